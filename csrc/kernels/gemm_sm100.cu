@@ -1,0 +1,112 @@
+// Host launcher for the tcgen05 bf16 GEMM (see gemm_sm100.cuh for the design).
+#include "gemm_sm100.h"
+
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
+
+#include "gemm_sm100.cuh"
+#include "tma_host.h"
+
+namespace hb {
+
+static std::atomic<int64_t> g_gemm_launches{0};
+int64_t gemm_launch_count() { return g_gemm_launches.load(); }
+
+namespace {
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int G, bool AMN, bool BMN, int ST, typename OutT>
+cudaError_t launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm_bf16_sm100_kernel<G, AMN, BMN, ST, OutT>;
+  constexpr int smem = gemm_detail::smem_bytes(G, ST);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles_m = (p.M + 128 * G - 1) / (128 * G);
+  const int tiles_n = (p.N + 255) / 256;
+  int clusters = num_sms() / G;
+  if (clusters > tiles_m * tiles_n) clusters = tiles_m * tiles_n;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * G);
+  cfg.blockDim = dim3(gemm_detail::kNumThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = G;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  g_gemm_launches.fetch_add(1);
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+}
+
+template <int G, int ST, typename OutT>
+cudaError_t dispatch_major(bool amn, bool bmn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                           cudaStream_t s) {
+  if (!amn && !bmn) return launch_cfg<G, false, false, ST, OutT>(ta, tb, p, s);
+  if (!amn && bmn) return launch_cfg<G, false, true, ST, OutT>(ta, tb, p, s);
+  if (amn && !bmn) return launch_cfg<G, true, false, ST, OutT>(ta, tb, p, s);
+  return launch_cfg<G, true, true, ST, OutT>(ta, tb, p, s);
+}
+
+}  // namespace
+
+cudaError_t gemm_bf16(const GemmCall& c, cudaStream_t stream) {
+  if (c.M <= 0 || c.N <= 0) return cudaSuccess;
+  if (c.K <= 0) return cudaErrorInvalidValue;
+  // TMA needs 16-byte aligned bases and row strides.
+  if ((reinterpret_cast<uintptr_t>(c.A) & 15) || (reinterpret_cast<uintptr_t>(c.B) & 15) || (c.lda & 7) || (c.ldb & 7))
+    return cudaErrorMisalignedAddress;
+  const int out_elem = c.out == GemmOut::BF16 ? 2 : 4;
+  if ((reinterpret_cast<uintptr_t>(c.C) & 15) || ((c.ldc * out_elem) & 15)) return cudaErrorMisalignedAddress;
+  if ((c.aux_in || c.aux_out) && (c.ld_aux & 7)) return cudaErrorMisalignedAddress;
+
+  int G = c.cta_group == 0 ? 2 : c.cta_group;
+  const int load_n = 256 / G;
+
+  CUtensorMap ta, tb;
+  bool ok;
+  if (!c.a_mn_major) ok = make_tmap_2d_bf16(&ta, c.A, (uint64_t)c.K, (uint64_t)c.M, (uint64_t)c.lda, 64, 128);
+  else ok = make_tmap_2d_bf16(&ta, c.A, (uint64_t)c.M, (uint64_t)c.K, (uint64_t)c.lda, 64, 64);
+  if (!ok) return cudaErrorInvalidValue;
+  if (!c.b_mn_major) ok = make_tmap_2d_bf16(&tb, c.B, (uint64_t)c.K, (uint64_t)c.N, (uint64_t)c.ldb, 64, load_n);
+  else ok = make_tmap_2d_bf16(&tb, c.B, (uint64_t)c.N, (uint64_t)c.K, (uint64_t)c.ldb, 64, 64);
+  if (!ok) return cudaErrorInvalidValue;
+
+  GemmParams p;
+  p.M = c.M; p.N = c.N; p.K = c.K;
+  p.C = c.C; p.ldc = c.ldc;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(c.bias);
+  p.aux_in = reinterpret_cast<const __nv_bfloat16*>(c.aux_in);
+  p.aux_out = reinterpret_cast<__nv_bfloat16*>(c.aux_out);
+  p.ld_aux = c.ld_aux;
+  p.act = c.act;
+  p.aux_mode = c.aux_in ? c.aux_mode : 0;
+  p.accumulate = c.accumulate ? 1 : 0;
+  p.alpha = c.alpha;
+
+  if (G == 2) {
+    if (c.out == GemmOut::BF16) return dispatch_major<2, 6, __nv_bfloat16>(c.a_mn_major, c.b_mn_major, ta, tb, p, stream);
+    return dispatch_major<2, 6, float>(c.a_mn_major, c.b_mn_major, ta, tb, p, stream);
+  } else {
+    if (c.out == GemmOut::BF16) return dispatch_major<1, 4, __nv_bfloat16>(c.a_mn_major, c.b_mn_major, ta, tb, p, stream);
+    return dispatch_major<1, 4, float>(c.a_mn_major, c.b_mn_major, ta, tb, p, stream);
+  }
+}
+
+}  // namespace hb

@@ -1,0 +1,421 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a.
+//
+//   C[M,N] = epilogue( A[M,K] * B[K,N] )        fp32 accumulation in TMEM
+//
+// Design (B200-first, not a cuBLAS wrapper):
+//   * one CTA per SM (or a CTA *pair* on one TPC when kCtaGroup == 2, issuing
+//     tcgen05.mma.cta_group::2 with a 256 x 256 x 16 instruction shape),
+//   * warp 0 = TMA producer, warp 1 = single-thread MMA issuer, warp 2 = TMEM
+//     allocator, warps 4..7 = epilogue (TMEM -> registers -> fused epilogue ->
+//     global),
+//   * kStages-deep smem ring (128B-swizzled tiles written by TMA, read by
+//     tcgen05.mma through shared-memory descriptors),
+//   * two 256-column TMEM accumulator stages so the epilogue of tile i overlaps
+//     the main loop of tile i+1,
+//   * both operands may be K-major ("row-major [rows, K]") or MN-major
+//     ("[K, rows]"), which covers forward (X * W^T), dgrad (dY * W) and wgrad
+//     (dY^T * X) of a linear layer without any transposing copies.
+//
+// Capability parity: replaces the cuBLAS call sites of the reference
+// (hetu/impl/kernel/MatMul.cu:29-77, Linear.cu:25-105, CUDABlas.cc:119-213).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+
+namespace hb {
+
+enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_GELU_TANH = 3, ACT_SILU = 4 };
+enum GemmAuxMode : int {
+  AUX_NONE = 0,
+  AUX_ADD = 1,        // out = acc + aux_in                       (residual add)
+  AUX_DGELU = 2,      // out = acc * gelu'(aux_in)                (fc2 dgrad -> d(pre-activation))
+  AUX_DRELU = 3,      // out = acc * (aux_in > 0)
+  AUX_DGELU_TANH = 4,
+  AUX_DSILU = 5,
+};
+
+struct GemmParams {
+  int M, N, K;
+  void* C;               // [M, ldc] bf16 or fp32
+  int64_t ldc;
+  const __nv_bfloat16* bias;    // [N] or nullptr
+  const __nv_bfloat16* aux_in;  // [M, ld_aux] or nullptr
+  __nv_bfloat16* aux_out;       // [M, ld_aux] (value before activation) or nullptr
+  int64_t ld_aux;
+  int act;
+  int aux_mode;
+  int accumulate;        // C += result (read-modify-write)
+  float alpha;           // scale applied to the accumulator
+};
+
+namespace gemm_detail {
+
+constexpr int BLOCK_M = 128;   // rows of A per CTA
+constexpr int BLOCK_N = 256;   // UMMA N (columns of the accumulator)
+constexpr int BLOCK_K = 64;    // 128 bytes of bf16 = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kEpiWarps = 8;     // 2 warps per TMEM lane quarter, each owning half the columns
+constexpr int kNumThreads = 128 + kEpiWarps * 32;
+constexpr int kAccumStages = 2;
+constexpr int kTmemCols = 512;
+
+__host__ __device__ constexpr int a_stage_bytes() { return BLOCK_M * BLOCK_K * 2; }
+__host__ __device__ constexpr int b_stage_bytes(int cta_group) { return (BLOCK_N / cta_group) * BLOCK_K * 2; }
+__host__ __device__ constexpr int smem_bytes(int cta_group, int stages) {
+  return stages * (a_stage_bytes() + b_stage_bytes(cta_group)) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+// erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): two MUFU ops + a short FMA chain,
+// ~6x cheaper than erff() in the epilogue where 128..256 threads cover a whole tile.
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float r = 1.0f - p * __expf(-ax * ax);
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float dgelu_erf(float x) {
+  const float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f));
+  const float pdf = 0.39894228040143267f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(u));
+}
+__device__ __forceinline__ float dgelu_tanh(float x) {
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  const float t = tanhf(u);
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * x * x);
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float dsilu(float x) {
+  const float s = 1.0f / (1.0f + __expf(-x));
+  return s * (1.0f + x * (1.0f - s));
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case ACT_GELU: return gelu_erf(v);
+    case ACT_RELU: return fmaxf(v, 0.0f);
+    case ACT_GELU_TANH: return gelu_tanh(v);
+    case ACT_SILU: return silu(v);
+    default: return v;
+  }
+}
+__device__ __forceinline__ float apply_aux(float v, float a, int mode) {
+  switch (mode) {
+    case AUX_ADD: return v + a;
+    case AUX_DGELU: return v * dgelu_erf(a);
+    case AUX_DRELU: return a > 0.0f ? v : 0.0f;
+    case AUX_DGELU_TANH: return v * dgelu_tanh(a);
+    case AUX_DSILU: return v * dsilu(a);
+    default: return v;
+  }
+}
+
+// Group-swizzled tile order: consecutive tile ids walk down a band of kGroupM
+// M-blocks before moving to the next N-block, so the ~74 clusters in flight
+// share a small set of A and B panels in L2.
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
+  constexpr int kGroupM = 8;
+  const int per_group = kGroupM * tiles_n;
+  const int g = tile / per_group;
+  const int first_m = g * kGroupM;
+  const int gm = min(tiles_m - first_m, kGroupM);
+  const int in_g = tile - g * per_group;
+  tm = first_m + in_g % gm;
+  tn = in_g / gm;
+}
+
+}  // namespace gemm_detail
+
+template <int kCtaGroup, bool kAMN, bool kBMN, int kStages, typename OutT>
+__global__ void __launch_bounds__(gemm_detail::kNumThreads, 1)
+gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                       const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  using namespace gemm_detail;
+  constexpr int A_STAGE = a_stage_bytes();
+  constexpr int B_STAGE = b_stage_bytes(kCtaGroup);
+  constexpr int LOAD_N = BLOCK_N / kCtaGroup;
+  constexpr int TILE_M = BLOCK_M * kCtaGroup;
+  constexpr uint32_t kTxBytes = (A_STAGE + B_STAGE) * kCtaGroup;
+  constexpr int kAtomBytes = BLOCK_K * 64 * 2;  // one 64(MN) x BLOCK_K MN-major box
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (A_STAGE + B_STAGE));
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tfull_bar = bars + 2 * kStages;
+  uint64_t* tempty_bar = bars + 2 * kStages + kAccumStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccumStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = (kCtaGroup == 2) ? ptx::cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+
+  const int tiles_m = (p.M + TILE_M - 1) / TILE_M;
+  const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int cluster_id = blockIdx.x / kCtaGroup;
+  const int num_clusters = gridDim.x / kCtaGroup;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full_bar[i], kCtaGroup);  // one producer arrive per CTA (+ tx bytes)
+      ptx::mbar_init(&empty_bar[i], 1);         // one tcgen05.commit
+    }
+    for (int i = 0; i < kAccumStages; ++i) {
+      ptx::mbar_init(&tfull_bar[i], 1);                 // one tcgen05.commit
+      ptx::mbar_init(&tempty_bar[i], kEpiWarps * kCtaGroup);  // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<kCtaGroup>(tmem_ptr_smem, kTmemCols);
+    ptx::tmem_relinquish<kCtaGroup>();
+  }
+  ptx::tc_fence_before();
+  if constexpr (kCtaGroup == 2) ptx::cluster_sync(); else __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ========================= TMA producer =========================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        int tm, tn; tile_coords(tile, tiles_m, tiles_n, tm, tn);
+        const int m0 = tm * TILE_M + int(rank) * BLOCK_M;
+        const int n0 = tn * BLOCK_N + int(rank) * LOAD_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+          if (kCtaGroup == 1 || leader) ptx::mbar_arrive_expect_tx(&full_bar[s], kTxBytes);
+          uint8_t* sa = smem_a + s * A_STAGE;
+          uint8_t* sb = smem_b + s * B_STAGE;
+          const int k0 = kb * BLOCK_K;
+          if constexpr (kCtaGroup == 1) {
+            if constexpr (!kAMN) ptx::tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m0);
+            else
+              for (int i = 0; i < BLOCK_M / 64; ++i) ptx::tma_load_2d(sa + i * kAtomBytes, &tmap_a, &full_bar[s], m0 + i * 64, k0);
+            if constexpr (!kBMN) ptx::tma_load_2d(sb, &tmap_b, &full_bar[s], k0, n0);
+            else
+              for (int i = 0; i < LOAD_N / 64; ++i) ptx::tma_load_2d(sb + i * kAtomBytes, &tmap_b, &full_bar[s], n0 + i * 64, k0);
+          } else {
+            if constexpr (!kAMN) ptx::tma_load_2d_2sm(sa, &tmap_a, &full_bar[s], k0, m0);
+            else
+              for (int i = 0; i < BLOCK_M / 64; ++i) ptx::tma_load_2d_2sm(sa + i * kAtomBytes, &tmap_a, &full_bar[s], m0 + i * 64, k0);
+            if constexpr (!kBMN) ptx::tma_load_2d_2sm(sb, &tmap_b, &full_bar[s], k0, n0);
+            else
+              for (int i = 0; i < LOAD_N / 64; ++i) ptx::tma_load_2d_2sm(sb + i * kAtomBytes, &tmap_b, &full_bar[s], n0 + i * 64, k0);
+            if (!leader) ptx::mbar_arrive_cluster(&full_bar[s], 0);
+          }
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ========================= MMA issuer (leader CTA, one thread) =========================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc(TILE_M, BLOCK_N, 1, 1, kAMN, kBMN);
+      const uint64_t a_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a), kAMN ? kAtomBytes : 0, 1024);
+      const uint64_t b_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b), kBMN ? kAtomBytes : 0, 1024);
+      // descriptor-address increments (units of 16 B) per UMMA_K step
+      constexpr uint32_t a_kstep = kAMN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      constexpr uint32_t b_kstep = kBMN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      int s = 0; uint32_t ph = 0;
+      int as = 0; uint32_t aph = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        ptx::mbar_wait(&tempty_bar[as], aph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after();
+          const uint64_t a_desc = a_desc0 + uint64_t(s * (A_STAGE >> 4));
+          const uint64_t b_desc = b_desc0 + uint64_t(s * (B_STAGE >> 4));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            ptx::mma_f16_ss<kCtaGroup>(tmem_d, a_desc + uint64_t(k * a_kstep), b_desc + uint64_t(k * b_kstep), idesc,
+                                       (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          ptx::mma_commit<kCtaGroup>(&empty_bar[s]);
+          if (kb == num_kb - 1) ptx::mma_commit<kCtaGroup>(&tfull_bar[as]);
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+        if (++as == kAccumStages) { as = 0; aph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ========================= epilogue =========================
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int chalf = (warp - 4) >> 2;  // which half of the accumulator columns this warp drains
+    constexpr int kChunksPerWarp = BLOCK_N / 32 / (kEpiWarps / 4);
+    int as = 0; uint32_t aph = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int tm, tn; tile_coords(tile, tiles_m, tiles_n, tm, tn);
+      const int row = tm * TILE_M + int(rank) * BLOCK_M + q * 32 + lane;
+      const int n_base = tn * BLOCK_N;
+      ptx::mbar_wait(&tfull_bar[as], aph);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N;
+      const bool row_ok = row < p.M;
+      OutT* crow = reinterpret_cast<OutT*>(p.C) + int64_t(row) * p.ldc;
+#pragma unroll 1
+      for (int cc = 0; cc < kChunksPerWarp; ++cc) {
+        const int c = chalf * kChunksPerWarp + cc;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+        ptx::tmem_ld_wait();
+        const int col0 = n_base + c * 32;
+        if (col0 >= p.N) continue;  // warp-uniform
+        const bool full_chunk = (col0 + 32 <= p.N);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.alpha != 1.0f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+        }
+        if (p.bias != nullptr) {
+          if (full_chunk) {
+            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint4 b = __ldg(bp + j4);
+              const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = __bfloat1622float2(b2[t]);
+                v[j4 * 8 + t * 2] += f.x; v[j4 * 8 + t * 2 + 1] += f.y;
+              }
+            }
+          } else {
+            for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __bfloat162float(p.bias[col0 + j]);
+          }
+        }
+        if (row_ok) {
+          if (p.aux_out != nullptr) {
+            __nv_bfloat16* ao = p.aux_out + int64_t(row) * p.ld_aux + col0;
+            if (full_chunk) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                uint4 o; __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) o2[t] = __floats2bfloat162_rn(v[j4 * 8 + t * 2], v[j4 * 8 + t * 2 + 1]);
+                reinterpret_cast<uint4*>(ao)[j4] = o;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j) if (col0 + j < p.N) ao[j] = __float2bfloat16(v[j]);
+            }
+          }
+          if (p.act != ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+          }
+          if (p.aux_mode != AUX_NONE) {
+            const __nv_bfloat16* ai = p.aux_in + int64_t(row) * p.ld_aux + col0;
+            if (full_chunk) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const uint4 a = reinterpret_cast<const uint4*>(ai)[j4];
+                const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 f = __bfloat1622float2(a2[t]);
+                  v[j4 * 8 + t * 2] = apply_aux(v[j4 * 8 + t * 2], f.x, p.aux_mode);
+                  v[j4 * 8 + t * 2 + 1] = apply_aux(v[j4 * 8 + t * 2 + 1], f.y, p.aux_mode);
+                }
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) v[j] = apply_aux(v[j], __bfloat162float(ai[j]), p.aux_mode);
+            }
+          }
+          if constexpr (sizeof(OutT) == 2) {
+            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(crow) + col0;
+            if (full_chunk) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                if (p.accumulate) {
+                  const uint4 old = reinterpret_cast<const uint4*>(cp)[j4];
+                  const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    const float2 f = __bfloat1622float2(o2[t]);
+                    v[j4 * 8 + t * 2] += f.x; v[j4 * 8 + t * 2 + 1] += f.y;
+                  }
+                }
+                uint4 o; __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) o2[t] = __floats2bfloat162_rn(v[j4 * 8 + t * 2], v[j4 * 8 + t * 2 + 1]);
+                reinterpret_cast<uint4*>(cp)[j4] = o;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) {
+                  float x = v[j];
+                  if (p.accumulate) x += __bfloat162float(cp[j]);
+                  cp[j] = __float2bfloat16(x);
+                }
+            }
+          } else {
+            float* cp = reinterpret_cast<float*>(crow) + col0;
+            if (full_chunk) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                float4 o = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                if (p.accumulate) {
+                  const float4 old = reinterpret_cast<const float4*>(cp)[j4];
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                reinterpret_cast<float4*>(cp)[j4] = o;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) cp[j] = p.accumulate ? cp[j] + v[j] : v[j];
+            }
+          }
+        }
+      }
+      // release this accumulator stage back to the MMA issuer (leader CTA's barrier)
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kCtaGroup == 1) ptx::mbar_arrive(&tempty_bar[as]);
+        else ptx::mbar_arrive_cluster(&tempty_bar[as], 0);
+      }
+      if (++as == kAccumStages) { as = 0; aph ^= 1; }
+    }
+  }
+
+  // ========================= teardown =========================
+  ptx::tc_fence_before();
+  if constexpr (kCtaGroup == 2) ptx::cluster_sync(); else __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kCtaGroup>(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace hb

@@ -1,0 +1,38 @@
+// Host API of the hand-written sm_100a GEMM family (no torch dependency).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hb {
+
+enum class GemmOut : int { BF16 = 0, FP32 = 1 };
+
+// C[M,N] = epi(alpha * A[M,K] * B[K,N]).
+//   a_mn_major == false: A stored [M, lda] (K contiguous);  true: A stored [K, lda] (M contiguous)
+//   b_mn_major == false: B stored [N, ldb] (K contiguous);  true: B stored [K, ldb] (N contiguous)
+struct GemmCall {
+  const void* A = nullptr;
+  const void* B = nullptr;
+  void* C = nullptr;
+  int M = 0, N = 0, K = 0;
+  int64_t lda = 0, ldb = 0, ldc = 0;
+  bool a_mn_major = false, b_mn_major = false;
+  GemmOut out = GemmOut::BF16;
+  const void* bias = nullptr;     // bf16 [N]
+  const void* aux_in = nullptr;   // bf16 [M, ld_aux]
+  void* aux_out = nullptr;        // bf16 [M, ld_aux]
+  int64_t ld_aux = 0;
+  int act = 0;        // GemmAct
+  int aux_mode = 0;   // GemmAuxMode
+  bool accumulate = false;
+  float alpha = 1.0f;
+  int cta_group = 0;  // 0 = auto (2), 1 or 2 to force
+};
+
+// Returns cudaSuccess or an error; never silently falls back to a library.
+cudaError_t gemm_bf16(const GemmCall& call, cudaStream_t stream);
+
+// Number of kernel launches issued by this module since process start.
+int64_t gemm_launch_count();
+
+}  // namespace hb

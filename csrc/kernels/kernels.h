@@ -1,0 +1,125 @@
+// C++ host API for the hand-written sm_100a kernels (everything except the GEMM /
+// attention families, which have their own headers).  No torch dependency: raw
+// pointers + sizes + stream.  bf16 is the activation dtype; statistics, losses,
+// optimizer state and gradient accumulators are fp32.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hb {
+
+int64_t kernel_launch_count();   // total launches issued through this API
+
+// ---------------------------------------------------------------- norms
+// y = (x - mean) * rstd * gamma + beta      (ref: hetu/impl/kernel/FusedLayerNorm.cu:456-1004)
+cudaError_t layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
+                          int64_t rows, int cols, float eps, cudaStream_t s);
+// dgamma/dbeta are fp32 [cols]; accumulate=true adds into them. workspace: fp32 [2 * ln_bwd_parts() * cols]
+int ln_bwd_parts();
+cudaError_t layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                          void* dx, float* dgamma, float* dbeta, float* workspace, int64_t rows, int cols,
+                          bool accumulate, cudaStream_t s);
+// y = x * rstd * gamma                       (ref: hetu/impl/kernel/FusedLayerNorm.cu:1004, RMSNorm.cu)
+cudaError_t rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, int64_t rows, int cols, float eps,
+                        cudaStream_t s);
+cudaError_t rmsnorm_bwd(const void* dy, const void* x, const void* gamma, const float* rstd, void* dx, float* dgamma,
+                        float* workspace, int64_t rows, int cols, bool accumulate, cudaStream_t s);
+
+// ---------------------------------------------------------------- elementwise (bf16 in/out)
+enum UnaryOp : int { U_GELU = 0, U_RELU, U_SILU, U_SIGMOID, U_TANH, U_GELU_TANH, U_EXP, U_NEG, U_SQRT, U_RSQRT, U_ABS };
+cudaError_t unary_fwd(int op, const void* x, void* y, int64_t n, cudaStream_t s);
+// dx = dy * f'(x)
+cudaError_t unary_bwd(int op, const void* dy, const void* x, void* dx, int64_t n, cudaStream_t s);
+// y[r, :] = silu(x[r, :d]) * x[r, d:2d]        (ref: hetu/impl/kernel/SwiGLU.cu:79,116)
+cudaError_t swiglu_fwd(const void* x, void* y, int64_t rows, int d, cudaStream_t s);
+cudaError_t swiglu_bwd(const void* dy, const void* x, void* dx, int64_t rows, int d, cudaStream_t s);
+// out = a + b (bf16), out may alias a
+cudaError_t add_bf16(const void* a, const void* b, void* out, int64_t n, cudaStream_t s);
+// dst(fp32) (+)= src(bf16)
+cudaError_t accum_bf16_into_fp32(const void* src, float* dst, int64_t n, bool accumulate, cudaStream_t s);
+cudaError_t cast_fp32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t s);
+cudaError_t cast_bf16_to_fp32(const void* src, float* dst, int64_t n, cudaStream_t s);
+// Philox dropout: y = x * mask / (1-p); the mask is recomputed in bwd from (seed, offset)
+cudaError_t dropout_fwd(const void* x, void* y, int64_t n, float p, uint64_t seed, uint64_t offset, cudaStream_t s);
+// out[c] (+)= sum_r x[r, c]   (bias gradient)  fp32 out
+cudaError_t colsum_bf16(const void* x, float* out, int64_t rows, int cols, bool accumulate, cudaStream_t s);
+
+// ---------------------------------------------------------------- rotary (ref: hetu/impl/kernel/rotary.cu:249-400)
+// x: [tokens, heads, head_dim] bf16, half-split convention; pos[token] gives the position id.
+// inverse=true applies the transposed rotation (backward).
+cudaError_t rotary_apply(const void* x, void* y, const int32_t* pos, int64_t tokens, int heads, int head_dim,
+                         int rot_dim, float base, bool inverse, int64_t token_stride, cudaStream_t s);
+
+// ---------------------------------------------------------------- embedding (ref: hetu/impl/kernel/EmbeddingLookup.cu:91,140)
+// y[t, :] = wte[ids[t], :] (+ wpe[pos[t], :])
+cudaError_t embedding_fwd(const int64_t* ids, const int32_t* pos, const void* wte, const void* wpe, void* y,
+                          int64_t tokens, int hidden, int64_t vocab, cudaStream_t s);
+// dwte[ids[t], :] += dy[t, :]   (fp32 accumulators), dwpe likewise when non-null
+cudaError_t embedding_bwd(const int64_t* ids, const int32_t* pos, const void* dy, float* dwte, float* dwpe,
+                          int64_t tokens, int hidden, int64_t vocab, cudaStream_t s);
+
+// ---------------------------------------------------------------- softmax cross-entropy
+// Fused fwd+bwd over bf16 logits [rows, ld] (only the first `cols` are valid):
+//   loss[r] = logsumexp(logits[r]) - logits[r, label]  (0 when label == ignore_index)
+//   logits[r, :] <- (softmax - onehot) * grad_scale    (in place, when write_grad)
+// (ref: hetu/impl/kernel/SoftmaxCrossEntropySparse.cu, VocabParallelCrossEntropyLoss.cu:57,114)
+cudaError_t softmax_ce_fwd_bwd(void* logits, const int64_t* labels, float* loss, float* lse, int64_t rows, int cols,
+                               int64_t ld, int64_t ignore_index, float grad_scale, bool write_grad, cudaStream_t s);
+// Vocab-parallel pieces: local max / local sum-exp & target logit, with a collective between them.
+cudaError_t vp_ce_local_max(const void* logits, float* row_max, int64_t rows, int cols, int64_t ld, cudaStream_t s);
+cudaError_t vp_ce_local_sum(const void* logits, const int64_t* labels, const float* row_max, float* sum_exp,
+                            float* target_logit, int64_t rows, int cols, int64_t ld, int64_t vocab_start,
+                            cudaStream_t s);
+cudaError_t vp_ce_finish(void* logits, const int64_t* labels, const float* row_max, const float* sum_exp,
+                         const float* target_logit, float* loss, int64_t rows, int cols, int64_t ld,
+                         int64_t vocab_start, int64_t ignore_index, float grad_scale, bool write_grad, cudaStream_t s);
+
+// ---------------------------------------------------------------- optimizers (ref: hetu/impl/kernel/Optimizers.cu:13-188)
+// Flat fused Adam(W) over a contiguous shard: fp32 master params / m / v, fp32 or bf16 grads, writes the
+// bf16 compute copy in the same pass.  step/bias-correction are computed on device from *step_ptr (int64)
+// so the launch is CUDA-graph capturable; grad_scale_ptr (optional) multiplies grads (loss-scale / 1/N).
+struct AdamArgs {
+  float* master = nullptr;     // fp32 [n]
+  float* m = nullptr;          // fp32 [n]
+  float* v = nullptr;          // fp32 [n]
+  const void* grad = nullptr;  // fp32 or bf16 [n]
+  bool grad_is_bf16 = false;
+  void* param_bf16 = nullptr;  // optional bf16 [n] compute copy
+  int64_t n = 0;
+  float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, weight_decay = 0.0f;
+  const int64_t* step_ptr = nullptr;     // device pointer; value already incremented for this step
+  const float* grad_scale_ptr = nullptr; // device pointer or null
+  const float* lr_ptr = nullptr;         // device pointer overriding lr (scheduler) or null
+  bool zero_grad = false;                // clear the grad buffer in the same pass
+};
+cudaError_t adam_update(const AdamArgs& a, cudaStream_t s);
+cudaError_t sgd_update(float* master, float* momentum_buf, const void* grad, bool grad_is_bf16, void* param_bf16,
+                       int64_t n, float lr, float momentum, bool nesterov, float weight_decay, cudaStream_t s);
+cudaError_t increment_step(int64_t* step_ptr, cudaStream_t s);
+// found_inf[0] = 1 if any non-finite value in x (fp32)
+cudaError_t check_finite(const float* x, int64_t n, float* found_inf, cudaStream_t s);
+// sum of squares into out[0] (fp32) for grad-norm clipping
+cudaError_t sumsq_fp32(const float* x, int64_t n, float* out, bool accumulate, cudaStream_t s);
+
+// ---------------------------------------------------------------- MoE (ref: hetu/v1/src/ops/{TopKIdx,LayoutTransform,...}.cu)
+// probs: softmax(logits) fp32 [tokens, experts]; top-k indices/values.
+cudaError_t moe_gate_topk(const void* logits_bf16, float* probs, int32_t* topk_idx, float* topk_val, int64_t tokens,
+                          int experts, int k, cudaStream_t s);
+// capacity-based slot assignment: location[t,k] = position of token t inside expert e's buffer (or -1 when dropped)
+cudaError_t moe_assign_slots(const int32_t* topk_idx, int32_t* location, int32_t* expert_count, int64_t tokens,
+                             int experts, int k, int capacity, cudaStream_t s);
+// dispatched[e, slot, :] = (scale ? scale[t,k] : 1) * x[t, :]; unassigned slots are zero-filled.
+// (with scale = gates this is also the backward of moe_combine w.r.t. expert_out)
+cudaError_t moe_dispatch(const void* x, const int32_t* topk_idx, const int32_t* location, const float* scale,
+                         void* dispatched, int64_t tokens, int hidden, int experts, int k, int capacity,
+                         cudaStream_t s);
+// y[t, :] = sum_k (gate ? gate[t,k] : 1) * expert_out[e_k, slot_k, :]
+// (with gate = null this is also the backward of moe_dispatch w.r.t. x)
+cudaError_t moe_combine(const void* expert_out, const int32_t* topk_idx, const int32_t* location, const float* gate,
+                        void* y, int64_t tokens, int hidden, int experts, int k, int capacity, cudaStream_t s);
+// backward of combine wrt gates: dgate[t,k] = <dy[t], expert_out[e_k, slot_k]>
+cudaError_t moe_combine_bwd_gate(const void* dy, const void* expert_out, const int32_t* topk_idx,
+                                 const int32_t* location, float* dgate, int64_t tokens, int hidden, int experts, int k,
+                                 int capacity, cudaStream_t s);
+
+}  // namespace hb

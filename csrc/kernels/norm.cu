@@ -1,0 +1,317 @@
+// LayerNorm / RMSNorm forward + backward for bf16 activations (fp32 statistics).
+//
+// Forward: one 128-thread CTA per row, the row lives in registers between the
+// statistics pass and the normalise pass (one HBM read, one write).
+// Backward: persistent CTAs stride over rows, keep per-column dgamma/dbeta
+// partials in registers, and a tiny second kernel folds the per-CTA partials,
+// so dx needs exactly one read of (x, dy) and one write.
+//
+// Capability parity: hetu/impl/kernel/FusedLayerNorm.cu:456-1004 (cuApplyLayerNorm,
+// cuApplyRMSNorm, cuComputePartGradGammaBeta, cuComputeGradInput).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace hb {
+
+std::atomic<int64_t> g_kernel_launches{0};
+int64_t kernel_launch_count() { return g_kernel_launches.load(); }
+
+namespace {
+
+constexpr int kFwdThreads = 128;
+constexpr int kFwdMaxV = 8;   // up to 8192 columns
+constexpr int kBwdThreads = 256;
+constexpr int kBwdMaxV = 4;   // up to 8192 columns
+
+template <bool kRMS>
+__global__ void __launch_bounds__(kFwdThreads) norm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ gamma,
+                                                               const void* __restrict__ beta, void* __restrict__ y,
+                                                               float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                               int cols, float eps) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const int nvec = cols >> 3;
+  const int tid = threadIdx.x;
+  const char* xr = reinterpret_cast<const char*>(x) + row * int64_t(cols) * 2;
+  char* yr = reinterpret_cast<char*>(y) + row * int64_t(cols) * 2;
+  float xv[kFwdMaxV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kFwdMaxV; ++i) {
+    const int v = tid + i * kFwdThreads;
+    if (v < nvec) {
+      unpack8(ld8_stream(xr, v), xv[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += kRMS ? xv[i][j] * xv[i][j] : xv[i][j];
+    }
+  }
+  float mean = 0.f, rstd;
+  if constexpr (kRMS) {
+    const float ms = block_sum(sum, red) / cols;
+    rstd = rsqrtf(ms + eps);
+  } else {
+    mean = block_sum(sum, red) / cols;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < kFwdMaxV; ++i) {
+      const int v = tid + i * kFwdThreads;
+      if (v < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = xv[i][j] - mean; var += d * d; }
+      }
+    }
+    var = block_sum(var, red) / cols;
+    rstd = rsqrtf(var + eps);
+  }
+  if (tid == 0) {
+    if (mean_out) mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < kFwdMaxV; ++i) {
+    const int v = tid + i * kFwdThreads;
+    if (v < nvec) {
+      float g[8], b[8], o[8];
+      unpack8(ld8(gamma, v), g);
+      if (!kRMS && beta != nullptr) unpack8(ld8(beta, v), b);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (xv[i][j] - mean) * rstd * g[j] + b[j];
+      st8(yr, v, pack8(o));
+    }
+  }
+}
+
+// Generic fallback (any column count): block per row, scalar loops.
+template <bool kRMS>
+__global__ void norm_fwd_generic_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                                        const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                        float* mean_out, float* rstd_out, int cols, float eps) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const __nv_bfloat16* xr = x + row * cols;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float v = __bfloat162float(xr[c]);
+    s += kRMS ? v * v : v;
+  }
+  float mean = 0.f, rstd;
+  if constexpr (kRMS) {
+    rstd = rsqrtf(block_sum(s, red) / cols + eps);
+  } else {
+    mean = block_sum(s, red) / cols;
+    float var = 0.f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+      const float d = __bfloat162float(xr[c]) - mean;
+      var += d * d;
+    }
+    rstd = rsqrtf(block_sum(var, red) / cols + eps);
+  }
+  if (threadIdx.x == 0) {
+    if (mean_out) mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float v = (__bfloat162float(xr[c]) - mean) * rstd * __bfloat162float(gamma[c]) +
+                    ((!kRMS && beta) ? __bfloat162float(beta[c]) : 0.f);
+    y[row * cols + c] = __float2bfloat16(v);
+  }
+}
+
+__device__ __forceinline__ float2 block_sum2(float2 v, float2* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v.x = warp_sum(v.x);
+  v.y = warp_sum(v.y);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float2 r = (lane < nw) ? red[lane] : make_float2(0.f, 0.f);
+  r.x = warp_sum(r.x);
+  r.y = warp_sum(r.y);
+  return r;
+}
+
+template <bool kRMS>
+__global__ void __launch_bounds__(kBwdThreads) norm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x,
+                                                               const void* __restrict__ gamma, const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd, void* __restrict__ dx,
+                                                               float* __restrict__ part_dg, float* __restrict__ part_db,
+                                                               int64_t rows, int cols) {
+  __shared__ float2 red[32];
+  const int nvec = cols >> 3;
+  const int tid = threadIdx.x;
+  float g[kBwdMaxV][8], dg[kBwdMaxV][8], db[kBwdMaxV][8];
+#pragma unroll
+  for (int i = 0; i < kBwdMaxV; ++i) {
+    const int v = tid + i * kBwdThreads;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; g[i][j] = 0.f; }
+    if (v < nvec) unpack8(ld8(gamma, v), g[i]);
+  }
+  const float inv_cols = 1.0f / cols;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const char* xr = reinterpret_cast<const char*>(x) + row * int64_t(cols) * 2;
+    const char* dyr = reinterpret_cast<const char*>(dy) + row * int64_t(cols) * 2;
+    char* dxr = reinterpret_cast<char*>(dx) + row * int64_t(cols) * 2;
+    const float mu = kRMS ? 0.f : mean[row];
+    const float rs = rstd[row];
+    float xh[kBwdMaxV][8], dyv[kBwdMaxV][8];
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kBwdMaxV; ++i) {
+      const int v = tid + i * kBwdThreads;
+      if (v < nvec) {
+        unpack8(ld8_stream(xr, v), xh[i]);
+        unpack8(ld8_stream(dyr, v), dyv[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (xh[i][j] - mu) * rs;
+          const float dyg = dyv[i][j] * g[i][j];
+          s.x += dyg;
+          s.y += dyg * xh[i][j];
+          dg[i][j] += dyv[i][j] * xh[i][j];
+          db[i][j] += dyv[i][j];
+        }
+      }
+    }
+    s = block_sum2(s, red);
+    const float m1 = kRMS ? 0.f : s.x * inv_cols;
+    const float m2 = s.y * inv_cols;
+#pragma unroll
+    for (int i = 0; i < kBwdMaxV; ++i) {
+      const int v = tid + i * kBwdThreads;
+      if (v < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs * (dyv[i][j] * g[i][j] - m1 - xh[i][j] * m2);
+        st8(dxr, v, pack8(o));
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kBwdMaxV; ++i) {
+    const int v = tid + i * kBwdThreads;
+    if (v < nvec) {
+      float* pg = part_dg + int64_t(blockIdx.x) * cols + v * 8;
+      reinterpret_cast<float4*>(pg)[0] = make_float4(dg[i][0], dg[i][1], dg[i][2], dg[i][3]);
+      reinterpret_cast<float4*>(pg)[1] = make_float4(dg[i][4], dg[i][5], dg[i][6], dg[i][7]);
+      if (!kRMS) {
+        float* pb = part_db + int64_t(blockIdx.x) * cols + v * 8;
+        reinterpret_cast<float4*>(pb)[0] = make_float4(db[i][0], db[i][1], db[i][2], db[i][3]);
+        reinterpret_cast<float4*>(pb)[1] = make_float4(db[i][4], db[i][5], db[i][6], db[i][7]);
+      }
+    }
+  }
+}
+
+template <bool kRMS>
+__global__ void norm_bwd_generic_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                        const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean,
+                                        const float* __restrict__ rstd, __nv_bfloat16* __restrict__ dx,
+                                        float* part_dg, float* part_db, int64_t rows, int cols) {
+  // one block per "part"; columns strided over threads; rows strided over blocks
+  __shared__ float2 red[32];
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    part_dg[int64_t(blockIdx.x) * cols + c] = 0.f;
+    if (!kRMS) part_db[int64_t(blockIdx.x) * cols + c] = 0.f;
+  }
+  __syncthreads();
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float mu = kRMS ? 0.f : mean[row];
+    const float rs = rstd[row];
+    float2 s = make_float2(0.f, 0.f);
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+      const float xh = (__bfloat162float(x[row * cols + c]) - mu) * rs;
+      const float d = __bfloat162float(dy[row * cols + c]);
+      const float dyg = d * __bfloat162float(gamma[c]);
+      s.x += dyg;
+      s.y += dyg * xh;
+      part_dg[int64_t(blockIdx.x) * cols + c] += d * xh;
+      if (!kRMS) part_db[int64_t(blockIdx.x) * cols + c] += d;
+    }
+    s = block_sum2(s, red);
+    const float m1 = kRMS ? 0.f : s.x / cols, m2 = s.y / cols;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+      const float xh = (__bfloat162float(x[row * cols + c]) - mu) * rs;
+      const float dyg = __bfloat162float(dy[row * cols + c]) * __bfloat162float(gamma[c]);
+      dx[row * cols + c] = __float2bfloat16(rs * (dyg - m1 - xh * m2));
+    }
+  }
+}
+
+__global__ void fold_parts_kernel(const float* __restrict__ parts, float* __restrict__ out, int nparts, int cols,
+                                  int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += parts[int64_t(p) * cols + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+}  // namespace
+
+int ln_bwd_parts() { return sm_count() * 2; }
+
+template <bool kRMS>
+static cudaError_t norm_fwd_impl(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
+                                 int64_t rows, int cols, float eps, cudaStream_t s) {
+  if (rows == 0) return cudaSuccess;
+  if ((cols & 7) == 0 && cols <= kFwdMaxV * kFwdThreads * 8) {
+    norm_fwd_kernel<kRMS><<<(unsigned)rows, kFwdThreads, 0, s>>>(x, gamma, beta, y, mean, rstd, cols, eps);
+  } else {
+    norm_fwd_generic_kernel<kRMS><<<(unsigned)rows, 256, 0, s>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, (__nv_bfloat16*)y, mean, rstd,
+        cols, eps);
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <bool kRMS>
+static cudaError_t norm_bwd_impl(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                                 void* dx, float* dgamma, float* dbeta, float* ws, int64_t rows, int cols,
+                                 bool accumulate, cudaStream_t s) {
+  if (rows == 0) return cudaSuccess;
+  int parts = ln_bwd_parts();
+  if (parts > rows) parts = (int)rows;
+  float* part_dg = ws;
+  float* part_db = ws + int64_t(ln_bwd_parts()) * cols;
+  if ((cols & 7) == 0 && cols <= kBwdMaxV * kBwdThreads * 8) {
+    norm_bwd_kernel<kRMS><<<parts, kBwdThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, part_dg, part_db, rows, cols);
+  } else {
+    norm_bwd_generic_kernel<kRMS><<<parts, 256, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+                                                        (const __nv_bfloat16*)gamma, mean, rstd, (__nv_bfloat16*)dx,
+                                                        part_dg, part_db, rows, cols);
+  }
+  fold_parts_kernel<<<(cols + 255) / 256, 256, 0, s>>>(part_dg, dgamma, parts, cols, accumulate ? 1 : 0);
+  count_launch(2);
+  if (!kRMS && dbeta != nullptr) {
+    fold_parts_kernel<<<(cols + 255) / 256, 256, 0, s>>>(part_db, dbeta, parts, cols, accumulate ? 1 : 0);
+    count_launch();
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
+                          int64_t rows, int cols, float eps, cudaStream_t s) {
+  return norm_fwd_impl<false>(x, gamma, beta, y, mean, rstd, rows, cols, eps, s);
+}
+cudaError_t layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                          void* dx, float* dgamma, float* dbeta, float* workspace, int64_t rows, int cols,
+                          bool accumulate, cudaStream_t s) {
+  return norm_bwd_impl<false>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, workspace, rows, cols, accumulate, s);
+}
+cudaError_t rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, int64_t rows, int cols, float eps,
+                        cudaStream_t s) {
+  return norm_fwd_impl<true>(x, gamma, nullptr, y, nullptr, rstd, rows, cols, eps, s);
+}
+cudaError_t rmsnorm_bwd(const void* dy, const void* x, const void* gamma, const float* rstd, void* dx, float* dgamma,
+                        float* workspace, int64_t rows, int cols, bool accumulate, cudaStream_t s) {
+  return norm_bwd_impl<true>(dy, x, gamma, nullptr, rstd, dx, dgamma, nullptr, workspace, rows, cols, accumulate, s);
+}
+
+}  // namespace hb
