@@ -311,6 +311,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
               }
             }
           } else {
+#pragma unroll
             for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __bfloat162float(p.bias[col0 + j]);
           }
         }
@@ -326,10 +327,14 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 reinterpret_cast<uint4*>(ao)[j4] = o;
               }
             } else {
+#pragma unroll
               for (int j = 0; j < 32; ++j) if (col0 + j < p.N) ao[j] = __float2bfloat16(v[j]);
             }
           }
-          if (p.act != ACT_NONE) {
+          if (p.act == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (p.act != ACT_NONE) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
           }
@@ -348,6 +353,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 }
               }
             } else {
+#pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.N) v[j] = apply_aux(v[j], __bfloat162float(ai[j]), p.aux_mode);
             }
@@ -372,6 +378,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 reinterpret_cast<uint4*>(cp)[j4] = o;
               }
             } else {
+#pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.N) {
                   float x = v[j];
@@ -392,6 +399,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 reinterpret_cast<float4*>(cp)[j4] = o;
               }
             } else {
+#pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.N) cp[j] = p.accumulate ? cp[j] + v[j] : v[j];
             }
