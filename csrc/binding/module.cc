@@ -1,0 +1,523 @@
+// Python binding of the native core (module hetu_b200._C).
+// (capability parity: python/hetu/_binding/** -- device, DeviceGroup, dtype, IntSymbol, Tensor,
+//  DistributedStates(+Union), Graph, graph.run, comm-group init, plus the generic op entry point
+//  that the generated Python op wrappers call)
+#include <pybind11/functional.h>
+#include <pybind11/stl.h>
+#include <torch/extension.h>
+
+#include "../core/device.h"
+#include "../core/ds.h"
+#include "../core/symbol.h"
+#include "../graph/exec.h"
+#include "../graph/ir.h"
+#include "../graph/op_utils.h"
+#include "../kernels/attention_sm100.h"
+#include "../kernels/gemm_sm100.h"
+#include "../kernels/kernels.h"
+#include "../planner/dp_core.h"
+#include "../v1/embedding_cache.h"
+
+namespace py = pybind11;
+using namespace hb;
+
+namespace {
+
+AttrMap attrs_from_dict(const py::dict& d) {
+  AttrMap a;
+  for (auto item : d) {
+    const std::string k = py::cast<std::string>(item.first);
+    py::handle v = item.second;
+    if (v.is_none()) continue;
+    if (py::isinstance<py::bool_>(v)) a.set(k, py::cast<bool>(v));
+    else if (py::isinstance<py::int_>(v)) a.set(k, py::cast<int64_t>(v));
+    else if (py::isinstance<py::float_>(v)) a.set(k, py::cast<double>(v));
+    else if (py::isinstance<py::str>(v)) a.set(k, py::cast<std::string>(v));
+    else if (py::isinstance<py::sequence>(v)) {
+      py::sequence s = py::reinterpret_borrow<py::sequence>(v);
+      bool all_int = true;
+      for (auto e : s) if (!py::isinstance<py::int_>(e) || py::isinstance<py::bool_>(e)) all_int = false;
+      if (all_int) a.set(k, py::cast<std::vector<int64_t>>(v));
+      else a.set(k, py::cast<std::vector<double>>(v));
+    } else throw std::runtime_error("unsupported attribute type for key " + k);
+  }
+  return a;
+}
+py::dict attrs_to_dict(const AttrMap& a) {
+  py::dict d;
+  for (auto& kv : a.raw()) std::visit([&](auto&& v) { d[py::str(kv.first)] = py::cast(v); }, kv.second);
+  return d;
+}
+DeviceGroupHierarchy dgh_from_py(const py::object& o) {
+  DeviceGroupHierarchy h;
+  if (o.is_none()) return h;
+  for (auto u : py::reinterpret_borrow<py::sequence>(o)) {
+    if (py::isinstance<DeviceGroupUnion>(u)) { h.add(py::cast<DeviceGroupUnion>(u)); continue; }
+    if (py::isinstance<DeviceGroup>(u)) { h.add(DeviceGroupUnion({py::cast<DeviceGroup>(u)})); continue; }
+    DeviceGroupUnion un;
+    for (auto g : py::reinterpret_borrow<py::sequence>(u)) un.add(py::cast<DeviceGroup>(g));
+    h.add(un);
+  }
+  return h;
+}
+DistributedStatesHierarchy dsh_from_py(const py::object& o) {
+  DistributedStatesHierarchy h;
+  if (o.is_none()) return h;
+  for (auto u : py::reinterpret_borrow<py::sequence>(o)) {
+    if (py::isinstance<DistributedStatesUnion>(u)) h.add(py::cast<DistributedStatesUnion>(u));
+    else if (py::isinstance<DistributedStates>(u)) h.add(DistributedStatesUnion({py::cast<DistributedStates>(u)}));
+    else {
+      DistributedStatesUnion un;
+      for (auto d : py::reinterpret_borrow<py::sequence>(u)) un.add(py::cast<DistributedStates>(d));
+      h.add(un);
+    }
+  }
+  return h;
+}
+
+}  // namespace
+
+PYBIND11_MODULE(_C, m) {
+  m.doc() = "hetu_b200 native core";
+  py::register_exception<hb::Error>(m, "HetuError");
+
+  // ---------------------------------------------------------------- core
+  py::class_<Device>(m, "device")
+      .def(py::init<const std::string&>())
+      .def_property_readonly("index", &Device::index)
+      .def_property_readonly("hostname", &Device::hostname)
+      .def_property_readonly("multiplex", &Device::multiplex)
+      .def_property_readonly("is_cpu", &Device::is_cpu)
+      .def_property_readonly("is_cuda", &Device::is_cuda)
+      .def_property_readonly("local", &Device::local)
+      .def("__str__", &Device::str)
+      .def("__repr__", [](const Device& d) { return "device(" + d.str() + ")"; })
+      .def("__eq__", [](const Device& a, const Device& b) { return a == b; })
+      .def("__lt__", [](const Device& a, const Device& b) { return a < b; })
+      .def("__hash__", &Device::hash);
+
+  py::class_<DeviceGroup>(m, "DeviceGroup")
+      .def(py::init<>())
+      .def(py::init<std::vector<std::string>>())
+      .def(py::init<std::vector<Device>>())
+      .def_property_readonly("num_devices", &DeviceGroup::num_devices)
+      .def_property_readonly("empty", &DeviceGroup::empty)
+      .def("contains", &DeviceGroup::contains)
+      .def("get", &DeviceGroup::get)
+      .def("get_index", &DeviceGroup::get_index)
+      .def_property_readonly("devices", &DeviceGroup::devices)
+      .def("indices", [](const DeviceGroup& g) {
+        std::vector<int> v;
+        for (auto& d : g.devices()) v.push_back(d.index());
+        return v;
+      })
+      .def("__len__", &DeviceGroup::num_devices)
+      .def("__eq__", [](const DeviceGroup& a, const DeviceGroup& b) { return a == b; })
+      .def("__repr__", &DeviceGroup::str);
+
+  py::class_<DeviceGroupUnion>(m, "DeviceGroupUnion")
+      .def(py::init<std::vector<DeviceGroup>>())
+      .def("size", &DeviceGroupUnion::size)
+      .def("get", &DeviceGroupUnion::get)
+      .def("all", &DeviceGroupUnion::all)
+      .def("get_index", &DeviceGroupUnion::get_index)
+      .def("raw", &DeviceGroupUnion::raw);
+
+  py::class_<IntSymbol>(m, "IntSymbol")
+      .def(py::init<>())
+      .def(py::init<int64_t>())
+      .def_property("data", &IntSymbol::get_val, &IntSymbol::set_val)
+      .def("get_data", &IntSymbol::get_val)
+      .def("set_data", &IntSymbol::set_val)
+      .def("reset_data", &IntSymbol::reset)
+      .def("is_leaf", &IntSymbol::is_leaf)
+      .def("is_instantiated", &IntSymbol::is_instantiated)
+      .def("__add__", [](const IntSymbol& a, const IntSymbol& b) { return a + b; })
+      .def("__add__", [](const IntSymbol& a, int64_t b) { return a + IntSymbol(b); })
+      .def("__radd__", [](const IntSymbol& a, int64_t b) { return IntSymbol(b) + a; })
+      .def("__sub__", [](const IntSymbol& a, const IntSymbol& b) { return a - b; })
+      .def("__sub__", [](const IntSymbol& a, int64_t b) { return a - IntSymbol(b); })
+      .def("__rsub__", [](const IntSymbol& a, int64_t b) { return IntSymbol(b) - a; })
+      .def("__mul__", [](const IntSymbol& a, const IntSymbol& b) { return a * b; })
+      .def("__mul__", [](const IntSymbol& a, int64_t b) { return a * IntSymbol(b); })
+      .def("__rmul__", [](const IntSymbol& a, int64_t b) { return IntSymbol(b) * a; })
+      .def("__truediv__", [](const IntSymbol& a, const IntSymbol& b) { return a / b; })
+      .def("__truediv__", [](const IntSymbol& a, int64_t b) { return a / IntSymbol(b); })
+      .def("__floordiv__", [](const IntSymbol& a, const IntSymbol& b) { return a / b; })
+      .def("__floordiv__", [](const IntSymbol& a, int64_t b) { return a / IntSymbol(b); })
+      .def("__mod__", [](const IntSymbol& a, const IntSymbol& b) { return a % b; })
+      .def("__mod__", [](const IntSymbol& a, int64_t b) { return a % IntSymbol(b); })
+      .def("__repr__", [](const IntSymbol& s) {
+        return s.is_instantiated() ? "IntSymbol(" + std::to_string(s.get_val()) + ")" : std::string("IntSymbol(?)");
+      });
+
+  py::class_<DistributedStates>(m, "DistributedStates")
+      .def(py::init<>())
+      .def(py::init<int, std::map<int, int>, std::vector<int>, bool>(), py::arg("device_num"), py::arg("states"),
+           py::arg("order") = std::vector<int>{}, py::arg("zero") = false)
+      .def_property_readonly("device_num", &DistributedStates::device_num)
+      .def_property_readonly("states", [](const DistributedStates& d) { return d.states(); })
+      .def_property_readonly("order", &DistributedStates::order)
+      .def_property("zero", &DistributedStates::zero, &DistributedStates::set_zero)
+      .def_property_readonly("is_none", &DistributedStates::is_none)
+      .def_property_readonly("is_valid", &DistributedStates::is_valid)
+      .def("get_dim", &DistributedStates::get_dim)
+      .def("check_equal", &DistributedStates::check_equal)
+      .def("check_pure_duplicate", &DistributedStates::check_pure_duplicate)
+      .def("check_max_dim", &DistributedStates::check_max_dim)
+      .def("combine_states", [](const DistributedStates& d, const std::vector<int>& src, int dst) { return d.combine_states(src, dst); })
+      .def("combine_order", [](const DistributedStates& d, const std::vector<int>& src, int dst) { return d.combine_order(src, dst); })
+      .def("check_combine", &DistributedStates::check_combine)
+      .def("reduce_states", &DistributedStates::reduce_states)
+      .def("reduce_order", &DistributedStates::reduce_order)
+      .def("check_split", &DistributedStates::check_split)
+      .def("check_scatter", &DistributedStates::check_scatter)
+      .def("check_allreduce", &DistributedStates::check_allreduce)
+      .def("check_allgather", &DistributedStates::check_allgather)
+      .def("check_reducescatter", &DistributedStates::check_reducescatter)
+      .def("check_broadcast", &DistributedStates::check_broadcast)
+      .def("check_reduce", &DistributedStates::check_reduce)
+      .def("get_split_dim", &DistributedStates::get_split_dim)
+      .def("get_loop_sizes", &DistributedStates::get_loop_sizes)
+      .def("map_device_to_state_index", &DistributedStates::map_device_to_state_index)
+      .def("get_dup_group_index", &DistributedStates::get_dup_group_index)
+      .def("get_device_indices_by_dim", &DistributedStates::get_device_indices_by_dim)
+      .def("get_devices_by_dim", &DistributedStates::get_devices_by_dim)
+      .def("local_shape", &DistributedStates::local_shape)
+      .def("global_shape", &DistributedStates::global_shape)
+      .def("local_slice", [](const DistributedStates& d, const std::vector<int64_t>& g, int idx) {
+        std::vector<int64_t> b, s;
+        d.local_slice(g, idx, &b, &s);
+        return std::make_pair(b, s);
+      })
+      .def("__eq__", [](const DistributedStates& a, const DistributedStates& b) { return a.check_equal(b); })
+      .def("__repr__", &DistributedStates::str);
+
+  py::class_<DistributedStatesUnion>(m, "DistributedStatesUnion")
+      .def(py::init<>())
+      .def(py::init<std::vector<DistributedStates>, int, bool>(), py::arg("ds_list"), py::arg("hetero_dim") = kNullHeteroDim,
+           py::arg("contiguous") = true)
+      .def("size", &DistributedStatesUnion::size)
+      .def("get", &DistributedStatesUnion::get)
+      .def("get_local", &DistributedStatesUnion::get_local)
+      .def("is_hetero", &DistributedStatesUnion::is_hetero)
+      .def_property("hetero_dim", &DistributedStatesUnion::hetero_dim, &DistributedStatesUnion::set_hetero_dim)
+      .def_property_readonly("ds_list", &DistributedStatesUnion::raw)
+      .def("check_equal", &DistributedStatesUnion::check_equal)
+      .def("to_hetero", &DistributedStatesUnion::to_hetero)
+      .def("__repr__", &DistributedStatesUnion::str);
+
+  py::enum_<CommType>(m, "CommType")
+      .value("UNUSED", CommType::UNUSED).value("P2P", CommType::P2P).value("COMM_SPLIT", CommType::COMM_SPLIT)
+      .value("SCATTER", CommType::SCATTER).value("ALL_REDUCE", CommType::ALL_REDUCE).value("ALL_GATHER", CommType::ALL_GATHER)
+      .value("REDUCE_SCATTER", CommType::REDUCE_SCATTER).value("BROADCAST", CommType::BROADCAST).value("REDUCE", CommType::REDUCE)
+      .value("SPLIT_ALL_REDUCE", CommType::SPLIT_ALL_REDUCE).value("SPLIT_REDUCE_SCATTER", CommType::SPLIT_REDUCE_SCATTER)
+      .value("SPLIT_ALL_GATHER", CommType::SPLIT_ALL_GATHER).value("BATCHED_ISEND_IRECV", CommType::BATCHED_ISEND_IRECV)
+      .value("ALL_TO_ALL", CommType::ALL_TO_ALL);
+  m.def("classify_comm", &classify_comm);
+  m.def("classify_comm_union", &classify_comm_union);
+  m.def("plan_comm", [](const DistributedStates& s, const DistributedStates& d, const DeviceGroup& g, int idx) {
+    CommPlan p = plan_comm(s, d, g, idx);
+    return py::make_tuple(p.type, p.dim, p.group);
+  });
+  m.def("plan_resharding", [](const std::vector<int64_t>& gshape, const DistributedStates& s, const std::vector<int>& sr,
+                              const DistributedStates& d, const std::vector<int>& dr, const std::string& algo, int per_node) {
+    SwitchAlgorithm a = SwitchAlgorithm::NEW_GREEDY;
+    if (algo == "FCFS") a = SwitchAlgorithm::FCFS;
+    else if (algo == "ROUND_ROBIN") a = SwitchAlgorithm::ROUND_ROBIN;
+    else if (algo == "MULTI_NODE_ROUND_ROBIN") a = SwitchAlgorithm::MULTI_NODE_ROUND_ROBIN;
+    else if (algo == "GREEDY") a = SwitchAlgorithm::GREEDY;
+    std::vector<int64_t> load;
+    auto plan = plan_resharding(gshape, s, sr, d, dr, a, &load, per_node);
+    py::list items;
+    for (auto& t : plan) items.append(py::make_tuple(t.src_device, t.dst_device, t.global.begin, t.global.size));
+    return py::make_tuple(items, load);
+  }, py::arg("global_shape"), py::arg("src_ds"), py::arg("src_ranks"), py::arg("dst_ds"), py::arg("dst_ranks"),
+     py::arg("algorithm") = "NEW_GREEDY", py::arg("devices_per_node") = 8);
+
+  // ---------------------------------------------------------------- graph
+  py::class_<TensorDef, Tensor>(m, "Tensor")
+      .def_readonly("id", &TensorDef::id)
+      .def_readwrite("name", &TensorDef::name)
+      .def_property_readonly("shape", [](const TensorDef& t) { return t.shape; })
+      .def_property_readonly("dtype", [](const TensorDef& t) { return std::string(dtype_name(t.dtype)); })
+      .def_readwrite("requires_grad", &TensorDef::requires_grad)
+      .def_readonly("is_grad", &TensorDef::is_grad)
+      .def_property_readonly("ndim", &TensorDef::ndim)
+      .def_property_readonly("global_shape", [](const TensorDef& t) { return t.global_shape(t.graph ? t.graph->cur_strategy() : 0); })
+      .def_property_readonly("symbolic_shape", [](const TensorDef& t) { return t.symbolic_shape; })
+      .def("set_symbolic_shape", [](TensorDef& t, const SyShape& s) { t.symbolic_shape = s; })
+      .def_property_readonly("ds_hierarchy", [](const TensorDef& t) { return t.ds_hierarchy.raw(); })
+      .def_property_readonly("distributed_states", [](const TensorDef& t) -> py::object {
+        const size_t s = t.graph ? t.graph->cur_strategy() : 0;
+        if (!t.has_ds(s)) return py::none();
+        return py::cast(t.ds(s));
+      })
+      .def("get_ds", [](const TensorDef& t, size_t s) -> py::object { return t.has_ds(s) ? py::cast(t.ds(s)) : py::none(); })
+      .def("get_ds_union", [](const TensorDef& t, size_t s) { return t.ds_hierarchy.get(s); })
+      .def_property_readonly("producer_type", [](const TensorDef& t) { return t.producer ? t.producer->type : std::string(); })
+      .def_property_readonly("producer_id", [](const TensorDef& t) { return t.producer ? t.producer->id : (OpId)-1; })
+      .def_property_readonly("device_group", [](const TensorDef& t) {
+        return t.producer ? t.producer->placement(t.graph ? t.graph->cur_strategy() : 0) : DeviceGroup();
+      })
+      .def_property_readonly("grad", [](const TensorDef& t) { return t.grad; })
+      .def_property_readonly("graph_id", [](const TensorDef& t) { return (uintptr_t)t.graph; })
+      .def("eager_data", [](const TensorDef& t) { return t.eager_data; })
+      .def("set_eager_data", [](TensorDef& t, const at::Tensor& v) { t.eager_data = v; t.shape = v.sizes().vec(); })
+      .def("__hash__", [](const TensorDef& t) { return (size_t)t.id ^ ((size_t)(uintptr_t)t.graph << 20); })
+      .def("__eq__", [](const Tensor& a, const py::object& b) {
+        if (!py::isinstance<TensorDef>(b)) return false;
+        return a.get() == py::cast<Tensor>(b).get();
+      })
+      .def("__repr__", [](const TensorDef& t) {
+        std::ostringstream os;
+        os << "Tensor(" << t.name << ", shape=" << t.shape << ", dtype=" << dtype_name(t.dtype) << ")";
+        return os.str();
+      });
+
+  py::enum_<GraphKind>(m, "GraphKind")
+      .value("EAGER", GraphKind::EAGER).value("DEFINE_BY_RUN", GraphKind::DEFINE_BY_RUN)
+      .value("DEFINE_AND_RUN", GraphKind::DEFINE_AND_RUN).value("EXECUTABLE", GraphKind::EXECUTABLE);
+
+  py::class_<Graph, std::shared_ptr<Graph>>(m, "Graph")
+      .def(py::init([](GraphKind k, const std::string& name, int ns) { return Graph::make(k, name, ns); }))
+      .def_static("default_eager", &Graph::default_eager)
+      .def_property_readonly("kind", &Graph::kind)
+      .def_property_readonly("id", [](const Graph& g) { return (uintptr_t)&g; })
+      .def_property_readonly("name", &Graph::name)
+      .def_property("num_strategy", &Graph::num_strategy, &Graph::set_num_strategy)
+      .def_property("cur_strategy", &Graph::cur_strategy, &Graph::set_cur_strategy)
+      .def_property_readonly("num_ops", &Graph::num_ops)
+      .def("op_types", [](const Graph& g) {
+        std::vector<std::string> v;
+        for (auto& op : g.ops()) v.push_back(op->type);
+        return v;
+      })
+      .def("op_info", [](const Graph& g, OpId id) {
+        auto op = g.op(id);
+        py::dict d;
+        d["type"] = op->type;
+        d["name"] = op->name();
+        d["attrs"] = attrs_to_dict(op->attrs);
+        d["inputs"] = op->inputs;
+        d["outputs"] = op->outputs;
+        d["is_bwd"] = op->is_bwd;
+        d["fw_op_id"] = op->fw_op_id;
+        d["subgraph"] = op->meta.subgraph;
+        d["placement"] = op->placement(g.cur_strategy());
+        return d;
+      })
+      .def("parameters", &Graph::parameters)
+      .def("push_subgraph", &Graph::push_subgraph)
+      .def("pop_subgraph", &Graph::pop_subgraph)
+      .def("subgraphs", [](Graph& g) {
+        py::dict d;
+        for (auto& kv : g.subgraphs()) {
+          py::dict e;
+          e["module_type"] = kv.second.module_type;
+          e["parent"] = kv.second.parent;
+          e["fwd_ops"] = kv.second.fwd_ops;
+          e["bwd_ops"] = kv.second.bwd_ops;
+          e["update_ops"] = kv.second.update_ops;
+          d[py::str(kv.first)] = e;
+        }
+        return d;
+      })
+      .def("push_ctx", [](Graph& g, const py::object& dgh, int stream_index, const TensorList& deps, const std::vector<bool>& rec,
+                          const std::vector<bool>& off) {
+        g.ctx_stack().push_back(g.ctx());
+        if (!dgh.is_none()) g.ctx().dg_hierarchy = dgh_from_py(dgh);
+        if (stream_index >= 0) g.ctx().stream_index = stream_index;
+        for (auto& d : deps) g.ctx().extra_deps.push_back(d);
+        if (!rec.empty()) g.ctx().recompute = rec;
+        if (!off.empty()) g.ctx().cpu_offload = off;
+      }, py::arg("device_group_hierarchy") = py::none(), py::arg("stream_index") = -1, py::arg("extra_deps") = TensorList{},
+         py::arg("recompute") = std::vector<bool>{}, py::arg("cpu_offload") = std::vector<bool>{})
+      .def("pop_ctx", [](Graph& g) {
+        HB_CHECK(!g.ctx_stack().empty()) << "context stack underflow";
+        g.ctx() = g.ctx_stack().back();
+        g.ctx_stack().pop_back();
+      })
+      .def("gradients", &Graph::gradients, py::arg("ys"), py::arg("xs"), py::arg("grad_ys") = TensorList{},
+           py::call_guard<py::gil_scoped_release>())
+      .def("backward", &Graph::eager_backward, py::arg("loss"), py::arg("grad") = nullptr, py::call_guard<py::gil_scoped_release>())
+      .def("make_op", [](Graph& g, const std::string& type, const TensorList& inputs, const py::dict& attrs, const std::string& name,
+                         const py::object& dgh, const py::object& dst_ds, const SyShape& sy_shape, const py::object& const_data,
+                         int stream_index, const TensorList& extra_deps) {
+        OpMeta meta;
+        meta.name = name;
+        meta.dg_hierarchy = dgh_from_py(dgh);
+        meta.stream_index = stream_index;
+        meta.extra_deps = extra_deps;
+        DistributedStatesHierarchy ds = dsh_from_py(dst_ds);
+        at::Tensor cd;
+        if (!const_data.is_none()) cd = py::cast<at::Tensor>(const_data);
+        AttrMap amap = attrs_from_dict(attrs);
+        py::gil_scoped_release nogil;
+        return g.make_op(type, inputs, amap, meta, [&](OpDef& op) {
+          op.dst_ds = ds;
+          op.sy_shape = sy_shape;
+          if (cd.defined()) op.const_data = cd;
+        });
+      }, py::arg("type"), py::arg("inputs"), py::arg("attrs") = py::dict(), py::arg("name") = "",
+         py::arg("device_group_hierarchy") = py::none(), py::arg("dst_ds") = py::none(), py::arg("sy_shape") = SyShape{},
+         py::arg("const_data") = py::none(), py::arg("stream_index") = -1, py::arg("extra_deps") = TensorList{})
+      .def("run", [](Graph& g, const Tensor& loss, const TensorList& fetches, const py::dict& feed, int num_micro_batches,
+                     int strategy, int run_level, double grad_scale, bool save_checkpoint) {
+        std::unordered_map<TensorId, std::vector<at::Tensor>> f;
+        for (auto item : feed) {
+          Tensor t = py::cast<Tensor>(item.first);
+          std::vector<at::Tensor> vs;
+          if (py::isinstance<py::list>(item.second) || py::isinstance<py::tuple>(item.second))
+            for (auto e : py::reinterpret_borrow<py::sequence>(item.second)) vs.push_back(py::cast<at::Tensor>(e));
+          else vs.push_back(py::cast<at::Tensor>(item.second));
+          f[t->id] = vs;
+        }
+        RunOptions o;
+        o.num_micro_batches = num_micro_batches;
+        o.strategy = strategy;
+        o.run_level = (RunLevel)run_level;
+        o.grad_scale = grad_scale;
+        o.save_checkpoint = save_checkpoint;
+        py::gil_scoped_release nogil;
+        return g.executor()->run(loss, fetches, f, o);
+      }, py::arg("loss"), py::arg("fetches"), py::arg("feed_dict") = py::dict(), py::arg("num_micro_batches") = 1,
+         py::arg("strategy") = 0, py::arg("run_level") = 0, py::arg("grad_scale") = 1.0, py::arg("save_checkpoint") = false)
+      .def("get_param", [](Graph& g, const Tensor& t) { return g.executor()->get_param(t); })
+      .def("set_param", [](Graph& g, const Tensor& t, const at::Tensor& v) { g.executor()->set_param(t, v); })
+      .def("has_param", [](Graph& g, const Tensor& t) { return g.has_param_data(t->id); })
+      .def("switch_strategy", [](Graph& g, int from, int to) { g.executor()->switch_strategy(from, to); })
+      .def("reinfer_shapes", &Graph::reinfer_shapes)
+      .def("set_profile", [](Graph& g, bool on) { g.executor()->set_profile(on); })
+      .def("op_times", [](Graph& g) { return g.executor()->op_times(); })
+      .def("step_breakdown", [](Graph& g) { return g.executor()->step_breakdown(); })
+      .def("accumulated_grad", [](Graph& g, const Tensor& param) -> py::object {
+        auto& m2 = g.executor()->accumulated_grads();
+        auto it = m2.find(param->id);
+        if (it == m2.end()) return py::none();
+        return py::cast(it->second);
+      });
+
+  m.def("list_ops", [] { return OpRegistry::get().list(); });
+  m.def("has_op", [](const std::string& t) { return OpRegistry::get().find(t) != nullptr; });
+
+  // ---------------------------------------------------------------- communication
+  m.def("init_comm", [](int rank, int world, const PG& world_pg, py::function factory) {
+    auto fac = [factory](const std::vector<int>& ranks) {
+      py::gil_scoped_acquire gil;
+      return py::cast<PG>(factory(ranks));
+    };
+    CommRuntime::get().init(rank, world, world_pg, fac);
+  });
+  m.def("comm_initialized", [] { return CommRuntime::get().initialized(); });
+  m.def("comm_rank", [] { return CommRuntime::get().rank(); });
+  m.def("comm_world", [] { return CommRuntime::get().world(); });
+  m.def("comm_barrier", [] { CommRuntime::get().barrier(); });
+  m.def("comm_stats", [] { return py::make_tuple(CommRuntime::get().bytes(), CommRuntime::get().calls()); });
+  m.def("comm_all_reduce", [](const at::Tensor& x, const std::vector<int>& r, const std::string& red) {
+    return CommRuntime::get().all_reduce(x, r, reduction_from_name(red));
+  }, py::arg("x"), py::arg("ranks"), py::arg("reduction") = "sum");
+  m.def("comm_all_gather", [](const at::Tensor& x, const std::vector<int>& r, int dim) { return CommRuntime::get().all_gather(x, r, dim); });
+  m.def("comm_reduce_scatter", [](const at::Tensor& x, const std::vector<int>& r, int dim) { return CommRuntime::get().reduce_scatter(x, r, dim); });
+  m.def("comm_all_to_all", [](const at::Tensor& x, const std::vector<int>& r, int sd, int cd) { return CommRuntime::get().all_to_all(x, r, sd, cd); });
+  m.def("comm_broadcast", [](const at::Tensor& x, const std::vector<int>& r, int root) { return CommRuntime::get().broadcast(x, r, root); });
+
+  // ---------------------------------------------------------------- schedules / planner / cache
+  m.def("generate_gpipe_schedule", [](int S, int M, bool inf) {
+    std::vector<std::vector<std::pair<int, int>>> out;
+    for (auto& st : generate_gpipe_schedule(S, M, inf)) {
+      out.emplace_back();
+      for (auto& t : st) out.back().push_back({(int)t.kind, t.micro_batch});
+    }
+    return out;
+  }, py::arg("num_stages"), py::arg("num_micro_batches"), py::arg("inference") = false);
+  m.def("generate_1f1b_schedule", [](int S, int M, bool inf) {
+    std::vector<std::vector<std::pair<int, int>>> out;
+    for (auto& st : generate_1f1b_schedule(S, M, inf)) {
+      out.emplace_back();
+      for (auto& t : st) out.back().push_back({(int)t.kind, t.micro_batch});
+    }
+    return out;
+  }, py::arg("num_stages"), py::arg("num_micro_batches"), py::arg("inference") = false);
+  m.def("galvatron_dp", [](int layers, int max_mem, int S, const std::vector<int>& mem, const std::vector<double>& intra,
+                           const std::vector<double>& inter) {
+    DpResult r = galvatron_dp(layers, max_mem, S, mem, intra, inter);
+    return py::make_tuple(r.cost, r.strategies, r.mem_remaining);
+  });
+
+  py::enum_<CachePolicy>(m, "CachePolicy").value("LRU", CachePolicy::LRU).value("LFU", CachePolicy::LFU).value("LFUOPT", CachePolicy::LFUOPT);
+  py::class_<EmbeddingCache>(m, "EmbeddingCache")
+      .def(py::init<int64_t, int, CachePolicy, int64_t, int64_t>(), py::arg("capacity"), py::arg("width"),
+           py::arg("policy") = CachePolicy::LRU, py::arg("pull_bound") = 0, py::arg("push_bound") = 0)
+      .def_property_readonly("size", &EmbeddingCache::size)
+      .def_property_readonly("capacity", &EmbeddingCache::capacity)
+      .def("contains", &EmbeddingCache::contains)
+      .def("stats", [](const EmbeddingCache& c) {
+        py::dict d;
+        d["lookups"] = c.stats().lookups; d["hits"] = c.stats().hits; d["evictions"] = c.stats().evictions;
+        d["pushes"] = c.stats().pushes; d["pulls"] = c.stats().pulls;
+        return d;
+      })
+      .def("lookup", [](EmbeddingCache& c, const std::vector<int64_t>& keys, const std::vector<int64_t>& versions) {
+        at::Tensor out = at::zeros({(int64_t)keys.size(), c.width()}, at::kFloat);
+        auto miss = c.lookup(keys, versions, out.data_ptr<float>());
+        return py::make_tuple(out, miss);
+      })
+      .def("insert", [](EmbeddingCache& c, const std::vector<int64_t>& keys, const at::Tensor& rows, const std::vector<int64_t>& versions) {
+        at::Tensor r = rows.to(at::kFloat).contiguous();
+        std::vector<int64_t> ek;
+        std::vector<float> eg;
+        c.insert(keys, r.data_ptr<float>(), versions, &ek, &eg);
+        at::Tensor g = at::from_blob(eg.data(), {(int64_t)ek.size(), c.width()}, at::kFloat).clone();
+        return py::make_tuple(ek, g);
+      })
+      .def("update", [](EmbeddingCache& c, const std::vector<int64_t>& keys, const at::Tensor& grads, float lr) {
+        at::Tensor g = grads.to(at::kFloat).contiguous();
+        std::vector<int64_t> pk;
+        std::vector<float> pg;
+        c.update(keys, g.data_ptr<float>(), lr, &pk, &pg);
+        at::Tensor out = at::from_blob(pg.data(), {(int64_t)pk.size(), c.width()}, at::kFloat).clone();
+        return py::make_tuple(pk, out);
+      })
+      .def("flush", [](EmbeddingCache& c) {
+        std::vector<int64_t> pk;
+        std::vector<float> pg;
+        c.flush(&pk, &pg);
+        at::Tensor out = at::from_blob(pg.data(), {(int64_t)pk.size(), c.width()}, at::kFloat).clone();
+        return py::make_tuple(pk, out);
+      });
+
+  // ---------------------------------------------------------------- diagnostics
+  m.def("kernel_launch_count", [] { return kernel_launch_count() + gemm_launch_count() + attn_launch_count(); });
+  m.def("gemm_launch_count", &gemm_launch_count);
+  m.def("attn_launch_count", &attn_launch_count);
+  m.def("fallback_count", &fallback_count);
+  m.def("set_log_level", [](const std::string& l) {
+    std::string s = l;
+    for (auto& c : s) c = toupper(c);
+    set_log_level(s == "TRACE" ? LogLevel::TRACE : s == "DEBUG" ? LogLevel::DEBUG : s == "INFO" ? LogLevel::INFO
+                  : s == "ERROR" ? LogLevel::ERROR : s == "FATAL" ? LogLevel::FATAL : LogLevel::WARN);
+  });
+  m.def("dtype_size", [](const std::string& n) { return dtype_size(dtype_from_name(n)); });
+
+  // direct kernel entry points (benchmarks / numerics tests)
+  m.def("gemm", [](const at::Tensor& a, const at::Tensor& b, bool a_mn, bool b_mn, const py::object& bias, const std::string& act,
+                   bool out_fp32, int cta_group) {
+    HB_CHECK(a.is_cuda() && a.scalar_type() == at::kBFloat16 && a.dim() == 2 && b.dim() == 2) << "gemm expects 2-D CUDA bf16";
+    const int64_t M = a_mn ? a.size(1) : a.size(0), K = a_mn ? a.size(0) : a.size(1), N = b_mn ? b.size(1) : b.size(0);
+    at::Tensor c = at::empty({M, N}, a.options().dtype(out_fp32 ? at::kFloat : at::kBFloat16));
+    GemmCall g;
+    g.A = a.data_ptr(); g.B = b.data_ptr(); g.C = c.data_ptr();
+    g.M = (int)M; g.N = (int)N; g.K = (int)K;
+    g.lda = a.stride(0); g.ldb = b.stride(0); g.ldc = N;
+    g.a_mn_major = a_mn; g.b_mn_major = b_mn;
+    g.out = out_fp32 ? GemmOut::FP32 : GemmOut::BF16;
+    at::Tensor bt;
+    if (!bias.is_none()) { bt = py::cast<at::Tensor>(bias); g.bias = bt.data_ptr(); }
+    g.act = act == "gelu" ? 1 : act == "relu" ? 2 : act == "gelu_tanh" ? 3 : act == "silu" ? 4 : 0;
+    g.cta_group = cta_group;
+    cuda_ok(gemm_bf16(g, cur_stream()), "gemm");
+    return c;
+  }, py::arg("a"), py::arg("b"), py::arg("a_mn_major") = false, py::arg("b_mn_major") = false, py::arg("bias") = py::none(),
+     py::arg("act") = "none", py::arg("out_fp32") = false, py::arg("cta_group") = 0);
+}

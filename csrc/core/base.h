@@ -37,6 +37,16 @@ class LogMessage {
   } else                                                    \
     ::hb::LogMessage(::hb::LogLevel::LVL, __FILE__, __LINE__).stream()
 
+template <typename T>
+std::ostream& operator<<(std::ostream& os, const std::vector<T>& v) {
+  os << "[";
+  for (size_t i = 0; i < v.size(); ++i) {
+    if (i) os << ", ";
+    os << v[i];
+  }
+  return os << "]";
+}
+
 class Error : public std::runtime_error {
  public:
   explicit Error(const std::string& m) : std::runtime_error(m) {}
@@ -64,16 +74,6 @@ class ErrorBuilder {
   } else               \
     ::hb::ErrorBuilder(__FILE__, __LINE__, #cond)
 #define HB_FAIL() ::hb::ErrorBuilder(__FILE__, __LINE__, "unreachable")
-
-template <typename T>
-std::ostream& operator<<(std::ostream& os, const std::vector<T>& v) {
-  os << "[";
-  for (size_t i = 0; i < v.size(); ++i) {
-    if (i) os << ", ";
-    os << v[i];
-  }
-  return os << "]";
-}
 
 inline double now_ms() {
   using namespace std::chrono;

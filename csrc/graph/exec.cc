@@ -1,0 +1,833 @@
+#include "exec.h"
+
+#include <ATen/ATen.h>
+#include <torch/csrc/distributed/c10d/Types.hpp>
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+#include "op_utils.h"
+
+namespace hb {
+
+// =============================================================================================
+// CommRuntime
+// =============================================================================================
+CommRuntime& CommRuntime::get() {
+  static CommRuntime r;
+  return r;
+}
+void CommRuntime::init(int rank, int world, PG world_pg, std::function<PG(const std::vector<int>&)> factory) {
+  rank_ = rank;
+  world_ = world;
+  world_pg_ = std::move(world_pg);
+  factory_ = std::move(factory);
+  groups_.clear();
+  set_log_prefix("[rank " + std::to_string(rank) + "]");
+}
+PG CommRuntime::group(const std::vector<int>& ranks) {
+  if ((int)ranks.size() == world_) {
+    bool ident = true;
+    for (int i = 0; i < world_; ++i) ident &= (ranks[i] == i);
+    if (ident) return world_pg_;
+  }
+  auto it = groups_.find(ranks);
+  if (it != groups_.end()) return it->second;
+  HB_CHECK(factory_) << "CommRuntime has no group factory (call hetu.init_comm_group first)";
+  PG pg = factory_(ranks);
+  groups_[ranks] = pg;
+  return pg;
+}
+void CommRuntime::barrier() {
+  if (!initialized()) return;
+  world_pg_->barrier()->wait();
+}
+static c10d::ReduceOp to_c10d(ReductionType r) {
+  switch (r) {
+    case ReductionType::SUM: case ReductionType::MEAN: return c10d::ReduceOp::SUM;
+    case ReductionType::MAX: return c10d::ReduceOp::MAX;
+    case ReductionType::MIN: return c10d::ReduceOp::MIN;
+    case ReductionType::PROD: return c10d::ReduceOp::PRODUCT;
+    default: return c10d::ReduceOp::SUM;
+  }
+}
+at::Tensor CommRuntime::all_reduce(const at::Tensor& x, const std::vector<int>& ranks, ReductionType red, bool fp32) {
+  if (ranks.size() <= 1 || !initialized()) return x;
+  at::Tensor buf = (fp32 && x.scalar_type() != at::kFloat) ? x.to(at::kFloat) : x.contiguous().clone();
+  std::vector<at::Tensor> v = {buf};
+  c10d::AllreduceOptions o;
+  o.reduceOp = to_c10d(red);
+  group(ranks)->allreduce(v, o)->wait();
+  if (red == ReductionType::MEAN) buf.div_((double)ranks.size());
+  bytes_["all_reduce"] += buf.nbytes();
+  calls_["all_reduce"] += 1;
+  return buf.scalar_type() == x.scalar_type() ? buf : buf.to(x.scalar_type());
+}
+at::Tensor CommRuntime::all_gather(const at::Tensor& x, const std::vector<int>& ranks, int dim) {
+  if (ranks.size() <= 1 || !initialized()) return x;
+  const int64_t n = (int64_t)ranks.size();
+  at::Tensor in = x.contiguous();
+  std::vector<int64_t> shp = in.sizes().vec();
+  shp.insert(shp.begin(), n);
+  at::Tensor out = at::empty(shp, in.options());
+  c10d::AllgatherOptions o;
+  group(ranks)->_allgather_base(out, in, o)->wait();
+  bytes_["all_gather"] += out.nbytes();
+  calls_["all_gather"] += 1;
+  if (dim == 0) {
+    std::vector<int64_t> f = in.sizes().vec();
+    f[0] *= n;
+    return out.reshape(f);
+  }
+  std::vector<at::Tensor> parts;
+  for (int64_t i = 0; i < n; ++i) parts.push_back(out[i]);
+  return at::cat(parts, dim);
+}
+at::Tensor CommRuntime::reduce_scatter(const at::Tensor& x, const std::vector<int>& ranks, int dim, ReductionType red,
+                                       bool fp32) {
+  if (ranks.size() <= 1 || !initialized()) return x;
+  const int64_t n = (int64_t)ranks.size();
+  at::Tensor in = (fp32 && x.scalar_type() != at::kFloat) ? x.to(at::kFloat) : x;
+  if (dim != 0) {
+    auto parts = at::chunk(in, n, dim);
+    in = at::cat(parts, 0);
+  }
+  in = in.contiguous();
+  std::vector<int64_t> shp = in.sizes().vec();
+  HB_CHECK(shp[0] % n == 0) << "reduce_scatter: dim not divisible by group size";
+  shp[0] /= n;
+  at::Tensor out = at::empty(shp, in.options());
+  c10d::ReduceScatterOptions o;
+  o.reduceOp = to_c10d(red);
+  group(ranks)->_reduce_scatter_base(out, in, o)->wait();
+  if (red == ReductionType::MEAN) out.div_((double)n);
+  bytes_["reduce_scatter"] += in.nbytes();
+  calls_["reduce_scatter"] += 1;
+  return out.scalar_type() == x.scalar_type() ? out : out.to(x.scalar_type());
+}
+at::Tensor CommRuntime::broadcast(const at::Tensor& x, const std::vector<int>& ranks, int root_rank) {
+  if (ranks.size() <= 1 || !initialized()) return x;
+  at::Tensor buf = x.contiguous().clone();
+  std::vector<at::Tensor> v = {buf};
+  c10d::BroadcastOptions o;
+  int root_in_group = 0;
+  for (size_t i = 0; i < ranks.size(); ++i) if (ranks[i] == root_rank) root_in_group = (int)i;
+  o.rootRank = root_in_group;
+  group(ranks)->broadcast(v, o)->wait();
+  bytes_["broadcast"] += buf.nbytes();
+  calls_["broadcast"] += 1;
+  return buf;
+}
+at::Tensor CommRuntime::all_to_all(const at::Tensor& x, const std::vector<int>& ranks, int split_dim, int concat_dim) {
+  if (ranks.size() <= 1 || !initialized()) return x;
+  const int64_t n = (int64_t)ranks.size();
+  at::Tensor in = x;
+  if (split_dim != 0) in = at::cat(at::chunk(x, n, split_dim), 0);
+  in = in.contiguous();
+  at::Tensor out = at::empty_like(in);
+  std::vector<int64_t> none;
+  c10d::AllToAllOptions o;
+  group(ranks)->alltoall_base(out, in, none, none, o)->wait();
+  bytes_["all_to_all"] += in.nbytes();
+  calls_["all_to_all"] += 1;
+  if (concat_dim == 0) return out;
+  return at::cat(at::chunk(out, n, 0), concat_dim);
+}
+void CommRuntime::send(const at::Tensor& x, int dst_rank) {
+  std::vector<at::Tensor> v = {x.contiguous()};
+  auto w = world_pg_->send(v, dst_rank, 0);
+  w->wait();
+  bytes_["p2p"] += x.nbytes();
+  calls_["p2p"] += 1;
+}
+at::Tensor CommRuntime::recv(const std::vector<int64_t>& shape, at::ScalarType dtype, const at::Device& dev, int src) {
+  at::Tensor t = at::empty(shape, at::TensorOptions().dtype(dtype).device(dev));
+  std::vector<at::Tensor> v = {t};
+  world_pg_->recv(v, src, 0)->wait();
+  return t;
+}
+void CommRuntime::batched_send_recv(const std::vector<std::pair<at::Tensor, int>>& sends,
+                                    std::vector<std::pair<at::Tensor, int>>& recvs) {
+  if (!initialized()) return;
+  std::vector<c10::intrusive_ptr<c10d::Work>> works;
+  std::vector<at::Tensor> keep;
+  const bool is_nccl = world_pg_->getBackendName() == "nccl";
+  // NCCL wants paired sends/recvs inside one group call; gloo is fine with async isend/irecv
+  if (is_nccl) world_pg_->startCoalescing(c10::DeviceType::CUDA);
+  for (auto& r : recvs) {
+    std::vector<at::Tensor> v = {r.first};
+    works.push_back(world_pg_->recv(v, r.second, 0));
+  }
+  for (auto& s : sends) {
+    keep.push_back(s.first.contiguous());
+    std::vector<at::Tensor> v = {keep.back()};
+    works.push_back(world_pg_->send(v, s.second, 0));
+    bytes_["p2p"] += s.first.nbytes();
+  }
+  if (is_nccl) {
+    auto w = world_pg_->endCoalescing(c10::DeviceType::CUDA);
+    if (w) w->wait();
+  } else {
+    for (auto& w : works) if (w) w->wait();
+  }
+  calls_["batched_p2p"] += 1;
+}
+
+// =============================================================================================
+// RunCtx
+// =============================================================================================
+at::Tensor RunCtx::scratch(const std::string& key, std::vector<int64_t> shape, at::ScalarType dt, const at::Device& dev) {
+  HB_CHECK(workspace != nullptr) << "no workspace bound";
+  auto it = workspace->find(key);
+  int64_t need = 1;
+  for (auto s : shape) need *= s;
+  if (it == workspace->end() || it->second.numel() < need || it->second.scalar_type() != dt || it->second.device() != dev) {
+    (*workspace)[key] = at::empty({need}, at::TensorOptions().dtype(dt).device(dev));
+    it = workspace->find(key);
+  }
+  return it->second.narrow(0, 0, need).view(shape);
+}
+
+// =============================================================================================
+// pipeline schedules
+// =============================================================================================
+std::vector<std::vector<PipeTask>> generate_gpipe_schedule(int S, int M, bool inference) {
+  std::vector<std::vector<PipeTask>> sched(S);
+  for (int s = 0; s < S; ++s) {
+    for (int m = 0; m < M; ++m) sched[s].push_back({PipeTask::FORWARD, m});
+    if (!inference) for (int m = 0; m < M; ++m) sched[s].push_back({PipeTask::BACKWARD, m});
+  }
+  return sched;
+}
+std::vector<std::vector<PipeTask>> generate_1f1b_schedule(int S, int M, bool inference) {
+  std::vector<std::vector<PipeTask>> sched(S);
+  for (int s = 0; s < S; ++s) {
+    if (inference) {
+      for (int m = 0; m < M; ++m) sched[s].push_back({PipeTask::FORWARD, m});
+      continue;
+    }
+    const int warmup = std::min(S - s - 1, M);
+    const int steady = M - warmup;
+    int f = 0, b = 0;
+    for (int i = 0; i < warmup; ++i) sched[s].push_back({PipeTask::FORWARD, f++});
+    for (int i = 0; i < steady; ++i) {
+      sched[s].push_back({PipeTask::FORWARD, f++});
+      sched[s].push_back({PipeTask::BACKWARD, b++});
+    }
+    // a flush marker lets the executor close an open send/recv group before the cool-down phase
+    if (warmup > 0) sched[s].push_back({PipeTask::FLUSH, -1});
+    for (int i = 0; i < warmup; ++i) sched[s].push_back({PipeTask::BACKWARD, b++});
+  }
+  return sched;
+}
+
+// =============================================================================================
+// Executor: devices / parameters
+// =============================================================================================
+Device Executor::local_device() const {
+  auto& c = CommRuntime::get();
+  const bool cuda = at::hasCUDA() && env_int("HETU_B200_FORCE_CPU", 0) == 0;
+  return Device(cuda ? DeviceType::CUDA : DeviceType::CPU, c.initialized() ? c.rank() : 0);
+}
+int Executor::local_device_index(const DeviceGroup& g) const {
+  // devices are identified by their global rank (index); type is ignored so that CPU (gloo) test runs and
+  // GPU runs share strategy files
+  const int me = CommRuntime::get().initialized() ? CommRuntime::get().rank() : 0;
+  for (size_t i = 0; i < g.num_devices(); ++i) if (g.get(i).index() == me) return (int)i;
+  return -1;
+}
+static at::Device aten_device() {
+  const bool cuda = at::hasCUDA() && env_int("HETU_B200_FORCE_CPU", 0) == 0;
+  if (!cuda) return at::Device(at::kCPU);
+  return at::Device(at::kCUDA, (c10::DeviceIndex)at::cuda::current_device());
+}
+
+static at::Tensor run_initializer(const OpDef& op, const std::vector<int64_t>& gshape) {
+  const std::string kind = op.attrs.s("init", "zeros");
+  auto o = at::TensorOptions().dtype(at::kFloat);
+  const uint64_t seed = (uint64_t)op.attrs.i("seed", 0) * 1000003ull + (uint64_t)op.id * 7919ull + 12345ull;
+  auto gen = at::detail::createCPUGenerator(seed);
+  int64_t fan_in = gshape.size() >= 2 ? gshape[1] : (gshape.empty() ? 1 : gshape[0]);
+  int64_t fan_out = gshape.empty() ? 1 : gshape[0];
+  if (gshape.size() > 2) {
+    int64_t rf = 1;
+    for (size_t i = 2; i < gshape.size(); ++i) rf *= gshape[i];
+    fan_in *= rf;
+    fan_out *= rf;
+  }
+  const double gain = op.attrs.f("gain", 1.0);
+  if (kind == "zeros") return at::zeros(gshape, o);
+  if (kind == "ones") return at::ones(gshape, o);
+  if (kind == "constant") return at::full(gshape, op.attrs.f("value", 0.0), o);
+  if (kind == "uniform") return at::empty(gshape, o).uniform_(op.attrs.f("lb", -1.0), op.attrs.f("ub", 1.0), gen);
+  if (kind == "normal") return at::empty(gshape, o).normal_(op.attrs.f("mean", 0.0), op.attrs.f("stddev", 1.0), gen);
+  if (kind == "truncated_normal") {
+    const double mean = op.attrs.f("mean", 0.0), std = op.attrs.f("stddev", 1.0);
+    const double lb = op.attrs.f("lb", -2.0), ub = op.attrs.f("ub", 2.0);
+    at::Tensor t = at::empty(gshape, o).normal_(0.0, 1.0, gen);
+    for (int it = 0; it < 8; ++it) {
+      at::Tensor bad = (t < lb).logical_or(t > ub);
+      if (!bad.any().item<bool>()) break;
+      t = at::where(bad, at::empty(gshape, o).normal_(0.0, 1.0, gen), t);
+    }
+    return t.clamp(lb, ub) * std + mean;
+  }
+  auto mode_fan = [&](const std::string& m) { return m == "fan_out" ? (double)fan_out : m == "avg" ? 0.5 * (fan_in + fan_out) : (double)fan_in; };
+  if (kind == "xavier_uniform") { const double a = gain * std::sqrt(6.0 / (fan_in + fan_out)); return at::empty(gshape, o).uniform_(-a, a, gen); }
+  if (kind == "xavier_normal") return at::empty(gshape, o).normal_(0.0, gain * std::sqrt(2.0 / (fan_in + fan_out)), gen);
+  if (kind == "he_uniform") { const double a = gain * std::sqrt(6.0 / mode_fan(op.attrs.s("mode", "fan_in"))); return at::empty(gshape, o).uniform_(-a, a, gen); }
+  if (kind == "he_normal") return at::empty(gshape, o).normal_(0.0, gain * std::sqrt(2.0 / mode_fan(op.attrs.s("mode", "fan_in"))), gen);
+  if (kind == "lecun_uniform") { const double a = gain * std::sqrt(3.0 / fan_in); return at::empty(gshape, o).uniform_(-a, a, gen); }
+  if (kind == "lecun_normal") return at::empty(gshape, o).normal_(0.0, gain * std::sqrt(1.0 / fan_in), gen);
+  if (kind == "provided") {
+    HB_CHECK(op.const_data.defined()) << "provided initializer without data for " << op.name();
+    return op.const_data.to(at::kFloat);
+  }
+  HB_FAIL() << "unknown initializer '" << kind << "'";
+}
+
+void Executor::ensure_param(OpDef* var, int strategy) {
+  Tensor t = var->outputs[0];
+  if (g_->has_param_data(t->id)) return;
+  const auto gshape = var->attrs.ints("global_shape");
+  if (var->attrs.s("init") == "copy_of") {
+    // fp32 master (possibly ZeRO-sharded) of a low-precision parameter: slice the parameter's own shard
+    OpDef* src = g_->op(var->attrs.i("copy_of_op")).get();
+    ensure_param(src, strategy);
+    at::Tensor pdata = g_->param_data()[src->outputs[0]->id];
+    at::Tensor local = pdata;
+    if (var->dst_ds.size() > 0 && src->dst_ds.size() > 0) {
+      const size_t s = var->dst_ds.size() > (size_t)strategy ? strategy : 0;
+      const DistributedStates& mds = var->dst_ds.get(s).get(0);
+      const DistributedStates& pds = src->dst_ds.get(std::min(s, src->dst_ds.size() - 1)).get(0);
+      DeviceGroup grp = var->placement(s);
+      int idx = grp.empty() ? 0 : local_device_index(grp);
+      if (idx < 0) idx = 0;
+      std::vector<int64_t> mb, ms, pb, ps;
+      mds.local_slice(gshape, idx % std::max(1, mds.device_num()), &mb, &ms);
+      pds.local_slice(gshape, idx % std::max(1, pds.device_num()), &pb, &ps);
+      for (size_t d = 0; d < mb.size(); ++d) local = local.narrow((int64_t)d, mb[d] - pb[d], ms[d]);
+    }
+    g_->param_data()[t->id] = local.to(to_aten_dtype(t->dtype)).contiguous().clone();
+    return;
+  }
+  // every shard is a slice of the same seeded global tensor, so any strategy sees identical weights
+  at::Tensor full = run_initializer(*var, gshape);
+  at::Tensor local = full;
+  if (var->dst_ds.size() > 0) {
+    const size_t s = var->dst_ds.size() > (size_t)strategy ? strategy : 0;
+    const DistributedStates& ds = var->dst_ds.get(s).get(0);
+    DeviceGroup grp = var->placement(s);
+    int idx = grp.empty() ? 0 : local_device_index(grp);
+    if (idx < 0) idx = 0;
+    if (ds.device_num() > 1) {
+      std::vector<int64_t> begin, size;
+      ds.local_slice(gshape, idx % ds.device_num(), &begin, &size);
+      for (size_t d = 0; d < begin.size(); ++d) local = local.narrow((int64_t)d, begin[d], size[d]);
+    }
+  }
+  g_->param_data()[t->id] = local.to(to_aten_dtype(t->dtype)).to(aten_device()).contiguous();
+}
+at::Tensor Executor::get_param(const Tensor& t) {
+  if (!g_->has_param_data(t->id) && t->producer && t->producer->has_flag(kFlagVariable))
+    ensure_param(t->producer, std::max(active_strategy_, 0));
+  HB_CHECK(g_->has_param_data(t->id)) << "tensor " << t->name << " has no materialised data";
+  return g_->param_data()[t->id];
+}
+void Executor::set_param(const Tensor& t, const at::Tensor& v) {
+  auto& store = g_->param_data();
+  auto it = store.find(t->id);
+  if (it != store.end() && it->second.sizes() == v.sizes()) it->second.copy_(v);  // keep flat-buffer views alive
+  else store[t->id] = v.to(to_aten_dtype(t->dtype)).to(aten_device()).contiguous();
+}
+
+// =============================================================================================
+// plan construction
+// =============================================================================================
+static std::vector<int> group_ranks(const DeviceGroup& g, const std::vector<int>& idx) {
+  std::vector<int> r;
+  for (int i : idx) r.push_back(g.get(i).index());
+  return r;
+}
+
+void Executor::lower_comm(ExecPlan& plan, OpDef* op, int strategy) {
+  CommStep cs;
+  const Tensor& x = op->inputs[0];
+  const Tensor& y = op->outputs[0];
+  DeviceGroup src_group = x->producer ? x->producer->placement(strategy) : DeviceGroup();
+  DeviceGroup dst_group = op->placement(strategy);
+  if (dst_group.empty()) dst_group = src_group;
+  if (src_group.empty()) src_group = dst_group;
+  if (!x->has_ds(strategy) || !y->has_ds(strategy) || src_group.empty() || !CommRuntime::get().initialized()) {
+    cs.type = CommType::UNUSED;
+    plan.comm[op->id] = cs;
+    return;
+  }
+  const DistributedStates& src = x->ds(strategy);
+  const DistributedStates& dst = y->ds(strategy);
+  cs.type = classify_comm(src, src_group, dst, dst_group);
+  cs.global_shape = src.global_shape(x->shape);
+  const int me_src = local_device_index(src_group), me_dst = local_device_index(dst_group);
+  switch (cs.type) {
+    case CommType::UNUSED: break;
+    case CommType::P2P: {
+      cs.is_sender = me_src >= 0;
+      cs.is_receiver = me_dst >= 0;
+      if (cs.is_sender) cs.peer = dst_group.get(me_src).index();
+      if (cs.is_receiver) cs.peer = src_group.get(me_dst).index();
+      break;
+    }
+    case CommType::ALL_REDUCE:
+      cs.ranks = group_ranks(src_group, src.get_device_indices_by_dim(kPartialDim, me_src));
+      break;
+    case CommType::ALL_GATHER:
+      cs.dim = src.get_split_dim(dst);
+      cs.ranks = group_ranks(src_group, dst.get_device_indices_by_dim(kDupDim, me_src));
+      break;
+    case CommType::REDUCE_SCATTER:
+      cs.dim = dst.get_split_dim(src);
+      cs.ranks = group_ranks(src_group, src.get_device_indices_by_dim(kPartialDim, me_src));
+      break;
+    case CommType::SCATTER:
+    case CommType::COMM_SPLIT: {
+      // local slicing of a replicated tensor
+      cs.dim = dst.get_split_dim(src);
+      break;
+    }
+    case CommType::BATCHED_ISEND_IRECV: {
+      std::vector<int> sr, dr;
+      for (auto& d : src_group.devices()) sr.push_back(d.index());
+      for (auto& d : dst_group.devices()) dr.push_back(d.index());
+      cs.transfers = plan_resharding(cs.global_shape, src, sr, dst, dr, switch_algorithm_from_env());
+      break;
+    }
+    default: break;
+  }
+  plan.comm[op->id] = cs;
+}
+
+ExecPlan& Executor::get_plan(const Tensor& loss, const TensorList& fetches, int strategy) {
+  std::vector<TensorId> key;
+  if (loss) key.push_back(loss->id);
+  for (auto& f : fetches) key.push_back(f->id);
+  auto k = std::make_pair(strategy, key);
+  auto it = plans_.find(k);
+  if (it == plans_.end()) {
+    ExecPlan& p = plans_[k];
+    build_plan(p, loss, fetches, strategy);
+    return p;
+  }
+  return it->second;
+}
+
+void Executor::build_plan(ExecPlan& plan, const Tensor& loss, const TensorList& fetches, int strategy) {
+  plan.strategy = strategy;
+  if (g_->cur_strategy() != strategy || shapes_strategy_ != strategy) {
+    if (shapes_strategy_ != -1 || strategy != 0) g_->reinfer_shapes(strategy);
+    shapes_strategy_ = strategy;
+  }
+  g_->set_cur_strategy(strategy);
+  TensorList targets = fetches;
+  if (loss) targets.push_back(loss);
+  std::vector<OpDef*> order = g_->topo_sort(targets);
+  // pipeline stages = distinct placement groups in order of first appearance (forward ops only)
+  for (OpDef* op : order) {
+    if (op->is_bwd || op->has_flag(kFlagOptimizerUpdate)) continue;
+    DeviceGroup grp = op->placement(strategy);
+    if (grp.empty()) continue;
+    bool seen = false;
+    for (auto& s : plan.stage_groups) if (s == grp) seen = true;
+    if (!seen) plan.stage_groups.push_back(grp);
+  }
+  plan.num_stages = std::max<int>(1, (int)plan.stage_groups.size());
+  plan.stage = 0;
+  for (size_t i = 0; i < plan.stage_groups.size(); ++i)
+    if (local_device_index(plan.stage_groups[i]) >= 0) { plan.stage = (int)i; break; }
+
+  // optimizer bookkeeping: (param, grad) pairs and deferred grad-sync comm ops
+  std::set<OpId> deferred;
+  for (OpDef* op : order) {
+    if (!op->has_flag(kFlagOptimizerUpdate) || op->inputs.size() < 2) continue;
+    Tensor param = op->inputs[0], grad = op->inputs[1];
+    plan.update_of_param[param->id] = op;
+    if (grad->producer && grad->producer->type == "comm") {
+      deferred.insert(grad->producer->id);
+      plan.param_of_grad[grad->producer->inputs[0]->id] = param->id;
+    } else {
+      plan.param_of_grad[grad->id] = param->id;
+    }
+  }
+  for (OpDef* op : order) {
+    if (op->type == "comm") lower_comm(plan, op, strategy);
+    DeviceGroup grp = op->placement(strategy);
+    bool local = grp.empty() || local_device_index(grp) >= 0;
+    if (op->type == "comm") {
+      const CommStep& cs = plan.comm[op->id];
+      if (cs.type == CommType::P2P) local = cs.is_sender || cs.is_receiver;
+      if (cs.type == CommType::BATCHED_ISEND_IRECV) {
+        const int me = CommRuntime::get().rank();
+        local = false;
+        for (auto& t : cs.transfers) local |= (t.src_device == me || t.dst_device == me);
+      }
+    }
+    if (!local) continue;
+    if (op->has_flag(kFlagOptimizerUpdate) || op->has_flag(kFlagGroup)) plan.update_ops.push_back(op);
+    else if (deferred.count(op->id)) plan.update_ops.push_back(op);
+    else if (op->is_bwd) plan.bw_ops.push_back(op);
+    else plan.fw_ops.push_back(op);
+  }
+  // static last-use analysis over [fw | bw]
+  auto note = [&](const Tensor& t, int pos) { plan.last_use_fw[t->id] = pos; };
+  int pos = 0;
+  for (OpDef* op : plan.fw_ops) { for (auto& in : op->inputs) note(in, pos); ++pos; }
+  for (OpDef* op : plan.bw_ops) { for (auto& in : op->inputs) note(in, pos); ++pos; }
+  for (auto& f : targets) plan.fetch_ids.push_back(f->id);
+  plan.built = true;
+  HB_LOG(DEBUG) << "plan built: strategy " << strategy << " stage " << plan.stage << "/" << plan.num_stages << " fw "
+                << plan.fw_ops.size() << " bw " << plan.bw_ops.size() << " update " << plan.update_ops.size();
+}
+
+// =============================================================================================
+// comm execution
+// =============================================================================================
+std::vector<at::Tensor> Executor::exec_comm(const CommStep& cs, OpDef* op, const std::vector<at::Tensor>& in, RunCtx&) {
+  auto& comm = CommRuntime::get();
+  const bool fp32 = env_int("HETU_FP32_COMM_REDUCE", 0) != 0;
+  switch (cs.type) {
+    case CommType::UNUSED: return {in[0]};
+    case CommType::ALL_REDUCE: return {comm.all_reduce(in[0], cs.ranks, ReductionType::SUM, fp32)};
+    case CommType::ALL_GATHER: return {comm.all_gather(in[0], cs.ranks, cs.dim)};
+    case CommType::REDUCE_SCATTER: return {comm.reduce_scatter(in[0], cs.ranks, cs.dim, ReductionType::SUM, fp32)};
+    case CommType::SCATTER:
+    case CommType::COMM_SPLIT: {
+      const Tensor& y = op->outputs[0];
+      const DistributedStates& dst = y->ds(std::max(active_strategy_, 0));
+      DeviceGroup grp = op->placement(std::max(active_strategy_, 0));
+      const int me = local_device_index(grp);
+      std::vector<int64_t> begin, size;
+      // slice of the *source-local* tensor: compute both global slices and subtract
+      const Tensor& x = op->inputs[0];
+      const DistributedStates& src = x->ds(std::max(active_strategy_, 0));
+      std::vector<int64_t> sb, ss;
+      src.local_slice(cs.global_shape, me, &sb, &ss);
+      dst.local_slice(cs.global_shape, me, &begin, &size);
+      at::Tensor t = in[0];
+      for (size_t d = 0; d < begin.size(); ++d) t = t.narrow((int64_t)d, begin[d] - sb[d], size[d]);
+      return {t.contiguous()};
+    }
+    case CommType::P2P: {
+      if (cs.is_sender && cs.is_receiver && cs.peer == comm.rank()) return {in[0]};
+      if (cs.is_sender) {
+        comm.send(in[0], cs.peer);
+        if (!cs.is_receiver) return {at::Tensor()};
+      }
+      const Tensor& y = op->outputs[0];
+      return {comm.recv(y->shape, to_aten_dtype(y->dtype), aten_device(), cs.peer)};
+    }
+    case CommType::BATCHED_ISEND_IRECV: {
+      const int me = comm.rank();
+      const Tensor& x = op->inputs[0];
+      const Tensor& y = op->outputs[0];
+      const int s = std::max(active_strategy_, 0);
+      DeviceGroup sg = x->producer ? x->producer->placement(s) : op->placement(s);
+      DeviceGroup dg = op->placement(s);
+      std::vector<int64_t> sb, ss, db, dsz;
+      const int si = local_device_index(sg), di = local_device_index(dg);
+      if (si >= 0) x->ds(s).local_slice(cs.global_shape, si, &sb, &ss);
+      at::Tensor out;
+      if (di >= 0) {
+        y->ds(s).local_slice(cs.global_shape, di, &db, &dsz);
+        out = at::empty(dsz, at::TensorOptions().dtype(to_aten_dtype(y->dtype)).device(aten_device()));
+      }
+      std::vector<std::pair<at::Tensor, int>> sends, recvs;
+      std::vector<std::pair<at::Tensor, at::Tensor>> copy_back;
+      for (auto& t : cs.transfers) {
+        if (t.src_device == me) {
+          at::Tensor piece = in[0];
+          for (size_t d = 0; d < sb.size(); ++d) piece = piece.narrow((int64_t)d, t.global.begin[d] - sb[d], t.global.size[d]);
+          if (t.dst_device == me) {
+            at::Tensor dstv = out;
+            for (size_t d = 0; d < db.size(); ++d) dstv = dstv.narrow((int64_t)d, t.global.begin[d] - db[d], t.global.size[d]);
+            dstv.copy_(piece);
+          } else sends.push_back({piece.contiguous(), t.dst_device});
+        } else if (t.dst_device == me) {
+          at::Tensor dstv = out;
+          for (size_t d = 0; d < db.size(); ++d) dstv = dstv.narrow((int64_t)d, t.global.begin[d] - db[d], t.global.size[d]);
+          at::Tensor buf = at::empty(t.global.size, out.options());
+          recvs.push_back({buf, t.src_device});
+          copy_back.push_back({dstv, buf});
+        }
+      }
+      comm.batched_send_recv(sends, recvs);
+      for (auto& cb : copy_back) cb.first.copy_(cb.second);
+      return {out};
+    }
+    default:
+      HB_FAIL() << "comm type " << comm_type_name(cs.type) << " is not executable in this build";
+  }
+}
+
+// =============================================================================================
+// run
+// =============================================================================================
+void Executor::run_ops(ExecPlan& plan, const std::vector<OpDef*>& ops, bool backward, int mb, RunCtx& rc,
+                       std::unordered_map<TensorId, at::Tensor>& vals) {
+  const int base = backward ? (int)plan.fw_ops.size() : 0;
+  std::set<TensorId> keep(plan.fetch_ids.begin(), plan.fetch_ids.end());
+  for (size_t i = 0; i < ops.size(); ++i) {
+    OpDef* op = ops[i];
+    const double t0 = profile_ ? now_ms() : 0.0;
+    std::vector<at::Tensor> outs;
+    if (op->has_flag(kFlagVariable)) {
+      ensure_param(op, plan.strategy);
+      outs = {g_->param_data()[op->outputs[0]->id]};
+    } else if (op->has_flag(kFlagPlaceholder)) {
+      auto it = vals.find(op->outputs[0]->id);
+      HB_CHECK(it != vals.end()) << "placeholder " << op->name() << " was not fed";
+      continue;
+    } else {
+      std::vector<at::Tensor> ins;
+      ins.reserve(op->inputs.size());
+      bool missing = false;
+      for (auto& t : op->inputs) {
+        auto it = vals.find(t->id);
+        if (it == vals.end()) {
+          if (g_->has_param_data(t->id)) { ins.push_back(g_->param_data()[t->id]); continue; }
+          missing = true;
+          break;
+        }
+        ins.push_back(it->second);
+      }
+      if (missing) {
+        // input produced on another pipeline stage and not routed here: the op is not runnable locally
+        if (op->type == "comm") {
+          const CommStep& cs = plan.comm[op->id];
+          if (cs.type == CommType::P2P && cs.is_receiver && !cs.is_sender) {
+            outs = exec_comm(cs, op, {}, rc);
+            vals[op->outputs[0]->id] = outs[0];
+          }
+        }
+        continue;
+      }
+      if (op->type == "comm") outs = exec_comm(plan.comm[op->id], op, ins, rc);
+      else outs = op->kernel->compute(*op, ins, &rc);
+    }
+    HB_CHECK(outs.size() == op->outputs.size()) << "op " << op->name() << " returned " << outs.size() << " outputs";
+    for (size_t k = 0; k < outs.size(); ++k) {
+      if (!outs[k].defined()) continue;
+      const TensorId oid = op->outputs[k]->id;
+      auto pg = plan.param_of_grad.find(oid);
+      if (pg != plan.param_of_grad.end()) {
+        // raw parameter gradient: fold into the (fp32) accumulation buffer, do not keep it alive
+        auto acc = accum_grads_.find(pg->second);
+        if (acc == accum_grads_.end()) {
+          const bool fp32 = env_int("HETU_FP32_GRAD_ACCUMULATION", 1) != 0;
+          accum_grads_[pg->second] = fp32 ? outs[k].to(at::kFloat) : outs[k].clone();
+        } else acc->second.add_(outs[k]);
+        continue;
+      }
+      vals[oid] = outs[k];
+    }
+    // free inputs whose last consumer was this op
+    const int pos = base + (int)i;
+    for (auto& t : op->inputs) {
+      auto lu = plan.last_use_fw.find(t->id);
+      if (lu != plan.last_use_fw.end() && lu->second == pos && !keep.count(t->id)) vals.erase(t->id);
+    }
+    if (profile_) {
+      if (at::hasCUDA() && env_int("HETU_B200_FORCE_CPU", 0) == 0) at::cuda::getCurrentCUDAStream().synchronize();
+      op_times_.push_back({op->type + ":" + op->name(), now_ms() - t0});
+    }
+  }
+  (void)mb;
+}
+
+std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetches,
+                                      const std::unordered_map<TensorId, std::vector<at::Tensor>>& feed,
+                                      const RunOptions& opt) {
+  at::NoGradGuard ng;
+  ExecPlan& plan = get_plan(loss, fetches, opt.strategy);
+  if (active_strategy_ >= 0 && active_strategy_ != opt.strategy) switch_strategy(active_strategy_, opt.strategy);
+  active_strategy_ = opt.strategy;
+  if (shapes_strategy_ != -1 && shapes_strategy_ != opt.strategy) {
+    g_->reinfer_shapes(opt.strategy);
+    shapes_strategy_ = opt.strategy;
+  }
+  g_->set_cur_strategy(opt.strategy);
+  if (opt.run_level == RunLevel::TOPO) return {};
+  for (OpDef* op : plan.fw_ops) if (op->has_flag(kFlagVariable)) ensure_param(op, opt.strategy);
+  for (OpDef* op : plan.update_ops)
+    for (auto& t : op->inputs) if (t->producer && t->producer->has_flag(kFlagVariable)) ensure_param(t->producer, opt.strategy);
+  if (opt.run_level == RunLevel::ALLOC) return {};
+  op_times_.clear();
+  const int M = std::max(1, opt.num_micro_batches);
+  const bool inference = plan.bw_ops.empty() || opt.run_level == RunLevel::COMPUTE_ONLY;
+  const bool gpipe = env_str("HETU_PIPELINE", "1F1B") == "GPIPE";
+  auto sched = (plan.num_stages > 1 && !gpipe) ? generate_1f1b_schedule(plan.num_stages, M, inference)
+                                               : generate_gpipe_schedule(plan.num_stages, M, inference);
+  std::vector<PipeTask> tasks;
+  if (plan.num_stages == 1 && !inference) {
+    for (int m = 0; m < M; ++m) { tasks.push_back({PipeTask::FORWARD, m}); tasks.push_back({PipeTask::BACKWARD, m}); }
+  } else tasks = sched[plan.stage];
+
+  std::vector<std::unordered_map<TensorId, at::Tensor>> vals(M);
+  std::vector<std::vector<at::Tensor>> fetched(plan.fetch_ids.size());
+  RunCtx rc;
+  rc.graph = g_;
+  rc.exec = this;
+  rc.num_micro_batches = M;
+  rc.strategy = opt.strategy;
+  rc.training = !inference;
+  rc.seed = 0x5DEECE66Dull + step_ * 1315423911ull;
+  rc.workspace = &workspace_;
+  const double t_start = now_ms();
+  for (auto& task : tasks) {
+    if (task.kind == PipeTask::FLUSH) continue;
+    const int mb = task.micro_batch;
+    rc.micro_batch = mb;
+    if (task.kind == PipeTask::FORWARD) {
+      for (auto& kv : feed) {
+        if (kv.second.empty()) continue;
+        at::Tensor v;
+        if ((int)kv.second.size() == M) v = kv.second[mb];
+        else if (kv.second.size() == 1) {
+          v = M == 1 ? kv.second[0] : at::chunk(kv.second[0], M, 0)[mb];
+        } else HB_FAIL() << "feed has " << kv.second.size() << " entries for " << M << " micro-batches";
+        vals[mb][kv.first] = v.device() == aten_device() ? v : v.to(aten_device(), /*non_blocking=*/true);
+      }
+      run_ops(plan, plan.fw_ops, false, mb, rc, vals[mb]);
+      if (inference) {
+        for (size_t i = 0; i < plan.fetch_ids.size(); ++i) {
+          auto it = vals[mb].find(plan.fetch_ids[i]);
+          if (it != vals[mb].end()) fetched[i].push_back(it->second);
+        }
+        vals[mb].clear();
+      }
+    } else {
+      run_ops(plan, plan.bw_ops, true, mb, rc, vals[mb]);
+      for (size_t i = 0; i < plan.fetch_ids.size(); ++i) {
+        auto it = vals[mb].find(plan.fetch_ids[i]);
+        if (it != vals[mb].end()) fetched[i].push_back(it->second);
+      }
+      vals[mb].clear();
+    }
+  }
+  breakdown_["compute_ms"] = now_ms() - t_start;
+
+  if (!inference && opt.run_level == RunLevel::UPDATE) {
+    const double t_u = now_ms();
+    std::unordered_map<TensorId, at::Tensor> uvals;
+    const double scale = opt.grad_scale / (double)M;
+    for (OpDef* op : plan.update_ops) {
+      if (op->has_flag(kFlagGroup)) continue;
+      if (op->type == "comm") {
+        // deferred gradient synchronisation (DP all-reduce / ZeRO reduce-scatter) on the accumulated gradient
+        const TensorId raw = op->inputs[0]->id;
+        auto pg = plan.param_of_grad.find(raw);
+        if (pg == plan.param_of_grad.end()) continue;
+        auto acc = accum_grads_.find(pg->second);
+        if (acc == accum_grads_.end()) continue;
+        at::Tensor g = acc->second;
+        if (scale != 1.0) g = g * scale;
+        uvals[op->outputs[0]->id] = exec_comm(plan.comm[op->id], op, {g}, rc)[0];
+        continue;
+      }
+      if (!op->has_flag(kFlagOptimizerUpdate)) continue;
+      std::vector<at::Tensor> ins;
+      bool ok = true;
+      for (size_t i = 0; i < op->inputs.size(); ++i) {
+        const Tensor& t = op->inputs[i];
+        if (i == 1) {
+          auto it = uvals.find(t->id);
+          if (it != uvals.end()) { ins.push_back(it->second); continue; }
+          auto acc = accum_grads_.find(op->inputs[0]->id);
+          if (acc == accum_grads_.end()) { ok = false; break; }
+          ins.push_back(scale != 1.0 ? acc->second * scale : acc->second);
+          continue;
+        }
+        ins.push_back(get_param(t));
+      }
+      if (!ok) continue;  // parameter received no gradient in this run
+      op->kernel->compute(*op, ins, &rc);
+    }
+    accum_grads_.clear();
+    breakdown_["update_ms"] = now_ms() - t_u;
+  }
+  ++step_;
+  std::vector<at::Tensor> result;
+  for (size_t i = 0; i < plan.fetch_ids.size(); ++i) {
+    if (fetched[i].empty()) { result.push_back(at::Tensor()); continue; }
+    if (fetched[i].size() == 1) { result.push_back(fetched[i][0]); continue; }
+    if (fetched[i][0].dim() == 0) result.push_back(at::stack(fetched[i]));
+    else result.push_back(at::cat(fetched[i], 0));
+  }
+  breakdown_["total_ms"] = now_ms() - t_start;
+  return result;
+}
+
+// =============================================================================================
+// hot switching: re-shard parameters / optimizer states between two strategies
+// =============================================================================================
+void Executor::switch_strategy(int from, int to) {
+  if (from == to) return;
+  auto& comm = CommRuntime::get();
+  const double t0 = now_ms();
+  int64_t moved = 0;
+  for (auto& opp : g_->ops()) {
+    OpDef* op = opp.get();
+    if (!op->has_flag(kFlagVariable)) continue;
+    Tensor t = op->outputs[0];
+    if (!g_->has_param_data(t->id)) continue;
+    if (op->dst_ds.size() <= (size_t)std::max(from, to)) continue;
+    const DistributedStates& src = op->dst_ds.get(from).get(0);
+    const DistributedStates& dst = op->dst_ds.get(to).get(0);
+    DeviceGroup sg = op->placement(from), dg = op->placement(to);
+    if (src.check_equal(dst) && sg == dg) continue;
+    const auto gshape = op->attrs.ints("global_shape");
+    std::vector<int> sr, dr;
+    for (auto& d : sg.devices()) sr.push_back(d.index());
+    for (auto& d : dg.devices()) dr.push_back(d.index());
+    if (!comm.initialized() || sr.empty() || dr.empty()) continue;
+    auto transfers = plan_resharding(gshape, src, sr, dst, dr, switch_algorithm_from_env());
+    const int me = comm.rank();
+    const int si = local_device_index(sg), di = local_device_index(dg);
+    at::Tensor cur = g_->param_data()[t->id];
+    std::vector<int64_t> sb, ss, db, dsz;
+    if (si >= 0) src.local_slice(gshape, si, &sb, &ss);
+    at::Tensor out;
+    if (di >= 0) {
+      dst.local_slice(gshape, di, &db, &dsz);
+      out = at::empty(dsz, cur.options());
+    }
+    std::vector<std::pair<at::Tensor, int>> sends, recvs;
+    std::vector<std::pair<at::Tensor, at::Tensor>> copy_back;
+    for (auto& tr : transfers) {
+      if (tr.src_device == me) {
+        at::Tensor piece = cur;
+        for (size_t d = 0; d < sb.size(); ++d) piece = piece.narrow((int64_t)d, tr.global.begin[d] - sb[d], tr.global.size[d]);
+        if (tr.dst_device == me) {
+          at::Tensor dv = out;
+          for (size_t d = 0; d < db.size(); ++d) dv = dv.narrow((int64_t)d, tr.global.begin[d] - db[d], tr.global.size[d]);
+          dv.copy_(piece);
+        } else { sends.push_back({piece.contiguous(), tr.dst_device}); moved += piece.numel(); }
+      } else if (tr.dst_device == me) {
+        at::Tensor dv = out;
+        for (size_t d = 0; d < db.size(); ++d) dv = dv.narrow((int64_t)d, tr.global.begin[d] - db[d], tr.global.size[d]);
+        at::Tensor buf = at::empty(tr.global.size, cur.options());
+        recvs.push_back({buf, tr.src_device});
+        copy_back.push_back({dv, buf});
+      }
+    }
+    comm.batched_send_recv(sends, recvs);
+    for (auto& cb : copy_back) cb.first.copy_(cb.second);
+    if (di >= 0) g_->param_data()[t->id] = out;
+    else g_->param_data().erase(t->id);
+    t->shape = dst.local_shape(gshape);
+  }
+  breakdown_["switch_ms"] = now_ms() - t0;
+  breakdown_["switch_elems_sent"] = (double)moved;
+  HB_LOG(INFO) << "hot switch " << from << " -> " << to << " moved " << moved << " elements in " << (now_ms() - t0) << " ms";
+}
+
+}  // namespace hb

@@ -1,0 +1,449 @@
+#include <torch/csrc/autograd/autograd.h>
+#include <torch/csrc/autograd/grad_mode.h>
+
+#include <algorithm>
+#include <deque>
+#include <queue>
+
+#include "exec.h"
+#include "ir.h"
+
+namespace hb {
+
+// ------------------------------------------------------------------ dtype bridge
+at::ScalarType to_aten_dtype(DataType t) {
+  switch (t) {
+    case DataType::UINT8: return at::kByte;
+    case DataType::INT8: return at::kChar;
+    case DataType::INT16: return at::kShort;
+    case DataType::INT32: return at::kInt;
+    case DataType::INT64: return at::kLong;
+    case DataType::FLOAT16: return at::kHalf;
+    case DataType::FLOAT32: return at::kFloat;
+    case DataType::FLOAT64: return at::kDouble;
+    case DataType::BFLOAT16: return at::kBFloat16;
+    case DataType::BOOL: return at::kBool;
+    case DataType::FLOAT8_E4M3: return at::kFloat8_e4m3fn;
+    case DataType::FLOAT8_E5M2: return at::kFloat8_e5m2;
+    case DataType::FLOAT4: case DataType::NFLOAT4: return at::kByte;  // packed storage
+    default: HB_FAIL() << "dtype has no ATen equivalent";
+  }
+}
+DataType from_aten_dtype(at::ScalarType t) {
+  switch (t) {
+    case at::kByte: return DataType::UINT8;
+    case at::kChar: return DataType::INT8;
+    case at::kShort: return DataType::INT16;
+    case at::kInt: return DataType::INT32;
+    case at::kLong: return DataType::INT64;
+    case at::kHalf: return DataType::FLOAT16;
+    case at::kFloat: return DataType::FLOAT32;
+    case at::kDouble: return DataType::FLOAT64;
+    case at::kBFloat16: return DataType::BFLOAT16;
+    case at::kBool: return DataType::BOOL;
+    case at::kFloat8_e4m3fn: return DataType::FLOAT8_E4M3;
+    case at::kFloat8_e5m2: return DataType::FLOAT8_E5M2;
+    default: HB_FAIL() << "unsupported ATen dtype " << int(t);
+  }
+}
+
+// ------------------------------------------------------------------ registry
+OpRegistry& OpRegistry::get() {
+  static OpRegistry r;
+  return r;
+}
+void OpRegistry::add(OpKernel k) {
+  const std::string t = k.type;
+  kernels_[t] = std::move(k);
+}
+const OpKernel* OpRegistry::find(const std::string& type) const {
+  auto it = kernels_.find(type);
+  return it == kernels_.end() ? nullptr : &it->second;
+}
+std::vector<std::string> OpRegistry::list() const {
+  std::vector<std::string> v;
+  for (auto& kv : kernels_) v.push_back(kv.first);
+  std::sort(v.begin(), v.end());
+  return v;
+}
+
+// ------------------------------------------------------------------ graph
+Graph::Graph(GraphKind kind, const std::string& name, int num_strategy)
+    : kind_(kind), name_(name), num_strategy_(num_strategy < 1 ? 1 : num_strategy) {}
+Graph::~Graph() = default;
+
+std::shared_ptr<Graph> Graph::make(GraphKind kind, const std::string& name, int num_strategy) {
+  return std::make_shared<Graph>(kind, name, num_strategy);
+}
+std::shared_ptr<Graph> Graph::default_eager() {
+  static std::shared_ptr<Graph> g = std::make_shared<Graph>(GraphKind::EAGER, "default_eager", 1);
+  return g;
+}
+
+Executor* Graph::executor() {
+  if (!executor_) executor_ = std::make_unique<Executor>(this);
+  return executor_.get();
+}
+
+void Graph::push_subgraph(const std::string& name, const std::string& module_type) {
+  const std::string parent = cur_subgraph();
+  const std::string full = parent.empty() ? name : parent + "." + name;
+  if (!subgraphs_.count(full)) {
+    SubGraphInfo info;
+    info.name = full;
+    info.module_type = module_type;
+    info.parent = parent;
+    subgraphs_[full] = info;
+  }
+  subgraph_stack_.push_back(full);
+}
+void Graph::pop_subgraph() {
+  HB_CHECK(!subgraph_stack_.empty()) << "subgraph stack underflow";
+  subgraph_stack_.pop_back();
+}
+
+void infer_meta_by_meta_exec(OpDef& op) {
+  std::vector<at::Tensor> ins;
+  for (auto& t : op.inputs)
+    ins.push_back(at::empty(t->shape, at::TensorOptions().dtype(to_aten_dtype(t->dtype)).device(at::kMeta)));
+  HB_CHECK(op.kernel->compute) << "op " << op.type << " has no compute function";
+  std::vector<at::Tensor> outs = op.kernel->compute(op, ins, nullptr);
+  HB_CHECK(op.kernel->num_outputs < 0 || (int)outs.size() == op.kernel->num_outputs)
+      << "op " << op.type << " produced " << outs.size() << " outputs, expected " << op.kernel->num_outputs;
+  op.outputs.resize(outs.size());
+  for (size_t i = 0; i < outs.size(); ++i) {
+    if (!op.outputs[i]) op.outputs[i] = std::make_shared<TensorDef>();
+    op.outputs[i]->shape = outs[i].sizes().vec();
+    op.outputs[i]->dtype = from_aten_dtype(outs[i].scalar_type());
+  }
+}
+
+void deduce_states_like_input(OpDef& op, size_t strategy, size_t input_index) {
+  if (op.inputs.size() <= input_index) return;
+  const Tensor& in = op.inputs[input_index];
+  if (!in->has_ds(strategy)) return;
+  for (auto& out : op.outputs) {
+    while (out->ds_hierarchy.size() <= strategy) out->ds_hierarchy.add(DistributedStatesUnion());
+    out->ds_hierarchy.get_mut(strategy) = in->ds_hierarchy.get(strategy);
+  }
+}
+
+void Graph::infer_meta(OpDef& op) {
+  if (op.kernel->infer_meta) op.kernel->infer_meta(op);
+  else infer_meta_by_meta_exec(op);
+}
+void Graph::deduce_states(OpDef& op) {
+  for (int s = 0; s < num_strategy_; ++s) {
+    if (op.kernel->deduce_states) op.kernel->deduce_states(op, s);
+    else deduce_states_like_input(op, s, 0);
+  }
+}
+
+TensorList Graph::make_op(const std::string& type, const TensorList& inputs, AttrMap attrs, OpMeta meta,
+                          std::function<void(OpDef&)> init) {
+  const OpKernel* k = OpRegistry::get().find(type);
+  HB_CHECK(k != nullptr) << "unknown op type '" << type << "'";
+  auto op = std::make_shared<OpDef>();
+  op->id = (OpId)ops_.size();
+  op->type = type;
+  op->inputs = inputs;
+  op->attrs = std::move(attrs);
+  op->meta = std::move(meta);
+  op->kernel = k;
+  op->graph = this;
+  op->is_bwd = ctx_.building_backward;
+  for (auto& t : inputs) HB_CHECK(t != nullptr) << "null input to op " << type;
+  // inherit context
+  if (op->meta.dg_hierarchy.size() == 0) {
+    if (ctx_.dg_hierarchy.size() > 0) op->meta.dg_hierarchy = ctx_.dg_hierarchy;
+    else {
+      for (auto& t : inputs)
+        if (t->producer && t->producer->meta.dg_hierarchy.size() > 0) {
+          op->meta.dg_hierarchy = t->producer->meta.dg_hierarchy;
+          break;
+        }
+    }
+  }
+  if (op->meta.stream_index < 0) op->meta.stream_index = ctx_.stream_index;
+  for (auto& d : ctx_.extra_deps) op->meta.extra_deps.push_back(d);
+  if (op->meta.recompute.empty()) op->meta.recompute = ctx_.recompute;
+  if (op->meta.cpu_offload.empty()) op->meta.cpu_offload = ctx_.cpu_offload;
+  if (op->meta.subgraph.empty()) op->meta.subgraph = cur_subgraph();
+  if (op->meta.name.empty()) op->meta.name = type + "_" + std::to_string(op->id);
+  if (init) init(*op);
+
+  infer_meta(*op);
+  bool any_grad = false;
+  for (auto& t : inputs) any_grad |= t->requires_grad;
+  for (size_t i = 0; i < op->outputs.size(); ++i) {
+    auto& o = op->outputs[i];
+    o->id = next_tensor_id();
+    o->producer = op.get();
+    o->output_index = (int)i;
+    o->graph = this;
+    if (o->name.empty()) o->name = op->meta.name + (op->outputs.size() > 1 ? ":" + std::to_string(i) : "");
+    if (!(k->flags & (kFlagVariable | kFlagPlaceholder | kFlagConst)))
+      o->requires_grad = any_grad && dtype_is_float(o->dtype) && !(k->flags & kFlagNondiff);
+    o->is_grad = op->is_bwd;
+  }
+  deduce_states(*op);
+  for (auto& t : inputs) t->consumers.push_back(op.get());
+  ops_.push_back(op);
+  if (!op->meta.subgraph.empty()) {
+    auto& sg = subgraphs_[op->meta.subgraph];
+    if (sg.name.empty()) sg.name = op->meta.subgraph;
+    if (k->flags & kFlagOptimizerUpdate) sg.update_ops.push_back(op->id);
+    else if (op->is_bwd) sg.bwd_ops.push_back(op->id);
+    else sg.fwd_ops.push_back(op->id);
+  }
+
+  if (kind_ == GraphKind::EAGER) {
+    std::vector<at::Tensor> ins;
+    for (auto& t : inputs) {
+      HB_CHECK(t->eager_data.defined()) << "eager op " << type << " got input " << t->name << " without data";
+      ins.push_back(t->eager_data);
+    }
+    RunCtx rc;
+    rc.graph = this;
+    at::NoGradGuard ng;
+    auto outs = k->compute(*op, ins, &rc);
+    HB_CHECK(outs.size() == op->outputs.size()) << "eager op " << type << " output count mismatch";
+    for (size_t i = 0; i < outs.size(); ++i) {
+      op->outputs[i]->eager_data = outs[i];
+      op->outputs[i]->shape = outs[i].sizes().vec();
+    }
+  }
+  return op->outputs;
+}
+
+void Graph::reinfer_shapes(int strategy) {
+  const int saved = cur_strategy_;
+  cur_strategy_ = strategy;
+  for (auto& op : ops_) {
+    std::vector<Tensor> outs = op->outputs;  // keep tensor identities, refresh shapes in place
+    infer_meta(*op);
+    HB_CHECK(op->outputs.size() == outs.size()) << "shape re-inference changed the arity of " << op->name();
+    for (size_t i = 0; i < outs.size(); ++i) {
+      if (op->outputs[i] != outs[i]) {
+        outs[i]->shape = op->outputs[i]->shape;
+        outs[i]->dtype = op->outputs[i]->dtype;
+        op->outputs[i] = outs[i];
+      }
+    }
+  }
+  cur_strategy_ = saved;
+}
+
+std::vector<Tensor> Graph::parameters() const {
+  std::vector<Tensor> v;
+  for (auto& op : ops_)
+    if (op->has_flag(kFlagVariable) && op->outputs[0]->requires_grad) v.push_back(op->outputs[0]);
+  return v;
+}
+
+// ------------------------------------------------------------------ topo sort
+std::vector<OpDef*> Graph::topo_sort(const TensorList& fetches) const {
+  // collect the ancestor set
+  std::set<OpId> needed;
+  std::vector<OpDef*> stack;
+  for (auto& t : fetches) if (t && t->producer) stack.push_back(t->producer);
+  while (!stack.empty()) {
+    OpDef* op = stack.back();
+    stack.pop_back();
+    if (!needed.insert(op->id).second) continue;
+    for (auto& in : op->inputs) if (in->producer) stack.push_back(in->producer);
+    for (auto& d : op->meta.extra_deps) if (d && d->producer) stack.push_back(d->producer);
+  }
+  // ops are created in a valid topological order (inputs precede consumers), so ascending id is a
+  // topological order that also preserves program order for in-place ops; this is deterministic across ranks
+  std::vector<OpDef*> order;
+  order.reserve(needed.size());
+  for (OpId id : needed) order.push_back(ops_[id].get());
+  return order;
+}
+
+// ------------------------------------------------------------------ autodiff
+TensorList Graph::gradients(const TensorList& ys, const TensorList& xs, const TensorList& grad_ys) {
+  HB_CHECK(grad_ys.empty() || grad_ys.size() == ys.size()) << "grad_ys must match ys";
+  auto order = topo_sort(ys);
+  // which ops lie on a path from xs to ys
+  std::set<TensorId> from_x;
+  for (auto& x : xs) from_x.insert(x->id);
+  std::set<OpId> on_path;
+  for (OpDef* op : order) {
+    bool dep = false;
+    for (auto& in : op->inputs) if (from_x.count(in->id)) dep = true;
+    if (dep) {
+      on_path.insert(op->id);
+      for (auto& o : op->outputs) from_x.insert(o->id);
+    }
+  }
+  std::unordered_map<TensorId, TensorList> pending;
+  const bool prev_bwd = ctx_.building_backward;
+  ctx_.building_backward = true;
+  for (size_t i = 0; i < ys.size(); ++i) {
+    Tensor g = grad_ys.empty() ? nullptr : grad_ys[i];
+    if (!g) {
+      OpMeta m;
+      if (ys[i]->producer) m.dg_hierarchy = ys[i]->producer->meta.dg_hierarchy;
+      g = make_op1("ones_like", {ys[i]}, {}, m);
+    }
+    pending[ys[i]->id].push_back(g);
+  }
+  auto sum_grads = [&](const Tensor& of, TensorList& gs) -> Tensor {
+    if (gs.empty()) return nullptr;
+    if (gs.size() == 1) return gs[0];
+    OpMeta m;
+    if (of->producer) m.dg_hierarchy = of->producer->meta.dg_hierarchy;
+    return make_op1("sum_n", gs, {}, m);
+  };
+  for (auto it = order.rbegin(); it != order.rend(); ++it) {
+    OpDef* op = *it;
+    if (!on_path.count(op->id)) continue;
+    TensorList gouts(op->outputs.size());
+    bool any = false;
+    for (size_t i = 0; i < op->outputs.size(); ++i) {
+      auto pit = pending.find(op->outputs[i]->id);
+      if (pit != pending.end()) {
+        gouts[i] = sum_grads(op->outputs[i], pit->second);
+        any |= (gouts[i] != nullptr);
+      }
+    }
+    if (!any) continue;
+    // gradient ops inherit placement / recompute context of the forward op
+    Ctx saved = ctx_;
+    ctx_.dg_hierarchy = op->meta.dg_hierarchy;
+    ctx_.recompute.clear();
+    ctx_.cpu_offload.clear();
+    const size_t first_new = ops_.size();
+    TensorList gins;
+    if (op->kernel->gradient) gins = op->kernel->gradient(*op, gouts);
+    else if (!(op->kernel->flags & (kFlagNondiff | kFlagPlaceholder | kFlagVariable | kFlagConst)))
+      gins = autograd_gradient(*op, gouts);
+    ctx_ = saved;
+    ctx_.building_backward = true;
+    for (size_t j = first_new; j < ops_.size(); ++j) {
+      ops_[j]->fw_op_id = op->id;
+      if (!op->meta.subgraph.empty() && ops_[j]->meta.subgraph.empty()) ops_[j]->meta.subgraph = op->meta.subgraph;
+    }
+    for (size_t i = 0; i < gins.size() && i < op->inputs.size(); ++i) {
+      if (!gins[i]) continue;
+      if (!op->inputs[i]->requires_grad && !from_x.count(op->inputs[i]->id)) continue;
+      pending[op->inputs[i]->id].push_back(gins[i]);
+    }
+  }
+  TensorList out;
+  for (auto& x : xs) {
+    auto pit = pending.find(x->id);
+    out.push_back(pit == pending.end() ? nullptr : sum_grads(x, pit->second));
+  }
+  ctx_.building_backward = prev_bwd;
+  return out;
+}
+
+void Graph::eager_backward(const Tensor& loss, const Tensor& grad) {
+  HB_CHECK(kind_ == GraphKind::EAGER) << "backward() is only available on eager graphs";
+  TensorList xs;
+  for (auto& op : ops_)
+    if ((op->has_flag(kFlagVariable) || op->has_flag(kFlagConst)) && op->outputs[0]->requires_grad)
+      xs.push_back(op->outputs[0]);
+  TensorList gy;
+  if (grad) gy.push_back(grad);
+  TensorList gs = gradients({loss}, xs, gy);
+  for (size_t i = 0; i < xs.size(); ++i) {
+    if (!gs[i]) continue;
+    if (xs[i]->grad && xs[i]->grad->eager_data.defined() && gs[i]->eager_data.defined()) {
+      xs[i]->grad->eager_data = xs[i]->grad->eager_data + gs[i]->eager_data;
+    } else {
+      xs[i]->grad = gs[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ generic VJP through ATen autograd
+// op "autograd_vjp": inputs = [fw inputs..., grad_outputs (non-null ones)...]; attrs carry the forward op id.
+TensorList autograd_gradient(OpDef& fw, const TensorList& gouts) {
+  Graph* g = fw.graph;
+  TensorList ins = fw.inputs;
+  std::vector<int64_t> gout_idx;
+  for (size_t i = 0; i < gouts.size(); ++i)
+    if (gouts[i]) {
+      ins.push_back(gouts[i]);
+      gout_idx.push_back((int64_t)i);
+    }
+  std::vector<int64_t> diff_inputs;
+  for (size_t i = 0; i < fw.inputs.size(); ++i)
+    if (dtype_is_float(fw.inputs[i]->dtype)) diff_inputs.push_back((int64_t)i);
+  if (diff_inputs.empty()) return TensorList(fw.inputs.size());
+  AttrMap a;
+  a.set("fw_op", (int64_t)fw.id);
+  a.set("gout_idx", gout_idx);
+  a.set("diff_inputs", diff_inputs);
+  a.set("num_fw_inputs", (int64_t)fw.inputs.size());
+  TensorList outs = g->make_op("autograd_vjp", ins, a);
+  TensorList res(fw.inputs.size());
+  for (size_t k = 0; k < diff_inputs.size(); ++k) res[diff_inputs[k]] = outs[k];
+  return res;
+}
+
+static std::vector<at::Tensor> vjp_compute(const OpDef& op, const std::vector<at::Tensor>& in, RunCtx* rc) {
+  const OpDef& fw = *op.graph->op(op.attrs.i("fw_op"));
+  const auto gout_idx = op.attrs.ints("gout_idx");
+  const auto diff_inputs = op.attrs.ints("diff_inputs");
+  const int64_t nfw = op.attrs.i("num_fw_inputs");
+  if (in.size() > 0 && in[0].is_meta()) {
+    std::vector<at::Tensor> outs;
+    for (auto i : diff_inputs) outs.push_back(at::empty_like(in[i]));
+    return outs;
+  }
+  std::vector<at::Tensor> fw_in(in.begin(), in.begin() + nfw);
+  std::vector<at::Tensor> leaves;
+  {
+    at::AutoGradMode gm(true);
+    for (auto i : diff_inputs) {
+      fw_in[i] = fw_in[i].detach().requires_grad_(true);
+      leaves.push_back(fw_in[i]);
+    }
+    std::vector<at::Tensor> fw_out = fw.kernel->compute(fw, fw_in, rc);
+    std::vector<at::Tensor> outs_sel, gouts_sel;
+    for (size_t k = 0; k < gout_idx.size(); ++k) {
+      const at::Tensor& o = fw_out[gout_idx[k]];
+      if (!o.requires_grad()) continue;
+      outs_sel.push_back(o);
+      gouts_sel.push_back(in[nfw + k].to(o.scalar_type()).expand_as(o));
+    }
+    std::vector<at::Tensor> grads;
+    if (!outs_sel.empty())
+      grads = torch::autograd::grad(outs_sel, leaves, gouts_sel, /*retain_graph=*/false, /*create_graph=*/false,
+                                    /*allow_unused=*/true);
+    std::vector<at::Tensor> res;
+    for (size_t k = 0; k < leaves.size(); ++k) {
+      if (k < grads.size() && grads[k].defined()) res.push_back(grads[k].detach());
+      else res.push_back(at::zeros_like(leaves[k]).detach());
+    }
+    return res;
+  }
+}
+
+static void vjp_infer(OpDef& op) {
+  const auto diff_inputs = op.attrs.ints("diff_inputs");
+  op.outputs.resize(diff_inputs.size());
+  for (size_t k = 0; k < diff_inputs.size(); ++k) {
+    if (!op.outputs[k]) op.outputs[k] = std::make_shared<TensorDef>();
+    op.outputs[k]->shape = op.inputs[diff_inputs[k]]->shape;
+    op.outputs[k]->dtype = op.inputs[diff_inputs[k]]->dtype;
+  }
+}
+static void vjp_deduce(OpDef& op, size_t s) {
+  const auto diff_inputs = op.attrs.ints("diff_inputs");
+  for (size_t k = 0; k < diff_inputs.size(); ++k) {
+    const Tensor& in = op.inputs[diff_inputs[k]];
+    if (!in->has_ds(s)) continue;
+    auto& out = op.outputs[k];
+    while (out->ds_hierarchy.size() <= s) out->ds_hierarchy.add(DistributedStatesUnion());
+    out->ds_hierarchy.get_mut(s) = in->ds_hierarchy.get(s);
+  }
+}
+static OpRegistrar _reg_vjp(OpKernel{"autograd_vjp", -1, kFlagNondiff, vjp_compute, nullptr, vjp_deduce, vjp_infer});
+
+}  // namespace hb

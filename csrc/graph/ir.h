@@ -271,6 +271,9 @@ class Graph {
   Executor* executor();   // lazily created (define-and-run)
   int64_t next_tensor_id() { return next_tensor_id_++; }
 
+  // re-run shape inference for every op under `strategy` (local shapes are strategy dependent)
+  void reinfer_shapes(int strategy);
+
   // eager helpers
   void eager_backward(const Tensor& loss, const Tensor& grad = nullptr);
 

@@ -1,0 +1,54 @@
+// Glue between at::Tensor and the raw-pointer kernel APIs, plus DS helpers shared by op definitions.
+#pragma once
+#include <ATen/ATen.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <cuda_runtime.h>
+
+#include "../kernels/attention_sm100.h"
+#include "../kernels/gemm_sm100.h"
+#include "../kernels/kernels.h"
+#include "ir.h"
+
+namespace hb {
+
+// the hand-written sm_100a path is taken for CUDA bf16 tensors; anything else (CPU tests, fp32
+// unit tests) goes through ATen with identical semantics
+inline bool is_native(const at::Tensor& t) { return t.is_cuda() && t.scalar_type() == at::kBFloat16; }
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+inline void cuda_ok(cudaError_t e, const char* what) {
+  HB_CHECK(e == cudaSuccess) << what << " failed: " << cudaGetErrorString(e);
+}
+// set HETU_B200_STRICT=1 (the GPU test suite does) to make any silent ATen fallback on a CUDA bf16 hot op an error
+bool strict_native();
+void note_fallback(const char* op);
+int64_t fallback_count();
+
+at::Tensor native_add(const at::Tensor& a, const at::Tensor& b);
+
+inline at::Tensor flatten_rows(const at::Tensor& x) { return x.reshape({-1, x.size(-1)}); }
+
+inline void set_out_ds(OpDef& op, size_t out_idx, size_t strategy, const DistributedStates& ds) {
+  auto& out = op.outputs[out_idx];
+  while (out->ds_hierarchy.size() <= strategy) out->ds_hierarchy.add(DistributedStatesUnion());
+  out->ds_hierarchy.get_mut(strategy) = DistributedStatesUnion({ds});
+}
+inline void copy_out_ds(OpDef& op, size_t out_idx, size_t strategy, const Tensor& from) {
+  if (!from->has_ds(strategy)) return;
+  auto& out = op.outputs[out_idx];
+  while (out->ds_hierarchy.size() <= strategy) out->ds_hierarchy.add(DistributedStatesUnion());
+  out->ds_hierarchy.get_mut(strategy) = from->ds_hierarchy.get(strategy);
+}
+
+// Layout of Y = A x B for a contraction: A has `a_nd` dims and contracts dim `a_k`; B is 2-D and contracts
+// dim `b_k`, its free dim `b_n` becomes Y's last dim.  Contracted shards become partial sums.
+DistributedStates matmul_ds(const DistributedStates& a, int a_nd, int a_k, const DistributedStates& b, int b_k, int b_n,
+                            int out_n_dim, const std::vector<int>& a_dim_to_out);
+
+inline void make_out(OpDef& op, size_t i, const std::vector<int64_t>& shape, DataType dt) {
+  if (op.outputs.size() <= i) op.outputs.resize(i + 1);
+  if (!op.outputs[i]) op.outputs[i] = std::make_shared<TensorDef>();
+  op.outputs[i]->shape = shape;
+  op.outputs[i]->dtype = dt;
+}
+
+}  // namespace hb

@@ -1,0 +1,402 @@
+// Communication ops: the abstract `comm` op (declares a target layout; lowered by
+// the executor), explicit collectives with rank lists, vocab-parallel cross entropy
+// and context-parallel (ring) attention.
+// (capability parity: hetu/graph/ops/Communication.{h,cc}, VocabParallelCrossEntropyLoss.cc,
+//  ParallelAttention.{h,cc})
+#include <ATen/ATen.h>
+
+#include "exec.h"
+#include "ir.h"
+#include "op_utils.h"
+
+namespace hb {
+
+using Ts = std::vector<at::Tensor>;
+
+// ------------------------------------------------------------------ abstract comm
+static void comm_infer(OpDef& op) {
+  const Tensor& x = op.inputs[0];
+  make_out(op, 0, x->shape, x->dtype);
+  const int s = op.graph ? op.graph->cur_strategy() : 0;
+  if (x->has_ds(s) && op.dst_ds.size() > (size_t)s && op.dst_ds.get(s).size() > 0) {
+    const auto g = x->ds(s).global_shape(x->shape);
+    op.outputs[0]->shape = op.dst_ds.get(s).get(0).local_shape(g);
+  }
+  if (!x->symbolic_shape.empty()) op.outputs[0]->symbolic_shape.clear();
+}
+static void comm_deduce(OpDef& op, size_t s) {
+  auto& out = op.outputs[0];
+  while (out->ds_hierarchy.size() <= s) out->ds_hierarchy.add(DistributedStatesUnion());
+  if (op.dst_ds.size() > s) out->ds_hierarchy.get_mut(s) = op.dst_ds.get(s);
+  else if (op.dst_ds.size() == 1) out->ds_hierarchy.get_mut(s) = op.dst_ds.get(0);
+}
+static Ts comm_compute(const OpDef&, const Ts& in, RunCtx*) {
+  // single-process / eager graphs: a layout change is the identity
+  return {in[0]};
+}
+static TensorList comm_grad(OpDef& op, const TensorList& g) {
+  // the gradient returns to the layout of the forward input, with "partial" read as "duplicate"
+  // (every contributor of a partial sum receives the same gradient)
+  const Tensor& x = op.inputs[0];
+  DistributedStatesHierarchy target;
+  for (size_t s = 0; s < x->ds_hierarchy.size(); ++s) {
+    DistributedStatesUnion u;
+    const auto& src_u = x->ds_hierarchy.get(s);
+    for (size_t i = 0; i < src_u.size(); ++i) {
+      const DistributedStates& ds = src_u.get(i);
+      if (ds.get_dim(kPartialDim) > 1) {
+        auto st = ds.combine_states({kPartialDim}, kDupDim);
+        auto order = ds.combine_order({kPartialDim}, kDupDim);
+        u.add(DistributedStates(ds.device_num(), st, order));
+      } else u.add(ds);
+    }
+    u.set_hetero_dim(src_u.hetero_dim() == kPartialDim ? kDupDim : src_u.hetero_dim());
+    target.add(u);
+  }
+  OpMeta m;
+  if (x->producer) m.dg_hierarchy = x->producer->meta.dg_hierarchy;  // gradient lives where the input lived
+  Tensor gx = op.graph->make_op1("comm", {g[0]}, {}, m, [&](OpDef& o) { o.dst_ds = target; });
+  return {gx};
+}
+HB_REGISTER_OP(comm, "comm", 1, kFlagComm | kFlagNoMetaExec, comm_compute, comm_grad, comm_deduce, comm_infer);
+
+// ------------------------------------------------------------------ explicit collectives (rank lists in attrs)
+static std::vector<int> ranks_attr(const OpDef& op) {
+  std::vector<int> r;
+  for (auto v : op.attrs.ints("ranks")) r.push_back((int)v);
+  return r;
+}
+static bool single(const OpDef& op) { return !CommRuntime::get().initialized() || op.attrs.ints("ranks").size() <= 1; }
+
+static Ts all_reduce_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  if (in[0].is_meta() || single(op)) return {in[0]};
+  return {CommRuntime::get().all_reduce(in[0], ranks_attr(op), reduction_from_name(op.attrs.s("reduction", "sum")),
+                                        op.attrs.b("fp32_reduce"))};
+}
+static TensorList all_reduce_grad(OpDef& op, const TensorList& g) { return {g[0]}; }
+HB_REGISTER_OP(all_reduce, "all_reduce", 1, kFlagComm, all_reduce_compute, all_reduce_grad, nullptr, nullptr);
+
+static Ts all_gather_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const int64_t n = (int64_t)op.attrs.ints("ranks").size();
+  const int64_t dim = op.attrs.i("dim", 0);
+  if (in[0].is_meta()) {
+    auto shp = in[0].sizes().vec();
+    shp[dim] *= std::max<int64_t>(n, 1);
+    return {at::empty(shp, in[0].options())};
+  }
+  if (single(op)) return {in[0]};
+  return {CommRuntime::get().all_gather(in[0], ranks_attr(op), (int)dim)};
+}
+static Ts reduce_scatter_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const int64_t n = (int64_t)op.attrs.ints("ranks").size();
+  const int64_t dim = op.attrs.i("dim", 0);
+  if (in[0].is_meta()) {
+    auto shp = in[0].sizes().vec();
+    shp[dim] /= std::max<int64_t>(n, 1);
+    return {at::empty(shp, in[0].options())};
+  }
+  if (single(op)) return {in[0]};
+  return {CommRuntime::get().reduce_scatter(in[0], ranks_attr(op), (int)dim, ReductionType::SUM, op.attrs.b("fp32_reduce"))};
+}
+static TensorList all_gather_grad(OpDef& op, const TensorList& g) {
+  return {op.graph->make_op1("reduce_scatter", {g[0]}, op.attrs)};
+}
+static TensorList reduce_scatter_grad(OpDef& op, const TensorList& g) {
+  return {op.graph->make_op1("all_gather", {g[0]}, op.attrs)};
+}
+HB_REGISTER_OP(all_gather, "all_gather", 1, kFlagComm, all_gather_compute, all_gather_grad, nullptr, nullptr);
+HB_REGISTER_OP(reduce_scatter, "reduce_scatter", 1, kFlagComm, reduce_scatter_compute, reduce_scatter_grad, nullptr, nullptr);
+
+// all_to_all over `ranks`: split dim `split_dim` into n chunks, chunk j goes to rank j, received chunks are
+// concatenated along `concat_dim` (MoE dispatch / combine, Ulysses-style head<->sequence exchange)
+static Ts all_to_all_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const int64_t n = std::max<int64_t>((int64_t)op.attrs.ints("ranks").size(), 1);
+  const int64_t sd = op.attrs.i("split_dim", 0), cd = op.attrs.i("concat_dim", 0);
+  if (in[0].is_meta()) {
+    auto shp = in[0].sizes().vec();
+    shp[sd] /= n;
+    shp[cd] *= n;
+    return {at::empty(shp, in[0].options())};
+  }
+  if (single(op)) return {in[0]};
+  return {CommRuntime::get().all_to_all(in[0], ranks_attr(op), (int)sd, (int)cd)};
+}
+static TensorList all_to_all_grad(OpDef& op, const TensorList& g) {
+  AttrMap a = op.attrs;
+  a.set("split_dim", op.attrs.i("concat_dim", 0));
+  a.set("concat_dim", op.attrs.i("split_dim", 0));
+  return {op.graph->make_op1("all_to_all", {g[0]}, a)};
+}
+HB_REGISTER_OP(all_to_all, "all_to_all", 1, kFlagComm, all_to_all_compute, all_to_all_grad, nullptr, nullptr);
+
+static Ts broadcast_comm_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  if (in[0].is_meta() || single(op)) return {in[0]};
+  return {CommRuntime::get().broadcast(in[0], ranks_attr(op), (int)op.attrs.i("root"))};
+}
+HB_REGISTER_OP(broadcast_comm, "broadcast_comm", 1, kFlagComm | kFlagNondiff, broadcast_comm_compute, nullptr, nullptr, nullptr);
+
+// ------------------------------------------------------------------ vocab-parallel cross entropy
+// logits [T, V/t] sharded on the vocab dim, labels hold *global* vocabulary ids.
+// Three small all-reduces (max, sum-exp, target logit) between local kernels.
+static std::vector<int> tp_ranks(const OpDef& op, RunCtx* rc) {
+  auto explicit_ranks = op.attrs.ints("ranks");
+  std::vector<int> r;
+  if (!explicit_ranks.empty()) {
+    for (auto v : explicit_ranks) r.push_back((int)v);
+    return r;
+  }
+  // derive from the logits layout: peers along the vocab (last) dim
+  const Tensor& lg = op.inputs[0];
+  const int s = rc ? rc->strategy : 0;
+  if (!lg->has_ds(s) || !rc || !rc->exec) return {};
+  const DistributedStates& ds = lg->ds(s);
+  const DeviceGroup grp = op.placement(s);
+  if (grp.empty()) return {};
+  const int me = rc->exec->local_device_index(grp);
+  if (me < 0) return {};
+  for (int i : ds.get_device_indices_by_dim(lg->ndim() - 1, me)) r.push_back(grp.get(i).index());
+  return r;
+}
+static Ts vp_ce_compute(const OpDef& op, const Ts& in, RunCtx* rc) {
+  const at::Tensor& logits = in[0];
+  const at::Tensor& labels = in[1];
+  const int64_t ignore = op.attrs.i("ignore_index", -1);
+  const std::string red = op.attrs.s("reduction", "mean");
+  const int64_t Vl = logits.size(-1);
+  std::vector<int64_t> lshape(logits.sizes().begin(), logits.sizes().end() - 1);
+  auto fopt = logits.options().dtype(at::kFloat);
+  if (logits.is_meta()) return {red == "none" ? at::empty(lshape, fopt) : at::empty({}, fopt), at::empty_like(logits)};
+  std::vector<int> ranks = tp_ranks(op, rc);
+  auto& comm = CommRuntime::get();
+  int my_pos = 0;
+  for (size_t i = 0; i < ranks.size(); ++i) if (ranks[i] == comm.rank()) my_pos = (int)i;
+  const bool dist = comm.initialized() && ranks.size() > 1;
+  const int64_t vstart = op.attrs.has("vocab_start") ? op.attrs.i("vocab_start") : (int64_t)my_pos * Vl;
+  at::Tensor lab = labels.to(at::kLong).reshape({-1}).contiguous();
+  const int64_t rows = lab.numel();
+  at::Tensor per_tok = at::empty({rows}, fopt), unit;
+  if (is_native(logits) && logits.is_contiguous() && Vl % 8 == 0) {
+    unit = op.attrs.b("donate_logits") ? logits : logits.clone();
+    at::Tensor rmax = at::empty({rows}, fopt), sexp = at::empty({rows}, fopt), tgt = at::empty({rows}, fopt);
+    cuda_ok(vp_ce_local_max(unit.data_ptr(), rmax.data_ptr<float>(), rows, (int)Vl, Vl, cur_stream()), "vp_ce_max");
+    if (dist) rmax = comm.all_reduce(rmax, ranks, ReductionType::MAX);
+    cuda_ok(vp_ce_local_sum(unit.data_ptr(), lab.data_ptr<int64_t>(), rmax.data_ptr<float>(), sexp.data_ptr<float>(),
+                            tgt.data_ptr<float>(), rows, (int)Vl, Vl, vstart, cur_stream()), "vp_ce_sum");
+    if (dist) {
+      at::Tensor both = at::stack({sexp, tgt});
+      both = comm.all_reduce(both, ranks, ReductionType::SUM);
+      sexp = both[0].contiguous();
+      tgt = both[1].contiguous();
+    }
+    cuda_ok(vp_ce_finish(unit.data_ptr(), lab.data_ptr<int64_t>(), rmax.data_ptr<float>(), sexp.data_ptr<float>(),
+                         tgt.data_ptr<float>(), per_tok.data_ptr<float>(), rows, (int)Vl, Vl, vstart, ignore, 1.0f, true,
+                         cur_stream()), "vp_ce_finish");
+  } else {
+    at::Tensor lf = logits.to(at::kFloat).reshape({rows, Vl});
+    at::Tensor rmax = std::get<0>(lf.max(-1));
+    if (dist) rmax = comm.all_reduce(rmax, ranks, ReductionType::MAX);
+    at::Tensor ex = at::exp(lf - rmax.unsqueeze(1));
+    at::Tensor sexp = ex.sum(-1);
+    at::Tensor local = lab - vstart;
+    at::Tensor mine = (local >= 0).logical_and(local < Vl);
+    at::Tensor safe = at::where(mine, local, at::zeros_like(local));
+    at::Tensor tgt = lf.gather(1, safe.unsqueeze(1)).squeeze(1) * mine.to(at::kFloat);
+    if (dist) {
+      at::Tensor both = comm.all_reduce(at::stack({sexp, tgt}), ranks, ReductionType::SUM);
+      sexp = both[0];
+      tgt = both[1];
+    }
+    at::Tensor valid = (lab != ignore).to(at::kFloat);
+    at::Tensor lse = rmax + at::log(sexp);
+    per_tok = (lse - tgt) * valid;
+    at::Tensor u = ex / sexp.unsqueeze(1);
+    u.scatter_add_(1, safe.unsqueeze(1), -mine.to(at::kFloat).unsqueeze(1));
+    unit = (u * valid.unsqueeze(1)).to(logits.scalar_type()).reshape(logits.sizes());
+  }
+  at::Tensor loss;
+  if (red == "none") loss = per_tok.reshape(lshape);
+  else if (red == "sum") loss = per_tok.sum();
+  else loss = per_tok.sum() / (lab != ignore).sum().to(at::kFloat).clamp_min(1.0);
+  return {loss, unit.reshape(logits.sizes())};
+}
+static TensorList vp_ce_grad(OpDef& op, const TensorList& g) {
+  AttrMap a;
+  a.set("reduction", op.attrs.s("reduction", "mean"));
+  a.set("ignore_index", op.attrs.i("ignore_index", -1));
+  return {op.graph->make_op1("softmax_ce_sparse_bwd", {g[0], op.outputs[1], op.inputs[1]}, a), nullptr};
+}
+static void vp_ce_deduce(OpDef& op, size_t s) {
+  const Tensor& lg = op.inputs[0];
+  const Tensor& lab = op.inputs[1];
+  if (!lg->has_ds(s)) return;
+  copy_out_ds(op, 1, s, lg);
+  const std::string red = op.attrs.s("reduction", "mean");
+  if (red == "none" && lab->has_ds(s)) { copy_out_ds(op, 0, s, lab); return; }
+  const int n = lg->ds(s).device_num();
+  set_out_ds(op, 0, s, DistributedStates(n, {{kDupDim, n}}, {kDupDim}));
+}
+HB_REGISTER_OP(vocab_parallel_cross_entropy, "vocab_parallel_cross_entropy", 2, 0, vp_ce_compute, vp_ce_grad, vp_ce_deduce,
+               nullptr);
+
+// ------------------------------------------------------------------ context-parallel attention
+// q, k, v hold this rank's sequence chunk(s); KV blocks travel around the CP ring with batched
+// send/recv while the local flash-attention kernel runs, and partial results are merged with their
+// log-sum-exp.  Causal load balance: SYM (zig-zag) split -- rank i owns chunks i and 2c-1-i.
+// Backward re-walks the ring, circulating dK/dV accumulators with the KV blocks.
+static std::vector<int> cp_ranks(const OpDef& op) {
+  std::vector<int> r;
+  for (auto v : op.attrs.ints("ranks")) r.push_back((int)v);
+  return r;
+}
+struct AttnPiece { at::Tensor o, lse; };
+static AttnPiece local_attn(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, double scale, bool causal) {
+  static const OpKernel* kern = OpRegistry::get().find("attn");
+  OpDef tmp;
+  tmp.attrs.set("causal", causal);
+  tmp.attrs.set("softmax_scale", scale);
+  tmp.kernel = kern;
+  auto r = kern->compute(tmp, {q, k, v}, nullptr);
+  return {r[0], r[1]};
+}
+// merge two normalised partial attention results
+static void merge_piece(at::Tensor& o, at::Tensor& lse, const AttnPiece& p) {
+  if (!o.defined()) { o = p.o.to(at::kFloat); lse = p.lse.clone(); return; }
+  at::Tensor nl = at::logaddexp(lse, p.lse);
+  at::Tensor w0 = at::exp(lse - nl).permute({0, 2, 1}).unsqueeze(-1);   // [B,S,H,1]
+  at::Tensor w1 = at::exp(p.lse - nl).permute({0, 2, 1}).unsqueeze(-1);
+  w0 = at::where(at::isfinite(w0), w0, at::zeros_like(w0));
+  w1 = at::where(at::isfinite(w1), w1, at::zeros_like(w1));
+  o = o * w0 + p.o.to(at::kFloat) * w1;
+  lse = nl;
+}
+// position of this rank's chunks: SYM -> two half-chunks (i, 2c-1-i); NORMAL -> one chunk i
+static std::vector<int> owned_chunks(int idx, int c, bool sym) {
+  if (sym) return {idx, 2 * c - 1 - idx};
+  return {idx};
+}
+static Ts parallel_attn_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& q = in[0];
+  const at::Tensor& k = in[1];
+  const at::Tensor& v = in[2];
+  auto fopt = q.options().dtype(at::kFloat);
+  if (q.is_meta()) return {at::empty(q.sizes(), q.options()), at::empty({q.size(0), q.size(2), q.size(1)}, fopt)};
+  const bool causal = op.attrs.b("causal", true);
+  const double scale = op.attrs.f("softmax_scale", 0.0) > 0 ? op.attrs.f("softmax_scale") : 1.0 / std::sqrt((double)q.size(3));
+  std::vector<int> ranks = cp_ranks(op);
+  auto& comm = CommRuntime::get();
+  const int c = (int)ranks.size();
+  if (c <= 1 || !comm.initialized()) {
+    AttnPiece p = local_attn(q, k, v, scale, causal);
+    return {p.o, p.lse};
+  }
+  int idx = 0;
+  for (int i = 0; i < c; ++i) if (ranks[i] == comm.rank()) idx = i;
+  const bool sym = causal && op.attrs.s("split_pattern", env_str("HETU_PARALLEL_ATTN_SPLIT_PATTERN", "SYM")) == "SYM";
+  const int64_t S = q.size(1);
+  const int nchunk = sym ? 2 : 1;
+  HB_CHECK(S % nchunk == 0) << "sequence chunk not divisible for the SYM split";
+  const int64_t cs = S / nchunk;
+  auto my_chunks = owned_chunks(idx, c, sym);
+  std::vector<at::Tensor> o_acc(nchunk), lse_acc(nchunk);
+  at::Tensor kv_cur = at::stack({k, v}).contiguous();
+  const int next = ranks[(idx + 1) % c], prev = ranks[(idx - 1 + c) % c];
+  for (int round = 0; round < c; ++round) {
+    at::Tensor kv_next;
+    const int src_idx = (idx - round + c) % c;  // owner of the KV block we hold this round
+    std::vector<std::pair<at::Tensor, int>> sends, recvs;
+    if (round + 1 < c) {
+      kv_next = at::empty_like(kv_cur);
+      sends.push_back({kv_cur, next});
+      recvs.push_back({kv_next, prev});
+      comm.batched_send_recv(sends, recvs);   // overlaps with the attention kernels below (async on NCCL)
+    }
+    auto src_chunks = owned_chunks(src_idx, c, sym);
+    for (int qi = 0; qi < nchunk; ++qi) {
+      at::Tensor qc = q.narrow(1, qi * cs, cs);
+      for (int ki = 0; ki < nchunk; ++ki) {
+        const int qpos = my_chunks[qi], kpos = src_chunks[ki];
+        if (causal && kpos > qpos) continue;  // fully masked block: skipped
+        at::Tensor kc = kv_cur[0].narrow(1, ki * cs, cs), vc = kv_cur[1].narrow(1, ki * cs, cs);
+        AttnPiece p = local_attn(qc, kc, vc, scale, causal && kpos == qpos);
+        merge_piece(o_acc[qi], lse_acc[qi], p);
+      }
+    }
+    if (round + 1 < c) kv_cur = kv_next;
+  }
+  at::Tensor o = at::cat(o_acc, 1).to(q.scalar_type());
+  at::Tensor lse = at::cat(lse_acc, 2);
+  return {o, lse};
+}
+// inputs: do, q, k, v, o, lse -> dq, dk, dv
+static Ts parallel_attn_bwd_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& d_o = in[0];
+  const at::Tensor& q = in[1];
+  const at::Tensor& k = in[2];
+  const at::Tensor& v = in[3];
+  const at::Tensor& o = in[4];
+  const at::Tensor& lse = in[5];
+  if (q.is_meta()) return {at::empty(q.sizes(), q.options()), at::empty(k.sizes(), k.options()), at::empty(v.sizes(), v.options())};
+  const bool causal = op.attrs.b("causal", true);
+  const double scale = op.attrs.f("softmax_scale", 0.0) > 0 ? op.attrs.f("softmax_scale") : 1.0 / std::sqrt((double)q.size(3));
+  static const OpKernel* bwd = OpRegistry::get().find("attn_bwd");
+  auto run_bwd = [&](const at::Tensor& dO, const at::Tensor& Q, const at::Tensor& K, const at::Tensor& V, const at::Tensor& O,
+                     const at::Tensor& L, bool cz) {
+    OpDef tmp;
+    tmp.attrs.set("causal", cz);
+    tmp.attrs.set("softmax_scale", scale);
+    tmp.kernel = bwd;
+    return bwd->compute(tmp, {dO.contiguous(), Q.contiguous(), K.contiguous(), V.contiguous(), O.contiguous(), L.contiguous()}, nullptr);
+  };
+  std::vector<int> ranks = cp_ranks(op);
+  auto& comm = CommRuntime::get();
+  const int c = (int)ranks.size();
+  if (c <= 1 || !comm.initialized()) return run_bwd(d_o, q, k, v, o, lse, causal);
+  int idx = 0;
+  for (int i = 0; i < c; ++i) if (ranks[i] == comm.rank()) idx = i;
+  const bool sym = causal && op.attrs.s("split_pattern", env_str("HETU_PARALLEL_ATTN_SPLIT_PATTERN", "SYM")) == "SYM";
+  const int64_t S = q.size(1);
+  const int nchunk = sym ? 2 : 1;
+  const int64_t cs = S / nchunk;
+  auto my_chunks = owned_chunks(idx, c, sym);
+  at::Tensor dq = at::zeros(q.sizes(), q.options().dtype(at::kFloat));
+  // the travelling buffer carries [k, v, dk, dv] so gradients return to the owner after a full loop
+  at::Tensor buf = at::stack({k.to(at::kFloat), v.to(at::kFloat), at::zeros_like(k, at::kFloat), at::zeros_like(v, at::kFloat)}).contiguous();
+  const int next = ranks[(idx + 1) % c], prev = ranks[(idx - 1 + c) % c];
+  for (int round = 0; round < c; ++round) {
+    const int src_idx = (idx - round + c) % c;
+    auto src_chunks = owned_chunks(src_idx, c, sym);
+    at::Tensor kb = buf[0].to(q.scalar_type()), vb = buf[1].to(q.scalar_type());
+    for (int qi = 0; qi < nchunk; ++qi) {
+      for (int ki = 0; ki < nchunk; ++ki) {
+        const int qpos = my_chunks[qi], kpos = src_chunks[ki];
+        if (causal && kpos > qpos) continue;
+        // the local kernel recomputes P from the *global* lse of the query rows, so per-block calls compose
+        auto r = run_bwd(d_o.narrow(1, qi * cs, cs), q.narrow(1, qi * cs, cs), kb.narrow(1, ki * cs, cs), vb.narrow(1, ki * cs, cs),
+                         o.narrow(1, qi * cs, cs), lse.narrow(2, qi * cs, cs), causal && kpos == qpos);
+        dq.narrow(1, qi * cs, cs).add_(r[0].to(at::kFloat));
+        buf[2].narrow(1, ki * cs, cs).add_(r[1].to(at::kFloat));
+        buf[3].narrow(1, ki * cs, cs).add_(r[2].to(at::kFloat));
+      }
+    }
+    // rotate (after the last round the buffer is sent once more so every block returns home)
+    at::Tensor nb = at::empty_like(buf);
+    std::vector<std::pair<at::Tensor, int>> sends = {{buf, next}}, recvs = {{nb, prev}};
+    comm.batched_send_recv(sends, recvs);
+    buf = nb;
+  }
+  return {dq.to(q.scalar_type()), buf[2].to(k.scalar_type()), buf[3].to(v.scalar_type())};
+}
+static TensorList parallel_attn_grad(OpDef& op, const TensorList& g) {
+  TensorList r = op.graph->make_op("parallel_attn_bwd", {g[0], op.inputs[0], op.inputs[1], op.inputs[2], op.outputs[0], op.outputs[1]}, op.attrs);
+  return {r[0], r[1], r[2]};
+}
+static void pattn_deduce(OpDef& op, size_t s) { copy_out_ds(op, 0, s, op.inputs[0]); }
+static void pattn_bwd_deduce(OpDef& op, size_t s) {
+  copy_out_ds(op, 0, s, op.inputs[1]);
+  copy_out_ds(op, 1, s, op.inputs[2]);
+  copy_out_ds(op, 2, s, op.inputs[3]);
+}
+HB_REGISTER_OP(parallel_attn, "parallel_attn", 2, kFlagAttention | kFlagComm, parallel_attn_compute, parallel_attn_grad, pattn_deduce, nullptr);
+HB_REGISTER_OP(parallel_attn_bwd, "parallel_attn_bwd", 3, kFlagAttention | kFlagComm, parallel_attn_bwd_compute, nullptr, pattn_bwd_deduce, nullptr);
+
+}  // namespace hb

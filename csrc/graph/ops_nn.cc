@@ -1,0 +1,921 @@
+// Hot-path ops of transformer training, bound to the hand-written sm_100a kernels
+// (tcgen05 GEMM / flash attention, fused norms, activations, embedding, losses),
+// with ATen reference implementations for CPU / fp32 so the same graph runs in the
+// CPU test-suite.  Every op has an explicit gradient (no recompute-VJP here).
+// (capability parity: hetu/graph/ops/{Linear,matmul,LayerNorm,RMSNorm,Gelu,Relu,SwiGLU,
+//  EmbeddingLookup,SoftmaxCrossEntropySparse,Attention,Rotary,Dropout}.cc)
+#include <ATen/ATen.h>
+
+#include <atomic>
+
+#include "exec.h"
+#include "ir.h"
+#include "op_utils.h"
+
+namespace hb {
+
+using Ts = std::vector<at::Tensor>;
+
+static std::atomic<int64_t> g_fallbacks{0};
+bool strict_native() {
+  static bool s = env_int("HETU_B200_STRICT", 0) != 0;
+  return s;
+}
+void note_fallback(const char* op) {
+  g_fallbacks.fetch_add(1);
+  HB_CHECK(!strict_native()) << "op " << op << " fell back to ATen on a CUDA bf16 tensor (HETU_B200_STRICT=1)";
+}
+int64_t fallback_count() { return g_fallbacks.load(); }
+
+at::Tensor native_add(const at::Tensor& a, const at::Tensor& b) {
+  if (is_native(a) && is_native(b) && a.sizes() == b.sizes() && a.is_contiguous() && b.is_contiguous()) {
+    at::Tensor out = at::empty_like(a);
+    cuda_ok(add_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), cur_stream()), "add_bf16");
+    return out;
+  }
+  return a + b;
+}
+
+// ------------------------------------------------------------------ DS rule for contractions
+DistributedStates matmul_ds(const DistributedStates& a, int a_nd, int a_k, const DistributedStates& b, int b_k, int b_n,
+                            int out_n_dim, const std::vector<int>& a_dim_to_out) {
+  (void)a_nd;
+  const int n = a.device_num();
+  HB_CHECK(n == b.device_num()) << "matmul operands live on different numbers of devices";
+  const int k_split = a.get_dim(a_k);
+  HB_CHECK(k_split == b.get_dim(b_k)) << "contraction dim is split " << k_split << "-way on one operand and "
+                                      << b.get_dim(b_k) << "-way on the other";
+  std::map<int, int> st;
+  int used = 1;
+  for (auto& kv : a.states()) {
+    if (kv.second <= 1 || kv.first < 0 || kv.first == a_k) continue;
+    st[a_dim_to_out[kv.first]] = kv.second;
+    used *= kv.second;
+  }
+  const int n_split = b.get_dim(b_n);
+  if (n_split > 1) { st[out_n_dim] = (st.count(out_n_dim) ? st[out_n_dim] : 1) * n_split; used *= n_split; }
+  const int partial = k_split * a.get_dim(kPartialDim) * b.get_dim(kPartialDim);
+  if (partial > 1) { st[kPartialDim] = partial; used *= partial; }
+  HB_CHECK(n % used == 0) << "inconsistent layouts in matmul: " << a << " x " << b;
+  if (n / used > 1) st[kDupDim] = n / used;
+  // device order: follow A's order, k -> partial, A's duplicate axis -> B's n split (or stays duplicate)
+  std::vector<int> order;
+  auto push = [&](int d) {
+    if (st.count(d) && st[d] > 1 && std::find(order.begin(), order.end(), d) == order.end()) order.push_back(d);
+  };
+  for (int o : a.order()) {
+    if (o == a_k || o == kPartialDim) push(kPartialDim);
+    else if (o == kDupDim) { if (n_split > 1) push(out_n_dim); push(kDupDim); }
+    else push(a_dim_to_out[o]);
+  }
+  for (auto& kv : st) push(kv.first);
+  return DistributedStates(n, st, order);
+}
+
+// ------------------------------------------------------------------ GEMM helpers
+static int act_code(const std::string& a) {
+  if (a.empty() || a == "none") return ACT_NONE;
+  if (a == "gelu") return ACT_GELU;
+  if (a == "relu") return ACT_RELU;
+  if (a == "gelu_tanh") return ACT_GELU_TANH;
+  if (a == "silu") return ACT_SILU;
+  HB_FAIL() << "unknown activation " << a;
+}
+static at::Tensor aten_act(const at::Tensor& x, int code) {
+  switch (code) {
+    case ACT_GELU: return at::gelu(x);
+    case ACT_RELU: return at::relu(x);
+    case ACT_GELU_TANH: return at::gelu(x, "tanh");
+    case ACT_SILU: return at::silu(x);
+    default: return x;
+  }
+}
+
+// C[M,N] = A * B with explicit operand majors on raw 2-D contiguous tensors
+static void run_gemm(const at::Tensor& A, bool a_mn, const at::Tensor& B, bool b_mn, at::Tensor& C, int64_t M, int64_t N,
+                     int64_t K, const at::Tensor* bias, const at::Tensor* aux_in, int aux_mode, at::Tensor* aux_out,
+                     int act, bool accumulate, float alpha = 1.0f) {
+  GemmCall c;
+  c.A = A.data_ptr(); c.B = B.data_ptr(); c.C = C.data_ptr();
+  c.M = (int)M; c.N = (int)N; c.K = (int)K;
+  c.lda = A.stride(0); c.ldb = B.stride(0); c.ldc = C.stride(0);
+  c.a_mn_major = a_mn; c.b_mn_major = b_mn;
+  c.out = C.scalar_type() == at::kFloat ? GemmOut::FP32 : GemmOut::BF16;
+  if (bias) c.bias = bias->data_ptr();
+  if (aux_in) { c.aux_in = aux_in->data_ptr(); c.aux_mode = aux_mode; c.ld_aux = aux_in->stride(0); }
+  if (aux_out) { c.aux_out = aux_out->data_ptr(); c.ld_aux = aux_out->stride(0); }
+  c.act = act;
+  c.accumulate = accumulate;
+  c.alpha = alpha;
+  cuda_ok(gemm_bf16(c, cur_stream()), "tcgen05 gemm");
+}
+static bool gemm_ok(const at::Tensor& t) {
+  return is_native(t) && t.dim() == 2 && t.stride(1) == 1 && (t.stride(0) % 8) == 0 &&
+         (reinterpret_cast<uintptr_t>(t.data_ptr()) % 16) == 0;
+}
+
+// ------------------------------------------------------------------ linear
+// inputs: x [..., K], w ([N, K] when trans_b else [K, N]), [bias [N]], [residual [..., N]]
+// outputs: y (and the pre-activation when an activation is fused)
+static Ts linear_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const bool trans_b = op.attrs.b("trans_b", true);
+  const bool has_bias = op.attrs.b("has_bias"), has_res = op.attrs.b("has_residual");
+  const int act = act_code(op.attrs.s("act"));
+  const at::Tensor& x = in[0];
+  const at::Tensor& w = in[1];
+  const at::Tensor* bias = has_bias ? &in[2] : nullptr;
+  const at::Tensor* res = has_res ? &in[has_bias ? 3 : 2] : nullptr;
+  const int64_t N = trans_b ? w.size(0) : w.size(1);
+  const int64_t K = x.size(-1);
+  std::vector<int64_t> oshape = x.sizes().vec();
+  oshape.back() = N;
+  if (x.is_meta()) {
+    Ts r = {at::empty(oshape, x.options())};
+    if (act != ACT_NONE) r.push_back(at::empty(oshape, x.options()));
+    return r;
+  }
+  at::Tensor x2 = flatten_rows(x).contiguous();
+  const int64_t M = x2.size(0);
+  if (gemm_ok(x2) && gemm_ok(w) && (!bias || is_native(*bias)) && (N % 8) == 0) {
+    at::Tensor y = at::empty({M, N}, x.options());
+    at::Tensor pre;
+    at::Tensor r2;
+    if (res) r2 = flatten_rows(*res).contiguous();
+    if (act != ACT_NONE) pre = at::empty({M, N}, x.options());
+    run_gemm(x2, false, w, !trans_b, y, M, N, K, bias, res ? &r2 : nullptr, AUX_ADD, act != ACT_NONE ? &pre : nullptr, act,
+             false);
+    Ts out = {y.reshape(oshape)};
+    if (act != ACT_NONE) out.push_back(pre.reshape(oshape));
+    return out;
+  }
+  if (is_native(x)) note_fallback("linear");
+  at::Tensor y = trans_b ? at::matmul(x2, w.t()) : at::matmul(x2, w);
+  if (bias) y = y + *bias;
+  Ts out;
+  if (act != ACT_NONE) {
+    at::Tensor pre = y;
+    y = aten_act(pre, act);
+    if (res) y = y + flatten_rows(*res);
+    out = {y.reshape(oshape), pre.reshape(oshape)};
+  } else {
+    if (res) y = y + flatten_rows(*res);
+    out = {y.reshape(oshape)};
+  }
+  return out;
+}
+
+// dgrad: dx[..., K] = dy[..., N] * W    (W [N,K] when trans_b)
+static Ts linear_dgrad_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const bool trans_b = op.attrs.b("trans_b", true);
+  const at::Tensor& dy = in[0];
+  const at::Tensor& w = in[1];
+  const int64_t K = trans_b ? w.size(1) : w.size(0);
+  std::vector<int64_t> oshape = dy.sizes().vec();
+  oshape.back() = K;
+  if (dy.is_meta()) return {at::empty(oshape, dy.options())};
+  at::Tensor d2 = flatten_rows(dy).contiguous();
+  const int64_t M = d2.size(0), N = d2.size(1);
+  if (gemm_ok(d2) && gemm_ok(w) && (K % 8) == 0) {
+    at::Tensor dx = at::empty({M, K}, dy.options());
+    // dx[M,K] = dy[M,N] * W[N,K]: B must be [K(out-n), N(contract)]; W[N,K] row-major = MN-major B
+    run_gemm(d2, false, w, trans_b, dx, M, K, N, nullptr, nullptr, 0, nullptr, ACT_NONE, false);
+    return {dx.reshape(oshape)};
+  }
+  if (is_native(dy)) note_fallback("linear_dgrad");
+  return {(trans_b ? at::matmul(d2, w) : at::matmul(d2, w.t())).reshape(oshape)};
+}
+// wgrad: dw = dy^T * x  ([N,K] when trans_b else [K,N])
+static Ts linear_wgrad_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const bool trans_b = op.attrs.b("trans_b", true);
+  const at::Tensor& dy = in[0];
+  const at::Tensor& x = in[1];
+  const int64_t N = dy.size(-1), K = x.size(-1);
+  std::vector<int64_t> wshape = trans_b ? std::vector<int64_t>{N, K} : std::vector<int64_t>{K, N};
+  if (dy.is_meta()) return {at::empty(wshape, dy.options())};
+  at::Tensor d2 = flatten_rows(dy).contiguous(), x2 = flatten_rows(x).contiguous();
+  const int64_t T = d2.size(0);
+  if (gemm_ok(d2) && gemm_ok(x2) && (N % 8) == 0 && (K % 8) == 0) {
+    at::Tensor dw = at::empty(wshape, dy.options());
+    if (trans_b) run_gemm(d2, true, x2, true, dw, N, K, T, nullptr, nullptr, 0, nullptr, ACT_NONE, false);
+    else run_gemm(x2, true, d2, true, dw, K, N, T, nullptr, nullptr, 0, nullptr, ACT_NONE, false);
+    return {dw};
+  }
+  if (is_native(dy)) note_fallback("linear_wgrad");
+  return {trans_b ? at::matmul(d2.t(), x2) : at::matmul(x2.t(), d2)};
+}
+static Ts bias_grad_compute(const OpDef&, const Ts& in, RunCtx*) {
+  const at::Tensor& dy = in[0];
+  if (dy.is_meta()) return {at::empty({dy.size(-1)}, dy.options())};
+  at::Tensor d2 = flatten_rows(dy).contiguous();
+  if (is_native(d2)) {
+    at::Tensor acc = at::empty({d2.size(1)}, d2.options().dtype(at::kFloat));
+    cuda_ok(colsum_bf16(d2.data_ptr(), acc.data_ptr<float>(), d2.size(0), (int)d2.size(1), false, cur_stream()), "colsum");
+    return {acc.to(dy.scalar_type())};
+  }
+  return {d2.sum(0)};
+}
+
+static void linear_deduce(OpDef& op, size_t s) {
+  const Tensor& x = op.inputs[0];
+  const Tensor& w = op.inputs[1];
+  if (!x->has_ds(s) || !w->has_ds(s)) { deduce_states_like_input(op, s, 0); return; }
+  const bool trans_b = op.attrs.b("trans_b", true);
+  const int nd = x->ndim();
+  std::vector<int> map(nd);
+  for (int i = 0; i < nd; ++i) map[i] = i;
+  DistributedStates out = matmul_ds(x->ds(s), nd, nd - 1, w->ds(s), trans_b ? 1 : 0, trans_b ? 0 : 1, nd - 1, map);
+  for (size_t i = 0; i < op.outputs.size(); ++i) set_out_ds(op, i, s, out);
+}
+static void dgrad_deduce(OpDef& op, size_t s) {
+  const Tensor& dy = op.inputs[0];
+  const Tensor& w = op.inputs[1];
+  if (!dy->has_ds(s) || !w->has_ds(s)) { deduce_states_like_input(op, s, 0); return; }
+  const bool trans_b = op.attrs.b("trans_b", true);
+  const int nd = dy->ndim();
+  std::vector<int> map(nd);
+  for (int i = 0; i < nd; ++i) map[i] = i;
+  set_out_ds(op, 0, s, matmul_ds(dy->ds(s), nd, nd - 1, w->ds(s), trans_b ? 0 : 1, trans_b ? 1 : 0, nd - 1, map));
+}
+static void wgrad_deduce(OpDef& op, size_t s) {
+  const Tensor& dy = op.inputs[0];
+  const Tensor& x = op.inputs[1];
+  if (!dy->has_ds(s) || !x->has_ds(s)) return;
+  const bool trans_b = op.attrs.b("trans_b", true);
+  // collapse leading (token) dims: they are all contracted.  Treat operands as 2-D [T, feat].
+  auto collapse = [](const DistributedStates& ds, int nd) {
+    std::map<int, int> st;
+    int tok = 1;
+    for (auto& kv : ds.states()) {
+      if (kv.second <= 1) continue;
+      if (kv.first < 0) st[kv.first] = kv.second;
+      else if (kv.first == nd - 1) st[1] = kv.second;
+      else tok *= kv.second;
+    }
+    if (tok > 1) st[0] = tok;
+    std::vector<int> order;
+    for (int o : ds.order()) {
+      int m = o < 0 ? o : (o == nd - 1 ? 1 : 0);
+      if (std::find(order.begin(), order.end(), m) == order.end()) order.push_back(m);
+    }
+    return DistributedStates(ds.device_num(), st, order);
+  };
+  DistributedStates a = collapse(dy->ds(s), dy->ndim());  // [T, N]
+  DistributedStates b = collapse(x->ds(s), x->ndim());    // [T, K]
+  DistributedStates out = trans_b ? matmul_ds(a, 2, 0, b, 0, 1, 1, {0, 0})   // dW[N,K]: rows from dy dim1
+                                  : matmul_ds(b, 2, 0, a, 0, 1, 1, {0, 0});
+  set_out_ds(op, 0, s, out);
+}
+static void bias_grad_deduce(OpDef& op, size_t s) {
+  const Tensor& dy = op.inputs[0];
+  if (!dy->has_ds(s)) return;
+  const DistributedStates& ds = dy->ds(s);
+  const int nd = dy->ndim();
+  std::map<int, int> st;
+  int partial = ds.get_dim(kPartialDim);
+  for (auto& kv : ds.states()) {
+    if (kv.second <= 1) continue;
+    if (kv.first == kDupDim) st[kDupDim] = kv.second;
+    else if (kv.first == nd - 1) st[0] = kv.second;
+    else if (kv.first >= 0) partial *= kv.second;
+  }
+  if (partial > 1) st[kPartialDim] = partial;
+  std::vector<int> order;
+  for (int o : ds.order()) {
+    int m = (o == nd - 1) ? 0 : (o >= 0 ? kPartialDim : o);
+    if (std::find(order.begin(), order.end(), m) == order.end()) order.push_back(m);
+  }
+  set_out_ds(op, 0, s, DistributedStates(ds.device_num(), st, order));
+}
+
+static TensorList linear_grad(OpDef& op, const TensorList& g) {
+  Graph* gr = op.graph;
+  const bool has_bias = op.attrs.b("has_bias"), has_res = op.attrs.b("has_residual");
+  const std::string act = op.attrs.s("act");
+  Tensor dy = g[0];
+  HB_CHECK(dy != nullptr) << "linear without an output gradient";
+  TensorList res(op.inputs.size());
+  if (has_res) res[has_bias ? 3 : 2] = dy;
+  Tensor dpre = dy;
+  if (!act.empty() && act != "none") {
+    AttrMap a;
+    a.set("kind", act);
+    dpre = gr->make_op1("unary_act_bwd", {dy, op.outputs[1]}, a);
+  }
+  AttrMap a;
+  a.set("trans_b", op.attrs.b("trans_b", true));
+  if (op.inputs[0]->requires_grad) res[0] = gr->make_op1("linear_dgrad", {dpre, op.inputs[1]}, a);
+  if (op.inputs[1]->requires_grad) res[1] = gr->make_op1("linear_wgrad", {dpre, op.inputs[0]}, a);
+  if (has_bias && op.inputs[2]->requires_grad) res[2] = gr->make_op1("bias_grad", {dpre});
+  return res;
+}
+static void linear_infer(OpDef& op) { infer_meta_by_meta_exec(op); }
+HB_REGISTER_OP(linear, "linear", -1, 0, linear_compute, linear_grad, linear_deduce, linear_infer);
+HB_REGISTER_OP(linear_dgrad, "linear_dgrad", 1, 0, linear_dgrad_compute, nullptr, dgrad_deduce, nullptr);
+HB_REGISTER_OP(linear_wgrad, "linear_wgrad", 1, 0, linear_wgrad_compute, nullptr, wgrad_deduce, nullptr);
+HB_REGISTER_OP(bias_grad, "bias_grad", 1, 0, bias_grad_compute, nullptr, bias_grad_deduce, nullptr);
+
+// matmul(a, b, trans_a, trans_b): general 2-D matmul (autograd VJP for the long tail)
+static Ts matmul_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const bool ta = op.attrs.b("trans_a"), tb = op.attrs.b("trans_b");
+  const at::Tensor& a = in[0];
+  const at::Tensor& b = in[1];
+  if (!a.is_meta() && gemm_ok(a) && gemm_ok(b) && a.dim() == 2 && b.dim() == 2) {
+    const int64_t M = ta ? a.size(1) : a.size(0), K = ta ? a.size(0) : a.size(1), N = tb ? b.size(0) : b.size(1);
+    if (M % 8 == 0 && N % 8 == 0 && K % 8 == 0) {
+      at::Tensor c = at::empty({M, N}, a.options());
+      run_gemm(a, ta, b, !tb, c, M, N, K, nullptr, nullptr, 0, nullptr, ACT_NONE, false);
+      return {c};
+    }
+  }
+  return {at::matmul(ta ? a.transpose(-1, -2) : a, tb ? b.transpose(-1, -2) : b)};
+}
+static void matmul_deduce(OpDef& op, size_t s) {
+  const Tensor& a = op.inputs[0];
+  const Tensor& b = op.inputs[1];
+  if (!a->has_ds(s) || !b->has_ds(s) || a->ndim() != 2 || b->ndim() != 2) { deduce_states_like_input(op, s, 0); return; }
+  const bool ta = op.attrs.b("trans_a"), tb = op.attrs.b("trans_b");
+  std::vector<int> map = ta ? std::vector<int>{0, 0} : std::vector<int>{0, 1};
+  set_out_ds(op, 0, s, matmul_ds(a->ds(s), 2, ta ? 0 : 1, b->ds(s), tb ? 1 : 0, tb ? 0 : 1, 1, map));
+}
+HB_REGISTER_OP(matmul, "matmul", 1, 0, matmul_compute, nullptr, matmul_deduce, nullptr);
+
+// ------------------------------------------------------------------ unary activations on the hot path
+static int unary_code(const std::string& k) {
+  if (k == "gelu") return U_GELU;
+  if (k == "relu") return U_RELU;
+  if (k == "silu") return U_SILU;
+  if (k == "gelu_tanh") return U_GELU_TANH;
+  HB_FAIL() << "unknown activation kind " << k;
+}
+static Ts unary_act_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const int code = unary_code(op.attrs.s("kind"));
+  const at::Tensor& x = in[0];
+  if (!x.is_meta() && is_native(x) && x.is_contiguous()) {
+    at::Tensor y = at::empty_like(x);
+    cuda_ok(unary_fwd(code, x.data_ptr(), y.data_ptr(), x.numel(), cur_stream()), "unary_fwd");
+    return {y};
+  }
+  switch (code) {
+    case U_GELU: return {at::gelu(x)};
+    case U_RELU: return {at::relu(x)};
+    case U_SILU: return {at::silu(x)};
+    default: return {at::gelu(x, "tanh")};
+  }
+}
+static Ts unary_act_bwd_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const int code = unary_code(op.attrs.s("kind"));
+  const at::Tensor& dy = in[0];
+  const at::Tensor& x = in[1];
+  if (dy.is_meta()) return {at::empty_like(x)};
+  if (is_native(x) && is_native(dy) && x.is_contiguous() && dy.is_contiguous()) {
+    at::Tensor dx = at::empty_like(x);
+    cuda_ok(unary_bwd(code, dy.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel(), cur_stream()), "unary_bwd");
+    return {dx};
+  }
+  at::Tensor xf = x.to(at::kFloat), d;
+  switch (code) {
+    case U_GELU: d = 0.5 * (1 + at::erf(xf * M_SQRT1_2)) + xf * at::exp(-0.5 * xf * xf) * 0.3989422804014327; break;
+    case U_RELU: d = (xf > 0).to(at::kFloat); break;
+    case U_SILU: { auto sg = at::sigmoid(xf); d = sg * (1 + xf * (1 - sg)); break; }
+    default: {
+      auto u = 0.7978845608028654 * (xf + 0.044715 * xf * xf * xf);
+      auto t = at::tanh(u);
+      d = 0.5 * (1 + t) + 0.5 * xf * (1 - t * t) * 0.7978845608028654 * (1 + 0.134145 * xf * xf);
+    }
+  }
+  return {(dy.to(at::kFloat) * d).to(x.scalar_type())};
+}
+static TensorList unary_act_grad(OpDef& op, const TensorList& g) {
+  AttrMap a;
+  a.set("kind", op.attrs.s("kind"));
+  return {op.graph->make_op1("unary_act_bwd", {g[0], op.inputs[0]}, a)};
+}
+HB_REGISTER_OP(unary_act, "unary_act", 1, 0, unary_act_compute, unary_act_grad, nullptr, nullptr);
+HB_REGISTER_OP(unary_act_bwd, "unary_act_bwd", 1, 0, unary_act_bwd_compute, nullptr, nullptr, nullptr);
+
+// swiglu: y = silu(x[..., :d]) * x[..., d:]
+static Ts swiglu_compute(const OpDef&, const Ts& in, RunCtx*) {
+  const at::Tensor& x = in[0];
+  const int64_t d = x.size(-1) / 2;
+  std::vector<int64_t> oshape = x.sizes().vec();
+  oshape.back() = d;
+  if (x.is_meta()) return {at::empty(oshape, x.options())};
+  if (is_native(x) && x.is_contiguous() && d % 8 == 0) {
+    at::Tensor y = at::empty(oshape, x.options());
+    cuda_ok(swiglu_fwd(x.data_ptr(), y.data_ptr(), x.numel() / (2 * d), (int)d, cur_stream()), "swiglu_fwd");
+    return {y};
+  }
+  return {at::silu(x.narrow(-1, 0, d)) * x.narrow(-1, d, d)};
+}
+static Ts swiglu_bwd_compute(const OpDef&, const Ts& in, RunCtx*) {
+  const at::Tensor& dy = in[0];
+  const at::Tensor& x = in[1];
+  if (dy.is_meta()) return {at::empty_like(x)};
+  const int64_t d = x.size(-1) / 2;
+  if (is_native(x) && is_native(dy) && x.is_contiguous() && dy.is_contiguous() && d % 8 == 0) {
+    at::Tensor dx = at::empty_like(x);
+    cuda_ok(swiglu_bwd(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel() / (2 * d), (int)d, cur_stream()), "swiglu_bwd");
+    return {dx};
+  }
+  auto a = x.narrow(-1, 0, d).to(at::kFloat), b = x.narrow(-1, d, d).to(at::kFloat), g = dy.to(at::kFloat);
+  auto sg = at::sigmoid(a);
+  auto da = g * b * sg * (1 + a * (1 - sg));
+  auto db = g * a * sg;
+  return {at::cat({da, db}, -1).to(x.scalar_type())};
+}
+static TensorList swiglu_grad(OpDef& op, const TensorList& g) {
+  return {op.graph->make_op1("swiglu_bwd", {g[0], op.inputs[0]})};
+}
+HB_REGISTER_OP(swiglu, "swiglu", 1, 0, swiglu_compute, swiglu_grad, nullptr, nullptr);
+HB_REGISTER_OP(swiglu_bwd, "swiglu_bwd", 1, 0, swiglu_bwd_compute, nullptr,
+               [](OpDef& op, size_t s) { copy_out_ds(op, 0, s, op.inputs[1]); }, nullptr);
+
+// ------------------------------------------------------------------ layer / rms norm
+// outputs: y, mean (layernorm only), rstd
+static Ts norm_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const bool rms = op.attrs.b("rms");
+  const double eps = op.attrs.f("eps", 1e-5);
+  const at::Tensor& x = in[0];
+  const at::Tensor& gamma = in[1];
+  const int64_t cols = x.size(-1);
+  std::vector<int64_t> sshape(x.sizes().begin(), x.sizes().end() - 1);
+  auto fopt = x.options().dtype(at::kFloat);
+  if (x.is_meta()) return {at::empty_like(x), at::empty(sshape, fopt), at::empty(sshape, fopt)};
+  const int64_t rows = x.numel() / cols;
+  if (is_native(x) && x.is_contiguous() && is_native(gamma)) {
+    at::Tensor y = at::empty_like(x), mean = at::empty(sshape, fopt), rstd = at::empty(sshape, fopt);
+    if (rms) {
+      cuda_ok(rmsnorm_fwd(x.data_ptr(), gamma.data_ptr(), y.data_ptr(), rstd.data_ptr<float>(), rows, (int)cols,
+                          (float)eps, cur_stream()), "rmsnorm_fwd");
+    } else {
+      const void* beta = in.size() > 2 ? in[2].data_ptr() : nullptr;
+      cuda_ok(layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta, y.data_ptr(), mean.data_ptr<float>(),
+                            rstd.data_ptr<float>(), rows, (int)cols, (float)eps, cur_stream()), "layernorm_fwd");
+    }
+    return {y, mean, rstd};
+  }
+  at::Tensor xf = x.to(at::kFloat);
+  at::Tensor mean, rstd, y;
+  if (rms) {
+    mean = at::zeros(sshape, fopt);
+    rstd = at::rsqrt(xf.pow(2).mean(-1) + eps);
+    y = xf * rstd.unsqueeze(-1) * gamma.to(at::kFloat);
+  } else {
+    mean = xf.mean(-1);
+    at::Tensor var = (xf - mean.unsqueeze(-1)).pow(2).mean(-1);
+    rstd = at::rsqrt(var + eps);
+    y = (xf - mean.unsqueeze(-1)) * rstd.unsqueeze(-1) * gamma.to(at::kFloat);
+    if (in.size() > 2) y = y + in[2].to(at::kFloat);
+  }
+  return {y.to(x.scalar_type()), mean, rstd};
+}
+// inputs: dy, x, gamma, mean, rstd -> dx, dgamma, (dbeta)
+static Ts norm_bwd_compute(const OpDef& op, const Ts& in, RunCtx* rc) {
+  const bool rms = op.attrs.b("rms");
+  const at::Tensor& dy = in[0];
+  const at::Tensor& x = in[1];
+  const at::Tensor& gamma = in[2];
+  const at::Tensor& mean = in[3];
+  const at::Tensor& rstd = in[4];
+  const int64_t cols = x.size(-1);
+  if (dy.is_meta()) {
+    Ts r = {at::empty_like(x), at::empty_like(gamma)};
+    if (!rms) r.push_back(at::empty_like(gamma));
+    return r;
+  }
+  const int64_t rows = x.numel() / cols;
+  if (is_native(x) && is_native(dy) && x.is_contiguous() && dy.is_contiguous()) {
+    auto fopt = x.options().dtype(at::kFloat);
+    at::Tensor dx = at::empty_like(x), dg = at::empty({cols}, fopt), db = at::empty({cols}, fopt);
+    at::Tensor ws = rc && rc->workspace ? rc->scratch("norm_bwd_ws", {2 * (int64_t)ln_bwd_parts() * cols}, at::kFloat, x.device())
+                                        : at::empty({2 * (int64_t)ln_bwd_parts() * cols}, fopt);
+    if (rms) {
+      cuda_ok(rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), rstd.data_ptr<float>(), dx.data_ptr(),
+                          dg.data_ptr<float>(), ws.data_ptr<float>(), rows, (int)cols, false, cur_stream()), "rmsnorm_bwd");
+      return {dx, dg.to(gamma.scalar_type())};
+    }
+    cuda_ok(layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
+                          dx.data_ptr(), dg.data_ptr<float>(), db.data_ptr<float>(), ws.data_ptr<float>(), rows,
+                          (int)cols, false, cur_stream()), "layernorm_bwd");
+    return {dx, dg.to(gamma.scalar_type()), db.to(gamma.scalar_type())};
+  }
+  at::Tensor xf = x.to(at::kFloat), g = dy.to(at::kFloat), gm = gamma.to(at::kFloat);
+  at::Tensor xhat = rms ? xf * rstd.unsqueeze(-1) : (xf - mean.unsqueeze(-1)) * rstd.unsqueeze(-1);
+  at::Tensor dyg = g * gm;
+  at::Tensor m2 = (dyg * xhat).mean(-1, true);
+  at::Tensor dx = rms ? rstd.unsqueeze(-1) * (dyg - xhat * m2) : rstd.unsqueeze(-1) * (dyg - dyg.mean(-1, true) - xhat * m2);
+  at::Tensor dgm = (g * xhat).reshape({-1, cols}).sum(0);
+  Ts r = {dx.to(x.scalar_type()), dgm.to(gamma.scalar_type())};
+  if (!rms) r.push_back(g.reshape({-1, cols}).sum(0).to(gamma.scalar_type()));
+  return r;
+}
+static void norm_infer(OpDef& op) { infer_meta_by_meta_exec(op); }
+static TensorList norm_grad(OpDef& op, const TensorList& g) {
+  AttrMap a;
+  a.set("rms", op.attrs.b("rms"));
+  TensorList outs = op.graph->make_op("norm_bwd", {g[0], op.inputs[0], op.inputs[1], op.outputs[1], op.outputs[2]}, a);
+  TensorList r(op.inputs.size());
+  r[0] = outs[0];
+  r[1] = outs[1];
+  if (op.inputs.size() > 2 && outs.size() > 2) r[2] = outs[2];
+  return r;
+}
+static void norm_bwd_deduce(OpDef& op, size_t s) {
+  copy_out_ds(op, 0, s, op.inputs[1]);
+  // dgamma / dbeta: token dims are reduced -> partial over every split of x
+  const Tensor& x = op.inputs[1];
+  if (!x->has_ds(s)) return;
+  const DistributedStates& ds = x->ds(s);
+  int partial = ds.get_dim(kPartialDim);
+  std::map<int, int> st;
+  for (auto& kv : ds.states()) {
+    if (kv.second <= 1) continue;
+    if (kv.first >= 0) partial *= kv.second;
+    else if (kv.first == kDupDim) st[kDupDim] = kv.second;
+  }
+  if (partial > 1) st[kPartialDim] = partial;
+  std::vector<int> order;
+  for (int o : ds.order()) {
+    int m = o >= 0 ? kPartialDim : o;
+    if (std::find(order.begin(), order.end(), m) == order.end()) order.push_back(m);
+  }
+  DistributedStates gds(ds.device_num(), st, order);
+  for (size_t i = 1; i < op.outputs.size(); ++i) set_out_ds(op, i, s, gds);
+}
+HB_REGISTER_OP(norm_op, "fused_norm", 3, 0, norm_compute, norm_grad, nullptr, norm_infer);
+HB_REGISTER_OP(norm_bwd, "norm_bwd", -1, 0, norm_bwd_compute, nullptr, norm_bwd_deduce, nullptr);
+
+// ------------------------------------------------------------------ embedding
+// inputs: table [V, H], ids [...]   (ids outside [0, V) produce zeros: vocab-parallel shards rely on it)
+static Ts embedding_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& table = in[0];
+  const at::Tensor& ids = in[1];
+  std::vector<int64_t> oshape = ids.sizes().vec();
+  oshape.push_back(table.size(1));
+  if (table.is_meta()) return {at::empty(oshape, table.options())};
+  const int64_t offset = op.attrs.i("vocab_offset", 0);
+  at::Tensor idl = ids.to(at::kLong).contiguous();
+  if (offset != 0) idl = idl - offset;
+  if (is_native(table) && table.is_contiguous() && table.size(1) % 8 == 0) {
+    at::Tensor y = at::empty(oshape, table.options());
+    cuda_ok(embedding_fwd(idl.data_ptr<int64_t>(), nullptr, table.data_ptr(), nullptr, y.data_ptr(), idl.numel(),
+                          (int)table.size(1), table.size(0), cur_stream()), "embedding_fwd");
+    return {y};
+  }
+  at::Tensor valid = (idl >= 0).logical_and(idl < table.size(0));
+  at::Tensor safe = at::where(valid, idl, at::zeros_like(idl));
+  at::Tensor y = at::embedding(table, safe) * valid.unsqueeze(-1).to(table.scalar_type());
+  return {y};
+}
+static Ts embedding_grad_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& dy = in[0];
+  const at::Tensor& ids = in[1];
+  const int64_t V = op.attrs.i("vocab"), H = dy.size(-1);
+  if (dy.is_meta()) return {at::empty({V, H}, dy.options())};
+  const int64_t offset = op.attrs.i("vocab_offset", 0);
+  at::Tensor idl = ids.to(at::kLong).contiguous();
+  if (offset != 0) idl = idl - offset;
+  at::Tensor d2 = dy.reshape({-1, H}).contiguous();
+  if (is_native(d2) && H % 8 == 0) {
+    at::Tensor acc = at::zeros({V, H}, dy.options().dtype(at::kFloat));
+    cuda_ok(embedding_bwd(idl.data_ptr<int64_t>(), nullptr, d2.data_ptr(), acc.data_ptr<float>(), nullptr, idl.numel(),
+                          (int)H, V, cur_stream()), "embedding_bwd");
+    return {acc.to(dy.scalar_type())};
+  }
+  at::Tensor flat = idl.reshape({-1});
+  at::Tensor valid = (flat >= 0).logical_and(flat < V);
+  at::Tensor safe = at::where(valid, flat, at::zeros_like(flat));
+  at::Tensor acc = at::zeros({V, H}, dy.options().dtype(at::kFloat));
+  acc.index_add_(0, safe, d2.to(at::kFloat) * valid.unsqueeze(-1).to(at::kFloat));
+  return {acc.to(dy.scalar_type())};
+}
+static TensorList embedding_grad(OpDef& op, const TensorList& g) {
+  AttrMap a;
+  a.set("vocab", op.inputs[0]->shape[0]);
+  a.set("vocab_offset", op.attrs.i("vocab_offset", 0));
+  return {op.graph->make_op1("embedding_grad", {g[0], op.inputs[1]}, a), nullptr};
+}
+static void embedding_deduce(OpDef& op, size_t s) {
+  const Tensor& table = op.inputs[0];
+  const Tensor& ids = op.inputs[1];
+  if (!ids->has_ds(s)) return;
+  const DistributedStates& ids_ds = ids->ds(s);
+  if (!table->has_ds(s) || table->ds(s).get_dim(0) <= 1) { copy_out_ds(op, 0, s, ids); return; }
+  // vocab-parallel table: the replicas of ids along the table's vocab split hold partial sums
+  const int vsplit = table->ds(s).get_dim(0);
+  std::map<int, int> st;
+  for (auto& kv : ids_ds.states()) if (kv.second > 1) st[kv.first] = kv.second;
+  HB_CHECK(st.count(kDupDim) && st[kDupDim] % vsplit == 0) << "vocab-parallel embedding needs ids duplicated over the vocab split";
+  st[kDupDim] /= vsplit;
+  st[kPartialDim] = (st.count(kPartialDim) ? st[kPartialDim] : 1) * vsplit;
+  std::vector<int> order;
+  for (int o : ids_ds.order()) {
+    if (o == kDupDim) { order.push_back(kPartialDim); if (st[kDupDim] > 1) order.push_back(kDupDim); }
+    else order.push_back(o);
+  }
+  set_out_ds(op, 0, s, DistributedStates(ids_ds.device_num(), st, order));
+}
+static void embedding_grad_deduce(OpDef& op, size_t s) {
+  // dense table gradient: partial over every token split of dy; split on vocab handled by the caller's comm
+  const Tensor& dy = op.inputs[0];
+  if (!dy->has_ds(s)) return;
+  const DistributedStates& ds = dy->ds(s);
+  const int nd = dy->ndim();
+  int partial = ds.get_dim(kPartialDim);
+  std::map<int, int> st;
+  for (auto& kv : ds.states()) {
+    if (kv.second <= 1) continue;
+    if (kv.first == kDupDim) st[kDupDim] = kv.second;
+    else if (kv.first == nd - 1) st[1] = kv.second;
+    else if (kv.first >= 0) partial *= kv.second;
+  }
+  if (partial > 1) st[kPartialDim] = partial;
+  std::vector<int> order;
+  for (int o : ds.order()) {
+    int m = (o == nd - 1) ? 1 : (o >= 0 ? kPartialDim : o);
+    if (std::find(order.begin(), order.end(), m) == order.end()) order.push_back(m);
+  }
+  set_out_ds(op, 0, s, DistributedStates(ds.device_num(), st, order));
+}
+HB_REGISTER_OP(embedding_lookup, "embedding_lookup", 1, 0, embedding_compute, embedding_grad, embedding_deduce, nullptr);
+HB_REGISTER_OP(embedding_grad, "embedding_grad", 1, 0, embedding_grad_compute, nullptr, embedding_grad_deduce, nullptr);
+
+// ------------------------------------------------------------------ sparse softmax cross entropy
+// inputs: logits [..., V], labels [...]; outputs: loss (reduced per attrs), dlogits_unit = softmax - onehot (saved)
+static Ts ce_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& logits = in[0];
+  const at::Tensor& labels = in[1];
+  const int64_t ignore = op.attrs.i("ignore_index", -1);
+  const std::string red = op.attrs.s("reduction", "mean");
+  const int64_t V = logits.size(-1);
+  std::vector<int64_t> lshape(logits.sizes().begin(), logits.sizes().end() - 1);
+  auto fopt = logits.options().dtype(at::kFloat);
+  if (logits.is_meta()) {
+    at::Tensor l = red == "none" ? at::empty(lshape, fopt) : at::empty({}, fopt);
+    return {l, at::empty_like(logits)};
+  }
+  at::Tensor lab = labels.to(at::kLong).reshape({-1}).contiguous();
+  const int64_t rows = lab.numel();
+  at::Tensor per_tok, unit;
+  if (is_native(logits) && logits.is_contiguous() && V % 8 == 0) {
+    // the kernel overwrites its input with (softmax - onehot): work on a copy only when the logits are
+    // still needed elsewhere (the executor marks single-consumer inputs as donatable)
+    unit = op.attrs.b("donate_logits") ? logits : logits.clone();
+    per_tok = at::empty({rows}, fopt);
+    cuda_ok(softmax_ce_fwd_bwd(unit.data_ptr(), lab.data_ptr<int64_t>(), per_tok.data_ptr<float>(), nullptr, rows, (int)V, V,
+                               ignore, 1.0f, true, cur_stream()), "softmax_ce");
+  } else {
+    at::Tensor lf = logits.to(at::kFloat).reshape({rows, V});
+    at::Tensor lsm = at::log_softmax(lf, -1);
+    at::Tensor valid = (lab != ignore);
+    at::Tensor safe = at::where(valid, lab, at::zeros_like(lab));
+    per_tok = -lsm.gather(1, safe.unsqueeze(1)).squeeze(1) * valid.to(at::kFloat);
+    at::Tensor u = at::exp(lsm);
+    u.scatter_add_(1, safe.unsqueeze(1), -at::ones({rows, 1}, fopt));
+    unit = (u * valid.unsqueeze(1).to(at::kFloat)).to(logits.scalar_type()).reshape(logits.sizes());
+  }
+  at::Tensor loss;
+  if (red == "none") loss = per_tok.reshape(lshape);
+  else if (red == "sum") loss = per_tok.sum();
+  else {
+    at::Tensor cnt = (lab != ignore).sum().to(at::kFloat).clamp_min(1.0);
+    loss = per_tok.sum() / cnt;
+  }
+  return {loss, unit.reshape(logits.sizes())};
+}
+// inputs: dloss, unit, labels -> dlogits
+static Ts ce_bwd_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& dl = in[0];
+  const at::Tensor& unit = in[1];
+  const at::Tensor& labels = in[2];
+  if (unit.is_meta()) return {at::empty_like(unit)};
+  const std::string red = op.attrs.s("reduction", "mean");
+  const int64_t ignore = op.attrs.i("ignore_index", -1);
+  at::Tensor scale;
+  if (red == "none") scale = dl.to(at::kFloat).unsqueeze(-1);
+  else if (red == "sum") scale = dl.to(at::kFloat);
+  else scale = dl.to(at::kFloat) / (labels.to(at::kLong) != ignore).sum().to(at::kFloat).clamp_min(1.0);
+  return {(unit.to(at::kFloat) * scale).to(unit.scalar_type())};
+}
+static TensorList ce_grad(OpDef& op, const TensorList& g) {
+  AttrMap a;
+  a.set("reduction", op.attrs.s("reduction", "mean"));
+  a.set("ignore_index", op.attrs.i("ignore_index", -1));
+  return {op.graph->make_op1("softmax_ce_sparse_bwd", {g[0], op.outputs[1], op.inputs[1]}, a), nullptr};
+}
+static void ce_deduce(OpDef& op, size_t s) {
+  const Tensor& lg = op.inputs[0];
+  if (!lg->has_ds(s)) return;
+  copy_out_ds(op, 1, s, lg);
+  const std::string red = op.attrs.s("reduction", "mean");
+  const DistributedStates& ds = lg->ds(s);
+  const int nd = lg->ndim();
+  std::map<int, int> st;
+  std::vector<int> order;
+  if (red == "none") {
+    for (auto& kv : ds.states()) if (kv.second > 1 && kv.first != nd - 1) st[kv.first] = kv.second;
+    for (int o : ds.order()) if (o != nd - 1) order.push_back(o);
+  } else {
+    // scalar loss: every token split holds the loss of its own tokens (kept as "duplicate" like the
+    // reference: the trainer averages per-rank losses explicitly)
+    st[kDupDim] = ds.device_num();
+    order = {kDupDim};
+  }
+  set_out_ds(op, 0, s, DistributedStates(ds.device_num(), st, order));
+}
+HB_REGISTER_OP(softmax_ce_sparse, "softmax_cross_entropy_sparse", 2, 0, ce_compute, ce_grad, ce_deduce, nullptr);
+HB_REGISTER_OP(softmax_ce_sparse_bwd, "softmax_ce_sparse_bwd", 1, 0, ce_bwd_compute, nullptr,
+               [](OpDef& op, size_t s) { copy_out_ds(op, 0, s, op.inputs[1]); }, nullptr);
+
+// ------------------------------------------------------------------ attention
+// inputs: q [B,Sq,Hq,D], k [B,Sk,Hkv,D], v [B,Sk,Hkv,D]  (any strides with D contiguous) -> o, lse [B,Hq,Sq]
+static AttnTensor as_attn(const at::Tensor& t) {
+  AttnTensor a;
+  a.ptr = t.data_ptr();
+  a.stride_b = t.stride(0); a.stride_s = t.stride(1); a.stride_h = t.stride(2);
+  return a;
+}
+static bool attn_ok(const at::Tensor& t) {
+  return is_native(t) && t.dim() == 4 && t.stride(3) == 1 && t.stride(0) % 8 == 0 && t.stride(1) % 8 == 0 &&
+         t.stride(2) % 8 == 0 && (reinterpret_cast<uintptr_t>(t.data_ptr()) % 16) == 0;
+}
+static std::pair<at::Tensor, at::Tensor> aten_attention(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
+                                                        double scale, bool causal) {
+  // reference math in fp32: returns (o [B,Sq,Hq,D], lse [B,Hq,Sq])
+  const int64_t Hq = q.size(2), Hkv = k.size(2), Sq = q.size(1), Sk = k.size(1);
+  at::Tensor qf = q.to(at::kFloat).permute({0, 2, 1, 3});
+  at::Tensor kf = k.to(at::kFloat).permute({0, 2, 1, 3});
+  at::Tensor vf = v.to(at::kFloat).permute({0, 2, 1, 3});
+  if (Hq != Hkv) {
+    kf = kf.repeat_interleave(Hq / Hkv, 1);
+    vf = vf.repeat_interleave(Hq / Hkv, 1);
+  }
+  at::Tensor s = at::matmul(qf, kf.transpose(-1, -2)) * scale;
+  if (causal) {
+    at::Tensor mask = at::ones({Sq, Sk}, s.options().dtype(at::kBool)).tril(Sk - Sq);
+    s = s.masked_fill(mask.logical_not(), -INFINITY);
+  }
+  at::Tensor lse = at::logsumexp(s, -1);
+  at::Tensor p = at::exp(s - lse.unsqueeze(-1));
+  p = at::where(at::isfinite(lse).unsqueeze(-1), p, at::zeros_like(p));
+  at::Tensor o = at::matmul(p, vf).permute({0, 2, 1, 3}).contiguous();
+  return {o, lse};
+}
+static Ts attn_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& q = in[0];
+  const at::Tensor& k = in[1];
+  const at::Tensor& v = in[2];
+  const bool causal = op.attrs.b("causal", true);
+  const double scale = op.attrs.f("softmax_scale", 0.0) > 0 ? op.attrs.f("softmax_scale") : 1.0 / std::sqrt((double)q.size(3));
+  auto fopt = q.options().dtype(at::kFloat);
+  if (q.is_meta()) return {at::empty(q.sizes(), q.options()), at::empty({q.size(0), q.size(2), q.size(1)}, fopt)};
+  if (attn_ok(q) && attn_ok(k) && attn_ok(v) && (q.size(3) == 64 || q.size(3) == 128)) {
+    at::Tensor o = at::empty(q.sizes(), q.options());
+    at::Tensor lse = at::empty({q.size(0), q.size(2), q.size(1)}, fopt);
+    AttnFwdCall c;
+    c.q = as_attn(q); c.k = as_attn(k); c.v = as_attn(v); c.o = as_attn(o);
+    c.lse = lse.data_ptr<float>();
+    c.B = (int)q.size(0); c.Sq = (int)q.size(1); c.Hq = (int)q.size(2); c.D = (int)q.size(3);
+    c.Sk = (int)k.size(1); c.Hkv = (int)k.size(2);
+    c.softmax_scale = (float)scale; c.causal = causal;
+    cuda_ok(attn_fwd(c, cur_stream()), "attn_fwd");
+    return {o, lse};
+  }
+  if (is_native(q)) note_fallback("attn");
+  auto r = aten_attention(q, k, v, scale, causal);
+  return {r.first.to(q.scalar_type()), r.second};
+}
+// inputs: do, q, k, v, o, lse -> dq, dk, dv
+static Ts attn_bwd_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& d_o = in[0];
+  const at::Tensor& q = in[1];
+  const at::Tensor& k = in[2];
+  const at::Tensor& v = in[3];
+  const at::Tensor& o = in[4];
+  const at::Tensor& lse = in[5];
+  const bool causal = op.attrs.b("causal", true);
+  const double scale = op.attrs.f("softmax_scale", 0.0) > 0 ? op.attrs.f("softmax_scale") : 1.0 / std::sqrt((double)q.size(3));
+  if (q.is_meta()) return {at::empty(q.sizes(), q.options()), at::empty(k.sizes(), k.options()), at::empty(v.sizes(), v.options())};
+  at::Tensor doc = d_o.stride(3) == 1 ? d_o : d_o.contiguous();
+  if (attn_ok(q) && attn_ok(k) && attn_ok(v) && attn_ok(o) && attn_ok(doc) && (q.size(3) == 64 || q.size(3) == 128)) {
+    at::Tensor dq = at::empty(q.sizes(), q.options()), dk = at::empty(k.sizes(), k.options()), dv = at::empty(v.sizes(), v.options());
+    at::Tensor delta = at::empty_like(lse);
+    AttnBwdCall c;
+    c.q = as_attn(q); c.k = as_attn(k); c.v = as_attn(v); c.o = as_attn(o); c.d_o = as_attn(doc);
+    c.dq = as_attn(dq); c.dk = as_attn(dk); c.dv = as_attn(dv);
+    c.lse = lse.data_ptr<float>(); c.delta = delta.data_ptr<float>();
+    c.B = (int)q.size(0); c.Sq = (int)q.size(1); c.Hq = (int)q.size(2); c.D = (int)q.size(3);
+    c.Sk = (int)k.size(1); c.Hkv = (int)k.size(2);
+    c.softmax_scale = (float)scale; c.causal = causal;
+    cuda_ok(attn_bwd(c, cur_stream()), "attn_bwd");
+    return {dq, dk, dv};
+  }
+  if (is_native(q)) note_fallback("attn_bwd");
+  // reference backward through autograd of the reference forward
+  at::AutoGradMode gm(true);
+  at::Tensor qf = q.detach().to(at::kFloat).requires_grad_(true);
+  at::Tensor kf = k.detach().to(at::kFloat).requires_grad_(true);
+  at::Tensor vf = v.detach().to(at::kFloat).requires_grad_(true);
+  auto r = aten_attention(qf, kf, vf, scale, causal);
+  r.first.backward(d_o.to(at::kFloat));
+  return {qf.grad().to(q.scalar_type()), kf.grad().to(k.scalar_type()), vf.grad().to(v.scalar_type())};
+}
+static TensorList attn_grad(OpDef& op, const TensorList& g) {
+  AttrMap a;
+  a.set("causal", op.attrs.b("causal", true));
+  a.set("softmax_scale", op.attrs.f("softmax_scale", 0.0));
+  TensorList r = op.graph->make_op("attn_bwd", {g[0], op.inputs[0], op.inputs[1], op.inputs[2], op.outputs[0], op.outputs[1]}, a);
+  return {r[0], r[1], r[2]};
+}
+static void attn_deduce(OpDef& op, size_t s) {
+  copy_out_ds(op, 0, s, op.inputs[0]);
+  const Tensor& q = op.inputs[0];
+  if (!q->has_ds(s)) return;
+  // lse [B,H,S]: batch split 0 -> 0, head split 2 -> 1, seq split 1 -> 2
+  const DistributedStates& ds = q->ds(s);
+  std::map<int, int> st;
+  auto m = [](int d) { return d == 2 ? 1 : (d == 1 ? 2 : d); };
+  for (auto& kv : ds.states()) if (kv.second > 1 && kv.first != 3) st[m(kv.first)] = kv.second;
+  std::vector<int> order;
+  for (int o : ds.order()) if (o != 3) order.push_back(m(o));
+  set_out_ds(op, 1, s, DistributedStates(ds.device_num(), st, order));
+}
+static void attn_bwd_deduce(OpDef& op, size_t s) {
+  copy_out_ds(op, 0, s, op.inputs[1]);
+  copy_out_ds(op, 1, s, op.inputs[2]);
+  copy_out_ds(op, 2, s, op.inputs[3]);
+}
+HB_REGISTER_OP(attn, "attn", 2, kFlagAttention, attn_compute, attn_grad, attn_deduce, nullptr);
+HB_REGISTER_OP(attn_bwd, "attn_bwd", 3, kFlagAttention, attn_bwd_compute, nullptr, attn_bwd_deduce, nullptr);
+
+// ------------------------------------------------------------------ rotary
+// x [T..., H, D] with positions [T...]; half-split convention; inverse rotation is the gradient
+static Ts rotary_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& x = in[0];
+  if (x.is_meta()) return {at::empty_like(x)};
+  const bool inverse = op.attrs.b("inverse");
+  const double base = op.attrs.f("base", 10000.0);
+  const int64_t D = x.size(-1), H = x.size(-2);
+  const int64_t rot = op.attrs.i("rot_dim", 0) > 0 ? op.attrs.i("rot_dim") : D;
+  const int64_t tokens = x.numel() / (H * D);
+  at::Tensor pos;
+  if (in.size() > 1) pos = in[1].to(at::kInt).reshape({-1}).contiguous();
+  else {
+    // default positions: index inside the second-to-last token dim (sequence), plus an offset (CP slot)
+    const int64_t S = x.dim() >= 3 ? x.size(-3) : tokens;
+    pos = (at::arange(tokens, x.options().dtype(at::kInt)) % S + (int64_t)op.attrs.i("pos_offset", 0)).contiguous();
+  }
+  if (is_native(x) && x.is_contiguous()) {
+    at::Tensor y = at::empty_like(x);
+    cuda_ok(rotary_apply(x.data_ptr(), y.data_ptr(), pos.data_ptr<int32_t>(), tokens, (int)H, (int)D, (int)rot,
+                         (float)base, inverse, H * D, cur_stream()), "rotary");
+    return {y};
+  }
+  at::Tensor xf = x.to(at::kFloat).reshape({tokens, H, D});
+  const int64_t half = rot / 2;
+  at::Tensor inv_freq = at::pow(base, -at::arange(0, half, xf.options()) * 2.0 / (double)rot);
+  at::Tensor ang = pos.to(at::kFloat).unsqueeze(1) * inv_freq.unsqueeze(0);  // [T, half]
+  at::Tensor cs = at::cos(ang).unsqueeze(1), sn = at::sin(ang).unsqueeze(1);
+  if (inverse) sn = -sn;
+  at::Tensor a = xf.narrow(-1, 0, half), b = xf.narrow(-1, half, half);
+  at::Tensor ya = a * cs - b * sn, yb = b * cs + a * sn;
+  at::Tensor y = xf.clone();
+  y.narrow(-1, 0, half).copy_(ya);
+  y.narrow(-1, half, half).copy_(yb);
+  return {y.reshape(x.sizes()).to(x.scalar_type())};
+}
+static TensorList rotary_grad(OpDef& op, const TensorList& g) {
+  AttrMap a = op.attrs;
+  a.set("inverse", !op.attrs.b("inverse"));
+  TensorList ins = {g[0]};
+  if (op.inputs.size() > 1) ins.push_back(op.inputs[1]);
+  TensorList r = {op.graph->make_op1("rotary", ins, a)};
+  if (op.inputs.size() > 1) r.push_back(nullptr);
+  return r;
+}
+HB_REGISTER_OP(rotary, "rotary", 1, 0, rotary_compute, rotary_grad, nullptr, nullptr);
+
+// ------------------------------------------------------------------ dropout (mask recomputed from seed in bwd)
+static Ts dropout_compute(const OpDef& op, const Ts& in, RunCtx* rc) {
+  const at::Tensor& x = in[0];
+  const double p = op.attrs.f("p", 0.0);
+  if (x.is_meta() || p <= 0.0 || (rc && !rc->training)) return {x.is_meta() ? at::empty_like(x) : x};
+  const uint64_t seed = (rc ? rc->seed : 0) + 0x9E3779B97F4A7C15ull * (uint64_t)(op.attrs.i("seed_op", op.id) + 1);
+  const uint64_t offset = rc ? (uint64_t)rc->micro_batch << 40 : 0;
+  if (is_native(x) && x.is_contiguous() && x.numel() % 8 == 0) {
+    at::Tensor y = at::empty_like(x);
+    cuda_ok(dropout_fwd(x.data_ptr(), y.data_ptr(), x.numel(), (float)p, seed, offset, cur_stream()), "dropout");
+    return {y};
+  }
+  auto gen = at::detail::createCPUGenerator(seed ^ offset);
+  at::Tensor mask = at::empty(x.sizes(), at::TensorOptions().dtype(at::kFloat)).uniform_(0, 1, gen).to(x.device()) >= p;
+  return {(x * mask.to(x.scalar_type())) / (1.0 - p)};
+}
+static TensorList dropout_grad(OpDef& op, const TensorList& g) {
+  AttrMap a = op.attrs;
+  a.set("seed_op", op.attrs.i("seed_op", op.id));
+  return {op.graph->make_op1("dropout", {g[0]}, a)};
+}
+HB_REGISTER_OP(dropout, "dropout", 1, 0, dropout_compute, dropout_grad, nullptr, nullptr);
+
+}  // namespace hb

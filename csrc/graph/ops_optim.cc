@@ -1,0 +1,251 @@
+// Optimizer update ops, loss-scaling helpers and MoE ops.
+// The update ops declare (param, grad, states, hyper-parameters); on the training hot
+// path the executor fuses all of them into one flat multi-tensor Adam launch per
+// parameter buffer (see exec.cc), the per-tensor compute below serves eager graphs
+// and parameters that are not part of a flat buffer.
+// (capability parity: hetu/graph/ops/optimizer_update.cc:21-83, graph/optim/optimizer.cc,
+//  graph/autocast/gradscaler; hetu/v1/python/hetu/layers/{moe_layer,TopGate}.py)
+#include <ATen/ATen.h>
+
+#include "exec.h"
+#include "ir.h"
+#include "op_utils.h"
+
+namespace hb {
+
+using Ts = std::vector<at::Tensor>;
+
+static void scalar_out_infer(OpDef& op) { make_out(op, 0, {1}, DataType::FLOAT32); }
+
+// inputs: param, grad, m, v, step, [master]
+static Ts adam_update_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  at::Tensor param = in[0];
+  const at::Tensor& grad = in[1];
+  at::Tensor m = in[2], v = in[3], step = in[4];
+  at::Tensor master = in.size() > 5 ? in[5] : param;
+  if (param.is_meta()) return {at::empty({1}, param.options().dtype(at::kFloat))};
+  const double lr = op.attrs.f("lr", 1e-3), b1 = op.attrs.f("beta1", 0.9), b2 = op.attrs.f("beta2", 0.999),
+               eps = op.attrs.f("eps", 1e-8), wd = op.attrs.f("weight_decay", 0.0);
+  step.add_(1);
+  if (master.is_cuda() && master.scalar_type() == at::kFloat && master.is_contiguous() && m.is_contiguous() &&
+      v.is_contiguous() && grad.is_contiguous() && (grad.scalar_type() == at::kFloat || grad.scalar_type() == at::kBFloat16)) {
+    AdamArgs a;
+    a.master = master.data_ptr<float>(); a.m = m.data_ptr<float>(); a.v = v.data_ptr<float>();
+    a.grad = grad.data_ptr(); a.grad_is_bf16 = grad.scalar_type() == at::kBFloat16;
+    a.param_bf16 = (param.scalar_type() == at::kBFloat16 && param.data_ptr() != master.data_ptr()) ? param.data_ptr() : nullptr;
+    a.n = master.numel();
+    a.lr = (float)lr; a.beta1 = (float)b1; a.beta2 = (float)b2; a.eps = (float)eps; a.weight_decay = (float)wd;
+    at::Tensor step_dev = step.is_cuda() ? step : step.to(master.device());
+    a.step_ptr = step_dev.data_ptr<int64_t>();
+    cuda_ok(adam_update(a, cur_stream()), "adam_update");
+    return {at::zeros({1}, master.options())};
+  }
+  const double t = (double)step.item<int64_t>();
+  at::Tensor g = grad.to(at::kFloat).to(master.device());
+  m.mul_(b1).add_(g, 1 - b1);
+  v.mul_(b2).addcmul_(g, g, 1 - b2);
+  const double bc1 = 1 - std::pow(b1, t), bc2 = 1 - std::pow(b2, t);
+  at::Tensor denom = (v.sqrt() / std::sqrt(bc2)).add_(eps);
+  at::Tensor mf = master.to(at::kFloat);
+  mf = mf - (lr / bc1) * (m / denom) - lr * wd * mf;
+  master.copy_(mf);
+  if (param.data_ptr() != master.data_ptr()) param.copy_(mf);
+  return {at::zeros({1}, at::TensorOptions().dtype(at::kFloat))};
+}
+HB_REGISTER_OP(adam_update, "adam_update", 1, kFlagOptimizerUpdate | kFlagNondiff | kFlagNoMetaExec | kFlagInplace,
+               adam_update_compute, nullptr, nullptr, scalar_out_infer);
+
+// inputs: param, grad, [velocity]
+static Ts sgd_update_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  at::Tensor param = in[0];
+  const at::Tensor& grad = in[1];
+  if (param.is_meta()) return {at::empty({1}, param.options().dtype(at::kFloat))};
+  const double lr = op.attrs.f("lr", 0.01), mom = op.attrs.f("momentum", 0.0), wd = op.attrs.f("weight_decay", 0.0);
+  const bool nesterov = op.attrs.b("nesterov");
+  at::Tensor g = grad.to(param.scalar_type());
+  if (wd != 0.0) g = g + wd * param;
+  if (mom != 0.0 && in.size() > 2) {
+    at::Tensor vel = in[2];
+    vel.mul_(mom).add_(g);
+    g = nesterov ? g + mom * vel : vel;
+  }
+  param.sub_(g * lr);
+  return {at::zeros({1}, at::TensorOptions().dtype(at::kFloat))};
+}
+HB_REGISTER_OP(sgd_update, "sgd_update", 1, kFlagOptimizerUpdate | kFlagNondiff | kFlagNoMetaExec | kFlagInplace,
+               sgd_update_compute, nullptr, nullptr, scalar_out_infer);
+
+// update_scale(scale, growth_tracker, found_inf): dynamic loss scaling (GradScaler)
+static Ts update_scale_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  at::Tensor scale = in[0], tracker = in[1];
+  const at::Tensor& found = in[2];
+  if (scale.is_meta()) return {at::empty({1}, scale.options())};
+  const double growth = op.attrs.f("growth_factor", 2.0), backoff = op.attrs.f("backoff_factor", 0.5);
+  const int64_t interval = op.attrs.i("growth_interval", 2000);
+  if (found.item<float>() > 0) {
+    scale.mul_(backoff);
+    tracker.zero_();
+  } else {
+    tracker.add_(1);
+    if (tracker.item<int64_t>() >= interval) {
+      scale.mul_(growth);
+      tracker.zero_();
+    }
+  }
+  return {scale.clone()};
+}
+HB_REGISTER_OP(update_scale, "update_scale", 1, kFlagNondiff | kFlagNoMetaExec | kFlagInplace, update_scale_compute, nullptr,
+               nullptr, scalar_out_infer);
+
+// ------------------------------------------------------------------ MoE (HetuMoE)
+// moe_gate: logits [T, E] -> (gates [T,k] fp32, topk_idx [T,k] int32, location [T,k] int32, aux_loss [1])
+static Ts moe_gate_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& logits = in[0];
+  const int64_t T = logits.size(0), E = logits.size(1);
+  const int64_t k = op.attrs.i("k", 1), capacity = op.attrs.i("capacity");
+  auto fopt = logits.options().dtype(at::kFloat);
+  auto iopt = logits.options().dtype(at::kInt);
+  if (logits.is_meta()) return {at::empty({T, k}, fopt), at::empty({T, k}, iopt), at::empty({T, k}, iopt), at::empty({1}, fopt)};
+  at::Tensor probs, idx, val, loc = at::empty({T, k}, iopt);
+  if (is_native(logits) && logits.is_contiguous() && E <= 256 && k <= 8) {
+    probs = at::empty({T, E}, fopt);
+    idx = at::empty({T, k}, iopt);
+    val = at::empty({T, k}, fopt);
+    cuda_ok(moe_gate_topk(logits.data_ptr(), probs.data_ptr<float>(), idx.data_ptr<int32_t>(), val.data_ptr<float>(), T, (int)E,
+                          (int)k, cur_stream()), "moe_gate_topk");
+    cuda_ok(moe_assign_slots(idx.data_ptr<int32_t>(), loc.data_ptr<int32_t>(), nullptr, T, (int)E, (int)k, (int)capacity,
+                             cur_stream()), "moe_assign_slots");
+  } else {
+    probs = at::softmax(logits.to(at::kFloat), -1);
+    auto tk = at::topk(probs, k, -1);
+    val = std::get<0>(tk).contiguous();
+    idx = std::get<1>(tk).to(at::kInt).contiguous();
+    // GShard ordering: all first choices before any second choice, token order inside a choice
+    at::Tensor idx_cpu = idx.cpu();
+    at::Tensor loc_cpu = at::empty({T, k}, at::TensorOptions().dtype(at::kInt));
+    std::vector<int> count(E, 0);
+    auto ia = idx_cpu.accessor<int, 2>();
+    auto la = loc_cpu.accessor<int, 2>();
+    for (int64_t kk = 0; kk < k; ++kk)
+      for (int64_t t = 0; t < T; ++t) {
+        const int e = ia[t][kk];
+        la[t][kk] = count[e] < capacity ? count[e] : -1;
+        count[e]++;
+      }
+    loc = loc_cpu.to(logits.device());
+  }
+  // normalise the kept gates (dropped tokens contribute zero), load-balancing aux loss as in GShard
+  at::Tensor kept = (loc >= 0).to(at::kFloat);
+  at::Tensor gates = val * kept;
+  if (k > 1) gates = gates / gates.sum(-1, true).clamp_min(1e-9);
+  at::Tensor me = probs.mean(0);
+  at::Tensor ce = at::one_hot(idx.select(1, 0).to(at::kLong), E).to(at::kFloat).mean(0);
+  at::Tensor aux = (me * ce).sum().reshape({1}) * (double)E;
+  return {gates, idx, loc, aux};
+}
+HB_REGISTER_OP(moe_gate, "moe_gate", 4, kFlagNondiff, moe_gate_compute, nullptr, nullptr, nullptr);
+
+// moe_dispatch: x [T,H], idx, loc -> [E, capacity, H]
+static Ts moe_dispatch_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& x = in[0];
+  const at::Tensor& idx = in[1];
+  const at::Tensor& loc = in[2];
+  const int64_t E = op.attrs.i("experts"), C = op.attrs.i("capacity"), H = x.size(1), T = x.size(0), k = idx.size(1);
+  if (x.is_meta()) return {at::empty({E, C, H}, x.options())};
+  const bool scaled = in.size() > 3;
+  if (is_native(x) && x.is_contiguous() && H % 8 == 0) {
+    at::Tensor out = at::empty({E, C, H}, x.options());
+    cuda_ok(moe_dispatch(x.data_ptr(), idx.data_ptr<int32_t>(), loc.data_ptr<int32_t>(),
+                         scaled ? in[3].contiguous().data_ptr<float>() : nullptr, out.data_ptr(), T, (int)H, (int)E, (int)k,
+                         (int)C, cur_stream()), "moe_dispatch");
+    return {out};
+  }
+  at::Tensor out = at::zeros({E * C, H}, x.options());
+  at::Tensor flat = idx.to(at::kLong) * C + loc.to(at::kLong);  // [T,k]
+  at::Tensor valid = loc >= 0;
+  for (int64_t kk = 0; kk < k; ++kk) {
+    at::Tensor sel = valid.select(1, kk).nonzero().squeeze(1);
+    at::Tensor rows = x.index_select(0, sel);
+    if (scaled) rows = rows * in[3].select(1, kk).index_select(0, sel).unsqueeze(1).to(x.scalar_type());
+    out.index_copy_(0, flat.select(1, kk).index_select(0, sel), rows);
+  }
+  return {out.reshape({E, C, H})};
+}
+// moe_combine: expert_out [E,C,H], idx, loc, [gates] -> [T,H]
+static Ts moe_combine_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& eo = in[0];
+  const at::Tensor& idx = in[1];
+  const at::Tensor& loc = in[2];
+  const int64_t E = eo.size(0), C = eo.size(1), H = eo.size(2), T = idx.size(0), k = idx.size(1);
+  (void)op;
+  if (eo.is_meta()) return {at::empty({T, H}, eo.options())};
+  const bool gated = in.size() > 3;
+  if (is_native(eo) && eo.is_contiguous() && H % 8 == 0) {
+    at::Tensor y = at::empty({T, H}, eo.options());
+    cuda_ok(moe_combine(eo.data_ptr(), idx.data_ptr<int32_t>(), loc.data_ptr<int32_t>(),
+                        gated ? in[3].contiguous().data_ptr<float>() : nullptr, y.data_ptr(), T, (int)H, (int)E, (int)k, (int)C,
+                        cur_stream()), "moe_combine");
+    return {y};
+  }
+  at::Tensor flat = (idx.to(at::kLong) * C + loc.to(at::kLong).clamp_min(0)).reshape({-1});
+  at::Tensor rows = eo.reshape({E * C, H}).index_select(0, flat).reshape({T, k, H}).to(at::kFloat);
+  at::Tensor w = (loc >= 0).to(at::kFloat);
+  if (gated) w = w * in[3];
+  return {(rows * w.unsqueeze(-1)).sum(1).to(eo.scalar_type())};
+}
+// d gates of combine: <dy[t], expert_out[e_k, slot_k]>
+static Ts moe_combine_gate_grad_compute(const OpDef&, const Ts& in, RunCtx*) {
+  const at::Tensor& dy = in[0];
+  const at::Tensor& eo = in[1];
+  const at::Tensor& idx = in[2];
+  const at::Tensor& loc = in[3];
+  const int64_t E = eo.size(0), C = eo.size(1), H = eo.size(2), T = idx.size(0), k = idx.size(1);
+  if (dy.is_meta()) return {at::empty({T, k}, dy.options().dtype(at::kFloat))};
+  if (is_native(eo) && is_native(dy) && eo.is_contiguous() && dy.is_contiguous() && H % 8 == 0) {
+    at::Tensor dg = at::empty({T, k}, dy.options().dtype(at::kFloat));
+    cuda_ok(moe_combine_bwd_gate(dy.data_ptr(), eo.data_ptr(), idx.data_ptr<int32_t>(), loc.data_ptr<int32_t>(),
+                                 dg.data_ptr<float>(), T, (int)H, (int)E, (int)k, (int)C, cur_stream()), "moe_combine_bwd_gate");
+    return {dg};
+  }
+  at::Tensor flat = (idx.to(at::kLong) * C + loc.to(at::kLong).clamp_min(0)).reshape({-1});
+  at::Tensor rows = eo.reshape({E * C, H}).index_select(0, flat).reshape({T, k, H}).to(at::kFloat);
+  return {(rows * dy.to(at::kFloat).unsqueeze(1)).sum(-1) * (loc >= 0).to(at::kFloat)};
+}
+static TensorList moe_dispatch_grad(OpDef& op, const TensorList& g) {
+  // dx = combine(d_dispatched) with the same scale; d scale is not propagated (gates flow through combine)
+  TensorList ins = {g[0], op.inputs[1], op.inputs[2]};
+  if (op.inputs.size() > 3) ins.push_back(op.inputs[3]);
+  TensorList r(op.inputs.size());
+  r[0] = op.graph->make_op1("moe_combine", ins);
+  return r;
+}
+static TensorList moe_combine_grad(OpDef& op, const TensorList& g) {
+  AttrMap a;
+  a.set("experts", op.inputs[0]->shape[0]);
+  a.set("capacity", op.inputs[0]->shape[1]);
+  TensorList ins = {g[0], op.inputs[1], op.inputs[2]};
+  if (op.inputs.size() > 3) ins.push_back(op.inputs[3]);
+  TensorList r(op.inputs.size());
+  r[0] = op.graph->make_op1("moe_dispatch", ins, a);
+  if (op.inputs.size() > 3) r[3] = op.graph->make_op1("moe_combine_gate_grad", {g[0], op.inputs[0], op.inputs[1], op.inputs[2]});
+  return r;
+}
+HB_REGISTER_OP(moe_dispatch, "moe_dispatch", 1, 0, moe_dispatch_compute, moe_dispatch_grad, nullptr, nullptr);
+HB_REGISTER_OP(moe_combine, "moe_combine", 1, 0, moe_combine_compute, moe_combine_grad, nullptr, nullptr);
+HB_REGISTER_OP(moe_combine_gate_grad, "moe_combine_gate_grad", 1, kFlagNondiff, moe_combine_gate_grad_compute, nullptr, nullptr, nullptr);
+
+// differentiable gate values: gates = normalise(softmax(logits)[topk]) for fixed routing decisions
+static Ts moe_gate_values_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& logits = in[0];
+  const at::Tensor& idx = in[1];
+  const at::Tensor& loc = in[2];
+  (void)op;
+  if (logits.is_meta()) return {at::empty(idx.sizes(), logits.options().dtype(at::kFloat))};
+  at::Tensor probs = at::softmax(logits.to(at::kFloat), -1);
+  at::Tensor val = probs.gather(1, idx.to(at::kLong)) * (loc >= 0).to(at::kFloat);
+  if (idx.size(1) > 1) val = val / val.sum(-1, true).clamp_min(1e-9);
+  return {val};
+}
+HB_REGISTER_OP(moe_gate_values, "moe_gate_values", 1, 0, moe_gate_values_compute, nullptr, nullptr, nullptr);
+
+}  // namespace hb

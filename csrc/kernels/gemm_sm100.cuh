@@ -24,19 +24,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "gemm_sm100.h"
 #include "ptx.cuh"
 
 namespace hb {
-
-enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_GELU_TANH = 3, ACT_SILU = 4 };
-enum GemmAuxMode : int {
-  AUX_NONE = 0,
-  AUX_ADD = 1,        // out = acc + aux_in                       (residual add)
-  AUX_DGELU = 2,      // out = acc * gelu'(aux_in)                (fc2 dgrad -> d(pre-activation))
-  AUX_DRELU = 3,      // out = acc * (aux_in > 0)
-  AUX_DGELU_TANH = 4,
-  AUX_DSILU = 5,
-};
 
 struct GemmParams {
   int M, N, K;

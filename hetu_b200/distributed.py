@@ -1,0 +1,82 @@
+"""Process bootstrap: one process per GPU, rendezvous through torch.distributed (NCCL on GPUs, gloo on CPU).
+
+API parity: hetu.init_comm_group / local_device / global_device_group / global_comm_barrier_* and
+hetu.utils.parallel.distributed.distributed_init (ref: python/hetu/_binding/distributed/comm_group.cc:55-60,
+hetu/impl/communication/rpc_comm.cc:36-266).  The reference's gRPC DeviceController is replaced by the
+torch.distributed TCPStore (same role: rank assignment, id exchange, barrier, KV) -- see hetu_b200.rpc for the
+stand-alone KV / heartbeat / elastic servers.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _C
+from .core import DeviceGroup, device
+
+_local_device = None
+_global_group = None
+
+
+def _factory(ranks: List[int]):
+    return dist.new_group(ranks=list(ranks))
+
+
+def init_comm_group(device_num: Optional[int] = None, device_idxs=(), server_address: str = "127.0.0.1:23457", backend: Optional[str] = None):
+    """Join the job.  World size / rank come from the launcher environment (RANK, WORLD_SIZE, LOCAL_RANK, MASTER_*)."""
+    global _local_device, _global_group
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", str(device_num or 1)))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    use_cuda = torch.cuda.is_available() and os.environ.get("HETU_B200_FORCE_CPU", "0") == "0"
+    if use_cuda:
+        torch.cuda.set_device(local_rank % torch.cuda.device_count())
+    if world > 1 or "RANK" in os.environ:
+        if not dist.is_initialized():
+            if "MASTER_ADDR" not in os.environ:
+                host, port = server_address.split(":")
+                os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = host, port
+            be = backend or ("nccl" if use_cuda else "gloo")
+            kw = {}
+            if use_cuda:
+                kw["device_id"] = torch.device("cuda", local_rank % torch.cuda.device_count())
+            dist.init_process_group(backend=be, rank=rank, world_size=world, **kw)
+        pg = dist.distributed_c10d._get_default_group()
+        _C.init_comm(rank, world, pg, _factory)
+    kind = "cuda" if use_cuda else "cpu"
+    _local_device = device(f"{kind}:{rank}")
+    _global_group = DeviceGroup([f"{kind}:{i}" for i in range(world)])
+    os.environ.setdefault("HETU_LOCAL_HOSTNAME", os.uname().nodename)
+    return _local_device
+
+
+def local_device():
+    return _local_device if _local_device is not None else device("cuda:0" if torch.cuda.is_available() else "cpu:0")
+
+
+def global_device_group():
+    return _global_group if _global_group is not None else DeviceGroup([str(local_device())])
+
+
+def global_comm_barrier_rpc():
+    if dist.is_initialized():
+        dist.barrier()
+
+
+global_comm_barrier_mpi = global_comm_barrier_rpc
+
+
+def world_size() -> int:
+    return dist.get_world_size() if dist.is_initialized() else 1
+
+
+def rank() -> int:
+    return dist.get_rank() if dist.is_initialized() else 0
+
+
+def map_to_local_data(ds, device_index: int):
+    """{split dim -> shard index} of a device under a DistributedStates (ref: hetu.map_to_local_data)."""
+    return {k: v for k, v in ds.map_device_to_state_index(device_index).items() if k >= 0}
