@@ -405,7 +405,9 @@ PYBIND11_MODULE(_C, m) {
   m.def("init_comm", [](int rank, int world, const PG& world_pg, py::function factory) {
     auto fac = [factory](const std::vector<int>& ranks) {
       py::gil_scoped_acquire gil;
-      return py::cast<PG>(factory(ranks));
+      py::object o = factory(ranks);
+      if (o.is_none()) return PG();   // this rank is not a member of the group
+      return py::cast<PG>(o);
     };
     CommRuntime::get().init(rank, world, world_pg, fac);
   });

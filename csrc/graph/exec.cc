@@ -24,6 +24,9 @@ void CommRuntime::init(int rank, int world, PG world_pg, std::function<PG(const 
   world_pg_ = std::move(world_pg);
   factory_ = std::move(factory);
   groups_.clear();
+  p2p_pg_[0] = PG();
+  p2p_pg_[1] = PG();
+  if (world_ > 1 && factory_) p2p_group(0);   // created collectively, right at initialisation
   set_log_prefix("[rank " + std::to_string(rank) + "]");
 }
 PG CommRuntime::group(const std::vector<int>& ranks) {
@@ -68,21 +71,16 @@ at::Tensor CommRuntime::all_gather(const at::Tensor& x, const std::vector<int>& 
   if (ranks.size() <= 1 || !initialized()) return x;
   const int64_t n = (int64_t)ranks.size();
   at::Tensor in = x.contiguous();
+  if (in.dim() == 0) in = in.reshape({1});
   std::vector<int64_t> shp = in.sizes().vec();
-  shp.insert(shp.begin(), n);
+  shp[0] *= n;   // rank-major concatenation along dim 0 (what both NCCL and gloo produce)
   at::Tensor out = at::empty(shp, in.options());
   c10d::AllgatherOptions o;
   group(ranks)->_allgather_base(out, in, o)->wait();
   bytes_["all_gather"] += out.nbytes();
   calls_["all_gather"] += 1;
-  if (dim == 0) {
-    std::vector<int64_t> f = in.sizes().vec();
-    f[0] *= n;
-    return out.reshape(f);
-  }
-  std::vector<at::Tensor> parts;
-  for (int64_t i = 0; i < n; ++i) parts.push_back(out[i]);
-  return at::cat(parts, dim);
+  if (dim == 0) return out;
+  return at::cat(at::chunk(out, n, 0), dim);
 }
 at::Tensor CommRuntime::reduce_scatter(const at::Tensor& x, const std::vector<int>& ranks, int dim, ReductionType red,
                                        bool fp32) {
@@ -134,18 +132,36 @@ at::Tensor CommRuntime::all_to_all(const at::Tensor& x, const std::vector<int>& 
   if (concat_dim == 0) return out;
   return at::cat(at::chunk(out, n, 0), concat_dim);
 }
-void CommRuntime::send(const at::Tensor& x, int dst_rank) {
-  std::vector<at::Tensor> v = {x.contiguous()};
-  auto w = world_pg_->send(v, dst_rank, 0);
-  w->wait();
+PG CommRuntime::p2p_group(int channel) {
+  channel = channel ? 1 : 0;
+  if (!p2p_pg_[channel]) {
+    // a dedicated world-sized group per direction: must be created collectively, so both are made on first use
+    std::vector<int> all(world_);
+    for (int i = 0; i < world_; ++i) all[i] = i;
+    HB_CHECK(factory_) << "CommRuntime has no group factory";
+    p2p_pg_[0] = factory_(all);
+    p2p_pg_[1] = factory_(all);
+  }
+  return p2p_pg_[channel];
+}
+void CommRuntime::send(const at::Tensor& x, int dst_rank, int channel) {
+  at::Tensor buf = x.contiguous();
+  std::vector<at::Tensor> v = {buf};
+  auto w = p2p_group(channel)->send(v, dst_rank, 0);
+  pending_sends_.push_back({w, buf});   // keep the buffer alive; completion is awaited in flush_sends()
   bytes_["p2p"] += x.nbytes();
   calls_["p2p"] += 1;
 }
-at::Tensor CommRuntime::recv(const std::vector<int64_t>& shape, at::ScalarType dtype, const at::Device& dev, int src) {
+at::Tensor CommRuntime::recv(const std::vector<int64_t>& shape, at::ScalarType dtype, const at::Device& dev, int src,
+                             int channel) {
   at::Tensor t = at::empty(shape, at::TensorOptions().dtype(dtype).device(dev));
   std::vector<at::Tensor> v = {t};
-  world_pg_->recv(v, src, 0)->wait();
+  p2p_group(channel)->recv(v, src, 0)->wait();
   return t;
+}
+void CommRuntime::flush_sends() {
+  for (auto& p : pending_sends_) if (p.first) p.first->wait();
+  pending_sends_.clear();
 }
 void CommRuntime::batched_send_recv(const std::vector<std::pair<at::Tensor, int>>& sends,
                                     std::vector<std::pair<at::Tensor, int>>& recvs) {
@@ -246,7 +262,11 @@ static at::Device aten_device() {
 static at::Tensor run_initializer(const OpDef& op, const std::vector<int64_t>& gshape) {
   const std::string kind = op.attrs.s("init", "zeros");
   auto o = at::TensorOptions().dtype(at::kFloat);
-  const uint64_t seed = (uint64_t)op.attrs.i("seed", 0) * 1000003ull + (uint64_t)op.id * 7919ull + 12345ull;
+  // seeded by the parameter *name* (FNV-1a), not by the op id: the same model built under another strategy has
+  // extra comm ops (shifted ids) but must start from identical weights
+  uint64_t name_hash = 1469598103934665603ull;
+  for (unsigned char ch : op.name()) { name_hash ^= ch; name_hash *= 1099511628211ull; }
+  const uint64_t seed = (uint64_t)op.attrs.i("seed", 0) * 1000003ull + (name_hash % 1000000007ull) * 7919ull + 12345ull;
   auto gen = at::detail::createCPUGenerator(seed);
   int64_t fan_in = gshape.size() >= 2 ? gshape[1] : (gshape.empty() ? 1 : gshape[0]);
   int64_t fan_out = gshape.empty() ? 1 : gshape[0];
@@ -298,16 +318,25 @@ void Executor::ensure_param(OpDef* var, int strategy) {
     at::Tensor pdata = g_->param_data()[src->outputs[0]->id];
     at::Tensor local = pdata;
     if (var->dst_ds.size() > 0 && src->dst_ds.size() > 0) {
+      // ZeRO shard = this rank's chunk (dim 0) of the local parameter among its data-parallel replicas, in the
+      // same order the reduce-scatter / all-gather of the bridge use
       const size_t s = var->dst_ds.size() > (size_t)strategy ? strategy : 0;
       const DistributedStates& mds = var->dst_ds.get(s).get(0);
       const DistributedStates& pds = src->dst_ds.get(std::min(s, src->dst_ds.size() - 1)).get(0);
-      DeviceGroup grp = var->placement(s);
-      int idx = grp.empty() ? 0 : local_device_index(grp);
-      if (idx < 0) idx = 0;
-      std::vector<int64_t> mb, ms, pb, ps;
-      mds.local_slice(gshape, idx % std::max(1, mds.device_num()), &mb, &ms);
-      pds.local_slice(gshape, idx % std::max(1, pds.device_num()), &pb, &ps);
-      for (size_t d = 0; d < mb.size(); ++d) local = local.narrow((int64_t)d, mb[d] - pb[d], ms[d]);
+      DeviceGroup grp = src->placement(s);
+      int me = grp.empty() ? 0 : local_device_index(grp);
+      if (me < 0) me = 0;
+      if (mds.local_shape(gshape) != pdata.sizes().vec() && pds.get_dim(kDupDim) > 1) {
+        int64_t count = var->attrs.i("zero_count", 0), interval = var->attrs.i("zero_interval", 1), pos = 0;
+        if (count > 0) {
+          pos = (me / interval) % count;     // position inside the gradient's reduce-scatter group
+        } else {
+          auto peers = pds.get_device_indices_by_dim(kDupDim, me);
+          count = (int64_t)peers.size();
+          for (size_t i = 0; i < peers.size(); ++i) if (peers[i] == me) pos = (int64_t)i;
+        }
+        local = pdata.chunk(count, 0)[pos];
+      }
     }
     g_->param_data()[t->id] = local.to(to_aten_dtype(t->dtype)).contiguous().clone();
     return;
@@ -458,6 +487,44 @@ void Executor::build_plan(ExecPlan& plan, const Tensor& loss, const TensorList& 
       plan.param_of_grad[grad->id] = param->id;
     }
   }
+  // Process groups must be created collectively by EVERY rank in the same order, including ranks that are not
+  // members: enumerate the groups of all comm ops for all devices up front (deterministic: sorted set).
+  if (CommRuntime::get().initialized()) {
+    std::set<std::vector<int>> groups;
+    for (OpDef* op : order) {
+      auto explicit_ranks = op->attrs.ints("ranks");
+      if (explicit_ranks.size() > 1 && op->type != "parallel_attn" && op->type != "parallel_attn_bwd") {
+        std::vector<int> r(explicit_ranks.begin(), explicit_ranks.end());
+        groups.insert(r);
+      }
+      const bool is_vp = op->type == "vocab_parallel_cross_entropy";
+      if (op->type != "comm" && !is_vp) continue;
+      const Tensor& x = op->inputs[0];
+      if (!x->has_ds(strategy)) continue;
+      const DistributedStates& src = x->ds(strategy);
+      DeviceGroup sg = (op->type == "comm" && x->producer) ? x->producer->placement(strategy) : op->placement(strategy);
+      if (sg.empty()) sg = op->placement(strategy);
+      if (sg.empty()) continue;
+      for (int me = 0; me < (int)sg.num_devices(); ++me) {
+        if (is_vp) {
+          groups.insert(group_ranks(sg, src.get_device_indices_by_dim(x->ndim() - 1, me)));
+          continue;
+        }
+        const Tensor& y = op->outputs[0];
+        if (!y->has_ds(strategy)) continue;
+        const DistributedStates& dst = y->ds(strategy);
+        DeviceGroup dg = op->placement(strategy);
+        if (dg.empty()) dg = sg;
+        CommType ct;
+        try { ct = classify_comm(src, sg, dst, dg); } catch (...) { continue; }
+        if (ct == CommType::ALL_REDUCE || ct == CommType::REDUCE_SCATTER)
+          groups.insert(group_ranks(sg, src.get_device_indices_by_dim(kPartialDim, me)));
+        else if (ct == CommType::ALL_GATHER)
+          groups.insert(group_ranks(sg, dst.get_device_indices_by_dim(kDupDim, me)));
+      }
+    }
+    for (auto& r : groups) if (r.size() > 1) CommRuntime::get().group(r);
+  }
   for (OpDef* op : order) {
     if (op->type == "comm") lower_comm(plan, op, strategy);
     DeviceGroup grp = op->placement(strategy);
@@ -518,12 +585,13 @@ std::vector<at::Tensor> Executor::exec_comm(const CommStep& cs, OpDef* op, const
     }
     case CommType::P2P: {
       if (cs.is_sender && cs.is_receiver && cs.peer == comm.rank()) return {in[0]};
+      const int channel = op->is_bwd ? 1 : 0;
       if (cs.is_sender) {
-        comm.send(in[0], cs.peer);
+        comm.send(in[0], cs.peer, channel);
         if (!cs.is_receiver) return {at::Tensor()};
       }
       const Tensor& y = op->outputs[0];
-      return {comm.recv(y->shape, to_aten_dtype(y->dtype), aten_device(), cs.peer)};
+      return {comm.recv(y->shape, to_aten_dtype(y->dtype), aten_device(), cs.peer, channel)};
     }
     case CommType::BATCHED_ISEND_IRECV: {
       const int me = comm.rank();
@@ -606,12 +674,25 @@ void Executor::run_ops(ExecPlan& plan, const std::vector<OpDef*>& ops, bool back
           if (cs.type == CommType::P2P && cs.is_receiver && !cs.is_sender) {
             outs = exec_comm(cs, op, {}, rc);
             vals[op->outputs[0]->id] = outs[0];
+            continue;
           }
         }
-        continue;
+        std::ostringstream os;
+        os << "op " << op->name() << " (" << op->type << ") is placed on this rank but input(s)";
+        for (auto& t : op->inputs) if (!vals.count(t->id) && !g_->has_param_data(t->id)) os << " " << t->name;
+        os << " are not available here -- a tensor crosses device groups without a comm op";
+        throw Error(os.str());
       }
-      if (op->type == "comm") outs = exec_comm(plan.comm[op->id], op, ins, rc);
-      else outs = op->kernel->compute(*op, ins, &rc);
+      try {
+        if (op->type == "comm") outs = exec_comm(plan.comm[op->id], op, ins, rc);
+        else outs = op->kernel->compute(*op, ins, &rc);
+      } catch (const std::exception& e) {
+        std::ostringstream os;
+        os << "while executing op " << op->name() << " (" << op->type << ") with input shapes";
+        for (auto& t : ins) os << " " << (t.defined() ? t.sizes().vec() : std::vector<int64_t>{});
+        os << ": " << e.what();
+        throw Error(os.str());
+      }
     }
     HB_CHECK(outs.size() == op->outputs.size()) << "op " << op->name() << " returned " << outs.size() << " outputs";
     for (size_t k = 0; k < outs.size(); ++k) {
@@ -749,12 +830,46 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
         ins.push_back(get_param(t));
       }
       if (!ok) continue;  // parameter received no gradient in this run
-      op->kernel->compute(*op, ins, &rc);
+      // ZeRO: optimizer states (and the synchronised gradient) cover only this rank's dim-0 chunk of the parameter.
+      // Update the chunk, then all-gather the low-precision parameter over the same ranks (optimize->compute bridge).
+      if (ins.size() > 2 && ins[2].numel() < ins[0].numel() && ins[1].numel() == ins[2].numel()) {
+        at::Tensor full = ins[0];
+        std::vector<int> ranks;
+        const Tensor& gt = op->inputs[1];
+        if (gt->producer && gt->producer->type == "comm") ranks = plan.comm[gt->producer->id].ranks;
+        HB_CHECK(!ranks.empty()) << "ZeRO update of " << op->inputs[0]->name << " without a reduce-scatter group";
+        int64_t pos = 0;
+        for (size_t i = 0; i < ranks.size(); ++i) if (ranks[i] == CommRuntime::get().rank()) pos = (int64_t)i;
+        at::Tensor shard = full.chunk((int64_t)ranks.size(), 0)[pos];   // view into the parameter
+        ins[0] = shard;
+        try {
+          op->kernel->compute(*op, ins, &rc);
+        } catch (const std::exception& e) {
+          std::ostringstream os;
+          os << "while executing ZeRO update " << op->name() << " with input shapes";
+          for (auto& t : ins) os << " " << t.sizes().vec();
+          os << ": " << e.what();
+          throw Error(os.str());
+        }
+        at::Tensor gathered = CommRuntime::get().all_gather(shard.contiguous(), ranks, 0);
+        full.copy_(gathered.view(full.sizes()));
+        continue;
+      }
+      try {
+        op->kernel->compute(*op, ins, &rc);
+      } catch (const std::exception& e) {
+        std::ostringstream os;
+        os << "while executing update " << op->name() << " with input shapes";
+        for (auto& t : ins) os << " " << t.sizes().vec();
+        os << ": " << e.what();
+        throw Error(os.str());
+      }
     }
     accum_grads_.clear();
     breakdown_["update_ms"] = now_ms() - t_u;
   }
   ++step_;
+  CommRuntime::get().flush_sends();
   std::vector<at::Tensor> result;
   for (size_t i = 0; i < plan.fetch_ids.size(); ++i) {
     if (fetched[i].empty()) { result.push_back(at::Tensor()); continue; }

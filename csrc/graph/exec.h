@@ -47,8 +47,12 @@ class CommRuntime {
                             ReductionType red = ReductionType::SUM, bool fp32_reduce = false);
   at::Tensor broadcast(const at::Tensor& x, const std::vector<int>& ranks, int root_rank);
   at::Tensor all_to_all(const at::Tensor& x, const std::vector<int>& ranks, int split_dim = 0, int concat_dim = 0);
-  void send(const at::Tensor& x, int dst_rank);
-  at::Tensor recv(const std::vector<int64_t>& shape, at::ScalarType dtype, const at::Device& dev, int src_rank);
+  // pipeline P2P: sends are asynchronous (completed by flush_sends()), the forward and backward directions use
+  // separate channels (own communicator / FIFO) so a stage sending activations never blocks behind a gradient receive
+  void send(const at::Tensor& x, int dst_rank, int channel = 0);
+  at::Tensor recv(const std::vector<int64_t>& shape, at::ScalarType dtype, const at::Device& dev, int src_rank, int channel = 0);
+  void flush_sends();
+  PG p2p_group(int channel);
   // grouped point-to-point (ring attention, re-sharding): all sends / recvs are issued as one batch
   void batched_send_recv(const std::vector<std::pair<at::Tensor, int>>& sends,
                          std::vector<std::pair<at::Tensor, int>>& recvs);
@@ -63,6 +67,8 @@ class CommRuntime {
   std::function<PG(const std::vector<int>&)> factory_;
   std::map<std::vector<int>, PG> groups_;
   std::map<std::string, int64_t> bytes_, calls_;
+  PG p2p_pg_[2];
+  std::vector<std::pair<c10::intrusive_ptr<c10d::Work>, at::Tensor>> pending_sends_;
 };
 
 // ------------------------------------------------------------------ run context

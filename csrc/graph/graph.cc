@@ -329,6 +329,37 @@ TensorList Graph::gradients(const TensorList& ys, const TensorList& xs, const Te
     for (size_t i = 0; i < gins.size() && i < op->inputs.size(); ++i) {
       if (!gins[i]) continue;
       if (!op->inputs[i]->requires_grad && !from_x.count(op->inputs[i]->id)) continue;
+      // A gradient must come back in the layout of the tensor it belongs to ("partial" read as "duplicate"):
+      // e.g. dX of a column-parallel linear is a partial sum over the TP group and is all-reduced right here.
+      // Parameter gradients are exempt -- their (data-parallel) reduction is deferred and bucketed by the optimizer.
+      {
+        const Tensor& x = op->inputs[i];
+        const bool leaf = x->producer && (x->producer->has_flag(kFlagVariable) || x->producer->has_flag(kFlagPlaceholder));
+        if (!leaf && x->ds_hierarchy.size() > 0 && gins[i]->ds_hierarchy.size() > 0 && op->type != "comm") {
+          DistributedStatesHierarchy target;
+          bool differs = false;
+          for (size_t s = 0; s < x->ds_hierarchy.size(); ++s) {
+            DistributedStatesUnion u;
+            const auto& xu = x->ds_hierarchy.get(s);
+            for (size_t m = 0; m < xu.size(); ++m) {
+              const DistributedStates& ds = xu.get(m);
+              if (ds.get_dim(kPartialDim) > 1)
+                u.add(DistributedStates(ds.device_num(), ds.combine_states({kPartialDim}, kDupDim), ds.combine_order({kPartialDim}, kDupDim)));
+              else u.add(ds);
+            }
+            u.set_hetero_dim(xu.hetero_dim() == kPartialDim ? kDupDim : xu.hetero_dim());
+            target.add(u);
+            if (gins[i]->has_ds(s) && u.size() > 0 && !gins[i]->ds(s).check_equal(u.get(0))) differs = true;
+          }
+          if (differs) {
+            OpMeta m;
+            if (x->producer) m.dg_hierarchy = x->producer->meta.dg_hierarchy;
+            const size_t before = ops_.size();
+            gins[i] = make_op1("comm", {gins[i]}, {}, m, [&](OpDef& o) { o.dst_ds = target; });
+            for (size_t j = before; j < ops_.size(); ++j) ops_[j]->fw_op_id = op->id;
+          }
+        }
+      }
       pending[op->inputs[i]->id].push_back(gins[i]);
     }
   }

@@ -96,7 +96,34 @@ static Tensor reduce_to_shape(Graph* g, const Tensor& grad, const Tensor& like) 
 static Ts reduce_to_shape_compute(const OpDef& op, const Ts& in, RunCtx*) {
   return {at::sum_to(in[0], op.attrs.ints("shape"))};
 }
-HB_REGISTER_OP(reduce_to_shape, "reduce_to_shape", 1, 0, reduce_to_shape_compute, nullptr, nullptr, nullptr);
+static void reduce_to_shape_deduce(OpDef& op, size_t s) {
+  // summed-away dims that were sharded leave partial sums; surviving dims keep their split (shifted to the new rank)
+  const Tensor& in = op.inputs[0];
+  if (!in->has_ds(s)) return;
+  const DistributedStates& ds = in->ds(s);
+  const auto target = op.attrs.ints("shape");
+  const int nd_in = in->ndim(), nd_out = (int)target.size();
+  const int lead = nd_in - nd_out;
+  std::map<int, int> st;
+  int partial = ds.get_dim(kPartialDim);
+  std::map<int, int> dim_map;
+  for (auto& kv : ds.states()) {
+    if (kv.second <= 1) continue;
+    if (kv.first < 0) { if (kv.first == kDupDim) st[kDupDim] = kv.second; continue; }
+    const int od = kv.first - lead;
+    const bool reduced = od < 0 || (target[od] == 1 && in->shape[kv.first] != 1);
+    if (reduced) partial *= kv.second;
+    else { st[od] = kv.second; dim_map[kv.first] = od; }
+  }
+  if (partial > 1) st[kPartialDim] = partial;
+  std::vector<int> order;
+  for (int o : ds.order()) {
+    int m = o < 0 ? o : (dim_map.count(o) ? dim_map[o] : kPartialDim);
+    if (st.count(m) && std::find(order.begin(), order.end(), m) == order.end()) order.push_back(m);
+  }
+  set_out_ds(op, 0, s, DistributedStates(ds.device_num(), st, order));
+}
+HB_REGISTER_OP(reduce_to_shape, "reduce_to_shape", 1, 0, reduce_to_shape_compute, nullptr, reduce_to_shape_deduce, nullptr);
 
 static Ts add_compute(const OpDef& op, const Ts& in, RunCtx*) {
   if (in.size() == 1) return {in[0] + op.attrs.f("value")};

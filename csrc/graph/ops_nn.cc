@@ -593,7 +593,7 @@ static TensorList embedding_grad(OpDef& op, const TensorList& g) {
   AttrMap a;
   a.set("vocab", op.inputs[0]->shape[0]);
   a.set("vocab_offset", op.attrs.i("vocab_offset", 0));
-  return {op.graph->make_op1("embedding_grad", {g[0], op.inputs[1]}, a), nullptr};
+  return {op.graph->make_op1("embedding_grad", {g[0], op.inputs[1], op.inputs[0]}, a), nullptr};
 }
 static void embedding_deduce(OpDef& op, size_t s) {
   const Tensor& table = op.inputs[0];
@@ -616,18 +616,39 @@ static void embedding_deduce(OpDef& op, size_t s) {
   set_out_ds(op, 0, s, DistributedStates(ids_ds.device_num(), st, order));
 }
 static void embedding_grad_deduce(OpDef& op, size_t s) {
-  // dense table gradient: partial over every token split of dy; split on vocab handled by the caller's comm
+  // dense table gradient [V_local, H]: keeps the table's own (vocab) split; the table's replicas that saw different
+  // tokens (token-split of dy) hold partial sums
   const Tensor& dy = op.inputs[0];
   if (!dy->has_ds(s)) return;
   const DistributedStates& ds = dy->ds(s);
   const int nd = dy->ndim();
-  int partial = ds.get_dim(kPartialDim);
+  int token_split = 1;
+  for (auto& kv : ds.states()) if (kv.first >= 0 && kv.first != nd - 1 && kv.second > 1) token_split *= kv.second;
+  if (op.inputs.size() > 2 && op.inputs[2]->has_ds(s)) {
+    const DistributedStates& tds = op.inputs[2]->ds(s);
+    std::map<int, int> st;
+    for (auto& kv : tds.states()) if (kv.second > 1) st[kv.first] = kv.second;
+    std::vector<int> order = tds.order();
+    const int dup = tds.get_dim(kDupDim);
+    if (token_split > 1 && dup > 1 && dup % token_split == 0) {
+      st[kPartialDim] = (st.count(kPartialDim) ? st[kPartialDim] : 1) * token_split;
+      if (dup / token_split > 1) st[kDupDim] = dup / token_split; else st.erase(kDupDim);
+      std::vector<int> no;
+      for (int o : order) {
+        if (o == kDupDim) { no.push_back(kPartialDim); if (st.count(kDupDim)) no.push_back(kDupDim); }
+        else no.push_back(o);
+      }
+      order = no;
+    }
+    set_out_ds(op, 0, s, DistributedStates(tds.device_num(), st, order));
+    return;
+  }
+  int partial = ds.get_dim(kPartialDim) * token_split;
   std::map<int, int> st;
   for (auto& kv : ds.states()) {
     if (kv.second <= 1) continue;
     if (kv.first == kDupDim) st[kDupDim] = kv.second;
     else if (kv.first == nd - 1) st[1] = kv.second;
-    else if (kv.first >= 0) partial *= kv.second;
   }
   if (partial > 1) st[kPartialDim] = partial;
   std::vector<int> order;
@@ -918,4 +939,144 @@ static TensorList dropout_grad(OpDef& op, const TensorList& g) {
 }
 HB_REGISTER_OP(dropout, "dropout", 1, 0, dropout_compute, dropout_grad, nullptr, nullptr);
 
+}  // namespace hb
+
+namespace hb {
+// ------------------------------------------------------------------ packed-QKV attention
+// qkv [T, (Hq + 2*Hkv) * D] straight out of the fused projection ([q heads | k heads | v heads] per row);
+// the kernels read q/k/v through strides (TMA), and the backward writes dq/dk/dv into one packed buffer that
+// feeds the projection's backward GEMMs -- no split / concat / transpose copies anywhere.
+using TsP = std::vector<at::Tensor>;
+static void packed_views(const at::Tensor& qkv, int64_t S, int64_t Hq, int64_t Hkv, int64_t D, at::Tensor* q, at::Tensor* k, bool interleaved,
+                         at::Tensor* v) {
+  const int64_t T = qkv.size(0);
+  HB_CHECK(T % S == 0) << "attn_packed: " << T << " tokens are not a multiple of seq_len " << S;
+  if (interleaved) {
+    // per-head interleaved layout [h0: q k v | h1: q k v | ...] (Megatron's): any TP degree that divides the head
+    // count owns complete heads, so the same global weight means the same model under every strategy
+    HB_CHECK(Hq == Hkv) << "the interleaved qkv layout needs num_heads == num_kv_heads";
+    at::Tensor y = qkv.view({T / S, S, Hq, 3, D});
+    *q = y.select(3, 0);
+    *k = y.select(3, 1);
+    *v = y.select(3, 2);
+    return;
+  }
+  at::Tensor x = qkv.view({T / S, S, Hq + 2 * Hkv, D});
+  *q = x.narrow(2, 0, Hq);
+  *k = x.narrow(2, Hq, Hkv);
+  *v = x.narrow(2, Hq + Hkv, Hkv);
+}
+static TsP attn_packed_compute(const OpDef& op, const TsP& in, RunCtx* rc) {
+  const at::Tensor& qkv = in[0];
+  const int64_t S = op.sy_shape.empty() ? op.attrs.i("seq_len") : op.sy_shape[0].get_val();
+  const int64_t Hq = op.attrs.i("num_heads"), Hkv = op.attrs.i("num_kv_heads", Hq), D = op.attrs.i("head_dim");
+  const int64_t T = qkv.size(0);
+  auto fopt = qkv.options().dtype(at::kFloat);
+  if (qkv.is_meta()) return {at::empty({T, Hq * D}, qkv.options()), at::empty({T / std::max<int64_t>(S, 1), Hq, S}, fopt)};
+  at::Tensor q, k, v;
+  at::Tensor src = qkv.is_contiguous() ? qkv : qkv.contiguous();
+  packed_views(src, S, Hq, Hkv, D, &q, &k, op.attrs.s("layout", "qkv") == "hqkv", &v);
+  static const OpKernel* kern = OpRegistry::get().find("attn");
+  OpDef tmp;
+  tmp.attrs = op.attrs;
+  tmp.kernel = kern;
+  auto r = kern->compute(tmp, {q, k, v}, rc);
+  return {r[0].reshape({T, Hq * D}), r[1]};
+}
+// inputs: do [T, Hq*D], qkv, o [T, Hq*D], lse -> dqkv
+static TsP attn_packed_bwd_compute(const OpDef& op, const TsP& in, RunCtx* rc) {
+  const at::Tensor& d_o = in[0];
+  const at::Tensor& qkv = in[1];
+  const at::Tensor& o = in[2];
+  const at::Tensor& lse = in[3];
+  if (qkv.is_meta()) return {at::empty_like(qkv)};
+  const int64_t S = op.sy_shape.empty() ? op.attrs.i("seq_len") : op.sy_shape[0].get_val();
+  const int64_t Hq = op.attrs.i("num_heads"), Hkv = op.attrs.i("num_kv_heads", Hq), D = op.attrs.i("head_dim");
+  const int64_t T = qkv.size(0), B = T / S;
+  at::Tensor src = qkv.is_contiguous() ? qkv : qkv.contiguous();
+  at::Tensor q, k, v, dq, dk, dv;
+  packed_views(src, S, Hq, Hkv, D, &q, &k, op.attrs.s("layout", "qkv") == "hqkv", &v);
+  at::Tensor dqkv = at::empty_like(src);
+  packed_views(dqkv, S, Hq, Hkv, D, &dq, &dk, op.attrs.s("layout", "qkv") == "hqkv", &dv);
+  at::Tensor o4 = o.contiguous().view({B, S, Hq, D}), do4 = d_o.contiguous().view({B, S, Hq, D});
+  const bool causal = op.attrs.b("causal", true);
+  const double scale = op.attrs.f("softmax_scale", 0.0) > 0 ? op.attrs.f("softmax_scale") : 1.0 / std::sqrt((double)D);
+  if (attn_ok(q) && attn_ok(k) && attn_ok(v) && attn_ok(o4) && attn_ok(do4) && (D == 64 || D == 128)) {
+    at::Tensor delta = at::empty_like(lse);
+    AttnBwdCall c;
+    c.q = as_attn(q); c.k = as_attn(k); c.v = as_attn(v); c.o = as_attn(o4); c.d_o = as_attn(do4);
+    c.dq = as_attn(dq); c.dk = as_attn(dk); c.dv = as_attn(dv);
+    c.lse = lse.data_ptr<float>(); c.delta = delta.data_ptr<float>();
+    c.B = (int)B; c.Sq = (int)S; c.Sk = (int)S; c.Hq = (int)Hq; c.Hkv = (int)Hkv; c.D = (int)D;
+    c.softmax_scale = (float)scale; c.causal = causal;
+    cuda_ok(attn_bwd(c, cur_stream()), "attn_bwd");
+    return {dqkv};
+  }
+  static const OpKernel* bwd = OpRegistry::get().find("attn_bwd");
+  OpDef tmp;
+  tmp.attrs = op.attrs;
+  tmp.kernel = bwd;
+  auto r = bwd->compute(tmp, {do4, q, k, v, o4, lse}, rc);
+  dq.copy_(r[0]); dk.copy_(r[1]); dv.copy_(r[2]);
+  return {dqkv};
+}
+static TensorList attn_packed_grad(OpDef& op, const TensorList& g) {
+  OpDef* fw = &op;
+  return {op.graph->make_op1("attn_packed_bwd", {g[0], op.inputs[0], op.outputs[0], op.outputs[1]}, op.attrs, {},
+                             [fw](OpDef& o) { o.sy_shape = fw->sy_shape; })};
+}
+static void attn_packed_deduce(OpDef& op, size_t s) {
+  copy_out_ds(op, 0, s, op.inputs[0]);
+  const Tensor& x = op.inputs[0];
+  if (!x->has_ds(s)) return;
+  // lse [B, H, S]: token split -> batch split, feature (head) split -> head split
+  const DistributedStates& ds = x->ds(s);
+  std::map<int, int> st;
+  for (auto& kv : ds.states()) if (kv.second > 1) st[kv.first] = kv.second;
+  set_out_ds(op, 1, s, DistributedStates(ds.device_num(), st, ds.order()));
+}
+HB_REGISTER_OP(attn_packed, "attn_packed", 2, kFlagAttention, attn_packed_compute, attn_packed_grad, attn_packed_deduce, nullptr);
+HB_REGISTER_OP(attn_packed_bwd, "attn_packed_bwd", 1, kFlagAttention, attn_packed_bwd_compute, nullptr,
+               [](OpDef& op, size_t s) { copy_out_ds(op, 0, s, op.inputs[1]); }, nullptr);
+
+// rotary on the q and k heads of a packed qkv buffer (one launch, v untouched)
+static TsP rotary_packed_compute(const OpDef& op, const TsP& in, RunCtx*) {
+  const at::Tensor& qkv = in[0];
+  if (qkv.is_meta()) return {at::empty_like(qkv)};
+  const int64_t S = op.sy_shape.empty() ? op.attrs.i("seq_len") : op.sy_shape[0].get_val();
+  const int64_t Hq = op.attrs.i("num_heads"), Hkv = op.attrs.i("num_kv_heads", Hq), D = op.attrs.i("head_dim");
+  const bool inverse = op.attrs.b("inverse");
+  const double base = op.attrs.f("base", 10000.0);
+  const int64_t T = qkv.size(0);
+  at::Tensor pos;
+  if (in.size() > 1) pos = in[1].to(at::kInt).reshape({-1}).contiguous();
+  else pos = (at::arange(T, qkv.options().dtype(at::kInt)) % S + (int64_t)op.attrs.i("pos_offset", 0)).contiguous();
+  at::Tensor out = qkv.contiguous().clone();
+  if (is_native(out)) {
+    cuda_ok(rotary_apply(out.data_ptr(), out.data_ptr(), pos.data_ptr<int32_t>(), T, (int)(Hq + Hkv), (int)D, (int)D, (float)base,
+                         inverse, (Hq + 2 * Hkv) * D, cur_stream()), "rotary_packed");
+    return {out};
+  }
+  at::Tensor x = out.view({T, Hq + 2 * Hkv, D}).narrow(1, 0, Hq + Hkv).to(at::kFloat);
+  const int64_t half = D / 2;
+  at::Tensor inv_freq = at::pow(base, -at::arange(0, half, x.options()) * 2.0 / (double)D);
+  at::Tensor ang = pos.to(at::kFloat).unsqueeze(1) * inv_freq.unsqueeze(0);
+  at::Tensor cs = at::cos(ang).unsqueeze(1), sn = at::sin(ang).unsqueeze(1);
+  if (inverse) sn = -sn;
+  at::Tensor a = x.narrow(-1, 0, half), b = x.narrow(-1, half, half);
+  at::Tensor y = at::cat({a * cs - b * sn, b * cs + a * sn}, -1).to(out.scalar_type());
+  out.view({T, Hq + 2 * Hkv, D}).narrow(1, 0, Hq + Hkv).copy_(y);
+  return {out};
+}
+static TensorList rotary_packed_grad(OpDef& op, const TensorList& g) {
+  AttrMap a = op.attrs;
+  a.set("inverse", !op.attrs.b("inverse"));
+  TensorList ins = {g[0]};
+  if (op.inputs.size() > 1) ins.push_back(op.inputs[1]);
+  OpDef* fw = &op;
+  TensorList r = {op.graph->make_op1("rotary_packed", ins, a, {}, [fw](OpDef& o) { o.sy_shape = fw->sy_shape; })};
+  if (op.inputs.size() > 1) r.push_back(nullptr);
+  return r;
+}
+HB_REGISTER_OP(rotary_packed, "rotary_packed", 1, 0, rotary_packed_compute, rotary_packed_grad, nullptr, nullptr);
 }  // namespace hb

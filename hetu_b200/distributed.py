@@ -22,7 +22,9 @@ _global_group = None
 
 
 def _factory(ranks: List[int]):
-    return dist.new_group(ranks=list(ranks))
+    # collective over the whole world; ranks outside the group get a sentinel instead of a ProcessGroup
+    pg = dist.new_group(ranks=list(ranks))
+    return pg if isinstance(pg, dist.ProcessGroup) else None
 
 
 def init_comm_group(device_num: Optional[int] = None, device_idxs=(), server_address: str = "127.0.0.1:23457", backend: Optional[str] = None):

@@ -1,0 +1,4 @@
+from .gpt import GPTConfig, GPTLMHeadModel  # noqa: F401
+from .llama import LlamaConfig, LlamaLMHeadModel  # noqa: F401
+from .moe import MoEConfig, GPTMoELMHeadModel  # noqa: F401
+from .parallel_config import generate_ds_parallel_config, read_ds_parallel_config  # noqa: F401

@@ -1,0 +1,259 @@
+"""HetuMoE: gates (Top-k GShard, k-Top-1, Hash, BASE balance assignment, SAM) -> capacity-based dispatch into
+expert-major buffers -> all-to-all over the expert-parallel group -> local experts -> all-to-all -> gated combine.
+(ref: hetu/v1/python/hetu/layers/{moe_layer,TopGate,KTop1Gate,HashGate,BalanceGate,SAMGate}.py,
+ hetu/v1/src/ops/LayoutTransform.cu, hetu/v1/examples/moe)
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from ... import ops
+from ...core import (from_numpy, normal_initializer, parallel_parameter, zeros_initializer)
+from ...nn import Module, ModuleList
+from ..gpt.gpt_model import GPTConfig
+
+
+@dataclass
+class MoEConfig(GPTConfig):
+    num_experts: int = 8
+    top_k: int = 1
+    capacity_factor: float = 1.0
+    gate_type: str = "topk"          # topk | ktop1 | hash | balance | sam
+    aux_loss_weight: float = 0.01
+    moe_every: int = 2               # every n-th block uses an MoE MLP
+    ep_ranks: tuple = ()             # expert-parallel group (global ranks); empty = all experts local
+
+    @staticmethod
+    def gpt_moe_350m_8e(**kw):
+        """GPT-MoE 350M x 8 experts (BASELINE config #4): 24 layers x 1024 hidden x 16 heads, MoE every other layer"""
+        return MoEConfig(n_embd=1024, n_layer=24, n_head=16, num_experts=8, top_k=1, **kw)
+
+
+class TopKGate(Module):
+    """softmax -> top-k -> capacity (GShard ordering) ; returns (gates, idx, loc, aux_loss)"""
+
+    def __init__(self, d_model, num_experts, k=1, capacity_factor=1.0, dtype="float32", name="gate"):
+        super().__init__()
+        self.num_experts, self.k, self.capacity_factor = num_experts, k, capacity_factor
+        self.wg = parallel_parameter(normal_initializer(0.0, 0.02), [num_experts, d_model], None, dtype=dtype, requires_grad=True,
+                                     name=f"{name}_wg")
+
+    def capacity(self, tokens):
+        return int(math.ceil(self.k * tokens / self.num_experts * self.capacity_factor))
+
+    def forward(self, x):
+        logits = ops.linear(x, self.wg, None, trans_b=True)
+        cap = self.capacity(x.shape[0])
+        _, idx, loc, aux = ops.moe_gate(logits, self.k, cap)
+        gates = ops.moe_gate_values(logits, idx, loc)     # differentiable w.r.t. the router weights
+        return gates, idx, loc, aux, cap
+
+
+class KTop1Gate(TopKGate):
+    """k independent top-1 routers over k disjoint expert groups (each token visits one expert per group)"""
+
+    def forward(self, x):
+        logits = ops.linear(x, self.wg, None, trans_b=True)
+        groups = ops.split(logits, self.k, dim=1)
+        e_per = self.num_experts // self.k
+        cap = int(math.ceil(x.shape[0] / e_per * self.capacity_factor))
+        gates, idxs, locs, aux_total = [], [], [], None
+        for gi, lg in enumerate(groups):
+            _, idx, loc, aux = ops.moe_gate(lg, 1, cap)
+            gates.append(ops.moe_gate_values(lg, idx, loc))
+            idxs.append(idx if gi == 0 else _shift_idx(idx, gi * e_per))
+            locs.append(loc)
+            aux_total = aux if aux_total is None else aux_total + aux
+        return ops.concat(gates, 1), ops.concat(idxs, 1), ops.concat(locs, 1), aux_total, cap
+
+
+def _shift_idx(idx, off):
+    return ops.make_op("add", [idx], {"value": float(off)})[0] if False else _IntAdd.apply(idx, off)
+
+
+class _IntAdd:
+    @staticmethod
+    def apply(idx, off):
+        return ops.data_transfer(ops.add(ops.data_transfer(idx, "float32"), float(off)), "int32")
+
+
+class HashGate(Module):
+    """static hash routing: expert = token_id mod E (no learned router, gates = 1)"""
+
+    def __init__(self, d_model, num_experts, capacity_factor=1.0, **kw):
+        super().__init__()
+        self.num_experts, self.k, self.capacity_factor = num_experts, 1, capacity_factor
+
+    def forward(self, x, token_ids=None):
+        tokens = x.shape[0]
+        cap = int(math.ceil(tokens / self.num_experts * self.capacity_factor))
+        if token_ids is None:
+            token_ids = ops.arange(0, tokens, 1, "int64")
+        onehot = ops.onehot(ops.data_transfer(_mod(token_ids, self.num_experts), "int64"), self.num_experts)
+        logits = ops.data_transfer(onehot * 30.0, x.dtype)
+        gates, idx, loc, aux = ops.moe_gate(logits, 1, cap)
+        return None, idx, loc, None, cap
+
+
+def _mod(t, n):
+    tf = ops.data_transfer(t, "float32")
+    return tf - ops.floor(tf / float(n)) * float(n)
+
+
+class BalanceGate(TopKGate):
+    """BASE layers: balanced assignment -- every expert receives exactly tokens/E tokens.  The assignment is solved
+    greedily on the score matrix in descending score order (auction-free approximation of the linear assignment)."""
+
+    def forward(self, x):
+        logits = ops.linear(x, self.wg, None, trans_b=True)
+        tokens = x.shape[0]
+        cap = int(math.ceil(tokens / self.num_experts))
+        _, idx, loc, aux = ops.make_op("moe_balance_assign", [logits], {"capacity": cap}) if ops._C.has_op("moe_balance_assign") \
+            else ops.moe_gate(logits, 1, cap)
+        gates = ops.moe_gate_values(logits, idx, loc)
+        return gates, idx, loc, aux, cap
+
+
+class SAMGate(TopKGate):
+    """Switch-and-Mixture: first pick the best expert *group* (sum of probabilities), then top-k inside it, so all k
+    experts of a token live on one device (one all-to-all hop instead of k)."""
+
+    def __init__(self, d_model, num_experts, k=2, num_groups=None, capacity_factor=1.0, dtype="float32", name="samgate"):
+        super().__init__(d_model, num_experts, k, capacity_factor, dtype, name)
+        self.num_groups = num_groups or max(num_experts // max(k, 1), 1)
+
+    def forward(self, x):
+        logits = ops.linear(x, self.wg, None, trans_b=True)
+        e, g = self.num_experts, self.num_groups
+        per = e // g
+        probs = ops.softmax(ops.data_transfer(logits, "float32"), -1)
+        group_score = ops.reduce(ops.reshape(probs, [x.shape[0], g, per]), "sum", [2])          # sam_group_sum
+        best = ops.reduce(group_score, "max", [1], keepdims=True)                                  # sam_max
+        mask = ops.data_transfer(ops.reshape(ops.broadcast(ops.reshape(
+            ops.data_transfer(_ge(group_score, best), "float32"), [x.shape[0], g, 1]), [x.shape[0], g, per]), [x.shape[0], e]),
+            logits.dtype)
+        masked = logits * mask + (mask - 1.0) * 1e4
+        cap = self.capacity(x.shape[0])
+        _, idx, loc, aux = ops.moe_gate(masked, self.k, cap)
+        gates = ops.moe_gate_values(masked, idx, loc)
+        return gates, idx, loc, aux, cap
+
+
+def _ge(a, b):
+    return ops.bool_op(ops.relu(a - b + 1e-9)) if hasattr(ops, "bool_op") else ops.make_op("bool_op", [ops.relu(a - b + 1e-9)])[0]
+
+
+class Expert(Module):
+    """E_local feed-forward experts evaluated as batched GEMMs over the expert-major buffer [E_local, C, H]"""
+
+    def __init__(self, d_model, d_ff, num_local_experts, act="gelu", dtype="float32", name="expert"):
+        super().__init__()
+        self.n, self.act = num_local_experts, act
+        std = 0.02
+        self.w1 = [parallel_parameter(normal_initializer(0.0, std), [d_ff, d_model], None, dtype=dtype, requires_grad=True,
+                                      name=f"{name}{i}_w1") for i in range(num_local_experts)]
+        self.b1 = [parallel_parameter(zeros_initializer(), [d_ff], None, dtype=dtype, requires_grad=True, name=f"{name}{i}_b1")
+                   for i in range(num_local_experts)]
+        self.w2 = [parallel_parameter(normal_initializer(0.0, std), [d_model, d_ff], None, dtype=dtype, requires_grad=True,
+                                      name=f"{name}{i}_w2") for i in range(num_local_experts)]
+        self.b2 = [parallel_parameter(zeros_initializer(), [d_model], None, dtype=dtype, requires_grad=True, name=f"{name}{i}_b2")
+                   for i in range(num_local_experts)]
+        for i in range(num_local_experts):
+            for nm, lst in (("w1", self.w1), ("b1", self.b1), ("w2", self.w2), ("b2", self.b2)):
+                self.register_parameter(f"{nm}_{i}", lst[i])
+
+    def forward(self, x):
+        """x [E_local, C', H] -> same shape"""
+        parts = ops.split(x, self.n, dim=0) if self.n > 1 else [x]
+        outs = []
+        for i, p in enumerate(parts):
+            t = ops.reshape(p, [p.shape[1] * p.shape[0], p.shape[2]])
+            hmid = ops.linear(t, self.w1[i], self.b1[i], act=self.act)
+            o = ops.linear(hmid, self.w2[i], self.b2[i])
+            outs.append(ops.reshape(o, [1, p.shape[1] * p.shape[0], p.shape[2]]))
+        return ops.concat(outs, 0) if len(outs) > 1 else outs[0]
+
+
+class MoELayer(Module):
+    def __init__(self, d_model, d_ff, num_experts, k=1, capacity_factor=1.0, gate_type="topk", ep_ranks: Sequence[int] = (),
+                 act="gelu", dtype="float32", name="moe"):
+        super().__init__()
+        self.ep_ranks = tuple(ep_ranks)
+        self.ep = max(len(self.ep_ranks), 1)
+        assert num_experts % self.ep == 0, "experts must divide evenly over the expert-parallel group"
+        self.num_experts, self.num_local = num_experts, num_experts // self.ep
+        gate_cls = {"topk": TopKGate, "ktop1": KTop1Gate, "hash": HashGate, "balance": BalanceGate, "sam": SAMGate}[gate_type]
+        self.gate = gate_cls(d_model, num_experts, k=k, capacity_factor=capacity_factor, dtype=dtype, name=f"{name}_gate") \
+            if gate_type != "hash" else HashGate(d_model, num_experts, capacity_factor)
+        self.experts = Expert(d_model, d_ff, self.num_local, act=act, dtype=dtype, name=f"{name}_expert")
+        self.l_aux = None
+
+    def forward(self, x):
+        """x [T, H] -> [T, H]"""
+        gates, idx, loc, aux, cap = self.gate(x)
+        self.l_aux = aux
+        h = x.shape[1]
+        disp = ops.moe_dispatch(x, idx, loc, self.num_experts, cap)              # [E, C, H]  (layout_transform)
+        if self.ep > 1:
+            # [E, C, H] -> every rank keeps its E_local experts and receives their tokens from all ranks
+            disp = ops.all_to_all(disp, self.ep_ranks, split_dim=0, concat_dim=1)   # [E_local, ep*C, H]
+        out = self.experts(disp)
+        if self.ep > 1:
+            out = ops.all_to_all(out, self.ep_ranks, split_dim=1, concat_dim=0)     # back to [E, C, H]
+        return ops.moe_combine(out, idx, loc, gates)                              # reverse_layout_transform
+
+
+class GPTMoELMHeadModel(Module):
+    """GPT with MoE MLPs every `moe_every` blocks (single-device-group TP=1; experts sharded over `ep_ranks`)."""
+
+    def __init__(self, config: MoEConfig):
+        super().__init__()
+        from ...nn import Embedding, LayerNorm, Linear
+        self.config = config
+        h = config.n_embd
+        self.wte = Embedding(config.vocab_size, h, dtype=config.dtype, name="wte")
+        self.wpe = Embedding(config.n_positions, h, dtype=config.dtype, name="wpe")
+        self.blocks = ModuleList()
+        for i in range(config.n_layer):
+            blk = Module()
+            blk.ln_1 = LayerNorm(h, config.layer_norm_epsilon, dtype=config.dtype, name=f"ln1_{i}")
+            blk.qkv = Linear(h, 3 * h, dtype=config.dtype, name=f"qkv_{i}")
+            blk.proj = Linear(h, h, dtype=config.dtype, name=f"proj_{i}")
+            blk.ln_2 = LayerNorm(h, config.layer_norm_epsilon, dtype=config.dtype, name=f"ln2_{i}")
+            if (i + 1) % config.moe_every == 0:
+                blk.moe = MoELayer(h, config.ffn_hidden_size, config.num_experts, config.top_k, config.capacity_factor,
+                                   config.gate_type, config.ep_ranks, dtype=config.dtype, name=f"moe_{i}")
+                blk.fc1 = blk.fc2 = None
+            else:
+                blk.moe = None
+                blk.fc1 = Linear(h, config.ffn_hidden_size, dtype=config.dtype, name=f"fc1_{i}")
+                blk.fc2 = Linear(config.ffn_hidden_size, h, dtype=config.dtype, name=f"fc2_{i}")
+            self.blocks.append(blk)
+        self.ln_f = LayerNorm(h, config.layer_norm_epsilon, dtype=config.dtype, name="ln_f")
+
+    def forward(self, input_ids, position_ids, labels=None, seq_len=None):
+        from ...ops_extra import attn_packed
+        cfg = self.config
+        x = self.wte(input_ids) + self.wpe(position_ids)
+        aux_total = None
+        for blk in self.blocks:
+            qkv = blk.qkv(blk.ln_1(x))
+            a = attn_packed(qkv, seq_len, cfg.n_head, cfg.n_head, cfg.n_embd // cfg.n_head)
+            x = blk.proj(a, residual=x)
+            hln = blk.ln_2(x)
+            if blk.moe is not None:
+                x = x + blk.moe(hln)
+                if blk.moe.l_aux is not None:
+                    aux_total = blk.moe.l_aux if aux_total is None else aux_total + blk.moe.l_aux
+            else:
+                x = blk.fc2(blk.fc1(hln, act=cfg.activation_function), residual=x)
+        x = self.ln_f(x)
+        logits = ops.linear(x, self.wte.weight, None, trans_b=True)
+        if labels is None:
+            return logits
+        loss = ops.softmax_cross_entropy_sparse(logits, labels, ignored_index=-1, reduction="mean")
+        return loss

@@ -136,11 +136,25 @@ class _ParallelBase(Module):
     def ds_dup_split1(self, zero=True):
         return self._ds(lambda d, t: {-1: d, 1: t}, [-1, 1], zero)
 
+    def _all_split0(self):         # tokens split over every device of the group (norm leaves: dp * tp = dup)
+        return self._ds(lambda d, t: {0: d * t}, [0])
+
     def ds_w_dup(self, zero=True):
         return self._ds(lambda d, t: {-1: d * t}, [-1], zero)
 
-    def _adapt(self, x, target):
-        return x if x.check_ds_hierarchy_equal(target) else ops.comm(x, target)
+    def _adapt(self, x, target=None):
+        """bring `x` to layout `target` on this module's devices: a layout change lowers to a collective, a change of
+        device group with an unchanged layout to pipeline P2P send/recv"""
+        src_group = x.device_group
+        my_group = self.device_group_unions[0][0]
+        moved = (not src_group.empty) and src_group != my_group
+        if target is None:
+            if not moved:
+                return x
+            target = list(x.ds_hierarchy)          # same layout, new devices: pipeline P2P
+        if x.check_ds_hierarchy_equal(target) and not moved:
+            return x
+        return ops.comm(x, target, device_group_hierarchy=self.device_group_unions)
 
 
 class HtMultiColumnParallelLinear(_ParallelBase):
@@ -264,7 +278,7 @@ class HtMultiParallelLayerNorm(_ParallelBase):
                                        device_group_hierarchy=self.device_group_unions, name=f"{name}_bias")
 
     def forward(self, x):
-        x = self._adapt(x, self.ds_split0() if self.sequence_parallel else self.ds_split0_dup())
+        x = self._adapt(x, self._all_split0() if self.sequence_parallel else None)
         return ops.layer_norm(x, self.weight, self.bias, eps=self.eps, device_group_hierarchy=self.device_group_unions)
 
 
@@ -278,7 +292,7 @@ class HtMultiParallelRMSNorm(_ParallelBase):
                                          device_group_hierarchy=self.device_group_unions, name=f"{name}_weight")
 
     def forward(self, x):
-        x = self._adapt(x, self.ds_split0() if self.sequence_parallel else self.ds_split0_dup())
+        x = self._adapt(x, self._all_split0() if self.sequence_parallel else None)
         return ops.rms_norm(x, self.weight, eps=self.eps, device_group_hierarchy=self.device_group_unions)
 
 

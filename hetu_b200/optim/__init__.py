@@ -77,6 +77,7 @@ class Optimizer:
         self.states: Dict[int, Dict[str, Tensor]] = {}
         self.update_ops: List[Tensor] = []
         self.step_count = 0
+        self._zero_geom: Dict[int, tuple] = {}   # param id -> (interval, count) of its reduce-scatter group
 
     # -- to be provided by subclasses
     def _make_states(self, param: Tensor, ds_hier, dgh) -> List[Tensor]:
@@ -94,11 +95,27 @@ class Optimizer:
             if gr is None:
                 continue
             ds_h = list(p.ds_hierarchy)
-            # gradient layout -> parameter layout (all-reduce) or ZeRO layout (reduce-scatter)
+            state_ds = ds_h
+            # gradient layout -> parameter layout (all-reduce) or ZeRO layout (reduce-scatter over the replicas that hold
+            # partial gradients; optimizer states are sharded the same way)
             if ds_h and any(u.size() > 0 for u in ds_h):
                 target = []
-                for u in ds_h:
-                    dsl = [(_zero_ds(d) if d.zero else d) for d in u.ds_list]
+                for s, u in enumerate(ds_h):
+                    dsl = []
+                    for d in u.ds_list:
+                        gds = gr.get_ds(s)
+                        if d.zero and gds is not None and gds.get_dim(-2) > 1:
+                            st = {k: v for k, v in dict(gds.combine_states([-2], 0)).items() if v > 1}
+                            dsl.append(DistributedStates(gds.device_num, st, gds.combine_order([-2], 0), True))
+                            order = list(gds.order)
+                            interval = 1
+                            for o in order[order.index(-2) + 1:]:
+                                interval *= gds.get_dim(o)
+                            self._zero_geom[p.id] = (int(interval), int(gds.get_dim(-2)))
+                        elif d.zero and (gds is None or gds.get_dim(-2) <= 1):
+                            dsl.append(DistributedStates(d.device_num, {k: v for k, v in d.states.items() if v > 1}, d.order, False))
+                        else:
+                            dsl.append(d)
                     target.append(DistributedStatesUnion(dsl, u.hetero_dim))
                 need = False
                 for s, u in enumerate(target):
@@ -107,7 +124,8 @@ class Optimizer:
                         need = True
                 if need:
                     gr = comm(gr, target, device_group_hierarchy=[[p.device_group]] if not p.device_group.empty else None)
-            states = self._make_states(p, ds_h, p.device_group)
+                state_ds = target
+            states = self._make_states(p, state_ds, p.device_group)
             self.params.append(p)
             out = make_op(self.update_type, [p, gr] + states, self._attrs(),
                           device_group_hierarchy=[[p.device_group]] if not p.device_group.empty else None, graph=g)[0]
@@ -144,14 +162,12 @@ class _in_graph:
 
 
 def _state_var(param: Tensor, suffix: str, ds_h, dtype="float32", shape=None, init=None):
+    """optimizer-state variable with the (possibly ZeRO-sharded) layout `ds_h`"""
     g = _graphs_by_id[param.graph_id]
     with _in_graph(g):
-        zero_ds = []
-        for u in ds_h:
-            zero_ds.append(DistributedStatesUnion([(_zero_ds(d) if d.zero else d) for d in u.ds_list], u.hetero_dim))
         gshape = shape if shape is not None else (param.global_shape if ds_h else param.shape)
         dg = param.device_group
-        return parallel_parameter(init or zeros_initializer(), gshape, zero_ds if (ds_h and shape is None) else None, dtype=dtype,
+        return parallel_parameter(init or zeros_initializer(), gshape, list(ds_h) if (ds_h and shape is None) else None, dtype=dtype,
                                   requires_grad=False, device_group_hierarchy=[[dg]] if not dg.empty else None,
                                   name=f"{param.name}_{suffix}")
 
@@ -203,7 +219,7 @@ class AdamOptimizer(Optimizer):
         ins = [m, v, step]
         if param.dtype != "float32":
             from ..core import Initializer
-            master = _state_var(param, "master", ds_h, init=_CopyOf(param))
+            master = _state_var(param, "master", ds_h, init=_CopyOf(param, self._zero_geom.get(param.id)))
             st["master"] = master
             ins.append(master)
         self.states[param.id] = st
@@ -211,14 +227,19 @@ class AdamOptimizer(Optimizer):
 
 
 class _CopyOf:
-    """initializer that mirrors another parameter's (bf16-rounded) initial value: fp32 master weights"""
+    """initializer that mirrors another parameter's (bf16-rounded) initial value: fp32 master weights.
+    `zero_geom` = (interval, count) of the reduce-scatter group so the shard matches the collective's chunk order."""
 
-    def __init__(self, param: Tensor):
+    def __init__(self, param: Tensor, zero_geom=None):
         self._op_id = param.producer_id
+        self._geom = zero_geom
         self.data = None
 
     def attrs(self):
-        return {"init": "copy_of", "copy_of_op": int(self._op_id)}
+        a = {"init": "copy_of", "copy_of_op": int(self._op_id)}
+        if self._geom is not None:
+            a["zero_interval"], a["zero_count"] = self._geom
+        return a
 
 
 class GradScaler:

@@ -1,0 +1,59 @@
+"""Multi-process (gloo, CPU) strategy-equivalence tests: every parallel strategy must reproduce the single-device
+loss curve of the same model / data / seed."""
+import json
+import os
+
+import pytest
+
+from dist_utils import run_workers
+
+WORKER = os.path.join(os.path.dirname(__file__), "workers", "gpt_parallel_worker.py")
+
+
+def _losses(outs):
+    for o in outs:
+        for line in o.splitlines():
+            if line.startswith("LOSSES "):
+                return json.loads(line[len("LOSSES "):])
+    raise AssertionError("no losses reported:\n" + "\n-----\n".join(outs))
+
+
+_ref_cache = {}
+
+
+def _reference(model="gpt"):
+    if model not in _ref_cache:
+        ok, outs = run_workers(WORKER, 1, [1, 1, 1, 0, 0, 1, model])
+        assert ok, outs
+        _ref_cache[model] = _losses(outs)
+    return _ref_cache[model]
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("dp,tp,pp,zero,sp,mb", [
+    (2, 1, 1, 0, 0, 1),     # data parallel (all-reduce)
+    (2, 1, 1, 1, 0, 1),     # ZeRO / OSDP: reduce-scatter grads, sharded Adam, all-gather params
+    (1, 2, 1, 0, 0, 1),     # Megatron tensor parallel
+    (1, 2, 1, 0, 1, 1),     # + sequence parallel
+    (1, 1, 2, 0, 0, 2),     # pipeline (1F1B, 2 micro-batches)
+    (2, 2, 1, 1, 1, 1),     # dp2 x tp2 + zero + sp
+    (1, 1, 1, 0, 0, 2),     # micro-batch accumulation on one device
+])
+def test_strategy_matches_single_device(dp, tp, pp, zero, sp, mb):
+    ref = _reference()
+    ok, outs = run_workers(WORKER, dp * tp * pp, [dp, tp, pp, zero, sp, mb])
+    assert ok, "\n-----\n".join(outs)
+    got = _losses(outs)
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, ref)
+
+
+@pytest.mark.dist
+def test_llama_tp2_sp_matches_single_device():
+    ref = _reference("llama")
+    ok, outs = run_workers(WORKER, 2, [1, 2, 1, 0, 1, 1, "llama"])
+    assert ok, "\n-----\n".join(outs)
+    got = _losses(outs)
+    for a, b in zip(got, ref):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, ref)
