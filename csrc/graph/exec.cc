@@ -545,10 +545,34 @@ void Executor::build_plan(ExecPlan& plan, const Tensor& loss, const TensorList& 
     else plan.fw_ops.push_back(op);
   }
   // static last-use analysis over [fw | bw]
+  // Recompute (activation checkpointing): outputs of flagged forward ops are dropped after their last *forward* use
+  // and rebuilt on demand in backward; the flagged ops' external inputs (the checkpoints) live until backward ends.
+  auto is_recompute = [&](const OpDef* op) {
+    if (!op || op->is_bwd || op->has_flag(kFlagVariable) || op->has_flag(kFlagPlaceholder) || op->has_flag(kFlagConst)) return false;
+    if (op->type == "comm") {
+      auto it = plan.comm.find(op->id);
+      if (it != plan.comm.end() && (it->second.type == CommType::P2P || it->second.type == CommType::BATCHED_ISEND_IRECV)) return false;
+    }
+    const auto& r = op->meta.recompute;
+    return !r.empty() && r[std::min<size_t>(strategy, r.size() - 1)];
+  };
   auto note = [&](const Tensor& t, int pos) { plan.last_use_fw[t->id] = pos; };
   int pos = 0;
+  const int end_pos = (int)(plan.fw_ops.size() + plan.bw_ops.size());
   for (OpDef* op : plan.fw_ops) { for (auto& in : op->inputs) note(in, pos); ++pos; }
-  for (OpDef* op : plan.bw_ops) { for (auto& in : op->inputs) note(in, pos); ++pos; }
+  for (OpDef* op : plan.bw_ops) {
+    for (auto& in : op->inputs) {
+      if (is_recompute(in->producer)) plan.last_use_bw[in->id] = pos;   // freed again after its last backward use
+      else note(in, pos);
+    }
+    ++pos;
+  }
+  if (!plan.bw_ops.empty())
+    for (OpDef* op : plan.fw_ops)
+      if (is_recompute(op)) {
+        plan.recompute_ops.insert(op->id);
+        for (auto& in : op->inputs) if (!is_recompute(in->producer)) note(in, end_pos);
+      }
   for (auto& f : targets) plan.fetch_ids.push_back(f->id);
   plan.built = true;
   HB_LOG(DEBUG) << "plan built: strategy " << strategy << " stage " << plan.stage << "/" << plan.num_stages << " fw "
@@ -660,11 +684,17 @@ void Executor::run_ops(ExecPlan& plan, const std::vector<OpDef*>& ops, bool back
       bool missing = false;
       for (auto& t : op->inputs) {
         auto it = vals.find(t->id);
+        if (it == vals.end() && backward && t->producer && plan.recompute_ops.count(t->producer->id)) {
+          recompute_tensor(plan, t, rc, vals);
+          it = vals.find(t->id);
+        }
         if (it == vals.end()) {
           if (g_->has_param_data(t->id)) { ins.push_back(g_->param_data()[t->id]); continue; }
           missing = true;
           break;
         }
+        if (backward && it->second.defined() && it->second.is_cpu() && aten_device().is_cuda())
+          it->second = it->second.to(aten_device(), /*non_blocking=*/true);   // activation CPU offload: bring it back
         ins.push_back(it->second);
       }
       if (missing) {
@@ -715,6 +745,10 @@ void Executor::run_ops(ExecPlan& plan, const std::vector<OpDef*>& ops, bool back
     for (auto& t : op->inputs) {
       auto lu = plan.last_use_fw.find(t->id);
       if (lu != plan.last_use_fw.end() && lu->second == pos && !keep.count(t->id)) vals.erase(t->id);
+      if (backward) {
+        auto lb = plan.last_use_bw.find(t->id);
+        if (lb != plan.last_use_bw.end() && lb->second == pos && !keep.count(t->id)) vals.erase(t->id);
+      }
     }
     if (profile_) {
       if (at::hasCUDA() && env_int("HETU_B200_FORCE_CPU", 0) == 0) at::cuda::getCurrentCUDAStream().synchronize();
@@ -722,6 +756,46 @@ void Executor::run_ops(ExecPlan& plan, const std::vector<OpDef*>& ops, bool back
     }
   }
   (void)mb;
+}
+
+void Executor::recompute_tensor(ExecPlan& plan, const Tensor& t, RunCtx& rc, std::unordered_map<TensorId, at::Tensor>& vals) {
+  OpDef* op = t->producer;
+  std::vector<at::Tensor> ins;
+  for (auto& in : op->inputs) {
+    auto it = vals.find(in->id);
+    if (it == vals.end() && in->producer && plan.recompute_ops.count(in->producer->id)) {
+      recompute_tensor(plan, in, rc, vals);
+      it = vals.find(in->id);
+    }
+    if (it == vals.end()) {
+      HB_CHECK(g_->has_param_data(in->id)) << "recompute of " << op->name() << ": checkpoint " << in->name << " was freed";
+      ins.push_back(g_->param_data()[in->id]);
+    } else {
+      if (it->second.is_cpu() && aten_device().is_cuda()) it->second = it->second.to(aten_device(), true);
+      ins.push_back(it->second);
+    }
+  }
+  std::vector<at::Tensor> outs = op->type == "comm" ? exec_comm(plan.comm[op->id], op, ins, rc) : op->kernel->compute(*op, ins, &rc);
+  for (size_t k = 0; k < outs.size(); ++k) vals[op->outputs[k]->id] = outs[k];
+  breakdown_["recomputed_ops"] += 1;
+}
+
+void Executor::offload_activations(ExecPlan& plan, std::unordered_map<TensorId, at::Tensor>& vals) {
+  // activation CPU offload: tensors produced by flagged forward ops and still alive after the forward pass are
+  // parked in pinned host memory until backward needs them
+  for (OpDef* op : plan.fw_ops) {
+    const auto& f = op->meta.cpu_offload;
+    if (f.empty() || !f[std::min<size_t>(plan.strategy, f.size() - 1)]) continue;
+    if (op->has_flag(kFlagVariable) || op->has_flag(kFlagPlaceholder)) continue;
+    for (auto& o : op->outputs) {
+      auto it = vals.find(o->id);
+      if (it == vals.end() || !it->second.defined() || !it->second.is_cuda()) continue;
+      at::Tensor host = at::empty(it->second.sizes(), it->second.options().device(at::kCPU).pinned_memory(true));
+      host.copy_(it->second, /*non_blocking=*/true);
+      it->second = host;
+      breakdown_["offloaded_bytes"] += (double)host.nbytes();
+    }
+  }
 }
 
 std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetches,
@@ -778,6 +852,7 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
         vals[mb][kv.first] = v.device() == aten_device() ? v : v.to(aten_device(), /*non_blocking=*/true);
       }
       run_ops(plan, plan.fw_ops, false, mb, rc, vals[mb]);
+      if (!inference) offload_activations(plan, vals[mb]);
       if (inference) {
         for (size_t i = 0; i < plan.fetch_ids.size(); ++i) {
           auto it = vals[mb].find(plan.fetch_ids[i]);

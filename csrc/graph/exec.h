@@ -113,6 +113,7 @@ struct ExecPlan {
   int num_stages = 1, stage = 0;
   std::vector<DeviceGroup> stage_groups;
   std::unordered_map<TensorId, int> last_use_fw, last_use_bw;   // position of last consumer in fw/bw lists
+  std::set<OpId> recompute_ops;                                  // forward ops re-executed on demand in backward
   std::vector<TensorId> fetch_ids;
   std::unordered_map<TensorId, TensorId> param_of_grad;    // grad tensor id -> param tensor id
   std::unordered_map<TensorId, OpDef*> update_of_param;
@@ -157,6 +158,8 @@ class Executor {
   void run_ops(ExecPlan& plan, const std::vector<OpDef*>& ops, bool backward, int mb, RunCtx& rc,
                std::unordered_map<TensorId, at::Tensor>& vals);
   std::vector<at::Tensor> exec_comm(const CommStep& cs, OpDef* op, const std::vector<at::Tensor>& in, RunCtx& rc);
+  void recompute_tensor(ExecPlan& plan, const Tensor& t, RunCtx& rc, std::unordered_map<TensorId, at::Tensor>& vals);
+  void offload_activations(ExecPlan& plan, std::unordered_map<TensorId, at::Tensor>& vals);
 
   Graph* g_;
   std::map<std::pair<int, std::vector<TensorId>>, ExecPlan> plans_;

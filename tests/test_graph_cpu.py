@@ -1,0 +1,157 @@
+"""Define-and-run graphs on CPU (BASELINE config #1: 2-layer MLP, world_size 1) plus executor features:
+micro-batch accumulation, run levels, recompute, module API, symbolic shapes, multi-strategy shape plans."""
+import numpy as np
+import pytest
+import torch
+
+import hetu_b200 as ht
+
+
+def build_mlp(g, din=16, dh=32, dout=4):
+    x = ht.placeholder("float32", [8, din], name="x")
+    y = ht.placeholder("int64", [8], name="y")
+    fc1, fc2 = ht.nn.Linear(din, dh, name="fc1"), ht.nn.Linear(dh, dout, name="fc2")
+    loss = ht.softmax_cross_entropy_sparse(fc2(fc1(x, act="relu")), y)
+    return x, y, fc1, fc2, loss
+
+
+def test_two_layer_mlp_matches_torch():
+    ht.set_seed(1)
+    X = np.random.RandomState(0).randn(8, 16).astype(np.float32)
+    Y = np.random.RandomState(1).randint(0, 4, (8,))
+    with ht.graph("define_and_run", create_new=True) as g:
+        x, y, fc1, fc2, loss = build_mlp(g)
+        opt = ht.SGDOptimizer(lr=0.1)
+        train = opt.minimize(loss)
+        w1, b1, w2, b2 = (g.get_param(p).clone() for p in (fc1.weight, fc1.bias, fc2.weight, fc2.bias))
+        losses = [float(g.run(loss, [loss, train], {x: X, y: Y})[0]) for _ in range(5)]
+    tw1, tb1, tw2, tb2 = (t.clone().requires_grad_() for t in (w1, b1, w2, b2))
+    ref = []
+    for _ in range(5):
+        l = torch.nn.functional.cross_entropy(torch.relu(torch.tensor(X) @ tw1.t() + tb1) @ tw2.t() + tb2, torch.tensor(Y))
+        ref.append(float(l))
+        gs = torch.autograd.grad(l, [tw1, tb1, tw2, tb2])
+        with torch.no_grad():
+            for p, gr in zip((tw1, tb1, tw2, tb2), gs):
+                p -= 0.1 * gr
+    np.testing.assert_allclose(losses, ref, rtol=1e-5)
+
+
+def test_micro_batches_equal_full_batch():
+    X = np.random.RandomState(0).randn(8, 16).astype(np.float32)
+    Y = np.random.RandomState(1).randint(0, 4, (8,))
+
+    def run(mb):
+        ht.set_seed(5)
+        with ht.graph("define_and_run", create_new=True) as g:
+            x = ht.placeholder("float32", [8 // mb, 16], name="x")
+            y = ht.placeholder("int64", [8 // mb], name="y")
+            fc = ht.nn.Linear(16, 4, name="fc")
+            loss = ht.softmax_cross_entropy_sparse(fc(x), y)
+            train = ht.AdamOptimizer(lr=1e-2).minimize(loss)
+            for _ in range(3):
+                out = g.run(loss, [loss, train], {x: X, y: Y}, num_micro_batches=mb)
+            return g.get_param(fc.weight).clone()
+
+    np.testing.assert_allclose(run(1).numpy(), run(4).numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_run_levels_grad_then_update():
+    X = np.random.RandomState(0).randn(8, 16).astype(np.float32)
+    Y = np.random.RandomState(1).randint(0, 4, (8,))
+    ht.set_seed(2)
+    with ht.graph("define_and_run", create_new=True) as g:
+        x, y, fc1, fc2, loss = build_mlp(g)
+        train = ht.SGDOptimizer(lr=0.5).minimize(loss)
+        w0 = g.get_param(fc2.weight).clone()
+        g.run(loss, [loss, train], {x: X, y: Y}, run_level="grad")          # accumulate only
+        assert torch.equal(w0, g.get_param(fc2.weight))
+        assert g.accumulated_grad(fc2.weight) is not None
+        g.run(loss, [loss, train], {x: X, y: Y}, run_level="update")        # second gradient + update
+        assert not torch.equal(w0, g.get_param(fc2.weight))
+        g.run(loss, [loss], {x: X, y: Y}, run_level="compute_only")
+        with ht.run_level("topo"):
+            assert g.run(loss, [loss, train], {x: X, y: Y}) == []
+
+
+def test_recompute_gives_identical_gradients():
+    X = np.random.RandomState(0).randn(8, 16).astype(np.float32)
+
+    def run(rc):
+        ht.set_seed(9)
+        with ht.graph("define_and_run", create_new=True) as g:
+            x = ht.placeholder("float32", [8, 16], name="x")
+            a, b, c = ht.nn.Linear(16, 32, name="a"), ht.nn.Linear(32, 32, name="b"), ht.nn.Linear(32, 1, name="c")
+            h = a(x, act="gelu")
+            if rc:
+                with ht.recompute([True]):
+                    h = ht.layer_norm(b(h, act="gelu"), ht.ones([32], requires_grad=False), ht.zeros([32], requires_grad=False))
+            else:
+                h = ht.layer_norm(b(h, act="gelu"), ht.ones([32], requires_grad=False), ht.zeros([32], requires_grad=False))
+            loss = ht.sum(c(h))
+            train = ht.SGDOptimizer(lr=0.1).minimize(loss)
+            g.run(loss, [loss, train], {x: X})
+            bd = g.step_breakdown()
+            return g.get_param(a.weight).clone(), bd.get("recomputed_ops", 0)
+
+    w_plain, n0 = run(False)
+    w_rc, n1 = run(True)
+    assert n0 == 0 and n1 > 0
+    np.testing.assert_allclose(w_plain.numpy(), w_rc.numpy(), rtol=1e-6)
+
+
+def test_module_api_and_state_dict():
+    with ht.graph("define_and_run", create_new=True) as g:
+        m = ht.nn.Sequential(ht.nn.Linear(4, 8, name="l0"), ht.nn.ReLU(), ht.nn.Linear(8, 2, name="l1"))
+        names = [n for n, _ in m.named_parameters()]
+        assert names == ["0.weight", "0.bias", "2.weight", "2.bias"]
+        sd = m.state_dict()
+        assert sd["0.weight"].shape == (8, 4)
+        sd["2.bias"] = torch.ones(2)
+        m.load_state_dict(sd)
+        x = ht.placeholder("float32", [3, 4], name="x")
+        out = g.run(None, [m(x)], {x: np.zeros((3, 4), np.float32)})[0]
+        l0b = sd["0.bias"]
+        ref = torch.relu(l0b) @ sd["2.weight"].t() + 1.0
+        np.testing.assert_allclose(out[0].numpy(), ref.numpy(), rtol=1e-5)
+        subs = g.subgraphs()
+        assert any(k.endswith("0") for k in subs) and all("fwd_ops" in v for v in subs.values())
+
+
+def test_symbolic_reshape_follows_int_symbol():
+    with ht.graph("define_and_run", create_new=True) as g:
+        seq = ht.IntSymbol(4)
+        x = ht.placeholder("float32", [2, 8], name="x")
+        y = ht.reshape(x, [ht.IntSymbol(2) * (ht.IntSymbol(8) // seq), seq])
+        out = g.run(None, [y], {x: np.arange(16, dtype=np.float32).reshape(2, 8)})[0]
+        assert list(out.shape) == [4, 4]
+        out = g.run(None, [y], {x: np.arange(16, dtype=np.float32).reshape(2, 8)}, int_symbol_dict={seq: 2})[0]
+        assert list(out.shape) == [8, 2]
+
+
+def test_gradients_api_and_eager_mix():
+    with ht.graph("define_and_run", create_new=True) as g:
+        x = ht.placeholder("float32", [3, 3], name="x")
+        w = ht.parameter(ht.ones_initializer(), [3, 3], name="w")
+        y = ht.sum(ht.matmul(x, w) * 2.0)
+        gw, = ht.gradients(y, [w])
+        out = g.run(None, [gw], {x: np.eye(3, dtype=np.float32)})[0]
+        np.testing.assert_allclose(out.numpy(), 2 * np.ones((3, 3)))
+    # eager graph keeps working afterwards
+    a = ht.from_numpy(np.ones((2, 2), np.float32), requires_grad=True)
+    ht.sum(a * 3.0).backward()
+    np.testing.assert_allclose(a.grad.numpy(), 3 * np.ones((2, 2)))
+
+
+def test_lr_schedule_and_grad_scaler():
+    from hetu_b200.optim import OptimizerParamScheduler
+    s = OptimizerParamScheduler(0.0, 1.0, 0.1, lr_warmup_steps=10, lr_decay_steps=110, lr_decay_style="cosine")
+    assert abs(s.get_lr(5) - 0.5) < 1e-9 and abs(s.get_lr(10) - 1.0) < 1e-9
+    assert abs(s.get_lr(60) - (0.1 + 0.9 * 0.5)) < 1e-9 and s.get_lr(500) == 0.1
+    lin = OptimizerParamScheduler(0.0, 1.0, 0.0, 0, 100, "linear")
+    assert abs(lin.get_lr(25) - 0.75) < 1e-9
+    sc = ht.GradScaler(init_scale=8.0, growth_interval=2)
+    sc.update(True)
+    assert sc.get_scale() == 4.0
+    sc.update(False); sc.update(False)
+    assert sc.get_scale() == 8.0

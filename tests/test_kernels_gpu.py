@@ -1,0 +1,240 @@
+"""Numerics of the hand-written sm_100a kernels against plain PyTorch fp32 references of the same op.
+Every test goes through the public op API on an eager graph with CUDA bf16 tensors; HETU_B200_STRICT=1 (set by
+conftest for gpu tests) turns any silent ATen fallback into an error, so a pass means the native kernel ran."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import hetu_b200 as ht
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(t):
+    return t.cuda()
+
+
+def bf(*shape, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).cuda()
+
+
+def leaf(t, grad=True):
+    return ht.from_numpy(t, requires_grad=grad)
+
+
+def close(a, b, atol, rtol):
+    a, b = a.float().cpu(), b.float().cpu()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    assert bool((err <= tol).all()), f"max err {err.max().item():.5f} (tol {atol}+{rtol}*|ref|), ref max {b.abs().max().item():.4f}"
+
+
+def launches():
+    return ht._C.kernel_launch_count()
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 512, 384), (1000, 520, 264), (2048, 1024, 2048)])
+@pytest.mark.parametrize("act", ["none", "gelu"])
+def test_linear_fwd_bwd(M, N, K, act):
+    x, w, b = bf(M, K, seed=1), bf(N, K, scale=1 / math.sqrt(K), seed=2), bf(N, seed=3)
+    n0 = launches()
+    X, W, B = leaf(x), leaf(w), leaf(b)
+    y = ht.linear(X, W, B, act=act)
+    loss = ht.sum(y * leaf(bf(M, N, seed=4), False))
+    loss.backward()
+    assert launches() - n0 >= 3   # fwd GEMM + dgrad + wgrad at least
+    xr, wr, br = x.float().requires_grad_(), w.float().requires_grad_(), b.float().requires_grad_()
+    yr = xr @ wr.t() + br
+    if act == "gelu":
+        yr = torch.nn.functional.gelu(yr)
+    (yr * bf(M, N, seed=4).float()).sum().backward()
+    close(torch.as_tensor(y.numpy()), yr.detach(), 0.03, 0.02)
+    close(torch.as_tensor(X.grad.numpy()), xr.grad, 0.06, 0.03)
+    close(torch.as_tensor(W.grad.numpy()), wr.grad, 0.3, 0.03)
+    close(torch.as_tensor(B.grad.numpy()), br.grad, 0.6, 0.03)
+
+
+def test_linear_residual_epilogue():
+    x, w, r = bf(512, 256, seed=1), bf(384, 256, scale=0.06, seed=2), bf(512, 384, seed=3)
+    y = ht.linear(leaf(x, False), leaf(w, False), None, residual=leaf(r, False))
+    close(torch.as_tensor(y.numpy()), x.float() @ w.float().t() + r.float(), 0.03, 0.02)
+
+
+@pytest.mark.parametrize("B,S,H,Hkv,D,causal", [(2, 256, 4, 4, 128, True), (1, 384, 4, 2, 64, True), (2, 200, 2, 2, 128, False)])
+def test_flash_attention_fwd_bwd(B, S, H, Hkv, D, causal):
+    q, k, v, g = bf(B, S, H, D, seed=1), bf(B, S, Hkv, D, seed=2), bf(B, S, Hkv, D, seed=3), bf(B, S, H, D, seed=4)
+    Q, K, V = leaf(q), leaf(k), leaf(v)
+    n0 = ht._C.attn_launch_count()
+    o = ht.attn(Q, K, V, is_causal=causal)
+    ht.sum(o * leaf(g, False)).backward()
+    assert ht._C.attn_launch_count() - n0 >= 4   # fwd + delta + dq + dkv
+    qr, kr, vr = q.float().requires_grad_(), k.float().requires_grad_(), v.float().requires_grad_()
+    kk = kr.repeat_interleave(H // Hkv, 2)
+    vv = vr.repeat_interleave(H // Hkv, 2)
+    orf = torch.nn.functional.scaled_dot_product_attention(qr.transpose(1, 2), kk.transpose(1, 2), vv.transpose(1, 2),
+                                                           is_causal=causal).transpose(1, 2)
+    (orf * g.float()).sum().backward()
+    close(torch.as_tensor(o.numpy()), orf.detach(), 0.02, 0.02)
+    close(torch.as_tensor(Q.grad.numpy()), qr.grad, 0.03, 0.03)
+    close(torch.as_tensor(K.grad.numpy()), kr.grad, 0.03, 0.03)
+    close(torch.as_tensor(V.grad.numpy()), vr.grad, 0.03, 0.03)
+
+
+@pytest.mark.parametrize("rows,cols", [(512, 2048), (300, 768), (64, 8192)])
+def test_layernorm_and_rmsnorm(rows, cols):
+    x, w, b, g = bf(rows, cols, seed=1), bf(cols, seed=2) * 0.1 + 1, bf(cols, seed=3) * 0.1, bf(rows, cols, seed=4)
+    X, W, Bb = leaf(x), leaf(w), leaf(b)
+    y = ht.layer_norm(X, W, Bb, eps=1e-5)
+    ht.sum(y * leaf(g, False)).backward()
+    xr, wr, br = x.float().requires_grad_(), w.float().requires_grad_(), b.float().requires_grad_()
+    yr = torch.nn.functional.layer_norm(xr, (cols,), wr, br, 1e-5)
+    (yr * g.float()).sum().backward()
+    close(torch.as_tensor(y.numpy()), yr.detach(), 0.03, 0.02)
+    close(torch.as_tensor(X.grad.numpy()), xr.grad, 0.05, 0.03)
+    close(torch.as_tensor(W.grad.numpy()), wr.grad, 0.5, 0.03)
+    close(torch.as_tensor(Bb.grad.numpy()), br.grad, 0.5, 0.03)
+    X2, W2 = leaf(x), leaf(w)
+    y2 = ht.rms_norm(X2, W2, eps=1e-6)
+    ht.sum(y2 * leaf(g, False)).backward()
+    xr2, wr2 = x.float().requires_grad_(), w.float().requires_grad_()
+    yr2 = xr2 * torch.rsqrt(xr2.pow(2).mean(-1, keepdim=True) + 1e-6) * wr2
+    (yr2 * g.float()).sum().backward()
+    close(torch.as_tensor(y2.numpy()), yr2.detach(), 0.03, 0.02)
+    close(torch.as_tensor(X2.grad.numpy()), xr2.grad, 0.05, 0.03)
+    close(torch.as_tensor(W2.grad.numpy()), wr2.grad, 0.5, 0.03)
+
+
+def test_softmax_cross_entropy_and_embedding():
+    T, V, H = 512, 2048, 256
+    logits = bf(T, V, seed=1)
+    labels = torch.randint(0, V, (T,), generator=torch.Generator().manual_seed(5)).cuda()
+    labels[::7] = -1
+    Lg = leaf(logits)
+    loss = ht.softmax_cross_entropy_sparse(Lg, ht.from_numpy(labels), ignored_index=-1, reduction="mean")
+    loss.backward()
+    lr = logits.float().requires_grad_()
+    lref = torch.nn.functional.cross_entropy(lr, labels, ignore_index=-1)
+    lref.backward()
+    assert abs(float(loss.numpy()) - float(lref)) < 2e-2
+    close(torch.as_tensor(Lg.grad.numpy()), lr.grad, 2e-4, 0.03)
+    table = bf(V, H, seed=2)
+    ids = torch.randint(0, V, (T,), generator=torch.Generator().manual_seed(6)).cuda()
+    Tb = leaf(table)
+    e = ht.embedding_lookup(Tb, ht.from_numpy(ids))
+    g = bf(T, H, seed=7)
+    ht.sum(e * leaf(g, False)).backward()
+    close(torch.as_tensor(e.numpy()), table.float()[ids], 1e-6, 0)
+    ref = torch.zeros(V, H, device="cuda").index_add_(0, ids, g.float())
+    close(torch.as_tensor(Tb.grad.numpy()), ref, 0.05, 0.02)
+
+
+def test_activations_swiglu_rotary():
+    x, g = bf(512, 1024, seed=1), bf(512, 1024, seed=2)
+    for name, ref in [("gelu", torch.nn.functional.gelu), ("relu", torch.relu), ("silu", torch.nn.functional.silu)]:
+        X = leaf(x)
+        y = getattr(ht, name)(X)
+        ht.sum(y * leaf(g, False)).backward()
+        xr = x.float().requires_grad_()
+        (ref(xr) * g.float()).sum().backward()
+        close(torch.as_tensor(y.numpy()), ref(x.float()), 0.02, 0.02)
+        close(torch.as_tensor(X.grad.numpy()), xr.grad, 0.03, 0.03)
+    X = leaf(x)
+    y = ht.swiglu(X)
+    ht.sum(y * leaf(g[:, :512].contiguous(), False)).backward()
+    xr = x.float().requires_grad_()
+    yr = torch.nn.functional.silu(xr[:, :512]) * xr[:, 512:]
+    (yr * g[:, :512].float()).sum().backward()
+    close(torch.as_tensor(y.numpy()), yr.detach(), 0.03, 0.02)
+    close(torch.as_tensor(X.grad.numpy()), xr.grad, 0.05, 0.03)
+    # rotary (half-split convention)
+    B, S, Hh, D = 2, 64, 4, 64
+    q = bf(B, S, Hh, D, seed=3)
+    y = ht.rotary(leaf(q, False))
+    half = D // 2
+    inv = 10000.0 ** (-torch.arange(half, dtype=torch.float32) * 2 / D)
+    ang = torch.arange(S, dtype=torch.float32)[:, None] * inv[None]
+    cs, sn = ang.cos()[None, :, None, :].cuda(), ang.sin()[None, :, None, :].cuda()
+    qa, qb = q.float()[..., :half], q.float()[..., half:]
+    ref = torch.cat([qa * cs - qb * sn, qb * cs + qa * sn], -1)
+    close(torch.as_tensor(y.numpy()), ref, 0.03, 0.02)
+
+
+def test_fused_adam_matches_torch():
+    n = 4096 * 33 + 5
+    p = torch.randn(n, generator=torch.Generator().manual_seed(1)).cuda()
+    with ht.graph("define_and_run", create_new=True) as g, ht.autocast("bfloat16"):
+        w = ht.parallel_parameter(ht.provided_initializer(p), [n], None, requires_grad=True, name="w")
+        x = ht.placeholder("bfloat16", [n], name="x")
+        loss = ht.sum(w * x)
+        opt = ht.AdamOptimizer(lr=1e-2, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.1)
+        train = opt.minimize(loss)
+        xs = torch.randn(n, generator=torch.Generator().manual_seed(2)).cuda().to(torch.bfloat16)
+        pt = p.to(torch.bfloat16).float().clone().requires_grad_()
+        topt = torch.optim.AdamW([pt], lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+        for _ in range(3):
+            g.run(loss, [loss, train], {x: xs})
+            topt.zero_grad()
+            (pt * xs.float()).sum().backward()
+            topt.step()
+        master = g.get_param(opt.get_states(w)["master"])
+    close(master, pt.detach(), 2e-4, 1e-3)
+
+
+def test_moe_dispatch_combine_roundtrip():
+    T, H, E, k = 1024, 256, 8, 2
+    x = bf(T, H, seed=1)
+    logits = bf(T, E, seed=2)
+    cap = int(math.ceil(k * T / E * 1.25))
+    gates, idx, loc, aux = ht.moe_gate(leaf(logits, False), k, cap)
+    disp = ht.moe_dispatch(leaf(x, False), idx, loc, E, cap)
+    y = ht.moe_combine(disp, idx, loc, gates)
+    gt, it, lt = torch.as_tensor(gates.numpy()).cuda(), torch.as_tensor(idx.numpy()).cuda().long(), torch.as_tensor(loc.numpy()).cuda()
+    # identity experts: y = sum_k gate_k * x for kept assignments
+    ref = x.float() * (gt * (lt >= 0)).sum(-1, keepdim=True)
+    close(torch.as_tensor(y.numpy()), ref, 0.03, 0.02)
+    # capacity respected and slots unique per expert
+    for e in range(E):
+        slots = lt[(it == e) & (lt >= 0)]
+        assert slots.numel() == slots.unique().numel() and slots.numel() <= cap
+
+
+def test_gpt_block_training_matches_fp32_reference():
+    """tiny GPT: native bf16 training vs the same graph on CPU fp32 -- loss curves must agree to bf16 accuracy"""
+    from hetu_b200.models import GPTConfig, GPTLMHeadModel, generate_ds_parallel_config
+    cfg = GPTConfig(vocab_size=512, n_positions=128, n_embd=256, n_layer=2, n_head=2)
+    B, S = 2, 128
+    rng = np.random.RandomState(0)
+    X = rng.randint(0, 512, (B * S,))
+    P = np.tile(np.arange(S), B)
+    L = np.roll(X, -1)
+
+    def train(native):
+        ht.set_seed(3)
+        import contextlib
+        ctx = ht.autocast("bfloat16") if native else contextlib.nullcontext()
+        import os
+        if not native:
+            os.environ["HETU_B200_FORCE_CPU"] = "1"
+        try:
+            with ht.graph("define_and_run", create_new=True) as g, ctx:
+                model = GPTLMHeadModel(cfg, [generate_ds_parallel_config(cfg.n_layer, 1, 1, 1, 1)])
+                ids, pos, lab = (ht.placeholder("int64", [B * S], name=n) for n in ("ids", "pos", "lab"))
+                loss = model(ids, pos, lab, seq_len=S)
+                train_op = ht.AdamOptimizer(lr=1e-3).minimize(loss)
+                out = []
+                for _ in range(5):
+                    out.append(float(g.run(loss, [loss, train_op], {ids: X, pos: P, lab: L})[0]))
+            return out
+        finally:
+            os.environ.pop("HETU_B200_FORCE_CPU", None)
+
+    n0 = launches()
+    native = train(True)
+    assert launches() - n0 > 100
+    ref = train(False)
+    for a, b in zip(native, ref):
+        assert abs(a - b) < 0.08, (native, ref)
+    assert native[-1] < native[0]

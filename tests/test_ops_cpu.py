@@ -1,0 +1,218 @@
+"""Op library on CPU: forward vs NumPy/PyTorch, backward (eager .backward() and define-and-run gradients) vs torch
+autograd -- the reference's tests/test_cpu_ops.py / test_graphcpu_ops.py strategy."""
+import numpy as np
+import pytest
+import torch
+
+import hetu_b200 as ht
+
+rng = np.random.RandomState(0)
+
+
+def arr(*shape, pos=False):
+    a = rng.randn(*shape).astype(np.float32)
+    return np.abs(a) + 0.5 if pos else a
+
+
+UNARY = [
+    ("abs", torch.abs, False), ("exp", torch.exp, False), ("log", torch.log, True), ("sqrt", torch.sqrt, True),
+    ("rsqrt", torch.rsqrt, True), ("sin", torch.sin, False), ("cos", torch.cos, False), ("sigmoid", torch.sigmoid, False),
+    ("tanh", torch.tanh, False), ("relu", torch.relu, False), ("gelu", torch.nn.functional.gelu, False),
+    ("silu", torch.nn.functional.silu, False), ("reciprocal", torch.reciprocal, True), ("neg", torch.neg, False),
+    ("mish", torch.nn.functional.mish, False), ("hardswish", torch.nn.functional.hardswish, False),
+    ("hardsigmoid", torch.nn.functional.hardsigmoid, False), ("logsigmoid", torch.nn.functional.logsigmoid, False),
+    ("ceil", torch.ceil, False), ("floor", torch.floor, False), ("round", torch.round, False),
+]
+
+
+@pytest.mark.parametrize("name,ref,pos", UNARY)
+def test_unary_forward_backward(name, ref, pos):
+    x = arr(5, 7, pos=pos)
+    X = ht.from_numpy(x, requires_grad=True)
+    y = getattr(ht, name)(X)
+    np.testing.assert_allclose(y.numpy(), ref(torch.tensor(x)).numpy(), rtol=1e-5, atol=1e-6)
+    if name in ("ceil", "floor", "round"):
+        return
+    ht.sum(y).backward()
+    xt = torch.tensor(x, requires_grad=True)
+    ref(xt).sum().backward()
+    np.testing.assert_allclose(X.grad.numpy(), xt.grad.numpy(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape_a,shape_b", [((4, 5), (4, 5)), ((4, 5), (5,)), ((3, 1, 5), (4, 5))])
+@pytest.mark.parametrize("op", ["add", "sub", "mul", "div"])
+def test_binary_broadcast(op, shape_a, shape_b):
+    a, b = arr(*shape_a), arr(*shape_b, pos=True)
+    A, B = ht.from_numpy(a, requires_grad=True), ht.from_numpy(b, requires_grad=True)
+    y = getattr(ht, op)(A, B)
+    ta, tb = torch.tensor(a, requires_grad=True), torch.tensor(b, requires_grad=True)
+    ty = {"add": ta + tb, "sub": ta - tb, "mul": ta * tb, "div": ta / tb}[op]
+    np.testing.assert_allclose(y.numpy(), ty.detach().numpy(), rtol=1e-5, atol=1e-6)
+    ht.sum(y * y).backward()
+    (ty * ty).sum().backward()
+    np.testing.assert_allclose(A.grad.numpy(), ta.grad.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(B.grad.numpy(), tb.grad.numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_scalar_arithmetic_and_operators():
+    x = arr(3, 4)
+    X = ht.from_numpy(x)
+    np.testing.assert_allclose((X * 2.0 + 1.0).numpy(), x * 2 + 1, rtol=1e-6)
+    np.testing.assert_allclose((3.0 - X).numpy(), 3 - x, rtol=1e-6)
+    np.testing.assert_allclose((1.0 / ht.from_numpy(np.abs(x) + 1)).numpy(), 1 / (np.abs(x) + 1), rtol=1e-6)
+    np.testing.assert_allclose((-X).numpy(), -x)
+    np.testing.assert_allclose(ht.pow(ht.from_numpy(np.abs(x) + 1), 1.5).numpy(), (np.abs(x) + 1) ** 1.5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("mode", ["sum", "mean", "max", "min", "prod"])
+@pytest.mark.parametrize("axes,keep", [(None, False), ([1], False), ([0, 2], True)])
+def test_reduce(mode, axes, keep):
+    x = arr(3, 4, 5)
+    y = ht.reduce(ht.from_numpy(x), mode, axes, keep)
+    fn = {"sum": np.sum, "mean": np.mean, "max": np.max, "min": np.min, "prod": np.prod}[mode]
+    ref = fn(x, axis=tuple(axes) if axes else None, keepdims=keep)
+    np.testing.assert_allclose(y.numpy(), ref, rtol=1e-4, atol=1e-5)
+
+
+def test_shape_ops():
+    x = arr(2, 3, 4)
+    X = ht.from_numpy(x, requires_grad=True)
+    np.testing.assert_allclose(ht.reshape(X, [6, 4]).numpy(), x.reshape(6, 4))
+    np.testing.assert_allclose(ht.transpose(X, [2, 0, 1]).numpy(), x.transpose(2, 0, 1))
+    np.testing.assert_allclose(ht.slice(X, [0, 1, 1], [2, 2, 2]).numpy(), x[:, 1:3, 1:3])
+    parts = ht.split(X, 2, dim=2)
+    np.testing.assert_allclose(parts[1].numpy(), x[:, :, 2:])
+    np.testing.assert_allclose(ht.concat([X, X], 1).numpy(), np.concatenate([x, x], 1))
+    np.testing.assert_allclose(ht.repeat(X, [1, 2, 1]).numpy(), np.tile(x, (1, 2, 1)))
+    np.testing.assert_allclose(ht.roll(X, [1], [2]).numpy(), np.roll(x, 1, 2))
+    np.testing.assert_allclose(ht.pad(X, [1, 1]).numpy(), np.pad(x, ((0, 0), (0, 0), (1, 1))))
+    np.testing.assert_allclose(ht.broadcast(ht.from_numpy(x[0]), [5, 3, 4], [0]).numpy(), np.broadcast_to(x[0], (5, 3, 4)))
+    np.testing.assert_allclose(ht.triu(ht.from_numpy(x[0])).numpy(), np.triu(x[0]))
+    # gradient through reshape / transpose / slice / split+concat
+    y = ht.concat(ht.split(ht.transpose(ht.reshape(X, [6, 4]), [1, 0]), 2, dim=0), 1)
+    ht.sum(y * y).backward()
+    xt = torch.tensor(x, requires_grad=True)
+    yt = torch.cat(torch.chunk(xt.reshape(6, 4).t(), 2, 0), 1)
+    (yt * yt).sum().backward()
+    np.testing.assert_allclose(X.grad.numpy(), xt.grad.numpy(), rtol=1e-5)
+
+
+def test_linear_and_matmul_grads():
+    x, w, b = arr(6, 5), arr(4, 5), arr(4)
+    X, W, B = (ht.from_numpy(v, requires_grad=True) for v in (x, w, b))
+    y = ht.linear(X, W, B, act="gelu")
+    ht.sum(y * y).backward()
+    xt, wt, bt = (torch.tensor(v, requires_grad=True) for v in (x, w, b))
+    yt = torch.nn.functional.gelu(xt @ wt.t() + bt)
+    (yt * yt).sum().backward()
+    for a, t in ((X, xt), (W, wt), (B, bt)):
+        np.testing.assert_allclose(a.grad.numpy(), t.grad.numpy(), rtol=1e-4, atol=1e-5)
+    A, Bm = ht.from_numpy(arr(3, 4), requires_grad=True), ht.from_numpy(arr(5, 4), requires_grad=True)
+    c = ht.matmul(A, Bm, trans_b=True)
+    assert c.shape == [3, 5]
+    ht.sum(c).backward()
+    assert A.grad.shape == [3, 4] and Bm.grad.shape == [5, 4]
+
+
+def test_norms_embedding_losses():
+    x, w, b = arr(4, 8), arr(8), arr(8)
+    X, W, B = (ht.from_numpy(v, requires_grad=True) for v in (x, w, b))
+    y = ht.layer_norm(X, W, B, eps=1e-5)
+    ht.sum(y * y).backward()
+    xt, wt, bt = (torch.tensor(v, requires_grad=True) for v in (x, w, b))
+    yt = torch.nn.functional.layer_norm(xt, (8,), wt, bt, 1e-5)
+    (yt * yt).sum().backward()
+    np.testing.assert_allclose(y.numpy(), yt.detach().numpy(), rtol=1e-4, atol=1e-5)
+    for a, t in ((X, xt), (W, wt), (B, bt)):
+        np.testing.assert_allclose(a.grad.numpy(), t.grad.numpy(), rtol=1e-3, atol=1e-4)
+    X2, W2 = ht.from_numpy(x, requires_grad=True), ht.from_numpy(w, requires_grad=True)
+    y2 = ht.rms_norm(X2, W2, eps=1e-6)
+    ht.sum(y2 * y2).backward()
+    xt2, wt2 = torch.tensor(x, requires_grad=True), torch.tensor(w, requires_grad=True)
+    yt2 = xt2 * torch.rsqrt(xt2.pow(2).mean(-1, keepdim=True) + 1e-6) * wt2
+    (yt2 * yt2).sum().backward()
+    np.testing.assert_allclose(X2.grad.numpy(), xt2.grad.numpy(), rtol=1e-3, atol=1e-4)
+    # sparse CE with ignore index
+    logits, labels = arr(6, 10), np.array([1, 2, -1, 4, 9, 0])
+    Lg = ht.from_numpy(logits, requires_grad=True)
+    loss = ht.softmax_cross_entropy_sparse(Lg, ht.from_numpy(labels), ignored_index=-1)
+    loss.backward()
+    lt = torch.tensor(logits, requires_grad=True)
+    ref = torch.nn.functional.cross_entropy(lt, torch.tensor(labels), ignore_index=-1)
+    ref.backward()
+    np.testing.assert_allclose(loss.numpy(), ref.item(), rtol=1e-5)
+    np.testing.assert_allclose(Lg.grad.numpy(), lt.grad.numpy(), rtol=1e-4, atol=1e-6)
+    # embedding
+    table, ids = arr(10, 4), np.array([1, 3, 3, 7])
+    Tb = ht.from_numpy(table, requires_grad=True)
+    e = ht.embedding_lookup(Tb, ht.from_numpy(ids))
+    ht.sum(e * e).backward()
+    tt = torch.tensor(table, requires_grad=True)
+    et = torch.nn.functional.embedding(torch.tensor(ids), tt)
+    (et * et).sum().backward()
+    np.testing.assert_allclose(Tb.grad.numpy(), tt.grad.numpy(), rtol=1e-5)
+    # dense losses
+    p, t = np.clip(np.abs(arr(5, 3)) / 3, 0.05, 0.95), (rng.rand(5, 3) > 0.5).astype(np.float32)
+    np.testing.assert_allclose(ht.binary_cross_entropy(ht.from_numpy(p), ht.from_numpy(t)).numpy(),
+                               torch.nn.functional.binary_cross_entropy(torch.tensor(p), torch.tensor(t)).item(), rtol=1e-5)
+    np.testing.assert_allclose(ht.mse_loss(ht.from_numpy(p), ht.from_numpy(t)).numpy(), ((p - t) ** 2).mean(), rtol=1e-5)
+
+
+def test_attention_rotary_swiglu_cpu():
+    B, S, H, D = 2, 8, 2, 16
+    q, k, v = arr(B, S, H, D), arr(B, S, H, D), arr(B, S, H, D)
+    Q, K, V = (ht.from_numpy(t, requires_grad=True) for t in (q, k, v))
+    o = ht.attn(Q, K, V, is_causal=True)
+    ht.sum(o * o).backward()
+    qt, kt, vt = (torch.tensor(t, requires_grad=True) for t in (q, k, v))
+    ot = torch.nn.functional.scaled_dot_product_attention(qt.transpose(1, 2), kt.transpose(1, 2), vt.transpose(1, 2),
+                                                          is_causal=True).transpose(1, 2)
+    (ot * ot).sum().backward()
+    np.testing.assert_allclose(o.numpy(), ot.detach().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(Q.grad.numpy(), qt.grad.numpy(), rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(V.grad.numpy(), vt.grad.numpy(), rtol=1e-3, atol=1e-4)
+    # rotary is orthogonal: backward = inverse rotation
+    X = ht.from_numpy(q, requires_grad=True)
+    y = ht.rotary(X)
+    ht.sum(y * ht.from_numpy(k)).backward()
+    np.testing.assert_allclose(np.linalg.norm(y.numpy()), np.linalg.norm(q), rtol=1e-5)
+    yk = ht.rotary(ht.from_numpy(q.copy()))
+    np.testing.assert_allclose((yk.numpy() * k).sum(), (q * X.grad.numpy()).sum(), rtol=1e-4)
+    x = arr(4, 12)
+    Xs = ht.from_numpy(x, requires_grad=True)
+    ys = ht.swiglu(Xs)
+    ht.sum(ys).backward()
+    xt = torch.tensor(x, requires_grad=True)
+    (torch.nn.functional.silu(xt[:, :6]) * xt[:, 6:]).sum().backward()
+    np.testing.assert_allclose(Xs.grad.numpy(), xt.grad.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_cnn_ops():
+    x, w, b = arr(2, 3, 8, 8), arr(4, 3, 3, 3), arr(4)
+    X, W, B = (ht.from_numpy(v, requires_grad=True) for v in (x, w, b))
+    y = ht.maxpool(ht.relu(ht.conv2d(X, W, B, padding=1, stride=1)), 2, 2, 0, 2)
+    ht.sum(y).backward()
+    xt, wt, bt = (torch.tensor(v, requires_grad=True) for v in (x, w, b))
+    yt = torch.nn.functional.max_pool2d(torch.relu(torch.nn.functional.conv2d(xt, wt, bt, padding=1)), 2, 2)
+    yt.sum().backward()
+    np.testing.assert_allclose(y.numpy(), yt.detach().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(W.grad.numpy(), wt.grad.numpy(), rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(ht.avgpool(ht.from_numpy(x), 2, 2, 0, 2).numpy(),
+                               torch.nn.functional.avg_pool2d(torch.tensor(x), 2, 2).numpy(), rtol=1e-5)
+    np.testing.assert_allclose(ht.einsum("ij,kj->ik", ht.from_numpy(arr(3, 4)), ht.from_numpy(arr(5, 4))).shape, [3, 5])
+
+
+def test_moe_ops_cpu():
+    T, H, E, k = 32, 8, 4, 2
+    x, logits = arr(T, H), arr(T, E)
+    gates, idx, loc, aux = ht.moe_gate(ht.from_numpy(logits), k, 12)
+    X = ht.from_numpy(x, requires_grad=True)
+    disp = ht.moe_dispatch(X, idx, loc, E, 12)
+    y = ht.moe_combine(disp, idx, loc, gates)
+    g_, i_, l_ = gates.numpy(), idx.numpy(), loc.numpy()
+    ref = x * (g_ * (l_ >= 0)).sum(-1, keepdims=True)
+    np.testing.assert_allclose(y.numpy(), ref, rtol=1e-5, atol=1e-6)
+    ht.sum(y).backward()
+    np.testing.assert_allclose(X.grad.numpy(), np.ones_like(x) * (g_ * (l_ >= 0)).sum(-1, keepdims=True), rtol=1e-5, atol=1e-6)
+    probs = torch.softmax(torch.tensor(logits), -1)
+    np.testing.assert_array_equal(np.sort(i_, 1), np.sort(torch.topk(probs, k, -1).indices.numpy(), 1))
