@@ -17,6 +17,7 @@
 #include "../kernels/kernels.h"
 #include "../planner/dp_core.h"
 #include "../v1/embedding_cache.h"
+#include "../runtime/symm_mem.h"
 
 namespace py = pybind11;
 using namespace hb;
@@ -501,6 +502,65 @@ PYBIND11_MODULE(_C, m) {
                   : s == "ERROR" ? LogLevel::ERROR : s == "FATAL" ? LogLevel::FATAL : LogLevel::WARN);
   });
   m.def("dtype_size", [](const std::string& n) { return dtype_size(dtype_from_name(n)); });
+
+  // ---------------------------------------------------------------- symmetric memory (NVLink peer access)
+  m.def("symm_alloc", [](const std::string& name, size_t bytes, int rank, int world) {
+    return py::bytes(SymmMem::get().alloc(name, bytes, rank, world));
+  });
+  m.def("symm_open", [](const std::string& name, const std::vector<py::bytes>& handles) {
+    std::vector<std::string> hs;
+    for (auto& h : handles) hs.push_back(std::string(h));
+    SymmMem::get().open(name, hs);
+  });
+  m.def("symm_has", [](const std::string& name) { return SymmMem::get().has(name); });
+  m.def("symm_free_all", [] { SymmMem::get().free_all(); });
+  m.def("symm_tensor", [](const std::string& name, size_t byte_offset, const std::vector<int64_t>& shape, const std::string& dtype) {
+    SymmBuffer& b = SymmMem::get().buffer(name);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto opts = at::TensorOptions().dtype(to_aten_dtype(dtype_from_name(dtype))).device(at::kCUDA, dev);
+    return at::from_blob(reinterpret_cast<char*>(b.local) + byte_offset, shape, opts);
+  });
+  m.def("symm_barrier", [](const std::string& name) { cuda_ok(symm_barrier(SymmMem::get().buffer(name), cur_stream()), "symm_barrier"); });
+  m.def("symm_all_gather", [](const std::string& name, size_t src_off, at::Tensor out, size_t bytes_per_rank) {
+    cuda_ok(symm_all_gather(SymmMem::get().buffer(name), src_off, out.data_ptr(), bytes_per_rank, cur_stream()), "symm_all_gather");
+  });
+  m.def("symm_reduce_scatter", [](const std::string& name, size_t src_off, at::Tensor out, size_t elems_per_rank) {
+    cuda_ok(symm_reduce_scatter(SymmMem::get().buffer(name), src_off, out.data_ptr(), elems_per_rank,
+                                out.scalar_type() == at::kBFloat16, cur_stream()), "symm_reduce_scatter");
+  });
+  m.def("symm_all_reduce", [](const std::string& name, size_t src_off, size_t elems, bool bf16) {
+    cuda_ok(symm_all_reduce(SymmMem::get().buffer(name), src_off, elems, bf16, cur_stream()), "symm_all_reduce");
+  });
+  m.def("symm_all_to_all", [](const std::string& name, size_t src_off, at::Tensor out, size_t bytes_per_chunk) {
+    cuda_ok(symm_all_to_all(SymmMem::get().buffer(name), src_off, out.data_ptr(), bytes_per_chunk, cur_stream()), "symm_all_to_all");
+  });
+  m.def("symm_launch_count", &symm_launch_count);
+  // fused row-parallel GEMM -> reduce-scatter: y[T/world, N] = sum_ranks(x_r[T, K_local] * w_r[N, K_local]^T) (+bias +residual).
+  // Output tiles are stored from the GEMM epilogue straight into the owner rank's staging slots over NVLink.
+  m.def("gemm_reduce_scatter", [](const at::Tensor& x, const at::Tensor& w, const std::string& staging, const py::object& bias,
+                                  const py::object& residual) {
+    SymmBuffer& b = SymmMem::get().buffer(staging);
+    const int64_t T = x.size(0), K = x.size(1), N = w.size(0);
+    HB_CHECK(T % b.world == 0 && (T / b.world) % 128 == 0) << "gemm_reduce_scatter: rows per rank must be a multiple of 128";
+    HB_CHECK(size_t(T) * N * 2 <= b.bytes) << "staging buffer too small";
+    const int64_t rpr = T / b.world;
+    GemmCall g;
+    g.A = x.data_ptr(); g.B = w.data_ptr(); g.C = b.local;
+    g.M = (int)T; g.N = (int)N; g.K = (int)K;
+    g.lda = x.stride(0); g.ldb = w.stride(0); g.ldc = N;
+    g.peer_c = b.peer; g.world = b.world; g.my_rank = b.rank; g.rows_per_rank = (int)rpr;
+    cuda_ok(symm_barrier(b, cur_stream()), "barrier");           // previous consumers of the staging slots are done
+    cuda_ok(gemm_bf16(g, cur_stream()), "gemm (peer epilogue)");
+    cuda_ok(symm_barrier(b, cur_stream()), "barrier");           // every rank's partial tiles have landed
+    at::Tensor out = at::empty({rpr, N}, x.options());
+    at::Tensor bt, rt;
+    if (!bias.is_none()) bt = py::cast<at::Tensor>(bias);
+    if (!residual.is_none()) rt = py::cast<at::Tensor>(residual);
+    cuda_ok(symm_reduce_slots(b.local, b.world, out.data_ptr(), bt.defined() ? bt.data_ptr() : nullptr,
+                              rt.defined() ? rt.data_ptr() : nullptr, rpr, (int)N, cur_stream()), "reduce_slots");
+    return out;
+  }, py::arg("x"), py::arg("w"), py::arg("staging"), py::arg("bias") = py::none(), py::arg("residual") = py::none());
 
   // direct kernel entry points (benchmarks / numerics tests)
   m.def("gemm", [](const at::Tensor& a, const at::Tensor& b, bool a_mn, bool b_mn, const py::object& bias, const std::string& act,

@@ -99,6 +99,14 @@ cudaError_t gemm_bf16(const GemmCall& c, cudaStream_t stream) {
   p.aux_mode = c.aux_in ? c.aux_mode : 0;
   p.accumulate = c.accumulate ? 1 : 0;
   p.alpha = c.alpha;
+  p.rows_per_rank = 0;
+  p.my_rank = c.my_rank;
+  for (int i = 0; i < 8; ++i) p.peer_c[i] = nullptr;
+  if (c.peer_c != nullptr && c.rows_per_rank > 0) {
+    if (c.world > 8 || (c.rows_per_rank % 128) != 0) return cudaErrorInvalidValue;   // a CTA's 128 rows have one owner
+    p.rows_per_rank = c.rows_per_rank;
+    for (int i = 0; i < c.world; ++i) p.peer_c[i] = c.peer_c[i];
+  }
 
   if (G == 2) {
     if (c.out == GemmOut::BF16) return dispatch_major<2, 6, __nv_bfloat16>(c.a_mn_major, c.b_mn_major, ta, tb, p, stream);

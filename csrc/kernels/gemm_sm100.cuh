@@ -41,6 +41,11 @@ struct GemmParams {
   int aux_mode;
   int accumulate;        // C += result (read-modify-write)
   float alpha;           // scale applied to the accumulator
+  // fused GEMM -> reduce-scatter: when rows_per_rank > 0 the tile owning rows [o*rows_per_rank, (o+1)*rows_per_rank) is
+  // stored straight into rank o's staging buffer (mapped peer memory over NVLink), slot `my_rank`; ldc = N
+  void* peer_c[8];
+  int rows_per_rank;
+  int my_rank;
 };
 
 namespace gemm_detail {
@@ -272,6 +277,11 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N;
       const bool row_ok = row < p.M;
       OutT* crow = reinterpret_cast<OutT*>(p.C) + int64_t(row) * p.ldc;
+      if (p.rows_per_rank > 0 && row_ok) {
+        const int owner = row / p.rows_per_rank;
+        crow = reinterpret_cast<OutT*>(p.peer_c[owner]) +
+               (int64_t(p.my_rank) * p.rows_per_rank + (row - owner * p.rows_per_rank)) * p.ldc;
+      }
 #pragma unroll 1
       for (int cc = 0; cc < kChunksPerWarp; ++cc) {
         const int c = chalf * kChunksPerWarp + cc;

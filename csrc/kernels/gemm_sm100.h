@@ -36,6 +36,9 @@ struct GemmCall {
   int aux_mode = 0;   // GemmAuxMode
   bool accumulate = false;
   float alpha = 1.0f;
+  // fused GEMM -> reduce-scatter over symmetric memory (see GemmParams::peer_c)
+  void* const* peer_c = nullptr;   // host array of `world` mapped staging buffers, each [world, rows_per_rank, N]
+  int world = 1, my_rank = 0, rows_per_rank = 0;
   int cta_group = 0;  // 0 = auto (2), 1 or 2 to force
 };
 

@@ -1,0 +1,63 @@
+// Symmetric memory over NVLink/NVSwitch: every rank allocates the same buffer, exchanges CUDA IPC handles and maps all
+// peers' buffers, so kernels can load / store / reduce peer memory directly (no NCCL in the data path).
+// A small flag pad per buffer provides system-scope release/acquire signalling for device-side barriers and per-tile
+// readiness flags of the fused compute+collective kernels.
+// (the reference has no equivalent: all GPU traffic goes through NCCL -- hetu/impl/communication/nccl_comm_group.cu)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../core/base.h"
+
+namespace hb {
+
+constexpr int kMaxPeers = 8;
+constexpr int kFlagWords = 1024;   // uint32 flags per rank per buffer
+
+struct SymmBuffer {
+  std::string name;
+  size_t bytes = 0;
+  int rank = 0, world = 1;
+  void* local = nullptr;                 // this rank's allocation (data followed by the flag pad)
+  void* peer[kMaxPeers] = {nullptr};     // mapped pointer of every rank's allocation (peer[rank] == local)
+  void** d_peer = nullptr;               // device copy of peer[] (data region)
+  uint32_t** d_flags = nullptr;          // device copy of every rank's flag pad pointer
+  uint32_t* flags_local = nullptr;
+  uint32_t epoch = 0;                    // barrier generation (host-tracked, identical on all ranks)
+};
+
+class SymmMem {
+ public:
+  static SymmMem& get();
+  // step 1: allocate locally, returns the 64-byte IPC handle to publish
+  std::string alloc(const std::string& name, size_t bytes, int rank, int world);
+  // step 2: map the peers (handles[r] = handle published by rank r)
+  void open(const std::string& name, const std::vector<std::string>& handles);
+  SymmBuffer& buffer(const std::string& name);
+  bool has(const std::string& name) const { return bufs_.count(name) > 0; }
+  void free_all();
+
+ private:
+  std::map<std::string, SymmBuffer> bufs_;
+};
+
+// ---- device-side collectives over a symmetric buffer (symm_comm.cu) ----------------------------------------
+// all ranks must call these in the same order; `stream` is the launching stream on every rank
+cudaError_t symm_barrier(SymmBuffer& b, cudaStream_t s);
+// out[r * n : (r+1) * n] = rank r's `n` elements at byte offset `src_off` of the symmetric buffer
+cudaError_t symm_all_gather(SymmBuffer& b, size_t src_off, void* out, size_t bytes_per_rank, cudaStream_t s);
+// out[0 : n] = sum_r (rank r's chunk `rank` of the `world * n`-element bf16/fp32 array at src_off); fp32 accumulation
+cudaError_t symm_reduce_scatter(SymmBuffer& b, size_t src_off, void* out, size_t elems_per_rank, bool bf16, cudaStream_t s);
+// in-place all-reduce of `elems` elements at src_off (two-shot: reduce-scatter into place, then all-gather)
+cudaError_t symm_all_reduce(SymmBuffer& b, size_t src_off, size_t elems, bool bf16, cudaStream_t s);
+// GEMM->reduce-scatter second stage: out[rows, cols] = sum over `world` staging slots (+ bias + residual), bf16
+cudaError_t symm_reduce_slots(const void* slots, int world, void* out, const void* bias, const void* residual, int64_t rows,
+                              int cols, cudaStream_t s);
+// all-to-all of equal chunks: out chunk r = rank r's chunk `rank`
+cudaError_t symm_all_to_all(SymmBuffer& b, size_t src_off, void* out, size_t bytes_per_chunk, cudaStream_t s);
+int64_t symm_launch_count();
+
+}  // namespace hb

@@ -53,8 +53,9 @@ def test_linear_fwd_bwd(M, N, K, act):
     (yr * bf(M, N, seed=4).float()).sum().backward()
     close(torch.as_tensor(y.numpy()), yr.detach(), 0.03, 0.02)
     close(torch.as_tensor(X.grad.numpy()), xr.grad, 0.06, 0.03)
-    close(torch.as_tensor(W.grad.numpy()), wr.grad, 0.3, 0.03)
-    close(torch.as_tensor(B.grad.numpy()), br.grad, 0.6, 0.03)
+    # dW / db sum over M rows of bf16 products: error grows ~ sqrt(M) * eps_bf16 * |terms|
+    close(torch.as_tensor(W.grad.numpy()), wr.grad, 0.02 * math.sqrt(M), 0.03)
+    close(torch.as_tensor(B.grad.numpy()), br.grad, 0.03 * math.sqrt(M), 0.03)
 
 
 def test_linear_residual_epilogue():
