@@ -215,12 +215,13 @@ def merge_strategy(target_graph: Graph = None, num_strategy: int = -1):
 class profiler:
     """`with hetu.profiler(enabled=True) as prof: ...; prof.summary()` -- per-op timing of executor runs."""
 
-    def __init__(self, enabled=True, use_cpu=False, use_cuda=True, record_shapes=False, profile_memory=False):
+    def __init__(self, enabled=True, use_cpu=False, use_cuda=True, record_shapes=False, profile_memory=False, graph=None):
         self.enabled = enabled
-        self.graph = None
+        self.graph = graph
 
     def __enter__(self):
-        self.graph = cur_graph()
+        if self.graph is None:
+            self.graph = cur_graph()
         if self.enabled:
             self.graph.set_profile(True)
         return self

@@ -22,9 +22,13 @@ import time
 t0 = time.perf_counter(); 
 for _ in range(3): g.run(loss, [loss, train_op], feed)
 torch.cuda.synchronize(); print("step ms (async)", (time.perf_counter() - t0) / 3 * 1e3)
-with ht.profiler() as prof:
-    g.run(loss, [loss, train_op], feed)
-summ = prof.summary()
+g.set_profile(True)
+g.run(loss, [loss, train_op], feed)
+g.set_profile(False)
+agg = {}
+for name, ms in g.op_times():
+    agg.setdefault(name.split(":")[0], []).append(ms)
+summ = {"by_optype": sorted(((k, sum(v), len(v)) for k, v in agg.items()), key=lambda r: -r[1]), "breakdown": g.step_breakdown()}
 tot = sum(r[1] for r in summ["by_optype"])
 print("sum of per-op (synchronised) ms", tot)
 for name, ms, n in summ["by_optype"][:30]:

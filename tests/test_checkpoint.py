@@ -1,0 +1,98 @@
+"""Checkpoint format: virtual-block split keys, strategy-independent reassembly, ModelSaver rotation, cross-strategy
+reload in a real multi-process job (save under tp=2, load under dp=2)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import hetu_b200 as ht
+from hetu_b200.utils.checkpoint import ht_safetensors as hs
+from hetu_b200.utils.checkpoint import ModelSaver, convert_llama_hf_to_ht
+from dist_utils import run_workers
+
+DS = ht.DistributedStates
+
+
+def test_split_keys_follow_reference_numbering():
+    # [64, 32] tensor, unsplit: 8 x 8 virtual blocks, key index = i1 * 8 + i0
+    keys = hs.split_keys_for_shard("w", [64, 32], {}, [0, 0], [64, 32])
+    assert len(keys) == 64
+    assert keys[0][0] == "w_split_0" and keys[1][0] == "w_split_8" and keys[8][0] == "w_split_1"
+    # a tp=2 shard of dim 0 owns block rows 4..7
+    keys = hs.split_keys_for_shard("w", [64, 32], {0: 2}, [32, 0], [32, 32])
+    idx = sorted(int(k.rsplit("_", 1)[1]) for k, _ in keys)
+    assert idx == sorted(i1 * 8 + i0 for i1 in range(8) for i0 in range(4, 8))
+    # 1-D tensors use a single digit
+    assert [k for k, _ in hs.split_keys_for_shard("b", [16], {}, [0], [16])] == [f"b_split_{i}" for i in range(8)]
+
+
+def test_save_under_tp4_reassemble_under_dp2_tp2(tmp_path):
+    full = torch.arange(64 * 32, dtype=torch.float32).reshape(64, 32)
+    src = DS(4, {0: 4}, [0])
+    for r in range(4):
+        b, s = src.local_slice([64, 32], r)
+        local = full[b[0]:b[0] + s[0], b[1]:b[1] + s[1]]
+        blocks, meta = hs._tensor_blocks("w", local, [64, 32], src, r)
+        meta["device_group"] = [0, 1, 2, 3]
+        hs.save_file(blocks, str(tmp_path / f"{hs.WEIGHTS_NAME}-{r + 1}-of-4{hs.WEIGHTS_FORMAT}"))
+        json.dump({"w": meta}, open(tmp_path / f"param_states-{r + 1}-of-4.json", "w"))
+    index = hs._SplitIndex(str(tmp_path))
+    dst = DS(4, {-1: 2, 1: 2}, [-1, 1])       # now split along dim 1 instead
+    for r in range(4):
+        b, s = dst.local_slice([64, 32], r)
+        got = hs.assemble_from_splits(index, "w", [64, 32], b, s)
+        assert torch.equal(got, full[b[0]:b[0] + s[0], b[1]:b[1] + s[1]])
+
+
+def test_model_saver_rotation_and_resume(tmp_path):
+    with ht.graph("define_and_run", create_new=True) as g:
+        m = ht.nn.Linear(8, 4, name="lin")
+        x = ht.placeholder("float32", [2, 8], name="x")
+        loss = ht.sum(m(x))
+        opt = ht.AdamOptimizer(lr=0.1)
+        train = opt.minimize(loss)
+        saver = ModelSaver(str(tmp_path), save_copies=2, save_interval=1)
+        X = np.ones((2, 8), np.float32)
+        snaps = {}
+        for step in range(1, 5):
+            g.run(loss, [loss, train], {x: X})
+            saver.save(m, opt, step, consumed_samples=step * 2, loss=0.0)
+            snaps[step] = g.get_param(m.weight).clone()
+        assert sorted(d for d in os.listdir(tmp_path) if d.startswith("step") and d[4:].isdigit()) == ["step3", "step4"]
+        g.run(loss, [loss, train], {x: X})                       # drift away, then restore
+        step, consumed = saver.load_latest(m, opt)
+        assert (step, consumed) == (4, 8)
+        assert torch.equal(g.get_param(m.weight), snaps[4])
+        st = opt.get_states(m.weight)
+        assert int(g.get_param(st["step"])) == 4
+
+
+def test_hf_llama_converter_shapes():
+    H, KV, D, L, F, V = 4, 2, 8, 2, 48, 64
+    hf = {"model.embed_tokens.weight": torch.randn(V, H * D), "model.norm.weight": torch.ones(H * D), "lm_head.weight": torch.randn(V, H * D)}
+    for i in range(L):
+        p = f"model.layers.{i}."
+        hf.update({p + "input_layernorm.weight": torch.ones(H * D), p + "post_attention_layernorm.weight": torch.ones(H * D),
+                   p + "self_attn.q_proj.weight": torch.randn(H * D, H * D), p + "self_attn.k_proj.weight": torch.randn(KV * D, H * D),
+                   p + "self_attn.v_proj.weight": torch.randn(KV * D, H * D), p + "self_attn.o_proj.weight": torch.randn(H * D, H * D),
+                   p + "mlp.gate_proj.weight": torch.randn(F, H * D), p + "mlp.up_proj.weight": torch.randn(F, H * D),
+                   p + "mlp.down_proj.weight": torch.randn(H * D, F)})
+    out = convert_llama_hf_to_ht(hf, L, H, KV)
+    assert out["transformer.h.1.attn.qkv_dense.weight"].shape == ((H + 2 * KV) * D, H * D)
+    assert out["transformer.h.0.mlp.dense_h_to_4h.weight"].shape == (2 * F, H * D)
+
+
+WORKER = os.path.join(os.path.dirname(__file__), "workers", "ckpt_worker.py")
+
+
+@pytest.mark.dist
+def test_cross_strategy_reload(tmp_path):
+    ok, outs = run_workers(WORKER, 2, ["save", 1, 2, str(tmp_path)])
+    assert ok, "\n---\n".join(outs)
+    saved = [json.loads(l[5:]) for o in outs for l in o.splitlines() if l.startswith("CKPT ")][0]
+    ok, outs = run_workers(WORKER, 2, ["load", 2, 1, str(tmp_path)])
+    assert ok, "\n---\n".join(outs)
+    loaded = [json.loads(l[5:]) for o in outs for l in o.splitlines() if l.startswith("CKPT ")][0]
+    assert abs(saved["next_loss"] - loaded["next_loss"]) < 2e-3 * max(1.0, abs(saved["next_loss"])), (saved, loaded)
