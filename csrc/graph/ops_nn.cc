@@ -90,6 +90,26 @@ static at::Tensor aten_act(const at::Tensor& x, int code) {
     default: return x;
   }
 }
+static int act_bwd_mode(const std::string& k) {
+  if (k == "gelu") return AUX_DGELU;
+  if (k == "relu") return AUX_DRELU;
+  if (k == "gelu_tanh") return AUX_DGELU_TANH;
+  if (k == "silu") return AUX_DSILU;
+  HB_FAIL() << "no fused backward for activation " << k;
+}
+// dy * act'(x) in fp32 with ATen (CPU path / reference numerics)
+static at::Tensor aten_act_bwd(const at::Tensor& dy, const at::Tensor& x, const std::string& kind) {
+  at::Tensor xf = x.to(at::kFloat), d;
+  if (kind == "gelu") d = 0.5 * (1 + at::erf(xf * M_SQRT1_2)) + xf * at::exp(-0.5 * xf * xf) * 0.3989422804014327;
+  else if (kind == "relu") d = (xf > 0).to(at::kFloat);
+  else if (kind == "silu") { auto sg = at::sigmoid(xf); d = sg * (1 + xf * (1 - sg)); }
+  else {
+    auto u = 0.7978845608028654 * (xf + 0.044715 * xf * xf * xf);
+    auto t = at::tanh(u);
+    d = 0.5 * (1 + t) + 0.5 * xf * (1 - t * t) * 0.7978845608028654 * (1 + 0.134145 * xf * xf);
+  }
+  return (dy.to(at::kFloat) * d).to(x.scalar_type());
+}
 
 // C[M,N] = A * B with explicit operand majors on raw 2-D contiguous tensors
 static void run_gemm(const at::Tensor& A, bool a_mn, const at::Tensor& B, bool b_mn, at::Tensor& C, int64_t M, int64_t N,
@@ -178,11 +198,18 @@ static Ts linear_dgrad_compute(const OpDef& op, const Ts& in, RunCtx*) {
   if (gemm_ok(d2) && gemm_ok(w) && (K % 8) == 0) {
     at::Tensor dx = at::empty({M, K}, dy.options());
     // dx[M,K] = dy[M,N] * W[N,K]: B must be [K(out-n), N(contract)]; W[N,K] row-major = MN-major B
-    run_gemm(d2, false, w, trans_b, dx, M, K, N, nullptr, nullptr, 0, nullptr, ACT_NONE, false);
+    if (in.size() > 2) {
+      at::Tensor pre = flatten_rows(in[2]).contiguous();
+      run_gemm(d2, false, w, trans_b, dx, M, K, N, nullptr, &pre, act_bwd_mode(op.attrs.s("act_bwd")), nullptr, ACT_NONE, false);
+    } else {
+      run_gemm(d2, false, w, trans_b, dx, M, K, N, nullptr, nullptr, 0, nullptr, ACT_NONE, false);
+    }
     return {dx.reshape(oshape)};
   }
   if (is_native(dy)) note_fallback("linear_dgrad");
-  return {(trans_b ? at::matmul(d2, w) : at::matmul(d2, w.t())).reshape(oshape)};
+  at::Tensor dxa = (trans_b ? at::matmul(d2, w) : at::matmul(d2, w.t())).reshape(oshape);
+  if (in.size() > 2) dxa = aten_act_bwd(dxa, in[2], op.attrs.s("act_bwd"));
+  return {dxa};
 }
 // wgrad: dw = dy^T * x  ([N,K] when trans_b else [K,N])
 static Ts linear_wgrad_compute(const OpDef& op, const Ts& in, RunCtx*) {
@@ -297,9 +324,18 @@ static TensorList linear_grad(OpDef& op, const TensorList& g) {
   if (has_res) res[has_bias ? 3 : 2] = dy;
   Tensor dpre = dy;
   if (!act.empty() && act != "none") {
-    AttrMap a;
-    a.set("kind", act);
-    dpre = gr->make_op1("unary_act_bwd", {dy, op.outputs[1]}, a);
+    OpDef* p = dy->producer;
+    if (p != nullptr && p->type == "linear_dgrad" && p->inputs.size() == 2 && dy->consumers.empty()) {
+      // dy is the dgrad of the next linear and nobody else reads it: recompute it with act'(pre) applied in the GEMM
+      // epilogue (AUX_DGELU...) -- the un-fused dgrad op becomes dead and is never scheduled
+      AttrMap a = p->attrs;
+      a.set("act_bwd", act);
+      dpre = gr->make_op1("linear_dgrad", {p->inputs[0], p->inputs[1], op.outputs[1]}, a);
+    } else {
+      AttrMap a;
+      a.set("kind", act);
+      dpre = gr->make_op1("unary_act_bwd", {dy, op.outputs[1]}, a);
+    }
   }
   AttrMap a;
   a.set("trans_b", op.attrs.b("trans_b", true));
@@ -372,18 +408,7 @@ static Ts unary_act_bwd_compute(const OpDef& op, const Ts& in, RunCtx*) {
     cuda_ok(unary_bwd(code, dy.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel(), cur_stream()), "unary_bwd");
     return {dx};
   }
-  at::Tensor xf = x.to(at::kFloat), d;
-  switch (code) {
-    case U_GELU: d = 0.5 * (1 + at::erf(xf * M_SQRT1_2)) + xf * at::exp(-0.5 * xf * xf) * 0.3989422804014327; break;
-    case U_RELU: d = (xf > 0).to(at::kFloat); break;
-    case U_SILU: { auto sg = at::sigmoid(xf); d = sg * (1 + xf * (1 - sg)); break; }
-    default: {
-      auto u = 0.7978845608028654 * (xf + 0.044715 * xf * xf * xf);
-      auto t = at::tanh(u);
-      d = 0.5 * (1 + t) + 0.5 * xf * (1 - t * t) * 0.7978845608028654 * (1 + 0.134145 * xf * xf);
-    }
-  }
-  return {(dy.to(at::kFloat) * d).to(x.scalar_type())};
+  return {aten_act_bwd(dy, x, op.attrs.s("kind"))};
 }
 static TensorList unary_act_grad(OpDef& op, const TensorList& g) {
   AttrMap a;
@@ -394,37 +419,60 @@ HB_REGISTER_OP(unary_act, "unary_act", 1, 0, unary_act_compute, unary_act_grad, 
 HB_REGISTER_OP(unary_act_bwd, "unary_act_bwd", 1, 0, unary_act_bwd_compute, nullptr, nullptr, nullptr);
 
 // swiglu: y = silu(x[..., :d]) * x[..., d:]
-static Ts swiglu_compute(const OpDef&, const Ts& in, RunCtx*) {
+// attr interleaved: x[..., 2i] = gate_i, x[..., 2i+1] = up_i (the tensor-parallel friendly layout of the fused gate/up GEMM)
+static Ts swiglu_compute(const OpDef& op, const Ts& in, RunCtx*) {
   const at::Tensor& x = in[0];
+  const bool il = op.attrs.b("interleaved");
   const int64_t d = x.size(-1) / 2;
   std::vector<int64_t> oshape = x.sizes().vec();
   oshape.back() = d;
   if (x.is_meta()) return {at::empty(oshape, x.options())};
   if (is_native(x) && x.is_contiguous() && d % 8 == 0) {
     at::Tensor y = at::empty(oshape, x.options());
-    cuda_ok(swiglu_fwd(x.data_ptr(), y.data_ptr(), x.numel() / (2 * d), (int)d, cur_stream()), "swiglu_fwd");
+    if (il) cuda_ok(swiglu_interleaved_fwd(x.data_ptr(), y.data_ptr(), x.numel() / (2 * d), (int)d, cur_stream()), "swiglu_fwd");
+    else cuda_ok(swiglu_fwd(x.data_ptr(), y.data_ptr(), x.numel() / (2 * d), (int)d, cur_stream()), "swiglu_fwd");
     return {y};
+  }
+  if (il) {
+    std::vector<int64_t> ps = oshape;
+    ps.push_back(2);
+    at::Tensor xp = x.reshape(ps);
+    return {at::silu(xp.select(-1, 0)) * xp.select(-1, 1)};
   }
   return {at::silu(x.narrow(-1, 0, d)) * x.narrow(-1, d, d)};
 }
-static Ts swiglu_bwd_compute(const OpDef&, const Ts& in, RunCtx*) {
+static Ts swiglu_bwd_compute(const OpDef& op, const Ts& in, RunCtx*) {
   const at::Tensor& dy = in[0];
   const at::Tensor& x = in[1];
+  const bool il = op.attrs.b("interleaved");
   if (dy.is_meta()) return {at::empty_like(x)};
   const int64_t d = x.size(-1) / 2;
   if (is_native(x) && is_native(dy) && x.is_contiguous() && dy.is_contiguous() && d % 8 == 0) {
     at::Tensor dx = at::empty_like(x);
-    cuda_ok(swiglu_bwd(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel() / (2 * d), (int)d, cur_stream()), "swiglu_bwd");
+    if (il) cuda_ok(swiglu_interleaved_bwd(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel() / (2 * d), (int)d, cur_stream()), "swiglu_bwd");
+    else cuda_ok(swiglu_bwd(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel() / (2 * d), (int)d, cur_stream()), "swiglu_bwd");
     return {dx};
   }
-  auto a = x.narrow(-1, 0, d).to(at::kFloat), b = x.narrow(-1, d, d).to(at::kFloat), g = dy.to(at::kFloat);
+  at::Tensor a, b;
+  if (il) {
+    std::vector<int64_t> ps = dy.sizes().vec();
+    ps.push_back(2);
+    at::Tensor xp = x.reshape(ps).to(at::kFloat);
+    a = xp.select(-1, 0);
+    b = xp.select(-1, 1);
+  } else {
+    a = x.narrow(-1, 0, d).to(at::kFloat);
+    b = x.narrow(-1, d, d).to(at::kFloat);
+  }
+  auto g = dy.to(at::kFloat);
   auto sg = at::sigmoid(a);
   auto da = g * b * sg * (1 + a * (1 - sg));
   auto db = g * a * sg;
+  if (il) return {at::stack({da, db}, -1).reshape(x.sizes()).to(x.scalar_type())};
   return {at::cat({da, db}, -1).to(x.scalar_type())};
 }
 static TensorList swiglu_grad(OpDef& op, const TensorList& g) {
-  return {op.graph->make_op1("swiglu_bwd", {g[0], op.inputs[0]})};
+  return {op.graph->make_op1("swiglu_bwd", {g[0], op.inputs[0]}, op.attrs)};
 }
 HB_REGISTER_OP(swiglu, "swiglu", 1, 0, swiglu_compute, swiglu_grad, nullptr, nullptr);
 HB_REGISTER_OP(swiglu_bwd, "swiglu_bwd", 1, 0, swiglu_bwd_compute, nullptr,
@@ -678,13 +726,16 @@ static Ts ce_compute(const OpDef& op, const Ts& in, RunCtx*) {
   at::Tensor lab = labels.to(at::kLong).reshape({-1}).contiguous();
   const int64_t rows = lab.numel();
   at::Tensor per_tok, unit;
+  at::Tensor inv_cnt;   // mean reduction: 1 / #valid tokens, folded into the saved gradient (native path)
   if (is_native(logits) && logits.is_contiguous() && V % 8 == 0) {
-    // the kernel overwrites its input with (softmax - onehot): work on a copy only when the logits are
+    // the kernel overwrites its input with (softmax - onehot) [/ #valid]: work on a copy only when the logits are
     // still needed elsewhere (the executor marks single-consumer inputs as donatable)
     unit = op.attrs.b("donate_logits") ? logits : logits.clone();
     per_tok = at::empty({rows}, fopt);
+    if (red == "mean") inv_cnt = (lab != ignore).sum().to(at::kFloat).clamp_min(1.0).reciprocal();
     cuda_ok(softmax_ce_fwd_bwd(unit.data_ptr(), lab.data_ptr<int64_t>(), per_tok.data_ptr<float>(), nullptr, rows, (int)V, V,
-                               ignore, 1.0f, true, cur_stream()), "softmax_ce");
+                               ignore, 1.0f, true, cur_stream(), inv_cnt.defined() ? inv_cnt.data_ptr<float>() : nullptr),
+            "softmax_ce");
   } else {
     at::Tensor lf = logits.to(at::kFloat).reshape({rows, V});
     at::Tensor lsm = at::log_softmax(lf, -1);
@@ -698,6 +749,7 @@ static Ts ce_compute(const OpDef& op, const Ts& in, RunCtx*) {
   at::Tensor loss;
   if (red == "none") loss = per_tok.reshape(lshape);
   else if (red == "sum") loss = per_tok.sum();
+  else if (inv_cnt.defined()) loss = per_tok.sum() * inv_cnt;
   else {
     at::Tensor cnt = (lab != ignore).sum().to(at::kFloat).clamp_min(1.0);
     loss = per_tok.sum() / cnt;
@@ -712,6 +764,16 @@ static Ts ce_bwd_compute(const OpDef& op, const Ts& in, RunCtx*) {
   if (unit.is_meta()) return {at::empty_like(unit)};
   const std::string red = op.attrs.s("reduction", "mean");
   const int64_t ignore = op.attrs.i("ignore_index", -1);
+  const int64_t V = unit.size(-1);
+  if (is_native(unit) && unit.is_contiguous() && V % 8 == 0) {
+    // native forward already folded 1/#valid into `unit` (mean); a unit seed (dloss == 1 by construction) is free
+    if (op.attrs.b("unit_dloss") && red != "none") return {unit};
+    at::Tensor sc = dl.to(at::kFloat).contiguous();
+    at::Tensor out = at::empty_like(unit);
+    cuda_ok(scale_rows_bf16(unit.data_ptr(), out.data_ptr(), sc.data_ptr<float>(), red == "none", unit.numel() / V, V, cur_stream()),
+            "ce_bwd scale");
+    return {out};
+  }
   at::Tensor scale;
   if (red == "none") scale = dl.to(at::kFloat).unsqueeze(-1);
   else if (red == "sum") scale = dl.to(at::kFloat);
@@ -722,6 +784,8 @@ static TensorList ce_grad(OpDef& op, const TensorList& g) {
   AttrMap a;
   a.set("reduction", op.attrs.s("reduction", "mean"));
   a.set("ignore_index", op.attrs.i("ignore_index", -1));
+  // loss seeded with ones_like(loss): the scale is the constant 1, the saved (softmax - onehot)/count IS the gradient
+  if (g[0]->producer != nullptr && g[0]->producer->type == "ones_like") a.set("unit_dloss", true);
   return {op.graph->make_op1("softmax_ce_sparse_bwd", {g[0], op.outputs[1], op.inputs[1]}, a), nullptr};
 }
 static void ce_deduce(OpDef& op, size_t s) {
@@ -754,7 +818,17 @@ static AttnTensor as_attn(const at::Tensor& t) {
   AttnTensor a;
   a.ptr = t.data_ptr();
   a.stride_b = t.stride(0); a.stride_s = t.stride(1); a.stride_h = t.stride(2);
+  if (t.dim() == 5) {   // grouped [B, S, G, rep, D]: slots of stride(3) elements, group stride(2)
+    a.stride_h = t.stride(3);
+    a.h_div = (int)t.size(3);
+    a.h_mul = (int)(t.stride(2) / t.stride(3));
+    a.h_slots = (int)(t.size(2) * a.h_mul);
+  }
   return a;
+}
+static bool attn5_ok(const at::Tensor& t) {
+  return is_native(t) && t.dim() == 5 && t.stride(4) == 1 && t.stride(3) == t.size(4) && t.stride(2) % t.stride(3) == 0 &&
+         t.stride(0) % 8 == 0 && t.stride(1) % 8 == 0 && (reinterpret_cast<uintptr_t>(t.data_ptr()) % 16) == 0;
 }
 static bool attn_ok(const at::Tensor& t) {
   return is_native(t) && t.dim() == 4 && t.stride(3) == 1 && t.stride(0) % 8 == 0 && t.stride(1) % 8 == 0 &&
@@ -954,11 +1028,13 @@ static void packed_views(const at::Tensor& qkv, int64_t S, int64_t Hq, int64_t H
   if (interleaved) {
     // per-head interleaved layout [h0: q k v | h1: q k v | ...] (Megatron's): any TP degree that divides the head
     // count owns complete heads, so the same global weight means the same model under every strategy
-    HB_CHECK(Hq == Hkv) << "the interleaved qkv layout needs num_heads == num_kv_heads";
-    at::Tensor y = qkv.view({T / S, S, Hq, 3, D});
-    *q = y.select(3, 0);
-    *k = y.select(3, 1);
-    *v = y.select(3, 2);
+    // with grouped-query attention the unit is a kv head: [g0: q x rep, k, v | g1: ...]; q is then a 5-D view
+    // [B, S, G, rep, D] (two head strides) that the kernels address through their head-slot mapping
+    const int64_t rep = Hq / Hkv;
+    at::Tensor y = qkv.view({T / S, S, Hkv, rep + 2, D});
+    *q = rep == 1 ? y.select(3, 0) : y.narrow(3, 0, rep);
+    *k = y.select(3, rep);
+    *v = y.select(3, rep + 1);
     return;
   }
   at::Tensor x = qkv.view({T / S, S, Hq + 2 * Hkv, D});
@@ -976,6 +1052,22 @@ static TsP attn_packed_compute(const OpDef& op, const TsP& in, RunCtx* rc) {
   at::Tensor q, k, v;
   at::Tensor src = qkv.is_contiguous() ? qkv : qkv.contiguous();
   packed_views(src, S, Hq, Hkv, D, &q, &k, op.attrs.s("layout", "qkv") == "hqkv", &v);
+  if (q.dim() == 5) {
+    const int64_t B = T / S;
+    if (attn5_ok(q) && attn_ok(k) && attn_ok(v) && (D == 64 || D == 128)) {
+      at::Tensor o = at::empty({B, S, Hq, D}, qkv.options());
+      at::Tensor lse = at::empty({B, Hq, S}, fopt);
+      AttnFwdCall c;
+      c.q = as_attn(q); c.k = as_attn(k); c.v = as_attn(v); c.o = as_attn(o);
+      c.lse = lse.data_ptr<float>();
+      c.B = (int)B; c.Sq = (int)S; c.Sk = (int)S; c.Hq = (int)Hq; c.Hkv = (int)Hkv; c.D = (int)D;
+      c.softmax_scale = (float)(op.attrs.f("softmax_scale", 0.0) > 0 ? op.attrs.f("softmax_scale") : 1.0 / std::sqrt((double)D));
+      c.causal = op.attrs.b("causal", true);
+      cuda_ok(attn_fwd(c, cur_stream()), "attn_fwd");
+      return {o.reshape({T, Hq * D}), lse};
+    }
+    q = q.reshape({B, S, Hq, D});   // fallback: gather the heads
+  }
   static const OpKernel* kern = OpRegistry::get().find("attn");
   OpDef tmp;
   tmp.attrs = op.attrs;
@@ -1001,7 +1093,8 @@ static TsP attn_packed_bwd_compute(const OpDef& op, const TsP& in, RunCtx* rc) {
   at::Tensor o4 = o.contiguous().view({B, S, Hq, D}), do4 = d_o.contiguous().view({B, S, Hq, D});
   const bool causal = op.attrs.b("causal", true);
   const double scale = op.attrs.f("softmax_scale", 0.0) > 0 ? op.attrs.f("softmax_scale") : 1.0 / std::sqrt((double)D);
-  if (attn_ok(q) && attn_ok(k) && attn_ok(v) && attn_ok(o4) && attn_ok(do4) && (D == 64 || D == 128)) {
+  const bool grouped = q.dim() == 5;
+  if ((grouped ? attn5_ok(q) : attn_ok(q)) && attn_ok(k) && attn_ok(v) && attn_ok(o4) && attn_ok(do4) && (D == 64 || D == 128)) {
     at::Tensor delta = at::empty_like(lse);
     AttnBwdCall c;
     c.q = as_attn(q); c.k = as_attn(k); c.v = as_attn(v); c.o = as_attn(o4); c.d_o = as_attn(do4);
@@ -1016,8 +1109,8 @@ static TsP attn_packed_bwd_compute(const OpDef& op, const TsP& in, RunCtx* rc) {
   OpDef tmp;
   tmp.attrs = op.attrs;
   tmp.kernel = bwd;
-  auto r = bwd->compute(tmp, {do4, q, k, v, o4, lse}, rc);
-  dq.copy_(r[0]); dk.copy_(r[1]); dv.copy_(r[2]);
+  auto r = bwd->compute(tmp, {do4, grouped ? q.reshape({B, S, Hq, D}) : q, k, v, o4, lse}, rc);
+  dq.copy_(grouped ? r[0].reshape(dq.sizes()) : r[0]); dk.copy_(r[1]); dv.copy_(r[2]);
   return {dqkv};
 }
 static TensorList attn_packed_grad(OpDef& op, const TensorList& g) {
@@ -1052,12 +1145,17 @@ static TsP rotary_packed_compute(const OpDef& op, const TsP& in, RunCtx*) {
   if (in.size() > 1) pos = in[1].to(at::kInt).reshape({-1}).contiguous();
   else pos = (at::arange(T, qkv.options().dtype(at::kInt)) % S + (int64_t)op.attrs.i("pos_offset", 0)).contiguous();
   at::Tensor out = qkv.contiguous().clone();
+  const bool grouped = op.attrs.s("layout", "qkv") == "hqkv";   // [g: q x rep, k, v] per kv head: rotate rep + 1 heads of each group
+  const int64_t rep = Hq / Hkv;
   if (is_native(out)) {
     cuda_ok(rotary_apply(out.data_ptr(), out.data_ptr(), pos.data_ptr<int32_t>(), T, (int)(Hq + Hkv), (int)D, (int)D, (float)base,
-                         inverse, (Hq + 2 * Hkv) * D, cur_stream()), "rotary_packed");
+                         inverse, (Hq + 2 * Hkv) * D, cur_stream(), grouped ? (int)(rep + 1) : 0, grouped ? (int)((rep + 2) * D) : 0),
+            "rotary_packed");
     return {out};
   }
-  at::Tensor x = out.view({T, Hq + 2 * Hkv, D}).narrow(1, 0, Hq + Hkv).to(at::kFloat);
+  at::Tensor rot_view = grouped ? out.view({T, Hkv, rep + 2, D}).narrow(2, 0, rep + 1)
+                                : out.view({T, 1, Hq + 2 * Hkv, D}).narrow(2, 0, Hq + Hkv);
+  at::Tensor x = rot_view.reshape({T, Hq + Hkv, D}).to(at::kFloat);
   const int64_t half = D / 2;
   at::Tensor inv_freq = at::pow(base, -at::arange(0, half, x.options()) * 2.0 / (double)D);
   at::Tensor ang = pos.to(at::kFloat).unsqueeze(1) * inv_freq.unsqueeze(0);
@@ -1065,7 +1163,7 @@ static TsP rotary_packed_compute(const OpDef& op, const TsP& in, RunCtx*) {
   if (inverse) sn = -sn;
   at::Tensor a = x.narrow(-1, 0, half), b = x.narrow(-1, half, half);
   at::Tensor y = at::cat({a * cs - b * sn, b * cs + a * sn}, -1).to(out.scalar_type());
-  out.view({T, Hq + 2 * Hkv, D}).narrow(1, 0, Hq + Hkv).copy_(y);
+  rot_view.copy_(y.reshape(rot_view.sizes()));
   return {out};
 }
 static TensorList rotary_packed_grad(OpDef& op, const TensorList& g) {

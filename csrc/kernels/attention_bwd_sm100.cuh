@@ -29,6 +29,7 @@
 namespace hb {
 
 struct AttnBwdParams {
+  int q_div, q_mul;   // grouped-layout slot mapping of Q / dQ heads (q_div == 0: identity)
   int B, Hq, Hkv, Sq, Sk;
   float scale_log2, scale;
   int causal, causal_off;
@@ -98,6 +99,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int hk = h / (p.Hq / p.Hkv);
+  const int hslot = p.q_div ? (h / p.q_div) * p.q_mul + (h % p.q_div) : h;
   const int q0 = qt * 128;
   int n_kv = (p.Sk + 127) / 128;
   if (p.causal) {
@@ -133,7 +135,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     if (lane == 0 && n_kv > 0) {
       ptx::mbar_arrive_expect_tx(qdo_full, 2 * T);
       for (int bx = 0; bx < NBOX; ++bx) {
-        ptx::tma_load_4d(sQ + bx * kBoxBytes, &tmap_q, qdo_full, bx * 64, h, q0, b);
+        ptx::tma_load_4d(sQ + bx * kBoxBytes, &tmap_q, qdo_full, bx * 64, hslot, q0, b);
         ptx::tma_load_4d(sDO + bx * kBoxBytes, &tmap_do, qdo_full, bx * 64, h, q0, b);
       }
       for (int j = 0; j < n_kv; ++j) {
@@ -251,7 +253,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&ds_ready[st]);
     }
-    __nv_bfloat16* orow = p.dQ + int64_t(b) * p.dq_sb + int64_t(grow) * p.dq_ss + int64_t(h) * p.dq_sh;
+    __nv_bfloat16* orow = p.dQ + int64_t(b) * p.dq_sb + int64_t(grow) * p.dq_ss + int64_t(hslot) * p.dq_sh;
     if (n_kv > 0) {
       ptx::mbar_wait(dq_done, 0);
       ptx::tc_fence_after();
@@ -372,7 +374,8 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         ptx::mbar_wait(&q_empty[st], ph ^ 1);
         ptx::mbar_arrive_expect_tx(&q_full[st], T);
         for (int bx = 0; bx < NBOX; ++bx)
-          ptx::tma_load_4d(sQ + st * T + bx * kBoxBytes, &tmap_q, &q_full[st], bx * 64, hq, q0, b);
+          ptx::tma_load_4d(sQ + st * T + bx * kBoxBytes, &tmap_q, &q_full[st], bx * 64,
+                           p.q_div ? (hq / p.q_div) * p.q_mul + (hq % p.q_div) : hq, q0, b);
         ptx::mbar_wait(&do_empty[st], ph ^ 1);
         ptx::mbar_arrive_expect_tx(&do_full[st], T);
         for (int bx = 0; bx < NBOX; ++bx)
@@ -565,7 +568,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
 // host launcher
 // ---------------------------------------------------------------------------------------------
 inline bool make_attn_tmap_bwd(CUtensorMap* out, const AttnTensor& t, int D, int H, int S, int B) {
-  uint64_t dims[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)S, (uint64_t)B};
+  uint64_t dims[4] = {(uint64_t)D, (uint64_t)(t.h_div ? t.h_slots : H), (uint64_t)S, (uint64_t)B};
   uint64_t strides[3] = {(uint64_t)t.stride_h * 2, (uint64_t)t.stride_s * 2, (uint64_t)t.stride_b * 2};
   uint32_t box[4] = {64, 1, 128, 1};
   return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t.ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -592,6 +595,7 @@ cudaError_t attn_bwd_launch(const AttnBwdCall& c, cudaStream_t s, std::atomic<in
   p.causal_off = c.Sk - c.Sq;
   p.LSE = c.lse; p.DELTA = c.delta;
   p.dQ = (__nv_bfloat16*)c.dq.ptr; p.dK = (__nv_bfloat16*)c.dk.ptr; p.dV = (__nv_bfloat16*)c.dv.ptr;
+  p.q_div = c.q.h_div; p.q_mul = c.q.h_mul;
   p.dq_sb = c.dq.stride_b; p.dq_ss = c.dq.stride_s; p.dq_sh = c.dq.stride_h;
   p.dk_sb = c.dk.stride_b; p.dk_ss = c.dk.stride_s; p.dk_sh = c.dk.stride_h;
   p.dv_sb = c.dv.stride_b; p.dv_ss = c.dv.stride_s; p.dv_sh = c.dv.stride_h;

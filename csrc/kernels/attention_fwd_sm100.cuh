@@ -24,6 +24,7 @@
 namespace hb {
 
 struct AttnFwdParams {
+  int q_div, q_mul;   // grouped-layout slot mapping of Q heads (q_div == 0: identity)
   int B, Hq, Hkv, Sq, Sk;
   float scale_log2;  // softmax_scale * log2(e)
   int causal;
@@ -73,6 +74,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int hk = h / (p.Hq / p.Hkv);
+  const int hslot = p.q_div ? (h / p.q_div) * p.q_mul + (h % p.q_div) : h;
   const int q0 = qt * 128;
 
   int n_kv = (p.Sk + 127) / 128;
@@ -112,7 +114,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   if (warp == 0) {
     if (lane == 0 && n_kv > 0) {
       ptx::mbar_arrive_expect_tx(q_full, TILE_BYTES);
-      for (int bx = 0; bx < NBOX; ++bx) ptx::tma_load_4d(sQ + bx * kBoxBytes, &tmap_q, q_full, bx * 64, h, q0, b);
+      for (int bx = 0; bx < NBOX; ++bx) ptx::tma_load_4d(sQ + bx * kBoxBytes, &tmap_q, q_full, bx * 64, hslot, q0, b);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;

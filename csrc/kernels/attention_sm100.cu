@@ -16,7 +16,7 @@ namespace {
 
 // 4-D map (D, H, S, B) with a {64, 1, rows, 1} box; strides in elements.
 bool make_attn_tmap(CUtensorMap* out, const AttnTensor& t, int D, int H, int S, int B, int box_rows) {
-  uint64_t dims[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)S, (uint64_t)B};
+  uint64_t dims[4] = {(uint64_t)D, (uint64_t)(t.h_div ? t.h_slots : H), (uint64_t)S, (uint64_t)B};
   uint64_t strides[3] = {(uint64_t)t.stride_h * 2, (uint64_t)t.stride_s * 2, (uint64_t)t.stride_b * 2};
   uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
   return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t.ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -35,6 +35,7 @@ cudaError_t launch_fwd(const AttnFwdCall& c, cudaStream_t s) {
   if (!make_attn_tmap(&tv, c.v, D, c.Hkv, c.Sk, c.B, 128)) return cudaErrorInvalidValue;
   AttnFwdParams p;
   p.B = c.B; p.Hq = c.Hq; p.Hkv = c.Hkv; p.Sq = c.Sq; p.Sk = c.Sk;
+  p.q_div = c.q.h_div; p.q_mul = c.q.h_mul;
   p.scale_log2 = c.softmax_scale * 1.4426950408889634f;
   p.causal = c.causal ? 1 : 0;
   p.causal_off = c.Sk - c.Sq;

@@ -11,6 +11,9 @@ namespace hb {
 struct AttnTensor {
   const void* ptr = nullptr;
   int64_t stride_b = 0, stride_s = 0, stride_h = 0;
+  // Grouped (GQA, kv-head-major) packed layouts: logical head h lives in slot (h / h_div) * h_mul + h % h_div of a
+  // row made of `h_slots` head-sized slots (stride_h apart).  h_div == 0: plain layout, slot == h.
+  int h_div = 0, h_mul = 0, h_slots = 0;
 };
 
 struct AttnFwdCall {

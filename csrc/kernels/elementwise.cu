@@ -141,6 +141,39 @@ __global__ void swiglu_bwd_kernel(const void* __restrict__ dy, const void* __res
   }
 }
 
+// interleaved layout: x[r, 2i] = gate_i, x[r, 2i+1] = up_i (tensor-parallel splits keep the pairs together)
+__global__ void swiglu_il_fwd_kernel(const void* __restrict__ x, void* __restrict__ y, int64_t nvec_out) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < nvec_out; i += int64_t(gridDim.x) * blockDim.x) {
+    float a[8], b[8], o[8];
+    unpack8(ld8_stream(x, 2 * i), a);
+    unpack8(ld8_stream(x, 2 * i + 1), b);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      o[j] = a[2 * j] / (1.0f + __expf(-a[2 * j])) * a[2 * j + 1];
+      o[4 + j] = b[2 * j] / (1.0f + __expf(-b[2 * j])) * b[2 * j + 1];
+    }
+    st8(y, i, pack8(o));
+  }
+}
+__global__ void swiglu_il_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, void* __restrict__ dx,
+                                     int64_t nvec_out) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < nvec_out; i += int64_t(gridDim.x) * blockDim.x) {
+    float a[16], g[8], d[16];
+    unpack8(ld8_stream(x, 2 * i), a);
+    unpack8(ld8_stream(x, 2 * i + 1), a + 8);
+    unpack8(ld8_stream(dy, i), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gate = a[2 * j], up = a[2 * j + 1];
+      const float s = 1.0f / (1.0f + __expf(-gate));
+      d[2 * j] = g[j] * up * s * (1.0f + gate * (1.0f - s));
+      d[2 * j + 1] = g[j] * gate * s;
+    }
+    st8(dx, 2 * i, pack8(d));
+    st8(dx, 2 * i + 1, pack8(d + 8));
+  }
+}
+
 __global__ void add_kernel(const void* __restrict__ a, const void* __restrict__ b, void* __restrict__ out, int64_t n) {
   const int64_t nvec = n >> 3;
   for (int64_t v = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; v < nvec; v += int64_t(gridDim.x) * blockDim.x) {
@@ -248,13 +281,71 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __rest
     atomicAdd(out + c, s);
   }
 }
+// Vectorised column sum: a warp covers 256 columns with 16-byte loads, the 8 warps of a CTA take interleaved rows
+// (4 independent loads in flight each), partial sums meet in shared memory and one atomicAdd per column leaves the CTA.
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
+                                                         int64_t rows, int cols, int rows_per_block) {
+  __shared__ float sm[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  const int64_t r0 = int64_t(blockIdx.y) * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c0 < cols) {
+    const char* base = reinterpret_cast<const char*>(x + c0);
+    const int64_t pitch = int64_t(cols) * 2;
+    int64_t r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {
+      bf16x8 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = ld8_stream(base + (r + u * 8) * pitch, 0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(q[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    }
+    for (; r < r1; r += 8) {
+      float f[8];
+      unpack8(ld8_stream(base + r * pitch, 0), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sm[w][threadIdx.x];
+    atomicAdd(out + c, s);
+  }
+}
+__global__ void scale_rows_kernel(const void* __restrict__ x, void* __restrict__ y, const float* __restrict__ scale,
+                                  int per_row, int64_t nvec, int64_t vec_per_row) {
+  for (int64_t v = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; v < nvec; v += int64_t(gridDim.x) * blockDim.x) {
+    const float sc = per_row ? scale[v / vec_per_row] : scale[0];
+    float f[8];
+    unpack8(ld8_stream(x, v), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= sc;
+    st8(y, v, pack8(f));
+  }
+}
 __global__ void zero_f32_kernel(float* p, int64_t n) {
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) p[i] = 0.f;
 }
 
 __global__ void rotary_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                               const int32_t* __restrict__ pos, int64_t tokens, int heads, int head_dim, int rot_dim,
-                              float log2_base, int inverse, int64_t token_stride) {
+                              float log2_base, int inverse, int64_t token_stride, int group_size, int group_stride) {
   // one thread per (token, head, pair i < rot_dim/2): (x[i], x[i + rot/2]) rotated by pos * base^(-2i/rot)
   const int half = rot_dim >> 1;
   const int64_t total = tokens * heads * half;
@@ -268,7 +359,9 @@ __global__ void rotary_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16
     float sn, cs;
     sincosf(ang, &sn, &cs);
     if (inverse) sn = -sn;
-    const int64_t base = t * token_stride + int64_t(h) * head_dim;
+    // grouped layouts: rotated heads come in runs of `group_size`, runs are `group_stride` elements apart
+    const int64_t base = t * token_stride + (group_size > 0 ? int64_t(h / group_size) * group_stride + int64_t(h % group_size) * head_dim
+                                                            : int64_t(h) * head_dim);
     const float a = __bfloat162float(x[base + i]);
     const float b = __bfloat162float(x[base + i + half]);
     y[base + i] = __float2bfloat16(a * cs - b * sn);
@@ -292,6 +385,22 @@ cudaError_t unary_bwd(int op, const void* dy, const void* x, void* dx, int64_t n
   if (n == 0) return cudaSuccess;
   CHECK_ALIGN16(x); CHECK_ALIGN16(dy); CHECK_ALIGN16(dx);
   unary_bwd_kernel<<<grid_for(n >> 3), kThreads, 0, s>>>(op, dy, x, dx, n);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t swiglu_interleaved_fwd(const void* x, void* y, int64_t rows, int d, cudaStream_t s) {
+  if (rows == 0) return cudaSuccess;
+  CHECK_ALIGN16(x); CHECK_ALIGN16(y);
+  const int64_t nv = rows * (d >> 3);
+  swiglu_il_fwd_kernel<<<grid_for(nv), kThreads, 0, s>>>(x, y, nv);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t swiglu_interleaved_bwd(const void* dy, const void* x, void* dx, int64_t rows, int d, cudaStream_t s) {
+  if (rows == 0) return cudaSuccess;
+  CHECK_ALIGN16(x); CHECK_ALIGN16(dy); CHECK_ALIGN16(dx);
+  const int64_t nv = rows * (d >> 3);
+  swiglu_il_bwd_kernel<<<grid_for(nv), kThreads, 0, s>>>(dy, x, dx, nv);
   count_launch();
   return cudaGetLastError();
 }
@@ -346,6 +455,16 @@ cudaError_t colsum_bf16(const void* x, float* out, int64_t rows, int cols, bool 
     count_launch();
   }
   if (rows == 0) return cudaGetLastError();
+  if ((cols & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int cb = (cols + 255) / 256;
+    int rb = (sm_count() * 8 + cb - 1) / cb;
+    if (rb > (rows + 31) / 32) rb = (int)((rows + 31) / 32);
+    const int rpb = (int)((rows + rb - 1) / rb);
+    rb = (int)((rows + rpb - 1) / rpb);
+    colsum_vec_kernel<<<dim3(cb, rb), 256, 0, s>>>((const __nv_bfloat16*)x, out, rows, cols, rpb);
+    count_launch();
+    return cudaGetLastError();
+  }
   const int col_blocks = (cols + 63) / 64;
   int row_blocks = (sm_count() * 4 + col_blocks - 1) / col_blocks;
   if (row_blocks > rows) row_blocks = (int)rows;
@@ -355,12 +474,23 @@ cudaError_t colsum_bf16(const void* x, float* out, int64_t rows, int cols, bool 
   count_launch();
   return cudaGetLastError();
 }
+cudaError_t scale_rows_bf16(const void* x, void* y, const float* scale, bool per_row, int64_t rows, int64_t cols,
+                            cudaStream_t s) {
+  if (rows * cols == 0) return cudaSuccess;
+  if ((cols & 7) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return cudaErrorMisalignedAddress;
+  const int64_t nvec = rows * cols / 8;
+  scale_rows_kernel<<<grid_for(nvec), kThreads, 0, s>>>(x, y, scale, per_row ? 1 : 0, nvec, cols / 8);
+  count_launch();
+  return cudaGetLastError();
+}
 cudaError_t rotary_apply(const void* x, void* y, const int32_t* pos, int64_t tokens, int heads, int head_dim,
-                         int rot_dim, float base, bool inverse, int64_t token_stride, cudaStream_t s) {
+                         int rot_dim, float base, bool inverse, int64_t token_stride, cudaStream_t s, int group_size,
+                         int group_stride) {
   if (tokens == 0) return cudaSuccess;
   const int64_t total = tokens * heads * (rot_dim / 2);
   rotary_kernel<<<grid_for(total), kThreads, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, pos, tokens, heads,
-                                                     head_dim, rot_dim, log2f(base), inverse ? 1 : 0, token_stride);
+                                                     head_dim, rot_dim, log2f(base), inverse ? 1 : 0, token_stride, group_size,
+                                                     group_stride);
   count_launch();
   return cudaGetLastError();
 }

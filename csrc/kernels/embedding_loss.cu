@@ -121,8 +121,10 @@ __global__ void __launch_bounds__(kCeThreads) ce_fwd_bwd_kernel(__nv_bfloat16* _
                                                                 const int64_t* __restrict__ labels,
                                                                 float* __restrict__ loss, float* __restrict__ lse_out,
                                                                 int cols, int64_t ld, int64_t ignore_index,
-                                                                float grad_scale, int write_grad) {
+                                                                float grad_scale, const float* __restrict__ grad_scale_ptr,
+                                                                int write_grad) {
   __shared__ MS red[32];
+  if (grad_scale_ptr != nullptr) grad_scale *= *grad_scale_ptr;
   const int64_t r = blockIdx.x;
   __nv_bfloat16* row = logits + r * ld;
   const int64_t label = labels[r];
@@ -262,11 +264,12 @@ cudaError_t embedding_bwd(const int64_t* ids, const int32_t* pos, const void* dy
   return cudaGetLastError();
 }
 cudaError_t softmax_ce_fwd_bwd(void* logits, const int64_t* labels, float* loss, float* lse, int64_t rows, int cols,
-                               int64_t ld, int64_t ignore_index, float grad_scale, bool write_grad, cudaStream_t s) {
+                               int64_t ld, int64_t ignore_index, float grad_scale, bool write_grad, cudaStream_t s,
+                               const float* grad_scale_ptr) {
   if (rows == 0) return cudaSuccess;
   if ((ld & 7) || (reinterpret_cast<uintptr_t>(logits) & 15)) return cudaErrorMisalignedAddress;
   ce_fwd_bwd_kernel<<<(unsigned)rows, kCeThreads, 0, s>>>((__nv_bfloat16*)logits, labels, loss, lse, cols, ld,
-                                                          ignore_index, grad_scale, write_grad ? 1 : 0);
+                                                          ignore_index, grad_scale, grad_scale_ptr, write_grad ? 1 : 0);
   count_launch();
   return cudaGetLastError();
 }

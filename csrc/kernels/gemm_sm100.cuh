@@ -79,10 +79,19 @@ __device__ __forceinline__ float fast_erf(float x) {
   return copysignf(r, x);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f)); }
+// d/dx gelu(x) = Phi(x) + x * phi(x); the erf polynomial and the density share one exponential (exp(-x^2/2))
 __device__ __forceinline__ float dgelu_erf(float x) {
-  const float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143267f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  const float ax = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = __expf(-ax * ax);
+  const float erf_abs = 1.0f - p * e;
+  const float cdf = fmaf(0.5f, copysignf(erf_abs, x), 0.5f);
+  return fmaf(x * 0.39894228040143267f, e, cdf);
 }
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
@@ -282,9 +291,25 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
         crow = reinterpret_cast<OutT*>(p.peer_c[owner]) +
                (int64_t(p.my_rank) * p.rows_per_rank + (row - owner * p.rows_per_rank)) * p.ldc;
       }
+      // aux operand (residual / pre-activation) of the NEXT chunk is fetched while the current one is processed: the
+      // ~1 us global latency would otherwise sit between every TMEM drain and its store
+      uint4 aux_next[4];
+      auto fetch_aux = [&](int cc_) {
+        const int col0_ = n_base + (chalf * kChunksPerWarp + cc_) * 32;
+        if (p.aux_mode != AUX_NONE && row_ok && col0_ + 32 <= p.N) {
+          const uint4* ai4 = reinterpret_cast<const uint4*>(p.aux_in + int64_t(row) * p.ld_aux + col0_);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) aux_next[j4] = __ldcs(ai4 + j4);
+        }
+      };
+      fetch_aux(0);
 #pragma unroll 1
       for (int cc = 0; cc < kChunksPerWarp; ++cc) {
         const int c = chalf * kChunksPerWarp + cc;
+        uint4 aux_cur[4];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) aux_cur[j4] = aux_next[j4];
+        if (cc + 1 < kChunksPerWarp) fetch_aux(cc + 1);
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
         ptx::tmem_ld_wait();
@@ -342,16 +367,28 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (p.aux_mode != AUX_NONE) {
             const __nv_bfloat16* ai = p.aux_in + int64_t(row) * p.ld_aux + col0;
             if (full_chunk) {
+              float a[32];
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
-                const uint4 a = reinterpret_cast<const uint4*>(ai)[j4];
-                const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+                const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&aux_cur[j4]);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                   const float2 f = __bfloat1622float2(a2[t]);
-                  v[j4 * 8 + t * 2] = apply_aux(v[j4 * 8 + t * 2], f.x, p.aux_mode);
-                  v[j4 * 8 + t * 2 + 1] = apply_aux(v[j4 * 8 + t * 2 + 1], f.y, p.aux_mode);
+                  a[j4 * 8 + t * 2] = f.x; a[j4 * 8 + t * 2 + 1] = f.y;
                 }
+              }
+              if (p.aux_mode == AUX_ADD) {          // the mode is uniform: keep the switch out of the unrolled loops
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += a[j];
+              } else if (p.aux_mode == AUX_DGELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= dgelu_erf(a[j]);
+              } else if (p.aux_mode == AUX_DSILU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= dsilu(a[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = apply_aux(v[j], a[j], p.aux_mode);
               }
             } else {
 #pragma unroll

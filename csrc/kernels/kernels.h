@@ -33,6 +33,9 @@ cudaError_t unary_bwd(int op, const void* dy, const void* x, void* dx, int64_t n
 // y[r, :] = silu(x[r, :d]) * x[r, d:2d]        (ref: hetu/impl/kernel/SwiGLU.cu:79,116)
 cudaError_t swiglu_fwd(const void* x, void* y, int64_t rows, int d, cudaStream_t s);
 cudaError_t swiglu_bwd(const void* dy, const void* x, void* dx, int64_t rows, int d, cudaStream_t s);
+// interleaved layout x[r, 2i] = gate_i, x[r, 2i+1] = up_i (pairs stay together under any tensor-parallel split)
+cudaError_t swiglu_interleaved_fwd(const void* x, void* y, int64_t rows, int d, cudaStream_t s);
+cudaError_t swiglu_interleaved_bwd(const void* dy, const void* x, void* dx, int64_t rows, int d, cudaStream_t s);
 // out = a + b (bf16), out may alias a
 cudaError_t add_bf16(const void* a, const void* b, void* out, int64_t n, cudaStream_t s);
 // dst(fp32) (+)= src(bf16)
@@ -48,7 +51,8 @@ cudaError_t colsum_bf16(const void* x, float* out, int64_t rows, int cols, bool 
 // x: [tokens, heads, head_dim] bf16, half-split convention; pos[token] gives the position id.
 // inverse=true applies the transposed rotation (backward).
 cudaError_t rotary_apply(const void* x, void* y, const int32_t* pos, int64_t tokens, int heads, int head_dim,
-                         int rot_dim, float base, bool inverse, int64_t token_stride, cudaStream_t s);
+                         int rot_dim, float base, bool inverse, int64_t token_stride, cudaStream_t s, int group_size = 0,
+                         int group_stride = 0);   // grouped layouts: head h -> (h / group_size) * group_stride + (h % group_size) * head_dim
 
 // ---------------------------------------------------------------- embedding (ref: hetu/impl/kernel/EmbeddingLookup.cu:91,140)
 // y[t, :] = wte[ids[t], :] (+ wpe[pos[t], :])
@@ -64,7 +68,11 @@ cudaError_t embedding_bwd(const int64_t* ids, const int32_t* pos, const void* dy
 //   logits[r, :] <- (softmax - onehot) * grad_scale    (in place, when write_grad)
 // (ref: hetu/impl/kernel/SoftmaxCrossEntropySparse.cu, VocabParallelCrossEntropyLoss.cu:57,114)
 cudaError_t softmax_ce_fwd_bwd(void* logits, const int64_t* labels, float* loss, float* lse, int64_t rows, int cols,
-                               int64_t ld, int64_t ignore_index, float grad_scale, bool write_grad, cudaStream_t s);
+                               int64_t ld, int64_t ignore_index, float grad_scale, bool write_grad, cudaStream_t s,
+                               const float* grad_scale_ptr = nullptr);   // device scalar multiplied into grad_scale
+// y[r, :] = x[r, :] * scale[per_row ? r : 0]   (scale lives on the device; bf16 rows of `cols` elements)
+cudaError_t scale_rows_bf16(const void* x, void* y, const float* scale, bool per_row, int64_t rows, int64_t cols,
+                            cudaStream_t s);
 // Vocab-parallel pieces: local max / local sum-exp & target logit, with a collective between them.
 cudaError_t vp_ce_local_max(const void* logits, float* row_max, int64_t rows, int cols, int64_t ld, cudaStream_t s);
 cudaError_t vp_ce_local_sum(const void* logits, const int64_t* labels, const float* row_max, float* sum_exp,

@@ -21,7 +21,6 @@ namespace {
 constexpr int kFwdThreads = 128;
 constexpr int kFwdMaxV = 8;   // up to 8192 columns
 constexpr int kBwdThreads = 256;
-constexpr int kBwdMaxV = 4;   // up to 8192 columns
 
 template <bool kRMS>
 __global__ void __launch_bounds__(kFwdThreads) norm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ gamma,
@@ -70,6 +69,69 @@ __global__ void __launch_bounds__(kFwdThreads) norm_fwd_kernel(const void* __res
 #pragma unroll
   for (int i = 0; i < kFwdMaxV; ++i) {
     const int v = tid + i * kFwdThreads;
+    if (v < nvec) {
+      float g[8], b[8], o[8];
+      unpack8(ld8(gamma, v), g);
+      if (!kRMS && beta != nullptr) unpack8(ld8(beta, v), b);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (xv[i][j] - mean) * rstd * g[j] + b[j];
+      st8(yr, v, pack8(o));
+    }
+  }
+}
+
+// Warp-per-row forward for cols <= 4096: no block barrier at all, the row lives in registers (kV vectors of 8 per lane),
+// 4 rows per CTA and many CTAs per SM keep enough loads in flight to saturate HBM.
+template <bool kRMS, int kV>
+__global__ void __launch_bounds__(128) norm_fwd_warp_kernel(const void* __restrict__ x, const void* __restrict__ gamma,
+                                                            const void* __restrict__ beta, void* __restrict__ y,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            int64_t rows, int cols, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = int64_t(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = cols >> 3;
+  const char* xr = reinterpret_cast<const char*>(x) + row * int64_t(cols) * 2;
+  char* yr = reinterpret_cast<char*>(y) + row * int64_t(cols) * 2;
+  float xv[kV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      unpack8(ld8_stream(xr, v), xv[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += kRMS ? xv[i][j] * xv[i][j] : xv[i][j];
+    }
+  }
+  float mean = 0.f, rstd;
+  const float inv = 1.0f / cols;
+  if constexpr (kRMS) {
+    rstd = rsqrtf(warp_sum(sum) * inv + eps);
+  } else {
+    mean = warp_sum(sum) * inv;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = xv[i][j] - mean; var += d * d; }
+      }
+    }
+    rstd = rsqrtf(warp_sum(var) * inv + eps);
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < kV; ++i) {
+    const int v = lane + i * 32;
     if (v < nvec) {
       float g[8], b[8], o[8];
       unpack8(ld8(gamma, v), g);
@@ -135,65 +197,106 @@ __device__ __forceinline__ float2 block_sum2(float2 v, float2* red) {
   return r;
 }
 
-template <bool kRMS>
+// kVPT vectors (of 8 columns) per thread, kR rows per iteration: kR*kVPT*2 16-byte loads are in flight per thread and
+// the 2*kR row statistics are reduced with ONE block barrier per iteration (double-buffered scratch).
+template <bool kRMS, int kVPT, int kR>
 __global__ void __launch_bounds__(kBwdThreads) norm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x,
                                                                const void* __restrict__ gamma, const float* __restrict__ mean,
                                                                const float* __restrict__ rstd, void* __restrict__ dx,
                                                                float* __restrict__ part_dg, float* __restrict__ part_db,
                                                                int64_t rows, int cols) {
-  __shared__ float2 red[32];
+  constexpr int kWarps = kBwdThreads / 32;
+  __shared__ float red[2][kWarps][2 * kR];
   const int nvec = cols >> 3;
-  const int tid = threadIdx.x;
-  float g[kBwdMaxV][8], dg[kBwdMaxV][8], db[kBwdMaxV][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float g[kVPT][8], dg[kVPT][8], db[kVPT][8];
 #pragma unroll
-  for (int i = 0; i < kBwdMaxV; ++i) {
+  for (int i = 0; i < kVPT; ++i) {
     const int v = tid + i * kBwdThreads;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; g[i][j] = 0.f; }
     if (v < nvec) unpack8(ld8(gamma, v), g[i]);
   }
   const float inv_cols = 1.0f / cols;
-  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
-    const char* xr = reinterpret_cast<const char*>(x) + row * int64_t(cols) * 2;
-    const char* dyr = reinterpret_cast<const char*>(dy) + row * int64_t(cols) * 2;
-    char* dxr = reinterpret_cast<char*>(dx) + row * int64_t(cols) * 2;
-    const float mu = kRMS ? 0.f : mean[row];
-    const float rs = rstd[row];
-    float xh[kBwdMaxV][8], dyv[kBwdMaxV][8];
-    float2 s = make_float2(0.f, 0.f);
+  int buf = 0;
+  for (int64_t row0 = int64_t(blockIdx.x) * kR; row0 < rows; row0 += int64_t(gridDim.x) * kR) {
+    float xh[kR][kVPT][8], dyv[kR][kVPT][8];
+    float s1[kR], s2[kR], rs[kR];
 #pragma unroll
-    for (int i = 0; i < kBwdMaxV; ++i) {
-      const int v = tid + i * kBwdThreads;
-      if (v < nvec) {
-        unpack8(ld8_stream(xr, v), xh[i]);
-        unpack8(ld8_stream(dyr, v), dyv[i]);
+    for (int r = 0; r < kR; ++r) {
+      const int64_t row = row0 + r;
+      const bool live = row < rows;
+      const char* xr = reinterpret_cast<const char*>(x) + row * int64_t(cols) * 2;
+      const char* dyr = reinterpret_cast<const char*>(dy) + row * int64_t(cols) * 2;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xh[i][j] - mu) * rs;
-          const float dyg = dyv[i][j] * g[i][j];
-          s.x += dyg;
-          s.y += dyg * xh[i][j];
-          dg[i][j] += dyv[i][j] * xh[i][j];
-          db[i][j] += dyv[i][j];
+      for (int i = 0; i < kVPT; ++i) {
+        const int v = tid + i * kBwdThreads;
+        if (live && v < nvec) {
+          unpack8(ld8_stream(xr, v), xh[r][i]);
+          unpack8(ld8_stream(dyr, v), dyv[r][i]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { xh[r][i][j] = 0.f; dyv[r][i][j] = 0.f; }
         }
       }
     }
-    s = block_sum2(s, red);
-    const float m1 = kRMS ? 0.f : s.x * inv_cols;
-    const float m2 = s.y * inv_cols;
 #pragma unroll
-    for (int i = 0; i < kBwdMaxV; ++i) {
-      const int v = tid + i * kBwdThreads;
-      if (v < nvec) {
-        float o[8];
+    for (int r = 0; r < kR; ++r) {
+      const int64_t row = row0 + r;
+      const bool live = row < rows;
+      const float mu = (kRMS || !live) ? 0.f : mean[row];
+      rs[r] = live ? rstd[row] : 0.f;
+      s1[r] = 0.f; s2[r] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rs * (dyv[i][j] * g[i][j] - m1 - xh[i][j] * m2);
-        st8(dxr, v, pack8(o));
+      for (int i = 0; i < kVPT; ++i) {
+        const int v = tid + i * kBwdThreads;
+        if (v < nvec) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xn = (xh[r][i][j] - mu) * rs[r];
+            xh[r][i][j] = xn;
+            const float dyg = dyv[r][i][j] * g[i][j];
+            s1[r] += dyg;
+            s2[r] += dyg * xn;
+            dg[i][j] += dyv[r][i][j] * xn;
+            db[i][j] += dyv[r][i][j];
+          }
+        }
+      }
+      s1[r] = warp_sum(s1[r]);
+      s2[r] = warp_sum(s2[r]);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < kR; ++r) { red[buf][warp][2 * r] = s1[r]; red[buf][warp][2 * r + 1] = s2[r]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) { a += red[buf][w][2 * r]; b += red[buf][w][2 * r + 1]; }
+      const float m1 = kRMS ? 0.f : a * inv_cols;
+      const float m2 = b * inv_cols;
+      const int64_t row = row0 + r;
+      if (row < rows) {
+        char* dxr = reinterpret_cast<char*>(dx) + row * int64_t(cols) * 2;
+#pragma unroll
+        for (int i = 0; i < kVPT; ++i) {
+          const int v = tid + i * kBwdThreads;
+          if (v < nvec) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = rs[r] * (dyv[r][i][j] * g[i][j] - m1 - xh[r][i][j] * m2);
+            st8(dxr, v, pack8(o));
+          }
+        }
       }
     }
+    buf ^= 1;
   }
 #pragma unroll
-  for (int i = 0; i < kBwdMaxV; ++i) {
+  for (int i = 0; i < kVPT; ++i) {
     const int v = tid + i * kBwdThreads;
     if (v < nvec) {
       float* pg = part_dg + int64_t(blockIdx.x) * cols + v * 8;
@@ -247,8 +350,16 @@ __global__ void fold_parts_kernel(const float* __restrict__ parts, float* __rest
                                   int accumulate) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
-  float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += parts[int64_t(p) * cols + c];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int p = 0;
+  for (; p + 3 < nparts; p += 4) {
+    s0 += parts[int64_t(p) * cols + c];
+    s1 += parts[int64_t(p + 1) * cols + c];
+    s2 += parts[int64_t(p + 2) * cols + c];
+    s3 += parts[int64_t(p + 3) * cols + c];
+  }
+  for (; p < nparts; ++p) s0 += parts[int64_t(p) * cols + c];
+  const float s = (s0 + s1) + (s2 + s3);
   out[c] = accumulate ? out[c] + s : s;
 }
 
@@ -260,7 +371,16 @@ template <bool kRMS>
 static cudaError_t norm_fwd_impl(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
                                  int64_t rows, int cols, float eps, cudaStream_t s) {
   if (rows == 0) return cudaSuccess;
-  if ((cols & 7) == 0 && cols <= kFwdMaxV * kFwdThreads * 8) {
+  const unsigned wgrid = (unsigned)((rows + 3) / 4);
+  if ((cols & 7) == 0 && cols <= 512) {
+    norm_fwd_warp_kernel<kRMS, 2><<<wgrid, 128, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, cols, eps);
+  } else if ((cols & 7) == 0 && cols <= 1024) {
+    norm_fwd_warp_kernel<kRMS, 4><<<wgrid, 128, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, cols, eps);
+  } else if ((cols & 7) == 0 && cols <= 2048) {
+    norm_fwd_warp_kernel<kRMS, 8><<<wgrid, 128, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, cols, eps);
+  } else if ((cols & 7) == 0 && cols <= 4096) {
+    norm_fwd_warp_kernel<kRMS, 16><<<wgrid, 128, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, cols, eps);
+  } else if ((cols & 7) == 0 && cols <= kFwdMaxV * kFwdThreads * 8) {
     norm_fwd_kernel<kRMS><<<(unsigned)rows, kFwdThreads, 0, s>>>(x, gamma, beta, y, mean, rstd, cols, eps);
   } else {
     norm_fwd_generic_kernel<kRMS><<<(unsigned)rows, 256, 0, s>>>(
@@ -280,8 +400,12 @@ static cudaError_t norm_bwd_impl(const void* dy, const void* x, const void* gamm
   if (parts > rows) parts = (int)rows;
   float* part_dg = ws;
   float* part_db = ws + int64_t(ln_bwd_parts()) * cols;
-  if ((cols & 7) == 0 && cols <= kBwdMaxV * kBwdThreads * 8) {
-    norm_bwd_kernel<kRMS><<<parts, kBwdThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, part_dg, part_db, rows, cols);
+  if ((cols & 7) == 0 && cols <= 2048) {
+    norm_bwd_kernel<kRMS, 1, 4><<<parts, kBwdThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, part_dg, part_db, rows, cols);
+  } else if ((cols & 7) == 0 && cols <= 4096) {
+    norm_bwd_kernel<kRMS, 2, 2><<<parts, kBwdThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, part_dg, part_db, rows, cols);
+  } else if ((cols & 7) == 0 && cols <= 8192) {
+    norm_bwd_kernel<kRMS, 4, 1><<<parts, kBwdThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, part_dg, part_db, rows, cols);
   } else {
     norm_bwd_generic_kernel<kRMS><<<parts, 256, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
                                                         (const __nv_bfloat16*)gamma, mean, rstd, (__nv_bfloat16*)dx,

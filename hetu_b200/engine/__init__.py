@@ -1,0 +1,7 @@
+from .trainer_config import TrainingConfig, SFTConfig, DataLoadLevel  # noqa: F401
+from .wrapper import ModelWrapper, ModelWrapperFromConfig, OptimizerWrapper, DatasetWrapper  # noqa: F401
+from .trainer import Trainer, TrainerStates  # noqa: F401
+from .sft_trainer import SFTTrainer  # noqa: F401
+from .straggler import Straggler, WorkloadInfo  # noqa: F401
+from .strategy import StrategyModel, TPGroup, LayersProp, TrainerCtxs, TrainerStrategyArgs  # noqa: F401
+from .data_collator import DataCollatorForLanguageModel  # noqa: F401

@@ -1,0 +1,328 @@
+"""Trainer: builds the define-and-run graph for a model under one or several parallel strategies, feeds it padded or
+packed micro-batches, drives the optimizer, logging, profiling, checkpoints and hot strategy switching.
+(ref: python/hetu/engine/trainer.py:66-828 -- Trainer.build/create_define_graph/prepare_feed_dict/train/save_model)
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import core, distributed
+from ..core import IntSymbol
+from ..data import Bucket, build_data_loader, build_tokenizer
+from ..utils.parallel import StrategyConfig, convert_strategy, parse_multi_ds_parallel_config, read_ds_parallel_config
+from .data_collator import DataCollatorForLanguageModel
+from .trainer_config import DataLoadLevel, TrainingConfig
+from .wrapper import ModelWrapper, ModelWrapperFromConfig, OptimizerWrapper
+
+
+@dataclass
+class TrainerStates:
+    """everything `build()` creates (ref: trainer.py:27 TrainerStates)"""
+    graph: object = None
+    model: object = None
+    optimizer: object = None
+    input_ids: object = None
+    position_ids: object = None
+    labels: object = None
+    loss: object = None
+    train_op: object = None
+    seq_len_symbol: object = None
+    config: object = None
+
+
+def _strategy_sizes(cfg: dict):
+    """(dp, tp, pp) of a ds_parallel_config from its input leaf and block ranges"""
+    inp = cfg["input"]
+    dp = int(inp["split"].get("0", [1])[0]) if inp.get("split") else 1
+    tp = int(inp["dup"][0]) if inp.get("dup") else 1
+    stages = {tuple(map(tuple, b["layernorm1"]["device_group_union"])) for b in cfg["blocks"].values()}
+    return dp, tp, max(len(stages), 1)
+
+
+class Trainer:
+    def __init__(self, pretrain_config: TrainingConfig, model, tokenizer=None, optimizer=None, train_dataset=None,
+                 data_collator: Optional[Callable] = None, **kwargs):
+        self.pretrain_config = cfg = pretrain_config
+        if cfg.packing and cfg.micro_batch_size:
+            raise ValueError("micro_batch_size is only valid when packing is off")
+        self.model_wrapper = model
+        self.optimizer_wrapper = optimizer if not isinstance(optimizer, dict) else OptimizerWrapper(optimizer)
+        if self.optimizer_wrapper is None:
+            self.optimizer_wrapper = OptimizerWrapper({"type": "adam", "lr": cfg.learning_rate, "weight_decay": cfg.weight_decay,
+                                                       "lr_warmup_steps": cfg.warmup_steps, "lr_decay_steps": cfg.steps,
+                                                       "lr_decay_style": cfg.lr_decay_style, "min_lr": cfg.min_lr})
+        if isinstance(tokenizer, dict):
+            tokenizer = build_tokenizer(tokenizer.pop("type", "byte"), **tokenizer)
+        self.tokenizer = tokenizer
+        self.train_dataset = train_dataset
+        self.data_collator = data_collator or DataCollatorForLanguageModel(tokenizer)
+        self.precision = "bfloat16" if cfg.bf16 else "float32"
+        self.epoch, self.consumed_samples, self.global_step = 0, 0, 0
+        self.trainer_states: Optional[TrainerStates] = None
+        self.is_model_built = False
+        self.loss_history: List[float] = []
+        self.step_times: List[float] = []
+        self.callbacks: List[Callable] = list(kwargs.get("callbacks", []))
+
+        dspc = kwargs.get("ds_parallel_configs")
+        if dspc is None:
+            sc: Optional[StrategyConfig] = cfg.ds_parallel
+            if sc is not None and sc.ds_parallel_config_path and sc.ds_parallel_config_name:
+                dspc = read_ds_parallel_config(os.path.join(sc.ds_parallel_config_path, sc.ds_parallel_config_name))
+            elif sc is not None:
+                dspc = [convert_strategy(sc, self._num_layers())]
+            else:
+                dspc = [convert_strategy(StrategyConfig(dp=max(distributed.world_size(), 1)), self._num_layers())]
+        self.ds_parallel_configs = dspc
+        self.num_strategy = len(dspc)
+        self.cur_strategy_id = 0
+
+    # ------------------------------------------------------------------ build
+    def _num_layers(self):
+        mc = getattr(self.model_wrapper, "model_config", None)
+        if mc is None and isinstance(self.model_wrapper, ModelWrapperFromConfig):
+            c = self.model_wrapper.config
+            return int(c.get("n_layer", c.get("num_hidden_layers", 12)))
+        for k in ("n_layer", "num_hidden_layers"):
+            if hasattr(mc, k):
+                return int(getattr(mc, k))
+        return 12
+
+    def get_train_data_loader(self):
+        cfg = self.pretrain_config
+        dp, _, _ = _strategy_sizes(self.ds_parallel_configs[self.cur_strategy_id])
+        level = cfg.data_load_level.value if isinstance(cfg.data_load_level, DataLoadLevel) else str(cfg.data_load_level)
+        kw = dict(global_batch_size=cfg.global_load_size) if level == "SAMPLE" else dict(global_token_num=cfg.global_load_size)
+        return build_data_loader(self.train_dataset, self.consumed_samples, load_level=level, dp_rank=self._dp_rank(), dp_size=dp,
+                                 seed=cfg.seed, collate_fn=self.data_collator, **kw)
+
+    def _dp_rank(self):
+        dp, tp, pp = _strategy_sizes(self.ds_parallel_configs[self.cur_strategy_id])
+        r = distributed.rank()
+        return (r % (dp * tp)) // tp
+
+    def build(self):
+        if self.is_model_built:
+            return self.trainer_states
+        self.trainer_states = self.create_define_graph()
+        self.is_model_built = True
+        return self.trainer_states
+
+    def create_define_graph(self) -> TrainerStates:
+        cfg = self.pretrain_config
+        st = TrainerStates()
+        in_dsh, in_dgh = parse_multi_ds_parallel_config(self.ds_parallel_configs, "input")
+        lb_dsh, lb_dgh = parse_multi_ds_parallel_config(self.ds_parallel_configs, "label")
+        dp, _, _ = _strategy_sizes(self.ds_parallel_configs[0])
+        seq = int(cfg.max_seq_length or 1024)
+        mbs = int(cfg.micro_batch_size or 1)
+        tokens = mbs * seq * dp
+        ac = core.autocast("bfloat16") if cfg.bf16 else _null()
+        with core.graph("define_and_run", create_new=True, num_strategy=self.num_strategy) as g, ac:
+            st.seq_len_symbol = IntSymbol(seq)
+            if hasattr(self.model_wrapper, "create_model"):
+                st.model = self.model_wrapper.create_model(self.ds_parallel_configs)
+                st.config = getattr(self.model_wrapper, "model_config", None)
+            else:
+                st.model = self.model_wrapper
+                st.config = getattr(st.model, "config", None)
+            st.input_ids = core.parallel_placeholder("int64", [tokens], in_dsh, device_group_hierarchy=in_dgh, name="input_ids")
+            st.position_ids = core.parallel_placeholder("int64", [tokens], in_dsh, device_group_hierarchy=in_dgh, name="position_ids")
+            st.labels = core.parallel_placeholder("int64", [tokens], lb_dsh, device_group_hierarchy=lb_dgh, name="labels")
+            st.loss = st.model(st.input_ids, st.position_ids, st.labels, seq_len=st.seq_len_symbol)
+            st.optimizer = self.optimizer_wrapper.create_optimizer() if isinstance(self.optimizer_wrapper, OptimizerWrapper) \
+                else self.optimizer_wrapper
+            st.train_op = st.optimizer.minimize(st.loss)
+            st.graph = g
+        return st
+
+    # ------------------------------------------------------------------ data
+    def prepare_feed_dict(self, batch: Sequence, strategy_id: int = 0):
+        """batch: [(inputs, labels)] of this data-parallel rank -> (feed_dict, num_micro_batches, seq_len, stats).
+        Padding mode: micro-batches of [micro_batch_size, width]; packing mode: one packed row per micro-batch
+        (documents aligned to `pack_alignment` tokens so attention tiles never straddle two documents)."""
+        cfg = self.pretrain_config
+        st = self.trainer_states
+        max_len = int(cfg.max_seq_length or 1024)
+        pad_id = getattr(self.tokenizer, "pad_id", 0) if self.tokenizer is not None else 0
+        ins, labs = Bucket(pad_id, max_len, cfg.pack_alignment), Bucket(-1, max_len, cfg.pack_alignment)
+        for x, y in batch:
+            ins.add_data(x)
+            labs.add_data(y)
+        feeds_i, feeds_p, feeds_l = [], [], []
+        if cfg.packing:
+            order = np.argsort([-len(x) for x, _ in batch], kind="stable")
+            rows_i = ins.pack_data()
+            # pack labels with the identical assignment: re-pack (input, label) jointly
+            rows = _pack_pairs([batch[i] for i in order], max_len, pad_id, cfg.pack_alignment)
+            width = max(len(r[0]) for r in rows)
+            width = (width + cfg.pack_alignment - 1) // cfg.pack_alignment * cfg.pack_alignment
+            for toks, lab, pos in rows:
+                n = len(toks)
+                feeds_i.append(np.concatenate([toks, np.full(width - n, pad_id, np.int64)]))
+                feeds_l.append(np.concatenate([lab, np.full(width - n, -1, np.int64)]))
+                feeds_p.append(np.concatenate([pos, np.zeros(width - n, np.int64)]))
+            seq = width
+            stats = {"real_tokens": int(sum(len(x) for x, _ in batch)), "fed_tokens": int(width * len(rows)), "rows": len(rows_i)}
+        else:
+            mbs = int(cfg.micro_batch_size or len(batch))
+            pi, pl = ins.pad_data(), labs.pad_data()
+            width = pi.shape[1]
+            nmb = (len(batch) + mbs - 1) // mbs
+            for m in range(nmb):
+                bi, bl = pi[m * mbs:(m + 1) * mbs], pl[m * mbs:(m + 1) * mbs]
+                if len(bi) < mbs:   # ragged tail: pad with fully-masked rows so every micro-batch has the same shape
+                    k = mbs - len(bi)
+                    bi = np.concatenate([bi, np.full((k, width), pad_id, np.int64)])
+                    bl = np.concatenate([bl, np.full((k, width), -1, np.int64)])
+                feeds_i.append(bi.reshape(-1))
+                feeds_l.append(bl.reshape(-1))
+                feeds_p.append(np.tile(np.arange(width), mbs))
+            seq = width
+            stats = {"real_tokens": int(sum(len(x) for x, _ in batch)), "fed_tokens": int(width * mbs * nmb), "rows": len(batch)}
+        to_t = (lambda a: torch.as_tensor(a).pin_memory()) if torch.cuda.is_available() else torch.as_tensor
+        feed = {st.input_ids: [to_t(a) for a in feeds_i], st.position_ids: [to_t(a) for a in feeds_p],
+                st.labels: [to_t(a) for a in feeds_l]}
+        return feed, len(feeds_i), seq, stats
+
+    def train_data_iterator(self):
+        while True:
+            loader = self.get_train_data_loader()
+            got = False
+            for batch in loader:
+                got = True
+                self.consumed_samples += self.pretrain_config.global_load_size if \
+                    str(getattr(self.pretrain_config.data_load_level, "value", self.pretrain_config.data_load_level)) == "SAMPLE" else len(batch)
+                yield batch
+            self.epoch += 1
+            self.consumed_samples = 0
+            if not got:
+                raise RuntimeError("the training dataset produced no batch (global_load_size larger than the dataset?)")
+
+    # ------------------------------------------------------------------ train
+    def _train_step(self, batch, strategy_id=0):
+        st = self.trainer_states
+        feed, nmb, seq, stats = self.prepare_feed_dict(batch, strategy_id)
+        dp, _, _ = _strategy_sizes(self.ds_parallel_configs[strategy_id])
+        st.seq_len_symbol.set_data(int(seq))
+        out = st.graph.run(st.loss, [st.loss, st.train_op], feed, num_micro_batches=nmb, cur_strategy_id=strategy_id,
+                           grad_scale=1.0 / dp)
+        loss = out[0]
+        return (float(loss.float().mean()) if loss is not None else None), stats
+
+    def train(self, steps: Optional[int] = None, strategy_schedule: Optional[Callable[[int], int]] = None):
+        """run `steps` optimizer steps; `strategy_schedule(step) -> strategy id` enables hot switching between the
+        strategies of ds_parallel_configs (HotSPa: e.g. by the step's max sequence length)"""
+        cfg = self.pretrain_config
+        self.build()
+        it = self.train_data_iterator()
+        steps = int(steps if steps is not None else cfg.steps)
+        saver = None
+        if cfg.save_interval:
+            from ..utils.checkpoint import ModelSaver
+            saver = ModelSaver(cfg.output_dir, save_interval=cfg.save_interval)
+        prof = None
+        for _ in range(steps):
+            batch = next(it)
+            sid = int(strategy_schedule(self.global_step)) if strategy_schedule else self.cur_strategy_id
+            if sid != self.cur_strategy_id:
+                self.trainer_states.graph.switch_strategy(sid)
+                self.cur_strategy_id = sid
+            if cfg.torch_profile and self.global_step == cfg.start_profile_step:
+                prof = core.profiler(graph=self.trainer_states.graph)
+                prof.__enter__()
+            t0 = time.perf_counter()
+            loss, stats = self._train_step(batch, sid)
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            self.step_times.append(dt)
+            if loss is not None:
+                self.loss_history.append(loss)
+            if prof is not None and self.global_step == cfg.end_profile_step:
+                prof.__exit__(None, None, None)
+                os.makedirs(cfg.profile_save_path, exist_ok=True)
+                with open(os.path.join(cfg.profile_save_path, f"trace_rank{distributed.rank()}.json"), "w") as f:
+                    json.dump(prof.summary(), f)
+                prof = None
+            self.global_step += 1
+            if loss is not None and cfg.log_interval and self.global_step % cfg.log_interval == 0 and distributed.rank() in self._loss_ranks():
+                print(f"[trainer] step {self.global_step} loss {loss:.4f} time {dt * 1e3:.1f} ms "
+                      f"tokens {stats['real_tokens']}/{stats['fed_tokens']} strategy {sid}", flush=True)
+            for cb in self.callbacks:
+                cb(self, loss, stats)
+            if saver is not None and self.global_step % cfg.save_interval == 0:
+                saver.save(self.trainer_states.model, self.trainer_states.optimizer, self.global_step, self.consumed_samples,
+                           loss if loss is not None else float("nan"))
+            if cfg.plot_loss and self.global_step % cfg.plot_update_freq == 0:
+                self.plot_training_loss()
+        if saver is not None:
+            saver.wait()
+        return self.loss_history
+
+    def _loss_ranks(self):
+        cfg = self.ds_parallel_configs[self.cur_strategy_id]
+        return {g[0] for g in cfg["label"]["device_group_union"]}
+
+    def save_model(self, output_dir: Optional[str] = None):
+        from ..utils.checkpoint import ModelSaver
+        sv = ModelSaver(output_dir or self.pretrain_config.output_dir)
+        sv.save(self.trainer_states.model, self.trainer_states.optimizer, self.global_step, self.consumed_samples,
+                self.loss_history[-1] if self.loss_history else float("nan"))
+        sv.wait()
+
+    def plot_training_loss(self):
+        """loss curve as CSV + (when matplotlib exists) PNG under output_dir"""
+        os.makedirs(self.pretrain_config.output_dir, exist_ok=True)
+        with open(os.path.join(self.pretrain_config.output_dir, "loss.csv"), "w") as f:
+            f.write("step,loss\n" + "\n".join(f"{i + 1},{v}" for i, v in enumerate(self.loss_history)))
+        try:
+            import matplotlib
+            matplotlib.use("Agg")
+            import matplotlib.pyplot as plt
+            plt.figure()
+            plt.plot(range(1, len(self.loss_history) + 1), self.loss_history)
+            plt.xlabel("step")
+            plt.ylabel("loss")
+            plt.savefig(os.path.join(self.pretrain_config.output_dir, "loss.png"))
+            plt.close()
+        except Exception:
+            pass
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def _pack_pairs(pairs, max_len, pad_id, alignment):
+    """first-fit-decreasing packing of (inputs, labels) pairs -> [(tokens, labels, positions)] per packed row"""
+    def al(n):
+        return min((n + alignment - 1) // alignment * alignment, max_len)
+    rows, space = [], []
+    for x, y in pairs:
+        x, y = np.asarray(x[:max_len], np.int64), np.asarray(y[:max_len], np.int64)
+        need = al(len(x))
+        for r in range(len(rows)):
+            if space[r] >= need:
+                break
+        else:
+            rows.append([[], [], []])
+            space.append(max_len)
+            r = len(rows) - 1
+        pad = need - len(x)
+        rows[r][0].append(np.concatenate([x, np.full(pad, pad_id, np.int64)]))
+        rows[r][1].append(np.concatenate([y, np.full(pad, -1, np.int64)]))
+        rows[r][2].append(np.concatenate([np.arange(len(x)), np.zeros(pad, np.int64)]))
+        space[r] -= need
+    return [(np.concatenate(a), np.concatenate(b), np.concatenate(c)) for a, b, c in rows]

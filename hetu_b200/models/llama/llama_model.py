@@ -65,20 +65,24 @@ class LlamaAttention(Module):
 
     def forward(self, x, seq_len, residual=None, pos_offset=0):
         tp = self.qkv_dense.tp[0]
-        hq, hkv, d = self.num_heads // tp, max(self.kv_heads // tp, 1), self.head_dim
+        assert self.kv_heads % tp == 0, "tensor parallel degree must divide the number of kv heads"
+        hq, hkv, d = self.num_heads // tp, self.kv_heads // tp, self.head_dim
+        rep = hq // hkv
+        # kv-head-major packed layout [g: q x rep, k, v]: any tp | kv_heads owns whole groups (strategy independent weights)
         qkv = self.qkv_dense(x)
-        qkv = rotary_packed(qkv, seq_len, hq, hkv, d, base=self.config.rope_theta, pos_offset=pos_offset)
+        qkv = rotary_packed(qkv, seq_len, hq, hkv, d, base=self.config.rope_theta, pos_offset=pos_offset, layout="hqkv")
         if self.config.cp_ranks and len(self.config.cp_ranks) > 1:
             t = qkv.shape[0]
             s = seq_len if isinstance(seq_len, int) else seq_len.get_data()
-            q, k, v = ops.split(qkv, [hq * d, hkv * d, hkv * d], dim=1)
+            g5 = ops.reshape(qkv, [t // s, s, hkv, rep + 2, d])
+            q, k, v = ops.split(g5, [rep, 1, 1], dim=3)
             q = ops.reshape(q, [t // s, s, hq, d])
             k = ops.reshape(k, [t // s, s, hkv, d])
             v = ops.reshape(v, [t // s, s, hkv, d])
             a = ops.parallel_attn(q, k, v, self.config.cp_ranks, is_causal=True)
             a = ops.reshape(a, [t, hq * d])
         else:
-            a = attn_packed(qkv, seq_len, hq, hkv, d, is_causal=True)
+            a = attn_packed(qkv, seq_len, hq, hkv, d, is_causal=True, layout="hqkv")
         return self.dense(a, residual=residual)
 
 
@@ -87,7 +91,8 @@ class LlamaMLP(Module):
         super().__init__()
         h, f = config.hidden_size, config.intermediate_size
         std = config.initializer_range
-        # gate and up projections are fused in one column-parallel GEMM: [T, 2f/tp] -> swiglu -> [T, f/tp]
+        # gate and up projections are fused in one column-parallel GEMM with interleaved rows (gate_0, up_0, gate_1, ...):
+        # [T, 2f/tp] -> swiglu -> [T, f/tp], the same global weight under every tensor-parallel degree
         self.dense_h_to_4h = HtMultiColumnParallelLinear(h, 2 * f, get_multi_ds_parallel_config(ds_parallel_configs, "dense_h_to_4h", layer_idx),
                                                          bias=False, gather_output=False, dtype=config.dtype, name=f"{name}_gate_up",
                                                          init_std=std)
@@ -96,7 +101,7 @@ class LlamaMLP(Module):
                                                       name=f"{name}_down", init_std=std / math.sqrt(2.0 * config.num_hidden_layers))
 
     def forward(self, x, residual=None):
-        return self.dense_4h_to_h(ops.swiglu(self.dense_h_to_4h(x)), residual=residual)
+        return self.dense_4h_to_h(ops.swiglu(self.dense_h_to_4h(x), interleaved=True), residual=residual)
 
 
 class LlamaBlock(Module):

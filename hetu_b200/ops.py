@@ -133,8 +133,9 @@ def log_softmax(x, dim=-1, **kw):
     return _op1("log_softmax", [x], {"dim": int(dim)}, **kw)
 
 
-def swiglu(x, **kw):
-    return _op1("swiglu", [x], **kw)
+def swiglu(x, interleaved=False, **kw):
+    """silu(gate) * up of a fused gate/up projection; interleaved: columns are (gate_0, up_0, gate_1, up_1, ...)"""
+    return _op1("swiglu", [x], {"interleaved": bool(interleaved)}, **kw)
 
 
 def clamp(x, min=-math.inf, max=math.inf, **kw):  # noqa: A002

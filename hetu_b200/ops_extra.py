@@ -21,11 +21,12 @@ def attn_packed(qkv, seq_len, num_heads, num_kv_heads=None, head_dim=None, is_ca
     return make_op("attn_packed", [qkv], a, sy_shape=sy, **_meta(kw))[0]
 
 
-def rotary_packed(qkv, seq_len, num_heads, num_kv_heads=None, head_dim=None, positions=None, base=10000.0, pos_offset=0, **kw):
+def rotary_packed(qkv, seq_len, num_heads, num_kv_heads=None, head_dim=None, positions=None, base=10000.0, pos_offset=0,
+                  layout="qkv", **kw):
     num_kv_heads = num_kv_heads or num_heads
     head_dim = head_dim or qkv.shape[-1] // (num_heads + 2 * num_kv_heads)
     a, sy = _seq(seq_len)
     a.update({"num_heads": int(num_heads), "num_kv_heads": int(num_kv_heads), "head_dim": int(head_dim), "base": float(base),
-              "pos_offset": int(pos_offset)})
+              "pos_offset": int(pos_offset), "layout": str(layout)})
     ins = [qkv] if positions is None else [qkv, positions]
     return make_op("rotary_packed", ins, a, sy_shape=sy, **_meta(kw))[0]

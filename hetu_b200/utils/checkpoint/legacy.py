@@ -23,11 +23,20 @@ def load_checkpoint(model, path: str, strict: bool = False):
 
 
 def _interleave_qkv(q, k, v, num_heads, num_kv_heads, head_dim, layout):
-    """HF stores q | k | v blocked; our fused projection wants per-head [q k v] (MHA, GPT) or [q.. | k.. | v..] (GQA, Llama)"""
+    """HF stores q | k | v blocked; our fused projection is kv-head-major [g: q x rep, k, v] ('hqkv'; per-head [q k v]
+    when num_heads == num_kv_heads) so that any tensor-parallel degree dividing the kv heads owns whole groups."""
     if layout == "hqkv":
-        qh, kh, vh = (t.view(num_heads, head_dim, -1) for t in (q, k, v))
-        return torch.stack([qh, kh, vh], 1).reshape(3 * num_heads * head_dim, -1)
+        rep = num_heads // num_kv_heads
+        qh = q.reshape(num_kv_heads, rep, head_dim, -1)
+        kh = k.reshape(num_kv_heads, 1, head_dim, -1)
+        vh = v.reshape(num_kv_heads, 1, head_dim, -1)
+        return torch.cat([qh, kh, vh], 1).reshape((num_heads + 2 * num_kv_heads) * head_dim, -1)
     return torch.cat([q, k, v], 0)
+
+
+def _interleave_gate_up(gate, up):
+    """rows (gate_0, up_0, gate_1, up_1, ...): the layout of the fused gate/up projection (swiglu interleaved=True)"""
+    return torch.stack([gate, up], 1).reshape(2 * gate.shape[0], -1)
 
 
 def convert_llama_hf_to_ht(hf_state: Dict[str, torch.Tensor], num_layers: int, num_heads: int, num_kv_heads: int) -> Dict[str, torch.Tensor]:
@@ -44,9 +53,9 @@ def convert_llama_hf_to_ht(hf_state: Dict[str, torch.Tensor], num_layers: int, n
         out[o + "rmsnorm_1.weight"] = hf_state[p + "input_layernorm.weight"]
         out[o + "rmsnorm_2.weight"] = hf_state[p + "post_attention_layernorm.weight"]
         out[o + "attn.qkv_dense.weight"] = _interleave_qkv(hf_state[p + "self_attn.q_proj.weight"], hf_state[p + "self_attn.k_proj.weight"],
-                                                            hf_state[p + "self_attn.v_proj.weight"], num_heads, num_kv_heads, hd, "qkv")
+                                                            hf_state[p + "self_attn.v_proj.weight"], num_heads, num_kv_heads, hd, "hqkv")
         out[o + "attn.dense.weight"] = hf_state[p + "self_attn.o_proj.weight"]
-        out[o + "mlp.dense_h_to_4h.weight"] = torch.cat([hf_state[p + "mlp.gate_proj.weight"], hf_state[p + "mlp.up_proj.weight"]], 0)
+        out[o + "mlp.dense_h_to_4h.weight"] = _interleave_gate_up(hf_state[p + "mlp.gate_proj.weight"], hf_state[p + "mlp.up_proj.weight"])
         out[o + "mlp.dense_4h_to_h.weight"] = hf_state[p + "mlp.down_proj.weight"]
     return out
 

@@ -34,3 +34,11 @@ print("sum of per-op (synchronised) ms", tot)
 for name, ms, n in summ["by_optype"][:30]:
     print(f"{name:32s} {ms:9.3f} ms  x{n}")
 print(json.dumps(summ["breakdown"]))
+# the same, grouped by op name with the layer index masked (which GEMM of the block is slow?)
+import re
+byname = {}
+for name, ms in g.op_times():
+    byname.setdefault(re.sub(r"\d+", "#", name), []).append(ms)
+print("---- by masked op name (mean ms per instance)")
+for k, v in sorted(byname.items(), key=lambda kv: -sum(kv[1]))[:40]:
+    print(f"{k:72s} {sum(v):9.3f} ms  x{len(v):3d}  mean {sum(v) / len(v) * 1e3:8.1f} us")

@@ -1,0 +1,139 @@
+"""Trainer / data / LoRA / Malleus planner on CPU (ref test model: tests/ci_test + examples/pretrain scripts)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import hetu_b200 as ht
+from hetu_b200.data import (Bucket, ByteTokenizer, DataLoader, IndexedTokenDataset, JsonDataset, SyntheticDataset,
+                            build_chat_sample, generate_cp_pack_data, pack_sequences)
+from hetu_b200.engine import (ModelWrapper, OptimizerWrapper, SFTConfig, SFTTrainer, StrategyModel, Trainer, TrainerCtxs,
+                              TrainerStrategyArgs, TrainingConfig)
+from hetu_b200.engine.strategy import dispatch_sequences
+from hetu_b200.models import GPTConfig, GPTLMHeadModel
+
+
+def _mcfg():
+    return GPTConfig(vocab_size=259, n_positions=64, n_embd=32, n_layer=2, n_head=4)
+
+
+def test_pack_sequences_alignment_and_cu_seqlens():
+    seqs = [np.arange(n) for n in (5, 30, 17, 64, 9)]
+    rows = pack_sequences(seqs, 64, pad_id=-7, alignment=16)
+    tot = 0
+    for toks, cu in rows:
+        assert len(toks) <= 64 and cu[0] == 0 and cu[-1] == len(toks)
+        assert all(c % 16 == 0 for c in cu)
+        tot += len(cu) - 1
+    assert tot == len(seqs)
+    b = Bucket(0, 64, 16)
+    for s in seqs:
+        b.add_data(s)
+    b.pad_data()
+    b.pack_data()
+    st = b.padding_stats()
+    assert st["pack_efficiency"] >= st["pad_efficiency"]
+
+
+def test_cp_pack_sym_split_is_balanced_and_complete():
+    toks = np.arange(64)
+    cu = np.array([0, 32, 64], dtype=np.int32)
+    parts = generate_cp_pack_data(toks, cu, cp=2, pattern="SYM")
+    assert sorted(np.concatenate([p[0] for p in parts]).tolist()) == list(range(64))
+    # causal work of rank r ~ sum of positions: symmetric split equalises it
+    w = [p[0].sum() for p in parts]
+    assert abs(w[0] - w[1]) <= 2
+
+
+def test_dataloader_resume_and_dp_sharding(tmp_path):
+    ds = SyntheticDataset(40, 100, 16, seed=3)
+    a = DataLoader(ds, global_batch_size=8, dp_rank=0, dp_size=2, prefetch=0)
+    b = DataLoader(ds, global_batch_size=8, dp_rank=1, dp_size=2, prefetch=0)
+    ba, bb = next(iter(a)), next(iter(b))
+    assert len(ba) == len(bb) == 4 and not any(np.array_equal(x, y) for x in ba for y in bb)
+    full = [x for batch in DataLoader(ds, global_batch_size=8, prefetch=0) for x in batch]
+    r = DataLoader(ds, global_batch_size=8, prefetch=2)
+    r.restart(16)
+    rest = [x for batch in r for x in batch]
+    assert len(rest) == 24 and np.array_equal(rest[0], full[16])
+    IndexedTokenDataset.build(str(tmp_path / "tok"), [[1, 2, 3], [4, 5]])
+    it = IndexedTokenDataset(str(tmp_path / "tok"))
+    assert len(it) == 2 and it[1].tolist() == [4, 5]
+    p = tmp_path / "d.jsonl"
+    p.write_text("\n".join(json.dumps({"text": "hello world %d" % i}) for i in range(3)))
+    jd = JsonDataset(str(p), "text", ByteTokenizer(), max_seq_len=8)
+    assert len(jd) == 3 and len(jd[0]) == 9
+
+
+def test_chat_sample_masks_non_assistant_tokens():
+    tok = ByteTokenizer()
+    ids, labels = build_chat_sample([{"role": "user", "content": "hi"}, {"role": "assistant", "content": "yo"}], tok)
+    assert len(ids) == len(labels) and (labels != -1).sum() == len("yo\n")
+
+
+def test_trainer_padding_and_packing_run():
+    ht.init_comm_group(1)
+    ds = SyntheticDataset(64, 259, 32, min_seq_len=8, seed=1, length_distribution="uniform")
+    cfg = TrainingConfig(packing=False, micro_batch_size=2, global_load_size=4, max_seq_length=32, steps=3, learning_rate=1e-2,
+                         log_interval=0, pack_alignment=16)
+    tr = Trainer(cfg, ModelWrapper(GPTLMHeadModel, _mcfg()), ByteTokenizer(), OptimizerWrapper({"type": "adam", "lr": 1e-2}), ds)
+    losses = tr.train()
+    assert len(losses) == 3 and all(np.isfinite(losses))
+    cfg2 = TrainingConfig(packing=True, global_load_size=8, max_seq_length=64, steps=3, learning_rate=1e-2, pack_alignment=16, log_interval=0)
+    tr2 = Trainer(cfg2, ModelWrapper(GPTLMHeadModel, _mcfg()), ByteTokenizer(), None, ds)
+    assert len(tr2.train()) == 3
+
+
+def test_trainer_overfits_fixed_text():
+    ht.init_comm_group(1)
+
+    class Fixed:
+        def __len__(self):
+            return 8
+
+        def __getitem__(self, i):
+            return np.asarray(ByteTokenizer().encode("the quick brown fox jumps")[:25], np.int64)
+    cfg = TrainingConfig(packing=False, micro_batch_size=4, global_load_size=4, max_seq_length=32, steps=30, log_interval=0,
+                         pack_alignment=8)
+    tr = Trainer(cfg, ModelWrapper(GPTLMHeadModel, _mcfg()), ByteTokenizer(), OptimizerWrapper({"type": "adam", "lr": 1e-2}), Fixed())
+    losses = tr.train()
+    assert losses[-1] < 0.5 * losses[0]
+
+
+def test_sft_trainer_with_lora_trains_only_adapters(tmp_path):
+    ht.init_comm_group(1)
+    from hetu_b200.peft import lora_state_dict, merge_lora_weights
+    recs = [{"messages": [{"role": "user", "content": f"say {i}"}, {"role": "assistant", "content": f"number {i} it is"}]} for i in range(16)]
+    scfg = SFTConfig(packing=False, micro_batch_size=4, global_load_size=4, max_seq_length=64, steps=6, learning_rate=1e-2, lora_rank=4,
+                     log_interval=0, pack_alignment=16)
+    st = SFTTrainer(scfg, ModelWrapper(GPTLMHeadModel, _mcfg()), ByteTokenizer(), None, recs)
+    base_before = {k: v.clone() for k, v in st.build().model.state_dict().items() if "lora_" not in k}
+    losses = st.train()
+    assert losses[-1] < losses[0]
+    m = st.trainer_states.model
+    after = m.state_dict()
+    for k, v in base_before.items():
+        assert torch.equal(after[k], v), f"frozen weight {k} changed"
+    assert len(lora_state_dict(m)) == 16
+    merged = merge_lora_weights(m)
+    assert not any("lora_" in k or ".base." in k for k in merged)
+
+
+def test_malleus_planner_gives_stragglers_fewer_layers():
+    ctx = TrainerCtxs(normal_layers=8, normal_mbn=8)
+    old = TrainerStrategyArgs(dp=2, tp=2, pp=2, rank_to_device_mapping={i: i for i in range(8)})
+    sr = {i: 1.0 for i in range(8)}
+    sr[3] = 2.5
+    m = StrategyModel(ctx, old, sr)
+    st, cfg = m.make_plans()
+    assert sum(st.hetero_micro_batch_num_list) == 16 and all(sum(l) == 16 for l in st.hetero_layers)
+    slow = [(pl, i) for pl in m.plans for i, g in enumerate(pl["groups"]) if 3 in g.devices]
+    pl, i = slow[0]
+    assert pl["layers"][i] < 8      # the stage containing the straggler holds fewer layers
+    assert cfg["hetero"] and len(cfg["blocks"]) == 16
+    same = StrategyModel(ctx, old, dict(sr))
+    assert same == m
+    bal = dispatch_sequences([100, 4000, 300, 2000, 1500, 800], [1.0, 0.5])
+    assert sorted(sum(bal, [])) == list(range(6))

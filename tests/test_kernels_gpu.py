@@ -84,7 +84,7 @@ def test_flash_attention_fwd_bwd(B, S, H, Hkv, D, causal):
     close(torch.as_tensor(V.grad.numpy()), vr.grad, 0.03, 0.03)
 
 
-@pytest.mark.parametrize("rows,cols", [(512, 2048), (300, 768), (64, 8192)])
+@pytest.mark.parametrize("rows,cols", [(512, 2048), (300, 768), (64, 8192), (1001, 4096), (37, 1024), (16384, 2048)])
 def test_layernorm_and_rmsnorm(rows, cols):
     x, w, b, g = bf(rows, cols, seed=1), bf(cols, seed=2) * 0.1 + 1, bf(cols, seed=3) * 0.1, bf(rows, cols, seed=4)
     X, W, Bb = leaf(x), leaf(w), leaf(b)
@@ -121,6 +121,16 @@ def test_softmax_cross_entropy_and_embedding():
     lref.backward()
     assert abs(float(loss.numpy()) - float(lref)) < 2e-2
     close(torch.as_tensor(Lg.grad.numpy()), lr.grad, 2e-4, 0.03)
+    # non-unit seed (device-scalar scale kernel) and per-token losses
+    Lg2 = leaf(logits)
+    (ht.softmax_cross_entropy_sparse(Lg2, ht.from_numpy(labels), ignored_index=-1, reduction="mean") * 3.0).backward()
+    close(torch.as_tensor(Lg2.grad.numpy()), 3.0 * lr.grad, 6e-4, 0.03)
+    Lg3 = leaf(logits)
+    wts = bf(T, seed=9).abs()
+    ht.sum(ht.softmax_cross_entropy_sparse(Lg3, ht.from_numpy(labels), ignored_index=-1, reduction="none") * leaf(wts, False)).backward()
+    lr3 = logits.float().requires_grad_()
+    (torch.nn.functional.cross_entropy(lr3, labels, ignore_index=-1, reduction="none") * wts.float()).sum().backward()
+    close(torch.as_tensor(Lg3.grad.numpy()), lr3.grad, 0.02, 0.03)
     table = bf(V, H, seed=2)
     ids = torch.randint(0, V, (T,), generator=torch.Generator().manual_seed(6)).cuda()
     Tb = leaf(table)
@@ -161,6 +171,70 @@ def test_activations_swiglu_rotary():
     qa, qb = q.float()[..., :half], q.float()[..., half:]
     ref = torch.cat([qa * cs - qb * sn, qb * cs + qa * sn], -1)
     close(torch.as_tensor(y.numpy()), ref, 0.03, 0.02)
+
+
+def test_mlp_backward_fuses_activation_grad_into_dgrad():
+    """linear(gelu) -> linear: the second linear's dgrad GEMM applies gelu'(pre) in its epilogue (no unary_act_bwd pass)"""
+    M, H, F = 1024, 512, 2048
+    x, w1, b1, w2 = bf(M, H, seed=1), bf(F, H, scale=1 / math.sqrt(H), seed=2), bf(F, seed=3), bf(H, F, scale=1 / math.sqrt(F), seed=4)
+    g = bf(M, H, seed=5)
+    for act, ref in [("gelu", torch.nn.functional.gelu), ("relu", torch.relu)]:
+        X, W1, B1, W2 = leaf(x), leaf(w1), leaf(b1), leaf(w2)
+        y = ht.linear(ht.linear(X, W1, B1, act=act), W2, None)
+        ht.sum(y * leaf(g, False)).backward()
+        xr, w1r, b1r, w2r = (t.float().requires_grad_() for t in (x, w1, b1, w2))
+        yr = ref(xr @ w1r.t() + b1r) @ w2r.t()
+        (yr * g.float()).sum().backward()
+        close(torch.as_tensor(y.numpy()), yr.detach(), 0.05, 0.03)
+        close(torch.as_tensor(X.grad.numpy()), xr.grad, 0.1, 0.04)
+        close(torch.as_tensor(W1.grad.numpy()), w1r.grad, 0.03 * math.sqrt(M), 0.04)
+        close(torch.as_tensor(B1.grad.numpy()), b1r.grad, 0.04 * math.sqrt(M), 0.04)
+        close(torch.as_tensor(W2.grad.numpy()), w2r.grad, 0.03 * math.sqrt(M), 0.04)
+
+
+@pytest.mark.parametrize("Hq,Hkv,D", [(8, 2, 64), (4, 4, 128), (8, 1, 128)])
+def test_packed_grouped_qkv_rotary_attention(Hq, Hkv, D):
+    """kv-head-major packed projection [g: q x rep, k, v]: rotary + flash attention read/write it through head slots"""
+    from hetu_b200.ops_extra import attn_packed, rotary_packed
+    B, S = 2, 256
+    rep = Hq // Hkv
+    T = B * S
+    qkv = bf(T, (Hq + 2 * Hkv) * D, seed=1)
+    g = bf(T, Hq * D, seed=2)
+    X = leaf(qkv)
+    r = rotary_packed(X, S, Hq, Hkv, D, layout="hqkv")
+    o = attn_packed(r, S, Hq, Hkv, D, is_causal=True, layout="hqkv")
+    ht.sum(o * leaf(g, False)).backward()
+    xr = qkv.float().requires_grad_()
+    x5 = xr.view(B, S, Hkv, rep + 2, D)
+    half = D // 2
+    inv = 10000.0 ** (-torch.arange(half, dtype=torch.float32, device="cuda") * 2 / D)
+    ang = torch.arange(S, dtype=torch.float32, device="cuda")[:, None] * inv[None]
+    cs, sn = ang.cos()[None, :, None, None, :], ang.sin()[None, :, None, None, :]
+
+    def rot(t):
+        a, b = t[..., :half], t[..., half:]
+        return torch.cat([a * cs - b * sn, b * cs + a * sn], -1)
+    q = rot(x5[:, :, :, :rep]).reshape(B, S, Hq, D)
+    k = rot(x5[:, :, :, rep:rep + 1]).reshape(B, S, Hkv, D).repeat_interleave(rep, 2)
+    v = x5[:, :, :, rep + 1].repeat_interleave(rep, 2)
+    orf = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True)
+    orf = orf.transpose(1, 2).reshape(T, Hq * D)
+    (orf * g.float()).sum().backward()
+    close(torch.as_tensor(o.numpy()), orf.detach(), 0.03, 0.03)
+    close(torch.as_tensor(X.grad.numpy()), xr.grad, 0.06, 0.04)
+
+
+def test_swiglu_interleaved():
+    x, g = bf(512, 1024, seed=1), bf(512, 512, seed=2)
+    X = leaf(x)
+    y = ht.swiglu(X, interleaved=True)
+    ht.sum(y * leaf(g, False)).backward()
+    xr = x.float().requires_grad_()
+    yr = torch.nn.functional.silu(xr[:, 0::2]) * xr[:, 1::2]
+    (yr * g.float()).sum().backward()
+    close(torch.as_tensor(y.numpy()), yr.detach(), 0.03, 0.02)
+    close(torch.as_tensor(X.grad.numpy()), xr.grad, 0.05, 0.03)
 
 
 def test_fused_adam_matches_torch():
