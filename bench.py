@@ -68,7 +68,8 @@ def reference_arm(args):
     none of MPI / protoc / grpc_cpp_plugin exist in this image, so it cannot be built offline."""
     ref = os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline", "_ref")
     ok = os.path.isdir(ref) and any(f.startswith("hetu") for f in os.listdir(ref)) if os.path.isdir(ref) else False
-    why = ("reference build requires MPI, gRPC/protoc, oneDNN and bitsandbytes (absent offline) and only targets sm_80-89"
+    why = ("pip: /root/reference has no setup.py/pyproject.toml; its CMake build needs MPI>=3.1, gRPC/protoc, oneDNN, bitsandbytes "
+           "(none available offline) and targets sm_80-89 only -- see DESIGN.md section 4"
            if not ok else "reference installed but its CUDA extension does not load on sm_100")
     if int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps({"impl": "reference", "unavailable": why}))

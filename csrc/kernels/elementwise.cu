@@ -298,12 +298,12 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const __nv_bfloat16* __
     const char* base = reinterpret_cast<const char*>(x + c0);
     const int64_t pitch = int64_t(cols) * 2;
     int64_t r = r0 + warp;
-    for (; r + 24 < r1; r += 32) {
-      bf16x8 q[4];
+    for (; r + 56 < r1; r += 64) {
+      bf16x8 q[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) q[u] = ld8_stream(base + (r + u * 8) * pitch, 0);
+      for (int u = 0; u < 8; ++u) q[u] = ld8_stream(base + (r + u * 8) * pitch, 0);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         float f[8];
         unpack8(q[u], f);
 #pragma unroll
@@ -457,8 +457,9 @@ cudaError_t colsum_bf16(const void* x, float* out, int64_t rows, int cols, bool 
   if (rows == 0) return cudaGetLastError();
   if ((cols & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
     const int cb = (cols + 255) / 256;
-    int rb = (sm_count() * 8 + cb - 1) / cb;
-    if (rb > (rows + 31) / 32) rb = (int)((rows + 31) / 32);
+    int rb = (sm_count() * 4 + cb - 1) / cb;
+    if (rb > (rows + 63) / 64) rb = (int)((rows + 63) / 64);
+    if (rb < 1) rb = 1;
     const int rpb = (int)((rows + rb - 1) / rb);
     rb = (int)((rows + rpb - 1) / rpb);
     colsum_vec_kernel<<<dim3(cb, rb), 256, 0, s>>>((const __nv_bfloat16*)x, out, rows, cols, rpb);

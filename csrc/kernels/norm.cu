@@ -346,21 +346,35 @@ __global__ void norm_bwd_generic_kernel(const __nv_bfloat16* __restrict__ dy, co
   }
 }
 
-__global__ void fold_parts_kernel(const float* __restrict__ parts, float* __restrict__ out, int nparts, int cols,
-                                  int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+// Folds the per-CTA partials: block (32 columns, 8 part-lanes), coalesced 128-byte rows, 8 independent chains per
+// column and BOTH outputs (dgamma, dbeta) in one launch (blockIdx.y).
+__global__ void __launch_bounds__(256) fold_parts_kernel(const float* __restrict__ parts0, float* __restrict__ out0,
+                                                         const float* __restrict__ parts1, float* __restrict__ out1,
+                                                         int nparts, int cols, int accumulate) {
+  __shared__ float sm[8][33];
+  const float* parts = blockIdx.y == 0 ? parts0 : parts1;
+  float* out = blockIdx.y == 0 ? out0 : out1;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int p = 0;
-  for (; p + 3 < nparts; p += 4) {
-    s0 += parts[int64_t(p) * cols + c];
-    s1 += parts[int64_t(p + 1) * cols + c];
-    s2 += parts[int64_t(p + 2) * cols + c];
-    s3 += parts[int64_t(p + 3) * cols + c];
+  if (c < cols) {
+    int p = ty;
+    for (; p + 24 < nparts; p += 32) {
+      s0 += parts[int64_t(p) * cols + c];
+      s1 += parts[int64_t(p + 8) * cols + c];
+      s2 += parts[int64_t(p + 16) * cols + c];
+      s3 += parts[int64_t(p + 24) * cols + c];
+    }
+    for (; p < nparts; p += 8) s0 += parts[int64_t(p) * cols + c];
   }
-  for (; p < nparts; ++p) s0 += parts[int64_t(p) * cols + c];
-  const float s = (s0 + s1) + (s2 + s3);
-  out[c] = accumulate ? out[c] + s : s;
+  sm[ty][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sm[w][tx];
+    out[c] = accumulate ? out[c] + s : s;
+  }
 }
 
 }  // namespace
@@ -411,12 +425,10 @@ static cudaError_t norm_bwd_impl(const void* dy, const void* x, const void* gamm
                                                         (const __nv_bfloat16*)gamma, mean, rstd, (__nv_bfloat16*)dx,
                                                         part_dg, part_db, rows, cols);
   }
-  fold_parts_kernel<<<(cols + 255) / 256, 256, 0, s>>>(part_dg, dgamma, parts, cols, accumulate ? 1 : 0);
+  const bool two = !kRMS && dbeta != nullptr;
+  fold_parts_kernel<<<dim3((cols + 31) / 32, two ? 2 : 1), 256, 0, s>>>(part_dg, dgamma, part_db, dbeta, parts, cols,
+                                                                        accumulate ? 1 : 0);
   count_launch(2);
-  if (!kRMS && dbeta != nullptr) {
-    fold_parts_kernel<<<(cols + 255) / 256, 256, 0, s>>>(part_db, dbeta, parts, cols, accumulate ? 1 : 0);
-    count_launch();
-  }
   return cudaGetLastError();
 }
 

@@ -1,0 +1,62 @@
+"""Galvatron planner: C++ DP core vs brute force, memory-pressure behaviour of the search, plan emission."""
+import itertools
+
+import numpy as np
+
+import hetu_b200 as ht
+from hetu_b200 import _C
+from hetu_b200.planner import GalvatronSearchEngine, HardwareProfile, LayerProfile, galvatron_plan_to_ds_parallel_config
+
+
+def test_dp_core_matches_brute_force():
+    rng = np.random.RandomState(0)
+    L, S, M = 5, 3, 14
+    mem = rng.randint(1, 5, (L, S))
+    intra = rng.rand(L, S)
+    inter = rng.rand(L, S, S) * 0.3
+    inter[0] = 0
+    cost, picks, rem = _C.galvatron_dp(L, M + 1, S,   # table rows 0..max_mem-1: budget = max_mem - 1 units (as the reference)
+                                         mem.reshape(-1).tolist(), intra.reshape(-1).tolist(), inter.reshape(-1).tolist())
+    best = (1e18, None)
+    for combo in itertools.product(range(S), repeat=L):
+        m = sum(mem[i, c] for i, c in enumerate(combo))
+        if m > M:
+            continue
+        c = sum(intra[i, s] for i, s in enumerate(combo)) + sum(inter[i, combo[i - 1], combo[i]] for i in range(1, L))
+        best = min(best, (c, combo))
+    assert abs(cost - best[0]) < 1e-9 and tuple(picks) == best[1]
+    assert _C.galvatron_dp(L, 3, S, mem.reshape(-1).tolist(), intra.reshape(-1).tolist(), inter.reshape(-1).tolist())[1] == []
+
+
+def test_search_prefers_plain_dp_when_memory_is_plentiful_and_shards_when_tight():
+    lp = LayerProfile.transformer(4096, 11008, 4096, 32, swiglu=True)
+    roomy = GalvatronSearchEngine(32, 8, lp, vocab=32000, hidden=4096, seq=4096, memory_mb=180 * 1024).search(batch_sizes=(16, 32))
+    assert roomy is not None and roomy["pp"] == 1 and all(s.tp == 1 for s in roomy["strategies"])
+    tight = GalvatronSearchEngine(32, 8, lp, vocab=32000, hidden=4096, seq=4096, memory_mb=24 * 1024).search(batch_sizes=(16, 32))
+    assert tight is not None
+    ss = tight["strategies"]
+    assert tight["pp"] > 1 or any(s.tp > 1 or s.sdp == 3 or s.ckpt for s in ss)     # had to trade speed for memory
+    assert tight["throughput_samples_per_s"] <= roomy["throughput_samples_per_s"] * 1.0001
+    none = GalvatronSearchEngine(32, 8, lp, vocab=32000, hidden=4096, seq=4096, memory_mb=2 * 1024).search(batch_sizes=(16,))
+    assert none is None
+
+
+def test_plan_json_and_ds_parallel_config_roundtrip(tmp_path):
+    lp = LayerProfile.transformer(2048, 8192, 1024, 16)
+    eng = GalvatronSearchEngine(8, 4, lp, hidden=2048, seq=1024, memory_mb=40 * 1024)
+    plan = eng.search(batch_sizes=(8, 16))
+    js = GalvatronSearchEngine.to_json(plan)
+    assert len(js["tp_sizes_enc"].split(",")) == 8 and js["pp_deg"] == plan["pp"]
+    GalvatronSearchEngine.save(plan, str(tmp_path / "plan.json"))
+    cfg = galvatron_plan_to_ds_parallel_config(plan, 4)
+    assert len(cfg["blocks"]) == 8
+    ds, dg = ht.nn.parallel.config2ds(cfg["blocks"]["blocks3"]["attn"]["qkv"])
+    assert ds.get(0).device_num == plan["strategies"][3].tp * plan["strategies"][3].dp
+
+
+def test_hetu_alias_package():
+    import hetu
+    from hetu.engine import Trainer   # noqa: F401
+    from hetu.utils.parallel import read_ds_parallel_config   # noqa: F401
+    import hetu.nn as nn
+    assert hetu.AdamOptimizer is ht.AdamOptimizer and nn.Module is ht.nn.Module
