@@ -29,6 +29,8 @@ CXX_SOURCES = [
     "csrc/core/ds.cc",
     "csrc/graph/graph.cc",
     "csrc/graph/exec.cc",
+    "csrc/graph/zero_fused.cc",
+    "csrc/graph/tp_fused.cc",
     "csrc/graph/ops_basic.cc",
     "csrc/graph/ops_nn.cc",
     "csrc/graph/ops_comm.cc",

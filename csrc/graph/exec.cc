@@ -1,4 +1,5 @@
 #include "exec.h"
+#include "zero_fused.h"
 
 #include <ATen/ATen.h>
 #include <torch/csrc/distributed/c10d/Types.hpp>
@@ -253,7 +254,7 @@ int Executor::local_device_index(const DeviceGroup& g) const {
   for (size_t i = 0; i < g.num_devices(); ++i) if (g.get(i).index() == me) return (int)i;
   return -1;
 }
-static at::Device aten_device() {
+at::Device aten_device() {
   const bool cuda = at::hasCUDA() && env_int("HETU_B200_FORCE_CPU", 0) == 0;
   if (!cuda) return at::Device(at::kCPU);
   return at::Device(at::kCUDA, (c10::DeviceIndex)at::cuda::current_device());
@@ -714,7 +715,10 @@ void Executor::run_ops(ExecPlan& plan, const std::vector<OpDef*>& ops, bool back
         throw Error(os.str());
       }
       try {
-        if (op->type == "comm") outs = exec_comm(plan.comm[op->id], op, ins, rc);
+        if (op->type == "comm") {
+          if (!tp_fused_comm(plan, op, outs)) outs = exec_comm(plan.comm[op->id], op, ins, rc);
+        } else if (backward && zf_active_ != nullptr && zero_fused_wgrad(*zf_active_, op, ins)) outs = {at::Tensor()};
+        else if ((op->type == "linear" || op->type == "linear_dgrad") && tp_fused_gemm(plan, op, ins, rc, outs)) {}
         else outs = op->kernel->compute(*op, ins, &rc);
       } catch (const std::exception& e) {
         std::ostringstream os;
@@ -733,8 +737,9 @@ void Executor::run_ops(ExecPlan& plan, const std::vector<OpDef*>& ops, bool back
         // raw parameter gradient: fold into the (fp32) accumulation buffer, do not keep it alive
         auto acc = accum_grads_.find(pg->second);
         if (acc == accum_grads_.end()) {
-          const bool fp32 = env_int("HETU_FP32_GRAD_ACCUMULATION", 1) != 0;
-          accum_grads_[pg->second] = fp32 ? outs[k].to(at::kFloat) : outs[k].clone();
+          // a single micro-batch (and no cross-run accumulation) needs no accumulator: keep the gradient itself
+          const bool fp32 = env_int("HETU_FP32_GRAD_ACCUMULATION", 1) != 0 && !single_shot_grads_;
+          accum_grads_[pg->second] = fp32 ? outs[k].to(at::kFloat) : (single_shot_grads_ ? outs[k] : outs[k].clone());
         } else acc->second.add_(outs[k]);
         continue;
       }
@@ -826,6 +831,20 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
     for (int m = 0; m < M; ++m) { tasks.push_back({PipeTask::FORWARD, m}); tasks.push_back({PipeTask::BACKWARD, m}); }
   } else tasks = sched[plan.stage];
 
+  // gradients of a one-micro-batch UPDATE run are consumed by the optimizer directly (no fp32 accumulation copy)
+  single_shot_grads_ = !inference && M == 1 && opt.run_level == RunLevel::UPDATE && accum_grads_.empty();
+  // ZeRO over symmetric memory (fused with the wgrad GEMM epilogues and the optimizer); prepared once per plan
+  if (!tp_fused_.count(&plan)) tp_fused_scan(plan);
+  zf_active_ = nullptr;
+  if (!inference && opt.run_level == RunLevel::UPDATE) {
+    auto zit = zero_fused_.find(&plan);
+    if (zit == zero_fused_.end()) zit = zero_fused_.emplace(&plan, zero_fused_prepare(plan)).first;
+    if (zit->second && zit->second->ok) {
+      zf_active_ = zit->second.get();
+      zf_active_->epilogue_this_run = single_shot_grads_;
+    }
+  }
+
   std::vector<std::unordered_map<TensorId, at::Tensor>> vals(M);
   std::vector<std::vector<at::Tensor>> fetched(plan.fetch_ids.size());
   RunCtx rc;
@@ -875,8 +894,12 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
     const double t_u = now_ms();
     std::unordered_map<TensorId, at::Tensor> uvals;
     const double scale = opt.grad_scale / (double)M;
+    std::vector<at::Tensor> deferred_steps;
+    if (aten_device().is_cuda()) rc.deferred_steps = &deferred_steps;
+    if (zf_active_ != nullptr) zero_fused_update(plan, *zf_active_, scale);
     for (OpDef* op : plan.update_ops) {
       if (op->has_flag(kFlagGroup)) continue;
+      if (zf_active_ != nullptr && zf_active_->handled_ops.count(op->id)) continue;
       if (op->type == "comm") {
         // deferred gradient synchronisation (DP all-reduce / ZeRO reduce-scatter) on the accumulated gradient
         const TensorId raw = op->inputs[0]->id;
@@ -939,6 +962,19 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
         os << ": " << e.what();
         throw Error(os.str());
       }
+    }
+    if (!deferred_steps.empty()) {
+      // all optimizer step counters advance in one launch (pointer table cached per plan)
+      at::Tensor& tab = workspace_["__step_table_" + std::to_string((uintptr_t)&plan)];
+      std::vector<int64_t> ptrs;
+      for (auto& t : deferred_steps) ptrs.push_back((int64_t)(uintptr_t)t.data_ptr<int64_t>());
+      std::vector<int64_t>& cached = step_tables_host_[&plan];
+      if (!tab.defined() || cached != ptrs) {
+        tab = at::tensor(ptrs, at::TensorOptions().dtype(at::kLong)).to(aten_device());
+        cached = ptrs;
+      }
+      cuda_ok(increment_many_i64(reinterpret_cast<int64_t* const*>(tab.data_ptr()), (int)deferred_steps.size(), cur_stream()),
+              "step counters");
     }
     accum_grads_.clear();
     breakdown_["update_ms"] = now_ms() - t_u;

@@ -82,6 +82,8 @@ struct RunCtx {
   bool training = true;
   uint64_t seed = 0;
   std::unordered_map<std::string, at::Tensor>* workspace = nullptr;  // persistent scratch keyed by name
+  // optimizer step counters whose increment is deferred to ONE batched kernel at the end of the update phase
+  std::vector<at::Tensor>* deferred_steps = nullptr;
   at::Tensor scratch(const std::string& key, std::vector<int64_t> shape, at::ScalarType dt, const at::Device& dev);
 };
 
@@ -128,6 +130,10 @@ struct RunOptions {
   bool save_checkpoint = false;
 };
 
+struct ZeroFusedState;
+struct TpFusedState;
+at::Device aten_device();   // device this process computes on (cuda:LOCAL_RANK, or cpu)
+
 class Executor {
  public:
   explicit Executor(Graph* g) : g_(g) {}
@@ -160,11 +166,24 @@ class Executor {
   std::vector<at::Tensor> exec_comm(const CommStep& cs, OpDef* op, const std::vector<at::Tensor>& in, RunCtx& rc);
   void recompute_tensor(ExecPlan& plan, const Tensor& t, RunCtx& rc, std::unordered_map<TensorId, at::Tensor>& vals);
   void offload_activations(ExecPlan& plan, std::unordered_map<TensorId, at::Tensor>& vals);
+  // ZeRO over symmetric memory fused with wgrad GEMMs and the optimizer (zero_fused.cc)
+  std::shared_ptr<ZeroFusedState> zero_fused_prepare(ExecPlan& plan);
+  bool zero_fused_wgrad(ZeroFusedState& st, OpDef* op, const std::vector<at::Tensor>& ins);
+  void zero_fused_update(ExecPlan& plan, ZeroFusedState& st, double scale);
+  // tensor-parallel GEMM -> reduce-scatter over symmetric memory (tp_fused.cc)
+  void tp_fused_scan(ExecPlan& plan);
+  bool tp_fused_gemm(ExecPlan& plan, OpDef* op, const std::vector<at::Tensor>& ins, RunCtx& rc, std::vector<at::Tensor>& outs);
+  bool tp_fused_comm(ExecPlan& plan, OpDef* op, std::vector<at::Tensor>& outs);
 
   Graph* g_;
   std::map<std::pair<int, std::vector<TensorId>>, ExecPlan> plans_;
   std::unordered_map<std::string, at::Tensor> workspace_;
   std::unordered_map<TensorId, at::Tensor> accum_grads_;
+  std::map<const ExecPlan*, std::shared_ptr<ZeroFusedState>> zero_fused_;
+  std::map<const ExecPlan*, std::shared_ptr<TpFusedState>> tp_fused_;
+  bool single_shot_grads_ = false;
+  std::map<const ExecPlan*, std::vector<int64_t>> step_tables_host_;
+  ZeroFusedState* zf_active_ = nullptr;   // set while run() executes a plan on the fused ZeRO path
   std::vector<std::pair<std::string, double>> op_times_;
   std::map<std::string, double> breakdown_;
   bool profile_ = false;

@@ -25,6 +25,18 @@ int64_t fallback_count();
 
 at::Tensor native_add(const at::Tensor& a, const at::Tensor& b);
 
+// Destination override for the next GEMM issued on this thread: when set (by the executor's tensor-parallel fusion),
+// a GEMM whose output is [world * rows_per_rank, cols] stores its tiles into the owner ranks' symmetric staging slots
+// (peer stores from the epilogue) instead of its own output tensor.
+struct GemmSink {
+  void* local = nullptr;
+  void* peers[8] = {nullptr};
+  int world = 1, my_rank = 0;
+  int64_t rows_per_rank = 0, cols = 0;
+  bool used = false;
+};
+extern thread_local GemmSink* tls_gemm_sink;
+
 inline at::Tensor flatten_rows(const at::Tensor& x) { return x.reshape({-1, x.size(-1)}); }
 
 inline void set_out_ds(OpDef& op, size_t out_idx, size_t strategy, const DistributedStates& ds) {

@@ -127,7 +127,30 @@ static void run_gemm(const at::Tensor& A, bool a_mn, const at::Tensor& B, bool b
   c.act = act;
   c.accumulate = accumulate;
   c.alpha = alpha;
+  GemmSink* sink = tls_gemm_sink;
+  if (sink != nullptr && !sink->used && bias == nullptr && aux_in == nullptr && aux_out == nullptr && act == ACT_NONE && !accumulate &&
+      c.out == GemmOut::BF16 && M == sink->rows_per_rank * sink->world && N == sink->cols) {
+    c.C = sink->local; c.ldc = N;
+    c.peer_c = sink->peers; c.world = sink->world; c.my_rank = sink->my_rank; c.rows_per_rank = (int)sink->rows_per_rank;
+    sink->used = true;
+  }
   cuda_ok(gemm_bf16(c, cur_stream()), "tcgen05 gemm");
+}
+// weight gradient dW[N,K] = dy^T x with the GEMM -> reduce-scatter epilogue: every 128-row block of dW is stored into
+// the staging slot `my_rank` of the rank owning those rows (peer memory over NVLink); see graph/zero_fused.cc
+void wgrad_to_peer_slots(const at::Tensor& dy, const at::Tensor& x, bool trans_b, void* local_c, void* const* peer_c, int world,
+                         int my_rank, int64_t rows_per_rank) {
+  HB_CHECK(trans_b) << "fused ZeRO weight gradients need [out, in] weights";
+  at::Tensor d2 = flatten_rows(dy).contiguous(), x2 = flatten_rows(x).contiguous();
+  const int64_t T = d2.size(0), N = d2.size(1), K = x2.size(1);
+  GemmCall c;
+  c.A = d2.data_ptr(); c.B = x2.data_ptr(); c.C = local_c;
+  c.M = (int)N; c.N = (int)K; c.K = (int)T;
+  c.lda = d2.stride(0); c.ldb = x2.stride(0); c.ldc = K;
+  c.a_mn_major = true; c.b_mn_major = true;
+  c.out = GemmOut::BF16;
+  c.peer_c = peer_c; c.world = world; c.my_rank = my_rank; c.rows_per_rank = (int)rows_per_rank;
+  cuda_ok(gemm_bf16(c, cur_stream()), "tcgen05 wgrad -> peer slots");
 }
 static bool gemm_ok(const at::Tensor& t) {
   return is_native(t) && t.dim() == 2 && t.stride(1) == 1 && (t.stride(0) % 8) == 0 &&

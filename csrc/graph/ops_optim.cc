@@ -18,7 +18,7 @@ using Ts = std::vector<at::Tensor>;
 static void scalar_out_infer(OpDef& op) { make_out(op, 0, {1}, DataType::FLOAT32); }
 
 // inputs: param, grad, m, v, step, [master]
-static Ts adam_update_compute(const OpDef& op, const Ts& in, RunCtx*) {
+static Ts adam_update_compute(const OpDef& op, const Ts& in, RunCtx* rc) {
   at::Tensor param = in[0];
   const at::Tensor& grad = in[1];
   at::Tensor m = in[2], v = in[3], step = in[4];
@@ -26,7 +26,10 @@ static Ts adam_update_compute(const OpDef& op, const Ts& in, RunCtx*) {
   if (param.is_meta()) return {at::empty({1}, param.options().dtype(at::kFloat))};
   const double lr = op.attrs.f("lr", 1e-3), b1 = op.attrs.f("beta1", 0.9), b2 = op.attrs.f("beta2", 0.999),
                eps = op.attrs.f("eps", 1e-8), wd = op.attrs.f("weight_decay", 0.0);
-  step.add_(1);
+  const bool native = master.is_cuda() && master.scalar_type() == at::kFloat && master.is_contiguous() && m.is_contiguous() &&
+                      v.is_contiguous() && grad.is_contiguous() && (grad.scalar_type() == at::kFloat || grad.scalar_type() == at::kBFloat16);
+  const bool defer_step = native && rc != nullptr && rc->deferred_steps != nullptr && step.is_cuda();
+  if (!defer_step) step.add_(1);
   if (master.is_cuda() && master.scalar_type() == at::kFloat && master.is_contiguous() && m.is_contiguous() &&
       v.is_contiguous() && grad.is_contiguous() && (grad.scalar_type() == at::kFloat || grad.scalar_type() == at::kBFloat16)) {
     AdamArgs a;
@@ -37,7 +40,9 @@ static Ts adam_update_compute(const OpDef& op, const Ts& in, RunCtx*) {
     a.lr = (float)lr; a.beta1 = (float)b1; a.beta2 = (float)b2; a.eps = (float)eps; a.weight_decay = (float)wd;
     at::Tensor step_dev = step.is_cuda() ? step : step.to(master.device());
     a.step_ptr = step_dev.data_ptr<int64_t>();
+    if (defer_step) { a.step_add = 1; rc->deferred_steps->push_back(step); }
     cuda_ok(adam_update(a, cur_stream()), "adam_update");
+    if (rc != nullptr && rc->workspace != nullptr) return {rc->scratch("__update_done", {1}, at::kFloat, master.device())};
     return {at::zeros({1}, master.options())};
   }
   const double t = (double)step.item<int64_t>();

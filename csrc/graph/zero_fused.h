@@ -1,0 +1,46 @@
+// ZeRO ("OSDP" sharded data parallelism) over NVLink symmetric memory, fused with the compute it follows:
+//   * weight-gradient GEMMs store every output tile straight into the staging slot of the rank that owns those rows
+//     (peer stores from the tcgen05 GEMM epilogue): the gradient reduce-scatter rides inside backward, tile by tile;
+//   * one kernel per parameter then sums the slots, applies AdamW to this rank's fp32 master shard and stores the
+//     new bf16 shard into EVERY rank's parameter tensor (peer stores): reduce + optimizer + all-gather in one pass;
+//   * small / irregular parameters share ONE flat in-kernel all-reduce instead of a collective each.
+// The reference runs these as separate NCCL reduce-scatter / all-gather calls around the optimizer
+// (hetu/graph/executable_graph.cc: grad reduce comm ops + optimize-compute bridge, hetu/graph/ops/Optimizer*.cc).
+#pragma once
+#include <memory>
+#include <set>
+#include <unordered_map>
+#include <vector>
+
+#include "exec.h"
+
+namespace hb {
+
+struct SymmBuffer;
+
+struct ZeroEntry {
+  OpDef* update = nullptr;      // adam_update op
+  OpDef* comm = nullptr;        // deferred reduce-scatter comm op feeding it
+  OpDef* wgrad = nullptr;       // linear_wgrad producing the raw gradient (fused entries only)
+  TensorId param = -1, raw_grad = -1;
+  int64_t rows = 0, cols = 0, numel = 0;
+  size_t slots_off = 0;         // fused: [world, rows / world, cols] bf16 staging slots in the arena
+  size_t param_off = 0;         // bf16 parameter inside the arena
+  size_t flat_off = 0;          // leftover: element offset inside the flat gradient buffer
+  bool fused = false;
+};
+
+struct ZeroFusedState {
+  bool ok = false;
+  std::vector<int> ranks;
+  int world = 1, pos = 0;
+  std::string arena_name;
+  std::vector<ZeroEntry> entries;
+  std::unordered_map<OpId, size_t> by_wgrad;    // wgrad op id -> entry
+  std::set<OpId> handled_ops;                    // update + comm ops executed by this path in the CURRENT run
+  size_t flat_off = 0, flat_elems = 0;           // leftover flat gradient buffer (2x: all-reduce scratch)
+  at::Tensor step_table;                         // device int64*[] of all step counters
+  bool epilogue_this_run = false;
+};
+
+}  // namespace hb

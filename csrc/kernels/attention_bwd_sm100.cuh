@@ -39,27 +39,33 @@ struct AttnBwdParams {
   int64_t dq_sb, dq_ss, dq_sh, dk_sb, dk_ss, dk_sh, dv_sb, dv_ss, dv_sh;
 };
 
-// delta[b,h,s] = sum_d dO * O   (one warp per row)
+// delta[b,h,s] = sum_d dO * O: D/8 lanes per row, one 16-byte load of each tensor per lane (2 or 4 rows per warp)
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
                                   float* __restrict__ delta, int B, int H, int S, int D, int64_t o_sb, int64_t o_ss,
                                   int64_t o_sh, int64_t do_sb, int64_t do_ss, int64_t do_sh) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= int64_t(B) * H * S) return;
-  const int s = int(row % S);
-  const int h = int((row / S) % H);
-  const int b = int(row / (int64_t(S) * H));
-  const __nv_bfloat16* op = o + b * o_sb + s * o_ss + h * o_sh;
-  const __nv_bfloat16* dp = d_o + b * do_sb + s * do_ss + h * do_sh;
+  const int lpr = D >> 3;                                   // lanes per row: 8 (D = 64) or 16 (D = 128)
+  const int64_t gt = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  const int64_t row = gt / lpr;
+  const int c = int(gt % lpr) * 8;
   float acc = 0.f;
-  for (int c = lane * 2; c < D; c += 64) {
-    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(op + c));
-    const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dp + c));
-    acc += a.x * g.x + a.y * g.y;
-  }
+  const bool live = row < int64_t(B) * H * S;
+  int s = 0, h = 0, b = 0;
+  if (live) {
+    s = int(row % S);
+    h = int((row / S) % H);
+    b = int(row / (int64_t(S) * H));
+    const uint4 ra = __ldg(reinterpret_cast<const uint4*>(o + b * o_sb + s * o_ss + h * o_sh + c));
+    const uint4 rg = __ldg(reinterpret_cast<const uint4*>(d_o + b * do_sb + s * do_ss + h * do_sh + c));
+    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&ra);
+    const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&rg);
 #pragma unroll
-  for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
-  if (lane == 0) delta[(int64_t(b) * H + h) * S + s] = acc;
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = __bfloat1622float2(a2[j]), g = __bfloat1622float2(g2[j]);
+      acc += a.x * g.x + a.y * g.y;
+    }
+  }
+  for (int o2 = lpr >> 1; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+  if (live && c == 0) delta[(int64_t(b) * H + h) * S + s] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -583,7 +589,8 @@ cudaError_t attn_bwd_launch(const AttnBwdCall& c, cudaStream_t s, std::atomic<in
   if (!make_attn_tmap_bwd(&tv, c.v, D, c.Hkv, c.Sk, c.B)) return cudaErrorInvalidValue;
   {
     const int64_t rows = int64_t(c.B) * c.Hq * c.Sq;
-    attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(
+    const int64_t threads = rows * (D / 8);
+    attn_delta_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
         (const __nv_bfloat16*)c.o.ptr, (const __nv_bfloat16*)c.d_o.ptr, c.delta, c.B, c.Hq, c.Sq, D, c.o.stride_b,
         c.o.stride_s, c.o.stride_h, c.d_o.stride_b, c.d_o.stride_s, c.d_o.stride_h);
   }

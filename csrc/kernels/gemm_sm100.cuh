@@ -62,7 +62,8 @@ constexpr int kTmemCols = 512;
 __host__ __device__ constexpr int a_stage_bytes() { return BLOCK_M * BLOCK_K * 2; }
 __host__ __device__ constexpr int b_stage_bytes(int cta_group) { return (BLOCK_N / cta_group) * BLOCK_K * 2; }
 __host__ __device__ constexpr int smem_bytes(int cta_group, int stages) {
-  return stages * (a_stage_bytes() + b_stage_bytes(cta_group)) + 1024 /*align slack*/ + 256 /*barriers*/;
+  return stages * (a_stage_bytes() + b_stage_bytes(cta_group)) + 1024 /*align slack*/ + 256 /*barriers*/ +
+         kEpiWarps * 4096 /*epilogue store staging*/;
 }
 
 // erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): two MUFU ops + a short FMA chain,
@@ -166,6 +167,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* tfull_bar = bars + 2 * kStages;
   uint64_t* tempty_bar = bars + 2 * kStages + kAccumStages;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccumStages);
+  uint8_t* epi_staging = smem + kStages * (A_STAGE + B_STAGE) + 256;   // kEpiWarps x 4 KB
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -291,6 +293,16 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
         crow = reinterpret_cast<OutT*>(p.peer_c[owner]) +
                (int64_t(p.my_rank) * p.rows_per_rank + (row - owner * p.rows_per_rank)) * p.ldc;
       }
+      const int row_base = tm * TILE_M + int(rank) * BLOCK_M + q * 32;   // global row of lane 0
+      uint8_t* stg = epi_staging + (warp - 4) * 4096;
+      auto c_row_ptr = [&](int grow) -> OutT* {
+        if (p.rows_per_rank > 0) {   // fused GEMM -> reduce-scatter: the row lives in its owner's staging slot
+          const int owner = grow / p.rows_per_rank;
+          return reinterpret_cast<OutT*>(p.peer_c[owner]) +
+                 (int64_t(p.my_rank) * p.rows_per_rank + (grow - owner * p.rows_per_rank)) * p.ldc;
+        }
+        return reinterpret_cast<OutT*>(p.C) + int64_t(grow) * p.ldc;
+      };
       // aux operand (residual / pre-activation) of the NEXT chunk is fetched while the current one is processed: the
       // ~1 us global latency would otherwise sit between every TMEM drain and its store
       uint4 aux_next[4];
@@ -341,21 +353,37 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
             for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __bfloat162float(p.bias[col0 + j]);
           }
         }
-        if (row_ok) {
+        // ---- stores go through a per-warp 32-row x 128-byte staging tile (16-byte units XOR-swizzled by row): every
+        // lane parks its own row, then the warp writes 4 rows x 128 contiguous bytes per instruction (full lines for
+        // HBM and for NVLink peer stores) instead of 32 scattered 16-byte pieces.
+        {
           if (p.aux_out != nullptr) {
-            __nv_bfloat16* ao = p.aux_out + int64_t(row) * p.ld_aux + col0;
-            if (full_chunk) {
+            // pre-activation (bf16): staged in this chunk's half of the tile, flushed at once (64-byte row pieces)
 #pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                uint4 o; __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              uint4 o; __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-                for (int t = 0; t < 4; ++t) o2[t] = __floats2bfloat162_rn(v[j4 * 8 + t * 2], v[j4 * 8 + t * 2 + 1]);
-                reinterpret_cast<uint4*>(ao)[j4] = o;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (col0 + j < p.N) ao[j] = __float2bfloat16(v[j]);
+              for (int t = 0; t < 4; ++t) o2[t] = __floats2bfloat162_rn(v[j4 * 8 + t * 2], v[j4 * 8 + t * 2 + 1]);
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((((cc & 1) * 4 + j4) ^ (lane & 7)) << 4)) = o;
             }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int rl = it * 8 + (lane >> 2), u = lane & 3;
+              const int grow = row_base + rl, gcol = col0 + u * 8;
+              if (grow < p.M && gcol < p.N) {
+                const uint4 val = *reinterpret_cast<const uint4*>(stg + rl * 128 + ((((cc & 1) * 4 + u) ^ (rl & 7)) << 4));
+                __nv_bfloat16* dst = p.aux_out + int64_t(grow) * p.ld_aux + gcol;
+                if (gcol + 8 <= p.N) *reinterpret_cast<uint4*>(dst) = val;
+                else {
+                  const uint32_t w4[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+                  for (int t = 0; t < 8; ++t)
+                    if (gcol + t < p.N) dst[t] = __ushort_as_bfloat16((unsigned short)(w4[t >> 1] >> ((t & 1) * 16)));
+                }
+              }
+            }
+            __syncwarp();
           }
           if (p.act == ACT_GELU) {
 #pragma unroll
@@ -393,54 +421,75 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) v[j] = apply_aux(v[j], __bfloat162float(ai[j]), p.aux_mode);
+                if (row_ok && col0 + j < p.N) v[j] = apply_aux(v[j], __bfloat162float(ai[j]), p.aux_mode);
             }
           }
           if constexpr (sizeof(OutT) == 2) {
-            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(crow) + col0;
-            if (full_chunk) {
+            if (p.accumulate && row_ok) {   // rare (bf16 accumulation): old values fetched by the owning lane
+              const __nv_bfloat16* cp = reinterpret_cast<const __nv_bfloat16*>(crow) + col0;
 #pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                if (p.accumulate) {
-                  const uint4 old = reinterpret_cast<const uint4*>(cp)[j4];
-                  const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&old);
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) v[j] += __bfloat162float(cp[j]);
+            }
+            // stage this chunk's 32 bf16 columns into its half of the 64-column tile
 #pragma unroll
-                  for (int t = 0; t < 4; ++t) {
-                    const float2 f = __bfloat1622float2(o2[t]);
-                    v[j4 * 8 + t * 2] += f.x; v[j4 * 8 + t * 2 + 1] += f.y;
+            for (int j4 = 0; j4 < 4; ++j4) {
+              uint4 o; __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) o2[t] = __floats2bfloat162_rn(v[j4 * 8 + t * 2], v[j4 * 8 + t * 2 + 1]);
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((((cc & 1) * 4 + j4) ^ (lane & 7)) << 4)) = o;
+            }
+            const bool flush = (cc & 1) || (cc + 1 == kChunksPerWarp) || (col0 + 32 >= p.N);
+            if (flush) {
+              __syncwarp();
+              const int span0 = col0 - (cc & 1) * 32;
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int rl = it * 4 + (lane >> 3), u = lane & 7;
+                const int grow = row_base + rl, gcol = span0 + u * 8;
+                if (grow < p.M && gcol < p.N && (u < 4 || (cc & 1))) {
+                  const uint4 val = *reinterpret_cast<const uint4*>(stg + rl * 128 + ((u ^ (rl & 7)) << 4));
+                  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(c_row_ptr(grow)) + gcol;
+                  if (gcol + 8 <= p.N) *reinterpret_cast<uint4*>(dst) = val;
+                  else {
+                    const uint32_t w4[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+                      if (gcol + t < p.N) dst[t] = __ushort_as_bfloat16((unsigned short)(w4[t >> 1] >> ((t & 1) * 16)));
                   }
                 }
-                uint4 o; __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) o2[t] = __floats2bfloat162_rn(v[j4 * 8 + t * 2], v[j4 * 8 + t * 2 + 1]);
-                reinterpret_cast<uint4*>(cp)[j4] = o;
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) {
-                  float x = v[j];
-                  if (p.accumulate) x += __bfloat162float(cp[j]);
-                  cp[j] = __float2bfloat16(x);
-                }
+              __syncwarp();
             }
           } else {
-            float* cp = reinterpret_cast<float*>(crow) + col0;
-            if (full_chunk) {
+            // fp32 output: the 32 columns of this chunk are one 128-byte row of the staging tile
 #pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                float4 o = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-                if (p.accumulate) {
-                  const float4 old = reinterpret_cast<const float4*>(cp)[j4];
-                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            for (int j4 = 0; j4 < 8; ++j4)
+              *reinterpret_cast<float4*>(stg + lane * 128 + ((j4 ^ (lane & 7)) << 4)) =
+                  make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rl = it * 4 + (lane >> 3), u = lane & 7;
+              const int grow = row_base + rl, gcol = col0 + u * 4;
+              if (grow < p.M && gcol < p.N) {
+                float4 val = *reinterpret_cast<const float4*>(stg + rl * 128 + ((u ^ (rl & 7)) << 4));
+                float* dst = reinterpret_cast<float*>(c_row_ptr(grow)) + gcol;
+                if (gcol + 4 <= p.N) {
+                  if (p.accumulate) {
+                    const float4 old = *reinterpret_cast<const float4*>(dst);
+                    val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+                  }
+                  *reinterpret_cast<float4*>(dst) = val;
+                } else {
+                  const float e4[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+                  for (int t = 0; t < 4; ++t)
+                    if (gcol + t < p.N) dst[t] = p.accumulate ? dst[t] + e4[t] : e4[t];
                 }
-                reinterpret_cast<float4*>(cp)[j4] = o;
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) cp[j] = p.accumulate ? cp[j] + v[j] : v[j];
             }
+            __syncwarp();
           }
         }
       }

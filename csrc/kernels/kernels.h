@@ -95,12 +95,33 @@ struct AdamArgs {
   void* param_bf16 = nullptr;  // optional bf16 [n] compute copy
   int64_t n = 0;
   float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, weight_decay = 0.0f;
-  const int64_t* step_ptr = nullptr;     // device pointer; value already incremented for this step
+  const int64_t* step_ptr = nullptr;     // device step counter
+  int step_add = 0;                      // bias correction uses *step_ptr + step_add (counter bumped later, in one batch)
   const float* grad_scale_ptr = nullptr; // device pointer or null
   const float* lr_ptr = nullptr;         // device pointer overriding lr (scheduler) or null
   bool zero_grad = false;                // clear the grad buffer in the same pass
 };
 cudaError_t adam_update(const AdamArgs& a, cudaStream_t s);
+// ZeRO fused update over symmetric memory: ONE kernel per parameter
+//   grad   = grad_scale * sum over `nslots` bf16 gradient slots (the GEMM->peer-store epilogue of the weight-gradient
+//            GEMMs filled slot s with rank s's partial sum of this rank's rows)          -> the reduce-scatter
+//   m, v, fp32 master of this rank's shard are updated (AdamW)                            -> the optimizer
+//   the new bf16 shard is stored into EVERY rank's parameter tensor through peer pointers -> the all-gather
+struct AdamZeroArgs {
+  float* master = nullptr; float* m = nullptr; float* v = nullptr;   // fp32 shard [n]
+  const void* slots = nullptr;      // bf16 [nslots, slot_stride] (this rank's symmetric staging area)
+  int nslots = 1;
+  int64_t slot_stride = 0;          // elements between slots
+  void* peer_param[8] = {nullptr};  // bf16 destination of this shard inside each rank's (symmetric) parameter tensor
+  int world = 1;
+  int64_t n = 0;
+  float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, weight_decay = 0.0f, grad_scale = 1.0f;
+  const int64_t* step_ptr = nullptr;   // device step counter
+  int step_add = 0;                    // bias correction uses *step_ptr + step_add (counter bumped later in one batch)
+};
+cudaError_t adam_zero_fused(const AdamZeroArgs& a, cudaStream_t s);
+// counters[i] += 1 for a device table of int64 pointers (one launch for all optimizer step counters)
+cudaError_t increment_many_i64(int64_t* const* table, int count, cudaStream_t s);
 cudaError_t sgd_update(float* master, float* momentum_buf, const void* grad, bool grad_is_bf16, void* param_bf16,
                        int64_t n, float lr, float momentum, bool nesterov, float weight_decay, cudaStream_t s);
 cudaError_t increment_step(int64_t* step_ptr, cudaStream_t s);

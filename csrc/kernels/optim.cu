@@ -18,14 +18,14 @@ struct AdamDev {
   void* param_bf16;
   int64_t n;
   float lr, beta1, beta2, eps, wd;
-  const int64_t* step_ptr;
+  const int64_t* step_ptr; int step_add;
   const float* grad_scale_ptr;
   const float* lr_ptr;
   int zero_grad;
 };
 
 __global__ void __launch_bounds__(256) adam_kernel(AdamDev a) {
-  const float step = a.step_ptr ? float(*a.step_ptr) : 1.0f;
+  const float step = a.step_ptr ? float(*a.step_ptr + a.step_add) : 1.0f;
   const float gscale = a.grad_scale_ptr ? *a.grad_scale_ptr : 1.0f;
   const float lr = a.lr_ptr ? *a.lr_ptr : a.lr;
   const float bc1 = 1.0f - __powf(a.beta1, step);
@@ -143,9 +143,112 @@ cudaError_t adam_update(const AdamArgs& a, cudaStream_t s) {
   AdamDev d;
   d.master = a.master; d.m = a.m; d.v = a.v; d.grad = a.grad; d.grad_is_bf16 = a.grad_is_bf16 ? 1 : 0;
   d.param_bf16 = a.param_bf16; d.n = a.n; d.lr = a.lr; d.beta1 = a.beta1; d.beta2 = a.beta2; d.eps = a.eps;
-  d.wd = a.weight_decay; d.step_ptr = a.step_ptr; d.grad_scale_ptr = a.grad_scale_ptr; d.lr_ptr = a.lr_ptr;
+  d.wd = a.weight_decay; d.step_ptr = a.step_ptr; d.step_add = a.step_add; d.grad_scale_ptr = a.grad_scale_ptr; d.lr_ptr = a.lr_ptr;
   d.zero_grad = a.zero_grad ? 1 : 0;
   adam_kernel<<<grid_for(a.n >> 2), 256, 0, s>>>(d);
+  count_launch();
+  return cudaGetLastError();
+}
+namespace {
+struct AdamZeroDev {
+  float* master; float* m; float* v;
+  const __nv_bfloat16* slots; int nslots; int64_t slot_stride;
+  __nv_bfloat16* peer[8]; int world;
+  int64_t n;
+  float lr, beta1, beta2, eps, wd, gscale;
+  const int64_t* step_ptr; int step_add;
+};
+__global__ void __launch_bounds__(256) adam_zero_fused_kernel(AdamZeroDev a) {
+  const float step = float((a.step_ptr ? *a.step_ptr : 0) + a.step_add);
+  const float bc1 = 1.0f - __powf(a.beta1, step);
+  const float bc2 = 1.0f - __powf(a.beta2, step);
+  const float step_size = a.lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const int64_t nvec = a.n >> 3;   // 8 elements (16 bytes of bf16) per thread-iteration
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < nvec; i += int64_t(gridDim.x) * blockDim.x) {
+    float g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = 0.f;
+    for (int s = 0; s < a.nslots; ++s) {
+      const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(a.slots + int64_t(s) * a.slot_stride) + i);
+      const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(b[j]);
+        g[2 * j] += f.x; g[2 * j + 1] += f.y;
+      }
+    }
+    float p[8], m[8], v[8];
+    *reinterpret_cast<float4*>(p) = reinterpret_cast<const float4*>(a.master)[2 * i];
+    *reinterpret_cast<float4*>(p + 4) = reinterpret_cast<const float4*>(a.master)[2 * i + 1];
+    *reinterpret_cast<float4*>(m) = reinterpret_cast<const float4*>(a.m)[2 * i];
+    *reinterpret_cast<float4*>(m + 4) = reinterpret_cast<const float4*>(a.m)[2 * i + 1];
+    *reinterpret_cast<float4*>(v) = reinterpret_cast<const float4*>(a.v)[2 * i];
+    *reinterpret_cast<float4*>(v + 4) = reinterpret_cast<const float4*>(a.v)[2 * i + 1];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gj = g[j] * a.gscale;
+      m[j] = a.beta1 * m[j] + (1.0f - a.beta1) * gj;
+      v[j] = a.beta2 * v[j] + (1.0f - a.beta2) * gj * gj;
+      const float denom = sqrtf(v[j]) * inv_sqrt_bc2 + a.eps;
+      p[j] = p[j] - step_size * (m[j] / denom) - a.lr * a.wd * p[j];
+    }
+    reinterpret_cast<float4*>(a.master)[2 * i] = *reinterpret_cast<const float4*>(p);
+    reinterpret_cast<float4*>(a.master)[2 * i + 1] = *reinterpret_cast<const float4*>(p + 4);
+    reinterpret_cast<float4*>(a.m)[2 * i] = *reinterpret_cast<const float4*>(m);
+    reinterpret_cast<float4*>(a.m)[2 * i + 1] = *reinterpret_cast<const float4*>(m + 4);
+    reinterpret_cast<float4*>(a.v)[2 * i] = *reinterpret_cast<const float4*>(v);
+    reinterpret_cast<float4*>(a.v)[2 * i + 1] = *reinterpret_cast<const float4*>(v + 4);
+    uint4 o;
+    __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(p[2 * j], p[2 * j + 1]);
+    for (int r = 0; r < a.world; ++r) reinterpret_cast<uint4*>(a.peer[r])[i] = o;   // all-gather by peer stores
+  }
+  if (blockIdx.x == 0) {   // scalar tail (n not a multiple of 8)
+    for (int64_t i = (nvec << 3) + threadIdx.x; i < a.n; i += blockDim.x) {
+      float g = 0.f;
+      for (int s = 0; s < a.nslots; ++s) g += __bfloat162float(a.slots[int64_t(s) * a.slot_stride + i]);
+      g *= a.gscale;
+      const float m = a.beta1 * a.m[i] + (1.0f - a.beta1) * g;
+      const float v = a.beta2 * a.v[i] + (1.0f - a.beta2) * g * g;
+      float p = a.master[i];
+      p = p - step_size * (m / (sqrtf(v) * inv_sqrt_bc2 + a.eps)) - a.lr * a.wd * p;
+      a.master[i] = p; a.m[i] = m; a.v[i] = v;
+      for (int r = 0; r < a.world; ++r) a.peer[r][i] = __float2bfloat16(p);
+    }
+  }
+}
+__global__ void increment_many_kernel(int64_t* const* table, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) *table[i] += 1;
+}
+}  // namespace
+
+cudaError_t adam_zero_fused(const AdamZeroArgs& a, cudaStream_t s) {
+  if (a.n == 0) return cudaSuccess;
+  if (a.world > 8 || a.nslots < 1) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(a.master) | reinterpret_cast<uintptr_t>(a.m) | reinterpret_cast<uintptr_t>(a.v) |
+       reinterpret_cast<uintptr_t>(a.slots)) & 15)
+    return cudaErrorMisalignedAddress;
+  if ((a.slot_stride & 7) != 0 && a.nslots > 1) return cudaErrorMisalignedAddress;
+  AdamZeroDev d;
+  d.master = a.master; d.m = a.m; d.v = a.v;
+  d.slots = reinterpret_cast<const __nv_bfloat16*>(a.slots); d.nslots = a.nslots; d.slot_stride = a.slot_stride;
+  for (int r = 0; r < 8; ++r) {
+    d.peer[r] = reinterpret_cast<__nv_bfloat16*>(r < a.world ? a.peer_param[r] : nullptr);
+    if (r < a.world && (reinterpret_cast<uintptr_t>(a.peer_param[r]) & 15)) return cudaErrorMisalignedAddress;
+  }
+  d.world = a.world; d.n = a.n;
+  d.lr = a.lr; d.beta1 = a.beta1; d.beta2 = a.beta2; d.eps = a.eps; d.wd = a.weight_decay; d.gscale = a.grad_scale;
+  d.step_ptr = a.step_ptr; d.step_add = a.step_add;
+  adam_zero_fused_kernel<<<grid_for(a.n >> 3), 256, 0, s>>>(d);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t increment_many_i64(int64_t* const* table, int count, cudaStream_t s) {
+  if (count <= 0) return cudaSuccess;
+  increment_many_kernel<<<(count + 255) / 256, 256, 0, s>>>(table, count);
   count_launch();
   return cudaGetLastError();
 }
