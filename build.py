@@ -22,6 +22,7 @@ CUDA_SOURCES = [
     "csrc/kernels/embedding_loss.cu",
     "csrc/kernels/optim.cu",
     "csrc/kernels/moe.cu",
+    "csrc/kernels/quant_fp8.cu",
     "csrc/kernels/symm_comm.cu",
 ]
 CXX_SOURCES = [

@@ -373,6 +373,134 @@ HB_REGISTER_OP(linear_dgrad, "linear_dgrad", 1, 0, linear_dgrad_compute, nullptr
 HB_REGISTER_OP(linear_wgrad, "linear_wgrad", 1, 0, linear_wgrad_compute, nullptr, wgrad_deduce, nullptr);
 HB_REGISTER_OP(bias_grad, "bias_grad", 1, 0, bias_grad_compute, nullptr, bias_grad_deduce, nullptr);
 
+// ------------------------------------------------------------------ fp8 linear (block-scaled e4m3, fp32 accumulate)
+// y = act(x W^T + b) with x and W quantised per 1 x K block (one fp32 scale per row of the K-major operand); the scales
+// factor out of the contraction and are applied in the tcgen05 (kind::f8f6f4) GEMM epilogue.  Backward: the input
+// gradient runs in fp8 as well (dy rows x W^T rows), the weight gradient stays in bf16.
+static void run_gemm_fp8(const at::Tensor& qa, const at::Tensor& sa, const at::Tensor& qb, const at::Tensor& sb, at::Tensor& C,
+                         int64_t M, int64_t N, int64_t K, const at::Tensor* bias, int act, at::Tensor* aux_out, const at::Tensor* aux_in,
+                         int aux_mode) {
+  GemmCall c;
+  c.A = qa.data_ptr(); c.B = qb.data_ptr(); c.C = C.data_ptr();
+  c.M = (int)M; c.N = (int)N; c.K = (int)K;
+  c.lda = qa.stride(0); c.ldb = qb.stride(0); c.ldc = C.stride(0);
+  c.fp8 = true; c.row_scale = sa.data_ptr<float>(); c.col_scale = sb.data_ptr<float>();
+  c.out = C.scalar_type() == at::kFloat ? GemmOut::FP32 : GemmOut::BF16;
+  if (bias) c.bias = bias->data_ptr();
+  if (aux_in) { c.aux_in = aux_in->data_ptr(); c.aux_mode = aux_mode; c.ld_aux = aux_in->stride(0); }
+  if (aux_out) { c.aux_out = aux_out->data_ptr(); c.ld_aux = aux_out->stride(0); }
+  c.act = act;
+  cuda_ok(gemm_bf16(c, cur_stream()), "tcgen05 fp8 gemm");
+}
+static std::pair<at::Tensor, at::Tensor> quant_rows(const at::Tensor& x2) {
+  at::Tensor q = at::empty(x2.sizes(), x2.options().dtype(at::kByte));
+  at::Tensor s = at::empty({x2.size(0)}, x2.options().dtype(at::kFloat));
+  cuda_ok(quantize_rowwise_e4m3(x2.data_ptr(), q.data_ptr(), s.data_ptr<float>(), x2.size(0), (int)x2.size(1), x2.stride(0), q.stride(0),
+                                cur_stream()), "quantize_rowwise_e4m3");
+  return {q, s};
+}
+// emulation of the same numerics with ATen (CPU tests / reference): round operands through e4m3 with row scales
+static at::Tensor fake_quant_rows(const at::Tensor& x2) {
+  at::Tensor xf = x2.to(at::kFloat);
+  at::Tensor sc = (xf.abs().amax(-1, true) / 448.0).clamp_min(1e-30);
+  at::Tensor y = xf / sc;
+  if (at::hasCUDA() || true) y = y.to(at::kFloat8_e4m3fn).to(at::kFloat);
+  return y * sc;
+}
+static Ts linear_fp8_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const bool has_bias = op.attrs.b("has_bias");
+  const int act = act_code(op.attrs.s("act"));
+  const at::Tensor& x = in[0];
+  const at::Tensor& w = in[1];
+  const at::Tensor* bias = has_bias ? &in[2] : nullptr;
+  const int64_t N = w.size(0), K = x.size(-1);
+  std::vector<int64_t> oshape = x.sizes().vec();
+  oshape.back() = N;
+  if (x.is_meta()) {
+    Ts out = {at::empty(oshape, x.options())};
+    if (act != ACT_NONE) out.push_back(at::empty(oshape, x.options()));
+    return out;
+  }
+  at::Tensor x2 = flatten_rows(x).contiguous();
+  const int64_t M = x2.size(0);
+  if (gemm_ok(x2) && gemm_ok(w) && K % 16 == 0 && N % 8 == 0) {
+    auto qx = quant_rows(x2);
+    auto qw = quant_rows(w);
+    at::Tensor y = at::empty({M, N}, x.options()), pre;
+    if (act != ACT_NONE) pre = at::empty({M, N}, x.options());
+    run_gemm_fp8(qx.first, qx.second, qw.first, qw.second, y, M, N, K, bias, act, act != ACT_NONE ? &pre : nullptr, nullptr, 0);
+    Ts out = {y.reshape(oshape)};
+    if (act != ACT_NONE) out.push_back(pre.reshape(oshape));
+    return out;
+  }
+  if (is_native(x)) note_fallback("linear_fp8");
+  at::Tensor y = at::matmul(fake_quant_rows(x2), fake_quant_rows(w).t());
+  if (bias) y = y + bias->to(at::kFloat);
+  Ts out;
+  if (act != ACT_NONE) {
+    at::Tensor pre = y.to(x.scalar_type());
+    out = {aten_act(pre, act).reshape(oshape), pre.reshape(oshape)};
+  } else out = {y.to(x.scalar_type()).reshape(oshape)};
+  return out;
+}
+// dx = dy W  in fp8: dy [M, N] quantised per row, W^T [K, N] quantised per row of W^T (= per input feature)
+static Ts linear_fp8_dgrad_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& dy = in[0];
+  const at::Tensor& w = in[1];
+  const int64_t N = w.size(0), K = w.size(1);
+  std::vector<int64_t> oshape = dy.sizes().vec();
+  oshape.back() = K;
+  if (dy.is_meta()) return {at::empty(oshape, dy.options())};
+  at::Tensor d2 = flatten_rows(dy).contiguous();
+  const int64_t M = d2.size(0);
+  if (gemm_ok(d2) && gemm_ok(w) && N % 16 == 0 && K % 8 == 0) {
+    auto qd = quant_rows(d2);
+    at::Tensor qwt = at::empty({K, N}, w.options().dtype(at::kByte));
+    at::Tensor swt = at::empty({K}, w.options().dtype(at::kFloat));
+    cuda_ok(quantize_transpose_e4m3(w.data_ptr(), qwt.data_ptr(), swt.data_ptr<float>(), N, (int)K, N, cur_stream()),
+            "quantize_transpose_e4m3");
+    at::Tensor dx = at::empty({M, K}, dy.options());
+    if (in.size() > 2) {
+      at::Tensor pre = flatten_rows(in[2]).contiguous();
+      run_gemm_fp8(qd.first, qd.second, qwt, swt, dx, M, K, N, nullptr, ACT_NONE, nullptr, &pre, act_bwd_mode(op.attrs.s("act_bwd")));
+    } else run_gemm_fp8(qd.first, qd.second, qwt, swt, dx, M, K, N, nullptr, ACT_NONE, nullptr, nullptr, 0);
+    return {dx.reshape(oshape)};
+  }
+  if (is_native(dy)) note_fallback("linear_fp8_dgrad");
+  at::Tensor dxa = at::matmul(fake_quant_rows(d2), fake_quant_rows(w.t().contiguous()).t()).to(dy.scalar_type()).reshape(oshape);
+  if (in.size() > 2) dxa = aten_act_bwd(dxa, in[2], op.attrs.s("act_bwd"));
+  return {dxa};
+}
+static TensorList linear_fp8_grad(OpDef& op, const TensorList& g) {
+  Graph* gr = op.graph;
+  const bool has_bias = op.attrs.b("has_bias");
+  const std::string act = op.attrs.s("act");
+  Tensor dy = g[0];
+  HB_CHECK(dy != nullptr) << "linear_fp8 without an output gradient";
+  TensorList res(op.inputs.size());
+  Tensor dpre = dy;
+  if (!act.empty() && act != "none") {
+    OpDef* p = dy->producer;
+    if (p != nullptr && (p->type == "linear_fp8_dgrad" || p->type == "linear_dgrad") && p->inputs.size() == 2 && dy->consumers.empty()) {
+      AttrMap a = p->attrs;
+      a.set("act_bwd", act);
+      dpre = gr->make_op1(p->type, {p->inputs[0], p->inputs[1], op.outputs[1]}, a);
+    } else {
+      AttrMap a;
+      a.set("kind", act);
+      dpre = gr->make_op1("unary_act_bwd", {dy, op.outputs[1]}, a);
+    }
+  }
+  AttrMap a;
+  a.set("trans_b", true);
+  if (op.inputs[0]->requires_grad) res[0] = gr->make_op1("linear_fp8_dgrad", {dpre, op.inputs[1]}, a);
+  if (op.inputs[1]->requires_grad) res[1] = gr->make_op1("linear_wgrad", {dpre, op.inputs[0]}, a);
+  if (has_bias && op.inputs[2]->requires_grad) res[2] = gr->make_op1("bias_grad", {dpre});
+  return res;
+}
+HB_REGISTER_OP(linear_fp8, "linear_fp8", -1, 0, linear_fp8_compute, linear_fp8_grad, linear_deduce, linear_infer);
+HB_REGISTER_OP(linear_fp8_dgrad, "linear_fp8_dgrad", 1, 0, linear_fp8_dgrad_compute, nullptr, dgrad_deduce, nullptr);
+
 // matmul(a, b, trans_a, trans_b): general 2-D matmul (autograd VJP for the long tail)
 static Ts matmul_compute(const OpDef& op, const Ts& in, RunCtx*) {
   const bool ta = op.attrs.b("trans_a"), tb = op.attrs.b("trans_b");

@@ -25,9 +25,9 @@ int num_sms() {
   return n;
 }
 
-template <int G, bool AMN, bool BMN, int ST, typename OutT>
+template <int G, bool AMN, bool BMN, int ST, typename OutT, bool FP8 = false>
 cudaError_t launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  auto kern = gemm_bf16_sm100_kernel<G, AMN, BMN, ST, OutT>;
+  auto kern = gemm_bf16_sm100_kernel<G, AMN, BMN, ST, OutT, FP8>;
   constexpr int smem = gemm_detail::smem_bytes(G, ST);
   static bool attr_set = false;
   if (!attr_set) {
@@ -70,7 +70,8 @@ cudaError_t gemm_bf16(const GemmCall& c, cudaStream_t stream) {
   if (c.M <= 0 || c.N <= 0) return cudaSuccess;
   if (c.K <= 0) return cudaErrorInvalidValue;
   // TMA needs 16-byte aligned bases and row strides.
-  if ((reinterpret_cast<uintptr_t>(c.A) & 15) || (reinterpret_cast<uintptr_t>(c.B) & 15) || (c.lda & 7) || (c.ldb & 7))
+  if ((reinterpret_cast<uintptr_t>(c.A) & 15) || (reinterpret_cast<uintptr_t>(c.B) & 15)) return cudaErrorMisalignedAddress;
+  if (c.fp8 ? ((c.lda & 15) || (c.ldb & 15) || c.a_mn_major || c.b_mn_major) : ((c.lda & 7) || (c.ldb & 7)))
     return cudaErrorMisalignedAddress;
   const int out_elem = c.out == GemmOut::BF16 ? 2 : 4;
   if ((reinterpret_cast<uintptr_t>(c.C) & 15) || ((c.ldc * out_elem) & 15)) return cudaErrorMisalignedAddress;
@@ -81,12 +82,18 @@ cudaError_t gemm_bf16(const GemmCall& c, cudaStream_t stream) {
 
   CUtensorMap ta, tb;
   bool ok;
+  if (c.fp8) {
+    ok = make_tmap_2d_u8(&ta, c.A, (uint64_t)c.K, (uint64_t)c.M, (uint64_t)c.lda, 128, 128) &&
+         make_tmap_2d_u8(&tb, c.B, (uint64_t)c.K, (uint64_t)c.N, (uint64_t)c.ldb, 128, load_n);
+    if (!ok) return cudaErrorInvalidValue;
+  } else {
   if (!c.a_mn_major) ok = make_tmap_2d_bf16(&ta, c.A, (uint64_t)c.K, (uint64_t)c.M, (uint64_t)c.lda, 64, 128);
   else ok = make_tmap_2d_bf16(&ta, c.A, (uint64_t)c.M, (uint64_t)c.K, (uint64_t)c.lda, 64, 64);
   if (!ok) return cudaErrorInvalidValue;
   if (!c.b_mn_major) ok = make_tmap_2d_bf16(&tb, c.B, (uint64_t)c.K, (uint64_t)c.N, (uint64_t)c.ldb, 64, load_n);
   else ok = make_tmap_2d_bf16(&tb, c.B, (uint64_t)c.N, (uint64_t)c.K, (uint64_t)c.ldb, 64, 64);
   if (!ok) return cudaErrorInvalidValue;
+  }
 
   GemmParams p;
   p.M = c.M; p.N = c.N; p.K = c.K;
@@ -108,6 +115,15 @@ cudaError_t gemm_bf16(const GemmCall& c, cudaStream_t stream) {
     for (int i = 0; i < c.world; ++i) p.peer_c[i] = c.peer_c[i];
   }
 
+  p.row_scale = c.row_scale; p.col_scale = c.col_scale;
+  if (c.fp8) {
+    if (G == 2) {
+      if (c.out == GemmOut::BF16) return launch_cfg<2, false, false, 6, __nv_bfloat16, true>(ta, tb, p, stream);
+      return launch_cfg<2, false, false, 6, float, true>(ta, tb, p, stream);
+    }
+    if (c.out == GemmOut::BF16) return launch_cfg<1, false, false, 4, __nv_bfloat16, true>(ta, tb, p, stream);
+    return launch_cfg<1, false, false, 4, float, true>(ta, tb, p, stream);
+  }
   if (G == 2) {
     if (c.out == GemmOut::BF16) return dispatch_major<2, 6, __nv_bfloat16>(c.a_mn_major, c.b_mn_major, ta, tb, p, stream);
     return dispatch_major<2, 6, float>(c.a_mn_major, c.b_mn_major, ta, tb, p, stream);

@@ -46,6 +46,9 @@ struct GemmParams {
   void* peer_c[8];
   int rows_per_rank;
   int my_rank;
+  // fp8 (e4m3) operands: C = (A8 * B8) * row_scale[m] * col_scale[n]  -- scales of a 1 x K block-scaled quantisation
+  const float* row_scale;   // [M] or nullptr
+  const float* col_scale;   // [N] or nullptr
 };
 
 namespace gemm_detail {
@@ -145,7 +148,9 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
 
 }  // namespace gemm_detail
 
-template <int kCtaGroup, bool kAMN, bool kBMN, int kStages, typename OutT>
+// kFp8: both operands are e4m3 bytes (K-major only); a 128-byte swizzle row then holds 128 K elements and one
+// tcgen05.mma.kind::f8f6f4 consumes 32 of them -- the smem stage size, descriptor strides and pipeline are unchanged.
+template <int kCtaGroup, bool kAMN, bool kBMN, int kStages, typename OutT, bool kFp8 = false>
 __global__ void __launch_bounds__(gemm_detail::kNumThreads, 1)
 gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
                        const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
@@ -177,7 +182,9 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int tiles_m = (p.M + TILE_M - 1) / TILE_M;
   const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = tiles_m * tiles_n;
-  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  constexpr int BLOCK_K_E = kFp8 ? BLOCK_K * 2 : BLOCK_K;   // K elements per stage (128 bytes per row either way)
+  static_assert(!kFp8 || (!kAMN && !kBMN), "fp8 operands must be K-major");
+  const int num_kb = (p.K + BLOCK_K_E - 1) / BLOCK_K_E;
   const int cluster_id = blockIdx.x / kCtaGroup;
   const int num_clusters = gridDim.x / kCtaGroup;
 
@@ -218,7 +225,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (kCtaGroup == 1 || leader) ptx::mbar_arrive_expect_tx(&full_bar[s], kTxBytes);
           uint8_t* sa = smem_a + s * A_STAGE;
           uint8_t* sb = smem_b + s * B_STAGE;
-          const int k0 = kb * BLOCK_K;
+          const int k0 = kb * BLOCK_K_E;
           if constexpr (kCtaGroup == 1) {
             if constexpr (!kAMN) ptx::tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m0);
             else
@@ -243,7 +250,8 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp == 1) {
     // ========================= MMA issuer (leader CTA, one thread) =========================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc(TILE_M, BLOCK_N, 1, 1, kAMN, kBMN);
+      constexpr uint32_t idesc = kFp8 ? ptx::make_idesc(TILE_M, BLOCK_N, 0, 0, false, false)      // e4m3 x e4m3 -> f32
+                                      : ptx::make_idesc(TILE_M, BLOCK_N, 1, 1, kAMN, kBMN);
       const uint64_t a_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a), kAMN ? kAtomBytes : 0, 1024);
       const uint64_t b_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b), kBMN ? kAtomBytes : 0, 1024);
       // descriptor-address increments (units of 16 B) per UMMA_K step
@@ -262,8 +270,12 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const uint64_t b_desc = b_desc0 + uint64_t(s * (B_STAGE >> 4));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            ptx::mma_f16_ss<kCtaGroup>(tmem_d, a_desc + uint64_t(k * a_kstep), b_desc + uint64_t(k * b_kstep), idesc,
-                                       (kb > 0 || k > 0) ? 1u : 0u);
+            if constexpr (kFp8)
+              ptx::mma_f8_ss<kCtaGroup>(tmem_d, a_desc + uint64_t(k * a_kstep), b_desc + uint64_t(k * b_kstep), idesc,
+                                        (kb > 0 || k > 0) ? 1u : 0u);
+            else
+              ptx::mma_f16_ss<kCtaGroup>(tmem_d, a_desc + uint64_t(k * a_kstep), b_desc + uint64_t(k * b_kstep), idesc,
+                                         (kb > 0 || k > 0) ? 1u : 0u);
           }
           ptx::mma_commit<kCtaGroup>(&empty_bar[s]);
           if (kb == num_kb - 1) ptx::mma_commit<kCtaGroup>(&tfull_bar[as]);
@@ -334,6 +346,20 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (p.alpha != 1.0f) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+        }
+        if constexpr (kFp8) {
+          const float rs = (p.row_scale != nullptr && row_ok) ? p.row_scale[row] : 1.0f;
+          if (p.col_scale != nullptr && full_chunk) {
+            const float4* cs4 = reinterpret_cast<const float4*>(p.col_scale + col0);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 c4 = __ldg(cs4 + j4);
+              v[j4 * 4] *= rs * c4.x; v[j4 * 4 + 1] *= rs * c4.y; v[j4 * 4 + 2] *= rs * c4.z; v[j4 * 4 + 3] *= rs * c4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= rs * ((p.col_scale != nullptr && col0 + j < p.N) ? p.col_scale[col0 + j] : 1.0f);
+          }
         }
         if (p.bias != nullptr) {
           if (full_chunk) {

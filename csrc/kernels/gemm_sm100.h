@@ -40,6 +40,10 @@ struct GemmCall {
   void* const* peer_c = nullptr;   // host array of `world` mapped staging buffers, each [world, rows_per_rank, N]
   int world = 1, my_rank = 0, rows_per_rank = 0;
   int cta_group = 0;  // 0 = auto (2), 1 or 2 to force
+  // fp8 path: A [M, lda] and B [N, ldb] hold e4m3 bytes (K-major), the result is scaled by row_scale[m] * col_scale[n]
+  bool fp8 = false;
+  const float* row_scale = nullptr;
+  const float* col_scale = nullptr;
 };
 
 // Returns cudaSuccess or an error; never silently falls back to a library.

@@ -54,6 +54,13 @@ cudaError_t rotary_apply(const void* x, void* y, const int32_t* pos, int64_t tok
                          int rot_dim, float base, bool inverse, int64_t token_stride, cudaStream_t s, int group_size = 0,
                          int group_stride = 0);   // grouped layouts: head h -> (h / group_size) * group_stride + (h % group_size) * head_dim
 
+// ---------------------------------------------------------------- fp8 quantisation (quant_fp8.cu)
+// q[r, :] = e4m3(x[r, :] / scale[r]) with scale[r] = amax(row r) / 448
+cudaError_t quantize_rowwise_e4m3(const void* x, void* q, float* scale, int64_t rows, int cols, int64_t ldx, int64_t ldq,
+                                  cudaStream_t s);
+// q[c, r] = e4m3(x[r, c] / scale[c]) with one scale per column of x (transposed, K-major operand of the dgrad GEMM)
+cudaError_t quantize_transpose_e4m3(const void* x, void* q, float* scale, int64_t rows, int cols, int64_t ldq, cudaStream_t s);
+
 // ---------------------------------------------------------------- embedding (ref: hetu/impl/kernel/EmbeddingLookup.cu:91,140)
 // y[t, :] = wte[ids[t], :] (+ wpe[pos[t], :])
 cudaError_t embedding_fwd(const int64_t* ids, const int32_t* pos, const void* wte, const void* wpe, void* y,

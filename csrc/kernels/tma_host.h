@@ -63,4 +63,12 @@ inline bool make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner
   return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+inline bool make_tmap_2d_u8(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
+                            uint32_t box_inner, uint32_t box_outer) {
+  uint64_t dims[2] = {inner, outer};
+  uint64_t strides[1] = {outer_stride_bytes};
+  uint32_t box[2] = {box_inner, box_outer};
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 }  // namespace hb

@@ -19,6 +19,7 @@ from ..parallel_config import generate_ds_parallel_config
 
 @dataclass
 class LlamaConfig:
+    # (fp8=True runs the four projection GEMMs of every block in block-scaled e4m3, see ops.linear_fp8)
     vocab_size: int = 32000
     hidden_size: int = 4096
     intermediate_size: int = 11008
@@ -33,6 +34,7 @@ class LlamaConfig:
     dtype: str = "float32"
     cp_ranks: tuple = ()            # context-parallel ring (global ranks); empty = no CP
     recompute_layers: tuple = ()
+    fp8: bool = False               # projection GEMMs in block-scaled e4m3 (fwd + dgrad), weight gradients in bf16
 
     @property
     def kv_heads(self):
@@ -62,6 +64,7 @@ class LlamaAttention(Module):
         self.dense = HtMultiRowParallelLinear(h, h, get_multi_ds_parallel_config(ds_parallel_configs, "dense", layer_idx),
                                               sequence_parallel=config.sequence_parallel, bias=False, dtype=config.dtype,
                                               name=f"{name}_dense", init_std=std / math.sqrt(2.0 * config.num_hidden_layers))
+        self.qkv_dense.fp8 = self.dense.fp8 = config.fp8
 
     def forward(self, x, seq_len, residual=None, pos_offset=0):
         tp = self.qkv_dense.tp[0]
@@ -99,6 +102,7 @@ class LlamaMLP(Module):
         self.dense_4h_to_h = HtMultiRowParallelLinear(f, h, get_multi_ds_parallel_config(ds_parallel_configs, "dense_4h_to_h", layer_idx),
                                                       sequence_parallel=config.sequence_parallel, bias=False, dtype=config.dtype,
                                                       name=f"{name}_down", init_std=std / math.sqrt(2.0 * config.num_hidden_layers))
+        self.dense_h_to_4h.fp8 = self.dense_4h_to_h.fp8 = config.fp8
 
     def forward(self, x, residual=None):
         return self.dense_4h_to_h(ops.swiglu(self.dense_h_to_4h(x), interleaved=True), residual=residual)

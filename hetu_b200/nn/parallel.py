@@ -171,10 +171,16 @@ class HtMultiColumnParallelLinear(_ParallelBase):
         self.bias = parallel_parameter(zeros_initializer(), [out_features], self.ds_dup_split0(), dtype=dtype, requires_grad=True,
                                        device_group_hierarchy=self.device_group_unions, name=f"{name}_bias") if bias else None
 
+    fp8 = False   # set per instance (or via model config) to run the GEMM in block-scaled e4m3
+
     def forward(self, x, act="none"):
         x = self._adapt(x, self.ds_split0_dup())   # sequence-parallel inputs are all-gathered here
-        y = ops.linear(x, self.weight, self.bias, trans_b=True, act=act, device_group_hierarchy=self.device_group_unions,
-                       name=f"linear_{self.name}")
+        if self.fp8:
+            y = ops.linear_fp8(x, self.weight, self.bias, act=act, device_group_hierarchy=self.device_group_unions,
+                               name=f"linear_{self.name}")
+        else:
+            y = ops.linear(x, self.weight, self.bias, trans_b=True, act=act, device_group_hierarchy=self.device_group_unions,
+                           name=f"linear_{self.name}")
         if self.gather_output:
             y = self._adapt(y, self.ds_split0_dup())
         return y
@@ -206,14 +212,22 @@ class HtMultiRowParallelLinear(_ParallelBase):
         self.bias = parallel_parameter(zeros_initializer(), [out_features], self.ds_w_dup(), dtype=dtype, requires_grad=True,
                                        device_group_hierarchy=self.device_group_unions, name=f"{name}_bias") if bias else None
 
+    fp8 = False
+
     def forward(self, x, residual=None):
         x = self._adapt(x, self.ds_split01())
         tp_any = any(t > 1 for t in self.tp)
         if not tp_any:
+            if self.fp8:
+                y = ops.linear_fp8(x, self.weight, self.bias, device_group_hierarchy=self.device_group_unions, name=f"linear_{self.name}")
+                return y if residual is None else y + residual
             return ops.linear(x, self.weight, self.bias, trans_b=True, residual=residual,
                               device_group_hierarchy=self.device_group_unions, name=f"linear_{self.name}")
-        y = ops.linear(x, self.weight, None, trans_b=True, device_group_hierarchy=self.device_group_unions,
-                       name=f"linear_{self.name}")                      # partial sums
+        if self.fp8:
+            y = ops.linear_fp8(x, self.weight, None, device_group_hierarchy=self.device_group_unions, name=f"linear_{self.name}")
+        else:
+            y = ops.linear(x, self.weight, None, trans_b=True, device_group_hierarchy=self.device_group_unions,
+                           name=f"linear_{self.name}")                      # partial sums
         y = ops.comm(y, self.ds_split0() if self.sequence_parallel else self.ds_split0_dup())
         if self.bias is not None:
             y = y + self.bias

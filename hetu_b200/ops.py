@@ -319,6 +319,14 @@ def linear(x, w, bias=None, trans_a=False, trans_b=True, act="none", residual=No
     return make_op("linear", ins, attrs, **_meta(kw))[0]
 
 
+def linear_fp8(x, w, bias=None, act="none", **kw):
+    """y = act(x @ w^T + bias) with both operands quantised to e4m3 per 1 x K block (fp32 scales applied in the tcgen05 GEMM
+    epilogue); the input-gradient GEMM also runs in fp8, the weight gradient in bf16.  w is [out, in]."""
+    ins = [x, w] + ([bias] if bias is not None else [])
+    attrs = {"trans_b": True, "has_bias": bias is not None, "has_residual": False, "act": str(act)}
+    return make_op("linear_fp8", ins, attrs, **_meta(kw))[0]
+
+
 def bmm(a, b, **kw):
     return _op1("bmm", [a, b], **kw)
 

@@ -237,6 +237,34 @@ def test_swiglu_interleaved():
     close(torch.as_tensor(X.grad.numpy()), xr.grad, 0.05, 0.03)
 
 
+@pytest.mark.parametrize("M,N,K,act", [(1024, 768, 512, "none"), (2048, 1024, 2048, "gelu"), (384, 520, 272, "none")])
+def test_linear_fp8_block_scaled(M, N, K, act):
+    """e4m3 operands with one fp32 scale per 1 x K block, tcgen05 kind::f8f6f4, scales applied in the epilogue"""
+    x, w, b, g = bf(M, K, seed=1), bf(N, K, scale=1 / math.sqrt(K), seed=2), bf(N, seed=3), bf(M, N, seed=4)
+    X, W, B = leaf(x), leaf(w), leaf(b)
+    n0 = ht._C.gemm_launch_count()
+    y = ht.linear_fp8(X, W, B, act=act)
+    ht.sum(y * leaf(g, False)).backward()
+    assert ht._C.gemm_launch_count() - n0 >= 3
+
+    def fq(t):      # the same quantisation in torch: per-row scale, round through e4m3
+        tf = t.float()
+        sc = (tf.abs().amax(-1, keepdim=True) / 448.0).clamp_min(1e-30)
+        return (tf / sc).to(torch.float8_e4m3fn).float() * sc
+    pre = fq(x) @ fq(w).t() + b.float()
+    yq = torch.nn.functional.gelu(pre) if act == "gelu" else pre
+    close(torch.as_tensor(y.numpy()), yq, 0.03, 0.02)                      # exact emulation of the quantised product
+    xr, wr = x.float().requires_grad_(), w.float().requires_grad_()
+    yr = xr @ wr.t() + b.float()
+    yr = torch.nn.functional.gelu(yr) if act == "gelu" else yr
+    (yr * g.float()).sum().backward()
+    # against the unquantised reference: e4m3 carries ~2^-4 relative precision per element, errors average over K
+    assert float((torch.as_tensor(y.numpy()).float().cpu() - yr.detach().cpu()).abs().mean()) < 0.03
+    gerr = (torch.as_tensor(X.grad.numpy()).float().cpu() - xr.grad.cpu()).abs().mean() / xr.grad.abs().mean().cpu()
+    assert float(gerr) < 0.06, float(gerr)
+    close(torch.as_tensor(W.grad.numpy()), wr.grad, 0.05 * math.sqrt(M), 0.06)
+
+
 def test_fused_adam_matches_torch():
     n = 4096 * 33 + 5
     p = torch.randn(n, generator=torch.Generator().manual_seed(1)).cuda()
