@@ -99,6 +99,8 @@ def main():
         cfg = GPTConfig.gpt2_small()
     else:
         raise SystemExit(f"unknown model {args.model}")
+    if int(os.environ.get("BENCH_SP", "0")):
+        cfg.sequence_parallel = True
     S, B = args.seq_len, args.batch_per_gpu
     tp = args.tp
     dp = world // tp
@@ -186,7 +188,7 @@ def main():
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic (random token ids, random-init weights)", "impl": "ours",
             "config": {"model": args.model, "layers": cfg.n_layer, "hidden": cfg.n_embd, "heads": cfg.n_head, "vocab": cfg.vocab_size,
-                       "global_batch": B * dp, "seq_len": S, "parallelism": f"dp{dp}" + (f"tp{tp}" if tp > 1 else "") + " zero (OSDP)",
+                       "global_batch": B * dp, "seq_len": S, "parallelism": f"dp{dp}" + (f"tp{tp}" if tp > 1 else "") + (" sp" if cfg.sequence_parallel else "") + " zero (OSDP)",
                        "l2": "working set per step >> 126 MB L2 (inputs larger than L2)", "optimizer": "AdamW fp32 master"},
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": int(3 * T * 8), "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps},

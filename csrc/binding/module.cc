@@ -562,6 +562,37 @@ PYBIND11_MODULE(_C, m) {
     return out;
   }, py::arg("x"), py::arg("w"), py::arg("staging"), py::arg("bias") = py::none(), py::arg("residual") = py::none());
 
+  // fp8 building blocks (numerics tests / benchmarks)
+  m.def("quantize_rowwise_e4m3", [](const at::Tensor& x) {
+    HB_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 2 && x.is_contiguous()) << "expects contiguous 2-D CUDA bf16";
+    at::Tensor q = at::empty(x.sizes(), x.options().dtype(at::kByte));
+    at::Tensor sc = at::empty({x.size(0)}, x.options().dtype(at::kFloat));
+    cuda_ok(quantize_rowwise_e4m3(x.data_ptr(), q.data_ptr(), sc.data_ptr<float>(), x.size(0), (int)x.size(1), x.stride(0), q.stride(0),
+                                  cur_stream()), "quantize_rowwise_e4m3");
+    return py::make_tuple(q, sc);
+  });
+  m.def("quantize_transpose_e4m3", [](const at::Tensor& x) {
+    HB_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 2 && x.is_contiguous()) << "expects contiguous 2-D CUDA bf16";
+    at::Tensor q = at::empty({x.size(1), x.size(0)}, x.options().dtype(at::kByte));
+    at::Tensor sc = at::empty({x.size(1)}, x.options().dtype(at::kFloat));
+    cuda_ok(quantize_transpose_e4m3(x.data_ptr(), q.data_ptr(), sc.data_ptr<float>(), x.size(0), (int)x.size(1), x.size(0), cur_stream()),
+            "quantize_transpose_e4m3");
+    return py::make_tuple(q, sc);
+  });
+  m.def("gemm_fp8", [](const at::Tensor& qa, const at::Tensor& sa, const at::Tensor& qb, const at::Tensor& sb, bool out_fp32, int cta_group) {
+    const int64_t M = qa.size(0), K = qa.size(1), N = qb.size(0);
+    at::Tensor c = at::empty({M, N}, qa.options().dtype(out_fp32 ? at::kFloat : at::kBFloat16));
+    GemmCall g;
+    g.A = qa.data_ptr(); g.B = qb.data_ptr(); g.C = c.data_ptr();
+    g.M = (int)M; g.N = (int)N; g.K = (int)K;
+    g.lda = qa.stride(0); g.ldb = qb.stride(0); g.ldc = N;
+    g.fp8 = true; g.row_scale = sa.data_ptr<float>(); g.col_scale = sb.data_ptr<float>();
+    g.out = out_fp32 ? GemmOut::FP32 : GemmOut::BF16;
+    g.cta_group = cta_group;
+    cuda_ok(gemm_bf16(g, cur_stream()), "gemm_fp8");
+    return c;
+  }, py::arg("qa"), py::arg("sa"), py::arg("qb"), py::arg("sb"), py::arg("out_fp32") = false, py::arg("cta_group") = 0);
+
   // direct kernel entry points (benchmarks / numerics tests)
   m.def("gemm", [](const at::Tensor& a, const at::Tensor& b, bool a_mn, bool b_mn, const py::object& bias, const std::string& act,
                    bool out_fp32, int cta_group) {

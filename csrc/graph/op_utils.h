@@ -36,6 +36,8 @@ struct GemmSink {
   bool used = false;
 };
 extern thread_local GemmSink* tls_gemm_sink;
+// collective over `ranks`: allocate a symmetric buffer, exchange the CUDA IPC handles and map every peer (tp_fused.cc)
+void symm_exchange_and_open(const std::string& name, size_t bytes, const std::vector<int>& ranks, int pos);
 
 inline at::Tensor flatten_rows(const at::Tensor& x) { return x.reshape({-1, x.size(-1)}); }
 

@@ -10,6 +10,8 @@
 #include "exec.h"
 #include "ir.h"
 #include "op_utils.h"
+#include "../runtime/symm_mem.h"
+#include "exec.h"
 
 namespace hb {
 
@@ -148,16 +150,78 @@ static Ts moe_gate_compute(const OpDef& op, const Ts& in, RunCtx*) {
   at::Tensor aux = (me * ce).sum().reshape({1}) * (double)E;
   return {gates, idx, loc, aux};
 }
-HB_REGISTER_OP(moe_gate, "moe_gate", 4, kFlagNondiff, moe_gate_compute, nullptr, nullptr, nullptr);
+// routing decisions are per token: they inherit the token layout of the logits; the auxiliary loss is a per-rank scalar
+static void moe_gate_deduce(OpDef& op, size_t s) {
+  const Tensor& lg = op.inputs[0];
+  if (!lg->has_ds(s)) return;
+  for (size_t i = 0; i < 3 && i < op.outputs.size(); ++i) copy_out_ds(op, i, s, lg);
+  if (op.outputs.size() > 3) {
+    const int n = lg->ds(s).device_num();
+    set_out_ds(op, 3, s, DistributedStates(n, {{kDupDim, n}}, {kDupDim}));
+  }
+}
+HB_REGISTER_OP(moe_gate, "moe_gate", 4, kFlagNondiff, moe_gate_compute, nullptr, moe_gate_deduce, nullptr);
 
+
+// ------------------------------------------------------------------ expert parallelism over peer memory
+// Symmetric buffer of an expert-parallel MoE op (persistent per op and micro-batch, so the forward activations stay
+// valid for backward): every rank of `ranks` allocates [experts_per_rank, ep * capacity, hidden] and maps its peers.
+struct EpBuffer {
+  SymmBuffer* buf = nullptr;
+  MoePeers peers;
+  at::Tensor local;   // [epr, ep * C, H] view of this rank's copy
+};
+static bool ep_native(const at::Tensor& x, const std::vector<int64_t>& ranks) {
+  return is_native(x) && ranks.size() > 1 && ranks.size() <= 8 && CommRuntime::get().initialized() && env_int("HETU_EP_FUSED", 1) != 0;
+}
+static EpBuffer ep_buffer(const OpDef& op, RunCtx* rc, const char* tag, const std::vector<int64_t>& ranks64, int64_t epr, int64_t C, int64_t H,
+                          const at::TensorOptions& opt) {
+  std::vector<int> ranks(ranks64.begin(), ranks64.end());
+  const int ep = (int)ranks.size();
+  int pos = -1;
+  for (int i = 0; i < ep; ++i) if (ranks[i] == CommRuntime::get().rank()) pos = i;
+  HB_CHECK(pos >= 0) << "rank " << CommRuntime::get().rank() << " is not in the expert-parallel group of " << op.name();
+  const size_t bytes = (size_t)epr * ep * C * H * 2;
+  const std::string name = std::string("ep_") + tag + "_" + std::to_string(op.id) + "_mb" + std::to_string(rc ? rc->micro_batch : 0);
+  auto& sm = SymmMem::get();
+  if (!sm.has(name) || sm.buffer(name).bytes < bytes) symm_exchange_and_open(name, bytes, ranks, pos);
+  EpBuffer b;
+  b.buf = &sm.buffer(name);
+  for (int r = 0; r < ep; ++r) b.peers.base[r] = b.buf->peer[r];
+  b.peers.ep = ep; b.peers.experts_per_rank = (int)epr; b.peers.src_rank = pos;
+  b.local = at::from_blob(b.buf->local, {epr, (int64_t)ep * C, H}, opt);
+  return b;
+}
 // moe_dispatch: x [T,H], idx, loc -> [E, capacity, H]
-static Ts moe_dispatch_compute(const OpDef& op, const Ts& in, RunCtx*) {
+static Ts moe_dispatch_compute(const OpDef& op, const Ts& in, RunCtx* rc) {
   const at::Tensor& x = in[0];
   const at::Tensor& idx = in[1];
   const at::Tensor& loc = in[2];
   const int64_t E = op.attrs.i("experts"), C = op.attrs.i("capacity"), H = x.size(1), T = x.size(0), k = idx.size(1);
-  if (x.is_meta()) return {at::empty({E, C, H}, x.options())};
+  const std::vector<int64_t> ep_ranks = op.attrs.ints("ep_ranks");
+  const int64_t ep = std::max<int64_t>(1, (int64_t)ep_ranks.size());
+  if (x.is_meta()) return {ep > 1 ? at::empty({E / ep, ep * C, H}, x.options()) : at::empty({E, C, H}, x.options())};
   const bool scaled = in.size() > 3;
+  if (ep > 1 && ep_native(x, ep_ranks) && x.is_contiguous() && H % 8 == 0) {
+    // fused layout transform + all-to-all: every token row is stored straight into its expert's rank over NVLink
+    EpBuffer b = ep_buffer(op, rc, "disp", ep_ranks, E / ep, C, H, x.options());
+    cudaStream_t st = cur_stream();
+    cuda_ok(cudaMemsetAsync(b.buf->local, 0, (size_t)(E / ep) * ep * C * H * 2, st), "memset");
+    cuda_ok(symm_barrier(*b.buf, st), "ep barrier");      // every destination buffer is cleared
+    cuda_ok(moe_dispatch_peers(x.data_ptr(), idx.data_ptr<int32_t>(), loc.data_ptr<int32_t>(),
+                               scaled ? in[3].contiguous().data_ptr<float>() : nullptr, b.peers, T, (int)H, (int)k, (int)C, st),
+            "moe_dispatch_peers");
+    cuda_ok(symm_barrier(*b.buf, st), "ep barrier");      // every rank's tokens have landed
+    return {b.local};
+  }
+  if (ep > 1) {
+    // unfused: local layout transform, then an all-to-all of the expert blocks
+    OpDef local = op;
+    local.attrs.set("ep_ranks", std::vector<int64_t>{});
+    at::Tensor disp = moe_dispatch_compute(local, in, rc)[0];
+    std::vector<int> ranks(ep_ranks.begin(), ep_ranks.end());
+    return {CommRuntime::get().all_to_all(disp, ranks, 0, 1)};
+  }
   if (is_native(x) && x.is_contiguous() && H % 8 == 0) {
     at::Tensor out = at::empty({E, C, H}, x.options());
     cuda_ok(moe_dispatch(x.data_ptr(), idx.data_ptr<int32_t>(), loc.data_ptr<int32_t>(),
@@ -177,14 +241,38 @@ static Ts moe_dispatch_compute(const OpDef& op, const Ts& in, RunCtx*) {
   return {out.reshape({E, C, H})};
 }
 // moe_combine: expert_out [E,C,H], idx, loc, [gates] -> [T,H]
-static Ts moe_combine_compute(const OpDef& op, const Ts& in, RunCtx*) {
-  const at::Tensor& eo = in[0];
+static Ts moe_combine_compute(const OpDef& op, const Ts& in, RunCtx* rc) {
   const at::Tensor& idx = in[1];
   const at::Tensor& loc = in[2];
-  const int64_t E = eo.size(0), C = eo.size(1), H = eo.size(2), T = idx.size(0), k = idx.size(1);
-  (void)op;
-  if (eo.is_meta()) return {at::empty({T, H}, eo.options())};
+  const std::vector<int64_t> ep_ranks = op.attrs.ints("ep_ranks");
+  const int64_t ep = std::max<int64_t>(1, (int64_t)ep_ranks.size());
   const bool gated = in.size() > 3;
+  if (ep > 1 && !in[0].is_meta()) {
+    const at::Tensor& src = in[0];                      // [E / ep, ep * C, H] on the experts' rank
+    const int64_t epr = src.size(0), C = src.size(1) / ep, H = src.size(2), T = idx.size(0), k = idx.size(1);
+    if (ep_native(src, ep_ranks) && H % 8 == 0) {
+      // fused all-to-all + reverse layout transform: expert outputs are read from their rank over NVLink
+      EpBuffer b = ep_buffer(op, rc, "comb", ep_ranks, epr, C, H, src.options());
+      cudaStream_t st = cur_stream();
+      if (src.data_ptr() != b.buf->local) b.local.copy_(src);
+      cuda_ok(symm_barrier(*b.buf, st), "ep barrier");    // every rank published its expert outputs
+      at::Tensor y = at::empty({T, H}, src.options());
+      cuda_ok(moe_combine_peers(b.peers, idx.data_ptr<int32_t>(), loc.data_ptr<int32_t>(),
+                                gated ? in[3].contiguous().data_ptr<float>() : nullptr, y.data_ptr(), T, (int)H, (int)k, (int)C, st),
+              "moe_combine_peers");
+      return {y};
+    }
+    std::vector<int> ranks(ep_ranks.begin(), ep_ranks.end());
+    at::Tensor back = CommRuntime::get().all_to_all(src.contiguous(), ranks, 1, 0);    // [E, C, H]
+    OpDef local = op;
+    local.attrs.set("ep_ranks", std::vector<int64_t>{});
+    Ts lin = in;
+    lin[0] = back;
+    return moe_combine_compute(local, lin, rc);
+  }
+  const at::Tensor& eo = in[0];
+  const int64_t E = eo.size(0), C = eo.size(1), H = eo.size(2), T = idx.size(0), k = idx.size(1);
+  if (eo.is_meta()) return {at::empty({T, H}, eo.options())};
   if (is_native(eo) && eo.is_contiguous() && H % 8 == 0) {
     at::Tensor y = at::empty({T, H}, eo.options());
     cuda_ok(moe_combine(eo.data_ptr(), idx.data_ptr<int32_t>(), loc.data_ptr<int32_t>(),
@@ -199,11 +287,34 @@ static Ts moe_combine_compute(const OpDef& op, const Ts& in, RunCtx*) {
   return {(rows * w.unsqueeze(-1)).sum(1).to(eo.scalar_type())};
 }
 // d gates of combine: <dy[t], expert_out[e_k, slot_k]>
-static Ts moe_combine_gate_grad_compute(const OpDef&, const Ts& in, RunCtx*) {
+static Ts moe_combine_gate_grad_compute(const OpDef& op, const Ts& in, RunCtx* rc) {
   const at::Tensor& dy = in[0];
-  const at::Tensor& eo = in[1];
   const at::Tensor& idx = in[2];
   const at::Tensor& loc = in[3];
+  const std::vector<int64_t> ep_ranks = op.attrs.ints("ep_ranks");
+  const int64_t ep = std::max<int64_t>(1, (int64_t)ep_ranks.size());
+  if (ep > 1 && !dy.is_meta()) {
+    const at::Tensor& src = in[1];
+    const int64_t epr = src.size(0), C = src.size(1) / ep, H = src.size(2), T = idx.size(0), k = idx.size(1);
+    if (ep_native(src, ep_ranks) && is_native(dy) && dy.is_contiguous() && H % 8 == 0) {
+      EpBuffer b = ep_buffer(op, rc, "gateg", ep_ranks, epr, C, H, src.options());
+      cudaStream_t st = cur_stream();
+      if (src.data_ptr() != b.buf->local) b.local.copy_(src);
+      cuda_ok(symm_barrier(*b.buf, st), "ep barrier");
+      at::Tensor dg = at::empty({T, k}, dy.options().dtype(at::kFloat));
+      cuda_ok(moe_combine_bwd_gate_peers(dy.data_ptr(), b.peers, idx.data_ptr<int32_t>(), loc.data_ptr<int32_t>(), dg.data_ptr<float>(), T,
+                                         (int)H, (int)k, (int)C, st), "moe_combine_bwd_gate_peers");
+      return {dg};
+    }
+    std::vector<int> ranks(ep_ranks.begin(), ep_ranks.end());
+    at::Tensor back = CommRuntime::get().all_to_all(src.contiguous(), ranks, 1, 0);
+    OpDef local = op;
+    local.attrs.set("ep_ranks", std::vector<int64_t>{});
+    Ts lin = in;
+    lin[1] = back;
+    return moe_combine_gate_grad_compute(local, lin, rc);
+  }
+  const at::Tensor& eo = in[1];
   const int64_t E = eo.size(0), C = eo.size(1), H = eo.size(2), T = idx.size(0), k = idx.size(1);
   if (dy.is_meta()) return {at::empty({T, k}, dy.options().dtype(at::kFloat))};
   if (is_native(eo) && is_native(dy) && eo.is_contiguous() && dy.is_contiguous() && H % 8 == 0) {
@@ -221,23 +332,36 @@ static TensorList moe_dispatch_grad(OpDef& op, const TensorList& g) {
   TensorList ins = {g[0], op.inputs[1], op.inputs[2]};
   if (op.inputs.size() > 3) ins.push_back(op.inputs[3]);
   TensorList r(op.inputs.size());
-  r[0] = op.graph->make_op1("moe_combine", ins);
+  AttrMap a;
+  a.set("ep_ranks", op.attrs.ints("ep_ranks"));
+  r[0] = op.graph->make_op1("moe_combine", ins, a);
   return r;
 }
 static TensorList moe_combine_grad(OpDef& op, const TensorList& g) {
   AttrMap a;
-  a.set("experts", op.inputs[0]->shape[0]);
-  a.set("capacity", op.inputs[0]->shape[1]);
+  const std::vector<int64_t> epr = op.attrs.ints("ep_ranks");
+  const int64_t ep = std::max<int64_t>(1, (int64_t)epr.size());
+  a.set("experts", op.inputs[0]->shape[0] * ep);
+  a.set("capacity", op.inputs[0]->shape[1] / ep);
+  a.set("ep_ranks", epr);
   TensorList ins = {g[0], op.inputs[1], op.inputs[2]};
   if (op.inputs.size() > 3) ins.push_back(op.inputs[3]);
   TensorList r(op.inputs.size());
   r[0] = op.graph->make_op1("moe_dispatch", ins, a);
-  if (op.inputs.size() > 3) r[3] = op.graph->make_op1("moe_combine_gate_grad", {g[0], op.inputs[0], op.inputs[1], op.inputs[2]});
+  if (op.inputs.size() > 3) {
+    AttrMap ga;
+    ga.set("ep_ranks", epr);
+    r[3] = op.graph->make_op1("moe_combine_gate_grad", {g[0], op.inputs[0], op.inputs[1], op.inputs[2]}, ga);
+  }
   return r;
 }
-HB_REGISTER_OP(moe_dispatch, "moe_dispatch", 1, 0, moe_dispatch_compute, moe_dispatch_grad, nullptr, nullptr);
-HB_REGISTER_OP(moe_combine, "moe_combine", 1, 0, moe_combine_compute, moe_combine_grad, nullptr, nullptr);
-HB_REGISTER_OP(moe_combine_gate_grad, "moe_combine_gate_grad", 1, kFlagNondiff, moe_combine_gate_grad_compute, nullptr, nullptr, nullptr);
+// expert-major buffers are rank-local (no global layout); token-major results take the layout of the routing tensors
+static void moe_no_ds(OpDef&, size_t) {}
+HB_REGISTER_OP(moe_dispatch, "moe_dispatch", 1, 0, moe_dispatch_compute, moe_dispatch_grad, moe_no_ds, nullptr);
+HB_REGISTER_OP(moe_combine, "moe_combine", 1, 0, moe_combine_compute, moe_combine_grad,
+               [](OpDef& op, size_t s) { copy_out_ds(op, 0, s, op.inputs[1]); if (op.outputs[0]->has_ds(s) && op.inputs[1]->has_ds(s)) {} }, nullptr);
+HB_REGISTER_OP(moe_combine_gate_grad, "moe_combine_gate_grad", 1, kFlagNondiff, moe_combine_gate_grad_compute, nullptr,
+               [](OpDef& op, size_t s) { copy_out_ds(op, 0, s, op.inputs[2]); }, nullptr);
 
 // differentiable gate values: gates = normalise(softmax(logits)[topk]) for fixed routing decisions
 static Ts moe_gate_values_compute(const OpDef& op, const Ts& in, RunCtx*) {
@@ -251,6 +375,7 @@ static Ts moe_gate_values_compute(const OpDef& op, const Ts& in, RunCtx*) {
   if (idx.size(1) > 1) val = val / val.sum(-1, true).clamp_min(1e-9);
   return {val};
 }
-HB_REGISTER_OP(moe_gate_values, "moe_gate_values", 1, 0, moe_gate_values_compute, nullptr, nullptr, nullptr);
+HB_REGISTER_OP(moe_gate_values, "moe_gate_values", 1, 0, moe_gate_values_compute, nullptr,
+               [](OpDef& op, size_t s) { copy_out_ds(op, 0, s, op.inputs[0]); }, nullptr);
 
 }  // namespace hb

@@ -23,7 +23,7 @@ struct TpFusedState {
   std::unordered_map<OpId, std::pair<std::string, std::vector<int64_t>>> pending;   // comm op -> (buffer, [rows_per_rank, cols])
 };
 
-static void exchange_and_open(const std::string& name, size_t bytes, const std::vector<int>& ranks, int pos) {
+void symm_exchange_and_open(const std::string& name, size_t bytes, const std::vector<int>& ranks, int pos) {
   auto& sm = SymmMem::get();
   auto& comm = CommRuntime::get();
   std::string handle = sm.alloc(name, bytes, pos, (int)ranks.size());
@@ -92,7 +92,7 @@ bool Executor::tp_fused_gemm(ExecPlan& plan, OpDef* op, const std::vector<at::Te
     static int seq = 0;
     for (int k = 0; k < 2; ++k) {
       sg.name[k] = "tp_stage_" + std::to_string(seq++);
-      exchange_and_open(sg.name[k], need, cs.ranks, pos);
+      symm_exchange_and_open(sg.name[k], need, cs.ranks, pos);
     }
     sg.bytes = need;
   }

@@ -153,6 +153,21 @@ cudaError_t moe_dispatch(const void* x, const int32_t* topk_idx, const int32_t* 
 // (with gate = null this is also the backward of moe_dispatch w.r.t. x)
 cudaError_t moe_combine(const void* expert_out, const int32_t* topk_idx, const int32_t* location, const float* gate,
                         void* y, int64_t tokens, int hidden, int experts, int k, int capacity, cudaStream_t s);
+// Expert-parallel variants over NVLink peer memory (the dispatch / combine all-to-all fused into the layout transform):
+// expert e lives on rank e / experts_per_rank; its buffer there is [experts_per_rank, ep * capacity, hidden] and tokens of
+// source rank r occupy rows [r * capacity, (r + 1) * capacity).  base[r] = rank r's (symmetric) buffer.
+struct MoePeers {
+  void* base[8] = {nullptr};
+  int ep = 1, experts_per_rank = 1, src_rank = 0;
+};
+// scatter: peer[e / epr][(e % epr), src_rank * C + slot, :] = scale * x[t, :]   (buffers must have been zero-filled)
+cudaError_t moe_dispatch_peers(const void* x, const int32_t* topk_idx, const int32_t* location, const float* scale,
+                               const MoePeers& peers, int64_t tokens, int hidden, int k, int capacity, cudaStream_t s);
+// gather: y[t, :] = sum_k gate * peer[e / epr][(e % epr), src_rank * C + slot, :]
+cudaError_t moe_combine_peers(const MoePeers& peers, const int32_t* topk_idx, const int32_t* location, const float* gate,
+                              void* y, int64_t tokens, int hidden, int k, int capacity, cudaStream_t s);
+cudaError_t moe_combine_bwd_gate_peers(const void* dy, const MoePeers& peers, const int32_t* topk_idx, const int32_t* location,
+                                       float* dgate, int64_t tokens, int hidden, int k, int capacity, cudaStream_t s);
 // backward of combine wrt gates: dgate[t,k] = <dy[t], expert_out[e_k, slot_k]>
 cudaError_t moe_combine_bwd_gate(const void* dy, const void* expert_out, const int32_t* topk_idx,
                                  const int32_t* location, float* dgate, int64_t tokens, int hidden, int experts, int k,

@@ -160,6 +160,80 @@ __global__ void combine_bwd_gate_kernel(const void* __restrict__ dy, const void*
   if (lane == 0) dgate[tk] = s;
 }
 
+__device__ __forceinline__ char* peer_row(const MoePeers& pr, int e, int loc, int capacity, int hidden) {
+  const int r = e / pr.experts_per_rank, el = e - r * pr.experts_per_rank;
+  return static_cast<char*>(pr.base[r]) + ((int64_t(el) * pr.ep + pr.src_rank) * capacity + loc) * int64_t(hidden) * 2;
+}
+__global__ void dispatch_peers_kernel(const void* __restrict__ x, const int32_t* __restrict__ topk_idx,
+                                      const int32_t* __restrict__ location, const float* __restrict__ scale, MoePeers pr,
+                                      int64_t tokens, int hidden, int k, int capacity) {
+  const int hv = hidden >> 3;
+  const int64_t total = tokens * k * hv;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % hv);
+    const int64_t tk = i / hv;
+    const int loc = location[tk];
+    if (loc < 0) continue;
+    const int64_t t = tk / k;
+    bf16x8 val = ld8(x, t * hv + c);
+    if (scale) {
+      float f[8];
+      unpack8(val, f);
+      const float sc = scale[tk];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] *= sc;
+      val = pack8(f);
+    }
+    st8(peer_row(pr, topk_idx[tk], loc, capacity, hidden), c, val);     // store over NVLink into the expert's rank
+  }
+}
+__global__ void combine_peers_kernel(MoePeers pr, const int32_t* __restrict__ topk_idx, const int32_t* __restrict__ location,
+                                     const float* __restrict__ gate, void* __restrict__ y, int64_t tokens, int hidden, int k,
+                                     int capacity) {
+  const int hv = hidden >> 3;
+  const int64_t total = tokens * hv;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % hv);
+    const int64_t t = i / hv;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int kk = 0; kk < k; ++kk) {
+      const int loc = location[t * k + kk];
+      if (loc < 0) continue;
+      const float gt = gate ? gate[t * k + kk] : 1.0f;
+      float f[8];
+      unpack8(ld8_stream(peer_row(pr, topk_idx[t * k + kk], loc, capacity, hidden), c), f);   // load over NVLink
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += gt * f[j];
+    }
+    st8(y, i, pack8(acc));
+  }
+}
+__global__ void combine_bwd_gate_peers_kernel(const void* __restrict__ dy, MoePeers pr, const int32_t* __restrict__ topk_idx,
+                                              const int32_t* __restrict__ location, float* __restrict__ dgate, int64_t tokens,
+                                              int hidden, int k, int capacity) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tk = blockIdx.x * int64_t(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tk >= tokens * k) return;
+  const int loc = location[tk];
+  float s = 0.f;
+  if (loc >= 0) {
+    const int64_t t = tk / k;
+    const int hv = hidden >> 3;
+    const char* row = peer_row(pr, topk_idx[tk], loc, capacity, hidden);
+    for (int c = lane; c < hv; c += 32) {
+      float a[8], b[8];
+      unpack8(ld8(dy, t * hv + c), a);
+      unpack8(ld8_stream(row, c), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += a[j] * b[j];
+    }
+  }
+  s = warp_sum(s);
+  if (lane == 0) dgate[tk] = s;
+}
+
 inline int grid_for(int64_t n) {
   int64_t blocks = (n + 255) / 256;
   const int64_t cap = int64_t(sm_count()) * 8;
@@ -203,6 +277,31 @@ cudaError_t moe_combine(const void* expert_out, const int32_t* topk_idx, const i
   if (tokens == 0) return cudaSuccess;
   combine_kernel<<<grid_for(tokens * (hidden >> 3)), 256, 0, s>>>(expert_out, topk_idx, location, gate, y, tokens,
                                                                   hidden, k, capacity);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t moe_dispatch_peers(const void* x, const int32_t* topk_idx, const int32_t* location, const float* scale,
+                               const MoePeers& peers, int64_t tokens, int hidden, int k, int capacity, cudaStream_t s) {
+  if (hidden & 7) return cudaErrorInvalidValue;
+  if (tokens == 0) return cudaSuccess;
+  dispatch_peers_kernel<<<grid_for(tokens * k * (hidden >> 3)), 256, 0, s>>>(x, topk_idx, location, scale, peers, tokens, hidden, k,
+                                                                             capacity);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t moe_combine_peers(const MoePeers& peers, const int32_t* topk_idx, const int32_t* location, const float* gate,
+                              void* y, int64_t tokens, int hidden, int k, int capacity, cudaStream_t s) {
+  if (hidden & 7) return cudaErrorInvalidValue;
+  if (tokens == 0) return cudaSuccess;
+  combine_peers_kernel<<<grid_for(tokens * (hidden >> 3)), 256, 0, s>>>(peers, topk_idx, location, gate, y, tokens, hidden, k, capacity);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t moe_combine_bwd_gate_peers(const void* dy, const MoePeers& peers, const int32_t* topk_idx, const int32_t* location,
+                                       float* dgate, int64_t tokens, int hidden, int k, int capacity, cudaStream_t s) {
+  if (tokens == 0) return cudaSuccess;
+  combine_bwd_gate_peers_kernel<<<(unsigned)((tokens * k + 7) / 8), 256, 0, s>>>(dy, peers, topk_idx, location, dgate, tokens, hidden, k,
+                                                                                 capacity);
   count_launch();
   return cudaGetLastError();
 }

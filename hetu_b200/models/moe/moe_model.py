@@ -148,23 +148,26 @@ def _ge(a, b):
 
 
 class Expert(Module):
-    """E_local feed-forward experts evaluated as batched GEMMs over the expert-major buffer [E_local, C, H]"""
+    """E_local feed-forward experts evaluated over the expert-major buffer [E_local, C', H].  Parameters are named by the
+    GLOBAL expert index, so expert e has the same weights whichever rank / expert-parallel degree holds it."""
 
-    def __init__(self, d_model, d_ff, num_local_experts, act="gelu", dtype="float32", name="expert"):
+    def __init__(self, d_model, d_ff, num_local_experts, act="gelu", dtype="float32", name="expert", expert_offset=0,
+                 device_group=None):
         super().__init__()
         self.n, self.act = num_local_experts, act
         std = 0.02
-        self.w1 = [parallel_parameter(normal_initializer(0.0, std), [d_ff, d_model], None, dtype=dtype, requires_grad=True,
-                                      name=f"{name}{i}_w1") for i in range(num_local_experts)]
-        self.b1 = [parallel_parameter(zeros_initializer(), [d_ff], None, dtype=dtype, requires_grad=True, name=f"{name}{i}_b1")
-                   for i in range(num_local_experts)]
-        self.w2 = [parallel_parameter(normal_initializer(0.0, std), [d_model, d_ff], None, dtype=dtype, requires_grad=True,
-                                      name=f"{name}{i}_w2") for i in range(num_local_experts)]
-        self.b2 = [parallel_parameter(zeros_initializer(), [d_model], None, dtype=dtype, requires_grad=True, name=f"{name}{i}_b2")
-                   for i in range(num_local_experts)]
-        for i in range(num_local_experts):
+        dgh = [[device_group]] if device_group is not None else None
+
+        def param(init, shape, nm):
+            return parallel_parameter(init, shape, None, dtype=dtype, requires_grad=True, name=nm, device_group_hierarchy=dgh)
+        gl = [expert_offset + i for i in range(num_local_experts)]
+        self.w1 = [param(normal_initializer(0.0, std), [d_ff, d_model], f"{name}{g}_w1") for g in gl]
+        self.b1 = [param(zeros_initializer(), [d_ff], f"{name}{g}_b1") for g in gl]
+        self.w2 = [param(normal_initializer(0.0, std), [d_model, d_ff], f"{name}{g}_w2") for g in gl]
+        self.b2 = [param(zeros_initializer(), [d_model], f"{name}{g}_b2") for g in gl]
+        for i, g in enumerate(gl):
             for nm, lst in (("w1", self.w1), ("b1", self.b1), ("w2", self.w2), ("b2", self.b2)):
-                self.register_parameter(f"{nm}_{i}", lst[i])
+                self.register_parameter(f"{nm}_{g}", lst[i])
 
     def forward(self, x):
         """x [E_local, C', H] -> same shape"""
@@ -180,80 +183,101 @@ class Expert(Module):
 
 class MoELayer(Module):
     def __init__(self, d_model, d_ff, num_experts, k=1, capacity_factor=1.0, gate_type="topk", ep_ranks: Sequence[int] = (),
-                 act="gelu", dtype="float32", name="moe"):
+                 act="gelu", dtype="float32", name="moe", gate_ds=None):
         super().__init__()
+        from ... import distributed
         self.ep_ranks = tuple(ep_ranks)
         self.ep = max(len(self.ep_ranks), 1)
         assert num_experts % self.ep == 0, "experts must divide evenly over the expert-parallel group"
         self.num_experts, self.num_local = num_experts, num_experts // self.ep
+        me = distributed.rank()
+        pos = self.ep_ranks.index(me) if me in self.ep_ranks else 0
         gate_cls = {"topk": TopKGate, "ktop1": KTop1Gate, "hash": HashGate, "balance": BalanceGate, "sam": SAMGate}[gate_type]
         self.gate = gate_cls(d_model, num_experts, k=k, capacity_factor=capacity_factor, dtype=dtype, name=f"{name}_gate") \
             if gate_type != "hash" else HashGate(d_model, num_experts, capacity_factor)
-        self.experts = Expert(d_model, d_ff, self.num_local, act=act, dtype=dtype, name=f"{name}_expert")
+        if gate_ds is not None and hasattr(self.gate, "wg"):
+            # router weights are replicated over the data-parallel group: re-create them with that layout so their
+            # gradient is all-reduced like every other replicated parameter
+            ds_h, dg_h = gate_ds
+            self.gate.wg = parallel_parameter(normal_initializer(0.0, 0.02), list(self.gate.wg.shape), ds_h, dtype=dtype, requires_grad=True,
+                                              device_group_hierarchy=dg_h, name=f"{name}_gate_wg")
+        self.experts = Expert(d_model, d_ff, self.num_local, act=act, dtype=dtype, name=f"{name}_expert", expert_offset=pos * self.num_local)
         self.l_aux = None
 
     def forward(self, x):
-        """x [T, H] -> [T, H]"""
+        """x [T_local, H] -> [T_local, H]"""
         gates, idx, loc, aux, cap = self.gate(x)
         self.l_aux = aux
-        h = x.shape[1]
-        disp = ops.moe_dispatch(x, idx, loc, self.num_experts, cap)              # [E, C, H]  (layout_transform)
-        if self.ep > 1:
-            # [E, C, H] -> every rank keeps its E_local experts and receives their tokens from all ranks
-            disp = ops.all_to_all(disp, self.ep_ranks, split_dim=0, concat_dim=1)   # [E_local, ep*C, H]
+        ranks = self.ep_ranks if self.ep > 1 else ()
+        # layout_transform (+ the dispatch all-to-all fused in: token rows go straight to their expert's rank over
+        # NVLink peer memory) -> [E_local, ep * C, H]
+        disp = ops.moe_dispatch(x, idx, loc, self.num_experts, cap, ep_ranks=ranks)
         out = self.experts(disp)
-        if self.ep > 1:
-            out = ops.all_to_all(out, self.ep_ranks, split_dim=1, concat_dim=0)     # back to [E, C, H]
-        return ops.moe_combine(out, idx, loc, gates)                              # reverse_layout_transform
+        # reverse_layout_transform (+ the combine all-to-all fused in: expert outputs are read from their rank)
+        return ops.moe_combine(out, idx, loc, gates, ep_ranks=ranks)
 
 
 class GPTMoELMHeadModel(Module):
-    """GPT with MoE MLPs every `moe_every` blocks (single-device-group TP=1; experts sharded over `ep_ranks`)."""
+    """GPT whose MLP is an MoE layer every `moe_every` blocks.  Attention / norms / embeddings are the data-parallel
+    (replicated) GPT modules over `ds_parallel_configs`; the experts are sharded over `config.ep_ranks` (usually the same
+    ranks: expert parallelism rides on the data-parallel group, HetuMoE style)."""
 
-    def __init__(self, config: MoEConfig):
+    def __init__(self, config: MoEConfig, ds_parallel_configs=None, num_gpus: int = 1):
         super().__init__()
-        from ...nn import Embedding, LayerNorm, Linear
-        self.config = config
-        h = config.n_embd
-        self.wte = Embedding(config.vocab_size, h, dtype=config.dtype, name="wte")
-        self.wpe = Embedding(config.n_positions, h, dtype=config.dtype, name="wpe")
+        from ...nn import HtMultiParallelLayerNorm, HtMultiParallelEmbedding, HtMultiVocabParallelEmbedding
+        from ...nn.parallel import get_multi_ds_parallel_config
+        from ..gpt.gpt_model import GPTAttention, GPTMLP
+        from ..parallel_config import generate_ds_parallel_config
+        if ds_parallel_configs is None:
+            ds_parallel_configs = [generate_ds_parallel_config(config.n_layer, num_gpus, num_gpus, 1, 1, zero=False)]
+        self.config, self.ds_parallel_configs = config, ds_parallel_configs
+        dsc, h = ds_parallel_configs, config.n_embd
+        std = config.initializer_range
+        self.wte = HtMultiVocabParallelEmbedding(config.vocab_size, h, get_multi_ds_parallel_config(dsc, "wte"), dtype=config.dtype, name="wte",
+                                                 init_std=std)
+        self.wpe = HtMultiParallelEmbedding(config.n_positions, h, get_multi_ds_parallel_config(dsc, "wpe"), dtype=config.dtype, name="wpe",
+                                            init_std=std)
         self.blocks = ModuleList()
         for i in range(config.n_layer):
             blk = Module()
-            blk.ln_1 = LayerNorm(h, config.layer_norm_epsilon, dtype=config.dtype, name=f"ln1_{i}")
-            blk.qkv = Linear(h, 3 * h, dtype=config.dtype, name=f"qkv_{i}")
-            blk.proj = Linear(h, h, dtype=config.dtype, name=f"proj_{i}")
-            blk.ln_2 = LayerNorm(h, config.layer_norm_epsilon, dtype=config.dtype, name=f"ln2_{i}")
+            blk.ln_1 = HtMultiParallelLayerNorm(h, get_multi_ds_parallel_config(dsc, "layernorm1", i), eps=config.layer_norm_epsilon,
+                                                dtype=config.dtype, name=f"ln1_block{i}")
+            blk.attn = GPTAttention(config, dsc, i, name=f"attn_block{i}")
+            blk.ln_2 = HtMultiParallelLayerNorm(h, get_multi_ds_parallel_config(dsc, "layernorm2", i), eps=config.layer_norm_epsilon,
+                                                dtype=config.dtype, name=f"ln2_block{i}")
             if (i + 1) % config.moe_every == 0:
-                blk.moe = MoELayer(h, config.ffn_hidden_size, config.num_experts, config.top_k, config.capacity_factor,
-                                   config.gate_type, config.ep_ranks, dtype=config.dtype, name=f"moe_{i}")
-                blk.fc1 = blk.fc2 = None
+                blk.moe = MoELayer(h, config.ffn_hidden_size, config.num_experts, config.top_k, config.capacity_factor, config.gate_type,
+                                   config.ep_ranks, act=config.activation_function, dtype=config.dtype, name=f"moe_{i}",
+                                   gate_ds=(blk.ln_2.ds_dup(), blk.ln_2.device_group_unions))
+                blk.mlp = None
             else:
                 blk.moe = None
-                blk.fc1 = Linear(h, config.ffn_hidden_size, dtype=config.dtype, name=f"fc1_{i}")
-                blk.fc2 = Linear(config.ffn_hidden_size, h, dtype=config.dtype, name=f"fc2_{i}")
+                blk.mlp = GPTMLP(config, dsc, i, name=f"mlp_block{i}")
             self.blocks.append(blk)
-        self.ln_f = LayerNorm(h, config.layer_norm_epsilon, dtype=config.dtype, name="ln_f")
+        self.ln_f = HtMultiParallelLayerNorm(h, get_multi_ds_parallel_config(dsc, "layernorm_final"), eps=config.layer_norm_epsilon,
+                                             dtype=config.dtype, name="ln_final")
 
     def forward(self, input_ids, position_ids, labels=None, seq_len=None):
-        from ...ops_extra import attn_packed
         cfg = self.config
         x = self.wte(input_ids) + self.wpe(position_ids)
         aux_total = None
         for blk in self.blocks:
-            qkv = blk.qkv(blk.ln_1(x))
-            a = attn_packed(qkv, seq_len, cfg.n_head, cfg.n_head, cfg.n_embd // cfg.n_head)
-            x = blk.proj(a, residual=x)
+            x = blk.attn(blk.ln_1(x), seq_len, residual=x)
             hln = blk.ln_2(x)
             if blk.moe is not None:
                 x = x + blk.moe(hln)
                 if blk.moe.l_aux is not None:
                     aux_total = blk.moe.l_aux if aux_total is None else aux_total + blk.moe.l_aux
             else:
-                x = blk.fc2(blk.fc1(hln, act=cfg.activation_function), residual=x)
+                x = blk.mlp(hln, residual=x)
         x = self.ln_f(x)
-        logits = ops.linear(x, self.wte.weight, None, trans_b=True)
+        logits = ops.linear(x, self.wte.embedding_table, None, trans_b=True, name="lm_head")
         if labels is None:
             return logits
         loss = ops.softmax_cross_entropy_sparse(logits, labels, ignored_index=-1, reduction="mean")
+        if aux_total is not None and cfg.aux_loss_weight > 0:
+            loss = loss + aux_total * cfg.aux_loss_weight
         return loss
+
+
+MoELMHeadModel = GPTMoELMHeadModel

@@ -504,14 +504,17 @@ def moe_gate_values(logits, idx, loc, **kw):
     return _op1("moe_gate_values", [logits, idx, loc], **kw)
 
 
-def moe_dispatch(x, idx, loc, experts, capacity, scale=None, **kw):
+def moe_dispatch(x, idx, loc, experts, capacity, scale=None, ep_ranks=(), **kw):
+    """layout transform [T, H] -> [E, C, H]; with `ep_ranks` (expert parallel group) the dispatch all-to-all is fused in:
+    rows are stored straight into the expert's rank over NVLink and the result is [E / ep, ep * C, H]"""
     ins = [x, idx, loc] + ([scale] if scale is not None else [])
-    return _op1("moe_dispatch", ins, {"experts": int(experts), "capacity": int(capacity)}, **kw)
+    return _op1("moe_dispatch", ins, {"experts": int(experts), "capacity": int(capacity), "ep_ranks": [int(r) for r in ep_ranks]}, **kw)
 
 
-def moe_combine(expert_out, idx, loc, gates=None, **kw):
+def moe_combine(expert_out, idx, loc, gates=None, ep_ranks=(), **kw):
+    """reverse layout transform (+ gate weighting); with `ep_ranks` the combine all-to-all is fused in (peer loads)"""
     ins = [expert_out, idx, loc] + ([gates] if gates is not None else [])
-    return _op1("moe_combine", ins, **kw)
+    return _op1("moe_combine", ins, {"ep_ranks": [int(r) for r in ep_ranks]}, **kw)
 
 
 # ----------------------------------------------------------------------------- quantization (blockwise absmax)

@@ -57,3 +57,21 @@ def test_llama_tp2_sp_matches_single_device():
     got = _losses(outs)
     for a, b in zip(got, ref):
         assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, ref)
+
+
+MOE_WORKER = os.path.join(os.path.dirname(__file__), "workers", "moe_worker.py")
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("gate", ["topk"])
+def test_moe_expert_parallel_matches_single_device(gate):
+    """GPT-MoE with the experts sharded over the data-parallel ranks (dispatch / combine all-to-all inside the layout
+    transform ops) reproduces the single-device loss curve when no token is dropped"""
+    ok, outs = run_workers(MOE_WORKER, 1, [1, gate])
+    assert ok, "\n".join(outs)
+    ref = _losses(outs)
+    ok, outs = run_workers(MOE_WORKER, 2, [2, gate])
+    assert ok, "\n-----\n".join(outs)
+    got = _losses(outs)
+    for a, b in zip(got, ref):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, ref)
