@@ -40,6 +40,8 @@ CXX_SOURCES = [
     "csrc/v1/embedding_cache.cc",
     "csrc/v1/ps_server.cc",
     "csrc/runtime/symm_mem.cc",
+    "csrc/runtime/memory_pool.cc",
+    "csrc/runtime/runtime.cc",
     "csrc/binding/module.cc",
 ]
 NVCC_FLAGS = "-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr"

@@ -18,6 +18,8 @@
 #include "../planner/dp_core.h"
 #include "../v1/embedding_cache.h"
 #include "../runtime/symm_mem.h"
+#include "../runtime/memory_pool.h"
+#include "../runtime/runtime.h"
 
 namespace py = pybind11;
 using namespace hb;
@@ -561,6 +563,50 @@ PYBIND11_MODULE(_C, m) {
                               rt.defined() ? rt.data_ptr() : nullptr, rpr, (int)N, cur_stream()), "reduce_slots");
     return out;
   }, py::arg("x"), py::arg("w"), py::arg("staging"), py::arg("bias") = py::none(), py::arg("residual") = py::none());
+
+  // ---------------------------------------------------------------- native runtime: memory pool, streams, RNG state, data loader
+  py::class_<CachingMemoryPool, std::shared_ptr<CachingMemoryPool>>(m, "MemoryPool")
+      .def(py::init([](const std::string& backend, int device, int64_t limit_mb, int64_t max_split_mb, int64_t pre_allocate_mb) {
+        CachingMemoryPool::Options o = CachingMemoryPool::options_from_env();
+        if (limit_mb > 0) o.limit = (size_t)limit_mb << 20;
+        if (max_split_mb > 0) o.max_split_size = (size_t)max_split_mb << 20;
+        if (pre_allocate_mb > 0) o.pre_allocate = (size_t)pre_allocate_mb << 20;
+        std::unique_ptr<MemoryBackend> be = backend == "cuda" ? make_cuda_backend(device) : make_host_backend(backend == "pinned");
+        return std::make_shared<CachingMemoryPool>(std::move(be), o);
+      }), py::arg("backend") = "host", py::arg("device") = 0, py::arg("limit_mb") = 0, py::arg("max_split_mb") = 0,
+           py::arg("pre_allocate_mb") = 0)
+      .def("alloc", [](CachingMemoryPool& p, int64_t bytes, int64_t stream) { return (uint64_t)(uintptr_t)p.alloc((size_t)bytes, stream); },
+           py::arg("bytes"), py::arg("stream") = 0)
+      .def("free", [](CachingMemoryPool& p, uint64_t ptr) { p.free((void*)(uintptr_t)ptr); })
+      .def("mark_used_by_stream", [](CachingMemoryPool& p, uint64_t ptr, int64_t stream) { p.mark_used_by_stream((void*)(uintptr_t)ptr, stream); })
+      .def("wait", [](CachingMemoryPool& p, uint64_t ptr) { p.wait((void*)(uintptr_t)ptr); })
+      .def("empty_cache", [](CachingMemoryPool& p) { return (int64_t)p.empty_cache(); })
+      .def("summary", &CachingMemoryPool::summary)
+      .def("stats", [](const CachingMemoryPool& p) {
+        PoolStats s = p.stats();
+        py::dict d;
+        d["reserved"] = s.reserved; d["allocated"] = s.allocated; d["peak_reserved"] = s.peak_reserved; d["peak_allocated"] = s.peak_allocated;
+        d["num_alloc"] = s.num_alloc; d["num_free"] = s.num_free; d["num_segment_alloc"] = s.num_segment_alloc; d["num_split"] = s.num_split;
+        d["num_merge"] = s.num_merge; d["cache_hits"] = s.cache_hits;
+        return d;
+      });
+  m.def("stream_role_name", &stream_role_name);
+  m.def("logical_stream", [](int device, int index) { return (uint64_t)(uintptr_t)logical_stream(device, index); });
+  m.def("sync_logical_stream", &sync_logical_stream);
+  m.def("random_seed", [] { return RandomState::get().seed(); });
+  m.def("random_set_seed", [](uint64_t s) { RandomState::get().set_seed(s); });
+  m.def("random_next_offset", [](uint64_t n) { return RandomState::get().next_offset(n); });
+  m.def("random_offset", [] { return RandomState::get().offset(); });
+  m.def("random_set_offset", [](uint64_t o) { RandomState::get().set_offset(o); });
+  py::class_<NativeDataloader, std::shared_ptr<NativeDataloader>>(m, "Dataloader")
+      .def(py::init([](const at::Tensor& data, int64_t batch_size, bool shuffle, bool drop_last, int dp_rank, int dp_size, uint64_t seed,
+                       int prefetch, bool pin_memory) {
+        return std::make_shared<NativeDataloader>(data, batch_size, shuffle, drop_last, dp_rank, dp_size, seed, prefetch, pin_memory);
+      }), py::arg("data"), py::arg("batch_size"), py::arg("shuffle") = false, py::arg("drop_last") = true, py::arg("dp_rank") = 0,
+           py::arg("dp_size") = 1, py::arg("seed") = 0, py::arg("prefetch") = 2, py::arg("pin_memory") = false)
+      .def("next", [](NativeDataloader& d) { py::gil_scoped_release rel; return d.next(); })
+      .def("reset", &NativeDataloader::reset, py::arg("start_batch") = 0)
+      .def_property_readonly("num_batches", &NativeDataloader::num_batches);
 
   // fp8 building blocks (numerics tests / benchmarks)
   m.def("quantize_rowwise_e4m3", [](const at::Tensor& x) {

@@ -36,19 +36,18 @@ __global__ void __launch_bounds__(256) quant_rowwise_kernel(const __nv_bfloat16*
   for (int c = (nvec << 3) + threadIdx.x; c < cols; c += blockDim.x) amax = fmaxf(amax, fabsf(__bfloat162float(row[c])));
   amax = block_max(amax, red);
   const float sc = amax > 0.f ? amax / kE4M3Max : 1.0f;
-  const float inv = 1.0f / sc;
   if (threadIdx.x == 0) scale[r] = sc;
   uint8_t* qrow = q + r * ldq;
   for (int v = threadIdx.x; v < nvec; v += blockDim.x) {   // second read of the row hits L1/L2
     float f[8];
     unpack8(ld8(row, v), f);
     uint2 o;
-    o.x = pack4_e4m3(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv);
-    o.y = pack4_e4m3(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv);
+    o.x = pack4_e4m3(f[0] / sc, f[1] / sc, f[2] / sc, f[3] / sc);     // true division: bit-identical to x / scale references
+    o.y = pack4_e4m3(f[4] / sc, f[5] / sc, f[6] / sc, f[7] / sc);
     reinterpret_cast<uint2*>(qrow)[v] = o;
   }
   for (int c = (nvec << 3) + threadIdx.x; c < cols; c += blockDim.x)
-    qrow[c] = (uint8_t)__nv_cvt_float_to_fp8(__bfloat162float(row[c]) * inv, __NV_SATFINITE, __NV_E4M3);
+    qrow[c] = (uint8_t)__nv_cvt_float_to_fp8(__bfloat162float(row[c]) / sc, __NV_SATFINITE, __NV_E4M3);
 }
 
 // column-wise absolute maximum -> scale[c] (atomicMax on the float bit pattern: values are non-negative)

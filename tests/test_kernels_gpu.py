@@ -251,9 +251,15 @@ def test_linear_fp8_block_scaled(M, N, K, act):
         tf = t.float()
         sc = (tf.abs().amax(-1, keepdim=True) / 448.0).clamp_min(1e-30)
         return (tf / sc).to(torch.float8_e4m3fn).float() * sc
-    pre = fq(x) @ fq(w).t() + b.float()
+    # exact check of the tensor-core product: dequantise what the quantisation kernel produced and multiply in fp32
+    qx, sx = ht._C.quantize_rowwise_e4m3(x)
+    qw, sw = ht._C.quantize_rowwise_e4m3(w)
+    dx, dw = qx.view(torch.float8_e4m3fn).float() * sx[:, None], qw.view(torch.float8_e4m3fn).float() * sw[:, None]
+    pre = dx @ dw.t() + b.float()
     yq = torch.nn.functional.gelu(pre) if act == "gelu" else pre
-    close(torch.as_tensor(y.numpy()), yq, 0.03, 0.02)                      # exact emulation of the quantised product
+    close(torch.as_tensor(y.numpy()), yq, 0.03, 0.02)
+    # and the quantiser itself against the torch formula (per-row amax / 448, round-to-nearest-even)
+    assert float((dx - fq(x)).abs().max()) < 1e-6 and float((dw - fq(w)).abs().max()) < 1e-6
     xr, wr = x.float().requires_grad_(), w.float().requires_grad_()
     yr = xr @ wr.t() + b.float()
     yr = torch.nn.functional.gelu(yr) if act == "gelu" else yr

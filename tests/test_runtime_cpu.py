@@ -1,0 +1,69 @@
+"""Native runtime pieces (C++): caching memory pool, random-state bookkeeping, prefetching data loader, stream roles."""
+import numpy as np
+import torch
+
+from hetu_b200 import _C
+
+
+def test_memory_pool_split_merge_reuse_and_limits():
+    pool = _C.MemoryPool("host", limit_mb=64)
+    a = pool.alloc(300 << 10)          # small pool: carved from a 2 MiB segment
+    b = pool.alloc(300 << 10)
+    st = pool.stats()
+    assert st["num_segment_alloc"] == 1 and st["num_split"] >= 2 and st["allocated"] >= 600 << 10
+    pool.free(a)
+    c = pool.alloc(200 << 10)          # fits in the hole left by `a`
+    assert c == a and pool.stats()["cache_hits"] >= 1
+    pool.free(b)
+    pool.free(c)
+    st = pool.stats()
+    assert st["allocated"] == 0 and st["num_merge"] >= 2
+    assert pool.empty_cache() == 2 << 20 and pool.stats()["reserved"] == 0
+    big = pool.alloc(30 << 20)
+    assert pool.stats()["reserved"] >= 30 << 20
+    try:
+        pool.alloc(60 << 20)
+        raised = False
+    except Exception as e:     # noqa: BLE001
+        raised = "out of memory" in str(e)
+    assert raised
+    pool.free(big)
+    # per-stream free lists: a block freed on stream 1 is not handed to stream 2
+    p1 = pool.alloc(4 << 20, stream=1)
+    pool.free(p1)
+    p2 = pool.alloc(4 << 20, stream=2)
+    assert p2 != p1
+    p3 = pool.alloc(4 << 20, stream=1)
+    assert p3 == p1
+    assert "host pool" in pool.summary()
+
+
+def test_random_state_offsets_are_reserved_monotonically():
+    _C.random_set_seed(123)
+    assert _C.random_seed() == 123 and _C.random_offset() == 0
+    a = _C.random_next_offset(1000)
+    b = _C.random_next_offset(10)
+    assert (a, b) == (0, 1000) and _C.random_offset() == 1010
+    _C.random_set_offset(a)          # replay (activation recompute) starts from the recorded offset
+    assert _C.random_next_offset(1000) == 0
+
+
+def test_native_dataloader_dp_slices_prefetch_and_reset():
+    data = torch.arange(40).reshape(20, 2)
+    d0 = _C.Dataloader(data, 8, dp_rank=0, dp_size=2)
+    d1 = _C.Dataloader(data, 8, dp_rank=1, dp_size=2)
+    assert d0.num_batches == 2
+    a, b = d0.next(), d1.next()
+    assert a[:, 0].tolist() == [0, 4, 8, 12] and b[:, 0].tolist() == [2, 6, 10, 14]
+    d0.next()
+    wrap = d0.next()                    # second epoch starts over
+    assert wrap[:, 0].tolist() == [0, 4, 8, 12]
+    d0.reset(1)
+    assert d0.next()[:, 0].tolist() == [16, 20, 24, 28]
+    sh = _C.Dataloader(data, 10, shuffle=True, seed=5)
+    x, y = sh.next(), sh.next()
+    assert sorted(torch.cat([x, y])[:, 0].tolist()) == list(range(0, 40, 2))
+
+
+def test_stream_role_names():
+    assert _C.stream_role_name(1) == "computing" and _C.stream_role_name(6) == "collective" and _C.stream_role_name(3) == "h2d"
