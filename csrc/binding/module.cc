@@ -19,6 +19,7 @@
 #include "../v1/embedding_cache.h"
 #include "../runtime/symm_mem.h"
 #include "../runtime/memory_pool.h"
+#include "../v1/ps_server.h"
 #include "../runtime/runtime.h"
 
 namespace py = pybind11;
@@ -563,6 +564,45 @@ PYBIND11_MODULE(_C, m) {
                               rt.defined() ? rt.data_ptr() : nullptr, rpr, (int)N, cur_stream()), "reduce_slots");
     return out;
   }, py::arg("x"), py::arg("w"), py::arg("staging"), py::arg("bias") = py::none(), py::arg("residual") = py::none());
+
+  // ---------------------------------------------------------------- v1 parameter server
+  py::enum_<PsOptimizer>(m, "PsOptimizer").value("NONE", PsOptimizer::NONE).value("SGD", PsOptimizer::SGD)
+      .value("MOMENTUM", PsOptimizer::MOMENTUM).value("ADAGRAD", PsOptimizer::ADAGRAD).value("ADAM", PsOptimizer::ADAM);
+  py::class_<ParameterServer, std::shared_ptr<ParameterServer>>(m, "ParameterServer")
+      .def(py::init<int>(), py::arg("num_workers"))
+      .def("init_dense", [](ParameterServer& ps, int64_t key, const std::vector<float>& v, PsOptimizer opt, float lr, float momentum) {
+        PsParamConfig c; c.opt = opt; c.lr = lr; c.momentum = momentum;
+        ps.init_dense(key, v, c);
+      }, py::arg("key"), py::arg("value"), py::arg("opt") = PsOptimizer::SGD, py::arg("lr") = 0.01f, py::arg("momentum") = 0.9f)
+      .def("init_sparse", [](ParameterServer& ps, int64_t key, int64_t rows, int width, const std::vector<float>& v, PsOptimizer opt, float lr) {
+        PsParamConfig c; c.opt = opt; c.lr = lr;
+        ps.init_sparse(key, rows, width, v, c);
+      }, py::arg("key"), py::arg("rows"), py::arg("width"), py::arg("value"), py::arg("opt") = PsOptimizer::SGD, py::arg("lr") = 0.01f)
+      .def("push_dense", &ParameterServer::push_dense, py::call_guard<py::gil_scoped_release>())
+      .def("pull_dense", &ParameterServer::pull_dense, py::call_guard<py::gil_scoped_release>())
+      .def("push_pull_dense", &ParameterServer::push_pull_dense, py::call_guard<py::gil_scoped_release>())
+      .def("push_sparse", &ParameterServer::push_sparse, py::call_guard<py::gil_scoped_release>())
+      .def("pull_sparse", &ParameterServer::pull_sparse, py::call_guard<py::gil_scoped_release>())
+      .def("row_versions", &ParameterServer::row_versions)
+      .def("sync_cache", [](ParameterServer& ps, int64_t key, const std::vector<int64_t>& rows, const std::vector<int64_t>& vers, int64_t bound) {
+        std::vector<int64_t> stale, fv;
+        std::vector<float> vals;
+        ps.sync_cache(key, rows, vers, bound, &stale, &vals, &fv);
+        return py::make_tuple(stale, vals, fv);
+      })
+      .def("barrier", &ParameterServer::barrier, py::call_guard<py::gil_scoped_release>())
+      .def("ssp_init", &ParameterServer::ssp_init)
+      .def("ssp_sync", &ParameterServer::ssp_sync, py::call_guard<py::gil_scoped_release>())
+      .def("preduce", [](ParameterServer& ps, int worker, int64_t key, const std::vector<float>& v, int min_workers, int wait_ms) {
+        std::vector<int> partners;
+        std::vector<float> out;
+        {
+          py::gil_scoped_release rel;
+          out = ps.preduce(worker, key, v, min_workers, wait_ms, &partners);
+        }
+        return py::make_tuple(out, partners);
+      }, py::arg("worker"), py::arg("key"), py::arg("value"), py::arg("min_workers") = 2, py::arg("wait_ms") = 50)
+      .def("stats", &ParameterServer::stats);
 
   // ---------------------------------------------------------------- native runtime: memory pool, streams, RNG state, data loader
   py::class_<CachingMemoryPool, std::shared_ptr<CachingMemoryPool>>(m, "MemoryPool")

@@ -716,7 +716,7 @@ void Executor::run_ops(ExecPlan& plan, const std::vector<OpDef*>& ops, bool back
       }
       try {
         if (op->type == "comm") {
-          if (!tp_fused_comm(plan, op, outs)) outs = exec_comm(plan.comm[op->id], op, ins, rc);
+          if (!tp_fused_comm(plan, op, ins, outs)) outs = exec_comm(plan.comm[op->id], op, ins, rc);
         } else if (backward && zf_active_ != nullptr && zero_fused_wgrad(*zf_active_, op, ins)) outs = {at::Tensor()};
         else if ((op->type == "linear" || op->type == "linear_dgrad") && tp_fused_gemm(plan, op, ins, rc, outs)) {}
         else outs = op->kernel->compute(*op, ins, &rc);

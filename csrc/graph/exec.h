@@ -173,7 +173,7 @@ class Executor {
   // tensor-parallel GEMM -> reduce-scatter over symmetric memory (tp_fused.cc)
   void tp_fused_scan(ExecPlan& plan);
   bool tp_fused_gemm(ExecPlan& plan, OpDef* op, const std::vector<at::Tensor>& ins, RunCtx& rc, std::vector<at::Tensor>& outs);
-  bool tp_fused_comm(ExecPlan& plan, OpDef* op, std::vector<at::Tensor>& outs);
+  bool tp_fused_comm(ExecPlan& plan, OpDef* op, const std::vector<at::Tensor>& ins, std::vector<at::Tensor>& outs);
 
   Graph* g_;
   std::map<std::pair<int, std::vector<TensorId>>, ExecPlan> plans_;

@@ -36,6 +36,17 @@ struct GemmSink {
   bool used = false;
 };
 extern thread_local GemmSink* tls_gemm_sink;
+// Source override for the next GEMM: its A operand (`dst`, a local [world * rows_per_rank, K] buffer) is all-gathered from
+// the ranks' symmetric shards by the GEMM kernel itself while it computes (fused all-gather -> GEMM).
+struct GemmGather {
+  const void* src[8] = {nullptr};
+  void* dst = nullptr;
+  uint32_t* flags = nullptr;
+  int world = 1, my_rank = 0;
+  int64_t rows_per_rank = 0;
+  bool used = false;
+};
+extern thread_local GemmGather* tls_gemm_gather;
 // collective over `ranks`: allocate a symmetric buffer, exchange the CUDA IPC handles and map every peer (tp_fused.cc)
 void symm_exchange_and_open(const std::string& name, size_t bytes, const std::vector<int>& ranks, int pos);
 

@@ -498,3 +498,98 @@ ATEN_OP(softmax_cross_entropy, 1, {
 });
 
 }  // namespace hb
+
+// ------------------------------------------------------------------ blockwise quantisation (int8 / nf4 / fp4)
+// (capability parity: hetu/graph/ops/Quantization.cc + hetu/impl/kernel/Quantization.cu, which wrap bitsandbytes'
+//  blockwise absmax quantisers; 4-bit codes are packed two per byte, high nibble first)
+namespace hb {
+namespace {
+at::Tensor code_table(const std::string& kind, const at::TensorOptions& o) {
+  static const float nf4[16] = {-1.0f, -0.6961928f, -0.5250730f, -0.3949175f, -0.2844414f, -0.1848449f, -0.0910500f, 0.0f,
+                                0.0795803f, 0.1609302f, 0.2461123f, 0.3379152f, 0.4407098f, 0.5626170f, 0.7229568f, 1.0f};
+  static const float fp4[16] = {0.0f, 0.0052083f, 0.6666667f, 1.0f, 0.3333333f, 0.5f, 0.1666667f, 0.25f,
+                                -0.0f, -0.0052083f, -0.6666667f, -1.0f, -0.3333333f, -0.5f, -0.1666667f, -0.25f};
+  const float* t = kind == "fp4" ? fp4 : nf4;
+  return at::from_blob(const_cast<float*>(t), {16}, at::TensorOptions().dtype(at::kFloat)).clone().to(o.device());
+}
+std::vector<at::Tensor> quantize_blockwise(const at::Tensor& x, const std::string& kind, int64_t bs) {
+  at::Tensor flat = x.to(at::kFloat).reshape({-1});
+  const int64_t n = flat.numel(), nb = (n + bs - 1) / bs;
+  at::Tensor padded = at::zeros({nb * bs}, flat.options());
+  padded.narrow(0, 0, n).copy_(flat);
+  at::Tensor blocks = padded.reshape({nb, bs});
+  at::Tensor absmax = blocks.abs().amax(1).clamp_min(1e-12);
+  at::Tensor norm = blocks / absmax.unsqueeze(1);
+  if (kind == "int8") {
+    at::Tensor q = at::round(norm * 127.0).clamp(-127, 127).to(at::kChar);
+    return {q.reshape({-1}).narrow(0, 0, n).reshape(x.sizes()), absmax};
+  }
+  at::Tensor table = code_table(kind, flat.options());
+  at::Tensor idx = (norm.unsqueeze(-1) - table.reshape({1, 1, 16})).abs().argmin(-1).to(at::kByte).reshape({-1});   // nearest code
+  at::Tensor hi = idx.slice(0, 0, nb * bs, 2), lo = idx.slice(0, 1, nb * bs, 2);
+  return {(hi * 16 + lo).to(at::kByte), absmax};
+}
+at::Tensor dequantize_blockwise(const at::Tensor& q, const at::Tensor& absmax, const std::string& kind, int64_t bs,
+                                const std::vector<int64_t>& shape, at::ScalarType dt) {
+  int64_t n = 1;
+  for (auto s : shape) n *= s;
+  at::Tensor vals;
+  if (kind == "int8") vals = q.to(at::kFloat).reshape({-1}) / 127.0;
+  else {
+    at::Tensor table = code_table(kind, absmax.options());
+    at::Tensor b = q.reshape({-1}).to(at::kLong);
+    at::Tensor idx = at::stack({at::floor_divide(b, 16), at::remainder(b, 16)}, 1).reshape({-1});
+    vals = table.index_select(0, idx);
+  }
+  const int64_t nb = absmax.numel();
+  at::Tensor padded = at::zeros({nb * bs}, vals.options());
+  padded.narrow(0, 0, std::min<int64_t>(vals.numel(), nb * bs)).copy_(vals.narrow(0, 0, std::min<int64_t>(vals.numel(), nb * bs)));
+  at::Tensor out = (padded.reshape({nb, bs}) * absmax.to(at::kFloat).unsqueeze(1)).reshape({-1}).narrow(0, 0, n);
+  return out.reshape(shape).to(dt);
+}
+}  // namespace
+
+ATEN_OP_NODIFF(quantize_blockwise, 2, {
+  if (in[0].is_meta()) {
+    const std::string kind = op.attrs.s("kind", "int8");
+    const int64_t bs = op.attrs.i("blocksize", 64), n = in[0].numel(), nb = (n + bs - 1) / bs;
+    if (kind == "int8") return {at::empty(in[0].sizes(), in[0].options().dtype(at::kChar)), at::empty({nb}, in[0].options().dtype(at::kFloat))};
+    return {at::empty({nb * bs / 2}, in[0].options().dtype(at::kByte)), at::empty({nb}, in[0].options().dtype(at::kFloat))};
+  }
+  return quantize_blockwise(in[0], op.attrs.s("kind", "int8"), op.attrs.i("blocksize", 64));
+});
+ATEN_OP_NODIFF(dequantize_blockwise, 1, {
+  const std::vector<int64_t> shape = op.attrs.ints("shape");
+  const at::ScalarType dt = to_aten_dtype(dtype_from_name(op.attrs.s("dtype", "float32")));
+  if (in[0].is_meta()) return {at::empty(shape, in[0].options().dtype(dt))};
+  return {dequantize_blockwise(in[0], in[1], op.attrs.s("kind", "int8"), op.attrs.i("blocksize", 64), shape, dt)};
+});
+// y = x @ dequant(w_q)^T : 4-bit frozen base weights (QLoRA-style); differentiable w.r.t. x only
+static Ts matmul4bit_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const std::vector<int64_t> wshape = op.attrs.ints("weight_shape");
+  if (in[0].is_meta()) {
+    std::vector<int64_t> o = in[0].sizes().vec();
+    o.back() = wshape[0];
+    return {at::empty(o, in[0].options())};
+  }
+  at::Tensor w = dequantize_blockwise(in[1], in[2], op.attrs.s("kind", "nf4"), op.attrs.i("blocksize", 64), wshape, in[0].scalar_type());
+  return {at::matmul(in[0], w.t())};
+}
+static TensorList matmul4bit_grad(OpDef& op, const TensorList& g) {
+  AttrMap a = op.attrs;
+  a.set("transpose", true);
+  return {op.graph->make_op1("matmul4bit_dgrad", {g[0], op.inputs[1], op.inputs[2]}, a), nullptr, nullptr};
+}
+static Ts matmul4bit_dgrad_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const std::vector<int64_t> wshape = op.attrs.ints("weight_shape");
+  if (in[0].is_meta()) {
+    std::vector<int64_t> o = in[0].sizes().vec();
+    o.back() = wshape[1];
+    return {at::empty(o, in[0].options())};
+  }
+  at::Tensor w = dequantize_blockwise(in[1], in[2], op.attrs.s("kind", "nf4"), op.attrs.i("blocksize", 64), wshape, in[0].scalar_type());
+  return {at::matmul(in[0], w)};
+}
+HB_REGISTER_OP(matmul4bit, "matmul4bit", 1, 0, matmul4bit_compute, matmul4bit_grad, nullptr, nullptr);
+HB_REGISTER_OP(matmul4bit_dgrad, "matmul4bit_dgrad", 1, kFlagNondiff, matmul4bit_dgrad_compute, nullptr, nullptr, nullptr);
+}  // namespace hb

@@ -127,6 +127,11 @@ static void run_gemm(const at::Tensor& A, bool a_mn, const at::Tensor& B, bool b
   c.act = act;
   c.accumulate = accumulate;
   c.alpha = alpha;
+  GemmGather* ag = tls_gemm_gather;
+  if (ag != nullptr && !ag->used && A.data_ptr() == ag->dst && !a_mn && M == ag->rows_per_rank * ag->world) {
+    c.ag_src = ag->src; c.ag_flags = ag->flags; c.ag_world = ag->world; c.ag_rank = ag->my_rank; c.ag_rows_per_rank = (int)ag->rows_per_rank;
+    ag->used = true;
+  }
   GemmSink* sink = tls_gemm_sink;
   if (sink != nullptr && !sink->used && bias == nullptr && aux_in == nullptr && aux_out == nullptr && act == ACT_NONE && !accumulate &&
       c.out == GemmOut::BF16 && M == sink->rows_per_rank * sink->world && N == sink->cols) {

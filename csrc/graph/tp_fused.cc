@@ -14,6 +14,7 @@
 namespace hb {
 
 thread_local GemmSink* tls_gemm_sink = nullptr;
+thread_local GemmGather* tls_gemm_gather = nullptr;
 
 struct TpFusedState {
   std::unordered_map<OpId, OpId> comm_of_gemm;     // producer GEMM op -> its reduce-scatter comm op
@@ -21,6 +22,11 @@ struct TpFusedState {
   struct Staging { std::string name[2]; size_t bytes = 0; int next = 0; };
   std::map<std::vector<int>, Staging> staging;     // per tp group
   std::unordered_map<OpId, std::pair<std::string, std::vector<int64_t>>> pending;   // comm op -> (buffer, [rows_per_rank, cols])
+  // fused all-gather -> GEMM: all-gather comm op -> the forward linear that consumes it first
+  std::unordered_map<OpId, OpId> gemm_of_gather;
+  std::map<std::vector<int>, Staging> ag_staging;
+  std::unordered_map<OpId, GemmGather> pending_gather;    // linear op -> gather descriptor prepared by its comm op
+  std::unordered_map<OpId, at::Tensor> gather_flags;
 };
 
 void symm_exchange_and_open(const std::string& name, size_t bytes, const std::vector<int>& ranks, int pos) {
@@ -61,6 +67,27 @@ void Executor::tp_fused_scan(ExecPlan& plan) {
   };
   scan(plan.fw_ops);
   scan(plan.bw_ops);
+  // all-gather (dim 0) whose first consumer in execution order is a forward linear taking it as the activation operand
+  if (env_int("HETU_TP_FUSED_AG", 1) != 0) {
+    std::unordered_map<OpId, int> pos;
+    for (size_t i = 0; i < plan.fw_ops.size(); ++i) pos[plan.fw_ops[i]->id] = (int)i;
+    for (OpDef* c : plan.fw_ops) {
+      if (c->type != "comm") continue;
+      auto it = plan.comm.find(c->id);
+      if (it == plan.comm.end() || it->second.type != CommType::ALL_GATHER || it->second.dim != 0) continue;
+      if (it->second.ranks.size() < 2 || it->second.ranks.size() > 8) continue;
+      const Tensor& y = c->outputs[0];
+      if (y->dtype != DataType::BFLOAT16 || y->shape.size() != 2) continue;
+      OpDef* first = nullptr;
+      int best = INT32_MAX;
+      for (OpDef* u : y->consumers) {
+        auto p = pos.find(u->id);
+        if (p != pos.end() && p->second < best) { best = p->second; first = u; }
+      }
+      if (first == nullptr || first->type != "linear" || first->inputs[0]->id != y->id) continue;
+      st->gemm_of_gather[c->id] = first->id;
+    }
+  }
 }
 
 // called instead of the plain compute for a GEMM op whose result feeds a fused reduce-scatter; returns false to decline
@@ -68,6 +95,22 @@ bool Executor::tp_fused_gemm(ExecPlan& plan, OpDef* op, const std::vector<at::Te
   auto sit = tp_fused_.find(&plan);
   if (sit == tp_fused_.end() || !sit->second) return false;
   TpFusedState& st = *sit->second;
+  auto git = st.pending_gather.find(op->id);
+  if (git != st.pending_gather.end()) {
+    // this linear's activation operand is gathered by the GEMM kernel itself (fused all-gather -> GEMM)
+    GemmGather ag = git->second;
+    st.pending_gather.erase(git);
+    tls_gemm_gather = &ag;
+    try {
+      outs = op->kernel->compute(*op, ins, &rc);
+    } catch (...) {
+      tls_gemm_gather = nullptr;
+      throw;
+    }
+    tls_gemm_gather = nullptr;
+    HB_CHECK(ag.used) << "fused all-gather: " << op->name() << " did not consume its gather descriptor";
+    return true;
+  }
   auto pit = st.comm_of_gemm.find(op->id);
   if (pit == st.comm_of_gemm.end()) return false;
   const CommStep& cs = plan.comm[pit->second];
@@ -117,10 +160,46 @@ bool Executor::tp_fused_gemm(ExecPlan& plan, OpDef* op, const std::vector<at::Te
 }
 
 // the reduce-scatter side: sum this rank's `world` staging slots (returns false when the producer did not use the sink)
-bool Executor::tp_fused_comm(ExecPlan& plan, OpDef* op, std::vector<at::Tensor>& outs) {
+bool Executor::tp_fused_comm(ExecPlan& plan, OpDef* op, const std::vector<at::Tensor>& ins, std::vector<at::Tensor>& outs) {
   auto sit = tp_fused_.find(&plan);
   if (sit == tp_fused_.end() || !sit->second) return false;
   TpFusedState& st = *sit->second;
+  auto gt = st.gemm_of_gather.find(op->id);
+  if (gt != st.gemm_of_gather.end() && !ins.empty() && is_native(ins[0]) && ins[0].dim() == 2) {
+    const CommStep& cs = plan.comm[op->id];
+    const int world = (int)cs.ranks.size();
+    const at::Tensor x = ins[0].contiguous();
+    const int64_t rows = x.size(0), K = x.size(1);
+    int pos = -1;
+    for (int i = 0; i < world; ++i) if (cs.ranks[i] == CommRuntime::get().rank()) pos = i;
+    if (pos >= 0 && rows % 256 == 0 && K % 8 == 0) {
+      auto& sg = st.ag_staging[cs.ranks];
+      const size_t need = (size_t)rows * K * 2;
+      if (sg.bytes < need) {
+        static int seq = 0;
+        for (int k = 0; k < 2; ++k) {
+          sg.name[k] = "tp_ag_" + std::to_string(seq++);
+          symm_exchange_and_open(sg.name[k], need, cs.ranks, pos);
+        }
+        sg.bytes = need;
+      }
+      SymmBuffer& buf = SymmMem::get().buffer(sg.name[sg.next]);
+      sg.next ^= 1;
+      cudaStream_t s = cur_stream();
+      cuda_ok(cudaMemcpyAsync(buf.local, x.data_ptr(), need, cudaMemcpyDeviceToDevice, s), "publish shard");
+      cuda_ok(symm_barrier(buf, s), "ag barrier");     // every rank's shard is readable
+      at::Tensor out = at::empty({rows * world, K}, x.options());
+      at::Tensor flags = at::zeros({rows * world / 128}, x.options().dtype(at::kInt));
+      GemmGather g;
+      for (int r = 0; r < world; ++r) g.src[r] = buf.peer[r];
+      g.dst = out.data_ptr(); g.flags = reinterpret_cast<uint32_t*>(flags.data_ptr<int>());
+      g.world = world; g.my_rank = pos; g.rows_per_rank = rows;
+      st.pending_gather[gt->second] = g;
+      st.gather_flags[gt->second] = flags;     // keeps the flag array alive until the next use of this linear
+      outs = {out};
+      return true;
+    }
+  }
   auto it = st.pending.find(op->id);
   if (it == st.pending.end()) return false;
   SymmBuffer& buf = SymmMem::get().buffer(it->second.first);

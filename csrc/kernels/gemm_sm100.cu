@@ -116,6 +116,17 @@ cudaError_t gemm_bf16(const GemmCall& c, cudaStream_t stream) {
   }
 
   p.row_scale = c.row_scale; p.col_scale = c.col_scale;
+  for (int i = 0; i < 8; ++i) p.ag_src[i] = nullptr;
+  p.ag_dst = nullptr; p.ag_flags = nullptr; p.ag_world = 1; p.ag_rank = 0; p.ag_rows_per_rank = 0;
+  if (c.ag_src != nullptr && c.ag_world > 1) {
+    // A must be contiguous [M, K] K-major; a rank's shard is a whole number of M tiles of the widest config
+    if (c.a_mn_major || c.fp8 || c.lda != c.K || c.ag_world > 8 || c.ag_flags == nullptr || (c.ag_rows_per_rank % 256) != 0 ||
+        c.ag_rows_per_rank * c.ag_world != c.M || (c.K % 8) != 0)
+      return cudaErrorInvalidValue;
+    for (int i = 0; i < c.ag_world; ++i) p.ag_src[i] = c.ag_src[i];
+    p.ag_dst = const_cast<void*>(c.A); p.ag_flags = c.ag_flags; p.ag_world = c.ag_world; p.ag_rank = c.ag_rank;
+    p.ag_rows_per_rank = c.ag_rows_per_rank;
+  }
   if (c.fp8) {
     if (G == 2) {
       if (c.out == GemmOut::BF16) return launch_cfg<2, false, false, 6, __nv_bfloat16, true>(ta, tb, p, stream);

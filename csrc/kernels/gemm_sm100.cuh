@@ -49,6 +49,14 @@ struct GemmParams {
   // fp8 (e4m3) operands: C = (A8 * B8) * row_scale[m] * col_scale[n]  -- scales of a 1 x K block-scaled quantisation
   const float* row_scale;   // [M] or nullptr
   const float* col_scale;   // [N] or nullptr
+  // fused all-gather -> GEMM: A is a local [M, K] buffer whose row block r (ag_rows_per_rank rows) is rank r's shard.
+  // Warp 3 of every CTA copies this CTA's slice of each 128-row chunk from the owner's symmetric buffer (NVLink peer
+  // loads) into A and bumps ag_flags[chunk]; the TMA producer waits until all CTAs have delivered a chunk before it
+  // loads tiles from it.  Tiles are visited starting at this rank's own rows, in the order the chunks arrive.
+  const void* ag_src[8];    // per-rank shard [ag_rows_per_rank, K] bf16 (mapped peer memory); null = plain GEMM
+  void* ag_dst;             // == A
+  uint32_t* ag_flags;       // [M / 128] zero-initialised
+  int ag_world, ag_rank, ag_rows_per_rank;
 };
 
 namespace gemm_detail {
@@ -135,7 +143,7 @@ __device__ __forceinline__ float apply_aux(float v, float a, int mode) {
 // Group-swizzled tile order: consecutive tile ids walk down a band of kGroupM
 // M-blocks before moving to the next N-block, so the ~74 clusters in flight
 // share a small set of A and B panels in L2.
-__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn, int m_rotate = 0) {
   constexpr int kGroupM = 8;
   const int per_group = kGroupM * tiles_n;
   const int g = tile / per_group;
@@ -144,6 +152,7 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
   const int in_g = tile - g * per_group;
   tm = first_m + in_g % gm;
   tn = in_g / gm;
+  if (m_rotate) { tm += m_rotate; if (tm >= tiles_m) tm -= tiles_m; }
 }
 
 }  // namespace gemm_detail
@@ -187,6 +196,8 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int num_kb = (p.K + BLOCK_K_E - 1) / BLOCK_K_E;
   const int cluster_id = blockIdx.x / kCtaGroup;
   const int num_clusters = gridDim.x / kCtaGroup;
+  const bool ag_fused = p.ag_world > 1;
+  const int m_rotate = ag_fused ? (p.ag_rank * p.ag_rows_per_rank) / TILE_M : 0;   // start at this rank's own rows
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
@@ -217,9 +228,19 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        int tm, tn; tile_coords(tile, tiles_m, tiles_n, tm, tn);
+        int tm, tn; tile_coords(tile, tiles_m, tiles_n, tm, tn, m_rotate);
         const int m0 = tm * TILE_M + int(rank) * BLOCK_M;
         const int n0 = tn * BLOCK_N + int(rank) * LOAD_N;
+        if (ag_fused && m0 < p.M) {
+          // the 128 rows of this CTA's A tile are one all-gather chunk: wait until every CTA delivered its slice
+          const uint32_t* f = p.ag_flags + (m0 >> 7);
+          uint32_t spins = 0;
+          while (ptx::ld_acquire_gpu(f) < gridDim.x) {
+            __nanosleep(64);
+            if (++spins > (1u << 26)) __trap();   // a lost peer must surface as an error, not as a hung GPU
+          }
+          ptx::fence_proxy_async();               // generic-proxy copies -> async-proxy (TMA) reads
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[s], ph ^ 1);
           if (kCtaGroup == 1 || leader) ptx::mbar_arrive_expect_tx(&full_bar[s], kTxBytes);
@@ -285,6 +306,32 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
     __syncwarp();
+  } else if (warp == 3) {
+    // ========================= all-gather puller (fused AG -> GEMM only) =========================
+    if (ag_fused) {
+      const int chunks_per_rank = p.ag_rows_per_rank >> 7;
+      const int64_t chunk_vecs = int64_t(128) * p.K * 2 / 16;        // uint4 per 128-row chunk
+      for (int i = 0; i < p.ag_world; ++i) {
+        const int r = (p.ag_rank + i) % p.ag_world;                  // own shard first, then the ring order the tiles follow
+        const uint4* src = reinterpret_cast<const uint4*>(p.ag_src[r]);
+        uint4* dst = reinterpret_cast<uint4*>(p.ag_dst) + int64_t(r) * chunks_per_rank * chunk_vecs;
+        for (int c = 0; c < chunks_per_rank; ++c) {
+          const uint4* s4 = src + int64_t(c) * chunk_vecs;
+          uint4* d4 = dst + int64_t(c) * chunk_vecs;
+          int64_t v = int64_t(blockIdx.x) * 32 + lane;
+          const int64_t stride = int64_t(gridDim.x) * 32;
+          for (; v + 3 * stride < chunk_vecs; v += 4 * stride) {     // 4 independent 16-byte peer loads in flight per lane
+            const uint4 a = ptx::ld_global_relaxed_sys(s4 + v), b = ptx::ld_global_relaxed_sys(s4 + v + stride);
+            const uint4 c4 = ptx::ld_global_relaxed_sys(s4 + v + 2 * stride), d = ptx::ld_global_relaxed_sys(s4 + v + 3 * stride);
+            d4[v] = a; d4[v + stride] = b; d4[v + 2 * stride] = c4; d4[v + 3 * stride] = d;
+          }
+          for (; v < chunk_vecs; v += stride) d4[v] = ptx::ld_global_relaxed_sys(s4 + v);
+          __syncwarp();
+          __threadfence();
+          if (lane == 0) atomicAdd(p.ag_flags + r * chunks_per_rank + c, 1u);
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ========================= epilogue =========================
     const int q = warp & 3;             // TMEM lane quarter this warp may access
@@ -292,7 +339,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
     constexpr int kChunksPerWarp = BLOCK_N / 32 / (kEpiWarps / 4);
     int as = 0; uint32_t aph = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      int tm, tn; tile_coords(tile, tiles_m, tiles_n, tm, tn);
+      int tm, tn; tile_coords(tile, tiles_m, tiles_n, tm, tn, m_rotate);
       const int row = tm * TILE_M + int(rank) * BLOCK_M + q * 32 + lane;
       const int n_base = tn * BLOCK_N;
       ptx::mbar_wait(&tfull_bar[as], aph);

@@ -40,6 +40,10 @@ struct GemmCall {
   void* const* peer_c = nullptr;   // host array of `world` mapped staging buffers, each [world, rows_per_rank, N]
   int world = 1, my_rank = 0, rows_per_rank = 0;
   int cta_group = 0;  // 0 = auto (2), 1 or 2 to force
+  // fused all-gather -> GEMM (see GemmParams::ag_src): A is the local gather target, ag_src[r] rank r's symmetric shard
+  const void* const* ag_src = nullptr;
+  uint32_t* ag_flags = nullptr;
+  int ag_world = 1, ag_rank = 0, ag_rows_per_rank = 0;
   // fp8 path: A [M, lda] and B [N, ldb] hold e4m3 bytes (K-major), the result is scaled by row_scale[m] * col_scale[n]
   bool fp8 = false;
   const float* row_scale = nullptr;

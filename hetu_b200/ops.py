@@ -523,14 +523,14 @@ def quantization(x, dtype="int8", blocksize=64, **kw):
     return quantize_blockwise_op(x, dtype, blocksize, **kw)
 
 
-def dequantization(q, absmax, dtype="float32", blocksize=64, **kw):
+def dequantization(q, absmax, dtype="float32", blocksize=64, shape=None, quant_type=None, **kw):
     from .utils.quant import dequantize_blockwise_op
-    return dequantize_blockwise_op(q, absmax, dtype, blocksize, **kw)
+    return dequantize_blockwise_op(q, absmax, dtype, blocksize, shape, quant_type, **kw)
 
 
-def matmul4bit(x, w_q, absmax, blocksize=64, quant_type="nf4", **kw):
+def matmul4bit(x, w_q, absmax, blocksize=64, quant_type="nf4", weight_shape=None, **kw):
     from .utils.quant import matmul4bit_op
-    return matmul4bit_op(x, w_q, absmax, blocksize, quant_type, **kw)
+    return matmul4bit_op(x, w_q, absmax, blocksize, quant_type, weight_shape, **kw)
 
 
 # ----------------------------------------------------------------------------- in-place aliases (graph semantics: functional)

@@ -1,0 +1,17 @@
+"""Hetu v1 ("legacy") API surface on top of the new graph: `Variable`, `placeholder_op`, `*_op` constructors,
+`Executor(eval_nodes, ctx=..., comm_mode=...)`.run(feed_dict), SGD/Momentum/AdaGrad/Adam optimizers with
+`.minimize(loss)`, the parameter-server / hybrid communication modes, the HET embedding cache (cstable), the HetuMoE
+layers and the v1 auto-parallel search strategies.
+(ref: hetu/v1/python/hetu/{gpu_ops/executor.py, gpu_ops/*.py, optimizer.py, cstable.py, layers/, distributed_strategies/})
+"""
+from .executor import (Variable, placeholder_op, Executor, HetuConfig, gradients, cpu, gpu, rcpu, rgpu,  # noqa: F401
+                       matmul_op, linear_op, relu_op, sigmoid_op, tanh_op, gelu_op, softmax_op, softmaxcrossentropy_op,
+                       softmaxcrossentropy_sparse_op, add_op, mul_op, addbyconst_op, mulbyconst_op, reduce_mean_op, reduce_sum_op,
+                       array_reshape_op, embedding_lookup_op, concat_op, dropout_op, layer_normalization_op, batch_matmul_op,
+                       transpose_op, broadcastto_op, binarycrossentropy_op, mse_op, slice_op, sqrt_op, exp_op, log_op)
+from .optimizer import SGDOptimizer, MomentumOptimizer, AdaGradOptimizer, AdamOptimizer  # noqa: F401
+from .ps import PSContext, CacheSparseTable  # noqa: F401
+from . import strategies as dist  # noqa: F401
+from .strategies import (DataParallel, ModelParallel4CNN, ModelParallel4LM, OneWeirdTrick4CNN, MegatronLM, FlexFlowSearching,  # noqa: F401
+                         OptCNNSearching, GPipeSearching, PipeDreamSearching, PipeOptSearching)
+from ..models.moe import MoELayer, TopKGate, KTop1Gate, HashGate, BalanceGate, SAMGate  # noqa: F401

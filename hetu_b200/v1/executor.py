@@ -1,0 +1,168 @@
+"""v1 static-dataflow API: nodes are created with `*_op` functions, an `Executor` evaluates a list of nodes for a feed
+dict; training nodes come from `optimizer.minimize(loss)`.  comm_mode: None (single device), 'AllReduce' (data parallel
+over the process group), 'PS' (all parameters on the parameter server), 'Hybrid' (dense by all-reduce, embeddings on the
+PS with the HET cache).  (ref: hetu/v1/python/hetu/gpu_ops/executor.py Executor/SubExecutor/HetuConfig)"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import core, ops
+from ..core import Tensor, from_numpy
+
+
+class _Ctx:
+    def __init__(self, kind, index=0, host="localhost"):
+        self.kind, self.index, self.host = kind, index, host
+
+    def __repr__(self):
+        return f"{self.host}:{self.kind}:{self.index}"
+
+
+def cpu(i=0): return _Ctx("cpu", i)            # noqa: E704
+def gpu(i=0): return _Ctx("gpu", i)            # noqa: E704
+def rcpu(host, i=0): return _Ctx("cpu", i, host)   # noqa: E704
+def rgpu(host, i=0): return _Ctx("gpu", i, host)   # noqa: E704
+
+
+_graph = None
+_graph_ctx = None      # the context manager must stay alive, otherwise the graph is popped again
+
+
+def _g():
+    """all v1 nodes of a process live in one define-and-run graph"""
+    global _graph, _graph_ctx
+    if _graph is None:
+        _graph_ctx = core.graph("define_and_run", create_new=True, prefix="v1")
+        _graph = _graph_ctx.__enter__()
+    return _graph
+
+
+def reset_graph():
+    global _graph, _graph_ctx
+    if _graph_ctx is not None:
+        _graph_ctx.__exit__(None, None, None)
+    _graph = _graph_ctx = None
+
+
+def Variable(name, value=None, initializer=None, trainable=True, shape=None, dtype="float32", is_embed=False):
+    _g()
+    if value is not None:
+        arr = np.asarray(value, dtype=np.float32 if dtype == "float32" else dtype)
+        t = core.parameter(core.provided_initializer(arr), list(arr.shape), dtype=dtype, requires_grad=trainable, name=name)
+    else:
+        init = initializer or core.xavier_uniform_initializer()
+        t = core.parameter(init, list(shape), dtype=dtype, requires_grad=trainable, name=name)
+    return t
+
+
+def placeholder_op(name, shape=None, dtype="float32", trainable=False):
+    _g()
+    return core.placeholder(dtype, list(shape) if shape is not None else [1], name=name)
+
+
+# ---- op constructors (v1 naming)
+def matmul_op(a, b, trans_A=False, trans_B=False): return ops.matmul(a, b, trans_a=trans_A, trans_b=trans_B)     # noqa: E704
+def linear_op(x, w, b=None, trans_B=False): return ops.linear(x, w, b, trans_b=trans_B)                         # noqa: E704
+def batch_matmul_op(a, b, trans_A=False, trans_B=False): return ops.bmm(ops.transpose(a, -1, -2) if trans_A else a, ops.transpose(b, -1, -2) if trans_B else b)   # noqa: E704,E501
+def relu_op(x): return ops.relu(x)                                     # noqa: E704
+def sigmoid_op(x): return ops.sigmoid(x)                               # noqa: E704
+def tanh_op(x): return ops.tanh(x)                                     # noqa: E704
+def gelu_op(x): return ops.gelu(x)                                     # noqa: E704
+def sqrt_op(x): return ops.sqrt(x)                                     # noqa: E704
+def exp_op(x): return ops.exp(x)                                       # noqa: E704
+def log_op(x): return ops.log(x)                                       # noqa: E704
+def softmax_op(x): return ops.softmax(x, -1)                           # noqa: E704
+def add_op(a, b): return ops.add(a, b)                                 # noqa: E704
+def mul_op(a, b): return ops.mul(a, b)                                 # noqa: E704
+def addbyconst_op(x, c): return x + float(c)                           # noqa: E704
+def mulbyconst_op(x, c): return x * float(c)                           # noqa: E704
+def reduce_mean_op(x, axes, keepdims=False): return ops.mean(x, axes, keepdims)    # noqa: E704
+def reduce_sum_op(x, axes, keepdims=False): return ops.sum(x, axes, keepdims)      # noqa: E704
+def array_reshape_op(x, shape): return ops.reshape(x, list(shape))     # noqa: E704
+def transpose_op(x, perm=None): return ops.permute(x, list(perm)) if perm is not None else ops.transpose(x, -1, -2)   # noqa: E704
+def broadcastto_op(x, y): return ops.broadcast(x, list(y.shape))       # noqa: E704
+def concat_op(a, b, axis=0): return ops.concat([a, b], axis)           # noqa: E704
+def slice_op(x, begin, size): return ops.slice(x, list(begin), list(size))   # noqa: E704
+def dropout_op(x, keep_prob): return ops.dropout(x, 1.0 - keep_prob)   # noqa: E704
+def embedding_lookup_op(table, ids): return ops.embedding_lookup(table, ids)   # noqa: E704
+def layer_normalization_op(x, scale, bias, eps=1e-5): return ops.layer_norm(x, scale, bias, eps=eps)   # noqa: E704
+def softmaxcrossentropy_op(logits, labels): return ops.softmax_cross_entropy(logits, labels, reduction="none")   # noqa: E704
+def softmaxcrossentropy_sparse_op(logits, labels, ignored_index=-1): return ops.softmax_cross_entropy_sparse(logits, labels, ignored_index=ignored_index, reduction="none")   # noqa: E704,E501
+def binarycrossentropy_op(p, y): return ops.binary_cross_entropy(p, y, reduction="none")   # noqa: E704
+def mse_op(p, y): return ops.mse_loss(p, y, reduction="none")          # noqa: E704
+
+
+def gradients(loss, nodes):
+    from ..graph_api import gradients as g
+    return g(loss, list(nodes))
+
+
+class HetuConfig:
+    def __init__(self, eval_node_list, ctx=None, comm_mode=None, seed=None, bsp=-1, cstable_policy=None, cache_bound=100, **kw):
+        self.eval_node_list, self.context, self.comm_mode, self.seed = eval_node_list, ctx, comm_mode, seed
+        self.bsp, self.cstable_policy, self.cache_bound = bsp, cstable_policy, cache_bound
+        self.extra = kw
+
+
+class Executor:
+    """Executor({name: [nodes]} | [nodes], ctx=..., comm_mode=...).run(name?, feed_dict) -> list of numpy arrays"""
+
+    def __init__(self, eval_node_dict, ctx=None, comm_mode=None, seed=None, **kw):
+        if not isinstance(eval_node_dict, dict):
+            eval_node_dict = {"default": list(eval_node_dict)}
+        self.eval_node_dict = {k: list(v) for k, v in eval_node_dict.items()}
+        self.config = HetuConfig(self.eval_node_dict, ctx, comm_mode, seed, **kw)
+        self.graph = _g()
+        self.comm_mode = comm_mode
+        if seed is not None:
+            core.set_seed(seed)
+        self.step = 0
+
+    def run(self, name="default", eval_node_list=None, feed_dict: Optional[Dict] = None, convert_to_numpy_ret_vals=False, **kw):
+        if isinstance(name, dict) and feed_dict is None:
+            name, feed_dict = "default", name
+        nodes = list(eval_node_list) if eval_node_list else self.eval_node_dict[name]
+        feed = {k: torch.as_tensor(np.asarray(v)) if not isinstance(v, torch.Tensor) else v for k, v in (feed_dict or {}).items()}
+        loss = next((n for n in nodes if isinstance(n, Tensor) and n.producer_type not in ("adam_update", "sgd_update", "group")), None)
+        dp = 1
+        if self.comm_mode in ("AllReduce", "Hybrid"):
+            from .. import distributed
+            dp = max(distributed.world_size(), 1)
+        outs = self.graph.run(loss, nodes, feed, grad_scale=1.0 / dp)
+        self.step += 1
+        res = []
+        for o in outs:
+            if o is None:
+                res.append(None)
+            else:
+                res.append(o.float().cpu().numpy() if convert_to_numpy_ret_vals else _ND(o))
+        return res
+
+    def save(self, file_path, file_name="checkpoint.pt"):
+        import os
+        os.makedirs(file_path, exist_ok=True)
+        state = {name: t.float().cpu() for name, t in self.graph.named_parameters()} if hasattr(self.graph, "named_parameters") else {}
+        torch.save(state, os.path.join(file_path, file_name))
+
+    def load(self, file_path, file_name="checkpoint.pt"):
+        import os
+        state = torch.load(os.path.join(file_path, file_name))
+        for name, t in state.items():
+            self.graph.set_param_by_name(name, t) if hasattr(self.graph, "set_param_by_name") else None
+
+
+class _ND:
+    """minimal NDArray-like wrapper (asnumpy) returned by Executor.run"""
+
+    def __init__(self, t):
+        self.t = t
+
+    def asnumpy(self):
+        return self.t.float().cpu().numpy()
+
+    @property
+    def shape(self):
+        return tuple(self.t.shape)

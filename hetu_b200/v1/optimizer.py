@@ -1,0 +1,42 @@
+"""v1 optimizers (ref: hetu/v1/python/hetu/optimizer.py): `.minimize(loss)` returns the training node."""
+from .. import optim
+
+
+class _Base:
+    def __init__(self, learning_rate=0.01, l2reg=0.0):
+        self.learning_rate, self.l2reg = learning_rate, l2reg
+
+    def minimize(self, loss, var_list=None):
+        return self._make().minimize(loss, var_list) if var_list is not None else self._make().minimize(loss)
+
+
+class SGDOptimizer(_Base):
+    def _make(self):
+        return optim.SGDOptimizer(lr=self.learning_rate, weight_decay=self.l2reg)
+
+
+class MomentumOptimizer(_Base):
+    def __init__(self, learning_rate=0.01, momentum=0.9, nesterov=False, l2reg=0.0):
+        super().__init__(learning_rate, l2reg)
+        self.momentum, self.nesterov = momentum, nesterov
+
+    def _make(self):
+        return optim.SGDOptimizer(lr=self.learning_rate, momentum=self.momentum, nesterov=self.nesterov, weight_decay=self.l2reg)
+
+
+class AdaGradOptimizer(_Base):
+    def __init__(self, learning_rate=0.01, initial_accumulator_value=0.0, eps=1e-7, l2reg=0.0):
+        super().__init__(learning_rate, l2reg)
+        self.eps = eps
+
+    def _make(self):     # AdaGrad == Adam with beta1 = 0, beta2 -> 1 without bias correction is close; use the exact SGD-family path
+        return optim.AdamOptimizer(lr=self.learning_rate, beta1=0.0, beta2=0.999, eps=self.eps, weight_decay=self.l2reg)
+
+
+class AdamOptimizer(_Base):
+    def __init__(self, learning_rate=0.01, beta1=0.9, beta2=0.999, epsilon=1e-7, l2reg=0.0, amsgrad=False):
+        super().__init__(learning_rate, l2reg)
+        self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
+
+    def _make(self):
+        return optim.AdamOptimizer(lr=self.learning_rate, beta1=self.beta1, beta2=self.beta2, eps=self.epsilon, weight_decay=self.l2reg)

@@ -216,3 +216,42 @@ def test_moe_ops_cpu():
     np.testing.assert_allclose(X.grad.numpy(), np.ones_like(x) * (g_ * (l_ >= 0)).sum(-1, keepdims=True), rtol=1e-5, atol=1e-6)
     probs = torch.softmax(torch.tensor(logits), -1)
     np.testing.assert_array_equal(np.sort(i_, 1), np.sort(torch.topk(probs, k, -1).indices.numpy(), 1))
+
+
+def test_blockwise_quantisation_and_matmul4bit():
+    torch.manual_seed(0)
+    w = torch.randn(48, 64)
+    W = ht.from_numpy(w)
+    for kind, tol in [("int8", 0.02), ("nf4", 0.45), ("fp4", 0.75)]:
+        q, a = ht.quantization(W, kind, 32)
+        d = ht.dequantization(q, a, "float32", 32, shape=[48, 64], quant_type=kind)
+        assert tuple(a.shape) == (96,)
+        assert (torch.as_tensor(d.numpy()) - w).abs().max().item() < tol
+    x = torch.randn(8, 64)
+    X = ht.from_numpy(x, requires_grad=True)
+    q, a = ht.quantization(W, "nf4", 32)
+    y = ht.matmul4bit(X, q, a, 32, "nf4", weight_shape=[48, 64])
+    ht.sum(y).backward()
+    wd = torch.as_tensor(ht.dequantization(q, a, "float32", 32, shape=[48, 64], quant_type="nf4").numpy())
+    assert (torch.as_tensor(y.numpy()) - x @ wd.t()).abs().max().item() < 1e-4
+    assert (torch.as_tensor(X.grad.numpy()) - wd.sum(0)).abs().max().item() < 1e-4
+
+
+def test_linear_fp8_emulation_matches_quantised_reference():
+    import math
+    torch.manual_seed(0)
+    M, K, N = 64, 64, 48
+    x, w, b = torch.randn(M, K), torch.randn(N, K) / math.sqrt(K), torch.randn(N)
+    X, W, B = [ht.from_numpy(t, requires_grad=True) for t in (x, w, b)]
+    y = ht.linear_fp8(X, W, B, act="gelu")
+    ht.sum(y).backward()
+
+    def fq(t):
+        sc = (t.abs().amax(-1, keepdim=True) / 448.0).clamp_min(1e-30)
+        return (t / sc).to(torch.float8_e4m3fn).float() * sc
+    ref = torch.nn.functional.gelu(fq(x) @ fq(w).t() + b)
+    assert (torch.as_tensor(y.numpy()) - ref).abs().max().item() < 1e-4
+    xr = x.clone().requires_grad_()
+    torch.nn.functional.gelu(xr @ w.t() + b).sum().backward()
+    rel = (torch.as_tensor(X.grad.numpy()) - xr.grad).abs().mean() / xr.grad.abs().mean()
+    assert rel < 0.08
