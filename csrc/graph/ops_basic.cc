@@ -593,3 +593,37 @@ static Ts matmul4bit_dgrad_compute(const OpDef& op, const Ts& in, RunCtx*) {
 HB_REGISTER_OP(matmul4bit, "matmul4bit", 1, 0, matmul4bit_compute, matmul4bit_grad, nullptr, nullptr);
 HB_REGISTER_OP(matmul4bit_dgrad, "matmul4bit_dgrad", 1, kFlagNondiff, matmul4bit_dgrad_compute, nullptr, nullptr, nullptr);
 }  // namespace hb
+
+// ------------------------------------------------------------------ integer id arithmetic, sparse matmul (CTR / GNN / compression)
+namespace hb {
+ATEN_OP_NODIFF(remainder, 1, return {at::remainder(in[0], (int64_t)op.attrs.i("divisor"))};);
+ATEN_OP_NODIFF(floor_divide, 1, return {at::floor_divide(in[0], (int64_t)op.attrs.i("divisor"))};);
+// universal hashing of ids: ((a * id + b) mod p) mod m   (p a Mersenne prime, computed in int64)
+ATEN_OP_NODIFF(hash_ids, 1, {
+  const int64_t a = op.attrs.i("a", 1000003), b = op.attrs.i("b", 12345), p = op.attrs.i("p", 2147483647), m = op.attrs.i("buckets");
+  at::Tensor x = in[0].to(at::kLong);
+  return {at::remainder(at::remainder(x * a + b, p), m)};
+});
+// y = A x with A given in COO form (indices [2, nnz], values [nnz]) -- differentiable w.r.t. values and x (generic VJP)
+ATEN_OP(spmm, 1, {
+  const int64_t rows = op.attrs.i("rows");
+  if (in[2].is_meta()) return {at::empty({rows, in[2].size(1)}, in[2].options())};
+  at::Tensor A = at::sparse_coo_tensor(in[0].to(at::kLong), in[1].to(in[2].scalar_type()), {rows, in[2].size(0)});
+  return {at::_sparse_mm(A, in[2])};
+});
+}  // namespace hb
+
+namespace hb {
+// value passes through, gradient does not (straight-through estimators, frozen branches)
+ATEN_OP_NODIFF(stop_gradient, 1, return {in[0]};);
+}  // namespace hb
+
+namespace hb {
+// elementwise comparison against a scalar -> 0/1 mask in `dtype` (float32 by default)
+ATEN_OP_NODIFF(compare_scalar, 1, {
+  const std::string m = op.attrs.s("mode", "lt");
+  const double v = op.attrs.f("value");
+  at::Tensor r = m == "lt" ? in[0] < v : m == "le" ? in[0] <= v : m == "gt" ? in[0] > v : m == "ge" ? in[0] >= v : m == "eq" ? in[0] == v : in[0] != v;
+  return {r.to(to_aten_dtype(dtype_from_name(op.attrs.s("dtype", "float32"))))};
+});
+}  // namespace hb

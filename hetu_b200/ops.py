@@ -517,6 +517,56 @@ def moe_combine(expert_out, idx, loc, gates=None, ep_ranks=(), **kw):
     return _op1("moe_combine", ins, {"ep_ranks": [int(r) for r in ep_ranks]}, **kw)
 
 
+def compare(x, mode, value, dtype="float32", **kw):
+    """0/1 mask of x <mode> value, mode in lt | le | gt | ge | eq | ne"""
+    return _op1("compare_scalar", [x], {"mode": str(mode), "value": float(value), "dtype": dtype_name(dtype)}, **kw)
+
+
+def less(x, v, **kw): return compare(x, "lt", v, **kw)              # noqa: E704
+def less_equal(x, v, **kw): return compare(x, "le", v, **kw)        # noqa: E704
+def greater(x, v, **kw): return compare(x, "gt", v, **kw)           # noqa: E704
+def greater_equal(x, v, **kw): return compare(x, "ge", v, **kw)     # noqa: E704
+def equal(x, v, **kw): return compare(x, "eq", v, **kw)             # noqa: E704
+def not_equal(x, v, **kw): return compare(x, "ne", v, **kw)         # noqa: E704
+
+
+def stop_gradient(x, **kw):
+    return _op1("stop_gradient", [x], **kw)
+
+
+detach = stop_gradient
+
+
+def cast(x, dtype, **kw):
+    return data_transfer(x, dtype, **kw)
+
+
+def permute(x, dims, **kw):
+    return transpose(x, list(dims), **kw)
+
+
+# ----------------------------------------------------------------------------- id arithmetic / sparse
+def remainder(x, divisor, **kw):
+    return _op1("remainder", [x], {"divisor": int(divisor)}, **kw)
+
+
+def floor_divide(x, divisor, **kw):
+    return _op1("floor_divide", [x], {"divisor": int(divisor)}, **kw)
+
+
+def hash_ids(ids, buckets, a=1000003, b=12345, p=2147483647, **kw):
+    """universal hash ((a * id + b) mod p) mod buckets of an integer id tensor"""
+    return _op1("hash_ids", [ids], {"buckets": int(buckets), "a": int(a), "b": int(b), "p": int(p)}, **kw)
+
+
+def spmm(indices, values, dense, rows, **kw):
+    """sparse (COO: indices [2, nnz], values [nnz], `rows` x dense.shape[0]) times dense"""
+    return _op1("spmm", [indices, values, dense], {"rows": int(rows)}, **kw)
+
+
+csrmm = spmm
+
+
 # ----------------------------------------------------------------------------- quantization (blockwise absmax)
 def quantization(x, dtype="int8", blocksize=64, **kw):
     from .utils.quant import quantize_blockwise_op

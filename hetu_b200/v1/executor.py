@@ -66,7 +66,7 @@ def placeholder_op(name, shape=None, dtype="float32", trainable=False):
 # ---- op constructors (v1 naming)
 def matmul_op(a, b, trans_A=False, trans_B=False): return ops.matmul(a, b, trans_a=trans_A, trans_b=trans_B)     # noqa: E704
 def linear_op(x, w, b=None, trans_B=False): return ops.linear(x, w, b, trans_b=trans_B)                         # noqa: E704
-def batch_matmul_op(a, b, trans_A=False, trans_B=False): return ops.bmm(ops.transpose(a, -1, -2) if trans_A else a, ops.transpose(b, -1, -2) if trans_B else b)   # noqa: E704,E501
+def batch_matmul_op(a, b, trans_A=False, trans_B=False): return ops.bmm(ops.transpose(a, [0, 2, 1]) if trans_A else a, ops.transpose(b, [0, 2, 1]) if trans_B else b)   # noqa: E704,E501
 def relu_op(x): return ops.relu(x)                                     # noqa: E704
 def sigmoid_op(x): return ops.sigmoid(x)                               # noqa: E704
 def tanh_op(x): return ops.tanh(x)                                     # noqa: E704
@@ -82,7 +82,7 @@ def mulbyconst_op(x, c): return x * float(c)                           # noqa: E
 def reduce_mean_op(x, axes, keepdims=False): return ops.mean(x, axes, keepdims)    # noqa: E704
 def reduce_sum_op(x, axes, keepdims=False): return ops.sum(x, axes, keepdims)      # noqa: E704
 def array_reshape_op(x, shape): return ops.reshape(x, list(shape))     # noqa: E704
-def transpose_op(x, perm=None): return ops.permute(x, list(perm)) if perm is not None else ops.transpose(x, -1, -2)   # noqa: E704
+def transpose_op(x, perm=None): return ops.transpose(x, list(perm) if perm is not None else list(range(len(x.shape)))[::-1])   # noqa: E704
 def broadcastto_op(x, y): return ops.broadcast(x, list(y.shape))       # noqa: E704
 def concat_op(a, b, axis=0): return ops.concat([a, b], axis)           # noqa: E704
 def slice_op(x, begin, size): return ops.slice(x, list(begin), list(size))   # noqa: E704
