@@ -810,7 +810,27 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
   ExecPlan& plan = get_plan(loss, fetches, opt.strategy);
   if (active_strategy_ >= 0 && active_strategy_ != opt.strategy) switch_strategy(active_strategy_, opt.strategy);
   active_strategy_ = opt.strategy;
-  if (shapes_strategy_ != -1 && shapes_strategy_ != opt.strategy) {
+  // dynamic shapes: a placeholder fed with a different token count (sequence-length buckets, packed batches) updates its
+  // global shape; static shapes are re-inferred when that happens or when the strategy (hence every local shape) changes
+  bool shapes_changed = false;
+  {
+    const int Mq = std::max(1, opt.num_micro_batches);
+    for (OpDef* op : plan.fw_ops) {
+      if (!op->has_flag(kFlagPlaceholder)) continue;
+      auto it = feed.find(op->outputs[0]->id);
+      if (it == feed.end() || it->second.empty() || !it->second[0].defined()) continue;
+      std::vector<int64_t> local = it->second[0].sizes().vec();
+      if ((int)it->second.size() == 1 && Mq > 1 && !local.empty()) local[0] /= Mq;
+      std::vector<int64_t> global = local;
+      if (op->dst_ds.size() > (size_t)opt.strategy && op->dst_ds.get(opt.strategy).size() > 0)
+        global = op->dst_ds.get(opt.strategy).get(0).global_shape(local);
+      if (op->attrs.ints("global_shape") != global) {
+        op->attrs.set("global_shape", global);
+        shapes_changed = true;
+      }
+    }
+  }
+  if (shapes_changed || (shapes_strategy_ != -1 && shapes_strategy_ != opt.strategy)) {
     g_->reinfer_shapes(opt.strategy);
     shapes_strategy_ = opt.strategy;
   }

@@ -221,7 +221,15 @@ void Graph::reinfer_shapes(int strategy) {
   cur_strategy_ = strategy;
   for (auto& op : ops_) {
     std::vector<Tensor> outs = op->outputs;  // keep tensor identities, refresh shapes in place
-    infer_meta(*op);
+    try {
+      infer_meta(*op);
+    } catch (const std::exception& e) {
+      std::ostringstream os;
+      os << "shape re-inference of op " << op->name() << " (" << op->type << ") under strategy " << strategy << " with input shapes";
+      for (auto& t : op->inputs) os << " " << t->name << t->shape;
+      os << ": " << e.what();
+      throw Error(os.str());
+    }
     HB_CHECK(op->outputs.size() == outs.size()) << "shape re-inference changed the arity of " << op->name();
     for (size_t i = 0; i < outs.size(); ++i) {
       if (op->outputs[i] != outs[i]) {

@@ -751,13 +751,20 @@ HB_REGISTER_OP(norm_bwd, "norm_bwd", -1, 0, norm_bwd_compute, nullptr, norm_bwd_
 
 // ------------------------------------------------------------------ embedding
 // inputs: table [V, H], ids [...]   (ids outside [0, V) produce zeros: vocab-parallel shards rely on it)
+// vocab-parallel shards: first row of this rank's shard, per strategy (hot switching changes the tensor-parallel degree)
+static int64_t vocab_offset_of(const OpDef& op) {
+  const std::vector<int64_t> per = op.attrs.ints("vocab_offsets");
+  const int s = op.graph ? op.graph->cur_strategy() : 0;
+  if (!per.empty() && s >= 0 && (size_t)s < per.size()) return per[s];
+  return op.attrs.i("vocab_offset", 0);
+}
 static Ts embedding_compute(const OpDef& op, const Ts& in, RunCtx*) {
   const at::Tensor& table = in[0];
   const at::Tensor& ids = in[1];
   std::vector<int64_t> oshape = ids.sizes().vec();
   oshape.push_back(table.size(1));
   if (table.is_meta()) return {at::empty(oshape, table.options())};
-  const int64_t offset = op.attrs.i("vocab_offset", 0);
+  const int64_t offset = vocab_offset_of(op);
   at::Tensor idl = ids.to(at::kLong).contiguous();
   if (offset != 0) idl = idl - offset;
   if (is_native(table) && table.is_contiguous() && table.size(1) % 8 == 0) {
@@ -774,9 +781,10 @@ static Ts embedding_compute(const OpDef& op, const Ts& in, RunCtx*) {
 static Ts embedding_grad_compute(const OpDef& op, const Ts& in, RunCtx*) {
   const at::Tensor& dy = in[0];
   const at::Tensor& ids = in[1];
-  const int64_t V = op.attrs.i("vocab"), H = dy.size(-1);
+  // the table (input 2) gives the local vocabulary size of the CURRENT strategy; the attribute is the build-time value
+  const int64_t V = in.size() > 2 ? in[2].size(0) : op.attrs.i("vocab"), H = dy.size(-1);
   if (dy.is_meta()) return {at::empty({V, H}, dy.options())};
-  const int64_t offset = op.attrs.i("vocab_offset", 0);
+  const int64_t offset = vocab_offset_of(op);
   at::Tensor idl = ids.to(at::kLong).contiguous();
   if (offset != 0) idl = idl - offset;
   at::Tensor d2 = dy.reshape({-1, H}).contiguous();
@@ -797,6 +805,7 @@ static TensorList embedding_grad(OpDef& op, const TensorList& g) {
   AttrMap a;
   a.set("vocab", op.inputs[0]->shape[0]);
   a.set("vocab_offset", op.attrs.i("vocab_offset", 0));
+  a.set("vocab_offsets", op.attrs.ints("vocab_offsets"));
   return {op.graph->make_op1("embedding_grad", {g[0], op.inputs[1], op.inputs[0]}, a), nullptr};
 }
 static void embedding_deduce(OpDef& op, size_t s) {
@@ -1201,7 +1210,11 @@ static void packed_views(const at::Tensor& qkv, int64_t S, int64_t Hq, int64_t H
 static TsP attn_packed_compute(const OpDef& op, const TsP& in, RunCtx* rc) {
   const at::Tensor& qkv = in[0];
   const int64_t S = op.sy_shape.empty() ? op.attrs.i("seq_len") : op.sy_shape[0].get_val();
-  const int64_t Hq = op.attrs.i("num_heads"), Hkv = op.attrs.i("num_kv_heads", Hq), D = op.attrs.i("head_dim");
+  // head counts follow the width of the packed projection actually fed (the tensor-parallel degree may change between
+  // strategies); the attributes fix the q : kv ratio and the head size
+  const int64_t D = op.attrs.i("head_dim");
+  const int64_t rep_ = std::max<int64_t>(1, op.attrs.i("num_heads") / std::max<int64_t>(1, op.attrs.i("num_kv_heads", op.attrs.i("num_heads"))));
+  const int64_t Hkv = qkv.size(-1) / ((rep_ + 2) * D), Hq = Hkv * rep_;
   const int64_t T = qkv.size(0);
   auto fopt = qkv.options().dtype(at::kFloat);
   if (qkv.is_meta()) return {at::empty({T, Hq * D}, qkv.options()), at::empty({T / std::max<int64_t>(S, 1), Hq, S}, fopt)};
@@ -1239,7 +1252,11 @@ static TsP attn_packed_bwd_compute(const OpDef& op, const TsP& in, RunCtx* rc) {
   const at::Tensor& lse = in[3];
   if (qkv.is_meta()) return {at::empty_like(qkv)};
   const int64_t S = op.sy_shape.empty() ? op.attrs.i("seq_len") : op.sy_shape[0].get_val();
-  const int64_t Hq = op.attrs.i("num_heads"), Hkv = op.attrs.i("num_kv_heads", Hq), D = op.attrs.i("head_dim");
+  // head counts follow the width of the packed projection actually fed (the tensor-parallel degree may change between
+  // strategies); the attributes fix the q : kv ratio and the head size
+  const int64_t D = op.attrs.i("head_dim");
+  const int64_t rep_ = std::max<int64_t>(1, op.attrs.i("num_heads") / std::max<int64_t>(1, op.attrs.i("num_kv_heads", op.attrs.i("num_heads"))));
+  const int64_t Hkv = qkv.size(-1) / ((rep_ + 2) * D), Hq = Hkv * rep_;
   const int64_t T = qkv.size(0), B = T / S;
   at::Tensor src = qkv.is_contiguous() ? qkv : qkv.contiguous();
   at::Tensor q, k, v, dq, dk, dv;
@@ -1293,7 +1310,11 @@ static TsP rotary_packed_compute(const OpDef& op, const TsP& in, RunCtx*) {
   const at::Tensor& qkv = in[0];
   if (qkv.is_meta()) return {at::empty_like(qkv)};
   const int64_t S = op.sy_shape.empty() ? op.attrs.i("seq_len") : op.sy_shape[0].get_val();
-  const int64_t Hq = op.attrs.i("num_heads"), Hkv = op.attrs.i("num_kv_heads", Hq), D = op.attrs.i("head_dim");
+  // head counts follow the width of the packed projection actually fed (the tensor-parallel degree may change between
+  // strategies); the attributes fix the q : kv ratio and the head size
+  const int64_t D = op.attrs.i("head_dim");
+  const int64_t rep_ = std::max<int64_t>(1, op.attrs.i("num_heads") / std::max<int64_t>(1, op.attrs.i("num_kv_heads", op.attrs.i("num_heads"))));
+  const int64_t Hkv = qkv.size(-1) / ((rep_ + 2) * D), Hq = Hkv * rep_;
   const bool inverse = op.attrs.b("inverse");
   const double base = op.attrs.f("base", 10000.0);
   const int64_t T = qkv.size(0);

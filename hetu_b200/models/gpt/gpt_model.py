@@ -199,8 +199,7 @@ class GPTLMHeadModel(Module):
             logits = self.lm_head(hidden)
         if labels is None:
             return logits
-        tp = wte.tp[0]
-        if tp > 1:
+        if any(t > 1 for t in wte.tp):     # any strategy with a vocab split needs the vocab-parallel loss (it degenerates for tp = 1)
             loss = ops.vocab_parallel_cross_entropy(logits, labels, ignored_index=-1, reduction="mean")
         else:
             loss = ops.softmax_cross_entropy_sparse(logits, labels, ignored_index=-1, reduction="mean")

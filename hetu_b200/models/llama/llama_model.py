@@ -173,6 +173,6 @@ class LlamaLMHeadModel(Module):
         logits = self.lm_head(hidden)
         if labels is None:
             return logits
-        if self.lm_head.tp[0] > 1:
+        if any(t > 1 for t in self.lm_head.tp):
             return ops.vocab_parallel_cross_entropy(logits, labels, ignored_index=-1, reduction="mean")
         return ops.softmax_cross_entropy_sparse(logits, labels, ignored_index=-1, reduction="mean")

@@ -263,17 +263,18 @@ class HtMultiVocabParallelEmbedding(_ParallelBase):
                                                   requires_grad=True, device_group_hierarchy=self.device_group_unions,
                                                   name=f"{name}_table")
 
-    def _vocab_offset(self):
+    def _vocab_offset(self, strategy=0):
         from ..distributed import rank
-        dgs = self.device_group_unions[0]
+        dgs = self.device_group_unions[strategy]
         idx = dgs[0].indices().index(rank()) if rank() in dgs[0].indices() else 0
-        ds = self.embedding_table.get_ds(0)
+        ds = self.embedding_table.get_ds(strategy)
         shard = ds.map_device_to_state_index(idx).get(0, 0)
-        return shard * (self.num_embeddings // max(self.tp[0], 1))
+        return shard * (self.num_embeddings // max(self.tp[strategy], 1))
 
     def forward(self, ids, sequence_parallel=False):
         ids = self._adapt(ids, self.ds_split0_dup())
-        y = ops.embedding_lookup(self.embedding_table, ids, vocab_offset=self._vocab_offset(),
+        offs = [self._vocab_offset(s) for s in range(len(self.device_group_unions))]
+        y = ops.embedding_lookup(self.embedding_table, ids, vocab_offset=offs[0], vocab_offsets=offs,
                                  device_group_hierarchy=self.device_group_unions)
         if any(t > 1 for t in self.tp):
             y = ops.comm(y, self.ds_split0() if sequence_parallel else self.ds_split0_dup())

@@ -361,8 +361,9 @@ def fused_rmsnorm(x, weight, normalized_shape=None, eps=1e-6, **kw):
     return rms_norm(x, weight, eps, **kw)
 
 
-def embedding_lookup(table, ids, vocab_offset=0, **kw):
-    return _op1("embedding_lookup", [table, ids], {"vocab_offset": int(vocab_offset)}, **kw)
+def embedding_lookup(table, ids, vocab_offset=0, vocab_offsets=(), **kw):
+    """vocab_offset: first row of this rank's shard of a vocab-parallel table; vocab_offsets: the same per strategy"""
+    return _op1("embedding_lookup", [table, ids], {"vocab_offset": int(vocab_offset), "vocab_offsets": [int(v) for v in vocab_offsets]}, **kw)
 
 
 def dropout(x, p=0.5, inplace=False, **kw):

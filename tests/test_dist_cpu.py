@@ -75,3 +75,19 @@ def test_moe_expert_parallel_matches_single_device(gate):
     got = _losses(outs)
     for a, b in zip(got, ref):
         assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, ref)
+
+
+HOT_WORKER = os.path.join(os.path.dirname(__file__), "workers", "hot_switch_worker.py")
+
+
+@pytest.mark.dist
+def test_hot_switching_between_dp_and_tp_keeps_the_loss_curve():
+    """HotSPa: parameters and optimizer states are re-sharded in place when the strategy changes between steps"""
+    ok, outs = run_workers(HOT_WORKER, 2, ["single"])
+    assert ok, "\n-----\n".join(outs)
+    ref = _losses(outs)
+    ok, outs = run_workers(HOT_WORKER, 2, ["switch"])
+    assert ok, "\n-----\n".join(outs)
+    got = _losses(outs)
+    for a, b in zip(got, ref):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, ref)
