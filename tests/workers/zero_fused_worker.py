@@ -15,7 +15,7 @@ rank, world = dist.get_rank(), dist.get_world_size()
 dev = torch.device("cuda", torch.cuda.current_device())
 os.environ["HETU_B200_STRICT"] = "1"
 S, B = 128, 4
-cfg = GPTConfig(vocab_size=1024, n_positions=S, n_embd=256 * world // 2 if world > 2 else 256, n_layer=2, n_head=4)
+cfg = GPTConfig(vocab_size=1024, n_positions=S, n_embd=256 * world // 2 if world > 2 else 256, n_layer=2, n_head=max(4, (256 * world // 2 if world > 2 else 256) // 64))
 T = B * S
 
 
