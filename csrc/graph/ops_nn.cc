@@ -506,6 +506,52 @@ static TensorList linear_fp8_grad(OpDef& op, const TensorList& g) {
 HB_REGISTER_OP(linear_fp8, "linear_fp8", -1, 0, linear_fp8_compute, linear_fp8_grad, linear_deduce, linear_infer);
 HB_REGISTER_OP(linear_fp8_dgrad, "linear_fp8_dgrad", 1, 0, linear_fp8_dgrad_compute, nullptr, dgrad_deduce, nullptr);
 
+// ------------------------------------------------------------------ scaled masked softmax (Megatron fused softmax parity)
+// x [B, H, Sq, Sk]; attrs: scale, causal; optional input 1: boolean mask [B, 1, Sq, Sk] (true = masked out)
+static Ts scaled_masked_softmax_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& x = in[0];
+  const double scale = op.attrs.f("scale", 1.0);
+  const bool causal = op.attrs.b("causal");
+  if (x.is_meta()) return {at::empty_like(x)};
+  const int64_t Sk = x.size(-1), Sq = x.dim() >= 2 ? x.size(-2) : 1;
+  if (is_native(x) && x.is_contiguous() && x.dim() == 4) {
+    at::Tensor y = at::empty_like(x), m;
+    if (in.size() > 1) m = in[1].to(at::kByte).expand({x.size(0), 1, Sq, Sk}).contiguous();
+    cuda_ok(scaled_softmax_fwd(x.data_ptr(), m.defined() ? m.data_ptr<uint8_t>() : nullptr, y.data_ptr(), x.numel() / Sk, (int)Sk,
+                               (int)(x.size(1) * Sq), (int)Sq, (float)scale, causal ? 2 : (m.defined() ? 1 : 0), cur_stream()),
+            "scaled_softmax_fwd");
+    return {y};
+  }
+  at::Tensor s = x.to(at::kFloat) * scale;
+  if (in.size() > 1) s = s.masked_fill(in[1].to(at::kBool), -INFINITY);
+  if (causal) s = s.masked_fill(at::ones({Sq, Sk}, s.options().dtype(at::kBool)).tril(Sk - Sq).logical_not(), -INFINITY);
+  at::Tensor y = at::softmax(s, -1);
+  y = at::where(at::isnan(y), at::zeros_like(y), y);
+  return {y.to(x.scalar_type())};
+}
+static Ts scaled_masked_softmax_bwd_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& dy = in[0];
+  const at::Tensor& y = in[1];
+  const double scale = op.attrs.f("scale", 1.0);
+  if (dy.is_meta()) return {at::empty_like(y)};
+  if (is_native(y) && is_native(dy) && y.is_contiguous() && dy.is_contiguous()) {
+    at::Tensor dx = at::empty_like(y);
+    cuda_ok(scaled_softmax_bwd(dy.data_ptr(), y.data_ptr(), dx.data_ptr(), y.numel() / y.size(-1), (int)y.size(-1), (float)scale, cur_stream()),
+            "scaled_softmax_bwd");
+    return {dx};
+  }
+  at::Tensor yf = y.to(at::kFloat), df = dy.to(at::kFloat);
+  return {(scale * yf * (df - (df * yf).sum(-1, true))).to(y.scalar_type())};
+}
+static TensorList scaled_masked_softmax_grad(OpDef& op, const TensorList& g) {
+  TensorList r(op.inputs.size());
+  r[0] = op.graph->make_op1("scaled_masked_softmax_bwd", {g[0], op.outputs[0]}, op.attrs);
+  return r;
+}
+HB_REGISTER_OP(scaled_masked_softmax, "scaled_masked_softmax", 1, 0, scaled_masked_softmax_compute, scaled_masked_softmax_grad, nullptr, nullptr);
+HB_REGISTER_OP(scaled_masked_softmax_bwd, "scaled_masked_softmax_bwd", 1, kFlagNondiff, scaled_masked_softmax_bwd_compute, nullptr, nullptr,
+               nullptr);
+
 // matmul(a, b, trans_a, trans_b): general 2-D matmul (autograd VJP for the long tail)
 static Ts matmul_compute(const OpDef& op, const Ts& in, RunCtx*) {
   const bool ta = op.attrs.b("trans_a"), tb = op.attrs.b("trans_b");

@@ -54,6 +54,13 @@ cudaError_t rotary_apply(const void* x, void* y, const int32_t* pos, int64_t tok
                          int rot_dim, float base, bool inverse, int64_t token_stride, cudaStream_t s, int group_size = 0,
                          int group_stride = 0);   // grouped layouts: head h -> (h / group_size) * group_stride + (h % group_size) * head_dim
 
+// ---------------------------------------------------------------- scaled masked softmax (softmax.cu)
+// y = softmax(scale * x) over the last dim of [rows, cols] bf16; mode 0 plain, 1 boolean mask [b, 1, sq, cols] (1 = masked),
+// 2 causal (bottom-right aligned); rows are ordered [b, h, sq], rows_per_batch = h * sq
+cudaError_t scaled_softmax_fwd(const void* x, const uint8_t* mask, void* y, int64_t rows, int cols, int rows_per_batch, int sq, float scale,
+                               int mode, cudaStream_t s);
+cudaError_t scaled_softmax_bwd(const void* dy, const void* y, void* dx, int64_t rows, int cols, float scale, cudaStream_t s);
+
 // ---------------------------------------------------------------- fp8 quantisation (quant_fp8.cu)
 // q[r, :] = e4m3(x[r, :] / scale[r]) with scale[r] = amax(row r) / 448
 cudaError_t quantize_rowwise_e4m3(const void* x, void* q, float* scale, int64_t rows, int cols, int64_t ldx, int64_t ldq,

@@ -531,6 +531,16 @@ def equal(x, v, **kw): return compare(x, "eq", v, **kw)             # noqa: E704
 def not_equal(x, v, **kw): return compare(x, "ne", v, **kw)         # noqa: E704
 
 
+def scaled_masked_softmax(x, mask=None, scale=1.0, **kw):
+    """softmax(scale * x) over the last dim of [B, H, Sq, Sk] with an optional boolean mask [B, 1, Sq, Sk] (true = masked)"""
+    return _op1("scaled_masked_softmax", [x] + ([mask] if mask is not None else []), {"scale": float(scale), "causal": False}, **kw)
+
+
+def scaled_upper_triang_masked_softmax(x, scale=1.0, **kw):
+    """causal variant: entries above the (bottom-right aligned) diagonal are masked"""
+    return _op1("scaled_masked_softmax", [x], {"scale": float(scale), "causal": True}, **kw)
+
+
 def stop_gradient(x, **kw):
     return _op1("stop_gradient", [x], **kw)
 

@@ -271,6 +271,23 @@ def test_linear_fp8_block_scaled(M, N, K, act):
     close(torch.as_tensor(W.grad.numpy()), wr.grad, 0.05 * math.sqrt(M), 0.06)
 
 
+def test_scaled_masked_softmax_kernels():
+    B, H, Sq, Sk = 2, 4, 64, 96
+    x, g = bf(B, H, Sq, Sk, seed=1), bf(B, H, Sq, Sk, seed=2)
+    X = leaf(x)
+    y = ht.scaled_upper_triang_masked_softmax(X, 0.25)
+    ht.sum(y * leaf(g, False)).backward()
+    xr = x.float().requires_grad_()
+    s = (xr * 0.25).masked_fill(torch.ones(Sq, Sk, dtype=torch.bool, device="cuda").tril(Sk - Sq).logical_not(), float("-inf"))
+    yr = torch.softmax(s, -1)
+    (yr * g.float()).sum().backward()
+    close(torch.as_tensor(y.numpy()), yr.detach(), 0.01, 0.02)
+    close(torch.as_tensor(X.grad.numpy()), xr.grad, 0.01, 0.03)
+    m = (torch.rand(B, 1, Sq, Sk, device="cuda") > 0.7)
+    y2 = ht.scaled_masked_softmax(leaf(x, False), ht.from_numpy(m), 2.0)
+    close(torch.as_tensor(y2.numpy()), torch.softmax((x.float() * 2).masked_fill(m, float("-inf")), -1), 0.01, 0.02)
+
+
 def test_fused_adam_matches_torch():
     n = 4096 * 33 + 5
     p = torch.randn(n, generator=torch.Generator().manual_seed(1)).cuda()
