@@ -475,6 +475,18 @@ void Executor::build_plan(ExecPlan& plan, const Tensor& loss, const TensorList& 
   for (size_t i = 0; i < plan.stage_groups.size(); ++i)
     if (local_device_index(plan.stage_groups[i]) >= 0) { plan.stage = (int)i; break; }
 
+  // the cross-entropy kernels overwrite their logits with (softmax - onehot): let them work in place when nothing else
+  // reads the logits (saves a copy of the largest activation of the step)
+  {
+    std::set<TensorId> fetched(plan.fetch_ids.begin(), plan.fetch_ids.end());
+    for (OpDef* op : order) {
+      if (op->type != "softmax_cross_entropy_sparse" && op->type != "vocab_parallel_cross_entropy") continue;
+      const Tensor& lg = op->inputs[0];
+      if (lg->consumers.size() == 1 && !fetched.count(lg->id) && lg->producer && !lg->producer->has_flag(kFlagVariable) &&
+          !lg->producer->has_flag(kFlagPlaceholder))
+        op->attrs.set("donate_logits", true);
+    }
+  }
   // optimizer bookkeeping: (param, grad) pairs and deferred grad-sync comm ops
   std::set<OpId> deferred;
   for (OpDef* op : order) {

@@ -303,6 +303,25 @@ TensorList Graph::gradients(const TensorList& ys, const TensorList& xs, const Te
     if (gs.size() == 1) return gs[0];
     OpMeta m;
     if (of->producer) m.dg_hierarchy = of->producer->meta.dg_hierarchy;
+    if (gs.size() == 2) {
+      // residual stream: d(x) = d(skip) + dgrad(branch).  Fold the addition into the dgrad GEMM epilogue (its residual
+      // operand) instead of a separate elementwise pass; the plain dgrad op becomes dead and is never scheduled.
+      for (int k = 0; k < 2; ++k) {
+        const Tensor& a = gs[k];
+        const Tensor& other = gs[1 - k];
+        OpDef* p = a->producer;
+        if (p != nullptr && p->type == "linear_dgrad" && p->inputs.size() == 2 && a->consumers.empty() && a->shape == other->shape &&
+            a->dtype == other->dtype && a->ds_hierarchy.size() == other->ds_hierarchy.size()) {
+          bool same = true;
+          for (size_t s = 0; s < a->ds_hierarchy.size() && same; ++s)
+            if (a->has_ds((int)s) != other->has_ds((int)s) || (a->has_ds((int)s) && !a->ds((int)s).check_equal(other->ds((int)s)))) same = false;
+          if (!same) continue;
+          AttrMap at = p->attrs;
+          at.set("residual_add", true);
+          return make_op1("linear_dgrad", {p->inputs[0], p->inputs[1], other}, at, p->meta);
+        }
+      }
+    }
     return make_op1("sum_n", gs, {}, m);
   };
   for (auto it = order.rbegin(); it != order.rend(); ++it) {

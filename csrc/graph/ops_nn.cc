@@ -227,8 +227,10 @@ static Ts linear_dgrad_compute(const OpDef& op, const Ts& in, RunCtx*) {
     at::Tensor dx = at::empty({M, K}, dy.options());
     // dx[M,K] = dy[M,N] * W[N,K]: B must be [K(out-n), N(contract)]; W[N,K] row-major = MN-major B
     if (in.size() > 2) {
-      at::Tensor pre = flatten_rows(in[2]).contiguous();
-      run_gemm(d2, false, w, trans_b, dx, M, K, N, nullptr, &pre, act_bwd_mode(op.attrs.s("act_bwd")), nullptr, ACT_NONE, false);
+      // third operand: pre-activation (dx *= act'(pre)) or, with residual_add, a gradient to add (dx += other)
+      at::Tensor aux = flatten_rows(in[2]).contiguous();
+      const int mode = op.attrs.b("residual_add") ? (int)AUX_ADD : act_bwd_mode(op.attrs.s("act_bwd"));
+      run_gemm(d2, false, w, trans_b, dx, M, K, N, nullptr, &aux, mode, nullptr, ACT_NONE, false);
     } else {
       run_gemm(d2, false, w, trans_b, dx, M, K, N, nullptr, nullptr, 0, nullptr, ACT_NONE, false);
     }
@@ -236,7 +238,7 @@ static Ts linear_dgrad_compute(const OpDef& op, const Ts& in, RunCtx*) {
   }
   if (is_native(dy)) note_fallback("linear_dgrad");
   at::Tensor dxa = (trans_b ? at::matmul(d2, w) : at::matmul(d2, w.t())).reshape(oshape);
-  if (in.size() > 2) dxa = aten_act_bwd(dxa, in[2], op.attrs.s("act_bwd"));
+  if (in.size() > 2) dxa = op.attrs.b("residual_add") ? dxa + in[2].reshape(oshape) : aten_act_bwd(dxa, in[2], op.attrs.s("act_bwd"));
   return {dxa};
 }
 // wgrad: dw = dy^T * x  ([N,K] when trans_b else [K,N])

@@ -235,7 +235,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
           // the 128 rows of this CTA's A tile are one all-gather chunk: wait until every CTA delivered its slice
           const uint32_t* f = p.ag_flags + (m0 >> 7);
           uint32_t spins = 0;
-          while (ptx::ld_acquire_gpu(f) < gridDim.x) {
+          while (ptx::ld_acquire_gpu(f) < 2 * gridDim.x) {        // two puller warps per CTA
             __nanosleep(64);
             if (++spins > (1u << 26)) __trap();   // a lost peer must surface as an error, not as a hung GPU
           }
@@ -306,11 +306,15 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
     __syncwarp();
-  } else if (warp == 3) {
-    // ========================= all-gather puller (fused AG -> GEMM only) =========================
+  } else if (warp == 2 || warp == 3) {
+    // ========================= all-gather pullers (fused AG -> GEMM only) =========================
+    // warps 2 (idle after the TMEM allocation) and 3 of every CTA stream this CTA's slice of each 128-row chunk from the
+    // owner's symmetric shard into A: 8 independent 16-byte peer loads in flight per lane
     if (ag_fused) {
       const int chunks_per_rank = p.ag_rows_per_rank >> 7;
       const int64_t chunk_vecs = int64_t(128) * p.K * 2 / 16;        // uint4 per 128-row chunk
+      const int64_t lane_id = (int64_t(blockIdx.x) * 2 + (warp - 2)) * 32 + lane;
+      const int64_t stride = int64_t(gridDim.x) * 64;
       for (int i = 0; i < p.ag_world; ++i) {
         const int r = (p.ag_rank + i) % p.ag_world;                  // own shard first, then the ring order the tiles follow
         const uint4* src = reinterpret_cast<const uint4*>(p.ag_src[r]);
@@ -318,12 +322,13 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int c = 0; c < chunks_per_rank; ++c) {
           const uint4* s4 = src + int64_t(c) * chunk_vecs;
           uint4* d4 = dst + int64_t(c) * chunk_vecs;
-          int64_t v = int64_t(blockIdx.x) * 32 + lane;
-          const int64_t stride = int64_t(gridDim.x) * 32;
-          for (; v + 3 * stride < chunk_vecs; v += 4 * stride) {     // 4 independent 16-byte peer loads in flight per lane
-            const uint4 a = ptx::ld_global_relaxed_sys(s4 + v), b = ptx::ld_global_relaxed_sys(s4 + v + stride);
-            const uint4 c4 = ptx::ld_global_relaxed_sys(s4 + v + 2 * stride), d = ptx::ld_global_relaxed_sys(s4 + v + 3 * stride);
-            d4[v] = a; d4[v + stride] = b; d4[v + 2 * stride] = c4; d4[v + 3 * stride] = d;
+          int64_t v = lane_id;
+          for (; v + 7 * stride < chunk_vecs; v += 8 * stride) {
+            uint4 t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = ptx::ld_global_relaxed_sys(s4 + v + u * stride);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) d4[v + u * stride] = t[u];
           }
           for (; v < chunk_vecs; v += stride) d4[v] = ptx::ld_global_relaxed_sys(s4 + v);
           __syncwarp();
