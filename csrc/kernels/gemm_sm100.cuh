@@ -319,21 +319,25 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int r = (p.ag_rank + i) % p.ag_world;                  // own shard first, then the ring order the tiles follow
         const uint4* src = reinterpret_cast<const uint4*>(p.ag_src[r]);
         uint4* dst = reinterpret_cast<uint4*>(p.ag_dst) + int64_t(r) * chunks_per_rank * chunk_vecs;
-        for (int c = 0; c < chunks_per_rank; ++c) {
-          const uint4* s4 = src + int64_t(c) * chunk_vecs;
-          uint4* d4 = dst + int64_t(c) * chunk_vecs;
+        // 8 chunks (1024 rows) are pulled as one batch: a lane owns only a few 16-byte pieces of a single chunk, batching
+        // gives it ~8x more independent peer loads in flight; the 8 chunk flags are raised together afterwards
+        for (int c0 = 0; c0 < chunks_per_rank; c0 += 8) {
+          const int nc = min(8, chunks_per_rank - c0);
+          const int64_t batch_vecs = int64_t(nc) * chunk_vecs;
+          const uint4* s4 = src + int64_t(c0) * chunk_vecs;
+          uint4* d4 = dst + int64_t(c0) * chunk_vecs;
           int64_t v = lane_id;
-          for (; v + 7 * stride < chunk_vecs; v += 8 * stride) {
+          for (; v + 7 * stride < batch_vecs; v += 8 * stride) {
             uint4 t[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) t[u] = ptx::ld_global_relaxed_sys(s4 + v + u * stride);
 #pragma unroll
             for (int u = 0; u < 8; ++u) d4[v + u * stride] = t[u];
           }
-          for (; v < chunk_vecs; v += stride) d4[v] = ptx::ld_global_relaxed_sys(s4 + v);
+          for (; v < batch_vecs; v += stride) d4[v] = ptx::ld_global_relaxed_sys(s4 + v);
           __syncwarp();
           __threadfence();
-          if (lane == 0) atomicAdd(p.ag_flags + r * chunks_per_rank + c, 1u);
+          if (lane < nc) atomicAdd(p.ag_flags + r * chunks_per_rank + c0 + lane, 1u);
         }
       }
     }

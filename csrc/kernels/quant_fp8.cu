@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(256) quant_rowwise_kernel(const __nv_bfloat16*
   }
   for (int c = (nvec << 3) + threadIdx.x; c < cols; c += blockDim.x) amax = fmaxf(amax, fabsf(__bfloat162float(row[c])));
   amax = block_max(amax, red);
-  const float sc = amax > 0.f ? amax / kE4M3Max : 1.0f;
+  // amax * (1 / 448) (not amax / 448): the same rounding as frameworks that divide by a scalar through its reciprocal
+  const float sc = amax > 0.f ? amax * (1.0f / kE4M3Max) : 1.0f;
   if (threadIdx.x == 0) scale[r] = sc;
   uint8_t* qrow = q + r * ldq;
   for (int v = threadIdx.x; v < nvec; v += blockDim.x) {   // second read of the row hits L1/L2
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(256) col_amax_kernel(const __nv_bfloat16* __re
 }
 __global__ void amax_to_scale_kernel(float* __restrict__ s, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) s[i] = s[i] > 0.f ? s[i] / kE4M3Max : 1.0f;
+  if (i < n) s[i] = s[i] > 0.f ? s[i] * (1.0f / kE4M3Max) : 1.0f;
 }
 // q[c, r] = e4m3(x[r, c] / scale[c]) through a 32 x 32 shared tile
 __global__ void __launch_bounds__(256) quant_transpose_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale,
