@@ -1119,14 +1119,28 @@ static Ts attn_bwd_compute(const OpDef& op, const Ts& in, RunCtx*) {
     return {dq, dk, dv};
   }
   if (is_native(q)) note_fallback("attn_bwd");
-  // reference backward through autograd of the reference forward
-  at::AutoGradMode gm(true);
-  at::Tensor qf = q.detach().to(at::kFloat).requires_grad_(true);
-  at::Tensor kf = k.detach().to(at::kFloat).requires_grad_(true);
-  at::Tensor vf = v.detach().to(at::kFloat).requires_grad_(true);
-  auto r = aten_attention(qf, kf, vf, scale, causal);
-  r.first.backward(d_o.to(at::kFloat));
-  return {qf.grad().to(q.scalar_type()), kf.grad().to(k.scalar_type()), vf.grad().to(v.scalar_type())};
+  // reference backward in fp32 from the SAVED statistics (o, lse), exactly like the kernels: P is rebuilt as
+  // exp(S - lse), so a call on one (q-block, kv-block) pair with the global lse composes into ring attention
+  const int64_t Hq = q.size(2), Hkv = k.size(2), Sq = q.size(1), Sk = k.size(1), rep = Hq / Hkv;
+  at::Tensor qf = q.to(at::kFloat).permute({0, 2, 1, 3}), kf = k.to(at::kFloat).permute({0, 2, 1, 3}), vf = v.to(at::kFloat).permute({0, 2, 1, 3});
+  at::Tensor of = in[4].to(at::kFloat).permute({0, 2, 1, 3}), dof = d_o.to(at::kFloat).permute({0, 2, 1, 3});
+  if (rep > 1) { kf = kf.repeat_interleave(rep, 1); vf = vf.repeat_interleave(rep, 1); }
+  at::Tensor sc = at::matmul(qf, kf.transpose(-1, -2)) * scale;                     // [B, Hq, Sq, Sk]
+  if (causal) sc = sc.masked_fill(at::ones({Sq, Sk}, sc.options().dtype(at::kBool)).tril(Sk - Sq).logical_not(), -INFINITY);
+  at::Tensor pr = at::exp(sc - lse.to(at::kFloat).unsqueeze(-1));
+  pr = at::where(at::isfinite(pr), pr, at::zeros_like(pr));
+  at::Tensor dv = at::matmul(pr.transpose(-1, -2), dof);
+  at::Tensor dp = at::matmul(dof, vf.transpose(-1, -2));
+  at::Tensor delta = (dof * of).sum(-1, true);
+  at::Tensor ds = pr * (dp - delta);
+  at::Tensor dq = at::matmul(ds, kf) * scale;
+  at::Tensor dk = at::matmul(ds.transpose(-1, -2), qf) * scale;
+  if (rep > 1) {
+    dk = dk.reshape({dk.size(0), Hkv, rep, Sk, dk.size(3)}).sum(2);
+    dv = dv.reshape({dv.size(0), Hkv, rep, Sk, dv.size(3)}).sum(2);
+  }
+  return {dq.permute({0, 2, 1, 3}).contiguous().to(q.scalar_type()), dk.permute({0, 2, 1, 3}).contiguous().to(k.scalar_type()),
+          dv.permute({0, 2, 1, 3}).contiguous().to(v.scalar_type())};
 }
 static TensorList attn_grad(OpDef& op, const TensorList& g) {
   AttrMap a;
