@@ -1269,9 +1269,7 @@ static void packed_views(const at::Tensor& qkv, int64_t S, int64_t Hq, int64_t H
   *k = x.narrow(2, Hq, Hkv);
   *v = x.narrow(2, Hq + Hkv, Hkv);
 }
-static TsP attn_packed_compute(const OpDef& op, const TsP& in, RunCtx* rc) {
-  const at::Tensor& qkv = in[0];
-  const int64_t S = op.sy_shape.empty() ? op.attrs.i("seq_len") : op.sy_shape[0].get_val();
+static TsP attn_packed_rows(const OpDef& op, const at::Tensor& qkv, int64_t S, RunCtx* rc) {
   // head counts follow the width of the packed projection actually fed (the tensor-parallel degree may change between
   // strategies); the attributes fix the q : kv ratio and the head size
   const int64_t D = op.attrs.i("head_dim");
@@ -1307,13 +1305,71 @@ static TsP attn_packed_compute(const OpDef& op, const TsP& in, RunCtx* rc) {
   return {r[0].reshape({T, Hq * D}), r[1]};
 }
 // inputs: do [T, Hq*D], qkv, o [T, Hq*D], lse -> dqkv
+// document boundaries of a packed batch (varlen attention): host copy of cu_seqlens, cached for the current step
+static std::vector<int64_t> host_cu_seqlens(const at::Tensor& cu, RunCtx* rc) {
+  static thread_local std::unordered_map<const void*, std::pair<uint64_t, std::vector<int64_t>>> cache;
+  const uint64_t stamp = rc ? rc->seed * 131 + (uint64_t)rc->micro_batch : 0;
+  auto it = cache.find(cu.data_ptr());
+  if (rc != nullptr && it != cache.end() && it->second.first == stamp && (int64_t)it->second.second.size() == cu.numel()) return it->second.second;
+  at::Tensor h = cu.to(at::kCPU, at::kLong).contiguous();
+  std::vector<int64_t> v(h.data_ptr<int64_t>(), h.data_ptr<int64_t>() + h.numel());
+  if (cache.size() > 64) cache.clear();
+  cache[cu.data_ptr()] = {stamp, v};
+  return v;
+}
+// forward.  inputs: qkv [T, W], [cu_seqlens int32 [n + 1]] -- with cu_seqlens every document [cu[i], cu[i+1]) attends
+// (causally) only to itself: one kernel launch per document over strided views of the packed buffer; the saved lse is the
+// concatenation of the per-document [Hq, len] blocks (shape [1, Hq, T])
+static TsP attn_packed_compute(const OpDef& op, const TsP& in, RunCtx* rc) {
+  const at::Tensor& qkv = in[0];
+  const int64_t S = op.sy_shape.empty() ? op.attrs.i("seq_len") : op.sy_shape[0].get_val();
+  if (in.size() < 2) return attn_packed_rows(op, qkv, S, rc);
+  const int64_t T = qkv.size(0), D = op.attrs.i("head_dim");
+  const int64_t rep_ = std::max<int64_t>(1, op.attrs.i("num_heads") / std::max<int64_t>(1, op.attrs.i("num_kv_heads", op.attrs.i("num_heads"))));
+  const int64_t Hq = qkv.size(-1) / ((rep_ + 2) * D) * rep_;
+  auto fopt = qkv.options().dtype(at::kFloat);
+  if (qkv.is_meta()) return {at::empty({T, Hq * D}, qkv.options()), at::empty({1, Hq, T}, fopt)};
+  const std::vector<int64_t> cu = host_cu_seqlens(in[1], rc);
+  HB_CHECK(cu.size() >= 2 && cu.front() == 0 && cu.back() <= T) << "attn_packed: bad cu_seqlens";
+  at::Tensor src = qkv.is_contiguous() ? qkv : qkv.contiguous();
+  at::Tensor o = at::zeros({T, Hq * D}, qkv.options());
+  at::Tensor lse = at::zeros({Hq * T}, fopt);
+  for (size_t i = 0; i + 1 < cu.size(); ++i) {
+    const int64_t lo = cu[i], len = cu[i + 1] - cu[i];
+    if (len <= 0) continue;
+    TsP r = attn_packed_rows(op, src.narrow(0, lo, len), len, rc);
+    o.narrow(0, lo, len).copy_(r[0]);
+    lse.narrow(0, Hq * lo, Hq * len).copy_(r[1].reshape({-1}));
+  }
+  return {o, lse.reshape({1, Hq, T})};
+}
+static TsP attn_packed_bwd_rows(const OpDef& op, const at::Tensor& d_o, const at::Tensor& qkv, const at::Tensor& o, const at::Tensor& lse,
+                                int64_t S, RunCtx* rc);
+// inputs: do [T, Hq*D], qkv, o, lse, [cu_seqlens] -> dqkv
 static TsP attn_packed_bwd_compute(const OpDef& op, const TsP& in, RunCtx* rc) {
-  const at::Tensor& d_o = in[0];
   const at::Tensor& qkv = in[1];
-  const at::Tensor& o = in[2];
-  const at::Tensor& lse = in[3];
   if (qkv.is_meta()) return {at::empty_like(qkv)};
   const int64_t S = op.sy_shape.empty() ? op.attrs.i("seq_len") : op.sy_shape[0].get_val();
+  if (in.size() < 5) return attn_packed_bwd_rows(op, in[0], qkv, in[2], in[3], S, rc);
+  const int64_t T = qkv.size(0), D = op.attrs.i("head_dim");
+  const int64_t rep_ = std::max<int64_t>(1, op.attrs.i("num_heads") / std::max<int64_t>(1, op.attrs.i("num_kv_heads", op.attrs.i("num_heads"))));
+  const int64_t Hq = qkv.size(-1) / ((rep_ + 2) * D) * rep_;
+  const std::vector<int64_t> cu = host_cu_seqlens(in[4], rc);
+  at::Tensor src = qkv.is_contiguous() ? qkv : qkv.contiguous();
+  at::Tensor dqkv = at::zeros_like(src);
+  at::Tensor lflat = in[3].reshape({-1}), dof = in[0].contiguous(), of = in[2].contiguous();
+  for (size_t i = 0; i + 1 < cu.size(); ++i) {
+    const int64_t lo = cu[i], len = cu[i + 1] - cu[i];
+    if (len <= 0) continue;
+    TsP r = attn_packed_bwd_rows(op, dof.narrow(0, lo, len), src.narrow(0, lo, len), of.narrow(0, lo, len),
+                                 lflat.narrow(0, Hq * lo, Hq * len).reshape({1, Hq, len}), len, rc);
+    dqkv.narrow(0, lo, len).copy_(r[0]);
+  }
+  (void)T;
+  return {dqkv};
+}
+static TsP attn_packed_bwd_rows(const OpDef& op, const at::Tensor& d_o, const at::Tensor& qkv, const at::Tensor& o, const at::Tensor& lse,
+                                int64_t S, RunCtx* rc) {
   // head counts follow the width of the packed projection actually fed (the tensor-parallel degree may change between
   // strategies); the attributes fix the q : kv ratio and the head size
   const int64_t D = op.attrs.i("head_dim");
@@ -1350,8 +1406,11 @@ static TsP attn_packed_bwd_compute(const OpDef& op, const TsP& in, RunCtx* rc) {
 }
 static TensorList attn_packed_grad(OpDef& op, const TensorList& g) {
   OpDef* fw = &op;
-  return {op.graph->make_op1("attn_packed_bwd", {g[0], op.inputs[0], op.outputs[0], op.outputs[1]}, op.attrs, {},
-                             [fw](OpDef& o) { o.sy_shape = fw->sy_shape; })};
+  TensorList ins = {g[0], op.inputs[0], op.outputs[0], op.outputs[1]};
+  if (op.inputs.size() > 1) ins.push_back(op.inputs[1]);      // cu_seqlens
+  TensorList r = {op.graph->make_op1("attn_packed_bwd", ins, op.attrs, {}, [fw](OpDef& o) { o.sy_shape = fw->sy_shape; })};
+  if (op.inputs.size() > 1) r.push_back(nullptr);
+  return r;
 }
 static void attn_packed_deduce(OpDef& op, size_t s) {
   copy_out_ds(op, 0, s, op.inputs[0]);

@@ -34,6 +34,7 @@ class TrainerStates:
     loss: object = None
     train_op: object = None
     seq_len_symbol: object = None
+    cu_seqlens: object = None
     config: object = None
 
 
@@ -70,6 +71,7 @@ class Trainer:
         self.loss_history: List[float] = []
         self.step_times: List[float] = []
         self.callbacks: List[Callable] = list(kwargs.get("callbacks", []))
+        self.max_docs_per_row = int(kwargs.get("max_docs_per_row", 64))
 
         dspc = kwargs.get("ds_parallel_configs")
         if dspc is None:
@@ -136,7 +138,12 @@ class Trainer:
             st.input_ids = core.parallel_placeholder("int64", [tokens], in_dsh, device_group_hierarchy=in_dgh, name="input_ids")
             st.position_ids = core.parallel_placeholder("int64", [tokens], in_dsh, device_group_hierarchy=in_dgh, name="position_ids")
             st.labels = core.parallel_placeholder("int64", [tokens], lb_dsh, device_group_hierarchy=lb_dgh, name="labels")
-            st.loss = st.model(st.input_ids, st.position_ids, st.labels, seq_len=st.seq_len_symbol)
+            if cfg.packing:
+                # document boundaries of every packed row (padded with repeats of the row length): variable-length attention
+                st.cu_seqlens = core.placeholder("int32", [self.max_docs_per_row + 1], name="cu_seqlens")
+                st.loss = st.model(st.input_ids, st.position_ids, st.labels, seq_len=st.seq_len_symbol, cu_seqlens=st.cu_seqlens)
+            else:
+                st.loss = st.model(st.input_ids, st.position_ids, st.labels, seq_len=st.seq_len_symbol)
             st.optimizer = self.optimizer_wrapper.create_optimizer() if isinstance(self.optimizer_wrapper, OptimizerWrapper) \
                 else self.optimizer_wrapper
             st.train_op = st.optimizer.minimize(st.loss)
@@ -164,11 +171,14 @@ class Trainer:
             rows = _pack_pairs([batch[i] for i in order], max_len, pad_id, cfg.pack_alignment)
             width = max(len(r[0]) for r in rows)
             width = (width + cfg.pack_alignment - 1) // cfg.pack_alignment * cfg.pack_alignment
-            for toks, lab, pos in rows:
+            feeds_cu = []
+            for toks, lab, pos, cu in rows:
                 n = len(toks)
                 feeds_i.append(np.concatenate([toks, np.full(width - n, pad_id, np.int64)]))
                 feeds_l.append(np.concatenate([lab, np.full(width - n, -1, np.int64)]))
                 feeds_p.append(np.concatenate([pos, np.zeros(width - n, np.int64)]))
+                cu = list(cu[: self.max_docs_per_row]) + [width]          # the padding tail is one more (label-masked) document
+                feeds_cu.append(np.asarray(cu + [width] * (self.max_docs_per_row + 1 - len(cu)), np.int32))
             seq = width
             stats = {"real_tokens": int(sum(len(x) for x, _ in batch)), "fed_tokens": int(width * len(rows)), "rows": len(rows_i)}
         else:
@@ -190,6 +200,8 @@ class Trainer:
         to_t = (lambda a: torch.as_tensor(a).pin_memory()) if torch.cuda.is_available() else torch.as_tensor
         feed = {st.input_ids: [to_t(a) for a in feeds_i], st.position_ids: [to_t(a) for a in feeds_p],
                 st.labels: [to_t(a) for a in feeds_l]}
+        if cfg.packing and st.cu_seqlens is not None:
+            feed[st.cu_seqlens] = [to_t(a) for a in feeds_cu]
         return feed, len(feeds_i), seq, stats
 
     def train_data_iterator(self):
@@ -325,4 +337,8 @@ def _pack_pairs(pairs, max_len, pad_id, alignment):
         rows[r][1].append(np.concatenate([y, np.full(pad, -1, np.int64)]))
         rows[r][2].append(np.concatenate([np.arange(len(x)), np.zeros(pad, np.int64)]))
         space[r] -= need
-    return [(np.concatenate(a), np.concatenate(b), np.concatenate(c)) for a, b, c in rows]
+    out = []
+    for a, b, c in rows:
+        cu = np.concatenate([[0], np.cumsum([len(t) for t in a])])
+        out.append((np.concatenate(a), np.concatenate(b), np.concatenate(c), cu))
+    return out

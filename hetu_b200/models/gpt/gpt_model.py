@@ -72,10 +72,11 @@ class GPTAttention(Module):
             h, h, get_multi_ds_parallel_config(ds_parallel_configs, "dense", layer_idx), sequence_parallel=config.sequence_parallel,
             bias=True, dtype=config.dtype, name=f"{name}_dense", init_std=std / math.sqrt(2.0 * config.n_layer))
 
-    def forward(self, x, seq_len, residual=None):
+    def forward(self, x, seq_len, residual=None, cu_seqlens=None):
         tp = self.qkv_dense.tp[0]
         qkv = self.qkv_dense(x)                                     # [T, 3h/tp]
-        a = attn_packed(qkv, seq_len, self.num_heads // tp, self.num_heads // tp, self.head_dim, is_causal=True, layout="hqkv")
+        a = attn_packed(qkv, seq_len, self.num_heads // tp, self.num_heads // tp, self.head_dim, is_causal=True, layout="hqkv",
+                        cu_seqlens=cu_seqlens)
         return self.dense(a, residual=residual)
 
 
@@ -112,10 +113,10 @@ class GPTBlock(Module):
                                              name=f"ln2_block{layer_idx}")
         self.mlp = GPTMLP(config, ds_parallel_configs, layer_idx, name=f"mlp_block{layer_idx}")
 
-    def forward(self, x, seq_len):
+    def forward(self, x, seq_len, cu_seqlens=None):
         # entering a new pipeline stage: receive the residual stream once (P2P), both branches then use the local copy
         x = self.ln_1._adapt(x, self.ln_1._all_split0() if self.ln_1.sequence_parallel else None)
-        x = self.attn(self.ln_1(x), seq_len, residual=x)    # residual add fused into the row-parallel GEMM epilogue
+        x = self.attn(self.ln_1(x), seq_len, residual=x, cu_seqlens=cu_seqlens)    # residual add fused into the row-parallel GEMM epilogue
         x = self.mlp(self.ln_2(x), residual=x)
         return x
 
@@ -136,8 +137,8 @@ class GPTModel(Module):
                                              sequence_parallel=config.sequence_parallel, eps=config.layer_norm_epsilon,
                                              dtype=config.dtype, name="ln_final")
 
-    def forward(self, input_ids, position_ids, seq_len):
-        """input_ids / position_ids: flattened [tokens]"""
+    def forward(self, input_ids, position_ids, seq_len, cu_seqlens=None):
+        """input_ids / position_ids: flattened [tokens]; cu_seqlens: document boundaries of a packed batch"""
         pe = self.wpe(position_ids)
         if self.config.sequence_parallel and any(t > 1 for t in self.wte.tp):
             pe = self.wte._adapt(pe, self.wte.ds_split0())      # local slice: keep this rank's token shard
@@ -146,7 +147,7 @@ class GPTModel(Module):
             x = ops.dropout(x, self.config.embd_pdrop)
         for blk in self.h:
             with _placement(blk):
-                x = blk(x, seq_len)
+                x = blk(x, seq_len, cu_seqlens)
         return self.ln_f(x)
 
 
@@ -182,8 +183,8 @@ class GPTLMHeadModel(Module):
                                                        gather_output=False, dtype=config.dtype, name="lm_head",
                                                        init_std=config.initializer_range)
 
-    def forward(self, input_ids, position_ids=None, labels=None, seq_len=None):
-        hidden = self.transformer(input_ids, position_ids, seq_len)
+    def forward(self, input_ids, position_ids=None, labels=None, seq_len=None, cu_seqlens=None):
+        hidden = self.transformer(input_ids, position_ids, seq_len, cu_seqlens)
         wte = self.transformer.wte
         if self.lm_head is None:
             last = self.transformer.ln_f.device_group_unions

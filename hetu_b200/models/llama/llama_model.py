@@ -66,14 +66,14 @@ class LlamaAttention(Module):
                                               name=f"{name}_dense", init_std=std / math.sqrt(2.0 * config.num_hidden_layers))
         self.qkv_dense.fp8 = self.dense.fp8 = config.fp8
 
-    def forward(self, x, seq_len, residual=None, pos_offset=0):
+    def forward(self, x, seq_len, residual=None, pos_offset=0, position_ids=None, cu_seqlens=None):
         tp = self.qkv_dense.tp[0]
         assert self.kv_heads % tp == 0, "tensor parallel degree must divide the number of kv heads"
         hq, hkv, d = self.num_heads // tp, self.kv_heads // tp, self.head_dim
         rep = hq // hkv
         # kv-head-major packed layout [g: q x rep, k, v]: any tp | kv_heads owns whole groups (strategy independent weights)
         qkv = self.qkv_dense(x)
-        qkv = rotary_packed(qkv, seq_len, hq, hkv, d, base=self.config.rope_theta, pos_offset=pos_offset, layout="hqkv")
+        qkv = rotary_packed(qkv, seq_len, hq, hkv, d, positions=position_ids, base=self.config.rope_theta, pos_offset=pos_offset, layout="hqkv")
         if self.config.cp_ranks and len(self.config.cp_ranks) > 1:
             t = qkv.shape[0]
             s = seq_len if isinstance(seq_len, int) else seq_len.get_data()
@@ -85,7 +85,7 @@ class LlamaAttention(Module):
             a = ops.parallel_attn(q, k, v, self.config.cp_ranks, is_causal=True)
             a = ops.reshape(a, [t, hq * d])
         else:
-            a = attn_packed(qkv, seq_len, hq, hkv, d, is_causal=True, layout="hqkv")
+            a = attn_packed(qkv, seq_len, hq, hkv, d, is_causal=True, layout="hqkv", cu_seqlens=cu_seqlens)
         return self.dense(a, residual=residual)
 
 
@@ -122,10 +122,10 @@ class LlamaBlock(Module):
                                                 name=f"rmsnorm2_block{layer_idx}")
         self.mlp = LlamaMLP(config, ds_parallel_configs, layer_idx, name=f"mlp_block{layer_idx}")
 
-    def forward(self, x, seq_len, pos_offset=0):
+    def forward(self, x, seq_len, pos_offset=0, position_ids=None, cu_seqlens=None):
         n1 = self.rmsnorm_1
         x = n1._adapt(x, n1._all_split0() if n1.sequence_parallel else None)   # pipeline-stage entry (P2P)
-        x = self.attn(self.rmsnorm_1(x), seq_len, residual=x, pos_offset=pos_offset)
+        x = self.attn(self.rmsnorm_1(x), seq_len, residual=x, pos_offset=pos_offset, position_ids=position_ids, cu_seqlens=cu_seqlens)
         return self.mlp(self.rmsnorm_2(x), residual=x)
 
 
@@ -141,7 +141,7 @@ class LlamaModel(Module):
                                                 sequence_parallel=config.sequence_parallel, eps=config.rms_norm_eps,
                                                 dtype=config.dtype, name="rmsnorm_final")
 
-    def forward(self, input_ids, seq_len, pos_offset=0):
+    def forward(self, input_ids, seq_len, pos_offset=0, position_ids=None, cu_seqlens=None):
         from ..gpt.gpt_model import _placement
         x = self.wte(input_ids, sequence_parallel=self.config.sequence_parallel)
         for i, blk in enumerate(self.h):
@@ -149,9 +149,9 @@ class LlamaModel(Module):
             with _placement(blk):
                 if i in self.config.recompute_layers:
                     with recompute_ctx([True]):
-                        x = blk(x, seq_len, pos_offset)
+                        x = blk(x, seq_len, pos_offset, position_ids, cu_seqlens)
                 else:
-                    x = blk(x, seq_len, pos_offset)
+                    x = blk(x, seq_len, pos_offset, position_ids, cu_seqlens)
         return self.rmsnorm_f(x)
 
 
@@ -168,8 +168,10 @@ class LlamaLMHeadModel(Module):
                                                    gather_output=False, dtype=config.dtype, name="lm_head",
                                                    init_std=config.initializer_range)
 
-    def forward(self, input_ids, position_ids=None, labels=None, seq_len=None, pos_offset=0):
-        hidden = self.transformer(input_ids, seq_len, pos_offset)
+    def forward(self, input_ids, position_ids=None, labels=None, seq_len=None, pos_offset=0, cu_seqlens=None):
+        """position_ids (optional): explicit rotary positions, needed when a batch row packs several documents;
+        cu_seqlens: their boundaries (variable-length attention)"""
+        hidden = self.transformer(input_ids, seq_len, pos_offset, position_ids if cu_seqlens is not None else None, cu_seqlens)
         logits = self.lm_head(hidden)
         if labels is None:
             return logits

@@ -225,6 +225,28 @@ def test_packed_grouped_qkv_rotary_attention(Hq, Hkv, D):
     close(torch.as_tensor(X.grad.numpy()), xr.grad, 0.06, 0.04)
 
 
+def test_varlen_packed_attention_native():
+    """documents of a packed row attend only to themselves (one launch per document over strided views)"""
+    from hetu_b200.ops_extra import attn_packed
+    T, H, D = 640, 4, 64
+    qkv, g = bf(T, 3 * H * D, seed=1), bf(T, H * D, seed=2)
+    bounds = [0, 128, 328, 640]
+    cu = torch.tensor(bounds + [640, 640], dtype=torch.int32).cuda()
+    X = leaf(qkv)
+    o = attn_packed(X, T, H, H, D, is_causal=True, layout="hqkv", cu_seqlens=ht.from_numpy(cu))
+    ht.sum(o * leaf(g, False)).backward()
+    xr = qkv.float().requires_grad_()
+    y = xr.view(T, H, 3, D)
+    outs = []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        q, k, v = (y[a:b, :, i].transpose(0, 1).unsqueeze(0) for i in range(3))
+        outs.append(torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True)[0].transpose(0, 1).reshape(b - a, H * D))
+    ref = torch.cat(outs)
+    (ref * g.float()).sum().backward()
+    close(torch.as_tensor(o.numpy()), ref.detach(), 0.02, 0.02)
+    close(torch.as_tensor(X.grad.numpy()), xr.grad, 0.04, 0.04)
+
+
 def test_swiglu_interleaved():
     x, g = bf(512, 1024, seed=1), bf(512, 512, seed=2)
     X = leaf(x)

@@ -255,3 +255,24 @@ def test_linear_fp8_emulation_matches_quantised_reference():
     torch.nn.functional.gelu(xr @ w.t() + b).sum().backward()
     rel = (torch.as_tensor(X.grad.numpy()) - xr.grad).abs().mean() / xr.grad.abs().mean()
     assert rel < 0.08
+
+
+def test_varlen_packed_attention_equals_per_document_attention():
+    from hetu_b200.ops_extra import attn_packed
+    torch.manual_seed(0)
+    T, H, D = 48, 2, 8
+    qkv, g = torch.randn(T, 3 * H * D), torch.randn(T, H * D)
+    cu = torch.tensor([0, 16, 40, 48, 48], dtype=torch.int32)       # trailing repeat = padding entry
+    X = ht.from_numpy(qkv, requires_grad=True)
+    o = attn_packed(X, T, H, H, D, is_causal=True, layout="hqkv", cu_seqlens=ht.from_numpy(cu))
+    ht.sum(o * ht.from_numpy(g)).backward()
+    xr = qkv.clone().requires_grad_()
+    y = xr.view(T, H, 3, D)
+    outs = []
+    for a, b in [(0, 16), (16, 40), (40, 48)]:
+        q, k, v = (y[a:b, :, i].transpose(0, 1).unsqueeze(0) for i in range(3))
+        outs.append(torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True)[0].transpose(0, 1).reshape(b - a, H * D))
+    ref = torch.cat(outs)
+    (ref * g).sum().backward()
+    assert (torch.as_tensor(o.numpy()) - ref).abs().max().item() < 1e-5
+    assert (torch.as_tensor(X.grad.numpy()) - xr.grad).abs().max().item() < 1e-5
