@@ -408,16 +408,17 @@ void Executor::lower_comm(ExecPlan& plan, OpDef* op, int strategy) {
       if (cs.is_receiver) cs.peer = src_group.get(me_dst).index();
       break;
     }
+    // (ranks of another pipeline stage lower the op too -- every rank walks the whole graph -- but are not members)
     case CommType::ALL_REDUCE:
-      cs.ranks = group_ranks(src_group, src.get_device_indices_by_dim(kPartialDim, me_src));
+      if (me_src >= 0) cs.ranks = group_ranks(src_group, src.get_device_indices_by_dim(kPartialDim, me_src));
       break;
     case CommType::ALL_GATHER:
       cs.dim = src.get_split_dim(dst);
-      cs.ranks = group_ranks(src_group, dst.get_device_indices_by_dim(kDupDim, me_src));
+      if (me_src >= 0) cs.ranks = group_ranks(src_group, dst.get_device_indices_by_dim(kDupDim, me_src));
       break;
     case CommType::REDUCE_SCATTER:
       cs.dim = dst.get_split_dim(src);
-      cs.ranks = group_ranks(src_group, src.get_device_indices_by_dim(kPartialDim, me_src));
+      if (me_src >= 0) cs.ranks = group_ranks(src_group, src.get_device_indices_by_dim(kPartialDim, me_src));
       break;
     case CommType::SCATTER:
     case CommType::COMM_SPLIT: {

@@ -361,7 +361,12 @@ TensorList Graph::gradients(const TensorList& ys, const TensorList& xs, const Te
       // Parameter gradients are exempt -- their (data-parallel) reduction is deferred and bucketed by the optimizer.
       {
         const Tensor& x = op->inputs[i];
-        const bool leaf = x->producer && (x->producer->has_flag(kFlagVariable) || x->producer->has_flag(kFlagPlaceholder));
+        bool leaf = x->producer && (x->producer->has_flag(kFlagVariable) || x->producer->has_flag(kFlagPlaceholder));
+        // a parameter shipped to another pipeline stage (tied embedding / lm_head: "share_weight_comm") is still that
+        // parameter: its gradient travels back un-reduced and joins the owner's deferred data-parallel reduction once
+        if (x->producer && x->producer->type == "comm" && !x->producer->inputs.empty() && x->producer->inputs[0]->producer &&
+            x->producer->inputs[0]->producer->has_flag(kFlagVariable))
+          leaf = true;
         if (!leaf && x->ds_hierarchy.size() > 0 && gins[i]->ds_hierarchy.size() > 0 && op->type != "comm") {
           DistributedStatesHierarchy target;
           bool differs = false;

@@ -39,7 +39,11 @@ static TensorList comm_grad(OpDef& op, const TensorList& g) {
   // (every contributor of a partial sum receives the same gradient)
   const Tensor& x = op.inputs[0];
   DistributedStatesHierarchy target;
-  for (size_t s = 0; s < x->ds_hierarchy.size(); ++s) {
+  // a parameter moved to another device group (tied weights across pipeline stages): its gradient comes home in the layout it
+  // has -- still a partial sum over the data-parallel replicas -- and is reduced once, by the owner's deferred gradient sync
+  const bool param_in = x->producer && x->producer->has_flag(kFlagVariable) && g[0] && g[0]->ds_hierarchy.size() == x->ds_hierarchy.size();
+  if (param_in) target = g[0]->ds_hierarchy;
+  for (size_t s = 0; !param_in && s < x->ds_hierarchy.size(); ++s) {
     DistributedStatesUnion u;
     const auto& src_u = x->ds_hierarchy.get(s);
     for (size_t i = 0; i < src_u.size(); ++i) {

@@ -38,6 +38,8 @@ def _reference(model="gpt"):
     (1, 1, 2, 0, 0, 2),     # pipeline (1F1B, 2 micro-batches)
     (2, 2, 1, 1, 1, 1),     # dp2 x tp2 + zero + sp
     (1, 1, 1, 0, 0, 2),     # micro-batch accumulation on one device
+    (2, 1, 2, 0, 0, 2),     # dp x pp: tied embedding gradient crosses stages un-reduced, reduced once by the owner
+    (2, 2, 2, 1, 1, 2),     # 3-D: dp2 x tp2 x pp2 + zero + sp + micro-batches (8 ranks)
 ])
 def test_strategy_matches_single_device(dp, tp, pp, zero, sp, mb):
     ref = _reference()
@@ -53,6 +55,17 @@ def test_strategy_matches_single_device(dp, tp, pp, zero, sp, mb):
 def test_llama_tp2_sp_matches_single_device():
     ref = _reference("llama")
     ok, outs = run_workers(WORKER, 2, [1, 2, 1, 0, 1, 1, "llama"])
+    assert ok, "\n-----\n".join(outs)
+    got = _losses(outs)
+    for a, b in zip(got, ref):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, ref)
+
+
+@pytest.mark.dist
+def test_llama_3d_parallel_matches_single_device():
+    """Llama (GQA, rotary, SwiGLU, untied head) under dp2 x tp2 x pp2 + ZeRO + sequence parallel + 2 micro-batches"""
+    ref = _reference("llama")
+    ok, outs = run_workers(WORKER, 8, [2, 2, 2, 1, 1, 2, "llama"])
     assert ok, "\n-----\n".join(outs)
     got = _losses(outs)
     for a, b in zip(got, ref):
