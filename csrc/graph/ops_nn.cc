@@ -440,6 +440,8 @@ static Ts linear_fp8_compute(const OpDef& op, const Ts& in, RunCtx*) {
     if (act != ACT_NONE) out.push_back(pre.reshape(oshape));
     return out;
   }
+  // shapes the e4m3 TMA maps cannot address (K not a multiple of 16 bytes): run the same product on the bf16 tensor cores
+  if (gemm_ok(x2) && gemm_ok(w) && (K % 8) == 0 && (N % 8) == 0) return linear_compute(op, in, nullptr);
   if (is_native(x)) note_fallback("linear_fp8");
   at::Tensor y = at::matmul(fake_quant_rows(x2), fake_quant_rows(w).t());
   if (bias) y = y + bias->to(at::kFloat);
@@ -473,6 +475,7 @@ static Ts linear_fp8_dgrad_compute(const OpDef& op, const Ts& in, RunCtx*) {
     } else run_gemm_fp8(qd.first, qd.second, qwt, swt, dx, M, K, N, nullptr, ACT_NONE, nullptr, nullptr, 0);
     return {dx.reshape(oshape)};
   }
+  if (gemm_ok(d2) && gemm_ok(w) && (K % 8) == 0) return linear_dgrad_compute(op, in, nullptr);     // bf16 tensor-core fallback
   if (is_native(dy)) note_fallback("linear_fp8_dgrad");
   at::Tensor dxa = at::matmul(fake_quant_rows(d2), fake_quant_rows(w.t().contiguous()).t()).to(dy.scalar_type()).reshape(oshape);
   if (in.size() > 2) dxa = aten_act_bwd(dxa, in[2], op.attrs.s("act_bwd"));

@@ -137,3 +137,11 @@ def test_malleus_planner_gives_stragglers_fewer_layers():
     assert same == m
     bal = dispatch_sequences([100, 4000, 300, 2000, 1500, 800], [1.0, 0.5])
     assert sorted(sum(bal, [])) == list(range(6))
+
+
+def test_yaml_experiment_config_with_overrides():
+    from hetu_b200.engine.config_loader import load_experiment
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "pretrain", "config", "gpt_small_dp2_tp2.yaml")
+    e = load_experiment(path, ["trainer.steps=7", "ds_parallel.tp=4"])
+    assert e["trainer"].steps == 7 and e["strategy"].tp == 4 and e["strategy"].world() == 8
+    assert e["trainer"].ds_parallel is e["strategy"] and e["model"]["type"] == "gpt" and e["optimizer"]["weight_decay"] == 0.1
