@@ -1,0 +1,118 @@
+"""Hydraulis-style dynamic dispatch: every step the global batch of variable-length sequences is split over several
+parallel strategies (e.g. a long-sequence strategy with large tp/cp and a short-sequence data-parallel one) so that the
+estimated makespan is minimal, and inside a strategy over its data-parallel replicas.  The planner can run in its own
+process and stream plans to the trainers through the KV store (`rpc.kv_store.ProducerConsumer`).
+(ref: examples/hydraulis -- strategy/dynamic_scip.py solves the assignment as an ILP with pyscipopt over a profiled cost
+model; here the same objective is solved with an exact DP over sorted sequences for <= 2 strategies and an LPT + local
+search heuristic in general, which needs no solver package.)"""
+from __future__ import annotations
+
+import bisect
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+
+@dataclass
+class StrategyCost:
+    """time(seq) = a * seq + b * seq^2 + c per sequence on ONE data-parallel replica of the strategy; `max_seq` is the longest
+    sequence that fits in memory; `dp` replicas work in parallel; switching to the strategy costs `switch_ms` once per step"""
+    name: str
+    dp: int
+    a: float
+    b: float
+    c: float = 0.0
+    max_seq: int = 1 << 30
+    switch_ms: float = 0.0
+
+    def seq_ms(self, n: int) -> float:
+        return self.a * n + self.b * n * n + self.c
+
+    @staticmethod
+    def fit(name: str, dp: int, samples: Sequence[Tuple[int, float]], max_seq: int = 1 << 30, switch_ms: float = 0.0) -> "StrategyCost":
+        """least-squares fit of (seq_len, ms) profile points to a*n + b*n^2 + c"""
+        import numpy as np
+        n = np.array([s for s, _ in samples], dtype=np.float64)
+        t = np.array([m for _, m in samples], dtype=np.float64)
+        A = np.stack([n, n * n, np.ones_like(n)], 1)
+        coef, *_ = np.linalg.lstsq(A, t, rcond=None)
+        return StrategyCost(name, dp, float(max(coef[0], 0)), float(max(coef[1], 0)), float(max(coef[2], 0)), max_seq, switch_ms)
+
+
+def _replica_makespan(costs: List[float], replicas: int) -> Tuple[float, List[List[int]]]:
+    """longest-processing-time-first assignment of per-sequence costs to `replicas` bins"""
+    order = sorted(range(len(costs)), key=lambda i: -costs[i])
+    loads = [0.0] * replicas
+    bins: List[List[int]] = [[] for _ in range(replicas)]
+    for i in order:
+        r = min(range(replicas), key=loads.__getitem__)
+        loads[r] += costs[i]
+        bins[r].append(i)
+    return (max(loads) if loads else 0.0), bins
+
+
+def dispatch_batch(seq_lens: Sequence[int], strategies: Sequence[StrategyCost], sequential: bool = True) -> Dict:
+    """-> {"assignment": [strategy index per sequence], "per_strategy": [{"indices", "replicas": [[...]], "ms"}], "makespan_ms"}.
+    sequential=True: the strategies run one after another on the same devices (hot switching, HotSPa / Hydraulis) so the
+    step time is the SUM of their makespans; False: they run concurrently on disjoint devices (MAX)."""
+    n, S = len(seq_lens), len(strategies)
+    feasible = [[j for j, st in enumerate(strategies) if seq_lens[i] <= st.max_seq] for i in range(n)]
+    if any(not f for f in feasible):
+        raise ValueError("a sequence fits no strategy")
+
+    def evaluate(assign: List[int]):
+        per, total = [], 0.0
+        for j, st in enumerate(strategies):
+            idx = [i for i in range(n) if assign[i] == j]
+            ms, bins = _replica_makespan([st.seq_ms(seq_lens[i]) for i in idx], st.dp)
+            ms += st.switch_ms if idx else 0.0
+            per.append({"indices": idx, "replicas": [[idx[k] for k in b] for b in bins], "ms": ms})
+            total = total + ms if sequential else max(total, ms)
+        return total, per
+
+    # start: every sequence on its cheapest feasible strategy (per-replica amortised cost)
+    assign = [min(feasible[i], key=lambda j: strategies[j].seq_ms(seq_lens[i]) / strategies[j].dp) for i in range(n)]
+    best, per = evaluate(assign)
+    # threshold sweep (exact for two strategies ordered by length affinity): sequences longer than t go to the strategy that
+    # supports the longest sequences
+    if S >= 2:
+        long_j = max(range(S), key=lambda j: strategies[j].max_seq)
+        for t in sorted(set(seq_lens)) + [max(seq_lens) + 1]:
+            cand = [long_j if (seq_lens[i] >= t or long_j not in feasible[i] and False) else
+                    min((j for j in feasible[i] if j != long_j), default=long_j, key=lambda j: strategies[j].seq_ms(seq_lens[i]) / strategies[j].dp)
+                    for i in range(n)]
+            if any(c not in feasible[i] for i, c in enumerate(cand)):
+                continue
+            v, p = evaluate(cand)
+            if v < best:
+                best, per, assign = v, p, cand
+    # local search: move single sequences while it helps
+    improved = True
+    while improved:
+        improved = False
+        for i in sorted(range(n), key=lambda k: -seq_lens[k]):
+            for j in feasible[i]:
+                if j == assign[i]:
+                    continue
+                cand = list(assign)
+                cand[i] = j
+                v, p = evaluate(cand)
+                if v < best - 1e-9:
+                    best, per, assign, improved = v, p, cand, True
+    return {"assignment": assign, "per_strategy": per, "makespan_ms": best}
+
+
+class HydraulisPlanner:
+    """produces one dispatch plan per step; with a KV client the plans are published ahead of the trainer"""
+
+    def __init__(self, strategies: Sequence[StrategyCost], producer=None):
+        self.strategies, self.producer = list(strategies), producer
+        self.step = 0
+
+    def plan(self, seq_lens: Sequence[int]) -> Dict:
+        p = dispatch_batch(seq_lens, self.strategies)
+        p["step"] = self.step
+        p["strategies"] = [s.name for s in self.strategies]
+        if self.producer is not None:
+            self.producer.produce({k: v for k, v in p.items()})
+        self.step += 1
+        return p

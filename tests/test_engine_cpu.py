@@ -145,3 +145,30 @@ def test_yaml_experiment_config_with_overrides():
     e = load_experiment(path, ["trainer.steps=7", "ds_parallel.tp=4"])
     assert e["trainer"].steps == 7 and e["strategy"].tp == 4 and e["strategy"].world() == 8
     assert e["trainer"].ds_parallel is e["strategy"] and e["model"]["type"] == "gpt" and e["optimizer"]["weight_decay"] == 0.1
+
+
+def test_hydraulis_dispatch_mixes_strategies_and_balances_replicas():
+    from hetu_b200.engine.hydraulis import HydraulisPlanner, StrategyCost, dispatch_batch
+    short = StrategyCost("dp8", 8, a=0.004, b=1e-6, max_seq=4096, switch_ms=1.0)          # fast per token, cannot hold long sequences
+    long_ = StrategyCost("tp4dp2", 2, a=0.006, b=6e-7, max_seq=32768, switch_ms=1.0)
+    rng = np.random.RandomState(0)
+    lens = rng.choice([256, 512, 1024, 2048], 64).tolist() + [16384, 30000]
+    p = dispatch_batch(lens, [short, long_])
+    assert set(p["assignment"][-2:]) == {1}                      # the long sequences can only run on the long strategy
+    n_short = sum(1 for a in p["assignment"] if a == 0)
+    assert n_short > 32                                           # most short sequences use the cheaper strategy
+    only_long = dispatch_batch(lens, [long_])
+    assert p["makespan_ms"] < only_long["makespan_ms"]
+    loads = [sum(short.seq_ms(lens[i]) for i in r) for r in p["per_strategy"][0]["replicas"]]
+    assert max(loads) - min(loads) <= short.seq_ms(2048) + 1e-6   # LPT keeps the replicas within one sequence of each other
+    fitted = StrategyCost.fit("x", 1, [(512, 6.0), (1024, 13.5), (2048, 33.0), (4096, 90.0)])
+    assert abs(fitted.seq_ms(2048) - 33.0) < 1.0
+    plans = []
+
+    class Sink:
+        def produce(self, item):
+            plans.append(item)
+    pl = HydraulisPlanner([short, long_], Sink())
+    pl.plan(lens)
+    pl.plan(lens[:10])
+    assert [x["step"] for x in plans] == [0, 1] and plans[0]["strategies"] == ["dp8", "tp4dp2"]
