@@ -12,7 +12,7 @@ import math
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
-from ..models.parallel_config import generate_hetero_ds_parallel_config
+from ..models.parallel_config import generate_ds_parallel_config, generate_hetero_ds_parallel_config
 
 DEVICES_PER_NODE = 8
 
@@ -263,6 +263,17 @@ class StrategyModel:
             hetero_micro_batch_num_list=[pl["micro_batches"] for pl in plans])
         self.ds_parallel_configs = generate_hetero_ds_parallel_config(self.total_layers, pipelines, zero=self.zero)
         self.plans = plans
+        # When all groups kept the full tp degree and the pipelines ended up identical in depth and layer split, the plan is
+        # also expressible as a homogeneous (dp, tp, pp) strategy with uneven stages on re-ordered devices -- directly
+        # executable by the current executor (heterogeneous unions are planned but not yet executed)
+        self.executable_config = None
+        full = all(g.tp == self.tp for pl in plans for g in pl["groups"])
+        same = len({(tuple(pl["layers"]), len(pl["groups"])) for pl in plans}) == 1
+        if full and same:
+            pp = len(plans[0]["groups"])
+            devices = [d for s in range(pp) for pl in plans for d in pl["groups"][s].devices]
+            self.executable_config = generate_ds_parallel_config(self.total_layers, len(devices), len(plans), self.tp, pp, zero=self.zero,
+                                                                 devices=devices, layer_split=plans[0]["layers"])
         return self.strategies, self.ds_parallel_configs
 
 

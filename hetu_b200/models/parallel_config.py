@@ -20,17 +20,21 @@ def _leaf(split: Dict[str, List[int]], dup: List[int], groups: List[List[int]], 
 
 
 def generate_ds_parallel_config(num_layers: int, num_gpus: int, dp: int, tp: int, pp: int, cp: int = 1, zero: bool = True,
-                                recompute_layers: Sequence[int] = (), model: str = "gpt", devices: Optional[List[int]] = None) -> dict:
-    """devices are laid out [pp][dp*cp][tp] (tp innermost = NVLink neighbours)"""
+                                recompute_layers: Sequence[int] = (), model: str = "gpt", devices: Optional[List[int]] = None,
+                                layer_split: Optional[Sequence[int]] = None) -> dict:
+    """devices are laid out [pp][dp*cp][tp] (tp innermost = NVLink neighbours).  layer_split: layers per pipeline stage
+    (uneven splits move work away from slow stages -- the homogeneous-tp form of Malleus' hetero_layers)"""
     assert dp * cp * tp * pp == num_gpus, f"dp{dp} x cp{cp} x tp{tp} x pp{pp} != {num_gpus}"
     devices = list(devices) if devices is not None else list(range(num_gpus))
     dcp = dp * cp
     per_stage = dcp * tp
     stage_devs = [devices[s * per_stage:(s + 1) * per_stage] for s in range(pp)]
     base, rem = divmod(num_layers, pp)
+    if layer_split is not None:
+        assert len(layer_split) == pp and sum(layer_split) == num_layers and all(n > 0 for n in layer_split), "bad layer_split"
     ranges, lo = [], 0
     for s in range(pp):
-        n = base + (1 if s < rem else 0)
+        n = layer_split[s] if layer_split is not None else base + (1 if s < rem else 0)
         ranges.append([lo, lo + n - 1])
         lo += n
 

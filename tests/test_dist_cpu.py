@@ -72,6 +72,17 @@ def test_llama_3d_parallel_matches_single_device():
         assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, ref)
 
 
+@pytest.mark.dist
+def test_uneven_pipeline_layer_split_matches_single_device():
+    """Malleus-style layer re-balancing: stage 0 holds 1 layer, stage 1 holds 3 (dp2 x pp2, 2 micro-batches)"""
+    ref = _reference("gpt")
+    ok, outs = run_workers(WORKER, 4, [2, 1, 2, 0, 0, 2, "gpt", "1,3"])
+    assert ok, "\n-----\n".join(outs)
+    got = _losses(outs)
+    for a, b in zip(got, ref):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, ref)
+
+
 MOE_WORKER = os.path.join(os.path.dirname(__file__), "workers", "moe_worker.py")
 
 

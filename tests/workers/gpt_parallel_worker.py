@@ -16,6 +16,7 @@ zero = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 sp = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 num_mb = int(sys.argv[6]) if len(sys.argv) > 6 else 1
 model_kind = sys.argv[7] if len(sys.argv) > 7 else "gpt"
+layer_split = [int(v) for v in sys.argv[8].split(",")] if len(sys.argv) > 8 else None
 world = dp * tp * pp
 ht.init_comm_group(world)
 rank = int(os.environ.get("RANK", "0"))
@@ -30,7 +31,7 @@ else:
     cfg = GPTConfig(vocab_size=128, n_positions=S, n_embd=32, n_layer=4, n_head=4, sequence_parallel=bool(sp))
     n_layer = cfg.n_layer
 with ht.graph("define_and_run", create_new=True) as g:
-    dsc = [generate_ds_parallel_config(n_layer, world, dp, tp, pp, zero=bool(zero))]
+    dsc = [generate_ds_parallel_config(n_layer, world, dp, tp, pp, zero=bool(zero), layer_split=layer_split)]
     model = (LlamaLMHeadModel if model_kind == "llama" else GPTLMHeadModel)(cfg, dsc)
     in_ds, in_dg = ht.nn.parallel.config2ds(dsc[0]["input"])
     lb_ds, lb_dg = ht.nn.parallel.config2ds(dsc[0]["label"])
