@@ -172,3 +172,32 @@ def test_hydraulis_dispatch_mixes_strategies_and_balances_replicas():
     pl.plan(lens)
     pl.plan(lens[:10])
     assert [x["step"] for x in plans] == [0, 1] and plans[0]["strategies"] == ["dp8", "tp4dp2"]
+
+
+def test_hotspa_trainer_picks_strategy_by_sequence_bucket_and_malleus_trainer_replans():
+    from hetu_b200.engine import HotSPaTrainer, MalleusTrainer
+    from hetu_b200.models import generate_ds_parallel_config
+    ht.init_comm_group(1)
+    ds = SyntheticDataset(64, 259, 48, min_seq_len=8, seed=2, length_distribution="uniform")
+    dsc = [generate_ds_parallel_config(2, 1, 1, 1, 1), generate_ds_parallel_config(2, 1, 1, 1, 1)]
+    cfg = TrainingConfig(packing=False, micro_batch_size=2, global_load_size=2, max_seq_length=48, steps=6, learning_rate=1e-2, log_interval=0,
+                         pack_alignment=8)
+    tr = HotSPaTrainer(cfg, ModelWrapper(GPTLMHeadModel, _mcfg()), ByteTokenizer(), None, ds, ds_parallel_configs=dsc, bucket_sizes=[24, 0])
+    assert tr.strategy_for(40) == 0 and tr.strategy_for(10) == 1
+    losses = tr.train()
+    assert len(losses) == 6 and all(np.isfinite(losses))
+    before = tr.switch_count
+    short = [(np.arange(9), np.arange(9)), (np.arange(7), np.arange(7))]
+    long_ = [(np.arange(40) % 200, np.arange(40) % 200), (np.arange(30), np.arange(30))]
+    for b in (short, long_, short):
+        l, _ = tr._train_step(b)
+        assert np.isfinite(l)
+    assert tr.switch_count - before >= 2 and tr.cur_strategy_id == 1
+    ratios = {i: 1.0 for i in range(8)}
+    ratios[5] = 2.0
+    mt = MalleusTrainer(cfg, ModelWrapper(GPTLMHeadModel, _mcfg()), ByteTokenizer(), None, ds, ctxs=TrainerCtxs(normal_layers=8, normal_mbn=8),
+                        strategy_args=TrainerStrategyArgs(dp=2, tp=2, pp=2, rank_to_device_mapping={i: i for i in range(8)}), replan_interval=2,
+                        ratio_source=lambda: ratios)
+    mt.train(steps=5)
+    assert len(mt.plans_log) == 1 and mt.plans_log[0]["step"] == 2      # second measurement equals the first -> no new plan
+    assert any(sum(l) == 16 for l in mt.plans_log[0]["hetero_layers"])
