@@ -416,6 +416,8 @@ PYBIND11_MODULE(_C, m) {
     CommRuntime::get().init(rank, world, world_pg, fac);
   });
   m.def("comm_initialized", [] { return CommRuntime::get().initialized(); });
+  m.def("comm_create_group", [](const std::vector<int>& ranks) { return (bool)CommRuntime::get().group(ranks); },
+        "create (or look up) the process group over `ranks`; collective among its members");
   m.def("comm_rank", [] { return CommRuntime::get().rank(); });
   m.def("comm_world", [] { return CommRuntime::get().world(); });
   m.def("comm_barrier", [] { CommRuntime::get().barrier(); });

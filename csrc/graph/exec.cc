@@ -16,8 +16,10 @@ namespace hb {
 // CommRuntime
 // =============================================================================================
 CommRuntime& CommRuntime::get() {
-  static CommRuntime r;
-  return r;
+  // intentionally immortal: it owns Python-created process groups and the Python group factory, which must not be
+  // released by a static destructor after the interpreter has been finalised
+  static CommRuntime* r = new CommRuntime();
+  return *r;
 }
 void CommRuntime::init(int rank, int world, PG world_pg, std::function<PG(const std::vector<int>&)> factory) {
   rank_ = rank;
@@ -494,7 +496,7 @@ void Executor::build_plan(ExecPlan& plan, const Tensor& loss, const TensorList& 
     if (!op->has_flag(kFlagOptimizerUpdate) || op->inputs.size() < 2) continue;
     Tensor param = op->inputs[0], grad = op->inputs[1];
     plan.update_of_param[param->id] = op;
-    if (grad->producer && grad->producer->type == "comm") {
+    if (grad->producer && (grad->producer->type == "comm" || grad->producer->type == "grouped_all_reduce")) {
       deferred.insert(grad->producer->id);
       plan.param_of_grad[grad->producer->inputs[0]->id] = param->id;
     } else {
@@ -933,6 +935,18 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
     for (OpDef* op : plan.update_ops) {
       if (op->has_flag(kFlagGroup)) continue;
       if (zf_active_ != nullptr && zf_active_->handled_ops.count(op->id)) continue;
+      if (op->type == "grouped_all_reduce") {
+        // heterogeneous data parallelism: slice-wise synchronisation of the accumulated gradient across pipelines
+        const TensorId raw = op->inputs[0]->id;
+        auto pg = plan.param_of_grad.find(raw);
+        if (pg == plan.param_of_grad.end()) continue;
+        auto acc = accum_grads_.find(pg->second);
+        if (acc == accum_grads_.end()) continue;
+        at::Tensor g = acc->second;
+        if (scale != 1.0) g = g * scale;
+        uvals[op->outputs[0]->id] = op->kernel->compute(*op, {g}, &rc)[0];
+        continue;
+      }
       if (op->type == "comm") {
         // deferred gradient synchronisation (DP all-reduce / ZeRO reduce-scatter) on the accumulated gradient
         const TensorId raw = op->inputs[0]->id;

@@ -64,6 +64,38 @@ static TensorList comm_grad(OpDef& op, const TensorList& g) {
 }
 HB_REGISTER_OP(comm, "comm", 1, kFlagComm | kFlagNoMetaExec, comm_compute, comm_grad, comm_deduce, comm_infer);
 
+// ------------------------------------------------------------------ heterogeneous data parallelism (Malleus / Ampelos unions)
+// grouped_all_reduce: the gradient of a parameter that other pipelines shard with a DIFFERENT tensor-parallel degree is
+// synchronised slice by slice -- slice i (offset, length along `dim`) is all-reduced over group i (the holders of that finest
+// shard in every pipeline); replicated parameters are all-reduced among one leader per pipeline and broadcast inside the
+// pipeline's tensor-parallel group.  (ref: SplitAllReduce / hetero CommOp lowering in hetu/graph/ops/Communication.cc)
+static Ts grouped_all_reduce_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  at::Tensor g = in[0];
+  if (g.is_meta()) return {at::empty_like(g)};
+  auto& comm = CommRuntime::get();
+  if (!comm.initialized()) return {g};
+  const int64_t dim = op.attrs.i("dim", 0);
+  const std::vector<int64_t> offs = op.attrs.ints("offsets"), lens = op.attrs.ints("lengths"), sizes = op.attrs.ints("group_sizes"),
+                             flat = op.attrs.ints("ranks_flat"), bcast = op.attrs.ints("bcast_ranks");
+  at::Tensor out = g.contiguous().clone();
+  size_t pos = 0;
+  for (size_t i = 0; i < sizes.size(); ++i) {
+    std::vector<int> ranks(flat.begin() + pos, flat.begin() + pos + sizes[i]);
+    pos += sizes[i];
+    if (ranks.size() < 2) continue;
+    at::Tensor piece = out.narrow(dim, offs[i], lens[i]);
+    at::Tensor red = comm.all_reduce(piece.contiguous(), ranks, ReductionType::SUM);
+    piece.copy_(red);
+  }
+  if (bcast.size() > 1) {
+    std::vector<int> ranks(bcast.begin(), bcast.end());
+    out = comm.broadcast(out, ranks, ranks[0]);
+  }
+  return {out};
+}
+HB_REGISTER_OP(grouped_all_reduce, "grouped_all_reduce", 1, kFlagComm | kFlagNondiff, grouped_all_reduce_compute, nullptr,
+               [](OpDef& op, size_t s) { copy_out_ds(op, 0, s, op.inputs[0]); }, nullptr);
+
 // ------------------------------------------------------------------ explicit collectives (rank lists in attrs)
 static std::vector<int> ranks_attr(const OpDef& op) {
   std::vector<int> r;

@@ -8,3 +8,4 @@ from .data_collator import DataCollatorForLanguageModel  # noqa: F401
 from .hydraulis import StrategyCost, dispatch_batch, HydraulisPlanner  # noqa: F401
 from .config_loader import load_experiment, build_trainer  # noqa: F401
 from .hot_trainers import HotSPaTrainer, MalleusTrainer  # noqa: F401
+from .hetero import HeteroSession  # noqa: F401

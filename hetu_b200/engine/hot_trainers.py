@@ -42,8 +42,9 @@ class HotSPaTrainer(Trainer):
 
 class MalleusTrainer(Trainer):
     """every `replan_interval` steps: measure slow-down ratios (Straggler workload), solve the Malleus plan; when the plan
-    is executable on the current executor (full tensor-parallel groups) it is appended as a new strategy and training hot
-    switches to it"""
+    is expressible as a homogeneous strategy (full tensor-parallel groups, identical pipelines) it is appended as a new
+    strategy and training hot switches to it; genuinely heterogeneous plans (different tp degrees / stage counts per
+    pipeline) are executed through engine.hetero.HeteroSession (member-local graphs + grouped gradient all-reduce)"""
 
     def __init__(self, *args, ctxs: Optional[TrainerCtxs] = None, strategy_args: Optional[TrainerStrategyArgs] = None, replan_interval: int = 50,
                  ratio_source: Optional[Callable[[], Dict[int, float]]] = None, **kwargs):
@@ -70,7 +71,8 @@ class MalleusTrainer(Trainer):
         strategy, cfg = model.make_plans()
         self.last_model = model
         rec = {"step": self.global_step, "ratios": ratios, "hetero_layers": strategy.hetero_layers,
-               "micro_batches": strategy.hetero_micro_batch_num_list, "executable": model.executable_config is not None,
+               "micro_batches": strategy.hetero_micro_batch_num_list, "executable": model.executable_config is not None,     # adoptable by in-place hot switching
+               "hetero_session": model.executable_config is None,     # otherwise: rebuild through engine.hetero.HeteroSession
                "estimated_time": model.estimate_time(model.plans)}
         self.plans_log.append(rec)
         return rec

@@ -264,8 +264,10 @@ class StrategyModel:
         self.ds_parallel_configs = generate_hetero_ds_parallel_config(self.total_layers, pipelines, zero=self.zero)
         self.plans = plans
         # When all groups kept the full tp degree and the pipelines ended up identical in depth and layer split, the plan is
-        # also expressible as a homogeneous (dp, tp, pp) strategy with uneven stages on re-ordered devices -- directly
-        # executable by the current executor (heterogeneous unions are planned but not yet executed)
+        # also expressible as a homogeneous (dp, tp, pp) strategy with uneven stages on re-ordered devices, which hot
+        # switching can adopt in place (`executable_config`).  Every other plan runs through the member-local path:
+        # engine.hetero.HeteroSession(self.ds_parallel_configs, shares=micro-batch counts) gives each rank the homogeneous
+        # graph of its own pipeline plus the cross-pipeline gradient synchronisation.
         self.executable_config = None
         full = all(g.tp == self.tp for pl in plans for g in pl["groups"])
         same = len({(tuple(pl["layers"]), len(pl["groups"])) for pl in plans}) == 1

@@ -98,6 +98,59 @@ def generate_hetero_ds_parallel_config(num_layers: int, pipelines: List[dict], z
     return cfg
 
 
+def localize_hetero_config(cfg: dict, rank: int) -> dict:
+    """Member-local view of a heterogeneous strategy: the pipeline (union member) that contains `rank` as an ordinary
+    homogeneous (dp = 1, tp_m, pp_m) ds_parallel_config on its own devices.  Every localized leaf keeps a reference to the
+    original leaf (`_hetero_orig`) and its member index, from which the cross-pipeline gradient synchronisation groups are
+    derived (hetu_b200.nn.parallel.hetero_grad_sync_spec)."""
+    import copy
+
+    pipe = [None]
+
+    def find_pipe(node):
+        if isinstance(node, dict):
+            if "device_group_union" in node and "type" in node:
+                for m, devs in enumerate(node["device_group_union"]):
+                    if rank in devs and pipe[0] is None:
+                        pipe[0] = m
+            else:
+                for v in node.values():
+                    find_pipe(v)
+
+    find_pipe(cfg)
+    assert pipe[0] is not None, f"rank {rank} does not appear in the heterogeneous strategy"
+
+    def member_of(leaf):
+        return pipe[0]
+
+    def walk(node):
+        if isinstance(node, dict) and "device_group_union" in node and "type" in node:
+            m = member_of(node)
+            devs = list(node["device_group_union"][m])
+            split = {k: [v[m] if isinstance(v, (list, tuple)) else v] for k, v in node.get("split", {}).items()}
+            tp_m = len(devs)
+            if node["type"] == "placeholder":
+                loc = {"split": {"0": [1]}, "dup": [tp_m], "device_group_union": [devs], "type": "placeholder"}
+            else:
+                has_split = any(v[0] > 1 for v in split.values())
+                loc = {"split": {k: v for k, v in split.items() if v[0] > 1}, "dup": [1 if has_split else tp_m], "device_group_union": [devs],
+                       "type": "variable", "zero": False}
+            loc["_hetero_orig"], loc["_hetero_member"] = node, m
+            return loc
+        if isinstance(node, dict):
+            return {k: (walk(v) if isinstance(v, (dict, list)) else copy.copy(v)) for k, v in node.items()}
+        if isinstance(node, list):
+            return [walk(v) if isinstance(v, (dict, list)) else v for v in node]
+        return node
+
+    # blocks: a member only instantiates each layer once, on the stage that holds it in THIS member
+    out = walk(cfg)
+    out["hetero"], out["zero"] = False, False
+    for name, blk in list(out.get("blocks", {}).items()):
+        blk["recompute"], blk["cpu_offload"] = [False], [False]
+    return out
+
+
 def read_ds_parallel_config(path_or_list) -> List[dict]:
     """one file per strategy (comma separated) -> list of configs"""
     if isinstance(path_or_list, (list, tuple)) and path_or_list and isinstance(path_or_list[0], dict):

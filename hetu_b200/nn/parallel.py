@@ -89,8 +89,111 @@ def get_multi_ds_parallel_config(ds_parallel_configs: List[dict], module_name: s
     return out
 
 
+# name of a parameter -> (original heterogeneous leaf, member index, split dim or None): filled by the parallel modules when
+# they are built from a localized heterogeneous config, consumed by hetero_grad_sync_spec()
+HETERO_PARAMS: dict = {}
+
+
+def _lcm(a, b):
+    import math
+    return a * b // math.gcd(a, b)
+
+
+def hetero_grad_sync_spec(name: str, local_shape, rank: int):
+    """slices / rank groups that synchronise the gradient of parameter `name` across the pipelines of a heterogeneous
+    strategy -> dict(dim, offsets, lengths, groups, bcast_ranks) or None when nothing has to be exchanged"""
+    if name not in HETERO_PARAMS:
+        return None
+    leaf, m, split_dim = HETERO_PARAMS[name]
+    members = [list(d) for d in leaf["device_group_union"]]
+    if len(members) < 2:
+        return None
+    me = members[m]
+    if rank not in me:
+        return None
+    t = me.index(rank)
+    if split_dim is None:
+        leaders = [d[0] for d in members]
+        spec = {"dim": 0, "offsets": [], "lengths": [], "groups": [], "bcast_ranks": me if len(me) > 1 else []}
+        if t == 0:
+            spec["offsets"], spec["lengths"], spec["groups"] = [0], [int(local_shape[0]) if local_shape else 1], [leaders]
+        return spec
+    tps = [len(d) for d in members]
+    G = 1
+    for v in tps:
+        G = _lcm(G, v)
+    n_local = int(local_shape[split_dim])
+    per = G // tps[m]                      # finest pieces held by this rank
+    f = n_local // per
+    assert f * per == n_local, f"parameter {name}: local extent {n_local} is not divisible into {per} pieces"
+    offs, lens, groups = [], [], []
+    for j in range(per):
+        k = t * per + j
+        ranks = [members[q][k // (G // tps[q])] for q in range(len(members))]
+        if groups and groups[-1] == ranks and offs[-1] + lens[-1] == j * f:
+            lens[-1] += f
+        else:
+            offs.append(j * f); lens.append(f); groups.append(ranks)
+    return {"dim": split_dim, "offsets": offs, "lengths": lens, "groups": groups, "bcast_ranks": []}
+
+
+def precreate_hetero_groups(hetero_cfg: dict, extra=()):
+    """Every rank of a heterogeneous job builds a different (member-local) graph, so the process groups cannot be created
+    lazily: ALL ranks create, in one global order, the tensor-parallel group of every pipeline stage, the cross-pipeline
+    gradient groups and the caller's `extra` groups."""
+    from .. import _C
+    groups = []
+
+    def walk(node):
+        if isinstance(node, dict):
+            if "device_group_union" in node and "type" in node:
+                for devs in node["device_group_union"]:
+                    if len(devs) > 1 and list(devs) not in groups:
+                        groups.append(list(devs))
+            else:
+                for k in sorted(node):
+                    walk(node[k])
+
+    walk(hetero_cfg)
+    for r in all_hetero_groups() + [list(e) for e in extra]:
+        if len(r) > 1 and r not in groups:
+            groups.append(r)
+    if _C.comm_initialized():
+        for r in groups:
+            _C.comm_create_group(r)
+    return groups
+
+
+def all_hetero_groups():
+    """every rank group any rank needs for the heterogeneous gradient synchronisation (deterministic order)"""
+    seen = []
+    for name, (leaf, m, split_dim) in sorted(HETERO_PARAMS.items()):
+        members = [list(d) for d in leaf["device_group_union"]]
+        if len(members) < 2:
+            continue
+        if split_dim is None:
+            cand = [[d[0] for d in members]] + [d for d in members if len(d) > 1]
+        else:
+            tps = [len(d) for d in members]
+            G = 1
+            for v in tps:
+                G = _lcm(G, v)
+            cand = [[members[q][k // (G // tps[q])] for q in range(len(members))] for k in range(G)]
+        for c in cand:
+            if c not in seen:
+                seen.append(c)
+    return seen
+
+
 class _ParallelBase(Module):
     """common bookkeeping: per-strategy (dp, tp, device groups) + the handful of layouts every module needs"""
+
+    def _hetero_register(self, param, split_dim):
+        """remember how `param` is laid out in the other pipelines of a heterogeneous strategy"""
+        leaf = self.ds_parallel_configs[0]
+        if "_hetero_orig" in leaf:
+            HETERO_PARAMS[param.name] = (leaf["_hetero_orig"], leaf["_hetero_member"], split_dim)
+        return param
 
     def __init__(self, multi_ds_parallel_config: List[dict]):
         super().__init__()
@@ -170,6 +273,9 @@ class HtMultiColumnParallelLinear(_ParallelBase):
                                          device_group_hierarchy=self.device_group_unions, name=f"{name}_weight")
         self.bias = parallel_parameter(zeros_initializer(), [out_features], self.ds_dup_split0(), dtype=dtype, requires_grad=True,
                                        device_group_hierarchy=self.device_group_unions, name=f"{name}_bias") if bias else None
+        self._hetero_register(self.weight, 0)
+        if self.bias is not None:
+            self._hetero_register(self.bias, 0)
 
     fp8 = False   # set per instance (or via model config) to run the GEMM in block-scaled e4m3
 
@@ -211,6 +317,9 @@ class HtMultiRowParallelLinear(_ParallelBase):
                                          device_group_hierarchy=self.device_group_unions, name=f"{name}_weight")
         self.bias = parallel_parameter(zeros_initializer(), [out_features], self.ds_w_dup(), dtype=dtype, requires_grad=True,
                                        device_group_hierarchy=self.device_group_unions, name=f"{name}_bias") if bias else None
+        self._hetero_register(self.weight, 1)
+        if self.bias is not None:
+            self._hetero_register(self.bias, None)
 
     fp8 = False
 
@@ -246,6 +355,7 @@ class HtMultiParallelEmbedding(_ParallelBase):
         self.embedding_table = parallel_parameter(init, [num_embeddings, embedding_dim], self.ds_w_dup(), dtype=dtype,
                                                   requires_grad=True, device_group_hierarchy=self.device_group_unions,
                                                   name=f"{name}_table")
+        self._hetero_register(self.embedding_table, None)
 
     def forward(self, ids):
         return ops.embedding_lookup(self.embedding_table, ids, device_group_hierarchy=self.device_group_unions)
@@ -262,6 +372,7 @@ class HtMultiVocabParallelEmbedding(_ParallelBase):
         self.embedding_table = parallel_parameter(init, [num_embeddings, embedding_dim], self.ds_dup_split0(), dtype=dtype,
                                                   requires_grad=True, device_group_hierarchy=self.device_group_unions,
                                                   name=f"{name}_table")
+        self._hetero_register(self.embedding_table, 0)
 
     def _vocab_offset(self, strategy=0):
         from ..distributed import rank
@@ -291,6 +402,8 @@ class HtMultiParallelLayerNorm(_ParallelBase):
                                          device_group_hierarchy=self.device_group_unions, name=f"{name}_weight")
         self.bias = parallel_parameter(zeros_initializer(), [n], self.ds_w_dup(), dtype=dtype, requires_grad=True,
                                        device_group_hierarchy=self.device_group_unions, name=f"{name}_bias")
+        self._hetero_register(self.weight, None)
+        self._hetero_register(self.bias, None)
 
     def forward(self, x):
         x = self._adapt(x, self._all_split0() if self.sequence_parallel else None)
@@ -305,6 +418,7 @@ class HtMultiParallelRMSNorm(_ParallelBase):
         self.eps, self.sequence_parallel = eps, sequence_parallel
         self.weight = parallel_parameter(ones_initializer(), [n], self.ds_w_dup(), dtype=dtype, requires_grad=True,
                                          device_group_hierarchy=self.device_group_unions, name=f"{name}_weight")
+        self._hetero_register(self.weight, None)
 
     def forward(self, x):
         x = self._adapt(x, self._all_split0() if self.sequence_parallel else None)

@@ -86,6 +86,23 @@ class Optimizer:
     def _attrs(self) -> dict:
         return {}
 
+    @staticmethod
+    def _hetero_sync(p, gr, g):
+        """heterogeneous strategies (one homogeneous graph per pipeline): synchronise the gradient across the pipelines
+        that hold the same parameter with a different tensor-parallel degree (grouped all-reduce, see ops_comm.cc)"""
+        from ..nn.parallel import HETERO_PARAMS, hetero_grad_sync_spec
+        if not HETERO_PARAMS or p.name not in HETERO_PARAMS:
+            return gr
+        from ..distributed import rank
+        spec = hetero_grad_sync_spec(p.name, list(p.shape), rank())
+        if spec is None:
+            return gr
+        attrs = {"dim": spec["dim"], "offsets": spec["offsets"], "lengths": spec["lengths"],
+                 "group_sizes": [len(r) for r in spec["groups"]], "ranks_flat": [x for r in spec["groups"] for x in r],
+                 "bcast_ranks": list(spec["bcast_ranks"])}
+        return make_op("grouped_all_reduce", [gr], attrs,
+                       device_group_hierarchy=[[p.device_group]] if not p.device_group.empty else None, graph=g)[0]
+
     def minimize(self, loss: Tensor, var_list: Optional[List[Tensor]] = None, grad_loss: Optional[Tensor] = None) -> Tensor:
         g = _graphs_by_id.get(loss.graph_id) or cur_graph()
         params = list(var_list) if var_list is not None else g.parameters()
@@ -125,6 +142,7 @@ class Optimizer:
                 if need:
                     gr = comm(gr, target, device_group_hierarchy=[[p.device_group]] if not p.device_group.empty else None)
                 state_ds = target
+            gr = self._hetero_sync(p, gr, g)
             states = self._make_states(p, state_ds, p.device_group)
             self.params.append(p)
             out = make_op(self.update_type, [p, gr] + states, self._attrs(),

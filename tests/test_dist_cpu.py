@@ -128,3 +128,19 @@ def test_context_parallel_ring_attention_matches_full_attention(pattern):
     ok, outs = run_workers(CP_WORKER, 2, [2, pattern])
     assert ok, "\n-----\n".join(outs)
     assert sum("CPERR" in o for o in outs) == 2
+
+
+HETERO_WORKER = os.path.join(os.path.dirname(__file__), "workers", "hetero_worker.py")
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("layout,world", [("tp2_tp1", 3), ("tp2pp2_tp1", 5)])
+def test_heterogeneous_pipelines_reproduce_the_single_device_loss(layout, world):
+    """Malleus / Ampelos unions: pipelines with different tp degrees (and stage counts) on unequal batch shares; parameter
+    gradients are synchronised per finest common shard (grouped_all_reduce)"""
+    ref = _reference()
+    ok, outs = run_workers(HETERO_WORKER, world, [layout])
+    assert ok, "\n-----\n".join(outs)
+    got = _losses(outs)
+    for a, b in zip(got, ref):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, ref)

@@ -201,3 +201,42 @@ def test_hotspa_trainer_picks_strategy_by_sequence_bucket_and_malleus_trainer_re
     mt.train(steps=5)
     assert len(mt.plans_log) == 1 and mt.plans_log[0]["step"] == 2      # second measurement equals the first -> no new plan
     assert any(sum(l) == 16 for l in mt.plans_log[0]["hetero_layers"])
+
+
+def test_hetero_session_localises_and_plans_gradient_sync():
+    """a heterogeneous strategy (tp4 | tp2 | tp1 pipelines) seen from single ranks: local config, batch shares and the
+    slice / group plan of the cross-pipeline gradient synchronisation"""
+    from hetu_b200.engine.hetero import HeteroSession
+    from hetu_b200.models.parallel_config import generate_hetero_ds_parallel_config
+    from hetu_b200.nn import parallel as P
+    pipes = [{"stages": [{"devices": [0, 1, 2, 3], "layers": [0, 1]}]},
+             {"stages": [{"devices": [4, 5], "layers": [0, 0]}, {"devices": [6, 7], "layers": [1, 1]}]},
+             {"stages": [{"devices": [8], "layers": [0, 1]}]}]
+    cfg = generate_hetero_ds_parallel_config(2, pipes, zero=False)
+    s = HeteroSession(cfg, rank=5, shares=[4, 2, 1])
+    assert s.pipeline == 1 and s.num_pipelines == 3
+    assert s.pipelines[1] == [[4, 5], [6, 7]] and s.first_stage_ranks == [0, 4, 8] and s.last_stage_ranks == [0, 6, 8]
+    assert s.split_batch(14) == [8, 4, 2] and s.batch_slice(14) == slice(8, 12)
+    assert sum(s.split_batch(9)) == 9 and min(s.split_batch(3)) == 1
+    loc = s.local_cfg
+    assert loc["blocks"]["blocks0"]["attn"]["qkv"]["device_group_union"] == [[4, 5]]
+    assert loc["blocks"]["blocks1"]["attn"]["qkv"]["device_group_union"] == [[6, 7]]
+    assert loc["blocks"]["blocks0"]["attn"]["qkv"]["split"] == {"0": [2]}
+    assert loc["wpe"]["dup"] == [2] and loc["input"]["device_group_union"] == [[4, 5]]
+    # gradient sync plan of a column-split parameter of layer 0: lcm(4, 2, 1) = 4 finest shards
+    leaf = cfg["blocks"]["blocks0"]["attn"]["qkv"]
+    P.HETERO_PARAMS.clear()
+    P.HETERO_PARAMS["w"] = (leaf, 1, 0)
+    spec = P.hetero_grad_sync_spec("w", [8, 16], 5)            # rank 5 = second tp rank of the tp2 pipeline: fine shards 2, 3
+    assert spec["dim"] == 0 and spec["offsets"] == [0, 4] and spec["lengths"] == [4, 4]
+    assert spec["groups"] == [[2, 5, 8], [3, 5, 8]] and spec["bcast_ranks"] == []
+    P.HETERO_PARAMS["w"] = (leaf, 2, 0)
+    spec = P.hetero_grad_sync_spec("w", [16, 16], 8)           # the tp1 pipeline holds all four
+    assert spec["offsets"] == [0, 4, 8, 12] and spec["groups"] == [[0, 4, 8], [1, 4, 8], [2, 5, 8], [3, 5, 8]]
+    # replicated parameter: leaders reduce, the tp group broadcasts
+    P.HETERO_PARAMS["ln"] = (cfg["blocks"]["blocks0"]["layernorm1"], 0, None)
+    lead, follower = P.hetero_grad_sync_spec("ln", [16], 0), P.hetero_grad_sync_spec("ln", [16], 2)
+    assert lead["groups"] == [[0, 4, 8]] and lead["lengths"] == [16] and lead["bcast_ranks"] == [0, 1, 2, 3]
+    assert follower["groups"] == [] and follower["bcast_ranks"] == [0, 1, 2, 3]
+    assert [0, 4, 8] in P.all_hetero_groups() and [3, 5, 8] in P.all_hetero_groups()
+    P.HETERO_PARAMS.clear()
