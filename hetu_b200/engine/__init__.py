@@ -9,3 +9,4 @@ from .hydraulis import StrategyCost, dispatch_batch, HydraulisPlanner  # noqa: F
 from .config_loader import load_experiment, build_trainer  # noqa: F401
 from .hot_trainers import HotSPaTrainer, MalleusTrainer  # noqa: F401
 from .hetero import HeteroSession  # noqa: F401
+from . import lobra  # noqa: F401

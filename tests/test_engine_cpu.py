@@ -240,3 +240,118 @@ def test_hetero_session_localises_and_plans_gradient_sync():
     assert follower["groups"] == [] and follower["bcast_ranks"] == [0, 1, 2, 3]
     assert [0, 4, 8] in P.all_hetero_groups() and [3, 5, 8] in P.all_hetero_groups()
     P.HETERO_PARAMS.clear()
+
+
+def _lobra_setup():
+    from hetu_b200.engine.lobra import LoraCostModel
+    rng = np.random.RandomState(0)
+    true = {1: (2e-7, 0.0, 4e-4, 0.0, 0.0, 0.05), 2: (1e-7, 0.0, 2.3e-4, 0.0, 0.0, 0.09), 4: (5e-8, 0.0, 1.4e-4, 0.0, 0.0, 0.12)}
+    recs = []
+    for tp, c in true.items():
+        for mbs in (1, 2, 4, 8):
+            for s in (256, 512, 1024, 2048, 4096, 8192):
+                t = float(np.dot(c, LoraCostModel.features(mbs, s)))
+                recs.append((tp, mbs, s, t * (1 + 0.01 * rng.randn())))
+    cm = LoraCostModel.fit(recs)
+    cands = [{"tp": 1, "pp": 1, "max_tokens": 2048, "throughput_per_gpu": 10.0}, {"tp": 2, "pp": 1, "max_tokens": 2048, "throughput_per_gpu": 8.0},
+             {"tp": 2, "pp": 1, "max_tokens": 8192, "throughput_per_gpu": 8.5}, {"tp": 4, "pp": 1, "max_tokens": 8192, "throughput_per_gpu": 7.0},
+             {"tp": 4, "pp": 1, "max_tokens": 16384, "throughput_per_gpu": 7.0}, {"tp": 2, "pp": 2, "max_tokens": 16384, "throughput_per_gpu": 7.5},
+             {"tp": 1, "pp": 1, "max_tokens": 0}]
+    tasks = [{256: 300, 512: 120, 1024: 20}, {512: 60, 2048: 30, 8192: 6}, {1024: 40, 4096: 10, 16384: 2}]
+    return cm, true, cands, tasks
+
+
+def test_lobra_cost_model_and_scheme_pool():
+    from hetu_b200.engine.lobra import LoraCostModel, Scheme, optimized_scheme_pool
+    cm, true, cands, _ = _lobra_setup()
+    for tp, c in true.items():
+        for mbs, s in ((3, 700), (6, 3000)):
+            ref = float(np.dot(c, LoraCostModel.features(mbs, s)))
+            assert abs(cm.layer_time(mbs, s, tp) - ref) < 0.03 * ref
+    assert cm.layer_time(0, 512, 1) == 0.0
+    assert cm.batch_time(2, 1024, Scheme(2, 2, 4096), 32) == pytest.approx(cm.layer_time(2, 1024, 2) * 16)
+    pool = optimized_scheme_pool(cands)
+    # per capacity the best-throughput scheme survives, plus cheaper alternatives; dominated / zero-capacity ones are dropped
+    assert Scheme(1, 1, 2048, 10.0) in pool and Scheme(2, 1, 2048, 8.0) not in pool
+    assert Scheme(2, 1, 8192, 8.5) in pool and Scheme(4, 1, 8192, 7.0) not in pool
+    assert Scheme(2, 2, 16384, 7.5) in pool and all(s.max_tokens > 0 for s in pool)
+    an = LoraCostModel.analytic(4096, 11008)
+    assert an.layer_time(1, 4096, 8) < an.layer_time(1, 4096, 1) and an.layer_time(2, 512, 2) > an.layer_time(1, 512, 2)
+
+
+def test_lobra_static_planners_and_dynamic_dispatch():
+    from hetu_b200.engine import lobra as L
+    cm, _, cands, tasks = _lobra_setup()
+    total = L._PlannerCore.merge_tasks(tasks)
+    kw = dict(cost_model=cm, num_layers=32, train_task_num=3, global_batch_size_list=[440, 96, 52], ngpus=16, scheme_candidates=cands)
+    plans = {}
+    for name, cls in (("group", L.GroupStaticPlanner), ("balance", L.BalanceStaticPlanner), ("prune", L.PruneStaticPlanner)):
+        pl = cls(**kw)
+        p = pl.schedule(tasks)
+        plans[name] = (p, pl)
+        assert p.gpus == 16 and np.isfinite(p.time) and p.time > 0
+        got = {}
+        for d in p.dispatch:
+            for s, n in d.items():
+                got[s] = got.get(s, 0) + n
+        assert got == total                                               # every sequence is dispatched exactly once
+        for j, d in enumerate(p.dispatch):                                # ... to a replica that can hold it
+            assert all(s <= p.schemes[j].max_tokens for s in d) and (p.dp[j] > 0 or not d)
+        for ti, t in enumerate(tasks):                                    # the per-task split adds up as well
+            for s, n in t.items():
+                assert sum(p.task_dispatch[ti][j].get(s, 0) for j in range(len(p.schemes))) == n
+        assert any(sc.max_tokens >= 16384 and d for sc, d in zip(p.schemes, p.dp))
+    g, b, pr = plans["group"][0], plans["balance"][0], plans["prune"][0]
+    assert b.time <= g.time * 1.02 and pr.time <= b.time * 1.02
+    assert plans["prune"][1].pruned > 0 and plans["prune"][1].evaluated < plans["balance"][1].evaluated
+    # the heterogeneous mix beats the best homogeneous deployment (only the 16384-token schemes can hold every sequence)
+    core = plans["balance"][1]
+    homo = []
+    for j, sc in enumerate(core.schemes):
+        if sc.max_tokens >= 16384:
+            dp = [0] * len(core.schemes)
+            dp[j] = 16 // sc.ngpus
+            homo.append(core.dispatch(dp, total, "balance").time)
+    assert b.time < 0.9 * min(homo)
+    assert len(b.strategy()) >= 2 and len(b.pipelines(32)) == sum(b.dp)
+    assert sorted(d for p in b.pipelines(32) for st in p["stages"] for d in st["devices"]) == list(range(16))
+    # dynamic dispatch of one step on the deployed mix
+    strategy = b.strategy()
+    mts = [sc.max_tokens for sc, d in zip(b.schemes, b.dp) if d]
+    step = [{256: 40, 512: 11}, {512: 5, 2048: 4, 8192: 1}, {1024: 6, 16384: 1}]
+    for cls in (L.GroupDynamicDispatcher, L.BalanceDynamicDispatcher):
+        p = cls(cm, 32, strategy, mts, train_task_num=3).schedule(step)
+        assert sum(n for d in p.dispatch for n in d.values()) == 68 and np.isfinite(p.time)
+    bal = L.BalanceDynamicDispatcher(cm, 32, strategy, mts, 3).schedule(step)
+    grp = L.GroupDynamicDispatcher(cm, 32, strategy, mts, 3).schedule(step)
+    assert bal.time <= grp.time * 1.02
+
+
+def test_lobra_batch_schedulers():
+    from hetu_b200.engine import lobra as L
+    cm, _, cands, _ = _lobra_setup()
+    rng = np.random.RandomState(1)
+    buckets = [256, 1024, 4096]
+    lens = [[int(v) for v in rng.randint(10, 250, 20)] + [900, 700], [int(v) for v in rng.randint(300, 1000, 8)] + [3000, 4000]]
+    batches = [[list(rng.randint(1, 100, n)) for n in task] for task in lens]
+    dist = L.seq_distribution(batches, buckets)
+    assert dist[0] == {256: 20, 1024: 2} and dist[1] == {1024: 8, 4096: 2}
+    strategy, mts = [(2, 1, 1), (1, 2, 1)], [1024, 4096]
+    plan = L.BalanceDynamicDispatcher(cm, 8, strategy, mts, 2).schedule(dist)
+    per = L.global_batch_scheduler(batches, plan, buckets)
+    assert len(per) == 2 and len(per[0]) == 2 and len(per[1]) == 1
+    assert sum(len(r) for sch in per for r in sch) == 32
+    want = sorted(int(sum(s)) for task in batches for s in task)
+    assert sorted(int(sum(t)) for sch in per for rep in sch for _, t, _ in rep) == want
+    for j, sch in enumerate(per):
+        for rep in sch:
+            mbs = L.greedy_local_batch_scheduler(rep, mts[j], 2)
+            assert all(m.token_num() <= mts[j] and m.batch_data.shape == (m.batch_size, m.seq_length) for m in mbs)
+            assert sum(m.batch_size for m in mbs) == len(rep)
+            for m in mbs:                                                # task rows are contiguous: [offset, offset + size)
+                assert sum(m.batch_size_list) == m.batch_size
+                assert all(m.batch_offset_list[t] + m.batch_size_list[t] <= m.batch_size for t in m.task_id())
+            packed = L.local_batch_pack_scheduler(rep, mts[j], 2)
+            assert sum(cu[-1] for _, cu in packed) == sum(len(t) for _, t, _ in rep)
+            assert all(cu[-1] <= mts[j] and m.batch_data.shape == (1, mts[j]) for m, cu in packed)
+            assert len(packed) <= len(mbs)                               # packing never needs more micro-batches than padding
