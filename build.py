@@ -43,6 +43,7 @@ CXX_SOURCES = [
     "csrc/runtime/symm_mem.cc",
     "csrc/runtime/memory_pool.cc",
     "csrc/runtime/runtime.cc",
+    "csrc/runtime/rpc_client.cc",
     "csrc/binding/module.cc",
 ]
 NVCC_FLAGS = "-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr"

@@ -21,6 +21,7 @@
 #include "../runtime/memory_pool.h"
 #include "../v1/ps_server.h"
 #include "../runtime/runtime.h"
+#include "../runtime/rpc_client.h"
 
 namespace py = pybind11;
 using namespace hb;
@@ -566,6 +567,42 @@ PYBIND11_MODULE(_C, m) {
                               rt.defined() ? rt.data_ptr() : nullptr, rpr, (int)N, cur_stream()), "reduce_slots");
     return out;
   }, py::arg("x"), py::arg("w"), py::arg("staging"), py::arg("bias") = py::none(), py::arg("residual") = py::none());
+
+  // ---------------------------------------------------------------- native rendezvous client
+  {
+    using R = RpcClient;
+    auto nogil = py::call_guard<py::gil_scoped_release>();
+    py::class_<R, std::shared_ptr<R>>(m, "RpcClient")
+        .def(py::init<std::string, int, std::string, double, double>(), py::arg("host"), py::arg("port"), py::arg("hostname") = "",
+             py::arg("heartbeat_interval") = 2.0, py::arg("connect_timeout") = 60.0, nogil)
+        .def("call", &R::call, py::arg("method"), py::arg("args_json") = "{}", nogil)
+        .def("connect", &R::connect, py::arg("start_heartbeat") = true, nogil)
+        .def_property_readonly("rank", &R::rank)
+        .def_property_readonly("local_device", &R::local_device)
+        .def_property_readonly("world_size", &R::world_size)
+        .def_property_readonly("client_id", &R::client_id)
+        .def_property_readonly("heartbeats_sent", &R::heartbeats_sent)
+        .def("put_int", &R::put_int, nogil).def("get_int", &R::get_int, nogil)
+        .def("put_double", &R::put_double, nogil).def("get_double", &R::get_double, nogil)
+        .def("put_string", &R::put_string, nogil).def("get_string", &R::get_string, nogil)
+        .def("put_bytes", [](R& c, const std::string& k, const py::bytes& v) { std::string b = v; py::gil_scoped_release g; c.put_bytes(k, b); })
+        .def("get_bytes", [](R& c, const std::string& k) { std::string b; { py::gil_scoped_release g; b = c.get_bytes(k); } return py::bytes(b); })
+        .def("put_json", &R::put_json, nogil).def("get_json", &R::get_json, nogil)
+        .def("remove", &R::remove, py::arg("key"), py::arg("kind") = "json", nogil)
+        .def("commit_hostname", &R::commit_hostname, nogil).def("get_hostname", &R::get_hostname, nogil)
+        .def("commit_nccl_id", [](R& c, std::vector<int> r, int st, const py::bytes& id) { std::string b = id; py::gil_scoped_release g; c.commit_nccl_id(std::move(r), st, b); })
+        .def("get_nccl_id", [](R& c, std::vector<int> r, int st) { std::string b; { py::gil_scoped_release g; b = c.get_nccl_id(std::move(r), st); } return py::bytes(b); })
+        .def("barrier", &R::barrier, py::arg("ranks") = std::vector<int>{}, py::arg("tag") = "", nogil)
+        .def("consistent", &R::consistent, py::arg("raw_json_value"), py::arg("ranks") = std::vector<int>{}, py::arg("tag") = "", nogil)
+        .def("worker_stop", &R::worker_stop, nogil).def("already_stop", &R::already_stop, nogil).def("exit", &R::exit, nogil);
+    m.def("json_field", [](const std::string& obj, const std::string& key) -> py::object {
+      std::string raw;
+      if (!json_field(obj, key, &raw)) return py::none();
+      return py::str(raw);
+    });
+    m.def("json_quote", &json_quote);
+    m.def("json_unquote", &json_unquote);
+  }
 
   // ---------------------------------------------------------------- v1 parameter server
   py::enum_<PsOptimizer>(m, "PsOptimizer").value("NONE", PsOptimizer::NONE).value("SGD", PsOptimizer::SGD)

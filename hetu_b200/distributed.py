@@ -19,6 +19,7 @@ from .core import DeviceGroup, device
 
 _local_device = None
 _global_group = None
+_rpc_client = None
 
 
 def _factory(ranks: List[int]):
@@ -29,7 +30,26 @@ def _factory(ranks: List[int]):
 
 def init_comm_group(device_num: Optional[int] = None, device_idxs=(), server_address: str = "127.0.0.1:23457", backend: Optional[str] = None):
     """Join the job.  World size / rank come from the launcher environment (RANK, WORLD_SIZE, LOCAL_RANK, MASTER_*)."""
-    global _local_device, _global_group
+    global _local_device, _global_group, _rpc_client
+    if "RANK" not in os.environ and os.environ.get("HETU_RENDEZVOUS", "") == "rpc":
+        # reference-style bootstrap: workers started by the pssh launcher know only the controller's address; the
+        # DeviceController hands out rank / local device / world size (native client, csrc/runtime/rpc_client.cc) and
+        # carries the address of the torch.distributed store chosen by rank 0
+        import socket
+
+        from .rpc import NativeDeviceClient
+        _rpc_client = NativeDeviceClient(server_address, hostname=os.environ.get("HETU_LOCAL_HOSTNAME"))
+        r, local, w = _rpc_client.connect()
+        if r == 0:
+            sk = socket.socket()
+            sk.bind(("", 0))
+            port = sk.getsockname()[1]
+            sk.close()
+            host = os.environ.get("HETU_MASTER_HOST", server_address.rsplit(":", 1)[0])
+            _rpc_client.put_string("torch_master", f"{host}:{port}")
+        master = _rpc_client.get_string("torch_master")
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = master.rsplit(":", 1)
+        os.environ["RANK"], os.environ["WORLD_SIZE"], os.environ["LOCAL_RANK"] = str(r), str(w), str(local)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", str(device_num or 1)))
     local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
@@ -64,11 +84,21 @@ def global_device_group():
 
 
 def global_comm_barrier_rpc():
+    """barrier through the DeviceController when the job was bootstrapped by it, else through the process group"""
+    if _rpc_client is not None:
+        _rpc_client.barrier(tag="global_comm_barrier")
+    elif dist.is_initialized():
+        dist.barrier()
+
+
+def global_comm_barrier_mpi():
     if dist.is_initialized():
         dist.barrier()
 
 
-global_comm_barrier_mpi = global_comm_barrier_rpc
+def rpc_client():
+    """the rendezvous client of this worker (None unless HETU_RENDEZVOUS=rpc)"""
+    return _rpc_client
 
 
 def world_size() -> int:

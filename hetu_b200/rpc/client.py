@@ -124,3 +124,69 @@ class DeviceClient:
                 self.exit()
         except Exception:   # noqa: BLE001
             pass
+
+
+class NativeDeviceClient:
+    """Same surface as `DeviceClient`, transported by the C++ client (`csrc/runtime/rpc_client.cc`: sockets, framing, JSON
+    scanning, base64 and the heart-beat thread are native; blocking calls release the GIL).  This is the client the runtime
+    bootstrap uses (ref: hetu/impl/communication/rpc_client.cc DeviceClientImpl)."""
+
+    def __init__(self, address: str = "127.0.0.1:23457", hostname: Optional[str] = None, heartbeat_interval: float = 2.0,
+                 connect_timeout: float = 60.0):
+        import json
+
+        from .. import _C
+        host, port = address.rsplit(":", 1)
+        self._json = json
+        self._c = _C.RpcClient(host, int(port), hostname or socket.gethostname(), float(heartbeat_interval), float(connect_timeout))
+        self.hostname = hostname or socket.gethostname()
+        self.rank = self.local_device = self.world_size = None
+
+    @property
+    def client_id(self):
+        return self._c.client_id
+
+    @property
+    def heartbeats_sent(self):
+        return self._c.heartbeats_sent
+
+    def call(self, method: str, **args) -> Any:
+        return self._json.loads(self._c.call(method, self._json.dumps(args)))
+
+    def connect(self, start_heartbeat: bool = True):
+        self._c.connect(start_heartbeat)
+        self.rank, self.local_device, self.world_size = self._c.rank, self._c.local_device, self._c.world_size
+        return self.rank, self.local_device, self.world_size
+
+    def all_gather_hostnames(self):
+        self._c.commit_hostname()
+        return [self._c.get_hostname(r) for r in range(self.world_size)]
+
+    def exchange_device_info(self, info):
+        self.call("CommitDeviceInfo", rank=self.rank, info=info)
+        return [self.call("GetDeviceInfo", rank=r) for r in range(self.world_size)]
+
+    def commit_nccl_id(self, ranks, stream, nccl_id: bytes): self._c.commit_nccl_id(list(ranks), int(stream), bytes(nccl_id))   # noqa: E704
+    def get_nccl_id(self, ranks, stream) -> bytes: return self._c.get_nccl_id(list(ranks), int(stream))                         # noqa: E704
+    def put_double(self, k, v): self._c.put_double(k, float(v))                 # noqa: E704
+    def get_double(self, k): return self._c.get_double(k)                        # noqa: E704
+    def put_int(self, k, v): self._c.put_int(k, int(v))                          # noqa: E704
+    def get_int(self, k): return self._c.get_int(k)                              # noqa: E704
+    def put_string(self, k, v): self._c.put_string(k, str(v))                    # noqa: E704
+    def get_string(self, k): return self._c.get_string(k)                        # noqa: E704
+    def put_bytes(self, k, v: bytes): self._c.put_bytes(k, bytes(v))             # noqa: E704
+    def get_bytes(self, k) -> bytes: return self._c.get_bytes(k)                 # noqa: E704
+    def put_json(self, k, v): self._c.put_json(k, self._json.dumps(v))           # noqa: E704
+    def get_json(self, k): return self._json.loads(self._c.get_json(k))          # noqa: E704
+    def remove(self, k, kind="json"): return self._c.remove(k, kind)             # noqa: E704
+
+    def barrier(self, ranks: Optional[Sequence[int]] = None, tag: str = ""):
+        self._c.barrier(list(ranks) if ranks else [], tag)
+        return True
+
+    def consistent(self, value, ranks: Optional[Sequence[int]] = None, tag: str = "") -> bool:
+        return self._c.consistent(self._json.dumps(value), list(ranks) if ranks else [], tag)
+
+    def worker_stop(self): self._c.worker_stop()                                 # noqa: E704
+    def already_stop(self) -> bool: return self._c.already_stop()                # noqa: E704
+    def exit(self): self._c.exit()                                               # noqa: E704

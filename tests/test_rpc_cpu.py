@@ -22,13 +22,17 @@ def _free_port():
     return p
 
 
-def test_rendezvous_ranks_kv_barrier_consistent():
+@pytest.mark.parametrize("client_cls", ["python", "native", "mixed"])
+def test_rendezvous_ranks_kv_barrier_consistent(client_cls):
+    from hetu_b200.rpc import NativeDeviceClient
     port = _free_port()
+    pick = {"python": lambda i: DeviceClient, "native": lambda i: NativeDeviceClient,
+            "mixed": lambda i: NativeDeviceClient if i % 2 == 0 else DeviceClient}[client_cls]
     srv = DeviceControllerServer(3, "127.0.0.1", port).start()
     out = {}
 
     def worker(i):
-        c = DeviceClient(f"127.0.0.1:{port}", hostname="nodeA" if i < 2 else "nodeB", heartbeat_interval=0.1)
+        c = pick(i)(f"127.0.0.1:{port}", hostname="nodeA" if i < 2 else "nodeB", heartbeat_interval=0.1)
         r, l, w = c.connect()
         hosts = c.all_gather_hostnames()
         infos = c.exchange_device_info({"rank": r, "mem": 180})
@@ -116,3 +120,58 @@ def test_pssh_dry_run_and_hosts_yaml(tmp_path):
     assert hosts == [{"addr": "127.0.0.1", "workers": 2}, {"addr": "node1", "workers": 1}]
     lines = pssh_start("python train.py", hosts, 29511, dry_run=True)
     assert len(lines) == 3 and lines[2][0] == "ssh" and "RANK=2" in lines[2][-1] and "WORLD_SIZE=3" in lines[0][-1]
+
+
+def test_native_client_json_scanner_typed_kv_and_heartbeat():
+    """C++ client: raw-JSON pass-through (nesting, escapes, unicode), typed KV round trips, heart-beats on a second
+    connection, stop flag propagation, error replies become exceptions"""
+    import hetu_b200 as ht
+    from hetu_b200.rpc import NativeDeviceClient
+    C = ht._C
+    obj = '{"a": [1, {"b": "x,}\\"]"}], "ok": true, "value": {"k": "v\\u00e9\\n", "n": -1.5e3}, "z": null}'
+    assert C.json_field(obj, "ok") == "true" and C.json_field(obj, "z") == "null" and C.json_field(obj, "missing") is None
+    assert C.json_field(obj, "a") == '[1, {"b": "x,}\\"]"}]'
+    assert C.json_unquote(C.json_field(C.json_field(obj, "value"), "k")) == "v\u00e9\n"
+    assert C.json_unquote(C.json_quote('q"\\\n\t\x01')) == 'q"\\\n\t\x01'
+    port = _free_port()
+    srv = DeviceControllerServer(1, "127.0.0.1", port, heartbeat_timeout=0.5).start()
+    c = NativeDeviceClient(f"127.0.0.1:{port}", hostname="n0", heartbeat_interval=0.05)
+    assert c.connect() == (0, 0, 1)
+    c.put_int("i", -(1 << 40)); c.put_double("d", 0.1); c.put_double("whole", 3.0); c.put_string("s", 'he said "hi"\n\u00e9')
+    blob = bytes(range(256)) * 3 + b"x"
+    c.put_bytes("b", blob); c.put_json("j", {"nested": [1, 2, {"x": None}], "t": True})
+    assert c.get_int("i") == -(1 << 40) and c.get_double("d") == 0.1 and c.get_double("whole") == 3.0
+    assert c.get_string("s") == 'he said "hi"\n\u00e9' and c.get_bytes("b") == blob
+    assert c.get_json("j") == {"nested": [1, 2, {"x": None}], "t": True}
+    assert c.remove("j") is True and c.remove("j") is False
+    assert c.consistent({"graph": [1, 2]}) is True
+    with pytest.raises(RuntimeError, match="unknown method"):
+        c.call("NoSuchMethod")
+    time.sleep(0.4)
+    assert c.heartbeats_sent >= 3 and srv.dead_ranks() == []
+    assert c.already_stop() is False
+    c.worker_stop()
+    time.sleep(0.2)
+    assert c.already_stop() is True
+    c.exit()
+    assert srv.all_exited()
+    srv.shutdown()
+
+
+def test_rpc_bootstrap_assigns_ranks_and_brings_up_the_process_group():
+    """no RANK / WORLD_SIZE in the environment: the controller assigns ranks, rank 0 publishes the store address, every
+    worker joins torch.distributed (gloo) and an all-reduce over the framework's comm runtime works"""
+    port = _free_port()
+    srv = DeviceControllerServer(2, "127.0.0.1", port).start()
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+    env.update({"HETU_RENDEZVOUS": "rpc", "HETU_B200_FORCE_CPU": "1", "CUDA_VISIBLE_DEVICES": "", "OMP_NUM_THREADS": "1",
+                "PYTHONPATH": ROOT + os.pathsep + env.get("PYTHONPATH", "")})
+    worker = os.path.join(ROOT, "tests", "workers", "rpc_bootstrap_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, f"127.0.0.1:{port}", "2"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for _ in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n----\n".join(outs)
+    lines = sorted(l for o in outs for l in o.splitlines() if l.startswith("BOOT"))
+    assert lines == ["BOOT rank=0 local=0 world=2 sum=3.0", "BOOT rank=1 local=1 world=2 sum=3.0"], outs
+    assert srv.all_exited()
+    srv.shutdown()
