@@ -261,6 +261,7 @@ PYBIND11_MODULE(_C, m) {
       .def("get_ds", [](const TensorDef& t, size_t s) -> py::object { return t.has_ds(s) ? py::cast(t.ds(s)) : py::none(); })
       .def("get_ds_union", [](const TensorDef& t, size_t s) { return t.ds_hierarchy.get(s); })
       .def_property_readonly("producer_type", [](const TensorDef& t) { return t.producer ? t.producer->type : std::string(); })
+      .def_property_readonly("producer_name", [](const TensorDef& t) { return t.producer ? t.producer->type + ":" + t.producer->name() : std::string(); })
       .def_property_readonly("producer_id", [](const TensorDef& t) { return t.producer ? t.producer->id : (OpId)-1; })
       .def_property_readonly("device_group", [](const TensorDef& t) {
         return t.producer ? t.producer->placement(t.graph ? t.graph->cur_strategy() : 0) : DeviceGroup();

@@ -15,4 +15,6 @@ from . import nn  # noqa: F401
 from .distributed import (init_comm_group, local_device, global_device_group, global_comm_barrier_rpc,  # noqa: F401
                           global_comm_barrier_mpi, map_to_local_data)
 
+Dataloader = _C.Dataloader       # native prefetching loader (ref: hetu.Dataloader, hetu/graph/data/dataloader.h)
+
 __version__ = "0.1.0"

@@ -38,6 +38,7 @@ def init_comm_group(device_num: Optional[int] = None, device_idxs=(), server_add
         import socket
 
         from .rpc import NativeDeviceClient
+        server_address = os.environ.get("HETU_RPC_SERVER", server_address)
         _rpc_client = NativeDeviceClient(server_address, hostname=os.environ.get("HETU_LOCAL_HOSTNAME"))
         r, local, w = _rpc_client.connect()
         if r == 0:

@@ -404,6 +404,33 @@ def attn_qkvpacked(qkv, num_heads, num_kv_heads=None, head_dim=None, is_causal=T
     return attn(q, k, v, is_causal=is_causal, softmax_scale=softmax_scale, **kw)
 
 
+def attn_varlen_qkvpacked(qkv, cu_seqlens, max_seqlen=None, num_heads=None, num_kv_heads=None, head_dim=None, p_dropout=0.0,
+                          softmax_scale=-1.0, is_causal=True, **kw):
+    """variable-length self attention over a packed batch: qkv [T, (H + 2*Hkv) * D] (or [T, 3, H, D]), cu_seqlens int32 [n + 1]
+    cumulative document boundaries; every document attends only to itself -> [T, H * D]
+    (ref: hetu.attn_varlen_qkvpacked / AttentionVarlenOp)"""
+    from .ops_extra import attn_packed
+    if len(qkv.shape) == 4:                        # [T, 3, H, D]
+        t, _, h, d = qkv.shape
+        num_heads, num_kv_heads, head_dim = h, h, d
+        qkv = reshape(qkv, [t, 3 * h * d])
+    assert num_heads is not None, "num_heads is required for a 2-D packed qkv"
+    return attn_packed(qkv, int(qkv.shape[0]), num_heads, num_kv_heads or num_heads, head_dim, is_causal=is_causal,
+                       softmax_scale=softmax_scale, layout="qkv", cu_seqlens=cu_seqlens, **kw)
+
+
+def attn_varlen(q, k, v, cu_seqlens_q, cu_seqlens_k=None, max_seqlen_q=None, max_seqlen_k=None, p_dropout=0.0, softmax_scale=-1.0,
+                is_causal=True, **kw):
+    """q [T, H, D], k / v [T, Hkv, D] packed along tokens, cu_seqlens_* the document boundaries (self attention: both lists
+    describe the same packing) -> [T, H, D]  (ref: hetu.attn_varlen)"""
+    t, h, d = q.shape
+    hkv = k.shape[1]
+    packed = concat([reshape(q, [t, h * d]), reshape(k, [t, hkv * d]), reshape(v, [t, hkv * d])], axis=1)
+    o = attn_varlen_qkvpacked(packed, cu_seqlens_q, max_seqlen_q, num_heads=h, num_kv_heads=hkv, head_dim=d, softmax_scale=softmax_scale,
+                              is_causal=is_causal, **kw)
+    return reshape(o, [t, h, d])
+
+
 def parallel_attn(q, k, v, ranks, is_causal=True, softmax_scale=-1.0, split_pattern="SYM", **kw):
     """Context-parallel attention over the ring `ranks` (ref: hetu.parallel_attn / ParallelAttentionOp)."""
     outs = make_op("parallel_attn", [q, k, v],
@@ -631,6 +658,11 @@ def _install_tensor_methods():
     g = globals()
     for n in self_ops:
         setattr(T, n, (lambda fn: lambda self, *a, **k: fn(self, *a, **k))(g[n]))
+    # every remaining public op is reachable as a method too (the tensor is the op's first argument), as in the reference's
+    # generated bindings (ref: python/hetu/_binding/codegen/ops.yml `self` entries)
+    for n in OP_NAMES:
+        if not hasattr(T, n) and not n.endswith("_initializer") and n not in ("placeholder", "parallel_placeholder", "parameter", "parallel_parameter"):
+            setattr(T, n, (lambda fn: lambda self, *a, **k: fn(self, *a, **k))(g[n]))
     T.__add__ = lambda a, b: add(a, b)
     T.__radd__ = lambda a, b: add(b, a)
     T.__sub__ = lambda a, b: sub(a, b)
@@ -662,14 +694,45 @@ def _install_tensor_methods():
         return NDArray(d)
 
     def reset_data(self, value):
-        from .core import _graphs_by_id, _to_torch
-        _graphs_by_id[self.graph_id].set_param(self, _to_torch(value.t if hasattr(value, "t") else value))
+        from .core import NDArray, _graphs_by_id, _to_torch
+        _graphs_by_id[self.graph_id].set_param(self, _to_torch(value.t if isinstance(value, NDArray) else value))
 
     def backward(self, grad=None):
         from .core import _graphs_by_id
         _graphs_by_id[self.graph_id].backward(self, grad)
 
+    def reset_data_from_splits(self, provided_datas):
+        """the local shard given as its ordered pieces (split-checkpoint loader): concatenated along the tensor's split
+        dimension (ref: ResetVariableDataFromSplits, hetu/graph/graph.h:1227)"""
+        from .core import NDArray, _to_torch
+        parts = [_to_torch(p.t if isinstance(p, NDArray) else p) for p in provided_datas]
+        ds = self.distributed_states
+        dims = [d for d, n in (dict(ds.states).items() if ds is not None else []) if d >= 0 and n > 1]
+        dim = dims[0] if len(dims) == 1 else 0
+        full = parts[0] if len(parts) == 1 else torch.cat(parts, dim=dim)
+        reset_data(self, full.reshape(list(self.shape)))
+
+    def timecost(self, micro_batch_id=0):
+        """ms the producer of this tensor took in micro-batch `micro_batch_id` of the last profiled run
+        (`with hetu.profiler(): graph.run(...)`; ref: Tensor.timecost / OpDef::TimeCost)"""
+        from .core import _graphs_by_id
+        key = self.producer_name
+        hits = [ms for name, ms in _graphs_by_id[self.graph_id].op_times() if name == key]
+        if not hits:
+            raise RuntimeError(f"no timing recorded for {key}: run the graph inside `with hetu.profiler():`")
+        return hits[micro_batch_id if micro_batch_id < len(hits) else len(hits) - 1]
+
+    def _device(self):
+        from .distributed import local_device
+        dg = self.device_group
+        dev = local_device()
+        return dev if (dg.empty or dg.contains(dev)) else None
+
     T.numpy = numpy
+    T.reset_data_from_splits = reset_data_from_splits
+    T.timecost = timecost
+    T.device = property(_device)
+    T.graph = property(lambda self: __import__("hetu_b200.core", fromlist=["_graphs_by_id"])._graphs_by_id.get(self.graph_id))
     T.get_data = get_data
     T.reset_data = reset_data
     T.backward = backward

@@ -19,21 +19,26 @@ def read_hosts_yaml(path: str) -> List[Dict]:
             for h in doc.get("hosts", [])]
 
 
-def _env(rank, local_rank, world, master_addr, master_port, extra):
+def _env(rank, local_rank, world, master_addr, master_port, extra, rendezvous_env=True):
     e = dict(os.environ)
-    e.update({"RANK": str(rank), "LOCAL_RANK": str(local_rank), "WORLD_SIZE": str(world), "MASTER_ADDR": master_addr,
-              "MASTER_PORT": str(master_port), "HETU_LOCAL_HOSTNAME": master_addr})
+    if rendezvous_env:
+        e.update({"RANK": str(rank), "LOCAL_RANK": str(local_rank), "WORLD_SIZE": str(world), "MASTER_ADDR": master_addr,
+                  "MASTER_PORT": str(master_port)})
+    else:       # ranks come from the DeviceController (HETU_RENDEZVOUS=rpc)
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+            e.pop(k, None)
+    e["HETU_LOCAL_HOSTNAME"] = master_addr
     e.update(extra or {})
     return e
 
 
 def local_start(command: Sequence[str], ngpus: int, master_port: int = 29500, env: Optional[Dict[str, str]] = None,
-                log_dir: Optional[str] = None, wait: bool = True):
+                log_dir: Optional[str] = None, wait: bool = True, rendezvous_env: bool = True):
     """spawn `ngpus` copies of `command` on this node with torchrun-style env; returns exit codes (or the Popen list)"""
     procs = []
     for r in range(ngpus):
         out = open(os.path.join(log_dir, f"rank{r}.log"), "w") if log_dir else None
-        procs.append(subprocess.Popen(list(command), env=_env(r, r, ngpus, "127.0.0.1", master_port, env), stdout=out,
+        procs.append(subprocess.Popen(list(command), env=_env(r, r, ngpus, "127.0.0.1", master_port, env, rendezvous_env), stdout=out,
                                       stderr=subprocess.STDOUT if out else None))
     if not wait:
         return procs
@@ -41,7 +46,7 @@ def local_start(command: Sequence[str], ngpus: int, master_port: int = 29500, en
 
 
 def pssh_start(command: str, hosts: List[Dict], master_port: int = 29500, envs: Optional[Dict[str, str]] = None,
-               env_script: Optional[str] = None, ssh_user: Optional[str] = None, dry_run: bool = False):
+               env_script: Optional[str] = None, ssh_user: Optional[str] = None, dry_run: bool = False, rendezvous_env: bool = True):
     """one ssh session per worker; hosts whose addr is local run without ssh.  Returns exit codes (or the command lines
     when dry_run)."""
     world = sum(h["workers"] for h in hosts)
@@ -50,8 +55,8 @@ def pssh_start(command: str, hosts: List[Dict], master_port: int = 29500, envs: 
     for h in hosts:
         for lr in range(h["workers"]):
             exports = " ".join(f"{k}={shlex.quote(str(v))}" for k, v in
-                               {"RANK": rank, "LOCAL_RANK": lr, "WORLD_SIZE": world, "MASTER_ADDR": master, "MASTER_PORT": master_port,
-                                **(envs or {})}.items())
+                               {**({"RANK": rank, "LOCAL_RANK": lr, "WORLD_SIZE": world, "MASTER_ADDR": master, "MASTER_PORT": master_port}
+                                   if rendezvous_env else {}), **(envs or {})}.items())
             inner = (f"source {shlex.quote(env_script)} && " if env_script else "") + f"env {exports} {command}"
             if h["addr"] in ("127.0.0.1", "localhost"):
                 line = ["bash", "-c", inner]

@@ -155,3 +155,20 @@ def test_lr_schedule_and_grad_scaler():
     assert sc.get_scale() == 4.0
     sc.update(False); sc.update(False)
     assert sc.get_scale() == 8.0
+
+
+def test_tensor_surface_timecost_splits_device_graph():
+    """reference Tensor API: .graph / .device / .timecost(µb) under the profiler / .reset_data_from_splits"""
+    with ht.graph("define_and_run", create_new=True) as g:
+        x = ht.placeholder("float32", [4, 8], name="x")
+        w = ht.parameter(ht.ones_initializer(), [8, 8], requires_grad=True, name="w_tc")
+        y = ht.matmul(x, w, name="mm_tc")
+        loss = ht.sum(y)
+    assert y.graph is g and w.graph is g and w.device is not None
+    with ht.profiler(enabled=True, graph=g):
+        out = g.run(loss, [loss], {x: torch.ones(4, 8)})
+    assert float(out[0]) == 4 * 8 * 8
+    assert y.timecost(0) >= 0.0 and loss.timecost() >= 0.0
+    w.reset_data_from_splits([np.full((3, 8), 2.0, dtype=np.float32), np.full((5, 8), 0.5, dtype=np.float32)])
+    out = g.run(loss, [loss], {x: torch.ones(4, 8)})
+    assert float(out[0]) == 4 * 8 * (3 * 2.0 + 5 * 0.5)

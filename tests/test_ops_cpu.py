@@ -276,3 +276,49 @@ def test_varlen_packed_attention_equals_per_document_attention():
     (ref * g).sum().backward()
     assert (torch.as_tensor(o.numpy()) - ref).abs().max().item() < 1e-5
     assert (torch.as_tensor(X.grad.numpy()) - xr.grad).abs().max().item() < 1e-5
+
+
+def test_attn_varlen_ops_and_tensor_method_surface():
+    """hetu.attn_varlen / attn_varlen_qkvpacked (cu_seqlens packing) == per-document attention; every op of the reference's
+    ops.yml is also reachable as a Tensor method"""
+    torch.manual_seed(0)
+    T, H, Hkv, D = 40, 4, 2, 8
+    q, k, v = torch.randn(T, H, D), torch.randn(T, Hkv, D), torch.randn(T, Hkv, D)
+    bounds = [0, 8, 24, 40]
+    cu = ht.from_numpy(torch.tensor(bounds, dtype=torch.int32))
+    Q, K, V = (ht.from_numpy(t, requires_grad=True) for t in (q, k, v))
+    o = ht.attn_varlen(Q, K, V, cu, cu, 16, 16, is_causal=True)
+    ht.sum(o * o).backward()
+    qr, kr, vr = (t.clone().requires_grad_() for t in (q, k, v))
+    outs = []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        qq = qr[a:b].transpose(0, 1).unsqueeze(0)
+        kk = kr[a:b].transpose(0, 1).repeat_interleave(H // Hkv, 0).unsqueeze(0)
+        vv = vr[a:b].transpose(0, 1).repeat_interleave(H // Hkv, 0).unsqueeze(0)
+        outs.append(torch.nn.functional.scaled_dot_product_attention(qq, kk, vv, is_causal=True)[0].transpose(0, 1))
+    ref = torch.cat(outs)
+    (ref * ref).sum().backward()
+    assert (torch.as_tensor(o.numpy()) - ref).abs().max().item() < 1e-5
+    for got, want in ((Q, qr), (K, kr), (V, vr)):
+        assert (torch.as_tensor(got.grad.numpy()) - want.grad).abs().max().item() < 1e-4
+    # [T, 3, H, D] packed form
+    qkv = torch.randn(T, 3, H, D)
+    o2 = ht.attn_varlen_qkvpacked(ht.from_numpy(qkv), cu, 16)
+    outs = []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        qq, kk, vv = (qkv[a:b, i].transpose(0, 1).unsqueeze(0) for i in range(3))
+        outs.append(torch.nn.functional.scaled_dot_product_attention(qq, kk, vv, is_causal=True)[0].transpose(0, 1).reshape(b - a, H * D))
+    assert (torch.as_tensor(o2.numpy()) - torch.cat(outs)).abs().max().item() < 1e-5
+    names = """abs abs_ add add_ as_strided attn attn_qkvpacked attn_varlen attn_varlen_qkvpacked avgpool batch_norm binary_cross_entropy
+        bmm broadcast ceil ceil_ checknumeric comm concat contiguous conv2d data_transfer dequantization diagonal div div_ dot dropout dropout_
+        dropout2d dropout2d_ einsum elu embedding_lookup exp exp_ flash_attn floor floor_ fused_layernorm fused_rmsnorm gather hardshrink
+        hardsigmoid hardswish hardtanh index_add_ instance_norm interpolate kl_div layer_norm leakyrelu leakyrelu_ linear log log_ logsigmoid
+        masked_fill matmul matmul4bit maxpool mean mish mse_loss mul mul_ neg neg_ nll_loss norm onehot pad parallel_attn pow pow_ quantization
+        range_mask reciprocal reciprocal_ reduce relu relu_ repeat reshape rms_norm roll rotary round round_ rsqrt rsqrt_ sigmoid sigmoid_ silu
+        sin sin_ slice softmax softmax_cross_entropy softmax_cross_entropy_sparse softplus softshrink split sqrt sqrt_ sub sub_ sum swiglu tanh
+        tanh_ transpose triu vocab_parallel_cross_entropy where where_""".split()
+    assert [n for n in names if not hasattr(ht, n)] == [] and [n for n in names if not hasattr(ht.Tensor, n)] == []
+    x = ht.from_numpy(torch.tensor([[1.0, -2.0], [3.0, 4.0]]))
+    assert torch.allclose(torch.as_tensor(x.matmul(x).numpy()), torch.tensor([[-5.0, -10.0], [15.0, 10.0]]))
+    assert torch.allclose(torch.as_tensor(x.add(x).softplus().numpy()), torch.nn.functional.softplus(torch.tensor([[2.0, -4.0], [6.0, 8.0]])))
+    assert hasattr(ht, "Dataloader")

@@ -175,3 +175,31 @@ def test_rpc_bootstrap_assigns_ranks_and_brings_up_the_process_group():
     assert lines == ["BOOT rank=0 local=0 world=2 sum=3.0", "BOOT rank=1 local=1 world=2 sum=3.0"], outs
     assert srv.all_exited()
     srv.shutdown()
+
+
+def test_pssh_start_config_launches_workers_that_rendezvous_through_the_controller(tmp_path):
+    """`python -m hetu.rpc.pssh_start_config rpc.command=...`: starts the controller, spawns the workers without ranks in their
+    environment; they obtain ranks from the controller (native client) and form the process group.  Also the hydra-style
+    YAML + override loader and the reference-named strategy generators."""
+    from hetu_b200.models.gpt.generate_gpt_4d_config import main as gen_main
+    from hetu_b200.rpc.pssh_start_config import main as launch_main
+    port = _free_port()
+    worker = os.path.join(ROOT, "tests", "workers", "rpc_bootstrap_worker.py")
+    (tmp_path / "config.yaml").write_text(
+        f"rpc:\n  num_gpus: 2\n  server_port: {port}\n  log_path: {tmp_path}/logs\n  envs: {{HETU_B200_FORCE_CPU: 1, CUDA_VISIBLE_DEVICES: '', OMP_NUM_THREADS: 1, PYTHONPATH: {ROOT}}}\n"
+        f"ds_parallel:\n  num_layers: 8\n  num_gpus: 8\n  dp: 2\n  tp: 2\n  pp: 2\n  zero: true\n  ds_parallel_config_path: {tmp_path}/ds\n  ds_parallel_config_name: s.json\n")
+    rc = launch_main(["--config-path", str(tmp_path), "--config-name", "config", f"rpc.command={sys.executable} {worker} 127.0.0.1:{port} 2"])
+    logs = sorted((tmp_path / "logs").glob("rank*.log"))
+    text = "\n".join(p.read_text() for p in logs)
+    assert rc == 0, text
+    assert sorted(l for l in text.splitlines() if l.startswith("BOOT")) == ["BOOT rank=0 local=0 world=2 sum=3.0", "BOOT rank=1 local=1 world=2 sum=3.0"]
+    out = gen_main(["--config-path", str(tmp_path), "ds_parallel.tp=4", "ds_parallel.dp=1"])
+    import json
+    cfg = json.load(open(out))
+    assert cfg["blocks"]["blocks0-3"]["attn"]["qkv"]["split"] == {"0": [4]} and cfg["zero"] in (True, False)
+    r = subprocess.run([sys.executable, "-m", "hetu.models.llama.generate_llama_hetero_4d_config", "--config-path", str(tmp_path),
+                        "ds_parallel.hetero_layers=[[4,4],[8]]", "ds_parallel.hetero_tp=[2,1]", "ds_parallel.ds_parallel_config_name=h.json"],
+                       env={**os.environ, "PYTHONPATH": ROOT, "HETU_B200_FORCE_CPU": "1"}, capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    h = json.load(open(tmp_path / "ds" / "h.json"))
+    assert h["blocks"]["blocks0"]["attn"]["qkv"]["device_group_union"] == [[0, 1], [4]] and h["blocks"]["blocks5"]["attn"]["qkv"]["device_group_union"] == [[2, 3], [4]]
