@@ -299,6 +299,12 @@ PYBIND11_MODULE(_C, m) {
         for (auto& op : g.ops()) v.push_back(op->type);
         return v;
       })
+      .def("set_op_attrs", [](Graph& g, OpId id, const py::dict& attrs) {
+        // attributes are read by the op bodies at execution time (e.g. the optimizer's lr / weight decay schedule)
+        AttrMap upd = attrs_from_dict(attrs);
+        auto op = g.op(id);
+        for (auto& kv : upd.raw()) op->attrs.set(kv.first, kv.second);
+      })
       .def("op_info", [](const Graph& g, OpId id) {
         auto op = g.op(id);
         py::dict d;

@@ -1,6 +1,7 @@
 #include "exec.h"
 #include "zero_fused.h"
 
+#include <fstream>
 #include <ATen/ATen.h>
 #include <torch/csrc/distributed/c10d/Types.hpp>
 
@@ -772,7 +773,25 @@ void Executor::run_ops(ExecPlan& plan, const std::vector<OpDef*>& ops, bool back
     }
     if (profile_) {
       if (at::hasCUDA() && env_int("HETU_B200_FORCE_CPU", 0) == 0) at::cuda::getCurrentCUDAStream().synchronize();
-      op_times_.push_back({op->type + ":" + op->name(), now_ms() - t0});
+      const double dt = now_ms() - t0;
+      op_times_.push_back({op->type + ":" + op->name(), dt});
+      // step breakdown buckets (ref: executable_graph.cc:2313-2500 -- attention fwd / bwd, tensor-parallel collectives with
+      // their traffic, pipeline p2p, data-parallel gradient reduction, other compute)
+      const std::string& ty = op->type;
+      std::string bucket = "other_compute_ms";
+      if (ty.find("attn") != std::string::npos) bucket = (op->is_bwd || ty.find("bwd") != std::string::npos) ? "attn_bwd_ms" : "attn_fwd_ms";
+      else if (ty == "comm") {
+        auto ci = plan.comm.find(op->id);
+        const CommType ct = ci != plan.comm.end() ? ci->second.type : CommType::UNUSED;
+        if (ct == CommType::P2P || ct == CommType::BATCHED_ISEND_IRECV) bucket = "pp_p2p_ms";
+        else if (ct == CommType::ALL_REDUCE || ct == CommType::ALL_GATHER || ct == CommType::REDUCE_SCATTER) {
+          bucket = "tp_collective_ms";
+          double bytes = 0;
+          for (auto& o : outs) if (o.defined()) bytes += (double)o.nbytes();
+          breakdown_["tp_collective_bytes"] += bytes;
+        } else bucket = "other_comm_ms";
+      } else if (op->has_flag(kFlagComm)) bucket = (ty == "all_to_all" || ty.find("moe") != std::string::npos) ? "ep_all_to_all_ms" : "tp_collective_ms";
+      breakdown_[bucket] += dt;
     }
   }
   (void)mb;
@@ -856,6 +875,13 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
     for (auto& t : op->inputs) if (t->producer && t->producer->has_flag(kFlagVariable)) ensure_param(t->producer, opt.strategy);
   if (opt.run_level == RunLevel::ALLOC) return {};
   op_times_.clear();
+  // HETU_STRAGGLER: per-rank step breakdown (per-op timing on) after every run, appended to HETU_STRAGGLER_LOG_FILE
+  // (".rank<r>" suffix) or printed -- what Malleus' planner consumes to detect slow devices
+  const bool straggler_report = !env_str("HETU_STRAGGLER", "").empty() && env_str("HETU_STRAGGLER", "") != "0";
+  if (straggler_report) profile_ = true;
+  for (const char* k : {"attn_fwd_ms", "attn_bwd_ms", "tp_collective_ms", "tp_collective_bytes", "pp_p2p_ms", "other_comm_ms",
+                        "ep_all_to_all_ms", "other_compute_ms", "dp_grad_reduce_ms", "optimizer_ms"})
+    breakdown_.erase(k);
   const int M = std::max(1, opt.num_micro_batches);
   const bool inference = plan.bw_ops.empty() || opt.run_level == RunLevel::COMPUTE_ONLY;
   const bool gpipe = env_str("HETU_PIPELINE", "1F1B") == "GPIPE";
@@ -944,7 +970,9 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
         if (acc == accum_grads_.end()) continue;
         at::Tensor g = acc->second;
         if (scale != 1.0) g = g * scale;
+        const double t_g = profile_ ? now_ms() : 0.0;
         uvals[op->outputs[0]->id] = op->kernel->compute(*op, {g}, &rc)[0];
+        if (profile_) breakdown_["dp_grad_reduce_ms"] += now_ms() - t_g;
         continue;
       }
       if (op->type == "comm") {
@@ -956,7 +984,12 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
         if (acc == accum_grads_.end()) continue;
         at::Tensor g = acc->second;
         if (scale != 1.0) g = g * scale;
+        const double t_g = profile_ ? now_ms() : 0.0;
         uvals[op->outputs[0]->id] = exec_comm(plan.comm[op->id], op, {g}, rc)[0];
+        if (profile_) {
+          if (aten_device().is_cuda()) at::cuda::getCurrentCUDAStream().synchronize();
+          breakdown_["dp_grad_reduce_ms"] += now_ms() - t_g;
+        }
         continue;
       }
       if (!op->has_flag(kFlagOptimizerUpdate)) continue;
@@ -1025,6 +1058,7 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
     }
     accum_grads_.clear();
     breakdown_["update_ms"] = now_ms() - t_u;
+    if (profile_) breakdown_["optimizer_ms"] = breakdown_["update_ms"] - breakdown_["dp_grad_reduce_ms"];
   }
   ++step_;
   CommRuntime::get().flush_sends();
@@ -1036,6 +1070,18 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
     else result.push_back(at::cat(fetched[i], 0));
   }
   breakdown_["total_ms"] = now_ms() - t_start;
+  if (straggler_report) {
+    std::ostringstream os;
+    os << "{\"rank\": " << CommRuntime::get().rank() << ", \"step\": " << step_;
+    for (auto& kv : breakdown_) os << ", \"" << kv.first << "\": " << kv.second;
+    os << "}";
+    const std::string path = env_str("HETU_STRAGGLER_LOG_FILE", "");
+    if (path.empty()) HB_LOG(INFO) << "[straggler] " << os.str();
+    else {
+      std::ofstream f(path + ".rank" + std::to_string(std::max(CommRuntime::get().rank(), 0)), std::ios::app);
+      f << os.str() << "\n";
+    }
+  }
   return result;
 }
 
@@ -1100,6 +1146,18 @@ void Executor::switch_strategy(int from, int to) {
   }
   breakdown_["switch_ms"] = now_ms() - t0;
   breakdown_["switch_elems_sent"] = (double)moved;
+  // HETU_SWITCH_PROFILE (TIME | NVLINK | MEMORY in the reference) + HETU_SWITCH_LOG_FILE: one line per hot switch and rank
+  if (!env_str("HETU_SWITCH_PROFILE", "").empty()) {
+    std::ostringstream os;
+    os << "{\"rank\": " << CommRuntime::get().rank() << ", \"from\": " << from << ", \"to\": " << to << ", \"algorithm\": \""
+       << env_str("HETU_SWITCH_ALGORITHM", "default") << "\", \"switch_ms\": " << breakdown_["switch_ms"] << ", \"elems_sent\": " << moved << "}";
+    const std::string path = env_str("HETU_SWITCH_LOG_FILE", "");
+    if (path.empty()) HB_LOG(INFO) << "[switch] " << os.str();
+    else {
+      std::ofstream f(path + ".rank" + std::to_string(std::max(CommRuntime::get().rank(), 0)), std::ios::app);
+      f << os.str() << "\n";
+    }
+  }
   HB_LOG(INFO) << "hot switch " << from << " -> " << to << " moved " << moved << " elements in " << (now_ms() - t0) << " ms";
 }
 

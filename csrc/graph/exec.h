@@ -148,7 +148,8 @@ class Executor {
   // accumulated gradients (RunLevel::GRAD keeps them across run() calls until an UPDATE run)
   std::unordered_map<TensorId, at::Tensor>& accumulated_grads() { return accum_grads_; }
   // per-op timing of the last run (ms), filled when profiling is enabled
-  void set_profile(bool on) { profile_ = on; }
+  // HETU_EVENT_TIMING=OFF vetoes per-op timing (it synchronises after every op)
+  void set_profile(bool on) { profile_ = on && env_str("HETU_EVENT_TIMING", "ON") != "OFF"; }
   const std::vector<std::pair<std::string, double>>& op_times() const { return op_times_; }
   std::map<std::string, double> step_breakdown() const { return breakdown_; }
   int local_device_index(const DeviceGroup& g) const;

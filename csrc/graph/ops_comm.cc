@@ -3,6 +3,9 @@
 // and context-parallel (ring) attention.
 // (capability parity: hetu/graph/ops/Communication.{h,cc}, VocabParallelCrossEntropyLoss.cc,
 //  ParallelAttention.{h,cc})
+#include <sstream>
+#include <fstream>
+#include <chrono>
 #include <ATen/ATen.h>
 
 #include "exec.h"
@@ -336,7 +339,18 @@ static Ts parallel_attn_compute(const OpDef& op, const Ts& in, RunCtx*) {
   std::vector<at::Tensor> o_acc(nchunk), lse_acc(nchunk);
   at::Tensor kv_cur = at::stack({k, v}).contiguous();
   const int next = ranks[(idx + 1) % c], prev = ranks[(idx - 1 + c) % c];
+  // HETU_PARALLEL_ATTN=ANALYSIS: per ring round, attention time, blocks computed / skipped by the causal mask and the KV
+  // bytes rotated (synchronising per round, so only for analysis); appended to HETU_PARALLEL_ATTN_LOG_FILE.rank<r>
+  // (ref: AttnCommRing::Profile, ops/ParallelAttention.cc:1140)
+  const bool analysis = env_str("HETU_PARALLEL_ATTN", "") == "ANALYSIS";
+  std::ostringstream report;
+  auto sync_now = [&]() {
+    if (q.is_cuda()) at::cuda::getCurrentCUDAStream().synchronize();
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  };
   for (int round = 0; round < c; ++round) {
+    const double t_round = analysis ? sync_now() : 0.0;
+    int blocks = 0, skipped = 0;
     at::Tensor kv_next;
     const int src_idx = (idx - round + c) % c;  // owner of the KV block we hold this round
     std::vector<std::pair<at::Tensor, int>> sends, recvs;
@@ -351,13 +365,31 @@ static Ts parallel_attn_compute(const OpDef& op, const Ts& in, RunCtx*) {
       at::Tensor qc = q.narrow(1, qi * cs, cs);
       for (int ki = 0; ki < nchunk; ++ki) {
         const int qpos = my_chunks[qi], kpos = src_chunks[ki];
-        if (causal && kpos > qpos) continue;  // fully masked block: skipped
+        if (causal && kpos > qpos) { ++skipped; continue; }  // fully masked block: skipped
         at::Tensor kc = kv_cur[0].narrow(1, ki * cs, cs), vc = kv_cur[1].narrow(1, ki * cs, cs);
         AttnPiece p = local_attn(qc, kc, vc, scale, causal && kpos == qpos);
         merge_piece(o_acc[qi], lse_acc[qi], p);
+        ++blocks;
       }
     }
+    if (analysis) {
+      const double t_attn = sync_now() - t_round;
+      if (round + 1 < c) comm.flush_sends();
+      report << (round ? ", " : "") << "{\"round\": " << round << ", \"kv_from\": " << ranks[src_idx] << ", \"attn_ms\": " << t_attn
+             << ", \"blocks\": " << blocks << ", \"skipped\": " << skipped << ", \"kv_bytes_sent\": "
+             << (round + 1 < c ? (double)kv_cur.nbytes() : 0.0) << "}";
+    }
     if (round + 1 < c) kv_cur = kv_next;
+  }
+  if (analysis) {
+    const std::string line = "{\"op\": \"" + op.name() + "\", \"rank\": " + std::to_string(comm.rank()) + ", \"cp\": " + std::to_string(c) +
+                             ", \"pattern\": \"" + (sym ? "SYM" : "NORMAL") + "\", \"rounds\": [" + report.str() + "]}";
+    const std::string path = env_str("HETU_PARALLEL_ATTN_LOG_FILE", "");
+    if (path.empty()) HB_LOG(INFO) << "[parallel_attn] " << line;
+    else {
+      std::ofstream f(path + ".rank" + std::to_string(comm.rank()), std::ios::app);
+      f << line << "\n";
+    }
   }
   at::Tensor o = at::cat(o_acc, 1).to(q.scalar_type());
   at::Tensor lse = at::cat(lse_acc, 2);

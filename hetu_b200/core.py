@@ -234,6 +234,20 @@ class profiler:
     def records(self):
         return self.graph.op_times() if self.graph is not None else []
 
+    def chrome_trace(self, pid: int = 0) -> dict:
+        """the recorded ops as a Chrome / Perfetto trace (`chrome://tracing`): complete events laid end to end in execution
+        order on one track per category (ref: the torch-profiler bridge of engine/trainer.py:713-730 writes one per device)"""
+        events, ts = [], 0.0
+        tracks = {"compute": 0, "attention": 1, "comm": 2, "optimizer": 3}
+        for name, ms in self.records():
+            ty = name.split(":")[0]
+            cat = "attention" if "attn" in ty else "comm" if ty in ("comm", "all_reduce", "all_gather", "reduce_scatter", "all_to_all",
+                                                                     "grouped_all_reduce") else "optimizer" if "update" in ty else "compute"
+            events.append({"name": name, "cat": cat, "ph": "X", "ts": ts * 1e3, "dur": max(ms, 0.0) * 1e3, "pid": pid, "tid": tracks[cat]})
+            ts += max(ms, 0.0)
+        meta = [{"name": "thread_name", "ph": "M", "pid": pid, "tid": t, "args": {"name": n}} for n, t in tracks.items()]
+        return {"traceEvents": meta + events, "displayTimeUnit": "ms"}
+
     def summary(self, group_by="optype"):
         agg: Dict[str, List[float]] = {}
         for name, ms in self.records():

@@ -251,7 +251,19 @@ class Trainer:
                 prof = core.profiler(graph=self.trainer_states.graph)
                 prof.__enter__()
             t0 = time.perf_counter()
-            loss, stats = self._train_step(batch, sid)
+            try:
+                loss, stats = self._train_step(batch, sid)
+            except RuntimeError as e:
+                # a failed rank must not leave its peers blocked in a collective: record the error where the launcher /
+                # elastic controller looks for it and (when asked) take the whole local worker group down
+                # (ref: engine/trainer.py:316-322 -- logs/exception.txt + os.killpg)
+                os.makedirs(os.path.join(cfg.output_dir, "logs"), exist_ok=True)
+                with open(os.path.join(cfg.output_dir, "logs", "exception.txt"), "a") as f:
+                    f.write(f"rank {distributed.rank()} step {self.global_step}: {type(e).__name__}: {e}\n")
+                if os.environ.get("HETU_KILL_GROUP_ON_ERROR", "0") == "1":
+                    import signal
+                    os.killpg(os.getpgrp(), signal.SIGTERM)
+                raise
             if torch.cuda.is_available():
                 torch.cuda.synchronize()
             dt = time.perf_counter() - t0
@@ -262,9 +274,13 @@ class Trainer:
                 prof.__exit__(None, None, None)
                 os.makedirs(cfg.profile_save_path, exist_ok=True)
                 with open(os.path.join(cfg.profile_save_path, f"trace_rank{distributed.rank()}.json"), "w") as f:
+                    json.dump(prof.chrome_trace(pid=distributed.rank()), f)           # open in chrome://tracing / Perfetto
+                with open(os.path.join(cfg.profile_save_path, f"summary_rank{distributed.rank()}.json"), "w") as f:
                     json.dump(prof.summary(), f)
                 prof = None
             self.global_step += 1
+            if hasattr(self.trainer_states.optimizer, "step_lr"):
+                self.trainer_states.optimizer.step_lr()        # lr warm-up / decay and weight-decay schedule for the next step
             if loss is not None and cfg.log_interval and self.global_step % cfg.log_interval == 0 and distributed.rank() in self._loss_ranks():
                 print(f"[trainer] step {self.global_step} loss {loss:.4f} time {dt * 1e3:.1f} ms "
                       f"tokens {stats['real_tokens']}/{stats['fed_tokens']} strategy {sid}", flush=True)

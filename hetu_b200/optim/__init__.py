@@ -160,9 +160,30 @@ class Optimizer:
         _graphs_by_id[st.graph_id].set_param(st, torch.as_tensor(value))
 
     def step_lr(self):
-        """advance the schedule; returns the lr that the next run() will use"""
+        """advance the lr / weight-decay schedule by one optimizer step and push the new values into the update ops (their
+        bodies read `lr` / `weight_decay` at execution time); returns the lr the next run() will use
+        (ref: OptimizerParamScheduler, hetu/graph/optim/optimizerParamScheduler.h)"""
         self.step_count += 1
+        sched = getattr(self, "scheduler", None)
+        if sched is not None:
+            nxt = self.step_count + 1                       # the step about to be executed
+            self.learning_rate = float(sched.get_lr(nxt))
+            if hasattr(sched, "get_wd"):
+                self.weight_decay = float(sched.get_wd(nxt))
+        self.apply_hyper_parameters()
         return self.learning_rate
+
+    def set_learning_rate(self, lr: float):
+        """external schedulers (e.g. the v1 lr_scheduler classes) drive the rate directly"""
+        self.learning_rate = float(lr)
+        self.apply_hyper_parameters()
+
+    def apply_hyper_parameters(self):
+        attrs = {"lr": float(self.learning_rate)}
+        if hasattr(self, "weight_decay"):
+            attrs["weight_decay"] = float(self.weight_decay)
+        for u in self.update_ops:
+            _graphs_by_id[u.graph_id].set_op_attrs(u.producer_id, attrs)
 
 
 class _in_graph:
@@ -223,7 +244,7 @@ class AdamOptimizer(Optimizer):
                                                  end_wd if end_wd is not None else weight_decay, wd_incr_steps, wd_incr_style)
         self.learning_rate = self.scheduler.get_lr(1) if lr_warmup_steps else peak
         self.beta1, self.beta2, self.eps = beta1, beta2, eps
-        self.weight_decay = end_wd if end_wd is not None else weight_decay
+        self.weight_decay = self.scheduler.get_wd(1)
 
     def _attrs(self):
         return {"lr": float(self.learning_rate), "beta1": float(self.beta1), "beta2": float(self.beta2), "eps": float(self.eps),

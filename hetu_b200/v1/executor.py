@@ -95,6 +95,35 @@ def binarycrossentropy_op(p, y): return ops.binary_cross_entropy(p, y, reduction
 def mse_op(p, y): return ops.mse_loss(p, y, reduction="none")          # noqa: E704
 
 
+def conv2d_op(x, w, padding=0, stride=1): return ops.conv2d(x, w, None, padding=padding, stride=stride)                    # noqa: E704
+def conv2d_add_bias_op(x, w, b, padding=0, stride=1): return ops.conv2d(x, w, b, padding=padding, stride=stride)            # noqa: E704
+def max_pool2d_op(x, kernel_H, kernel_W, padding=0, stride=1): return ops.maxpool(x, kernel_H, kernel_W, padding, stride)   # noqa: E704
+def avg_pool2d_op(x, kernel_H, kernel_W, padding=0, stride=1): return ops.avgpool(x, kernel_H, kernel_W, padding, stride)   # noqa: E704
+def batch_normalization_op(x, scale, bias, mean, var, momentum=0.1, eps=1e-5): return ops.batch_norm(x, scale, bias, mean, var, momentum, eps)   # noqa: E704,E501
+def instance_normalization2d_op(x, eps=1e-7): return ops.instance_norm(x, eps)   # noqa: E704
+def pad_op(x, paddings, mode="constant", constant_values=0.0): return ops.pad(x, paddings, mode, constant_values)   # noqa: E704
+def div_op(a, b): return ops.div(a, b)                                  # noqa: E704
+def minus_op(a, b): return ops.sub(a, b)                                # noqa: E704
+def opposite_op(x): return ops.neg(x)                                   # noqa: E704
+def abs_op(x): return ops.abs(x)                                        # noqa: E704
+def pow_op(x, p): return ops.pow(x, p)                                  # noqa: E704
+def rsqrt_op(x): return ops.rsqrt(x)                                    # noqa: E704
+def leaky_relu_op(x, alpha=0.1): return ops.leakyrelu(x, alpha)         # noqa: E704
+def mish_op(x): return ops.mish(x)                                      # noqa: E704
+def silu_op(x): return ops.silu(x)                                      # noqa: E704
+def where_op(c, a, b): return ops.where(c, a, b)                        # noqa: E704
+def one_hot_op(x, num_classes): return ops.onehot(x, num_classes)       # noqa: E704
+def reduce_max_op(x, axes, keepdims=False): return ops.reduce(x, "max", axes, keepdims)   # noqa: E704
+def reduce_min_op(x, axes, keepdims=False): return ops.reduce(x, "min", axes, keepdims)   # noqa: E704
+def concatenate_op(nodes, axis=0): return ops.concat(list(nodes), axis)   # noqa: E704
+def split_op(x, axes, indices, splits): return ops.split(x, splits[0], dim=axes[0])[indices[0]]   # noqa: E704
+def sum_op(nodes):                                                      # noqa: E704
+    y = nodes[0]
+    for n in nodes[1:]:
+        y = ops.add(y, n)
+    return y
+
+
 def gradients(loss, nodes):
     from ..graph_api import gradients as g
     return g(loss, list(nodes))
@@ -126,13 +155,29 @@ class Executor:
             name, feed_dict = "default", name
         nodes = list(eval_node_list) if eval_node_list else self.eval_node_dict[name]
         feed = {k: torch.as_tensor(np.asarray(v)) if not isinstance(v, torch.Tensor) else v for k, v in (feed_dict or {}).items()}
+        # dataloader_op nodes: the loader registered under this executor pass (`name`) provides the batch
+        from . import dataloader as _dl
+        fed = {k.id for k in feed}
+        for op in _dl.loaders_of(nodes):
+            if op.node.id not in fed and name in op.dataloaders and op.node.graph_id == self.graph.id:
+                feed[op.node] = torch.as_tensor(op.get_arr(name))
+        # an lr scheduler object as the optimizer's learning rate: apply the current value, advance after the step
+        for opt in self._optimizers():
+            sched = getattr(opt, "v1_scheduler", None)
+            if sched is not None:
+                opt.set_learning_rate(sched.get())
         loss = next((n for n in nodes if isinstance(n, Tensor) and n.producer_type not in ("adam_update", "sgd_update", "group")), None)
         dp = 1
         if self.comm_mode in ("AllReduce", "Hybrid"):
             from .. import distributed
             dp = max(distributed.world_size(), 1)
-        outs = self.graph.run(loss, nodes, feed, grad_scale=1.0 / dp)
+        training = any(isinstance(n, Tensor) and n.producer_type in ("adam_update", "sgd_update", "group") for n in nodes)
+        outs = self.graph.run(loss if training else None, nodes, feed, grad_scale=1.0 / dp)[:len(nodes)]
         self.step += 1
+        if any(isinstance(n, Tensor) and n.producer_type in ("adam_update", "sgd_update", "group") for n in nodes):
+            for opt in self._optimizers():
+                if getattr(opt, "v1_scheduler", None) is not None:
+                    opt.v1_scheduler.step()
         res = []
         for o in outs:
             if o is None:
@@ -140,6 +185,16 @@ class Executor:
             else:
                 res.append(o.float().cpu().numpy() if convert_to_numpy_ret_vals else _ND(o))
         return res
+
+    def _optimizers(self):
+        from .optimizer import _LIVE
+        return [o for o in _LIVE if o.update_ops and o.update_ops[0].graph_id == self.graph.id]
+
+    def get_batch_num(self, name="default"):
+        """batches per epoch of the loaders registered under `name` (ref: Executor.get_batch_num)"""
+        from . import dataloader as _dl
+        nums = [op.get_batch_num(name) for op in _dl.loaders_of([]) if name in op.dataloaders and op.node.graph_id == self.graph.id]
+        return min(nums) if nums else None
 
     def save(self, file_path, file_name="checkpoint.pt"):
         import os

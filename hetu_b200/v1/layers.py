@@ -1,0 +1,232 @@
+"""v1 layer library: small callable objects that create their Variables and emit `*_op` nodes
+(ref: hetu/v1/python/hetu/layers/{base,linear,conv,normalization,embedding,dropout,relu,gelu,mish,identity,reshape,
+sequence,concatenate,sum,slice,pooling,attention,loss}.py; the MoE layers / gates live in hetu_b200.models.moe)."""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional, Sequence
+
+from .. import ops
+from . import initializers as init
+
+
+class BaseLayer:
+    def __call__(self, *a, **k):
+        raise NotImplementedError
+
+    def make_dataloader_func(self):
+        return None
+
+
+class OpLayer(BaseLayer):
+    """wraps any `*_op` function as a layer"""
+
+    def __init__(self, op: Callable, *args, **kwargs):
+        self.op, self.args, self.kwargs = op, args, kwargs
+
+    def __call__(self, *x):
+        return self.op(*x, *self.args, **self.kwargs)
+
+
+class Linear(BaseLayer):
+    def __init__(self, in_features, out_features, initializer=None, bias=True, activation=None, weight_transpose=False, name="linear"):
+        shape = (out_features, in_features) if weight_transpose else (in_features, out_features)
+        self.weight_transpose, self.activation = weight_transpose, activation
+        self.weight_var = (initializer or init.GenXavierUniform())(shape, name=f"{name}_weight")
+        self.bias_var = init.zeros((out_features,), name=f"{name}_bias") if bias else None
+
+    def __call__(self, x):
+        w = self.weight_var if self.weight_transpose else ops.transpose(self.weight_var, [1, 0])
+        y = ops.linear(x, w, self.bias_var, trans_b=True)
+        return _act(self.activation, y)
+
+
+def _act(name, y):
+    if name is None:
+        return y
+    if callable(name):
+        return name(y)
+    return {"relu": ops.relu, "gelu": ops.gelu, "sigmoid": ops.sigmoid, "tanh": ops.tanh, "mish": ops.mish, "silu": ops.silu}[name](y)
+
+
+class Conv2d(BaseLayer):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, initializer=None, bias=True, activation=None, name="conv2d"):
+        k = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
+        self.stride, self.padding, self.activation = stride, padding, activation
+        self.weight_var = (initializer or init.GenHeUniform())((out_channels, in_channels) + k, name=f"{name}_weight")
+        self.bias_var = init.zeros((out_channels,), name=f"{name}_bias") if bias else None
+
+    def __call__(self, x):
+        return _act(self.activation, ops.conv2d(x, self.weight_var, self.bias_var, padding=self.padding, stride=self.stride))
+
+
+class MaxPool2d(BaseLayer):
+    def __init__(self, kernel_size, stride=None, padding=0):
+        self.k = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
+        self.stride, self.padding = stride or self.k[0], padding
+
+    def __call__(self, x):
+        return ops.maxpool(x, self.k[0], self.k[1], padding=self.padding, stride=self.stride)
+
+
+class AvgPool2d(MaxPool2d):
+    def __call__(self, x):
+        return ops.avgpool(x, self.k[0], self.k[1], padding=self.padding, stride=self.stride)
+
+
+class BatchNorm(BaseLayer):
+    def __init__(self, num_channels, momentum=0.1, eps=1e-5, name="batchnorm"):
+        self.scale, self.bias = init.ones((num_channels,), name=f"{name}_scale"), init.zeros((num_channels,), name=f"{name}_bias")
+        self.mean = init.zeros((num_channels,), name=f"{name}_running_mean", trainable=False)
+        self.var = init.ones((num_channels,), name=f"{name}_running_var", trainable=False)
+        self.momentum, self.eps = momentum, eps
+
+    def __call__(self, x):
+        return ops.batch_norm(x, self.scale, self.bias, self.mean, self.var, momentum=self.momentum, eps=self.eps)
+
+
+class LayerNorm(BaseLayer):
+    def __init__(self, num_channels, eps=1e-5, name="layernorm"):
+        self.scale, self.bias, self.eps = init.ones((num_channels,), name=f"{name}_scale"), init.zeros((num_channels,), name=f"{name}_bias"), eps
+
+    def __call__(self, x):
+        return ops.layer_norm(x, self.scale, self.bias, eps=self.eps)
+
+
+class InstanceNorm2d(BaseLayer):
+    def __init__(self, eps=1e-7):
+        self.eps = eps
+
+    def __call__(self, x):
+        return ops.instance_norm(x, eps=self.eps)
+
+
+class Embedding(BaseLayer):
+    def __init__(self, num_embeddings, embedding_dim, initializer=None, name="embedding"):
+        self.num_embeddings, self.embedding_dim = num_embeddings, embedding_dim
+        self.embedding_table = (initializer or init.GenXavierNormal())((num_embeddings, embedding_dim), name=f"{name}_table")
+
+    def __call__(self, ids):
+        return ops.embedding_lookup(self.embedding_table, ids)
+
+
+class DropOut(BaseLayer):
+    def __init__(self, p=0.5):
+        self.keep_prob = 1.0 - p
+
+    def __call__(self, x):
+        return ops.dropout(x, 1.0 - self.keep_prob)
+
+
+class Relu(OpLayer):
+    def __init__(self): super().__init__(ops.relu)                                 # noqa: E704
+
+
+class Gelu(OpLayer):
+    def __init__(self): super().__init__(ops.gelu)                                 # noqa: E704
+
+
+class Mish(OpLayer):
+    def __init__(self): super().__init__(ops.mish)                                 # noqa: E704
+
+
+class Sigmoid(OpLayer):
+    def __init__(self): super().__init__(ops.sigmoid)                              # noqa: E704
+
+
+class Tanh(OpLayer):
+    def __init__(self): super().__init__(ops.tanh)                                 # noqa: E704
+
+
+class Identity(BaseLayer):
+    def __call__(self, x):
+        return x
+
+
+class Reshape(BaseLayer):
+    def __init__(self, shape):
+        self.shape = list(shape)
+
+    def __call__(self, x):
+        return ops.reshape(x, self.shape)
+
+
+class Slice(BaseLayer):
+    def __init__(self, begin, size):
+        self.begin, self.size = list(begin), list(size)
+
+    def __call__(self, x):
+        return ops.slice(x, self.begin, self.size)
+
+
+class Sequence(BaseLayer):
+    def __init__(self, *layers):
+        self.layers = list(layers)
+
+    def __call__(self, x):
+        for layer in self.layers:
+            x = layer(x)
+        return x
+
+
+class ConcatenateLayers(BaseLayer):
+    """apply every branch to the input and concatenate the results"""
+
+    def __init__(self, layers: Sequence, axis=0):
+        self.layers, self.axis = list(layers), axis
+
+    def __call__(self, x):
+        return ops.concat([layer(x) for layer in self.layers], self.axis)
+
+
+class SumLayers(BaseLayer):
+    def __init__(self, layers: Sequence):
+        self.layers = list(layers)
+
+    def __call__(self, x):
+        outs = [layer(x) for layer in self.layers]
+        y = outs[0]
+        for o in outs[1:]:
+            y = ops.add(y, o)
+        return y
+
+
+class MultiHeadAttention(BaseLayer):
+    """[batch * seq, hidden] token-major self attention with fused qkv projection"""
+
+    def __init__(self, hidden_size, num_heads, seq_len, batch_size, dropout=0.0, causal=False, name="attn"):
+        assert hidden_size % num_heads == 0
+        self.h, self.nh, self.s, self.b, self.causal = hidden_size, num_heads, seq_len, batch_size, causal
+        self.qkv = Linear(hidden_size, 3 * hidden_size, name=f"{name}_qkv")
+        self.out = Linear(hidden_size, hidden_size, name=f"{name}_out")
+        self.drop = DropOut(dropout) if dropout > 0 else None
+
+    def __call__(self, x):
+        d = self.h // self.nh
+        qkv = ops.reshape(self.qkv(x), [self.b, self.s, 3 * self.h])
+        q, k, v = ops.split(qkv, 3, dim=2)
+        q, k, v = (ops.reshape(t, [self.b, self.s, self.nh, d]) for t in (q, k, v))
+        o = ops.attn(q, k, v, is_causal=self.causal, softmax_scale=1.0 / math.sqrt(d))
+        y = self.out(ops.reshape(o, [self.b * self.s, self.h]))
+        return self.drop(y) if self.drop is not None else y
+
+
+class SoftmaxCrossEntropyLoss(BaseLayer):
+    def __init__(self, sparse=False, ignored_index=-1, reduce_mean=True):
+        self.sparse, self.ignored_index, self.reduce_mean = sparse, ignored_index, reduce_mean
+
+    def __call__(self, logits, labels):
+        red = "mean" if self.reduce_mean else "none"
+        if self.sparse:
+            return ops.softmax_cross_entropy_sparse(logits, labels, ignored_index=self.ignored_index, reduction=red)
+        return ops.softmax_cross_entropy(logits, labels, reduction=red)
+
+
+class BCELoss(BaseLayer):
+    def __call__(self, p, y):
+        return ops.mean(ops.binary_cross_entropy(p, y, reduction="none"))
+
+
+class MSELoss(BaseLayer):
+    def __call__(self, p, y):
+        return ops.mean(ops.mse_loss(p, y, reduction="none"))

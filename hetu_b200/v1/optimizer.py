@@ -2,12 +2,25 @@
 from .. import optim
 
 
+_LIVE = []      # optimizers with update ops in a graph (the Executor applies their lr schedulers)
+
+
 class _Base:
+    """`learning_rate` is a float or an `lr_scheduler` object (its value is applied before, and stepped after, every
+    training run of the Executor)"""
+
     def __init__(self, learning_rate=0.01, l2reg=0.0):
-        self.learning_rate, self.l2reg = learning_rate, l2reg
+        self.scheduler = learning_rate if hasattr(learning_rate, "get") else None
+        self.learning_rate = float(learning_rate.get()) if self.scheduler is not None else learning_rate
+        self.l2reg = l2reg
 
     def minimize(self, loss, var_list=None):
-        return self._make().minimize(loss, var_list) if var_list is not None else self._make().minimize(loss)
+        opt = self._make()
+        opt.v1_scheduler = self.scheduler
+        self.backend = opt
+        node = opt.minimize(loss, var_list) if var_list is not None else opt.minimize(loss)
+        _LIVE.append(opt)
+        return node
 
 
 class SGDOptimizer(_Base):

@@ -110,9 +110,18 @@ def test_hot_switching_between_dp_and_tp_keeps_the_loss_curve():
     ok, outs = run_workers(HOT_WORKER, 2, ["single"])
     assert ok, "\n-----\n".join(outs)
     ref = _losses(outs)
-    ok, outs = run_workers(HOT_WORKER, 2, ["switch"])
+    log = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"hb_switch_{os.getpid()}.jsonl")
+    for r in range(2):
+        if os.path.exists(f"{log}.rank{r}"):
+            os.remove(f"{log}.rank{r}")
+    ok, outs = run_workers(HOT_WORKER, 2, ["switch"], env_extra={"HETU_SWITCH_PROFILE": "TIME", "HETU_SWITCH_LOG_FILE": log})
     assert ok, "\n-----\n".join(outs)
     got = _losses(outs)
+    for r in range(2):          # HETU_SWITCH_PROFILE: one record per hot switch and rank
+        rows = [json.loads(l) for l in open(f"{log}.rank{r}")]
+        assert rows and all(x["rank"] == r and x["from"] != x["to"] and x["switch_ms"] >= 0 for x in rows)
+        assert any(x["elems_sent"] > 0 for x in rows)
+        os.remove(f"{log}.rank{r}")
     for a, b in zip(got, ref):
         assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, ref)
 
@@ -130,6 +139,25 @@ def test_context_parallel_ring_attention_matches_full_attention(pattern):
     assert sum("CPERR" in o for o in outs) == 2
 
 
+@pytest.mark.dist
+def test_ring_attention_analysis_log(tmp_path):
+    """HETU_PARALLEL_ATTN=ANALYSIS: one JSON line per ring-attention op and rank with per-round attention time, computed /
+    mask-skipped blocks and rotated KV bytes; under the SYM split both ranks compute the same number of blocks"""
+    log = str(tmp_path / "ring.jsonl")
+    ok, outs = run_workers(CP_WORKER, 2, [2, "SYM"], env_extra={"HETU_PARALLEL_ATTN": "ANALYSIS", "HETU_PARALLEL_ATTN_LOG_FILE": log})
+    assert ok, "\n-----\n".join(outs)
+    per_rank = []
+    for r in range(2):
+        rows = [json.loads(l) for l in open(f"{log}.rank{r}")]
+        assert rows and all(x["cp"] == 2 and x["pattern"] == "SYM" and len(x["rounds"]) == 2 for x in rows)
+        first = rows[0]["rounds"]
+        assert first[0]["kv_from"] == r and first[1]["kv_from"] == 1 - r
+        assert first[0]["kv_bytes_sent"] > 0 and first[1]["kv_bytes_sent"] == 0
+        per_rank.append(sum(x["blocks"] for x in first))
+        assert sum(x["blocks"] + x["skipped"] for x in first) == 8          # 2 x 2 chunk pairs per round
+    assert per_rank[0] == per_rank[1]                                        # zig-zag split balances the causal work
+
+
 HETERO_WORKER = os.path.join(os.path.dirname(__file__), "workers", "hetero_worker.py")
 
 
@@ -144,3 +172,22 @@ def test_heterogeneous_pipelines_reproduce_the_single_device_loss(layout, world)
     got = _losses(outs)
     for a, b in zip(got, ref):
         assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, ref)
+
+
+@pytest.mark.dist
+def test_straggler_report_writes_per_rank_step_breakdown(tmp_path):
+    """HETU_STRAGGLER=1: every run appends this rank's step breakdown (attention fwd/bwd, tensor-parallel collectives and
+    their traffic, data-parallel gradient reduction, optimizer, other compute) to HETU_STRAGGLER_LOG_FILE.rank<r>"""
+    log = str(tmp_path / "straggler.jsonl")
+    ok, outs = run_workers(WORKER, 4, [2, 2, 1, 0, 0, 1, "gpt"], env_extra={"HETU_STRAGGLER": "1", "HETU_STRAGGLER_LOG_FILE": log})
+    assert ok, "\n-----\n".join(outs)
+    for r in range(4):
+        rows = [json.loads(l) for l in open(f"{log}.rank{r}")]
+        assert len(rows) == 4 and [x["step"] for x in rows] == [1, 2, 3, 4] and all(x["rank"] == r for x in rows)
+        last = rows[-1]
+        for k in ("attn_fwd_ms", "attn_bwd_ms", "tp_collective_ms", "tp_collective_bytes", "dp_grad_reduce_ms", "optimizer_ms",
+                  "other_compute_ms", "compute_ms", "update_ms", "total_ms"):
+            assert k in last and last[k] >= 0.0, (k, last)
+        assert last["tp_collective_bytes"] > 0 and last["dp_grad_reduce_ms"] > 0 and last["attn_fwd_ms"] > 0
+        parts = sum(last[k] for k in ("attn_fwd_ms", "attn_bwd_ms", "tp_collective_ms", "other_compute_ms", "update_ms") if k in last)
+        assert parts <= last["total_ms"] * 1.05

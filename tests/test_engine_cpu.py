@@ -355,3 +355,29 @@ def test_lobra_batch_schedulers():
             assert sum(cu[-1] for _, cu in packed) == sum(len(t) for _, t, _ in rep)
             assert all(cu[-1] <= mts[j] and m.batch_data.shape == (1, mts[j]) for m, cu in packed)
             assert len(packed) <= len(mbs)                               # packing never needs more micro-batches than padding
+
+
+def test_trainer_writes_chrome_trace_and_records_step_exceptions(tmp_path):
+    """torch_profile window -> one Chrome trace per rank (complete events on compute / attention / comm / optimizer tracks);
+    a RuntimeError inside a step is appended to <output_dir>/logs/exception.txt before it propagates"""
+    ht.init_comm_group(1)
+    ds = SyntheticDataset(64, 259, 32, min_seq_len=8, seed=1, length_distribution="uniform")
+    cfg = TrainingConfig(packing=False, micro_batch_size=2, global_load_size=4, max_seq_length=32, steps=4, learning_rate=1e-2, log_interval=0,
+                         pack_alignment=16, torch_profile=True, start_profile_step=1, end_profile_step=2, profile_save_path=str(tmp_path / "trace"),
+                         output_dir=str(tmp_path / "out"))
+    tr = Trainer(cfg, ModelWrapper(GPTLMHeadModel, _mcfg()), ByteTokenizer(), OptimizerWrapper({"type": "adam", "lr": 1e-2}), ds)
+    assert len(tr.train()) == 4
+    trace = json.load(open(tmp_path / "trace" / "trace_rank0.json"))
+    ev = [e for e in trace["traceEvents"] if e["ph"] == "X"]
+    assert len(ev) > 20 and all(e["dur"] >= 0 and e["pid"] == 0 for e in ev)
+    assert {e["cat"] for e in ev} >= {"compute", "attention"} and any(e["name"].startswith("linear") for e in ev)
+    assert all(b["ts"] >= a["ts"] for a, b in zip(ev, ev[1:]))
+    assert "breakdown" in json.load(open(tmp_path / "trace" / "summary_rank0.json"))
+
+    def boom(batch, sid=0):
+        raise RuntimeError("injected device failure")
+    tr._train_step = boom
+    with pytest.raises(RuntimeError, match="injected"):
+        tr.train(steps=1)
+    txt = (tmp_path / "out" / "logs" / "exception.txt").read_text()
+    assert "rank 0 step 4" in txt and "injected device failure" in txt

@@ -172,3 +172,46 @@ def test_tensor_surface_timecost_splits_device_graph():
     w.reset_data_from_splits([np.full((3, 8), 2.0, dtype=np.float32), np.full((5, 8), 0.5, dtype=np.float32)])
     out = g.run(loss, [loss], {x: torch.ones(4, 8)})
     assert float(out[0]) == 4 * 8 * (3 * 2.0 + 5 * 0.5)
+
+
+def test_lr_and_weight_decay_schedules_reach_the_update_ops():
+    """AdamOptimizer(lr_warmup_steps, lr_decay_steps, lr_decay_style, start_wd/end_wd...) + step_lr(): with a constant gradient
+    Adam moves every weight by exactly lr_t per step, so the trajectory exposes the schedule"""
+    with ht.graph("define_and_run", create_new=True) as g:
+        w = ht.parameter(ht.zeros_initializer(), [4], requires_grad=True, name="w_sched")
+        loss = ht.sum(w)
+        opt = ht.AdamOptimizer(lr=0.1, lr_warmup_steps=4, lr_decay_steps=8, lr_decay_style="linear", min_lr=0.02, eps=1e-12)
+        train = opt.minimize(loss)
+    want = [opt.scheduler.get_lr(s) for s in range(1, 11)]
+    assert want[0] == pytest.approx(0.025) and want[3] == pytest.approx(0.1) and want[5] == pytest.approx(0.06) and want[9] == pytest.approx(0.02)
+    pos, seen = 0.0, []
+    for s in range(10):
+        g.run(loss, [loss, train], {})
+        cur = float(torch.as_tensor(w.numpy())[0])
+        seen.append(pos - cur)
+        pos = cur
+        assert opt.step_lr() == pytest.approx(want[s + 1] if s + 1 < 10 else opt.scheduler.get_lr(11))
+    assert seen == pytest.approx(want, rel=1e-4)
+    # external control (v1 lr_scheduler classes): SGD step = lr * grad
+    with ht.graph("define_and_run", create_new=True) as g2:
+        v = ht.parameter(ht.zeros_initializer(), [2], requires_grad=True, name="v_sched")
+        l2 = ht.sum(v)
+        sgd = ht.SGDOptimizer(lr=1.0)
+        t2 = sgd.minimize(l2)
+    from hetu_b200.v1.lr_scheduler import ExponentialScheduler, MultiStepScheduler, ReduceOnPlateauScheduler, StepScheduler
+    sch = StepScheduler(1.0, step_size=2, gamma=0.5)
+    deltas, pos = [], 0.0
+    for s in range(5):
+        sgd.set_learning_rate(sch.get())
+        g2.run(l2, [l2, t2], {})
+        cur = float(torch.as_tensor(v.numpy())[0])
+        deltas.append(pos - cur)
+        pos = cur
+        sch.step()
+    assert deltas == pytest.approx([1.0, 1.0, 0.5, 0.5, 0.25])
+    ms = MultiStepScheduler(1.0, [2, 3], 0.1)
+    assert [round(ms.step(), 6) for _ in range(4)] == [1.0, 0.1, 0.01, 0.01]
+    ex = ExponentialScheduler(2.0, 0.5)
+    assert [ex.step() for _ in range(3)] == [1.0, 0.5, 0.25]
+    rp = ReduceOnPlateauScheduler(1.0, factor=0.5, patience=1)
+    assert [rp.step(x) for x in (1.0, 0.9, 0.9, 0.9, 0.9, 0.9)] == [1.0, 1.0, 1.0, 0.5, 0.5, 0.25]

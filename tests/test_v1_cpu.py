@@ -107,3 +107,51 @@ def test_search_strategies_are_feasible_and_no_worse_than_data_parallel():
     pd = v1.PipeDreamSearching(n).assign(layers)
     po = v1.PipeOptSearching(n).assign(layers)
     assert len(pd) == len(po) == len(layers)
+
+
+def test_v1_layers_dataloaders_schedulers_and_metrics():
+    """the legacy training loop: dataloader_op nodes fed per executor pass ('train' / 'validate'), layers building the graph,
+    an lr scheduler object as the optimizer's learning rate, numpy metrics on the outputs"""
+    import hetu_b200.v1 as v1
+    v1.reset_graph()
+    rng = np.random.RandomState(0)
+    X = rng.randn(256, 16).astype(np.float32)
+    wtrue = rng.randn(16, 3).astype(np.float32)
+    Y = np.eye(3, dtype=np.float32)[(X @ wtrue).argmax(1)]
+    x = v1.dataloader_op([v1.Dataloader(X[:192], 32, "train"), v1.Dataloader(X[192:], 32, "validate")])
+    y = v1.dataloader_op([v1.Dataloader(Y[:192], 32, "train"), v1.Dataloader(Y[192:], 32, "validate")])
+    net = v1.layers.Sequence(v1.layers.Linear(16, 32, activation="relu", name="fc1"), v1.layers.LayerNorm(32, name="ln"),
+                              v1.layers.Linear(32, 3, name="fc2"))
+    logits = net(x)
+    loss = v1.layers.SoftmaxCrossEntropyLoss()(logits, y)
+    sched = v1.lr_scheduler.StepScheduler(0.05, step_size=30, gamma=0.5)
+    train = v1.AdamOptimizer(learning_rate=sched).minimize(loss)
+    ex = v1.Executor({"train": [loss, train], "validate": [loss, logits, y]})
+    assert ex.get_batch_num("train") == 6 and ex.get_batch_num("validate") == 2
+    first = last = None
+    for epoch in range(12):
+        for _ in range(ex.get_batch_num("train")):
+            lv = float(ex.run("train", convert_to_numpy_ret_vals=True)[0])
+            first = lv if first is None else first
+            last = lv
+    assert last < 0.5 * first and sched.cnt == 72 and sched.get() == pytest.approx(0.05 * 0.25)
+    accs = []
+    for _ in range(ex.get_batch_num("validate")):
+        _, lg, yy = ex.run("validate", convert_to_numpy_ret_vals=True)
+        accs.append(v1.metrics.accuracy(yy, v1.metrics.softmax_func(lg)))
+        assert v1.metrics.f_score_one_hot(yy, lg, average="macro") > 0.5
+    assert np.mean(accs) > 0.8
+    # metrics against closed forms
+    lab = np.array([0, 0, 1, 1])
+    assert v1.metrics.auc(lab, np.array([0.1, 0.4, 0.35, 0.8])) == pytest.approx(0.75, abs=0.02)
+    assert v1.metrics.auc(lab, np.array([0.1, 0.2, 0.8, 0.9])) == pytest.approx(1.0, abs=0.02)
+    oh = np.eye(3)[[0, 1, 2, 2]]
+    pr = np.eye(3)[[0, 2, 2, 2]]
+    assert v1.metrics.precision_score_one_hot(oh, pr).tolist() == pytest.approx([1.0, 0.0, 2 / 3])
+    assert v1.metrics.recall_score_one_hot(oh, pr, average="micro") == pytest.approx(0.75)
+    # initializers: factories and direct constructors
+    w = v1.init.he_normal((64, 32), name="w_he")
+    assert tuple(w.shape) == (64, 32) and abs(float(np.std(w.numpy())) - np.sqrt(2.0 / 64)) < 0.03
+    c = v1.init.GenConstant(2.5)((3,), name="c25")
+    assert np.allclose(c.numpy(), 2.5)
+    v1.reset_graph()
