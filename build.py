@@ -40,6 +40,7 @@ CXX_SOURCES = [
     "csrc/planner/dp_core.cc",
     "csrc/v1/embedding_cache.cc",
     "csrc/v1/ps_server.cc",
+    "csrc/v1/ps_net.cc",
     "csrc/runtime/symm_mem.cc",
     "csrc/runtime/memory_pool.cc",
     "csrc/runtime/runtime.cc",

@@ -20,6 +20,7 @@
 #include "../runtime/symm_mem.h"
 #include "../runtime/memory_pool.h"
 #include "../v1/ps_server.h"
+#include "../v1/ps_net.h"
 #include "../runtime/runtime.h"
 #include "../runtime/rpc_client.h"
 
@@ -649,6 +650,47 @@ PYBIND11_MODULE(_C, m) {
         return py::make_tuple(out, partners);
       }, py::arg("worker"), py::arg("key"), py::arg("value"), py::arg("min_workers") = 2, py::arg("wait_ms") = 50)
       .def("stats", &ParameterServer::stats);
+
+  // network transport of the parameter server (multi-process PS / Hybrid jobs)
+  py::class_<PsNetServer, std::shared_ptr<PsNetServer>>(m, "PsNetServer")
+      .def(py::init<std::shared_ptr<ParameterServer>, int, const std::string&>(), py::arg("ps"), py::arg("port") = 0, py::arg("bind_addr") = "0.0.0.0")
+      .def_property_readonly("port", &PsNetServer::port)
+      .def_property_readonly("requests", &PsNetServer::requests)
+      .def("stop", &PsNetServer::stop, py::call_guard<py::gil_scoped_release>());
+  {
+    auto nogil = py::call_guard<py::gil_scoped_release>();
+    py::class_<PsNetClient, std::shared_ptr<PsNetClient>>(m, "PsNetClient")
+        .def(py::init<const std::string&, int, double>(), py::arg("host"), py::arg("port"), py::arg("connect_timeout") = 60.0, nogil)
+        .def("init_dense", [](PsNetClient& ps, int64_t key, const std::vector<float>& v, PsOptimizer opt, float lr, float momentum) {
+          PsParamConfig c; c.opt = opt; c.lr = lr; c.momentum = momentum;
+          py::gil_scoped_release rel;
+          ps.init_dense(key, v, c);
+        }, py::arg("key"), py::arg("value"), py::arg("opt") = PsOptimizer::SGD, py::arg("lr") = 0.01f, py::arg("momentum") = 0.9f)
+        .def("init_sparse", [](PsNetClient& ps, int64_t key, int64_t rows, int width, const std::vector<float>& v, PsOptimizer opt, float lr) {
+          PsParamConfig c; c.opt = opt; c.lr = lr;
+          py::gil_scoped_release rel;
+          ps.init_sparse(key, rows, width, v, c);
+        }, py::arg("key"), py::arg("rows"), py::arg("width"), py::arg("value"), py::arg("opt") = PsOptimizer::SGD, py::arg("lr") = 0.01f)
+        .def("push_dense", &PsNetClient::push_dense, nogil).def("pull_dense", &PsNetClient::pull_dense, nogil)
+        .def("push_pull_dense", &PsNetClient::push_pull_dense, nogil)
+        .def("push_sparse", &PsNetClient::push_sparse, nogil).def("pull_sparse", &PsNetClient::pull_sparse, nogil)
+        .def("row_versions", &PsNetClient::row_versions, nogil)
+        .def("sync_cache", [](PsNetClient& ps, int64_t key, const std::vector<int64_t>& rows, const std::vector<int64_t>& vers, int64_t bound) {
+          std::vector<int64_t> stale, fv;
+          std::vector<float> vals;
+          { py::gil_scoped_release rel; ps.sync_cache(key, rows, vers, bound, &stale, &vals, &fv); }
+          return py::make_tuple(stale, vals, fv);
+        })
+        .def("barrier", &PsNetClient::barrier, nogil).def("ssp_init", &PsNetClient::ssp_init, nogil).def("ssp_sync", &PsNetClient::ssp_sync, nogil)
+        .def("preduce", [](PsNetClient& ps, int worker, int64_t key, const std::vector<float>& v, int min_workers, int wait_ms) {
+          std::vector<int> partners;
+          std::vector<float> out;
+          { py::gil_scoped_release rel; out = ps.preduce(worker, key, v, min_workers, wait_ms, &partners); }
+          return py::make_tuple(out, partners);
+        }, py::arg("worker"), py::arg("key"), py::arg("value"), py::arg("min_workers") = 2, py::arg("wait_ms") = 50)
+        .def("stats", &PsNetClient::stats, nogil)
+        .def("num_workers", &PsNetClient::num_workers, nogil);
+  }
 
   // ---------------------------------------------------------------- native runtime: memory pool, streams, RNG state, data loader
   py::class_<CachingMemoryPool, std::shared_ptr<CachingMemoryPool>>(m, "MemoryPool")

@@ -12,7 +12,7 @@ from .executor import (Variable, placeholder_op, Executor, HetuConfig, gradients
                        conv2d_add_bias_op, max_pool2d_op, avg_pool2d_op, batch_normalization_op, instance_normalization2d_op, pad_op,
                        div_op, minus_op, opposite_op, abs_op, pow_op, rsqrt_op, leaky_relu_op, mish_op, silu_op, where_op, one_hot_op,
                        reduce_max_op, reduce_min_op, concatenate_op, split_op, sum_op, reset_graph)
-from . import initializers, initializers as init, layers, lr_scheduler, metrics, dataloader  # noqa: F401
+from . import initializers, initializers as init, layers, lr_scheduler, metrics, dataloader, onnx  # noqa: F401
 from .dataloader import Dataloader, dataloader_op  # noqa: F401
 from .optimizer import SGDOptimizer, MomentumOptimizer, AdaGradOptimizer, AdamOptimizer  # noqa: F401
 from .ps import PSContext, CacheSparseTable  # noqa: F401

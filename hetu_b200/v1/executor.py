@@ -101,7 +101,10 @@ def max_pool2d_op(x, kernel_H, kernel_W, padding=0, stride=1): return ops.maxpoo
 def avg_pool2d_op(x, kernel_H, kernel_W, padding=0, stride=1): return ops.avgpool(x, kernel_H, kernel_W, padding, stride)   # noqa: E704
 def batch_normalization_op(x, scale, bias, mean, var, momentum=0.1, eps=1e-5): return ops.batch_norm(x, scale, bias, mean, var, momentum, eps)   # noqa: E704,E501
 def instance_normalization2d_op(x, eps=1e-7): return ops.instance_norm(x, eps)   # noqa: E704
-def pad_op(x, paddings, mode="constant", constant_values=0.0): return ops.pad(x, paddings, mode, constant_values)   # noqa: E704
+def pad_op(x, paddings, mode="constant", constant_values=0.0):
+    """paddings: [[before, after] per dimension] (numpy style) -> the flat last-dimension-first list of the pad op"""
+    flat = [int(v) for pair in reversed([list(p) for p in paddings]) for v in pair]
+    return ops.pad(x, flat, mode, constant_values)
 def div_op(a, b): return ops.div(a, b)                                  # noqa: E704
 def minus_op(a, b): return ops.sub(a, b)                                # noqa: E704
 def opposite_op(x): return ops.neg(x)                                   # noqa: E704

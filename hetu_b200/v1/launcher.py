@@ -1,0 +1,72 @@
+"""heturun: start the roles of a parameter-server job on this node from a YAML file
+
+    python -m hetu.v1.launcher -c config.yaml python train.py --comm PS
+
+    shared:            # environment of every role
+      DMLC_PS_ROOT_PORT: 13100
+    launch:
+      worker: 4        # worker processes (HETU_PS_WORKER_ID = 0..3, HETU_PS_ADDRESS points at the server)
+      server: 1        # the parameter server is hosted by this launcher process (native transport, csrc/v1/ps_net.cc)
+      scheduler: 1     # accepted for compatibility: rendezvous is the server's listening socket
+
+(ref: hetu/v1/python/hetu/launcher.py `launch`, bin/heturun; ps-lite scheduler / server / worker roles)"""
+from __future__ import annotations
+
+import argparse
+import os
+import signal
+import subprocess
+import sys
+from typing import Dict, List, Optional, Sequence
+
+import yaml
+
+from .ps import PSContext
+
+
+def launch(command: Sequence[str], settings: Dict, log_dir: Optional[str] = None, wait: bool = True):
+    shared = {str(k): str(v) for k, v in (settings.get("shared") or {}).items()}
+    lc = settings.get("launch") or {}
+    n_worker, n_server = int(lc.get("worker", 1)), int(lc.get("server", 1))
+    port = int(shared.get("DMLC_PS_ROOT_PORT", 0))
+    server = PSContext.serve(n_worker, port) if n_server > 0 else None
+    procs: List[subprocess.Popen] = []
+    for w in range(n_worker):
+        env = dict(os.environ)
+        env.update(shared)
+        env.update({"DMLC_ROLE": "worker", "DMLC_NUM_WORKER": str(n_worker), "DMLC_NUM_SERVER": str(n_server), "HETU_PS_WORKER_ID": str(w),
+                    "WORKER_ID": str(w)})
+        if server is not None:
+            env["HETU_PS_ADDRESS"] = f"{shared.get('DMLC_PS_ROOT_URI', '127.0.0.1')}:{server.port}"
+        out = open(os.path.join(log_dir, f"worker{w}.log"), "w") if log_dir else None
+        procs.append(subprocess.Popen(list(command), env=env, stdout=out, stderr=subprocess.STDOUT if out else None))
+
+    def stop(*_):
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    signal.signal(signal.SIGINT, stop)
+    if not wait:
+        return procs, server
+    codes = [p.wait() for p in procs]
+    if server is not None:
+        server.stop()
+    return codes
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(prog="heturun")
+    ap.add_argument("-c", "--config", required=True)
+    ap.add_argument("--log-dir", default=None)
+    ap.add_argument("command", nargs=argparse.REMAINDER)
+    a = ap.parse_args(argv)
+    with open(a.config) as f:
+        settings = yaml.safe_load(f) or {}
+    if a.log_dir:
+        os.makedirs(a.log_dir, exist_ok=True)
+    cmd = a.command[1:] if a.command and a.command[0] == "--" else a.command
+    return max(launch(cmd, settings, a.log_dir))
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -36,8 +36,7 @@ class Linear(BaseLayer):
         self.bias_var = init.zeros((out_features,), name=f"{name}_bias") if bias else None
 
     def __call__(self, x):
-        w = self.weight_var if self.weight_transpose else ops.transpose(self.weight_var, [1, 0])
-        y = ops.linear(x, w, self.bias_var, trans_b=True)
+        y = ops.linear(x, self.weight_var, self.bias_var, trans_b=self.weight_transpose)
         return _act(self.activation, y)
 
 

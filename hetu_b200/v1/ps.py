@@ -1,6 +1,7 @@
 """Parameter-server context and the cache-enabled sparse table (HET) for the v1 PS / Hybrid modes.
-Workers are threads or processes: in-process they share one native `ParameterServer`; across processes `PSContext.serve`
-exposes it over the rpc transport.  (ref: hetu/v1/python/hetu/communicator + ps-lite worker API, hetu/cstable.py)"""
+Workers are threads or processes: in-process they share one native `ParameterServer`; across processes the server role
+(`PSContext.serve`, or `python -m hetu.v1.launcher`) exposes it through the native TCP transport (`csrc/v1/ps_net.cc`) and
+workers connect with `PSContext(address="host:port")` (or the HETU_PS_ADDRESS environment variable).  (ref: hetu/v1/python/hetu/communicator + ps-lite worker API, hetu/cstable.py)"""
 from __future__ import annotations
 
 from typing import Dict, Optional, Sequence
@@ -17,14 +18,33 @@ _OPT = {"none": _C.PsOptimizer.NONE, "sgd": _C.PsOptimizer.SGD, "momentum": _C.P
 class PSContext:
     _shared: Dict[str, "_C.ParameterServer"] = {}
 
-    def __init__(self, num_workers: int = 1, worker_id: int = 0, name: str = "default"):
-        if name not in PSContext._shared:
-            PSContext._shared[name] = _C.ParameterServer(num_workers)
-        self.server, self.worker_id, self.num_workers = PSContext._shared[name], worker_id, num_workers
+    def __init__(self, num_workers: int = 1, worker_id: Optional[int] = None, name: str = "default", address: Optional[str] = None):
+        import os
+        address = address or os.environ.get("HETU_PS_ADDRESS")
+        if worker_id is None:
+            worker_id = int(os.environ.get("HETU_PS_WORKER_ID", os.environ.get("WORKER_ID", "0")))
+        if address:
+            host, port = address.rsplit(":", 1)
+            self.server = _C.PsNetClient(host, int(port))
+            num_workers = self.server.num_workers()
+        else:
+            if name not in PSContext._shared:
+                PSContext._shared[name] = _C.ParameterServer(num_workers)
+            self.server = PSContext._shared[name]
+        self.worker_id, self.num_workers = worker_id, num_workers
         self._keys: Dict[str, int] = {}
 
+    @staticmethod
+    def serve(num_workers: int, port: int = 0, bind_addr: str = "0.0.0.0", name: str = "default"):
+        """server role: host the parameter store for `num_workers` remote workers -> the running `_C.PsNetServer`
+        (`.port`, `.requests`, `.stop()`)"""
+        ps = PSContext._shared.setdefault(name, _C.ParameterServer(num_workers))
+        return _C.PsNetServer(ps, int(port), bind_addr)
+
     def key(self, name: str) -> int:
-        return self._keys.setdefault(name, abs(hash(name)) % (1 << 40))
+        # stable across processes (Python's str hash is salted per process)
+        import zlib
+        return self._keys.setdefault(name, (zlib.crc32(name.encode()) | (len(name) << 32)) & ((1 << 40) - 1))
 
     # ---- dense
     def init_dense(self, name, value: np.ndarray, opt="sgd", lr=0.01):

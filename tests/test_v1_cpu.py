@@ -155,3 +155,101 @@ def test_v1_layers_dataloaders_schedulers_and_metrics():
     c = v1.init.GenConstant(2.5)((3,), name="c25")
     assert np.allclose(c.numpy(), 2.5)
     v1.reset_graph()
+
+
+def test_onnx_export_import_round_trip(tmp_path):
+    """hetu2onnx writes a real ONNX protobuf (wire format checked field by field), onnx2hetu rebuilds an equivalent graph:
+    a CNN + MLP head + embedding branch gives identical outputs after the round trip"""
+    import hetu_b200.v1 as v1
+    from hetu_b200.v1.onnx import proto as P
+    v1.reset_graph()
+    rng = np.random.RandomState(0)
+    x = v1.placeholder_op("image", [2, 3, 8, 8])
+    ids = v1.placeholder_op("ids", [2], dtype="int64")
+    h = v1.layers.Conv2d(3, 4, 3, padding=1, activation="relu", name="c1")(x)
+    h = v1.layers.BatchNorm(4, name="bn")(h)
+    h = v1.layers.MaxPool2d(2)(h)
+    h = v1.pad_op(h, [[0, 0], [0, 0], [1, 0], [0, 1]])
+    h = v1.layers.AvgPool2d(5)(h)                         # [2, 4, 1, 1]
+    f = v1.array_reshape_op(h, [2, 4])
+    e = v1.layers.Embedding(10, 4, name="emb")(ids)
+    z = v1.concat_op(f, e, axis=1)                        # [2, 8]
+    z = v1.layers.Linear(8, 16, activation="gelu", name="fc1")(z)
+    z = v1.layers.LayerNorm(16, name="ln")(z)
+    z = v1.layers.Linear(16, 6, name="fc2", weight_transpose=True)(z)
+    z = v1.slice_op(z, [0, 1], [2, 4]) * 0.5 + 1.0
+    z = v1.div_op(v1.leaky_relu_op(z, 0.2), v1.sqrt_op(v1.exp_op(z)))
+    probs = v1.softmax_op(z)
+    score = v1.reduce_sum_op(v1.matmul_op(probs, probs, trans_B=True), [1])
+    feed = {x: rng.randn(2, 3, 8, 8).astype(np.float32), ids: np.array([3, 7])}
+    ex = v1.Executor([probs, score])
+    want = ex.run(feed_dict=feed, convert_to_numpy_ret_vals=True)
+    path = v1.onnx.export([probs, score], str(tmp_path / "model.onnx"))
+    # the file is a well-formed ModelProto
+    m = P.dec_model(open(path, "rb").read())
+    assert m["ir_version"] == 8 and m["opset"][""] == 20 and m["producer"] == "hetu_b200"
+    types = [n["op_type"] for n in m["graph"]["nodes"]]
+    for t in ("Conv", "BatchNormalization", "MaxPool", "Pad", "AveragePool", "Reshape", "Gather", "Concat", "Gemm", "Gelu", "LayerNormalization",
+              "Slice", "LeakyRelu", "Softmax", "MatMul", "ReduceSum"):
+        assert t in types, t
+    assert sorted(i["name"].split("_")[0] for i in m["graph"]["inputs"]) == ["ids", "image"]
+    assert [i["shape"] for i in m["graph"]["inputs"] if i["name"].startswith("image")] == [[2, 3, 8, 8]]
+    assert [o["shape"] for o in m["graph"]["outputs"]] == [[2, 4], [2]]
+    conv = next(n for n in m["graph"]["nodes"] if n["op_type"] == "Conv")
+    assert conv["attrs"]["pads"] == [1, 1, 1, 1] and conv["attrs"]["strides"] == [1, 1]
+    assert any(a.shape == (4, 3, 3, 3) for a in m["graph"]["initializers"].values())
+    # import into a fresh graph and compare
+    v1.reset_graph()
+    inputs, outs = v1.onnx.load(path)
+    by = {k.split("_")[0]: v for k, v in inputs.items()}
+    ex2 = v1.Executor(outs)
+    got = ex2.run(feed_dict={by["image"]: feed[x], by["ids"]: feed[ids]}, convert_to_numpy_ret_vals=True)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and np.allclose(a, b, atol=1e-5), np.abs(a - b).max()
+    v1.reset_graph()
+    # codec details: negative ints, packed floats, scalar tensors
+    node = P.dec_node(P.enc_node("X", ["a"], ["b"], "n", {"i": -3, "f": 0.25, "s": "str", "ints": [1, -2, 3], "floats": [0.5, 1.5], "t": np.arange(6, dtype=np.int64).reshape(2, 3)}))
+    assert node["attrs"]["i"] == -3 and node["attrs"]["f"] == 0.25 and node["attrs"]["s"] == "str" and node["attrs"]["ints"] == [1, -2, 3]
+    assert node["attrs"]["floats"] == [0.5, 1.5] and node["attrs"]["t"].tolist() == [[0, 1, 2], [3, 4, 5]]
+    name, arr = P.dec_tensor(P.enc_tensor("s", np.float32(2.5)))
+    assert name == "s" and arr.shape == () and float(arr) == 2.5
+
+
+def test_parameter_server_over_the_network_with_heturun_launcher(tmp_path):
+    """multi-process PS job: the launcher hosts the native parameter server, 3 worker processes connect over TCP and run
+    BSP regression + HET-cached sparse updates + partial reduce + SSP clocks through it"""
+    import os
+    import sys
+    from hetu_b200 import _C
+    from hetu_b200.v1.launcher import launch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # in-process smoke of the transport first: errors travel back as exceptions, arrays round-trip exactly
+    ps = _C.ParameterServer(1)
+    srv = _C.PsNetServer(ps, 0, "127.0.0.1")
+    cl = _C.PsNetClient("127.0.0.1", srv.port)
+    cl.init_dense(7, [1.0, 2.0, 3.0], _C.PsOptimizer.SGD, 0.5)
+    cl.push_dense(7, [2.0, 2.0, 2.0])
+    assert cl.pull_dense(7) == [0.0, 1.0, 2.0] and ps.pull_dense(7) == [0.0, 1.0, 2.0] and cl.num_workers() == 1
+    with pytest.raises(RuntimeError):
+        cl.pull_dense(12345)
+    assert cl.pull_dense(7) == [0.0, 1.0, 2.0]            # the connection survives a failed request
+    assert srv.requests >= 6
+    del cl
+    srv.stop()
+    logs = tmp_path / "logs"
+    logs.mkdir()
+    env_keep = dict(os.environ)
+    os.environ.update({"PYTHONPATH": root, "HETU_B200_FORCE_CPU": "1", "CUDA_VISIBLE_DEVICES": "", "OMP_NUM_THREADS": "1"})
+    try:
+        codes = launch([sys.executable, os.path.join(root, "tests", "workers", "ps_net_worker.py")],
+                       {"shared": {"DMLC_PS_ROOT_URI": "127.0.0.1"}, "launch": {"worker": 3, "server": 1, "scheduler": 1}}, log_dir=str(logs))
+    finally:
+        os.environ.clear()
+        os.environ.update(env_keep)
+    text = "\n".join((logs / f"worker{w}.log").read_text() for w in range(3))
+    assert codes == [0, 0, 0], text
+    lines = sorted(l for l in text.splitlines() if l.startswith("PSNET"))
+    assert len(lines) == 3
+    for w, l in enumerate(lines):
+        assert f"worker={w} " in l and "preduce=[1.0, 1.0, 1.0, 1.0]" in l and "partners=[0, 1, 2]" in l
+        assert float(l.split("err=")[1].split()[0]) < 0.05
