@@ -693,13 +693,18 @@ PYBIND11_MODULE(_C, m) {
   }
 
   // ---------------------------------------------------------------- native runtime: memory pool, streams, RNG state, data loader
+  m.def("get_memory_pool", [](const std::string& device) { return MemoryPoolRegistry::instance().get(device); }, py::arg("device") = "cpu",
+        "the process-wide pool of a device: 'cuda:<i>', 'cpu', 'pinned', 'shm'");
+  m.def("memory_pool_devices", [] { return MemoryPoolRegistry::instance().devices(); });
+  m.def("empty_all_memory_caches", [] { return (uint64_t)MemoryPoolRegistry::instance().empty_all_caches(); });
   py::class_<CachingMemoryPool, std::shared_ptr<CachingMemoryPool>>(m, "MemoryPool")
       .def(py::init([](const std::string& backend, int device, int64_t limit_mb, int64_t max_split_mb, int64_t pre_allocate_mb) {
         CachingMemoryPool::Options o = CachingMemoryPool::options_from_env();
         if (limit_mb > 0) o.limit = (size_t)limit_mb << 20;
         if (max_split_mb > 0) o.max_split_size = (size_t)max_split_mb << 20;
         if (pre_allocate_mb > 0) o.pre_allocate = (size_t)pre_allocate_mb << 20;
-        std::unique_ptr<MemoryBackend> be = backend == "cuda" ? make_cuda_backend(device) : make_host_backend(backend == "pinned");
+        std::unique_ptr<MemoryBackend> be = backend == "cuda" ? make_cuda_backend(device)
+                                            : backend == "shm" ? make_shm_backend("hetu_b200") : make_host_backend(backend == "pinned");
         return std::make_shared<CachingMemoryPool>(std::move(be), o);
       }), py::arg("backend") = "host", py::arg("device") = 0, py::arg("limit_mb") = 0, py::arg("max_split_mb") = 0,
            py::arg("pre_allocate_mb") = 0)
@@ -707,6 +712,16 @@ PYBIND11_MODULE(_C, m) {
            py::arg("bytes"), py::arg("stream") = 0)
       .def("free", [](CachingMemoryPool& p, uint64_t ptr) { p.free((void*)(uintptr_t)ptr); })
       .def("mark_used_by_stream", [](CachingMemoryPool& p, uint64_t ptr, int64_t stream) { p.mark_used_by_stream((void*)(uintptr_t)ptr, stream); })
+      .def("shm_locate", [](CachingMemoryPool& p, uint64_t ptr) -> py::object {
+        std::string name;
+        size_t off = 0;
+        if (!shm_locate(p.backend(), (void*)(uintptr_t)ptr, &name, &off)) return py::none();
+        return py::make_tuple(name, (uint64_t)off);
+      }, "(shm segment name, offset) of a block of a shared-memory pool: another process maps it with mmap")
+      .def("as_tensor", [](std::shared_ptr<CachingMemoryPool> p, uint64_t ptr, std::vector<int64_t> shape, const std::string& dtype) {
+        // a host tensor viewing pool memory (no copy); the block stays allocated until the caller frees it
+        return at::from_blob((void*)(uintptr_t)ptr, shape, at::TensorOptions().dtype(to_aten_dtype(dtype_from_name(dtype))));
+      }, py::arg("ptr"), py::arg("shape"), py::arg("dtype") = "float32")
       .def("wait", [](CachingMemoryPool& p, uint64_t ptr) { p.wait((void*)(uintptr_t)ptr); })
       .def("empty_cache", [](CachingMemoryPool& p) { return (int64_t)p.empty_cache(); })
       .def("summary", &CachingMemoryPool::summary)

@@ -1,5 +1,9 @@
 #include "memory_pool.h"
 
+#include <map>
+#include <unistd.h>
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -82,7 +86,91 @@ class CudaBackend : public MemoryBackend {
   uint64_t next_ = 0;
   std::unordered_map<uint64_t, cudaEvent_t> events_;
 };
+// POSIX shared-memory segments (shm_open + mmap): host buffers another process can map by name -- the asynchronous
+// checkpoint writer reads the parameter snapshot from here while training continues
+// (ref: CPUMemoryPool::AllocShareMemory, hetu/impl/memory/CPUMemoryPool.cc)
+class ShmBackend : public MemoryBackend {
+ public:
+  explicit ShmBackend(std::string prefix) : prefix_(std::move(prefix)) {}
+  ~ShmBackend() override {
+    for (auto& kv : segs_) { munmap(kv.first, kv.second.second); shm_unlink(kv.second.first.c_str()); }
+  }
+  void* raw_alloc(size_t bytes) override {
+    const std::string name = "/" + prefix_ + "_" + std::to_string(getpid()) + "_" + std::to_string(++next_);
+    int fd = shm_open(name.c_str(), O_CREAT | O_RDWR | O_EXCL, 0600);
+    if (fd < 0) return nullptr;
+    if (ftruncate(fd, (off_t)bytes) != 0) { close(fd); shm_unlink(name.c_str()); return nullptr; }
+    void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) { shm_unlink(name.c_str()); return nullptr; }
+    segs_[p] = {name, bytes};
+    return p;
+  }
+  void raw_free(void* p) override {
+    auto it = segs_.find(p);
+    if (it == segs_.end()) return;
+    munmap(p, it->second.second);
+    shm_unlink(it->second.first.c_str());
+    segs_.erase(it);
+  }
+  uint64_t record_event(int64_t) override { return 0; }
+  bool event_done(uint64_t) override { return true; }
+  void event_sync(uint64_t) override {}
+  const char* name() const override { return "shm"; }
+  // segment that contains p -> (shm name, offset) so that a peer process can map the same bytes
+  bool locate(const void* p, std::string* shm_name, size_t* offset) const {
+    for (auto& kv : segs_) {
+      const char* base = static_cast<const char*>(kv.first);
+      if (p >= base && p < base + kv.second.second) { *shm_name = kv.second.first; *offset = (size_t)(static_cast<const char*>(p) - base); return true; }
+    }
+    return false;
+  }
+
+ private:
+  std::string prefix_;
+  uint64_t next_ = 0;
+  std::map<void*, std::pair<std::string, size_t>> segs_;
+};
 }  // namespace
+
+std::unique_ptr<MemoryBackend> make_shm_backend(const std::string& prefix) { return std::make_unique<ShmBackend>(prefix); }
+bool shm_locate(MemoryBackend* backend, const void* p, std::string* name, size_t* offset) {
+  auto* b = dynamic_cast<ShmBackend*>(backend);
+  return b != nullptr && b->locate(p, name, offset);
+}
+
+// ------------------------------------------------------------------ per-device registry (MemoryManager role)
+std::shared_ptr<CachingMemoryPool> MemoryPoolRegistry::get(const std::string& device) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = pools_.find(device);
+  if (it != pools_.end()) return it->second;
+  std::unique_ptr<MemoryBackend> be;
+  if (device.rfind("cuda", 0) == 0) {
+    const size_t c = device.find(':');
+    be = make_cuda_backend(c == std::string::npos ? 0 : std::stoi(device.substr(c + 1)));
+  } else if (device == "pinned") be = make_host_backend(true);
+  else if (device == "shm") be = make_shm_backend("hetu_b200");
+  else be = make_host_backend(false);
+  auto pool = std::make_shared<CachingMemoryPool>(std::move(be), CachingMemoryPool::options_from_env());
+  pools_[device] = pool;
+  return pool;
+}
+std::vector<std::string> MemoryPoolRegistry::devices() const {
+  std::lock_guard<std::mutex> lk(mu_);
+  std::vector<std::string> out;
+  for (auto& kv : pools_) out.push_back(kv.first);
+  return out;
+}
+size_t MemoryPoolRegistry::empty_all_caches() {
+  std::lock_guard<std::mutex> lk(mu_);
+  size_t n = 0;
+  for (auto& kv : pools_) n += kv.second->empty_cache();
+  return n;
+}
+MemoryPoolRegistry& MemoryPoolRegistry::instance() {
+  static MemoryPoolRegistry* r = new MemoryPoolRegistry();
+  return *r;
+}
 
 std::unique_ptr<MemoryBackend> make_host_backend(bool pinned) { return std::make_unique<HostBackend>(pinned); }
 std::unique_ptr<MemoryBackend> make_cuda_backend(int device) { return std::make_unique<CudaBackend>(device); }

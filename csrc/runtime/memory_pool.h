@@ -37,6 +37,8 @@ class MemoryBackend {
 };
 std::unique_ptr<MemoryBackend> make_host_backend(bool pinned);
 std::unique_ptr<MemoryBackend> make_cuda_backend(int device);
+std::unique_ptr<MemoryBackend> make_shm_backend(const std::string& prefix);     // POSIX shared memory (AllocShareMemory)
+bool shm_locate(MemoryBackend* backend, const void* p, std::string* shm_name, size_t* offset);
 
 class CachingMemoryPool {
  public:
@@ -62,6 +64,7 @@ class CachingMemoryPool {
   size_t empty_cache();                                          // release every fully free segment; returns bytes released
   PoolStats stats() const;
   std::string summary() const;
+  MemoryBackend* backend() { return backend_.get(); }
   static Options options_from_env();
 
  private:
@@ -87,6 +90,19 @@ class CachingMemoryPool {
   std::unordered_map<void*, Block*> live_;
   std::vector<Block*> pending_;       // freed but still referenced by another stream's events
   PoolStats st_;
+};
+
+// per-device registry of pools: "cuda:<i>", "cpu", "pinned", "shm" (ref: GetMemoryPool / RegisterMemoryPool, MemoryManager)
+class MemoryPoolRegistry {
+ public:
+  static MemoryPoolRegistry& instance();
+  std::shared_ptr<CachingMemoryPool> get(const std::string& device);
+  std::vector<std::string> devices() const;
+  size_t empty_all_caches();
+
+ private:
+  mutable std::mutex mu_;
+  std::map<std::string, std::shared_ptr<CachingMemoryPool>> pools_;
 };
 
 }  // namespace hb

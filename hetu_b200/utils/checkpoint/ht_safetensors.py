@@ -103,10 +103,18 @@ def _tensor_blocks(name: str, local: torch.Tensor, global_shape, ds, device_inde
 def temp_save_split(model, optimizer, filename: str, config=None, local_device=None, save_dtype=None, force_contiguous=False,
                     only_lora: bool = False, metadata: Optional[Dict[str, str]] = None, step: Optional[int] = None):
     """Save this rank's shards of `model` (+ optimizer states) under directory `filename`."""
+    return write_split_state(filename, collect_split_state(model, optimizer, save_dtype=save_dtype, only_lora=only_lora, metadata=metadata,
+                                                           step=step))
+
+
+def collect_split_state(model, optimizer, save_dtype=None, only_lora: bool = False, metadata: Optional[Dict[str, str]] = None,
+                        step: Optional[int] = None, snapshot=None) -> dict:
+    """Phase 1 of a split save, on the training thread: this rank's blocks as HOST tensors.  `snapshot(t) -> host tensor`
+    replaces the default `.cpu()` (asynchronous saving must own a private copy: pinned / shared memory)."""
     from ...core import _graphs_by_id
     from ...distributed import rank, world_size
     r, n = rank(), world_size()
-    os.makedirs(filename, exist_ok=True)
+    to_host = snapshot or (lambda t: t.cpu())
     tensors: Dict[str, torch.Tensor] = OrderedDict()
     ds_json = {}
     seen = set()
@@ -137,7 +145,7 @@ def temp_save_split(model, optimizer, filename: str, config=None, local_device=N
             gshape = list(ds.global_shape(list(data.shape))) if ds is not None else list(data.shape)
             if ds is not None and list(ds.local_shape(gshape)) != list(data.shape):
                 ds, gshape = None, list(data.shape)      # flat-sharded state: stored as an opaque local tensor
-            blocks, meta = _tensor_blocks(name, data.cpu(), gshape, ds, didx if ds is not None else 0)
+            blocks, meta = _tensor_blocks(name, to_host(data), gshape, ds, didx if ds is not None else 0)
             meta["device_group"] = ranks
             tensors.update(blocks)
             ds_json[name] = meta
@@ -145,10 +153,17 @@ def temp_save_split(model, optimizer, filename: str, config=None, local_device=N
     md.setdefault("format", "pt")
     if step is not None:
         md["step"] = str(step)
-    save_file(tensors, os.path.join(filename, f"{WEIGHTS_NAME}-{r + 1}-of-{n}{WEIGHTS_FORMAT}"), md)
+    return {"tensors": tensors, "ds_json": ds_json, "metadata": md, "rank": r, "world": n}
+
+
+def write_split_state(filename: str, state: dict):
+    """Phase 2: write the collected blocks (no framework state is touched: safe on a background thread / forked process)"""
+    os.makedirs(filename, exist_ok=True)
+    r, n = state["rank"], state["world"]
+    save_file(state["tensors"], os.path.join(filename, f"{WEIGHTS_NAME}-{r + 1}-of-{n}{WEIGHTS_FORMAT}"), state["metadata"])
     with open(os.path.join(filename, f"param_states-{r + 1}-of-{n}.json"), "w") as f:
-        json.dump(ds_json, f)
-    return list(tensors.keys())
+        json.dump(state["ds_json"], f)
+    return list(state["tensors"].keys())
 
 
 class _SplitIndex:

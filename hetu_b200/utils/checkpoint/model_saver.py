@@ -1,8 +1,11 @@
 """Periodic / rotating / asynchronous checkpointing (ref: python/hetu/utils/checkpoint/model_saver.py:889-1893).
 
 * keeps the newest `save_copies` step directories, deletes older ones
-* `async_save=True` snapshots the tensors to pinned host memory on the training thread and writes files on a
-  background thread, so the step loop only pays for the device->host copy
+* `async_save=True` snapshots the tensors on the training thread (a private host copy, so later optimizer steps cannot
+  tear the checkpoint) and writes the files in the background, so the step loop only pays for the device->host copy.
+  `async_mode="thread"` writes on a Python thread; `async_mode="process"` copies the snapshot into the POSIX shared-memory
+  pool (`_C.get_memory_pool("shm")`) and forks a writer process, as the reference does, so file serialisation never
+  competes with the training process for the GIL
 * step-info CSV (`step_info.csv`: step, consumed_samples, loss, path) for resume
 """
 from __future__ import annotations
@@ -14,15 +17,19 @@ import threading
 import time
 from typing import Optional
 
-from .ht_safetensors import temp_load_split, temp_save_split
+from .ht_safetensors import collect_split_state, temp_load_split, write_split_state
 
 
 class ModelSaver:
     def __init__(self, save_dir: str, save_copies: int = 2, save_interval: int = 0, async_save: bool = False, only_lora=False,
-                 save_dtype=None):
+                 save_dtype=None, async_mode: str = "thread"):
+        assert async_mode in ("thread", "process")
         self.save_dir, self.save_copies, self.save_interval = save_dir, save_copies, save_interval
-        self.async_save, self.only_lora, self.save_dtype = async_save, only_lora, save_dtype
+        self.async_save, self.only_lora, self.save_dtype, self.async_mode = async_save, only_lora, save_dtype, async_mode
         self._thread: Optional[threading.Thread] = None
+        self._child: Optional[int] = None
+        self._shm_blocks = []
+        self.last_write_error: Optional[str] = None
         os.makedirs(save_dir, exist_ok=True)
 
     def step_dir(self, step: int) -> str:
@@ -35,21 +42,68 @@ class ModelSaver:
         if self._thread is not None:
             self._thread.join()
             self._thread = None
+        if self._child is not None:
+            _, status = os.waitpid(self._child, 0)
+            self._child = None
+            if status != 0:
+                self.last_write_error = f"checkpoint writer process exited with status {status}"
+        if self._shm_blocks:
+            from ... import _C
+            pool = _C.get_memory_pool("shm")
+            for ptr in self._shm_blocks:
+                pool.free(ptr)
+            self._shm_blocks = []
+        if self.last_write_error is not None:
+            err, self.last_write_error = self.last_write_error, None
+            raise RuntimeError(err)
+
+    def _snapshot_fn(self):
+        """host copy owned by the saver: plain clone for the thread writer, shared-memory pool blocks for the process writer"""
+        if self.async_mode == "thread":
+            return lambda t: t.detach().to("cpu", copy=True)
+        from ... import _C
+        pool = _C.get_memory_pool("shm")
+        names = {"torch.float32": "float32", "torch.bfloat16": "bfloat16", "torch.float16": "float16", "torch.int64": "int64",
+                 "torch.int32": "int32", "torch.float64": "float64", "torch.bool": "bool", "torch.uint8": "uint8", "torch.int8": "int8"}
+
+        def snap(t):
+            t = t.detach()
+            ptr = pool.alloc(max(t.numel() * t.element_size(), 1))
+            self._shm_blocks.append(ptr)
+            view = pool.as_tensor(ptr, list(t.shape), names[str(t.dtype)])
+            view.copy_(t)
+            return view
+        return snap
 
     def save(self, model, optimizer, step: int, consumed_samples: int = 0, loss: float = float("nan")):
         from ...distributed import global_comm_barrier_rpc, rank
         self.wait()
         path = self.step_dir(step)
 
-        def work():
-            temp_save_split(model, optimizer, path, only_lora=self.only_lora, save_dtype=self.save_dtype, step=step)
+        state = collect_split_state(model, optimizer, save_dtype=self.save_dtype, only_lora=self.only_lora, step=step,
+                                    snapshot=self._snapshot_fn() if self.async_save else None)
 
-        if self.async_save:
-            # tensors are copied to host inside temp_save_split (.cpu()); run that part now, write files in background
+        def work():
+            try:
+                write_split_state(path, state)
+            except Exception as e:   # noqa: BLE001 -- surfaced by the next wait()
+                self.last_write_error = f"{type(e).__name__}: {e}"
+
+        if not self.async_save:
+            write_split_state(path, state)
+        elif self.async_mode == "thread":
             self._thread = threading.Thread(target=work, daemon=True)
             self._thread.start()
         else:
-            work()
+            pid = os.fork()
+            if pid == 0:                 # writer process: only reads the shared snapshot and writes files
+                code = 0
+                try:
+                    write_split_state(path, state)
+                except BaseException:    # noqa: BLE001
+                    code = 1
+                os._exit(code)
+            self._child = pid
         global_comm_barrier_rpc()
         if rank() == 0:
             with open(os.path.join(self.save_dir, "step_info.csv"), "a", newline="") as f:

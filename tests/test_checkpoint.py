@@ -69,6 +69,35 @@ def test_model_saver_rotation_and_resume(tmp_path):
         assert int(g.get_param(st["step"])) == 4
 
 
+@pytest.mark.parametrize("mode", ["thread", "process"])
+def test_async_model_saver_snapshots_before_training_continues(tmp_path, mode):
+    """async_save: the snapshot is taken on the training thread (thread mode: private clone; process mode: shared-memory
+    pool + forked writer), so optimizer steps issued right after save() cannot leak into the checkpoint"""
+    with ht.graph("define_and_run", create_new=True) as g:
+        m = ht.nn.Linear(64, 32, name=f"lin_{mode}")
+        x = ht.placeholder("float32", [2, 64], name="x")
+        loss = ht.sum(m(x))
+        opt = ht.AdamOptimizer(lr=0.1)
+        train = opt.minimize(loss)
+        saver = ModelSaver(str(tmp_path), save_copies=3, async_save=True, async_mode=mode)
+        X = np.ones((2, 64), np.float32)
+        g.run(loss, [loss, train], {x: X})
+        want_w = g.get_param(m.weight).clone()
+        want_m = g.get_param(opt.get_states(m.weight)["mean"]).clone()
+        saver.save(m, opt, 1, consumed_samples=2, loss=0.0)
+        for _ in range(3):                                        # training goes on while the files are written
+            g.run(loss, [loss, train], {x: X})
+        assert not torch.equal(g.get_param(m.weight), want_w)
+        saver.wait()
+        assert saver._shm_blocks == [] and saver._child is None and saver._thread is None
+        files = os.listdir(tmp_path / "step1")
+        assert any(f.endswith(".safetensors") for f in files) and any(f.startswith("param_states") for f in files)
+        assert saver.load_latest(m, opt) == (1, 2)
+        assert torch.equal(g.get_param(m.weight), want_w)
+        assert torch.equal(g.get_param(opt.get_states(m.weight)["mean"]), want_m)
+        assert int(g.get_param(opt.get_states(m.weight)["step"])) == 1
+
+
 def test_hf_llama_converter_shapes():
     H, KV, D, L, F, V = 4, 2, 8, 2, 48, 64
     hf = {"model.embed_tokens.weight": torch.randn(V, H * D), "model.norm.weight": torch.ones(H * D), "lm_head.weight": torch.randn(V, H * D)}

@@ -67,3 +67,32 @@ def test_native_dataloader_dp_slices_prefetch_and_reset():
 
 def test_stream_role_names():
     assert _C.stream_role_name(1) == "computing" and _C.stream_role_name(6) == "collective" and _C.stream_role_name(3) == "h2d"
+
+
+def test_shared_memory_pool_and_registry(tmp_path):
+    """POSIX shared-memory backend (AllocShareMemory): a block written through a zero-copy tensor view is readable from
+    another process that maps the segment by name; the per-device registry hands out one pool per device string"""
+    import subprocess
+    import sys
+    import torch
+    pool = _C.get_memory_pool("shm")
+    assert _C.get_memory_pool("shm") is pool and "shm" in _C.memory_pool_devices()
+    assert _C.get_memory_pool("cpu") is not pool
+    p = pool.alloc(4096 * 4)
+    t = pool.as_tensor(p, [64, 64], "float32")
+    t.copy_(torch.arange(4096, dtype=torch.float32).reshape(64, 64))
+    name, off = pool.shm_locate(p)
+    assert name.startswith("/hetu_b200_") and off >= 0
+    code = ("import mmap, os, sys, numpy as np\n"
+            f"fd = os.open('/dev/shm{name}', os.O_RDONLY)\n"
+            "m = mmap.mmap(fd, 0, prot=mmap.PROT_READ)\n"
+            f"a = np.frombuffer(m, dtype=np.float32, count=4096, offset={off})\n"
+            "print(float(a.sum()), float(a[4095]))\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == [str(float(sum(range(4096)))), "4095.0"]
+    q = pool.alloc(1024)
+    assert pool.shm_locate(q)[0] == name            # small blocks are carved out of the same segment
+    pool.free(p); pool.free(q)
+    assert _C.get_memory_pool("cpu").shm_locate(0) is None
+    assert _C.empty_all_memory_caches() >= 0
