@@ -114,8 +114,9 @@ class GPTBlock(Module):
         self.mlp = GPTMLP(config, ds_parallel_configs, layer_idx, name=f"mlp_block{layer_idx}")
 
     def forward(self, x, seq_len, cu_seqlens=None):
-        # entering a new pipeline stage: receive the residual stream once (P2P), both branches then use the local copy
-        x = self.ln_1._adapt(x, self.ln_1._all_split0() if self.ln_1.sequence_parallel else None)
+        # entering a new pipeline stage: receive the residual stream once (P2P), both branches then use the local copy; a
+        # block with another (tp, dp) than its predecessor (Galvatron layer-wise strategies) relocates the activations here
+        x = self.ln_1._adapt(x, self.ln_1._all_split0() if self.ln_1.sequence_parallel else self.attn.qkv_dense.ds_split0_dup())
         x = self.attn(self.ln_1(x), seq_len, residual=x, cu_seqlens=cu_seqlens)    # residual add fused into the row-parallel GEMM epilogue
         x = self.mlp(self.ln_2(x), residual=x)
         return x

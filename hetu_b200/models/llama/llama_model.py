@@ -124,7 +124,8 @@ class LlamaBlock(Module):
 
     def forward(self, x, seq_len, pos_offset=0, position_ids=None, cu_seqlens=None):
         n1 = self.rmsnorm_1
-        x = n1._adapt(x, n1._all_split0() if n1.sequence_parallel else None)   # pipeline-stage entry (P2P)
+        # pipeline-stage entry (P2P) / relocation when this block's (tp, dp) differs from its predecessor's
+        x = n1._adapt(x, n1._all_split0() if n1.sequence_parallel else self.attn.qkv_dense.ds_split0_dup())
         x = self.attn(self.rmsnorm_1(x), seq_len, residual=x, pos_offset=pos_offset, position_ids=position_ids, cu_seqlens=cu_seqlens)
         return self.mlp(self.rmsnorm_2(x), residual=x)
 

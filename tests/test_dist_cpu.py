@@ -191,3 +191,19 @@ def test_straggler_report_writes_per_rank_step_breakdown(tmp_path):
         assert last["tp_collective_bytes"] > 0 and last["dp_grad_reduce_ms"] > 0 and last["attn_fwd_ms"] > 0
         parts = sum(last[k] for k in ("attn_fwd_ms", "attn_bwd_ms", "tp_collective_ms", "other_compute_ms", "update_ms") if k in last)
         assert parts <= last["total_ms"] * 1.05
+
+
+GALVATRON_WORKER = os.path.join(os.path.dirname(__file__), "workers", "galvatron_worker.py")
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("tps,world", [("1,1,2,2", 2), ("2,1,2,1", 2), ("1,4,2,1", 4)])
+def test_galvatron_layerwise_strategies_reproduce_the_single_device_loss(tps, world):
+    """layers of one model under different (tp, dp) degrees on the same devices (the plan format of the Galvatron search):
+    activations are relocated at every layout change (dp -> tp: all-gather of the batch shards, tp -> dp: local slice)"""
+    ref = _reference()
+    ok, outs = run_workers(GALVATRON_WORKER, world, [tps, world])
+    assert ok, "\n-----\n".join(outs)
+    got = _losses(outs)
+    for a, b in zip(got, ref):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, ref)
