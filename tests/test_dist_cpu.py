@@ -207,3 +207,19 @@ def test_galvatron_layerwise_strategies_reproduce_the_single_device_loss(tps, wo
     got = _losses(outs)
     for a, b in zip(got, ref):
         assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, ref)
+
+
+CP_MODEL_WORKER = os.path.join(os.path.dirname(__file__), "workers", "cp_model_worker.py")
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("cp,tp", [(2, 1), (2, 2)])
+def test_whole_model_context_parallel_training_matches_single_device(cp, tp):
+    """Llama with every sequence split over a CP ring (SYM chunks): ring attention in every layer, rotary at the original
+    positions, parameter gradients reduced over the ring (and TP inside each ring member for cp x tp)"""
+    ref = _reference("llama")
+    ok, outs = run_workers(CP_MODEL_WORKER, cp * tp, [cp, tp])
+    assert ok, "\n-----\n".join(outs)
+    got = _losses(outs)
+    for a, b in zip(got, ref):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, ref)

@@ -40,7 +40,7 @@ with ht.graph("define_and_run", create_new=True) as g:
     pos = ht.parallel_placeholder("int64", [T], [in_ds], device_group_hierarchy=[in_dg], name="pos")
     lab = ht.parallel_placeholder("int64", [T], [lb_ds], device_group_hierarchy=[lb_dg], name="lab")
     loss = model(ids, pos, lab, seq_len=S)
-    opt = ht.AdamOptimizer(lr=1e-2)
+    opt = ht.SGDOptimizer(lr=0.5) if os.environ.get("WORKER_OPT") == "sgd" else ht.AdamOptimizer(lr=1e-2)
     train_op = opt.minimize(loss)
 
 rng = np.random.RandomState(0)
