@@ -618,8 +618,11 @@ std::vector<at::Tensor> Executor::exec_comm(const CommStep& cs, OpDef* op, const
       const Tensor& x = op->inputs[0];
       const DistributedStates& src = x->ds(std::max(active_strategy_, 0));
       std::vector<int64_t> sb, ss;
-      src.local_slice(cs.global_shape, me, &sb, &ss);
-      dst.local_slice(cs.global_shape, me, &begin, &size);
+      // the global shape follows the tensor that is actually flowing (feeds may change the token count from run to run;
+      // the shape recorded when the plan was lowered can be stale)
+      const std::vector<int64_t> gshape = src.global_shape(in[0].sizes().vec());
+      src.local_slice(gshape, me, &sb, &ss);
+      dst.local_slice(gshape, me, &begin, &size);
       at::Tensor t = in[0];
       for (size_t d = 0; d < begin.size(); ++d) t = t.narrow((int64_t)d, begin[d] - sb[d], size[d]);
       return {t.contiguous()};

@@ -47,6 +47,18 @@ def _strategy_sizes(cfg: dict):
     return dp, tp, max(len(stages), 1)
 
 
+def _cp_degree(cfg: dict) -> int:
+    """context-parallel degree of a strategy (the batch split of the input leaf counts dp * cp replicas)"""
+    return max(int(cfg.get("cp", 1) or 1), 1)
+
+
+def cp_rows(width: int, cp: int, cp_idx: int) -> np.ndarray:
+    """token positions of one sequence owned by ring member `cp_idx`: chunk i and its mirror 2cp-1-i of 2cp equal chunks
+    (the SYM split that balances causal attention work; ref: generate_cp_pack_data / ParallelAttention SYM pattern)"""
+    chunks = np.split(np.arange(width), 2 * cp)
+    return np.concatenate([chunks[cp_idx], chunks[2 * cp - 1 - cp_idx]])
+
+
 class Trainer:
     def __init__(self, pretrain_config: TrainingConfig, model, tokenizer=None, optimizer=None, train_dataset=None,
                  data_collator: Optional[Callable] = None, **kwargs):
@@ -100,15 +112,28 @@ class Trainer:
     def get_train_data_loader(self):
         cfg = self.pretrain_config
         dp, _, _ = _strategy_sizes(self.ds_parallel_configs[self.cur_strategy_id])
+        dp //= _cp_degree(self.ds_parallel_configs[self.cur_strategy_id])
         level = cfg.data_load_level.value if isinstance(cfg.data_load_level, DataLoadLevel) else str(cfg.data_load_level)
         kw = dict(global_batch_size=cfg.global_load_size) if level == "SAMPLE" else dict(global_token_num=cfg.global_load_size)
         return build_data_loader(self.train_dataset, self.consumed_samples, load_level=level, dp_rank=self._dp_rank(), dp_size=dp,
                                  seed=cfg.seed, collate_fn=self.data_collator, **kw)
 
     def _dp_rank(self):
-        dp, tp, pp = _strategy_sizes(self.ds_parallel_configs[self.cur_strategy_id])
+        """data-parallel replica of this rank (devices are laid out [pp][dp][cp][tp]: ring members share their replica's data)"""
+        dcp, tp, pp = _strategy_sizes(self.ds_parallel_configs[self.cur_strategy_id])
+        cp = _cp_degree(self.ds_parallel_configs[self.cur_strategy_id])
         r = distributed.rank()
-        return (r % (dp * tp)) // tp
+        return (r % (dcp * tp)) // tp // cp
+
+    def _cp_index_and_ring(self, strategy_id: int = 0):
+        """(position of this rank in its context-parallel ring, global ranks of the ring)"""
+        dcp, tp, pp = _strategy_sizes(self.ds_parallel_configs[strategy_id])
+        cp = _cp_degree(self.ds_parallel_configs[strategy_id])
+        r = distributed.rank()
+        stage, within = divmod(r, dcp * tp)
+        dcp_idx, tp_idx = divmod(within, tp)
+        d, c = divmod(dcp_idx, cp)
+        return c, tuple(stage * dcp * tp + (d * cp + k) * tp + tp_idx for k in range(cp))
 
     def build(self):
         if self.is_model_built:
@@ -129,6 +154,14 @@ class Trainer:
         ac = core.autocast("bfloat16") if cfg.bf16 else _null()
         with core.graph("define_and_run", create_new=True, num_strategy=self.num_strategy) as g, ac:
             st.seq_len_symbol = IntSymbol(seq)
+            cp = _cp_degree(self.ds_parallel_configs[0])
+            if cp > 1:
+                if cfg.packing:
+                    raise ValueError("context parallelism in the Trainer needs packing=False (use data.bucket.generate_cp_pack_data for packed CP feeds)")
+                mc = getattr(self.model_wrapper, "model_config", None) or getattr(self.model_wrapper, "config", None)
+                if mc is None or not hasattr(mc, "cp_ranks"):
+                    raise ValueError("this model has no context-parallel attention path (config.cp_ranks)")
+                mc.cp_ranks = self._cp_index_and_ring(0)[1]
             if hasattr(self.model_wrapper, "create_model"):
                 st.model = self.model_wrapper.create_model(self.ds_parallel_configs)
                 st.config = getattr(self.model_wrapper, "model_config", None)
@@ -196,6 +229,14 @@ class Trainer:
                 feeds_l.append(bl.reshape(-1))
                 feeds_p.append(np.tile(np.arange(width), mbs))
             seq = width
+            cp = _cp_degree(self.ds_parallel_configs[strategy_id])
+            if cp > 1:
+                # every ring member keeps its SYM chunks of each row (positions stay the original ones for the rotary embedding)
+                assert width % (2 * cp) == 0, f"padded width {width} must be a multiple of 2 * cp = {2 * cp} (set pack_alignment accordingly)"
+                cols = cp_rows(width, cp, self._cp_index_and_ring(strategy_id)[0])
+                take = lambda flat: flat.reshape(-1, width)[:, cols].reshape(-1)   # noqa: E731
+                feeds_i, feeds_l, feeds_p = [take(a) for a in feeds_i], [take(a) for a in feeds_l], [take(a) for a in feeds_p]
+                seq = len(cols)
             stats = {"real_tokens": int(sum(len(x) for x, _ in batch)), "fed_tokens": int(width * mbs * nmb), "rows": len(batch)}
         to_t = (lambda a: torch.as_tensor(a).pin_memory()) if torch.cuda.is_available() else torch.as_tensor
         feed = {st.input_ids: [to_t(a) for a in feeds_i], st.position_ids: [to_t(a) for a in feeds_p],

@@ -9,6 +9,7 @@ from dataclasses import dataclass
 from typing import List, Optional
 
 from ... import ops
+from ...core import IntSymbol
 from ...core import recompute as recompute_ctx
 from ...nn import (HtMultiColumnParallelLinear, HtMultiParallelRMSNorm, HtMultiQKVColumnParallelLinear, HtMultiRowParallelLinear,
                    HtMultiVocabParallelEmbedding, Module, ModuleList)
@@ -75,15 +76,21 @@ class LlamaAttention(Module):
         qkv = self.qkv_dense(x)
         qkv = rotary_packed(qkv, seq_len, hq, hkv, d, positions=position_ids, base=self.config.rope_theta, pos_offset=pos_offset, layout="hqkv")
         if self.config.cp_ranks and len(self.config.cp_ranks) > 1:
-            t = qkv.shape[0]
-            s = seq_len if isinstance(seq_len, int) else seq_len.get_data()
-            g5 = ops.reshape(qkv, [t // s, s, hkv, rep + 2, d])
+            s = seq_len            # int or IntSymbol: the per-ring-member sequence length may change every step
+            sym = (lambda t, shp: t.set_symbolic_shape([v if isinstance(v, IntSymbol) else IntSymbol(int(v)) for v in shp])) \
+                if isinstance(s, IntSymbol) else (lambda t, shp: None)
+            # the reshape gradients restore their input's shape: give the intermediates symbolic shapes so that follows `s`
+            sym(qkv, [-1, (hq + 2 * hkv) * d])
+            g5 = ops.reshape(qkv, [-1, s, hkv, rep + 2, d])
             q, k, v = ops.split(g5, [rep, 1, 1], dim=3)
-            q = ops.reshape(q, [t // s, s, hq, d])
-            k = ops.reshape(k, [t // s, s, hkv, d])
-            v = ops.reshape(v, [t // s, s, hkv, d])
+            for t, n in ((q, rep), (k, 1), (v, 1)):
+                sym(t, [-1, s, hkv, n, d])
+            q = ops.reshape(q, [-1, s, hq, d])
+            k = ops.reshape(k, [-1, s, hkv, d])
+            v = ops.reshape(v, [-1, s, hkv, d])
             a = ops.parallel_attn(q, k, v, self.config.cp_ranks, is_causal=True)
-            a = ops.reshape(a, [t, hq * d])
+            sym(a, [-1, s, hq, d])
+            a = ops.reshape(a, [-1, hq * d])
         else:
             a = attn_packed(qkv, seq_len, hq, hkv, d, is_causal=True, layout="hqkv", cu_seqlens=cu_seqlens)
         return self.dense(a, residual=residual)

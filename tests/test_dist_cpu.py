@@ -223,3 +223,22 @@ def test_whole_model_context_parallel_training_matches_single_device(cp, tp):
     got = _losses(outs)
     for a, b in zip(got, ref):
         assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, ref)
+
+
+TRAINER_CP_WORKER = os.path.join(os.path.dirname(__file__), "workers", "trainer_cp_worker.py")
+
+
+@pytest.mark.dist
+def test_trainer_with_context_parallel_strategies(tmp_path):
+    """`Trainer` on ds_parallel_configs with cp > 1: rows are cut into each ring member's SYM chunks, the model's ring is
+    derived from the device layout [pp][dp][cp][tp], sequence length is symbolic; loss histories equal the cp = 1 run"""
+    env = {"TRAINER_OUT": str(tmp_path)}
+    ok, outs = run_workers(TRAINER_CP_WORKER, 1, [1, 1, 1], env_extra=env)
+    assert ok, "\n-----\n".join(outs)
+    ref = _losses(outs)
+    for dp, cp, tp in ((1, 2, 1), (2, 2, 1), (1, 2, 2)):
+        ok, outs = run_workers(TRAINER_CP_WORKER, dp * cp * tp, [dp, cp, tp], env_extra=env)
+        assert ok, "\n-----\n".join(outs)
+        got = _losses(outs)
+        for a, b in zip(got, ref):
+            assert abs(a - b) < 1e-3 * max(1.0, abs(b)), ((dp, cp, tp), got, ref)
