@@ -94,6 +94,14 @@ class Trainer:
                 dspc = [convert_strategy(sc, self._num_layers())]
             else:
                 dspc = [convert_strategy(StrategyConfig(dp=max(distributed.world_size(), 1)), self._num_layers())]
+        # heterogeneous strategy (pipelines with different tp / stage counts, e.g. a Malleus plan): this rank trains the
+        # homogeneous member-local graph of its own pipeline on its share of every global batch (engine/hetero.py)
+        self.hetero = None
+        if len(dspc) == 1 and dspc[0].get("hetero") and "device_group_union" in dspc[0].get("input", {}) \
+                and len(dspc[0]["input"]["device_group_union"]) > 1:
+            from .hetero import HeteroSession
+            self.hetero = HeteroSession(dspc[0], shares=kwargs.get("hetero_shares"))
+            dspc = [self.hetero.local_cfg]
         self.ds_parallel_configs = dspc
         self.num_strategy = len(dspc)
         self.cur_strategy_id = 0
@@ -139,6 +147,8 @@ class Trainer:
         if self.is_model_built:
             return self.trainer_states
         self.trainer_states = self.create_define_graph()
+        if self.hetero is not None:
+            self.hetero.precreate_groups()        # collective over all ranks: tp groups of every stage + cross-pipeline groups
         self.is_model_built = True
         return self.trainer_states
 
@@ -262,13 +272,22 @@ class Trainer:
     # ------------------------------------------------------------------ train
     def _train_step(self, batch, strategy_id=0):
         st = self.trainer_states
+        scale = None
+        if self.hetero is not None:
+            # every rank loaded the whole global batch: keep this pipeline's share, weight its gradient by the share
+            n_global = len(batch)
+            batch = batch[self.hetero.batch_slice(n_global)]
+            scale = self.hetero.grad_scale(len(batch), n_global)
         feed, nmb, seq, stats = self.prepare_feed_dict(batch, strategy_id)
         dp, _, _ = _strategy_sizes(self.ds_parallel_configs[strategy_id])
         st.seq_len_symbol.set_data(int(seq))
         out = st.graph.run(st.loss, [st.loss, st.train_op], feed, num_micro_batches=nmb, cur_strategy_id=strategy_id,
-                           grad_scale=1.0 / dp)
+                           grad_scale=scale if scale is not None else 1.0 / dp)
         loss = out[0]
-        return (float(loss.float().mean()) if loss is not None else None), stats
+        lv = float(loss.float().mean()) if loss is not None else None
+        if self.hetero is not None and lv is not None and self.hetero.rank in self.hetero.last_stage_ranks:
+            lv = self.hetero.reduce_loss(lv, len(batch), n_global)      # global mean from the per-pipeline means
+        return lv, stats
 
     def train(self, steps: Optional[int] = None, strategy_schedule: Optional[Callable[[int], int]] = None):
         """run `steps` optimizer steps; `strategy_schedule(step) -> strategy id` enables hot switching between the
@@ -337,6 +356,8 @@ class Trainer:
         return self.loss_history
 
     def _loss_ranks(self):
+        if self.hetero is not None:
+            return {self.hetero.last_stage_ranks[0]}
         cfg = self.ds_parallel_configs[self.cur_strategy_id]
         return {g[0] for g in cfg["label"]["device_group_union"]}
 

@@ -242,3 +242,22 @@ def test_trainer_with_context_parallel_strategies(tmp_path):
         got = _losses(outs)
         for a, b in zip(got, ref):
             assert abs(a - b) < 1e-3 * max(1.0, abs(b)), ((dp, cp, tp), got, ref)
+
+
+TRAINER_HETERO_WORKER = os.path.join(os.path.dirname(__file__), "workers", "trainer_hetero_worker.py")
+
+
+@pytest.mark.dist
+def test_trainer_on_a_heterogeneous_strategy(tmp_path):
+    """`Trainer(ds_parallel_configs=[hetero config], hetero_shares=[3, 1])`: (tp2 x pp2) + tp1 pipelines, every pipeline takes
+    its share of each global batch; the loss history equals the single-device Trainer"""
+    env = {"TRAINER_OUT": str(tmp_path)}
+    ok, outs = run_workers(TRAINER_HETERO_WORKER, 1, ["single"], env_extra=env)
+    assert ok, "\n-----\n".join(outs)
+    ref = _losses(outs)
+    ok, outs = run_workers(TRAINER_HETERO_WORKER, 5, ["hetero"], env_extra=env)
+    assert ok, "\n-----\n".join(outs)
+    got = _losses(outs)
+    assert sum("INFO" in o and "True" in o for o in outs) == 5
+    for a, b in zip(got, ref):
+        assert abs(a - b) < 1e-3 * max(1.0, abs(b)), (got, ref)
