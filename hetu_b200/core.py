@@ -300,8 +300,24 @@ def make_op(op_type: str, inputs: Sequence[Tensor], attrs: Optional[dict] = None
             device_group_hierarchy=None, dst_ds=None, sy_shape=(), const_data=None, stream_index: int = -1,
             extra_deps: Sequence[Tensor] = (), graph: Optional[Graph] = None, **_ignored) -> List[Tensor]:
     g = graph or _graph_of(inputs) or cur_graph()
+    ac = autocast_dtype()
+    if ac is not None and op_type in _AUTOCAST_OPS:
+        # autocast: tensor-core ops run in the context's dtype -- fp32 operands (e.g. fed activations) are cast on entry,
+        # tensors already in a 16-bit type are left alone (ref: hetu/graph/autocast, DataTransferOp insertion)
+        cast = None
+        new = []
+        for t in inputs:
+            if t.dtype == "float32":
+                if cast is None:
+                    from .ops import data_transfer as cast
+                t = cast(t, ac)
+            new.append(t)
+        inputs = new
     return g.make_op(op_type, list(inputs), attrs or {}, name, _normalize_dgh(device_group_hierarchy), _normalize_dsh(dst_ds),
                      list(sy_shape), const_data, stream_index, list(extra_deps))
+
+
+_AUTOCAST_OPS = {"linear", "matmul", "bmm", "conv2d", "attn", "attn_packed", "einsum"}
 
 
 _graphs_by_id: Dict[int, Graph] = {}

@@ -44,8 +44,11 @@ def run_graph(g: Graph, loss: Optional[Tensor], fetches: Sequence[Tensor], feed_
         feed[t] = [x.to(want) if x.dtype != want else x for x in vals]
     lvl = cur_run_level() if run_level is None else (run_level if isinstance(run_level, int) else
                                                      {"update": 0, "grad": 1, "compute_only": 2, "alloc": 3, "topo": 4}[run_level])
-    return g.run_native(loss, list(fetches), feed, int(num_micro_batches), int(compute_strategy_id), int(lvl),
-                        float(grad_scale), bool(save_checkpoint))
+    fetches = list(fetches)
+    res = g.run_native(loss, fetches, feed, int(num_micro_batches), int(compute_strategy_id), int(lvl),
+                       float(grad_scale), bool(save_checkpoint))
+    # the executor also evaluates `loss` (it drives the backward pass); the caller gets exactly one value per fetch
+    return res[:len(fetches)] if (loss is not None and fetches and len(res) > len(fetches)) else res
 
 
 def _graph_run(self, loss, fetches=None, feed_dict=None, *args, **kwargs):

@@ -175,7 +175,7 @@ class Executor:
             from .. import distributed
             dp = max(distributed.world_size(), 1)
         training = any(isinstance(n, Tensor) and n.producer_type in ("adam_update", "sgd_update", "group") for n in nodes)
-        outs = self.graph.run(loss if training else None, nodes, feed, grad_scale=1.0 / dp)[:len(nodes)]
+        outs = self.graph.run(loss if training else None, nodes, feed, grad_scale=1.0 / dp)
         self.step += 1
         if any(isinstance(n, Tensor) and n.producer_type in ("adam_update", "sgd_update", "group") for n in nodes):
             for opt in self._optimizers():
