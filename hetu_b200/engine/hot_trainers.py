@@ -47,8 +47,9 @@ class MalleusTrainer(Trainer):
     pipeline) are executed through engine.hetero.HeteroSession (member-local graphs + grouped gradient all-reduce)"""
 
     def __init__(self, *args, ctxs: Optional[TrainerCtxs] = None, strategy_args: Optional[TrainerStrategyArgs] = None, replan_interval: int = 50,
-                 ratio_source: Optional[Callable[[], Dict[int, float]]] = None, **kwargs):
+                 ratio_source: Optional[Callable[[], Dict[int, float]]] = None, auto_apply: bool = False, **kwargs):
         super().__init__(*args, **kwargs)
+        self.auto_apply = auto_apply
         self.ctxs = ctxs or TrainerCtxs()
         self.strategy_args = strategy_args
         self.replan_interval, self.ratio_source = replan_interval, ratio_source
@@ -75,7 +76,23 @@ class MalleusTrainer(Trainer):
                "hetero_session": model.executable_config is None,     # otherwise: rebuild through engine.hetero.HeteroSession
                "estimated_time": model.estimate_time(model.plans)}
         self.plans_log.append(rec)
+        if self.auto_apply:
+            rec["applied"] = self.apply_plan(model)
         return rec
+
+    def apply_plan(self, model: StrategyModel) -> str:
+        """move the running job onto the plan: identical pipelines with equal micro-batch counts are an ordinary
+        (dp, tp, pp) strategy; anything else -- unequal batch shares, different tp degrees or stage counts -- runs through
+        the heterogeneous member-local path.  Both go through `Trainer.rebuild` (split checkpoint, re-sharded on load)."""
+        strategy = model.strategies
+        if strategy.unused_rank_list:
+            return "skipped: the plan leaves ranks without work (needs a restart with fewer workers)"
+        shares = list(strategy.hetero_micro_batch_num_list)
+        if model.executable_config is not None and len(set(shares)) == 1:
+            self.rebuild([model.executable_config])
+            return "homogeneous"
+        self.rebuild([model.ds_parallel_configs], hetero_shares=shares)
+        return "hetero"
 
     def train(self, steps=None, strategy_schedule=None):
         self.callbacks.append(lambda trainer, loss, stats: trainer.maybe_replan())

@@ -94,17 +94,50 @@ class Trainer:
                 dspc = [convert_strategy(sc, self._num_layers())]
             else:
                 dspc = [convert_strategy(StrategyConfig(dp=max(distributed.world_size(), 1)), self._num_layers())]
+        self._set_strategies(dspc, kwargs.get("hetero_shares"))
+
+    def _set_strategies(self, dspc, hetero_shares=None):
         # heterogeneous strategy (pipelines with different tp / stage counts, e.g. a Malleus plan): this rank trains the
         # homogeneous member-local graph of its own pipeline on its share of every global batch (engine/hetero.py)
         self.hetero = None
         if len(dspc) == 1 and dspc[0].get("hetero") and "device_group_union" in dspc[0].get("input", {}) \
                 and len(dspc[0]["input"]["device_group_union"]) > 1:
             from .hetero import HeteroSession
-            self.hetero = HeteroSession(dspc[0], shares=kwargs.get("hetero_shares"))
+            self.hetero = HeteroSession(dspc[0], shares=hetero_shares)
             dspc = [self.hetero.local_cfg]
         self.ds_parallel_configs = dspc
         self.num_strategy = len(dspc)
         self.cur_strategy_id = 0
+
+    def rebuild(self, ds_parallel_configs, hetero_shares=None, ckpt_dir: Optional[str] = None):
+        """Continue training under strategies that hot switching cannot reach (another device layout per pipeline, a
+        heterogeneous plan, ...): parameters and optimizer states go through a strategy-independent split checkpoint, the
+        graph is rebuilt under the new strategies and the state is re-sharded on load.  Step counters, consumed samples and
+        the loss history carry over.  (the in-process form of the reference's re-plan + restart-from-checkpoint path:
+        python/hetu/rpc/heturpc_elastic_server.py + ModelSaver)"""
+        from ..nn.parallel import HETERO_PARAMS
+        from ..utils.checkpoint import ModelSaver
+        self.build()
+        st = self.trainer_states
+        saver = ModelSaver(ckpt_dir or os.path.join(self.pretrain_config.output_dir, "_rebuild"), save_copies=1)
+        saver.save(st.model, st.optimizer, self.global_step, self.consumed_samples, self.loss_history[-1] if self.loss_history else float("nan"))
+        saver.wait()
+        distributed.global_comm_barrier_rpc()
+        self.trainer_states, self.is_model_built = None, False
+        HETERO_PARAMS.clear()
+        wrapper_cfg = getattr(self.model_wrapper, "model_config", None)
+        if wrapper_cfg is not None and hasattr(wrapper_cfg, "cp_ranks"):
+            wrapper_cfg.cp_ranks = ()
+        self._set_strategies(list(ds_parallel_configs), hetero_shares)
+        self._iter_version = getattr(self, "_iter_version", 0) + 1
+        self.build()
+        st = self.trainer_states
+        loaded = saver.load_latest(st.model, st.optimizer)
+        assert loaded is not None and loaded[0] == self.global_step, "the rebuild checkpoint could not be read back"
+        if hasattr(st.optimizer, "step_count"):
+            st.optimizer.step_count = self.global_step
+            st.optimizer.apply_hyper_parameters()
+        return self
 
     # ------------------------------------------------------------------ build
     def _num_layers(self):
@@ -294,7 +327,7 @@ class Trainer:
         strategies of ds_parallel_configs (HotSPa: e.g. by the step's max sequence length)"""
         cfg = self.pretrain_config
         self.build()
-        it = self.train_data_iterator()
+        it, it_version = self.train_data_iterator(), getattr(self, "_iter_version", 0)
         steps = int(steps if steps is not None else cfg.steps)
         saver = None
         if cfg.save_interval:
@@ -302,6 +335,9 @@ class Trainer:
             saver = ModelSaver(cfg.output_dir, save_interval=cfg.save_interval)
         prof = None
         for _ in range(steps):
+            if it_version != getattr(self, "_iter_version", 0):
+                # the strategy was rebuilt by a callback: the data-parallel sharding of the loader changed with it
+                it, it_version = self.train_data_iterator(), self._iter_version
             batch = next(it)
             sid = int(strategy_schedule(self.global_step)) if strategy_schedule else self.cur_strategy_id
             if sid != self.cur_strategy_id:

@@ -261,3 +261,20 @@ def test_trainer_on_a_heterogeneous_strategy(tmp_path):
     assert sum("INFO" in o and "True" in o for o in outs) == 5
     for a, b in zip(got, ref):
         assert abs(a - b) < 1e-3 * max(1.0, abs(b)), (got, ref)
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("worker,mode,world", [("trainer_rebuild_worker.py", "rebuild", 3), ("malleus_apply_worker.py", "malleus", 4)])
+def test_replanning_a_running_job_keeps_the_loss_curve(tmp_path, worker, mode, world):
+    """Trainer.rebuild (explicit) and MalleusTrainer(auto_apply=True) (straggler report -> plan -> rebuild inside the training
+    loop): the job moves from a homogeneous strategy to a heterogeneous one through a split checkpoint; parameters, Adam states,
+    step counters and the data position carry over, so the 4-step loss curve equals the single-device one"""
+    path = os.path.join(os.path.dirname(__file__), "workers", worker)
+    ok, outs = run_workers(path, 1, ["single"], env_extra={"TRAINER_OUT": str(tmp_path / "single")})
+    assert ok, "\n-----\n".join(outs)
+    ref = _losses(outs)
+    ok, outs = run_workers(path, world, [mode], env_extra={"TRAINER_OUT": str(tmp_path / mode)})
+    assert ok, "\n-----\n".join(outs)
+    got = _losses(outs)
+    for a, b in zip(got, ref):
+        assert abs(a - b) < 1e-3 * max(1.0, abs(b)), (got, ref)
