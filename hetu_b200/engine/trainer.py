@@ -94,7 +94,10 @@ class Trainer:
                 dspc = [convert_strategy(sc, self._num_layers())]
             else:
                 dspc = [convert_strategy(StrategyConfig(dp=max(distributed.world_size(), 1)), self._num_layers())]
-        self._set_strategies(dspc, kwargs.get("hetero_shares"))
+        shares = kwargs.get("hetero_shares")
+        if shares is None and cfg.ds_parallel is not None and getattr(cfg.ds_parallel, "micro_batch_num_list", None):
+            shares = list(cfg.ds_parallel.micro_batch_num_list)
+        self._set_strategies(dspc, shares)
 
     def _set_strategies(self, dspc, hetero_shares=None):
         # heterogeneous strategy (pipelines with different tp / stage counts, e.g. a Malleus plan): this rank trains the

@@ -36,7 +36,12 @@ class StrategyConfig:
     ds_parallel_config_path: Optional[str] = None
     ds_parallel_config_name: Optional[str] = None
     recompute: RecomputeConfig = field(default_factory=RecomputeConfig)
-    hetero_layers: Optional[List[List[int]]] = None
+    hetero: bool = False
+    hetero_layers: Optional[List[List[int]]] = None            # layers per stage, one list per pipeline
+    hetero_tp: Optional[List[int]] = None                      # tensor-parallel degree per pipeline (default: tp)
+    micro_batch_num_list: Optional[List[int]] = None           # micro-batches (= batch share) per pipeline
+    seq_len_list: Optional[List[int]] = None
+    cp_list: Optional[List[int]] = None
     rank_to_device_mapping: Optional[Dict[int, int]] = None
     unused_rank: List[int] = field(default_factory=list)
 
@@ -47,14 +52,17 @@ class StrategyConfig:
 def convert_strategy(strategy: StrategyConfig, num_layers: int) -> dict:
     """StrategyConfig -> ds_parallel_config dict"""
     if strategy.hetero_layers:
-        mapping = strategy.rank_to_device_mapping or {}
+        mapping = {int(k): int(v) for k, v in (strategy.rank_to_device_mapping or {}).items()}
         pipelines, rank = [], 0
-        for stages in strategy.hetero_layers:
-            pl = []
+        for p, stages in enumerate(strategy.hetero_layers):
+            tp = strategy.hetero_tp[p] if strategy.hetero_tp else strategy.tp
+            pl, lo = [], 0
             for nl in stages:
-                devs = [mapping.get(r, r) for r in range(rank, rank + strategy.tp) if r not in strategy.unused_rank]
-                pl.append({"layers": nl, "devices": devs})
-                rank += strategy.tp
+                devs = [mapping.get(r, r) for r in range(rank, rank + tp) if r not in strategy.unused_rank]
+                pl.append({"layers": [lo, lo + int(nl) - 1], "devices": devs})
+                lo += int(nl)
+                rank += tp
+            assert lo == num_layers, f"pipeline {p} covers {lo} layers, the model has {num_layers}"
             pipelines.append({"stages": pl})
         return generate_hetero_ds_parallel_config(num_layers, pipelines, zero=strategy.zero)
     return generate_ds_parallel_config(num_layers, strategy.world(), strategy.dp, strategy.tp, strategy.pp, strategy.cp, zero=strategy.zero)

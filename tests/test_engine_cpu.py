@@ -381,3 +381,26 @@ def test_trainer_writes_chrome_trace_and_records_step_exceptions(tmp_path):
         tr.train(steps=1)
     txt = (tmp_path / "out" / "logs" / "exception.txt").read_text()
     assert "rank 0 step 4" in txt and "injected device failure" in txt
+
+
+def test_strategy_config_hetero_fields_become_a_heterogeneous_ds_config(tmp_path):
+    """YAML `ds_parallel` with hetero_layers / hetero_tp / micro_batch_num_list / rank_to_device_mapping (the reference's hetero
+    experiment configs) -> StrategyConfig -> heterogeneous ds_parallel_config -> HeteroSession pipelines + batch shares"""
+    from hetu_b200.engine import HeteroSession, load_experiment
+    from hetu_b200.utils.parallel import convert_strategy
+    (tmp_path / "exp.yaml").write_text(
+        "ds_parallel:\n  hetero: true\n  tp: 2\n  hetero_layers: [[3, 5], [8]]\n  hetero_tp: [2, 1]\n  micro_batch_num_list: [6, 2]\n"
+        "  rank_to_device_mapping: {0: 0, 1: 1, 2: 2, 3: 3, 4: 7}\n  zero: false\n"
+        "trainer:\n  steps: 2\n  global_load_size: 8\nmodel:\n  n_layer: 8\n")
+    exp = load_experiment(str(tmp_path / "exp.yaml"), ["ds_parallel.micro_batch_num_list=[3, 1]"])
+    sc = exp["strategy"]
+    assert sc.hetero and sc.hetero_layers == [[3, 5], [8]] and sc.micro_batch_num_list == [3, 1] and sc.hetero_tp == [2, 1]
+    cfg = convert_strategy(sc, 8)
+    assert cfg["hetero"] and cfg["blocks"]["blocks2"]["attn"]["qkv"]["device_group_union"] == [[0, 1], [7]]
+    assert cfg["blocks"]["blocks3"]["attn"]["qkv"]["device_group_union"] == [[2, 3], [7]]
+    assert cfg["blocks"]["blocks3"]["attn"]["qkv"]["split"] == {"0": [2, 1]}
+    s = HeteroSession(cfg, rank=7, shares=sc.micro_batch_num_list)
+    assert s.pipelines == [[[0, 1], [2, 3]], [[7]]] and s.pipeline == 1 and s.split_batch(8) == [6, 2]
+    with pytest.raises(AssertionError, match="covers"):
+        sc.hetero_layers = [[3, 4], [8]]
+        convert_strategy(sc, 8)
