@@ -17,22 +17,20 @@ class ModelWrapperFromConfig:
     """{"type": "gpt" | "llama" | "moe", **config fields}"""
 
     def __init__(self, config: Dict[str, Any]):
+        from .. import models
         self.config = dict(config)
+        cfg = dict(self.config)
+        self.kind = cfg.pop("type", "gpt").lower()
+        table = {"gpt": (models.GPTConfig, models.GPTLMHeadModel), "llama": (models.LlamaConfig, models.LlamaLMHeadModel),
+                 "moe": (models.MoEConfig, models.GPTMoELMHeadModel), "gpt_moe": (models.MoEConfig, models.GPTMoELMHeadModel)}
+        if self.kind not in table:
+            raise ValueError(f"unknown model type {self.kind}")
+        cfg_cls, self.model_class = table[self.kind]
+        # the config object exists before the model: the Trainer adjusts it (e.g. the context-parallel ring) prior to building
+        self.model_config = cfg_cls(**cfg)
 
     def create_model(self, ds_parallel_configs):
-        from .. import models
-        cfg = dict(self.config)
-        kind = cfg.pop("type", "gpt").lower()
-        if kind == "gpt":
-            self.model_config = models.GPTConfig(**cfg)
-            return models.GPTLMHeadModel(self.model_config, ds_parallel_configs)
-        if kind == "llama":
-            self.model_config = models.LlamaConfig(**cfg)
-            return models.LlamaLMHeadModel(self.model_config, ds_parallel_configs)
-        if kind in ("moe", "gpt_moe"):
-            self.model_config = models.MoEConfig(**cfg)
-            return models.MoELMHeadModel(self.model_config, ds_parallel_configs)
-        raise ValueError(f"unknown model type {kind}")
+        return self.model_class(self.model_config, ds_parallel_configs)
 
 
 class OptimizerWrapper:

@@ -404,3 +404,23 @@ def test_strategy_config_hetero_fields_become_a_heterogeneous_ds_config(tmp_path
     with pytest.raises(AssertionError, match="covers"):
         sc.hetero_layers = [[3, 4], [8]]
         convert_strategy(sc, 8)
+
+
+def test_pretrain_yaml_configs_load_and_train():
+    """every experiment YAML under examples/pretrain/config parses into trainer / strategy / model sections; the context-
+    parallel one trains through `build_trainer` on one process with cp overridden to 1"""
+    import glob
+    from hetu_b200.engine import build_trainer, load_experiment
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "pretrain", "config")
+    files = sorted(glob.glob(os.path.join(root, "*.yaml")))
+    assert {os.path.basename(f) for f in files} >= {"gpt_small_dp2_tp2.yaml", "llama_pack_tp.yaml", "llama_pad_cp.yaml", "gpt_hetero.yaml"}
+    for f in files:
+        exp = load_experiment(f)
+        assert exp["model"]["type"] in ("gpt", "llama") and exp["trainer"].steps > 0 and exp["strategy"] is not None
+    assert load_experiment(os.path.join(root, "gpt_hetero.yaml"))["strategy"].micro_batch_num_list == [3, 1]
+    assert load_experiment(os.path.join(root, "llama_pad_cp.yaml"))["strategy"].cp == 2
+    ht.init_comm_group(1)
+    tr = build_trainer(os.path.join(root, "llama_pad_cp.yaml"), ["ds_parallel.cp=1", "trainer.steps=2", "trainer.log_interval=0"],
+                       train_dataset=SyntheticDataset(32, 259, 64, seed=0, length_distribution="fixed"))
+    losses = tr.train()
+    assert len(losses) == 2 and all(np.isfinite(losses)) and tr.model_wrapper.model_config.num_key_value_heads == 2
