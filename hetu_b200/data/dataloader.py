@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import queue
 import threading
-from typing import Iterator, List, Optional, Sequence
+from typing import Iterator, List
 
 import numpy as np
 import torch

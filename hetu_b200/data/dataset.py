@@ -2,8 +2,7 @@
 from __future__ import annotations
 
 import json
-import os
-from typing import Callable, List, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 

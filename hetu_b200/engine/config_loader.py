@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import copy
 import dataclasses
-from typing import Any, Dict, List, Optional, Sequence, Tuple
+from typing import Any, Dict, Sequence
 
 import yaml
 

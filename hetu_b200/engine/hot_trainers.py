@@ -7,7 +7,6 @@ from __future__ import annotations
 
 from typing import Callable, Dict, List, Optional, Sequence
 
-import numpy as np
 
 from .straggler import Straggler
 from .strategy import StrategyModel, TrainerCtxs, TrainerStrategyArgs

@@ -7,9 +7,8 @@ model; here the same objective is solved with an exact DP over sorted sequences 
 search heuristic in general, which needs no solver package.)"""
 from __future__ import annotations
 
-import bisect
-from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence, Tuple
+from dataclasses import dataclass
+from typing import Dict, List, Sequence, Tuple
 
 
 @dataclass

@@ -7,7 +7,6 @@ solve_pp_arrangement; engine/utils.py TrainerCtxs/TrainerStrategyArgs)
 """
 from __future__ import annotations
 
-import itertools
 import math
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple

@@ -7,8 +7,8 @@ from __future__ import annotations
 import json
 import os
 import time
-from dataclasses import dataclass, field
-from typing import Callable, Dict, List, Optional, Sequence
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence
 
 import numpy as np
 import torch
@@ -19,7 +19,7 @@ from ..data import Bucket, build_data_loader, build_tokenizer
 from ..utils.parallel import StrategyConfig, convert_strategy, parse_multi_ds_parallel_config, read_ds_parallel_config
 from .data_collator import DataCollatorForLanguageModel
 from .trainer_config import DataLoadLevel, TrainingConfig
-from .wrapper import ModelWrapper, ModelWrapperFromConfig, OptimizerWrapper
+from .wrapper import ModelWrapperFromConfig, OptimizerWrapper
 
 
 @dataclass

@@ -4,12 +4,11 @@ split into `p / c` row blocks, every block is replicated `c` times, each replica
 feature rows and the partial products are summed inside the replica group."""
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import List, Tuple
 
 import numpy as np
 
 from .. import ops
-from ..core import from_numpy
 from ..nn import Linear, Module, ModuleList
 
 

@@ -5,7 +5,7 @@ parallel modules; activations are kept as [tokens, hidden] so that sequence para
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Optional
 
 from ... import ops

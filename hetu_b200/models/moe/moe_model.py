@@ -7,12 +7,11 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass
-from typing import List, Optional, Sequence
+from typing import Sequence
 
-import torch
 
 from ... import ops
-from ...core import (from_numpy, normal_initializer, parallel_parameter, zeros_initializer)
+from ...core import normal_initializer, parallel_parameter, zeros_initializer
 from ...nn import Module, ModuleList
 from ..gpt.gpt_model import GPTConfig
 

@@ -10,7 +10,7 @@ from typing import Dict, Iterator, List, Optional, Tuple
 
 import torch
 
-from ..core import Tensor, _graphs_by_id, cur_graph, subgraph
+from ..core import Tensor, _graphs_by_id, subgraph
 
 
 class Module:

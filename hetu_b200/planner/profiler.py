@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import json
 import time
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, Optional, Sequence
 
 import torch
 

@@ -7,7 +7,7 @@ different TP degree (the parallel modules insert the re-sharding comm op where t
 from __future__ import annotations
 
 import json
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, List, Sequence
 
 from .cost_model import Strategy
 from .search_engine import galvatron_plan_to_ds_parallel_config

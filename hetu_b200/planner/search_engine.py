@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import json
 import math
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence
 
 from .. import _C
 from .cost_model import HardwareProfile, LayerProfile, MemoryCostModel, Strategy, TimeCostModel

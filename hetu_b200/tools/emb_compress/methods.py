@@ -1,12 +1,12 @@
 from __future__ import annotations
 
 import math
-from typing import Optional, Sequence
+from typing import Sequence
 
 import numpy as np
 
 from ... import ops
-from ...core import constant_initializer, from_numpy, normal_initializer, ones_initializer, parallel_parameter, uniform_initializer, zeros_initializer
+from ...core import constant_initializer, from_numpy, normal_initializer, ones_initializer, parallel_parameter, zeros_initializer
 from ...nn import Linear, Module, ModuleList
 
 

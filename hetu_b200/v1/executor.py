@@ -4,13 +4,13 @@ over the process group), 'PS' (all parameters on the parameter server), 'Hybrid'
 PS with the HET cache).  (ref: hetu/v1/python/hetu/gpu_ops/executor.py Executor/SubExecutor/HetuConfig)"""
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, Optional
 
 import numpy as np
 import torch
 
 from .. import core, ops
-from ..core import Tensor, from_numpy
+from ..core import Tensor
 
 
 class _Ctx:

@@ -4,7 +4,7 @@ sequence,concatenate,sum,slice,pooling,attention,loss}.py; the MoE layers / gate
 from __future__ import annotations
 
 import math
-from typing import Callable, Optional, Sequence
+from typing import Callable, Sequence
 
 from .. import ops
 from . import initializers as init

@@ -5,7 +5,7 @@ import numpy as np
 
 import hetu_b200 as ht
 from hetu_b200 import _C
-from hetu_b200.planner import GalvatronSearchEngine, HardwareProfile, LayerProfile, galvatron_plan_to_ds_parallel_config
+from hetu_b200.planner import GalvatronSearchEngine, LayerProfile, galvatron_plan_to_ds_parallel_config
 
 
 def test_dp_core_matches_brute_force():

@@ -1,5 +1,4 @@
 """Native runtime pieces (C++): caching memory pool, random-state bookkeeping, prefetching data loader, stream roles."""
-import numpy as np
 import torch
 
 from hetu_b200 import _C

@@ -1,6 +1,5 @@
 """worker process of a parameter-server job started by the heturun-style launcher: BSP linear regression through the remote
 parameter store (dense push / pull, barrier), a sparse table with the HET cache, SSP clocks and partial reduce"""
-import os
 
 import numpy as np
 

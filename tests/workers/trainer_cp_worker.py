@@ -9,7 +9,6 @@ from hetu_b200 import distributed
 from hetu_b200.data import ByteTokenizer, SyntheticDataset
 from hetu_b200.engine import ModelWrapper, OptimizerWrapper, Trainer, TrainingConfig
 from hetu_b200.models import LlamaConfig, LlamaLMHeadModel, generate_ds_parallel_config
-from hetu_b200.utils.parallel import StrategyConfig
 
 dp, cp, tp = (int(v) for v in sys.argv[1:4])
 world = dp * cp * tp
