@@ -213,3 +213,32 @@ class SoftmaxCrossEntropySparse(_Loss):
 
     def forward(self, logits, labels):
         return ops.softmax_cross_entropy_sparse(logits, labels, self.ignored_index, self.reduction)
+
+
+class NewGeLU(Module):
+    """tanh approximation used by GPT-2 (ref: nn/modules/activation.py NewGeLU)"""
+
+    def forward(self, x):
+        c = 0.7978845608028654   # sqrt(2 / pi)
+        return x * 0.5 * (ops.tanh((x + ops.pow(x, 3.0) * 0.044715) * c) + 1.0)
+
+
+class ConstantPad2d(Module):
+    """pad the last two dimensions: padding = int or (left, right, top, bottom) (ref: nn/modules/padding.py)"""
+
+    def __init__(self, padding, value: float = 0.0):
+        super().__init__()
+        self.padding = [int(padding)] * 4 if isinstance(padding, int) else [int(p) for p in padding]
+        assert len(self.padding) == 4
+        self.value = float(value)
+
+    def forward(self, x):
+        return ops.pad(x, self.padding, "constant", self.value)
+
+
+class ZeroPad2d(ConstantPad2d):
+    def __init__(self, padding):
+        super().__init__(padding, 0.0)
+
+
+__all__ += ["NewGeLU", "ConstantPad2d", "ZeroPad2d"]

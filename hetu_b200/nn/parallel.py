@@ -457,3 +457,33 @@ class ParallelLayerNorm(HtMultiParallelLayerNorm):
     def __init__(self, normalized_shape, device_group, dp=None, eps=1e-5, dtype="float32", name="ln"):
         ids = device_group.indices()
         super().__init__(normalized_shape, _one(device_group, dp or len(ids)), eps=eps, dtype=dtype, name=name)
+
+
+# ----------------------------------------------------------------------------- single-config DS modules (hetu.nn.parallel_ds)
+def _single(cls):
+    """Ht<X> takes ONE ds_parallel_config dict where HtMulti<X> takes the list of all strategies
+    (ref: python/hetu/nn/modules/parallel_ds.py)"""
+    pos = list(cls.__init__.__code__.co_varnames[:cls.__init__.__code__.co_argcount])
+    idx = pos.index("multi_ds_parallel_config") - 1
+
+    class _One(cls):
+        def __init__(self, *a, **k):
+            if "ds_parallel_config" in k:
+                k["multi_ds_parallel_config"] = [k.pop("ds_parallel_config")]
+            elif len(a) > idx and isinstance(a[idx], dict):
+                a = list(a)
+                a[idx] = [a[idx]]
+            super().__init__(*a, **k)
+    _One.__name__ = _One.__qualname__ = cls.__name__.replace("HtMulti", "Ht")
+    return _One
+
+
+HtParallelRMSNorm = _single(HtMultiParallelRMSNorm)
+HtParallelLayerNorm = _single(HtMultiParallelLayerNorm)
+HtParallelEmbedding = _single(HtMultiParallelEmbedding)
+HtVocabParallelEmbedding = _single(HtMultiVocabParallelEmbedding)
+HtColumnParallelLinear = _single(HtMultiColumnParallelLinear)
+HtRowParallelLinear = _single(HtMultiRowParallelLinear)
+
+__all__ += ["HtParallelRMSNorm", "HtParallelLayerNorm", "HtParallelEmbedding", "HtVocabParallelEmbedding", "HtColumnParallelLinear",
+            "HtRowParallelLinear", "HETERO_PARAMS", "hetero_grad_sync_spec", "precreate_hetero_groups", "all_hetero_groups"]

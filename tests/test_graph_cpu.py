@@ -215,3 +215,23 @@ def test_lr_and_weight_decay_schedules_reach_the_update_ops():
     assert [ex.step() for _ in range(3)] == [1.0, 0.5, 0.25]
     rp = ReduceOnPlateauScheduler(1.0, factor=0.5, patience=1)
     assert [rp.step(x) for x in (1.0, 0.9, 0.9, 0.9, 0.9, 0.9)] == [1.0, 1.0, 1.0, 0.5, 0.5, 0.25]
+
+
+def test_extra_nn_modules_pad_newgelu_single_config_parallel():
+    from hetu_b200.models.parallel_config import generate_ds_parallel_config
+    x = torch.randn(2, 3, 4, 5)
+    y = ht.nn.ConstantPad2d((1, 2, 0, 3), 1.5)(ht.from_numpy(x))
+    assert torch.equal(torch.as_tensor(y.numpy()), torch.nn.functional.pad(x, (1, 2, 0, 3), value=1.5))
+    assert torch.equal(torch.as_tensor(ht.nn.ZeroPad2d(2)(ht.from_numpy(x)).numpy()), torch.nn.functional.pad(x, (2, 2, 2, 2)))
+    g = ht.nn.NewGeLU()(ht.from_numpy(x))
+    assert torch.allclose(torch.as_tensor(g.numpy()), torch.nn.functional.gelu(x, approximate="tanh"), atol=1e-6)
+    cfg = generate_ds_parallel_config(2, 1, 1, 1, 1, zero=False)
+    blk = cfg["blocks"]["blocks0-1"]
+    with ht.graph("define_and_run", create_new=True) as gph:
+        col = ht.nn.HtColumnParallelLinear(8, 16, blk["mlp"]["dense_h_to_4h"], gather_output=False, name="c1")
+        row = ht.nn.HtRowParallelLinear(16, 8, ds_parallel_config=blk["mlp"]["dense_4h_to_h"], name="r1")
+        ln = ht.nn.HtParallelLayerNorm(8, blk["layernorm1"], name="l1")
+        inp = ht.placeholder("float32", [4, 8], name="inp")
+        out = row(col(ln(inp)))
+        res = gph.run(None, [out], {inp: torch.randn(4, 8)})[0]
+    assert tuple(res.shape) == (4, 8) and type(col).__name__ == "HtColumnParallelLinear" and isinstance(col, ht.nn.HtMultiColumnParallelLinear)
