@@ -12,6 +12,7 @@ from . import ops  # noqa: F401
 from .graph_api import gradients, run_graph  # noqa: F401
 from .optim import AdamOptimizer, SGDOptimizer, GradScaler  # noqa: F401
 from . import nn  # noqa: F401
+from . import logger  # noqa: F401  (module: hetu.logger.info(...), hetu.logger.get_logger(name))
 from .distributed import (init_comm_group, local_device, global_device_group, global_comm_barrier_rpc,  # noqa: F401
                           global_comm_barrier_mpi, map_to_local_data)
 

@@ -1,4 +1,5 @@
 """Galvatron planner: C++ DP core vs brute force, memory-pressure behaviour of the search, plan emission."""
+import pytest
 import itertools
 
 import numpy as np
@@ -60,3 +61,34 @@ def test_hetu_alias_package():
     from hetu.utils.parallel import read_ds_parallel_config   # noqa: F401
     import hetu.nn as nn
     assert hetu.AdamOptimizer is ht.AdamOptimizer and nn.Module is ht.nn.Module
+
+
+def test_reference_module_paths_resolve_under_the_hetu_alias():
+    """a user of the reference keeps their imports: every module path of python/hetu resolves (to the same module objects as
+    hetu_b200.*) through the alias hook"""
+    import importlib
+    paths = ["hetu.logger", "hetu.context", "hetu.nn.parallel", "hetu.optim", "hetu.data.data_collator", "hetu.data.bucket", "hetu.data.dataloader",
+             "hetu.data.dataset", "hetu.data.utils", "hetu.data.messages.message_template", "hetu.data.messages.prompt_template",
+             "hetu.data.tokenizers.gpt2_tokenizer", "hetu.data.tokenizers.hf_tokenizer", "hetu.data.tokenizers.sentencepiece_tokenizer",
+             "hetu.data.tokenizers.tiktoken_tokenizer", "hetu.data.tokenizers.tokenizer", "hetu.utils.common_utils", "hetu.utils.file_utils",
+             "hetu.utils.data.dataloader", "hetu.utils.parallel.distributed", "hetu.utils.parallel.ds_config", "hetu.utils.parallel.generate_ds",
+             "hetu.utils.parallel.read_ds", "hetu.utils.checkpoint.ht_safetensors", "hetu.utils.checkpoint.model_saver",
+             "hetu.utils.checkpoint.load_checkpoint", "hetu.utils.checkpoint.save_checkpoint", "hetu.engine.trainer", "hetu.engine.trainer_config",
+             "hetu.engine.sft_trainer", "hetu.engine.wrapper", "hetu.engine.parallel_config", "hetu.engine.straggler", "hetu.engine.strategy",
+             "hetu.models.gpt.gpt_model", "hetu.models.gpt.gpt_config", "hetu.models.gpt.gpt_tokenizer", "hetu.models.gpt.generate_gpt_4d_config",
+             "hetu.models.gpt.generate_gpt_hetero_4d_config", "hetu.models.llama.llama_model", "hetu.models.llama.llama_config",
+             "hetu.models.llama.llama_tokenizer", "hetu.models.llama.generate_llama_4d_config", "hetu.models.llama.generate_llama_hetero_4d_config",
+             "hetu.models.utils.converter.convert_llama_hf_to_ht", "hetu.peft.lora.layer", "hetu.peft.lora.model", "hetu.peft.lora.config",
+             "hetu.rpc.pssh_start", "hetu.rpc.pssh_start_config", "hetu.rpc.pssh_start_elastic", "hetu.rpc.local_start", "hetu.rpc.pssh_workers",
+             "hetu.rpc.elastic_arg_parser", "hetu.rpc.kv_store", "hetu.rpc.heturpc_elastic_server", "hetu.rpc.heturpc_polling_server",
+             "hetu.rpc.heturpc_async_server"]
+    for p in paths:
+        m = importlib.import_module(p)
+        assert m is importlib.import_module("hetu_b200." + p[len("hetu."):]), p
+    import hetu
+    from hetu.engine.parallel_config import config_spread_zero
+    from hetu.utils.parallel.ds_config import StrategyConfig
+    assert config_spread_zero({"zero": True, "w": {"type": "variable"}})["w"]["zero"] is True and StrategyConfig().world() == 1
+    assert hetu.logger is importlib.import_module("hetu_b200").logger and callable(hetu.logger.info)
+    with pytest.raises(ModuleNotFoundError):
+        importlib.import_module("hetu.no_such_module")
