@@ -308,6 +308,45 @@ static void merge_piece(at::Tensor& o, at::Tensor& lse, const AttnPiece& p) {
   o = o * w0 + p.o.to(at::kFloat) * w1;
   lse = nl;
 }
+// ---- variable-length (packed) rows under context parallelism: `cu` holds the document boundaries in the coordinates of
+// the whole row (length cs * number of chunks).  A (query chunk, key chunk) block decomposes into one sub-block per
+// document that intersects both chunks: the same document inside the diagonal block is causal, a document spanning an
+// earlier key chunk is fully visible, everything else is masked (ref: AttnInfo / valid_cu_seqlens, ParallelAttention.cc:125-330)
+struct DocPiece { int64_t q_off, q_len, k_off, k_len; bool causal; };
+static std::vector<int64_t> host_boundaries(const at::Tensor& cu, int64_t row_len) {
+  at::Tensor h = cu.to(at::kCPU, at::kLong).contiguous();
+  std::vector<int64_t> v(h.data_ptr<int64_t>(), h.data_ptr<int64_t>() + h.numel());
+  std::vector<int64_t> out;
+  for (int64_t b : v) {
+    b = std::min(b, row_len);
+    if (out.empty() || b > out.back()) out.push_back(b);
+  }
+  if (out.empty() || out.front() != 0) out.insert(out.begin(), 0);
+  if (out.back() != row_len) out.push_back(row_len);
+  return out;
+}
+static std::vector<DocPiece> doc_pieces(const std::vector<int64_t>& cu, int qpos, int kpos, int64_t cs, bool causal) {
+  std::vector<DocPiece> out;
+  const int64_t q_lo = qpos * cs, q_hi = q_lo + cs, k_lo = kpos * cs, k_hi = k_lo + cs;
+  for (size_t d = 0; d + 1 < cu.size(); ++d) {
+    const int64_t qa = std::max(q_lo, cu[d]), qb = std::min(q_hi, cu[d + 1]);
+    const int64_t ka = std::max(k_lo, cu[d]), kb = std::min(k_hi, cu[d + 1]);
+    if (qa >= qb || ka >= kb) continue;
+    out.push_back({qa - q_lo, qb - qa, ka - k_lo, kb - ka, causal && qpos == kpos});
+  }
+  return out;
+}
+// merge a partial result into rows [off, off + len) of the accumulators (o [B,cs,H,D] fp32, lse [B,H,cs], -inf = empty)
+static void merge_rows(at::Tensor& o, at::Tensor& lse, int64_t off, int64_t len, const AttnPiece& p) {
+  at::Tensor osub = o.narrow(1, off, len), lsub = lse.narrow(2, off, len);
+  at::Tensor nl = at::logaddexp(lsub, p.lse);
+  at::Tensor w0 = at::exp(lsub - nl).permute({0, 2, 1}).unsqueeze(-1);
+  at::Tensor w1 = at::exp(p.lse - nl).permute({0, 2, 1}).unsqueeze(-1);
+  w0 = at::where(at::isfinite(w0), w0, at::zeros_like(w0));
+  w1 = at::where(at::isfinite(w1), w1, at::zeros_like(w1));
+  osub.copy_(osub * w0 + p.o.to(at::kFloat) * w1);
+  lsub.copy_(nl);
+}
 // position of this rank's chunks: SYM -> two half-chunks (i, 2c-1-i); NORMAL -> one chunk i
 static std::vector<int> owned_chunks(int idx, int c, bool sym) {
   if (sym) return {idx, 2 * c - 1 - idx};
@@ -324,9 +363,18 @@ static Ts parallel_attn_compute(const OpDef& op, const Ts& in, RunCtx*) {
   std::vector<int> ranks = cp_ranks(op);
   auto& comm = CommRuntime::get();
   const int c = (int)ranks.size();
+  const bool varlen = in.size() > 3 && in[3].defined();
   if (c <= 1 || !comm.initialized()) {
-    AttnPiece p = local_attn(q, k, v, scale, causal);
-    return {p.o, p.lse};
+    if (!varlen) {
+      AttnPiece p = local_attn(q, k, v, scale, causal);
+      return {p.o, p.lse};
+    }
+    const std::vector<int64_t> cu1 = host_boundaries(in[3], q.size(1));
+    at::Tensor o1 = at::zeros(q.sizes(), fopt), l1 = at::full({q.size(0), q.size(2), q.size(1)}, -INFINITY, fopt);
+    for (auto& pc : doc_pieces(cu1, 0, 0, q.size(1), causal))
+      merge_rows(o1, l1, pc.q_off, pc.q_len, local_attn(q.narrow(1, pc.q_off, pc.q_len), k.narrow(1, pc.k_off, pc.k_len),
+                                                        v.narrow(1, pc.k_off, pc.k_len), scale, pc.causal));
+    return {o1.to(q.scalar_type()), l1};
   }
   int idx = 0;
   for (int i = 0; i < c; ++i) if (ranks[i] == comm.rank()) idx = i;
@@ -336,7 +384,14 @@ static Ts parallel_attn_compute(const OpDef& op, const Ts& in, RunCtx*) {
   HB_CHECK(S % nchunk == 0) << "sequence chunk not divisible for the SYM split";
   const int64_t cs = S / nchunk;
   auto my_chunks = owned_chunks(idx, c, sym);
+  std::vector<int64_t> cu;
+  if (varlen) cu = host_boundaries(in[3], cs * nchunk * c);
   std::vector<at::Tensor> o_acc(nchunk), lse_acc(nchunk);
+  if (varlen)
+    for (int qi = 0; qi < nchunk; ++qi) {
+      o_acc[qi] = at::zeros({q.size(0), cs, q.size(2), q.size(3)}, fopt);
+      lse_acc[qi] = at::full({q.size(0), q.size(2), cs}, -INFINITY, fopt);
+    }
   at::Tensor kv_cur = at::stack({k, v}).contiguous();
   const int next = ranks[(idx + 1) % c], prev = ranks[(idx - 1 + c) % c];
   // HETU_PARALLEL_ATTN=ANALYSIS: per ring round, attention time, blocks computed / skipped by the causal mask and the KV
@@ -367,6 +422,14 @@ static Ts parallel_attn_compute(const OpDef& op, const Ts& in, RunCtx*) {
         const int qpos = my_chunks[qi], kpos = src_chunks[ki];
         if (causal && kpos > qpos) { ++skipped; continue; }  // fully masked block: skipped
         at::Tensor kc = kv_cur[0].narrow(1, ki * cs, cs), vc = kv_cur[1].narrow(1, ki * cs, cs);
+        if (varlen) {
+          auto pieces = doc_pieces(cu, qpos, kpos, cs, causal);
+          for (auto& pc : pieces)
+            merge_rows(o_acc[qi], lse_acc[qi], pc.q_off, pc.q_len,
+                       local_attn(qc.narrow(1, pc.q_off, pc.q_len), kc.narrow(1, pc.k_off, pc.k_len), vc.narrow(1, pc.k_off, pc.k_len), scale, pc.causal));
+          if (pieces.empty()) ++skipped; else ++blocks;
+          continue;
+        }
         AttnPiece p = local_attn(qc, kc, vc, scale, causal && kpos == qpos);
         merge_piece(o_acc[qi], lse_acc[qi], p);
         ++blocks;
@@ -418,7 +481,20 @@ static Ts parallel_attn_bwd_compute(const OpDef& op, const Ts& in, RunCtx*) {
   std::vector<int> ranks = cp_ranks(op);
   auto& comm = CommRuntime::get();
   const int c = (int)ranks.size();
-  if (c <= 1 || !comm.initialized()) return run_bwd(d_o, q, k, v, o, lse, causal);
+  const bool varlen = in.size() > 6 && in[6].defined();
+  if (c <= 1 || !comm.initialized()) {
+    if (!varlen) return run_bwd(d_o, q, k, v, o, lse, causal);
+    const std::vector<int64_t> cu1 = host_boundaries(in[6], q.size(1));
+    at::Tensor dq1 = at::zeros(q.sizes(), q.options().dtype(at::kFloat)), dk1 = at::zeros_like(k, at::kFloat), dv1 = at::zeros_like(v, at::kFloat);
+    for (auto& pc : doc_pieces(cu1, 0, 0, q.size(1), causal)) {
+      auto r = run_bwd(d_o.narrow(1, pc.q_off, pc.q_len), q.narrow(1, pc.q_off, pc.q_len), k.narrow(1, pc.k_off, pc.k_len),
+                       v.narrow(1, pc.k_off, pc.k_len), o.narrow(1, pc.q_off, pc.q_len), lse.narrow(2, pc.q_off, pc.q_len), pc.causal);
+      dq1.narrow(1, pc.q_off, pc.q_len).add_(r[0].to(at::kFloat));
+      dk1.narrow(1, pc.k_off, pc.k_len).add_(r[1].to(at::kFloat));
+      dv1.narrow(1, pc.k_off, pc.k_len).add_(r[2].to(at::kFloat));
+    }
+    return {dq1.to(q.scalar_type()), dk1.to(k.scalar_type()), dv1.to(v.scalar_type())};
+  }
   int idx = 0;
   for (int i = 0; i < c; ++i) if (ranks[i] == comm.rank()) idx = i;
   const bool sym = causal && op.attrs.s("split_pattern", env_str("HETU_PARALLEL_ATTN_SPLIT_PATTERN", "SYM")) == "SYM";
@@ -426,6 +502,8 @@ static Ts parallel_attn_bwd_compute(const OpDef& op, const Ts& in, RunCtx*) {
   const int nchunk = sym ? 2 : 1;
   const int64_t cs = S / nchunk;
   auto my_chunks = owned_chunks(idx, c, sym);
+  std::vector<int64_t> cu;
+  if (varlen) cu = host_boundaries(in[6], cs * nchunk * c);
   at::Tensor dq = at::zeros(q.sizes(), q.options().dtype(at::kFloat));
   // the travelling buffer carries [k, v, dk, dv] so gradients return to the owner after a full loop
   at::Tensor buf = at::stack({k.to(at::kFloat), v.to(at::kFloat), at::zeros_like(k, at::kFloat), at::zeros_like(v, at::kFloat)}).contiguous();
@@ -438,6 +516,17 @@ static Ts parallel_attn_bwd_compute(const OpDef& op, const Ts& in, RunCtx*) {
       for (int ki = 0; ki < nchunk; ++ki) {
         const int qpos = my_chunks[qi], kpos = src_chunks[ki];
         if (causal && kpos > qpos) continue;
+        if (varlen) {
+          for (auto& pc : doc_pieces(cu, qpos, kpos, cs, causal)) {
+            const int64_t qo = qi * cs + pc.q_off, ko = ki * cs + pc.k_off;
+            auto r = run_bwd(d_o.narrow(1, qo, pc.q_len), q.narrow(1, qo, pc.q_len), kb.narrow(1, ko, pc.k_len), vb.narrow(1, ko, pc.k_len),
+                             o.narrow(1, qo, pc.q_len), lse.narrow(2, qo, pc.q_len), pc.causal);
+            dq.narrow(1, qo, pc.q_len).add_(r[0].to(at::kFloat));
+            buf[2].narrow(1, ko, pc.k_len).add_(r[1].to(at::kFloat));
+            buf[3].narrow(1, ko, pc.k_len).add_(r[2].to(at::kFloat));
+          }
+          continue;
+        }
         // the local kernel recomputes P from the *global* lse of the query rows, so per-block calls compose
         auto r = run_bwd(d_o.narrow(1, qi * cs, cs), q.narrow(1, qi * cs, cs), kb.narrow(1, ki * cs, cs), vb.narrow(1, ki * cs, cs),
                          o.narrow(1, qi * cs, cs), lse.narrow(2, qi * cs, cs), causal && kpos == qpos);
@@ -455,7 +544,10 @@ static Ts parallel_attn_bwd_compute(const OpDef& op, const Ts& in, RunCtx*) {
   return {dq.to(q.scalar_type()), buf[2].to(k.scalar_type()), buf[3].to(v.scalar_type())};
 }
 static TensorList parallel_attn_grad(OpDef& op, const TensorList& g) {
-  TensorList r = op.graph->make_op("parallel_attn_bwd", {g[0], op.inputs[0], op.inputs[1], op.inputs[2], op.outputs[0], op.outputs[1]}, op.attrs);
+  TensorList ins = {g[0], op.inputs[0], op.inputs[1], op.inputs[2], op.outputs[0], op.outputs[1]};
+  if (op.inputs.size() > 3) ins.push_back(op.inputs[3]);          // cu_seqlens of a packed row
+  TensorList r = op.graph->make_op("parallel_attn_bwd", ins, op.attrs);
+  if (op.inputs.size() > 3) return {r[0], r[1], r[2], nullptr};
   return {r[0], r[1], r[2]};
 }
 static void pattn_deduce(OpDef& op, size_t s) { copy_out_ds(op, 0, s, op.inputs[0]); }

@@ -202,8 +202,6 @@ class Trainer:
             st.seq_len_symbol = IntSymbol(seq)
             cp = _cp_degree(self.ds_parallel_configs[0])
             if cp > 1:
-                if cfg.packing:
-                    raise ValueError("context parallelism in the Trainer needs packing=False (use data.bucket.generate_cp_pack_data for packed CP feeds)")
                 mc = getattr(self.model_wrapper, "model_config", None) or getattr(self.model_wrapper, "config", None)
                 if mc is None or not hasattr(mc, "cp_ranks"):
                     raise ValueError("this model has no context-parallel attention path (config.cp_ranks)")
@@ -249,7 +247,9 @@ class Trainer:
             # pack labels with the identical assignment: re-pack (input, label) jointly
             rows = _pack_pairs([batch[i] for i in order], max_len, pad_id, cfg.pack_alignment)
             width = max(len(r[0]) for r in rows)
-            width = (width + cfg.pack_alignment - 1) // cfg.pack_alignment * cfg.pack_alignment
+            cp = _cp_degree(self.ds_parallel_configs[strategy_id])
+            unit = cfg.pack_alignment if cp == 1 else int(np.lcm(cfg.pack_alignment, 2 * cp))     # CP: 2 * cp equal chunks per row
+            width = (width + unit - 1) // unit * unit
             feeds_cu = []
             for toks, lab, pos, cu in rows:
                 n = len(toks)
@@ -259,6 +259,12 @@ class Trainer:
                 cu = list(cu[: self.max_docs_per_row]) + [width]          # the padding tail is one more (label-masked) document
                 feeds_cu.append(np.asarray(cu + [width] * (self.max_docs_per_row + 1 - len(cu)), np.int32))
             seq = width
+            if cp > 1:
+                # every ring member keeps its SYM chunks of each packed row; cu_seqlens stay in whole-row coordinates (the
+                # ring attention masks documents across chunk and rank borders)
+                cols = cp_rows(width, cp, self._cp_index_and_ring(strategy_id)[0])
+                feeds_i, feeds_l, feeds_p = [a[cols] for a in feeds_i], [a[cols] for a in feeds_l], [a[cols] for a in feeds_p]
+                seq = len(cols)
             stats = {"real_tokens": int(sum(len(x) for x, _ in batch)), "fed_tokens": int(width * len(rows)), "rows": len(rows_i)}
         else:
             mbs = int(cfg.micro_batch_size or len(batch))

@@ -88,7 +88,7 @@ class LlamaAttention(Module):
             q = ops.reshape(q, [-1, s, hq, d])
             k = ops.reshape(k, [-1, s, hkv, d])
             v = ops.reshape(v, [-1, s, hkv, d])
-            a = ops.parallel_attn(q, k, v, self.config.cp_ranks, is_causal=True)
+            a = ops.parallel_attn(q, k, v, self.config.cp_ranks, is_causal=True, cu_seqlens=cu_seqlens)   # packed rows: per-document masks
             sym(a, [-1, s, hq, d])
             a = ops.reshape(a, [-1, hq * d])
         else:

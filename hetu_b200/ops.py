@@ -431,9 +431,11 @@ def attn_varlen(q, k, v, cu_seqlens_q, cu_seqlens_k=None, max_seqlen_q=None, max
     return reshape(o, [t, h, d])
 
 
-def parallel_attn(q, k, v, ranks, is_causal=True, softmax_scale=-1.0, split_pattern="SYM", **kw):
-    """Context-parallel attention over the ring `ranks` (ref: hetu.parallel_attn / ParallelAttentionOp)."""
-    outs = make_op("parallel_attn", [q, k, v],
+def parallel_attn(q, k, v, ranks, is_causal=True, softmax_scale=-1.0, split_pattern="SYM", cu_seqlens=None, **kw):
+    """Context-parallel attention over the ring `ranks` (ref: hetu.parallel_attn / ParallelAttentionOp).
+    cu_seqlens (int tensor [n + 1], boundaries in the coordinates of the WHOLE row = local length x ring size) makes it
+    variable-length attention over packed rows: every document attends only to itself, across chunk and rank borders."""
+    outs = make_op("parallel_attn", [q, k, v] if cu_seqlens is None else [q, k, v, cu_seqlens],
                    {"causal": bool(is_causal), "softmax_scale": float(softmax_scale if softmax_scale > 0 else 0.0),
                     "ranks": [int(r) for r in ranks], "split_pattern": split_pattern}, **_meta(kw))
     return outs[0]

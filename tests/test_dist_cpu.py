@@ -140,6 +140,16 @@ def test_context_parallel_ring_attention_matches_full_attention(pattern):
 
 
 @pytest.mark.dist
+@pytest.mark.parametrize("cp,pattern", [(2, "SYM"), (2, "NORMAL"), (4, "SYM"), (1, "SYM")])
+def test_context_parallel_varlen_attention_over_packed_rows(cp, pattern):
+    """parallel_attn(cu_seqlens=...): documents of a packed row (crossing chunk and rank borders, one of length 1) attend only to
+    themselves; outputs and dq / dk / dv equal per-document causal attention on the gathered row"""
+    ok, outs = run_workers(CP_WORKER, cp, [cp, pattern, "varlen"])
+    assert ok, "\n-----\n".join(outs)
+    assert sum("CPERR" in o for o in outs) == cp
+
+
+@pytest.mark.dist
 def test_ring_attention_analysis_log(tmp_path):
     """HETU_PARALLEL_ATTN=ANALYSIS: one JSON line per ring-attention op and rank with per-round attention time, computed /
     mask-skipped blocks and rotated KV bytes; under the SYM split both ranks compute the same number of blocks"""
@@ -242,6 +252,14 @@ def test_trainer_with_context_parallel_strategies(tmp_path):
         got = _losses(outs)
         for a, b in zip(got, ref):
             assert abs(a - b) < 1e-3 * max(1.0, abs(b)), ((dp, cp, tp), got, ref)
+    # packing x context parallelism: packed rows (documents crossing chunk borders) through variable-length ring attention
+    ok, outs = run_workers(TRAINER_CP_WORKER, 1, [1, 1, 1, "pack"], env_extra=env)
+    assert ok, "\n-----\n".join(outs)
+    ref = _losses(outs)
+    ok, outs = run_workers(TRAINER_CP_WORKER, 2, [1, 2, 1, "pack"], env_extra=env)
+    assert ok, "\n-----\n".join(outs)
+    for a, b in zip(_losses(outs), ref):
+        assert abs(a - b) < 2e-4 * max(1.0, abs(b)), (_losses(outs), ref)
 
 
 TRAINER_HETERO_WORKER = os.path.join(os.path.dirname(__file__), "workers", "trainer_hetero_worker.py")

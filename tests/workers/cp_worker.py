@@ -10,6 +10,8 @@ import hetu_b200 as ht
 
 cp = int(sys.argv[1])
 pattern = sys.argv[2] if len(sys.argv) > 2 else "SYM"
+varlen = len(sys.argv) > 3 and sys.argv[3] == "varlen"
+bounds = [0, 5, 6, 19, 32] if varlen else None      # documents of a packed row: they straddle chunk and rank borders
 ht.init_comm_group(cp)
 rank = int(os.environ.get("RANK", "0"))
 B, S, H, D = 2, 32, 2, 8
@@ -26,10 +28,15 @@ def my_rows():
 rows = my_rows()
 os.environ["HETU_PARALLEL_ATTN_SPLIT_PATTERN"] = pattern
 Q, K, V = (ht.from_numpy(torch.as_tensor(t[:, rows]).contiguous(), requires_grad=True) for t in (q, k, v))
-o = ht.parallel_attn(Q, K, V, list(range(cp)), is_causal=True, split_pattern=pattern)
+cu = ht.from_numpy(torch.tensor(bounds + [32, 32], dtype=torch.int32)) if varlen else None     # trailing repeats = padding entries
+o = ht.parallel_attn(Q, K, V, list(range(cp)), is_causal=True, split_pattern=pattern, cu_seqlens=cu)
 ht.sum(o * ht.from_numpy(torch.as_tensor(g[:, rows]).contiguous())).backward()
 qr, kr, vr = (torch.as_tensor(t).requires_grad_() for t in (q, k, v))
-ref = torch.nn.functional.scaled_dot_product_attention(qr.transpose(1, 2), kr.transpose(1, 2), vr.transpose(1, 2), is_causal=True).transpose(1, 2)
+if varlen:
+    ref = torch.cat([torch.nn.functional.scaled_dot_product_attention(qr[:, a:b].transpose(1, 2), kr[:, a:b].transpose(1, 2), vr[:, a:b].transpose(1, 2),
+                                                                      is_causal=True).transpose(1, 2) for a, b in zip(bounds[:-1], bounds[1:])], dim=1)
+else:
+    ref = torch.nn.functional.scaled_dot_product_attention(qr.transpose(1, 2), kr.transpose(1, 2), vr.transpose(1, 2), is_causal=True).transpose(1, 2)
 (ref * torch.as_tensor(g)).sum().backward()
 errs = [float((torch.as_tensor(o.numpy()) - ref.detach()[:, rows]).abs().max()),
         float((torch.as_tensor(Q.grad.numpy()) - qr.grad[:, rows]).abs().max()),
