@@ -413,7 +413,7 @@ def test_pretrain_yaml_configs_load_and_train():
     from hetu_b200.engine import build_trainer, load_experiment
     root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "pretrain", "config")
     files = sorted(glob.glob(os.path.join(root, "*.yaml")))
-    assert {os.path.basename(f) for f in files} >= {"gpt_small_dp2_tp2.yaml", "llama_pack_tp.yaml", "llama_pad_cp.yaml", "gpt_hetero.yaml"}
+    assert {os.path.basename(f) for f in files} >= {"gpt_small_dp2_tp2.yaml", "llama_pack_tp.yaml", "llama_pad_cp.yaml", "llama_pack_cp.yaml", "gpt_hetero.yaml"}
     for f in files:
         exp = load_experiment(f)
         assert exp["model"]["type"] in ("gpt", "llama") and exp["trainer"].steps > 0 and exp["strategy"] is not None
