@@ -400,6 +400,9 @@ void Executor::lower_comm(ExecPlan& plan, OpDef* op, int strategy) {
   const DistributedStates& src = x->ds(strategy);
   const DistributedStates& dst = y->ds(strategy);
   cs.type = classify_comm(src, src_group, dst, dst_group);
+  // pipeline stages with different tensor-parallel degrees (a re-planned pipeline whose stage lost a device): the layouts
+  // look alike (all duplicate) but the groups differ in size -- a general re-sharding exchange instead of pairwise P2P
+  if (cs.type == CommType::P2P && src_group.num_devices() != dst_group.num_devices()) cs.type = CommType::BATCHED_ISEND_IRECV;
   cs.global_shape = src.global_shape(x->shape);
   const int me_src = local_device_index(src_group), me_dst = local_device_index(dst_group);
   switch (cs.type) {
@@ -522,6 +525,7 @@ void Executor::build_plan(ExecPlan& plan, const Tensor& loss, const TensorList& 
       DeviceGroup sg = (op->type == "comm" && x->producer) ? x->producer->placement(strategy) : op->placement(strategy);
       if (sg.empty()) sg = op->placement(strategy);
       if (sg.empty()) continue;
+      if ((int)sg.num_devices() != src.device_num()) continue;     // cross-group transfer between groups of different size
       for (int me = 0; me < (int)sg.num_devices(); ++me) {
         if (is_vp) {
           groups.insert(group_ranks(sg, src.get_device_indices_by_dim(x->ndim() - 1, me)));
@@ -543,7 +547,13 @@ void Executor::build_plan(ExecPlan& plan, const Tensor& loss, const TensorList& 
     for (auto& r : groups) if (r.size() > 1) CommRuntime::get().group(r);
   }
   for (OpDef* op : order) {
-    if (op->type == "comm") lower_comm(plan, op, strategy);
+    if (op->type == "comm") {
+      try {
+        lower_comm(plan, op, strategy);
+      } catch (const std::exception& e) {
+        throw Error("while lowering " + op->name() + " (input " + op->inputs[0]->name + "): " + e.what());
+      }
+    }
     DeviceGroup grp = op->placement(strategy);
     bool local = grp.empty() || local_device_index(grp) >= 0;
     if (op->type == "comm") {
@@ -671,7 +681,17 @@ std::vector<at::Tensor> Executor::exec_comm(const CommStep& cs, OpDef* op, const
           copy_back.push_back({dstv, buf});
         }
       }
-      comm.batched_send_recv(sends, recvs);
+      if (!(sg == dg)) {
+        // transfer between pipeline stages (groups of different size): asynchronous sends + blocking receives on the
+        // forward / backward channels, exactly like the pairwise P2P path, so the 1F1B steady state (one stage sending
+        // activations while its neighbour sends gradients) cannot dead-lock on mutually blocking exchanges
+        const int channel = op->is_bwd ? 1 : 0;
+        for (auto& sp : sends) comm.send(sp.first, sp.second, channel);
+        for (size_t i = 0; i < recvs.size(); ++i)
+          recvs[i].first.copy_(comm.recv(recvs[i].first.sizes().vec(), recvs[i].first.scalar_type(), recvs[i].first.device(), recvs[i].second, channel));
+      } else {
+        comm.batched_send_recv(sends, recvs);
+      }
       for (auto& cb : copy_back) cb.first.copy_(cb.second);
       return {out};
     }
@@ -721,8 +741,8 @@ void Executor::run_ops(ExecPlan& plan, const std::vector<OpDef*>& ops, bool back
         // input produced on another pipeline stage and not routed here: the op is not runnable locally
         if (op->type == "comm") {
           const CommStep& cs = plan.comm[op->id];
-          if (cs.type == CommType::P2P && cs.is_receiver && !cs.is_sender) {
-            outs = exec_comm(cs, op, {}, rc);
+          if ((cs.type == CommType::P2P && cs.is_receiver && !cs.is_sender) || cs.type == CommType::BATCHED_ISEND_IRECV) {
+            outs = exec_comm(cs, op, {}, rc);       // pure receiver of a cross-stage transfer
             vals[op->outputs[0]->id] = outs[0];
             continue;
           }

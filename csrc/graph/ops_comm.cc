@@ -44,7 +44,11 @@ static TensorList comm_grad(OpDef& op, const TensorList& g) {
   DistributedStatesHierarchy target;
   // a parameter moved to another device group (tied weights across pipeline stages): its gradient comes home in the layout it
   // has -- still a partial sum over the data-parallel replicas -- and is reduced once, by the owner's deferred gradient sync
-  const bool param_in = x->producer && x->producer->has_flag(kFlagVariable) && g[0] && g[0]->ds_hierarchy.size() == x->ds_hierarchy.size();
+  bool param_in = x->producer && x->producer->has_flag(kFlagVariable) && g[0] && g[0]->ds_hierarchy.size() == x->ds_hierarchy.size();
+  // (only when both ends use the same number of devices: stages with different tensor-parallel degrees need the re-sharding
+  // to the owner's layout below)
+  for (size_t s = 0; param_in && s < x->ds_hierarchy.size(); ++s)
+    if (g[0]->ds_hierarchy.get(s).get(0).device_num() != x->ds_hierarchy.get(s).get(0).device_num()) param_in = false;
   if (param_in) target = g[0]->ds_hierarchy;
   for (size_t s = 0; !param_in && s < x->ds_hierarchy.size(); ++s) {
     DistributedStatesUnion u;

@@ -189,19 +189,23 @@ class GPTLMHeadModel(Module):
         wte = self.transformer.wte
         if self.lm_head is None:
             last = self.transformer.ln_f.device_group_unions
-            if not hidden.check_ds_hierarchy_equal(wte.ds_split0_dup()):      # sequence-parallel hidden -> all-gather
-                hidden = ops.comm(hidden, wte.ds_split0_dup(), device_group_hierarchy=last)
+            # layouts of the head follow the LAST stage (its tensor-parallel degree may differ from the first stage's, e.g. a
+            # re-planned pipeline whose stage lost a device); on a single stage that is the embedding's own layout
+            head = wte if wte.device_group_unions == last else self.transformer.h[-1].attn.qkv_dense
+            if not hidden.check_ds_hierarchy_equal(head.ds_split0_dup()):      # sequence-parallel hidden -> all-gather
+                hidden = ops.comm(hidden, head.ds_split0_dup(), device_group_hierarchy=last)
             table = wte.embedding_table
             if wte.device_group_unions != last:
                 # tied head under pipeline parallelism: the table travels first stage -> last stage (and its gradient
-                # back) through a P2P comm with an unchanged layout ("share_weight_comm" in the reference)
-                table = ops.comm(table, wte.ds_dup_split0(), device_group_hierarchy=last, name="share_weight_comm")
+                # back) through a comm op ("share_weight_comm" in the reference), re-sharded when the tp degrees differ
+                table = ops.comm(table, head.ds_dup_split0(), device_group_hierarchy=last, name="share_weight_comm")
             logits = ops.linear(hidden, table, None, trans_b=True, device_group_hierarchy=last, name="lm_head")
+            head_tp = head.tp
         else:
             logits = self.lm_head(hidden)
         if labels is None:
             return logits
-        if any(t > 1 for t in wte.tp):     # any strategy with a vocab split needs the vocab-parallel loss (it degenerates for tp = 1)
+        if any(t > 1 for t in (head_tp if self.lm_head is None else wte.tp)):     # any strategy with a vocab split needs the vocab-parallel loss (it degenerates for tp = 1)
             loss = ops.vocab_parallel_cross_entropy(logits, labels, ignored_index=-1, reduction="mean")
         else:
             loss = ops.softmax_cross_entropy_sparse(logits, labels, ignored_index=-1, reduction="mean")

@@ -21,10 +21,16 @@ LAYOUTS = {
     "tp2_tp1": ([{"stages": [{"devices": [0, 1], "layers": [0, 3]}]}, {"stages": [{"devices": [2], "layers": [0, 3]}]}], [6, 2]),
     "tp2pp2_tp1": ([{"stages": [{"devices": [0, 1], "layers": [0, 1]}, {"devices": [2, 3], "layers": [2, 3]}]},
                     {"stages": [{"devices": [4], "layers": [0, 3]}]}], [5, 3]),
+    # one pipeline whose stages have DIFFERENT tensor-parallel degrees (a straggler left stage 1 with a single device)
+    "tp2to1_tp1": ([{"stages": [{"devices": [0, 1], "layers": [0, 1]}, {"devices": [2], "layers": [2, 3]}]},
+                    {"stages": [{"devices": [3], "layers": [0, 3]}]}], [5, 3]),
     "tp4_tp2_tp1": ([{"stages": [{"devices": [0, 1, 2, 3], "layers": [0, 3]}]}, {"stages": [{"devices": [4, 5], "layers": [0, 3]}]},
                      {"stages": [{"devices": [6], "layers": [0, 3]}]}], [4, 3, 1]),
 }
 pipelines, shares = LAYOUTS[layout]
+num_mb = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+if num_mb > 1:
+    shares = [6, 2] if len(shares) == 2 else shares      # divisible into micro-batches
 world = sum(len(st["devices"]) for p in pipelines for st in p["stages"])
 ht.init_comm_group(world)
 rank = int(os.environ.get("RANK", "0"))
@@ -40,7 +46,7 @@ with ht.graph("define_and_run", create_new=True) as g:
     model = GPTLMHeadModel(cfg, [local])
     in_ds, in_dg = ht.nn.parallel.config2ds(local["input"])
     lb_ds, lb_dg = ht.nn.parallel.config2ds(local["label"])
-    T = n_seq * S
+    T = n_seq * S // num_mb
     ids = ht.parallel_placeholder("int64", [T], [in_ds], device_group_hierarchy=[in_dg], name="ids")
     pos = ht.parallel_placeholder("int64", [T], [in_ds], device_group_hierarchy=[in_dg], name="pos")
     lab = ht.parallel_placeholder("int64", [T], [lb_ds], device_group_hierarchy=[lb_dg], name="lab")
@@ -54,10 +60,16 @@ X = rng.randint(0, 128, (Bg, S))
 L = np.roll(X, -1, axis=1)
 P = np.tile(np.arange(S), (Bg, 1))
 sl = bs
-feed = {ids: [torch.as_tensor(X[sl].reshape(-1))], pos: [torch.as_tensor(P[sl].reshape(-1))], lab: [torch.as_tensor(L[sl].reshape(-1))]}
+def mbs(a):
+    rows = a[sl]
+    per = len(rows) // num_mb
+    return [torch.as_tensor(rows[m * per:(m + 1) * per].reshape(-1)) for m in range(num_mb)]
+
+
+feed = {ids: mbs(X), pos: mbs(P), lab: mbs(L)}
 losses = []
 for step in range(4):
-    out = g.run(loss, [loss, train_op], feed, num_micro_batches=1, grad_scale=sess.grad_scale(n_seq, Bg))
+    out = g.run(loss, [loss, train_op], feed, num_micro_batches=num_mb, grad_scale=sess.grad_scale(n_seq, Bg))
     if rank in sess.last_stage_ranks:
         losses.append(sess.reduce_loss(out[0].float().mean(), n_seq, Bg))
 if rank == sess.last_stage_ranks[0]:
