@@ -172,14 +172,15 @@ HETERO_WORKER = os.path.join(os.path.dirname(__file__), "workers", "hetero_worke
 
 
 @pytest.mark.dist
-@pytest.mark.parametrize("layout,world,mb", [("tp2_tp1", 3, 1), ("tp2pp2_tp1", 5, 2), ("tp2to1_tp1", 4, 1), ("tp2to1_tp1", 4, 2)])
-def test_heterogeneous_pipelines_reproduce_the_single_device_loss(layout, world, mb):
+@pytest.mark.parametrize("layout,world,mb,kind", [("tp2_tp1", 3, 1, "gpt"), ("tp2pp2_tp1", 5, 2, "gpt"), ("tp2to1_tp1", 4, 2, "gpt"),
+                                                  ("tp2to1_tp1", 4, 2, "llama")])
+def test_heterogeneous_pipelines_reproduce_the_single_device_loss(layout, world, mb, kind):
     """Malleus / Ampelos unions: pipelines with different tp degrees (and stage counts) on unequal batch shares; parameter
     gradients are synchronised per finest common shard (grouped_all_reduce).  `tp2to1_tp1`: the stages of ONE pipeline have
     different tensor-parallel degrees -- activations / gradients cross the stage border through a re-sharding exchange and the
     tied embedding table is re-sharded on its way to the last stage; with 2 micro-batches the exchange runs inside 1F1B."""
-    ref = _reference()
-    ok, outs = run_workers(HETERO_WORKER, world, [layout, mb])
+    ref = _reference(kind)
+    ok, outs = run_workers(HETERO_WORKER, world, [layout, mb, kind])
     assert ok, "\n-----\n".join(outs)
     got = _losses(outs)
     for a, b in zip(got, ref):

@@ -35,7 +35,13 @@ world = sum(len(st["devices"]) for p in pipelines for st in p["stages"])
 ht.init_comm_group(world)
 rank = int(os.environ.get("RANK", "0"))
 ht.set_seed(7)
-cfg = GPTConfig(vocab_size=128, n_positions=S, n_embd=32, n_layer=NL, n_head=4)
+kind = sys.argv[3] if len(sys.argv) > 3 else "gpt"
+if kind == "llama":
+    from hetu_b200.models import LlamaConfig, LlamaLMHeadModel
+    cfg = LlamaConfig(vocab_size=128, hidden_size=32, intermediate_size=64, num_hidden_layers=NL, num_attention_heads=4, num_key_value_heads=2,
+                      sequence_parallel=False)
+else:
+    cfg = GPTConfig(vocab_size=128, n_positions=S, n_embd=32, n_layer=NL, n_head=4)
 hetero = generate_hetero_ds_parallel_config(NL, pipelines, zero=False)
 sess = HeteroSession(hetero, rank, shares=shares)
 local, me = sess.local_cfg, sess.pipeline
@@ -43,7 +49,7 @@ assert sess.split_batch(Bg) == shares
 bs = sess.batch_slice(Bg)
 n_seq = bs.stop - bs.start
 with ht.graph("define_and_run", create_new=True) as g:
-    model = GPTLMHeadModel(cfg, [local])
+    model = (LlamaLMHeadModel if kind == "llama" else GPTLMHeadModel)(cfg, [local])
     in_ds, in_dg = ht.nn.parallel.config2ds(local["input"])
     lb_ds, lb_dg = ht.nn.parallel.config2ds(local["label"])
     T = n_seq * S // num_mb
