@@ -41,12 +41,15 @@ class HeteroSession:
         self.rank = distributed.rank() if rank is None else rank
         self.pipelines = _pipelines_of(hetero_cfg)
         self.num_pipelines = len(self.pipelines)
-        self.pipeline = next(i for i, p in enumerate(self.pipelines) if any(self.rank in st for st in p))
+        # a rank the plan leaves without work (e.g. the other half of a tensor-parallel group that lost a device) is idle:
+        # it owns no graph but still takes part in the collective creation of process groups and in world barriers
+        self.pipeline = next((i for i, p in enumerate(self.pipelines) if any(self.rank in st for st in p)), None)
+        self.idle = self.pipeline is None
         self.first_stage_ranks = [p[0][0] for p in self.pipelines]
         self.last_stage_ranks = [p[-1][0] for p in self.pipelines]
         self.shares = list(shares) if shares is not None else [1] * self.num_pipelines
         HETERO_PARAMS.clear()
-        self.local_cfg = localize_hetero_config(hetero_cfg, self.rank)
+        self.local_cfg = None if self.idle else localize_hetero_config(hetero_cfg, self.rank)
 
     # -- batch split ----------------------------------------------------------------------------------------------
     def split_batch(self, global_batch: int) -> List[int]:
@@ -66,6 +69,8 @@ class HeteroSession:
 
     def batch_slice(self, global_batch: int) -> slice:
         per = self.split_batch(global_batch)
+        if self.idle:
+            return slice(0, 0)
         lo = sum(per[:self.pipeline])
         return slice(lo, lo + per[self.pipeline])
 

@@ -84,10 +84,11 @@ class MalleusTrainer(Trainer):
         (dp, tp, pp) strategy; anything else -- unequal batch shares, different tp degrees or stage counts -- runs through
         the heterogeneous member-local path.  Both go through `Trainer.rebuild` (split checkpoint, re-sharded on load)."""
         strategy = model.strategies
-        if strategy.unused_rank_list:
-            return "skipped: the plan leaves ranks without work (needs a restart with fewer workers)"
         shares = list(strategy.hetero_micro_batch_num_list)
-        if model.executable_config is not None and len(set(shares)) == 1:
+        from .. import distributed
+        used = {d for pl in model.plans for g in pl["groups"] for d in g.devices}
+        covers_world = len(used) >= max(distributed.world_size(), 1)      # otherwise some ranks idle: member-local path
+        if model.executable_config is not None and len(set(shares)) == 1 and covers_world:
             self.rebuild([model.executable_config])
             return "homogeneous"
         self.rebuild([model.ds_parallel_configs], hetero_shares=shares)

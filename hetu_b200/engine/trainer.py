@@ -102,12 +102,15 @@ class Trainer:
     def _set_strategies(self, dspc, hetero_shares=None):
         # heterogeneous strategy (pipelines with different tp / stage counts, e.g. a Malleus plan): this rank trains the
         # homogeneous member-local graph of its own pipeline on its share of every global batch (engine/hetero.py)
-        self.hetero = None
-        if len(dspc) == 1 and dspc[0].get("hetero") and "device_group_union" in dspc[0].get("input", {}) \
-                and len(dspc[0]["input"]["device_group_union"]) > 1:
-            from .hetero import HeteroSession
-            self.hetero = HeteroSession(dspc[0], shares=hetero_shares)
-            dspc = [self.hetero.local_cfg]
+        self.hetero, self.idle = None, False
+        if len(dspc) == 1 and dspc[0].get("hetero") and "device_group_union" in dspc[0].get("input", {}):
+            used = {d for grp in dspc[0]["input"]["device_group_union"] for d in grp} | \
+                   {d for b in dspc[0]["blocks"].values() for grp in b["layernorm1"]["device_group_union"] for d in grp}
+            if len(dspc[0]["input"]["device_group_union"]) > 1 or len(used) < max(distributed.world_size(), 1):
+                from .hetero import HeteroSession
+                self.hetero = HeteroSession(dspc[0], shares=hetero_shares)
+                self.idle = self.hetero.idle
+                dspc = [self.hetero.local_cfg]
         self.ds_parallel_configs = dspc
         self.num_strategy = len(dspc)
         self.cur_strategy_id = 0
@@ -123,8 +126,13 @@ class Trainer:
         self.build()
         st = self.trainer_states
         saver = ModelSaver(ckpt_dir or os.path.join(self.pretrain_config.output_dir, "_rebuild"), save_copies=1)
-        saver.save(st.model, st.optimizer, self.global_step, self.consumed_samples, self.loss_history[-1] if self.loss_history else float("nan"))
-        saver.wait()
+        if self.idle:
+            distributed.global_comm_barrier_rpc()             # the barrier inside the active ranks' saver.save()
+        else:
+            writer = min(d for p in self.hetero.pipelines for stg in p for d in stg) if self.hetero is not None else 0
+            saver.save(st.model, st.optimizer, self.global_step, self.consumed_samples, self.loss_history[-1] if self.loss_history else float("nan"),
+                       writer_rank=writer)
+            saver.wait()
         distributed.global_comm_barrier_rpc()
         self.trainer_states, self.is_model_built = None, False
         HETERO_PARAMS.clear()
@@ -134,6 +142,8 @@ class Trainer:
         self._set_strategies(list(ds_parallel_configs), hetero_shares)
         self._iter_version = getattr(self, "_iter_version", 0) + 1
         self.build()
+        if self.idle:
+            return self
         st = self.trainer_states
         loaded = saver.load_latest(st.model, st.optimizer)
         assert loaded is not None and loaded[0] == self.global_step, "the rebuild checkpoint could not be read back"
@@ -182,6 +192,13 @@ class Trainer:
     def build(self):
         if self.is_model_built:
             return self.trainer_states
+        if self.idle:
+            # this rank has no work under the current plan: join the collective group creation, build nothing
+            from ..nn.parallel import HETERO_PARAMS
+            HETERO_PARAMS.clear()
+            self.hetero.precreate_groups()
+            self.trainer_states, self.is_model_built = None, True
+            return None
         self.trainer_states = self.create_define_graph()
         if self.hetero is not None:
             self.hetero.precreate_groups()        # collective over all ranks: tp groups of every stage + cross-pipeline groups
@@ -344,6 +361,14 @@ class Trainer:
             saver = ModelSaver(cfg.output_dir, save_interval=cfg.save_interval)
         prof = None
         for _ in range(steps):
+            if self.idle:
+                # keep the step counter (and every world-collective the active ranks execute) in lock step
+                self.global_step += 1
+                for cb in self.callbacks:
+                    cb(self, None, {})
+                if cfg.save_interval and self.global_step % cfg.save_interval == 0:
+                    distributed.global_comm_barrier_rpc()
+                continue
             if it_version != getattr(self, "_iter_version", 0):
                 # the strategy was rebuilt by a callback: the data-parallel sharding of the loader changed with it
                 it, it_version = self.train_data_iterator(), self._iter_version

@@ -75,7 +75,7 @@ class ModelSaver:
             return view
         return snap
 
-    def save(self, model, optimizer, step: int, consumed_samples: int = 0, loss: float = float("nan")):
+    def save(self, model, optimizer, step: int, consumed_samples: int = 0, loss: float = float("nan"), writer_rank: int = 0):
         from ...distributed import global_comm_barrier_rpc, rank
         self.wait()
         path = self.step_dir(step)
@@ -105,7 +105,7 @@ class ModelSaver:
                 os._exit(code)
             self._child = pid
         global_comm_barrier_rpc()
-        if rank() == 0:
+        if rank() == writer_rank:                # the rank that keeps the step-info CSV (an active one when some ranks are idle)
             with open(os.path.join(self.save_dir, "step_info.csv"), "a", newline="") as f:
                 csv.writer(f).writerow([step, consumed_samples, loss, path, time.time()])
             self._cleanup(step)

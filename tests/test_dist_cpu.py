@@ -285,11 +285,14 @@ def test_trainer_on_a_heterogeneous_strategy(tmp_path):
 
 
 @pytest.mark.dist
-@pytest.mark.parametrize("worker,mode,world", [("trainer_rebuild_worker.py", "rebuild", 3), ("malleus_apply_worker.py", "malleus", 4)])
+@pytest.mark.parametrize("worker,mode,world", [("trainer_rebuild_worker.py", "rebuild", 3), ("malleus_apply_worker.py", "malleus", 4),
+                                               ("malleus_apply_worker.py", "shrink", 4)])
 def test_replanning_a_running_job_keeps_the_loss_curve(tmp_path, worker, mode, world):
     """Trainer.rebuild (explicit) and MalleusTrainer(auto_apply=True) (straggler report -> plan -> rebuild inside the training
     loop): the job moves from a homogeneous strategy to a heterogeneous one through a split checkpoint; parameters, Adam states,
-    step counters and the data position carry over, so the 4-step loss curve equals the single-device one"""
+    step counters and the data position carry over, so the 4-step loss curve equals the single-device one.  `shrink`: a device
+    becomes 50x slower, the planner dissolves its tensor-parallel group -- one tp2 pipeline over the healthy devices, the other
+    two ranks idle (they own no graph but keep taking part in group creation and barriers)"""
     path = os.path.join(os.path.dirname(__file__), "workers", worker)
     ok, outs = run_workers(path, 1, ["single"], env_extra={"TRAINER_OUT": str(tmp_path / "single")})
     assert ok, "\n-----\n".join(outs)
