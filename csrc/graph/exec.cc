@@ -500,7 +500,15 @@ void Executor::build_plan(ExecPlan& plan, const Tensor& loss, const TensorList& 
     if (!op->has_flag(kFlagOptimizerUpdate) || op->inputs.size() < 2) continue;
     Tensor param = op->inputs[0], grad = op->inputs[1];
     plan.update_of_param[param->id] = op;
-    if (grad->producer && (grad->producer->type == "comm" || grad->producer->type == "grouped_all_reduce")) {
+    if (grad->producer && grad->producer->type == "grouped_all_reduce" && grad->producer->inputs[0]->producer &&
+        grad->producer->inputs[0]->producer->type == "comm") {
+      // heterogeneous sync on top of the pipeline's own gradient sync (e.g. norm weights under sequence parallelism):
+      // both run once, in the update phase, on the accumulated gradient
+      OpDef* inner = grad->producer->inputs[0]->producer;
+      deferred.insert(grad->producer->id);
+      deferred.insert(inner->id);
+      plan.param_of_grad[inner->inputs[0]->id] = param->id;
+    } else if (grad->producer && (grad->producer->type == "comm" || grad->producer->type == "grouped_all_reduce")) {
       deferred.insert(grad->producer->id);
       plan.param_of_grad[grad->producer->inputs[0]->id] = param->id;
     } else {
@@ -987,12 +995,17 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
       if (op->type == "grouped_all_reduce") {
         // heterogeneous data parallelism: slice-wise synchronisation of the accumulated gradient across pipelines
         const TensorId raw = op->inputs[0]->id;
-        auto pg = plan.param_of_grad.find(raw);
-        if (pg == plan.param_of_grad.end()) continue;
-        auto acc = accum_grads_.find(pg->second);
-        if (acc == accum_grads_.end()) continue;
-        at::Tensor g = acc->second;
-        if (scale != 1.0) g = g * scale;
+        at::Tensor g;
+        auto pre = uvals.find(raw);
+        if (pre != uvals.end()) g = pre->second;          // already synchronised inside the pipeline by the deferred comm above
+        else {
+          auto pg = plan.param_of_grad.find(raw);
+          if (pg == plan.param_of_grad.end()) continue;
+          auto acc = accum_grads_.find(pg->second);
+          if (acc == accum_grads_.end()) continue;
+          g = acc->second;
+          if (scale != 1.0) g = g * scale;
+        }
         const double t_g = profile_ ? now_ms() : 0.0;
         uvals[op->outputs[0]->id] = op->kernel->compute(*op, {g}, &rc)[0];
         if (profile_) breakdown_["dp_grad_reduce_ms"] += now_ms() - t_g;

@@ -180,7 +180,9 @@ def test_heterogeneous_pipelines_reproduce_the_single_device_loss(layout, world,
     different tensor-parallel degrees -- activations / gradients cross the stage border through a re-sharding exchange and the
     tied embedding table is re-sharded on its way to the last stage; with 2 micro-batches the exchange runs inside 1F1B."""
     ref = _reference(kind)
-    ok, outs = run_workers(HETERO_WORKER, world, [layout, mb, kind])
+    # the (tp2 x pp2) + tp1 case also runs Megatron sequence parallelism inside the tp2 pipeline: norm-weight gradients are
+    # first reduced over the pipeline's tp group, then synchronised across pipelines (two chained deferred syncs)
+    ok, outs = run_workers(HETERO_WORKER, world, [layout, mb, kind], env_extra={"HETERO_SP": "1"} if layout == "tp2pp2_tp1" else None)
     assert ok, "\n-----\n".join(outs)
     got = _losses(outs)
     for a, b in zip(got, ref):

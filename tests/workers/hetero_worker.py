@@ -41,7 +41,7 @@ if kind == "llama":
     cfg = LlamaConfig(vocab_size=128, hidden_size=32, intermediate_size=64, num_hidden_layers=NL, num_attention_heads=4, num_key_value_heads=2,
                       sequence_parallel=False)
 else:
-    cfg = GPTConfig(vocab_size=128, n_positions=S, n_embd=32, n_layer=NL, n_head=4)
+    cfg = GPTConfig(vocab_size=128, n_positions=S, n_embd=32, n_layer=NL, n_head=4, sequence_parallel=os.environ.get("HETERO_SP") == "1")
 hetero = generate_hetero_ds_parallel_config(NL, pipelines, zero=False)
 sess = HeteroSession(hetero, rank, shares=shares)
 local, me = sess.local_cfg, sess.pipeline
