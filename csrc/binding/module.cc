@@ -376,7 +376,8 @@ PYBIND11_MODULE(_C, m) {
          py::arg("device_group_hierarchy") = py::none(), py::arg("dst_ds") = py::none(), py::arg("sy_shape") = SyShape{},
          py::arg("const_data") = py::none(), py::arg("stream_index") = -1, py::arg("extra_deps") = TensorList{})
       .def("run", [](Graph& g, const Tensor& loss, const TensorList& fetches, const py::dict& feed, int num_micro_batches,
-                     int strategy, int run_level, double grad_scale, bool save_checkpoint) {
+                     int strategy, int run_level, double grad_scale, bool save_checkpoint,
+                     const std::vector<std::pair<IntSymbol, std::vector<int64_t>>>& symbols) {
         std::unordered_map<TensorId, std::vector<at::Tensor>> f;
         for (auto item : feed) {
           Tensor t = py::cast<Tensor>(item.first);
@@ -392,10 +393,12 @@ PYBIND11_MODULE(_C, m) {
         o.run_level = (RunLevel)run_level;
         o.grad_scale = grad_scale;
         o.save_checkpoint = save_checkpoint;
+        o.symbols = symbols;
         py::gil_scoped_release nogil;
         return g.executor()->run(loss, fetches, f, o);
       }, py::arg("loss"), py::arg("fetches"), py::arg("feed_dict") = py::dict(), py::arg("num_micro_batches") = 1,
-         py::arg("strategy") = 0, py::arg("run_level") = 0, py::arg("grad_scale") = 1.0, py::arg("save_checkpoint") = false)
+         py::arg("strategy") = 0, py::arg("run_level") = 0, py::arg("grad_scale") = 1.0, py::arg("save_checkpoint") = false,
+         py::arg("symbols") = std::vector<std::pair<IntSymbol, std::vector<int64_t>>>{})
       .def("get_param", [](Graph& g, const Tensor& t) { return g.executor()->get_param(t); })
       .def("set_param", [](Graph& g, const Tensor& t, const at::Tensor& v) { g.executor()->set_param(t, v); })
       .def("has_param", [](Graph& g, const Tensor& t) { return g.has_param_data(t->id); })

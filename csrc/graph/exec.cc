@@ -876,29 +876,47 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
   if (active_strategy_ >= 0 && active_strategy_ != opt.strategy) switch_strategy(active_strategy_, opt.strategy);
   active_strategy_ = opt.strategy;
   // dynamic shapes: a placeholder fed with a different token count (sequence-length buckets, packed batches) updates its
-  // global shape; static shapes are re-inferred when that happens or when the strategy (hence every local shape) changes
-  bool shapes_changed = false;
-  {
+  // global shape; static shapes are re-inferred when that happens or when the strategy (hence every local shape) changes.
+  // With per-micro-batch symbol values / feeds of different widths the same happens before every micro-batch task.
+  auto sync_shapes = [&](int mb) {
+    bool changed = false;
     const int Mq = std::max(1, opt.num_micro_batches);
+    for (auto& sv : opt.symbols) {
+      if (sv.second.empty()) continue;
+      const int64_t v = sv.second[std::min<size_t>((size_t)mb, sv.second.size() - 1)];
+      IntSymbol sym = sv.first;
+      if (!sym.is_instantiated() || sym.get_val() != v) { sym.set_val(v); changed = true; }
+    }
     for (OpDef* op : plan.fw_ops) {
       if (!op->has_flag(kFlagPlaceholder)) continue;
       auto it = feed.find(op->outputs[0]->id);
-      if (it == feed.end() || it->second.empty() || !it->second[0].defined()) continue;
-      std::vector<int64_t> local = it->second[0].sizes().vec();
+      if (it == feed.end() || it->second.empty()) continue;
+      const at::Tensor& t0 = it->second[(int)it->second.size() == Mq ? (size_t)mb : 0];
+      if (!t0.defined()) continue;
+      std::vector<int64_t> local = t0.sizes().vec();
       if ((int)it->second.size() == 1 && Mq > 1 && !local.empty()) local[0] /= Mq;
       std::vector<int64_t> global = local;
       if (op->dst_ds.size() > (size_t)opt.strategy && op->dst_ds.get(opt.strategy).size() > 0)
         global = op->dst_ds.get(opt.strategy).get(0).global_shape(local);
       if (op->attrs.ints("global_shape") != global) {
         op->attrs.set("global_shape", global);
-        shapes_changed = true;
+        changed = true;
       }
     }
-  }
+    return changed;
+  };
+  const bool shapes_changed = sync_shapes(0);
   if (shapes_changed || (shapes_strategy_ != -1 && shapes_strategy_ != opt.strategy)) {
     g_->reinfer_shapes(opt.strategy);
     shapes_strategy_ = opt.strategy;
   }
+  // micro-batches of different widths: (a list of symbol values with more than one distinct entry, or feeds whose shapes differ)
+  bool per_mb_shapes = false;
+  for (auto& sv : opt.symbols)
+    for (size_t i = 1; i < sv.second.size(); ++i) per_mb_shapes |= sv.second[i] != sv.second[0];
+  for (auto& kv : feed)
+    for (size_t i = 1; i < kv.second.size(); ++i)
+      per_mb_shapes |= kv.second[i].defined() && kv.second[0].defined() && kv.second[i].sizes() != kv.second[0].sizes();
   g_->set_cur_strategy(opt.strategy);
   if (opt.run_level == RunLevel::TOPO) return {};
   for (OpDef* op : plan.fw_ops) if (op->has_flag(kFlagVariable)) ensure_param(op, opt.strategy);
@@ -952,6 +970,7 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
     if (task.kind == PipeTask::FLUSH) continue;
     const int mb = task.micro_batch;
     rc.micro_batch = mb;
+    if (per_mb_shapes && sync_shapes(mb)) g_->reinfer_shapes(opt.strategy);
     if (task.kind == PipeTask::FORWARD) {
       for (auto& kv : feed) {
         if (kv.second.empty()) continue;

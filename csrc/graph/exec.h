@@ -21,6 +21,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "../core/symbol.h"
 #include "ir.h"
 
 namespace hb {
@@ -128,6 +129,8 @@ struct RunOptions {
   RunLevel run_level = RunLevel::UPDATE;
   double grad_scale = 1.0;
   bool save_checkpoint = false;
+  // per-micro-batch values of symbolic ints (sequence length of each micro-batch, ...): symbols[i].second[mb]
+  std::vector<std::pair<IntSymbol, std::vector<int64_t>>> symbols;
 };
 
 struct ZeroFusedState;

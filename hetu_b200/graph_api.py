@@ -31,10 +31,14 @@ def run_graph(g: Graph, loss: Optional[Tensor], fetches: Sequence[Tensor], feed_
     (ref: python/hetu/_binding/graph/graph.cc:110-121).  Returns one torch tensor (or None) per fetch."""
     if cur_strategy_id is not None:
         compute_strategy_id = cur_strategy_id
+    symbols = []
     if int_symbol_dict:
+        # {IntSymbol: value | [value per micro-batch]}: the executor sets every symbol before each micro-batch task and
+        # re-infers static shapes when a micro-batch differs from the previous one
         for sym, vals in int_symbol_dict.items():
-            v = vals[0] if isinstance(vals, (list, tuple)) else vals
-            sym.set_data(int(v))
+            vs = [int(v) for v in vals] if isinstance(vals, (list, tuple)) else [int(vals)]
+            sym.set_data(vs[0])
+            symbols.append((sym, vs))
     feed = {}
     for t, v in (feed_dict or {}).items():
         vals = _feed_value(v)
@@ -46,7 +50,7 @@ def run_graph(g: Graph, loss: Optional[Tensor], fetches: Sequence[Tensor], feed_
                                                      {"update": 0, "grad": 1, "compute_only": 2, "alloc": 3, "topo": 4}[run_level])
     fetches = list(fetches)
     res = g.run_native(loss, fetches, feed, int(num_micro_batches), int(compute_strategy_id), int(lvl),
-                       float(grad_scale), bool(save_checkpoint))
+                       float(grad_scale), bool(save_checkpoint), symbols)
     # the executor also evaluates `loss` (it drives the backward pass); the caller gets exactly one value per fetch
     return res[:len(fetches)] if (loss is not None and fetches and len(res) > len(fetches)) else res
 

@@ -235,3 +235,49 @@ def test_extra_nn_modules_pad_newgelu_single_config_parallel():
         out = row(col(ln(inp)))
         res = gph.run(None, [out], {inp: torch.randn(4, 8)})[0]
     assert tuple(res.shape) == (4, 8) and type(col).__name__ == "HtColumnParallelLinear" and isinstance(col, ht.nn.HtMultiColumnParallelLinear)
+
+
+def test_micro_batches_of_different_sequence_lengths():
+    """graph.run(int_symbol_dict={seq_len: [16, 8]}, feeds of different widths per micro-batch): the executor sets the symbol
+    and re-infers static shapes before every micro-batch; the step equals accumulating the two micro-batches in separate runs"""
+    from hetu_b200.models import GPTConfig, GPTLMHeadModel, generate_ds_parallel_config
+    rng = np.random.RandomState(0)
+    cfg = GPTConfig(vocab_size=64, n_positions=16, n_embd=16, n_layer=2, n_head=2)
+    widths = [16, 8]
+    data = [(rng.randint(0, 64, (2, w)), np.tile(np.arange(w), (2, 1))) for w in widths]
+
+    def build():
+        ht.set_seed(11)
+        with ht.graph("define_and_run", create_new=True) as g:
+            sym = ht.IntSymbol(16)
+            model = GPTLMHeadModel(cfg, [generate_ds_parallel_config(2, 1, 1, 1, 1, zero=False)])
+            ids, pos, lab = (ht.placeholder("int64", [32], name=n) for n in ("ids", "pos", "lab"))
+            loss = model(ids, pos, lab, seq_len=sym)
+            train = ht.SGDOptimizer(lr=0.5).minimize(loss)
+        return g, sym, ids, pos, lab, loss, train, model
+
+    def feeds(ids, pos, lab, which):
+        f = {ids: [], pos: [], lab: []}
+        for k in which:
+            x, p = data[k]
+            f[ids].append(torch.as_tensor(x.reshape(-1)))
+            f[pos].append(torch.as_tensor(p.reshape(-1)))
+            f[lab].append(torch.as_tensor(np.roll(x, -1, axis=1).reshape(-1)))
+        return f
+
+    g, sym, ids, pos, lab, loss, train, model = build()
+    out = g.run(loss, [loss, train], feeds(ids, pos, lab, [0, 1]), int_symbol_dict={sym: widths}, num_micro_batches=2)
+    per_mb = [float(v) for v in out[0].reshape(-1)]
+    after_a = {n: g.get_param(p).clone() for n, p in model.named_parameters()}
+
+    g2, sym2, ids2, pos2, lab2, loss2, train2, model2 = build()
+    with ht.run_level("grad"):
+        l0 = g2.run(loss2, [loss2, train2], feeds(ids2, pos2, lab2, [0]), int_symbol_dict={sym2: 16}, grad_scale=0.5)
+    l1 = g2.run(loss2, [loss2, train2], feeds(ids2, pos2, lab2, [1]), int_symbol_dict={sym2: 8}, grad_scale=0.5)
+    assert per_mb[1] == pytest.approx(float(l1[0]), rel=1e-5) and len(per_mb) == 2
+    after_b = {n: g2.get_param(p) for n, p in model2.named_parameters()}
+    assert set(after_a) == set(after_b) and len(after_a) > 10
+    for n in after_a:
+        assert torch.allclose(after_a[n], after_b[n], atol=2e-6, rtol=1e-5), n
+    moved = sum(float((after_a[n] - g.get_param(p)).abs().sum()) for n, p in model.named_parameters())
+    assert moved == 0.0 and any(float(v.abs().sum()) > 0 for v in after_a.values())
