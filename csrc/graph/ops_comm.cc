@@ -103,6 +103,67 @@ static Ts grouped_all_reduce_compute(const OpDef& op, const Ts& in, RunCtx*) {
 HB_REGISTER_OP(grouped_all_reduce, "grouped_all_reduce", 1, kFlagComm | kFlagNondiff, grouped_all_reduce_compute, nullptr,
                [](OpDef& op, size_t s) { copy_out_ds(op, 0, s, op.inputs[0]); }, nullptr);
 
+// grouped_reduce_scatter / grouped_all_gather: the sharded-state (ZeRO) counterparts of grouped_all_reduce.  Slice i of the
+// gradient is reduce-scattered over group i along `dim` (every member keeps 1 / |group| of the reduced slice, in group
+// order); the kept parts are concatenated.  grouped_all_gather is the inverse: the parts are all-gathered slice by slice and
+// written back at the slice offsets.  (ref: SplitReduceScatterOp / SplitAllGatherOp, hetu/graph/ops/Communication.cc:660-852)
+static std::vector<std::vector<int>> slice_groups(const OpDef& op) {
+  const auto sizes = op.attrs.ints("group_sizes"), flat = op.attrs.ints("ranks_flat");
+  std::vector<std::vector<int>> out;
+  size_t pos = 0;
+  for (int64_t n : sizes) {
+    out.emplace_back(flat.begin() + pos, flat.begin() + pos + n);
+    pos += (size_t)n;
+  }
+  return out;
+}
+static Ts grouped_reduce_scatter_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& g = in[0];
+  const int64_t dim = op.attrs.i("dim", 0);
+  const auto offs = op.attrs.ints("offsets"), lens = op.attrs.ints("lengths");
+  auto groups = slice_groups(op);
+  int64_t kept = 0;
+  for (size_t i = 0; i < lens.size(); ++i) kept += lens[i] / std::max<int64_t>((int64_t)groups[i].size(), 1);
+  auto shp = g.sizes().vec();
+  shp[dim] = kept;
+  if (g.is_meta()) return {at::empty(shp, g.options())};
+  auto& comm = CommRuntime::get();
+  std::vector<at::Tensor> parts;
+  for (size_t i = 0; i < lens.size(); ++i) {
+    at::Tensor piece = g.narrow(dim, offs[i], lens[i]).contiguous();
+    if (groups[i].size() > 1 && comm.initialized()) {
+      HB_CHECK(lens[i] % (int64_t)groups[i].size() == 0) << "slice of " << lens[i] << " rows is not divisible over " << groups[i].size() << " holders";
+      piece = comm.reduce_scatter(piece, groups[i], (int)dim, ReductionType::SUM, op.attrs.b("fp32_reduce"));
+    }
+    parts.push_back(piece);
+  }
+  return {parts.empty() ? at::empty(shp, g.options()) : at::cat(parts, dim)};
+}
+static Ts grouped_all_gather_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& x = in[0];
+  const int64_t dim = op.attrs.i("dim", 0);
+  const auto offs = op.attrs.ints("offsets"), lens = op.attrs.ints("lengths");
+  auto groups = slice_groups(op);
+  int64_t full = 0;
+  for (size_t i = 0; i < lens.size(); ++i) full = std::max(full, offs[i] + lens[i]);
+  auto shp = x.sizes().vec();
+  shp[dim] = full;
+  if (x.is_meta()) return {at::empty(shp, x.options())};
+  auto& comm = CommRuntime::get();
+  at::Tensor out = at::zeros(shp, x.options());
+  int64_t pos = 0;
+  for (size_t i = 0; i < lens.size(); ++i) {
+    const int64_t n = std::max<int64_t>((int64_t)groups[i].size(), 1), part = lens[i] / n;
+    at::Tensor piece = x.narrow(dim, pos, part).contiguous();
+    pos += part;
+    if (n > 1 && comm.initialized()) piece = comm.all_gather(piece, groups[i], (int)dim);
+    out.narrow(dim, offs[i], lens[i]).copy_(piece);
+  }
+  return {out};
+}
+HB_REGISTER_OP(grouped_reduce_scatter, "grouped_reduce_scatter", 1, kFlagComm | kFlagNondiff, grouped_reduce_scatter_compute, nullptr, nullptr, nullptr);
+HB_REGISTER_OP(grouped_all_gather, "grouped_all_gather", 1, kFlagComm | kFlagNondiff, grouped_all_gather_compute, nullptr, nullptr, nullptr);
+
 // ------------------------------------------------------------------ explicit collectives (rank lists in attrs)
 static std::vector<int> ranks_attr(const OpDef& op) {
   std::vector<int> r;

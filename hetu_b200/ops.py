@@ -431,6 +431,29 @@ def attn_varlen(q, k, v, cu_seqlens_q, cu_seqlens_k=None, max_seqlen_q=None, max
     return reshape(o, [t, h, d])
 
 
+def _slice_group_attrs(dim, offsets, lengths, groups):
+    return {"dim": int(dim), "offsets": [int(o) for o in offsets], "lengths": [int(n) for n in lengths],
+            "group_sizes": [len(g) for g in groups], "ranks_flat": [int(r) for g in groups for r in g]}
+
+
+def grouped_all_reduce(x, dim, offsets, lengths, groups, bcast_ranks=(), **kw):
+    """slice i = x[offsets[i] : offsets[i] + lengths[i]] along `dim` is all-reduced over rank group groups[i]; optionally the
+    result is broadcast inside `bcast_ranks` (heterogeneous data parallelism, ref: SplitAllReduceOp)"""
+    a = _slice_group_attrs(dim, offsets, lengths, groups)
+    a["bcast_ranks"] = [int(r) for r in bcast_ranks]
+    return _op1("grouped_all_reduce", [x], a, **kw)
+
+
+def grouped_reduce_scatter(x, dim, offsets, lengths, groups, **kw):
+    """slice-wise reduce-scatter: every member of groups[i] keeps 1 / |group| of reduced slice i (ref: SplitReduceScatterOp)"""
+    return _op1("grouped_reduce_scatter", [x], _slice_group_attrs(dim, offsets, lengths, groups), **kw)
+
+
+def grouped_all_gather(x, dim, offsets, lengths, groups, **kw):
+    """inverse of grouped_reduce_scatter: parts are all-gathered slice by slice into the full tensor (ref: SplitAllGatherOp)"""
+    return _op1("grouped_all_gather", [x], _slice_group_attrs(dim, offsets, lengths, groups), **kw)
+
+
 def parallel_attn(q, k, v, ranks, is_causal=True, softmax_scale=-1.0, split_pattern="SYM", cu_seqlens=None, **kw):
     """Context-parallel attention over the ring `ranks` (ref: hetu.parallel_attn / ParallelAttentionOp).
     cu_seqlens (int tensor [n + 1], boundaries in the coordinates of the WHOLE row = local length x ring size) makes it

@@ -304,3 +304,12 @@ def test_replanning_a_running_job_keeps_the_loss_curve(tmp_path, worker, mode, w
     got = _losses(outs)
     for a, b in zip(got, ref):
         assert abs(a - b) < 1e-3 * max(1.0, abs(b)), (got, ref)
+
+
+@pytest.mark.dist
+def test_grouped_slice_collectives_over_heterogeneous_holders():
+    """grouped_all_reduce / grouped_reduce_scatter / grouped_all_gather (the Split* collectives of heterogeneous DP): a parameter
+    held as 2 shards by a tp2 pipeline and whole by a tp1 pipeline is reduced / scattered / gathered slice by slice"""
+    ok, outs = run_workers(os.path.join(os.path.dirname(__file__), "workers", "grouped_comm_worker.py"), 3, [])
+    assert ok, "\n-----\n".join(outs)
+    assert sum("GROUPED" in o and "True" in o for o in outs) == 3
