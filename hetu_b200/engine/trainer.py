@@ -285,28 +285,51 @@ class Trainer:
             stats = {"real_tokens": int(sum(len(x) for x, _ in batch)), "fed_tokens": int(width * len(rows)), "rows": len(rows_i)}
         else:
             mbs = int(cfg.micro_batch_size or len(batch))
-            pi, pl = ins.pad_data(), labs.pad_data()
-            width = pi.shape[1]
-            nmb = (len(batch) + mbs - 1) // mbs
-            for m in range(nmb):
-                bi, bl = pi[m * mbs:(m + 1) * mbs], pl[m * mbs:(m + 1) * mbs]
-                if len(bi) < mbs:   # ragged tail: pad with fully-masked rows so every micro-batch has the same shape
-                    k = mbs - len(bi)
-                    bi = np.concatenate([bi, np.full((k, width), pad_id, np.int64)])
-                    bl = np.concatenate([bl, np.full((k, width), -1, np.int64)])
-                feeds_i.append(bi.reshape(-1))
-                feeds_l.append(bl.reshape(-1))
-                feeds_p.append(np.tile(np.arange(width), mbs))
-            seq = width
             cp = _cp_degree(self.ds_parallel_configs[strategy_id])
+            unit = cfg.pack_alignment if cp == 1 else int(np.lcm(cfg.pack_alignment, 2 * cp))
+            if cfg.dynamic_micro_batch_padding:
+                # rows sorted by length so that a micro-batch holds rows of similar length, each micro-batch padded to its own
+                # (aligned) longest row: the executor re-infers shapes per micro-batch (graph.run int_symbol_dict lists)
+                order = np.argsort([-len(x) for x, _ in batch], kind="stable")
+                rows = [batch[i] for i in order]
+                nmb = (len(rows) + mbs - 1) // mbs
+                widths = []
+                for m in range(nmb):
+                    chunk = rows[m * mbs:(m + 1) * mbs]
+                    w = min(max(len(x) for x, _ in chunk), max_len)
+                    w = (w + unit - 1) // unit * unit
+                    bi = np.full((mbs, w), pad_id, np.int64)
+                    bl = np.full((mbs, w), -1, np.int64)
+                    for r, (x, y) in enumerate(chunk):
+                        n = min(len(x), w)
+                        bi[r, :n], bl[r, :n] = x[:n], y[:n]
+                    feeds_i.append(bi.reshape(-1)); feeds_l.append(bl.reshape(-1)); feeds_p.append(np.tile(np.arange(w), mbs))
+                    widths.append(w)
+                width = widths
+            else:
+                pi, pl = ins.pad_data(), labs.pad_data()
+                width = pi.shape[1]
+                nmb = (len(batch) + mbs - 1) // mbs
+                for m in range(nmb):
+                    bi, bl = pi[m * mbs:(m + 1) * mbs], pl[m * mbs:(m + 1) * mbs]
+                    if len(bi) < mbs:   # ragged tail: pad with fully-masked rows so every micro-batch has the same shape
+                        k = mbs - len(bi)
+                        bi = np.concatenate([bi, np.full((k, width), pad_id, np.int64)])
+                        bl = np.concatenate([bl, np.full((k, width), -1, np.int64)])
+                    feeds_i.append(bi.reshape(-1))
+                    feeds_l.append(bl.reshape(-1))
+                    feeds_p.append(np.tile(np.arange(width), mbs))
+            widths = width if isinstance(width, list) else [width] * nmb
+            seq = list(widths) if isinstance(width, list) else width
             if cp > 1:
                 # every ring member keeps its SYM chunks of each row (positions stay the original ones for the rotary embedding)
-                assert width % (2 * cp) == 0, f"padded width {width} must be a multiple of 2 * cp = {2 * cp} (set pack_alignment accordingly)"
-                cols = cp_rows(width, cp, self._cp_index_and_ring(strategy_id)[0])
-                take = lambda flat: flat.reshape(-1, width)[:, cols].reshape(-1)   # noqa: E731
-                feeds_i, feeds_l, feeds_p = [take(a) for a in feeds_i], [take(a) for a in feeds_l], [take(a) for a in feeds_p]
-                seq = len(cols)
-            stats = {"real_tokens": int(sum(len(x) for x, _ in batch)), "fed_tokens": int(width * mbs * nmb), "rows": len(batch)}
+                ci = self._cp_index_and_ring(strategy_id)[0]
+                for m, w in enumerate(widths):
+                    assert w % (2 * cp) == 0, f"padded width {w} must be a multiple of 2 * cp = {2 * cp} (set pack_alignment accordingly)"
+                    cols = cp_rows(w, cp, ci)
+                    feeds_i[m], feeds_l[m], feeds_p[m] = (a.reshape(-1, w)[:, cols].reshape(-1) for a in (feeds_i[m], feeds_l[m], feeds_p[m]))
+                seq = [w // cp for w in widths] if isinstance(width, list) else widths[0] // cp
+            stats = {"real_tokens": int(sum(len(x) for x, _ in batch)), "fed_tokens": int(sum(widths) * mbs), "rows": len(batch)}
         to_t = (lambda a: torch.as_tensor(a).pin_memory()) if torch.cuda.is_available() else torch.as_tensor
         feed = {st.input_ids: [to_t(a) for a in feeds_i], st.position_ids: [to_t(a) for a in feeds_p],
                 st.labels: [to_t(a) for a in feeds_l]}
@@ -339,9 +362,9 @@ class Trainer:
             scale = self.hetero.grad_scale(len(batch), n_global)
         feed, nmb, seq, stats = self.prepare_feed_dict(batch, strategy_id)
         dp, _, _ = _strategy_sizes(self.ds_parallel_configs[strategy_id])
-        st.seq_len_symbol.set_data(int(seq))
-        out = st.graph.run(st.loss, [st.loss, st.train_op], feed, num_micro_batches=nmb, cur_strategy_id=strategy_id,
-                           grad_scale=scale if scale is not None else 1.0 / dp)
+        # `seq` is one sequence length, or one per micro-batch (dynamic_micro_batch_padding)
+        out = st.graph.run(st.loss, [st.loss, st.train_op], feed, int_symbol_dict={st.seq_len_symbol: seq}, num_micro_batches=nmb,
+                           cur_strategy_id=strategy_id, grad_scale=scale if scale is not None else 1.0 / dp)
         loss = out[0]
         lv = float(loss.float().mean()) if loss is not None else None
         if self.hetero is not None and lv is not None and self.hetero.rank in self.hetero.last_stage_ranks:

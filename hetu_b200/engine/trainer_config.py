@@ -22,6 +22,7 @@ class TrainingConfig:
     bf16: bool = False
     packing: bool = True                       # pack variable-length samples into rows (varlen attention)
     micro_batch_size: Optional[int] = None     # padding mode only
+    dynamic_micro_batch_padding: bool = False  # padding mode: sort by length and pad every micro-batch to its OWN longest row
     ds_parallel: Optional[StrategyConfig] = None
     global_load_size: int = 64                 # samples (SAMPLE level) or tokens (TOKEN level) per step
     data_load_level: DataLoadLevel = DataLoadLevel.SAMPLE
