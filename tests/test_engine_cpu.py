@@ -448,3 +448,46 @@ def test_dynamic_micro_batch_padding_feeds_fewer_tokens_for_the_same_losses():
     # (sorted rows), so compare the quantity that does not depend on it: training must track closely
     for a, b in zip(base, dyn):
         assert abs(a - b) < 0.05 * abs(a)
+
+
+def test_multi_lora_routes_tokens_to_their_tasks_adapters():
+    """multi-tenant LoRA (LobRA): one frozen base model, one adapter pair per task, a [tokens, tasks] one-hot mask routes every
+    token; training on task-0 tokens only changes task-0 adapters, task-1 tokens still see the base model"""
+    from hetu_b200.peft import get_peft_model
+    from hetu_b200.peft.lora.config import LoraConfig
+    ht.init_comm_group(1)
+    ht.set_seed(9)
+    rng = np.random.RandomState(0)
+    S, B = 16, 4
+    X = rng.randint(0, 64, (B, S))
+    X[:, 1::2] = (X[:, 0::2] + 1) % 64
+    L = np.roll(X, -1, axis=1)
+    P = np.tile(np.arange(S), (B, 1))
+    with ht.graph("define_and_run", create_new=True) as g:
+        from hetu_b200.models import generate_ds_parallel_config
+        base = GPTLMHeadModel(GPTConfig(vocab_size=64, n_positions=S, n_embd=32, n_layer=2, n_head=2), [generate_ds_parallel_config(2, 1, 1, 1, 1, zero=False)])
+        model = get_peft_model(base, LoraConfig(rank=4, num_tasks=2, init_std=0.05))
+        ids, pos, lab = (ht.placeholder("int64", [B * S], name=n) for n in ("ids", "pos", "lab"))
+        mask = ht.placeholder("float32", [B * S, 2], name="task_mask")
+        model.set_task_mask(mask)
+        loss = model(ids, pos, lab, seq_len=S)
+        train = ht.AdamOptimizer(lr=2e-2).minimize(loss)
+    feed = {ids: torch.as_tensor(X.reshape(-1)), pos: torch.as_tensor(P.reshape(-1)), lab: torch.as_tensor(L.reshape(-1))}
+    task0 = torch.zeros(B * S, 2); task0[:, 0] = 1.0
+    task1 = torch.zeros(B * S, 2); task1[:, 1] = 1.0
+    params = dict(model.named_parameters())
+    trainable = [n for n, p in params.items() if p.requires_grad]
+    assert trainable and all("lora" in n for n in trainable) and any("task0" in n for n in trainable) and any("task1" in n for n in trainable)
+    before = {n: g.get_param(p).clone() for n, p in params.items()}
+    base_loss = float(g.run(loss, [loss], {**feed, mask: task1})[0])
+    losses = [float(g.run(loss, [loss, train], {**feed, mask: task0})[0]) for _ in range(25)]
+    assert losses[-1] < 0.97 * losses[0]
+    after = {n: g.get_param(p) for n, p in params.items()}
+    changed = {n for n in params if not torch.equal(before[n], after[n])}
+    assert changed and all("task0" in n for n in changed)                       # base weights and task-1 adapters untouched
+    assert float(g.run(loss, [loss], {**feed, mask: task1})[0]) == pytest.approx(base_loss, rel=1e-5)   # task 1 still = base model
+    assert float(g.run(loss, [loss], {**feed, mask: task0})[0]) < 0.97 * base_loss
+    # mixed batch: the first half of the tokens belongs to task 0, the rest to task 1
+    mixed = torch.cat([task0[:B * S // 2], task1[B * S // 2:]])
+    lm = float(g.run(loss, [loss], {**feed, mask: mixed})[0])
+    assert float(g.run(loss, [loss], {**feed, mask: task0})[0]) < lm < base_loss
