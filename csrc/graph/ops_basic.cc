@@ -91,10 +91,23 @@ static Tensor reduce_to_shape(Graph* g, const Tensor& grad, const Tensor& like) 
   if (grad->shape == like->shape) return grad;
   AttrMap a;
   a.set("shape", like->shape);
+  // which target dims were broadcast (size 1 against a larger gradient dim): the other dims follow the gradient's RUNTIME
+  // size, so the op stays valid when the token count changes from run to run
+  const int lead = (int)grad->shape.size() - (int)like->shape.size();
+  std::vector<int64_t> bcast;
+  for (size_t j = 0; j < like->shape.size(); ++j)
+    bcast.push_back(lead >= 0 && like->shape[j] == 1 && grad->shape[j + lead] != 1 ? 1 : 0);
+  if (lead >= 0) a.set("bcast", bcast);
   return g->make_op1("reduce_to_shape", {grad}, a);
 }
 static Ts reduce_to_shape_compute(const OpDef& op, const Ts& in, RunCtx*) {
-  return {at::sum_to(in[0], op.attrs.ints("shape"))};
+  std::vector<int64_t> target = op.attrs.ints("shape");
+  const auto bcast = op.attrs.ints("bcast");
+  if (bcast.size() == target.size()) {
+    const int64_t lead = in[0].dim() - (int64_t)target.size();
+    for (size_t j = 0; j < target.size(); ++j) target[j] = bcast[j] ? 1 : in[0].size((int64_t)j + lead);
+  }
+  return {at::sum_to(in[0], target)};
 }
 static void reduce_to_shape_deduce(OpDef& op, size_t s) {
   // summed-away dims that were sharded leave partial sums; surviving dims keep their split (shifted to the new rank)

@@ -97,9 +97,10 @@ class _MultiMixin:
         self._task_mask = mask
 
     def _route(self, deltas: List):
+        # one [tokens, 1] column per task (a split follows the fed token count; a static slice would pin it)
+        cols = ops.split(self._task_mask, len(deltas), dim=1) if len(deltas) > 1 else [self._task_mask]
         out = None
-        for i, d in enumerate(deltas):
-            m = ops.slice(self._task_mask, [0, i], [self._task_mask.shape[0], 1])
+        for d, m in zip(deltas, cols):
             out = d * m if out is None else out + d * m
         return out
 
