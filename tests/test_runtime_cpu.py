@@ -95,3 +95,21 @@ def test_shared_memory_pool_and_registry(tmp_path):
     pool.free(p); pool.free(q)
     assert _C.get_memory_pool("cpu").shm_locate(0) is None
     assert _C.empty_all_memory_caches() >= 0
+
+
+def test_cuda_profiler_degrades_gracefully_without_a_gpu(tmp_path):
+    """memory / NVLink / clock profiler (G17): without a GPU or NVML every probe returns zeros instead of failing, and the
+    per-micro-batch memory log is still written"""
+    import json
+    from hetu_b200.utils.profiler import CUDAProfiler, get_cuda_profiler
+    p = CUDAProfiler(log_file=str(tmp_path / "mem.jsonl"))
+    info = p.get_current_memory_info()
+    assert info.mempool_allocated >= 0 and info.all_reserved >= 0
+    p.record_micro_batch(True, 0, 1, info, info)
+    p.record_micro_batch(False, 0, 1, info, info)
+    rows = [json.loads(l) for l in open(tmp_path / "mem.jsonl")]
+    assert [r["is_forward"] for r in rows] == [True, False] and rows[0]["micro_batch_id"] == 1 and "begin" in rows[0]
+    p.profile_nvlink_start()
+    nv = p.profile_nvlink_end()
+    assert nv["tx_bytes"] >= 0 and nv["seconds"] >= 0 and isinstance(p.clocks(), dict)
+    assert get_cuda_profiler() is get_cuda_profiler()
