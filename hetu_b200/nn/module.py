@@ -102,6 +102,37 @@ class Module:
                     p.set_eager_data(g.get_param(p))
         return missing, unexpected
 
+    def buffers(self):
+        for _, b in self.named_buffers():
+            yield b
+
+    def named_children(self) -> Iterator[Tuple[str, "Module"]]:
+        for n, m in self._modules.items():
+            if m is not None:
+                yield n, m
+
+    def apply(self, fn):
+        """fn(module) on every sub-module (children first), then on self"""
+        for m in self.children():
+            m.apply(fn)
+        fn(self)
+        return self
+
+    def to(self, dtype=None, **kw):
+        """cast the floating-point parameters / buffers (device placement is decided by the graph's device groups)"""
+        if dtype is None:
+            return self
+        from ..core import to_torch_dtype
+        td = to_torch_dtype(dtype) if not isinstance(dtype, torch.dtype) else dtype
+        for _, p in list(self.named_parameters()) + list(self.named_buffers()):
+            g = _graphs_by_id.get(p.graph_id)
+            if g is None or not g.has_param(p):
+                continue
+            d = g.get_param(p)
+            if d.is_floating_point() and d.dtype != td:
+                g.set_param(p, d.to(td))
+        return self
+
     def train(self, mode: bool = True):
         for m in self.modules():
             object.__setattr__(m, "training", mode)

@@ -281,3 +281,15 @@ def test_micro_batches_of_different_sequence_lengths():
         assert torch.allclose(after_a[n], after_b[n], atol=2e-6, rtol=1e-5), n
     moved = sum(float((after_a[n] - g.get_param(p)).abs().sum()) for n, p in model.named_parameters())
     assert moved == 0.0 and any(float(v.abs().sum()) > 0 for v in after_a.values())
+
+
+def test_module_tree_helpers_buffers_children_apply():
+    with ht.graph("define_and_run", create_new=True):
+        seq = ht.nn.Sequential(ht.nn.Linear(4, 8, name="a"), ht.nn.ReLU(), ht.nn.Linear(8, 2, name="b"))
+        bn = ht.nn.BatchNorm(3)
+    assert [n for n, _ in seq.named_children()] == ["0", "1", "2"] and len(list(seq.children())) == 3
+    seen = []
+    seq.apply(lambda m: seen.append(type(m).__name__))
+    assert seen == ["Linear", "ReLU", "Linear", "Sequential"]
+    assert len(list(bn.buffers())) == len(list(bn.named_buffers())) >= 2
+    assert seq.eval().training is False and seq.train().training is True and seq.to(None) is seq
