@@ -371,11 +371,21 @@ class Trainer:
             lv = self.hetero.reduce_loss(lv, len(batch), n_global)      # global mean from the per-pipeline means
         return lv, stats
 
-    def train(self, steps: Optional[int] = None, strategy_schedule: Optional[Callable[[int], int]] = None):
+    def train(self, steps: Optional[int] = None, strategy_schedule: Optional[Callable[[int], int]] = None, strategy_id: Optional[int] = None,
+              cp_list=None, run_level=None):
         """run `steps` optimizer steps; `strategy_schedule(step) -> strategy id` enables hot switching between the
-        strategies of ds_parallel_configs (HotSPa: e.g. by the step's max sequence length)"""
+        strategies of ds_parallel_configs (HotSPa: e.g. by the step's max sequence length).  `strategy_id` (reference
+        signature `train(cp_list, strategy_id, run_level)`) starts under that strategy; the context-parallel layout comes
+        from the strategy's `cp` field, so `cp_list` is accepted for compatibility only; `run_level` wraps the loop in
+        `hetu.run_level(...)` (e.g. "compute_only" for a forward-only pass over the data)."""
+        if run_level is not None:
+            with core.run_level(run_level):
+                return self.train(steps, strategy_schedule, strategy_id, cp_list, None)
         cfg = self.pretrain_config
         self.build()
+        if strategy_id is not None and int(strategy_id) != self.cur_strategy_id and not self.idle:
+            self.trainer_states.graph.switch_strategy(int(strategy_id))
+            self.cur_strategy_id = int(strategy_id)
         it, it_version = self.train_data_iterator(), getattr(self, "_iter_version", 0)
         steps = int(steps if steps is not None else cfg.steps)
         saver = None
