@@ -313,3 +313,20 @@ def test_grouped_slice_collectives_over_heterogeneous_holders():
     ok, outs = run_workers(os.path.join(os.path.dirname(__file__), "workers", "grouped_comm_worker.py"), 3, [])
     assert ok, "\n-----\n".join(outs)
     assert sum("GROUPED" in o and "True" in o for o in outs) == 3
+
+
+@pytest.mark.dist
+def test_single_strategy_parallel_modules_are_tp_invariant():
+    """hetu.nn.{VocabParallelEmbedding, ColumnParallelLinear, RowParallelLinear, ParallelLayerNorm}(device_group, dp): outputs and
+    the effect of one SGD step are the same under tp = 1 and tp = 2 (the reference's tests/test_parallel.py scenario)"""
+    worker = os.path.join(os.path.dirname(__file__), "workers", "parallel_modules_worker.py")
+    res = []
+    for tp in (1, 2):
+        ok, outs = run_workers(worker, tp, [tp])
+        assert ok, "\n-----\n".join(outs)
+        line = next(l for o in outs for l in o.splitlines() if l.startswith("PM "))
+        res.append(json.loads(line[3:]))
+    a, b = res
+    assert abs(a["l0"] - b["l0"]) < 1e-5 and abs(a["l1"] - b["l1"]) < 1e-5 and a["l1"] < a["l0"]
+    for k in ("y0", "y1"):
+        assert max(abs(x - y) for x, y in zip(a[k], b[k])) < 1e-4
