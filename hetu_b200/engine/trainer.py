@@ -450,8 +450,9 @@ class Trainer:
             for cb in self.callbacks:
                 cb(self, loss, stats)
             if saver is not None and self.global_step % cfg.save_interval == 0:
+                writer = min(d for p in self.hetero.pipelines for stg in p for d in stg) if self.hetero is not None else 0
                 saver.save(self.trainer_states.model, self.trainer_states.optimizer, self.global_step, self.consumed_samples,
-                           loss if loss is not None else float("nan"))
+                           loss if loss is not None else float("nan"), writer_rank=writer)
             if cfg.plot_loss and self.global_step % cfg.plot_update_freq == 0:
                 self.plot_training_loss()
         if saver is not None:
