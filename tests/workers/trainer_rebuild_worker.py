@@ -22,18 +22,24 @@ cfg = TrainingConfig(packing=False, micro_batch_size=2, global_load_size=6, max_
 first = [generate_ds_parallel_config(2, world, world, 1, 1, zero=False)]
 tr = Trainer(cfg, ModelWrapper(GPTLMHeadModel, mcfg), ByteTokenizer(), OptimizerWrapper({"type": "adam", "lr": 1e-2}), ds, ds_parallel_configs=first)
 if mode == "single":
-    losses = tr.train(steps=4)
+    losses = tr.train(steps=5)
 else:
     tr.train(steps=2)
     pipelines = [{"stages": [{"devices": [0, 1], "layers": [0, 1]}]}, {"stages": [{"devices": [2], "layers": [0, 1]}]}]
     tr.rebuild([generate_hetero_ds_parallel_config(2, pipelines, zero=False)], hetero_shares=[2, 1])
     assert tr.hetero is not None and tr.global_step == 2
-    losses = tr.train(steps=2)
+    tr.train(steps=2)
+    # ... and back: the checkpoint written by the heterogeneous pipelines (each saves its own shards) re-shards onto plain dp3
+    tr.rebuild(first)
+    assert tr.hetero is None and tr.global_step == 4
+    losses = tr.train(steps=1)
 import torch
 t = torch.tensor([float(v) for v in losses], dtype=torch.float64)
 if mode == "rebuild":
-    # the first two entries are per-replica means of the dp3 phase: average them; the hetero phase already reports the global mean
+    # dp3 phases report per-replica means: average them; the hetero phase already reports the global mean (on the loss ranks)
+    t = torch.where(torch.isnan(t), torch.zeros_like(t), t) if len(t) == 5 else torch.cat([t, torch.zeros(5 - len(t), dtype=t.dtype)])
     head = ht._C.comm_all_reduce(t[:2].clone(), [0, 1, 2], "sum") / 3
-    t = torch.cat([head, t[2:]])
+    tail = ht._C.comm_all_reduce(t[4:].clone(), [0, 1, 2], "sum") / 3
+    t = torch.cat([head, t[2:4], tail])
 if distributed.rank() == 0:
     print("LOSSES " + json.dumps([float(v) for v in t]))
