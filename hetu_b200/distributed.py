@@ -66,6 +66,9 @@ def init_comm_group(device_num: Optional[int] = None, device_idxs=(), server_add
             kw = {}
             if use_cuda:
                 kw["device_id"] = torch.device("cuda", local_rank % torch.cuda.device_count())
+            if os.environ.get("HETU_PG_TIMEOUT_S"):       # collectives that cannot complete fail after this long (tests)
+                import datetime
+                kw["timeout"] = datetime.timedelta(seconds=float(os.environ["HETU_PG_TIMEOUT_S"]))
             dist.init_process_group(backend=be, rank=rank, world_size=world, **kw)
         pg = dist.distributed_c10d._get_default_group()
         _C.init_comm(rank, world, pg, _factory)

@@ -33,7 +33,7 @@ def _env(rank, local_rank, world, master_addr, master_port, extra, rendezvous_en
 
 
 def local_start(command: Sequence[str], ngpus: int, master_port: int = 29500, env: Optional[Dict[str, str]] = None,
-                log_dir: Optional[str] = None, wait: bool = True, rendezvous_env: bool = True):
+                log_dir: Optional[str] = None, wait: bool = True, rendezvous_env: bool = True, timeout: Optional[float] = None):
     """spawn `ngpus` copies of `command` on this node with torchrun-style env; returns exit codes (or the Popen list)"""
     procs = []
     for r in range(ngpus):
@@ -42,11 +42,26 @@ def local_start(command: Sequence[str], ngpus: int, master_port: int = 29500, en
                                       stderr=subprocess.STDOUT if out else None))
     if not wait:
         return procs
+    return _wait_all(procs, timeout)
+
+
+def _wait_all(procs, timeout: Optional[float] = None):
+    """exit codes; with a timeout the stragglers are killed when it expires (exit code -9)"""
+    import time
+    deadline = None if timeout is None else time.time() + float(timeout)
+    while any(p.poll() is None for p in procs):
+        if deadline is not None and time.time() > deadline:
+            for p in procs:
+                if p.poll() is None:
+                    p.kill()
+            break
+        time.sleep(0.1)
     return [p.wait() for p in procs]
 
 
 def pssh_start(command: str, hosts: List[Dict], master_port: int = 29500, envs: Optional[Dict[str, str]] = None,
-               env_script: Optional[str] = None, ssh_user: Optional[str] = None, dry_run: bool = False, rendezvous_env: bool = True):
+               env_script: Optional[str] = None, ssh_user: Optional[str] = None, dry_run: bool = False, rendezvous_env: bool = True,
+               timeout: Optional[float] = None):
     """one ssh session per worker; hosts whose addr is local run without ssh.  Returns exit codes (or the command lines
     when dry_run)."""
     world = sum(h["workers"] for h in hosts)
@@ -69,7 +84,7 @@ def pssh_start(command: str, hosts: List[Dict], master_port: int = 29500, envs: 
             rank += 1
     if dry_run:
         return lines
-    return [p.wait() for p in procs]
+    return _wait_all(procs, timeout)
 
 
 if __name__ == "__main__":

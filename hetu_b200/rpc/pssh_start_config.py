@@ -25,9 +25,9 @@ def main(argv=None):
         if c.get("hosts"):
             hosts = read_hosts_yaml(c.hosts)
             codes = pssh_start(c.command, hosts, master_port=port + 1, envs=envs, env_script=c.get("env_script"), ssh_user=c.get("ssh_user"),
-                               rendezvous_env=False)
+                               rendezvous_env=False, timeout=c.get("timeout"))
         else:
-            codes = local_start(shlex.split(c.command), n, master_port=port + 1, env=envs, log_dir=log_dir, rendezvous_env=False)
+            codes = local_start(shlex.split(c.command), n, master_port=port + 1, env=envs, log_dir=log_dir, rendezvous_env=False, timeout=c.get("timeout"))
     finally:
         srv.shutdown()
     return max(codes) if codes else 0

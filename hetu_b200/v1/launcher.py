@@ -24,7 +24,7 @@ import yaml
 from .ps import PSContext
 
 
-def launch(command: Sequence[str], settings: Dict, log_dir: Optional[str] = None, wait: bool = True):
+def launch(command: Sequence[str], settings: Dict, log_dir: Optional[str] = None, wait: bool = True, timeout: Optional[float] = None):
     shared = {str(k): str(v) for k, v in (settings.get("shared") or {}).items()}
     lc = settings.get("launch") or {}
     n_worker, n_server = int(lc.get("worker", 1)), int(lc.get("server", 1))
@@ -48,7 +48,8 @@ def launch(command: Sequence[str], settings: Dict, log_dir: Optional[str] = None
     signal.signal(signal.SIGINT, stop)
     if not wait:
         return procs, server
-    codes = [p.wait() for p in procs]
+    from ..rpc.launcher import _wait_all
+    codes = _wait_all(procs, timeout)
     if server is not None:
         server.stop()
     return codes

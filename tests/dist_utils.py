@@ -15,14 +15,14 @@ def free_port():
     return p
 
 
-def run_workers(script, world, args=(), force_cpu=True, timeout=600, env_extra=None):
+def _run_once(script, world, args, force_cpu, timeout, env_extra):
     port = free_port()
     procs = []
     for r in range(world):
         env = dict(os.environ)
         env.update({"RANK": str(r), "WORLD_SIZE": str(world), "LOCAL_RANK": str(r), "MASTER_ADDR": "127.0.0.1",
                     "MASTER_PORT": str(port), "PYTHONPATH": ROOT + os.pathsep + env.get("PYTHONPATH", ""),
-                    "OMP_NUM_THREADS": "1"})
+                    "OMP_NUM_THREADS": "1", "HETU_PG_TIMEOUT_S": str(max(int(timeout) // 2, 60))})
         if force_cpu:
             env["HETU_B200_FORCE_CPU"] = "1"
             env["CUDA_VISIBLE_DEVICES"] = ""
@@ -30,15 +30,29 @@ def run_workers(script, world, args=(), force_cpu=True, timeout=600, env_extra=N
             env.update(env_extra)
         procs.append(subprocess.Popen([sys.executable, script, *map(str, args)], env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.STDOUT, text=True))
-    outs = []
-    ok = True
-    for p in procs:
-        try:
-            o, _ = p.communicate(timeout=timeout)
-        except subprocess.TimeoutExpired:
-            p.kill()
-            o, _ = p.communicate()
-            ok = False
-        outs.append(o)
-        ok = ok and p.returncode == 0
+    # one deadline for the whole group: a hung rank must not cost `timeout` per process
+    import time
+    deadline = time.time() + timeout
+    timed_out = False
+    while any(p.poll() is None for p in procs):
+        if time.time() > deadline:
+            timed_out = True
+            for p in procs:
+                if p.poll() is None:
+                    p.kill()
+            break
+        time.sleep(0.1)
+    outs = [p.communicate()[0] for p in procs]
+    ok = (not timed_out) and all(p.returncode == 0 for p in procs)
+    return ok, outs, timed_out
+
+
+def run_workers(script, world, args=(), force_cpu=True, timeout=300, env_extra=None):
+    """-> (ok, [stdout+stderr per rank]).  A run that TIMES OUT (e.g. the rendezvous port was taken between `free_port()` and the
+    workers' bind) is retried once on a fresh port; failures with an exit code are never retried."""
+    ok, outs, timed_out = _run_once(script, world, args, force_cpu, timeout, env_extra)
+    if timed_out:
+        ok, outs, timed_out = _run_once(script, world, args, force_cpu, timeout, env_extra)
+        if timed_out:
+            outs = [o + "\n[run_workers] timed out twice" for o in outs]
     return ok, outs

@@ -186,7 +186,7 @@ def test_pssh_start_config_launches_workers_that_rendezvous_through_the_controll
     port = _free_port()
     worker = os.path.join(ROOT, "tests", "workers", "rpc_bootstrap_worker.py")
     (tmp_path / "config.yaml").write_text(
-        f"rpc:\n  num_gpus: 2\n  server_port: {port}\n  log_path: {tmp_path}/logs\n  envs: {{HETU_B200_FORCE_CPU: 1, CUDA_VISIBLE_DEVICES: '', OMP_NUM_THREADS: 1, PYTHONPATH: {ROOT}}}\n"
+        f"rpc:\n  num_gpus: 2\n  timeout: 240\n  server_port: {port}\n  log_path: {tmp_path}/logs\n  envs: {{HETU_B200_FORCE_CPU: 1, CUDA_VISIBLE_DEVICES: '', OMP_NUM_THREADS: 1, PYTHONPATH: {ROOT}}}\n"
         f"ds_parallel:\n  num_layers: 8\n  num_gpus: 8\n  dp: 2\n  tp: 2\n  pp: 2\n  zero: true\n  ds_parallel_config_path: {tmp_path}/ds\n  ds_parallel_config_name: s.json\n")
     rc = launch_main(["--config-path", str(tmp_path), "--config-name", "config", f"rpc.command={sys.executable} {worker} 127.0.0.1:{port} 2"])
     logs = sorted((tmp_path / "logs").glob("rank*.log"))
@@ -199,7 +199,7 @@ def test_pssh_start_config_launches_workers_that_rendezvous_through_the_controll
     assert cfg["blocks"]["blocks0-3"]["attn"]["qkv"]["split"] == {"0": [4]} and cfg["zero"] in (True, False)
     r = subprocess.run([sys.executable, "-m", "hetu.models.llama.generate_llama_hetero_4d_config", "--config-path", str(tmp_path),
                         "ds_parallel.hetero_layers=[[4,4],[8]]", "ds_parallel.hetero_tp=[2,1]", "ds_parallel.ds_parallel_config_name=h.json"],
-                       env={**os.environ, "PYTHONPATH": ROOT, "HETU_B200_FORCE_CPU": "1"}, capture_output=True, text=True, cwd=str(tmp_path))
+                       env={**os.environ, "PYTHONPATH": ROOT, "HETU_B200_FORCE_CPU": "1"}, capture_output=True, text=True, cwd=str(tmp_path), timeout=240)
     assert r.returncode == 0, r.stderr
     h = json.load(open(tmp_path / "ds" / "h.json"))
     assert h["blocks"]["blocks0"]["attn"]["qkv"]["device_group_union"] == [[0, 1], [4]] and h["blocks"]["blocks5"]["attn"]["qkv"]["device_group_union"] == [[2, 3], [4]]

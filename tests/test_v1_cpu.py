@@ -242,7 +242,7 @@ def test_parameter_server_over_the_network_with_heturun_launcher(tmp_path):
     os.environ.update({"PYTHONPATH": root, "HETU_B200_FORCE_CPU": "1", "CUDA_VISIBLE_DEVICES": "", "OMP_NUM_THREADS": "1"})
     try:
         codes = launch([sys.executable, os.path.join(root, "tests", "workers", "ps_net_worker.py")],
-                       {"shared": {"DMLC_PS_ROOT_URI": "127.0.0.1"}, "launch": {"worker": 3, "server": 1, "scheduler": 1}}, log_dir=str(logs))
+                       {"shared": {"DMLC_PS_ROOT_URI": "127.0.0.1"}, "launch": {"worker": 3, "server": 1, "scheduler": 1}}, log_dir=str(logs), timeout=240)
     finally:
         os.environ.clear()
         os.environ.update(env_keep)
