@@ -31,6 +31,7 @@ def _factory(ranks: List[int]):
 def init_comm_group(device_num: Optional[int] = None, device_idxs=(), server_address: str = "127.0.0.1:23457", backend: Optional[str] = None):
     """Join the job.  World size / rank come from the launcher environment (RANK, WORLD_SIZE, LOCAL_RANK, MASTER_*)."""
     global _local_device, _global_group, _rpc_client
+    _rpc_store = None
     if "RANK" not in os.environ and os.environ.get("HETU_RENDEZVOUS", "") == "rpc":
         # reference-style bootstrap: workers started by the pssh launcher know only the controller's address; the
         # DeviceController hands out rank / local device / world size (native client, csrc/runtime/rpc_client.cc) and
@@ -41,14 +42,30 @@ def init_comm_group(device_num: Optional[int] = None, device_idxs=(), server_add
         server_address = os.environ.get("HETU_RPC_SERVER", server_address)
         _rpc_client = NativeDeviceClient(server_address, hostname=os.environ.get("HETU_LOCAL_HOSTNAME"))
         r, local, w = _rpc_client.connect()
+        import datetime
+        st_timeout = datetime.timedelta(seconds=float(os.environ.get("HETU_PG_TIMEOUT_S", "1800")))
         if r == 0:
-            sk = socket.socket()
-            sk.bind(("", 0))
-            port = sk.getsockname()[1]
-            sk.close()
+            # rank 0 owns the torch.distributed store: it binds FIRST (retrying on another port if the candidate was taken in
+            # the meantime) and only then publishes the address, so the other ranks can never race a half-chosen port
             host = os.environ.get("HETU_MASTER_HOST", server_address.rsplit(":", 1)[0])
+            last = None
+            for _ in range(16):
+                sk = socket.socket()
+                sk.bind(("", 0))
+                port = sk.getsockname()[1]
+                sk.close()
+                try:
+                    _rpc_store = dist.TCPStore(host, port, w, True, st_timeout, wait_for_workers=False)
+                    break
+                except (RuntimeError, OSError) as e:      # address in use: try the next free port
+                    last = e
+            else:
+                raise RuntimeError(f"could not bind a store port: {last}")
             _rpc_client.put_string("torch_master", f"{host}:{port}")
         master = _rpc_client.get_string("torch_master")
+        if r != 0:
+            mh, mp = master.rsplit(":", 1)
+            _rpc_store = dist.TCPStore(mh, int(mp), w, False, st_timeout)
         os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = master.rsplit(":", 1)
         os.environ["RANK"], os.environ["WORLD_SIZE"], os.environ["LOCAL_RANK"] = str(r), str(w), str(local)
     rank = int(os.environ.get("RANK", "0"))
@@ -69,6 +86,8 @@ def init_comm_group(device_num: Optional[int] = None, device_idxs=(), server_add
             if os.environ.get("HETU_PG_TIMEOUT_S"):       # collectives that cannot complete fail after this long (tests)
                 import datetime
                 kw["timeout"] = datetime.timedelta(seconds=float(os.environ["HETU_PG_TIMEOUT_S"]))
+            if _rpc_store is not None:
+                kw["store"] = _rpc_store
             dist.init_process_group(backend=be, rank=rank, world_size=world, **kw)
         pg = dist.distributed_c10d._get_default_group()
         _C.init_comm(rank, world, pg, _factory)
