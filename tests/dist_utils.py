@@ -48,10 +48,11 @@ def _run_once(script, world, args, force_cpu, timeout, env_extra):
 
 
 def run_workers(script, world, args=(), force_cpu=True, timeout=300, env_extra=None):
-    """-> (ok, [stdout+stderr per rank]).  A run that TIMES OUT (e.g. the rendezvous port was taken between `free_port()` and the
-    workers' bind) is retried once on a fresh port; failures with an exit code are never retried."""
+    """-> (ok, [stdout+stderr per rank]).  A run that TIMES OUT or fails to bind the rendezvous port (taken between
+    `free_port()` and the workers' bind) is retried once on a fresh port; other failures are never retried."""
     ok, outs, timed_out = _run_once(script, world, args, force_cpu, timeout, env_extra)
-    if timed_out:
+    port_taken = (not ok) and any("Address already in use" in o or "EADDRINUSE" in o for o in outs)
+    if timed_out or port_taken:
         ok, outs, timed_out = _run_once(script, world, args, force_cpu, timeout, env_extra)
         if timed_out:
             outs = [o + "\n[run_workers] timed out twice" for o in outs]
