@@ -17,7 +17,8 @@ ht.init_comm_group(world)
 ht.set_seed(3)
 mcfg = GPTConfig(vocab_size=260, n_positions=32, n_embd=32, n_layer=4, n_head=4)
 ds = SyntheticDataset(64, 259, 32, seed=1, length_distribution="fixed")
-cfg = TrainingConfig(packing=False, micro_batch_size=2, global_load_size=8, max_seq_length=32, steps=4, learning_rate=1e-2, log_interval=0,
+PACK = os.environ.get("TRAINER_PACK") == "1"
+cfg = TrainingConfig(packing=PACK, micro_batch_size=None if PACK else 2, global_load_size=8, max_seq_length=32, steps=4, learning_rate=1e-2, log_interval=0,
                      pack_alignment=16, output_dir=os.environ.get("TRAINER_OUT", "/tmp/hb_trainer_hetero"), save_interval=int(os.environ.get("TRAINER_SAVE", "0")))
 if mode == "hetero":
     pipelines = [{"stages": [{"devices": [0, 1], "layers": [0, 1]}, {"devices": [2, 3], "layers": [2, 3]}]}, {"stages": [{"devices": [4], "layers": [0, 3]}]}]
