@@ -52,7 +52,7 @@ def run_workers(script, world, args=(), force_cpu=True, timeout=300, env_extra=N
     `free_port()` and the workers' bind) is retried once on a fresh port; other failures are never retried."""
     ok, outs, timed_out = _run_once(script, world, args, force_cpu, timeout, env_extra)
     port_taken = (not ok) and any("Address already in use" in o or "EADDRINUSE" in o for o in outs)
-    if timed_out or port_taken:
+    if (timed_out and force_cpu) or port_taken:       # GPU runs are not repeated after a timeout (they are long)
         ok, outs, timed_out = _run_once(script, world, args, force_cpu, timeout, env_extra)
         if timed_out:
             outs = [o + "\n[run_workers] timed out twice" for o in outs]
