@@ -16,8 +16,9 @@ def free_port():
 
 
 def _run_once(script, world, args, force_cpu, timeout, env_extra):
+    import tempfile
     port = free_port()
-    procs = []
+    procs, logs = [], []
     for r in range(world):
         env = dict(os.environ)
         env.update({"RANK": str(r), "WORLD_SIZE": str(world), "LOCAL_RANK": str(r), "MASTER_ADDR": "127.0.0.1",
@@ -28,8 +29,10 @@ def _run_once(script, world, args, force_cpu, timeout, env_extra):
             env["CUDA_VISIBLE_DEVICES"] = ""
         if env_extra:
             env.update(env_extra)
-        procs.append(subprocess.Popen([sys.executable, script, *map(str, args)], env=env, stdout=subprocess.PIPE,
-                                      stderr=subprocess.STDOUT, text=True))
+        # output goes to a file, not a pipe: a chatty worker (long tracebacks, NCCL_DEBUG) can never block on a full pipe
+        log = tempfile.TemporaryFile(mode="w+", prefix=f"hb_worker{r}_")
+        logs.append(log)
+        procs.append(subprocess.Popen([sys.executable, script, *map(str, args)], env=env, stdout=log, stderr=subprocess.STDOUT, text=True))
     # one deadline for the whole group: a hung rank must not cost `timeout` per process
     import time
     deadline = time.time() + timeout
@@ -42,7 +45,12 @@ def _run_once(script, world, args, force_cpu, timeout, env_extra):
                     p.kill()
             break
         time.sleep(0.1)
-    outs = [p.communicate()[0] for p in procs]
+    outs = []
+    for p, log in zip(procs, logs):
+        p.wait()
+        log.seek(0)
+        outs.append(log.read())
+        log.close()
     ok = (not timed_out) and all(p.returncode == 0 for p in procs)
     return ok, outs, timed_out
 
