@@ -405,6 +405,19 @@ PYBIND11_MODULE(_C, m) {
       .def("switch_strategy", [](Graph& g, int from, int to) { g.executor()->switch_strategy(from, to); })
       .def("reinfer_shapes", &Graph::reinfer_shapes)
       .def("set_profile", [](Graph& g, bool on) { g.executor()->set_profile(on); })
+      .def("set_loss_scaler", [](Graph& g, const Tensor& var, double init_scale, double growth, double backoff, int64_t interval) {
+        g.executor()->set_loss_scaler(var, init_scale, growth, backoff, interval);
+      })
+      .def("loss_scale", [](Graph& g) { return g.executor()->loss_scaler().scale; })
+      .def("set_loss_scale", [](Graph& g, double v) {
+        auto& s = g.executor()->loss_scaler();
+        s.scale = v;
+        if (s.scale_var) g.executor()->get_param(s.scale_var).fill_(v);
+      })
+      .def("loss_scaler_state", [](Graph& g) {
+        auto& s = g.executor()->loss_scaler();
+        return py::make_tuple(s.enabled, s.scale, s.tracker, s.skipped, s.last_found_inf);
+      })
       .def("op_times", [](Graph& g) { return g.executor()->op_times(); })
       .def("step_breakdown", [](Graph& g) { return g.executor()->step_breakdown(); })
       .def("accumulated_grad", [](Graph& g, const Tensor& param) -> py::object {

@@ -47,6 +47,10 @@ std::ostream& operator<<(std::ostream& os, const std::vector<T>& v) {
   return os << "]";
 }
 
+// "\n  at <module>+0x<offset> ..." for the calling frames (resolve with addr2line -e <module> <offset>); empty unless
+// HETU_BACKTRACE=1.  Makes a failed check on a remote GPU box diagnosable without a debugger.
+std::string capture_backtrace();
+
 class Error : public std::runtime_error {
  public:
   explicit Error(const std::string& m) : std::runtime_error(m) {}
@@ -63,7 +67,7 @@ class ErrorBuilder {
     os_ << v;
     return *this;
   }
-  [[noreturn]] ~ErrorBuilder() noexcept(false) { throw Error(os_.str()); }
+  [[noreturn]] ~ErrorBuilder() noexcept(false) { throw Error(os_.str() + capture_backtrace()); }
 
  private:
   std::ostringstream os_;

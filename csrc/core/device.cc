@@ -1,4 +1,7 @@
 #include "device.h"
+#include <dlfcn.h>
+#include <execinfo.h>
+#include <cstring>
 
 #include <cstring>
 #include <mutex>
@@ -21,6 +24,25 @@ static std::string g_prefix;
 static std::mutex g_log_mu;
 
 LogLevel log_level() { return g_level; }
+
+std::string capture_backtrace() {
+  const char* e = std::getenv("HETU_BACKTRACE");
+  if (!e || e[0] == '0') return "";
+  void* frames[48];
+  const int n = ::backtrace(frames, 48);
+  std::ostringstream os;
+  os << "\n  backtrace:";
+  for (int i = 1; i < n; ++i) {
+    Dl_info info;
+    if (dladdr(frames[i], &info) && info.dli_fname) {
+      const char* base = std::strrchr(info.dli_fname, '/');
+      os << "\n    " << (base ? base + 1 : info.dli_fname) << "+0x" << std::hex
+         << (uintptr_t)((char*)frames[i] - (char*)info.dli_fbase) << std::dec;
+      if (info.dli_sname) os << " (" << info.dli_sname << ")";
+    }
+  }
+  return os.str();
+}
 void set_log_level(LogLevel l) { g_level = l; }
 void set_log_prefix(const std::string& p) { g_prefix = p; }
 const std::string& log_prefix() { return g_prefix; }

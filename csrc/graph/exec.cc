@@ -250,6 +250,16 @@ Device Executor::local_device() const {
   const bool cuda = at::hasCUDA() && env_int("HETU_B200_FORCE_CPU", 0) == 0;
   return Device(cuda ? DeviceType::CUDA : DeviceType::CPU, c.initialized() ? c.rank() : 0);
 }
+void Executor::set_loss_scaler(const Tensor& scale_var, double init_scale, double growth, double backoff, int64_t interval) {
+  scaler_ = LossScaler();
+  scaler_.enabled = true;
+  scaler_.scale_var = scale_var;
+  scaler_.scale = init_scale;
+  scaler_.growth = growth;
+  scaler_.backoff = backoff;
+  scaler_.interval = interval;
+  if (scale_var) get_param(scale_var).fill_(init_scale);
+}
 int Executor::local_device_index(const DeviceGroup& g) const {
   // devices are identified by their global rank (index); type is ignored so that CPU (gloo) test runs and
   // GPU runs share strategy files
@@ -946,7 +956,8 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
   // ZeRO over symmetric memory (fused with the wgrad GEMM epilogues and the optimizer); prepared once per plan
   if (!tp_fused_.count(&plan)) tp_fused_scan(plan);
   zf_active_ = nullptr;
-  if (!inference && opt.run_level == RunLevel::UPDATE) {
+  // (with a loss scaler the gradients must be inspected before they are reduced into the optimizer: plain path)
+  if (!inference && opt.run_level == RunLevel::UPDATE && !scaler_.enabled) {
     auto zit = zero_fused_.find(&plan);
     if (zit == zero_fused_.end()) zit = zero_fused_.emplace(&plan, zero_fused_prepare(plan)).first;
     if (zit->second && zit->second->ok) {
@@ -1004,11 +1015,37 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
   if (!inference && opt.run_level == RunLevel::UPDATE) {
     const double t_u = now_ms();
     std::unordered_map<TensorId, at::Tensor> uvals;
-    const double scale = opt.grad_scale / (double)M;
+    double scale = opt.grad_scale / (double)M;
+    bool skip_update = false;
+    if (scaler_.enabled) {
+      // un-scale by folding 1/loss_scale into the gradient multiplier; look for inf/nan in what this rank accumulated
+      scale /= scaler_.scale;
+      at::Tensor found = at::zeros({1}, at::TensorOptions().dtype(at::kFloat).device(aten_device()));
+      for (auto& kv : accum_grads_)
+        found = at::maximum(found, at::logical_not(at::isfinite(kv.second)).any().to(at::kFloat).reshape({1}));
+      auto& comm = CommRuntime::get();
+      if (comm.initialized() && comm.world() > 1) {
+        std::vector<int> all(comm.world());
+        for (int i = 0; i < comm.world(); ++i) all[i] = i;
+        found = comm.all_reduce(found, all, ReductionType::MAX);
+      }
+      skip_update = found.item<float>() > 0.f;       // host sync, as in the reference's SGDUpdateWithGradScaler
+      scaler_.last_found_inf = skip_update;
+      if (skip_update) {
+        scaler_.scale *= scaler_.backoff;
+        scaler_.tracker = 0;
+        ++scaler_.skipped;
+      } else if (++scaler_.tracker >= scaler_.interval) {
+        scaler_.scale *= scaler_.growth;
+        scaler_.tracker = 0;
+      }
+      if (scaler_.scale_var) get_param(scaler_.scale_var).fill_(scaler_.scale);
+    }
     std::vector<at::Tensor> deferred_steps;
     if (aten_device().is_cuda()) rc.deferred_steps = &deferred_steps;
     if (zf_active_ != nullptr) zero_fused_update(plan, *zf_active_, scale);
     for (OpDef* op : plan.update_ops) {
+      if (skip_update) break;                  // inf/nan gradients: drop this step
       if (op->has_flag(kFlagGroup)) continue;
       if (zf_active_ != nullptr && zf_active_->handled_ops.count(op->id)) continue;
       if (op->type == "grouped_all_reduce") {

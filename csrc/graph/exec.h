@@ -160,6 +160,19 @@ class Executor {
   // hot switch: re-shard every parameter / optimizer state from strategy a to b
   void switch_strategy(int from, int to);
   int active_strategy() const { return active_strategy_; }
+  // dynamic loss scaling (ref: hetu/graph/autocast/gradscaler.h, optimizer_update.cc SGDUpdateWithGradScaler): the loss is
+  // multiplied by the value of `scale_var` inside the graph; the update phase un-scales the accumulated gradients, checks
+  // them for inf/nan on every rank (MAX all-reduce), skips the optimizer step and backs the scale off when one is found,
+  // and grows the scale after `growth_interval` clean steps.
+  struct LossScaler {
+    bool enabled = false;
+    Tensor scale_var;
+    double scale = 65536.0, growth = 2.0, backoff = 0.5;
+    int64_t interval = 2000, tracker = 0, skipped = 0;
+    bool last_found_inf = false;
+  };
+  void set_loss_scaler(const Tensor& scale_var, double init_scale, double growth, double backoff, int64_t interval);
+  LossScaler& loss_scaler() { return scaler_; }
 
  private:
   ExecPlan& get_plan(const Tensor& loss, const TensorList& fetches, int strategy);
@@ -194,6 +207,7 @@ class Executor {
   int active_strategy_ = -1;
   int shapes_strategy_ = -1;   // strategy whose local shapes are currently stored in the tensors
   uint64_t step_ = 0;
+  LossScaler scaler_;
 };
 
 }  // namespace hb
