@@ -7,6 +7,8 @@
 //  graph/autocast/gradscaler; hetu/v1/python/hetu/layers/{moe_layer,TopGate}.py)
 #include <ATen/ATen.h>
 
+#include <algorithm>
+
 #include "exec.h"
 #include "ir.h"
 #include "op_utils.h"
@@ -161,6 +163,69 @@ static void moe_gate_deduce(OpDef& op, size_t s) {
   }
 }
 HB_REGISTER_OP(moe_gate, "moe_gate", 4, kFlagNondiff, moe_gate_compute, nullptr, moe_gate_deduce, nullptr);
+
+
+// moe_balance_assign: BASE-layer balanced assignment.  scores [T, E] -> (gate prob of the assigned expert [T,1] fp32,
+// expert [T,1] int32, slot [T,1] int32, aux [1] = 0).  Every expert receives at most `capacity` tokens.  Rounds of
+// (propose to the best expert with room, experts keep their best proposers); the CUDA path runs the two kernels of
+// moe.cu for E rounds without touching the host, the CPU path is the same algorithm in plain loops.
+// (ref: hetu/v1/python/hetu/layers/BalanceGate.py:42 balance_assignment_op, gpu_ops/BalanceAssignment.py)
+static Ts moe_balance_assign_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  const at::Tensor& logits = in[0];
+  const int64_t T = logits.size(0), E = logits.size(1);
+  int64_t capacity = op.attrs.i("capacity", 0);
+  if (capacity <= 0) capacity = (T + E - 1) / E;
+  HB_CHECK(capacity * E >= T) << "balanced assignment needs capacity * experts >= tokens (" << capacity << " * " << E << " < " << T << ")";
+  auto fopt = logits.options().dtype(at::kFloat);
+  auto iopt = logits.options().dtype(at::kInt);
+  if (logits.is_meta()) return {at::empty({T, 1}, fopt), at::empty({T, 1}, iopt), at::empty({T, 1}, iopt), at::empty({1}, fopt)};
+  at::Tensor scores = logits.to(at::kFloat).contiguous();
+  at::Tensor idx = at::empty({T, 1}, iopt), loc = at::empty({T, 1}, iopt);
+  if (scores.is_cuda() && env_int("HETU_B200_FORCE_CPU", 0) == 0) {
+    at::Tensor filled = at::empty({E}, iopt), choice = at::empty({T}, iopt);
+    cuda_ok(moe_balance_assign(scores.data_ptr<float>(), idx.data_ptr<int32_t>(), loc.data_ptr<int32_t>(), filled.data_ptr<int32_t>(),
+                               choice.data_ptr<int32_t>(), T, (int)E, (int)capacity, cur_stream()), "moe_balance_assign");
+  } else {
+    at::Tensor sc = scores.cpu();
+    const float* sp = sc.data_ptr<float>();
+    std::vector<int> ia(T, -1), la(T, -1), filled(E, 0), choice(T, -1);
+    for (int64_t round = 0; round < E; ++round) {
+      bool any = false;
+      for (int64_t t = 0; t < T; ++t) {
+        choice[t] = -1;
+        if (ia[t] >= 0) continue;
+        float best = 0.f;
+        for (int64_t e = 0; e < E; ++e) {
+          if (filled[e] >= capacity) continue;
+          if (choice[t] < 0 || sp[t * E + e] > best) { best = sp[t * E + e]; choice[t] = (int)e; }
+        }
+        any = true;
+      }
+      if (!any) break;
+      for (int64_t e = 0; e < E; ++e) {
+        const int room = (int)capacity - filled[e];
+        if (room <= 0) continue;
+        std::vector<int64_t> cand;
+        for (int64_t t = 0; t < T; ++t) if (choice[t] == e) cand.push_back(t);
+        if ((int)cand.size() > room) {
+          // keep the `room` best scores, ties by token order; then place in token order
+          std::stable_sort(cand.begin(), cand.end(), [&](int64_t a, int64_t b) { return sp[a * E + e] > sp[b * E + e]; });
+          cand.resize(room);
+          std::sort(cand.begin(), cand.end());
+        }
+        for (int64_t t : cand) { ia[t] = (int)e; la[t] = filled[e]++; }
+      }
+    }
+    at::Tensor ic = at::empty({T, 1}, at::TensorOptions().dtype(at::kInt)), lc = at::empty({T, 1}, at::TensorOptions().dtype(at::kInt));
+    std::copy(ia.begin(), ia.end(), ic.data_ptr<int32_t>());
+    std::copy(la.begin(), la.end(), lc.data_ptr<int32_t>());
+    idx = ic.to(logits.device());
+    loc = lc.to(logits.device());
+  }
+  at::Tensor probs = at::softmax(scores, -1).gather(1, idx.to(at::kLong));
+  return {probs, idx, loc, at::zeros({1}, fopt)};
+}
+HB_REGISTER_OP(moe_balance_assign, "moe_balance_assign", 4, kFlagNondiff, moe_balance_assign_compute, nullptr, moe_gate_deduce, nullptr);
 
 
 // ------------------------------------------------------------------ expert parallelism over peer memory

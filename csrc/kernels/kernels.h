@@ -151,6 +151,11 @@ cudaError_t moe_gate_topk(const void* logits_bf16, float* probs, int32_t* topk_i
 // capacity-based slot assignment: location[t,k] = position of token t inside expert e's buffer (or -1 when dropped)
 cudaError_t moe_assign_slots(const int32_t* topk_idx, int32_t* location, int32_t* expert_count, int64_t tokens,
                              int experts, int k, int capacity, cudaStream_t s);
+// BASE balanced assignment (ref: hetu/v1/python/hetu/gpu_ops/BalanceAssignment.py): idx[t] = expert, loc[t] = slot, every
+// expert gets at most `capacity` tokens (exactly T/E when E divides T).  scores fp32 [tokens, experts];
+// filled [experts] and choice [tokens] are int32 scratch.
+cudaError_t moe_balance_assign(const float* scores, int32_t* idx, int32_t* loc, int32_t* filled, int32_t* choice,
+                               int64_t tokens, int experts, int capacity, cudaStream_t s);
 // dispatched[e, slot, :] = (scale ? scale[t,k] : 1) * x[t, :]; unassigned slots are zero-filled.
 // (with scale = gates this is also the backward of moe_combine w.r.t. expert_out)
 cudaError_t moe_dispatch(const void* x, const int32_t* topk_idx, const int32_t* location, const float* scale,

@@ -242,6 +242,116 @@ inline int grid_for(int64_t n) {
   return (int)blocks;
 }
 
+
+// ---------------------------------------------------------------- BASE-layer balanced assignment
+// Every expert receives exactly `capacity` (= ceil(T / E)) tokens.  Rounds of (choose, accept): each unassigned token
+// proposes to its best expert that still has room; an expert with more proposers than room keeps the highest scoring
+// ones (radix select of the r-th largest score, ties in token order).  Each round either places every remaining token or
+// fills at least one expert, so E rounds always suffice -- no host round trips (the reference's auction,
+// hetu/v1/python/hetu/gpu_ops/BalanceAssignment.py, copies bids to the host every iteration).
+__global__ void balance_choose_kernel(const float* __restrict__ scores, const int32_t* __restrict__ idx,
+                                      const int32_t* __restrict__ filled, int32_t* __restrict__ choice, int64_t tokens,
+                                      int experts, int capacity) {
+  const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (t >= tokens) return;
+  int c = -1;
+  if (idx[t] < 0) {
+    float best = -INFINITY;
+    for (int e = 0; e < experts; ++e) {
+      if (filled[e] >= capacity) continue;
+      const float v = scores[t * experts + e];
+      if (c < 0 || v > best) { best = v; c = e; }
+    }
+  }
+  choice[t] = c;
+}
+
+__device__ __forceinline__ uint32_t order_key(float v) {      // larger float <=> larger key (NaN-free inputs)
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ int block_sum_int(int v, int* smem) {
+  v = __reduce_add_sync(0xffffffffu, v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int tot = 0;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) tot += smem[w];
+  return tot;
+}
+
+__global__ void balance_accept_kernel(const float* __restrict__ scores, const int32_t* __restrict__ choice,
+                                      int32_t* __restrict__ idx, int32_t* __restrict__ loc, int32_t* __restrict__ filled,
+                                      int64_t tokens, int experts, int capacity) {
+  __shared__ int red[32];
+  __shared__ int scan_base[2];
+  const int e = blockIdx.x;
+  const int have = filled[e];
+  const int room = capacity - have;
+  if (room <= 0) return;
+  int n = 0;
+  for (int64_t t = threadIdx.x; t < tokens; t += blockDim.x) n += (choice[t] == e);
+  n = block_sum_int(n, red);
+  if (n == 0) return;
+  uint32_t thr = 0;          // accept keys > thr, plus the first `need_eq` proposers with key == thr
+  int need_eq = 0;
+  if (n > room) {
+    int need = room;
+    uint32_t prefix = 0;
+    for (int b = 31; b >= 0; --b) {
+      const uint32_t test = prefix | (1u << b);
+      const uint32_t mask = ~((1u << b) - 1u);
+      int c1 = 0;
+      for (int64_t t = threadIdx.x; t < tokens; t += blockDim.x)
+        if (choice[t] == e) c1 += ((order_key(scores[t * experts + e]) & mask) == test);
+      c1 = block_sum_int(c1, red);
+      if (c1 >= need) prefix = test;
+      else need -= c1;
+    }
+    thr = prefix;
+    need_eq = need;
+  } else {
+    need_eq = n;             // accept everything: treat all as "equal" candidates in token order
+  }
+  const bool all = n <= room;
+  // placement in token order: running counts of accepted (-> slot) and of accepted ties
+  if (threadIdx.x == 0) { scan_base[0] = 0; scan_base[1] = 0; }
+  __syncthreads();
+  for (int64_t base = 0; base < tokens; base += blockDim.x) {
+    const int64_t t = base + threadIdx.x;
+    bool mine = t < tokens && choice[t] == e;
+    uint32_t key = mine ? order_key(scores[t * experts + e]) : 0u;
+    const bool gt = mine && !all && key > thr;
+    const bool eq = mine && (all || key == thr);
+    // block-wide exclusive scans of eq and of (gt | accepted eq); two passes through warp ballots
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned eq_mask = __ballot_sync(0xffffffffu, eq);
+    __syncthreads();
+    if (lane == 0) red[warp] = __popc(eq_mask);
+    __syncthreads();
+    int eq_before = scan_base[1];
+    for (unsigned w = 0; w < warp; ++w) eq_before += red[w];
+    int eq_total = 0;
+    for (unsigned w = 0; w < (blockDim.x >> 5); ++w) eq_total += red[w];
+    eq_before += __popc(eq_mask & ((1u << lane) - 1u));
+    const bool take = gt || (eq && eq_before < need_eq);
+    const unsigned tk_mask = __ballot_sync(0xffffffffu, take);
+    __syncthreads();
+    if (lane == 0) red[warp] = __popc(tk_mask);
+    __syncthreads();
+    int tk_before = scan_base[0];
+    for (unsigned w = 0; w < warp; ++w) tk_before += red[w];
+    int tk_total = 0;
+    for (unsigned w = 0; w < (blockDim.x >> 5); ++w) tk_total += red[w];
+    tk_before += __popc(tk_mask & ((1u << lane) - 1u));
+    if (take) { idx[t] = e; loc[t] = have + tk_before; }
+    __syncthreads();
+    if (threadIdx.x == 0) { scan_base[0] += tk_total; scan_base[1] += eq_total; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) filled[e] = have + scan_base[0];
+}
 }  // namespace
 
 cudaError_t moe_gate_topk(const void* logits_bf16, float* probs, int32_t* topk_idx, float* topk_val, int64_t tokens,
@@ -315,4 +425,23 @@ cudaError_t moe_combine_bwd_gate(const void* dy, const void* expert_out, const i
   return cudaGetLastError();
 }
 
+}  // namespace hb
+
+namespace hb {
+cudaError_t moe_balance_assign(const float* scores, int32_t* idx, int32_t* loc, int32_t* filled, int32_t* choice,
+                               int64_t tokens, int experts, int capacity, cudaStream_t s) {
+  cudaError_t err = cudaMemsetAsync(idx, 0xff, sizeof(int32_t) * tokens, s);       // -1 = unassigned
+  if (err != cudaSuccess) return err;
+  err = cudaMemsetAsync(filled, 0, sizeof(int32_t) * experts, s);
+  if (err != cudaSuccess) return err;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((tokens + threads - 1) / threads);
+  for (int round = 0; round < experts; ++round) {
+    balance_choose_kernel<<<blocks, threads, 0, s>>>(scores, idx, filled, choice, tokens, experts, capacity);
+    balance_accept_kernel<<<experts, 1024, 0, s>>>(scores, choice, idx, loc, filled, tokens, experts, capacity);
+    count_launch();
+    count_launch();
+  }
+  return cudaGetLastError();
+}
 }  // namespace hb

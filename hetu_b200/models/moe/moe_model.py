@@ -32,6 +32,20 @@ class MoEConfig(GPTConfig):
         return MoEConfig(n_embd=1024, n_layer=24, n_head=16, num_experts=8, top_k=1, **kw)
 
 
+def balance_loss(logits, idx, num_experts):
+    """GShard / Switch load-balancing loss  E * sum_e mean_t(softmax(logits))[t, e] * ce[e]  with ce[e] the fraction of
+    tokens whose first choice is expert e.  `ce` comes from the (integer) routing decision and is a constant for autograd;
+    the mean gate probability is built from differentiable ops, so the router weights receive the balancing gradient
+    (ref: hetu/v1/python/hetu/layers/TopGate.py:28-45 builds it from the softmax gates the same way).  The aux output of the
+    `moe_gate` op itself is computed inside a non-differentiable op and only serves as a monitoring value."""
+    tokens = logits.shape[0]
+    probs = ops.softmax(ops.data_transfer(logits, "float32"), -1)                      # [T, E], differentiable
+    me = ops.reduce(probs, "mean", [0])                                                 # [E]
+    first = ops.reshape(ops.slice(idx, [0, 0], [tokens, 1]), [tokens])
+    ce = ops.reduce(ops.onehot(ops.data_transfer(first, "int64"), num_experts), "mean", [0])   # [E], constant
+    return ops.reduce(me * ops.data_transfer(ce, "float32"), "sum", [0]) * float(num_experts)
+
+
 class TopKGate(Module):
     """softmax -> top-k -> capacity (GShard ordering) ; returns (gates, idx, loc, aux_loss)"""
 
@@ -47,9 +61,9 @@ class TopKGate(Module):
     def forward(self, x):
         logits = ops.linear(x, self.wg, None, trans_b=True)
         cap = self.capacity(x.shape[0])
-        _, idx, loc, aux = ops.moe_gate(logits, self.k, cap)
+        _, idx, loc, _ = ops.moe_gate(logits, self.k, cap)
         gates = ops.moe_gate_values(logits, idx, loc)     # differentiable w.r.t. the router weights
-        return gates, idx, loc, aux, cap
+        return gates, idx, loc, balance_loss(logits, idx, self.num_experts), cap
 
 
 class KTop1Gate(TopKGate):
@@ -62,7 +76,8 @@ class KTop1Gate(TopKGate):
         cap = int(math.ceil(x.shape[0] / e_per * self.capacity_factor))
         gates, idxs, locs, aux_total = [], [], [], None
         for gi, lg in enumerate(groups):
-            _, idx, loc, aux = ops.moe_gate(lg, 1, cap)
+            _, idx, loc, _ = ops.moe_gate(lg, 1, cap)
+            aux = balance_loss(lg, idx, e_per)
             gates.append(ops.moe_gate_values(lg, idx, loc))
             idxs.append(idx if gi == 0 else _shift_idx(idx, gi * e_per))
             locs.append(loc)
@@ -71,13 +86,8 @@ class KTop1Gate(TopKGate):
 
 
 def _shift_idx(idx, off):
-    return ops.make_op("add", [idx], {"value": float(off)})[0] if False else _IntAdd.apply(idx, off)
-
-
-class _IntAdd:
-    @staticmethod
-    def apply(idx, off):
-        return ops.data_transfer(ops.add(ops.data_transfer(idx, "float32"), float(off)), "int32")
+    """expert indices of group `gi` are offset by gi * experts_per_group (small integers: exact through float32)"""
+    return ops.data_transfer(ops.add(ops.data_transfer(idx, "float32"), float(off)), "int32")
 
 
 class HashGate(Module):
@@ -104,17 +114,19 @@ def _mod(t, n):
 
 
 class BalanceGate(TopKGate):
-    """BASE layers: balanced assignment -- every expert receives exactly tokens/E tokens.  The assignment is solved
-    greedily on the score matrix in descending score order (auction-free approximation of the linear assignment)."""
+    """BASE layers: balanced assignment -- every expert receives exactly ceil(tokens / E) tokens, no token is dropped and
+    no auxiliary loss is needed.  The assignment runs on the device (`moe_balance_assign`, csrc/kernels/moe.cu): rounds in
+    which every unplaced token proposes to its best expert with room and over-subscribed experts keep their highest
+    scoring proposers.  (ref: hetu/v1/python/hetu/layers/BalanceGate.py, gpu_ops/BalanceAssignment.py -- an auction with a
+    host round trip per iteration)"""
 
     def forward(self, x):
         logits = ops.linear(x, self.wg, None, trans_b=True)
         tokens = x.shape[0]
         cap = int(math.ceil(tokens / self.num_experts))
-        _, idx, loc, aux = ops.make_op("moe_balance_assign", [logits], {"capacity": cap}) if ops._C.has_op("moe_balance_assign") \
-            else ops.moe_gate(logits, 1, cap)
+        _, idx, loc, _ = ops.make_op("moe_balance_assign", [logits], {"capacity": cap})
         gates = ops.moe_gate_values(logits, idx, loc)
-        return gates, idx, loc, aux, cap
+        return gates, idx, loc, None, cap
 
 
 class SAMGate(TopKGate):
@@ -137,9 +149,9 @@ class SAMGate(TopKGate):
             logits.dtype)
         masked = logits * mask + (mask - 1.0) * 1e4
         cap = self.capacity(x.shape[0])
-        _, idx, loc, aux = ops.moe_gate(masked, self.k, cap)
+        _, idx, loc, _ = ops.moe_gate(masked, self.k, cap)
         gates = ops.moe_gate_values(masked, idx, loc)
-        return gates, idx, loc, aux, cap
+        return gates, idx, loc, balance_loss(logits, idx, self.num_experts), cap
 
 
 def _ge(a, b):

@@ -282,19 +282,34 @@ class _CopyOf:
 
 
 class GradScaler:
-    """Dynamic loss scaling (ref: hetu/graph/autocast/gradscaler.h): scale(loss), unscale+check, update."""
+    """Dynamic loss scaling (ref: hetu/graph/autocast/gradscaler.h, optimizer_update.cc SGDUpdateWithGradScaler).
+
+    `minimize(optimizer, loss)` multiplies the loss by a scale *variable* inside the graph and registers the scaler with the
+    graph's executor, whose update phase un-scales the accumulated gradients, checks them for inf/nan on every rank, skips
+    the optimizer step when one is found (backing the scale off) and grows the scale after `growth_interval` clean steps.
+    `scale()/update()` remain for hand-written loops (eager graphs)."""
 
     def __init__(self, init_scale=65536.0, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000, enabled=True):
         self.scale_value = float(init_scale)
         self.growth_factor, self.backoff_factor, self.growth_interval = growth_factor, backoff_factor, growth_interval
         self.enabled = enabled
         self._tracker = 0
+        self._graph = None
 
     def scale(self, loss: Tensor) -> Tensor:
         return loss * self.scale_value if self.enabled else loss
 
     def get_scale(self):
+        if self._graph is not None:
+            self.scale_value = float(self._graph.loss_scale())
         return self.scale_value
+
+    def found_inf(self) -> bool:
+        """whether the last executed step was skipped because of a non-finite gradient"""
+        return bool(self._graph.loss_scaler_state()[4]) if self._graph is not None else False
+
+    def skipped_steps(self) -> int:
+        return int(self._graph.loss_scaler_state()[3]) if self._graph is not None else 0
 
     def update(self, found_inf: bool):
         if not self.enabled:
@@ -307,6 +322,18 @@ class GradScaler:
             if self._tracker >= self.growth_interval:
                 self.scale_value *= self.growth_factor
                 self._tracker = 0
+        if self._graph is not None:
+            self._graph.set_loss_scale(self.scale_value)
 
     def minimize(self, optimizer: Optimizer, loss: Tensor, var_list=None):
-        return optimizer.minimize(self.scale(loss), var_list)
+        if not self.enabled:
+            return optimizer.minimize(loss, var_list)
+        g = _graphs_by_id.get(loss.graph_id) or cur_graph()
+        with _in_graph(g):
+            scale_var = parallel_parameter(constant_initializer(self.scale_value), [1], None, dtype="float32", requires_grad=False,
+                                           name="loss_scale")
+            scaled = loss * scale_var
+        train_op = optimizer.minimize(scaled, var_list)
+        g.set_loss_scaler(scale_var, self.scale_value, float(self.growth_factor), float(self.backoff_factor), int(self.growth_interval))
+        self._graph = g
+        return train_op

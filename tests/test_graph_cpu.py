@@ -293,3 +293,36 @@ def test_module_tree_helpers_buffers_children_apply():
     assert seen == ["Linear", "ReLU", "Linear", "Sequential"]
     assert len(list(bn.buffers())) == len(list(bn.named_buffers())) >= 2
     assert seq.eval().training is False and seq.train().training is True and seq.to(None) is seq
+
+
+def test_grad_scaler_minimize_unscales_checks_and_skips():
+    """scaled-loss training must follow the unscaled trajectory; a non-finite gradient skips the step and backs the scale off
+    (ref: hetu/graph/autocast/gradscaler.h, optimizer_update.cc SGDUpdateWithGradScaler)"""
+    def train(scaler, feeds):
+        with ht.graph("define_and_run", create_new=True) as g:
+            x = ht.placeholder("float32", [4, 3], name="x")
+            w = ht.parameter(ht.ones_initializer(), [3, 1], requires_grad=True, name="w_gs")
+            loss = ht.sum(ht.matmul(x, w)) * 0.25
+            opt = ht.SGDOptimizer(lr=0.01)
+            train_op = scaler.minimize(opt, loss) if scaler is not None else opt.minimize(loss)
+            ws = []
+            for f in feeds:
+                g.run(loss, [loss, train_op], {x: f})
+                ws.append(g.get_param(w).clone())
+        return ws
+
+    ones = torch.ones(4, 3)
+    plain = train(None, [ones, ones, ones])
+    sc = ht.GradScaler(init_scale=1024.0, growth_interval=2)
+    scaled = train(sc, [ones, ones, ones])
+    for a, b in zip(plain, scaled):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-6)
+    assert abs(plain[0][0, 0].item() - 0.99) < 1e-6           # one SGD step of size lr * dL/dw = 0.01 * 1.0
+    assert sc.get_scale() == 2048.0 and sc.skipped_steps() == 0   # grew once after two clean steps
+    # an inf in the batch: the step is dropped, the scale halves, the weights stay
+    sc2 = ht.GradScaler(init_scale=64.0, growth_interval=100)
+    bad = ones.clone(); bad[0, 0] = float("inf")
+    ws = train(sc2, [ones, bad, ones])
+    np.testing.assert_allclose(ws[1].numpy(), ws[0].numpy())
+    assert sc2.found_inf() is False and sc2.skipped_steps() == 1 and sc2.get_scale() == 32.0
+    np.testing.assert_allclose(ws[2].numpy(), plain[1].numpy(), rtol=1e-6)

@@ -355,6 +355,26 @@ def test_moe_dispatch_combine_roundtrip():
         assert slots.numel() == slots.unique().numel() and slots.numel() <= cap
 
 
+def test_moe_balanced_assignment_kernel_matches_host_algorithm():
+    """BASE balanced assignment on the device (csrc/kernels/moe.cu, E rounds of choose/accept without host round trips) must
+    produce the same assignment as the plain-loop host implementation of the same algorithm"""
+    g = torch.Generator().manual_seed(5)
+    for T, E in [(4096, 8), (1000, 16), (16384, 64)]:
+        scores = torch.randn(T, E, generator=g)
+        scores[:, 1] += 1.5
+        cap = (T + E - 1) // E
+        before = launches()
+        _, idx, loc, _ = ht.make_op("moe_balance_assign", [ht.from_numpy(scores.cuda())], {"capacity": cap})
+        assert launches() > before
+        _, ridx, rloc, _ = ht.make_op("moe_balance_assign", [ht.from_numpy(scores)], {"capacity": cap})     # CPU tensors: host loops
+        i_ = torch.as_tensor(idx.numpy()).cpu()[:, 0]
+        l_ = torch.as_tensor(loc.numpy()).cpu()[:, 0]
+        assert torch.equal(i_, torch.as_tensor(ridx.numpy()).cpu()[:, 0])
+        assert torch.equal(l_, torch.as_tensor(rloc.numpy()).cpu()[:, 0])
+        counts = torch.bincount(i_.long(), minlength=E)
+        assert int(counts.max()) <= cap and int(counts.sum()) == T
+
+
 def test_gpt_block_training_matches_fp32_reference():
     """tiny GPT: native bf16 training vs the same graph on CPU fp32 -- loss curves must agree to bf16 accuracy"""
     from hetu_b200.models import GPTConfig, GPTLMHeadModel, generate_ds_parallel_config

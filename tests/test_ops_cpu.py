@@ -218,6 +218,52 @@ def test_moe_ops_cpu():
     np.testing.assert_array_equal(np.sort(i_, 1), np.sort(torch.topk(probs, k, -1).indices.numpy(), 1))
 
 
+def test_moe_balanced_assignment_gives_every_expert_its_share():
+    """BASE layers: exactly T/E tokens per expert, slots 0..cap-1 used once, tokens prefer their best expert when it has room
+    (ref: hetu/v1/python/hetu/layers/BalanceGate.py balance_assignment_op)"""
+    rng = np.random.RandomState(3)
+    T, E = 64, 4
+    scores = rng.randn(T, E).astype(np.float32)
+    scores[:, 0] += 2.0                                    # everybody's favourite: must be rationed
+    _, idx, loc, _ = ht.make_op("moe_balance_assign", [ht.from_numpy(scores)], {"capacity": T // E})
+    i_, l_ = idx.numpy()[:, 0], loc.numpy()[:, 0]
+    assert sorted(np.bincount(i_, minlength=E).tolist()) == [T // E] * E
+    for e in range(E):
+        assert sorted(l_[i_ == e].tolist()) == list(range(T // E))
+    # expert 0 keeps the T/E highest-scoring of its proposers (all tokens propose to it in round one)
+    fav = np.argsort(-scores[:, 0], kind="stable")[:T // E]
+    assert set(np.nonzero(i_ == 0)[0].tolist()) == set(fav.tolist())
+    # uneven T: nobody is dropped, no expert exceeds ceil(T / E)
+    _, idx2, loc2, _ = ht.make_op("moe_balance_assign", [ht.from_numpy(scores[:61])], {"capacity": 16})
+    assert (idx2.numpy() >= 0).all() and np.bincount(idx2.numpy()[:, 0], minlength=E).max() <= 16 and (loc2.numpy() >= 0).all()
+
+
+def test_moe_balance_loss_reaches_the_router_weights():
+    """the load-balancing loss must be differentiable w.r.t. the gate weights (the aux output of the moe_gate op is not)"""
+    from hetu_b200.models.moe.moe_model import TopKGate, BalanceGate
+    with ht.graph("define_and_run", create_new=True) as g:
+        x = ht.placeholder("float32", [16, 8], name="x")
+        gate = TopKGate(8, 4, k=2, capacity_factor=2.0, name="g0")
+        gates, idx, loc, aux, cap = gate(x)
+        d_aux, = ht.gradients(aux, [gate.wg])
+        assert d_aux is not None
+        xv = torch.randn(16, 8, generator=torch.Generator().manual_seed(0))
+        aux_v, dw, idx_v = g.run(None, [aux, d_aux, idx], {x: xv})
+        w = g.get_param(gate.wg).clone().requires_grad_(True)
+        probs = torch.softmax(xv @ w.t(), -1)
+        ce = torch.nn.functional.one_hot(idx_v[:, 0].long(), 4).float().mean(0)
+        ref = (probs.mean(0) * ce).sum() * 4
+        ref.backward()
+        np.testing.assert_allclose(float(aux_v), float(ref), rtol=1e-5)
+        np.testing.assert_allclose(dw.numpy(), w.grad.numpy(), rtol=1e-4, atol=1e-6)
+        assert float(dw.abs().sum()) > 0
+        bg = BalanceGate(8, 4, name="g1")
+        gates, idx, loc, aux, cap = bg(x)
+        assert aux is None and cap == 4
+        iv = g.run(None, [idx], {x: xv})[0]
+        assert np.bincount(iv.numpy()[:, 0], minlength=4).tolist() == [4, 4, 4, 4]
+
+
 def test_blockwise_quantisation_and_matmul4bit():
     torch.manual_seed(0)
     w = torch.randn(48, 64)
