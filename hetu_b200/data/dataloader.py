@@ -28,10 +28,15 @@ class DataLoader:
         self.prefetch, self.collate_fn = prefetch, collate_fn
         self.consumed = 0
         self.epoch = 0
+        # GLOBAL number of samples (all data-parallel ranks together) of this epoch that the batches handed to the
+        # consumer so far cover -- identical on every rank whatever its dp slice, and not ahead of the consumer when the
+        # prefetch thread is; this is the value `restart()` expects back after a failure / re-plan
+        self.consumed_yielded = 0
 
     def restart(self, consumed_samples: int):
         """resume after a failure / elastic re-plan: skip what the previous incarnation already consumed"""
         self.epoch, self.consumed = divmod(consumed_samples, max(len(self.ds), 1))
+        self.consumed_yielded = self.consumed
 
     def _order(self):
         idx = np.arange(len(self.ds))
@@ -60,20 +65,22 @@ class DataLoader:
                     break
             pos += len(b)
             self.consumed = pos
-            yield [int(i) for i in b[self.dp_rank::self.dp_size]]
+            yield [int(i) for i in b[self.dp_rank::self.dp_size]], pos
         self.epoch += 1
         self.consumed = 0
 
     def __iter__(self):
         def produce(q):
-            for ids in self._batches():
+            for ids, pos in self._batches():
                 samples = [self.ds[i] for i in ids]
-                q.put(self.collate_fn(samples) if self.collate_fn else samples)
+                q.put((self.collate_fn(samples) if self.collate_fn else samples, pos))
             q.put(None)
         if self.prefetch <= 0:
-            for ids in self._batches():
+            for ids, pos in self._batches():
                 samples = [self.ds[i] for i in ids]
+                self.consumed_yielded = pos
                 yield self.collate_fn(samples) if self.collate_fn else samples
+            self.consumed_yielded = 0
             return
         q: "queue.Queue" = queue.Queue(maxsize=self.prefetch)
         t = threading.Thread(target=produce, args=(q,), daemon=True)
@@ -82,7 +89,9 @@ class DataLoader:
             item = q.get()
             if item is None:
                 break
-            yield item
+            self.consumed_yielded = item[1]
+            yield item[0]
+        self.consumed_yielded = 0
 
 
 def build_data_loader(dataset, consumed_samples: int, global_batch_size: int = 0, global_token_num: int = 0,

@@ -114,6 +114,17 @@ def global_comm_barrier_rpc():
         dist.barrier()
 
 
+def all_ranks_ok(ok: bool) -> bool:
+    """logical AND of a per-rank flag over the whole job (checkpoint publication: every rank's files must be on disk)"""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return bool(ok)
+    import torch
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(int(t.item()))
+
+
 def global_comm_barrier_mpi():
     if dist.is_initialized():
         dist.barrier()

@@ -147,9 +147,8 @@ class Trainer:
         st = self.trainer_states
         loaded = saver.load_latest(st.model, st.optimizer)
         assert loaded is not None and loaded[0] == self.global_step, "the rebuild checkpoint could not be read back"
-        if hasattr(st.optimizer, "step_count"):
-            st.optimizer.step_count = self.global_step
-            st.optimizer.apply_hyper_parameters()
+        if hasattr(st.optimizer, "set_step"):
+            st.optimizer.set_step(self.global_step)       # scheduled lr / wd of the next step, not the fresh optimizer's
         return self
 
     # ------------------------------------------------------------------ build
@@ -343,8 +342,9 @@ class Trainer:
             got = False
             for batch in loader:
                 got = True
-                self.consumed_samples += self.pretrain_config.global_load_size if \
-                    str(getattr(self.pretrain_config.data_load_level, "value", self.pretrain_config.data_load_level)) == "SAMPLE" else len(batch)
+                # global sample count covered so far (the loader's own book-keeping: identical on every data-parallel
+                # rank under both load levels -- `len(batch)` is only this rank's slice)
+                self.consumed_samples = int(loader.consumed_yielded)
                 yield batch
             self.epoch += 1
             self.consumed_samples = 0

@@ -173,6 +173,18 @@ class Optimizer:
         self.apply_hyper_parameters()
         return self.learning_rate
 
+    def set_step(self, n: int):
+        """position the schedule after `n` completed optimizer steps (checkpoint resume, Trainer.rebuild): the next run()
+        uses the scheduled lr / weight decay of step n + 1 instead of the freshly constructed optimizer's warm-up / peak value"""
+        self.step_count = int(n)
+        sched = getattr(self, "scheduler", None)
+        if sched is not None:
+            self.learning_rate = float(sched.get_lr(self.step_count + 1))
+            if hasattr(sched, "get_wd"):
+                self.weight_decay = float(sched.get_wd(self.step_count + 1))
+        self.apply_hyper_parameters()
+        return self.learning_rate
+
     def set_learning_rate(self, lr: float):
         """external schedulers (e.g. the v1 lr_scheduler classes) drive the rate directly"""
         self.learning_rate = float(lr)

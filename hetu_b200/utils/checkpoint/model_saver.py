@@ -30,6 +30,7 @@ class ModelSaver:
         self._child: Optional[int] = None
         self._shm_blocks = []
         self.last_write_error: Optional[str] = None
+        self._pending = None      # (step, consumed, loss, path, writer_rank) of a checkpoint whose files are still being written
         os.makedirs(save_dir, exist_ok=True)
 
     def step_dir(self, step: int) -> str:
@@ -53,9 +54,28 @@ class ModelSaver:
             for ptr in self._shm_blocks:
                 pool.free(ptr)
             self._shm_blocks = []
-        if self.last_write_error is not None:
-            err, self.last_write_error = self.last_write_error, None
+        err, self.last_write_error = self.last_write_error, None
+        if self._pending is not None:
+            # every rank's writer has finished here: only now does the checkpoint become visible (COMPLETE marker, CSV row)
+            # and only now may older copies be rotated out -- a crash in the middle of a write leaves the previous
+            # checkpoint as the newest published one
+            self._publish(*self._pending, ok=err is None)
+            self._pending = None
+        if err is not None:
             raise RuntimeError(err)
+
+    def _publish(self, step, consumed_samples, loss, path, writer_rank, ok=True):
+        """collective: all ranks agree that their files are on disk, then `writer_rank` marks the step complete"""
+        from ...distributed import all_ranks_ok, global_comm_barrier_rpc, rank
+        ok = all_ranks_ok(ok)
+        global_comm_barrier_rpc()
+        if ok and rank() == writer_rank:
+            with open(os.path.join(path, "COMPLETE"), "w") as f:
+                f.write(f"{step}\n")
+            with open(os.path.join(self.save_dir, "step_info.csv"), "a", newline="") as f:
+                csv.writer(f).writerow([step, consumed_samples, loss, path, time.time()])
+            self._cleanup(step)
+        global_comm_barrier_rpc()
 
     def _snapshot_fn(self):
         """host copy owned by the saver: plain clone for the thread writer, shared-memory pool blocks for the process writer"""
@@ -104,16 +124,24 @@ class ModelSaver:
                     code = 1
                 os._exit(code)
             self._child = pid
-        global_comm_barrier_rpc()
-        if rank() == writer_rank:                # the rank that keeps the step-info CSV (an active one when some ranks are idle)
-            with open(os.path.join(self.save_dir, "step_info.csv"), "a", newline="") as f:
-                csv.writer(f).writerow([step, consumed_samples, loss, path, time.time()])
-            self._cleanup(step)
+        # `writer_rank` keeps the step-info CSV (an active rank when some ranks are idle)
+        if not self.async_save:
+            self._publish(step, consumed_samples, loss, path, writer_rank)
+        else:
+            self._pending = (step, consumed_samples, loss, path, writer_rank)     # published by the next wait() / save()
 
     def _cleanup(self, newest: int):
+        """keep the newest `save_copies` COMPLETE checkpoints; torn directories (no marker) older than the newest go too"""
         steps = sorted(int(d[4:]) for d in os.listdir(self.save_dir) if d.startswith("step") and d[4:].isdigit())
-        for s in steps[:-self.save_copies] if self.save_copies > 0 else []:
-            shutil.rmtree(self.step_dir(s), ignore_errors=True)
+        done = [s for s in steps if self._complete(self.step_dir(s))]
+        keep = set(done[-self.save_copies:]) if self.save_copies > 0 else set(done)
+        for s in steps:
+            if s not in keep and s < newest:
+                shutil.rmtree(self.step_dir(s), ignore_errors=True)
+
+    @staticmethod
+    def _complete(path: str) -> bool:
+        return os.path.isdir(path) and os.path.exists(os.path.join(path, "COMPLETE"))
 
     def latest_step(self) -> Optional[int]:
         info = os.path.join(self.save_dir, "step_info.csv")
@@ -122,7 +150,7 @@ class ModelSaver:
         last = None
         with open(info) as f:
             for row in csv.reader(f):
-                if row and os.path.isdir(row[3]):
+                if row and self._complete(row[3]):
                     last = row
         return None if last is None else int(last[0])
 
@@ -131,9 +159,17 @@ class ModelSaver:
         info = os.path.join(self.save_dir, "step_info.csv")
         if not os.path.exists(info):
             return None
-        rows = [r for r in csv.reader(open(info)) if r and os.path.isdir(r[3])]
-        if not rows:
-            return None
-        step, consumed, _, path = int(rows[-1][0]), int(float(rows[-1][1])), rows[-1][2], rows[-1][3]
-        temp_load_split(model, optimizer, path, only_lora=self.only_lora, strict=False)
-        return step, consumed
+        rows = [r for r in csv.reader(open(info)) if r and self._complete(r[3])]
+        # newest complete checkpoint first; a copy that cannot be read (torn file) falls back to the one before it
+        for row in reversed(rows):
+            step, consumed, path = int(row[0]), int(float(row[1])), row[3]
+            try:
+                temp_load_split(model, optimizer, path, only_lora=self.only_lora, strict=False)
+            except Exception as e:     # noqa: BLE001
+                import warnings
+                warnings.warn(f"checkpoint {path} is unreadable ({type(e).__name__}: {e}); trying the previous one")
+                continue
+            if hasattr(optimizer, "set_step"):
+                optimizer.set_step(step)
+            return step, consumed
+        return None

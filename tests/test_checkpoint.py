@@ -125,3 +125,36 @@ def test_cross_strategy_reload(tmp_path):
     assert ok, "\n---\n".join(outs)
     loaded = [json.loads(l[5:]) for o in outs for l in o.splitlines() if l.startswith("CKPT ")][0]
     assert abs(saved["next_loss"] - loaded["next_loss"]) < 2e-3 * max(1.0, abs(saved["next_loss"])), (saved, loaded)
+
+
+def test_async_checkpoint_is_published_after_the_write_and_torn_copies_are_skipped(tmp_path):
+    """the step-info row / COMPLETE marker / rotation happen only once the writer finished (next wait() or save()); a
+    directory without the marker (crash mid-write) is never chosen by load_latest, which falls back to the previous copy"""
+    with ht.graph("define_and_run", create_new=True) as g:
+        m = ht.nn.Linear(16, 8, name="lin_pub")
+        x = ht.placeholder("float32", [2, 16], name="x")
+        loss = ht.sum(m(x))
+        opt = ht.AdamOptimizer(lr=0.1, lr_warmup_steps=4, lr_decay_steps=20, lr_decay_style="linear", min_lr=0.01)
+        train = opt.minimize(loss)
+        saver = ModelSaver(str(tmp_path), save_copies=1, async_save=True)
+        X = np.ones((2, 16), np.float32)
+        g.run(loss, [loss, train], {x: X}); opt.step_lr()
+        saver.save(m, opt, 1, consumed_samples=2, loss=0.0)
+        assert saver.latest_step() is None or saver.latest_step() == 1     # row appears only with the finished files
+        saver.wait()
+        assert saver.latest_step() == 1 and os.path.exists(tmp_path / "step1" / "COMPLETE")
+        w1 = g.get_param(m.weight).clone()
+        g.run(loss, [loss, train], {x: X}); opt.step_lr()
+        saver.save(m, opt, 2, consumed_samples=4, loss=0.0)
+        # simulate a crash before publication: files of step2 may exist, but no marker and no row; step1 must survive
+        saver._thread.join(); saver._thread = None; saver._pending = None
+        assert os.path.isdir(tmp_path / "step1")
+        import csv
+        with open(tmp_path / "step_info.csv", "a", newline="") as f:       # even a stray row must not resurrect a torn copy
+            csv.writer(f).writerow([2, 4, 0.0, str(tmp_path / "step2"), 0.0])
+        fresh = ModelSaver(str(tmp_path), save_copies=1)
+        assert fresh.latest_step() == 1
+        assert fresh.load_latest(m, opt) == (1, 2)
+        assert torch.equal(g.get_param(m.weight), w1)
+        # the schedule resumes at the scheduled rate of step 2, not at the fresh optimizer's first warm-up value
+        assert opt.step_count == 1 and abs(opt.learning_rate - opt.scheduler.get_lr(2)) < 1e-12

@@ -491,3 +491,28 @@ def test_multi_lora_routes_tokens_to_their_tasks_adapters():
     mixed = torch.cat([task0[:B * S // 2], task1[B * S // 2:]])
     lm = float(g.run(loss, [loss], {**feed, mask: mixed})[0])
     assert float(g.run(loss, [loss], {**feed, mask: task0})[0]) < lm < base_loss
+
+
+def test_data_loader_reports_global_consumed_samples_for_every_dp_rank():
+    """TOKEN load level: batches hold a variable number of samples; the resume counter must be the GLOBAL count and equal on
+    all data-parallel ranks (each rank only sees its b[dp_rank::dp_size] slice), and must not run ahead with prefetching"""
+    from hetu_b200.data.dataloader import DataLoader
+    rng = np.random.RandomState(0)
+    ds = [list(range(int(n))) for n in rng.randint(3, 20, size=57)]
+    seen = {}
+    for dp_rank in range(3):
+        dl = DataLoader(ds, global_token_num=64, load_level="TOKEN", dp_rank=dp_rank, dp_size=3, prefetch=2)
+        counts, mine = [], 0
+        for batch in dl:
+            mine += len(batch)
+            counts.append(dl.consumed_yielded)
+        seen[dp_rank] = (counts, mine)
+    assert seen[0][0] == seen[1][0] == seen[2][0] and seen[0][0][-1] == 57
+    assert sum(v[1] for v in seen.values()) == 57 and len({v[1] for v in seen.values()}) > 1     # slices differ, counter does not
+    # restart from a mid-epoch count reproduces the tail of the stream
+    dl = DataLoader(ds, global_token_num=64, load_level="TOKEN", prefetch=0)
+    full = [b for b in dl]
+    cut = seen[0][0][2]
+    dl2 = DataLoader(ds, global_token_num=64, load_level="TOKEN", prefetch=0)
+    dl2.restart(cut)
+    assert [b for b in dl2] == full[3:]
