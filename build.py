@@ -42,6 +42,7 @@ CXX_SOURCES = [
     "csrc/v1/ps_server.cc",
     "csrc/v1/ps_net.cc",
     "csrc/runtime/symm_mem.cc",
+    "csrc/runtime/symm_vmm.cc",
     "csrc/runtime/memory_pool.cc",
     "csrc/runtime/runtime.cc",
     "csrc/runtime/rpc_client.cc",

@@ -566,6 +566,29 @@ PYBIND11_MODULE(_C, m) {
     cuda_ok(symm_all_to_all(SymmMem::get().buffer(name), src_off, out.data_ptr(), bytes_per_chunk, cur_stream()), "symm_all_to_all");
   });
   m.def("symm_launch_count", &symm_launch_count);
+  // VMM allocation + NVLS multicast mapping (csrc/runtime/symm_vmm.cc): alloc -> exchange descriptors -> open -> barrier -> bind
+  m.def("symm_multicast_supported", [] { return SymmMem::multicast_supported(); });
+  m.def("symm_alloc_vmm", [](const std::string& name, size_t bytes, int rank, int world) {
+    return py::bytes(SymmMem::get().alloc_vmm(name, bytes, rank, world));
+  });
+  m.def("symm_open_vmm", [](const std::string& name, const std::vector<py::bytes>& descs) {
+    std::vector<std::string> ds;
+    for (auto& d : descs) ds.push_back(std::string(d));
+    SymmMem::get().open_vmm(name, ds);
+  });
+  m.def("symm_bind_multicast", [](const std::string& name) { SymmMem::get().bind_multicast(name); });
+  m.def("symm_has_multicast", [](const std::string& name) { return SymmMem::get().buffer(name).mc != nullptr; });
+  m.def("symm_mc_all_reduce", [](const std::string& name, size_t src_off, size_t elems, bool bf16) {
+    cuda_ok(symm_mc_all_reduce(SymmMem::get().buffer(name), src_off, elems, bf16, cur_stream()), "symm_mc_all_reduce");
+  });
+  m.def("symm_mc_reduce_scatter", [](const std::string& name, size_t src_off, at::Tensor out, size_t elems_per_rank) {
+    cuda_ok(symm_mc_reduce_scatter(SymmMem::get().buffer(name), src_off, out.data_ptr(), elems_per_rank,
+                                   out.scalar_type() == at::kBFloat16, cur_stream()), "symm_mc_reduce_scatter");
+  });
+  m.def("symm_mc_all_gather", [](const std::string& name, const at::Tensor& src, size_t dst_off) {
+    cuda_ok(symm_mc_all_gather(SymmMem::get().buffer(name), src.data_ptr(), dst_off, (size_t)src.numel() * src.element_size(),
+                               cur_stream()), "symm_mc_all_gather");
+  });
   // fused row-parallel GEMM -> reduce-scatter: y[T/world, N] = sum_ranks(x_r[T, K_local] * w_r[N, K_local]^T) (+bias +residual).
   // Output tiles are stored from the GEMM epilogue straight into the owner rank's staging slots over NVLink.
   m.def("gemm_reduce_scatter", [](const at::Tensor& x, const at::Tensor& w, const std::string& staging, const py::object& bias,

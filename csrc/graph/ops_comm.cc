@@ -233,6 +233,64 @@ static TensorList all_to_all_grad(OpDef& op, const TensorList& g) {
 }
 HB_REGISTER_OP(all_to_all, "all_to_all", 1, kFlagComm, all_to_all_compute, all_to_all_grad, nullptr, nullptr);
 
+// hierarchical (two-level) all-to-all: ranks = nodes x gpus_per_node (node-major).  Stage 1 exchanges inside the node so
+// that local peer l holds everything this node sends to the GPUs with local index l; stage 2 exchanges between the nodes
+// among GPUs of equal local index -- every inter-node message is gpus_per_node times larger than in the flat algorithm
+// (one aggregated message per node pair and rail instead of one per GPU pair).  Between the stages the per-destination
+// chunks are regrouped by a layout-transform kernel.  Same result as all_to_all(split_dim=0, concat_dim=0).
+// (ref: hetu/v1/src/communication/mpi_nccl_communication.cu:152-243 _ncclHAllToAll / HA2AGather / HA2AScatter,
+//  hetu/v1/src/ops/H_A2A_LayoutTransform.cu, python halltoall_op)
+static at::Tensor chunk_transpose_any(const at::Tensor& x, int64_t a, int64_t b) {
+  const int64_t chunk_bytes = (int64_t)x.nbytes() / (a * b);
+  if (x.is_cuda() && x.is_contiguous() && chunk_bytes % 16 == 0) {
+    at::Tensor y = at::empty_like(x);
+    cuda_ok(chunk_transpose(x.data_ptr(), y.data_ptr(), (int)a, (int)b, chunk_bytes, cur_stream()), "chunk_transpose");
+    return y;
+  }
+  auto shp = x.sizes().vec();
+  at::Tensor v = x.reshape({a, b, -1}).transpose(0, 1).contiguous();
+  return v.reshape(shp);
+}
+static Ts hall_to_all_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  if (in[0].is_meta() || single(op)) return {in[0]};
+  const std::vector<int> ranks = ranks_attr(op);
+  const int64_t n = (int64_t)ranks.size();
+  int64_t local = op.attrs.i("gpus_per_node", n);
+  if (local <= 0 || n % local != 0) local = n;
+  const int64_t nodes = n / local;
+  auto& comm = CommRuntime::get();
+  if (nodes == 1 || local == 1) return {comm.all_to_all(in[0], ranks, 0, 0)};
+  HB_CHECK(in[0].size(0) % n == 0) << "hall_to_all: dim 0 (" << in[0].size(0) << ") must be divisible by " << n << " ranks";
+  int64_t me = -1;
+  for (int64_t i = 0; i < n; ++i) if (ranks[i] == comm.rank()) me = i;
+  HB_CHECK(me >= 0) << "hall_to_all: rank " << comm.rank() << " is not a member of the group";
+  const int64_t my_node = me / local, my_l = me % local;
+  // sub-groups are created collectively: every rank requests all node groups and all rail groups in the same order
+  std::vector<int> node_group, rail_group;
+  for (int64_t q = 0; q < nodes; ++q) {
+    std::vector<int> grp;
+    for (int64_t l = 0; l < local; ++l) grp.push_back(ranks[q * local + l]);
+    comm.group(grp);
+    if (q == my_node) node_group = grp;
+  }
+  for (int64_t l = 0; l < local; ++l) {
+    std::vector<int> grp;
+    for (int64_t q = 0; q < nodes; ++q) grp.push_back(ranks[q * local + l]);
+    comm.group(grp);
+    if (l == my_l) rail_group = grp;
+  }
+  at::Tensor x = in[0].contiguous();
+  // [node q][local l] -> [l][q]; intra-node exchange by l
+  at::Tensor s1 = comm.all_to_all(chunk_transpose_any(x, nodes, local), node_group, 0, 0);      // now [from p][to node q]
+  // [p][q] -> [q][p]; inter-node exchange by q
+  at::Tensor s2 = comm.all_to_all(chunk_transpose_any(s1, local, nodes), rail_group, 0, 0);     // now [from node q'][from local p]
+  return {s2};
+}
+static TensorList hall_to_all_grad(OpDef& op, const TensorList& g) {
+  return {op.graph->make_op1("hall_to_all", {g[0]}, op.attrs)};      // the exchange is its own transpose
+}
+HB_REGISTER_OP(hall_to_all, "hall_to_all", 1, kFlagComm, hall_to_all_compute, hall_to_all_grad, nullptr, nullptr);
+
 static Ts broadcast_comm_compute(const OpDef& op, const Ts& in, RunCtx*) {
   if (in[0].is_meta() || single(op)) return {in[0]};
   return {CommRuntime::get().broadcast(in[0], ranks_attr(op), (int)op.attrs.i("root"))};

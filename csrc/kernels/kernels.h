@@ -151,6 +151,8 @@ cudaError_t moe_gate_topk(const void* logits_bf16, float* probs, int32_t* topk_i
 // capacity-based slot assignment: location[t,k] = position of token t inside expert e's buffer (or -1 when dropped)
 cudaError_t moe_assign_slots(const int32_t* topk_idx, int32_t* location, int32_t* expert_count, int64_t tokens,
                              int experts, int k, int capacity, cudaStream_t s);
+// y[b][a][chunk] = x[a][b][chunk] (16-byte aligned chunks): layout transform of the hierarchical all-to-all
+cudaError_t chunk_transpose(const void* x, void* y, int a, int b, int64_t chunk_bytes, cudaStream_t s);
 // BASE balanced assignment (ref: hetu/v1/python/hetu/gpu_ops/BalanceAssignment.py): idx[t] = expert, loc[t] = slot, every
 // expert gets at most `capacity` tokens (exactly T/E when E divides T).  scores fp32 [tokens, experts];
 // filled [experts] and choice [tokens] are int32 scratch.

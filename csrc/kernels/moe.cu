@@ -352,6 +352,19 @@ __global__ void balance_accept_kernel(const float* __restrict__ scores, const in
   }
   if (threadIdx.x == 0) filled[e] = have + scan_base[0];
 }
+
+// ---------------------------------------------------------------- hierarchical all-to-all layout transform
+// x viewed as [a][b][chunk] -> y[b][a][chunk]: regroups the per-destination chunks between the intra-node and the
+// inter-node exchange of the two-level all-to-all (ref: hetu/v1/src/ops/H_A2A_LayoutTransform.cu, node-major <-> gpu-major)
+__global__ void chunk_transpose_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int a, int b, int64_t vecs) {
+  const int64_t total = int64_t(a) * b * vecs;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t v = i % vecs;
+    const int64_t ab = i / vecs;          // destination chunk index = bi * a + ai
+    const int ai = int(ab % a), bi = int(ab / a);
+    y[i] = x[(int64_t(ai) * b + bi) * vecs + v];
+  }
+}
 }  // namespace
 
 cudaError_t moe_gate_topk(const void* logits_bf16, float* probs, int32_t* topk_idx, float* topk_val, int64_t tokens,
@@ -442,6 +455,16 @@ cudaError_t moe_balance_assign(const float* scores, int32_t* idx, int32_t* loc, 
     count_launch();
     count_launch();
   }
+  return cudaGetLastError();
+}
+cudaError_t chunk_transpose(const void* x, void* y, int a, int b, int64_t chunk_bytes, cudaStream_t s) {
+  if ((chunk_bytes & 15) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return cudaErrorMisalignedAddress;
+  const int64_t vecs = chunk_bytes / 16, total = int64_t(a) * b * vecs;
+  if (total == 0) return cudaSuccess;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > int64_t(sm_count()) * 8) blocks = int64_t(sm_count()) * 8;
+  chunk_transpose_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), a, b, vecs);
+  count_launch();
   return cudaGetLastError();
 }
 }  // namespace hb

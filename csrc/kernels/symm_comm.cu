@@ -129,6 +129,41 @@ __global__ void reduce_slots_kernel(const __nv_bfloat16* __restrict__ slots, int
   }
 }
 
+
+// ---- NVLS: the NVSwitch reduces (multimem.ld_reduce) and replicates (multimem.st) -------------------------------------
+__device__ __forceinline__ uint4 mc_ld_reduce_bf16(const void* mc_addr) {       // 8 bf16, fp32 accumulation in the switch
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 mc_ld_reduce_f32(const void* mc_addr) {        // 4 fp32
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mc_st(void* mc_addr, const uint4& v) {           // 16 bytes into every rank's buffer
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(mc_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <bool kBf16, bool kBroadcast>
+__global__ void mc_reduce_kernel(char* mc_base, size_t src_off, uint4* __restrict__ out, size_t vecs_per_rank, int rank) {
+  char* mine = mc_base + src_off + size_t(rank) * vecs_per_rank * 16;
+  for (size_t v = blockIdx.x * size_t(blockDim.x) + threadIdx.x; v < vecs_per_rank; v += size_t(gridDim.x) * blockDim.x) {
+    const uint4 r = kBf16 ? mc_ld_reduce_bf16(mine + v * 16) : mc_ld_reduce_f32(mine + v * 16);
+    if (kBroadcast) mc_st(mine + v * 16, r);
+    else out[v] = r;
+  }
+}
+
+__global__ void mc_all_gather_kernel(char* mc_base, size_t dst_off, const uint4* __restrict__ src, size_t vecs_per_rank, int rank) {
+  char* dst = mc_base + dst_off + size_t(rank) * vecs_per_rank * 16;
+  for (size_t v = blockIdx.x * size_t(blockDim.x) + threadIdx.x; v < vecs_per_rank; v += size_t(gridDim.x) * blockDim.x)
+    mc_st(dst + v * 16, src[v]);
+}
+
 inline int grid_for(size_t n) {
   size_t blocks = (n + 255) / 256;
   const size_t cap = size_t(sm_count()) * 4;
@@ -216,6 +251,51 @@ cudaError_t symm_all_to_all(SymmBuffer& b, size_t src_off, void* out, size_t byt
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   return symm_barrier(b, s);
+}
+
+cudaError_t symm_mc_all_reduce(SymmBuffer& b, size_t src_off, size_t elems, bool bf16, cudaStream_t s) {
+  if (b.mc == nullptr) return cudaErrorNotSupported;
+  const size_t per = bf16 ? 8 : 4;
+  if (elems % (size_t(b.world) * per) || (src_off & 15)) return cudaErrorInvalidValue;
+  const size_t vecs = elems / b.world / per;
+  cudaError_t e = symm_barrier(b, s);                     // every rank's contribution is complete
+  if (e != cudaSuccess) return e;
+  char* mc = reinterpret_cast<char*>(b.mc);
+  if (bf16) mc_reduce_kernel<true, true><<<grid_for(vecs), 256, 0, s>>>(mc, src_off, nullptr, vecs, b.rank);
+  else mc_reduce_kernel<false, true><<<grid_for(vecs), 256, 0, s>>>(mc, src_off, nullptr, vecs, b.rank);
+  g_symm_launches.fetch_add(1);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return symm_barrier(b, s);                              // all slices have been replicated everywhere
+}
+
+cudaError_t symm_mc_reduce_scatter(SymmBuffer& b, size_t src_off, void* out, size_t elems_per_rank, bool bf16, cudaStream_t s) {
+  if (b.mc == nullptr) return cudaErrorNotSupported;
+  const size_t per = bf16 ? 8 : 4;
+  if ((elems_per_rank % per) || (src_off & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return cudaErrorMisalignedAddress;
+  const size_t vecs = elems_per_rank / per;
+  cudaError_t e = symm_barrier(b, s);
+  if (e != cudaSuccess) return e;
+  char* mc = reinterpret_cast<char*>(b.mc);
+  if (bf16) mc_reduce_kernel<true, false><<<grid_for(vecs), 256, 0, s>>>(mc, src_off, reinterpret_cast<uint4*>(out), vecs, b.rank);
+  else mc_reduce_kernel<false, false><<<grid_for(vecs), 256, 0, s>>>(mc, src_off, reinterpret_cast<uint4*>(out), vecs, b.rank);
+  g_symm_launches.fetch_add(1);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return symm_barrier(b, s);                              // sources may be overwritten again
+}
+
+cudaError_t symm_mc_all_gather(SymmBuffer& b, const void* src, size_t dst_off, size_t bytes_per_rank, cudaStream_t s) {
+  if (b.mc == nullptr) return cudaErrorNotSupported;
+  if ((bytes_per_rank & 15) || (dst_off & 15) || (reinterpret_cast<uintptr_t>(src) & 15)) return cudaErrorMisalignedAddress;
+  cudaError_t e = symm_barrier(b, s);                     // previous readers of the destination are done
+  if (e != cudaSuccess) return e;
+  mc_all_gather_kernel<<<grid_for(bytes_per_rank / 16), 256, 0, s>>>(reinterpret_cast<char*>(b.mc), dst_off,
+                                                                     reinterpret_cast<const uint4*>(src), bytes_per_rank / 16, b.rank);
+  g_symm_launches.fetch_add(1);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return symm_barrier(b, s);                              // every rank's shard has landed in every buffer
 }
 
 }  // namespace hb

@@ -63,6 +63,7 @@ SymmBuffer& SymmMem::buffer(const std::string& name) {
 void SymmMem::free_all() {
   for (auto& kv : bufs_) {
     SymmBuffer& b = kv.second;
+    if (b.vmm) { free_vmm(b); continue; }
     for (int r = 0; r < b.world; ++r)
       if (r != b.rank && b.peer[r]) cudaIpcCloseMemHandle(b.peer[r]);
     if (b.d_peer) cudaFree(b.d_peer);

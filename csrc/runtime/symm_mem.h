@@ -27,6 +27,14 @@ struct SymmBuffer {
   uint32_t** d_flags = nullptr;          // device copy of every rank's flag pad pointer
   uint32_t* flags_local = nullptr;
   uint32_t epoch = 0;                    // barrier generation (host-tracked, identical on all ranks)
+  // ---- VMM / NVLS multicast variant (symm_vmm.cc) ----
+  bool vmm = false;                      // allocated with cuMemCreate (shareable fd) instead of cudaMalloc + IPC
+  int device = 0;
+  size_t map_bytes = 0, granularity = 0;
+  unsigned long long mem_handle = 0, mc_handle = 0, peer_handles[kMaxPeers] = {0};
+  int mem_fd = -1, mc_fd = -1;
+  bool mc_joined = false;                // this device was added to the multicast object
+  void* mc = nullptr;                    // multicast mapping of the whole allocation: multimem.st / multimem.ld_reduce address
 };
 
 class SymmMem {
@@ -39,8 +47,14 @@ class SymmMem {
   SymmBuffer& buffer(const std::string& name);
   bool has(const std::string& name) const { return bufs_.count(name) > 0; }
   void free_all();
+  // ---- VMM allocation with an NVLS multicast mapping (symm_vmm.cc); three collective steps, see the file header
+  static bool multicast_supported();
+  std::string alloc_vmm(const std::string& name, size_t bytes, int rank, int world);
+  void open_vmm(const std::string& name, const std::vector<std::string>& descs);
+  void bind_multicast(const std::string& name);
 
  private:
+  void free_vmm(SymmBuffer& b);
   std::map<std::string, SymmBuffer> bufs_;
 };
 
@@ -58,6 +72,14 @@ cudaError_t symm_reduce_slots(const void* slots, int world, void* out, const voi
                               int cols, cudaStream_t s);
 // all-to-all of equal chunks: out chunk r = rank r's chunk `rank`
 cudaError_t symm_all_to_all(SymmBuffer& b, size_t src_off, void* out, size_t bytes_per_chunk, cudaStream_t s);
+// ---- NVLS (multicast) collectives: need b.mc != nullptr; the switch does the reduction / replication ----------
+// in-place all-reduce of `elems` bf16 / fp32 elements at src_off: every rank load-reduces its 1/world slice through the
+// multicast address (fp32 accumulation in the switch) and multicast-stores the result into all ranks' buffers
+cudaError_t symm_mc_all_reduce(SymmBuffer& b, size_t src_off, size_t elems, bool bf16, cudaStream_t s);
+// out[0 : n] = sum over ranks of chunk `rank` of the world * n element array at src_off
+cudaError_t symm_mc_reduce_scatter(SymmBuffer& b, size_t src_off, void* out, size_t elems_per_rank, bool bf16, cudaStream_t s);
+// every rank's buffer [dst_off + r * bytes_per_rank, ...) = rank r's `src` (local memory), one multicast store per rank
+cudaError_t symm_mc_all_gather(SymmBuffer& b, const void* src, size_t dst_off, size_t bytes_per_rank, cudaStream_t s);
 int64_t symm_launch_count();
 
 }  // namespace hb

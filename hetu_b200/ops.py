@@ -537,6 +537,15 @@ def reduce_scatter(x, ranks, dim=0, **kw):
     return _op1("reduce_scatter", [x], {"ranks": [int(r) for r in ranks], "dim": int(dim)}, **kw)
 
 
+def hall_to_all(x, ranks, gpus_per_node, **kw):
+    """hierarchical (intra-node, then inter-node) all-to-all of the dim-0 chunks; same result as all_to_all
+    (ref: hetu/v1 halltoall_op)"""
+    return _op1("hall_to_all", [x], {"ranks": [int(r) for r in ranks], "gpus_per_node": int(gpus_per_node)}, **kw)
+
+
+halltoall = hall_to_all
+
+
 def all_to_all(x, ranks, split_dim=0, concat_dim=0, **kw):
     return _op1("all_to_all", [x], {"ranks": [int(r) for r in ranks], "split_dim": int(split_dim), "concat_dim": int(concat_dim)}, **kw)
 

@@ -24,6 +24,8 @@ ap.add_argument("--seq", type=int, default=2048)
 ap.add_argument("--batch", type=int, default=4, help="sequences per data-parallel replica and step")
 ap.add_argument("--micro-batches", type=int, default=0)
 ap.add_argument("--no-fp8", action="store_true")
+ap.add_argument("--tp", type=int, default=0, help="override the tensor-parallel degree of the config")
+ap.add_argument("--pp", type=int, default=0, help="override the pipeline-parallel degree of the config")
 a = ap.parse_args()
 ht.init_comm_group()
 world, rank = dist.get_world_size(), dist.get_rank()
@@ -31,7 +33,7 @@ dev = torch.device("cuda", torch.cuda.current_device())
 os.environ.setdefault("HETU_B200_STRICT", "1")
 S, B = a.seq, a.batch
 if a.config == "llama2-7b":
-    tp, pp = 2, 2
+    tp, pp = a.tp or 2, a.pp or 2
     dp = world // (tp * pp)
     cfg = LlamaConfig.llama2_7b(sequence_parallel=True)
     mbs = a.micro_batches or 4

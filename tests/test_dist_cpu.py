@@ -330,3 +330,13 @@ def test_single_strategy_parallel_modules_are_tp_invariant():
     assert abs(a["l0"] - b["l0"]) < 1e-5 and abs(a["l1"] - b["l1"]) < 1e-5 and a["l1"] < a["l0"]
     for k in ("y0", "y1"):
         assert max(abs(x - y) for x, y in zip(a[k], b[k])) < 1e-4
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("world,local", [(4, 2), (6, 3), (8, 2)])
+def test_hierarchical_all_to_all_equals_flat(world, local):
+    """two-level all-to-all (node group, layout transform, rail group) == flat all-to-all, values and gradient"""
+    ok, outs = run_workers(os.path.join(os.path.dirname(__file__), "workers", "hall_to_all_worker.py"), world, [local])
+    assert ok, "\n-----\n".join(outs)
+    line = [l for o in outs for l in o.splitlines() if l.startswith("HA2A ")][0]
+    assert json.loads(line[5:])["ok"]

@@ -23,4 +23,8 @@ def test_symmetric_collectives_match_nccl():
     assert r["all_gather_ok"] and r["all_to_all_ok"]
     assert r["reduce_scatter_err"] < 0.05 and r["all_reduce_err"] < 0.05
     assert r["gemm_rs_err"] < 0.02 * max(1.0, r["gemm_rs_ref_max"])
+    if r.get("multicast_supported"):
+        # NVLS path (cuMulticast + multimem.*): must map on NVSwitch systems and agree with NCCL
+        assert r.get("multicast_mapped"), r.get("multicast_error")
+        assert r["mc_all_gather_ok"] and r["mc_reduce_scatter_err"] < 0.05 and r["mc_all_reduce_err"] < 0.05
     print(json.dumps(r, indent=1))

@@ -74,6 +74,38 @@ tmp = src.clone()
 res["ms_nccl_all_reduce"] = timed(lambda: dist.all_reduce(tmp))
 res["payload_MiB_per_rank"] = n * 2 / 2**20
 
+# --- NVLS: VMM allocation + multicast mapping; the NVSwitch reduces (multimem.ld_reduce) and replicates (multimem.st)
+from hetu_b200.parallel.symm import multicast_available
+res["multicast_supported"] = bool(multicast_available())
+if res["multicast_supported"] and os.environ.get("HETU_NVLS", "1") != "0":
+    try:
+        mbuf = SymmetricBuffer("mc", n * world * 2 + 1024, multicast=True)
+        res["multicast_mapped"] = bool(mbuf.has_multicast)
+    except Exception as e:                      # noqa: BLE001 -- reported, the IPC path above is still valid
+        res["multicast_mapped"] = False
+        res["multicast_error"] = f"{type(e).__name__}: {str(e)[:300]}"
+    if res.get("multicast_mapped"):
+        mx = mbuf.tensor([n * world], "bfloat16")
+        # all-reduce in place
+        mx.copy_(src)
+        mbuf.mc_all_reduce_(n * world, True)
+        res["mc_all_reduce_err"] = float((mx.float() - ref_ar).abs().max())
+        # reduce-scatter
+        mx.copy_(src)
+        mrs = torch.empty(n, dtype=torch.bfloat16, device=dev)
+        mbuf.mc_reduce_scatter(n, mrs)
+        res["mc_reduce_scatter_err"] = float((mrs.float() - ref_rs).abs().max())
+        # all-gather: every rank multicasts its first n elements into slot `rank` of every buffer
+        mx.zero_()
+        torch.cuda.synchronize(); dist.barrier()
+        mbuf.mc_all_gather(src[:n].contiguous())
+        res["mc_all_gather_ok"] = bool(torch.equal(mx, torch.cat(ref)))
+        mx.copy_(src)
+        res["ms_mc_all_reduce"] = timed(lambda: mbuf.mc_all_reduce_(n * world, True))
+        res["ms_mc_reduce_scatter"] = timed(lambda: mbuf.mc_reduce_scatter(n, mrs))
+        shard = src[:n].contiguous()
+        res["ms_mc_all_gather"] = timed(lambda: mbuf.mc_all_gather(shard))
+
 # --- fused GEMM -> reduce-scatter (row-parallel linear of a TP group = all ranks)
 T, K, N = 8192, 8192 // world, 2048
 stage = SymmetricBuffer("stage", T * N * 2)
