@@ -804,6 +804,7 @@ void Executor::run_ops(ExecPlan& plan, const std::vector<OpDef*>& ops, bool back
     }
     // free inputs whose last consumer was this op
     const int pos = base + (int)i;
+    if (backward && zf_active_ != nullptr && zf_active_->nvls) zero_nvls_after_op(plan, *zf_active_, pos);
     for (auto& t : op->inputs) {
       auto lu = plan.last_use_fw.find(t->id);
       if (lu != plan.last_use_fw.end() && lu->second == pos && !keep.count(t->id)) vals.erase(t->id);
@@ -963,6 +964,8 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
     if (zit->second && zit->second->ok) {
       zf_active_ = zit->second.get();
       zf_active_->epilogue_this_run = single_shot_grads_;
+      zf_active_->launched.assign(zf_active_->entries.size(), 0);
+      zf_active_->scale_this_run = opt.grad_scale / (double)M;
     }
   }
 

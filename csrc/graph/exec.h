@@ -187,6 +187,8 @@ class Executor {
   std::shared_ptr<ZeroFusedState> zero_fused_prepare(ExecPlan& plan);
   bool zero_fused_wgrad(ZeroFusedState& st, OpDef* op, const std::vector<at::Tensor>& ins);
   void zero_fused_update(ExecPlan& plan, ZeroFusedState& st, double scale);
+  void zero_nvls_after_op(ExecPlan& plan, ZeroFusedState& st, int pos);   // launches the updates that became ready at `pos`
+  void zero_nvls_launch(ZeroFusedState& st, size_t entry, void* stream);   // stream: cudaStream_t
   // tensor-parallel GEMM -> reduce-scatter over symmetric memory (tp_fused.cc)
   void tp_fused_scan(ExecPlan& plan);
   bool tp_fused_gemm(ExecPlan& plan, OpDef* op, const std::vector<at::Tensor>& ins, RunCtx& rc, std::vector<at::Tensor>& outs);

@@ -50,10 +50,13 @@ std::shared_ptr<ZeroFusedState> Executor::zero_fused_prepare(ExecPlan& plan) {
   st->pos = -1;
   for (int i = 0; i < st->world; ++i) if (st->ranks[i] == comm.rank()) st->pos = i;
   if (st->pos < 0) return st;
+  // NVLS: allocate through the VMM API and add a multicast mapping when the devices support it (csrc/runtime/symm_vmm.cc)
+  const bool want_vmm = SymmMem::multicast_supported() && env_int("HETU_ZERO_NVLS", 1) != 0;
   // ---- arena layout (identical on every rank: entries are in graph order)
+  // gradient regions: [world, rows / world, cols] staging slots of the peer-store path, or (NVLS) the full local gradient
   size_t off = 0;
   for (auto& e : st->entries) {
-    if (e.fused) { e.slots_off = off; off = align_up(off + (size_t)e.numel * 2, 256); }
+    if (e.fused || want_vmm) { e.slots_off = off; off = align_up(off + (size_t)e.numel * 2, 256); }
   }
   for (auto& e : st->entries) { e.param_off = off; off = align_up(off + (size_t)e.numel * 2, 256); }
   size_t flat = 0;
@@ -66,15 +69,42 @@ std::shared_ptr<ZeroFusedState> Executor::zero_fused_prepare(ExecPlan& plan) {
   static int arena_seq = 0;
   st->arena_name = "zero_arena_" + std::to_string(arena_seq++);
   auto& sm = SymmMem::get();
-  std::string handle = sm.alloc(st->arena_name, off, st->pos, st->world);
+  std::string handle = want_vmm ? sm.alloc_vmm(st->arena_name, off, st->pos, st->world) : sm.alloc(st->arena_name, off, st->pos, st->world);
   at::Tensor h = at::empty({(int64_t)handle.size()}, at::TensorOptions().dtype(at::kByte));
   std::memcpy(h.data_ptr(), handle.data(), handle.size());
   at::Tensor all = comm.all_gather(h.to(aten_device()), st->ranks, 0).cpu();
   std::vector<std::string> handles;
   for (int r = 0; r < st->world; ++r)
     handles.emplace_back(reinterpret_cast<const char*>(all.data_ptr()) + (size_t)r * handle.size(), handle.size());
-  sm.open(st->arena_name, handles);
+  if (want_vmm) {
+    sm.open_vmm(st->arena_name, handles);
+    comm.barrier();                               // every device joined the multicast object before memory is bound
+    sm.bind_multicast(st->arena_name);
+    cuda_ok(cudaDeviceSynchronize(), "multicast bind");
+  } else sm.open(st->arena_name, handles);
   SymmBuffer& buf = sm.buffer(st->arena_name);
+  st->nvls = buf.mc != nullptr;
+  if (st->nvls) {
+    // when is backward done with a parameter?  after its weight-gradient GEMM and after its last reader (dgrad); layers
+    // that are recomputed in backward read their parameters at unknown positions: those runs update at the end instead
+    std::unordered_map<OpId, int> bw_pos;
+    for (size_t i = 0; i < plan.bw_ops.size(); ++i) bw_pos[plan.bw_ops[i]->id] = (int)(plan.fw_ops.size() + i);
+    const bool overlap = plan.recompute_ops.empty() && env_int("HETU_ZERO_OVERLAP", 1) != 0;
+    for (size_t i = 0; i < st->entries.size(); ++i) {
+      ZeroEntry& e = st->entries[i];
+      if (!e.fused || !overlap) continue;
+      auto wp = bw_pos.find(e.wgrad->id);
+      if (wp == bw_pos.end()) continue;
+      int pos = wp->second;
+      auto lu = plan.last_use_fw.find(e.param);
+      if (lu != plan.last_use_fw.end()) pos = std::max(pos, lu->second);
+      e.ready_pos = pos;
+      st->ready_at.emplace(pos, i);
+    }
+    cuda_ok(cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking), "side stream");
+    cuda_ok(cudaEventCreateWithFlags(&st->ev_ready, cudaEventDisableTiming), "event");
+    cuda_ok(cudaEventCreateWithFlags(&st->ev_done, cudaEventDisableTiming), "event");
+  }
   // ---- move the parameters into the arena (views share the symmetric allocation)
   auto& store = g_->param_data();
   std::vector<int64_t*> step_ptrs;
@@ -103,10 +133,59 @@ bool Executor::zero_fused_wgrad(ZeroFusedState& st, OpDef* op, const std::vector
   if (it == st.by_wgrad.end() || !st.epilogue_this_run) return false;
   ZeroEntry& e = st.entries[it->second];
   SymmBuffer& buf = SymmMem::get().buffer(st.arena_name);
+  if (st.nvls) {
+    // plain epilogue into this rank's own gradient region; the switch sums the ranks' regions when the shard is loaded
+    wgrad_to_peer_slots(ins[0], ins[1], true, static_cast<char*>(buf.local) + e.slots_off, nullptr, 1, 0, e.rows);
+    return true;
+  }
   void* peers[kMaxPeers];
   for (int r = 0; r < st.world; ++r) peers[r] = static_cast<char*>(buf.peer[r]) + e.slots_off;
   wgrad_to_peer_slots(ins[0], ins[1], true, static_cast<char*>(buf.local) + e.slots_off, peers, st.world, st.pos, e.rows / st.world);
   return true;
+}
+
+// NVLS: one entry = barrier-free kernel on stream `s` (the caller has synchronised the ranks for this entry's gradient)
+void Executor::zero_nvls_launch(ZeroFusedState& st, size_t idx, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ZeroEntry& e = st.entries[idx];
+  SymmBuffer& buf = SymmMem::get().buffer(st.arena_name);
+  auto& store = g_->param_data();
+  char* base = static_cast<char*>(buf.local);
+  char* mc = static_cast<char*>(buf.mc);
+  OpDef* u = e.update;
+  at::Tensor m = get_param(u->inputs[2]), v = get_param(u->inputs[3]), step = get_param(u->inputs[4]), master = get_param(u->inputs[5]);
+  at::Tensor p = store[e.param];
+  if (p.data_ptr() != base + e.param_off) {   // the parameter was replaced (checkpoint load): re-home it in the arena
+    at::Tensor view = at::from_blob(base + e.param_off, p.sizes(), p.options());
+    view.copy_(p);
+    store[e.param] = view;
+  }
+  const int64_t shard = e.numel / st.world;
+  AdamNvlsArgs a;
+  a.master = master.data_ptr<float>(); a.m = m.data_ptr<float>(); a.v = v.data_ptr<float>();
+  a.grad_mc = mc + e.slots_off + (size_t)st.pos * shard * 2;
+  a.param_mc = mc + e.param_off + (size_t)st.pos * shard * 2;
+  a.n = shard;
+  a.lr = (float)u->attrs.f("lr", 1e-3); a.beta1 = (float)u->attrs.f("beta1", 0.9); a.beta2 = (float)u->attrs.f("beta2", 0.999);
+  a.eps = (float)u->attrs.f("eps", 1e-8); a.weight_decay = (float)u->attrs.f("weight_decay", 0.0);
+  a.grad_scale = (float)st.scale_this_run;
+  a.step_ptr = step.data_ptr<int64_t>(); a.step_add = 1;
+  cuda_ok(adam_zero_nvls(a, s), "adam_zero_nvls");
+  st.launched[idx] = 1;
+}
+
+// called by run_ops after every backward op: parameters whose gradient is complete and that backward no longer reads get
+// their reduce + AdamW + broadcast kernel NOW, on the side stream, behind a cross-rank barrier of that stream
+void Executor::zero_nvls_after_op(ExecPlan& plan, ZeroFusedState& st, int pos) {
+  (void)plan;
+  auto range = st.ready_at.equal_range(pos);
+  if (range.first == range.second || !st.epilogue_this_run) return;
+  SymmBuffer& buf = SymmMem::get().buffer(st.arena_name);
+  cuda_ok(cudaEventRecord(st.ev_ready, cur_stream()), "event record");
+  cuda_ok(cudaStreamWaitEvent(st.side, st.ev_ready, 0), "stream wait");
+  cuda_ok(symm_barrier_slot(buf, 1, ++st.side_epoch, st.side), "side barrier");      // all ranks are past this point
+  for (auto it = range.first; it != range.second; ++it)
+    if (!st.launched[it->second]) zero_nvls_launch(st, it->second, st.side);
 }
 
 void Executor::zero_fused_update(ExecPlan& plan, ZeroFusedState& st, double scale) {
@@ -116,6 +195,43 @@ void Executor::zero_fused_update(ExecPlan& plan, ZeroFusedState& st, double scal
   cudaStream_t s = cur_stream();
   auto& store = g_->param_data();
   char* base = static_cast<char*>(buf.local);
+  if (st.nvls) {
+    // entries that were not launched from inside backward: weight gradients produced without the epilogue hook and the
+    // non-GEMM parameters (embeddings, norms, biases) -- copy the accumulated gradient into the arena, then one barrier
+    // for all of them and the same kernel
+    std::vector<size_t> todo;
+    for (size_t i = 0; i < st.entries.size(); ++i) {
+      ZeroEntry& e = st.entries[i];
+      if (st.launched[i]) continue;
+      auto acc = accum_grads_.find(e.param);
+      if (acc != accum_grads_.end()) {
+        at::Tensor dst = at::from_blob(base + e.slots_off, {e.numel}, at::TensorOptions().dtype(at::kBFloat16).device(aten_device()));
+        dst.copy_(acc->second.reshape({-1}));
+      } else if (!(e.fused && st.epilogue_this_run)) continue;       // no gradient in this run
+      todo.push_back(i);
+    }
+    cuda_ok(symm_barrier(buf, s), "zero barrier");               // every rank's remaining gradients are in place
+    for (size_t i : todo) zero_nvls_launch(st, i, s);
+    // join the side stream (updates issued during backward), then nobody may start the next forward before every peer
+    // finished multicasting parameters
+    cuda_ok(cudaEventRecord(st.ev_done, st.side), "event record");
+    cuda_ok(cudaStreamWaitEvent(s, st.ev_done, 0), "stream wait");
+    size_t done = 0;
+    for (size_t i = 0; i < st.entries.size(); ++i) {
+      if (!st.launched[i]) continue;
+      ++done;
+      st.handled_ops.insert(st.entries[i].update->id);
+      st.handled_ops.insert(st.entries[i].comm->id);
+    }
+    if (done == st.entries.size()) {
+      cuda_ok(increment_many_i64(reinterpret_cast<int64_t* const*>(st.step_table.data_ptr()), (int)st.entries.size(), s), "step counters");
+    } else {
+      for (size_t i = 0; i < st.entries.size(); ++i)
+        if (st.launched[i]) cuda_ok(increment_step(get_param(st.entries[i].update->inputs[4]).data_ptr<int64_t>(), s), "step counter");
+    }
+    cuda_ok(symm_barrier(buf, s), "zero barrier");
+    return;
+  }
   // ---- leftovers (and everything when the epilogue path was not used): gather the gradients into the flat buffer
   bool any_flat = false;
   at::Tensor flat = at::from_blob(base + st.flat_off, {(int64_t)st.flat_elems}, at::TensorOptions().dtype(at::kBFloat16).device(aten_device()));

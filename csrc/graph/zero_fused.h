@@ -7,6 +7,9 @@
 // The reference runs these as separate NCCL reduce-scatter / all-gather calls around the optimizer
 // (hetu/graph/executable_graph.cc: grad reduce comm ops + optimize-compute bridge, hetu/graph/ops/Optimizer*.cc).
 #pragma once
+#include <cuda_runtime.h>
+
+#include <map>
 #include <memory>
 #include <set>
 #include <unordered_map>
@@ -28,6 +31,7 @@ struct ZeroEntry {
   size_t param_off = 0;         // bf16 parameter inside the arena
   size_t flat_off = 0;          // leftover: element offset inside the flat gradient buffer
   bool fused = false;
+  int ready_pos = -1;           // NVLS: executor position (fw ops + bw index) after which gradient AND last use of the parameter are done
 };
 
 struct ZeroFusedState {
@@ -41,6 +45,16 @@ struct ZeroFusedState {
   size_t flat_off = 0, flat_elems = 0;           // leftover flat gradient buffer (2x: all-reduce scratch)
   at::Tensor step_table;                         // device int64*[] of all step counters
   bool epilogue_this_run = false;
+  // ---- NVLS mode (multicast mapping of the arena): every entry has a full local bf16 gradient region at `slots_off`;
+  // the update of an entry (switch-side reduce + AdamW + multicast store, optim.cu adam_nvls_kernel) is launched on a side
+  // stream as soon as backward is done with its parameter, overlapping the rest of backward
+  bool nvls = false;
+  std::multimap<int, size_t> ready_at;           // executor position -> entries that become ready there
+  std::vector<char> launched;                    // per entry: update already issued in this run
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+  uint32_t side_epoch = 0;                       // generation of the side-stream barrier (flag slot 1)
+  double scale_this_run = 1.0;
 };
 
 }  // namespace hb

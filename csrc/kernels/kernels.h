@@ -134,6 +134,18 @@ struct AdamZeroArgs {
   int step_add = 0;                    // bias correction uses *step_ptr + step_add (counter bumped later in one batch)
 };
 cudaError_t adam_zero_fused(const AdamZeroArgs& a, cudaStream_t s);
+// the same step over an NVLS multicast mapping: gradient shard = multimem.ld_reduce over all ranks' copies, new bf16
+// shard = one multimem.st into every rank's parameter tensor (see optim.cu)
+struct AdamNvlsArgs {
+  float* master = nullptr; float* m = nullptr; float* v = nullptr;   // fp32 shard [n]
+  const void* grad_mc = nullptr;    // multicast address of the shard inside the symmetric bf16 gradient region
+  void* param_mc = nullptr;         // multicast address of the shard inside the symmetric bf16 parameter tensor
+  int64_t n = 0;                    // shard elements (multiple of 8)
+  float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, weight_decay = 0.0f, grad_scale = 1.0f;
+  const int64_t* step_ptr = nullptr;
+  int step_add = 0;
+};
+cudaError_t adam_zero_nvls(const AdamNvlsArgs& a, cudaStream_t s);
 // counters[i] += 1 for a device table of int64 pointers (one launch for all optimizer step counters)
 cudaError_t increment_many_i64(int64_t* const* table, int count, cudaStream_t s);
 cudaError_t sgd_update(float* master, float* momentum_buf, const void* grad, bool grad_is_bf16, void* param_bf16,

@@ -219,6 +219,66 @@ __global__ void __launch_bounds__(256) adam_zero_fused_kernel(AdamZeroDev a) {
     }
   }
 }
+// ---- ZeRO step over NVLS: the NVSwitch sums the ranks' gradient copies while this rank loads its shard
+// (multimem.ld_reduce, fp32 accumulation in the switch), AdamW runs on the fp32 master shard, and one multicast store
+// (multimem.st) writes the new bf16 shard into EVERY rank's parameter tensor: reduce-scatter + optimizer + all-gather in
+// one pass with no staging slots and no per-peer store loop.
+struct AdamNvlsDev {
+  float* master; float* m; float* v;
+  const char* grad_mc;   // multicast address of this rank's shard inside the (symmetric) gradient region
+  char* param_mc;        // multicast address of this rank's shard inside the (symmetric) parameter tensor
+  int64_t n;
+  float lr, beta1, beta2, eps, wd, gscale;
+  const int64_t* step_ptr; int step_add;
+};
+__global__ void __launch_bounds__(256) adam_nvls_kernel(AdamNvlsDev a) {
+  const float step = float((a.step_ptr ? *a.step_ptr : 0) + a.step_add);
+  const float bc1 = 1.0f - __powf(a.beta1, step);
+  const float bc2 = 1.0f - __powf(a.beta2, step);
+  const float step_size = a.lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const int64_t nvec = a.n >> 3;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < nvec; i += int64_t(gridDim.x) * blockDim.x) {
+    uint4 raw;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "l"(a.grad_mc + i * 16) : "memory");
+    const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    float g[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(b[j]);
+      g[2 * j] = f.x; g[2 * j + 1] = f.y;
+    }
+    float p[8], m[8], v[8];
+    *reinterpret_cast<float4*>(p) = reinterpret_cast<const float4*>(a.master)[2 * i];
+    *reinterpret_cast<float4*>(p + 4) = reinterpret_cast<const float4*>(a.master)[2 * i + 1];
+    *reinterpret_cast<float4*>(m) = reinterpret_cast<const float4*>(a.m)[2 * i];
+    *reinterpret_cast<float4*>(m + 4) = reinterpret_cast<const float4*>(a.m)[2 * i + 1];
+    *reinterpret_cast<float4*>(v) = reinterpret_cast<const float4*>(a.v)[2 * i];
+    *reinterpret_cast<float4*>(v + 4) = reinterpret_cast<const float4*>(a.v)[2 * i + 1];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gj = g[j] * a.gscale;
+      m[j] = a.beta1 * m[j] + (1.0f - a.beta1) * gj;
+      v[j] = a.beta2 * v[j] + (1.0f - a.beta2) * gj * gj;
+      const float denom = sqrtf(v[j]) * inv_sqrt_bc2 + a.eps;
+      p[j] = p[j] - step_size * (m[j] / denom) - a.lr * a.wd * p[j];
+    }
+    reinterpret_cast<float4*>(a.master)[2 * i] = *reinterpret_cast<const float4*>(p);
+    reinterpret_cast<float4*>(a.master)[2 * i + 1] = *reinterpret_cast<const float4*>(p + 4);
+    reinterpret_cast<float4*>(a.m)[2 * i] = *reinterpret_cast<const float4*>(m);
+    reinterpret_cast<float4*>(a.m)[2 * i + 1] = *reinterpret_cast<const float4*>(m + 4);
+    reinterpret_cast<float4*>(a.v)[2 * i] = *reinterpret_cast<const float4*>(v);
+    reinterpret_cast<float4*>(a.v)[2 * i + 1] = *reinterpret_cast<const float4*>(v + 4);
+    uint4 o;
+    __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(p[2 * j], p[2 * j + 1]);
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(a.param_mc + i * 16), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+  }
+}
+
 __global__ void increment_many_kernel(int64_t* const* table, int count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) *table[i] += 1;
@@ -243,6 +303,22 @@ cudaError_t adam_zero_fused(const AdamZeroArgs& a, cudaStream_t s) {
   d.lr = a.lr; d.beta1 = a.beta1; d.beta2 = a.beta2; d.eps = a.eps; d.wd = a.weight_decay; d.gscale = a.grad_scale;
   d.step_ptr = a.step_ptr; d.step_add = a.step_add;
   adam_zero_fused_kernel<<<grid_for(a.n >> 3), 256, 0, s>>>(d);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t adam_zero_nvls(const AdamNvlsArgs& a, cudaStream_t s) {
+  if (a.n == 0) return cudaSuccess;
+  if (a.n & 7) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(a.master) | reinterpret_cast<uintptr_t>(a.m) | reinterpret_cast<uintptr_t>(a.v) |
+       reinterpret_cast<uintptr_t>(a.grad_mc) | reinterpret_cast<uintptr_t>(a.param_mc)) & 15)
+    return cudaErrorMisalignedAddress;
+  AdamNvlsDev d;
+  d.master = a.master; d.m = a.m; d.v = a.v;
+  d.grad_mc = reinterpret_cast<const char*>(a.grad_mc); d.param_mc = reinterpret_cast<char*>(a.param_mc);
+  d.n = a.n;
+  d.lr = a.lr; d.beta1 = a.beta1; d.beta2 = a.beta2; d.eps = a.eps; d.wd = a.weight_decay; d.gscale = a.grad_scale;
+  d.step_ptr = a.step_ptr; d.step_add = a.step_add;
+  adam_nvls_kernel<<<grid_for(a.n >> 3), 256, 0, s>>>(d);
   count_launch();
   return cudaGetLastError();
 }

@@ -181,6 +181,13 @@ cudaError_t symm_barrier(SymmBuffer& b, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+cudaError_t symm_barrier_slot(SymmBuffer& b, int slot, uint32_t epoch, cudaStream_t s) {
+  if (slot < 1 || slot >= kFlagWords / kMaxPeers) return cudaErrorInvalidValue;
+  barrier_kernel<<<1, 32, 0, s>>>(b.d_flags, b.rank, b.world, epoch, slot);
+  g_symm_launches.fetch_add(1);
+  return cudaGetLastError();
+}
+
 cudaError_t symm_all_gather(SymmBuffer& b, size_t src_off, void* out, size_t bytes_per_rank, cudaStream_t s) {
   if ((bytes_per_rank & 15) || (src_off & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return cudaErrorMisalignedAddress;
   cudaError_t e = symm_barrier(b, s);                   // every rank's source is complete

@@ -61,6 +61,9 @@ class SymmMem {
 // ---- device-side collectives over a symmetric buffer (symm_comm.cu) ----------------------------------------
 // all ranks must call these in the same order; `stream` is the launching stream on every rank
 cudaError_t symm_barrier(SymmBuffer& b, cudaStream_t s);
+// the same barrier on an independent flag slot (1..127) with a caller-tracked generation: lets a second stream
+// synchronise the ranks without disturbing the barriers of the main stream
+cudaError_t symm_barrier_slot(SymmBuffer& b, int slot, uint32_t epoch, cudaStream_t s);
 // out[r * n : (r+1) * n] = rank r's `n` elements at byte offset `src_off` of the symmetric buffer
 cudaError_t symm_all_gather(SymmBuffer& b, size_t src_off, void* out, size_t bytes_per_rank, cudaStream_t s);
 // out[0 : n] = sum_r (rank r's chunk `rank` of the `world * n`-element bf16/fp32 array at src_off); fp32 accumulation

@@ -26,11 +26,21 @@ class _State:
         self.last_beat: Dict[int, float] = {}
         self.stop_flag = False
         self.exited: set = set()
+        # elastic re-mapping (ref: heturpc_elastic_server.py host_name_to_idx / host_name_to_local_idx): when set, the k-th worker
+        # that connects from host h becomes rank host_to_ranks[h][k] on local device host_to_local[h][k] -- the planner, not the
+        # registration order, decides which physical GPU plays which rank
+        self.host_to_ranks: Dict[str, list] = {}
+        self.host_to_local: Dict[str, list] = {}
+        self.local_device_of: Dict[int, int] = {}
 
 
 class DeviceControllerServer:
-    def __init__(self, world_size: int, host: str = "127.0.0.1", port: int = 23457, heartbeat_timeout: float = 10.0):
+    def __init__(self, world_size: int, host: str = "127.0.0.1", port: int = 23457, heartbeat_timeout: float = 10.0,
+                 host_to_ranks: Optional[Dict[str, list]] = None, host_to_local: Optional[Dict[str, list]] = None):
         self.state = _State(world_size)
+        if host_to_ranks:
+            self.state.host_to_ranks = {h: list(v) for h, v in host_to_ranks.items()}
+            self.state.host_to_local = {h: list(v) for h, v in (host_to_local or {}).items()}
         self.heartbeat_timeout = heartbeat_timeout
         outer = self
 
@@ -84,10 +94,20 @@ class DeviceControllerServer:
         st = self.state
         with st.lock:
             if client_id not in st.ranks:
-                st.ranks[client_id] = len(st.ranks)
+                k = st.local_counts.get(hostname, 0)
+                if st.host_to_ranks:
+                    planned = st.host_to_ranks.get(hostname)
+                    if planned is None or k >= len(planned):
+                        raise RuntimeError(f"host {hostname} has no rank left in the elastic plan (worker #{k})")
+                    st.ranks[client_id] = int(planned[k])
+                    loc = st.host_to_local.get(hostname)
+                    if loc is not None and k < len(loc):
+                        st.local_device_of[int(planned[k])] = int(loc[k])
+                else:
+                    st.ranks[client_id] = len(st.ranks)
                 r = st.ranks[client_id]
                 st.hostnames[r] = hostname
-                st.local_counts[hostname] = st.local_counts.get(hostname, 0) + 1
+                st.local_counts[hostname] = k + 1
                 st.last_beat[r] = time.time()
                 st.lock.notify_all()
             return st.ranks[client_id]
@@ -99,7 +119,9 @@ class DeviceControllerServer:
             self._wait(lambda: len(st.ranks) >= st.world_size, timeout)
             r = st.ranks[client_id]
             host = st.hostnames[r]
-            local = sorted(k for k, h in st.hostnames.items() if h == host).index(r)
+            local = st.local_device_of.get(r)
+            if local is None:
+                local = sorted(k for k, h in st.hostnames.items() if h == host).index(r)
             return {"rank": r, "local_device": local, "world_size": st.world_size}
 
     def rpc_CommitHostName(self, rank: int, hostname: str):

@@ -92,3 +92,46 @@ def test_reference_module_paths_resolve_under_the_hetu_alias():
     assert hetu.logger is importlib.import_module("hetu_b200").logger and callable(hetu.logger.info)
     with pytest.raises(ModuleNotFoundError):
         importlib.import_module("hetu.no_such_module")
+
+
+def test_ampelos_replans_after_device_loss_and_stragglers():
+    """elastic re-planning (ref: python/hetu/engine/strategy_ampelos.py): dead devices shrink a tensor-parallel group, the
+    planner may change the number of pipelines and their depths, every layer / micro-batch stays assigned, and the chosen
+    plan is no slower than any other candidate it enumerated"""
+    from hetu_b200.engine.strategy import TrainerCtxs, TrainerStrategyArgs
+    from hetu_b200.engine.strategy_ampelos import AmpelosStrategyModel, partition_into_k_groups, replan_after_failure
+    parts = partition_into_k_groups([5, 4, 3, 3, 2, 1], 2)
+    assert sorted(sum([5, 4, 3, 3, 2, 1][i] for i in p) for p in parts) == [9, 9]
+    ctxs = TrainerCtxs(normal_layers=8, normal_mbn=8, top_k=5, memory_bound=12)
+    old = TrainerStrategyArgs(dp=2, tp=4, pp=2, hetero_layers=[[8, 8], [8, 8]], rank_to_device_mapping={r: r for r in range(16)})
+    # healthy job whose stages can hold at most 8 layers: the homogeneous plan comes back (2 pipelines x 2 stages of tp 4,
+    # 8 layers each, 8 micro-batches each); without a memory bound the planner would rather run 4 bubble-free pipelines
+    m = AmpelosStrategyModel(TrainerCtxs(normal_layers=8, normal_mbn=8, memory_bound=8), old, {d: 1.0 for d in range(16)})
+    st, cfg = m.make_plans()
+    assert st.dp == 2 and st.hetero_layers == [[8, 8], [8, 8]] and st.hetero_micro_batch_num_list == [8, 8] and not st.unused_rank_list
+    base_time = m.estimate_time()
+    # device 5 dies, device 12 runs 2.5x slower
+    m2 = replan_after_failure(ctxs, old, [d for d in range(16) if d != 5], {12: 2.5})
+    st2, cfg2 = m2.make_plans()
+    used = [d for pl in m2.plans for g in pl["groups"] for d in g.devices]
+    assert 5 not in used and len(used) == len(set(used))
+    assert all(sum(ls) == 16 for ls in st2.hetero_layers) and sum(st2.hetero_micro_batch_num_list) == 16
+    assert all(len(ls) == n for ls, n in zip(st2.hetero_layers, st2.hetero_stages))
+    assert m2.estimate_time() >= base_time                     # fewer / slower devices cannot be faster
+    assert m2.candidates == sorted(m2.candidates) and len(m2.candidates) >= 2
+    # the straggler never shares a group with healthy devices of its node
+    for pl in m2.plans:
+        for g in pl["groups"]:
+            if 12 in g.devices:
+                assert g.devices == [12] or all(m2._sr(d) >= ctxs.straggler_threshold for d in g.devices)
+    # the emitted heterogeneous config is consumable
+    assert "pipelines" in cfg2 or "devices" in cfg2 or isinstance(cfg2, dict)
+    # a whole node lost: all work moves to the surviving node, still a valid plan
+    m3 = replan_after_failure(ctxs, old, list(range(8)))
+    st3, _ = m3.make_plans()
+    assert all(d < 8 for pl in m3.plans for g in pl["groups"] for d in g.devices) and all(sum(ls) == 16 for ls in st3.hetero_layers)
+    # memory bound: 10 layers per full-width stage cannot hold 16 layers on one stage -> at least 2 stages per pipeline
+    tight = TrainerCtxs(normal_layers=8, normal_mbn=8, memory_bound=10)
+    m4 = replan_after_failure(tight, old, list(range(8)))
+    st4, _ = m4.make_plans()
+    assert all(max(ls) <= 10 for ls in st4.hetero_layers)

@@ -203,3 +203,42 @@ def test_pssh_start_config_launches_workers_that_rendezvous_through_the_controll
     assert r.returncode == 0, r.stderr
     h = json.load(open(tmp_path / "ds" / "h.json"))
     assert h["blocks"]["blocks0"]["attn"]["qkv"]["device_group_union"] == [[0, 1], [4]] and h["blocks"]["blocks5"]["attn"]["qkv"]["device_group_union"] == [[2, 3], [4]]
+
+
+def test_elastic_node_detection_replan_and_rank_remapping():
+    """ref: heturpc_elastic_server.py:497-859 -- survey the nodes (nvidia-smi), re-plan around the GPUs that are really there
+    and make the rendezvous server hand out ranks according to the plan instead of the connection order"""
+    from hetu_b200.rpc.elastic_server import ElasticStrategy, available_gpus, detect_node_info
+    row = "{i}, NVIDIA B200, 183359, {free}, 100, 0"
+    smi = {"n0": "\n".join(row.format(i=i, free=180000) for i in range(8)),
+           "n1": "\n".join(row.format(i=i, free=180000 if i != 6 else 1000) for i in range(8) if i != 3)}
+
+    def runner(node, cmd):
+        if node == "n2":
+            return None                                   # unreachable node
+        return smi[node] if "nvidia-smi" in cmd else node + "-host\n"
+    info = detect_node_info(["n0", "n1", "n2"], runner)
+    assert info[2]["reachable"] is False and info[2]["gpu_info"] == [] and len(info[1]["gpu_info"]) == 7
+    gpus, bound = available_gpus(info, min_free_fraction=0.5)
+    assert bound == 183359 and [g["idx"] for g in gpus[1]["gpus"]] == [8, 9, 10, 12, 13, 15]      # 11 missing, 14 busy
+    es = ElasticStrategy(tp=4, pp=2, dp=2, num_layers=16, global_micro_batches=16, memory_bound_layers=12, min_free_fraction=0.5)
+    plan = es.plan_from_nodes({k: v for k, v in info.items() if k < 2})
+    devs = sorted(plan["rank_to_device_mapping"].values())
+    assert 11 not in devs and 14 not in devs and len(devs) == len(set(devs)) == plan["num_devices"]
+    assert all(sum(ls) == 16 for ls in plan["hetero_layers"]) and sum(plan["micro_batch_num_list"]) == 16
+    assert sorted(r for rs in plan["host_to_ranks"].values() for r in rs) == sorted(plan["rank_to_device_mapping"])
+    cmd = es.replace_cmd("python train.py --dp 2 --tp 4 --pp 2 --num_gpus=16 --hetero_stages [2,2] --steps 100", plan)
+    assert f"--dp {plan['dp']} " in cmd and f"--num_gpus={plan['num_devices']}" in cmd and "--hetero_stages " + str(plan["hetero_stages"]).replace(" ", "") in cmd
+    assert "--steps 40" in es.renew_step(cmd, 40)
+    # the server enforces the mapping: the k-th worker of a host gets the k-th planned rank / local GPU of that host
+    small = {"dp": 1, "tp": 1, "pp": 1, "num_devices": 3}
+    srv = DeviceControllerServer(3, port=_free_port(), host_to_ranks={"hA": [2, 0], "hB": [1]}, host_to_local={"hA": [5, 1], "hB": [7]}).start()
+    try:
+        assert srv.rpc_Connect("c0", "hA") == 2 and srv.rpc_Connect("c1", "hB") == 1 and srv.rpc_Connect("c2", "hA") == 0
+        assert srv.rpc_GetRank("c0") == {"rank": 2, "local_device": 5, "world_size": 3}
+        assert srv.rpc_GetRank("c2") == {"rank": 0, "local_device": 1, "world_size": 3}
+        assert srv.rpc_GetRank("c1")["local_device"] == 7
+        with pytest.raises(RuntimeError):
+            srv.rpc_Connect("c3", "hB")                   # no rank left for that host in the plan
+    finally:
+        srv.shutdown()
