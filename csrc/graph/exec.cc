@@ -108,6 +108,48 @@ at::Tensor CommRuntime::reduce_scatter(const at::Tensor& x, const std::vector<in
   calls_["reduce_scatter"] += 1;
   return out.scalar_type() == x.scalar_type() ? out : out.to(x.scalar_type());
 }
+CommRuntime::AsyncResult CommRuntime::all_reduce_async(const at::Tensor& x, const std::vector<int>& ranks, ReductionType red, bool fp32) {
+  AsyncResult r;
+  r.red = red; r.n = (int64_t)ranks.size(); r.want = x.scalar_type();
+  if (ranks.size() <= 1 || !initialized()) { r.out = x; return r; }
+  r.out = (fp32 && x.scalar_type() != at::kFloat) ? x.to(at::kFloat) : x.contiguous().clone();
+  std::vector<at::Tensor> v = {r.out};
+  c10d::AllreduceOptions o;
+  o.reduceOp = to_c10d(red);
+  r.work = group(ranks)->allreduce(v, o);
+  bytes_["all_reduce"] += r.out.nbytes();
+  calls_["all_reduce"] += 1;
+  return r;
+}
+CommRuntime::AsyncResult CommRuntime::reduce_scatter_async(const at::Tensor& x, const std::vector<int>& ranks, int dim, ReductionType red,
+                                                           bool fp32) {
+  AsyncResult r;
+  r.red = red; r.n = (int64_t)ranks.size(); r.want = x.scalar_type();
+  if (ranks.size() <= 1 || !initialized()) { r.out = x; return r; }
+  at::Tensor in = (fp32 && x.scalar_type() != at::kFloat) ? x.to(at::kFloat) : x;
+  if (dim != 0) in = at::cat(at::chunk(in, r.n, dim), 0);
+  in = in.contiguous();
+  std::vector<int64_t> shp = in.sizes().vec();
+  HB_CHECK(shp[0] % r.n == 0) << "reduce_scatter: dim not divisible by group size";
+  shp[0] /= r.n;
+  r.out = at::empty(shp, in.options());
+  r.keep = in;
+  c10d::ReduceScatterOptions o;
+  o.reduceOp = to_c10d(red);
+  r.work = group(ranks)->_reduce_scatter_base(r.out, in, o);
+  bytes_["reduce_scatter"] += in.nbytes();
+  calls_["reduce_scatter"] += 1;
+  return r;
+}
+at::Tensor CommRuntime::finish(AsyncResult& r) {
+  if (r.work) {
+    r.work->wait();                      // CUDA: the compute stream waits for the collective's event, the host does not block
+    r.work.reset();
+    r.keep = at::Tensor();
+    if (r.red == ReductionType::MEAN) r.out.div_((double)r.n);
+  }
+  return r.out.scalar_type() == r.want ? r.out : r.out.to(r.want);
+}
 at::Tensor CommRuntime::broadcast(const at::Tensor& x, const std::vector<int>& ranks, int root_rank) {
   if (ranks.size() <= 1 || !initialized()) return x;
   at::Tensor buf = x.contiguous().clone();
@@ -585,7 +627,10 @@ void Executor::build_plan(ExecPlan& plan, const Tensor& loss, const TensorList& 
     }
     if (!local) continue;
     if (op->has_flag(kFlagOptimizerUpdate) || op->has_flag(kFlagGroup)) plan.update_ops.push_back(op);
-    else if (deferred.count(op->id)) plan.update_ops.push_back(op);
+    else if (deferred.count(op->id)) {
+      plan.update_ops.push_back(op);
+      if (op->type == "comm" && !op->inputs.empty()) plan.deferred_comm_of_raw[op->inputs[0]->id] = op;
+    }
     else if (op->is_bwd) plan.bw_ops.push_back(op);
     else plan.fw_ops.push_back(op);
   }
@@ -798,6 +843,22 @@ void Executor::run_ops(ExecPlan& plan, const std::vector<OpDef*>& ops, bool back
           const bool fp32 = env_int("HETU_FP32_GRAD_ACCUMULATION", 1) != 0 && !single_shot_grads_;
           accum_grads_[pg->second] = fp32 ? outs[k].to(at::kFloat) : (single_shot_grads_ ? outs[k] : outs[k].clone());
         } else acc->second.add_(outs[k]);
+        // overlapped gradient synchronisation: this parameter's gradient is final (single micro-batch, UPDATE run), so its
+        // data-parallel all-reduce / ZeRO reduce-scatter starts NOW on the communication stream while backward continues;
+        // the update phase only waits for it (ref: HETU_OVERLAP_GRAD_REDUCE, executable_graph.cc:1137-1150)
+        if (single_shot_grads_ && overlap_grad_reduce_ && zf_active_ == nullptr && !scaler_.enabled) {
+          auto dc = plan.deferred_comm_of_raw.find(oid);
+          if (dc != plan.deferred_comm_of_raw.end()) {
+            const CommStep& cs = plan.comm[dc->second->id];
+            const bool fp32 = env_int("HETU_FP32_COMM_REDUCE", 0) != 0;
+            at::Tensor g = accum_grads_[pg->second];
+            if (cs.type == CommType::ALL_REDUCE && cs.ranks.size() > 1)
+              async_grad_comm_[dc->second->outputs[0]->id] = CommRuntime::get().all_reduce_async(g, cs.ranks, ReductionType::SUM, fp32);
+            else if (cs.type == CommType::REDUCE_SCATTER && cs.ranks.size() > 1)
+              async_grad_comm_[dc->second->outputs[0]->id] =
+                  CommRuntime::get().reduce_scatter_async(g, cs.ranks, cs.dim, ReductionType::SUM, fp32);
+          }
+        }
         continue;
       }
       vals[oid] = outs[k];
@@ -954,6 +1015,9 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
 
   // gradients of a one-micro-batch UPDATE run are consumed by the optimizer directly (no fp32 accumulation copy)
   single_shot_grads_ = !inference && M == 1 && opt.run_level == RunLevel::UPDATE && accum_grads_.empty();
+  // default: overlap on GPUs (the process group's own communication stream runs beside the compute stream)
+  overlap_grad_reduce_ = env_str("HETU_OVERLAP_GRAD_REDUCE", aten_device().is_cuda() ? "ON" : "OFF") != "OFF" &&
+                         env_str("HETU_OVERLAP_GRAD_REDUCE", "ON") != "0";
   // ZeRO over symmetric memory (fused with the wgrad GEMM epilogues and the optimizer); prepared once per plan
   if (!tp_fused_.count(&plan)) tp_fused_scan(plan);
   zf_active_ = nullptr;
@@ -1077,6 +1141,14 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
         if (pg == plan.param_of_grad.end()) continue;
         auto acc = accum_grads_.find(pg->second);
         if (acc == accum_grads_.end()) continue;
+        auto pending = async_grad_comm_.find(op->outputs[0]->id);
+        if (pending != async_grad_comm_.end()) {
+          // launched from inside backward: (sum commutes with the scale)
+          at::Tensor r = CommRuntime::get().finish(pending->second);
+          uvals[op->outputs[0]->id] = scale != 1.0 ? r * scale : r;
+          async_grad_comm_.erase(pending);
+          continue;
+        }
         at::Tensor g = acc->second;
         if (scale != 1.0) g = g * scale;
         const double t_g = profile_ ? now_ms() : 0.0;
@@ -1152,6 +1224,7 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
               "step counters");
     }
     accum_grads_.clear();
+    async_grad_comm_.clear();
     breakdown_["update_ms"] = now_ms() - t_u;
     if (profile_) breakdown_["optimizer_ms"] = breakdown_["update_ms"] - breakdown_["dp_grad_reduce_ms"];
   }

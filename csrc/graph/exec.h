@@ -48,6 +48,22 @@ class CommRuntime {
                             ReductionType red = ReductionType::SUM, bool fp32_reduce = false);
   at::Tensor broadcast(const at::Tensor& x, const std::vector<int>& ranks, int root_rank);
   at::Tensor all_to_all(const at::Tensor& x, const std::vector<int>& ranks, int split_dim = 0, int concat_dim = 0);
+  // asynchronous gradient synchronisation: the collective is enqueued on the communication stream of the process group
+  // (behind everything issued so far on the compute stream) and completed later by finish() -- the backward pass keeps
+  // computing in between (ref: executable_graph.cc:1137-1150 overlapped grad reduce on kBridgeStream)
+  struct AsyncResult {
+    c10::intrusive_ptr<c10d::Work> work;
+    at::Tensor out, keep;                 // result buffer, input kept alive until completion
+    ReductionType red = ReductionType::SUM;
+    int64_t n = 1;
+    at::ScalarType want = at::kFloat;
+    bool valid() const { return out.defined(); }
+  };
+  AsyncResult all_reduce_async(const at::Tensor& x, const std::vector<int>& ranks, ReductionType red = ReductionType::SUM,
+                               bool fp32_reduce = false);
+  AsyncResult reduce_scatter_async(const at::Tensor& x, const std::vector<int>& ranks, int dim,
+                                   ReductionType red = ReductionType::SUM, bool fp32_reduce = false);
+  at::Tensor finish(AsyncResult& r);
   // pipeline P2P: sends are asynchronous (completed by flush_sends()), the forward and backward directions use
   // separate channels (own communicator / FIFO) so a stage sending activations never blocks behind a gradient receive
   void send(const at::Tensor& x, int dst_rank, int channel = 0);
@@ -120,6 +136,7 @@ struct ExecPlan {
   std::vector<TensorId> fetch_ids;
   std::unordered_map<TensorId, TensorId> param_of_grad;    // grad tensor id -> param tensor id
   std::unordered_map<TensorId, OpDef*> update_of_param;
+  std::unordered_map<TensorId, OpDef*> deferred_comm_of_raw;   // raw gradient tensor -> its deferred (update-phase) comm op
   bool built = false;
 };
 
@@ -201,6 +218,7 @@ class Executor {
   std::map<const ExecPlan*, std::shared_ptr<ZeroFusedState>> zero_fused_;
   std::map<const ExecPlan*, std::shared_ptr<TpFusedState>> tp_fused_;
   bool single_shot_grads_ = false;
+  bool overlap_grad_reduce_ = false;
   std::map<const ExecPlan*, std::vector<int64_t>> step_tables_host_;
   ZeroFusedState* zf_active_ = nullptr;   // set while run() executes a plan on the fused ZeRO path
   std::vector<std::pair<std::string, double>> op_times_;
@@ -210,6 +228,8 @@ class Executor {
   int shapes_strategy_ = -1;   // strategy whose local shapes are currently stored in the tensors
   uint64_t step_ = 0;
   LossScaler scaler_;
+  // gradient collectives launched from inside backward (HETU_OVERLAP_GRAD_REDUCE), keyed by the comm op's output tensor
+  std::unordered_map<TensorId, CommRuntime::AsyncResult> async_grad_comm_;
 };
 
 }  // namespace hb

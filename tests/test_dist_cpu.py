@@ -340,3 +340,16 @@ def test_hierarchical_all_to_all_equals_flat(world, local):
     assert ok, "\n-----\n".join(outs)
     line = [l for o in outs for l in o.splitlines() if l.startswith("HA2A ")][0]
     assert json.loads(line[5:])["ok"]
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("zero", [0, 1])
+def test_overlapped_gradient_reduce_matches_the_serial_path(zero):
+    """HETU_OVERLAP_GRAD_REDUCE: the data-parallel all-reduce / ZeRO reduce-scatter of every parameter is launched from inside
+    backward as soon as its gradient is final and only awaited by the update phase -- same loss curve as the serial path"""
+    ref = _reference()
+    ok, outs = run_workers(WORKER, 2, [2, 1, 1, zero, 0, 1], env_extra={"HETU_OVERLAP_GRAD_REDUCE": "ON"})
+    assert ok, "\n-----\n".join(outs)
+    got = _losses(outs)
+    for a, b in zip(got, ref):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, ref)
