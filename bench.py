@@ -108,16 +108,20 @@ def main():
     tp = args.tp
     dp = world // tp
     T = B * S
-    with ht.graph("define_and_run", create_new=True) as g, ht.autocast("bfloat16"):
-        dsc = [generate_ds_parallel_config(cfg.n_layer, world, dp, tp, 1, zero=True)]
-        model = GPTLMHeadModel(cfg, dsc)
-        ids_cfg = ht.nn.parallel.config2ds(dsc[0]["input"])
-        ids = ht.parallel_placeholder("int64", [T * dp], [ids_cfg[0]], device_group_hierarchy=[ids_cfg[1]], name="input_ids")
-        pos = ht.parallel_placeholder("int64", [T * dp], [ids_cfg[0]], device_group_hierarchy=[ids_cfg[1]], name="position_ids")
-        lab = ht.parallel_placeholder("int64", [T * dp], [ids_cfg[0]], device_group_hierarchy=[ids_cfg[1]], name="labels")
-        loss = model(ids, pos, lab, seq_len=S)
-        opt = ht.AdamOptimizer(lr=1e-4, beta1=0.9, beta2=0.95, weight_decay=0.1)
-        train_op = opt.minimize(loss)
+    def build_graph():
+        with ht.graph("define_and_run", create_new=True) as g, ht.autocast("bfloat16"):
+            dsc = [generate_ds_parallel_config(cfg.n_layer, world, dp, tp, 1, zero=True)]
+            model = GPTLMHeadModel(cfg, dsc)
+            ids_cfg = ht.nn.parallel.config2ds(dsc[0]["input"])
+            ids = ht.parallel_placeholder("int64", [T * dp], [ids_cfg[0]], device_group_hierarchy=[ids_cfg[1]], name="input_ids")
+            pos = ht.parallel_placeholder("int64", [T * dp], [ids_cfg[0]], device_group_hierarchy=[ids_cfg[1]], name="position_ids")
+            lab = ht.parallel_placeholder("int64", [T * dp], [ids_cfg[0]], device_group_hierarchy=[ids_cfg[1]], name="labels")
+            loss = model(ids, pos, lab, seq_len=S)
+            opt = ht.AdamOptimizer(lr=1e-4, beta1=0.9, beta2=0.95, weight_decay=0.1)
+            train_op = opt.minimize(loss)
+        return g, model, ids, pos, lab, loss, train_op
+
+    g, model, ids, pos, lab, loss, train_op = build_graph()
 
     gen = torch.Generator().manual_seed(1234 + rank)
     n_host = 4
@@ -180,10 +184,41 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    verify = None
+    if world > 1 and os.environ.get("BENCH_VERIFY", "1") != "0":
+        # multi-GPU correctness, outside every timed region: a fresh copy of the model trained 3 steps on the fused
+        # (symmetric-memory / NVLS) path and another on the NCCL twin of the same graph, same weights (name-seeded
+        # initialisation) and data -- losses and parameters must agree
+        del g, model
+        torch.cuda.empty_cache()
+
+        def short_run(env):
+            old = {k: os.environ.get(k) for k in env}
+            os.environ.update(env)
+            try:
+                g2, m2, i2, p2, l2, ls2, tr2 = build_graph()
+                losses = [float(g2.run(ls2, [ls2, tr2], {i2: dev_ids[k % n_host], p2: dev_pos, l2: dev_lab[k % n_host]},
+                                       grad_scale=grad_scale)[0].float().cpu()) for k in range(3)]
+                named = dict(m2.named_parameters())
+                keep = {n: g2.get_param(named[n]).float().clone() for n in sorted(named)[:: max(len(named) // 12, 1)]}
+            finally:
+                for k, v in old.items():
+                    if v is None:
+                        os.environ.pop(k, None)
+                    else:
+                        os.environ[k] = v
+            return losses, keep
+        fused_l, fused_p = short_run({})
+        twin_l, twin_p = short_run({"HETU_ZERO_FUSED": "0", "HETU_TP_FUSED": "0", "HETU_TP_FUSED_AG": "0"})
+        pdiff = max(float((fused_p[n] - twin_p[n]).abs().max()) for n in fused_p)
+        pmax = max(float(twin_p[n].abs().max()) for n in twin_p)
+        verify = {"steps": 3, "loss_fused": fused_l, "loss_nccl_twin": twin_l,
+                  "max_loss_delta": max_over_ranks(max(abs(a - b) for a, b in zip(fused_l, twin_l))),
+                  "max_param_diff": max_over_ranks(pdiff), "param_abs_max": pmax, "params_compared": len(fused_p)}
     tokens_per_step = T * dp
     value = tokens_per_step * args.steps / (dev_ms / 1e3)
     e2e_value = tokens_per_step * args.steps / (e2e_ms / 1e3)
-    flops_per_token = 6 * cfg.num_parameters() + 12 * cfg.n_layer * cfg.n_embd * S  # dense + attention (causal, fwd+bwd)
+    flops_per_token = 6 * cfg.num_parameters() + 6 * cfg.n_layer * cfg.n_embd * S  # dense + causal attention (half of the 12*L*h*S of full attention), fwd+bwd
     if rank == 0:
         print(json.dumps({
             "metric": "tokens/sec (device-timed, max over ranks) GPT-2 1.3B DP+TP at 1/2/4/8 B200",
@@ -197,7 +232,7 @@ def main():
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "final_loss": float(last.float().cpu()), "e2e_final_loss": lv,
             "model_tflops_per_gpu": value / world * flops_per_token / 1e12,
-            "aten_fallbacks": int(ht._C.fallback_count()),
+            "aten_fallbacks": int(ht._C.fallback_count()), "verify": verify,
             "clocks": sampler.summary(),
         }))
     if world > 1:

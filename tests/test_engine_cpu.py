@@ -516,3 +516,32 @@ def test_data_loader_reports_global_consumed_samples_for_every_dp_rank():
     dl2 = DataLoader(ds, global_token_num=64, load_level="TOKEN", prefetch=0)
     dl2.restart(cut)
     assert [b for b in dl2] == full[3:]
+
+
+def test_hydraulis_ilp_dispatch_is_optimal_and_respects_limits():
+    """the MILP formulations of examples/hydraulis/strategy/dynamic_scip.py (solved with scipy/HiGHS): optimal on an instance
+    small enough to brute-force, never worse than the greedy heuristic, honours max_seq and the token bounds"""
+    import itertools
+    from hetu_b200.engine.hydraulis import StrategyCost, batching_strategy_ilp, dispatch_batch, dispatch_batch_ilp
+    long_s = StrategyCost("tp8", 1, a=1e-3, b=2e-8, max_seq=32768)
+    short_s = StrategyCost("tp2", 1, a=2e-3, b=8e-8, max_seq=8192)
+    mid_s = StrategyCost("tp4", 1, a=1.4e-3, b=4e-8, max_seq=16384)
+    sts, pps = [long_s, mid_s, short_s], [2, 1, 1]
+    seqs = [30000, 12000, 9000, 7000, 4000, 2500, 2000, 1000]
+    r = dispatch_batch_ilp(seqs, sts, pps)
+    assert all(seqs[i] <= sts[j].max_seq for i, j in enumerate(r["assignment"]))
+
+    def makespan(assign):
+        loads = [0.0] * 3
+        for i, j in enumerate(assign):
+            loads[j] += sts[j].seq_ms(seqs[i])
+        return max(loads[j] + (pps[j] - 1) * sts[j].seq_ms(min(max(seqs), sts[j].max_seq)) for j in range(3))
+    brute = min(makespan(a) for a in itertools.product(range(3), repeat=len(seqs))
+                if all(seqs[i] <= sts[j].max_seq for i, j in enumerate(a)))
+    assert abs(r["makespan_ms"] - brute) < 1e-6 * brute and abs(makespan(r["assignment"]) - brute) < 1e-6 * brute
+    h = dispatch_batch(seqs, [long_s, mid_s, short_s], sequential=False)
+    assert dispatch_batch_ilp(seqs, sts)["makespan_ms"] <= h["makespan_ms"] + 1e-9
+    b = batching_strategy_ilp([4000, 3000, 2500, 2000, 1500, 1000, 800, 600], short_s, pp=2, max_tokens=8192, min_tokens=2048)
+    toks = [sum([4000, 3000, 2500, 2000, 1500, 1000, 800, 600][i] for i in mb) for mb in b["micro_batches"]]
+    assert all(2048 <= t <= 8192 for t in toks) and sorted(i for mb in b["micro_batches"] for i in mb) == list(range(8))
+    assert b["e2e_ms"] == pytest.approx(b["max_micro_batch_ms"] * (2 - 1 + b["num_micro_batches"]))
