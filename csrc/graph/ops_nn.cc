@@ -1243,6 +1243,88 @@ static TensorList dropout_grad(OpDef& op, const TensorList& g) {
 }
 HB_REGISTER_OP(dropout, "dropout", 1, 0, dropout_compute, dropout_grad, nullptr, nullptr);
 
+// ------------------------------------------------------------------ fused dropout + residual add + norm
+// inputs: x, [residual], gamma, [beta]      attrs: rms, eps, p, has_residual
+// outputs: y = norm(z), z = residual + dropout(x) (the new residual stream), mean, rstd
+// One kernel in forward (csrc/kernels/norm.cu dropout_add_norm_fwd_kernel); the backward is composed of the norm
+// backward on z, the add of the residual-stream gradient and the dropout mask re-created from the same Philox counters.
+// (ref: hetu/impl/kernel/RMSNorm.cu:90 DropoutAddLnFwdCuda / :257 DropoutAddLnBwdCuda)
+static Ts dropout_add_norm_compute(const OpDef& op, const Ts& in, RunCtx* rc) {
+  const bool rms = op.attrs.b("rms"), has_res = op.attrs.b("has_residual");
+  const double eps = op.attrs.f("eps", 1e-5);
+  double p = op.attrs.f("p", 0.0);
+  if (rc && !rc->training) p = 0.0;
+  const at::Tensor& x = in[0];
+  const at::Tensor* res = has_res ? &in[1] : nullptr;
+  const at::Tensor& gamma = in[has_res ? 2 : 1];
+  const at::Tensor* beta = (!rms && in.size() > (size_t)(has_res ? 3 : 2)) ? &in[has_res ? 3 : 2] : nullptr;
+  const int64_t cols = x.size(-1);
+  std::vector<int64_t> sshape(x.sizes().begin(), x.sizes().end() - 1);
+  auto fopt = x.options().dtype(at::kFloat);
+  if (x.is_meta()) return {at::empty_like(x), at::empty_like(x), at::empty(sshape, fopt), at::empty(sshape, fopt)};
+  const int64_t rows = x.numel() / cols;
+  const uint64_t seed = (rc ? rc->seed : 0) + 0x9E3779B97F4A7C15ull * (uint64_t)(op.attrs.i("seed_op", op.id) + 1);
+  const uint64_t offset = rc ? (uint64_t)rc->micro_batch << 40 : 0;
+  if (is_native(x) && x.is_contiguous() && is_native(gamma) && cols % 8 == 0 && cols <= 8192 && (!res || (is_native(*res) && res->is_contiguous()))) {
+    at::Tensor y = at::empty_like(x), z = at::empty_like(x), mean = at::empty(sshape, fopt), rstd = at::empty(sshape, fopt);
+    if (rms)
+      cuda_ok(dropout_add_rmsnorm_fwd(x.data_ptr(), res ? res->data_ptr() : nullptr, gamma.data_ptr(), y.data_ptr(), z.data_ptr(),
+                                      rstd.data_ptr<float>(), rows, (int)cols, (float)eps, (float)p, seed, offset, cur_stream()),
+              "dropout_add_rmsnorm_fwd");
+    else
+      cuda_ok(dropout_add_layernorm_fwd(x.data_ptr(), res ? res->data_ptr() : nullptr, gamma.data_ptr(), beta ? beta->data_ptr() : nullptr,
+                                        y.data_ptr(), z.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(), rows, (int)cols,
+                                        (float)eps, (float)p, seed, offset, cur_stream()), "dropout_add_layernorm_fwd");
+    if (rms) mean.zero_();
+    return {y, z, mean, rstd};
+  }
+  if (is_native(x)) note_fallback("dropout_add_norm");
+  at::Tensor d = x;
+  if (p > 0.0) {
+    auto gen = at::detail::createCPUGenerator(seed ^ offset);
+    at::Tensor mask = at::empty(x.sizes(), at::TensorOptions().dtype(at::kFloat)).uniform_(0, 1, gen).to(x.device()) >= p;
+    d = (x * mask.to(x.scalar_type())) / (1.0 - p);
+  }
+  at::Tensor z = (res ? d + *res : d).to(x.scalar_type());
+  at::Tensor zf = z.to(at::kFloat), mean, rstd, y;
+  if (rms) {
+    mean = at::zeros(sshape, fopt);
+    rstd = at::rsqrt(zf.pow(2).mean(-1) + eps);
+    y = zf * rstd.unsqueeze(-1) * gamma.to(at::kFloat);
+  } else {
+    mean = zf.mean(-1);
+    rstd = at::rsqrt((zf - mean.unsqueeze(-1)).pow(2).mean(-1) + eps);
+    y = (zf - mean.unsqueeze(-1)) * rstd.unsqueeze(-1) * gamma.to(at::kFloat);
+    if (beta) y = y + beta->to(at::kFloat);
+  }
+  return {y.to(x.scalar_type()), z, mean, rstd};
+}
+static TensorList dropout_add_norm_grad(OpDef& op, const TensorList& g) {
+  const bool rms = op.attrs.b("rms"), has_res = op.attrs.b("has_residual");
+  const Tensor& gamma = op.inputs[has_res ? 2 : 1];
+  TensorList r(op.inputs.size());
+  Tensor dz = g.size() > 1 ? g[1] : Tensor();
+  if (g[0]) {
+    AttrMap a;
+    a.set("rms", rms);
+    TensorList nb = op.graph->make_op("norm_bwd", {g[0], op.outputs[1], gamma, op.outputs[2], op.outputs[3]}, a);
+    dz = dz ? op.graph->make_op1("add", {nb[0], dz}, AttrMap()) : nb[0];
+    r[has_res ? 2 : 1] = nb[1];
+    if (!rms && op.inputs.size() > (size_t)(has_res ? 3 : 2) && nb.size() > 2) r[has_res ? 3 : 2] = nb[2];
+  }
+  if (!dz) return r;
+  if (has_res) r[1] = dz;
+  if (op.attrs.f("p", 0.0) > 0.0) {
+    AttrMap a;
+    a.set("p", op.attrs.f("p", 0.0));
+    a.set("seed_op", op.attrs.i("seed_op", op.id));
+    r[0] = op.graph->make_op1("dropout", {dz}, a);
+  } else r[0] = dz;
+  return r;
+}
+static void dropout_add_norm_infer(OpDef& op) { infer_meta_by_meta_exec(op); }
+HB_REGISTER_OP(dropout_add_norm, "dropout_add_norm", 4, 0, dropout_add_norm_compute, dropout_add_norm_grad, nullptr, dropout_add_norm_infer);
+
 }  // namespace hb
 
 namespace hb {

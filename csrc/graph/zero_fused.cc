@@ -2,6 +2,7 @@
 
 #include <ATen/cuda/CUDAContext.h>
 
+#include "../runtime/runtime.h"
 #include "../runtime/symm_mem.h"
 #include "op_utils.h"
 
@@ -101,7 +102,11 @@ std::shared_ptr<ZeroFusedState> Executor::zero_fused_prepare(ExecPlan& plan) {
       e.ready_pos = pos;
       st->ready_at.emplace(pos, i);
     }
-    cuda_ok(cudaStreamCreateWithFlags(&st->side, cudaStreamNonBlocking), "side stream");
+    // the ZeRO bridge work (gradient reduce + optimizer + parameter broadcast) runs on the device's logical bridge stream
+    // (ref: hetu/core/stream.h kBridgeStream -- "ZeRO param-gather / grad-reduce")
+    int cur_dev = 0;
+    cuda_ok(cudaGetDevice(&cur_dev), "cudaGetDevice");
+    st->side = logical_stream(cur_dev, kBridgeStream);
     cuda_ok(cudaEventCreateWithFlags(&st->ev_ready, cudaEventDisableTiming), "event");
     cuda_ok(cudaEventCreateWithFlags(&st->ev_done, cudaEventDisableTiming), "event");
   }

@@ -89,4 +89,32 @@ inline int sm_count() {
   return n;
 }
 
+// counter-based RNG: 4 uniform floats per (seed, counter)
+__device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {
+  *hi = __umulhi(a, b);
+  return a * b;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, hi1;
+    const uint32_t lo0 = mulhilo32(M0, ctr.x, &hi0);
+    const uint32_t lo1 = mulhilo32(M1, ctr.z, &hi1);
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+// keep / drop decision of dropout for the 8 elements of vector `v` (16 bits of Philox output per element): shared by the
+// standalone dropout kernel and the fused dropout + residual + norm kernel so their masks agree
+__device__ __forceinline__ void dropout_keep8(uint64_t counter, uint64_t seed, uint32_t thresh, bool keep[8]) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)counter, (uint32_t)(counter >> 32), 0u, 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) keep[j] = ((rr[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu) >= thresh;
+}
+
 }  // namespace hb

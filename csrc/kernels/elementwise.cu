@@ -223,41 +223,18 @@ __global__ void cast_f2b_kernel(const float* __restrict__ src, void* __restrict_
     for (int64_t i = (nvec << 3) + threadIdx.x; i < n; i += blockDim.x) ((__nv_bfloat16*)dst)[i] = __float2bfloat16(src[i]);
 }
 
-// counter-based RNG: 4 uniform floats per (seed, counter)
-__device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {
-  *hi = __umulhi(a, b);
-  return a * b;
-}
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t hi0, hi1;
-    const uint32_t lo0 = mulhilo32(M0, ctr.x, &hi0);
-    const uint32_t lo1 = mulhilo32(M1, ctr.z, &hi1);
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
-}
 __global__ void dropout_kernel(const void* __restrict__ x, void* __restrict__ y, int64_t n, float p, uint64_t seed,
                                uint64_t offset) {
   const int64_t nvec = n >> 3;
   const float scale = 1.0f / (1.0f - p);
   const uint32_t thresh = (uint32_t)(p * 65536.0f);
   for (int64_t v = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; v < nvec; v += int64_t(gridDim.x) * blockDim.x) {
-    const uint64_t c = uint64_t(v) + offset;
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
-                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+    bool keep[8];
+    dropout_keep8(uint64_t(v) + offset, seed, thresh, keep);
     float f[8];
     unpack8(ld8_stream(x, v), f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t u16 = (rr[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
-      f[j] = (u16 >= thresh) ? f[j] * scale : 0.f;
-    }
+    for (int j = 0; j < 8; ++j) f[j] = keep[j] ? f[j] * scale : 0.f;
     st8(y, v, pack8(f));
   }
 }

@@ -42,6 +42,13 @@ cudaError_t add_bf16(const void* a, const void* b, void* out, int64_t n, cudaStr
 cudaError_t accum_bf16_into_fp32(const void* src, float* dst, int64_t n, bool accumulate, cudaStream_t s);
 cudaError_t cast_fp32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t s);
 cudaError_t cast_bf16_to_fp32(const void* src, float* dst, int64_t n, cudaStream_t s);
+// fused z = residual + dropout(x); y = norm(z): one pass (ref: hetu/impl/kernel/RMSNorm.cu:90,257 DropoutAddLn*);
+// residual may be null, p may be 0; cols % 8 == 0 and cols <= 8192
+cudaError_t dropout_add_layernorm_fwd(const void* x, const void* residual, const void* gamma, const void* beta, void* y, void* z,
+                                      float* mean, float* rstd, int64_t rows, int cols, float eps, float p, uint64_t seed,
+                                      uint64_t offset, cudaStream_t s);
+cudaError_t dropout_add_rmsnorm_fwd(const void* x, const void* residual, const void* gamma, void* y, void* z, float* rstd,
+                                    int64_t rows, int cols, float eps, float p, uint64_t seed, uint64_t offset, cudaStream_t s);
 // Philox dropout: y = x * mask / (1-p); the mask is recomputed in bwd from (seed, offset)
 cudaError_t dropout_fwd(const void* x, void* y, int64_t n, float p, uint64_t seed, uint64_t offset, cudaStream_t s);
 // out[c] (+)= sum_r x[r, c]   (bias gradient)  fp32 out

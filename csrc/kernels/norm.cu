@@ -432,6 +432,117 @@ static cudaError_t norm_bwd_impl(const void* dy, const void* x, const void* gamm
   return cudaGetLastError();
 }
 
+// Fused dropout + residual add + LayerNorm / RMSNorm forward (pre-norm transformer block glue):
+//     z = residual + dropout(x)          (written out: it is the next block's residual stream)
+//     y = norm(z) * gamma (+ beta)
+// one pass over x / residual instead of three kernels; warp per row, the row stays in registers.
+// The dropout mask uses the same Philox counters as the standalone dropout kernel (vector index of the flattened
+// tensor + offset), so the backward re-creates it with that kernel.
+// (ref: hetu/impl/kernel/RMSNorm.cu:90 DropoutAddLnFwdCuda, :257 DropoutAddLnBwd, FlashAttention's layer_norm library)
+template <bool kRMS, int kV>
+__global__ void __launch_bounds__(128) dropout_add_norm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ residual,
+                                                                   const void* __restrict__ gamma, const void* __restrict__ beta,
+                                                                   void* __restrict__ y, void* __restrict__ z,
+                                                                   float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                                   int64_t rows, int cols, float eps, float p, uint64_t seed,
+                                                                   uint64_t offset) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = int64_t(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = cols >> 3;
+  const int64_t rbytes = row * int64_t(cols) * 2;
+  const char* xr = reinterpret_cast<const char*>(x) + rbytes;
+  const char* rr = residual ? reinterpret_cast<const char*>(residual) + rbytes : nullptr;
+  char* yr = reinterpret_cast<char*>(y) + rbytes;
+  char* zr = reinterpret_cast<char*>(z) + rbytes;
+  const float scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  const uint32_t thresh = (uint32_t)(p * 65536.0f);
+  float zv[kV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      unpack8(ld8_stream(xr, v), zv[i]);
+      if (p > 0.f) {
+        bool keep[8];
+        dropout_keep8(uint64_t(row) * nvec + v + offset, seed, thresh, keep);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) zv[i][j] = keep[j] ? zv[i][j] * scale : 0.f;
+      }
+      if (rr) {
+        float r8[8];
+        unpack8(ld8_stream(rr, v), r8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) zv[i][j] += r8[j];
+      }
+      // the residual stream is stored in bf16: normalise exactly what the next block will read
+      const bf16x8 packed = pack8(zv[i]);
+      st8(zr, v, packed);
+      unpack8(packed, zv[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += kRMS ? zv[i][j] * zv[i][j] : zv[i][j];
+    }
+  }
+  float mean = 0.f, rstd;
+  const float inv = 1.0f / cols;
+  if constexpr (kRMS) {
+    rstd = rsqrtf(warp_sum(sum) * inv + eps);
+  } else {
+    mean = warp_sum(sum) * inv;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < kV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = zv[i][j] - mean; var += d * d; }
+      }
+    }
+    rstd = rsqrtf(warp_sum(var) * inv + eps);
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < kV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      float g[8], b[8], o[8];
+      unpack8(ld8(gamma, v), g);
+      if (!kRMS && beta != nullptr) unpack8(ld8(beta, v), b);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (zv[i][j] - mean) * rstd * g[j] + b[j];
+      st8(yr, v, pack8(o));
+    }
+  }
+}
+
+template <bool kRMS>
+cudaError_t dropout_add_norm_impl(const void* x, const void* residual, const void* gamma, const void* beta, void* y, void* z,
+                                  float* mean, float* rstd, int64_t rows, int cols, float eps, float p, uint64_t seed,
+                                  uint64_t offset, cudaStream_t s) {
+  if (rows == 0) return cudaSuccess;
+  if ((cols & 7) || cols > 8192) return cudaErrorInvalidValue;
+  const unsigned grid = (unsigned)((rows + 3) / 4);
+  const int nvec = cols >> 3;
+#define HB_DAN(V) dropout_add_norm_fwd_kernel<kRMS, V><<<grid, 128, 0, s>>>(x, residual, gamma, beta, y, z, mean, rstd, rows, cols, eps, p, seed, offset)
+  if (nvec <= 32) HB_DAN(1);
+  else if (nvec <= 64) HB_DAN(2);
+  else if (nvec <= 128) HB_DAN(4);
+  else if (nvec <= 256) HB_DAN(8);
+  else if (nvec <= 512) HB_DAN(16);
+  else HB_DAN(32);
+#undef HB_DAN
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
                           int64_t rows, int cols, float eps, cudaStream_t s) {
   return norm_fwd_impl<false>(x, gamma, beta, y, mean, rstd, rows, cols, eps, s);
@@ -448,6 +559,16 @@ cudaError_t rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, 
 cudaError_t rmsnorm_bwd(const void* dy, const void* x, const void* gamma, const float* rstd, void* dx, float* dgamma,
                         float* workspace, int64_t rows, int cols, bool accumulate, cudaStream_t s) {
   return norm_bwd_impl<true>(dy, x, gamma, nullptr, rstd, dx, dgamma, nullptr, workspace, rows, cols, accumulate, s);
+}
+
+cudaError_t dropout_add_layernorm_fwd(const void* x, const void* residual, const void* gamma, const void* beta, void* y, void* z,
+                                      float* mean, float* rstd, int64_t rows, int cols, float eps, float p, uint64_t seed,
+                                      uint64_t offset, cudaStream_t s) {
+  return dropout_add_norm_impl<false>(x, residual, gamma, beta, y, z, mean, rstd, rows, cols, eps, p, seed, offset, s);
+}
+cudaError_t dropout_add_rmsnorm_fwd(const void* x, const void* residual, const void* gamma, void* y, void* z, float* rstd,
+                                    int64_t rows, int cols, float eps, float p, uint64_t seed, uint64_t offset, cudaStream_t s) {
+  return dropout_add_norm_impl<true>(x, residual, gamma, nullptr, y, z, nullptr, rstd, rows, cols, eps, p, seed, offset, s);
 }
 
 }  // namespace hb

@@ -537,6 +537,23 @@ def reduce_scatter(x, ranks, dim=0, **kw):
     return _op1("reduce_scatter", [x], {"ranks": [int(r) for r in ranks], "dim": int(dim)}, **kw)
 
 
+def dropout_add_norm(x, gamma, beta=None, residual=None, p=0.0, eps=1e-5, rms=False, **kw):
+    """fused  z = residual + dropout(x);  y = norm(z)  ->  (y, z)   (z is the next block's residual stream)
+    (ref: hetu/impl/kernel/RMSNorm.cu:90,257 DropoutAddLn{Fwd,Bwd}Cuda; hetu.fused_layernorm / fused_rmsnorm with residual)"""
+    ins = [x] + ([residual] if residual is not None else []) + [gamma] + ([beta] if (beta is not None and not rms) else [])
+    outs = make_op("dropout_add_norm", ins, {"rms": bool(rms), "eps": float(eps), "p": float(p), "has_residual": residual is not None},
+                   **_meta(kw))
+    return outs[0], outs[1]
+
+
+def dropout_add_layer_norm(x, residual, gamma, beta, p=0.0, eps=1e-5, **kw):
+    return dropout_add_norm(x, gamma, beta, residual, p, eps, rms=False, **kw)
+
+
+def dropout_add_rms_norm(x, residual, gamma, p=0.0, eps=1e-5, **kw):
+    return dropout_add_norm(x, gamma, None, residual, p, eps, rms=True, **kw)
+
+
 def hall_to_all(x, ranks, gpus_per_node, **kw):
     """hierarchical (intra-node, then inter-node) all-to-all of the dim-0 chunks; same result as all_to_all
     (ref: hetu/v1 halltoall_op)"""

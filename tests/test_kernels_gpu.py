@@ -375,6 +375,43 @@ def test_moe_balanced_assignment_kernel_matches_host_algorithm():
         assert int(counts.max()) <= cap and int(counts.sum()) == T
 
 
+@pytest.mark.parametrize("rms", [False, True])
+@pytest.mark.parametrize("cols", [1024, 2048, 5120])
+def test_fused_dropout_add_norm(rms, cols):
+    """one-pass z = residual + dropout(x); y = norm(z) (csrc/kernels/norm.cu) against an fp32 reference; with p > 0 the mask
+    of the fused kernel must be the one the standalone dropout kernel produces for the same op seed (the backward relies on it)"""
+    rows = 777
+    x, r = bf(rows, cols, seed=1), bf(rows, cols, seed=2)
+    gamma, beta = (torch.rand(cols) + 0.5).to(torch.bfloat16).cuda(), bf(cols, seed=3)
+    before = launches()
+    X, R = leaf(x), leaf(r)
+    y, z = ht.dropout_add_norm(X, leaf(gamma), None if rms else leaf(beta), residual=R, p=0.0, eps=1e-5, rms=rms)
+    assert launches() > before
+    zt = (x.float() + r.float()).to(torch.bfloat16).float()
+    if rms:
+        yt = zt * torch.rsqrt(zt.pow(2).mean(-1, keepdim=True) + 1e-5) * gamma.float()
+    else:
+        yt = torch.nn.functional.layer_norm(zt, (cols,), gamma.float(), beta.float(), 1e-5)
+    close(torch.as_tensor(z.numpy()), zt, 1e-6, 1e-6)
+    close(torch.as_tensor(y.numpy()), yt, 0.03, 0.02)
+    w = bf(rows, cols, seed=4)
+    ht.sum(y * leaf(w, False) + z * leaf(w, False)).backward()
+    xr = x.float().clone().requires_grad_(True)
+    zz = (xr + r.float())
+    yy = zz * torch.rsqrt(zz.pow(2).mean(-1, keepdim=True) + 1e-5) * gamma.float() if rms else \
+        torch.nn.functional.layer_norm(zz, (cols,), gamma.float(), beta.float(), 1e-5)
+    ((yy + zz) * w.float()).sum().backward()
+    close(torch.as_tensor(X.grad.numpy()), xr.grad, 0.06, 0.04)
+    close(torch.as_tensor(R.grad.numpy()), xr.grad, 0.06, 0.04)
+    # dropout: ones in, z = mask / (1 - p); the gradient through z must carry exactly the same mask
+    X1 = leaf(torch.ones(rows, cols, dtype=torch.bfloat16).cuda())
+    _, z1 = ht.dropout_add_norm(X1, leaf(gamma), None if rms else leaf(beta), residual=None, p=0.25, rms=rms)
+    ht.sum(z1).backward()
+    zn, gn = torch.as_tensor(z1.numpy()).float(), torch.as_tensor(X1.grad.numpy()).float()
+    keep = (zn > 0).float().mean().item()
+    assert abs(keep - 0.75) < 0.01 and torch.equal(zn > 0, gn > 0)
+
+
 def test_gpt_block_training_matches_fp32_reference():
     """tiny GPT: native bf16 training vs the same graph on CPU fp32 -- loss curves must agree to bf16 accuracy"""
     from hetu_b200.models import GPTConfig, GPTLMHeadModel, generate_ds_parallel_config

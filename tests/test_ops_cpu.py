@@ -368,3 +368,37 @@ def test_attn_varlen_ops_and_tensor_method_surface():
     assert torch.allclose(torch.as_tensor(x.matmul(x).numpy()), torch.tensor([[-5.0, -10.0], [15.0, 10.0]]))
     assert torch.allclose(torch.as_tensor(x.add(x).softplus().numpy()), torch.nn.functional.softplus(torch.tensor([[2.0, -4.0], [6.0, 8.0]])))
     assert hasattr(ht, "Dataloader")
+
+
+@pytest.mark.parametrize("rms", [False, True])
+def test_dropout_add_norm_forward_and_gradients(rms):
+    """fused z = residual + dropout(x); y = norm(z) (ref: RMSNorm.cu DropoutAddLn*): p = 0 must equal the unfused ops in value
+    and in every gradient (x, residual, gamma, beta), including the gradient that arrives through the residual stream z"""
+    rng = np.random.RandomState(1)
+    x, r = rng.randn(6, 16).astype(np.float32), rng.randn(6, 16).astype(np.float32)
+    g, b = rng.rand(16).astype(np.float32) + 0.5, rng.randn(16).astype(np.float32)
+    X, R, G, B = (ht.from_numpy(a, requires_grad=True) for a in (x, r, g, b))
+    y, z = ht.dropout_add_norm(X, G, None if rms else B, residual=R, p=0.0, eps=1e-5, rms=rms)
+    wy, wz = rng.randn(6, 16).astype(np.float32), rng.randn(6, 16).astype(np.float32)
+    ht.sum(y * ht.from_numpy(wy) + z * ht.from_numpy(wz)).backward()
+    xt, rt, gt, bt = (torch.tensor(a, requires_grad=True) for a in (x, r, g, b))
+    zt = xt + rt
+    if rms:
+        yt = zt * torch.rsqrt(zt.pow(2).mean(-1, keepdim=True) + 1e-5) * gt
+    else:
+        yt = torch.nn.functional.layer_norm(zt, (16,), gt, bt, 1e-5)
+    (yt * torch.tensor(wy) + zt * torch.tensor(wz)).sum().backward()
+    np.testing.assert_allclose(y.numpy(), yt.detach().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(z.numpy(), zt.detach().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(X.grad.numpy(), xt.grad.numpy(), rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(R.grad.numpy(), rt.grad.numpy(), rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(G.grad.numpy(), gt.grad.numpy(), rtol=1e-3, atol=1e-5)
+    if not rms:
+        np.testing.assert_allclose(B.grad.numpy(), bt.grad.numpy(), rtol=1e-3, atol=1e-5)
+    # with dropout: the gradient w.r.t. x is masked exactly like the forward (zero where the activation was dropped)
+    X2 = ht.from_numpy(np.ones((6, 16), np.float32), requires_grad=True)
+    y2, z2 = ht.dropout_add_norm(X2, G, None if rms else B, residual=None, p=0.5, rms=rms)
+    ht.sum(z2).backward()
+    zn, gn = z2.numpy(), X2.grad.numpy()
+    assert set(np.unique(zn).round(4).tolist()) <= {0.0, 2.0} and 0.2 < (zn == 0).mean() < 0.8
+    np.testing.assert_allclose(gn, zn, rtol=1e-6)               # d sum(z) / dx = mask / (1 - p) = z for x = 1
