@@ -23,6 +23,7 @@ CUDA_SOURCES = [
     "csrc/kernels/optim.cu",
     "csrc/kernels/moe.cu",
     "csrc/kernels/quant_fp8.cu",
+    "csrc/kernels/quant_block.cu",
     "csrc/kernels/softmax.cu",
     "csrc/kernels/symm_comm.cu",
 ]

@@ -525,7 +525,21 @@ at::Tensor code_table(const std::string& kind, const at::TensorOptions& o) {
   const float* t = kind == "fp4" ? fp4 : nf4;
   return at::from_blob(const_cast<float*>(t), {16}, at::TensorOptions().dtype(at::kFloat)).clone().to(o.device());
 }
+int kind_code(const std::string& kind) { return kind == "int8" ? 0 : (kind == "fp4" ? 2 : 1); }
+bool quant_native(const at::Tensor& t) {
+  return t.is_cuda() && env_int("HETU_B200_FORCE_CPU", 0) == 0 && (t.scalar_type() == at::kBFloat16 || t.scalar_type() == at::kFloat);
+}
 std::vector<at::Tensor> quantize_blockwise(const at::Tensor& x, const std::string& kind, int64_t bs) {
+  if (quant_native(x) && bs % 2 == 0) {
+    // native sm_100a kernel: one warp per block, absmax + encode in a single pass (csrc/kernels/quant_block.cu)
+    at::Tensor xc = x.contiguous();
+    const int64_t n = xc.numel(), nb = (n + bs - 1) / bs;
+    at::Tensor absmax = at::empty({nb}, xc.options().dtype(at::kFloat));
+    at::Tensor q = kind == "int8" ? at::empty(xc.sizes(), xc.options().dtype(at::kChar)) : at::empty({nb * bs / 2}, xc.options().dtype(at::kByte));
+    cuda_ok(hb::quantize_blockwise(xc.data_ptr(), xc.scalar_type() == at::kBFloat16, q.data_ptr(), absmax.data_ptr<float>(), n, (int)bs,
+                                   kind_code(kind), cur_stream()), "quantize_blockwise");
+    return {q, absmax};
+  }
   at::Tensor flat = x.to(at::kFloat).reshape({-1});
   const int64_t n = flat.numel(), nb = (n + bs - 1) / bs;
   at::Tensor padded = at::zeros({nb * bs}, flat.options());
@@ -546,6 +560,13 @@ at::Tensor dequantize_blockwise(const at::Tensor& q, const at::Tensor& absmax, c
                                 const std::vector<int64_t>& shape, at::ScalarType dt) {
   int64_t n = 1;
   for (auto s : shape) n *= s;
+  if (q.is_cuda() && env_int("HETU_B200_FORCE_CPU", 0) == 0 && absmax.scalar_type() == at::kFloat && q.is_contiguous() &&
+      (dt == at::kBFloat16 || dt == at::kFloat)) {
+    at::Tensor out = at::empty(shape, q.options().dtype(dt));
+    cuda_ok(hb::dequantize_blockwise(q.data_ptr(), absmax.contiguous().data_ptr<float>(), out.data_ptr(), dt == at::kBFloat16, n, (int)bs,
+                                     kind_code(kind), cur_stream()), "dequantize_blockwise");
+    return out;
+  }
   at::Tensor vals;
   if (kind == "int8") vals = q.to(at::kFloat).reshape({-1}) / 127.0;
   else {
@@ -586,6 +607,19 @@ static Ts matmul4bit_compute(const OpDef& op, const Ts& in, RunCtx*) {
     return {at::empty(o, in[0].options())};
   }
   at::Tensor w = dequantize_blockwise(in[1], in[2], op.attrs.s("kind", "nf4"), op.attrs.i("blocksize", 64), wshape, in[0].scalar_type());
+  // bf16 on the GPU: 4-bit weights are expanded once into a bf16 tile stream and multiplied on the tcgen05 GEMM
+  at::Tensor x2 = in[0].reshape({-1, in[0].size(-1)}).contiguous();
+  if (is_native(x2) && is_native(w) && x2.size(1) % 8 == 0 && (reinterpret_cast<uintptr_t>(x2.data_ptr()) % 16) == 0) {
+    std::vector<int64_t> o = in[0].sizes().vec();
+    o.back() = wshape[0];
+    at::Tensor y = at::empty({x2.size(0), wshape[0]}, x2.options());
+    GemmCall g;
+    g.A = x2.data_ptr(); g.B = w.data_ptr(); g.C = y.data_ptr();
+    g.M = (int)x2.size(0); g.N = (int)wshape[0]; g.K = (int)x2.size(1);
+    g.lda = x2.stride(0); g.ldb = w.stride(0); g.ldc = wshape[0];
+    g.out = GemmOut::BF16;
+    if (gemm_bf16(g, cur_stream()) == cudaSuccess) return {y.reshape(o)};
+  }
   return {at::matmul(in[0], w.t())};
 }
 static TensorList matmul4bit_grad(OpDef& op, const TensorList& g) {

@@ -49,6 +49,12 @@ cudaError_t dropout_add_layernorm_fwd(const void* x, const void* residual, const
                                       uint64_t offset, cudaStream_t s);
 cudaError_t dropout_add_rmsnorm_fwd(const void* x, const void* residual, const void* gamma, void* y, void* z, float* rstd,
                                     int64_t rows, int cols, float eps, float p, uint64_t seed, uint64_t offset, cudaStream_t s);
+// blockwise absmax quantisation (quant_block.cu); kind: 0 int8, 1 nf4, 2 fp4; 4-bit codes packed two per byte
+// q: int8 [n] (kind 0) or uint8 [ceil(n / blocksize) * blocksize / 2]; absmax: fp32 [ceil(n / blocksize)]
+cudaError_t quantize_blockwise(const void* x, bool x_is_bf16, void* q, float* absmax, int64_t n, int blocksize, int kind,
+                               cudaStream_t s);
+cudaError_t dequantize_blockwise(const void* q, const float* absmax, void* y, bool y_is_bf16, int64_t n, int blocksize, int kind,
+                                 cudaStream_t s);
 // Philox dropout: y = x * mask / (1-p); the mask is recomputed in bwd from (seed, offset)
 cudaError_t dropout_fwd(const void* x, void* y, int64_t n, float p, uint64_t seed, uint64_t offset, cudaStream_t s);
 // out[c] (+)= sum_r x[r, c]   (bias gradient)  fp32 out

@@ -412,6 +412,29 @@ def test_fused_dropout_add_norm(rms, cols):
     assert abs(keep - 0.75) < 0.01 and torch.equal(zn > 0, gn > 0)
 
 
+@pytest.mark.parametrize("kind", ["int8", "nf4", "fp4"])
+def test_blockwise_quantisation_kernels_match_host_reference(kind):
+    """native absmax quantise / dequantise (csrc/kernels/quant_block.cu) against the ATen formulation of the same scheme run on
+    the CPU, and the 4-bit matmul (dequantise + tcgen05 GEMM) against an fp32 product of the dequantised weight"""
+    g = torch.Generator().manual_seed(2)
+    w = (torch.randn(384, 512, generator=g) * 0.3)
+    before = launches()
+    q, a = ht.quantization(ht.from_numpy(w.to(torch.bfloat16).cuda()), kind, 64)
+    assert launches() > before
+    qr, ar = ht.quantization(ht.from_numpy(w.to(torch.bfloat16).float()), kind, 64)       # CPU tensors: host path
+    close(torch.as_tensor(a.numpy()), torch.as_tensor(ar.numpy()), 1e-6, 1e-6)
+    qa, qb = torch.as_tensor(q.numpy()).cpu(), torch.as_tensor(qr.numpy()).cpu()
+    assert (qa != qb).float().mean().item() < 1e-3           # identical codes up to exact .5 ties of the rounding mode
+    d = ht.dequantization(q, a, "bfloat16", 64, shape=[384, 512], quant_type=kind)
+    dr = ht.dequantization(qr, ar, "float32", 64, shape=[384, 512], quant_type=kind)
+    close(torch.as_tensor(d.numpy()), torch.as_tensor(dr.numpy()), 0.01, 0.01)
+    if kind != "int8":
+        x = bf(256, 512, seed=9)
+        y = ht.matmul4bit(leaf(x, False), q, a, 64, kind, weight_shape=[384, 512])
+        ref = x.float() @ torch.as_tensor(d.numpy()).float().cuda().t()
+        close(torch.as_tensor(y.numpy()), ref, 0.08, 0.02)
+
+
 def test_gpt_block_training_matches_fp32_reference():
     """tiny GPT: native bf16 training vs the same graph on CPU fp32 -- loss curves must agree to bf16 accuracy"""
     from hetu_b200.models import GPTConfig, GPTLMHeadModel, generate_ds_parallel_config
