@@ -367,6 +367,7 @@ PYBIND11_MODULE(_C, m) {
         if (!const_data.is_none()) cd = py::cast<at::Tensor>(const_data);
         AttrMap amap = attrs_from_dict(attrs);
         py::gil_scoped_release nogil;
+        if (ds.size() == 0 && sy_shape.empty() && !cd.defined()) return g.make_op(type, inputs, amap, meta);   // plain op (reusable)
         return g.make_op(type, inputs, amap, meta, [&](OpDef& op) {
           op.dst_ds = ds;
           op.sy_shape = sy_shape;
@@ -404,6 +405,10 @@ PYBIND11_MODULE(_C, m) {
       .def("has_param", [](Graph& g, const Tensor& t) { return g.has_param_data(t->id); })
       .def("switch_strategy", [](Graph& g, int from, int to) { g.executor()->switch_strategy(from, to); })
       .def("reinfer_shapes", &Graph::reinfer_shapes)
+      .def("materialize", [](Graph& g, const Tensor& t) { return g.materialize(t); }, py::call_guard<py::gil_scoped_release>())
+      .def("prune", &Graph::prune)
+      .def("num_live_ops", &Graph::num_live_ops)
+      .def("reuse_hits", &Graph::reuse_hits)
       .def("set_profile", [](Graph& g, bool on) { g.executor()->set_profile(on); })
       .def("set_loss_scaler", [](Graph& g, const Tensor& var, double init_scale, double growth, double backoff, int64_t interval) {
         g.executor()->set_loss_scaler(var, init_scale, growth, backoff, interval);

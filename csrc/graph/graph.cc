@@ -147,6 +147,12 @@ TensorList Graph::make_op(const std::string& type, const TensorList& inputs, Att
   op->id = (OpId)ops_.size();
   op->type = type;
   op->inputs = inputs;
+  if (kind_ == GraphKind::DEFINE_BY_RUN && !init && !ctx_.building_backward) {
+    if (Operator hit = find_reusable_op(k, type, inputs, attrs)) {
+      ++reuse_hits_;
+      return hit->outputs;
+    }
+  }
   op->attrs = std::move(attrs);
   op->meta = std::move(meta);
   op->kernel = k;
@@ -214,6 +220,89 @@ TensorList Graph::make_op(const std::string& type, const TensorList& inputs, Att
     }
   }
   return op->outputs;
+}
+
+// ---------------------------------------------------------------------------------------- define-by-run
+Operator Graph::find_reusable_op(const OpKernel* k, const std::string& type, const TensorList& inputs, const AttrMap& attrs) const {
+  // only pure ops: no variables / placeholders / constants (identity matters), nothing in place, nothing that draws random
+  // numbers or communicates
+  if (inputs.empty() || (k->flags & (kFlagVariable | kFlagPlaceholder | kFlagConst | kFlagInplace | kFlagOptimizerUpdate | kFlagComm)))
+    return nullptr;
+  if (type == "dropout" || type == "dropout_add_norm" || type.find("rand") != std::string::npos) return nullptr;
+  for (OpDef* c : inputs[0]->consumers) {
+    if (c->pruned || c->type != type || c->inputs.size() != inputs.size() || c->is_bwd) continue;
+    bool same = true;
+    for (size_t i = 0; i < inputs.size() && same; ++i) same = c->inputs[i] == inputs[i];
+    if (!same || !(c->attrs.raw() == attrs.raw())) continue;
+    return ops_.at(c->id);
+  }
+  return nullptr;
+}
+
+at::Tensor Graph::materialize(const Tensor& t) {
+  HB_CHECK(t != nullptr) << "materialize(null)";
+  if (t->eager_data.defined()) return t->eager_data;
+  if (has_param_data(t->id)) return param_data_[t->id];
+  HB_CHECK(t->producer != nullptr) << "tensor " << t->name << " has no producer and no data";
+  RunCtx rc;
+  rc.graph = this;
+  at::NoGradGuard ng;
+  for (OpDef* op : topo_sort({t})) {
+    bool done = !op->outputs.empty();
+    for (auto& o : op->outputs) done = done && (o->eager_data.defined() || has_param_data(o->id));
+    if (done) continue;
+    HB_CHECK(!op->pruned) << "op " << op->name() << " was pruned but is needed again";
+    std::vector<at::Tensor> ins;
+    for (auto& in : op->inputs) {
+      if (in->eager_data.defined()) ins.push_back(in->eager_data);
+      else if (has_param_data(in->id)) ins.push_back(param_data_[in->id]);
+      else HB_CHECK(false) << "input " << in->name << " of " << op->name() << " has no value (unfed placeholder in a define-by-run graph?)";
+    }
+    if (op->has_flag(kFlagVariable)) {
+      at::Tensor v = executor()->get_param(op->outputs[0]);
+      op->outputs[0]->eager_data = v;
+      continue;
+    }
+    auto outs = op->kernel->compute(*op, ins, &rc);
+    HB_CHECK(outs.size() == op->outputs.size()) << "op " << op->name() << " output count mismatch";
+    for (size_t i = 0; i < outs.size(); ++i) {
+      op->outputs[i]->eager_data = outs[i];
+      if (outs[i].defined()) op->outputs[i]->shape = outs[i].sizes().vec();
+    }
+  }
+  return t->eager_data;
+}
+
+size_t Graph::prune() {
+  // reverse creation order: consumers are visited before their producers, so whole dead chains disappear in one call
+  size_t removed = 0;
+  for (auto it = ops_.rbegin(); it != ops_.rend(); ++it) {
+    OpDef* op = it->get();
+    if (op->pruned || op->has_flag(kFlagVariable) || op->has_flag(kFlagPlaceholder)) continue;
+    bool dead = true;
+    for (auto& o : op->outputs) {
+      // referenced from outside (python handle, another container)?  the op itself holds exactly one reference
+      if (o.use_count() > 1) { dead = false; break; }
+      for (OpDef* c : o->consumers) if (!c->pruned) { dead = false; break; }
+      if (!dead) break;
+    }
+    if (!dead) continue;
+    for (auto& in : op->inputs) {
+      auto& cs = in->consumers;
+      cs.erase(std::remove(cs.begin(), cs.end(), op), cs.end());
+    }
+    for (auto& o : op->outputs) o->eager_data = at::Tensor();
+    op->inputs.clear();
+    op->pruned = true;
+    ++removed;
+  }
+  return removed;
+}
+
+size_t Graph::num_live_ops() const {
+  size_t n = 0;
+  for (auto& op : ops_) n += op->pruned ? 0 : 1;
+  return n;
 }
 
 void Graph::reinfer_shapes(int strategy) {

@@ -187,6 +187,7 @@ class OpDef {
   Graph* graph = nullptr;
   OpId fw_op_id = -1;       // forward op this gradient op belongs to (-1 for forward ops)
   bool is_bwd = false;
+  bool pruned = false;      // define-by-run: removed by Graph::prune()
   // side payloads that do not fit AttrMap
   DistributedStatesHierarchy dst_ds;      // comm / placeholder / variable target layouts
   SyShape sy_shape;                        // symbolic target shape (reshape / slice ...)
@@ -277,6 +278,18 @@ class Graph {
   // eager helpers
   void eager_backward(const Tensor& loss, const Tensor& grad = nullptr);
 
+  // ---- define-by-run graphs (ref: hetu/graph/define_by_run_graph.{h,cc}): ops are recorded, not executed;
+  // * an op identical to an existing one (same type, inputs, attributes; deterministic, not in place) is not created
+  //   again -- its outputs are reused (FindReusableOp);
+  // * a tensor's value is computed on demand by running exactly the not-yet-evaluated part of its ancestry, results
+  //   are cached on the tensors (materialise);
+  // * ops none of whose outputs is referenced any more (by user handles or by live consumers) are pruned: their cached
+  //   values are dropped and they leave the consumer lists (prune)
+  at::Tensor materialize(const Tensor& t);
+  size_t prune();
+  size_t num_live_ops() const;
+  int64_t reuse_hits() const { return reuse_hits_; }
+
   static std::shared_ptr<Graph> make(GraphKind kind, const std::string& name, int num_strategy = 1);
   static std::shared_ptr<Graph> default_eager();
 
@@ -295,6 +308,8 @@ class Graph {
   Ctx ctx_;
   std::vector<Ctx> ctx_stack_;
   std::unique_ptr<Executor> executor_;
+  Operator find_reusable_op(const OpKernel* k, const std::string& type, const TensorList& inputs, const AttrMap& attrs) const;
+  int64_t reuse_hits_ = 0;
 };
 
 // helpers used by op definitions -----------------------------------------------------------

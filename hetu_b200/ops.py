@@ -731,7 +731,8 @@ def _install_tensor_methods():
         d = self.eager_data()
         if d is None or not d.defined() if hasattr(d, "defined") else d is None:
             gr = _graphs_by_id.get(self.graph_id)
-            d = gr.get_param(self)
+            # define-by-run: evaluate (only) the part of the ancestry that has no cached value yet
+            d = gr.materialize(self) if gr.kind == _C.GraphKind.DEFINE_BY_RUN else gr.get_param(self)
         d = d.detach().cpu()
         if d.dtype == torch.bfloat16:
             d = d.float()
@@ -741,7 +742,8 @@ def _install_tensor_methods():
         from .core import NDArray, _graphs_by_id
         d = self.eager_data()
         if d is None:
-            d = _graphs_by_id[self.graph_id].get_param(self)
+            gr = _graphs_by_id[self.graph_id]
+            d = gr.materialize(self) if gr.kind == _C.GraphKind.DEFINE_BY_RUN else gr.get_param(self)
         return NDArray(d)
 
     def reset_data(self, value):

@@ -326,3 +326,31 @@ def test_grad_scaler_minimize_unscales_checks_and_skips():
     np.testing.assert_allclose(ws[1].numpy(), ws[0].numpy())
     assert sc2.found_inf() is False and sc2.skipped_steps() == 1 and sc2.get_scale() == 32.0
     np.testing.assert_allclose(ws[2].numpy(), plain[1].numpy(), rtol=1e-6)
+
+
+def test_define_by_run_graph_reuses_ops_evaluates_lazily_and_prunes():
+    """ref: hetu/graph/define_by_run_graph.{h,cc}: FindReusableOp (identical pure ops are not duplicated), lazy evaluation of
+    exactly the needed ancestry with cached results, pruning of ops nobody references any more"""
+    with ht.graph("define_by_run", create_new=True) as g:
+        a = ht.from_numpy(np.arange(6, dtype=np.float32).reshape(2, 3))
+        b = ht.from_numpy(np.ones((2, 3), np.float32))
+        n0 = g.num_ops
+        s1 = ht.exp(a + b)
+        s2 = ht.exp(a + b)                       # same expression: both ops are reused
+        assert g.num_ops == n0 + 2 and g.reuse_hits() == 2 and s1.id == s2.id
+        d1, d2 = ht.dropout(a, 0.5), ht.dropout(a, 0.5)
+        assert d1.id != d2.id                    # random ops are never merged
+        big = ht.matmul(s1, ht.from_numpy(np.ones((3, 4), np.float32)))
+        side = ht.sum(ht.relu(a - 3.0))          # an unrelated branch
+        assert s1.eager_data() is None           # nothing has run yet
+        np.testing.assert_allclose(big.numpy(), np.exp(np.arange(6).reshape(2, 3) + 1.0) @ np.ones((3, 4)), rtol=1e-5)
+        assert s1.eager_data() is not None and side.eager_data() is None      # only big's ancestry was evaluated
+        np.testing.assert_allclose(float(side.numpy()), 1.0 + 2.0)
+        live = g.num_live_ops()
+        del big, side, d1, d2, s2
+        removed = g.prune()
+        # matmul + its const, the relu/sub/sum chain and both dropouts go; exp(a + b) stays (s1 is still referenced)
+        assert removed >= 7 and g.num_live_ops() == live - removed
+        np.testing.assert_allclose(s1.numpy(), np.exp(np.arange(6).reshape(2, 3) + 1.0), rtol=1e-5)
+        again = ht.exp(a + b)
+        assert again.id == s1.id                 # still reusable after pruning its consumers
