@@ -11,10 +11,6 @@
 //
 // No atomics, no transposes through shared memory: the same 128B-swizzled TMA tile
 // is consumed K-major by the score GEMM and MN-major by the accumulate GEMM.
-// 384 threads per CTA: warps 0-2 TMA / MMA issue / TMEM allocation, warps 4-11 the
-// elementwise stage -- two warpgroups that split the 128 score columns of a tile
-// (64 exp2 + 64 dS per thread and tile), two warps per SM sub-partition so the MUFU
-// pipe and the TMEM load/store path stay busy while the partner warp waits.
 //
 // Capability parity: hetu/impl/kernel/FlashAttention.cu:592 (FlashAttnGradientCuda ->
 // run_mha_bwd_), causal, GQA.
@@ -76,7 +72,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
 // dQ kernel
 // ---------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(256, 1)
 attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                          const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                          const AttnBwdParams p) {
@@ -126,7 +122,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&k_full[i], 1); ptx::mbar_init(&k_empty[i], 1);
       ptx::mbar_init(&v_full[i], 1); ptx::mbar_init(&v_empty[i], 1);
-      ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&ds_ready[i], 8);
+      ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&ds_ready[i], 4);
     }
     ptx::mbar_init(dp_full, 1);
     ptx::mbar_init(dq_done, 1);
@@ -213,10 +209,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // two warpgroups split the 128 key columns of a tile (thread (half, row): columns [64*half, 64*half+64) of query row
-    // `row`); everything here is elementwise, so the halves never have to talk to each other
     const int qd = warp & 3;
-    const int half = (warp - 4) >> 2;
     const int row = qd * 32 + lane;
     const int grow = q0 + row;
     const bool row_ok = grow < p.Sq;
@@ -230,14 +223,16 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       ptx::mbar_wait(&s_full[st], (j >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + lane_base + st * 128;
-      uint32_t sr[64];
-      ptx::tmem_ld_32x32b_x32(taddr + half * 64, sr);
-      ptx::tmem_ld_32x32b_x32(taddr + half * 64 + 32, sr + 32);
+      uint32_t sr[128];
+      ptx::tmem_ld_32x32b_x32(taddr, sr);
+      ptx::tmem_ld_32x32b_x32(taddr + 32, sr + 32);
+      ptx::tmem_ld_32x32b_x32(taddr + 64, sr + 64);
+      ptx::tmem_ld_32x32b_x32(taddr + 96, sr + 96);
       ptx::tmem_ld_wait();
-      const int k0 = j * 128 + half * 64;
+      const int k0 = j * 128;
       const int lim = p.causal ? min(p.Sk - 1, grow + p.causal_off) : p.Sk - 1;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
+      for (int c = 0; c < 128; ++c) {
         float pv = ex2(fmaf(__uint_as_float(sr[c]), p.scale_log2, -lse2));
         if (k0 + c > lim) pv = 0.f;
         sr[c] = __float_as_uint(pv);
@@ -245,9 +240,9 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       ptx::mbar_wait(dp_full, j & 1);
       ptx::tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint32_t dpr[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + DP_COL + half * 64 + c * 32, dpr);
+        ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + DP_COL + c * 32, dpr);
         ptx::tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
@@ -257,7 +252,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           const __nv_bfloat162 v2 = __floats2bfloat162_rn(d0, d1);
           pk[t] = *reinterpret_cast<const uint32_t*>(&v2);
         }
-        ptx::tmem_st_32x32b_x16(taddr + half * 32 + c * 16, pk);
+        ptx::tmem_st_32x32b_x16(taddr + c * 16, pk);
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
@@ -265,13 +260,11 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       if (lane == 0) ptx::mbar_arrive(&ds_ready[st]);
     }
     __nv_bfloat16* orow = p.dQ + int64_t(b) * p.dq_sb + int64_t(grow) * p.dq_ss + int64_t(hslot) * p.dq_sh;
-    constexpr int OCH = D / 64;     // 32-column dQ chunks per half
     if (n_kv > 0) {
       ptx::mbar_wait(dq_done, 0);
       ptx::tc_fence_after();
 #pragma unroll
-      for (int cc = 0; cc < OCH; ++cc) {
-        const int c = half * OCH + cc;
+      for (int c = 0; c < D / 32; ++c) {
         uint32_t orr[32];
         ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + DQ_COL + c * 32, orr);
         ptx::tmem_ld_wait();
@@ -288,7 +281,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         }
       }
     } else if (row_ok) {
-      for (int c = half * (D / 16); c < (half + 1) * (D / 16); ++c) reinterpret_cast<uint4*>(orow)[c] = make_uint4(0u, 0u, 0u, 0u);
+      for (int c = 0; c < D / 8; ++c) reinterpret_cast<uint4*>(orow)[c] = make_uint4(0u, 0u, 0u, 0u);
     }
   }
   ptx::tc_fence_before();
@@ -303,7 +296,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 // dK/dV kernel
 // ---------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(256, 1)
 attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                           const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                           const AttnBwdParams p) {
@@ -359,7 +352,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       ptx::mbar_init(&do_full[i], 1); ptx::mbar_init(&do_empty[i], 1);
     }
     ptx::mbar_init(st_full, 1); ptx::mbar_init(dpt_full, 1);
-    ptx::mbar_init(pt_ready, 8); ptx::mbar_init(dst_ready, 8);
+    ptx::mbar_init(pt_ready, 4); ptx::mbar_init(dst_ready, 4);
     ptx::mbar_init(acc_done, 1);
     ptx::fence_barrier_init();
   }
@@ -449,63 +442,58 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // two warpgroups split the 128 query columns of S^T / dP^T (thread (half, row): queries [64*half, 64*half+64) of key
-    // row `row`); half 0 writes dV, half 1 writes dK at the end
     const int qd = warp & 3;
-    const int half = (warp - 4) >> 2;
     const int row = qd * 32 + lane;   // key row inside the tile
     const int gk = k0 + row;
-    const int tid = threadIdx.x - 128;  // 0..255
+    const int tid = threadIdx.x - 128;  // 0..127
     const uint32_t lane_base = uint32_t(qd * 32) << 16;
     for (int it = 0; it < n_it; ++it) {
       const int hq = hk * group + it / nq_iters;
       const int q0 = (i_start + it % nq_iters) * 128;
       float* stat = sStat + (it & 1) * 256;
       {
-        // threads 0..127 stage the log-sum-exp of the tile's query rows, threads 128..255 their delta
-        const int gq = q0 + (tid & 127);
+        const int gq = q0 + tid;
         const bool ok = gq < p.Sq;
         const int64_t si = (int64_t(b) * p.Hq + hq) * p.Sq + gq;
-        if (tid < 128) {
-          float l2 = ok ? p.LSE[si] * 1.4426950408889634f : INFINITY;
-          if (l2 == -INFINITY) l2 = INFINITY;  // fully masked row: P = 0
-          stat[tid] = l2;
-        } else {
-          stat[tid] = ok ? p.DELTA[si] : 0.f;
-        }
+        float l2 = ok ? p.LSE[si] * 1.4426950408889634f : INFINITY;
+        if (l2 == -INFINITY) l2 = INFINITY;  // fully masked row: P = 0
+        stat[tid] = l2;
+        stat[128 + tid] = ok ? p.DELTA[si] : 0.f;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       ptx::mbar_wait(st_full, it & 1);
       ptx::tc_fence_after();
-      uint32_t sr[64];
+      uint32_t sr[128];
       const uint32_t ta = tmem_base + lane_base + ST_COL;
-      ptx::tmem_ld_32x32b_x32(ta + half * 64, sr);
-      ptx::tmem_ld_32x32b_x32(ta + half * 64 + 32, sr + 32);
+      ptx::tmem_ld_32x32b_x32(ta, sr);
+      ptx::tmem_ld_32x32b_x32(ta + 32, sr + 32);
+      ptx::tmem_ld_32x32b_x32(ta + 64, sr + 64);
+      ptx::tmem_ld_32x32b_x32(ta + 96, sr + 96);
       ptx::tmem_ld_wait();
       // visible iff key gk <= min(Sk-1, qrow + off)  <=>  qrow >= gk - off (causal) and gk < Sk
       const int first_q = p.causal ? gk - p.causal_off : -0x3fffffff;
       const bool key_ok = gk < p.Sk;
-      const int qc0 = half * 64;
 #pragma unroll
-      for (int c4 = 0; c4 < 16; ++c4) {
-        const float4 l4 = *reinterpret_cast<const float4*>(stat + qc0 + c4 * 4);
+      for (int c4 = 0; c4 < 32; ++c4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(stat + c4 * 4);
         const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int c = c4 * 4 + t;
           float pv = ex2(fmaf(__uint_as_float(sr[c]), p.scale_log2, -ls[t]));
-          if (!key_ok || (q0 + qc0 + c) < first_q) pv = 0.f;
+          if (!key_ok || (q0 + c) < first_q) pv = 0.f;
           sr[c] = __float_as_uint(pv);
         }
       }
       {
-        uint32_t pk[32];
+        uint32_t pk[64];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
+        for (int c = 0; c < 64; ++c) {
           const __nv_bfloat162 v2 = __floats2bfloat162_rn(__uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1]));
           pk[c] = *reinterpret_cast<const uint32_t*>(&v2);
         }
-        ptx::tmem_st_32x32b_x32(ta + half * 32, pk);
+        ptx::tmem_st_32x32b_x32(ta, pk);
+        ptx::tmem_st_32x32b_x32(ta + 32, pk + 32);
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
@@ -515,14 +503,14 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       ptx::tc_fence_after();
       const uint32_t td = tmem_base + lane_base + DPT_COL;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint32_t dpr[32];
-        ptx::tmem_ld_32x32b_x32(td + half * 64 + c * 32, dpr);
+        ptx::tmem_ld_32x32b_x32(td + c * 32, dpr);
         ptx::tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int t4 = 0; t4 < 8; ++t4) {
-          const float4 d4 = *reinterpret_cast<const float4*>(stat + 128 + qc0 + c * 32 + t4 * 4);
+          const float4 d4 = *reinterpret_cast<const float4*>(stat + 128 + c * 32 + t4 * 4);
           const float d0 = __uint_as_float(sr[c * 32 + t4 * 4 + 0]) * (__uint_as_float(dpr[t4 * 4 + 0]) - d4.x) * p.scale;
           const float d1 = __uint_as_float(sr[c * 32 + t4 * 4 + 1]) * (__uint_as_float(dpr[t4 * 4 + 1]) - d4.y) * p.scale;
           const float d2 = __uint_as_float(sr[c * 32 + t4 * 4 + 2]) * (__uint_as_float(dpr[t4 * 4 + 2]) - d4.z) * p.scale;
@@ -532,7 +520,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
           pk[t4 * 2] = *reinterpret_cast<const uint32_t*>(&a2);
           pk[t4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&b2);
         }
-        ptx::tmem_st_32x32b_x16(td + half * 32 + c * 16, pk);
+        ptx::tmem_st_32x32b_x16(td + c * 16, pk);
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
@@ -542,30 +530,36 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
     const bool row_ok = gk < p.Sk;
     __nv_bfloat16* dvrow = p.dV + int64_t(b) * p.dv_sb + int64_t(gk) * p.dv_ss + int64_t(hk) * p.dv_sh;
     __nv_bfloat16* dkrow = p.dK + int64_t(b) * p.dk_sb + int64_t(gk) * p.dk_ss + int64_t(hk) * p.dk_sh;
-    __nv_bfloat16* orow = half == 0 ? dvrow : dkrow;
     if (n_it > 0) {
       ptx::mbar_wait(acc_done, 0);
       ptx::tc_fence_after();
-      const uint32_t col = half == 0 ? DV_COL : DK_COL;
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
-        uint32_t orr[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + col + c * 32, orr);
-        ptx::tmem_ld_wait();
-        if (row_ok) {
+      for (int which = 0; which < 2; ++which) {
+        __nv_bfloat16* orow = which == 0 ? dvrow : dkrow;
+        const uint32_t col = which == 0 ? DV_COL : DK_COL;
 #pragma unroll
-          for (int t4 = 0; t4 < 4; ++t4) {
-            uint4 o;
-            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t orr[32];
+          ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + col + c * 32, orr);
+          ptx::tmem_ld_wait();
+          if (row_ok) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-              o2[t] = __floats2bfloat162_rn(__uint_as_float(orr[t4 * 8 + t * 2]), __uint_as_float(orr[t4 * 8 + t * 2 + 1]));
-            reinterpret_cast<uint4*>(orow + c * 32)[t4] = o;
+            for (int t4 = 0; t4 < 4; ++t4) {
+              uint4 o;
+              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+                o2[t] = __floats2bfloat162_rn(__uint_as_float(orr[t4 * 8 + t * 2]), __uint_as_float(orr[t4 * 8 + t * 2 + 1]));
+              reinterpret_cast<uint4*>(orow + c * 32)[t4] = o;
+            }
           }
         }
       }
     } else if (row_ok) {
-      for (int c = 0; c < D / 8; ++c) reinterpret_cast<uint4*>(orow)[c] = make_uint4(0u, 0u, 0u, 0u);
+      for (int c = 0; c < D / 8; ++c) {
+        reinterpret_cast<uint4*>(dvrow)[c] = make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4*>(dkrow)[c] = make_uint4(0u, 0u, 0u, 0u);
+      }
     }
   }
   ptx::tc_fence_before();
@@ -623,8 +617,8 @@ cudaError_t attn_bwd_launch(const AttnBwdCall& c, cudaStream_t s, std::atomic<in
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kq<<<dim3((c.Sq + 127) / 128, c.Hq, c.B), 384, smem, s>>>(tq, tdo, tk, tv, p);
-  kkv<<<dim3((c.Sk + 127) / 128, c.Hkv, c.B), 384, smem, s>>>(tq, tdo, tk, tv, p);
+  kq<<<dim3((c.Sq + 127) / 128, c.Hq, c.B), 256, smem, s>>>(tq, tdo, tk, tv, p);
+  kkv<<<dim3((c.Sk + 127) / 128, c.Hkv, c.B), 256, smem, s>>>(tq, tdo, tk, tv, p);
   counter->fetch_add(3);
   return cudaGetLastError();
 }

@@ -4,15 +4,9 @@
 // A operand straight from TMEM).  Q/K/V tiles arrive by TMA into 128B-swizzled
 // shared memory; K and V are double buffered.
 //
-// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer (one thread),
-// warp 2 TMEM allocator, warps 4..11 softmax + lazy O rescale + epilogue.  The two
-// softmax warpgroups split the 128 score columns of a tile: thread (half, row) owns
-// columns [64*half, 64*half+64) of query row `row` (a warp can only touch the TMEM
-// lanes 32*(warp%4)..+31, so warps w and w+4 share their rows).  The halves exchange
-// their partial row maxima through shared memory (one 256-thread named barrier per
-// KV tile, double buffered), the row sums only at the end.  Two warps per SM
-// sub-partition keep the MUFU (ex2) pipe and the TMEM load/store path busy while
-// the partner waits -- the softmax warps, not the tensor pipe, bound this kernel.
+// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer (one thread),
+// warp 2 TMEM allocator, warps 4..7 softmax + lazy O rescale + epilogue (thread i
+// owns query row i, matching the 32x32b TMEM access pattern).
 //
 // Online softmax uses a *lazy* reference maximum: the running max is only
 // refreshed (and O rescaled in TMEM) when the new row max exceeds it by more
@@ -50,7 +44,7 @@ constexpr int kBoxBytes = 128 * 128;  // 128 rows x 64 bf16 (one 128B-swizzled T
 }  // namespace attn_detail
 
 template <int D>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(256, 1)
 attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                       const __grid_constant__ CUtensorMap tmap_v, const AttnFwdParams p) {
   using namespace attn_detail;
@@ -73,7 +67,6 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   uint64_t* p_ready = bars + 11;  // [2]
   uint64_t* o_done = bars + 13;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
-  float* s_xchg = reinterpret_cast<float*>(bars + 16);   // [2 buffers][2 halves][128 rows] partial row max / row sum
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -104,7 +97,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       ptx::mbar_init(&v_full[i], 1);
       ptx::mbar_init(&v_empty[i], 1);
       ptx::mbar_init(&s_full[i], 1);
-      ptx::mbar_init(&p_ready[i], 8);
+      ptx::mbar_init(&p_ready[i], 4);
     }
     ptx::mbar_init(o_done, 1);
     ptx::fence_barrier_init();
@@ -178,38 +171,33 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     __syncwarp();
   } else if (warp >= 4) {
     const int qd = warp & 3;
-    const int half = (warp - 4) >> 2;            // which 64 score columns of the tile
     const int row = qd * 32 + lane;
     const int grow = q0 + row;
     const uint32_t lane_base = uint32_t(qd * 32) << 16;
-    constexpr int OCH = D / 64;                  // 32-column O chunks per half (rescale / epilogue)
     float m_ref = -INFINITY;
-    float l = 0.f;                               // partial row sum over this half's columns
+    float l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       const int st = j & 1;
       ptx::mbar_wait(&s_full[st], (j >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + lane_base + st * 128;
-      uint32_t sr[64];
-      ptx::tmem_ld_32x32b_x32(taddr + half * 64, sr);
-      ptx::tmem_ld_32x32b_x32(taddr + half * 64 + 32, sr + 32);
+      uint32_t sr[128];
+      ptx::tmem_ld_32x32b_x32(taddr, sr);
+      ptx::tmem_ld_32x32b_x32(taddr + 32, sr + 32);
+      ptx::tmem_ld_32x32b_x32(taddr + 64, sr + 64);
+      ptx::tmem_ld_32x32b_x32(taddr + 96, sr + 96);
       ptx::tmem_ld_wait();
-      const int k0 = j * 128 + half * 64;
-      const bool need_mask = (k0 + 64 > p.Sk) || (p.causal && (k0 + 63 > q0 + p.causal_off));
+      const int k0 = j * 128;
+      const bool need_mask = (k0 + 128 > p.Sk) || (p.causal && (k0 + 127 > q0 + p.causal_off));
       if (need_mask) {
         const int lim = p.causal ? min(p.Sk - 1, grow + p.causal_off) : p.Sk - 1;  // last visible column
 #pragma unroll
-        for (int c = 0; c < 64; ++c)
+        for (int c = 0; c < 128; ++c)
           if (k0 + c > lim) sr[c] = 0xff800000u;  // -inf
       }
       float mx = __uint_as_float(sr[0]);
 #pragma unroll
-      for (int c = 1; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(sr[c]));
-      // row max over both halves
-      float* xb = s_xchg + (j & 1) * 256;
-      xb[half * 128 + row] = mx;
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
+      for (int c = 1; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(sr[c]));
       mx *= p.scale_log2;
       if (j == 0) {
         m_ref = mx;
@@ -223,23 +211,22 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           if (need) m_ref = mx;
           l *= alpha;
 #pragma unroll
-          for (int c = 0; c < OCH; ++c) {
+          for (int c = 0; c < D / 32; ++c) {
             uint32_t orr[32];
-            const uint32_t oa = tmem_base + lane_base + O_COL + (half * OCH + c) * 32;
-            ptx::tmem_ld_32x32b_x32(oa, orr);
+            ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + O_COL + c * 32, orr);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int t = 0; t < 32; ++t) orr[t] = __float_as_uint(__uint_as_float(orr[t]) * alpha);
-            ptx::tmem_st_32x32b_x32(oa, orr);
+            ptx::tmem_st_32x32b_x32(tmem_base + lane_base + O_COL + c * 32, orr);
           }
           ptx::tmem_st_wait();
         }
       }
       const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
-      uint32_t pk[32];
+      uint32_t pk[64];
       float lsum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
+      for (int c = 0; c < 64; ++c) {
         const float p0 = ex2(fmaf(__uint_as_float(sr[2 * c]), p.scale_log2, -m_use));
         const float p1 = ex2(fmaf(__uint_as_float(sr[2 * c + 1]), p.scale_log2, -m_use));
         lsum += p0 + p1;
@@ -247,20 +234,14 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         pk[c] = *reinterpret_cast<const uint32_t*>(&pb);
       }
       l += lsum;
-      ptx::tmem_st_32x32b_x32(taddr + half * 32, pk);
+      ptx::tmem_st_32x32b_x32(taddr, pk);
+      ptx::tmem_st_32x32b_x32(taddr + 32, pk + 32);
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&p_ready[st]);
     }
-    // total row sum = both halves' partial sums (same m_ref history on both sides)
-    {
-      float* xb = s_xchg + (n_kv & 1) * 256;
-      xb[half * 128 + row] = l;
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      l += xb[(half ^ 1) * 128 + row];
-    }
-    // epilogue: O / l -> bf16 -> global (each half writes its D/2 columns), LSE
+    // epilogue: O / l -> bf16 -> global, LSE
     const bool row_ok = grow < p.Sq;
     __nv_bfloat16* orow = p.O + int64_t(b) * p.o_sb + int64_t(grow) * p.o_ss + int64_t(h) * p.o_sh;
     if (n_kv > 0) {
@@ -268,8 +249,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       ptx::tc_fence_after();
       const float inv_l = l > 0.f ? 1.0f / l : 0.f;
 #pragma unroll
-      for (int cc = 0; cc < OCH; ++cc) {
-        const int c = half * OCH + cc;
+      for (int c = 0; c < D / 32; ++c) {
         uint32_t orr[32];
         ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + O_COL + c * 32, orr);
         ptx::tmem_ld_wait();
@@ -286,12 +266,12 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           }
         }
       }
-      if (row_ok && p.LSE && half == 0)
+      if (row_ok && p.LSE)
         p.LSE[(int64_t(b) * p.Hq + h) * p.Sq + grow] =
             (l > 0.f) ? (m_ref + log2f(l)) * 0.6931471805599453f : -INFINITY;
     } else if (row_ok) {
-      for (int c = half * (D / 16); c < (half + 1) * (D / 16); ++c) reinterpret_cast<uint4*>(orow)[c] = make_uint4(0u, 0u, 0u, 0u);
-      if (p.LSE && half == 0) p.LSE[(int64_t(b) * p.Hq + h) * p.Sq + grow] = -INFINITY;
+      for (int c = 0; c < D / 8; ++c) reinterpret_cast<uint4*>(orow)[c] = make_uint4(0u, 0u, 0u, 0u);
+      if (p.LSE) p.LSE[(int64_t(b) * p.Hq + h) * p.Sq + grow] = -INFINITY;
     }
   }
 

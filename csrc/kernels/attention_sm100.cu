@@ -42,7 +42,7 @@ cudaError_t launch_fwd(const AttnFwdCall& c, cudaStream_t s) {
   p.O = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(c.o.ptr));
   p.o_sb = c.o.stride_b; p.o_ss = c.o.stride_s; p.o_sh = c.o.stride_h;
   p.LSE = c.lse;
-  constexpr int smem = 5 * 128 * D * 2 + 1024 + 256 + 2048;   // tiles, alignment slack, barriers, row-stat exchange
+  constexpr int smem = 5 * 128 * D * 2 + 1024 + 256;
   auto kern = attn_fwd_sm100_kernel<D>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -51,7 +51,7 @@ cudaError_t launch_fwd(const AttnFwdCall& c, cudaStream_t s) {
     attr_set = true;
   }
   dim3 grid((c.Sq + 127) / 128, c.Hq, c.B);
-  kern<<<grid, 384, smem, s>>>(tq, tk, tv, p);
+  kern<<<grid, 256, smem, s>>>(tq, tk, tv, p);
   g_attn_launches.fetch_add(1);
   return cudaGetLastError();
 }
