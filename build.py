@@ -78,7 +78,7 @@ def main():
         "  description = NVCC $in", "",
         "rule cxx", "  command = g++ $cxxflags -MD -MF $out.d -c $in -o $out", "  depfile = $out.d", "  deps = gcc",
         "  description = CXX $in", "",
-        "rule link", "  command = g++ $in $ldflags -o $out", "  description = LINK $out", "",
+        "rule link", "  command = g++ $in $ldflags -o $out.tmp && mv -f $out.tmp $out", "  description = LINK $out", "",
         "rule cudaexe", "  command = $nvcc $nvflags $in -o $out $libs", "  description = NVCC-EXE $out", "",
     ]
     objs = []

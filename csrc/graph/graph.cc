@@ -409,6 +409,26 @@ TensorList Graph::gradients(const TensorList& ys, const TensorList& xs, const Te
           at.set("residual_add", true);
           return make_op1("linear_dgrad", {p->inputs[0], p->inputs[1], other}, at, p->meta);
         }
+        // the same for a norm: d(x) = norm_bwd(...).dx + d(skip) -- the skip gradient becomes the norm backward's `dx_add`
+        // operand.  The replaced op's dgamma / dbeta outputs are re-pointed in the pending lists; the old op is dead.
+        if (p != nullptr && p->type == "norm_bwd" && p->inputs.size() == 5 && a == p->outputs[0] && a->consumers.empty() &&
+            a->shape == other->shape && a->dtype == other->dtype && a->ds_hierarchy.size() == other->ds_hierarchy.size() &&
+            env_int("HETU_FUSE_NORM_BWD_ADD", 1) != 0) {
+          bool same = true;
+          for (size_t s = 0; s < a->ds_hierarchy.size() && same; ++s)
+            if (a->has_ds((int)s) != other->has_ds((int)s) || (a->has_ds((int)s) && !a->ds((int)s).check_equal(other->ds((int)s)))) same = false;
+          bool params_unused = true;
+          for (size_t o = 1; o < p->outputs.size(); ++o) params_unused = params_unused && p->outputs[o]->consumers.empty();
+          if (!same || !params_unused) continue;
+          TensorList ins = p->inputs;
+          ins.push_back(other);
+          TensorList outs = make_op("norm_bwd", ins, p->attrs, p->meta);
+          for (auto& kv : pending)
+            for (auto& t : kv.second)
+              for (size_t o = 1; o < p->outputs.size() && o < outs.size(); ++o)
+                if (t == p->outputs[o]) t = outs[o];
+          return outs[0];
+        }
       }
     }
     return make_op1("sum_n", gs, {}, m);

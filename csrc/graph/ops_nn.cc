@@ -724,9 +724,12 @@ static Ts norm_compute(const OpDef& op, const Ts& in, RunCtx*) {
   }
   return {y.to(x.scalar_type()), mean, rstd};
 }
-// inputs: dy, x, gamma, mean, rstd -> dx, dgamma, (dbeta)
+// inputs: dy, x, gamma, mean, rstd, [dx_add] -> dx (+ dx_add), dgamma, (dbeta)
+// dx_add is the gradient that reaches the norm's input through the residual stream; Graph::gradients folds that addition
+// in here (see sum_grads) so the backward pass has no separate elementwise add per norm
 static Ts norm_bwd_compute(const OpDef& op, const Ts& in, RunCtx* rc) {
   const bool rms = op.attrs.b("rms");
+  const at::Tensor* dx_add = in.size() > 5 ? &in[5] : nullptr;
   const at::Tensor& dy = in[0];
   const at::Tensor& x = in[1];
   const at::Tensor& gamma = in[2];
@@ -739,19 +742,21 @@ static Ts norm_bwd_compute(const OpDef& op, const Ts& in, RunCtx* rc) {
     return r;
   }
   const int64_t rows = x.numel() / cols;
-  if (is_native(x) && is_native(dy) && x.is_contiguous() && dy.is_contiguous()) {
+  if (is_native(x) && is_native(dy) && x.is_contiguous() && dy.is_contiguous() &&
+      (!dx_add || (is_native(*dx_add) && dx_add->is_contiguous() && dx_add->sizes() == x.sizes()))) {
     auto fopt = x.options().dtype(at::kFloat);
+    const void* addp = dx_add ? dx_add->data_ptr() : nullptr;
     at::Tensor dx = at::empty_like(x), dg = at::empty({cols}, fopt), db = at::empty({cols}, fopt);
     at::Tensor ws = rc && rc->workspace ? rc->scratch("norm_bwd_ws", {2 * (int64_t)ln_bwd_parts() * cols}, at::kFloat, x.device())
                                         : at::empty({2 * (int64_t)ln_bwd_parts() * cols}, fopt);
     if (rms) {
       cuda_ok(rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), rstd.data_ptr<float>(), dx.data_ptr(),
-                          dg.data_ptr<float>(), ws.data_ptr<float>(), rows, (int)cols, false, cur_stream()), "rmsnorm_bwd");
+                          dg.data_ptr<float>(), ws.data_ptr<float>(), rows, (int)cols, false, cur_stream(), addp), "rmsnorm_bwd");
       return {dx, dg.to(gamma.scalar_type())};
     }
     cuda_ok(layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
                           dx.data_ptr(), dg.data_ptr<float>(), db.data_ptr<float>(), ws.data_ptr<float>(), rows,
-                          (int)cols, false, cur_stream()), "layernorm_bwd");
+                          (int)cols, false, cur_stream(), addp), "layernorm_bwd");
     return {dx, dg.to(gamma.scalar_type()), db.to(gamma.scalar_type())};
   }
   at::Tensor xf = x.to(at::kFloat), g = dy.to(at::kFloat), gm = gamma.to(at::kFloat);
@@ -760,6 +765,7 @@ static Ts norm_bwd_compute(const OpDef& op, const Ts& in, RunCtx* rc) {
   at::Tensor m2 = (dyg * xhat).mean(-1, true);
   at::Tensor dx = rms ? rstd.unsqueeze(-1) * (dyg - xhat * m2) : rstd.unsqueeze(-1) * (dyg - dyg.mean(-1, true) - xhat * m2);
   at::Tensor dgm = (g * xhat).reshape({-1, cols}).sum(0);
+  if (dx_add) dx = dx + dx_add->to(at::kFloat);
   Ts r = {dx.to(x.scalar_type()), dgm.to(gamma.scalar_type())};
   if (!rms) r.push_back(g.reshape({-1, cols}).sum(0).to(gamma.scalar_type()));
   return r;
@@ -1227,9 +1233,12 @@ static Ts dropout_compute(const OpDef& op, const Ts& in, RunCtx* rc) {
   if (x.is_meta() || p <= 0.0 || (rc && !rc->training)) return {x.is_meta() ? at::empty_like(x) : x};
   const uint64_t seed = (rc ? rc->seed : 0) + 0x9E3779B97F4A7C15ull * (uint64_t)(op.attrs.i("seed_op", op.id) + 1);
   const uint64_t offset = rc ? (uint64_t)rc->micro_batch << 40 : 0;
-  if (is_native(x) && x.is_contiguous() && x.numel() % 8 == 0) {
-    at::Tensor y = at::empty_like(x);
-    cuda_ok(dropout_fwd(x.data_ptr(), y.data_ptr(), x.numel(), (float)p, seed, offset, cur_stream()), "dropout");
+  if (is_native(x) && x.numel() % 8 == 0) {
+    // (an expanded / strided gradient is materialised first: the mask is defined on the flattened element index and must
+    // be the one the forward -- possibly the fused dropout_add_norm kernel -- used)
+    at::Tensor xc = x.contiguous();
+    at::Tensor y = at::empty_like(xc);
+    cuda_ok(dropout_fwd(xc.data_ptr(), y.data_ptr(), xc.numel(), (float)p, seed, offset, cur_stream()), "dropout");
     return {y};
   }
   auto gen = at::detail::createCPUGenerator(seed ^ offset);

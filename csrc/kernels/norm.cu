@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kBwdThreads) norm_bwd_kernel(const void* __res
                                                                const void* __restrict__ gamma, const float* __restrict__ mean,
                                                                const float* __restrict__ rstd, void* __restrict__ dx,
                                                                float* __restrict__ part_dg, float* __restrict__ part_db,
-                                                               int64_t rows, int cols) {
+                                                               int64_t rows, int cols, const void* __restrict__ dx_add) {
   constexpr int kWarps = kBwdThreads / 32;
   __shared__ float red[2][kWarps][2 * kR];
   const int nvec = cols >> 3;
@@ -288,6 +288,14 @@ __global__ void __launch_bounds__(kBwdThreads) norm_bwd_kernel(const void* __res
             float o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = rs[r] * (dyv[r][i][j] * g[i][j] - m1 - xh[r][i][j] * m2);
+            if (dx_add != nullptr) {
+              // gradient arriving through the residual stream: d(input) = d(norm branch) + d(skip), added here instead of a
+              // separate elementwise pass over the activation
+              float e[8];
+              unpack8(ld8_stream(reinterpret_cast<const char*>(dx_add) + row * int64_t(cols) * 2, v), e);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] += e[j];
+            }
             st8(dxr, v, pack8(o));
           }
         }
@@ -315,7 +323,7 @@ template <bool kRMS>
 __global__ void norm_bwd_generic_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                         const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean,
                                         const float* __restrict__ rstd, __nv_bfloat16* __restrict__ dx,
-                                        float* part_dg, float* part_db, int64_t rows, int cols) {
+                                        float* part_dg, float* part_db, int64_t rows, int cols, const __nv_bfloat16* __restrict__ dx_add) {
   // one block per "part"; columns strided over threads; rows strided over blocks
   __shared__ float2 red[32];
   for (int c = threadIdx.x; c < cols; c += blockDim.x) {
@@ -341,7 +349,7 @@ __global__ void norm_bwd_generic_kernel(const __nv_bfloat16* __restrict__ dy, co
     for (int c = threadIdx.x; c < cols; c += blockDim.x) {
       const float xh = (__bfloat162float(x[row * cols + c]) - mu) * rs;
       const float dyg = __bfloat162float(dy[row * cols + c]) * __bfloat162float(gamma[c]);
-      dx[row * cols + c] = __float2bfloat16(rs * (dyg - m1 - xh * m2));
+      dx[row * cols + c] = __float2bfloat16(rs * (dyg - m1 - xh * m2) + (dx_add ? __bfloat162float(dx_add[row * cols + c]) : 0.f));
     }
   }
 }
@@ -408,22 +416,22 @@ static cudaError_t norm_fwd_impl(const void* x, const void* gamma, const void* b
 template <bool kRMS>
 static cudaError_t norm_bwd_impl(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
                                  void* dx, float* dgamma, float* dbeta, float* ws, int64_t rows, int cols,
-                                 bool accumulate, cudaStream_t s) {
+                                 bool accumulate, cudaStream_t s, const void* dx_add) {
   if (rows == 0) return cudaSuccess;
   int parts = ln_bwd_parts();
   if (parts > rows) parts = (int)rows;
   float* part_dg = ws;
   float* part_db = ws + int64_t(ln_bwd_parts()) * cols;
   if ((cols & 7) == 0 && cols <= 2048) {
-    norm_bwd_kernel<kRMS, 1, 4><<<parts, kBwdThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, part_dg, part_db, rows, cols);
+    norm_bwd_kernel<kRMS, 1, 4><<<parts, kBwdThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, part_dg, part_db, rows, cols, dx_add);
   } else if ((cols & 7) == 0 && cols <= 4096) {
-    norm_bwd_kernel<kRMS, 2, 2><<<parts, kBwdThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, part_dg, part_db, rows, cols);
+    norm_bwd_kernel<kRMS, 2, 2><<<parts, kBwdThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, part_dg, part_db, rows, cols, dx_add);
   } else if ((cols & 7) == 0 && cols <= 8192) {
-    norm_bwd_kernel<kRMS, 4, 1><<<parts, kBwdThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, part_dg, part_db, rows, cols);
+    norm_bwd_kernel<kRMS, 4, 1><<<parts, kBwdThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, part_dg, part_db, rows, cols, dx_add);
   } else {
     norm_bwd_generic_kernel<kRMS><<<parts, 256, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
                                                         (const __nv_bfloat16*)gamma, mean, rstd, (__nv_bfloat16*)dx,
-                                                        part_dg, part_db, rows, cols);
+                                                        part_dg, part_db, rows, cols, (const __nv_bfloat16*)dx_add);
   }
   const bool two = !kRMS && dbeta != nullptr;
   fold_parts_kernel<<<dim3((cols + 31) / 32, two ? 2 : 1), 256, 0, s>>>(part_dg, dgamma, part_db, dbeta, parts, cols,
@@ -549,16 +557,16 @@ cudaError_t layernorm_fwd(const void* x, const void* gamma, const void* beta, vo
 }
 cudaError_t layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
                           void* dx, float* dgamma, float* dbeta, float* workspace, int64_t rows, int cols,
-                          bool accumulate, cudaStream_t s) {
-  return norm_bwd_impl<false>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, workspace, rows, cols, accumulate, s);
+                          bool accumulate, cudaStream_t s, const void* dx_add) {
+  return norm_bwd_impl<false>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, workspace, rows, cols, accumulate, s, dx_add);
 }
 cudaError_t rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, int64_t rows, int cols, float eps,
                         cudaStream_t s) {
   return norm_fwd_impl<true>(x, gamma, nullptr, y, nullptr, rstd, rows, cols, eps, s);
 }
 cudaError_t rmsnorm_bwd(const void* dy, const void* x, const void* gamma, const float* rstd, void* dx, float* dgamma,
-                        float* workspace, int64_t rows, int cols, bool accumulate, cudaStream_t s) {
-  return norm_bwd_impl<true>(dy, x, gamma, nullptr, rstd, dx, dgamma, nullptr, workspace, rows, cols, accumulate, s);
+                        float* workspace, int64_t rows, int cols, bool accumulate, cudaStream_t s, const void* dx_add) {
+  return norm_bwd_impl<true>(dy, x, gamma, nullptr, rstd, dx, dgamma, nullptr, workspace, rows, cols, accumulate, s, dx_add);
 }
 
 cudaError_t dropout_add_layernorm_fwd(const void* x, const void* residual, const void* gamma, const void* beta, void* y, void* z,

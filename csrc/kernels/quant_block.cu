@@ -51,12 +51,11 @@ __global__ void quantize_blockwise_kernel(const T* __restrict__ x, void* __restr
   }
   m = fmaxf(warp_max(m), 1e-12f);
   if (lane == 0) absmax[blk] = m;
-  const float inv = 1.0f / m;
   if (kind == 0) {
     int8_t* out = reinterpret_cast<int8_t*>(q);
     for (int i = lane; i < bs; i += 32) {
       const int64_t k = base + i;
-      if (k < n) out[k] = (int8_t)fminf(fmaxf(rintf(load_as_float(x, k) * inv * 127.0f), -127.f), 127.f);
+      if (k < n) out[k] = (int8_t)fminf(fmaxf(rintf(load_as_float(x, k) / m * 127.0f), -127.f), 127.f);
     }
     return;
   }
@@ -64,8 +63,8 @@ __global__ void quantize_blockwise_kernel(const T* __restrict__ x, void* __restr
   uint8_t* out = reinterpret_cast<uint8_t*>(q);
   for (int i = lane; i < bs / 2; i += 32) {                 // one byte = elements (2i, 2i+1) of the block
     const int64_t k0 = base + 2 * i, k1 = k0 + 1;
-    const float v0 = k0 < n ? load_as_float(x, k0) * inv : 0.f;
-    const float v1 = k1 < n ? load_as_float(x, k1) * inv : 0.f;
+    const float v0 = k0 < n ? load_as_float(x, k0) / m : 0.f;     // true division: same normalised value as the host formulation
+    const float v1 = k1 < n ? load_as_float(x, k1) / m : 0.f;
     out[(base >> 1) + i] = (uint8_t)((nearest_code(v0, table) << 4) | nearest_code(v1, table));
   }
 }

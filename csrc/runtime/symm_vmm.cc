@@ -1,8 +1,9 @@
 // Symmetric memory on the CUDA virtual-memory-management API with an NVLink-SHARP (NVLS) multicast mapping.
 //
 // Every rank creates one physical allocation (cuMemCreate, exportable as a POSIX file descriptor), the ranks import each
-// other's allocations (the descriptor is duplicated out of the owning process with pidfd_getfd -- no unix-socket
-// side channel) and map them into their address space, exactly like the IPC path of symm_mem.cc.  In addition rank 0
+// other's allocations (the descriptor is duplicated out of the owning process with pidfd_getfd, or -- where the
+// container forbids that -- received as an SCM_RIGHTS message over an abstract unix socket) and map them into their
+// address space, exactly like the IPC path of symm_mem.cc.  In addition rank 0
 // creates a *multicast object* spanning all GPUs of the group; every rank adds its device, binds its physical
 // allocation and maps the object: a store to the multicast address is replicated by the NVSwitch into every rank's
 // buffer (multimem.st), a load-reduce returns the sum over all ranks' buffers computed inside the switch
@@ -17,11 +18,19 @@
 // module still imports on a machine without a driver.
 // (the reference has no equivalent: all GPU traffic goes through NCCL -- hetu/impl/communication/nccl_comm_group.cu)
 #include <cuda.h>
+#include <sys/prctl.h>
+#include <sys/socket.h>
 #include <sys/syscall.h>
+#include <sys/un.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <cerrno>
 #include <cstring>
+#include <thread>
+
+#include <map>
+#include <memory>
 
 #include "symm_mem.h"
 
@@ -91,19 +100,108 @@ struct VmmDesc {          // what a rank publishes (plain bytes, exchanged by th
   int32_t mc_fd;          // rank 0 only, -1 elsewhere (or when multicast is unsupported)
   int32_t mc_ok;          // this rank's device supports multicast
   uint64_t size;          // physical size (rounded to the granularity)
+  int32_t sock_seq;       // this rank serves its descriptors on the abstract unix socket "hetu_symm_<pid>_<sock_seq>"
+  int32_t pad;
 };
 
-// duplicate file descriptor `fd` of process `pid` into this process (Linux >= 5.6)
-int dup_from_process(int pid, int fd) {
+// ---- handing a file descriptor to a peer process.  Fast path: pidfd_getfd (needs ptrace permission over the owner --
+// granted to everybody by the owner through PR_SET_PTRACER_ANY when Yama's ptrace_scope is 1).  Containers that forbid it
+// fall back to the classic SCM_RIGHTS message over an abstract unix socket served by a thread of the owner.
+void fill_addr(sockaddr_un* a, socklen_t* len, int pid, int seq) {
+  std::memset(a, 0, sizeof(*a));
+  a->sun_family = AF_UNIX;
+  const std::string name = "hetu_symm_" + std::to_string(pid) + "_" + std::to_string(seq);
+  std::memcpy(a->sun_path + 1, name.data(), name.size());          // leading NUL: abstract namespace, nothing on disk
+  *len = (socklen_t)(offsetof(sockaddr_un, sun_path) + 1 + name.size());
+}
+
+struct FdServer {
+  int listen_fd = -1;
+  int fds[2] = {-1, -1};            // [0] memory handle, [1] multicast handle
+  std::thread th;
+  std::atomic<bool> stop{false};
+  void start(int seq) {
+    listen_fd = socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
+    HB_CHECK(listen_fd >= 0) << "socket(AF_UNIX) failed: " << std::strerror(errno);
+    sockaddr_un a;
+    socklen_t len;
+    fill_addr(&a, &len, (int)getpid(), seq);
+    HB_CHECK(bind(listen_fd, (sockaddr*)&a, len) == 0) << "bind of the descriptor socket failed: " << std::strerror(errno);
+    HB_CHECK(listen(listen_fd, 32) == 0) << "listen failed: " << std::strerror(errno);
+    th = std::thread([this] {
+      while (!stop.load()) {
+        const int c = accept(listen_fd, nullptr, nullptr);
+        if (c < 0) break;
+        int32_t which = 0;
+        if (recv(c, &which, sizeof(which), MSG_WAITALL) == (ssize_t)sizeof(which) && which >= 0 && which < 2 && fds[which] >= 0) {
+          char payload = 'f';
+          iovec io{&payload, 1};
+          alignas(cmsghdr) char ctrl[CMSG_SPACE(sizeof(int))];
+          std::memset(ctrl, 0, sizeof(ctrl));
+          msghdr msg{};
+          msg.msg_iov = &io; msg.msg_iovlen = 1;
+          msg.msg_control = ctrl; msg.msg_controllen = sizeof(ctrl);
+          cmsghdr* cm = CMSG_FIRSTHDR(&msg);
+          cm->cmsg_level = SOL_SOCKET; cm->cmsg_type = SCM_RIGHTS; cm->cmsg_len = CMSG_LEN(sizeof(int));
+          std::memcpy(CMSG_DATA(cm), &fds[which], sizeof(int));
+          sendmsg(c, &msg, 0);
+        }
+        close(c);
+      }
+    });
+  }
+  ~FdServer() { shutdown_server(); }
+  void shutdown_server() {
+    stop.store(true);
+    if (listen_fd >= 0) { ::shutdown(listen_fd, SHUT_RDWR); close(listen_fd); listen_fd = -1; }
+    if (th.joinable()) th.join();
+  }
+};
+std::map<std::string, std::unique_ptr<FdServer>>& servers() {
+  static std::map<std::string, std::unique_ptr<FdServer>> m;
+  return m;
+}
+
+int recv_fd_over_socket(int pid, int seq, int which) {
+  const int c = socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
+  HB_CHECK(c >= 0) << "socket(AF_UNIX) failed: " << std::strerror(errno);
+  sockaddr_un a;
+  socklen_t len;
+  fill_addr(&a, &len, pid, seq);
+  int rc = -1;
+  for (int attempt = 0; attempt < 200 && rc != 0; ++attempt) {        // the peer's server thread may not be listening yet
+    rc = connect(c, (sockaddr*)&a, len);
+    if (rc != 0) usleep(10000);
+  }
+  HB_CHECK(rc == 0) << "cannot reach the descriptor socket of process " << pid << ": " << std::strerror(errno);
+  const int32_t w = which;
+  HB_CHECK(send(c, &w, sizeof(w), 0) == (ssize_t)sizeof(w)) << "descriptor request failed";
+  char payload = 0;
+  iovec io{&payload, 1};
+  alignas(cmsghdr) char ctrl[CMSG_SPACE(sizeof(int))];
+  msghdr msg{};
+  msg.msg_iov = &io; msg.msg_iovlen = 1;
+  msg.msg_control = ctrl; msg.msg_controllen = sizeof(ctrl);
+  const ssize_t n = recvmsg(c, &msg, 0);
+  close(c);
+  HB_CHECK(n == 1) << "no descriptor received from process " << pid;
+  cmsghdr* cm = CMSG_FIRSTHDR(&msg);
+  HB_CHECK(cm != nullptr && cm->cmsg_level == SOL_SOCKET && cm->cmsg_type == SCM_RIGHTS) << "malformed descriptor message";
+  int fd = -1;
+  std::memcpy(&fd, CMSG_DATA(cm), sizeof(int));
+  return fd;
+}
+
+// a duplicate of descriptor `fd` (which: 0 memory handle, 1 multicast handle) of the peer described by (pid, seq)
+int dup_from_process(int pid, int fd, int seq, int which) {
   if (pid == (int)getpid()) return dup(fd);
   const int pidfd = (int)syscall(SYS_pidfd_open, pid, 0);
-  HB_CHECK(pidfd >= 0) << "pidfd_open(" << pid << ") failed: " << std::strerror(errno);
-  const int got = (int)syscall(SYS_pidfd_getfd, pidfd, fd, 0);
-  const int err = errno;
-  close(pidfd);
-  HB_CHECK(got >= 0) << "pidfd_getfd(pid " << pid << ", fd " << fd << ") failed: " << std::strerror(err)
-                     << " (needs ptrace permission over the peer process: same user and kernel.yama.ptrace_scope <= 1, or CAP_SYS_PTRACE)";
-  return got;
+  if (pidfd >= 0) {
+    const int got = (int)syscall(SYS_pidfd_getfd, pidfd, fd, 0);
+    close(pidfd);
+    if (got >= 0) return got;
+  }
+  return recv_fd_over_socket(pid, seq, which);
 }
 
 CUmemAccessDesc rw_access(int device) {
@@ -188,12 +286,16 @@ std::string SymmMem::alloc_vmm(const std::string& name, size_t bytes, int rank, 
   HB_CHECK(cudaDeviceSynchronize() == cudaSuccess) << "sync";
   b.flags_local = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(b.local) + b.bytes);
 
+  static std::atomic<int> sock_seq{0};
   VmmDesc d;
+  std::memset(&d, 0, sizeof(d));
   d.pid = (int32_t)getpid();
   d.mem_fd = fd;
   d.mc_fd = -1;
   d.mc_ok = mc_ok ? 1 : 0;
   d.size = b.map_bytes;
+  d.sock_seq = sock_seq.fetch_add(1);
+  prctl(PR_SET_PTRACER, PR_SET_PTRACER_ANY, 0, 0, 0);      // let the peers use pidfd_getfd under Yama ptrace_scope = 1
   if (mc_ok && rank == 0 && world > 1) {
     mp.size = b.map_bytes;
     CUmemGenericAllocationHandle mc;
@@ -203,6 +305,13 @@ std::string SymmMem::alloc_vmm(const std::string& name, size_t bytes, int rank, 
     DRV_OK(D().memExport(&mfd, mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
     b.mc_fd = mfd;
     d.mc_fd = mfd;
+  }
+  {
+    auto srv = std::make_unique<FdServer>();
+    srv->fds[0] = b.mem_fd;
+    srv->fds[1] = b.mc_fd;
+    srv->start(d.sock_seq);
+    servers()[name] = std::move(srv);
   }
   bufs_[name] = b;
   return std::string(reinterpret_cast<const char*>(&d), sizeof(d));
@@ -225,7 +334,7 @@ void SymmMem::open_vmm(const std::string& name, const std::vector<std::string>& 
   for (int r = 0; r < b.world; ++r) {
     if (r == b.rank) b.peer[r] = b.local;
     else {
-      const int fd = dup_from_process(ds[r].pid, ds[r].mem_fd);
+      const int fd = dup_from_process(ds[r].pid, ds[r].mem_fd, ds[r].sock_seq, 0);
       CUmemGenericAllocationHandle h;
       DRV_OK(D().memImport(&h, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
       close(fd);
@@ -242,7 +351,7 @@ void SymmMem::open_vmm(const std::string& name, const std::vector<std::string>& 
   CUmemGenericAllocationHandle mc;
   if (b.rank == 0) mc = (CUmemGenericAllocationHandle)b.mc_handle;
   else {
-    const int fd = dup_from_process(ds[0].pid, ds[0].mc_fd);
+    const int fd = dup_from_process(ds[0].pid, ds[0].mc_fd, ds[0].sock_seq, 1);
     DRV_OK(D().memImport(&mc, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
     close(fd);
     b.mc_handle = (unsigned long long)mc;
@@ -262,6 +371,8 @@ void SymmMem::bind_multicast(const std::string& name) {
 }
 
 void SymmMem::free_vmm(SymmBuffer& b) {
+  auto sit = servers().find(b.name);
+  if (sit != servers().end()) { sit->second->shutdown_server(); servers().erase(sit); }
   auto unmap = [&](void* p) {
     if (!p) return;
     D().memUnmap((CUdeviceptr)p, b.map_bytes);

@@ -4,6 +4,7 @@
 N=${1:-2}
 mkdir -p gpurun_out
 export HETU_BACKTRACE=1
+export PYTHONPATH=$PWD:$PYTHONPATH
 timeout 900 python -m pytest tests/test_kernels_gpu.py -q > gpurun_out/pytest_kernels.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_kernels.log | cut -c1-300
 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
   tests/workers/symm_worker.py > gpurun_out/symm_nvls_$N.log 2>&1; echo "symm rc=$?"
