@@ -1363,6 +1363,27 @@ static void packed_views(const at::Tensor& qkv, int64_t S, int64_t Hq, int64_t H
   *k = x.narrow(2, Hq, Hkv);
   *v = x.narrow(2, Hq + Hkv, Hkv);
 }
+// single-launch variable-length attention: per-token document start / end (device int32 [T]), set by attn_packed_compute /
+// attn_packed_bwd_compute around ONE call of the row helpers over the whole packed buffer (B = 1, S = T)
+struct VarlenCtx { const int* row_start = nullptr; const int* row_end = nullptr; };
+static thread_local VarlenCtx tls_varlen;
+static bool varlen_fused_enabled() { return env_int("HETU_ATTN_VARLEN_FUSED", 1) != 0; }
+// (row_start, row_end) tensors of a cu_seqlens list, cached for the current step like the host copy
+static std::pair<at::Tensor, at::Tensor> varlen_rows(const std::vector<int64_t>& cu, int64_t T, const at::Device& dev) {
+  static thread_local std::vector<int64_t> last_cu;
+  static thread_local at::Tensor last_start, last_end;
+  if (last_cu == cu && last_start.defined() && last_start.size(0) == T && last_start.device() == dev) return {last_start, last_end};
+  at::Tensor hs = at::empty({T}, at::TensorOptions().dtype(at::kInt)), he = at::empty({T}, at::TensorOptions().dtype(at::kInt));
+  int32_t* ps = hs.data_ptr<int32_t>();
+  int32_t* pe = he.data_ptr<int32_t>();
+  for (int64_t t = 0; t < T; ++t) { ps[t] = (int32_t)t; pe[t] = (int32_t)(t + 1); }      // tokens outside every document: alone
+  for (size_t i = 0; i + 1 < cu.size(); ++i)
+    for (int64_t t = cu[i]; t < cu[i + 1] && t < T; ++t) { ps[t] = (int32_t)cu[i]; pe[t] = (int32_t)cu[i + 1]; }
+  last_cu = cu;
+  last_start = hs.to(dev);
+  last_end = he.to(dev);
+  return {last_start, last_end};
+}
 static TsP attn_packed_rows(const OpDef& op, const at::Tensor& qkv, int64_t S, RunCtx* rc) {
   // head counts follow the width of the packed projection actually fed (the tensor-parallel degree may change between
   // strategies); the attributes fix the q : kv ratio and the head size
@@ -1386,11 +1407,26 @@ static TsP attn_packed_rows(const OpDef& op, const at::Tensor& qkv, int64_t S, R
       c.B = (int)B; c.Sq = (int)S; c.Sk = (int)S; c.Hq = (int)Hq; c.Hkv = (int)Hkv; c.D = (int)D;
       c.softmax_scale = (float)(op.attrs.f("softmax_scale", 0.0) > 0 ? op.attrs.f("softmax_scale") : 1.0 / std::sqrt((double)D));
       c.causal = op.attrs.b("causal", true);
+      c.row_start = tls_varlen.row_start;
       cuda_ok(attn_fwd(c, cur_stream()), "attn_fwd");
       return {o.reshape({T, Hq * D}), lse};
     }
     q = q.reshape({B, S, Hq, D});   // fallback: gather the heads
+  } else if (tls_varlen.row_start != nullptr && attn_ok(q) && attn_ok(k) && attn_ok(v) && (D == 64 || D == 128)) {
+    const int64_t B = T / S;
+    at::Tensor o = at::empty({B, S, Hq, D}, qkv.options());
+    at::Tensor lse = at::empty({B, Hq, S}, fopt);
+    AttnFwdCall c;
+    c.q = as_attn(q); c.k = as_attn(k); c.v = as_attn(v); c.o = as_attn(o);
+    c.lse = lse.data_ptr<float>();
+    c.B = (int)B; c.Sq = (int)S; c.Sk = (int)S; c.Hq = (int)Hq; c.Hkv = (int)Hkv; c.D = (int)D;
+    c.softmax_scale = (float)(op.attrs.f("softmax_scale", 0.0) > 0 ? op.attrs.f("softmax_scale") : 1.0 / std::sqrt((double)D));
+    c.causal = true;
+    c.row_start = tls_varlen.row_start;
+    cuda_ok(attn_fwd(c, cur_stream()), "attn_fwd");
+    return {o.reshape({T, Hq * D}), lse};
   }
+  HB_CHECK(tls_varlen.row_start == nullptr) << "single-launch varlen attention needs the native kernel path";
   static const OpKernel* kern = OpRegistry::get().find("attn");
   OpDef tmp;
   tmp.attrs = op.attrs;
@@ -1426,6 +1462,18 @@ static TsP attn_packed_compute(const OpDef& op, const TsP& in, RunCtx* rc) {
   const std::vector<int64_t> cu = host_cu_seqlens(in[1], rc);
   HB_CHECK(cu.size() >= 2 && cu.front() == 0 && cu.back() <= T) << "attn_packed: bad cu_seqlens";
   at::Tensor src = qkv.is_contiguous() ? qkv : qkv.contiguous();
+  if (is_native(src) && (D == 64 || D == 128) && op.attrs.b("causal", true) && varlen_fused_enabled()) {
+    // ONE launch over the whole packed buffer: block-diagonal causal mask from the per-token document starts, KV tiles
+    // outside a query tile's documents are skipped inside the kernel; lse comes back in the natural [1, Hq, T] layout
+    auto rows = varlen_rows(cu, T, src.device());
+    tls_varlen.row_start = rows.first.data_ptr<int32_t>();
+    tls_varlen.row_end = rows.second.data_ptr<int32_t>();
+    TsP r;
+    bool ok = true;
+    try { r = attn_packed_rows(op, src, T, rc); } catch (const Error&) { ok = false; }     // layout not addressable: per-document path
+    tls_varlen = VarlenCtx();
+    if (ok) return {r[0], r[1].reshape({1, Hq, T})};
+  }
   at::Tensor o = at::zeros({T, Hq * D}, qkv.options());
   at::Tensor lse = at::zeros({Hq * T}, fopt);
   for (size_t i = 0; i + 1 < cu.size(); ++i) {
@@ -1450,6 +1498,16 @@ static TsP attn_packed_bwd_compute(const OpDef& op, const TsP& in, RunCtx* rc) {
   const int64_t Hq = qkv.size(-1) / ((rep_ + 2) * D) * rep_;
   const std::vector<int64_t> cu = host_cu_seqlens(in[4], rc);
   at::Tensor src = qkv.is_contiguous() ? qkv : qkv.contiguous();
+  if (is_native(src) && (D == 64 || D == 128) && op.attrs.b("causal", true) && varlen_fused_enabled()) {
+    auto rows = varlen_rows(cu, T, src.device());
+    tls_varlen.row_start = rows.first.data_ptr<int32_t>();
+    tls_varlen.row_end = rows.second.data_ptr<int32_t>();
+    TsP r;
+    bool ok = true;
+    try { r = attn_packed_bwd_rows(op, in[0], src, in[2], in[3].reshape({1, Hq, T}), T, rc); } catch (const Error&) { ok = false; }
+    tls_varlen = VarlenCtx();
+    if (ok) return r;
+  }
   at::Tensor dqkv = at::zeros_like(src);
   at::Tensor lflat = in[3].reshape({-1}), dof = in[0].contiguous(), of = in[2].contiguous();
   for (size_t i = 0; i + 1 < cu.size(); ++i) {
@@ -1487,9 +1545,11 @@ static TsP attn_packed_bwd_rows(const OpDef& op, const at::Tensor& d_o, const at
     c.lse = lse.data_ptr<float>(); c.delta = delta.data_ptr<float>();
     c.B = (int)B; c.Sq = (int)S; c.Sk = (int)S; c.Hq = (int)Hq; c.Hkv = (int)Hkv; c.D = (int)D;
     c.softmax_scale = (float)scale; c.causal = causal;
+    c.row_start = tls_varlen.row_start; c.row_end = tls_varlen.row_end;
     cuda_ok(attn_bwd(c, cur_stream()), "attn_bwd");
     return {dqkv};
   }
+  HB_CHECK(tls_varlen.row_start == nullptr) << "single-launch varlen attention backward needs the native kernel path";
   static const OpKernel* bwd = OpRegistry::get().find("attn_bwd");
   OpDef tmp;
   tmp.attrs = op.attrs;

@@ -37,6 +37,9 @@ struct AttnBwdParams {
   const float* DELTA;  // [B, Hq, Sq]
   __nv_bfloat16 *dQ, *dK, *dV;
   int64_t dq_sb, dq_ss, dq_sh, dk_sb, dk_ss, dk_sh, dv_sb, dv_ss, dv_sh;
+  // packed variable-length rows in one launch (B == 1, causal): document start / end (exclusive) of every token
+  const int* row_start = nullptr;
+  const int* row_end = nullptr;
 };
 
 // delta[b,h,s] = sum_d dO * O: D/8 lanes per row, one 16-byte load of each tensor per lane (2 or 4 rows per warp)
@@ -107,12 +110,14 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   const int hk = h / (p.Hq / p.Hkv);
   const int hslot = p.q_div ? (h / p.q_div) * p.q_mul + (h % p.q_div) : h;
   const int q0 = qt * 128;
-  int n_kv = (p.Sk + 127) / 128;
+  int n_kv_end = (p.Sk + 127) / 128;
   if (p.causal) {
     const int last = q0 + 127 + p.causal_off;
     const int lim = last < 0 ? 0 : last / 128 + 1;
-    n_kv = min(n_kv, lim);
+    n_kv_end = min(n_kv_end, lim);
   }
+  const int j_begin = (p.row_start != nullptr) ? min(p.row_start[min(q0, p.Sq - 1)] / 128, n_kv_end) : 0;
+  const int n_kv = n_kv_end - j_begin;          // KV tiles visited: tile index = j_begin + j
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_q); ptx::prefetch_tmap(&tmap_do); ptx::prefetch_tmap(&tmap_k); ptx::prefetch_tmap(&tmap_v);
@@ -150,11 +155,11 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         ptx::mbar_wait(&k_empty[st], ph ^ 1);
         ptx::mbar_arrive_expect_tx(&k_full[st], T);
         for (int bx = 0; bx < NBOX; ++bx)
-          ptx::tma_load_4d(sK + st * T + bx * kBoxBytes, &tmap_k, &k_full[st], bx * 64, hk, j * 128, b);
+          ptx::tma_load_4d(sK + st * T + bx * kBoxBytes, &tmap_k, &k_full[st], bx * 64, hk, (j_begin + j) * 128, b);
         ptx::mbar_wait(&v_empty[st], ph ^ 1);
         ptx::mbar_arrive_expect_tx(&v_full[st], T);
         for (int bx = 0; bx < NBOX; ++bx)
-          ptx::tma_load_4d(sV + st * T + bx * kBoxBytes, &tmap_v, &v_full[st], bx * 64, hk, j * 128, b);
+          ptx::tma_load_4d(sV + st * T + bx * kBoxBytes, &tmap_v, &v_full[st], bx * 64, hk, (j_begin + j) * 128, b);
       }
     }
     __syncwarp();
@@ -218,6 +223,11 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     float lse2 = row_ok ? p.LSE[stat_idx] * 1.4426950408889634f : INFINITY;
     if (lse2 == -INFINITY) lse2 = INFINITY;  // fully masked row: P = 0
     const float delta = row_ok ? p.DELTA[stat_idx] : 0.f;
+    // visible keys of this row: [doc_lo, lim] (doc_lo = 0 without packing); one unsigned compare per element tests both ends
+    const int lim = p.causal ? min(p.Sk - 1, grow + p.causal_off) : p.Sk - 1;
+    const int doc_lo = (p.row_start != nullptr && row_ok) ? p.row_start[grow] : 0;
+    const unsigned span = lim >= doc_lo ? unsigned(lim - doc_lo) : 0u;
+    const int vis_lo = lim >= doc_lo ? doc_lo : -(1 << 29);          // nothing visible: every column compares above `span`
     for (int j = 0; j < n_kv; ++j) {
       const int st = j & 1;
       ptx::mbar_wait(&s_full[st], (j >> 1) & 1);
@@ -229,12 +239,11 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       ptx::tmem_ld_32x32b_x32(taddr + 64, sr + 64);
       ptx::tmem_ld_32x32b_x32(taddr + 96, sr + 96);
       ptx::tmem_ld_wait();
-      const int k0 = j * 128;
-      const int lim = p.causal ? min(p.Sk - 1, grow + p.causal_off) : p.Sk - 1;
+      const int kb = (j_begin + j) * 128 - vis_lo;
 #pragma unroll
       for (int c = 0; c < 128; ++c) {
         float pv = ex2(fmaf(__uint_as_float(sr[c]), p.scale_log2, -lse2));
-        if (k0 + c > lim) pv = 0.f;
+        if (unsigned(kb + c) > span) pv = 0.f;
         sr[c] = __float_as_uint(pv);
       }
       ptx::mbar_wait(dp_full, j & 1);
@@ -311,8 +320,8 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
   uint8_t* sV = smem + T;
   uint8_t* sQ = smem + 2 * T;   // 2 stages
   uint8_t* sDO = smem + 4 * T;  // 2 stages
-  float* sStat = reinterpret_cast<float*>(smem + 6 * T);  // [2 stages][2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * T + 2048);
+  float* sStat = reinterpret_cast<float*>(smem + 6 * T);  // [2 stages][3][128]: lse, delta, document start of the tile's queries
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * T + 3072);
   uint64_t* kv_full = bars;
   uint64_t* q_full = bars + 1;
   uint64_t* q_empty = bars + 3;
@@ -339,7 +348,10 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
     i_start = first_row <= 0 ? 0 : first_row / 128;
     if (i_start > n_q) i_start = n_q;
   }
-  const int nq_iters = n_q - i_start;
+  // varlen: queries past the end of the last document that starts inside this key tile never see these keys
+  int i_end = n_q;
+  if (p.row_end != nullptr) i_end = min(n_q, (p.row_end[min(k0 + 127, p.Sk - 1)] + 127) / 128);
+  const int nq_iters = max(i_end - i_start, 0);
   const int n_it = nq_iters * group;
 
   if (warp == 0 && lane == 0) {
@@ -450,7 +462,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
     for (int it = 0; it < n_it; ++it) {
       const int hq = hk * group + it / nq_iters;
       const int q0 = (i_start + it % nq_iters) * 128;
-      float* stat = sStat + (it & 1) * 256;
+      float* stat = sStat + (it & 1) * 384;
       {
         const int gq = q0 + tid;
         const bool ok = gq < p.Sq;
@@ -459,6 +471,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         if (l2 == -INFINITY) l2 = INFINITY;  // fully masked row: P = 0
         stat[tid] = l2;
         stat[128 + tid] = ok ? p.DELTA[si] : 0.f;
+        reinterpret_cast<int*>(stat)[256 + tid] = (p.row_start != nullptr && ok) ? p.row_start[gq] : 0;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       ptx::mbar_wait(st_full, it & 1);
@@ -481,7 +494,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         for (int t = 0; t < 4; ++t) {
           const int c = c4 * 4 + t;
           float pv = ex2(fmaf(__uint_as_float(sr[c]), p.scale_log2, -ls[t]));
-          if (!key_ok || (q0 + c) < first_q) pv = 0.f;
+          if (!key_ok || (q0 + c) < first_q || gk < reinterpret_cast<const int*>(stat)[256 + c]) pv = 0.f;   // (other document)
           sr[c] = __float_as_uint(pv);
         }
       }
@@ -601,12 +614,13 @@ cudaError_t attn_bwd_launch(const AttnBwdCall& c, cudaStream_t s, std::atomic<in
   p.causal = c.causal ? 1 : 0;
   p.causal_off = c.Sk - c.Sq;
   p.LSE = c.lse; p.DELTA = c.delta;
+  p.row_start = c.row_start; p.row_end = c.row_end;
   p.dQ = (__nv_bfloat16*)c.dq.ptr; p.dK = (__nv_bfloat16*)c.dk.ptr; p.dV = (__nv_bfloat16*)c.dv.ptr;
   p.q_div = c.q.h_div; p.q_mul = c.q.h_mul;
   p.dq_sb = c.dq.stride_b; p.dq_ss = c.dq.stride_s; p.dq_sh = c.dq.stride_h;
   p.dk_sb = c.dk.stride_b; p.dk_ss = c.dk.stride_s; p.dk_sh = c.dk.stride_h;
   p.dv_sb = c.dv.stride_b; p.dv_ss = c.dv.stride_s; p.dv_sh = c.dv.stride_h;
-  constexpr int smem = 6 * 128 * D * 2 + 2048 + 1024 + 256;
+  constexpr int smem = 6 * 128 * D * 2 + 3072 + 1024 + 256;
   auto kq = attn_bwd_dq_sm100_kernel<D>;
   auto kkv = attn_bwd_dkv_sm100_kernel<D>;
   static bool attr_set = false;

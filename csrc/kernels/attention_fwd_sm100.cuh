@@ -32,6 +32,9 @@ struct AttnFwdParams {
   __nv_bfloat16* O;
   int64_t o_sb, o_ss, o_sh;
   float* LSE;        // [B, Hq, Sq]
+  // packed variable-length rows in ONE launch (B == 1, causal): row_start[t] = first token of the document that token t
+  // belongs to.  A query attends to keys in [row_start[q], q]; KV tiles wholly before the first row's document are skipped.
+  const int* row_start = nullptr;
 };
 
 namespace attn_detail {
@@ -77,12 +80,15 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   const int hslot = p.q_div ? (h / p.q_div) * p.q_mul + (h % p.q_div) : h;
   const int q0 = qt * 128;
 
-  int n_kv = (p.Sk + 127) / 128;
+  int n_kv_end = (p.Sk + 127) / 128;
   if (p.causal) {
     const int last = q0 + 127 + p.causal_off;  // last visible key column for this tile
     const int lim = last < 0 ? 0 : last / 128 + 1;
-    n_kv = min(n_kv, lim);
+    n_kv_end = min(n_kv_end, lim);
   }
+  // varlen: documents are contiguous, so the first row of the tile has the smallest document start
+  const int j_begin = (p.row_start != nullptr) ? min(p.row_start[min(q0, p.Sq - 1)] / 128, n_kv_end) : 0;
+  const int n_kv = n_kv_end - j_begin;          // number of KV tiles this CTA visits: tile index = j_begin + j
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_q);
@@ -121,11 +127,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         ptx::mbar_wait(&k_empty[st], ph ^ 1);
         ptx::mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
         for (int bx = 0; bx < NBOX; ++bx)
-          ptx::tma_load_4d(sK + st * TILE_BYTES + bx * kBoxBytes, &tmap_k, &k_full[st], bx * 64, hk, j * 128, b);
+          ptx::tma_load_4d(sK + st * TILE_BYTES + bx * kBoxBytes, &tmap_k, &k_full[st], bx * 64, hk, (j_begin + j) * 128, b);
         ptx::mbar_wait(&v_empty[st], ph ^ 1);
         ptx::mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
         for (int bx = 0; bx < NBOX; ++bx)
-          ptx::tma_load_4d(sV + st * TILE_BYTES + bx * kBoxBytes, &tmap_v, &v_full[st], bx * 64, hk, j * 128, b);
+          ptx::tma_load_4d(sV + st * TILE_BYTES + bx * kBoxBytes, &tmap_v, &v_full[st], bx * 64, hk, (j_begin + j) * 128, b);
       }
     }
     __syncwarp();
@@ -176,6 +182,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const uint32_t lane_base = uint32_t(qd * 32) << 16;
     float m_ref = -INFINITY;
     float l = 0.f;
+    const int doc_lo = (p.row_start != nullptr) ? p.row_start[min(grow, p.Sq - 1)] : 0;   // first visible key of this row
     for (int j = 0; j < n_kv; ++j) {
       const int st = j & 1;
       ptx::mbar_wait(&s_full[st], (j >> 1) & 1);
@@ -187,13 +194,13 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       ptx::tmem_ld_32x32b_x32(taddr + 64, sr + 64);
       ptx::tmem_ld_32x32b_x32(taddr + 96, sr + 96);
       ptx::tmem_ld_wait();
-      const int k0 = j * 128;
-      const bool need_mask = (k0 + 128 > p.Sk) || (p.causal && (k0 + 127 > q0 + p.causal_off));
+      const int k0 = (j_begin + j) * 128;
+      const bool need_mask = (k0 + 128 > p.Sk) || (p.causal && (k0 + 127 > q0 + p.causal_off)) || (k0 < doc_lo);
       if (need_mask) {
         const int lim = p.causal ? min(p.Sk - 1, grow + p.causal_off) : p.Sk - 1;  // last visible column
 #pragma unroll
         for (int c = 0; c < 128; ++c)
-          if (k0 + c > lim) sr[c] = 0xff800000u;  // -inf
+          if (k0 + c > lim || k0 + c < doc_lo) sr[c] = 0xff800000u;  // -inf
       }
       float mx = __uint_as_float(sr[0]);
 #pragma unroll

@@ -42,6 +42,7 @@ cudaError_t launch_fwd(const AttnFwdCall& c, cudaStream_t s) {
   p.O = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(c.o.ptr));
   p.o_sb = c.o.stride_b; p.o_ss = c.o.stride_s; p.o_sh = c.o.stride_h;
   p.LSE = c.lse;
+  p.row_start = c.row_start;
   constexpr int smem = 5 * 128 * D * 2 + 1024 + 256;
   auto kern = attn_fwd_sm100_kernel<D>;
   static bool attr_set = false;
@@ -62,6 +63,7 @@ cudaError_t attn_fwd(const AttnFwdCall& c, cudaStream_t s) {
   if (c.B == 0 || c.Sq == 0) return cudaSuccess;
   if (!strides_ok(c.q) || !strides_ok(c.k) || !strides_ok(c.v) || !strides_ok(c.o)) return cudaErrorMisalignedAddress;
   if (c.Hkv <= 0 || c.Hq % c.Hkv != 0) return cudaErrorInvalidValue;
+  if (c.row_start != nullptr && (c.B != 1 || !c.causal || c.Sq != c.Sk)) return cudaErrorInvalidValue;
   if (c.D == 64) return launch_fwd<64>(c, s);
   if (c.D == 128) return launch_fwd<128>(c, s);
   return cudaErrorInvalidValue;
@@ -73,6 +75,8 @@ cudaError_t attn_bwd(const AttnBwdCall& c, cudaStream_t s) {
       !strides_ok(c.dq) || !strides_ok(c.dk) || !strides_ok(c.dv))
     return cudaErrorMisalignedAddress;
   if (c.Hkv <= 0 || c.Hq % c.Hkv != 0) return cudaErrorInvalidValue;
+  if ((c.row_start != nullptr) != (c.row_end != nullptr)) return cudaErrorInvalidValue;
+  if (c.row_start != nullptr && (c.B != 1 || !c.causal || c.Sq != c.Sk)) return cudaErrorInvalidValue;
   if (c.D == 64) return attn_bwd_launch<64>(c, s, &g_attn_launches);
   if (c.D == 128) return attn_bwd_launch<128>(c, s, &g_attn_launches);
   return cudaErrorInvalidValue;

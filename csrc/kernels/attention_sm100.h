@@ -23,6 +23,9 @@ struct AttnFwdCall {
   int B = 0, Hq = 0, Hkv = 0, Sq = 0, Sk = 0, D = 0;
   float softmax_scale = 1.0f;
   bool causal = true;   // bottom-right aligned when Sq != Sk (FlashAttention-2 convention)
+  // packed variable-length rows (B == 1, causal, Sq == Sk): device int32 [Sq], first token of every token's document.
+  // One launch covers all documents (block-diagonal causal mask, tiles outside a document are skipped).
+  const int* row_start = nullptr;
 };
 
 struct AttnBwdCall {
@@ -33,6 +36,8 @@ struct AttnBwdCall {
   int B = 0, Hq = 0, Hkv = 0, Sq = 0, Sk = 0, D = 0;
   float softmax_scale = 1.0f;
   bool causal = true;
+  const int* row_start = nullptr;   // varlen (see AttnFwdCall): document start and end (exclusive) of every token
+  const int* row_end = nullptr;
 };
 
 cudaError_t attn_fwd(const AttnFwdCall& c, cudaStream_t s);

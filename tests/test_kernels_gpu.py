@@ -225,15 +225,20 @@ def test_packed_grouped_qkv_rotary_attention(Hq, Hkv, D):
     close(torch.as_tensor(X.grad.numpy()), xr.grad, 0.06, 0.04)
 
 
-def test_varlen_packed_attention_native():
-    """documents of a packed row attend only to themselves (one launch per document over strided views)"""
+@pytest.mark.parametrize("T,H,D,bounds", [
+    (640, 4, 64, [0, 128, 328, 640]),
+    (1536, 2, 128, [0, 37, 38, 300, 1000, 1129, 1536]),      # 1-token document, documents crossing several 128-row tiles
+])
+def test_varlen_packed_attention_native(T, H, D, bounds):
+    """documents of a packed row attend only to themselves: ONE fwd launch and one delta + dQ + dK/dV launch set for the whole
+    packed buffer (block-diagonal causal mask from per-token document bounds inside the kernels)"""
     from hetu_b200.ops_extra import attn_packed
-    T, H, D = 640, 4, 64
     qkv, g = bf(T, 3 * H * D, seed=1), bf(T, H * D, seed=2)
-    bounds = [0, 128, 328, 640]
-    cu = torch.tensor(bounds + [640, 640], dtype=torch.int32).cuda()
+    cu = torch.tensor(bounds + [T, T], dtype=torch.int32).cuda()
     X = leaf(qkv)
+    n0 = ht._C.attn_launch_count()
     o = attn_packed(X, T, H, H, D, is_causal=True, layout="hqkv", cu_seqlens=ht.from_numpy(cu))
+    assert ht._C.attn_launch_count() - n0 == 1, "variable-length forward must be a single kernel launch"
     ht.sum(o * leaf(g, False)).backward()
     xr = qkv.float().requires_grad_()
     y = xr.view(T, H, 3, D)
