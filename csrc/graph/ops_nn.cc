@@ -1098,6 +1098,19 @@ static Ts attn_compute(const OpDef& op, const Ts& in, RunCtx*) {
     cuda_ok(attn_fwd(c, cur_stream()), "attn_fwd");
     return {o, lse};
   }
+  // other head sizes below 128 (32, 40, 80, 96, 112, ...): zero-pad the head dimension to the next supported size; the
+  // scores are unchanged (padding contributes 0 to q.k), the padded output columns are dropped.  The softmax scale of the
+  // ORIGINAL head size is passed explicitly.
+  if (is_native(q) && is_native(k) && is_native(v) && q.size(3) < 128 && q.size(3) != 64 && !op.attrs.b("_padded")) {
+    const int64_t D = q.size(3), Dp = D < 64 ? 64 : 128;
+    auto pad = [&](const at::Tensor& t) { return at::constant_pad_nd(t, {0, Dp - D}).contiguous(); };
+    OpDef tmp;
+    tmp.attrs = op.attrs;
+    tmp.attrs.set("softmax_scale", scale);
+    tmp.attrs.set("_padded", true);
+    Ts r = attn_compute(tmp, {pad(q), pad(k), pad(v)}, nullptr);
+    return {r[0].narrow(3, 0, D).contiguous(), r[1]};
+  }
   if (is_native(q)) note_fallback("attn");
   auto r = aten_attention(q, k, v, scale, causal);
   return {r.first.to(q.scalar_type()), r.second};
@@ -1126,6 +1139,16 @@ static Ts attn_bwd_compute(const OpDef& op, const Ts& in, RunCtx*) {
     c.softmax_scale = (float)scale; c.causal = causal;
     cuda_ok(attn_bwd(c, cur_stream()), "attn_bwd");
     return {dq, dk, dv};
+  }
+  if (is_native(q) && is_native(k) && is_native(v) && q.size(3) < 128 && q.size(3) != 64 && !op.attrs.b("_padded")) {
+    const int64_t D = q.size(3), Dp = D < 64 ? 64 : 128;
+    auto pad = [&](const at::Tensor& t) { return at::constant_pad_nd(t, {0, Dp - D}).contiguous(); };
+    OpDef tmp;
+    tmp.attrs = op.attrs;
+    tmp.attrs.set("softmax_scale", scale);
+    tmp.attrs.set("_padded", true);
+    Ts r = attn_bwd_compute(tmp, {pad(d_o), pad(q), pad(k), pad(v), pad(o), lse}, nullptr);
+    return {r[0].narrow(3, 0, D).contiguous(), r[1].narrow(3, 0, D).contiguous(), r[2].narrow(3, 0, D).contiguous()};
   }
   if (is_native(q)) note_fallback("attn_bwd");
   // reference backward in fp32 from the SAVED statistics (o, lse), exactly like the kernels: P is rebuilt as

@@ -64,7 +64,8 @@ def test_linear_residual_epilogue():
     close(torch.as_tensor(y.numpy()), x.float() @ w.float().t() + r.float(), 0.03, 0.02)
 
 
-@pytest.mark.parametrize("B,S,H,Hkv,D,causal", [(2, 256, 4, 4, 128, True), (1, 384, 4, 2, 64, True), (2, 200, 2, 2, 128, False)])
+@pytest.mark.parametrize("B,S,H,Hkv,D,causal", [(2, 256, 4, 4, 128, True), (1, 384, 4, 2, 64, True), (2, 200, 2, 2, 128, False),
+                                                (2, 256, 4, 2, 32, True), (1, 300, 3, 3, 96, True)])   # 32 / 96: zero-padded to 64 / 128
 def test_flash_attention_fwd_bwd(B, S, H, Hkv, D, causal):
     q, k, v, g = bf(B, S, H, D, seed=1), bf(B, S, Hkv, D, seed=2), bf(B, S, Hkv, D, seed=3), bf(B, S, H, D, seed=4)
     Q, K, V = leaf(q), leaf(k), leaf(v)
