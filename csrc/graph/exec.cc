@@ -1029,6 +1029,7 @@ std::vector<at::Tensor> Executor::run(const Tensor& loss, const TensorList& fetc
       zf_active_ = zit->second.get();
       zf_active_->epilogue_this_run = single_shot_grads_;
       zf_active_->launched.assign(zf_active_->entries.size(), 0);
+      zf_active_->ready_queue.clear();
       zf_active_->scale_this_run = opt.grad_scale / (double)M;
     }
   }

@@ -185,12 +185,20 @@ void Executor::zero_nvls_after_op(ExecPlan& plan, ZeroFusedState& st, int pos) {
   (void)plan;
   auto range = st.ready_at.equal_range(pos);
   if (range.first == range.second || !st.epilogue_this_run) return;
+  for (auto it = range.first; it != range.second; ++it)
+    if (!st.launched[it->second]) st.ready_queue.push_back(it->second);
+  // Buckets: the cross-rank barrier of the bridge stream is a spinning one-CTA kernel; while it waits for the slowest
+  // rank it holds a CTA slot and the next persistent GEMM of the compute stream cannot place its CTA on that SM.  One
+  // barrier per parameter (97 per step) cost ~4 ms of such stalls at 4 GPUs; with a bucket of parameters per barrier the
+  // barrier is also issued well after the first member became ready, so the peers have usually passed it already.
+  static const int bucket = std::max(1, (int)env_int("HETU_ZERO_BUCKET", 24));
+  if ((int)st.ready_queue.size() < bucket) return;
   SymmBuffer& buf = SymmMem::get().buffer(st.arena_name);
   cuda_ok(cudaEventRecord(st.ev_ready, cur_stream()), "event record");
   cuda_ok(cudaStreamWaitEvent(st.side, st.ev_ready, 0), "stream wait");
   cuda_ok(symm_barrier_slot(buf, 1, ++st.side_epoch, st.side), "side barrier");      // all ranks are past this point
-  for (auto it = range.first; it != range.second; ++it)
-    if (!st.launched[it->second]) zero_nvls_launch(st, it->second, st.side);
+  for (size_t idx : st.ready_queue) zero_nvls_launch(st, idx, st.side);
+  st.ready_queue.clear();
 }
 
 void Executor::zero_fused_update(ExecPlan& plan, ZeroFusedState& st, double scale) {
@@ -204,6 +212,7 @@ void Executor::zero_fused_update(ExecPlan& plan, ZeroFusedState& st, double scal
     // entries that were not launched from inside backward: weight gradients produced without the epilogue hook and the
     // non-GEMM parameters (embeddings, norms, biases) -- copy the accumulated gradient into the arena, then one barrier
     // for all of them and the same kernel
+    st.ready_queue.clear();          // what is still queued joins the final batch below
     std::vector<size_t> todo;
     for (size_t i = 0; i < st.entries.size(); ++i) {
       ZeroEntry& e = st.entries[i];

@@ -51,6 +51,7 @@ struct ZeroFusedState {
   bool nvls = false;
   std::multimap<int, size_t> ready_at;           // executor position -> entries that become ready there
   std::vector<char> launched;                    // per entry: update already issued in this run
+  std::vector<size_t> ready_queue;               // ready entries waiting for their bucket's barrier
   cudaStream_t side = nullptr;
   cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
   uint32_t side_epoch = 0;                       // generation of the side-stream barrier (flag slot 1)

@@ -81,7 +81,11 @@ def init_comm_group(device_num: Optional[int] = None, device_idxs=(), server_add
                 os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = host, port
             be = backend or ("nccl" if use_cuda else "gloo")
             kw = {}
-            if use_cuda:
+            # lazy communicator initialisation (no device_id): point-to-point sends / receives between pipeline stages then get
+            # their own 2-rank communicators.  With eager initialisation c10d runs unbatched p2p ops on the parent communicator
+            # "as independent collective ops, serialized with all other ops" of the group, which interlocks 1F1B schedules of
+            # tensor-parallel stages (observed as a hang of tp2 x pp2 on 4 B200s).  HETU_NCCL_EAGER_INIT=1 restores it.
+            if use_cuda and os.environ.get("HETU_NCCL_EAGER_INIT", "0") == "1":
                 kw["device_id"] = torch.device("cuda", local_rank % torch.cuda.device_count())
             if os.environ.get("HETU_PG_TIMEOUT_S"):       # collectives that cannot complete fail after this long (tests)
                 import datetime
