@@ -746,18 +746,21 @@ static Ts norm_bwd_compute(const OpDef& op, const Ts& in, RunCtx* rc) {
       (!dx_add || (is_native(*dx_add) && dx_add->is_contiguous() && dx_add->sizes() == x.sizes()))) {
     auto fopt = x.options().dtype(at::kFloat);
     const void* addp = dx_add ? dx_add->data_ptr() : nullptr;
-    at::Tensor dx = at::empty_like(x), dg = at::empty({cols}, fopt), db = at::empty({cols}, fopt);
+    // parameter gradients come out in the parameter's dtype straight from the fold kernel (no cast pass)
+    const bool pbf = gamma.scalar_type() == at::kBFloat16;
+    at::Tensor dx = at::empty_like(x), dg = at::empty({cols}, pbf ? gamma.options() : fopt), db = at::empty({cols}, pbf ? gamma.options() : fopt);
     at::Tensor ws = rc && rc->workspace ? rc->scratch("norm_bwd_ws", {2 * (int64_t)ln_bwd_parts() * cols}, at::kFloat, x.device())
                                         : at::empty({2 * (int64_t)ln_bwd_parts() * cols}, fopt);
     if (rms) {
       cuda_ok(rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), rstd.data_ptr<float>(), dx.data_ptr(),
-                          dg.data_ptr<float>(), ws.data_ptr<float>(), rows, (int)cols, false, cur_stream(), addp), "rmsnorm_bwd");
-      return {dx, dg.to(gamma.scalar_type())};
+                          pbf ? nullptr : dg.data_ptr<float>(), ws.data_ptr<float>(), rows, (int)cols, false, cur_stream(), addp,
+                          pbf ? dg.data_ptr() : nullptr), "rmsnorm_bwd");
+      return {dx, pbf ? dg : dg.to(gamma.scalar_type())};
     }
     cuda_ok(layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
-                          dx.data_ptr(), dg.data_ptr<float>(), db.data_ptr<float>(), ws.data_ptr<float>(), rows,
-                          (int)cols, false, cur_stream(), addp), "layernorm_bwd");
-    return {dx, dg.to(gamma.scalar_type()), db.to(gamma.scalar_type())};
+                          dx.data_ptr(), pbf ? nullptr : dg.data_ptr<float>(), pbf ? nullptr : db.data_ptr<float>(), ws.data_ptr<float>(), rows,
+                          (int)cols, false, cur_stream(), addp, pbf ? dg.data_ptr() : nullptr, pbf ? db.data_ptr() : nullptr), "layernorm_bwd");
+    return {dx, pbf ? dg : dg.to(gamma.scalar_type()), pbf ? db : db.to(gamma.scalar_type())};
   }
   at::Tensor xf = x.to(at::kFloat), g = dy.to(at::kFloat), gm = gamma.to(at::kFloat);
   at::Tensor xhat = rms ? xf * rstd.unsqueeze(-1) : (xf - mean.unsqueeze(-1)) * rstd.unsqueeze(-1);

@@ -18,12 +18,14 @@ cudaError_t layernorm_fwd(const void* x, const void* gamma, const void* beta, vo
 int ln_bwd_parts();
 cudaError_t layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
                           void* dx, float* dgamma, float* dbeta, float* workspace, int64_t rows, int cols,
-                          bool accumulate, cudaStream_t s, const void* dx_add = nullptr);   // dx_add: bf16 [rows, cols] added into dx
+                          bool accumulate, cudaStream_t s, const void* dx_add = nullptr,   // dx_add: bf16 [rows, cols] added into dx
+                          void* dgamma_bf16 = nullptr, void* dbeta_bf16 = nullptr);         // when set: results written as bf16 here
 // y = x * rstd * gamma                       (ref: hetu/impl/kernel/FusedLayerNorm.cu:1004, RMSNorm.cu)
 cudaError_t rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, int64_t rows, int cols, float eps,
                         cudaStream_t s);
 cudaError_t rmsnorm_bwd(const void* dy, const void* x, const void* gamma, const float* rstd, void* dx, float* dgamma,
-                        float* workspace, int64_t rows, int cols, bool accumulate, cudaStream_t s, const void* dx_add = nullptr);
+                        float* workspace, int64_t rows, int cols, bool accumulate, cudaStream_t s, const void* dx_add = nullptr,
+                        void* dgamma_bf16 = nullptr);
 
 // ---------------------------------------------------------------- elementwise (bf16 in/out)
 enum UnaryOp : int { U_GELU = 0, U_RELU, U_SILU, U_SIGMOID, U_TANH, U_GELU_TANH, U_EXP, U_NEG, U_SQRT, U_RSQRT, U_ABS };

@@ -358,10 +358,12 @@ __global__ void norm_bwd_generic_kernel(const __nv_bfloat16* __restrict__ dy, co
 // column and BOTH outputs (dgamma, dbeta) in one launch (blockIdx.y).
 __global__ void __launch_bounds__(256) fold_parts_kernel(const float* __restrict__ parts0, float* __restrict__ out0,
                                                          const float* __restrict__ parts1, float* __restrict__ out1,
-                                                         int nparts, int cols, int accumulate) {
+                                                         int nparts, int cols, int accumulate,
+                                                         __nv_bfloat16* __restrict__ outb0, __nv_bfloat16* __restrict__ outb1) {
   __shared__ float sm[8][33];
   const float* parts = blockIdx.y == 0 ? parts0 : parts1;
   float* out = blockIdx.y == 0 ? out0 : out1;
+  __nv_bfloat16* outb = blockIdx.y == 0 ? outb0 : outb1;      // bf16 result written directly (parameter-gradient dtype)
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -381,7 +383,8 @@ __global__ void __launch_bounds__(256) fold_parts_kernel(const float* __restrict
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += sm[w][tx];
-    out[c] = accumulate ? out[c] + s : s;
+    if (outb != nullptr) outb[c] = __float2bfloat16(s);
+    else out[c] = accumulate ? out[c] + s : s;
   }
 }
 
@@ -416,7 +419,8 @@ static cudaError_t norm_fwd_impl(const void* x, const void* gamma, const void* b
 template <bool kRMS>
 static cudaError_t norm_bwd_impl(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
                                  void* dx, float* dgamma, float* dbeta, float* ws, int64_t rows, int cols,
-                                 bool accumulate, cudaStream_t s, const void* dx_add) {
+                                 bool accumulate, cudaStream_t s, const void* dx_add, void* dgamma_bf16 = nullptr,
+                                 void* dbeta_bf16 = nullptr) {
   if (rows == 0) return cudaSuccess;
   int parts = ln_bwd_parts();
   if (parts > rows) parts = (int)rows;
@@ -433,9 +437,10 @@ static cudaError_t norm_bwd_impl(const void* dy, const void* x, const void* gamm
                                                         (const __nv_bfloat16*)gamma, mean, rstd, (__nv_bfloat16*)dx,
                                                         part_dg, part_db, rows, cols, (const __nv_bfloat16*)dx_add);
   }
-  const bool two = !kRMS && dbeta != nullptr;
+  const bool two = !kRMS && (dbeta != nullptr || dbeta_bf16 != nullptr);
   fold_parts_kernel<<<dim3((cols + 31) / 32, two ? 2 : 1), 256, 0, s>>>(part_dg, dgamma, part_db, dbeta, parts, cols,
-                                                                        accumulate ? 1 : 0);
+                                                                        accumulate ? 1 : 0, (__nv_bfloat16*)dgamma_bf16,
+                                                                        (__nv_bfloat16*)dbeta_bf16);
   count_launch(2);
   return cudaGetLastError();
 }
@@ -557,16 +562,19 @@ cudaError_t layernorm_fwd(const void* x, const void* gamma, const void* beta, vo
 }
 cudaError_t layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
                           void* dx, float* dgamma, float* dbeta, float* workspace, int64_t rows, int cols,
-                          bool accumulate, cudaStream_t s, const void* dx_add) {
-  return norm_bwd_impl<false>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, workspace, rows, cols, accumulate, s, dx_add);
+                          bool accumulate, cudaStream_t s, const void* dx_add, void* dgamma_bf16, void* dbeta_bf16) {
+  return norm_bwd_impl<false>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, workspace, rows, cols, accumulate, s, dx_add, dgamma_bf16,
+                              dbeta_bf16);
 }
 cudaError_t rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, int64_t rows, int cols, float eps,
                         cudaStream_t s) {
   return norm_fwd_impl<true>(x, gamma, nullptr, y, nullptr, rstd, rows, cols, eps, s);
 }
 cudaError_t rmsnorm_bwd(const void* dy, const void* x, const void* gamma, const float* rstd, void* dx, float* dgamma,
-                        float* workspace, int64_t rows, int cols, bool accumulate, cudaStream_t s, const void* dx_add) {
-  return norm_bwd_impl<true>(dy, x, gamma, nullptr, rstd, dx, dgamma, nullptr, workspace, rows, cols, accumulate, s, dx_add);
+                        float* workspace, int64_t rows, int cols, bool accumulate, cudaStream_t s, const void* dx_add,
+                        void* dgamma_bf16) {
+  return norm_bwd_impl<true>(dy, x, gamma, nullptr, rstd, dx, dgamma, nullptr, workspace, rows, cols, accumulate, s, dx_add, dgamma_bf16,
+                             nullptr);
 }
 
 cudaError_t dropout_add_layernorm_fwd(const void* x, const void* residual, const void* gamma, const void* beta, void* y, void* z,
