@@ -816,6 +816,13 @@ void Executor::run_ops(ExecPlan& plan, const std::vector<OpDef*>& ops, bool back
         os << " are not available here -- a tensor crosses device groups without a comm op";
         throw Error(os.str());
       }
+      static const bool trace_ops = env_int("HETU_TRACE_OPS", 0) != 0;     // last line per rank = where a hang sits
+      if (trace_ops) {
+        std::ostringstream os;
+        os << "[trace r" << CommRuntime::get().rank() << " mb" << mb << (backward ? " bw] " : " fw] ") << op->name() << " (" << op->type << ")";
+        if (op->type == "comm") os << " comm_type=" << (int)plan.comm[op->id].type << " peer=" << plan.comm[op->id].peer;
+        std::cerr << os.str() << std::endl;
+      }
       try {
         if (op->type == "comm") {
           if (!tp_fused_comm(plan, op, ins, outs)) outs = exec_comm(plan.comm[op->id], op, ins, rc);
