@@ -17,6 +17,8 @@
 #include "../kernels/kernels.h"
 #include "../planner/dp_core.h"
 #include "../v1/embedding_cache.h"
+#include <torch/csrc/cuda/CUDAPluggableAllocator.h>
+
 #include "../runtime/symm_mem.h"
 #include "../runtime/memory_pool.h"
 #include "../v1/ps_server.h"
@@ -537,6 +539,45 @@ PYBIND11_MODULE(_C, m) {
                   : s == "ERROR" ? LogLevel::ERROR : s == "FATAL" ? LogLevel::FATAL : LogLevel::WARN);
   });
   m.def("dtype_size", [](const std::string& n) { return dtype_size(dtype_from_name(n)); });
+
+  // ---------------------------------------------------------------- caching memory pool on the tensor path
+  // Replaces PyTorch's CUDA caching allocator by this framework's CachingMemoryPool (csrc/runtime/memory_pool.cc) through
+  // the pluggable-allocator interface: every at::Tensor the executor and the ops allocate then comes from the pool --
+  // per-stream free lists, split / merge, event-based cross-stream reuse (record_stream -> mark_used_by_stream), the
+  // HETU_MAX_SPLIT_SIZE_MB / HETU_MAX_INTERNAL_FRAGMENT_SIZE_MB / HETU_PRE_ALLOCATE_SIZE_MB knobs and the pool statistics.
+  // Must run before the first CUDA allocation of the process (hetu_b200/__init__.py does it when HETU_NATIVE_ALLOCATOR=1).
+  // (ref: hetu/impl/memory/CUDACachingMemoryPool.cu on the NDArray allocation path, hetu/core/memory_pool.h)
+  m.def("use_native_allocator", [] {
+    static bool installed = false;
+    if (installed) return true;
+    auto pool_of = [](int device) { return MemoryPoolRegistry::instance().get("cuda:" + std::to_string(device)); };
+    auto alloc = torch::cuda::CUDAPluggableAllocator::createCustomAllocator(
+        [pool_of](size_t size, int device, cudaStream_t stream) -> void* {
+          if (size == 0) return nullptr;
+          void* p = pool_of(device)->alloc(size, (int64_t)(uintptr_t)stream);
+          if (p == nullptr) {                       // out of memory: give cached segments back and retry once
+            MemoryPoolRegistry::instance().empty_all_caches();
+            p = pool_of(device)->alloc(size, (int64_t)(uintptr_t)stream);
+          }
+          HB_CHECK(p != nullptr) << "CUDA out of memory: native pool could not serve " << size << " bytes on device " << device << "\n"
+                                 << pool_of(device)->summary();
+          return p;
+        },
+        [pool_of](void* ptr, size_t, int device, cudaStream_t) {
+          if (ptr != nullptr) pool_of(device)->free(ptr);
+        });
+    auto* plug = dynamic_cast<torch::cuda::CUDAPluggableAllocator::CUDAPluggableAllocator*>(alloc.get());
+    HB_CHECK(plug != nullptr) << "unexpected allocator type";
+    plug->set_record_stream_fn([](void* ptr, cudaStream_t stream) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      MemoryPoolRegistry::instance().get("cuda:" + std::to_string(dev))->mark_used_by_stream(ptr, (int64_t)(uintptr_t)stream);
+    });
+    plug->set_reset_fn([] { MemoryPoolRegistry::instance().empty_all_caches(); });
+    torch::cuda::CUDAPluggableAllocator::changeCurrentAllocator(alloc);
+    installed = true;
+    return true;
+  });
 
   // ---------------------------------------------------------------- symmetric memory (NVLink peer access)
   m.def("symm_alloc", [](const std::string& name, size_t bytes, int rank, int world) {

@@ -441,6 +441,45 @@ def test_blockwise_quantisation_kernels_match_host_reference(kind):
         close(torch.as_tensor(y.numpy()), ref, 0.08, 0.02)
 
 
+def test_native_caching_pool_as_the_tensor_allocator():
+    """HETU_NATIVE_ALLOCATOR=1: the framework's CachingMemoryPool replaces PyTorch's CUDA allocator (pluggable allocator), a small
+    GPT trains on it with the same losses, and the pool's statistics show the traffic (cache hits, splits)"""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import os, sys, json, torch
+import hetu_b200 as ht
+from hetu_b200.models import GPTConfig, GPTLMHeadModel, generate_ds_parallel_config
+cfg = GPTConfig(vocab_size=1024, n_positions=256, n_embd=256, n_layer=2, n_head=2)
+with ht.graph("define_and_run", create_new=True) as g, ht.autocast("bfloat16"):
+    model = GPTLMHeadModel(cfg, [generate_ds_parallel_config(2, 1, 1, 1, 1)])
+    ids, pos, lab = (ht.placeholder("int64", [512], name=n) for n in ("ids", "pos", "lab"))
+    loss = model(ids, pos, lab, seq_len=256)
+    op = ht.AdamOptimizer(lr=1e-3).minimize(loss)
+    x = torch.randint(0, 1024, (512,), generator=torch.Generator().manual_seed(0)).cuda()
+    p = torch.arange(256).repeat(2).cuda()
+    ls = [float(g.run(loss, [loss, op], {ids: x, pos: p, lab: torch.roll(x, -1)})[0]) for _ in range(6)]
+torch.cuda.synchronize()
+st = ht._C.get_memory_pool("cuda:0").stats() if os.environ.get("HETU_NATIVE_ALLOCATOR") == "1" else None
+print("RESULT " + json.dumps({"losses": ls, "allocs": st.num_alloc if st else 0, "hits": st.cache_hits if st else 0,
+                              "reserved": st.reserved if st else 0, "torch_reserved": torch.cuda.memory_reserved()}))
+"""
+    outs = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, HETU_NATIVE_ALLOCATOR=flag, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+        assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-3000:]
+        import json
+        outs[flag] = json.loads(line[0][7:])
+    a, b = outs["0"], outs["1"]
+    assert b["allocs"] > 100 and b["hits"] > 0 and b["reserved"] > 0, b
+    assert b["torch_reserved"] == 0, "PyTorch's own caching allocator must be out of the picture"
+    for x, y in zip(a["losses"], b["losses"]):
+        assert abs(x - y) < 1e-3 * max(1.0, abs(x)), (a["losses"], b["losses"])
+
+
 def test_gpt_block_training_matches_fp32_reference():
     """tiny GPT: native bf16 training vs the same graph on CPU fp32 -- loss curves must agree to bf16 accuracy"""
     from hetu_b200.models import GPTConfig, GPTLMHeadModel, generate_ds_parallel_config
