@@ -461,6 +461,14 @@ PYBIND11_MODULE(_C, m) {
   m.def("comm_reduce_scatter", [](const at::Tensor& x, const std::vector<int>& r, int dim) { return CommRuntime::get().reduce_scatter(x, r, dim); });
   m.def("comm_all_to_all", [](const at::Tensor& x, const std::vector<int>& r, int sd, int cd) { return CommRuntime::get().all_to_all(x, r, sd, cd); });
   m.def("comm_broadcast", [](const at::Tensor& x, const std::vector<int>& r, int root) { return CommRuntime::get().broadcast(x, r, root); });
+  m.def("comm_all_reduce_coalesce", [](const std::vector<at::Tensor>& xs, const std::vector<int>& r, const std::string& red) {
+    return CommRuntime::get().all_reduce_coalesce(xs, r, reduction_from_name(red));
+  }, py::arg("tensors"), py::arg("ranks"), py::arg("reduction") = "sum");
+  m.def("comm_reduce", [](const at::Tensor& x, const std::vector<int>& r, int root, const std::string& red) {
+    return CommRuntime::get().reduce(x, r, root, reduction_from_name(red));
+  }, py::arg("x"), py::arg("ranks"), py::arg("root"), py::arg("reduction") = "sum");
+  m.def("comm_gather", [](const at::Tensor& x, const std::vector<int>& r, int root) { return CommRuntime::get().gather(x, r, root); });
+  m.def("comm_scatter", [](const at::Tensor& x, const std::vector<int>& r, int root) { return CommRuntime::get().scatter(x, r, root); });
 
   // ---------------------------------------------------------------- schedules / planner / cache
   m.def("generate_gpipe_schedule", [](int S, int M, bool inf) {

@@ -178,6 +178,65 @@ at::Tensor CommRuntime::all_to_all(const at::Tensor& x, const std::vector<int>& 
   if (concat_dim == 0) return out;
   return at::cat(at::chunk(out, n, 0), concat_dim);
 }
+std::vector<at::Tensor> CommRuntime::all_reduce_coalesce(const std::vector<at::Tensor>& xs, const std::vector<int>& ranks, ReductionType red) {
+  if (xs.empty() || ranks.size() <= 1 || !initialized()) return xs;
+  std::vector<at::Tensor> flat;
+  flat.reserve(xs.size());
+  const at::ScalarType dt = xs[0].scalar_type();
+  for (auto& x : xs) {
+    HB_CHECK(x.scalar_type() == dt && x.device() == xs[0].device()) << "all_reduce_coalesce: tensors of one bucket share dtype and device";
+    flat.push_back(x.reshape({-1}));
+  }
+  at::Tensor buf = at::cat(flat, 0);
+  std::vector<at::Tensor> v = {buf};
+  c10d::AllreduceOptions o;
+  o.reduceOp = to_c10d(red);
+  group(ranks)->allreduce(v, o)->wait();
+  if (red == ReductionType::MEAN) buf.div_((double)ranks.size());
+  bytes_["all_reduce"] += buf.nbytes();
+  calls_["all_reduce_coalesce"] += 1;
+  std::vector<at::Tensor> out;
+  int64_t off = 0;
+  for (auto& x : xs) {
+    out.push_back(buf.narrow(0, off, x.numel()).reshape(x.sizes()));
+    off += x.numel();
+  }
+  return out;
+}
+static int index_in(const std::vector<int>& ranks, int r) {
+  for (size_t i = 0; i < ranks.size(); ++i) if (ranks[i] == r) return (int)i;
+  return -1;
+}
+at::Tensor CommRuntime::reduce(const at::Tensor& x, const std::vector<int>& ranks, int root_rank, ReductionType red) {
+  if (ranks.size() <= 1 || !initialized()) return x;
+  at::Tensor buf = x.contiguous().clone();
+  std::vector<at::Tensor> v = {buf};
+  c10d::ReduceOptions o;
+  o.reduceOp = to_c10d(red);
+  o.rootRank = std::max(index_in(ranks, root_rank), 0);
+  group(ranks)->reduce(v, o)->wait();
+  if (red == ReductionType::MEAN && rank_ == root_rank) buf.div_((double)ranks.size());
+  calls_["reduce"] += 1;
+  bytes_["reduce"] += buf.nbytes();
+  return buf;          // meaningful on the root only
+}
+at::Tensor CommRuntime::gather(const at::Tensor& x, const std::vector<int>& ranks, int root_rank) {
+  if (ranks.size() <= 1 || !initialized()) return x.unsqueeze(0);
+  // every rank contributes equally sized pieces: an all-gather restricted to the root's view keeps this one collective on
+  // backends without a native gather (NCCL)
+  at::Tensor all = all_gather(x.contiguous().unsqueeze(0), ranks, 0);
+  calls_["gather"] += 1;
+  return rank_ == root_rank ? all : at::empty({0}, x.options());
+}
+at::Tensor CommRuntime::scatter(const at::Tensor& x, const std::vector<int>& ranks, int root_rank) {
+  if (ranks.size() <= 1 || !initialized()) return x.dim() > 0 && x.size(0) == 1 ? x[0] : x;
+  const int64_t n = (int64_t)ranks.size();
+  // the root's [n, ...] tensor travels as a broadcast and every rank keeps its slice (message count 1; NCCL has no scatter)
+  at::Tensor full = broadcast(x, ranks, root_rank);
+  HB_CHECK(full.dim() > 0 && full.size(0) == n) << "scatter: the root passes one slice per rank along dim 0";
+  calls_["scatter"] += 1;
+  return full[std::max(index_in(ranks, rank_), 0)].contiguous();
+}
 PG CommRuntime::p2p_group(int channel) {
   channel = channel ? 1 : 0;
   if (!p2p_pg_[channel]) {

@@ -48,6 +48,15 @@ class CommRuntime {
                             ReductionType red = ReductionType::SUM, bool fp32_reduce = false);
   at::Tensor broadcast(const at::Tensor& x, const std::vector<int>& ranks, int root_rank);
   at::Tensor all_to_all(const at::Tensor& x, const std::vector<int>& ranks, int split_dim = 0, int concat_dim = 0);
+  // bucketed all-reduce: the tensors are packed into one flat buffer, reduced in ONE collective and unpacked -- many small
+  // gradients cost one launch latency instead of one each (ref: NCCLCommunicationGroupDef::AllReduceCoalesce,
+  // hetu/impl/communication/nccl_comm_group.cu:246-313)
+  std::vector<at::Tensor> all_reduce_coalesce(const std::vector<at::Tensor>& xs, const std::vector<int>& ranks,
+                                              ReductionType red = ReductionType::SUM);
+  // rooted collectives (ref: nccl_comm_group.cu Reduce :354, Gather / Scatter :465-563 -- send/recv fans there)
+  at::Tensor reduce(const at::Tensor& x, const std::vector<int>& ranks, int root_rank, ReductionType red = ReductionType::SUM);
+  at::Tensor gather(const at::Tensor& x, const std::vector<int>& ranks, int root_rank);      // root: [n, ...]; others: empty
+  at::Tensor scatter(const at::Tensor& x, const std::vector<int>& ranks, int root_rank);     // root passes [n, ...], all get [...]
   // asynchronous gradient synchronisation: the collective is enqueued on the communication stream of the process group
   // (behind everything issued so far on the compute stream) and completed later by finish() -- the backward pass keeps
   // computing in between (ref: executable_graph.cc:1137-1150 overlapped grad reduce on kBridgeStream)

@@ -353,3 +353,11 @@ def test_overlapped_gradient_reduce_matches_the_serial_path(zero):
     got = _losses(outs)
     for a, b in zip(got, ref):
         assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, ref)
+
+
+@pytest.mark.dist
+def test_comm_group_api_coalesce_reduce_gather_scatter():
+    ok, outs = run_workers(os.path.join(os.path.dirname(__file__), "workers", "comm_api_worker.py"), 3)
+    assert ok, "\n-----\n".join(outs)
+    line = [l for o in outs for l in o.splitlines() if l.startswith("COMMAPI ")][0]
+    assert json.loads(line[8:])["ok"]
