@@ -13,6 +13,16 @@ void wgrad_to_peer_slots(const at::Tensor& dy, const at::Tensor& x, bool trans_b
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// barrier among the ranks of ONE ZeRO group.  (A world barrier here dead-locks pipeline-parallel jobs: the stages prepare
+// their groups at different times -- or not at all when a stage has nothing to shard -- while the other stage already
+// waits in a p2p transfer; observed as the tp2 x pp2 hang on 4 GPUs.)
+static void group_barrier(const std::vector<int>& ranks) {
+  auto& comm = CommRuntime::get();
+  at::Tensor t = at::zeros({1}, at::TensorOptions().dtype(at::kFloat).device(aten_device()));
+  t = comm.all_reduce(t, ranks, ReductionType::SUM);
+  if (t.is_cuda()) cuda_ok(cudaStreamSynchronize(cur_stream()), "group barrier");
+}
+
 std::shared_ptr<ZeroFusedState> Executor::zero_fused_prepare(ExecPlan& plan) {
   auto st = std::make_shared<ZeroFusedState>();
   auto& comm = CommRuntime::get();
@@ -79,7 +89,7 @@ std::shared_ptr<ZeroFusedState> Executor::zero_fused_prepare(ExecPlan& plan) {
     handles.emplace_back(reinterpret_cast<const char*>(all.data_ptr()) + (size_t)r * handle.size(), handle.size());
   if (want_vmm) {
     sm.open_vmm(st->arena_name, handles);
-    comm.barrier();                               // every device joined the multicast object before memory is bound
+    group_barrier(st->ranks);                     // every device joined the multicast object before memory is bound
     sm.bind_multicast(st->arena_name);
     cuda_ok(cudaDeviceSynchronize(), "multicast bind");
   } else sm.open(st->arena_name, handles);
@@ -127,7 +137,7 @@ std::shared_ptr<ZeroFusedState> Executor::zero_fused_prepare(ExecPlan& plan) {
   std::memcpy(tab.data_ptr(), step_ptrs.data(), step_ptrs.size() * sizeof(int64_t*));
   st->step_table = tab.to(aten_device());
   cuda_ok(cudaStreamSynchronize(cur_stream()), "zero arena setup");
-  comm.barrier();
+  group_barrier(st->ranks);
   st->ok = true;
   return st;
 }
