@@ -11,19 +11,7 @@ import hetu_b200 as _impl
 from hetu_b200 import *  # noqa: F401,F403
 
 
-class _AliasLoader(importlib.abc.Loader):
-    def __init__(self, real):
-        self.real = real
-        self.saved = (getattr(real, "__spec__", None), getattr(real, "__loader__", None))
-
-    def create_module(self, spec):
-        return self.real
-
-    def get_code(self, fullname):       # `python -m hetu.x.y` (runpy) executes the real module's code as __main__
-        return self.saved[1].get_code(self.real.__name__)
-
-    def exec_module(self, module):      # the import machinery re-stamped __spec__ / __loader__ with the alias: put the real ones back
-        module.__spec__, module.__loader__ = self.saved
+from hetu_b200._refpaths import AliasLoader as _AliasLoader
 
 
 class _AliasFinder(importlib.abc.MetaPathFinder):

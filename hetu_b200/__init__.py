@@ -5,6 +5,9 @@ hot switching, Galvatron planning) over hand-written sm_100a kernels.  `import h
 import os as _os
 
 from . import _C  # noqa: F401  native core (must be built in-tree: `python build.py`)
+from . import _refpaths as _refpaths
+
+_refpaths.install()      # reference module paths that are table entries instead of files
 
 if _os.environ.get("HETU_NATIVE_ALLOCATOR", "0") == "1":
     # put the framework's own caching memory pool under every CUDA tensor (must happen before the first CUDA allocation)

@@ -86,3 +86,24 @@ def build_tokenizer(tokenizer_type: str = "byte", vocab_file: Optional[str] = No
             decode = staticmethod(enc.decode)
         return _T()
     raise ValueError(f"unknown tokenizer type {tokenizer_type}")
+
+
+# class-style constructors of the reference's per-tokenizer modules (ref: python/hetu/data/tokenizers/{gpt2,hf,sentencepiece,
+# tiktoken}_tokenizer.py, models/llama/llama_tokenizer.py)
+def GPT2BPETokenizer(vocab_file, merge_file):
+    return build_tokenizer("gpt2", vocab_file=vocab_file, merge_file=merge_file)
+
+
+def HFTokenizer(name_or_path):
+    return build_tokenizer("hf", name_or_path=name_or_path)
+
+
+def SentencePieceTokenizer(model_file):
+    return build_tokenizer("sentencepiece", vocab_file=model_file)
+
+
+LlamaTokenizer = SentencePieceTokenizer
+
+
+def TikTokenizer(name="cl100k_base"):
+    return build_tokenizer("tiktoken", name_or_path=name)

@@ -26,7 +26,8 @@ class Module:
         if isinstance(value, Module):
             self._modules[name] = value
             object.__setattr__(value, "_module_name", name)
-        elif isinstance(value, Tensor) and (value.requires_grad or value.producer_type == "variable"):
+        elif isinstance(value, Tensor) and value.producer_type == "variable":
+            # only graph variables are parameters: an activation kept on the module (e.g. an auxiliary loss) is not
             self._parameters[name] = value
         object.__setattr__(self, name, value)
 

@@ -79,11 +79,14 @@ class HardwareProfiler:
 
     def profile(self, world: int, gpus_per_node: int = 8) -> HardwareProfile:
         hw = HardwareProfile(gpus_per_node=gpus_per_node)
-        from .. import distributed
+        from .. import _C, distributed
         r = distributed.rank()
         n = 2
         while n <= world:
             consecutive = [list(range(i, i + n)) for i in range(0, world, n)]
+            if world > 1 and _C.comm_initialized():
+                for g in consecutive:          # process groups are created collectively: every rank walks the same list
+                    _C.comm_create_group(g)
             mine = next(g for g in consecutive if r in g)
             hw.allreduce_bw[n] = self.allreduce_bandwidth(mine)
             n *= 2
