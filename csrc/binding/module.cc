@@ -877,7 +877,7 @@ PYBIND11_MODULE(_C, m) {
 
   // direct kernel entry points (benchmarks / numerics tests)
   m.def("gemm", [](const at::Tensor& a, const at::Tensor& b, bool a_mn, bool b_mn, const py::object& bias, const std::string& act,
-                   bool out_fp32, int cta_group) {
+                   bool out_fp32, int cta_group, int block_n) {
     HB_CHECK(a.is_cuda() && a.scalar_type() == at::kBFloat16 && a.dim() == 2 && b.dim() == 2) << "gemm expects 2-D CUDA bf16";
     const int64_t M = a_mn ? a.size(1) : a.size(0), K = a_mn ? a.size(0) : a.size(1), N = b_mn ? b.size(1) : b.size(0);
     at::Tensor c = at::empty({M, N}, a.options().dtype(out_fp32 ? at::kFloat : at::kBFloat16));
@@ -891,8 +891,9 @@ PYBIND11_MODULE(_C, m) {
     if (!bias.is_none()) { bt = py::cast<at::Tensor>(bias); g.bias = bt.data_ptr(); }
     g.act = act == "gelu" ? 1 : act == "relu" ? 2 : act == "gelu_tanh" ? 3 : act == "silu" ? 4 : 0;
     g.cta_group = cta_group;
+    g.block_n = block_n;
     cuda_ok(gemm_bf16(g, cur_stream()), "gemm");
     return c;
   }, py::arg("a"), py::arg("b"), py::arg("a_mn_major") = false, py::arg("b_mn_major") = false, py::arg("bias") = py::none(),
-     py::arg("act") = "none", py::arg("out_fp32") = false, py::arg("cta_group") = 0);
+     py::arg("act") = "none", py::arg("out_fp32") = false, py::arg("cta_group") = 0, py::arg("block_n") = 0);
 }

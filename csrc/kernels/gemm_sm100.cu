@@ -2,6 +2,7 @@
 #include "gemm_sm100.h"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -25,10 +26,11 @@ int num_sms() {
   return n;
 }
 
-template <int G, bool AMN, bool BMN, int ST, typename OutT, bool FP8 = false>
+template <int G, bool AMN, bool BMN, int ST, typename OutT, bool FP8 = false, int BN = 256>
 cudaError_t launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  auto kern = gemm_bf16_sm100_kernel<G, AMN, BMN, ST, OutT, FP8>;
-  constexpr int smem = gemm_detail::smem_bytes(G, ST);
+  auto kern = gemm_bf16_sm100_kernel<G, AMN, BMN, ST, OutT, FP8, BN>;
+  constexpr int smem = gemm_detail::smem_bytes(G, ST, BN);
+  static_assert(smem <= 227 * 1024, "shared memory per CTA");
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -36,7 +38,7 @@ cudaError_t launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     attr_set = true;
   }
   const int tiles_m = (p.M + 128 * G - 1) / (128 * G);
-  const int tiles_n = (p.N + 255) / 256;
+  const int tiles_n = (p.N + BN - 1) / BN;
   int clusters = num_sms() / G;
   if (clusters > tiles_m * tiles_n) clusters = tiles_m * tiles_n;
   cudaLaunchConfig_t cfg = {};
@@ -55,13 +57,32 @@ cudaError_t launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   return cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
 }
 
-template <int G, int ST, typename OutT>
+template <int G, int ST, typename OutT, int BN = 256>
 cudaError_t dispatch_major(bool amn, bool bmn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                            cudaStream_t s) {
-  if (!amn && !bmn) return launch_cfg<G, false, false, ST, OutT>(ta, tb, p, s);
-  if (!amn && bmn) return launch_cfg<G, false, true, ST, OutT>(ta, tb, p, s);
-  if (amn && !bmn) return launch_cfg<G, true, false, ST, OutT>(ta, tb, p, s);
-  return launch_cfg<G, true, true, ST, OutT>(ta, tb, p, s);
+  if (!amn && !bmn) return launch_cfg<G, false, false, ST, OutT, false, BN>(ta, tb, p, s);
+  if (!amn && bmn) return launch_cfg<G, false, true, ST, OutT, false, BN>(ta, tb, p, s);
+  if (amn && !bmn) return launch_cfg<G, true, false, ST, OutT, false, BN>(ta, tb, p, s);
+  return launch_cfg<G, true, true, ST, OutT, false, BN>(ta, tb, p, s);
+}
+
+// Persistent grid of `clusters` CTA pairs: fraction of the last wave that does work, for a given tile width.
+double wave_efficiency(int M, int N, int bn, int clusters) {
+  const int64_t tiles = int64_t((M + 255) / 256) * ((N + bn - 1) / bn);
+  const int64_t waves = (tiles + clusters - 1) / clusters;
+  return double(tiles) / double(waves * clusters);
+}
+
+// 128-column tiles when the 256-column tiling leaves a large part of the last wave idle and the narrower one does not
+// (HETU_GEMM_BN = 128 / 256 forces a width, 0 = this heuristic)
+int pick_block_n(const GemmCall& c) {
+  static const int forced = [] { const char* e = getenv("HETU_GEMM_BN"); return e ? atoi(e) : -1; }();
+  if (c.block_n == 128 || c.block_n == 256) return c.block_n;
+  if (forced == 128 || forced == 256) return forced;
+  if (forced != 0) return 256;            // heuristic is opt-in until measured: HETU_GEMM_BN=0
+  const int clusters = num_sms() / 2;
+  const double e256 = wave_efficiency(c.M, c.N, 256, clusters), e128 = wave_efficiency(c.M, c.N, 128, clusters);
+  return (e256 < 0.92 && e128 > e256 + 0.06) ? 128 : 256;
 }
 
 }  // namespace
@@ -78,7 +99,10 @@ cudaError_t gemm_bf16(const GemmCall& c, cudaStream_t stream) {
   if ((c.aux_in || c.aux_out) && (c.ld_aux & 7)) return cudaErrorMisalignedAddress;
 
   int G = c.cta_group == 0 ? 2 : c.cta_group;
-  const int load_n = 256 / G;
+  // the narrow tile exists for the plain bf16 pair kernel only (not fp8, not the fused all-gather / reduce-scatter variants)
+  const bool narrow_ok = G == 2 && !c.fp8 && c.ag_src == nullptr && !(c.peer_c != nullptr && c.rows_per_rank > 0);
+  const int BN = narrow_ok ? pick_block_n(c) : 256;
+  const int load_n = BN / G;
 
   CUtensorMap ta, tb;
   bool ok;
@@ -134,6 +158,10 @@ cudaError_t gemm_bf16(const GemmCall& c, cudaStream_t stream) {
     }
     if (c.out == GemmOut::BF16) return launch_cfg<1, false, false, 4, __nv_bfloat16, true>(ta, tb, p, stream);
     return launch_cfg<1, false, false, 4, float, true>(ta, tb, p, stream);
+  }
+  if (G == 2 && BN == 128) {
+    if (c.out == GemmOut::BF16) return dispatch_major<2, 8, __nv_bfloat16, 128>(c.a_mn_major, c.b_mn_major, ta, tb, p, stream);
+    return dispatch_major<2, 8, float, 128>(c.a_mn_major, c.b_mn_major, ta, tb, p, stream);
   }
   if (G == 2) {
     if (c.out == GemmOut::BF16) return dispatch_major<2, 6, __nv_bfloat16>(c.a_mn_major, c.b_mn_major, ta, tb, p, stream);

@@ -62,7 +62,7 @@ struct GemmParams {
 namespace gemm_detail {
 
 constexpr int BLOCK_M = 128;   // rows of A per CTA
-constexpr int BLOCK_N = 256;   // UMMA N (columns of the accumulator)
+constexpr int BLOCK_N = 256;   // default UMMA N (columns of the accumulator); the kernel's kBN parameter may narrow it to 128
 constexpr int BLOCK_K = 64;    // 128 bytes of bf16 = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;     // 2 warps per TMEM lane quarter, each owning half the columns
@@ -71,9 +71,9 @@ constexpr int kAccumStages = 2;
 constexpr int kTmemCols = 512;
 
 __host__ __device__ constexpr int a_stage_bytes() { return BLOCK_M * BLOCK_K * 2; }
-__host__ __device__ constexpr int b_stage_bytes(int cta_group) { return (BLOCK_N / cta_group) * BLOCK_K * 2; }
-__host__ __device__ constexpr int smem_bytes(int cta_group, int stages) {
-  return stages * (a_stage_bytes() + b_stage_bytes(cta_group)) + 1024 /*align slack*/ + 256 /*barriers*/ +
+__host__ __device__ constexpr int b_stage_bytes(int cta_group, int bn = BLOCK_N) { return (bn / cta_group) * BLOCK_K * 2; }
+__host__ __device__ constexpr int smem_bytes(int cta_group, int stages, int bn = BLOCK_N) {
+  return stages * (a_stage_bytes() + b_stage_bytes(cta_group, bn)) + 1024 /*align slack*/ + 256 /*barriers*/ +
          kEpiWarps * 4096 /*epilogue store staging*/;
 }
 
@@ -159,14 +159,16 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
 
 // kFp8: both operands are e4m3 bytes (K-major only); a 128-byte swizzle row then holds 128 K elements and one
 // tcgen05.mma.kind::f8f6f4 consumes 32 of them -- the smem stage size, descriptor strides and pipeline are unchanged.
-template <int kCtaGroup, bool kAMN, bool kBMN, int kStages, typename OutT, bool kFp8 = false>
+// kBN: accumulator columns per tile.  256 is the default; 128 halves the tile for outputs whose 256-wide tile count does not
+// fill the last wave of the persistent grid (e.g. 8192 x 2048: 256 tiles on 74 CTA pairs = 3.46 waves; 512 half tiles = 6.92).
+template <int kCtaGroup, bool kAMN, bool kBMN, int kStages, typename OutT, bool kFp8 = false, int kBN = 256>
 __global__ void __launch_bounds__(gemm_detail::kNumThreads, 1)
 gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
                        const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
   using namespace gemm_detail;
   constexpr int A_STAGE = a_stage_bytes();
-  constexpr int B_STAGE = b_stage_bytes(kCtaGroup);
-  constexpr int LOAD_N = BLOCK_N / kCtaGroup;
+  constexpr int B_STAGE = b_stage_bytes(kCtaGroup, kBN);
+  constexpr int LOAD_N = kBN / kCtaGroup;
   constexpr int TILE_M = BLOCK_M * kCtaGroup;
   constexpr uint32_t kTxBytes = (A_STAGE + B_STAGE) * kCtaGroup;
   constexpr int kAtomBytes = BLOCK_K * 64 * 2;  // one 64(MN) x BLOCK_K MN-major box
@@ -189,7 +191,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const bool leader = rank == 0;
 
   const int tiles_m = (p.M + TILE_M - 1) / TILE_M;
-  const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int tiles_n = (p.N + kBN - 1) / kBN;
   const int num_tiles = tiles_m * tiles_n;
   constexpr int BLOCK_K_E = kFp8 ? BLOCK_K * 2 : BLOCK_K;   // K elements per stage (128 bytes per row either way)
   static_assert(!kFp8 || (!kAMN && !kBMN), "fp8 operands must be K-major");
@@ -230,7 +232,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         int tm, tn; tile_coords(tile, tiles_m, tiles_n, tm, tn, m_rotate);
         const int m0 = tm * TILE_M + int(rank) * BLOCK_M;
-        const int n0 = tn * BLOCK_N + int(rank) * LOAD_N;
+        const int n0 = tn * kBN + int(rank) * LOAD_N;
         if (ag_fused && m0 < p.M) {
           // the 128 rows of this CTA's A tile are one all-gather chunk: wait until every CTA delivered its slice
           const uint32_t* f = p.ag_flags + (m0 >> 7);
@@ -271,8 +273,8 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp == 1) {
     // ========================= MMA issuer (leader CTA, one thread) =========================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = kFp8 ? ptx::make_idesc(TILE_M, BLOCK_N, 0, 0, false, false)      // e4m3 x e4m3 -> f32
-                                      : ptx::make_idesc(TILE_M, BLOCK_N, 1, 1, kAMN, kBMN);
+      constexpr uint32_t idesc = kFp8 ? ptx::make_idesc(TILE_M, kBN, 0, 0, false, false)      // e4m3 x e4m3 -> f32
+                                      : ptx::make_idesc(TILE_M, kBN, 1, 1, kAMN, kBMN);
       const uint64_t a_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a), kAMN ? kAtomBytes : 0, 1024);
       const uint64_t b_desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b), kBMN ? kAtomBytes : 0, 1024);
       // descriptor-address increments (units of 16 B) per UMMA_K step
@@ -283,7 +285,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         ptx::mbar_wait(&tempty_bar[as], aph ^ 1);
         ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        const uint32_t tmem_d = tmem_base + as * kBN;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[s], ph);
           ptx::tc_fence_after();
@@ -345,15 +347,15 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // ========================= epilogue =========================
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int chalf = (warp - 4) >> 2;  // which half of the accumulator columns this warp drains
-    constexpr int kChunksPerWarp = BLOCK_N / 32 / (kEpiWarps / 4);
+    constexpr int kChunksPerWarp = kBN / 32 / (kEpiWarps / 4);
     int as = 0; uint32_t aph = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       int tm, tn; tile_coords(tile, tiles_m, tiles_n, tm, tn, m_rotate);
       const int row = tm * TILE_M + int(rank) * BLOCK_M + q * 32 + lane;
-      const int n_base = tn * BLOCK_N;
+      const int n_base = tn * kBN;
       ptx::mbar_wait(&tfull_bar[as], aph);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N;
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * kBN;
       const bool row_ok = row < p.M;
       OutT* crow = reinterpret_cast<OutT*>(p.C) + int64_t(row) * p.ldc;
       if (p.rows_per_rank > 0 && row_ok) {

@@ -40,6 +40,7 @@ struct GemmCall {
   void* const* peer_c = nullptr;   // host array of `world` mapped staging buffers, each [world, rows_per_rank, N]
   int world = 1, my_rank = 0, rows_per_rank = 0;
   int cta_group = 0;  // 0 = auto (2), 1 or 2 to force
+  int block_n = 0;    // accumulator columns per tile: 0 = auto (wave-quantisation heuristic), 256 or 128 to force (128: bf16, cta_group 2)
   // fused all-gather -> GEMM (see GemmParams::ag_src): A is the local gather target, ag_src[r] rank r's symmetric shard
   const void* const* ag_src = nullptr;
   uint32_t* ag_flags = nullptr;

@@ -58,6 +58,27 @@ def test_linear_fwd_bwd(M, N, K, act):
     close(torch.as_tensor(B.grad.numpy()), br.grad, 0.03 * math.sqrt(M), 0.03)
 
 
+@pytest.mark.parametrize("M,N,K,amn,bmn", [(512, 384, 256, False, False), (1000, 520, 264, False, True), (768, 2048, 512, True, True),
+                                           (2048, 2048, 1024, True, False)])
+def test_gemm_narrow_accumulator_tile_matches_wide_tile_and_fp32(M, N, K, amn, bmn):
+    """the 128-column accumulator tile (wave-quantisation variant) against the 256-column one and an fp32 matmul, all four
+    operand majors, ragged edges, with a fused bias + GELU epilogue"""
+    C = ht._C
+    torch.manual_seed(0)
+    a = (torch.randn((K, M) if amn else (M, K), device="cuda") * 0.1).bfloat16()
+    b = (torch.randn((K, N) if bmn else (N, K), device="cuda") * 0.1).bfloat16()
+    bias = (torch.randn(N, device="cuda") * 0.1).bfloat16()
+    ref = (a.float().t() if amn else a.float()) @ (b.float() if bmn else b.float().t())
+    for kw in ({}, {"bias": bias, "act": "gelu"}):
+        o128 = C.gemm(a, b, amn, bmn, block_n=128, **kw).float()
+        o256 = C.gemm(a, b, amn, bmn, block_n=256, **kw).float()
+        want = torch.nn.functional.gelu(ref + bias.float()) if kw else ref
+        assert (o128 - want).abs().max() <= 2e-2 * want.abs().max() + 1e-3
+        assert torch.equal(o128, o256)          # same K order per output element -> bit-identical
+    o32 = C.gemm(a, b, amn, bmn, out_fp32=True, block_n=128)
+    assert o32.dtype == torch.float32 and (o32 - ref).abs().max() <= 1e-2 * ref.abs().max() + 1e-3
+
+
 def test_linear_residual_epilogue():
     x, w, r = bf(512, 256, seed=1), bf(384, 256, scale=0.06, seed=2), bf(512, 384, seed=3)
     y = ht.linear(leaf(x, False), leaf(w, False), None, residual=leaf(r, False))
