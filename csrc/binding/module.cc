@@ -9,6 +9,7 @@
 #include "../core/device.h"
 #include "../core/ds.h"
 #include "../core/symbol.h"
+#include "../core/utils.h"
 #include "../graph/exec.h"
 #include "../graph/ir.h"
 #include "../graph/op_utils.h"
@@ -874,6 +875,70 @@ PYBIND11_MODULE(_C, m) {
     cuda_ok(gemm_bf16(g, cur_stream()), "gemm_fp8");
     return c;
   }, py::arg("qa"), py::arg("sa"), py::arg("qb"), py::arg("sb"), py::arg("out_fp32") = false, py::arg("cta_group") = 0);
+
+  // ------------------------------------------------------------------ host utilities
+  py::class_<ContextStore, std::shared_ptr<ContextStore>>(m, "ContextStore")
+      .def(py::init<>())
+      .def("put", [](ContextStore& c, const std::string& k, const py::object& v) {
+        if (py::isinstance<py::bool_>(v)) c.put<bool>(k, v.cast<bool>());
+        else if (py::isinstance<py::int_>(v)) c.put<int64_t>(k, v.cast<int64_t>());
+        else if (py::isinstance<py::float_>(v)) c.put<double>(k, v.cast<double>());
+        else if (py::isinstance<py::str>(v)) c.put<std::string>(k, v.cast<std::string>());
+        else if (THPVariable_Check(v.ptr())) c.put<at::Tensor>(k, v.cast<at::Tensor>());
+        else if (py::isinstance<py::sequence>(v)) {
+          bool all_int = true;
+          for (auto e : v) all_int = all_int && py::isinstance<py::int_>(e) && !py::isinstance<py::bool_>(e);
+          if (all_int) c.put<std::vector<int64_t>>(k, v.cast<std::vector<int64_t>>());
+          else c.put<std::vector<double>>(k, v.cast<std::vector<double>>());
+        } else throw Error("ContextStore.put: unsupported value type for '" + k + "'");
+      })
+      .def("get", [](const ContextStore& c, const std::string& k, const py::object& dflt) -> py::object {
+        if (!c.has(k)) return dflt;
+        return std::visit([](const auto& x) -> py::object { return py::cast(x); }, c.raw(k));
+      }, py::arg("key"), py::arg("default") = py::none())
+      .def("pop", [](ContextStore& c, const std::string& k) -> py::object {
+        py::object o = std::visit([](const auto& x) -> py::object { return py::cast(x); }, c.raw(k));
+        c.erase(k);
+        return o;
+      })
+      .def("contains", &ContextStore::has)
+      .def("__contains__", &ContextStore::has)
+      .def("erase", &ContextStore::erase)
+      .def("migrate_from", &ContextStore::migrate_from, py::arg("src"), py::arg("key"), py::arg("new_key") = "")
+      .def("keys", &ContextStore::keys)
+      .def("clear", &ContextStore::clear)
+      .def("__len__", &ContextStore::size);
+  py::class_<TaskQueue, std::shared_ptr<TaskQueue>>(m, "TaskQueue")
+      .def(py::init([](const std::string& name, int workers, size_t max_pending) {
+        // the destructor joins the workers, which may still need the GIL for queued Python callables: drop it while joining
+        return std::shared_ptr<TaskQueue>(new TaskQueue(name, workers, max_pending), [](TaskQueue* q) {
+          py::gil_scoped_release rel;
+          delete q;
+        });
+      }), py::arg("name"), py::arg("num_workers") = 1, py::arg("max_pending") = 1024)
+      .def("add", [](TaskQueue& q, py::function fn) {
+        // the callable is kept alive by the task and runs with the GIL held; submission may block on a full queue
+        auto holder = std::make_shared<py::function>(std::move(fn));
+        py::gil_scoped_release rel;
+        q.add([holder]() mutable {
+          py::gil_scoped_acquire gil;
+          try {
+            (*holder)();
+          } catch (py::error_already_set& e) {
+            std::string msg = e.what();
+            holder.reset();
+            throw Error(msg);
+          }
+          holder.reset();
+        });
+      })
+      .def("wait", [](TaskQueue& q) { py::gil_scoped_release rel; q.wait(); })
+      .def("shutdown", [](TaskQueue& q) { py::gil_scoped_release rel; q.shutdown(); })
+      .def_property_readonly("num_workers", &TaskQueue::num_workers)
+      .def_property_readonly("running", &TaskQueue::running)
+      .def_property_readonly("pending", &TaskQueue::pending)
+      .def_property_readonly("completed", &TaskQueue::completed)
+      .def_property_readonly("name", &TaskQueue::name);
 
   // direct kernel entry points (benchmarks / numerics tests)
   m.def("gemm", [](const at::Tensor& a, const at::Tensor& b, bool a_mn, bool b_mn, const py::object& bias, const std::string& act,

@@ -26,7 +26,7 @@ class ModelSaver:
         assert async_mode in ("thread", "process")
         self.save_dir, self.save_copies, self.save_interval = save_dir, save_copies, save_interval
         self.async_save, self.only_lora, self.save_dtype, self.async_mode = async_save, only_lora, save_dtype, async_mode
-        self._thread: Optional[threading.Thread] = None
+        self._queue = None        # native TaskQueue (one writer thread) of the `thread` mode, created on first use
         self._child: Optional[int] = None
         self._shm_blocks = []
         self.last_write_error: Optional[str] = None
@@ -40,9 +40,8 @@ class ModelSaver:
         return self.save_interval > 0 and step > 0 and step % self.save_interval == 0
 
     def wait(self):
-        if self._thread is not None:
-            self._thread.join()
-            self._thread = None
+        if self._queue is not None:
+            self._queue.wait()
         if self._child is not None:
             _, status = os.waitpid(self._child, 0)
             self._child = None
@@ -112,8 +111,10 @@ class ModelSaver:
         if not self.async_save:
             write_split_state(path, state)
         elif self.async_mode == "thread":
-            self._thread = threading.Thread(target=work, daemon=True)
-            self._thread.start()
+            if self._queue is None:
+                from ... import _C
+                self._queue = _C.TaskQueue("checkpoint-writer", 1, 2)
+            self._queue.add(work)
         else:
             pid = os.fork()
             if pid == 0:                 # writer process: only reads the shared snapshot and writes files

@@ -1,6 +1,9 @@
 """Native runtime pieces (C++): caching memory pool, random-state bookkeeping, prefetching data loader, stream roles."""
 import torch
 
+import pytest
+
+import hetu_b200 as ht
 from hetu_b200 import _C
 
 
@@ -113,3 +116,61 @@ def test_cuda_profiler_degrades_gracefully_without_a_gpu(tmp_path):
     nv = p.profile_nvlink_end()
     assert nv["tx_bytes"] >= 0 and nv["seconds"] >= 0 and isinstance(p.clocks(), dict)
     assert get_cuda_profiler() is get_cuda_profiler()
+
+
+def test_context_store_typed_entries_pop_and_migrate():
+    """ref: hetu/utils/context_store.h -- typed put / get / pop, `contains`, migrate_from with a new key"""
+    C = ht._C
+    a, b = C.ContextStore(), C.ContextStore()
+    a.put("flag", True); a.put("n", 7); a.put("eps", 1e-5); a.put("name", "ln"); a.put("shape", [2, 3]); a.put("scales", [0.5, 2.0])
+    t = torch.arange(6.0).reshape(2, 3)
+    a.put("saved", t)
+    assert a.get("flag") is True and a.get("n") == 7 and a.get("eps") == 1e-5 and a.get("name") == "ln"
+    assert a.get("shape") == [2, 3] and a.get("scales") == [0.5, 2.0] and torch.equal(a.get("saved"), t)
+    assert a.get("missing") is None and a.get("missing", 3) == 3 and "n" in a and len(a) == 7
+    assert torch.equal(a.pop("saved"), t) and "saved" not in a
+    b.migrate_from(a, "n", "count")
+    assert b.get("count") == 7 and "n" not in a
+    b.migrate_from(a, "absent")              # nothing to move: no entry appears
+    assert b.keys() == ["count"]
+    with pytest.raises(ht.HetuError):
+        a.pop("saved")
+
+
+def test_task_queue_runs_tasks_on_workers_with_back_pressure_and_error_report():
+    """ref: hetu/utils/task_queue.h -- N workers drain a bounded queue; `wait` returns when everything submitted has run and
+    surfaces a task's exception; shutdown drains what is queued"""
+    import threading
+    import time
+    C = ht._C
+    q = C.TaskQueue("io", num_workers=3, max_pending=4)
+    seen, lock, tids = [], threading.Lock(), set()
+
+    def work(i):
+        def run():
+            time.sleep(0.005)
+            with lock:
+                seen.append(i); tids.add(threading.get_ident())
+        return run
+    for i in range(40):
+        q.add(work(i))                       # blocks whenever 4 tasks are pending
+    q.wait()
+    assert sorted(seen) == list(range(40)) and q.completed == 40 and q.pending == 0 and q.num_workers == 3
+    assert threading.get_ident() not in tids and len(tids) >= 2
+
+    def boom():
+        raise ValueError("disk full")
+    q.add(boom)
+    with pytest.raises(ht.HetuError, match="disk full"):
+        q.wait()
+    q.add(work(99)); q.wait()                # the queue stays usable after a failed task
+    assert seen[-1] == 99
+    for i in range(5):
+        q.add(work(100 + i))
+    q.shutdown()                             # drains
+    assert not q.running and sorted(seen)[-5:] == [100, 101, 102, 103, 104]
+    with pytest.raises(ht.HetuError):
+        q.add(work(0))
+    q2 = C.TaskQueue("gc", 1)
+    q2.add(work(7))
+    del q2                                   # destructor joins the worker without dead-locking on the GIL
