@@ -45,6 +45,7 @@ CXX_SOURCES = [
     "csrc/runtime/symm_mem.cc",
     "csrc/runtime/symm_vmm.cc",
     "csrc/runtime/memory_pool.cc",
+    "csrc/runtime/bfc_pool.cc",
     "csrc/runtime/runtime.cc",
     "csrc/runtime/rpc_client.cc",
     "csrc/binding/module.cc",

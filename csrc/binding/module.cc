@@ -559,7 +559,7 @@ PYBIND11_MODULE(_C, m) {
   m.def("use_native_allocator", [] {
     static bool installed = false;
     if (installed) return true;
-    auto pool_of = [](int device) { return MemoryPoolRegistry::instance().get("cuda:" + std::to_string(device)); };
+    auto pool_of = [](int device) { return MemoryPoolRegistry::instance().tensor_allocator("cuda:" + std::to_string(device)); };
     auto alloc = torch::cuda::CUDAPluggableAllocator::createCustomAllocator(
         [pool_of](size_t size, int device, cudaStream_t stream) -> void* {
           if (size == 0) return nullptr;
@@ -580,9 +580,14 @@ PYBIND11_MODULE(_C, m) {
     plug->set_record_stream_fn([](void* ptr, cudaStream_t stream) {
       int dev = 0;
       cudaGetDevice(&dev);
-      MemoryPoolRegistry::instance().get("cuda:" + std::to_string(dev))->mark_used_by_stream(ptr, (int64_t)(uintptr_t)stream);
+      MemoryPoolRegistry::instance().tensor_allocator("cuda:" + std::to_string(dev))->mark_used_by_stream(ptr, (int64_t)(uintptr_t)stream);
     });
-    plug->set_reset_fn([] { MemoryPoolRegistry::instance().empty_all_caches(); });
+    plug->set_reset_fn([] {
+      MemoryPoolRegistry::instance().empty_all_caches();
+      int n = 0;
+      if (cudaGetDeviceCount(&n) != cudaSuccess) n = 0;
+      for (int d = 0; d < n; ++d) MemoryPoolRegistry::instance().tensor_allocator("cuda:" + std::to_string(d))->empty_cache();
+    });
     torch::cuda::CUDAPluggableAllocator::changeCurrentAllocator(alloc);
     installed = true;
     return true;
@@ -791,7 +796,43 @@ PYBIND11_MODULE(_C, m) {
         "the process-wide pool of a device: 'cuda:<i>', 'cpu', 'pinned', 'shm'");
   m.def("memory_pool_devices", [] { return MemoryPoolRegistry::instance().devices(); });
   m.def("empty_all_memory_caches", [] { return (uint64_t)MemoryPoolRegistry::instance().empty_all_caches(); });
-  py::class_<CachingMemoryPool, std::shared_ptr<CachingMemoryPool>>(m, "MemoryPool")
+  auto stats_dict = [](const PoolStats& s) {
+    py::dict d;
+    d["reserved"] = s.reserved; d["allocated"] = s.allocated; d["peak_reserved"] = s.peak_reserved; d["peak_allocated"] = s.peak_allocated;
+    d["num_alloc"] = s.num_alloc; d["num_free"] = s.num_free; d["num_segment_alloc"] = s.num_segment_alloc; d["num_split"] = s.num_split;
+    d["num_merge"] = s.num_merge; d["cache_hits"] = s.cache_hits;
+    return d;
+  };
+  py::class_<DeviceAllocator, std::shared_ptr<DeviceAllocator>>(m, "DeviceAllocator")
+      .def("alloc", [](DeviceAllocator& p, int64_t bytes, int64_t stream) { return (uint64_t)(uintptr_t)p.alloc((size_t)bytes, stream); },
+           py::arg("bytes"), py::arg("stream") = 0)
+      .def("free", [](DeviceAllocator& p, uint64_t ptr) { p.free((void*)(uintptr_t)ptr); })
+      .def("mark_used_by_stream", [](DeviceAllocator& p, uint64_t ptr, int64_t stream) { p.mark_used_by_stream((void*)(uintptr_t)ptr, stream); })
+      .def("wait", [](DeviceAllocator& p, uint64_t ptr) { p.wait((void*)(uintptr_t)ptr); })
+      .def("empty_cache", &DeviceAllocator::empty_cache)
+      .def("stats", [stats_dict](DeviceAllocator& p) { return stats_dict(p.stats()); })
+      .def("summary", &DeviceAllocator::summary)
+      .def_property_readonly("kind", [](DeviceAllocator& p) { return std::string(p.kind()); });
+  py::class_<BFCMemoryPool, DeviceAllocator, std::shared_ptr<BFCMemoryPool>>(m, "BFCMemoryPool")
+      .def(py::init([](const std::string& backend, int device, int64_t initial_region_mb, int64_t limit_mb, int64_t min_chunk) {
+        BFCMemoryPool::Options o;
+        if (initial_region_mb > 0) o.initial_region = (size_t)initial_region_mb << 20;
+        if (limit_mb > 0) o.limit = (size_t)limit_mb << 20;
+        if (min_chunk > 0) o.min_chunk = (size_t)min_chunk;
+        return std::make_shared<BFCMemoryPool>(backend == "cuda" ? make_cuda_backend(device) : make_host_backend(backend == "pinned"), o);
+      }), py::arg("backend") = "host", py::arg("device") = 0, py::arg("initial_region_mb") = 0, py::arg("limit_mb") = 0, py::arg("min_chunk") = 0)
+      .def_property_readonly("num_regions", &BFCMemoryPool::num_regions)
+      .def("bin_occupancy", &BFCMemoryPool::bin_occupancy)
+      .def_property_readonly("largest_free_chunk", &BFCMemoryPool::largest_free_chunk)
+      .def_property_readonly("fragmentation", &BFCMemoryPool::fragmentation);
+  py::class_<StreamOrderedMemoryPool, DeviceAllocator, std::shared_ptr<StreamOrderedMemoryPool>>(m, "StreamOrderedMemoryPool")
+      .def(py::init([](int device, int64_t release_threshold_mb) {
+        return std::make_shared<StreamOrderedMemoryPool>(device, release_threshold_mb < 0 ? SIZE_MAX : (size_t)release_threshold_mb << 20);
+      }), py::arg("device") = 0, py::arg("release_threshold_mb") = -1)
+      .def_property_readonly("on_device", &StreamOrderedMemoryPool::on_device);
+  m.def("tensor_allocator", [](const std::string& device) { return MemoryPoolRegistry::instance().tensor_allocator(device); },
+        "the allocator that backs CUDA tensors of `device` under HETU_NATIVE_ALLOCATOR=1 (kind: HETU_MEMORY_POOL)");
+  py::class_<CachingMemoryPool, DeviceAllocator, std::shared_ptr<CachingMemoryPool>>(m, "MemoryPool")
       .def(py::init([](const std::string& backend, int device, int64_t limit_mb, int64_t max_split_mb, int64_t pre_allocate_mb) {
         CachingMemoryPool::Options o = CachingMemoryPool::options_from_env();
         if (limit_mb > 0) o.limit = (size_t)limit_mb << 20;

@@ -31,6 +31,8 @@ from .distributed import (init_comm_group, local_device, global_device_group, gl
 
 def memory_pool_summary(device: str = "cuda:0") -> str:
     """statistics of the native caching pool of `device` (reserved / allocated / peak, splits, merges, cache hits)"""
+    if _os.environ.get("HETU_NATIVE_ALLOCATOR", "0") == "1" and device.startswith("cuda"):
+        return _C.tensor_allocator(device).summary()      # caching / bfc / stream_ordered (HETU_MEMORY_POOL)
     return _C.get_memory_pool(device).summary()
 
 

@@ -462,9 +462,10 @@ def test_blockwise_quantisation_kernels_match_host_reference(kind):
         close(torch.as_tensor(y.numpy()), ref, 0.08, 0.02)
 
 
-def test_native_caching_pool_as_the_tensor_allocator():
-    """HETU_NATIVE_ALLOCATOR=1: the framework's CachingMemoryPool replaces PyTorch's CUDA allocator (pluggable allocator), a small
-    GPT trains on it with the same losses, and the pool's statistics show the traffic (cache hits, splits)"""
+def test_native_pools_as_the_tensor_allocator():
+    """HETU_NATIVE_ALLOCATOR=1: the framework's own pool -- caching, best-fit-with-coalescing or stream-ordered
+    (HETU_MEMORY_POOL) -- replaces PyTorch's CUDA allocator (pluggable allocator); a small GPT trains on each with the same
+    losses, and the pool's statistics show the traffic"""
     import os
     import subprocess
     import sys
@@ -482,23 +483,30 @@ with ht.graph("define_and_run", create_new=True) as g, ht.autocast("bfloat16"):
     p = torch.arange(256).repeat(2).cuda()
     ls = [float(g.run(loss, [loss, op], {ids: x, pos: p, lab: torch.roll(x, -1)})[0]) for _ in range(6)]
 torch.cuda.synchronize()
-st = ht._C.get_memory_pool("cuda:0").stats() if os.environ.get("HETU_NATIVE_ALLOCATOR") == "1" else None
+al = ht._C.tensor_allocator("cuda:0") if os.environ.get("HETU_NATIVE_ALLOCATOR") == "1" else None
+st = al.stats() if al is not None else None
 print("RESULT " + json.dumps({"losses": ls, "allocs": st["num_alloc"] if st else 0, "hits": st["cache_hits"] if st else 0,
-                              "reserved": st["reserved"] if st else 0,
+                              "reserved": st["reserved"] if st else 0, "kind": al.kind if al is not None else "torch",
+                              "summary": ht.memory_pool_summary("cuda:0") if al is not None else "",
                               "torch_reserved": torch.cuda.memory_reserved() if st is None else 0}))
 """
+    import json
     outs = {}
-    for flag in ("0", "1"):
-        env = dict(os.environ, HETU_NATIVE_ALLOCATOR=flag, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    for flag, kind in (("0", "torch"), ("1", "caching"), ("1", "bfc"), ("1", "stream_ordered")):
+        env = dict(os.environ, HETU_NATIVE_ALLOCATOR=flag, HETU_MEMORY_POOL=kind if flag == "1" else "caching",
+                   PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
         line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
-        assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-3000:]
-        import json
-        outs[flag] = json.loads(line[0][7:])
-    a, b = outs["0"], outs["1"]
-    assert b["allocs"] > 100 and b["hits"] > 0 and b["reserved"] > 0, b
-    for x, y in zip(a["losses"], b["losses"]):
-        assert abs(x - y) < 1e-3 * max(1.0, abs(x)), (a["losses"], b["losses"])
+        assert r.returncode == 0 and line, kind + "\n" + r.stdout[-2000:] + r.stderr[-3000:]
+        outs[kind] = json.loads(line[0][7:])
+    a = outs["torch"]
+    for kind in ("caching", "bfc", "stream_ordered"):
+        b = outs[kind]
+        assert b["kind"] == kind and b["allocs"] > 100 and b["reserved"] > 0, b
+        if kind != "stream_ordered":
+            assert b["hits"] > 0, b
+        for x, y in zip(a["losses"], b["losses"]):
+            assert abs(x - y) < 1e-3 * max(1.0, abs(x)), (kind, a["losses"], b["losses"])
 
 
 def test_gpt_block_training_matches_fp32_reference():

@@ -174,3 +174,78 @@ def test_task_queue_runs_tasks_on_workers_with_back_pressure_and_error_report():
     q2 = C.TaskQueue("gc", 1)
     q2.add(work(7))
     del q2                                   # destructor joins the worker without dead-locking on the GIL
+
+
+def test_bfc_pool_best_fit_split_coalesce_and_region_growth():
+    """ref: hetu/impl/memory/CUDABFCMemoryPool -- bins by power of two, best fit, split, coalescing with both neighbours,
+    doubling regions, limit, empty_cache returns whole free regions"""
+    MB = 1 << 20
+    pool = _C.BFCMemoryPool("host", initial_region_mb=4, limit_mb=64)
+    assert pool.kind == "bfc" and pool.num_regions == 0
+    a = pool.alloc(1 * MB); b = pool.alloc(1 * MB); c = pool.alloc(1 * MB)
+    assert pool.num_regions == 1 and b == a + MB and c == b + MB            # carved contiguously out of the first 4 MiB region
+    st = pool.stats()
+    assert st["reserved"] == 4 * MB and st["allocated"] == 3 * MB and st["num_split"] == 3
+    pool.free(b)
+    assert pool.largest_free_chunk == MB and pool.fragmentation == 0.5      # two free 1 MiB chunks, not adjacent
+    # best fit: a 512 KiB request takes the 1 MiB hole (smallest chunk that fits), not the tail
+    d = pool.alloc(512 << 10)
+    assert d == b
+    pool.free(d); pool.free(a)                                              # a + (d + its remainder) coalesce into 2 MiB
+    assert pool.largest_free_chunk == 2 * MB
+    pool.free(c)                                                            # everything merges back into one 4 MiB chunk
+    assert pool.largest_free_chunk == 4 * MB and pool.fragmentation == 0.0 and sum(pool.bin_occupancy()) == 1
+    assert pool.stats()["num_merge"] >= 4
+    # growth: a request beyond the first region opens a second, larger one (doubling schedule)
+    big = pool.alloc(6 * MB)
+    assert pool.num_regions == 2 and pool.stats()["reserved"] == 4 * MB + 8 * MB
+    # odd sizes are rounded to the 256-byte granularity and requests reuse freed chunks
+    x = pool.alloc(1000); pool.free(x)
+    assert pool.alloc(1024) == x
+    hits = pool.stats()["cache_hits"]
+    assert hits >= 3
+    # limit: 64 MiB cap refuses a request that cannot fit
+    assert pool.alloc(80 * MB) == 0
+    pool.free(big); pool.free(x)
+    released = pool.empty_cache()
+    assert released == 12 * MB and pool.num_regions == 0 and pool.stats()["reserved"] == 0
+    assert "bfc pool" in pool.summary()
+
+
+def test_bfc_pool_random_workload_never_overlaps_and_returns_to_one_chunk_per_region():
+    import random
+    rng = random.Random(0)
+    pool = _C.BFCMemoryPool("host", initial_region_mb=2, limit_mb=256)
+    live = {}
+    for step in range(3000):
+        if live and (rng.random() < 0.45 or len(live) > 200):
+            p = rng.choice(list(live)); pool.free(p); del live[p]
+        else:
+            n = rng.choice([300, 4096, 70_000, 1 << 20, 3 << 20]) + rng.randrange(0, 257)
+            p = pool.alloc(n, stream=rng.choice([0, 0, 0, 7]))
+            assert p != 0 and p % 256 == 0
+            live[p] = n
+        if step % 500 == 0:
+            spans = sorted((p, p + n) for p, n in live.items())
+            assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))      # no two live blocks overlap
+    for p in list(live):
+        pool.free(p)
+    assert sum(pool.bin_occupancy()) == pool.num_regions and pool.stats()["allocated"] == 0
+    st = pool.stats()
+    assert st["num_alloc"] == st["num_free"] and st["peak_allocated"] <= st["peak_reserved"]
+
+
+def test_stream_ordered_pool_bookkeeping_without_a_device_and_allocator_selection(monkeypatch):
+    """ref: hetu/impl/memory/CUDAStreamOrderedMemoryPool -- on a GPU this is cudaMallocAsync on the default mempool; without one the
+    same interface runs on host memory.  HETU_MEMORY_POOL picks the tensor allocator kind."""
+    pool = _C.StreamOrderedMemoryPool(0)
+    assert pool.kind == "stream_ordered" and (pool.on_device or not torch.cuda.is_available())
+    p = pool.alloc(1 << 20, stream=0); q = pool.alloc(4096, stream=0)
+    pool.mark_used_by_stream(p, 5)
+    assert pool.stats()["allocated"] == (1 << 20) + 4096 and pool.stats()["num_alloc"] == 2
+    pool.wait(p); pool.free(p); pool.free(q)
+    assert pool.stats()["allocated"] == 0 and pool.stats()["num_free"] == 2 and "stream-ordered" in pool.summary()
+    monkeypatch.setenv("HETU_MEMORY_POOL", "bfc")
+    assert _C.tensor_allocator("cpu:91").kind == "bfc"
+    monkeypatch.setenv("HETU_MEMORY_POOL", "caching")
+    assert _C.tensor_allocator("cpu:92").kind == "caching"
