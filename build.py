@@ -16,6 +16,7 @@ BUILD = os.path.join(ROOT, "build")
 
 CUDA_SOURCES = [
     "csrc/kernels/gemm_sm100.cu",
+    "csrc/kernels/generic.cu",
     "csrc/kernels/attention_sm100.cu",
     "csrc/kernels/norm.cu",
     "csrc/kernels/elementwise.cu",
@@ -35,6 +36,7 @@ CXX_SOURCES = [
     "csrc/graph/zero_fused.cc",
     "csrc/graph/tp_fused.cc",
     "csrc/graph/ops_basic.cc",
+    "csrc/graph/native_generic.cc",
     "csrc/graph/ops_nn.cc",
     "csrc/graph/ops_comm.cc",
     "csrc/graph/ops_optim.cc",

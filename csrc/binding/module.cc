@@ -981,6 +981,37 @@ PYBIND11_MODULE(_C, m) {
       .def_property_readonly("completed", &TaskQueue::completed)
       .def_property_readonly("name", &TaskQueue::name);
 
+  // generic long-tail kernels (csrc/kernels/generic.cu) behind at::Tensor; None = not applicable (the ops then use ATen)
+  {
+    auto opt = [](const at::Tensor& t) -> py::object { return t.defined() ? py::cast(t) : py::none(); };
+    py::dict u;
+    const char* un[] = {"neg", "reciprocal", "abs", "ceil", "floor", "round", "exp", "log", "sqrt", "rsqrt", "sin", "cos", "clamp", "sigmoid",
+                        "tanh", "leakyrelu", "elu", "hardshrink", "hardsigmoid", "hardtanh", "hardswish", "logsigmoid", "softplus", "mish",
+                        "softshrink", "pow", "add_scalar", "mul_scalar", "rsub_scalar", "rdiv_scalar", "div_scalar"};
+    for (int i = 0; i < (int)(sizeof(un) / sizeof(un[0])); ++i) u[un[i]] = i;
+    m.attr("GENERIC_UNARY") = u;
+    py::dict b;
+    const char* bn[] = {"add", "sub", "mul", "div", "max", "min", "pow"};
+    for (int i = 0; i < 7; ++i) b[bn[i]] = i;
+    m.attr("GENERIC_BINARY") = b;
+    py::dict r;
+    const char* rn[] = {"sum", "mean", "max", "min", "prod"};
+    for (int i = 0; i < 5; ++i) r[rn[i]] = i;
+    m.attr("GENERIC_REDUCE") = r;
+    m.def("g_unary", [opt](int op, const at::Tensor& x, float p0, float p1) { return opt(g_unary(op, x, p0, p1)); }, py::arg("op"), py::arg("x"),
+          py::arg("p0") = 0.f, py::arg("p1") = 0.f);
+    m.def("g_binary", [opt](int op, const at::Tensor& a, const at::Tensor& b2) { return opt(g_binary(op, a, b2)); });
+    m.def("g_reduce", [opt](int mode, const at::Tensor& x, std::vector<int64_t> axes, bool keep) { return opt(g_reduce(mode, x, axes, keep)); },
+          py::arg("mode"), py::arg("x"), py::arg("axes") = std::vector<int64_t>{}, py::arg("keepdims") = false);
+    m.def("g_softmax", [opt](bool log, const at::Tensor& x, int64_t dim) { return opt(g_softmax(log, x, dim)); });
+    m.def("g_concat", [opt](const std::vector<at::Tensor>& in, int64_t dim) { return opt(g_concat(in, dim)); });
+    m.def("g_contiguous", [opt](const at::Tensor& x) { return opt(g_contiguous(x)); });
+    m.def("g_cast", [opt](const at::Tensor& x, const std::string& dtype) { return opt(g_cast(x, to_aten_dtype(dtype_from_name(dtype)))); });
+    m.def("g_full", [opt](const std::vector<int64_t>& shape, const std::string& dtype, double value, const std::string& device) {
+      return opt(g_full(shape, at::TensorOptions().dtype(to_aten_dtype(dtype_from_name(dtype))).device(c10::Device(device)), value));
+    }, py::arg("shape"), py::arg("dtype"), py::arg("value"), py::arg("device") = "cuda");
+  }
+
   // direct kernel entry points (benchmarks / numerics tests)
   m.def("gemm", [](const at::Tensor& a, const at::Tensor& b, bool a_mn, bool b_mn, const py::object& bias, const std::string& act,
                    bool out_fp32, int cta_group, int block_n) {

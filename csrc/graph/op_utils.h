@@ -25,6 +25,16 @@ int64_t fallback_count();
 
 at::Tensor native_add(const at::Tensor& a, const at::Tensor& b);
 
+// generic device kernels behind at::Tensor (native_generic.cc); an UNDEFINED result means "not applicable, use ATen"
+at::Tensor g_contiguous(const at::Tensor& x);
+at::Tensor g_unary(int op, const at::Tensor& x, float p0 = 0.f, float p1 = 0.f);
+at::Tensor g_binary(int op, const at::Tensor& a, const at::Tensor& b);
+at::Tensor g_reduce(int mode, const at::Tensor& x, std::vector<int64_t> axes, bool keepdims);
+at::Tensor g_softmax(bool log, const at::Tensor& x, int64_t dim);
+at::Tensor g_concat(const std::vector<at::Tensor>& in, int64_t dim);
+at::Tensor g_cast(const at::Tensor& x, at::ScalarType to);
+at::Tensor g_full(at::IntArrayRef shape, const at::TensorOptions& opt, double value);
+
 // Destination override for the next GEMM issued on this thread: when set (by the executor's tensor-parallel fusion),
 // a GEMM whose output is [world * rows_per_rank, cols] stores its tiles into the owner ranks' symmetric staging slots
 // (peer stores from the epilogue) instead of its own output tensor.

@@ -64,11 +64,22 @@ HB_REGISTER_OP(const_tensor, "const", 1, kFlagConst | kFlagNondiff | kFlagNoMeta
   }                                                                                               \
   HB_REGISTER_OP(NAME, #NAME, NOUT, kFlagNondiff, NAME##_compute, nullptr, nullptr, nullptr)
 
-static at::Tensor like_const(const at::Tensor& ref, double v) { return at::full_like(ref, v); }
+// native generic kernel first, ATen when it does not apply (CPU, integer dtypes, ...)
+#define GEN_OR(EXPR, FALLBACK)                    \
+  {                                               \
+    at::Tensor _r = (EXPR);                       \
+    if (_r.defined()) return {_r};                \
+    return {FALLBACK};                            \
+  }
+
+static at::Tensor like_const(const at::Tensor& ref, double v) {
+  at::Tensor r = g_full(ref.sizes(), ref.options(), v);
+  return r.defined() ? r : at::full_like(ref, v);
+}
 
 // ------------------------------------------------------------------ creation-like
-ATEN_OP_NODIFF(ones_like, 1, return {at::ones_like(in[0])};);
-ATEN_OP_NODIFF(zeros_like, 1, return {at::zeros_like(in[0])};);
+ATEN_OP_NODIFF(ones_like, 1, return {like_const(in[0], 1.0)};);
+ATEN_OP_NODIFF(zeros_like, 1, return {like_const(in[0], 0.0)};);
 ATEN_OP_NODIFF(full_like, 1, return {like_const(in[0], op.attrs.f("value"))};);
 ATEN_OP_NODIFF(arange, 0 + 1, {
   auto o = at::TensorOptions().dtype(to_aten_dtype(dtype_from_name(op.attrs.s("dtype", "int64"))));
@@ -139,8 +150,9 @@ static void reduce_to_shape_deduce(OpDef& op, size_t s) {
 HB_REGISTER_OP(reduce_to_shape, "reduce_to_shape", 1, 0, reduce_to_shape_compute, nullptr, reduce_to_shape_deduce, nullptr);
 
 static Ts add_compute(const OpDef& op, const Ts& in, RunCtx*) {
-  if (in.size() == 1) return {in[0] + op.attrs.f("value")};
-  return {native_add(in[0], in[1])};
+  if (in.size() == 1) GEN_OR(g_unary(G_ADD_SCALAR, in[0], (float)op.attrs.f("value")), in[0] + op.attrs.f("value"));
+  if (in[0].sizes() == in[1].sizes()) return {native_add(in[0], in[1])};
+  GEN_OR(g_binary(B_ADD, in[0], in[1]), in[0] + in[1]);
 }
 static TensorList add_grad(OpDef& op, const TensorList& g) {
   TensorList r(op.inputs.size());
@@ -150,8 +162,11 @@ static TensorList add_grad(OpDef& op, const TensorList& g) {
 HB_REGISTER_OP(add, "add", 1, 0, add_compute, add_grad, nullptr, nullptr);
 
 static Ts sub_compute(const OpDef& op, const Ts& in, RunCtx*) {
-  if (in.size() == 1) return {op.attrs.b("from_const") ? op.attrs.f("value") - in[0] : in[0] - op.attrs.f("value")};
-  return {in[0] - in[1]};
+  if (in.size() == 1) {
+    if (op.attrs.b("from_const")) GEN_OR(g_unary(G_RSUB_SCALAR, in[0], (float)op.attrs.f("value")), op.attrs.f("value") - in[0]);
+    GEN_OR(g_unary(G_ADD_SCALAR, in[0], -(float)op.attrs.f("value")), in[0] - op.attrs.f("value"));
+  }
+  GEN_OR(g_binary(B_SUB, in[0], in[1]), in[0] - in[1]);
 }
 static TensorList sub_grad(OpDef& op, const TensorList& g) {
   Graph* gr = op.graph;
@@ -161,8 +176,8 @@ static TensorList sub_grad(OpDef& op, const TensorList& g) {
 HB_REGISTER_OP(sub, "sub", 1, 0, sub_compute, sub_grad, nullptr, nullptr);
 
 static Ts mul_compute(const OpDef& op, const Ts& in, RunCtx*) {
-  if (in.size() == 1) return {in[0] * op.attrs.f("value")};
-  return {in[0] * in[1]};
+  if (in.size() == 1) GEN_OR(g_unary(G_MUL_SCALAR, in[0], (float)op.attrs.f("value")), in[0] * op.attrs.f("value"));
+  GEN_OR(g_binary(B_MUL, in[0], in[1]), in[0] * in[1]);
 }
 static TensorList mul_grad(OpDef& op, const TensorList& g) {
   Graph* gr = op.graph;
@@ -177,23 +192,26 @@ static TensorList mul_grad(OpDef& op, const TensorList& g) {
 HB_REGISTER_OP(mul, "mul", 1, 0, mul_compute, mul_grad, nullptr, nullptr);
 
 ATEN_OP(div, 1, {
-  if (in.size() == 1) return {op.attrs.b("from_const") ? at::reciprocal(in[0]) * op.attrs.f("value") : in[0] / op.attrs.f("value")};
-  return {in[0] / in[1]};
+  if (in.size() == 1) {
+    if (op.attrs.b("from_const")) GEN_OR(g_unary(G_RDIV_SCALAR, in[0], (float)op.attrs.f("value")), at::reciprocal(in[0]) * op.attrs.f("value"));
+    GEN_OR(g_unary(G_DIV_SCALAR, in[0], (float)op.attrs.f("value")), in[0] / op.attrs.f("value"));
+  }
+  GEN_OR(g_binary(B_DIV, in[0], in[1]), in[0] / in[1]);
 });
-ATEN_OP(pow, 1, return {at::pow(in[0], op.attrs.f("exponent"))};);
-ATEN_OP(neg, 1, return {at::neg(in[0])};);
-ATEN_OP(reciprocal, 1, return {at::reciprocal(in[0])};);
-ATEN_OP(abs, 1, return {at::abs(in[0])};);
-ATEN_OP_NODIFF(ceil, 1, return {at::ceil(in[0])};);
-ATEN_OP_NODIFF(floor, 1, return {at::floor(in[0])};);
-ATEN_OP_NODIFF(round, 1, return {at::round(in[0])};);
-ATEN_OP(exp, 1, return {at::exp(in[0])};);
-ATEN_OP(log, 1, return {at::log(in[0])};);
-ATEN_OP(sqrt, 1, return {at::sqrt(in[0])};);
-ATEN_OP(rsqrt, 1, return {at::rsqrt(in[0])};);
-ATEN_OP(sin, 1, return {at::sin(in[0])};);
-ATEN_OP(cos, 1, return {at::cos(in[0])};);
-ATEN_OP(clamp, 1, return {at::clamp(in[0], op.attrs.f("min"), op.attrs.f("max"))};);
+ATEN_OP(pow, 1, GEN_OR(g_unary(G_POW, in[0], (float)op.attrs.f("exponent")), at::pow(in[0], op.attrs.f("exponent"))));
+ATEN_OP(neg, 1, GEN_OR(g_unary(G_NEG, in[0]), at::neg(in[0])));
+ATEN_OP(reciprocal, 1, GEN_OR(g_unary(G_RECIPROCAL, in[0]), at::reciprocal(in[0])));
+ATEN_OP(abs, 1, GEN_OR(g_unary(G_ABS, in[0]), at::abs(in[0])));
+ATEN_OP_NODIFF(ceil, 1, GEN_OR(g_unary(G_CEIL, in[0]), at::ceil(in[0])));
+ATEN_OP_NODIFF(floor, 1, GEN_OR(g_unary(G_FLOOR, in[0]), at::floor(in[0])));
+ATEN_OP_NODIFF(round, 1, GEN_OR(g_unary(G_ROUND, in[0]), at::round(in[0])));
+ATEN_OP(exp, 1, GEN_OR(g_unary(G_EXP, in[0]), at::exp(in[0])));
+ATEN_OP(log, 1, GEN_OR(g_unary(G_LOG, in[0]), at::log(in[0])));
+ATEN_OP(sqrt, 1, GEN_OR(g_unary(G_SQRT, in[0]), at::sqrt(in[0])));
+ATEN_OP(rsqrt, 1, GEN_OR(g_unary(G_RSQRT, in[0]), at::rsqrt(in[0])));
+ATEN_OP(sin, 1, GEN_OR(g_unary(G_SIN, in[0]), at::sin(in[0])));
+ATEN_OP(cos, 1, GEN_OR(g_unary(G_COS, in[0]), at::cos(in[0])));
+ATEN_OP(clamp, 1, GEN_OR(g_unary(G_CLAMP, in[0], (float)op.attrs.f("min"), (float)op.attrs.f("max")), at::clamp(in[0], op.attrs.f("min"), op.attrs.f("max"))));
 ATEN_OP_NODIFF(bool_op, 1, return {in[0] != 0};);
 ATEN_OP(where, 1, return {at::where(in[0].to(at::kBool), in[1], in[2])};);
 ATEN_OP(masked_fill, 1, return {at::masked_fill(in[0], in[1].to(at::kBool), op.attrs.f("value"))};);
@@ -207,20 +225,20 @@ ATEN_OP_NODIFF(range_mask, 1, {
 });
 
 // ------------------------------------------------------------------ activations (long tail; hot ones live in ops_nn.cc)
-ATEN_OP(sigmoid, 1, return {at::sigmoid(in[0])};);
-ATEN_OP(tanh, 1, return {at::tanh(in[0])};);
-ATEN_OP(leakyrelu, 1, return {at::leaky_relu(in[0], op.attrs.f("alpha", 0.01))};);
-ATEN_OP(elu, 1, return {at::elu(in[0], op.attrs.f("alpha", 1.0), op.attrs.f("scale", 1.0))};);
-ATEN_OP(hardshrink, 1, return {at::hardshrink(in[0], op.attrs.f("lambda", 0.5))};);
-ATEN_OP(hardsigmoid, 1, return {at::hardsigmoid(in[0])};);
-ATEN_OP(hardtanh, 1, return {at::hardtanh(in[0], op.attrs.f("min_val", -1.0), op.attrs.f("max_val", 1.0))};);
-ATEN_OP(hardswish, 1, return {at::hardswish(in[0])};);
-ATEN_OP(logsigmoid, 1, return {at::log_sigmoid(in[0])};);
-ATEN_OP(mish, 1, return {at::mish(in[0])};);
-ATEN_OP(softplus, 1, return {at::softplus(in[0], op.attrs.f("beta", 1.0), op.attrs.f("threshold", 20.0))};);
-ATEN_OP(softshrink, 1, return {at::softshrink(in[0], op.attrs.f("lambda", 0.5))};);
-ATEN_OP(softmax, 1, return {at::softmax(in[0], op.attrs.i("dim", -1))};);
-ATEN_OP(log_softmax, 1, return {at::log_softmax(in[0], op.attrs.i("dim", -1))};);
+ATEN_OP(sigmoid, 1, GEN_OR(g_unary(G_SIGMOID, in[0]), at::sigmoid(in[0])));
+ATEN_OP(tanh, 1, GEN_OR(g_unary(G_TANH, in[0]), at::tanh(in[0])));
+ATEN_OP(leakyrelu, 1, GEN_OR(g_unary(G_LEAKYRELU, in[0], (float)op.attrs.f("alpha", 0.01)), at::leaky_relu(in[0], op.attrs.f("alpha", 0.01))));
+ATEN_OP(elu, 1, GEN_OR(g_unary(G_ELU, in[0], (float)op.attrs.f("alpha", 1.0), (float)op.attrs.f("scale", 1.0)), at::elu(in[0], op.attrs.f("alpha", 1.0), op.attrs.f("scale", 1.0))));
+ATEN_OP(hardshrink, 1, GEN_OR(g_unary(G_HARDSHRINK, in[0], (float)op.attrs.f("lambda", 0.5)), at::hardshrink(in[0], op.attrs.f("lambda", 0.5))));
+ATEN_OP(hardsigmoid, 1, GEN_OR(g_unary(G_HARDSIGMOID, in[0]), at::hardsigmoid(in[0])));
+ATEN_OP(hardtanh, 1, GEN_OR(g_unary(G_HARDTANH, in[0], (float)op.attrs.f("min_val", -1.0), (float)op.attrs.f("max_val", 1.0)), at::hardtanh(in[0], op.attrs.f("min_val", -1.0), op.attrs.f("max_val", 1.0))));
+ATEN_OP(hardswish, 1, GEN_OR(g_unary(G_HARDSWISH, in[0]), at::hardswish(in[0])));
+ATEN_OP(logsigmoid, 1, GEN_OR(g_unary(G_LOGSIGMOID, in[0]), at::log_sigmoid(in[0])));
+ATEN_OP(mish, 1, GEN_OR(g_unary(G_MISH, in[0]), at::mish(in[0])));
+ATEN_OP(softplus, 1, GEN_OR(g_unary(G_SOFTPLUS, in[0], (float)op.attrs.f("beta", 1.0), (float)op.attrs.f("threshold", 20.0)), at::softplus(in[0], op.attrs.f("beta", 1.0), op.attrs.f("threshold", 20.0))));
+ATEN_OP(softshrink, 1, GEN_OR(g_unary(G_SOFTSHRINK, in[0], (float)op.attrs.f("lambda", 0.5)), at::softshrink(in[0], op.attrs.f("lambda", 0.5))));
+ATEN_OP(softmax, 1, GEN_OR(g_softmax(false, in[0], op.attrs.i("dim", -1)), at::softmax(in[0], op.attrs.i("dim", -1))));
+ATEN_OP(log_softmax, 1, GEN_OR(g_softmax(true, in[0], op.attrs.i("dim", -1)), at::log_softmax(in[0], op.attrs.i("dim", -1))));
 
 // ------------------------------------------------------------------ reductions
 static Ts reduce_compute(const OpDef& op, const Ts& in, RunCtx*) {
@@ -229,6 +247,14 @@ static Ts reduce_compute(const OpDef& op, const Ts& in, RunCtx*) {
   const bool keep = op.attrs.b("keepdims");
   const at::Tensor& x = in[0];
   if (axes.empty()) for (int64_t i = 0; i < x.dim(); ++i) axes.push_back(i);
+  {
+    const int gm = mode == "sum" ? R_SUM : (mode == "mean" || mode == "avg") ? R_MEAN : mode == "max" ? R_MAX : mode == "min" ? R_MIN
+                   : mode == "prod" ? R_PROD : -1;
+    if (gm >= 0) {
+      at::Tensor r = g_reduce(gm, x, axes, keep);
+      if (r.defined()) return {r};
+    }
+  }
   if (mode == "sum") return {at::sum(x, axes, keep)};
   if (mode == "mean" || mode == "avg") return {at::mean(x, axes, keep)};
   if (mode == "max") return {at::amax(x, axes, keep)};
@@ -280,7 +306,7 @@ static void reduce_deduce(OpDef& op, size_t s) {
   out->ds_hierarchy.get_mut(s) = DistributedStatesUnion({DistributedStates(ds.device_num(), st, order)});
 }
 HB_REGISTER_OP(reduce, "reduce", 1, 0, reduce_compute, nullptr, reduce_deduce, nullptr);
-ATEN_OP(mean, 1, return {at::mean(in[0])};);
+ATEN_OP(mean, 1, GEN_OR(g_reduce(R_MEAN, in[0], {}, false), at::mean(in[0])));
 ATEN_OP(norm, 1, return {at::norm(in[0], op.attrs.f("p", 2.0), op.attrs.ints("axes").empty() ? std::vector<int64_t>{} : op.attrs.ints("axes"), op.attrs.b("keepdims"))};);
 
 // ------------------------------------------------------------------ shape / view ops
@@ -422,7 +448,7 @@ static TensorList split_grad(OpDef& op, const TensorList& g) {
 }
 HB_REGISTER_OP(split, "split", -1, 0, split_compute, split_grad, nullptr, nullptr);
 
-static Ts concat_compute(const OpDef& op, const Ts& in, RunCtx*) { return {at::cat(in, op.attrs.i("dim"))}; }
+static Ts concat_compute(const OpDef& op, const Ts& in, RunCtx*) { GEN_OR(g_concat(in, op.attrs.i("dim")), at::cat(in, op.attrs.i("dim"))); }
 static TensorList concat_grad(OpDef& op, const TensorList& g) {
   std::vector<int64_t> sections;
   const int64_t dim = op.attrs.i("dim");
@@ -437,7 +463,8 @@ HB_REGISTER_OP(dynamic_concat, "dynamic_concat", 1, 0, concat_compute, concat_gr
 
 // dtype / device transfer (autocast inserts these)
 static Ts data_transfer_compute(const OpDef& op, const Ts& in, RunCtx*) {
-  return {in[0].to(to_aten_dtype(dtype_from_name(op.attrs.s("dtype"))))};
+  const at::ScalarType to = to_aten_dtype(dtype_from_name(op.attrs.s("dtype")));
+  GEN_OR(g_cast(in[0], to), in[0].to(to));
 }
 static TensorList data_transfer_grad(OpDef& op, const TensorList& g) {
   AttrMap a;

@@ -27,6 +27,35 @@ cudaError_t rmsnorm_bwd(const void* dy, const void* x, const void* gamma, const 
                         float* workspace, int64_t rows, int cols, bool accumulate, cudaStream_t s, const void* dx_add = nullptr,
                         void* dgamma_bf16 = nullptr);
 
+// ---------------------------------------------------------------- generic long-tail kernels (generic.cu)
+// dtype codes of the generic kernels
+enum GenericDtype : int { GD_F32 = 0, GD_BF16, GD_F16, GD_I64, GD_I32, GD_U8 };
+enum GenericUnary : int {
+  G_NEG = 0, G_RECIPROCAL, G_ABS, G_CEIL, G_FLOOR, G_ROUND, G_EXP, G_LOG, G_SQRT, G_RSQRT, G_SIN, G_COS, G_CLAMP /*p0 min, p1 max*/, G_SIGMOID,
+  G_TANH, G_LEAKYRELU /*p0 slope*/, G_ELU /*p0 alpha, p1 scale*/, G_HARDSHRINK /*p0 lambda*/, G_HARDSIGMOID, G_HARDTANH /*p0 min, p1 max*/,
+  G_HARDSWISH, G_LOGSIGMOID, G_SOFTPLUS /*p0 beta, p1 threshold*/, G_MISH, G_SOFTSHRINK /*p0 lambda*/, G_POW /*p0 exponent*/,
+  G_ADD_SCALAR, G_MUL_SCALAR, G_RSUB_SCALAR /*p0 - x*/, G_RDIV_SCALAR /*p0 / x*/, G_DIV_SCALAR
+};
+enum GenericBinary : int { B_ADD = 0, B_SUB, B_MUL, B_DIV, B_MAX, B_MIN, B_POW };
+enum GenericReduce : int { R_SUM = 0, R_MEAN, R_MAX, R_MIN, R_PROD };
+// dst[...] = src[...] for any-rank (<= 8) strided operands of one shape; strides in elements
+cudaError_t strided_copy(int elem_bytes, const void* src, void* dst, int ndim, const int64_t* shape, const int64_t* src_strides,
+                         const int64_t* dst_strides, cudaStream_t s);
+// y = f(x), contiguous, fp32 / bf16 / fp16 (fp32 arithmetic); cudaErrorMisalignedAddress when a pointer is not 16-byte aligned
+cudaError_t generic_unary(int op, int dtype, const void* x, void* y, int64_t n, float p0, float p1, cudaStream_t s);
+// out = a (op) b with broadcasting: `out` is contiguous of `out_shape`, operand strides in elements (0 on broadcast dims)
+cudaError_t generic_binary(int op, int dtype, const void* a, const void* b, void* out, int ndim, const int64_t* out_shape,
+                           const int64_t* a_strides, const int64_t* b_strides, cudaStream_t s);
+// x viewed as contiguous [outer, red, inner] -> y [outer, inner]; workspace (fp32, generic_reduce_workspace_floats) enables the
+// two-pass path for long reductions with little outer parallelism
+int64_t generic_reduce_workspace_floats(int64_t outer, int64_t inner);
+cudaError_t generic_reduce(int mode, int dtype, const void* x, void* y, float* workspace, int64_t outer, int64_t red, int64_t inner,
+                           cudaStream_t s);
+// softmax / log-softmax along the middle extent of a contiguous [outer, dim, inner] view
+cudaError_t generic_softmax(bool log, int dtype, const void* x, void* y, int64_t outer, int64_t dim, int64_t inner, cudaStream_t s);
+cudaError_t generic_cast(int src_dtype, int dst_dtype, const void* src, void* dst, int64_t n, cudaStream_t s);
+cudaError_t generic_fill(int dtype, void* dst, int64_t n, double value, cudaStream_t s);
+
 // ---------------------------------------------------------------- elementwise (bf16 in/out)
 enum UnaryOp : int { U_GELU = 0, U_RELU, U_SILU, U_SIGMOID, U_TANH, U_GELU_TANH, U_EXP, U_NEG, U_SQRT, U_RSQRT, U_ABS };
 cudaError_t unary_fwd(int op, const void* x, void* y, int64_t n, cudaStream_t s);

@@ -509,6 +509,122 @@ print("RESULT " + json.dumps({"losses": ls, "allocs": st["num_alloc"] if st else
             assert abs(x - y) < 1e-3 * max(1.0, abs(x)), (kind, a["losses"], b["losses"])
 
 
+def _close_to(a, b, dtype):
+    rtol, atol = (2e-5, 2e-6) if dtype == torch.float32 else (1.6e-2, 1e-2)
+    assert a.dtype == b.dtype and a.shape == b.shape, (a.dtype, b.dtype, a.shape, b.shape)
+    af, bf = a.float(), b.float()
+    both_nan = torch.isnan(af) & torch.isnan(bf)
+    ok = both_nan | (af == bf) | ((af - bf).abs() <= atol + rtol * bf.abs())
+    assert bool(ok.all()), float(((af - bf).abs() * (~ok)).max())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_generic_unary_family_matches_the_library(dtype):
+    """every function of the generic unary kernel against the same PyTorch function computed in fp32, on a size with a ragged tail
+    and on a non-contiguous view"""
+    C = ht._C
+    F = torch.nn.functional
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = (torch.randn(3, 1237, device="cuda", generator=g) * 2.0).to(dtype)
+    pos = x.abs() + 0.1
+    cases = {
+        "neg": (x, (), torch.neg), "reciprocal": (pos, (), torch.reciprocal), "abs": (x, (), torch.abs), "ceil": (x, (), torch.ceil),
+        "floor": (x, (), torch.floor), "round": (x, (), torch.round), "exp": (x, (), torch.exp), "log": (pos, (), torch.log),
+        "sqrt": (pos, (), torch.sqrt), "rsqrt": (pos, (), torch.rsqrt), "sin": (x, (), torch.sin), "cos": (x, (), torch.cos),
+        "clamp": (x, (-0.5, 0.7), lambda t: torch.clamp(t, -0.5, 0.7)), "sigmoid": (x, (), torch.sigmoid), "tanh": (x, (), torch.tanh),
+        "leakyrelu": (x, (0.1,), lambda t: F.leaky_relu(t, 0.1)), "elu": (x, (1.3, 1.0), lambda t: F.elu(t, 1.3)),
+        "hardshrink": (x, (0.4,), lambda t: F.hardshrink(t, 0.4)), "hardsigmoid": (x, (), F.hardsigmoid),
+        "hardtanh": (x, (-0.8, 0.9), lambda t: F.hardtanh(t, -0.8, 0.9)), "hardswish": (x, (), F.hardswish),
+        "logsigmoid": (x, (), F.logsigmoid), "softplus": (x, (2.0, 5.0), lambda t: F.softplus(t, 2.0, 5.0)), "mish": (x, (), F.mish),
+        "softshrink": (x, (0.3,), lambda t: F.softshrink(t, 0.3)), "pow": (pos, (1.7,), lambda t: torch.pow(t, 1.7)),
+        "add_scalar": (x, (0.37,), lambda t: t + 0.37), "mul_scalar": (x, (-1.9,), lambda t: t * -1.9), "rsub_scalar": (x, (2.5,), lambda t: 2.5 - t),
+        "rdiv_scalar": (pos, (3.0,), lambda t: 3.0 / t), "div_scalar": (x, (7.0,), lambda t: t / 7.0),
+    }
+    assert set(cases) == set(C.GENERIC_UNARY)
+    for name, (inp, params, fn) in cases.items():
+        p = list(params) + [0.0] * (2 - len(params))
+        out = C.g_unary(C.GENERIC_UNARY[name], inp, p[0], p[1])
+        assert out is not None, name
+        _close_to(out, fn(inp.float()).to(dtype), dtype)
+    view = x.t()                                           # non-contiguous input goes through the strided copy first
+    out = C.g_unary(C.GENERIC_UNARY["exp"], view)
+    _close_to(out, torch.exp(view.float()).to(dtype), dtype)
+    assert C.g_unary(C.GENERIC_UNARY["exp"], x.cpu()) is None and C.g_unary(0, torch.arange(4, device="cuda")) is None
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_generic_binary_broadcasting_reduce_softmax_concat_cast_fill(dtype):
+    C = ht._C
+    g = torch.Generator(device="cuda").manual_seed(1)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g).to(dtype)
+    a = rnd(4, 33, 65)
+    fns = {"add": torch.add, "sub": torch.sub, "mul": torch.mul, "div": torch.div, "max": torch.maximum, "min": torch.minimum}
+    for b in (rnd(4, 33, 65), rnd(65), rnd(33, 1), rnd(4, 1, 65), rnd(1), rnd(4, 33, 65).transpose(0, 1).contiguous().transpose(0, 1)):
+        for name, fn in fns.items():
+            bb = b.abs() + 0.5 if name == "div" else b
+            out = C.g_binary(C.GENERIC_BINARY[name], a, bb)
+            assert out is not None
+            _close_to(out, fn(a.float(), bb.float()).to(dtype), dtype)
+    base, expo = a.abs() + 0.1, rnd(65)
+    _close_to(C.g_binary(C.GENERIC_BINARY["pow"], base, expo), torch.pow(base.float(), expo.float()).to(dtype), dtype)
+    big = rnd(8192, 1031)
+    _close_to(C.g_binary(C.GENERIC_BINARY["add"], big, big), (big.float() + big.float()).to(dtype), dtype)       # flat 16-byte path + tail
+    assert C.g_binary(0, a, a.float() if dtype != torch.float32 else a.bfloat16()) is None                        # mixed dtypes: not ours
+
+    # reductions: last dim, first dim, middle dim, several dims, non-adjacent dims, everything; long single row (two-pass)
+    x = rnd(6, 50, 70)
+    lib = {"sum": torch.sum, "mean": torch.mean, "max": torch.amax, "min": torch.amin}
+    for axes in ([2], [0], [1], [1, 2], [0, 1], [0, 2], [0, 1, 2], [-1]):
+        for keep in (False, True):
+            for name, fn in lib.items():
+                out = C.g_reduce(C.GENERIC_REDUCE[name], x, axes, keep)
+                assert out is not None
+                ref = fn(x.float(), dim=axes, keepdim=keep).to(dtype)
+                if name in ("max", "min"):
+                    assert torch.equal(out, ref)
+                elif dtype == torch.float32:
+                    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)       # summation order differs from the library's
+                else:
+                    torch.testing.assert_close(out.float(), ref.float(), rtol=2e-2, atol=2e-2 * max(1.0, float(ref.float().abs().max())))
+    small = rnd(5, 6) * 0.3 + 1.0
+    torch.testing.assert_close(C.g_reduce(C.GENERIC_REDUCE["prod"], small, [1], False).float(), torch.prod(small.float(), 1), rtol=3e-2, atol=1e-3)
+    long_row = rnd(3, 300_000)
+    torch.testing.assert_close(C.g_reduce(C.GENERIC_REDUCE["sum"], long_row, [1], False).float(), long_row.float().sum(1), rtol=1e-2 if dtype != torch.float32 else 1e-4,
+                               atol=4.0 if dtype != torch.float32 else 5e-2)
+    tall = rnd(200_000, 40)
+    torch.testing.assert_close(C.g_reduce(C.GENERIC_REDUCE["mean"], tall, [0], False).float(), tall.float().mean(0), rtol=1e-2, atol=1e-2 if dtype != torch.float32 else 1e-5)
+    nanx = x.clone(); nanx[1, 2, 3] = float("nan")
+    assert bool(torch.isnan(C.g_reduce(C.GENERIC_REDUCE["max"], nanx, [2], False)[1, 2]))
+
+    # softmax / log-softmax along every dim, short and long rows
+    for t, dims in ((rnd(7, 33, 19), (0, 1, 2, -1)), (rnd(5, 50304), (1,)), (rnd(300, 200), (0, 1))):
+        for d in dims:
+            _close_to(C.g_softmax(False, t, d), torch.softmax(t.float(), d).to(dtype), dtype)
+            lo = C.g_softmax(True, t, d)
+            torch.testing.assert_close(lo.float(), torch.log_softmax(t.float(), d), rtol=2e-2 if dtype != torch.float32 else 1e-5,
+                                       atol=6e-2 if dtype != torch.float32 else 1e-5)
+
+    # concat along every dim (one input is a non-contiguous view), strided copy, casts, fill
+    parts = [rnd(3, 5, 8), rnd(3, 5, 8).transpose(0, 1).contiguous().transpose(0, 1), rnd(3, 5, 8)]
+    for d in (0, 1, 2, -1):
+        out = C.g_concat(parts, d)
+        assert out is not None and torch.equal(out, torch.cat(parts, d))
+    odd = [rnd(4, 3), rnd(4, 7), rnd(4, 1)]
+    assert torch.equal(C.g_concat(odd, 1), torch.cat(odd, 1))
+    v = rnd(6, 10, 14).permute(2, 0, 1)[1:, :, ::2]
+    assert torch.equal(C.g_contiguous(v), v.contiguous())
+    ints = torch.randint(-1000, 1000, (777,), device="cuda")
+    assert torch.equal(C.g_cast(ints, "float32"), ints.float()) and torch.equal(C.g_cast(ints, "int32"), ints.int())
+    f = rnd(1025) * 50
+    for name, td in (("float32", torch.float32), ("bfloat16", torch.bfloat16), ("float16", torch.float16), ("int64", torch.int64), ("int32", torch.int32)):
+        if td == dtype:
+            continue
+        assert torch.equal(C.g_cast(f, name), f.to(td)), name
+    for name, td in (("float32", torch.float32), ("bfloat16", torch.bfloat16), ("int64", torch.int64)):
+        out = C.g_full([3, 1001], name, 3.0)
+        assert out.dtype == td and out.shape == (3, 1001) and bool((out == 3).all())
+
+
 def test_gpt_block_training_matches_fp32_reference():
     """tiny GPT: native bf16 training vs the same graph on CPU fp32 -- loss curves must agree to bf16 accuracy"""
     from hetu_b200.models import GPTConfig, GPTLMHeadModel, generate_ds_parallel_config
