@@ -44,6 +44,7 @@ CXX_SOURCES = [
     "csrc/v1/embedding_cache.cc",
     "csrc/v1/ps_server.cc",
     "csrc/v1/ps_net.cc",
+    "csrc/v1/ps_scheduler.cc",
     "csrc/runtime/symm_mem.cc",
     "csrc/runtime/symm_vmm.cc",
     "csrc/runtime/memory_pool.cc",

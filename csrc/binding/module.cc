@@ -24,6 +24,7 @@
 #include "../runtime/memory_pool.h"
 #include "../v1/ps_server.h"
 #include "../v1/ps_net.h"
+#include "../v1/ps_scheduler.h"
 #include "../runtime/runtime.h"
 #include "../runtime/rpc_client.h"
 
@@ -758,6 +759,37 @@ PYBIND11_MODULE(_C, m) {
       .def("stop", &PsNetServer::stop, py::call_guard<py::gil_scoped_release>());
   {
     auto nogil = py::call_guard<py::gil_scoped_release>();
+    py::class_<PsNodeInfo>(m, "PsNodeInfo")
+        .def_readonly("role", &PsNodeInfo::role)
+        .def_readonly("rank", &PsNodeInfo::rank)
+        .def_readonly("host", &PsNodeInfo::host)
+        .def_readonly("port", &PsNodeInfo::port)
+        .def("__repr__", [](const PsNodeInfo& n) {
+          return std::string(n.role == 0 ? "server" : "worker") + "[" + std::to_string(n.rank) + "]@" + n.host + ":" + std::to_string(n.port);
+        });
+    py::class_<PsScheduler, std::shared_ptr<PsScheduler>>(m, "PsScheduler")
+        .def(py::init<int, int, int, const std::string&>(), py::arg("num_servers"), py::arg("num_workers"), py::arg("port") = 0,
+             py::arg("bind_addr") = "0.0.0.0")
+        .def_property_readonly("port", &PsScheduler::port)
+        .def("stop", &PsScheduler::stop, nogil)
+        .def("dead_nodes", &PsScheduler::dead_nodes, py::arg("timeout_s"))
+        .def_property_readonly("registered", &PsScheduler::registered)
+        .def_property_readonly("finalized", &PsScheduler::finalized)
+        .def("wait_finalized", &PsScheduler::wait_finalized, py::arg("timeout_s") = 60.0, nogil);
+    py::class_<PsSchedulerClient, std::shared_ptr<PsSchedulerClient>>(m, "PsSchedulerClient")
+        .def(py::init<const std::string&, int, int, const std::string&, int, double>(), py::arg("host"), py::arg("port"), py::arg("role"),
+             py::arg("my_host") = "127.0.0.1", py::arg("my_port") = 0, py::arg("connect_timeout") = 60.0, nogil)
+        .def_property_readonly("role", &PsSchedulerClient::role)
+        .def_property_readonly("rank", &PsSchedulerClient::rank)
+        .def_property_readonly("num_servers", &PsSchedulerClient::num_servers)
+        .def_property_readonly("num_workers", &PsSchedulerClient::num_workers)
+        .def_property_readonly("servers", &PsSchedulerClient::servers)
+        .def("barrier", &PsSchedulerClient::barrier, py::arg("group") = (int)kAllGroup, nogil)
+        .def("heartbeat", &PsSchedulerClient::heartbeat, nogil)
+        .def("dead_nodes", &PsSchedulerClient::dead_nodes, py::arg("timeout_s"), nogil)
+        .def("key_ranges", &PsSchedulerClient::key_ranges, py::arg("total"))
+        .def("finalize", &PsSchedulerClient::finalize, nogil)
+        .def("start_heartbeat", &PsSchedulerClient::start_heartbeat, py::arg("interval_s") = 1.0);
     py::class_<PsNetClient, std::shared_ptr<PsNetClient>>(m, "PsNetClient")
         .def(py::init<const std::string&, int, double>(), py::arg("host"), py::arg("port"), py::arg("connect_timeout") = 60.0, nogil)
         .def("init_dense", [](PsNetClient& ps, int64_t key, const std::vector<float>& v, PsOptimizer opt, float lr, float momentum) {

@@ -1,5 +1,7 @@
 #include "ps_net.h"
 
+#include "ps_wire.h"
+
 #include <arpa/inet.h>
 #include <netdb.h>
 #include <netinet/tcp.h>
@@ -11,80 +13,11 @@
 #include <stdexcept>
 
 namespace hb {
+using namespace ps_wire;
 namespace {
 
 enum Op : uint8_t { INIT_DENSE = 1, PUSH_DENSE, PULL_DENSE, PUSH_PULL_DENSE, INIT_SPARSE, PUSH_SPARSE, PULL_SPARSE, ROW_VERSIONS, SYNC_CACHE,
                     BARRIER, SSP_INIT, SSP_SYNC, PREDUCE, STATS, NUM_WORKERS };
-
-struct Writer {
-  std::string b;
-  template <typename T> void put(T v) { b.append(reinterpret_cast<const char*>(&v), sizeof v); }
-  template <typename T> void arr(const std::vector<T>& v) {
-    put<uint64_t>(v.size());
-    if (!v.empty()) b.append(reinterpret_cast<const char*>(v.data()), v.size() * sizeof(T));
-  }
-  void str(const std::string& s) { put<uint64_t>(s.size()); b += s; }
-  void cfg(const PsParamConfig& c) { put<int32_t>((int32_t)c.opt); put(c.lr); put(c.momentum); put(c.beta1); put(c.beta2); put(c.eps); }
-};
-struct Reader {
-  const std::string& b;
-  size_t i = 0;
-  explicit Reader(const std::string& s) : b(s) {}
-  template <typename T> T get() {
-    if (i + sizeof(T) > b.size()) throw std::runtime_error("ps: truncated frame");
-    T v;
-    memcpy(&v, b.data() + i, sizeof v);
-    i += sizeof v;
-    return v;
-  }
-  template <typename T> std::vector<T> arr() {
-    const uint64_t n = get<uint64_t>();
-    if (i + n * sizeof(T) > b.size()) throw std::runtime_error("ps: truncated array");
-    std::vector<T> v(n);
-    if (n) memcpy(v.data(), b.data() + i, n * sizeof(T));
-    i += n * sizeof(T);
-    return v;
-  }
-  std::string str() {
-    const uint64_t n = get<uint64_t>();
-    std::string s = b.substr(i, n);
-    i += n;
-    return s;
-  }
-  PsParamConfig cfg() {
-    PsParamConfig c;
-    c.opt = (PsOptimizer)get<int32_t>(); c.lr = get<float>(); c.momentum = get<float>(); c.beta1 = get<float>(); c.beta2 = get<float>(); c.eps = get<float>();
-    return c;
-  }
-};
-
-void write_all(int fd, const char* p, size_t n) {
-  while (n) {
-    ssize_t w = ::send(fd, p, n, MSG_NOSIGNAL);
-    if (w <= 0) throw std::runtime_error("ps: connection lost");
-    p += w; n -= (size_t)w;
-  }
-}
-bool read_all(int fd, char* p, size_t n) {
-  while (n) {
-    ssize_t r = ::recv(fd, p, n, 0);
-    if (r <= 0) return false;
-    p += r; n -= (size_t)r;
-  }
-  return true;
-}
-void send_frame(int fd, const std::string& s) {
-  uint32_t n = (uint32_t)s.size();
-  std::string buf(reinterpret_cast<const char*>(&n), 4);
-  buf += s;
-  write_all(fd, buf.data(), buf.size());
-}
-bool recv_frame(int fd, std::string* s) {
-  uint32_t n = 0;
-  if (!read_all(fd, reinterpret_cast<char*>(&n), 4)) return false;
-  s->assign(n, '\0');
-  return n == 0 || read_all(fd, &(*s)[0], n);
-}
 
 }  // namespace
 

@@ -6,8 +6,9 @@
       DMLC_PS_ROOT_PORT: 13100
     launch:
       worker: 4        # worker processes (HETU_PS_WORKER_ID = 0..3, HETU_PS_ADDRESS points at the server)
-      server: 1        # the parameter server is hosted by this launcher process (native transport, csrc/v1/ps_net.cc)
-      scheduler: 1     # accepted for compatibility: rendezvous is the server's listening socket
+      server: 1        # parameter servers hosted by this launcher process (native transport, csrc/v1/ps_net.cc)
+      scheduler: 1     # with more than one server the launcher also runs the native scheduler (csrc/v1/ps_scheduler.cc):
+                       # servers and workers register there, workers get HETU_PS_SCHEDULER and shard parameters over the servers
 
 (ref: hetu/v1/python/hetu/launcher.py `launch`, bin/heturun; ps-lite scheduler / server / worker roles)"""
 from __future__ import annotations
@@ -29,7 +30,21 @@ def launch(command: Sequence[str], settings: Dict, log_dir: Optional[str] = None
     lc = settings.get("launch") or {}
     n_worker, n_server = int(lc.get("worker", 1)), int(lc.get("server", 1))
     port = int(shared.get("DMLC_PS_ROOT_PORT", 0))
-    server = PSContext.serve(n_worker, port) if n_server > 0 else None
+    sched, shard_servers = None, []
+    if n_server > 1:
+        import threading
+
+        from .. import _C
+        from .ps import ShardedPSContext
+        sched = _C.PsScheduler(n_server, n_worker, port, "0.0.0.0")
+        addr = f"{shared.get('DMLC_PS_ROOT_URI', '127.0.0.1')}:{sched.port}"
+        # registration blocks until the workers are up too: the server roles register from threads
+        for _ in range(n_server):
+            t = threading.Thread(target=lambda: shard_servers.append(ShardedPSContext.serve(addr, num_workers=n_worker, heartbeat_s=1.0)), daemon=True)
+            t.start()
+        server = None
+    else:
+        server = PSContext.serve(n_worker, port) if n_server > 0 else None
     procs: List[subprocess.Popen] = []
     for w in range(n_worker):
         env = dict(os.environ)
@@ -38,6 +53,8 @@ def launch(command: Sequence[str], settings: Dict, log_dir: Optional[str] = None
                     "WORKER_ID": str(w)})
         if server is not None:
             env["HETU_PS_ADDRESS"] = f"{shared.get('DMLC_PS_ROOT_URI', '127.0.0.1')}:{server.port}"
+        if sched is not None:
+            env["HETU_PS_SCHEDULER"] = f"{shared.get('DMLC_PS_ROOT_URI', '127.0.0.1')}:{sched.port}"
         out = open(os.path.join(log_dir, f"worker{w}.log"), "w") if log_dir else None
         procs.append(subprocess.Popen(list(command), env=env, stdout=out, stderr=subprocess.STDOUT if out else None))
 
@@ -47,11 +64,16 @@ def launch(command: Sequence[str], settings: Dict, log_dir: Optional[str] = None
                 p.kill()
     signal.signal(signal.SIGINT, stop)
     if not wait:
-        return procs, server
+        return procs, (server if sched is None else sched)
     from ..rpc.launcher import _wait_all
     codes = _wait_all(procs, timeout)
     if server is not None:
         server.stop()
+    if sched is not None:
+        for net, client in shard_servers:
+            client.finalize()
+            net.stop()
+        sched.stop()
     return codes
 
 

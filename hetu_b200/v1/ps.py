@@ -121,3 +121,123 @@ class CacheSparseTable:
 
     def stats(self):
         return self.cache.stats()
+
+
+class ShardedPSContext:
+    """Worker-side view of a multi-server deployment managed by the native scheduler (`_C.PsScheduler`): the worker registers,
+    learns the server table, and partitions parameters over the servers the way ps-lite's key ranges do -- a dense parameter
+    is cut into `num_servers` contiguous slices (slice s lives on server s), a sparse table is split by `row % num_servers`.
+    Barriers go through the scheduler (worker group); every server sees `num_workers` workers.
+    (ref: hetu/v1/ps-lite/src/postoffice.cc GetServerKeyRanges, kv_app.h DefaultSlicer)"""
+
+    SERVER, WORKER = 0, 1
+
+    def __init__(self, scheduler: str, my_host: str = "127.0.0.1", heartbeat_s: float = 0.0):
+        host, port = scheduler.rsplit(":", 1)
+        self.sched = _C.PsSchedulerClient(host, int(port), self.WORKER, my_host, 0)
+        self.worker_id, self.num_workers, self.num_servers = self.sched.rank, self.sched.num_workers, self.sched.num_servers
+        self.servers = [_C.PsNetClient(s.host, s.port) for s in self.sched.servers]
+        self._keys: Dict[str, int] = {}
+        self._dense_len: Dict[str, int] = {}
+        if heartbeat_s > 0:
+            self.sched.start_heartbeat(heartbeat_s)
+
+    @staticmethod
+    def serve(scheduler: str, my_host: str = "127.0.0.1", port: int = 0, num_workers: Optional[int] = None, heartbeat_s: float = 0.0):
+        """server role: start the native store + its TCP transport, then register the address with the scheduler (blocks until
+        the whole deployment has registered).  The worker count is a property of the deployment (DMLC_NUM_WORKER /
+        HETU_PS_NUM_WORKERS, as in ps-lite) unless given.  -> (PsNetServer, PsSchedulerClient)"""
+        import os
+        if num_workers is None:
+            num_workers = int(os.environ.get("DMLC_NUM_WORKER", os.environ.get("HETU_PS_NUM_WORKERS", "1")))
+        host, sport = scheduler.rsplit(":", 1)
+        net = _C.PsNetServer(_C.ParameterServer(int(num_workers)), int(port), "0.0.0.0")
+        client = _C.PsSchedulerClient(host, int(sport), ShardedPSContext.SERVER, my_host, net.port)
+        if heartbeat_s > 0:
+            client.start_heartbeat(heartbeat_s)
+        return net, client
+
+    def key(self, name: str) -> int:
+        import zlib
+        return self._keys.setdefault(name, (zlib.crc32(name.encode()) | (len(name) << 32)) & ((1 << 40) - 1))
+
+    def _ranges(self, n: int):
+        b = self.sched.key_ranges(int(n))
+        return [(int(b[i]), int(b[i + 1])) for i in range(self.num_servers)]
+
+    # ---- dense: slice s of the flattened parameter lives on server s
+    def init_dense(self, name, value: np.ndarray, opt="sgd", lr=0.01):
+        v = np.asarray(value, np.float32).reshape(-1)
+        self._dense_len[name] = v.size
+        for s, (lo, hi) in enumerate(self._ranges(v.size)):
+            if hi > lo:
+                self.servers[s].init_dense(self.key(name), v[lo:hi].tolist(), _OPT[opt], lr)
+
+    def push(self, name, grad: np.ndarray):
+        g = np.asarray(grad, np.float32).reshape(-1)
+        for s, (lo, hi) in enumerate(self._ranges(g.size)):
+            if hi > lo:
+                self.servers[s].push_dense(self.key(name), g[lo:hi].tolist())
+
+    def pull(self, name, shape=None) -> np.ndarray:
+        n = self._dense_len.get(name) or (int(np.prod(shape)) if shape is not None else None)
+        assert n is not None, f"unknown size of dense parameter {name}: pass shape"
+        out = np.empty(n, np.float32)
+        for s, (lo, hi) in enumerate(self._ranges(n)):
+            if hi > lo:
+                out[lo:hi] = self.servers[s].pull_dense(self.key(name))
+        return out.reshape(shape) if shape is not None else out
+
+    def push_pull(self, name, grad, shape=None):
+        g = np.asarray(grad, np.float32).reshape(-1)
+        out = np.empty_like(g)
+        for s, (lo, hi) in enumerate(self._ranges(g.size)):
+            if hi > lo:
+                out[lo:hi] = self.servers[s].push_pull_dense(self.key(name), g[lo:hi].tolist())
+        return out.reshape(shape) if shape is not None else out
+
+    # ---- sparse: row r lives on server r % S as local row r // S
+    def init_sparse(self, name, value: np.ndarray, opt="sgd", lr=0.01):
+        value = np.asarray(value, np.float32)
+        for s in range(self.num_servers):
+            part = value[s::self.num_servers]
+            if part.shape[0]:
+                self.servers[s].init_sparse(self.key(name), part.shape[0], part.shape[1], part.reshape(-1).tolist(), _OPT[opt], lr)
+
+    def sparse_pull(self, name, rows: Sequence[int], width: int) -> np.ndarray:
+        rows = np.asarray(rows, np.int64).reshape(-1)
+        out = np.empty((rows.size, width), np.float32)
+        for s in range(self.num_servers):
+            sel = np.nonzero(rows % self.num_servers == s)[0]
+            if sel.size:
+                got = self.servers[s].pull_sparse(self.key(name), (rows[sel] // self.num_servers).tolist())
+                out[sel] = np.asarray(got, np.float32).reshape(sel.size, width)
+        return out
+
+    def sparse_push(self, name, rows: Sequence[int], grads: np.ndarray):
+        rows = np.asarray(rows, np.int64).reshape(-1)
+        grads = np.asarray(grads, np.float32).reshape(rows.size, -1)
+        for s in range(self.num_servers):
+            sel = np.nonzero(rows % self.num_servers == s)[0]
+            if sel.size:
+                self.servers[s].push_sparse(self.key(name), (rows[sel] // self.num_servers).tolist(), grads[sel].reshape(-1).tolist())
+
+    # ---- control plane
+    def barrier(self):
+        self.sched.barrier(2)          # worker group
+
+    def dead_nodes(self, timeout_s: float):
+        return self.sched.dead_nodes(float(timeout_s))
+
+    def finalize(self):
+        self.sched.finalize()
+
+
+def connect(**kw):
+    """the parameter-server context of this worker process: sharded over several servers when the launcher started a scheduler
+    (HETU_PS_SCHEDULER), a single server otherwise (HETU_PS_ADDRESS or in-process)"""
+    import os
+    sched = os.environ.get("HETU_PS_SCHEDULER")
+    if sched:
+        return ShardedPSContext(sched, heartbeat_s=float(kw.pop("heartbeat_s", 1.0)))
+    return PSContext(**kw)

@@ -242,3 +242,87 @@ def test_elastic_node_detection_replan_and_rank_remapping():
             srv.rpc_Connect("c3", "hB")                   # no rank left for that host in the plan
     finally:
         srv.shutdown()
+
+
+def test_ps_scheduler_sharded_servers_key_ranges_barriers_heartbeats():
+    """ref: ps-lite scheduler / postoffice -- 2 servers + 3 workers register with the scheduler, dense parameters are cut into
+    per-server key ranges, sparse rows go to row % S, worker barriers run through the scheduler, a silent node shows up as
+    dead, everybody checks out"""
+    import os
+    import threading
+    import time
+
+    import numpy as np
+
+    from hetu_b200 import _C
+    from hetu_b200.v1.ps import ShardedPSContext
+    S, W = 2, 3
+    sched = _C.PsScheduler(S, W, 0, "127.0.0.1")
+    addr = f"127.0.0.1:{sched.port}"
+    os.environ["HETU_PS_NUM_WORKERS"] = str(W)
+    servers, workers, errors = [None] * S, [None] * W, []
+
+    def start_server(i):
+        try:
+            servers[i] = ShardedPSContext.serve(addr)
+        except Exception as e:      # noqa: BLE001
+            errors.append(repr(e))
+
+    def start_worker(i):
+        try:
+            workers[i] = ShardedPSContext(addr)
+        except Exception as e:      # noqa: BLE001
+            errors.append(repr(e))
+    ts = [threading.Thread(target=start_server, args=(i,)) for i in range(S)] + [threading.Thread(target=start_worker, args=(i,)) for i in range(W)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(60)
+    assert not errors and sched.registered == S + W, errors
+    assert sorted(w.worker_id for w in workers) == [0, 1, 2] and sorted(c.rank for _, c in servers) == [0, 1]
+    w0 = workers[0]
+    assert w0.num_servers == S and w0.num_workers == W and [s.rank for s in w0.sched.servers] == [0, 1]
+    assert w0.sched.key_ranges(11) == [0, 6, 11] and w0.sched.key_ranges(4) == [0, 2, 4]
+
+    # dense: every worker pushes a gradient; SGD on the servers; each server holds only its slice
+    init = np.arange(11, dtype=np.float32)
+    w0.init_dense("w", init, opt="sgd", lr=0.5)
+    for w in workers[1:]:
+        w._dense_len["w"] = 11
+    done = []
+
+    def step(w):
+        w.push("w", np.ones(11, np.float32) * (w.worker_id + 1))
+        w.barrier()                                    # all pushes have landed once every worker passed the barrier
+        done.append(w.pull("w"))
+    ts = [threading.Thread(target=step, args=(w,)) for w in workers]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(60)
+    assert len(done) == W
+    for got in done:
+        np.testing.assert_allclose(got, init - 0.5 * (1 + 2 + 3), rtol=1e-6)
+    per_server = [w0.servers[s].pull_dense(w0.key("w")) for s in range(S)]
+    assert [len(p) for p in per_server] == [6, 5]
+
+    # sparse: rows split by row % S
+    table = np.arange(10 * 4, dtype=np.float32).reshape(10, 4)
+    w0.init_sparse("emb", table, opt="sgd", lr=1.0)
+    np.testing.assert_array_equal(workers[1].sparse_pull("emb", [9, 0, 3, 4], 4), table[[9, 0, 3, 4]])
+    workers[2].sparse_push("emb", [3, 4], np.ones((2, 4), np.float32))
+    np.testing.assert_array_equal(workers[0].sparse_pull("emb", [3, 4, 5], 4), np.stack([table[3] - 1, table[4] - 1, table[5]]))
+
+    # liveness: nobody heartbeats for 0.3 s except worker 0 and server 0 -> the others are reported
+    time.sleep(0.35)
+    w0.sched.heartbeat(); servers[0][1].heartbeat()
+    dead = w0.dead_nodes(0.3)
+    assert len(dead) == S + W - 2 and all(not (d.role == 1 and d.rank == w0.worker_id) for d in dead)
+    for w in workers:
+        w.finalize()
+    for net, c in servers:
+        c.finalize()
+    assert sched.wait_finalized(10.0) and sched.finalized == S + W
+    for net, _ in servers:
+        net.stop()
+    sched.stop()

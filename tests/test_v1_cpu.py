@@ -253,3 +253,29 @@ def test_parameter_server_over_the_network_with_heturun_launcher(tmp_path):
     for w, l in enumerate(lines):
         assert f"worker={w} " in l and "preduce=[1.0, 1.0, 1.0, 1.0]" in l and "partners=[0, 1, 2]" in l
         assert float(l.split("err=")[1].split()[0]) < 0.05
+
+
+def test_sharded_parameter_servers_behind_the_scheduler_with_heturun(tmp_path):
+    """`server: 2` in the launch file: the launcher runs the native scheduler and two server roles, 3 worker processes register,
+    shard the dense weight over the servers' key ranges and an embedding table over row % 2, synchronise through scheduler
+    barriers and converge"""
+    import os
+    import sys
+    from hetu_b200.v1.launcher import launch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    logs = tmp_path / "logs"
+    logs.mkdir()
+    env_keep = dict(os.environ)
+    os.environ.update({"PYTHONPATH": root, "HETU_B200_FORCE_CPU": "1", "CUDA_VISIBLE_DEVICES": "", "OMP_NUM_THREADS": "1"})
+    try:
+        codes = launch([sys.executable, os.path.join(root, "tests", "workers", "ps_sharded_worker.py")],
+                       {"shared": {"DMLC_PS_ROOT_URI": "127.0.0.1"}, "launch": {"worker": 3, "server": 2, "scheduler": 1}}, log_dir=str(logs), timeout=240)
+    finally:
+        os.environ.clear()
+        os.environ.update(env_keep)
+    text = "\n".join((logs / f"worker{w}.log").read_text() for w in range(3))
+    assert codes == [0, 0, 0], text
+    lines = sorted(l for l in text.splitlines() if l.startswith("PSSHARD"))
+    assert len(lines) == 3, text
+    for l in lines:
+        assert float(l.split("err=")[1].split()[0]) < 0.05 and "emb7=3.0" in l and "own=1.0" in l and "dead=0" in l, l
