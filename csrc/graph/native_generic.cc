@@ -23,13 +23,17 @@ static int gd_of(at::ScalarType t) {
     default: return -1;
   }
 }
+// Ops without a hand-written gradient are differentiated by re-running their compute function under ATen autograd
+// (graph.cc `autograd_vjp`): there the result must carry an autograd history, so the native kernels step aside.
+static bool traced(const at::Tensor& t) { return at::GradMode::is_enabled() && t.defined() && t.requires_grad(); }
 static bool float_cuda(const at::Tensor& t) {
-  return generic_enabled() && t.defined() && t.is_cuda() && t.numel() > 0 &&
+  return generic_enabled() && t.defined() && t.is_cuda() && t.numel() > 0 && !traced(t) &&
          (t.scalar_type() == at::kFloat || t.scalar_type() == at::kBFloat16 || t.scalar_type() == at::kHalf);
 }
 
 at::Tensor g_contiguous(const at::Tensor& x) {
-  if (!generic_enabled() || !x.is_cuda() || x.is_contiguous() || x.numel() == 0 || x.dim() > 8 || x.numel() >= (1ll << 31)) return at::Tensor();
+  if (!generic_enabled() || !x.is_cuda() || x.is_contiguous() || x.numel() == 0 || x.dim() > 8 || x.numel() >= (1ll << 31) || traced(x))
+    return at::Tensor();
   at::Tensor out = at::empty(x.sizes(), x.options());
   const auto dst = out.strides();
   if (strided_copy((int)x.element_size(), x.data_ptr(), out.data_ptr(), (int)x.dim(), x.sizes().data(), x.strides().data(), dst.data(),
@@ -161,7 +165,7 @@ at::Tensor g_concat(const std::vector<at::Tensor>& in, int64_t dim) {
   std::vector<int64_t> shape = in[0].sizes().vec();
   int64_t total = 0;
   for (auto& t : in) {
-    if (!t.is_cuda() || t.scalar_type() != in[0].scalar_type() || t.dim() != nd || t.device() != in[0].device()) return at::Tensor();
+    if (!t.is_cuda() || t.scalar_type() != in[0].scalar_type() || t.dim() != nd || t.device() != in[0].device() || traced(t)) return at::Tensor();
     for (int d = 0; d < nd; ++d) if (d != dim && t.size(d) != shape[d]) return at::Tensor();
     total += t.size(dim);
   }
@@ -184,7 +188,7 @@ at::Tensor g_concat(const std::vector<at::Tensor>& in, int64_t dim) {
 }
 
 at::Tensor g_cast(const at::Tensor& x, at::ScalarType to) {
-  if (!generic_enabled() || !x.is_cuda() || x.numel() == 0 || x.scalar_type() == to) return at::Tensor();
+  if (!generic_enabled() || !x.is_cuda() || x.numel() == 0 || x.scalar_type() == to || traced(x)) return at::Tensor();
   const int s = gd_of(x.scalar_type()), d = gd_of(to);
   if (s < 0 || d < 0 || d == GD_U8 || x.scalar_type() == at::kBool) return at::Tensor();
   at::Tensor xc = x.is_contiguous() ? x : g_contiguous(x);
