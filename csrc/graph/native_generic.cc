@@ -1,6 +1,8 @@
 // at::Tensor front-ends of the generic device kernels (csrc/kernels/generic.cu).  Every function returns an undefined tensor
 // when the native kernel does not apply (CPU tensor, integer dtype, rank > 8, HETU_NATIVE_GENERIC=0 ...); the caller then takes
 // the ATen path, so the op semantics never depend on which one ran.
+#include <ATen/core/grad_mode.h>
+
 #include <algorithm>
 
 #include "../kernels/kernels.h"
@@ -129,8 +131,8 @@ at::Tensor g_reduce(int mode, const at::Tensor& x, std::vector<int64_t> axes, bo
   at::Tensor out = at::empty(oshape, x.options());
   if (out.numel() == 0) return out;
   at::Tensor ws;
-  const bool long_red = red >= 4096 && (inner == 1 ? outer * 256 : outer * inner) < 148 * 1024;
-  if (long_red) ws = at::empty({generic_reduce_workspace_floats(outer, inner)}, x.options().dtype(at::kFloat));
+  const int64_t ws_floats = generic_reduce_workspace_floats(outer, red, inner);
+  if (ws_floats > 0) ws = at::empty({ws_floats}, x.options().dtype(at::kFloat));
   if (generic_reduce(mode, gd_of(x.scalar_type()), xc.data_ptr(), out.data_ptr(), ws.defined() ? ws.data_ptr<float>() : nullptr, outer, red, inner,
                      cur_stream()) != cudaSuccess) {
     cudaGetLastError();

@@ -476,12 +476,7 @@ namespace {
 template <int MODE, typename T>
 cudaError_t reduce_launch(const T* x, T* y, float* workspace, int64_t outer, int64_t red, int64_t inner, float scale, cudaStream_t s) {
   // one pass when it fills the machine; otherwise split the reduced extent into chunks -> fp32 partials -> second pass
-  const int64_t parallel = inner == 1 ? outer * 256 : outer * inner;
-  int chunks = 1;
-  if (parallel < 148 * 1024 && red >= 4096) {
-    chunks = (int)std::min<int64_t>(std::min<int64_t>(64, red / 1024), std::max<int64_t>(1, (148 * 2048) / std::max<int64_t>(parallel, 1)));
-    if (chunks < 2) chunks = 1;
-  }
+  int chunks = generic_reduce_chunks(outer, red, inner);
   if (chunks > 1 && workspace == nullptr) chunks = 1;
   const int64_t chunk_len = (red + chunks - 1) / chunks;
   if (inner == 1) {
@@ -515,7 +510,19 @@ cudaError_t reduce_dtype(int dtype, const void* x, void* y, float* ws, int64_t o
 }
 }  // namespace
 
-int64_t generic_reduce_workspace_floats(int64_t outer, int64_t inner) { return 64 * outer * inner; }
+// number of slices the reduced extent is cut into: enough (row, slice) blocks / (column, slice) threads to cover ~2 waves of the
+// machine, at least 1024 elements per slice, at most 1024 slices
+int generic_reduce_chunks(int64_t outer, int64_t red, int64_t inner) {
+  const int64_t parallel = inner == 1 ? outer * 256 : outer * inner;      // threads one pass would run
+  if (parallel >= 148 * 1024 || red < 4096) return 1;
+  const int64_t want = (148 * 2048 + parallel - 1) / std::max<int64_t>(parallel, 1);
+  const int64_t chunks = std::min<int64_t>(std::min<int64_t>(1024, red / 1024), want);
+  return chunks < 2 ? 1 : (int)chunks;
+}
+int64_t generic_reduce_workspace_floats(int64_t outer, int64_t red, int64_t inner) {
+  const int chunks = generic_reduce_chunks(outer, red, inner);
+  return chunks > 1 ? (int64_t)chunks * outer * inner : 0;
+}
 
 cudaError_t generic_reduce(int mode, int dtype, const void* x, void* y, float* workspace, int64_t outer, int64_t red, int64_t inner,
                            cudaStream_t s) {

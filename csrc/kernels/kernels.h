@@ -48,7 +48,8 @@ cudaError_t generic_binary(int op, int dtype, const void* a, const void* b, void
                            const int64_t* a_strides, const int64_t* b_strides, cudaStream_t s);
 // x viewed as contiguous [outer, red, inner] -> y [outer, inner]; workspace (fp32, generic_reduce_workspace_floats) enables the
 // two-pass path for long reductions with little outer parallelism
-int64_t generic_reduce_workspace_floats(int64_t outer, int64_t inner);
+int generic_reduce_chunks(int64_t outer, int64_t red, int64_t inner);
+int64_t generic_reduce_workspace_floats(int64_t outer, int64_t red, int64_t inner);     // 0: one pass, no workspace needed
 cudaError_t generic_reduce(int mode, int dtype, const void* x, void* y, float* workspace, int64_t outer, int64_t red, int64_t inner,
                            cudaStream_t s);
 // softmax / log-softmax along the middle extent of a contiguous [outer, dim, inner] view
