@@ -279,3 +279,38 @@ def test_sharded_parameter_servers_behind_the_scheduler_with_heturun(tmp_path):
     assert len(lines) == 3, text
     for l in lines:
         assert float(l.split("err=")[1].split()[0]) < 0.05 and "emb7=3.0" in l and "own=1.0" in l and "dead=0" in l, l
+
+
+def test_embedding_compression_trainer_schedules_and_rate_sizing():
+    """ref: tools/EmbeddingMemoryCompression run_compressed.py + methods/scheduler -- the harness sizes a method for a target rate,
+    trains a CTR model on the planted-signal stream, runs the method's schedule and reports AUC + achieved compression"""
+    from hetu_b200.tools.emb_compress.trainer import CompressionTrainer, SyntheticCTR, plan_for_rate
+    # sizing: the planned constructor arguments land near the requested parameter budget
+    from hetu_b200.tools.emb_compress import build_compressed_embedding
+    import hetu_b200 as ht
+    with ht.graph("define_and_run", create_new=True):
+        for m in ("hash", "robe", "adapt", "dpq"):
+            e = build_compressed_embedding(m, 8000, 16, **plan_for_rate(m, 8000, 16, 0.1))
+            assert 5.0 <= e.compression_ratio() <= 16.0, (m, e.compression_ratio())
+    data = SyntheticCTR(2000, 4, 3)
+    f = data.frequency(20000)
+    assert f.sum() > 0 and f[:500].sum() > 0                     # every field contributes ids; the head of each field dominates
+    common = dict(num_embeddings=2000, dim=8, num_fields=4, num_dense=3, batch_size=128, compress_rate=0.25, lr=0.02)
+    full = CompressionTrainer(None, "wdl", **common).run(steps=50, eval_batches=3)
+    assert full["auc"] > 0.62 and full["stage1_loss"][1] < full["stage1_loss"][0] and full["ratio"] == 1.0
+    hashed = CompressionTrainer("hash", "wdl", **common).run(steps=50, eval_batches=3)
+    assert 3.5 <= hashed["ratio"] <= 4.5 and 0.5 < hashed["auc"] <= full["auc"] + 0.05
+    # DeepLight: the mask refresh prunes towards the target while training continues
+    dl = CompressionTrainer("deeplight", "deepfm", **common)
+    r = dl.run(steps=40, eval_batches=2)
+    assert 0.0 < r["schedule"]["sparsity"] <= 0.75 and r["effective_ratio"] > 1.0
+    w, mask = dl.value_of(dl.embedding.weight), dl.value_of(dl.embedding.mask)
+    assert abs(float((mask == 0).mean()) - r["schedule"]["sparsity"]) < 1e-6
+    # AutoDim: search stage picks a width, stage 2 retrains a table of that width
+    ad = CompressionTrainer("autodim", "deepfm", **common)
+    r = ad.run(steps=25, eval_batches=2)
+    assert r["schedule"]["selected_dim"] in (2, 4, 8) and "stage1" in r and "stage2_loss" in r
+    assert ad.embedding.dim == r["schedule"]["selected_dim"]
+    # OptEmbed: supernet with sampled widths, then the width search
+    oe = CompressionTrainer("optembed", "deepfm", **common).run(steps=25, eval_batches=2)
+    assert oe["schedule"]["searched_dim"] in (2, 4, 6, 8) and len(oe["schedule"]["candidate_auc"]) >= 3
