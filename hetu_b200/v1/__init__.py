@@ -15,7 +15,8 @@ from .executor import (Variable, placeholder_op, Executor, HetuConfig, gradients
 from . import initializers, initializers as init, layers, lr_scheduler, metrics, dataloader, onnx  # noqa: F401
 from .dataloader import Dataloader, dataloader_op  # noqa: F401
 from .optimizer import SGDOptimizer, MomentumOptimizer, AdaGradOptimizer, AdamOptimizer  # noqa: F401
-from .ps import PSContext, CacheSparseTable  # noqa: F401
+from . import optimizer as optim  # noqa: F401  (v1: ht.optim.SGDOptimizer)
+from .ps import PSContext, ShardedPSContext, CacheSparseTable  # noqa: F401
 from . import strategies as dist  # noqa: F401
 from .strategies import (DataParallel, ModelParallel4CNN, ModelParallel4LM, OneWeirdTrick4CNN, MegatronLM, FlexFlowSearching,  # noqa: F401
                          OptCNNSearching, GPipeSearching, PipeDreamSearching, PipeOptSearching)

@@ -27,6 +27,7 @@ def rcpu(host, i=0): return _Ctx("cpu", i, host)   # noqa: E704
 def rgpu(host, i=0): return _Ctx("gpu", i, host)   # noqa: E704
 
 
+_EMBED_IDS = set()
 _graph = None
 _graph_ctx = None      # the context manager must stay alive, otherwise the graph is popped again
 
@@ -55,6 +56,8 @@ def Variable(name, value=None, initializer=None, trainable=True, shape=None, dty
     else:
         init = initializer or core.xavier_uniform_initializer()
         t = core.parameter(init, list(shape), dtype=dtype, requires_grad=trainable, name=name)
+    if is_embed:
+        _EMBED_IDS.add(t.id)         # Hybrid mode keeps these tables on the parameter server (sparse push / pull)
     return t
 
 
@@ -152,6 +155,76 @@ class Executor:
         if seed is not None:
             core.set_seed(seed)
         self.step = 0
+        self.ps = kw.get("ps")                    # a PSContext / ShardedPSContext; default: ps.connect() on first use
+        self._ps_plans = {}                       # train node id -> (params on the server, their gradient nodes, server optimizer)
+
+    # ---- parameter-server modes -----------------------------------------------------------------------------------
+    # 'PS': every trainable variable lives on the server(s); a step fetches the gradients instead of running the local update ops,
+    # pushes them, and installs the values the server answers with (the server applies the optimizer: BSP through the barrier).
+    # 'Hybrid': only the embedding tables (Variable(..., is_embed=True)) are on the server, as sparse tables -- a step pushes the
+    # rows that received gradient and pulls them back; dense variables keep the local optimizer behind the gradient all-reduce.
+    # (ref: hetu/v1/python/hetu/gpu_ops/executor.py comm_mode handling, ParameterServerCommunicate / ParameterServerSparsePull ops)
+    def _ps_context(self):
+        if self.ps is None:
+            from . import ps as _ps
+            self.ps = _ps.connect()
+        return self.ps
+
+    def _ps_plan(self, opt):
+        key = opt.v1_train_node.id
+        if key in self._ps_plans:
+            return self._ps_plans[key]
+        from ..graph_api import gradients as _grads
+        params = list(opt.v1_var_list) if opt.v1_var_list is not None else [p for p in self.graph.parameters() if p.requires_grad]
+        if self.comm_mode == "Hybrid":
+            params = [p for p in params if p.id in _EMBED_IDS]
+        grads = _grads(opt.v1_loss, params) if params else []
+        pairs = [(p, g) for p, g in zip(params, grads) if g is not None]
+        ps = self._ps_context()
+        kind, lr = opt.v1_server_opt
+        if getattr(ps, "worker_id", 0) == 0:
+            for p, _ in pairs:
+                value = self.graph.get_param(p).float().cpu().numpy()
+                if self.comm_mode == "Hybrid":
+                    ps.init_sparse(p.name, value.reshape(value.shape[0], -1), opt=kind, lr=lr)
+                else:
+                    ps.init_dense(p.name, value, opt=kind, lr=lr)
+        ps.barrier()
+        for p, _ in pairs:                         # every worker starts from the server's copy
+            if self.comm_mode == "Hybrid":
+                continue
+            if hasattr(ps, "_dense_len"):
+                ps._dense_len[p.name] = int(np.prod(p.shape))
+            self.graph.set_param(p, torch.as_tensor(ps.pull(p.name, list(p.shape))))
+        self._ps_plans[key] = (pairs, kind, lr)
+        return self._ps_plans[key]
+
+    def _ps_step(self, opt, grad_values):
+        ps = self._ps_context()
+        pairs, _, _ = self._ps_plan(opt)
+        nw = max(int(getattr(ps, "num_workers", 1)), 1)
+        if self.comm_mode == "PS":
+            for (p, _), g in zip(pairs, grad_values):
+                ps.push(p.name, g.float().cpu().numpy() / nw)           # the server sums the workers' shares
+            ps.barrier()                                                 # BSP: all pushes of the step are in
+            for p, _ in pairs:
+                self.graph.set_param(p, torch.as_tensor(ps.pull(p.name, list(p.shape))))
+            ps.barrier()                                                 # nobody pushes step t+1 before everyone pulled step t
+            return
+        for (p, _), g in zip(pairs, grad_values):                       # Hybrid: sparse rows of the embedding tables
+            g2 = g.float().cpu().numpy().reshape(p.shape[0], -1)
+            rows = np.nonzero(np.abs(g2).sum(1))[0]
+            if rows.size:
+                ps.sparse_push(p.name, rows.tolist(), g2[rows] / nw)
+        ps.barrier()
+        for (p, _), g in zip(pairs, grad_values):
+            g2 = g.float().cpu().numpy().reshape(p.shape[0], -1)
+            rows = np.nonzero(np.abs(g2).sum(1))[0]
+            if rows.size:
+                table = self.graph.get_param(p).float().cpu().clone()
+                table.reshape(p.shape[0], -1)[torch.as_tensor(rows)] = torch.as_tensor(ps.sparse_pull(p.name, rows.tolist(), g2.shape[1]))
+                self.graph.set_param(p, table)
+        ps.barrier()
 
     def run(self, name="default", eval_node_list=None, feed_dict: Optional[Dict] = None, convert_to_numpy_ret_vals=False, **kw):
         if isinstance(name, dict) and feed_dict is None:
@@ -175,7 +248,27 @@ class Executor:
             from .. import distributed
             dp = max(distributed.world_size(), 1)
         training = any(isinstance(n, Tensor) and n.producer_type in ("adam_update", "sgd_update", "group") for n in nodes)
-        outs = self.graph.run(loss if training else None, nodes, feed, grad_scale=1.0 / dp)
+        ps_opts = []
+        if training and self.comm_mode in ("PS", "Hybrid"):
+            ps_opts = [o for o in self._optimizers() if any(n is o.v1_train_node or getattr(n, "id", None) == o.v1_train_node.id for n in nodes)]
+        if ps_opts:
+            # fetch the gradients of the server-held variables next to the user's nodes; in 'PS' mode the local update ops are
+            # dropped from the fetch list (the server is the optimizer), in 'Hybrid' they still run for the dense variables
+            plans = [self._ps_plan(o) for o in ps_opts]
+            extra = [g for pairs, _, _ in plans for _, g in pairs]
+            train_ids = {o.v1_train_node.id for o in ps_opts}
+            fetch = [n for n in nodes if not (self.comm_mode == "PS" and getattr(n, "id", None) in train_ids)] + extra
+            got = self.graph.run(loss, fetch, feed, grad_scale=1.0 / dp)
+            n_user = len(fetch) - len(extra)
+            user_vals, grad_vals = got[:n_user], got[n_user:]
+            at = 0
+            for o, (pairs, _, _) in zip(ps_opts, plans):
+                self._ps_step(o, grad_vals[at:at + len(pairs)])
+                at += len(pairs)
+            it = iter(user_vals)
+            outs = [None if (self.comm_mode == "PS" and getattr(n, "id", None) in train_ids) else next(it) for n in nodes]
+        else:
+            outs = self.graph.run(loss if training else None, nodes, feed, grad_scale=1.0 / dp)
         self.step += 1
         if any(isinstance(n, Tensor) and n.producer_type in ("adam_update", "sgd_update", "group") for n in nodes):
             for opt in self._optimizers():

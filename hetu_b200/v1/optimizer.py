@@ -19,8 +19,15 @@ class _Base:
         opt.v1_scheduler = self.scheduler
         self.backend = opt
         node = opt.minimize(loss, var_list) if var_list is not None else opt.minimize(loss)
+        # what the parameter-server modes of the Executor need: which loss / variables this training node stands for and how the
+        # server should apply a gradient (the local update ops stay in the graph but are not fetched in PS mode)
+        opt.v1_loss, opt.v1_var_list, opt.v1_train_node = loss, var_list, node
+        opt.v1_server_opt = self._server_opt()
         _LIVE.append(opt)
         return node
+
+    def _server_opt(self):
+        return ("sgd", float(self.learning_rate))
 
 
 class SGDOptimizer(_Base):
@@ -36,11 +43,17 @@ class MomentumOptimizer(_Base):
     def _make(self):
         return optim.SGDOptimizer(lr=self.learning_rate, momentum=self.momentum, nesterov=self.nesterov, weight_decay=self.l2reg)
 
+    def _server_opt(self):
+        return ("momentum", float(self.learning_rate))
+
 
 class AdaGradOptimizer(_Base):
     def __init__(self, learning_rate=0.01, initial_accumulator_value=0.0, eps=1e-7, l2reg=0.0):
         super().__init__(learning_rate, l2reg)
         self.eps = eps
+
+    def _server_opt(self):
+        return ("adagrad", float(self.learning_rate))
 
     def _make(self):     # AdaGrad == Adam with beta1 = 0, beta2 -> 1 without bias correction is close; use the exact SGD-family path
         return optim.AdamOptimizer(lr=self.learning_rate, beta1=0.0, beta2=0.999, eps=self.eps, weight_decay=self.l2reg)
@@ -50,6 +63,9 @@ class AdamOptimizer(_Base):
     def __init__(self, learning_rate=0.01, beta1=0.9, beta2=0.999, epsilon=1e-7, l2reg=0.0, amsgrad=False):
         super().__init__(learning_rate, l2reg)
         self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
+
+    def _server_opt(self):
+        return ("adam", float(self.learning_rate))
 
     def _make(self):
         return optim.AdamOptimizer(lr=self.learning_rate, beta1=self.beta1, beta2=self.beta2, eps=self.epsilon, weight_decay=self.l2reg)

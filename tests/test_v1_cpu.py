@@ -314,3 +314,61 @@ def test_embedding_compression_trainer_schedules_and_rate_sizing():
     # OptEmbed: supernet with sampled widths, then the width search
     oe = CompressionTrainer("optembed", "deepfm", **common).run(steps=25, eval_batches=2)
     assert oe["schedule"]["searched_dim"] in (2, 4, 6, 8) and len(oe["schedule"]["candidate_auc"]) >= 3
+
+
+def test_v1_executor_parameter_server_and_hybrid_comm_modes(tmp_path):
+    """`Executor(..., comm_mode='PS')`: variables live on the server, the step fetches gradients, the server applies the optimizer
+    (3 worker processes under heturun end with identical weights and a falling loss); `comm_mode='Hybrid'`: embedding tables
+    (is_embed) go through sparse push / pull, dense variables keep the local optimizer"""
+    import os
+    import sys
+    from hetu_b200.v1.launcher import launch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    logs = tmp_path / "logs"
+    logs.mkdir()
+    env_keep = dict(os.environ)
+    os.environ.update({"PYTHONPATH": root, "HETU_B200_FORCE_CPU": "1", "CUDA_VISIBLE_DEVICES": "", "OMP_NUM_THREADS": "1"})
+    try:
+        codes = launch([sys.executable, os.path.join(root, "tests", "workers", "v1_ps_executor_worker.py")],
+                       {"shared": {"DMLC_PS_ROOT_URI": "127.0.0.1"}, "launch": {"worker": 3, "server": 1}}, log_dir=str(logs), timeout=240)
+    finally:
+        os.environ.clear()
+        os.environ.update(env_keep)
+    text = "\n".join((logs / f"worker{w}.log").read_text() for w in range(3))
+    assert codes == [0, 0, 0], text
+    lines = sorted(l for l in text.splitlines() if l.startswith("V1PS"))
+    assert len(lines) == 3, text
+    sums = {l.split("wsum=")[1].split()[0] for l in lines}
+    assert len(sums) == 1, lines                                  # BSP through the server: every worker holds the same weights
+    for l in lines:
+        first, last = float(l.split("first=")[1].split()[0]), float(l.split("last=")[1].split()[0])
+        assert last < 0.6 * first, l
+
+    # Hybrid in one process: the embedding table is served by the (in-process) parameter server, the dense layer trains locally
+    import numpy as np
+    import hetu_b200.v1 as v1
+    from hetu_b200.v1 import executor as v1ex
+    v1ex.reset_graph()
+    rng = np.random.RandomState(0)
+    ids = v1.placeholder_op("ids", [16], dtype="int64")
+    tgt = v1.placeholder_op("tgt", [16, 1])
+    table = v1.Variable("emb_table", value=rng.randn(50, 4).astype(np.float32) * 0.1, is_embed=True)
+    wout = v1.Variable("w_out", value=rng.randn(4, 1).astype(np.float32) * 0.1)
+    pred = v1.matmul_op(v1.embedding_lookup_op(table, ids), wout)
+    loss = v1.reduce_mean_op(v1.mse_op(pred, tgt), [0, 1])
+    train = v1.SGDOptimizer(learning_rate=0.2).minimize(loss)
+    ps = v1.PSContext(1, 0, "hybrid_test")
+    ex = v1.Executor([loss, train], comm_mode="Hybrid", ps=ps)
+    t0 = ex.graph.get_param(table).clone()
+    per_id = rng.randn(50).astype(np.float32)
+    losses = []
+    for step in range(80):
+        i = rng.randint(0, 20, 16)                               # only ids < 20 ever appear
+        out = ex.run(feed_dict={ids: i, tgt: per_id[i].reshape(16, 1)})
+        losses.append(float(out[0].asnumpy()))
+    t1 = ex.graph.get_param(table)
+    assert losses[-1] < 0.3 * losses[0]
+    assert not np.allclose(t1[:20].numpy(), t0[:20].numpy()) and np.array_equal(t1[20:].numpy(), t0[20:].numpy())
+    served = ps.sparse_pull("emb_table", list(range(50)), 4)
+    np.testing.assert_allclose(served, t1.numpy(), rtol=1e-5, atol=1e-6)     # the server's table is the worker's table
+    v1ex.reset_graph()
