@@ -303,3 +303,64 @@ def transformer_layers(num_layers: int, hidden: int, ffn: int, seq: int, batch: 
         L.append(LayerSpec(f"fc2_{i}", "linear", 2.0 * tok * hidden * ffn, hidden * ffn * bytes_per_el, tok * hidden * bytes_per_el))
     L.append(LayerSpec("head", "linear", 2.0 * tok * hidden * vocab, 0.0, tok * vocab * bytes_per_el, ("batch", "out")))
     return L
+
+
+# ---------------------------------------------------------------------------------------------------- strategy -> executable plan
+def summarize_placements(layers: Sequence[LayerSpec], placements: Sequence[Placement]) -> Dict:
+    """collapse a per-layer placement list of a transformer layer graph into the (dp, tp, pp, layers per stage) form the executor's
+    ds_parallel_config expresses: pipeline stages = maximal runs of layers on one device set; inside a stage the tensor-parallel
+    degree is the FLOP-weighted majority of the linear layers' non-batch split, data parallel takes the rest of the group"""
+    stages: List[Dict] = []
+    for l, p in zip(layers, placements):
+        devs = tuple(sorted(p.devices))
+        if not stages or stages[-1]["devices"] != devs:
+            stages.append({"devices": devs, "layers": [], "votes": {}})
+        st = stages[-1]
+        st["layers"].append(l.name)
+        if l.type == "linear":
+            tp = 1
+            for axis, parts in p.split.items():
+                if axis != "batch":
+                    tp *= parts
+            st["votes"][tp] = st["votes"].get(tp, 0.0) + max(l.flops, 1.0)
+    sizes = {len(s["devices"]) for s in stages}
+    assert len(sizes) == 1, f"pipeline stages of different widths {sorted(sizes)} need a heterogeneous plan (engine.HeteroSession)"
+    width = sizes.pop()
+    votes: Dict[int, float] = {}
+    for s in stages:
+        for tp, w in s["votes"].items():
+            votes[tp] = votes.get(tp, 0.0) + w
+    tp = max(votes, key=votes.get) if votes else 1
+    tp = max(1, min(tp, width))
+    while width % tp:
+        tp //= 2
+    blocks_per_stage = []
+    for s in stages:
+        ids = {int("".join(ch for ch in n if ch.isdigit())) for n in s["layers"] if n.startswith("qkv")}
+        blocks_per_stage.append(len(ids))
+    return {"pp": len(stages), "tp": tp, "dp": width // tp, "layer_split": blocks_per_stage,
+            "devices": [d for s in stages for d in s["devices"]]}
+
+
+def strategy_to_ds_parallel_config(strategy: Strategy, num_layers: int, hidden: int, ffn: int, seq: int, batch: int, model: str = "gpt",
+                                   zero: bool = True) -> Dict:
+    """run a v1 strategy (fixed or searching) on the layer graph of a GPT / Llama and emit the ds_parallel_config the graph
+    executor consumes -- the search result becomes a runnable plan (ref: distributed_strategies/base.py Strategy.set_raw_ctxs_n_states:
+    the reference writes contexts into the v1 graph; here the plan targets the DistributedStates executor)"""
+    from ..models.parallel_config import generate_ds_parallel_config
+    layers = transformer_layers(num_layers, hidden, ffn, seq, batch)
+    placements = strategy.assign(layers)
+    s = summarize_placements(layers, placements)
+    pp, tp = s["pp"], s["tp"]
+    split = s["layer_split"]
+    if sum(split) != num_layers or any(n <= 0 for n in split):      # a stage holding only the embedding / head: spread the blocks evenly
+        if num_layers >= pp:
+            base, rem = divmod(num_layers, pp)
+            split = [base + (1 if i < rem else 0) for i in range(pp)]
+        else:
+            pp, split = 1, None
+    dp = strategy.n // (tp * pp)
+    cfg = generate_ds_parallel_config(num_layers, strategy.n, dp, tp, pp, zero=zero, model=model, layer_split=split if pp > 1 else None)
+    cfg["searched_by"] = type(strategy).__name__
+    cfg["estimated_step_s"] = strategy.total_time(layers, placements)
+    return cfg

@@ -372,3 +372,28 @@ def test_v1_executor_parameter_server_and_hybrid_comm_modes(tmp_path):
     served = ps.sparse_pull("emb_table", list(range(50)), 4)
     np.testing.assert_allclose(served, t1.numpy(), rtol=1e-5, atol=1e-6)     # the server's table is the worker's table
     v1ex.reset_graph()
+
+
+def test_v1_strategies_emit_executable_ds_parallel_configs():
+    """ref: hetu/v1 distributed_strategies -- the fixed and searching strategies run on a GPT layer graph and their placement
+    becomes the ds_parallel_config of the DistributedStates executor (same dict the hand-written generator produces)"""
+    from hetu_b200.models import generate_ds_parallel_config
+    from hetu_b200.v1 import strategies as S
+    L, H, F, SEQ, B = 8, 1024, 4096, 1024, 16
+    layers = S.transformer_layers(L, H, F, SEQ, B)
+    summ = S.summarize_placements(layers, S.MegatronLM(8, tp=4).assign(layers))
+    assert (summ["pp"], summ["tp"], summ["dp"]) == (1, 4, 2)
+    cfg = S.strategy_to_ds_parallel_config(S.MegatronLM(8, tp=4), L, H, F, SEQ, B)
+    ref = generate_ds_parallel_config(L, 8, 2, 4, 1)
+    assert cfg["blocks"] == ref["blocks"] and cfg["wte"] == ref["wte"] and cfg["searched_by"] == "MegatronLM" and cfg["estimated_step_s"] > 0
+    cfg = S.strategy_to_ds_parallel_config(S.DataParallel(4), L, H, F, SEQ, B)
+    assert (cfg["dp"], cfg["tp"], cfg["pp"]) == (4, 1, 1)
+    g = S.GPipeSearching(8, num_stages=4, micro_batches=8)
+    cfg = S.strategy_to_ds_parallel_config(g, L, H, F, SEQ, B)
+    assert (cfg["dp"], cfg["tp"], cfg["pp"]) == (2, 1, 4)
+    ranges = sorted(b["range"] for b in cfg["blocks"].values())
+    assert ranges[0][0] == 0 and ranges[-1][1] == L - 1 and all(a[1] + 1 == b[0] for a, b in zip(ranges, ranges[1:]))
+    # the searching strategies return something the generator accepts, and never worse than plain data parallelism under their model
+    for strat in (S.FlexFlowSearching(8, budget=300), S.OptCNNSearching(8), S.PipeDreamSearching(8), S.PipeOptSearching(8)):
+        cfg = S.strategy_to_ds_parallel_config(strat, L, H, F, SEQ, B)
+        assert cfg["dp"] * cfg["tp"] * cfg["pp"] == 8 and len(cfg["devices"]) == 8 and cfg["estimated_step_s"] > 0
