@@ -61,3 +61,143 @@ def build_hybrid_parallel_model(plan: dict, num_gpus: int, model_class, model_co
     model = model_class(model_config, [cfg])
     dp = plan["strategies"][0].dp
     return model, cfg, {"num_micro_batches": int(plan["chunks"]), "grad_scale": 1.0 / dp}
+
+
+class GalvatronRuntime:
+    """A searched (or hand-written) plan as an object: validated against the device count and a memory budget, printable per layer,
+    buildable into a model + run arguments, and checkable against the cost model once step times have been measured.
+
+        rt = GalvatronRuntime.from_json("galvatron_config_llama2-7b_8gpus.json", num_gpus=8, layer=LayerProfile.transformer(...))
+        print(rt.describe())
+        with ht.graph("define_and_run", create_new=True) as g, ht.autocast("bfloat16"):
+            model, cfg, run_kw = rt.build(LlamaLMHeadModel, LlamaConfig.llama2_7b())
+        ...
+        rt.record_step(ms); print(rt.cost_model_report())
+
+    (ref: tools/Galvatron/galvatron/core/hybrid_parallel_config.py get_hybrid_parallel_configs_api / check_hp_config /
+    print_hp_config, core/hybrid_parallel_model.py construct_hybrid_parallel_model_api, profile hooks of core/profiler.py)"""
+
+    def __init__(self, plan: dict, num_gpus: int, layer=None, hardware=None, vocab: int = 50304, hidden: int = 2048, seq: int = 1024,
+                 memory_mb: float = None):
+        self.plan, self.num_gpus = plan, int(num_gpus)
+        self.layer, self.hw = layer, hardware
+        self.vocab, self.hidden, self.seq, self.memory_mb = vocab, hidden, seq, memory_mb
+        self.measured_ms: List[float] = []
+        for s in plan["strategies"]:
+            if s.dp * s.tp * plan["pp"] != self.num_gpus:
+                object.__setattr__(s, "dp", self.num_gpus // plan["pp"] // s.tp)
+        self.check()
+
+    @classmethod
+    def from_json(cls, path_or_dict, num_gpus: int, **kw):
+        js = json.load(open(path_or_dict)) if isinstance(path_or_dict, str) else dict(path_or_dict)
+        js.setdefault("world_size", num_gpus)
+        return cls(load_plan(js), num_gpus, **kw)
+
+    # -- validation ---------------------------------------------------------------------------------------------------
+    def check(self):
+        """structural rules of a hybrid-parallel plan (ref: check_hp_config)"""
+        p, ss = self.plan, self.plan["strategies"]
+        pp = int(p["pp"])
+        if self.num_gpus % pp:
+            raise ValueError(f"pp_deg {pp} does not divide {self.num_gpus} GPUs")
+        per_stage = self.num_gpus // pp
+        split = list(p["layer_split"])
+        if len(split) != pp or sum(split) != len(ss) or any(n <= 0 for n in split):
+            raise ValueError(f"pp_division {split} does not partition {len(ss)} layers into {pp} non-empty stages")
+        for i, s in enumerate(ss):
+            if s.tp < 1 or s.tp & (s.tp - 1) or per_stage % s.tp:
+                raise ValueError(f"layer {i}: tp {s.tp} must be a power of two dividing the {per_stage} GPUs of a stage")
+            if s.tp * s.dp != per_stage:
+                raise ValueError(f"layer {i}: tp {s.tp} x dp {s.dp} != {per_stage} GPUs per stage")
+            if s.sdp not in (0, 2, 3):
+                raise ValueError(f"layer {i}: dp type {s.sdp} is not ddp (0) / zero-2 (2) / zero-3 (3)")
+        gbs, chunks = int(p.get("global_bsz", 0)), max(int(p.get("chunks", 1)), 1)
+        min_dp = min(s.dp for s in ss)
+        if gbs and (gbs % chunks or (gbs // chunks) % min_dp):
+            raise ValueError(f"global batch {gbs} / {chunks} micro-batches is not divisible by the data-parallel degree {min_dp}")
+        if self.memory_mb is not None and self.layer is not None:
+            worst = max(self.memory_per_stage_mb())
+            if worst > self.memory_mb:
+                raise ValueError(f"plan needs {worst:.0f} MB on its fullest stage, budget is {self.memory_mb:.0f} MB")
+        return True
+
+    # -- cost model views ---------------------------------------------------------------------------------------------
+    def _models(self):
+        from .cost_model import HardwareProfile, MemoryCostModel, TimeCostModel
+        hw = self.hw or HardwareProfile()
+        return MemoryCostModel(self.layer), TimeCostModel(self.layer, hw), hw
+
+    def memory_per_stage_mb(self) -> List[float]:
+        mem, _, _ = self._models()
+        p, ss = self.plan, self.plan["strategies"]
+        chunks = max(int(p.get("chunks", 1)), 1)
+        out, lo = [], 0
+        for st, nl in enumerate(p["layer_split"]):
+            in_flight = min(chunks, p["pp"] - st)                    # 1F1B keeps (pp - stage) micro-batches alive
+            total = 0.0
+            for s in ss[lo:lo + nl]:
+                micro = max(int(p.get("global_bsz", s.dp)), 1) / chunks / s.dp
+                total += mem.layer_mb(s, micro, in_flight)
+            out.append(total)
+            lo += nl
+        return out
+
+    def predicted_step_ms(self) -> float:
+        _, tm, _ = self._models()
+        p, ss = self.plan, self.plan["strategies"]
+        chunks = max(int(p.get("chunks", 1)), 1)
+        gbs = max(int(p.get("global_bsz", ss[0].dp)), 1)
+        stage_ms, lo = [], 0
+        for nl in p["layer_split"]:
+            t = 0.0
+            for i in range(lo, lo + nl):
+                t += tm.layer_ms(ss[i], gbs, chunks)
+                if i + 1 < lo + nl:
+                    t += tm.transition_ms(ss[i], ss[i + 1], gbs / chunks / ss[i].dp) * chunks
+            stage_ms.append(t)
+            lo += nl
+        boundary = self.layer.boundary_mb * gbs / chunks / max(ss[0].dp, 1)
+        return tm.pipeline_ms(stage_ms, chunks, boundary, int(p["pp"]))
+
+    def record_step(self, ms: float):
+        self.measured_ms.append(float(ms))
+
+    def cost_model_report(self) -> Dict:
+        """measured vs predicted step time (the reference's profile-vs-model check); ratio > 1: the model is optimistic"""
+        pred = self.predicted_step_ms() if self.layer is not None else None
+        med = sorted(self.measured_ms)[len(self.measured_ms) // 2] if self.measured_ms else None
+        return {"predicted_ms": pred, "measured_ms": med, "ratio": (med / pred) if (pred and med) else None,
+                "memory_per_stage_mb": self.memory_per_stage_mb() if self.layer is not None else None}
+
+    # -- presentation -------------------------------------------------------------------------------------------------
+    def describe(self) -> str:
+        """one line per run of equal layers (ref: print_hp_config)"""
+        p, ss = self.plan, self.plan["strategies"]
+        lines = [f"hybrid parallel plan: {self.num_gpus} GPUs, pp {p['pp']} (layers per stage {list(p['layer_split'])}), "
+                 f"global batch {p.get('global_bsz')}, {p.get('chunks', 1)} micro-batches"]
+        lo = 0
+        stage_of = [st for st, nl in enumerate(p["layer_split"]) for _ in range(nl)]
+        while lo < len(ss):
+            hi = lo
+            while hi + 1 < len(ss) and ss[hi + 1].key() == ss[lo].key() and stage_of[hi + 1] == stage_of[lo]:
+                hi += 1
+            s = ss[lo]
+            dpt = {0: "ddp", 2: "zero-2", 3: "zero-3"}[s.sdp]
+            lines.append(f"  layers {lo:>3}-{hi:<3} stage {stage_of[lo]}  tp {s.tp} ({'consecutive' if s.tp_consec else 'strided'})"
+                         f"{' +sp' if s.sp else ''}  dp {s.dp} ({dpt})  recompute {'on' if s.ckpt else 'off'}")
+            lo = hi + 1
+        return "\n".join(lines)
+
+    def comm_groups(self):
+        ss = self.plan["strategies"]
+        return gen_comm_groups(self.num_gpus, self.plan["pp"], [s.tp for s in ss], [int(s.tp_consec) for s in ss])
+
+    def to_json(self) -> dict:
+        from .search_engine import GalvatronSearchEngine
+        js = GalvatronSearchEngine.to_json(self.plan)
+        js["world_size"] = self.num_gpus
+        return js
+
+    def build(self, model_class, model_config):
+        return build_hybrid_parallel_model(self.plan, self.num_gpus, model_class, model_config)

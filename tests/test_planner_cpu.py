@@ -135,3 +135,45 @@ def test_ampelos_replans_after_device_loss_and_stragglers():
     m4 = replan_after_failure(tight, old, list(range(8)))
     st4, _ = m4.make_plans()
     assert all(max(ls) <= 10 for ls in st4.hetero_layers)
+
+
+def test_galvatron_runtime_validates_describes_builds_and_checks_a_plan(tmp_path):
+    """ref: tools/Galvatron core/hybrid_parallel_config.py (check / print of a layer-wise plan) + hybrid_parallel_model.py"""
+    import json
+    from hetu_b200.planner import GalvatronRuntime, HardwareProfile
+    from hetu_b200.models import GPTConfig, GPTLMHeadModel
+    lp = LayerProfile.transformer(1024, 4096, 512, 8)
+    js = {"pp_deg": 2, "tp_sizes_enc": "2,2,1,1", "tp_consecutive_flags": "1,1,1,1", "dp_types_enc": "0,0,1,1", "checkpoint": "0,1,0,0",
+          "global_bsz": 16, "chunks": 4, "pp_division": "2,2", "default_dp_type": "zero2"}
+    rt = GalvatronRuntime.from_json(js, num_gpus=4, layer=lp, hardware=HardwareProfile(), hidden=1024, seq=512)
+    ss = rt.plan["strategies"]
+    assert [(s.tp, s.dp, s.sdp, s.ckpt) for s in ss] == [(2, 1, 2, False), (2, 1, 2, True), (1, 2, 3, False), (1, 2, 3, False)]
+    text = rt.describe()
+    assert "pp 2" in text and "tp 2 (consecutive) +sp  dp 1 (zero-2)  recompute off" in text and "zero-3" in text and len(text.splitlines()) == 4
+    groups = rt.comm_groups()
+    assert groups[0]["tp"] == [[0, 1], [2, 3]] and groups[2]["dp"] == [[0, 1], [2, 3]] and groups[0]["pp"] == [[0, 2], [1, 3]]
+    mem = rt.memory_per_stage_mb()
+    assert len(mem) == 2 and all(m > 0 for m in mem)
+    pred = rt.predicted_step_ms()
+    assert pred > 0
+    for ms in (pred * 1.3, pred * 1.2, pred * 1.25):
+        rt.record_step(ms)
+    rep = rt.cost_model_report()
+    assert abs(rep["ratio"] - 1.25) < 1e-6 and rep["memory_per_stage_mb"] == mem
+    # JSON round trip keeps the plan
+    (tmp_path / "p.json").write_text(json.dumps(rt.to_json()))
+    rt2 = GalvatronRuntime.from_json(str(tmp_path / "p.json"), num_gpus=4)
+    assert [s.key() for s in rt2.plan["strategies"]] == [s.key() for s in ss] and rt2.plan["layer_split"] == [2, 2]
+    # a plan that cannot run is rejected with the reason
+    for bad, msg in (({**js, "tp_sizes_enc": "4,2,1,1"}, "tp 4"), ({**js, "pp_division": "3,2"}, "pp_division"), ({**js, "pp_deg": 3}, "pp_deg 3"),
+                     ({**js, "global_bsz": 6}, "global batch")):
+        with pytest.raises(ValueError, match=msg):
+            GalvatronRuntime.from_json(bad, num_gpus=4)
+    with pytest.raises(ValueError, match="budget"):
+        GalvatronRuntime.from_json(js, num_gpus=4, layer=lp, memory_mb=1.0)
+    # build: world 1 plan -> model + run arguments
+    one = GalvatronRuntime.from_json({"pp_deg": 1, "tp_sizes_enc": "1,1", "tp_consecutive_flags": "1,1", "dp_types_enc": "0,0", "checkpoint": "0,1",
+                                      "global_bsz": 4, "chunks": 2}, num_gpus=1)
+    with ht.graph("define_and_run", create_new=True):
+        model, cfg, run_kw = one.build(GPTLMHeadModel, GPTConfig(vocab_size=64, n_positions=16, n_embd=32, n_layer=2, n_head=2))
+    assert run_kw == {"num_micro_batches": 2, "grad_scale": 1.0} and cfg["blocks"]["blocks1"]["recompute"] == [True]
