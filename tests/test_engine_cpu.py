@@ -545,3 +545,55 @@ def test_hydraulis_ilp_dispatch_is_optimal_and_respects_limits():
     toks = [sum([4000, 3000, 2500, 2000, 1500, 1000, 800, 600][i] for i in mb) for mb in b["micro_batches"]]
     assert all(2048 <= t <= 8192 for t in toks) and sorted(i for mb in b["micro_batches"] for i in mb) == list(range(8))
     assert b["e2e_ms"] == pytest.approx(b["max_micro_batch_ms"] * (2 - 1 + b["num_micro_batches"]))
+
+
+def test_hydra_lite_composition_interpolation_overrides_and_structured_merge(tmp_path, monkeypatch):
+    """ref: SURVEY 5.6 -- hydra/OmegaConf YAML tier: `defaults` composition with config groups, `${...}` interpolation incl.
+    `oc.env`, dotted overrides (+add, ~delete, group=option), merge onto dataclasses with type checks"""
+    import dataclasses
+    from hetu_b200.utils import hydra_lite as H
+    (tmp_path / "model").mkdir()
+    (tmp_path / "ds_parallel").mkdir()
+    (tmp_path / "base.yaml").write_text("trainer:\n  steps: 10\n  bf16: true\nseed: 1\n")
+    (tmp_path / "model" / "gpt_small.yaml").write_text("type: gpt\nn_embd: 256\nn_layer: 4\n")
+    (tmp_path / "model" / "llama_7b.yaml").write_text("type: llama\nn_embd: 4096\nn_layer: 32\n")
+    (tmp_path / "ds_parallel" / "dp2_tp2.yaml").write_text("# @package _global_\nds_parallel:\n  dp: 2\n  tp: 2\n  pp: 1\n")
+    (tmp_path / "exp.yaml").write_text(
+        "defaults:\n  - base\n  - model: gpt_small\n  - ds_parallel: dp2_tp2\n  - _self_\n"
+        "trainer:\n  steps: 20\n  max_seq_length: ${model.n_positions}\n  out_dir: runs/${model.type}_${trainer.steps}\n"
+        "model:\n  n_positions: 512\n  hidden4: ${model.n_embd}\nworld: ${oc.env:HYDRA_LITE_WORLD,4}\n")
+    cfg = H.load(["--config-path", str(tmp_path), "--config-name", "exp"])
+    assert cfg.trainer.steps == 20 and cfg.trainer.bf16 is True and cfg.seed == 1                     # _self_ after base
+    assert cfg.model.type == "gpt" and cfg.model.n_layer == 4 and cfg.ds_parallel.tp == 2             # group under its key / _global_ package
+    assert cfg.trainer.max_seq_length == 512 and cfg.model.hidden4 == 256 and cfg.trainer.out_dir == "runs/gpt_20" and cfg.world == 4
+    monkeypatch.setenv("HYDRA_LITE_WORLD", "8")
+    cfg = H.load(["--config-path", str(tmp_path), "--config-name", "exp", "model=llama_7b", "trainer.steps=5", "+trainer.log_interval=2", "~seed",
+                  "ds_parallel.recompute.layer_idxs=[[0,1],[2]]"])
+    assert cfg.model.type == "llama" and cfg.model.hidden4 == 4096 and cfg.trainer.out_dir == "runs/llama_5" and cfg.world == 8
+    assert cfg.trainer.log_interval == 2 and "seed" not in cfg and cfg.ds_parallel.recompute.layer_idxs == [[0, 1], [2]]
+    assert "n_embd: 4096" in H.to_yaml(cfg)
+    with pytest.raises(FileNotFoundError):
+        H.load(["--config-path", str(tmp_path), "--config-name", "exp", "model=nope"])
+    with pytest.raises(ValueError, match="cycle"):
+        H.resolve({"a": "${b}", "b": "${a}"})
+    with pytest.raises(KeyError):
+        H.resolve({"a": "${missing.key}"})
+
+    @dataclasses.dataclass
+    class Inner:
+        granularity: str = "full"
+        num_layers: int = 0
+
+    @dataclasses.dataclass
+    class Strat:
+        dp: int = 1
+        tp: int = 1
+        zero: bool = False
+        lr: float = 1e-3
+        recompute: Inner = dataclasses.field(default_factory=Inner)
+    st = H.merge_dataclass(Strat, {"dp": "2", "zero": "true", "lr": 3, "recompute": {"num_layers": "4"}})
+    assert (st.dp, st.tp, st.zero, st.lr, st.recompute.num_layers, st.recompute.granularity) == (2, 1, True, 3.0, 4, "full")
+    with pytest.raises(KeyError, match="no field"):
+        H.merge_dataclass(Strat, {"pipeline": 2})
+    with pytest.raises(TypeError):
+        H.merge_dataclass(Strat, {"dp": 2.5})
