@@ -368,6 +368,19 @@ int Executor::local_device_index(const DeviceGroup& g) const {
   for (size_t i = 0; i < g.num_devices(); ++i) if (g.get(i).index() == me) return (int)i;
   return -1;
 }
+int Executor::require_device_index(const DeviceGroup& g, const OpDef* op, const char* what) const {
+  const int i = local_device_index(g);
+  if (i >= 0) return i;
+  std::ostringstream os;
+  os << "[";
+  for (size_t k = 0; k < g.num_devices(); ++k) os << (k ? "," : "") << g.get(k).index();
+  os << "]";
+  const int me = CommRuntime::get().initialized() ? CommRuntime::get().rank() : 0;
+  HB_FAIL() << what << ": rank " << me << " executes op '" << (op ? op->name() : std::string("?")) << "' (" << (op ? op->type : std::string("?"))
+            << ") but is not a member of its device group " << os.str() << " under strategy " << std::max(active_strategy_, 0)
+            << " -- the op was scheduled on a rank its placement does not cover (check the ds_parallel_config device groups)";
+  return -1;
+}
 at::Device aten_device() {
   const bool cuda = at::hasCUDA() && env_int("HETU_B200_FORCE_CPU", 0) == 0;
   if (!cuda) return at::Device(at::kCPU);
@@ -744,7 +757,7 @@ std::vector<at::Tensor> Executor::exec_comm(const CommStep& cs, OpDef* op, const
       const Tensor& y = op->outputs[0];
       const DistributedStates& dst = y->ds(std::max(active_strategy_, 0));
       DeviceGroup grp = op->placement(std::max(active_strategy_, 0));
-      const int me = local_device_index(grp);
+      const int me = require_device_index(grp, op, "local split");
       std::vector<int64_t> begin, size;
       // slice of the *source-local* tensor: compute both global slices and subtract
       const Tensor& x = op->inputs[0];

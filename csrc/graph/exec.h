@@ -182,6 +182,8 @@ class Executor {
   const std::vector<std::pair<std::string, double>>& op_times() const { return op_times_; }
   std::map<std::string, double> step_breakdown() const { return breakdown_; }
   int local_device_index(const DeviceGroup& g) const;
+  // same, but a rank outside the group is an error that names the op and the group (instead of an index of -1 travelling on)
+  int require_device_index(const DeviceGroup& g, const OpDef* op, const char* what) const;
   Device local_device() const;
   // hot switch: re-shard every parameter / optimizer state from strategy a to b
   void switch_strategy(int from, int to);
