@@ -22,8 +22,13 @@ from .ht_safetensors import collect_split_state, temp_load_split, write_split_st
 
 class ModelSaver:
     def __init__(self, save_dir: str, save_copies: int = 2, save_interval: int = 0, async_save: bool = False, only_lora=False,
-                 save_dtype=None, async_mode: str = "thread"):
+                 save_dtype=None, async_mode: str = "thread", remote: Optional[str] = None):
+        """remote: URI of a mirror (`hdfs://namenode/ckpt`, `hdfs-cli://ckpt`, `file:///shared/ckpt`, ...): every published step is
+        uploaded there (each rank its own files, the bookkeeping rank the markers), rotation is applied remotely too, and
+        `load_latest` on a node whose local directory is empty restores from the mirror"""
         assert async_mode in ("thread", "process")
+        self.remote_uri = remote
+        self._remote = None
         self.save_dir, self.save_copies, self.save_interval = save_dir, save_copies, save_interval
         self.async_save, self.only_lora, self.save_dtype, self.async_mode = async_save, only_lora, save_dtype, async_mode
         self._queue = None        # native TaskQueue (one writer thread) of the `thread` mode, created on first use
@@ -68,13 +73,70 @@ class ModelSaver:
         from ...distributed import all_ranks_ok, global_comm_barrier_rpc, rank
         ok = all_ranks_ok(ok)
         global_comm_barrier_rpc()
+        if ok and self.remote_uri:
+            ok = all_ranks_ok(self._mirror_own_files(step, path))        # every rank uploads what it wrote
         if ok and rank() == writer_rank:
             with open(os.path.join(path, "COMPLETE"), "w") as f:
                 f.write(f"{step}\n")
             with open(os.path.join(self.save_dir, "step_info.csv"), "a", newline="") as f:
                 csv.writer(f).writerow([step, consumed_samples, loss, path, time.time()])
             self._cleanup(step)
+            if self.remote_uri:
+                self._mirror_markers(step, path)
         global_comm_barrier_rpc()
+
+    # ---- remote mirror ------------------------------------------------------------------------------------------------
+    def remote(self):
+        if self._remote is None and self.remote_uri:
+            from .remote_fs import open_remote
+            self._remote = open_remote(self.remote_uri)
+        return self._remote
+
+    def _mirror_own_files(self, step: int, path: str) -> bool:
+        """upload the files of this step directory that are not on the mirror yet (ranks sharing a filesystem skip each other's)"""
+        try:
+            fs = self.remote()
+            have = set(fs.listdir(f"step{step}"))
+            for f in sorted(os.listdir(path)):
+                if f != "COMPLETE" and f not in have:
+                    fs.put_file(os.path.join(path, f), f"step{step}/{f}")
+            return True
+        except Exception as e:      # noqa: BLE001 -- surfaced as "checkpoint not published"
+            self.last_write_error = f"remote mirror: {type(e).__name__}: {e}"
+            return False
+
+    def _mirror_markers(self, step: int, path: str):
+        fs = self.remote()
+        fs.put_file(os.path.join(path, "COMPLETE"), f"step{step}/COMPLETE")
+        fs.put_file(os.path.join(self.save_dir, "step_info.csv"), "step_info.csv")
+        steps = sorted(int(d[4:]) for d in fs.listdir("") if d.startswith("step") and d[4:].isdigit())
+        done = [s for s in steps if fs.exists(f"step{s}/COMPLETE")]
+        keep = set(done[-self.save_copies:]) if self.save_copies > 0 else set(done)
+        for s in steps:
+            if s not in keep and s < step:
+                fs.remove_dir(f"step{s}")
+
+    def restore_from_remote(self) -> Optional[int]:
+        """download the newest complete step (and the step-info file) from the mirror into save_dir -> its step number"""
+        fs = self.remote()
+        if fs is None:
+            return None
+        steps = sorted(int(d[4:]) for d in fs.listdir("") if d.startswith("step") and d[4:].isdigit())
+        done = [s for s in steps if fs.exists(f"step{s}/COMPLETE")]
+        if not done:
+            return None
+        s = done[-1]
+        fs.get_dir(f"step{s}", self.step_dir(s))
+        info = os.path.join(self.save_dir, "step_info.csv")
+        if fs.exists("step_info.csv"):
+            fs.get_file("step_info.csv", info)
+            # rows carry the path of the node that wrote them: point them at this node's directory
+            rows = [r for r in csv.reader(open(info)) if r]
+            with open(info, "w", newline="") as f:
+                for r in rows:
+                    r[3] = self.step_dir(int(r[0]))
+                    csv.writer(f).writerow(r)
+        return s
 
     def _snapshot_fn(self):
         """host copy owned by the saver: plain clone for the thread writer, shared-memory pool blocks for the process writer"""
@@ -158,6 +220,8 @@ class ModelSaver:
     def load_latest(self, model, optimizer):
         """-> (step, consumed_samples) or None"""
         info = os.path.join(self.save_dir, "step_info.csv")
+        if self.remote_uri and (not os.path.exists(info) or not any(self._complete(r[3]) for r in csv.reader(open(info)) if r)):
+            self.restore_from_remote()                  # a fresh node: pull the newest complete step from the mirror
         if not os.path.exists(info):
             return None
         rows = [r for r in csv.reader(open(info)) if r and self._complete(r[3])]

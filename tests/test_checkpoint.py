@@ -89,7 +89,7 @@ def test_async_model_saver_snapshots_before_training_continues(tmp_path, mode):
             g.run(loss, [loss, train], {x: X})
         assert not torch.equal(g.get_param(m.weight), want_w)
         saver.wait()
-        assert saver._shm_blocks == [] and saver._child is None and saver._thread is None
+        assert saver._shm_blocks == [] and saver._child is None and (saver._queue is None or saver._queue.pending == 0)
         files = os.listdir(tmp_path / "step1")
         assert any(f.endswith(".safetensors") for f in files) and any(f.startswith("param_states") for f in files)
         assert saver.load_latest(m, opt) == (1, 2)
@@ -147,7 +147,7 @@ def test_async_checkpoint_is_published_after_the_write_and_torn_copies_are_skipp
         g.run(loss, [loss, train], {x: X}); opt.step_lr()
         saver.save(m, opt, 2, consumed_samples=4, loss=0.0)
         # simulate a crash before publication: files of step2 may exist, but no marker and no row; step1 must survive
-        saver._thread.join(); saver._thread = None; saver._pending = None
+        saver._queue.wait(); saver._pending = None
         assert os.path.isdir(tmp_path / "step1")
         import csv
         with open(tmp_path / "step_info.csv", "a", newline="") as f:       # even a stray row must not resurrect a torn copy
@@ -158,3 +158,84 @@ def test_async_checkpoint_is_published_after_the_write_and_torn_copies_are_skipp
         assert torch.equal(g.get_param(m.weight), w1)
         # the schedule resumes at the scheduled rate of step 2, not at the fresh optimizer's first warm-up value
         assert opt.step_count == 1 and abs(opt.learning_rate - opt.scheduler.get_lr(2)) < 1e-12
+
+
+def _fake_hdfs(bin_dir, store):
+    """an `hdfs` executable that implements `hdfs dfs -mkdir -p / -put -f / -get [-f] / -ls / -test -e / -rm -r -f` on a local
+    directory (`store` plays the namenode) -- enough to drive HdfsCliFS without a Hadoop installation"""
+    script = f'''#!{__import__("sys").executable}
+import os, shutil, sys
+ROOT = {str(store)!r}
+a = sys.argv[1:]
+assert a[0] == "dfs", a
+cmd, rest = a[1], [x for x in a[2:] if not x.startswith("-")]
+m = lambda p: os.path.join(ROOT, p.replace("hdfs://nn", "").lstrip("/"))
+if cmd == "-mkdir":
+    os.makedirs(m(rest[0]), exist_ok=True)
+elif cmd == "-put":
+    src, dst = rest[0], m(rest[1])
+    if os.path.isdir(src):
+        shutil.rmtree(dst, ignore_errors=True); shutil.copytree(src, dst)
+    else:
+        os.makedirs(os.path.dirname(dst), exist_ok=True); shutil.copyfile(src, dst)
+elif cmd == "-get":
+    src, dst = m(rest[0]), rest[1]
+    if not os.path.exists(src): sys.exit(1)
+    shutil.copytree(src, dst) if os.path.isdir(src) else shutil.copyfile(src, dst)
+elif cmd == "-ls":
+    p = m(rest[0])
+    if not os.path.isdir(p): sys.exit(1)
+    names = sorted(os.listdir(p)); print(f"Found {{len(names)}} items")
+    for n in names: print("drwxr-xr-x   - u g 0 2026-01-01 00:00 " + os.path.join(rest[0], n))
+elif cmd == "-test":
+    sys.exit(0 if os.path.exists(m(rest[0])) else 1)
+elif cmd == "-rm":
+    shutil.rmtree(m(rest[0]), ignore_errors=True)
+else:
+    sys.exit(2)
+'''
+    path = os.path.join(bin_dir, "hdfs")
+    with open(path, "w") as f:
+        f.write(script)
+    os.chmod(path, 0o755)
+    return path
+
+
+@pytest.mark.parametrize("backend", ["arrow-file", "hdfs-cli"])
+def test_model_saver_mirrors_to_a_remote_filesystem_and_restores_on_a_fresh_node(tmp_path, backend, monkeypatch):
+    """ref: model_saver.py SAVER_DST.HDFS -- published steps are uploaded to the remote (pyarrow filesystem URI, or the `hdfs dfs`
+    command line), rotation applies remotely, and a node with an empty local directory resumes from the mirror"""
+    from hetu_b200.utils.checkpoint.remote_fs import HdfsCliFS, open_remote
+    store = tmp_path / "remote_store"
+    store.mkdir()
+    if backend == "arrow-file":
+        uri = "file://" + str(store / "ckpt")
+    else:
+        bin_dir = tmp_path / "bin"
+        bin_dir.mkdir()
+        monkeypatch.setenv("HETU_HDFS_BIN", _fake_hdfs(str(bin_dir), store))
+        uri = "hdfs-cli://ckpt"
+        assert isinstance(open_remote(uri), HdfsCliFS)
+    local_a, local_b = tmp_path / "node_a", tmp_path / "node_b"
+    with ht.graph("define_and_run", create_new=True) as g:
+        m = ht.nn.Linear(8, 4, name=f"lin_remote_{backend.replace('-', '_')}")
+        x = ht.placeholder("float32", [2, 8], name="x")
+        loss = ht.sum(m(x))
+        opt = ht.AdamOptimizer(lr=0.1)
+        train = opt.minimize(loss)
+        saver = ModelSaver(str(local_a), save_copies=2, save_interval=1, remote=uri)
+        X = np.ones((2, 8), np.float32)
+        snaps = {}
+        for step in range(1, 5):
+            g.run(loss, [loss, train], {x: X})
+            saver.save(m, opt, step, consumed_samples=step * 2, loss=0.0)
+            snaps[step] = g.get_param(m.weight).clone()
+        fs = saver.remote()
+        assert [d for d in fs.listdir("") if d.startswith("step") and d[4:].isdigit()] == ["step3", "step4"]       # rotated remotely too
+        assert fs.exists("step4/COMPLETE") and fs.exists("step_info.csv") and len(fs.listdir("step4")) >= 3
+        g.run(loss, [loss, train], {x: X})                                   # drift
+        fresh = ModelSaver(str(local_b), save_copies=2, remote=uri)          # another node: nothing on its disk
+        assert not os.path.exists(local_b / "step_info.csv")
+        step, consumed = fresh.load_latest(m, opt)
+        assert (step, consumed) == (4, 8) and torch.equal(g.get_param(m.weight), snaps[4])
+        assert os.path.exists(local_b / "step4" / "COMPLETE")
