@@ -382,8 +382,37 @@ def rotary(x, positions=None, base=10000.0, rot_dim=0, pos_offset=0, **kw):
     return _op1("rotary", ins, {"base": float(base), "rot_dim": int(rot_dim), "pos_offset": int(pos_offset)}, **kw)
 
 
+def _attn_with_dropout(q, k, v, p_dropout, softmax_scale, is_causal):
+    """attention with dropout on the softmax probabilities, composed from graph ops (scores -> mask -> softmax -> dropout -> PV).
+    The fused flash kernels have no in-kernel dropout, so p_dropout > 0 takes this path: same semantics as the reference's
+    flash-attention dropout (inverted dropout on P, mask replayed in backward from the op's Philox counters), O(S^2) memory."""
+    b, s, h, d = q.shape
+    sk, hkv = k.shape[1], k.shape[2]
+    g = h // hkv
+    scale = float(softmax_scale) if softmax_scale and softmax_scale > 0 else 1.0 / float(d) ** 0.5
+    qt = reshape(transpose(q, [0, 2, 1, 3]), [b * h, s, d])
+
+    def heads(t):                                     # [B, Sk, Hkv, D] -> [B * H, Sk, D] with every kv head repeated g times
+        t = transpose(t, [0, 2, 1, 3])
+        if g > 1:
+            t = broadcast(reshape(t, [b, hkv, 1, sk, d]), [b, hkv, g, sk, d])
+        return reshape(t, [b * h, sk, d])
+    kt, vt = heads(k), heads(v)
+    scores = bmm(qt, transpose(kt, [0, 2, 1])) * scale
+    if is_causal:
+        future = triu(ones_like(scores), False, 1 + (sk - s))      # 1 above the (bottom-right aligned) diagonal
+        scores = masked_fill(scores, future, -1e30)
+    probs = dropout(softmax(scores, -1), float(p_dropout))
+    out = bmm(probs, vt)
+    return transpose(reshape(out, [b, h, s, d]), [0, 2, 1, 3]), probs
+
+
 def attn(q, k, v, p_dropout=0.0, softmax_scale=-1.0, is_causal=True, return_softmax=False, **kw):
-    """q [B,S,H,D], k/v [B,S,Hkv,D] -> [B,S,H,D] (flash attention; tcgen05 kernels on B200)."""
+    """q [B,S,H,D], k/v [B,S,Hkv,D] -> [B,S,H,D] (flash attention; tcgen05 kernels on B200).  p_dropout > 0 (training-time
+    attention dropout) runs the composed path `_attn_with_dropout`."""
+    if p_dropout and float(p_dropout) > 0.0:
+        out, probs = _attn_with_dropout(q, k, v, float(p_dropout), softmax_scale, is_causal)
+        return (out, probs) if return_softmax else out
     outs = make_op("attn", [q, k, v], {"causal": bool(is_causal), "softmax_scale": float(softmax_scale if softmax_scale > 0 else 0.0)},
                    **_meta(kw))
     return outs if return_softmax else outs[0]

@@ -402,3 +402,36 @@ def test_dropout_add_norm_forward_and_gradients(rms):
     zn, gn = z2.numpy(), X2.grad.numpy()
     assert set(np.unique(zn).round(4).tolist()) <= {0.0, 2.0} and 0.2 < (zn == 0).mean() < 0.8
     np.testing.assert_allclose(gn, zn, rtol=1e-6)               # d sum(z) / dx = mask / (1 - p) = z for x = 1
+
+
+def test_attention_dropout_composed_path_matches_flash_semantics():
+    """ref: FlashAttention.cu p_dropout -- dropout acts on the softmax probabilities (inverted scaling), the mask of the forward is
+    replayed in backward; p_dropout == 0 keeps the fused op; GQA and causal masks as in the fused kernels"""
+    torch.manual_seed(0)
+    B, S, H, HKV, D = 2, 12, 4, 2, 8
+    q, k, v = torch.randn(B, S, H, D), torch.randn(B, S, HKV, D), torch.randn(B, S, HKV, D)
+    Q, K, V = (ht.from_numpy(t.clone(), requires_grad=True) for t in (q, k, v))
+    from hetu_b200 import ops
+    fused = ht.attn(Q, K, V, is_causal=True)
+    composed, probs = ops._attn_with_dropout(Q, K, V, 0.0, -1.0, True)
+    assert torch.allclose(torch.as_tensor(composed.numpy()), torch.as_tensor(fused.numpy()), atol=1e-5)
+    # reference with an explicit mask: out = (dropmask * softmax / (1 - p)) @ v
+    ht.set_seed(11)
+    out, P = ht.attn(Q, K, V, p_dropout=0.3, is_causal=True, return_softmax=True)
+    Pn = torch.as_tensor(P.numpy()).reshape(B, H, S, S)
+    kk, vv = k.repeat_interleave(H // HKV, 2), v.repeat_interleave(H // HKV, 2)
+    sc = torch.einsum("bshd,bthd->bhst", q, kk) / D ** 0.5
+    sc = sc.masked_fill(torch.triu(torch.ones(S, S), 1).bool(), float("-inf"))
+    sm = torch.softmax(sc, -1)
+    keep = Pn != 0
+    lower = torch.tril(torch.ones(S, S)).bool()
+    assert torch.allclose(Pn[keep], (sm / 0.7)[keep], atol=1e-5) and not bool(Pn[:, :, ~lower].any())     # survivors are scaled by 1 / (1 - p)
+    frac = float(keep[:, :, lower].float().mean())
+    assert 0.6 < frac < 0.8                                                                                   # about 70 % kept
+    want = torch.einsum("bhst,bthd->bshd", Pn, vv)
+    assert torch.allclose(torch.as_tensor(out.numpy()), want, atol=1e-5)
+    # backward replays the same mask: dV = P_dropped^T dO
+    ht.sum(out).backward()
+    dv = torch.einsum("bhst,bshd->bthd", Pn, torch.ones(B, S, H, D)).reshape(B, S, HKV, H // HKV, D).sum(3)
+    assert torch.allclose(torch.as_tensor(V.grad.numpy()), dv, atol=1e-4)
+    assert Q.grad is not None and float(torch.as_tensor(Q.grad.numpy()).abs().sum()) > 0
