@@ -439,6 +439,9 @@ def attn_varlen_qkvpacked(qkv, cu_seqlens, max_seqlen=None, num_heads=None, num_
     cumulative document boundaries; every document attends only to itself -> [T, H * D]
     (ref: hetu.attn_varlen_qkvpacked / AttentionVarlenOp)"""
     from .ops_extra import attn_packed
+    if p_dropout and float(p_dropout) > 0.0:
+        raise NotImplementedError("attention dropout on packed variable-length rows is not implemented (the fused kernels have no in-kernel "
+                                  "dropout); use p_dropout=0 here, or `attn(..., p_dropout=p)` on padded batches")
     if len(qkv.shape) == 4:                        # [T, 3, H, D]
         t, _, h, d = qkv.shape
         num_heads, num_kv_heads, head_dim = h, h, d
