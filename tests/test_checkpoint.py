@@ -239,3 +239,81 @@ def test_model_saver_mirrors_to_a_remote_filesystem_and_restores_on_a_fresh_node
         step, consumed = fresh.load_latest(m, opt)
         assert (step, consumed) == (4, 8) and torch.equal(g.get_param(m.weight), snaps[4])
         assert os.path.exists(local_b / "step4" / "COMPLETE")
+
+
+def test_huggingface_gpt2_weights_round_trip_and_logits_match():
+    """HF GPT2LMHeadModel (tiny, random) -> convert_gpt2_hf_to_ht -> GPTLMHeadModel: the logits of this framework equal the
+    HuggingFace forward; converting back reproduces the HF state dict bit for bit (ref: examples/hetero/gpt_hf_to_ht.py, gpt_hf_to_hf.py)"""
+    transformers = pytest.importorskip("transformers")
+    from hetu_b200.models import GPTConfig, GPTLMHeadModel, generate_ds_parallel_config
+    from hetu_b200.utils.checkpoint import convert_gpt2_hf_to_ht, convert_gpt2_ht_to_hf
+    torch.manual_seed(0)
+    L, H, NH, V, S = 2, 32, 4, 97, 12
+    hf = transformers.GPT2LMHeadModel(transformers.GPT2Config(vocab_size=V, n_positions=S, n_embd=H, n_layer=L, n_head=NH, activation_function="gelu",
+                                                              resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)).eval()
+    hf_sd = {k: v.detach().clone() for k, v in hf.state_dict().items() if not k.endswith((".attn.bias", ".attn.masked_bias"))}
+    ht_sd = convert_gpt2_hf_to_ht(hf_sd, L, NH)
+    ids = torch.randint(0, V, (2, S))
+    with torch.no_grad():
+        want = hf(ids).logits.reshape(2 * S, V)
+    with ht.graph("define_and_run", create_new=True) as g:
+        m = GPTLMHeadModel(GPTConfig(vocab_size=V, n_positions=S, n_embd=H, n_layer=L, n_head=NH), [generate_ds_parallel_config(L, 1, 1, 1, 1, zero=False)])
+        x = ht.placeholder("int64", [2 * S], name="ids")
+        p = ht.placeholder("int64", [2 * S], name="pos")
+        logits = m(x, p, None, seq_len=S)
+        missing = m.load_state_dict(ht_sd, strict=False)
+        got = g.run(logits, [logits], {x: ids.reshape(-1), p: torch.arange(S).repeat(2)})[0]
+    assert torch.allclose(got.float(), want, atol=2e-4, rtol=1e-4), float((got.float() - want).abs().max())
+    back = convert_gpt2_ht_to_hf(ht_sd, L, NH)
+    for k, v in hf_sd.items():
+        assert torch.equal(back[k], v), k
+
+
+def test_huggingface_llama_weights_round_trip_and_logits_match():
+    transformers = pytest.importorskip("transformers")
+    from hetu_b200.models import LlamaConfig, LlamaLMHeadModel, generate_ds_parallel_config
+    from hetu_b200.utils.checkpoint import convert_llama_hf_to_ht, convert_llama_ht_to_hf
+    torch.manual_seed(1)
+    L, H, NH, KV, F, V, S = 2, 32, 4, 2, 64, 89, 10
+    hf_cfg = transformers.LlamaConfig(vocab_size=V, hidden_size=H, intermediate_size=F, num_hidden_layers=L, num_attention_heads=NH, num_key_value_heads=KV,
+                                      max_position_embeddings=S, rms_norm_eps=1e-6, tie_word_embeddings=False, attention_dropout=0.0)
+    hf = transformers.LlamaForCausalLM(hf_cfg).eval()
+    hf_sd = {k: v.detach().clone() for k, v in hf.state_dict().items() if "rotary_emb" not in k}
+    ht_sd = convert_llama_hf_to_ht(hf_sd, L, NH, KV)
+    ids = torch.randint(0, V, (2, S))
+    with torch.no_grad():
+        want = hf(ids).logits.reshape(2 * S, V)
+    cfg = LlamaConfig(vocab_size=V, hidden_size=H, intermediate_size=F, num_hidden_layers=L, num_attention_heads=NH, num_key_value_heads=KV,
+                      max_position_embeddings=S, rms_norm_eps=1e-6)
+    with ht.graph("define_and_run", create_new=True) as g:
+        m = LlamaLMHeadModel(cfg, [generate_ds_parallel_config(L, 1, 1, 1, 1, zero=False, model="llama")])
+        x = ht.placeholder("int64", [2 * S], name="ids")
+        p = ht.placeholder("int64", [2 * S], name="pos")
+        logits = m(x, p, None, seq_len=S)
+        m.load_state_dict(ht_sd, strict=False)
+        got = g.run(logits, [logits], {x: ids.reshape(-1), p: torch.arange(S).repeat(2)})[0]
+    assert torch.allclose(got.float(), want, atol=2e-4, rtol=1e-4), float((got.float() - want).abs().max())
+    back = convert_llama_ht_to_hf(ht_sd, L, NH, KV)
+    for k, v in hf_sd.items():
+        assert torch.equal(back[k], v), k
+
+
+def test_examine_checkpoint_lists_tensors_layouts_and_states(tmp_path, capsys):
+    from hetu_b200.utils.checkpoint import examine_checkpoint
+    from hetu_b200.utils.checkpoint.converters import main as examine_main
+    with ht.graph("define_and_run", create_new=True) as g:
+        m = ht.nn.Linear(8, 4, name="lin_examine")
+        x = ht.placeholder("float32", [2, 8], name="x")
+        loss = ht.sum(m(x))
+        opt = ht.AdamOptimizer(lr=0.1)
+        train = opt.minimize(loss)
+        g.run(loss, [loss, train], {x: np.ones((2, 8), np.float32)})
+        ModelSaver(str(tmp_path), save_copies=1).save(m, opt, 1, consumed_samples=2, loss=0.0)
+    info = examine_checkpoint(str(tmp_path / "step1"))
+    assert info["complete"] and len(info["shard_files"]) == 1 and info["blocks"] > 0 and info["bytes"] > 0
+    w = next(t for n, t in info["parameters"].items() if n.endswith("weight"))
+    assert w["global_shape"] == [4, 8] and w["dtype"] == "float32" and w["device_num"] == 1
+    assert any(n.endswith("_mean") for n in info["optimizer_states"]) and any(n.endswith("_variance") for n in info["optimizer_states"])
+    examine_main([str(tmp_path / "step1")])
+    out = capsys.readouterr().out
+    assert "COMPLETE" in out and "weight" in out and "[4, 8]" in out
