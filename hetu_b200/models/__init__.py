@@ -4,3 +4,4 @@ from .moe import MoEConfig, GPTMoELMHeadModel  # noqa: F401
 from .parallel_config import generate_ds_parallel_config, read_ds_parallel_config  # noqa: F401
 from .ctr import WDL, DeepFM, DCN  # noqa: F401
 from .gnn import GCN, GCNLayer, GraphSageLayer, normalise_adjacency, partition_15d, dist_gcn_15d_forward  # noqa: F401
+from .bert import BertConfig, BertModel, BertForPreTraining, BertForMaskedLM, BertForSequenceClassification, convert_bert_hf_to_ht  # noqa: F401,E402
