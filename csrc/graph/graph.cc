@@ -544,8 +544,14 @@ TensorList autograd_gradient(OpDef& fw, const TensorList& gouts) {
       gout_idx.push_back((int64_t)i);
     }
   std::vector<int64_t> diff_inputs;
-  for (size_t i = 0; i < fw.inputs.size(); ++i)
-    if (dtype_is_float(fw.inputs[i]->dtype)) diff_inputs.push_back((int64_t)i);
+  for (size_t i = 0; i < fw.inputs.size(); ++i) {
+    const Tensor& t = fw.inputs[i];
+    if (!dtype_is_float(t->dtype)) continue;
+    // a variable that was declared non-trainable (running statistics, frozen tables, masks) never needs a gradient -- and some
+    // library ops refuse to be traced with respect to it (native_batch_norm and its running mean / variance)
+    if (t->producer != nullptr && t->producer->type == "variable" && !t->requires_grad) continue;
+    diff_inputs.push_back((int64_t)i);
+  }
   if (diff_inputs.empty()) return TensorList(fw.inputs.size());
   AttrMap a;
   a.set("fw_op", (int64_t)fw.id);

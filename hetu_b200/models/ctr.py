@@ -96,3 +96,47 @@ class DCN(_CTRBase):
             h = l(h, act="relu")
         logit = self.out(ops.concat([x, h], 1))
         return logit if label is None else (self.loss(logit, label), logit)
+
+
+class DeepCrossing(_CTRBase):
+    """Deep Crossing (DC): embeddings + dense features through a stack of residual units h = relu(h + W2 relu(W1 h))
+    (ref: hetu/v1/examples/ctr/models/dc_criteo.py)"""
+
+    def __init__(self, num_embeddings, embedding_dim=16, num_fields=26, num_dense=13, num_units=3, unit_hidden=256, **kw):
+        super().__init__(num_embeddings, embedding_dim, num_fields, num_dense, **kw)
+        d = num_fields * embedding_dim + num_dense
+        self.w1 = ModuleList([Linear(d, unit_hidden, name=f"dc_u{i}_w1") for i in range(num_units)])
+        self.w2 = ModuleList([Linear(unit_hidden, d, name=f"dc_u{i}_w2") for i in range(num_units)])
+        self.out = Linear(d, 1, name="dc_out")
+
+    def forward(self, dense, sparse_ids, label=None, embedded=None):
+        b = dense.shape[0]
+        h = ops.concat([ops.reshape(self.embed(sparse_ids, embedded), [b, self.num_fields * self.dim]), dense], 1)
+        for a, c in zip(self.w1, self.w2):
+            h = ops.relu(h + c(a(h, act="relu")))
+        logit = self.out(h)
+        return logit if label is None else (self.loss(logit, label), logit)
+
+
+class NCF(Module):
+    """Neural collaborative filtering (NeuMF): a GMF branch (element-wise product of user / item factors) and an MLP branch over
+    concatenated embeddings, fused by one linear layer; implicit-feedback BCE loss
+    (ref: hetu/v1/examples/rec -- hetu_ncf.py)"""
+
+    def __init__(self, num_users, num_items, factors=8, mlp_layers: Sequence[int] = (64, 32, 16, 8)):
+        super().__init__()
+        self.user_gmf, self.item_gmf = Embedding(num_users, factors, name="ncf_user_gmf"), Embedding(num_items, factors, name="ncf_item_gmf")
+        half = mlp_layers[0] // 2
+        self.user_mlp, self.item_mlp = Embedding(num_users, half, name="ncf_user_mlp"), Embedding(num_items, half, name="ncf_item_mlp")
+        self.mlp = ModuleList([Linear(a, b, name=f"ncf_mlp{i}") for i, (a, b) in enumerate(zip(mlp_layers[:-1], mlp_layers[1:]))])
+        self.out = Linear(factors + mlp_layers[-1], 1, name="ncf_out")
+
+    def forward(self, users, items, label=None):
+        gmf = self.user_gmf(users) * self.item_gmf(items)
+        h = ops.concat([self.user_mlp(users), self.item_mlp(items)], 1)
+        for l in self.mlp:
+            h = l(h, act="relu")
+        logit = self.out(ops.concat([gmf, h], 1))
+        if label is None:
+            return logit
+        return ops.binary_cross_entropy(ops.sigmoid(logit), label, reduction="mean"), logit

@@ -78,3 +78,79 @@ def test_bert_sequence_classifier_learns_a_separable_task():
             out = g.run(loss, [loss, logits, train], {X: torch.as_tensor(ids), Y: torch.as_tensor(y)})
             acc.append(float((out[1].float().argmax(1).numpy() == y).mean()))
     assert np.mean(acc[-10:]) > 0.9, acc[-10:]
+
+
+def test_lstm_matches_torch_lstm_with_shared_weights():
+    from hetu_b200.models import LSTM
+    torch.manual_seed(0)
+    B, T, F, Hd = 4, 6, 5, 7
+    ref = torch.nn.LSTM(F, Hd, batch_first=True)
+    x = torch.randn(B, T, F)
+    with torch.no_grad():
+        seq, (hn, cn) = ref(x)
+    with ht.graph("define_and_run", create_new=True) as g:
+        m = LSTM(F, Hd, num_classes=3)
+        X = ht.placeholder("float32", [B, T, F], name="x")
+        hs, (h, c) = m(X, return_sequence=True)
+        m.load_state_dict({"wx.weight": ref.weight_ih_l0.detach(), "wx.bias": ref.bias_ih_l0.detach(), "wh.weight": ref.weight_hh_l0.detach(),
+                           "wh.bias": ref.bias_hh_l0.detach()}, strict=False)
+        out = g.run(h, hs + [h, c], {X: x})
+    for t in range(T):
+        assert torch.allclose(out[t].float(), seq[:, t], atol=1e-5), t
+    assert torch.allclose(out[T].float(), hn[0], atol=1e-5) and torch.allclose(out[T + 1].float(), cn[0], atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["logreg", "mlp", "lenet", "cnn3", "alexnet", "vgg16", "resnet18", "rnn", "lstm"])
+def test_image_and_sequence_classifiers_fit_a_small_batch(name):
+    """every classifier of the zoo builds, back-propagates and drives the loss down on a memorisable batch"""
+    from hetu_b200 import models as M
+    rng = np.random.RandomState(0)
+    B = 8
+    if name in ("rnn", "lstm"):
+        x, shape = rng.randn(B, 6, 10).astype(np.float32), [B, 6, 10]
+        make = {"rnn": lambda: M.RNN(10, 32, 4), "lstm": lambda: M.LSTM(10, 32, 4)}[name]
+    elif name in ("logreg", "lenet"):
+        x, shape = rng.randn(B, 1, 28, 28).astype(np.float32), [B, 1, 28, 28]
+        make = {"logreg": lambda: M.LogReg(784, 4), "lenet": lambda: M.LeNet(1, 4, 28)}[name]
+    else:
+        x, shape = rng.randn(B, 3, 32, 32).astype(np.float32), [B, 3, 32, 32]
+        make = {"mlp": lambda: M.MLP(3072, (64,), 4), "cnn3": lambda: M.CNN3(3, 4, 32, width=8), "alexnet": lambda: M.AlexNet(3, 4, 32, dropout=0.0),
+                "vgg16": lambda: M.VGG(16, 3, 4, 32, width_div=8), "resnet18": lambda: M.ResNet(18, 3, 4, width=8)}[name]
+    y = rng.randint(0, 4, B)
+    with ht.graph("define_and_run", create_new=True) as g:
+        model = make()
+        X = ht.placeholder("float32", shape, name="x")
+        Y = ht.placeholder("int64", [B], name="y")
+        loss, logits = model(X, Y)
+        train = ht.AdamOptimizer(lr=3e-4 if name == "alexnet" else 3e-3).minimize(loss)      # no normalisation layers in AlexNet: smaller steps
+        assert list(logits.shape) == [B, 4]
+        losses = [float(g.run(loss, [loss, train], {X: torch.as_tensor(x), Y: torch.as_tensor(y)})[0]) for _ in range(60 if name == "alexnet" else 25)]
+    assert np.isfinite(losses).all() and losses[-1] < 0.7 * losses[0], (name, losses[0], losses[-1])
+
+
+def test_deep_crossing_and_ncf_train():
+    from hetu_b200.models import NCF, DeepCrossing
+    rng = np.random.RandomState(0)
+    B, F, N = 64, 6, 500
+    with ht.graph("define_and_run", create_new=True) as g:
+        m = DeepCrossing(N, 8, num_fields=F, num_dense=4, num_units=2, unit_hidden=32)
+        d, s, y = ht.placeholder("float32", [B, 4], name="d"), ht.placeholder("int64", [B, F], name="s"), ht.placeholder("float32", [B, 1], name="y")
+        loss, _ = m(d, s, y)
+        train = ht.AdamOptimizer(lr=1e-2).minimize(loss)
+        ls = []
+        for _ in range(40):
+            dense, sparse = rng.randn(B, 4).astype(np.float32), rng.randint(0, N, (B, F))
+            label = ((dense[:, :1] + (sparse[:, :1] % 2)) > 0.5).astype(np.float32)
+            ls.append(float(g.run(loss, [loss, train], {d: torch.as_tensor(dense), s: torch.as_tensor(sparse), y: torch.as_tensor(label)})[0]))
+    assert np.mean(ls[-5:]) < 0.85 * np.mean(ls[:5])
+    with ht.graph("define_and_run", create_new=True) as g:
+        m = NCF(50, 80, factors=4, mlp_layers=(16, 8, 4))
+        u, i, y = ht.placeholder("int64", [B], name="u"), ht.placeholder("int64", [B], name="i"), ht.placeholder("float32", [B, 1], name="y")
+        loss, logit = m(u, i, y)
+        train = ht.AdamOptimizer(lr=2e-2).minimize(loss)
+        like = (np.arange(50)[:, None] % 4) == (np.arange(80)[None, :] % 4)          # users like the items of their own group (low rank)
+        ls = []
+        for _ in range(150):
+            uu, ii = rng.randint(0, 50, B), rng.randint(0, 80, B)
+            ls.append(float(g.run(loss, [loss, train], {u: torch.as_tensor(uu), i: torch.as_tensor(ii), y: torch.as_tensor(like[uu, ii].astype(np.float32).reshape(B, 1))})[0]))
+    assert np.mean(ls[-10:]) < 0.7 * np.mean(ls[:10])
