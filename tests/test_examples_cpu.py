@@ -27,10 +27,14 @@ CASES = [
     ("moe/train_moe.py", "loss"),
     ("elastic/run_elastic.py", "generations"),
     ("efficiency/profile_attn.py --seq 256", "packed varlen"),
+    ("bert/pretrain_bert.py --steps 11", "nsp-acc"),
+    ("cnn/train_cnn.py --model resnet18 --steps 11 --batch 16 --width-div 8", "resnet18 step 10"),
+    ("rec/train_ncf.py --steps 51", "auc"),
+    ("hetero/convert_checkpoint.py examine .", "INCOMPLETE"),
 ]
 
 
-@pytest.mark.parametrize("cmd,expect", CASES, ids=[c[0].split()[0] for c in CASES])
+@pytest.mark.parametrize("cmd,expect", CASES, ids=[c[0].split()[0] + ("" if i < 16 else f"-{i}") for i, c in enumerate(CASES)])
 def test_example_runs(cmd, expect, tmp_path):
     env = dict(os.environ, HETU_B200_FORCE_CPU="1", CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2", PYTHONPATH=ROOT, TRAINER_OUT=str(tmp_path / "out"))
     parts = cmd.split()
