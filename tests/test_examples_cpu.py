@@ -30,6 +30,7 @@ CASES = [
     ("bert/pretrain_bert.py --steps 11", "nsp-acc"),
     ("cnn/train_cnn.py --model resnet18 --steps 11 --batch 16 --width-div 8", "resnet18 step 10"),
     ("rec/train_ncf.py --steps 51", "auc"),
+    ("nlp/train_transformer.py --steps 21 --batch 16 --seq 5 --vocab 12", "decoded"),
     ("hetero/convert_checkpoint.py examine .", "INCOMPLETE"),
 ]
 
