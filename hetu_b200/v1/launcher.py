@@ -44,7 +44,10 @@ def launch(command: Sequence[str], settings: Dict, log_dir: Optional[str] = None
             t.start()
         server = None
     else:
-        server = PSContext.serve(n_worker, port) if n_server > 0 else None
+        # a fresh store per job: the in-process registry is keyed by name and would otherwise hand a later job the parameters of
+        # an earlier one launched from the same interpreter
+        import uuid
+        server = PSContext.serve(n_worker, port, name=f"heturun-{uuid.uuid4().hex[:8]}") if n_server > 0 else None
     procs: List[subprocess.Popen] = []
     for w in range(n_worker):
         env = dict(os.environ)
