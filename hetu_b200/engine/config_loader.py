@@ -28,12 +28,20 @@ def _from_dict(cls, d: dict):
 def load_experiment(path: str, overrides: Sequence[str] = ()) -> Dict[str, Any]:
     """-> {"trainer": TrainingConfig | SFTConfig, "strategy": StrategyConfig, "model": dict, "optimizer": dict, "tokenizer": dict,
     "rpc": dict, "raw": dict}"""
-    with open(path) as f:
-        raw = yaml.safe_load(f) or {}
-    raw = copy.deepcopy(raw)
+    # hydra-style loading: `defaults` composition with config groups next to the file, dotted overrides (+add, ~delete,
+    # group=option), ${...} interpolation (utils/hydra_lite.py)
+    import os
+    from ..utils import hydra_lite
+    cfg_dir, cfg_name = os.path.split(os.path.abspath(path))
+    choices, values = {}, []
     for ov in overrides:
-        k, v = ov.split("=", 1)
-        _set(raw, k, yaml.safe_load(v))
+        k, eq, v = ov.partition("=")
+        if eq and not ov.startswith(("+", "~")) and "." not in k and os.path.isdir(os.path.join(cfg_dir, k)):
+            choices[k] = v
+        else:
+            values.append(ov)
+    raw = hydra_lite.compose(cfg_dir, cfg_name, choices)
+    raw = hydra_lite.resolve(hydra_lite.apply_overrides(copy.deepcopy(raw), values))
     ds = dict(raw.get("ds_parallel", {}))
     rc = ds.pop("recompute", None) or {}
     strat = _from_dict(StrategyConfig, {**ds, "recompute": _from_dict(RecomputeConfig, {
