@@ -597,3 +597,65 @@ def test_hydra_lite_composition_interpolation_overrides_and_structured_merge(tmp
         H.merge_dataclass(Strat, {"pipeline": 2})
     with pytest.raises(TypeError):
         H.merge_dataclass(Strat, {"dp": 2.5})
+
+
+def test_indexed_corpus_builder_preprocessor_gpt_samples_blending_and_splits(tmp_path):
+    """ref: examples/hydraulis/data_utils (MMapIndexedDataset + builder, HetuDataset sample mapping, BlendedDataset, split string)"""
+    import json as _json
+    from hetu_b200.data import (BlendedDataset, GPTSampleDataset, IndexedDatasetBuilder, blending_indices, open_indexed, preprocess_jsonl,
+                                split_documents)
+    rng = np.random.RandomState(0)
+    docs = [rng.randint(5, 250, rng.randint(3, 40)).tolist() for _ in range(57)]
+    b = IndexedDatasetBuilder(str(tmp_path / "a"), vocab_size=259)
+    for d in docs[:30]:
+        b.add_document(d)
+    ds_a = b.finalize()
+    b2 = IndexedDatasetBuilder(str(tmp_path / "b"), vocab_size=259)
+    for d in docs[30:]:
+        b2.add_document(d)
+    b2.finalize()
+    m = IndexedDatasetBuilder(str(tmp_path / "merged"), vocab_size=259)
+    m.merge(str(tmp_path / "a")); m.merge(str(tmp_path / "b"))
+    merged = m.finalize()
+    assert len(ds_a) == 30 and len(merged) == 57 and all(merged[i].tolist() == docs[i] for i in range(57))
+    assert merged.data.dtype == np.uint16 and _json.load(open(tmp_path / "merged.meta.json"))["tokens"] == sum(map(len, docs))
+    # JSONL preprocessing with 2 worker processes == 1 worker, documents in file order, EOD appended
+    lines = [{"text": "".join(chr(97 + (i + j) % 26) for j in range(5 + i % 9))} for i in range(400)]
+    with open(tmp_path / "corpus.jsonl", "w") as f:
+        for r in lines:
+            f.write(_json.dumps(r) + "\n")
+    one = preprocess_jsonl(str(tmp_path / "corpus.jsonl"), str(tmp_path / "tok1"), workers=1)
+    two = preprocess_jsonl(str(tmp_path / "corpus.jsonl"), str(tmp_path / "tok2"), workers=2)
+    assert len(one) == len(two) == 400 and all(np.array_equal(one[i], two[i]) for i in range(400))
+    from hetu_b200.data import ByteTokenizer
+    tok = ByteTokenizer()
+    assert one[7].tolist() == list(tok.encode(lines[7]["text"])) + [tok.eos_id]
+    assert not any(os.path.exists(str(tmp_path / f"tok2.shard{i}.bin")) for i in range(2))
+    # GPT samples: windows of seq+1 tokens over the shuffled document stream; an epoch covers its token stream exactly once
+    S = 16
+    g = GPTSampleDataset(merged, S, seed=3)
+    n = g.samples_per_epoch
+    assert n == (sum(map(len, docs)) - 1) // S and len(g) == n
+    samples = [g[i] for i in range(n)]
+    assert all(len(s) == S + 1 for s in samples)
+    order, starts, sample_order = g._epoch(0)
+    stream = np.concatenate([np.asarray(docs[d]) for d in order])
+    for i in range(n):
+        lo = int(sample_order[i]) * S
+        assert np.array_equal(samples[i], stream[lo:lo + S + 1])
+    assert sorted(int(x) for x in sample_order) == list(range(n))
+    again = GPTSampleDataset(open_indexed(str(tmp_path / "merged")), S, seed=3)
+    assert np.array_equal(again[5], samples[5])                               # resumable: a pure function of (seed, index)
+    two_epochs = GPTSampleDataset(merged, S, num_samples=2 * n, seed=3)
+    assert not np.array_equal(two_epochs[n], two_epochs[0]) or n == 1         # the second epoch is reshuffled
+    # blending: realised shares follow the weights at every prefix
+    which, inner = blending_indices([0.7, 0.2, 0.1], 1000)
+    for k, w in enumerate([0.7, 0.2, 0.1]):
+        assert abs((which == k).mean() - w) < 0.002 and abs((which[:100] == k).mean() - w) < 0.02
+        assert inner[which == k].tolist() == list(range(int((which == k).sum())))
+    mix = BlendedDataset([g, GPTSampleDataset(ds_a, S, seed=1)], [0.75, 0.25], 40)
+    assert len(mix) == 40 and len(mix[39]) == S + 1
+    tr, va, te = split_documents(1000, "969,30,1")
+    assert (len(tr), len(va), len(te)) == (969, 30, 1) and tr[-1] + 1 == va[0] and te[-1] == 999
+    tr, va, te = split_documents(10, "8,2")
+    assert (len(tr), len(va), len(te)) == (8, 2, 0)
