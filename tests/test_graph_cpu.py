@@ -354,3 +354,28 @@ def test_define_by_run_graph_reuses_ops_evaluates_lazily_and_prunes():
         np.testing.assert_allclose(s1.numpy(), np.exp(np.arange(6).reshape(2, 3) + 1.0), rtol=1e-5)
         again = ht.exp(a + b)
         assert again.id == s1.id                 # still reusable after pruning its consumers
+
+
+def test_graphboard_exports_dict_dot_and_html(tmp_path):
+    """ref: hetu/v1/python/graphboard -- the graph as data, as Graphviz source and as a standalone HTML page"""
+    import json as _json
+    from hetu_b200.utils import graphboard
+    with ht.graph("define_and_run", create_new=True) as g:
+        with ht.subgraph("encoder"):
+            lin = ht.nn.Linear(8, 4, name="gb_lin")
+            x = ht.placeholder("float32", [2, 8], name="gb_x")
+            h = ht.relu(lin(x))
+        loss = ht.sum(h)
+        train = ht.SGDOptimizer(lr=0.1).minimize(loss)
+    d = graphboard.graph_to_dict(g)
+    types = [o["type"] for o in d["ops"]]
+    assert "linear" in types and "unary_act" in types and any(t.endswith("_update") for t in types) and any(o["is_bwd"] for o in d["ops"])
+    relu = next(o for o in d["ops"] if o["type"] == "unary_act" and not o["is_bwd"])
+    assert d["tensors"][relu["outputs"][0]]["shape"] == [2, 4] and d["tensors"][relu["inputs"][0]]["producer"] is not None
+    dot = graphboard.to_dot(g)
+    assert dot.startswith("digraph") and "->" in dot and "cluster_" in dot and "linear" in dot and dot.count("[label=") == len(d["ops"])
+    path = graphboard.to_html(g, str(tmp_path / "graph.html"), title="toy")
+    page = open(path).read()
+    assert "<table" in page and "gb_lin" in page and 'id="graph"' in page
+    embedded = _json.loads(page.split('id="graph">')[1].split("</script>")[0])
+    assert len(embedded["ops"]) == len(d["ops"])
