@@ -81,6 +81,8 @@ class Trainer:
         self.trainer_states: Optional[TrainerStates] = None
         self.is_model_built = False
         self.loss_history: List[float] = []
+        self.eval_history: List[dict] = []
+        self.eval_dataset = None
         self.step_times: List[float] = []
         self.callbacks: List[Callable] = list(kwargs.get("callbacks", []))
         self.max_docs_per_row = int(kwargs.get("max_docs_per_row", 64))
@@ -449,6 +451,10 @@ class Trainer:
                       f"tokens {stats['real_tokens']}/{stats['fed_tokens']} strategy {sid}", flush=True)
             for cb in self.callbacks:
                 cb(self, loss, stats)
+            if getattr(cfg, "eval_interval", 0) and getattr(self, "eval_dataset", None) is not None and self.global_step % cfg.eval_interval == 0:
+                ev = self.evaluate(max_batches=getattr(cfg, "eval_iters", None) or None)
+                if ev is not None and cfg.log_interval:
+                    print(f"[trainer] step {self.global_step} eval loss {ev['loss']:.4f} ppl {ev['perplexity']:.2f} ({ev['tokens']} tokens)", flush=True)
             if saver is not None and self.global_step % cfg.save_interval == 0:
                 writer = min(d for p in self.hetero.pipelines for stg in p for d in stg) if self.hetero is not None else 0
                 saver.save(self.trainer_states.model, self.trainer_states.optimizer, self.global_step, self.consumed_samples,
@@ -458,6 +464,53 @@ class Trainer:
         if saver is not None:
             saver.wait()
         return self.loss_history
+
+    # ------------------------------------------------------------------ evaluation
+    def evaluate(self, eval_dataset=None, max_batches: Optional[int] = None, strategy_id: Optional[int] = None) -> Optional[dict]:
+        """forward-only pass over `eval_dataset` (default: `self.eval_dataset`) under the current strategy: no optimizer step, no
+        gradient ops are fetched.  -> {"loss": token-weighted mean, "perplexity", "batches", "tokens"} on the ranks that own the
+        loss, None elsewhere.  The data-parallel ranks see disjoint slices; their means are combined by token count."""
+        import math
+        ds = eval_dataset if eval_dataset is not None else getattr(self, "eval_dataset", None)
+        if ds is None:
+            raise ValueError("evaluate() needs an eval_dataset")
+        self.build()
+        if self.idle:
+            return None
+        cfg = self.pretrain_config
+        sid = self.cur_strategy_id if strategy_id is None else int(strategy_id)
+        dp, _, _ = _strategy_sizes(self.ds_parallel_configs[sid])
+        dp //= _cp_degree(self.ds_parallel_configs[sid])
+        level = cfg.data_load_level.value if isinstance(cfg.data_load_level, DataLoadLevel) else str(cfg.data_load_level)
+        kw = dict(global_batch_size=cfg.global_load_size) if level == "SAMPLE" else dict(global_token_num=cfg.global_load_size)
+        loader = build_data_loader(ds, 0, load_level=level, dp_rank=self._dp_rank(), dp_size=dp, seed=cfg.seed, collate_fn=self.data_collator, **kw)
+        st = self.trainer_states
+        tot_loss, tot_tok, nb = 0.0, 0, 0
+        for batch in loader:
+            if max_batches is not None and nb >= max_batches:
+                break
+            if self.hetero is not None:
+                batch = batch[self.hetero.batch_slice(len(batch))]
+            feed, nmb, seq, stats = self.prepare_feed_dict(batch, sid)
+            out = st.graph.run(st.loss, [st.loss], feed, int_symbol_dict={st.seq_len_symbol: seq}, num_micro_batches=nmb, cur_strategy_id=sid)
+            nb += 1
+            if out[0] is not None:
+                n = max(int(stats.get("real_tokens", 1)), 1)
+                tot_loss += float(out[0].float().mean()) * n
+                tot_tok += n
+        if tot_tok == 0:
+            return None
+        ranks = sorted(self._loss_ranks())
+        if len(ranks) > 1 and distributed.world_size() > 1 and distributed.rank() in ranks:
+            from .. import _C
+            t = _C.comm_all_reduce(torch.tensor([tot_loss, float(tot_tok)], dtype=torch.float64), ranks, "sum")
+            tot_loss, tot_tok = float(t[0]), int(t[1])
+        if distributed.rank() not in ranks:
+            return None
+        loss = tot_loss / tot_tok
+        res = {"loss": loss, "perplexity": math.exp(min(loss, 50.0)), "batches": nb, "tokens": tot_tok, "step": self.global_step}
+        self.eval_history.append(res)
+        return res
 
     def _loss_ranks(self):
         if self.hetero is not None:

@@ -41,6 +41,8 @@ class TrainingConfig:
     min_lr: float = 0.0
     clip_grad: float = 0.0
     save_interval: int = 0
+    eval_interval: int = 0                # evaluate on Trainer.eval_dataset every N steps (0 = never)
+    eval_iters: int = 0                   # batches per evaluation (0 = one pass over the evaluation set)
     log_interval: int = 1
     seed: int = 1234
     pack_alignment: int = 128

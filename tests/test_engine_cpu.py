@@ -659,3 +659,40 @@ def test_indexed_corpus_builder_preprocessor_gpt_samples_blending_and_splits(tmp
     assert (len(tr), len(va), len(te)) == (969, 30, 1) and tr[-1] + 1 == va[0] and te[-1] == 999
     tr, va, te = split_documents(10, "8,2")
     assert (len(tr), len(va), len(te)) == (8, 2, 0)
+
+
+def test_trainer_evaluate_and_periodic_evaluation():
+    """forward-only evaluation: token-weighted loss / perplexity over an evaluation set, no parameter changes; `eval_interval`
+    runs it inside the training loop and the evaluation loss falls as the model learns the pattern"""
+    from hetu_b200.engine import ModelWrapper, OptimizerWrapper, Trainer, TrainingConfig
+    from hetu_b200.models import GPTConfig, GPTLMHeadModel, generate_ds_parallel_config
+
+    class Pattern:
+        """sequences that count upwards modulo 50 from a per-sample start: learnable next-token structure"""
+
+        def __init__(self, n, seq, offset=0):
+            self.n, self.seq, self.offset = n, seq, offset
+
+        def __len__(self):
+            return self.n
+
+        def __getitem__(self, i):
+            return ((np.arange(self.seq + 1) + (i + self.offset) * 7) % 50 + 3).astype(np.int64)
+    ht.set_seed(5)
+    mcfg = GPTConfig(vocab_size=64, n_positions=16, n_embd=32, n_layer=2, n_head=2)
+    cfg = TrainingConfig(packing=False, micro_batch_size=4, global_load_size=8, max_seq_length=16, steps=30, learning_rate=3e-3, log_interval=0,
+                         pack_alignment=16, eval_interval=10, eval_iters=2)
+    tr = Trainer(cfg, ModelWrapper(GPTLMHeadModel, mcfg), ByteTokenizer(), OptimizerWrapper({"type": "adam", "lr": 3e-3}), Pattern(256, 16),
+                 ds_parallel_configs=[generate_ds_parallel_config(2, 1, 1, 1, 1, zero=False)])
+    tr.eval_dataset = Pattern(32, 16, offset=1000)
+    before = tr.evaluate()
+    assert before["batches"] == 4 and before["tokens"] == 32 * 16 and abs(before["perplexity"] - np.exp(before["loss"])) < 1e-6
+    w0 = tr.trainer_states.graph.get_param(next(iter(tr.trainer_states.model.parameters()))).clone()
+    again = tr.evaluate(max_batches=4)
+    assert abs(again["loss"] - before["loss"]) < 1e-6                                   # evaluation changes nothing
+    assert torch.equal(tr.trainer_states.graph.get_param(next(iter(tr.trainer_states.model.parameters()))), w0)
+    tr.train()
+    periodic = [e for e in tr.eval_history if e["step"] in (10, 20, 30)]
+    assert [e["step"] for e in periodic] == [10, 20, 30] and all(e["batches"] == 2 for e in periodic)
+    after = tr.evaluate()
+    assert after["loss"] < 0.7 * before["loss"] and periodic[-1]["loss"] < periodic[0]["loss"]
