@@ -530,6 +530,22 @@ class Trainer:
         os.makedirs(self.pretrain_config.output_dir, exist_ok=True)
         with open(os.path.join(self.pretrain_config.output_dir, "loss.csv"), "w") as f:
             f.write("step,loss\n" + "\n".join(f"{i + 1},{v}" for i, v in enumerate(self.loss_history)))
+        # dependency-free SVG of the same curve (train loss, plus evaluation points when there are any)
+        if self.loss_history:
+            W, H, pad = 720, 360, 40
+            lo, hi = min(self.loss_history), max(self.loss_history)
+            span = (hi - lo) or 1.0
+            n = max(len(self.loss_history) - 1, 1)
+            sx = lambda i: pad + (W - 2 * pad) * i / n                                   # noqa: E731
+            sy = lambda v: H - pad - (H - 2 * pad) * (min(max(v, lo), hi) - lo) / span   # noqa: E731
+            pts = " ".join(f"{sx(i):.1f},{sy(v):.1f}" for i, v in enumerate(self.loss_history))
+            dots = "".join(f'<circle cx="{sx(min(e["step"] - 1, n)):.1f}" cy="{sy(e["loss"]):.1f}" r="3" fill="#d62728"/>' for e in self.eval_history)
+            svg = (f'<svg xmlns="http://www.w3.org/2000/svg" width="{W}" height="{H}"><rect width="100%" height="100%" fill="white"/>'
+                   f'<polyline fill="none" stroke="#1f77b4" stroke-width="1.5" points="{pts}"/>{dots}'
+                   f'<text x="{pad}" y="{pad - 12}" font-size="12">loss {hi:.4f} (top) .. {lo:.4f} (bottom), {len(self.loss_history)} steps</text>'
+                   f'<line x1="{pad}" y1="{H - pad}" x2="{W - pad}" y2="{H - pad}" stroke="black"/><line x1="{pad}" y1="{pad}" x2="{pad}" y2="{H - pad}" stroke="black"/></svg>')
+            with open(os.path.join(self.pretrain_config.output_dir, "loss.svg"), "w") as f:
+                f.write(svg)
         try:
             import matplotlib
             matplotlib.use("Agg")
