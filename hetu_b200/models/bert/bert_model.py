@@ -6,7 +6,7 @@ from the graph's DistributedStates (replicated parameters, split batch), like th
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, Optional
+from typing import Dict
 
 from ... import ops
 from ...nn import Dropout, Embedding, LayerNorm, Linear, Module, ModuleList

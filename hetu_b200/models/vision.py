@@ -6,7 +6,7 @@ from __future__ import annotations
 from typing import List, Sequence
 
 from .. import ops
-from ..nn import AvgPool2d, BatchNorm, Conv2d, Dropout, Linear, MaxPool2d, Module, ModuleList
+from ..nn import BatchNorm, Conv2d, Dropout, Linear, MaxPool2d, Module, ModuleList
 
 
 class _Classifier(Module):

@@ -20,13 +20,11 @@ from typing import Callable, Dict, List, Optional, Tuple
 import numpy as np
 import torch
 
-from ... import core, ops
-from ...graph_api import gradients  # noqa: F401  (kept importable for users extending schedules)
+from ... import core
 from ...models.ctr import DCN, WDL, DeepFM
 from ...optim import AdamOptimizer
 from ...v1.metrics import auc as _auc
-from .methods import (AutoDimEmbedding, CafeEmbedding, DeepLightEmbedding, MixedDimEmbedding, OptEmbedEmbedding, PrunedEmbedding,
-                      build_compressed_embedding)
+from .methods import AutoDimEmbedding, CafeEmbedding, DeepLightEmbedding, OptEmbedEmbedding, PrunedEmbedding, build_compressed_embedding
 
 
 # ----------------------------------------------------------------------------------------------------------------- data
