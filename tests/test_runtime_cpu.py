@@ -249,3 +249,47 @@ def test_stream_ordered_pool_bookkeeping_without_a_device_and_allocator_selectio
     assert _C.tensor_allocator("cpu:91").kind == "bfc"
     monkeypatch.setenv("HETU_MEMORY_POOL", "caching")
     assert _C.tensor_allocator("cpu:92").kind == "caching"
+
+
+@pytest.mark.parametrize("kind", ["caching", "bfc"])
+def test_pools_are_thread_safe_under_concurrent_alloc_free(kind):
+    """four threads hammer one pool: every live block keeps its own byte pattern (no two live blocks overlap), all memory returns"""
+    import ctypes
+    import random
+    import threading
+    pool = _C.MemoryPool("host", limit_mb=512) if kind == "caching" else _C.BFCMemoryPool("host", initial_region_mb=4, limit_mb=512)
+    errors = []
+
+    def worker(tid):
+        rng = random.Random(tid)
+        live = []
+        try:
+            for step in range(1500):
+                if live and (rng.random() < 0.5 or len(live) > 40):
+                    ptr, n, tag = live.pop(rng.randrange(len(live)))
+                    buf = (ctypes.c_ubyte * n).from_address(ptr)
+                    if buf[0] != tag or buf[n - 1] != tag or buf[n // 2] != tag:
+                        errors.append(f"thread {tid}: block at {ptr:#x} was overwritten")
+                        return
+                    pool.free(ptr)
+                else:
+                    n = rng.choice([64, 700, 4096, 33_000, 260_000])
+                    ptr = pool.alloc(n, stream=tid)
+                    if ptr == 0:
+                        errors.append("allocation failed")
+                        return
+                    tag = (tid * 37 + step) % 251 + 1
+                    ctypes.memset(ptr, tag, n)
+                    live.append((ptr, n, tag))
+            for ptr, n, tag in live:
+                pool.free(ptr)
+        except Exception as e:      # noqa: BLE001
+            errors.append(repr(e))
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(120)
+    assert not errors, errors[:3]
+    st = pool.stats()
+    assert st["allocated"] == 0 and st["num_alloc"] == st["num_free"] > 1000
