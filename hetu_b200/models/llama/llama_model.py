@@ -20,7 +20,7 @@ from ..parallel_config import generate_ds_parallel_config
 
 @dataclass
 class LlamaConfig:
-    # (fp8=True runs the four projection GEMMs of every block in block-scaled e4m3, see ops.linear_fp8)
+    # (fp8=True runs the four projection GEMMs of every block in e4m3 with per-row (activations) and per-column (weights) scales, see ops.linear_fp8)
     vocab_size: int = 32000
     hidden_size: int = 4096
     intermediate_size: int = 11008
@@ -35,7 +35,7 @@ class LlamaConfig:
     dtype: str = "float32"
     cp_ranks: tuple = ()            # context-parallel ring (global ranks); empty = no CP
     recompute_layers: tuple = ()
-    fp8: bool = False               # projection GEMMs in block-scaled e4m3 (fwd + dgrad), weight gradients in bf16
+    fp8: bool = False               # projection GEMMs in row- / column-scaled e4m3 (fwd + dgrad), weight gradients in bf16
 
     @property
     def kv_heads(self):

@@ -320,8 +320,9 @@ def linear(x, w, bias=None, trans_a=False, trans_b=True, act="none", residual=No
 
 
 def linear_fp8(x, w, bias=None, act="none", **kw):
-    """y = act(x @ w^T + bias) with both operands quantised to e4m3 per 1 x K block (fp32 scales applied in the tcgen05 GEMM
-    epilogue); the input-gradient GEMM also runs in fp8, the weight gradient in bf16.  w is [out, in]."""
+    """y = act(x @ w^T + bias) with both operands quantised to e4m3 with one fp32 scale per row of x and per output row of w
+    (i.e. per 1 x K slice -- coarser than 1 x 128 / 128 x 128 block scaling; the scales are applied in the tcgen05 GEMM epilogue);
+    the input-gradient GEMM also runs in fp8, the weight gradient in bf16.  w is [out, in]."""
     ins = [x, w] + ([bias] if bias is not None else [])
     attrs = {"trans_b": True, "has_bias": bias is not None, "has_residual": False, "act": str(act)}
     return make_op("linear_fp8", ins, attrs, **_meta(kw))[0]

@@ -287,7 +287,7 @@ def test_swiglu_interleaved():
 
 
 @pytest.mark.parametrize("M,N,K,act", [(1024, 768, 512, "none"), (2048, 1024, 2048, "gelu"), (384, 520, 272, "none")])
-def test_linear_fp8_block_scaled(M, N, K, act):
+def test_linear_fp8_row_scaled(M, N, K, act):
     """e4m3 operands with one fp32 scale per 1 x K block, tcgen05 kind::f8f6f4, scales applied in the epilogue"""
     x, w, b, g = bf(M, K, seed=1), bf(N, K, scale=1 / math.sqrt(K), seed=2), bf(N, seed=3), bf(M, N, seed=4)
     X, W, B = leaf(x), leaf(w), leaf(b)
