@@ -45,6 +45,49 @@ TABLE = {
     "rpc.heturpc_elastic_server": [("rpc.elastic_server", None)],
     "rpc.elastic_arg_parser": [("rpc.elastic_server", None)],
     "rpc.heturpc_async_server": [("rpc.heturpc_polling_server", None)],   # one threaded controller serves both variants
+    "rpc.heturpc_async_server_exp": [("rpc.heturpc_polling_server", None)],
+    "rpc.pssh_start_exp": [("rpc.launcher", None)],
+    "rpc.kv_store.client": [("rpc.kv_store", ["KeyValueStoreClient", "RemoteDict"])],
+    "rpc.kv_store.server": [("rpc.kv_store", ["KeyValueStoreServer"])],
+    "rpc.kv_store.producer_consumer": [("rpc.kv_store", ["ProducerConsumer"])],
+    "rpc.kv_store.const": [("rpc.kv_store", ["TIMEOUT", "DEFAULT_PORT"])],
+    "engine.sft_config": [("engine.trainer_config", ["SFTConfig"])],
+    "engine.utils": [("engine.strategy", ["Args", "TrainerCtxs", "TrainerDatasetArgs", "TrainerStrategyArgs", "TrainerCommArgs", "TrainerCommAllArgs",
+                                          "TrainerEnvs"])],
+    "data.tokenizers.utils": [("data.tokenizers", ["SpecialToken", "BaseTokenizer"])],
+    "data.tokenizers.pretrained_tokenizer": [("data.tokenizers", ["PreTrainedTokenizer"])],
+    "models.utils.common_utils": [("models.utils.pretrained", ["split_hetu_state_dict_into_shards", "split_state_dict_into_shards", "parse_size"])],
+    "models.utils.config_utils": [("models.utils.pretrained", ["PreTrainedConfig", "CONFIG_NAME"])],
+    "models.utils.hub": [("models.utils.pretrained", ["is_remote_url"])],
+    "models.utils.model_utils": [("models.utils.pretrained", ["PreTrainedModel", "get_state_dict_dtype", "get_parameter_dtype", "WEIGHTS_INDEX_NAME"]),
+                                 ("peft.lora.model", ["lora_state_dict"])],
+    "models.utils.converter.convert_utils": [("utils.checkpoint.ht_safetensors", ["save_model", "save_file"])],
+    "nn.functional": [("nn.init", ["generalized_xavier_", "xavier_uniform_", "xavier_normal_", "kaiming_uniform_", "kaiming_normal_", "lecun_uniform_",
+                                   "lecun_normal_", "calculate_gain"])],
+    "nn.parameter": [("nn", ["Parameter"])],
+    "nn.modules": [("nn.module", "*"), ("nn.layers", "*"), ("nn.parallel", "*")],      # a package facade: its children are listed below
+    "nn.modules.activation": [("nn.layers", ["ReLU", "GELU", "SiLU", "Sigmoid", "Tanh", "LeakyReLU", "Softmax", "NewGeLU"])],
+    "nn.modules.batchnorm": [("nn.layers", ["BatchNorm"])],
+    "nn.modules.container": [("nn.module", ["ModuleList", "Sequential", "ModuleDict"])],
+    "nn.modules.conv": [("nn.layers", ["Conv2d"])],
+    "nn.modules.dropout": [("nn.layers", ["Dropout", "Dropout2d"])],
+    "nn.modules.instancenorm": [("nn.layers", ["InstanceNorm"])],
+    "nn.modules.linear": [("nn.layers", ["Linear", "Identity"])],
+    "nn.modules.loss": [("nn.layers", ["MSELoss", "BCELoss", "NLLLoss", "KLDivLoss", "CrossEntropyLoss", "SoftmaxCrossEntropySparse"])],
+    "nn.modules.module": [("nn.module", ["Module"])],
+    "nn.modules.normalization": [("nn.layers", ["LayerNorm", "RMSNorm"])],
+    "nn.modules.padding": [("nn.layers", ["ConstantPad2d", "ZeroPad2d"])],
+    "nn.modules.pooling": [("nn.layers", ["MaxPool2d", "AvgPool2d"])],
+    "nn.modules.sparse": [("nn.layers", ["Embedding"])],
+    "nn.modules.parallel": [("nn.parallel", None)],
+    "nn.modules.parallel_ds": [("nn.parallel", None)],
+    "nn.modules.parallel_multi_ds": [("nn.parallel", None)],
+    "nn.modules.parallel_utils": [("nn.parallel", ["config2ds", "get_multi_ds_parallel_config"]),
+                                  ("data.dataloader", ["parallel_data_provider"]),
+                                  ("utils.parallel", ["get_local_index", "get_device_index"])],
+    "nn.modules.utils": [("nn.layers", ["_nlist"])],
+    "optim.optimizer": [("optim", ["Optimizer"])],
+    "optim.sgd": [("optim", ["SGDOptimizer", "SGD"])],
     "utils.checkpoint.load_checkpoint": [("utils.checkpoint.legacy", ["convert_llama_hf_to_ht", "load_checkpoint", "load_checkpoint_from_megatron"])],
     "utils.checkpoint.save_checkpoint": [("utils.checkpoint.legacy", ["save_checkpoint"])],
     "utils.data.dataloader": [("data.dataloader", None)],
@@ -88,6 +131,8 @@ class FacadeLoader(importlib.abc.Loader):
         names = []
         for src, wanted in self.sources:
             real = importlib.import_module(f"{_PKG}.{src}")
+            if wanted == "*":
+                wanted = [n for n in getattr(real, "__all__", None) or dir(real) if not n.startswith("_")]
             for n in wanted:
                 setattr(module, n, getattr(real, n))
                 names.append(n)
@@ -105,7 +150,9 @@ class RefPathFinder(importlib.abc.MetaPathFinder):
         if len(sources) == 1 and sources[0][1] is None:
             real = importlib.import_module(f"{_PKG}.{sources[0][0]}")
             return importlib.util.spec_from_loader(fullname, AliasLoader(real), origin=getattr(real.__spec__, "origin", None))
-        return importlib.util.spec_from_loader(fullname, FacadeLoader(sources))
+        rel = fullname[len(_PKG) + 1:]
+        has_children = any(k.startswith(rel + ".") for k in TABLE)          # e.g. nn.modules -> nn.modules.linear
+        return importlib.util.spec_from_loader(fullname, FacadeLoader(sources), is_package=has_children)
 
 
 def install():

@@ -107,3 +107,74 @@ LlamaTokenizer = SentencePieceTokenizer
 
 def TikTokenizer(name="cl100k_base"):
     return build_tokenizer("tiktoken", name_or_path=name)
+
+
+# ---- base classes of the reference's tokenizer package (ref: python/hetu/data/tokenizers/{utils.py, pretrained_tokenizer.py})
+class SpecialToken:
+    """names of the special tokens a tokenizer may define"""
+    PAD, BOS, EOS, UNK, SEP, CLS, MASK = "pad", "bos", "eos", "unk", "sep", "cls", "mask"
+
+    def __init__(self, content: str, token_id: Optional[int] = None, kind: str = ""):
+        self.content, self.token_id, self.kind = content, token_id, kind
+
+    def __repr__(self):
+        return f"SpecialToken({self.content!r}, id={self.token_id}, kind={self.kind!r})"
+
+
+class BaseTokenizer:
+    """interface every tokenizer of this package satisfies: encode / decode, vocab_size, pad / bos / eos ids, batch helpers"""
+    vocab_size: int = 0
+    pad_id: int = 0
+    bos_id: int = 0
+    eos_id: int = 0
+
+    def encode(self, text: str, add_special_tokens: bool = True) -> List[int]:
+        raise NotImplementedError
+
+    def decode(self, ids) -> str:
+        raise NotImplementedError
+
+    def batch_encode(self, texts, max_length: Optional[int] = None, padding: bool = False, add_special_tokens: bool = True):
+        rows = [self.encode(t, add_special_tokens)[:max_length] if max_length else self.encode(t, add_special_tokens) for t in texts]
+        if padding:
+            width = max(len(r) for r in rows)
+            rows = [r + [self.pad_id] * (width - len(r)) for r in rows]
+        return rows
+
+    def batch_decode(self, rows):
+        return [self.decode([i for i in r if i != self.pad_id]) for r in rows]
+
+    @property
+    def pad(self):
+        return self.pad_id
+
+    @property
+    def eod(self):
+        return self.eos_id
+
+
+class PreTrainedTokenizer(BaseTokenizer):
+    """a tokenizer restored from a local directory (`from_pretrained(dir)`: HuggingFace files, a sentencepiece model or a GPT-2
+    vocab/merges pair are recognised) behind the BaseTokenizer interface"""
+
+    def __init__(self, inner):
+        self.inner = inner
+        for k in ("vocab_size", "pad_id", "bos_id", "eos_id"):
+            setattr(self, k, getattr(inner, k, 0))
+
+    @classmethod
+    def from_pretrained(cls, path: str):
+        import os
+        files = set(os.listdir(path)) if os.path.isdir(path) else set()
+        if {"vocab.json", "merges.txt"} <= files and "tokenizer.json" not in files and "tokenizer_config.json" not in files:
+            return cls(build_tokenizer("gpt2", vocab_file=os.path.join(path, "vocab.json"), merge_file=os.path.join(path, "merges.txt")))
+        sp = next((f for f in files if f.endswith(".model")), None)
+        if sp and "tokenizer.json" not in files:
+            return cls(build_tokenizer("sentencepiece", vocab_file=os.path.join(path, sp)))
+        return cls(build_tokenizer("hf", name_or_path=path))
+
+    def encode(self, text, add_special_tokens: bool = True):
+        return list(self.inner.encode(text, add_special_tokens=add_special_tokens))
+
+    def decode(self, ids):
+        return self.inner.decode(list(ids))

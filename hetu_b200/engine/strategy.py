@@ -35,6 +35,64 @@ class TrainerCtxs:
     top_k: int = 3
 
 
+class Args:
+    """attribute bundle printed field by field (ref: python/hetu/engine/utils.py Args)"""
+
+    def print_args(self):
+        for k, v in vars(self).items():
+            print(f"{type(self).__name__}.{k} = {v}")
+
+
+@dataclass
+class TrainerDatasetArgs(Args):
+    dataset: object = None
+    consumed_samples: int = 0
+    steps: int = 0
+    epochs: int = 1
+    step: int = 0
+    epoch: int = 0
+
+
+@dataclass
+class TrainerCommArgs(Args):
+    """one communicator of the straggler report: its members and how long they spent in it"""
+    input_ds_union: object = None
+    output_ds_union: object = None
+    device_group_union: object = None
+    local_device: object = None
+    is_hetero: bool = False
+
+
+@dataclass
+class TrainerCommAllArgs(Args):
+    comm_args_list: List[TrainerCommArgs] = field(default_factory=list)
+
+
+@dataclass
+class TrainerEnvs(Args):
+    """environment knobs a (re)launched trainer process is started with"""
+    run_straggler_experiment: bool = False
+    run_memory_experiment: bool = False
+    straggler_file: str = ""
+    memory_file: str = ""
+    elastic: bool = False
+    event_timing: bool = True
+
+    def as_env(self) -> Dict[str, str]:
+        e = {}
+        if self.run_straggler_experiment:
+            e["HETU_STRAGGLER"] = "EXP"
+            if self.straggler_file:
+                e["HETU_STRAGGLER_LOG_FILE"] = self.straggler_file
+        if self.run_memory_experiment:
+            e["HETU_MEMORY_PROFILE"] = "MICRO_BATCH"
+            if self.memory_file:
+                e["HETU_MEMORY_LOG_FILE"] = self.memory_file
+        if not self.event_timing:
+            e["HETU_EVENT_TIMING"] = "OFF"
+        return e
+
+
 @dataclass
 class TrainerStrategyArgs:
     dp: int = 1

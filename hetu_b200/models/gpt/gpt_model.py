@@ -14,10 +14,11 @@ from ...nn import (HtMultiColumnParallelLinear, HtMultiParallelEmbedding, HtMult
 from ...nn.parallel import get_multi_ds_parallel_config
 from ...ops_extra import attn_packed
 from ..parallel_config import generate_ds_parallel_config
+from ..utils.pretrained import PreTrainedConfig, PreTrainedModel
 
 
 @dataclass
-class GPTConfig:
+class GPTConfig(PreTrainedConfig):
     vocab_size: int = 50304
     n_positions: int = 1024
     n_embd: int = 768
@@ -168,7 +169,9 @@ class _placement:
         return False
 
 
-class GPTLMHeadModel(Module):
+class GPTLMHeadModel(Module, PreTrainedModel):
+    config_class = GPTConfig
+
     def __init__(self, config: GPTConfig, ds_parallel_configs: Optional[List[dict]] = None, num_gpus: int = 1):
         super().__init__()
         if ds_parallel_configs is None:

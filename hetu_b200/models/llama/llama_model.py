@@ -16,10 +16,11 @@ from ...nn import (HtMultiColumnParallelLinear, HtMultiParallelRMSNorm, HtMultiQ
 from ...nn.parallel import get_multi_ds_parallel_config
 from ...ops_extra import attn_packed, rotary_packed
 from ..parallel_config import generate_ds_parallel_config
+from ..utils.pretrained import PreTrainedConfig, PreTrainedModel
 
 
 @dataclass
-class LlamaConfig:
+class LlamaConfig(PreTrainedConfig):
     # (fp8=True runs the four projection GEMMs of every block in e4m3 with per-row (activations) and per-column (weights) scales, see ops.linear_fp8)
     vocab_size: int = 32000
     hidden_size: int = 4096
@@ -163,7 +164,9 @@ class LlamaModel(Module):
         return self.rmsnorm_f(x)
 
 
-class LlamaLMHeadModel(Module):
+class LlamaLMHeadModel(Module, PreTrainedModel):
+    config_class = LlamaConfig
+
     def __init__(self, config: LlamaConfig, ds_parallel_configs: Optional[List[dict]] = None, num_gpus: int = 1):
         super().__init__()
         if ds_parallel_configs is None:

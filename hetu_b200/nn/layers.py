@@ -242,3 +242,11 @@ class ZeroPad2d(ConstantPad2d):
 
 
 __all__ += ["NewGeLU", "ConstantPad2d", "ZeroPad2d"]
+
+
+def _nlist(x, n: int):
+    """an int (or a 1-element sequence) repeated n times, an n-sequence as a list (ref: python/hetu/nn/modules/utils.py)"""
+    if isinstance(x, (list, tuple)):
+        x = list(x)
+        return x * n if len(x) == 1 else x
+    return [x] * n

@@ -349,3 +349,6 @@ class GradScaler:
         g.set_loss_scaler(scale_var, self.scale_value, float(self.growth_factor), float(self.backoff_factor), int(self.growth_interval))
         self._graph = g
         return train_op
+
+
+SGD = SGDOptimizer      # ref: python/hetu/optim/sgd.py

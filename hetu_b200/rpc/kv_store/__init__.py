@@ -8,6 +8,9 @@ from typing import Any, Optional
 from ..client import DeviceClient
 from ..server import DeviceControllerServer
 
+TIMEOUT = 60.0           # seconds a blocking get waits for a key (ref: python/hetu/rpc/kv_store/const.py)
+DEFAULT_PORT = 23460
+
 
 class KeyValueStoreServer(DeviceControllerServer):
     def __init__(self, host: str = "127.0.0.1", port: int = 23458):

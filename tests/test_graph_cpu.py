@@ -1,5 +1,7 @@
 """Define-and-run graphs on CPU (BASELINE config #1: 2-layer MLP, world_size 1) plus executor features:
 micro-batch accumulation, run levels, recompute, module API, symbolic shapes, multi-strategy shape plans."""
+import math
+import os
 import numpy as np
 import pytest
 import torch
@@ -379,3 +381,65 @@ def test_graphboard_exports_dict_dot_and_html(tmp_path):
     assert "<table" in page and "gb_lin" in page and 'id="graph"' in page
     embedded = _json.loads(page.split('id="graph">')[1].split("</script>")[0])
     assert len(embedded["ops"]) == len(d["ops"])
+
+
+def test_nn_init_functions_parameter_and_pretrained_round_trip(tmp_path):
+    """ref: python/hetu/nn/{init,parameter}.py, models/utils/{config_utils,model_utils,common_utils}.py -- in-place initialisers with the
+    right statistics, `nn.Parameter`, HuggingFace-style save_pretrained / from_pretrained with sharded safetensors"""
+    from hetu_b200.models import GPTConfig, GPTLMHeadModel, generate_ds_parallel_config
+    from hetu_b200.models.utils.pretrained import PreTrainedModel, parse_size, split_state_dict_into_shards
+    from hetu_b200.nn import init
+    ht.set_seed(7)
+    with ht.graph("define_and_run", create_new=True) as g:
+        lin = ht.nn.Linear(400, 300, name="init_lin")
+        conv = ht.nn.Conv2d(8, 16, 3, name="init_conv")
+        w = lin.weight
+        init.xavier_uniform_(w)
+        v = g.get_param(w)
+        lim = math.sqrt(6.0 / (400 + 300))
+        assert float(v.abs().max()) <= lim + 1e-6 and abs(float(v.std()) - lim / math.sqrt(3)) < 0.05 * lim
+        init.kaiming_normal_(conv.weight, mode="fan_out", nonlinearity="relu")
+        assert abs(float(g.get_param(conv.weight).std()) - math.sqrt(2.0 / (16 * 9))) < 0.02
+        init.lecun_normal_(w)
+        assert abs(float(g.get_param(w).std()) - math.sqrt(1.0 / 400)) < 0.005
+        init.trunc_normal_(w, std=0.02, a=-0.04, b=0.04)
+        assert float(g.get_param(w).abs().max()) <= 0.04 and abs(float(g.get_param(w).std()) - 0.0176) < 0.002
+        init.constant_(lin.bias, 0.5); assert bool((g.get_param(lin.bias) == 0.5).all())
+        init.zeros_(lin.bias); init.ones_(lin.bias); assert bool((g.get_param(lin.bias) == 1).all())
+        init.uniform_(lin.bias, -2, 2); init.normal_(lin.bias, 1.0, 0.1)
+        assert init.calculate_gain("relu") == math.sqrt(2.0) and abs(init.calculate_gain("leaky_relu", 0.2) - math.sqrt(2 / 1.04)) < 1e-9
+        assert init._calculate_fan_in_and_fan_out(conv.weight) == (72, 144)
+        p = ht.nn.Parameter(np.arange(6, dtype=np.float32).reshape(2, 3), name="my_param")
+        assert p.requires_grad and list(p.shape) == [2, 3] and torch.equal(g.get_param(p), torch.arange(6.0).reshape(2, 3))
+    # pretrained IO: config.json + sharded safetensors + index; reload under a fresh graph reproduces the logits
+    files, index = split_state_dict_into_shards({"a": torch.zeros(1000), "b": torch.zeros(1000), "c": torch.zeros(10)}, max_shard_size=5000)
+    assert list(files) == ["model-00001-of-00002.safetensors", "model-00002-of-00002.safetensors"] and index["weight_map"]["c"].startswith("model-00002")
+    assert parse_size("5GB") == 5 * 10 ** 9 and parse_size("200MiB") == 200 * 2 ** 20
+    cfg = GPTConfig(vocab_size=64, n_positions=16, n_embd=32, n_layer=2, n_head=2)
+    ids = torch.randint(0, 64, (16,))
+    with ht.graph("define_and_run", create_new=True) as g:
+        m = GPTLMHeadModel(cfg, [generate_ds_parallel_config(2, 1, 1, 1, 1, zero=False)])
+        x, pos = ht.placeholder("int64", [16], name="ids"), ht.placeholder("int64", [16], name="pos")
+        logits = m(x, pos, None, seq_len=16)
+        want = g.run(logits, [logits], {x: ids, pos: torch.arange(16)})[0].clone()
+        written = m.save_pretrained(str(tmp_path / "gpt"), max_shard_size="20KB")
+    assert len(written) > 1 and os.path.exists(tmp_path / "gpt" / "config.json") and os.path.exists(tmp_path / "gpt" / "model.safetensors.index.json")
+    assert GPTConfig.from_pretrained(str(tmp_path / "gpt")) == cfg and isinstance(m, PreTrainedModel)
+    with ht.graph("define_and_run", create_new=True) as g:
+        m2 = GPTLMHeadModel.from_pretrained(str(tmp_path / "gpt"))
+        x, pos = ht.placeholder("int64", [16], name="ids"), ht.placeholder("int64", [16], name="pos")
+        logits = m2(x, pos, None, seq_len=16)
+        got = g.run(logits, [logits], {x: ids, pos: torch.arange(16)})[0]
+    assert torch.equal(got, want)
+    with pytest.raises(ValueError, match="remote"):
+        GPTLMHeadModel.from_pretrained("https://huggingface.co/gpt2")
+
+
+def test_tokenizer_base_classes():
+    from hetu_b200.data.tokenizers import BaseTokenizer, ByteTokenizer, PreTrainedTokenizer, SpecialToken
+    tok = PreTrainedTokenizer(ByteTokenizer())
+    assert isinstance(tok, BaseTokenizer) and tok.vocab_size == 259 and tok.pad == 256 and tok.eod == 258
+    rows = tok.batch_encode(["hi", "hello"], padding=True)
+    assert len(rows[0]) == len(rows[1]) and rows[0][-1] == tok.pad_id and tok.batch_decode(rows) == ["hi", "hello"]
+    assert tok.batch_encode(["abcdef"], max_length=4)[0] == tok.encode("abcdef")[:4]
+    assert "pad" in repr(SpecialToken("<pad>", 0, SpecialToken.PAD))

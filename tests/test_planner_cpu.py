@@ -82,6 +82,20 @@ def test_reference_module_paths_resolve_under_the_hetu_alias():
              "hetu.rpc.pssh_start", "hetu.rpc.pssh_start_config", "hetu.rpc.pssh_start_elastic", "hetu.rpc.local_start", "hetu.rpc.pssh_workers",
              "hetu.rpc.elastic_arg_parser", "hetu.rpc.kv_store", "hetu.rpc.heturpc_elastic_server", "hetu.rpc.heturpc_polling_server",
              "hetu.rpc.heturpc_async_server"]
+    # every python module of the reference resolves (only its op-binding code generator has no counterpart): facades for the finer
+    # grained reference layout -- nn.modules.*, nn.functional / init / parameter, optim.{optimizer,sgd}, engine.{utils,sft_config},
+    # models.utils.*, data.tokenizers.{utils,pretrained_tokenizer}, rpc.kv_store.{client,server,const,producer_consumer}
+    more = ["hetu.nn.modules", "hetu.nn.modules.linear", "hetu.nn.modules.activation", "hetu.nn.modules.parallel_multi_ds", "hetu.nn.modules.parallel_utils",
+            "hetu.nn.modules.container", "hetu.nn.functional", "hetu.nn.init", "hetu.nn.parameter", "hetu.optim.optimizer", "hetu.optim.sgd",
+            "hetu.engine.utils", "hetu.engine.sft_config", "hetu.models.utils.model_utils", "hetu.models.utils.config_utils", "hetu.models.utils.hub",
+            "hetu.models.utils.common_utils", "hetu.data.tokenizers.utils", "hetu.data.tokenizers.pretrained_tokenizer", "hetu.rpc.kv_store.client",
+            "hetu.rpc.kv_store.server", "hetu.rpc.kv_store.const", "hetu.rpc.kv_store.producer_consumer", "hetu.rpc.pssh_start_exp"]
+    for p in more:
+        importlib.import_module(p)
+    from hetu.nn.modules.linear import Linear
+    from hetu.nn.modules import HtMultiColumnParallelLinear, Module   # noqa: F401
+    from hetu.optim.sgd import SGD
+    assert Linear is ht.nn.Linear and SGD is ht.SGDOptimizer
     for p in paths:
         m = importlib.import_module(p)
         assert m is importlib.import_module("hetu_b200." + p[len("hetu."):]), p
