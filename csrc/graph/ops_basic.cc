@@ -407,6 +407,25 @@ ATEN_OP(repeat, 1, return {in[0].repeat(op.attrs.ints("repeats"))};);
 ATEN_OP(roll, 1, return {at::roll(in[0], op.attrs.ints("shifts"), op.attrs.ints("dims"))};);
 ATEN_OP(pad, 1, return {at::constant_pad_nd(in[0], op.attrs.ints("paddings"), op.attrs.f("value"))};);
 ATEN_OP(gather, 1, return {at::gather(in[0], op.attrs.i("dim"), in[1].to(at::kLong))};);
+// index / order statistics of the v1 op set (ref: hetu/v1 Argmax, Argsort, TopKIdx / TopKVal, Cumsum, Sign, Scatter)
+ATEN_OP_NODIFF(argmax, 1, return {at::argmax(in[0], op.attrs.i("dim", -1), op.attrs.b("keepdims"))};);
+ATEN_OP_NODIFF(argsort, 1, return {at::argsort(in[0], op.attrs.i("dim", -1), op.attrs.b("descending"))};);
+ATEN_OP(topk, 2, {
+  auto r = at::topk(in[0], op.attrs.i("k", 1), op.attrs.i("dim", -1), op.attrs.b("largest", true), true);
+  return {std::get<0>(r), std::get<1>(r)};
+});
+ATEN_OP(cumsum, 1, return {at::cumsum(in[0], op.attrs.i("dim", -1))};);
+ATEN_OP_NODIFF(sign, 1, return {at::sign(in[0])};);
+ATEN_OP(scatter, 1, return {at::scatter(in[0], op.attrs.i("dim"), in[1].to(at::kLong), in[2])};);
+ATEN_OP_NODIFF(unique_consecutive_count, 2, {
+  // sorted unique values of a 1-D tensor and, per input element, the index of its value among them (fixed-size outputs: the unique
+  // list is padded with the last value to the input length; `count` tells how many entries are real)
+  auto flat = in[0].reshape({-1});
+  auto r = at::_unique2(flat, true, true, false);
+  at::Tensor u = std::get<0>(r), inv = std::get<1>(r);
+  at::Tensor padded = u.numel() > 0 ? at::cat({u, u.slice(0, u.numel() - 1, u.numel()).expand({flat.numel() - u.numel()})}) : flat;
+  return {padded, inv};
+});
 ATEN_OP(index_add, 1, return {at::index_add(in[0], op.attrs.i("dim"), in[1].to(at::kLong), in[2])};);
 ATEN_OP(interpolate, 1, {
   auto size = op.attrs.ints("size");

@@ -285,6 +285,38 @@ def gather(x, dim, index, **kw):
     return _op1("gather", [x, index], {"dim": int(dim)}, **kw)
 
 
+def argmax(x, dim=-1, keepdims=False, **kw):
+    return _op1("argmax", [x], {"dim": int(dim), "keepdims": bool(keepdims)}, **kw)
+
+
+def argsort(x, dim=-1, descending=False, **kw):
+    return _op1("argsort", [x], {"dim": int(dim), "descending": bool(descending)}, **kw)
+
+
+def topk(x, k, dim=-1, largest=True, **kw):
+    """-> (values, indices)"""
+    outs = make_op("topk", [x], {"k": int(k), "dim": int(dim), "largest": bool(largest)}, **_meta(kw))
+    return outs[0], outs[1]
+
+
+def cumsum(x, dim=-1, **kw):
+    return _op1("cumsum", [x], {"dim": int(dim)}, **kw)
+
+
+def sign(x, **kw):
+    return _op1("sign", [x], **kw)
+
+
+def scatter(x, dim, index, src, **kw):
+    return _op1("scatter", [x, index, src], {"dim": int(dim)}, **kw)
+
+
+def unique(x, **kw):
+    """sorted unique values of a 1-D tensor padded to the input length, and every element's index among them -> (values, inverse)"""
+    outs = make_op("unique_consecutive_count", [x], {}, **_meta(kw))
+    return outs[0], outs[1]
+
+
 def index_add_(x, index, src, dim=0, **kw):
     return _op1("index_add", [x, index, src], {"dim": int(dim)}, **kw)
 

@@ -21,3 +21,5 @@ from . import strategies as dist  # noqa: F401
 from .strategies import (DataParallel, ModelParallel4CNN, ModelParallel4LM, OneWeirdTrick4CNN, MegatronLM, FlexFlowSearching,  # noqa: F401
                          OptCNNSearching, GPipeSearching, PipeDreamSearching, PipeOptSearching)
 from ..models.moe import MoELayer, TopKGate, KTop1Gate, HashGate, BalanceGate, SAMGate  # noqa: F401
+from .ops import *  # noqa: F401,F403,E402  (the long tail of v1 `*_op` constructors)
+from . import ops as gpu_ops  # noqa: F401,E402

@@ -397,3 +397,51 @@ def test_v1_strategies_emit_executable_ds_parallel_configs():
     for strat in (S.FlexFlowSearching(8, budget=300), S.OptCNNSearching(8), S.PipeDreamSearching(8), S.PipeOptSearching(8)):
         cfg = S.strategy_to_ds_parallel_config(strat, L, H, F, SEQ, B)
         assert cfg["dp"] * cfg["tp"] * cfg["pp"] == 8 and len(cfg["devices"]) == 8 and cfg["estimated_step_s"] > 0
+
+
+def test_v1_long_tail_op_constructors_match_numpy():
+    """ref: hetu/v1/python/hetu/gpu_ops -- the `*_op` constructors beyond the common set, checked against numpy / torch"""
+    import numpy as np
+    import torch
+    import hetu_b200.v1 as v1
+    from hetu_b200.v1 import executor as v1ex
+    v1ex.reset_graph()
+    rng = np.random.RandomState(0)
+    a, b, c = (rng.randn(4, 5).astype(np.float32) for _ in range(3))
+    m1, m2 = rng.randn(4, 3).astype(np.float32), rng.randn(3, 5).astype(np.float32)
+    A, B, C = (v1.Variable(n, value=v, trainable=False) for n, v in (("lt_a", a), ("lt_b", b), ("lt_c", c)))
+    M1, M2 = v1.Variable("lt_m1", value=m1, trainable=False), v1.Variable("lt_m2", value=m2, trainable=False)
+    pos = v1.Variable("lt_pos", value=np.abs(a) + 0.5, trainable=False)
+    ids = v1.Variable("lt_ids", value=np.array([7, 12, 5, 30], np.int64), dtype="int64", trainable=False)
+    nodes = {
+        "addmm": (v1.addmm_op(C, M1, M2, alpha=0.5, beta=2.0), 0.5 * m1 @ m2 + 2.0 * c),
+        "minus_byconst": (v1.minus_byconst_op(A, 3.0), 3.0 - a), "div_const": (v1.div_const_op(2.0, pos), 2.0 / (np.abs(a) + 0.5)),
+        "const_pow": (v1.const_pow_op(A, 2.0), 2.0 ** a), "power": (v1.power_op(pos, 1.5), (np.abs(a) + 0.5) ** 1.5),
+        "clamp": (v1.clamp_op(A, mmin=-0.3, mmax=0.4), np.clip(a, -0.3, 0.4)), "sign": (v1.sign_op(A), np.sign(a)), "bool": (v1.bool_op(A), (a != 0).astype(np.float32)),
+        "max": (v1.max_op(A, B), np.maximum(a, b)), "min": (v1.min_op(A, B), np.minimum(a, b)),
+        "reduce_mul": (v1.reduce_mul_op(pos, [1]), np.prod(np.abs(a) + 0.5, 1)), "reduce_norm1": (v1.reduce_norm1_op(A, [1]), np.abs(a).sum(1)),
+        "reduce_norm2": (v1.reduce_norm2_op(A, [0]), np.sqrt((a * a).sum(0))), "reducesumaxiszero": (v1.reducesumaxiszero_op(A), a.sum(0)),
+        "argmax": (v1.argmax_op(A, 1), a.argmax(1)), "argsort": (v1.argsort_op(A, 1, descending=True), np.argsort(-a, 1, kind="stable")),
+        "topk_val": (v1.topk_val_op(A, 2, 1), -np.sort(-a, 1)[:, :2]), "topk_idx": (v1.topk_idx_op(A, 2, 1), np.argsort(-a, 1, kind="stable")[:, :2]),
+        "cumsum": (v1.cumsum_with_bias_op(A, 1.0, dim=1), np.cumsum(a, 1) + 1.0), "tile": (v1.tile_op(A, [2, 1]), np.tile(a, (2, 1))),
+        "roll": (v1.roll_op(A, 2, 1), np.roll(a, 2, 1)), "where_const": (v1.where_const_op(v1.bool_op(v1.relu_op(A)), A, -1.0), np.where(a > 0, a, -1.0)),
+        "slice_assign": (v1.slice_assign_op(A, [1, 1], [2, 3], 9.0), (lambda t: (t.__setitem__((slice(1, 3), slice(1, 4)), 9.0), t)[1])(a.copy())),
+        "log_softmax": (v1.log_softmax_op(A), torch.log_softmax(torch.tensor(a), -1).numpy()),
+        "crossentropy": (v1.crossentropy_op(v1.softmax_op(A), v1.softmax_op(B)), -(torch.softmax(torch.tensor(b), -1) * torch.log_softmax(torch.tensor(a), -1)).sum(-1).numpy()),
+        "bce_logits": (v1.binarycrossentropywithlogits_op(A, v1.bool_op(v1.relu_op(B))),
+                       torch.nn.functional.binary_cross_entropy_with_logits(torch.tensor(a), torch.tensor((b > 0).astype(np.float32)), reduction="none").numpy()),
+        "mod_hash": (v1.mod_hash_op(ids, 5), np.array([2, 2, 0, 0])), "div_hash": (v1.div_hash_op(ids, 5), np.array([1, 2, 1, 6])),
+        "conv2d_reducesum": (v1.conv2d_reducesum_op(v1.array_reshape_op(A, [2, 2, 5, 1])), a.reshape(2, 2, 5, 1).sum((0, 2, 3))),
+        "tril_lookup": (v1.tril_lookup_op(v1.array_reshape_op(v1.slice_op(A, [0, 0], [4, 4]), [1, 4, 4])), a[:, :4][np.tril_indices(4)].reshape(1, -1)),
+        "min_dist": (v1.min_dist_op(A, B), ((a[:, None, :] - b[None]) ** 2).sum(-1).argmin(1)),
+        "prune": (v1.prune_low_magnitude_op(A, 0.5), a * (np.abs(a) > np.sort(np.abs(a).reshape(-1))[9])),
+    }
+    names = list(nodes)
+    ex = v1.Executor([nodes[n][0] for n in names])
+    outs = ex.run(feed_dict={}, convert_to_numpy_ret_vals=True)
+    for n, got in zip(names, outs):
+        np.testing.assert_allclose(np.asarray(got, dtype=np.float64), np.asarray(nodes[n][1], dtype=np.float64), rtol=2e-5, atol=2e-5, err_msg=n)
+    s1, s2 = v1.normal_sample_op([1000], 1.0, 2.0), v1.uniform_sample_op([1000], -1.0, 1.0)
+    r = v1.Executor([s1, s2, v1.randint_sample_op([50], 3, 9), v1.gumbel_sample_op([10])]).run(feed_dict={}, convert_to_numpy_ret_vals=True)
+    assert abs(r[0].mean() - 1.0) < 0.2 and abs(r[0].std() - 2.0) < 0.2 and -1.0 <= r[1].min() and r[1].max() <= 1.0 and 3 <= r[2].min() and r[2].max() < 9
+    v1ex.reset_graph()
