@@ -10,10 +10,11 @@ from typing import Dict
 
 from ... import ops
 from ...nn import Dropout, Embedding, LayerNorm, Linear, Module, ModuleList
+from ..utils.pretrained import PreTrainedConfig, PreTrainedModel
 
 
 @dataclass
-class BertConfig:
+class BertConfig(PreTrainedConfig):
     vocab_size: int = 30522
     hidden_size: int = 768
     num_hidden_layers: int = 12
@@ -144,7 +145,9 @@ class _MLMHead(Module):
         return ops.linear(h, self.decoder_weight, self.decoder_bias, trans_b=True)
 
 
-class BertForMaskedLM(Module):
+class BertForMaskedLM(Module, PreTrainedModel):
+    config_class = BertConfig
+
     def __init__(self, config: BertConfig):
         super().__init__()
         self.config = config
@@ -160,7 +163,9 @@ class BertForMaskedLM(Module):
         return ops.softmax_cross_entropy_sparse(logits, ops.reshape(labels, [b * s]), ignored_index=-100, reduction="mean"), logits
 
 
-class BertForPreTraining(Module):
+class BertForPreTraining(Module, PreTrainedModel):
+    config_class = BertConfig
+
     """masked-LM + next-sentence heads; loss = MLM cross entropy (labels -100 ignored) + NSP cross entropy"""
 
     def __init__(self, config: BertConfig):
@@ -182,7 +187,9 @@ class BertForPreTraining(Module):
         return loss, mlm, nsp
 
 
-class BertForSequenceClassification(Module):
+class BertForSequenceClassification(Module, PreTrainedModel):
+    config_class = BertConfig
+
     def __init__(self, config: BertConfig):
         super().__init__()
         self.config = config

@@ -144,11 +144,15 @@ class PreTrainedModel:
         """build the model inside the CURRENT graph context and load the weights -> model"""
         if is_remote_url(path):
             raise ValueError(f"{path}: remote model hubs are not reachable; pass a local directory")
+        import inspect
         cfg = config if config is not None else cls.config_class.from_pretrained(path, **config_overrides)
-        if ds_parallel_configs is None:
-            from ..parallel_config import generate_ds_parallel_config
-            layers = getattr(cfg, "n_layer", None) or getattr(cfg, "num_hidden_layers")
-            ds_parallel_configs = [generate_ds_parallel_config(int(layers), 1, 1, 1, 1, zero=False)]
-        model = cls(cfg, ds_parallel_configs)
+        if "ds_parallel_configs" in inspect.signature(cls.__init__).parameters:
+            if ds_parallel_configs is None:
+                from ..parallel_config import generate_ds_parallel_config
+                layers = getattr(cfg, "n_layer", None) or getattr(cfg, "num_hidden_layers")
+                ds_parallel_configs = [generate_ds_parallel_config(int(layers), 1, 1, 1, 1, zero=False)]
+            model = cls(cfg, ds_parallel_configs)
+        else:
+            model = cls(cfg)                          # model families without a parallel layout argument (BERT, seq2seq, ...)
         model.load_state_dict(cls.load_weights(path), strict=strict)
         return model
