@@ -55,6 +55,7 @@ TABLE = {
     "engine.utils": [("engine.strategy", ["Args", "TrainerCtxs", "TrainerDatasetArgs", "TrainerStrategyArgs", "TrainerCommArgs", "TrainerCommAllArgs",
                                           "TrainerEnvs"])],
     "data.tokenizers.utils": [("data.tokenizers", ["SpecialToken", "BaseTokenizer"])],
+    "data.tokenizers.bert_tokenizer": [("data.tokenizers.wordpiece", None)],
     "data.tokenizers.pretrained_tokenizer": [("data.tokenizers", ["PreTrainedTokenizer"])],
     "models.utils.common_utils": [("models.utils.pretrained", ["split_hetu_state_dict_into_shards", "split_state_dict_into_shards", "parse_size"])],
     "models.utils.config_utils": [("models.utils.pretrained", ["PreTrainedConfig", "CONFIG_NAME"])],

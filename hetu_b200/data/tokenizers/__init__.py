@@ -76,6 +76,9 @@ def build_tokenizer(tokenizer_type: str = "byte", vocab_file: Optional[str] = No
         return _HFWrapper(AutoTokenizer.from_pretrained(name_or_path, local_files_only=True))
     if t in ("sentencepiece", "sentencepiecetokenizer", "llama"):
         return _SPWrapper(vocab_file or name_or_path)
+    if t in ("bert", "wordpiece", "berttokenizer"):
+        from .wordpiece import BertTokenizer
+        return BertTokenizer(vocab_file or name_or_path)
     if t in ("tiktoken", "tiktokentokenizer"):
         import tiktoken
         enc = tiktoken.get_encoding(name_or_path or "cl100k_base")

@@ -696,3 +696,29 @@ def test_trainer_evaluate_and_periodic_evaluation():
     assert [e["step"] for e in periodic] == [10, 20, 30] and all(e["batches"] == 2 for e in periodic)
     after = tr.evaluate()
     assert after["loss"] < 0.7 * before["loss"] and periodic[-1]["loss"] < periodic[0]["loss"]
+
+
+def test_bert_wordpiece_tokenizer_matches_the_huggingface_reference_implementation(tmp_path):
+    """own WordPiece implementation (basic tokenisation + greedy longest match) against transformers.BertTokenizer on the same vocab"""
+    transformers = pytest.importorskip("transformers")
+    from hetu_b200.data.tokenizers import build_tokenizer
+    words = ["the", "quick", "brown", "fox", "jump", "##s", "##ed", "##ing", "over", "lazy", "dog", "un", "##believ", "##able", "cafe", "na", "##ive", "2024",
+             "hello", "world", "!", ",", ".", "?", "-", "'", "s", "中", "文", "token", "##izer", "##ization", "a", "b", "##c", "new", "york"]
+    vocab = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + words
+    (tmp_path / "vocab.txt").write_text("\n".join(vocab) + "\n", encoding="utf-8")
+    ours = build_tokenizer("bert", vocab_file=str(tmp_path / "vocab.txt"))
+    ref = transformers.BertTokenizer(str(tmp_path / "vocab.txt"), do_lower_case=True)
+    texts = ["The quick brown fox jumps over the lazy dog.", "Unbelievable!  Tokenization, tokenizer's naive café?", "hello 中文 world", "jumping jumped xyz-abc 2024",
+             "New   York\tnew\nyork", "[MASK] the [SEP] fox"]
+    for t in texts:
+        assert ours.tokenize(t) == ref.tokenize(t), t
+        assert ours.encode(t) == ref.encode(t), t
+    a, b = "the quick fox", "jumps over the lazy dog"
+    ids, types, mask = ours.encode_plus(a, b, max_length=12, padding=True)
+    enc = ref(a, b, max_length=12, padding="max_length", truncation="longest_first")
+    assert ids == enc["input_ids"] and types == enc["token_type_ids"] and mask == enc["attention_mask"]
+    ids, types, mask = ours.encode_plus(a, b, max_length=7)
+    enc = ref(a, b, max_length=7, truncation="longest_first")
+    assert ids == enc["input_ids"] and types == enc["token_type_ids"]
+    assert ours.decode(ours.encode("unbelievable tokenization")) == "unbelievable tokenization"
+    assert ours.vocab_size == len(vocab) and ours.pad == 0 and ours.mask_id == 4
