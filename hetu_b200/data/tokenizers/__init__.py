@@ -69,6 +69,9 @@ def build_tokenizer(tokenizer_type: str = "byte", vocab_file: Optional[str] = No
     if t in ("byte", "bytes"):
         return ByteTokenizer()
     if t in ("gpt2bpetokenizer", "gpt2", "gpt2bpe"):
+        from .bpe import GPT2BPE                      # own byte-level BPE (no dependency on the transformers tokenizers)
+        return GPT2BPE(vocab_file, merge_file)
+    if t in ("gpt2-hf", "gpt2_hf"):
         from transformers import GPT2TokenizerFast
         return _HFWrapper(GPT2TokenizerFast(vocab_file=vocab_file, merges_file=merge_file))
     if t in ("hf", "huggingface", "hftokenizer"):

@@ -722,3 +722,48 @@ def test_bert_wordpiece_tokenizer_matches_the_huggingface_reference_implementati
     assert ids == enc["input_ids"] and types == enc["token_type_ids"]
     assert ours.decode(ours.encode("unbelievable tokenization")) == "unbelievable tokenization"
     assert ours.vocab_size == len(vocab) and ours.pad == 0 and ours.mask_id == 4
+
+
+def test_gpt2_byte_level_bpe_matches_the_huggingface_reference_implementation(tmp_path):
+    """own byte-level BPE (pre-tokenisation pattern, byte symbols, ranked merges) against transformers.GPT2Tokenizer on a vocabulary
+    learned here from a tiny corpus"""
+    transformers = pytest.importorskip("transformers")
+    import json as _json
+    from collections import Counter
+    from hetu_b200.data.tokenizers import build_tokenizer
+    from hetu_b200.data.tokenizers.bpe import _PATTERN, bytes_to_unicode
+    import regex
+    corpus = "the quick brown fox jumps over the lazy dog. The dog's tokenization isn't naive: 2024 tokens, tokenizer tokens! héllo wörld 中文 \n\n  spaced   out"
+    be = bytes_to_unicode()
+    words = Counter("".join(be[b] for b in w.encode("utf-8")) for w in regex.findall(_PATTERN, corpus * 3))
+    vocab = {c: i for i, c in enumerate(sorted(set(be.values())))}
+    splits = {w: list(w) for w in words}
+    merges = []
+    for _ in range(60):                                    # learn 60 merges: most frequent adjacent pair first
+        pairs = Counter()
+        for w, n in words.items():
+            for p in zip(splits[w], splits[w][1:]):
+                pairs[p] += n
+        if not pairs:
+            break
+        (a, b), _n = max(sorted(pairs.items()), key=lambda kv: kv[1])
+        merges.append((a, b))
+        vocab.setdefault(a + b, len(vocab))
+        for w in splits:
+            s, out, i = splits[w], [], 0
+            while i < len(s):
+                if i < len(s) - 1 and s[i] == a and s[i + 1] == b:
+                    out.append(a + b); i += 2
+                else:
+                    out.append(s[i]); i += 1
+            splits[w] = out
+    vocab["<|endoftext|>"] = len(vocab)
+    (tmp_path / "vocab.json").write_text(_json.dumps(vocab), encoding="utf-8")
+    (tmp_path / "merges.txt").write_text("#version: 0.2\n" + "\n".join(f"{a} {b}" for a, b in merges) + "\n", encoding="utf-8")
+    ours = build_tokenizer("gpt2", vocab_file=str(tmp_path / "vocab.json"), merge_file=str(tmp_path / "merges.txt"))
+    ref = transformers.GPT2Tokenizer(str(tmp_path / "vocab.json"), str(tmp_path / "merges.txt"))
+    for t in (corpus, "the dog's tokens", "  leading spaces and a tab\there", "unseen ßtring with ünïcode 🙂", ""):
+        assert ours.tokenize(t) == ref.tokenize(t), t
+        assert ours.encode(t) == ref.encode(t), t
+        assert ours.decode(ours.encode(t)) == t
+    assert ours.encode("fox", add_special_tokens=True)[-1] == ours.eos_id == vocab["<|endoftext|>"] and ours.vocab_size == len(vocab)
