@@ -8,3 +8,4 @@ from .rnn import RNN, LSTM  # noqa: F401
 from .gnn import GCN, GCNLayer, GraphSageLayer, normalise_adjacency, partition_15d, dist_gcn_15d_forward  # noqa: F401
 from .bert import BertConfig, BertModel, BertForPreTraining, BertForMaskedLM, BertForSequenceClassification, convert_bert_hf_to_ht  # noqa: F401,E402
 from .transformer import Transformer, TransformerConfig, MultiHeadAttention  # noqa: F401,E402
+from .generation import Generator  # noqa: F401,E402

@@ -209,3 +209,42 @@ def test_encoder_decoder_transformer_learns_to_reverse_sequences_and_decodes_gre
         src = rng.randint(3, V, (4, S))
         dec = m.greedy_decode(g, src, max_len=S + 2, bos_id=BOS, eos_id=EOS)
         assert (dec[:, 1:S + 1] == src[:, ::-1]).mean() > 0.6, (dec, src)       # free-running decoding of the longest sequences: harder than teacher forcing
+
+
+def test_generator_greedy_and_sampling_continue_a_learned_pattern():
+    """a tiny GPT learns 'count upwards modulo 20'; greedy decoding continues the count from prompts of different lengths, nucleus /
+    top-k sampling with a low temperature does too, eos stops a sequence, and the filters keep exactly the requested candidate sets"""
+    from hetu_b200.models import Generator, GPTConfig, GPTLMHeadModel, generate_ds_parallel_config
+    from hetu_b200.models.generation import _filter_logits
+    V, S, B = 24, 16, 8
+    cfg = GPTConfig(vocab_size=V, n_positions=S, n_embd=32, n_layer=2, n_head=2)
+    dsc = [generate_ds_parallel_config(2, 1, 1, 1, 1, zero=False)]
+    rng = np.random.RandomState(0)
+    with ht.graph("define_and_run", create_new=True) as g:
+        m = GPTLMHeadModel(cfg, dsc)
+        X, P, Y = (ht.placeholder("int64", [B * S], name=n) for n in ("ids", "pos", "lab"))
+        loss = m(X, P, Y, seq_len=S)
+        train = ht.AdamOptimizer(lr=5e-3).minimize(loss)
+        for _ in range(150):
+            start = rng.randint(0, 20, B)
+            seq = (start[:, None] + np.arange(S + 1)[None]) % 20 + 2
+            g.run(loss, [loss, train], {X: torch.as_tensor(seq[:, :-1].reshape(-1)), P: torch.arange(S).repeat(B), Y: torch.as_tensor(seq[:, 1:].reshape(-1))})
+        state = m.state_dict()
+    gen = Generator(lambda: GPTLMHeadModel(cfg, dsc), batch=3, window=S)
+    gen.load_state_dict(state)
+    prompts = [[5, 6, 7], [12], [19, 20, 21, 2]]
+    out = gen.generate(prompts, max_new_tokens=6)
+    for p, o in zip(prompts, out):
+        assert o[:len(p)] == p and len(o) == len(p) + 6
+        want = [(p[-1] - 2 + k) % 20 + 2 for k in range(1, 7)]
+        assert o[len(p):] == want, (p, o)
+    sampled = gen.generate(prompts, max_new_tokens=4, temperature=0.2, top_k=3, top_p=0.9, seed=1)
+    assert all(s[:len(p)] == p and len(s) == len(p) + 4 for p, s in zip(prompts, sampled))
+    assert sum(s[len(p):] == o[len(p):len(p) + 4] for p, s, o in zip(prompts, sampled, out)) >= 2      # a sharp distribution: mostly the greedy path
+    stopped = gen.generate([[5, 6, 7]], max_new_tokens=10, eos_id=10)
+    assert stopped[0] == [5, 6, 7, 8, 9, 10]
+    full = gen.generate([list(range(2, 2 + S - 2))], max_new_tokens=10)
+    assert len(full[0]) == S                                                    # the window is the hard limit
+    z = np.log(np.array([[0.5, 0.25, 0.15, 0.07, 0.03]]))
+    assert np.isfinite(_filter_logits(z, 2, 1.0)).sum() == 2 and np.isfinite(_filter_logits(z, 0, 0.8)).sum() == 3
+    assert np.isfinite(_filter_logits(z, 0, 1.0)).all()
