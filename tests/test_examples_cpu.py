@@ -14,7 +14,7 @@ CASES = [
      "trainer.max_seq_length=32 model.n_positions=32 model.n_embd=32 model.n_layer=2 model.n_head=2 model.vocab_size=259 "
      "model.sequence_parallel=false ds_parallel.sequence_parallel=false", "steps 2"),
     ("sft/sft_lora.py", "adapter tensors"),
-    ("sft/sft_hetu.py --config-name gpt_lora trainer.steps=6 sft.lora_rank=4", "trainable parameters"),
+    ("sft/sft_hetu.py --config-name gpt_lora trainer.steps=6 sft.lora_rank=4 --prompt hello", "answer:"),
     ("malleus/replan.py", "estimated step time"),
     ("malleus/train_malleus.py --steps 5", "hetero path: False"),
     ("galvatron/search.py --gpus 8 --mem-gb 40", "galvatron_plan.json"),
