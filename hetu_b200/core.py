@@ -248,11 +248,39 @@ class profiler:
         meta = [{"name": "thread_name", "ph": "M", "pid": pid, "tid": t, "args": {"name": n}} for n, t in tracks.items()]
         return {"traceEvents": meta + events, "displayTimeUnit": "ms"}
 
+    def _op_index(self) -> Dict[str, tuple]:
+        """record name ("type:op name") -> (module path, first output shape)"""
+        idx = {}
+        if self.graph is None:
+            return idx
+        for i in range(self.graph.num_ops):
+            try:
+                info = self.graph.op_info(i)
+            except Exception:      # noqa: BLE001 -- pruned ops
+                continue
+            shape = tuple(info["outputs"][0].shape) if info["outputs"] else ()
+            idx[f'{info["type"]}:{info["name"]}'] = (info.get("subgraph") or "", shape)
+        return idx
+
     def summary(self, group_by="optype"):
+        """rows (key, total ms, calls) sorted by time.  group_by: "optype" | "op" (every op instance) | "optype_shape" (type + output
+        shape: which GEMM sizes cost what) | "subgraph" (module view: time per `hetu.subgraph` / nn.Module scope, children included in
+        their parents)  (ref: impl/profiler op / optype / optype+shape / graph views, Graph::SubGraphProfiling)"""
         agg: Dict[str, List[float]] = {}
+        index = self._op_index() if group_by in ("optype_shape", "subgraph") else {}
         for name, ms in self.records():
-            key = name.split(":")[0] if group_by == "optype" else name
-            agg.setdefault(key, []).append(ms)
+            if group_by == "optype":
+                keys = [name.split(":")[0]]
+            elif group_by == "optype_shape":
+                keys = [f'{name.split(":")[0]} {list(index.get(name, ("", ()))[1])}']
+            elif group_by == "subgraph":
+                path = index.get(name, ("", ()))[0]
+                parts = [p for p in path.split(".") if p]
+                keys = [".".join(parts[:i]) for i in range(1, len(parts) + 1)] or ["(top level)"]
+            else:
+                keys = [name]
+            for key in keys:
+                agg.setdefault(key, []).append(ms)
         rows = sorted(((k, sum(v), len(v)) for k, v in agg.items()), key=lambda r: -r[1])
         return {"by_" + group_by: rows, "breakdown": self.graph.step_breakdown() if self.graph is not None else {}}
 

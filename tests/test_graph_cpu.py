@@ -443,3 +443,28 @@ def test_tokenizer_base_classes():
     assert len(rows[0]) == len(rows[1]) and rows[0][-1] == tok.pad_id and tok.batch_decode(rows) == ["hi", "hello"]
     assert tok.batch_encode(["abcdef"], max_length=4)[0] == tok.encode("abcdef")[:4]
     assert "pad" in repr(SpecialToken("<pad>", 0, SpecialToken.PAD))
+
+
+def test_profiler_views_by_optype_shape_and_module():
+    """ref: hetu.profiler summary views -- op type, op type + shape, op instance, module (subgraph) with children rolled into parents"""
+    with ht.graph("define_and_run", create_new=True) as g:
+        with ht.subgraph("encoder"):
+            with ht.subgraph("block0"):
+                a = ht.nn.Linear(16, 32, name="pv_a")
+            with ht.subgraph("block1"):
+                b = ht.nn.Linear(32, 8, name="pv_b")
+            x = ht.placeholder("float32", [4, 16], name="pv_x")
+            with ht.subgraph("block0"):
+                h = a(x, act="relu")
+            with ht.subgraph("block1"):
+                y = b(h)
+        loss = ht.sum(y)
+        with ht.profiler(graph=g) as prof:
+            g.run(loss, [loss], {x: torch.randn(4, 16)})
+        by_type = dict((k, (t, n)) for k, t, n in prof.summary("optype")["by_optype"])
+        assert by_type["linear"][1] == 2
+        shapes = [k for k, _, _ in prof.summary("optype_shape")["by_optype_shape"]]
+        assert "linear [4, 32]" in shapes and "linear [4, 8]" in shapes
+        mods = dict((k, n) for k, _, n in prof.summary("subgraph")["by_subgraph"])
+        assert mods.get("encoder", 0) >= mods.get("encoder.block0", 0) + mods.get("encoder.block1", 0) >= 2
+        assert any(k.startswith("linear:") for k, _, _ in prof.summary("op")["by_op"])
