@@ -3,9 +3,13 @@ loss curve of the same model / data / seed."""
 import json
 import os
 
+import numpy as np
+
 import pytest
 
 from dist_utils import run_workers
+
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 WORKER = os.path.join(os.path.dirname(__file__), "workers", "gpt_parallel_worker.py")
 
@@ -361,3 +365,66 @@ def test_comm_group_api_coalesce_reduce_gather_scatter():
     assert ok, "\n-----\n".join(outs)
     line = [l for o in outs for l in o.splitlines() if l.startswith("COMMAPI ")][0]
     assert json.loads(line[8:])["ok"]
+
+
+@pytest.mark.parametrize("p,c,comm", [(4, 1, "groups"), (4, 2, "groups"), (6, 3, "groups"), (4, 2, "world"), (8, 2, "groups")])
+def test_distgcn_15d_training_matches_single_process(p, c, comm):
+    """ref: hetu/v1 DistGCN_15d -- p ranks, replication c: every step's loss and the final weights equal plain single-process training
+    of the same GCN.  The p ranks run as threads of this process over `ThreadCollectives` (same all-gather / all-reduce interface as
+    the process-group transport), so the partitioned forward + backward is checked without a network transport;
+    tests/workers/distgcn_worker.py is the same run over real process groups (torchrun)."""
+    import threading
+    import torch
+    from hetu_b200.models.gnn import DistGCN15D, ThreadCollectives, normalise_adjacency
+    rng = np.random.RandomState(0)
+    n, f, hdim, k, steps = 96, 12, 16, 4, 6
+    edges = rng.randint(0, n, (2, 400))
+    idx, val = normalise_adjacency(edges, n)
+    x = rng.randn(n, f).astype(np.float32)
+    y = rng.randint(0, k, n)
+    mask = rng.rand(n) < 0.7
+    ends = ThreadCollectives.world(p)
+    models = [DistGCN15D(idx, val, x, y, [f, hdim, k], r, p, c, lr=0.5, seed=3, train_mask=mask, comm=comm, collectives=ends[r])
+              for r in range(p)]
+    losses, errors = [None] * p, []
+
+    def run(r):
+        try:
+            losses[r] = [models[r].step() for _ in range(steps)]
+        except Exception as e:                                   # noqa: BLE001 - reported below
+            errors.append((r, repr(e)))
+    threads = [threading.Thread(target=run, args=(r,), daemon=True) for r in range(p)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errors and all(l is not None for l in losses), errors
+    A = torch.sparse_coo_tensor(torch.as_tensor(idx), torch.as_tensor(val), (n, n)).to_dense()
+    g = torch.Generator().manual_seed(3)
+    ws = [(torch.randn(a, b, generator=g) * (1.0 / np.sqrt(a))).requires_grad_() for a, b in ((f, hdim), (hdim, k))]
+    ref = []
+    X, Y, M = torch.as_tensor(x), torch.as_tensor(y), torch.as_tensor(mask)
+    for _ in range(steps):
+        h = torch.relu(A @ (X @ ws[0]))
+        z = A @ (h @ ws[1])
+        l = torch.nn.functional.cross_entropy(z[M], Y[M])
+        ref.append(float(l))
+        gs = torch.autograd.grad(l, ws)
+        with torch.no_grad():
+            for w, gg in zip(ws, gs):
+                w -= 0.5 * gg
+    for r in range(p):
+        np.testing.assert_allclose(losses[r], ref, rtol=2e-4, atol=2e-5)
+        assert max(float((a - b.detach()).abs().max()) for a, b in zip(models[r].weights, ws)) < 2e-4
+    assert ref[-1] < ref[0]
+    # replication trades memory for traffic: per step a rank gathers n/c feature rows and reduces n*c/p -- below the 1-D n rows
+    # once 1/c + c/p < 1
+    if comm == "groups" and c > 1 and c * c <= p:
+        base = [DistGCN15D(idx, val, x, y, [f, hdim, k], r, p, 1, lr=0.5, seed=3, train_mask=mask, collectives=e)
+                for r, e in enumerate(ThreadCollectives.world(p))]
+        ts = [threading.Thread(target=base[r].step, daemon=True) for r in range(p)]
+        [t.start() for t in ts]
+        [t.join(60) for t in ts]
+        ratio = (models[0].bytes_moved / steps) / base[0].bytes_moved
+        assert abs(ratio - (1.0 / c + c / p)) < 1e-6
+        assert (ratio < 1.0) == (1.0 / c + c / p < 1.0 - 1e-9)
