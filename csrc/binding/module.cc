@@ -463,6 +463,15 @@ PYBIND11_MODULE(_C, m) {
   m.def("comm_reduce_scatter", [](const at::Tensor& x, const std::vector<int>& r, int dim) { return CommRuntime::get().reduce_scatter(x, r, dim); });
   m.def("comm_all_to_all", [](const at::Tensor& x, const std::vector<int>& r, int sd, int cd) { return CommRuntime::get().all_to_all(x, r, sd, cd); });
   m.def("comm_broadcast", [](const at::Tensor& x, const std::vector<int>& r, int root) { return CommRuntime::get().broadcast(x, r, root); });
+  m.def("comm_send", [](const at::Tensor& x, int dst, int channel) {
+    py::gil_scoped_release nogil;
+    CommRuntime::get().send(x.contiguous(), dst, channel);
+    CommRuntime::get().flush_sends();
+  }, py::arg("x"), py::arg("dst"), py::arg("channel") = 0);
+  m.def("comm_recv", [](const std::vector<int64_t>& shape, const std::string& dtype, int src, int channel) {
+    py::gil_scoped_release nogil;
+    return CommRuntime::get().recv(shape, to_aten_dtype(dtype_from_name(dtype)), aten_device(), src, channel);
+  }, py::arg("shape"), py::arg("dtype"), py::arg("src"), py::arg("channel") = 0);
   m.def("comm_all_reduce_coalesce", [](const std::vector<at::Tensor>& xs, const std::vector<int>& r, const std::string& red) {
     return CommRuntime::get().all_reduce_coalesce(xs, r, reduction_from_name(red));
   }, py::arg("tensors"), py::arg("ranks"), py::arg("reduction") = "sum");

@@ -360,8 +360,16 @@ std::vector<OpDef*> Graph::topo_sort(const TensorList& fetches) const {
 }
 
 // ------------------------------------------------------------------ autodiff
+// tensors the caller of gradients() asked about by name: a frozen variable among them still gets its gradient
+static thread_local std::set<TensorId> tl_requested_xs;
+
 TensorList Graph::gradients(const TensorList& ys, const TensorList& xs, const TensorList& grad_ys) {
   HB_CHECK(grad_ys.empty() || grad_ys.size() == ys.size()) << "grad_ys must match ys";
+  struct Requested {
+    std::set<TensorId> saved;
+    explicit Requested(const TensorList& xs) : saved(tl_requested_xs) { for (auto& x : xs) tl_requested_xs.insert(x->id); }
+    ~Requested() { tl_requested_xs = saved; }
+  } requested(xs);
   auto order = topo_sort(ys);
   // which ops lie on a path from xs to ys
   std::set<TensorId> from_x;
@@ -549,7 +557,7 @@ TensorList autograd_gradient(OpDef& fw, const TensorList& gouts) {
     if (!dtype_is_float(t->dtype)) continue;
     // a variable that was declared non-trainable (running statistics, frozen tables, masks) never needs a gradient -- and some
     // library ops refuse to be traced with respect to it (native_batch_norm and its running mean / variance)
-    if (t->producer != nullptr && t->producer->type == "variable" && !t->requires_grad) continue;
+    if (t->producer != nullptr && t->producer->type == "variable" && !t->requires_grad && !tl_requested_xs.count(t->id)) continue;
     diff_inputs.push_back((int64_t)i);
   }
   if (diff_inputs.empty()) return TensorList(fw.inputs.size());

@@ -297,6 +297,35 @@ static Ts broadcast_comm_compute(const OpDef& op, const Ts& in, RunCtx*) {
 }
 HB_REGISTER_OP(broadcast_comm, "broadcast_comm", 1, kFlagComm | kFlagNondiff, broadcast_comm_compute, nullptr, nullptr, nullptr);
 
+// ------------------------------------------------------------------ explicit pipeline hand-off (v1 API: pipeline_send_op / pipeline_receive_op)
+// pipeline_send(x; dst, channel) ships x to rank dst and yields a 1-element token (so the node can be fetched / depended on);
+// pipeline_recv(; src, shape, dtype, channel) yields the tensor sent by rank src.  The DS-lowered pipelines never emit these --
+// their stage boundaries are `comm` ops the executor turns into batched P2P -- they serve hand-placed v1 graphs.
+static void pipeline_send_infer(OpDef& op) { make_out(op, 0, {1}, op.inputs[0]->dtype); }
+static Ts pipeline_send_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  if (in[0].is_meta()) return {at::empty({1}, in[0].options())};
+  auto& comm = CommRuntime::get();
+  if (comm.initialized() && (int)op.attrs.i("dst") != comm.rank()) {
+    comm.send(in[0].contiguous(), (int)op.attrs.i("dst"), (int)op.attrs.i("channel", 0));
+    comm.flush_sends();
+  }
+  return {at::zeros({1}, in[0].options())};
+}
+HB_REGISTER_OP(pipeline_send, "pipeline_send", 1, kFlagComm | kFlagNondiff | kFlagNoMetaExec, pipeline_send_compute, nullptr, nullptr,
+               pipeline_send_infer);
+
+static void pipeline_recv_infer(OpDef& op) { make_out(op, 0, op.attrs.ints("shape"), dtype_from_name(op.attrs.s("dtype", "float32"))); }
+static Ts pipeline_recv_compute(const OpDef& op, const Ts&, RunCtx* rc) {
+  auto& comm = CommRuntime::get();
+  const auto dt = to_aten_dtype(dtype_from_name(op.attrs.s("dtype", "float32")));
+  (void)rc;
+  const at::Device dev = aten_device();
+  HB_CHECK(comm.initialized()) << "pipeline_recv needs an initialised communication runtime";
+  return {comm.recv(op.attrs.ints("shape"), dt, dev, (int)op.attrs.i("src"), (int)op.attrs.i("channel", 0))};
+}
+HB_REGISTER_OP(pipeline_recv, "pipeline_recv", 1, kFlagComm | kFlagNondiff | kFlagNoMetaExec, pipeline_recv_compute, nullptr, nullptr,
+               pipeline_recv_infer);
+
 // ------------------------------------------------------------------ vocab-parallel cross entropy
 // logits [T, V/t] sharded on the vocab dim, labels hold *global* vocabulary ids.
 // Three small all-reduces (max, sum-exp, target logit) between local kernels.

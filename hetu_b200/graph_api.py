@@ -49,6 +49,9 @@ def run_graph(g: Graph, loss: Optional[Tensor], fetches: Sequence[Tensor], feed_
     lvl = cur_run_level() if run_level is None else (run_level if isinstance(run_level, int) else
                                                      {"update": 0, "grad": 1, "compute_only": 2, "alloc": 3, "topo": 4}[run_level])
     fetches = list(fetches)
+    for i, f in enumerate(fetches):
+        if not isinstance(f, Tensor):
+            raise TypeError(f"fetch {i} is {type(f).__name__}, not a graph tensor (a gradient that does not exist comes back as None)")
     res = g.run_native(loss, fetches, feed, int(num_micro_batches), int(compute_strategy_id), int(lvl),
                        float(grad_scale), bool(save_checkpoint), symbols)
     # the executor also evaluates `loss` (it drives the backward pass); the caller gets exactly one value per fetch

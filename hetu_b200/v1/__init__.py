@@ -22,4 +22,5 @@ from .strategies import (DataParallel, ModelParallel4CNN, ModelParallel4LM, OneW
                          OptCNNSearching, GPipeSearching, PipeDreamSearching, PipeOptSearching)
 from ..models.moe import MoELayer, TopKGate, KTop1Gate, HashGate, BalanceGate, SAMGate  # noqa: F401
 from .ops import *  # noqa: F401,F403,E402  (the long tail of v1 `*_op` constructors)
+from .grad_ops import *  # noqa: F401,F403,E402  (explicit gradient-node constructors, quantised tables, pipeline send / receive)
 from . import ops as gpu_ops  # noqa: F401,E402

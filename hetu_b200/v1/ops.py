@@ -1,7 +1,7 @@
 """The remaining `*_op` constructors of the v1 API (executor.py holds the most common ones): arithmetic and reductions, index /
 order statistics, sampling, hashing, MoE layout transforms and gates' helpers, collective-communication nodes, quantisation.
-Each maps onto an op of the graph library; gradients come from the graph's autodiff (so the reference's `*_gradient_op` constructors
-have no counterpart).  (ref: hetu/v1/python/hetu/gpu_ops/__init__.py and the per-op modules next to it)"""
+Each maps onto an op of the graph library; gradients come from the graph's autodiff (the reference's explicit `*_gradient_op`
+constructors live in grad_ops.py).  (ref: hetu/v1/python/hetu/gpu_ops/__init__.py and the per-op modules next to it)"""
 from __future__ import annotations
 
 import numpy as np
@@ -143,9 +143,23 @@ def robe_hash_op(ids, nbucket, a=1000003, b=12345): return ops.hash_ids(ids, int
 
 
 # ---- MoE layout transforms and gate helpers
-def layout_transform_op(x, indices, locations, capacity, num_experts): return ops.moe_dispatch(x, indices, locations, int(num_experts), int(capacity))   # noqa: E704,E501
-def reverse_layout_transform_op(y, indices, locations, gates, capacity, num_experts): return ops.moe_combine(y, indices, locations, gates)   # noqa: E704,E501
-def reverse_layout_transform_no_gate_op(y, indices, locations, capacity, num_experts): return ops.moe_combine(y, indices, locations, None)   # noqa: E704,E501
+def _routing(t, dtype="int32"):
+    """v1 passes routing data per choice: one [T] vector (top-1) or a list of k of them; the library ops take [T, k]"""
+    if isinstance(t, (list, tuple)):
+        cols = [ops.reshape(ops.cast(c, dtype), [-1, 1]) for c in t]
+        return cols[0] if len(cols) == 1 else ops.concat(cols, 1)
+    t = ops.cast(t, dtype)
+    return ops.reshape(t, [-1, 1]) if len(t.shape) == 1 else t
+def layout_transform_op(x, indices, locations, capacity, num_experts):                                       # noqa: E704
+    """tokens [T, d] -> expert-major slots [E * capacity, d]"""
+    y = ops.moe_dispatch(x, _routing(indices), _routing(locations), int(num_experts), int(capacity))
+    return ops.reshape(y, [int(num_experts) * int(capacity), x.shape[-1]])
+def _slots(y, capacity, num_experts):
+    return y if len(y.shape) == 3 else ops.reshape(y, [int(num_experts), int(capacity), y.shape[-1]])
+def reverse_layout_transform_op(y, indices, locations, gates, capacity, num_experts):                        # noqa: E704
+    return ops.moe_combine(_slots(y, capacity, num_experts), _routing(indices), _routing(locations), _routing(gates, "float32"))
+def reverse_layout_transform_no_gate_op(y, indices, locations, capacity, num_experts):                       # noqa: E704
+    return ops.moe_combine(_slots(y, capacity, num_experts), _routing(indices), _routing(locations), None)
 def balance_assignment_op(scores): return ops._op1("moe_balance_assign", [scores], {})                        # noqa: E704
 def group_topk_idx_op(x, top1_group, topk=1, num_local_gpus=8):
     """top-k experts restricted to the expert group chosen by `top1_group` (SAM gate): scores outside the group are masked out"""

@@ -445,3 +445,220 @@ def test_v1_long_tail_op_constructors_match_numpy():
     r = v1.Executor([s1, s2, v1.randint_sample_op([50], 3, 9), v1.gumbel_sample_op([10])]).run(feed_dict={}, convert_to_numpy_ret_vals=True)
     assert abs(r[0].mean() - 1.0) < 0.2 and abs(r[0].std() - 2.0) < 0.2 and -1.0 <= r[1].min() and r[1].max() <= 1.0 and 3 <= r[2].min() and r[2].max() < 9
     v1ex.reset_graph()
+
+
+def test_v1_explicit_gradient_node_constructors_match_torch_autograd():
+    """ref: hetu/v1/python/hetu/gpu_ops/{Relu,Conv2d,MaxPool,BatchNorm,Pad,Slice,Concat,...}.py -- `*_gradient_op(...)` built by hand
+    give the same values as torch autograd of the forward"""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    import hetu_b200.v1 as v1
+    from hetu_b200.v1 import executor as v1ex
+    v1ex.reset_graph()
+    rng = np.random.RandomState(1)
+
+    def var(name, val, dtype=None):
+        return v1.Variable("gn_" + name, value=val, trainable=False, **({"dtype": dtype} if dtype else {}))
+
+    def tgrad(fn, x, dy):
+        t = torch.tensor(x, requires_grad=True)
+        y = fn(t)
+        return torch.autograd.grad(y, t, torch.tensor(dy).reshape(y.shape))[0].numpy()
+
+    x, dy = rng.randn(4, 6).astype(np.float32), rng.randn(4, 6).astype(np.float32)
+    X, DY = var("x", x), var("dy", dy)
+    pos = np.abs(x) + 0.5
+    POS = var("pos", pos)
+    img, w = rng.randn(2, 3, 8, 8).astype(np.float32), rng.randn(4, 3, 3, 3).astype(np.float32)
+    dconv = rng.randn(2, 4, 8, 8).astype(np.float32)
+    IMG, W, DCONV = var("img", img), var("w", w), var("dconv", dconv)
+    dpool = rng.randn(2, 3, 4, 4).astype(np.float32)
+    DPOOL = var("dpool", dpool)
+    scale = rng.rand(3).astype(np.float32) + 0.5
+    SCALE = var("scale", scale)
+    dimg = rng.randn(2, 3, 8, 8).astype(np.float32)
+    DIMG = var("dimg", dimg)
+    idx = rng.randint(0, 6, (4, 3)).astype(np.int64)
+    IDX = var("idx", idx, "int64")
+    dg = rng.randn(4, 3).astype(np.float32)
+    DG = var("dg", dg)
+    tgt = rng.randint(0, 6, 4).astype(np.int64)
+    TGT = var("tgt", tgt, "int64")
+    bn = v1.batch_normalization_gradient_op(DIMG, IMG, SCALE, None, 1e-5)
+
+    def bn_ref(which):
+        t, s, b = torch.tensor(img, requires_grad=True), torch.tensor(scale, requires_grad=True), torch.zeros(3, requires_grad=True)
+        y = F.batch_norm(t, None, None, s, b, True, 0.1, 1e-5)
+        return torch.autograd.grad(y, [t, s, b], torch.tensor(dimg))[which].numpy()
+
+    fwd_tanh, fwd_sm, fwd_lsm = np.tanh(x), torch.softmax(torch.tensor(x), -1).numpy(), torch.log_softmax(torch.tensor(x), -1).numpy()
+    nodes = {
+        "relu": (v1.relu_gradient_op(X, DY), dy * (x > 0)),
+        "leaky_relu": (v1.leaky_relu_gradient_op(X, DY, 0.1), dy * np.where(x > 0, 1.0, 0.1)),
+        "gelu": (v1.gelu_gradient_op(X, DY), tgrad(F.gelu, x, dy)),
+        "tanh": (v1.tanh_gradient_op(var("tanh", fwd_tanh), DY), dy * (1 - fwd_tanh ** 2)),
+        "abs": (v1.abs_gradient_op(DY, X), dy * np.sign(x)),
+        "log": (v1.log_grad_op(DY, POS, 0.0), dy / pos),
+        "pow": (v1.pow_gradient_op(POS, DY, 2.5), tgrad(lambda t: t ** 2.5, pos, dy)),
+        "const_pow": (v1.const_pow_gradient_op(X, DY, 3.0), tgrad(lambda t: 3.0 ** t, x, dy)),
+        "softmax": (v1.softmax_gradient_op(var("sm", fwd_sm), DY), tgrad(lambda t: torch.softmax(t, -1), x, dy)),
+        "log_softmax": (v1.log_softmax_gradient_op(var("lsm", fwd_lsm), DY), tgrad(lambda t: torch.log_softmax(t, -1), x, dy)),
+        "bce_logits": (v1.binarycrossentropywithlogits_gradient_op(X, var("lab", (pos > 1).astype(np.float32)), DY),
+                       tgrad(lambda t: F.binary_cross_entropy_with_logits(t, torch.tensor((pos > 1).astype(np.float32)), reduction="none"), x, dy)),
+        "nll": (v1.nll_loss_grad_op(var("one", np.ones(1, np.float32)), TGT, 6), tgrad(lambda t: F.nll_loss(t, torch.tensor(tgt)), x, np.ones((), np.float32))),
+        "norm": (v1.norm_gradient_op(X, None, var("dn", dy[:, 0].copy()), 1, 2), tgrad(lambda t: t.norm(2, 1), x, dy[:, 0].copy())),
+        "addmm_bias": (v1.addmm_gradient_op(var("bias", np.zeros((1, 6), np.float32)), DY, 2.0), 2.0 * dy.sum(0, keepdims=True)),
+        "reshape": (v1.array_reshape_gradient_op(X, var("dflat", dy.reshape(-1))), dy),
+        "repeat": (v1.repeat_gradient_op(X, var("drep", np.tile(dy, (3, 2)))), 6.0 * dy),
+        "pad": (v1.pad_gradient_op(DY, [[1, 1], [2, 0]]), dy[1:3, 2:]),
+        "slice": (v1.slice_gradient_op(var("dsl", dy[:2, :3].copy()), [1, 2], [4, 6]), np.pad(dy[:2, :3], [[1, 1], [2, 1]])),
+        "concat0": (v1.concat_gradient_op(DY, var("c0", x[:, :2].copy()), 1, 0), dy[:, :2]),
+        "concat1": (v1.concat_gradient_op(DY, var("c1", x[:, 2:].copy()), 1, 1), dy[:, 2:]),
+        "concatenate": (v1.concatenate_gradient_op(DY, var("c2", x[:, 1:4].copy()), 1, offset=1), dy[:, 1:4]),
+        "split": (v1.split_gradient_op(var("dsp", dy[:, 2:4].copy()), [1], [1], [3]), np.pad(dy[:, 2:4], [[0, 0], [2, 2]])),
+        "gather": (v1.gather_gradient_op(X, DG, 1, IDX), tgrad(lambda t: t.gather(1, torch.tensor(idx)), x, dg)),
+        "scatter1d": (v1.scatter1d_grad_op(var("d1", dy[:, 0].copy().reshape(4, 1)), var("i1", np.array([2, 0, 3], np.int64), "int64")), dy[[2, 0, 3], 0].reshape(3, 1)),
+        "tril": (v1.tril_lookup_gradient_op(var("dtri", np.arange(1, 7, dtype=np.float32).reshape(1, 6))),
+                 (lambda m: (m.__setitem__(np.tril_indices(3), np.arange(1, 7)), m)[1])(np.zeros((3, 3), np.float32)).reshape(1, 3, 3)),
+        "interpolate": (v1.interpolate_grad_op(var("dint", np.ones((2, 3, 16, 16), np.float32)), IMG, "bilinear", False),
+                        tgrad(lambda t: F.interpolate(t, size=(16, 16), mode="bilinear", align_corners=False), img, np.ones((2, 3, 16, 16), np.float32))),
+        "conv_data": (v1.conv2d_gradient_of_data_op(W, DCONV, IMG, padding=1, stride=1), tgrad(lambda t: F.conv2d(t, torch.tensor(w), padding=1), img, dconv)),
+        "conv_filter": (v1.conv2d_gradient_of_filter_op(IMG, DCONV, W, padding=1, stride=1), tgrad(lambda t: F.conv2d(torch.tensor(img), t, padding=1), w, dconv)),
+        "max_pool": (v1.max_pool2d_gradient_op(None, DPOOL, IMG, 2, 2, 0, 2), tgrad(lambda t: F.max_pool2d(t, 2, 2), img, dpool)),
+        "avg_pool": (v1.avg_pool2d_gradient_op(None, DPOOL, IMG, 2, 2, 0, 2), tgrad(lambda t: F.avg_pool2d(t, 2, 2), img, dpool)),
+        "bn_data": (v1.batch_normalization_gradient_of_data_op(bn, IMG), bn_ref(0)),
+        "bn_scale": (v1.batch_normalization_gradient_of_scale_op(bn, SCALE), bn_ref(1)),
+        "bn_bias": (v1.batch_normalization_gradient_of_bias_op(bn, None), bn_ref(2)),
+    }
+    names = list(nodes)
+    outs = v1.Executor([nodes[n][0] for n in names]).run(feed_dict={}, convert_to_numpy_ret_vals=True)
+    for n, got in zip(names, outs):
+        np.testing.assert_allclose(np.asarray(got, dtype=np.float64), np.asarray(nodes[n][1], dtype=np.float64), rtol=2e-4, atol=2e-5, err_msg=n)
+    v1ex.reset_graph()
+
+
+def test_v1_quantised_table_sparse_row_and_moe_gradient_constructors():
+    """ref: hetu/v1/src/ops/{QuantizeEmbedding,SignedQuantize,SparseSet,AssignWithIndexedSlices,UniqueIndices}.cu and
+    gpu_ops/{LayoutTransform,ReverseLayoutTransform}.py -- quantised lookups, ALPT rounding with its LSQ step gradient, row
+    assignment, de-duplication and the hand-built MoE dispatch / combine gradients"""
+    import numpy as np
+    import torch
+    import hetu_b200.v1 as v1
+    from hetu_b200 import ops
+    from hetu_b200.v1 import executor as v1ex
+    v1ex.reset_graph()
+    rng = np.random.RandomState(2)
+
+    def var(name, val, dtype=None, trainable=False):
+        return v1.Variable("qt_" + name, value=val, trainable=trainable, **({"dtype": dtype} if dtype else {}))
+
+    q8 = rng.randint(0, 256, (10, 4)).astype(np.float32)
+    qp = np.stack([rng.rand(10) * 0.1 + 0.01, rng.randn(10)], 1).astype(np.float32)
+    ids = np.array([3, 7, 3, 9], np.int64)
+    Q8, QP, IDS = var("q8", q8), var("qp", qp), var("ids", ids, "int64")
+    step = (rng.rand(10, 1) * 0.05 + 0.01).astype(np.float32)
+    STEP = var("step", step)
+    s8 = rng.randint(-128, 128, (10, 4)).astype(np.float32)
+    S8 = var("s8", s8)
+    look = (rng.randn(4, 4) * 90).astype(np.float32)        # some values beyond the int8 range
+    LOOK, ST4 = var("look", look), var("st4", step[ids])
+    new_rows = rng.randn(4, 4).astype(np.float32)
+    NEW = var("new", new_rows)
+    uniq = np.array([3, 7, 9, -1], np.int64)
+    UNIQ = var("uniq", uniq, "int64")
+    table = rng.randn(10, 4).astype(np.float32)
+    TABLE = var("table", table)
+    inverse = np.array([0, 1, 0, 2], np.int64)
+    INV = var("inv", inverse, "int64")
+    rows = rng.randn(4, 4).astype(np.float32)
+    ROWS = var("rows", rows)
+
+    assigned = table.copy()
+    assigned[[3, 7, 9]] = new_rows[:3]
+    lsq = np.where(look >= 127, 127.0, np.where(look <= -128, -128.0, np.floor(look + 0.5) - look))
+    rounded = np.clip(np.floor(np.clip(look, -128, 127) + 0.5), -128, 127) * step[ids] + 0.25
+    dedup = np.zeros((4, 4), np.float32)
+    for j in range(3):
+        dedup[j] = rows[inverse == j].mean(0)
+    dgrad = np.zeros((4, 4), np.float32)
+    np.add.at(dgrad, inverse, rows)
+    unified_ids = np.array([2, -1, 11, 5], np.int64)
+    uni = np.where(((unified_ids >= 0) & (unified_ids < 10))[:, None], q8[np.clip(unified_ids, 0, 9)] * 0.02 - 1.5, 0.0)
+    nodes = {
+        "quantized_lookup": (v1.quantized_embedding_lookup_op(Q8, IDS, QP, 8), q8[ids] * qp[ids, :1] + qp[ids, 1:]),
+        "unified_lookup": (v1.unified_quantized_embedding_lookup_op(Q8, var("uids", unified_ids, "int64"), 0.02, -1.5, 8), uni),
+        "alpt_lookup": (v1.alpt_embedding_lookup_op(S8, IDS, STEP, 0.25, 8), s8[ids] * step[ids] + 0.25),
+        "alpt_rounding": (v1.alpt_rounding_op(LOOK, ST4, 0.25, 8), rounded),
+        "alpt_scale_grad": (v1.alpt_scale_gradient_op(LOOK, 8), lsq),
+        "assign_rows": (v1.assign_with_indexedslices_op(TABLE, UNIQ, NEW), assigned),
+        "sparse_set": (v1.sparse_set_op(TABLE, UNIQ, NEW), assigned),
+        "assign_unified": (v1.assign_quantized_embedding_op(Q8, var("u3", np.array([1, 4], np.int64), "int64"), var("n2", np.array([[0.0, 0.5, 1.0, 5.2]] * 2, np.float32)), 8,
+                                                            scale=0.02, minele=0.0),
+                           (lambda t: (t.__setitem__([1, 4], np.array([0, 25, 50, 255], np.float32)), t)[1])(q8.copy())),
+        "dedup_lookup": (v1.deduplicate_lookup_op(ROWS, (INV, None)), dedup),
+        "dedup_grad": (v1.deduplicate_grad_op(ROWS, (INV, None)), dgrad),
+        "sum_sparse": (v1.sum_sparse_gradient_op([10, 4], (IDS, ROWS), TABLE), (lambda t: (np.add.at(t, ids, rows), t)[1])(table.copy())),
+        "slice_by_matrix": (v1.slice_by_matrix_op(var("cube", np.arange(24, dtype=np.float32).reshape(2, 3, 4)), var("i1", np.array([1, 0], np.int64), "int64"),
+                                                  var("i2", np.array([2, 1], np.int64), "int64")), np.arange(24, dtype=np.float32).reshape(2, 3, 4)[[1, 0], [2, 1]]),
+        "slice_assign_matrix": (v1.slice_assign_matrix_op(TABLE, ROWS, [2, 1], [2, 2], [1, 0], [2, 2]),
+                                (lambda t: (t.__setitem__((slice(2, 4), slice(1, 3)), rows[1:3, 0:2]), t)[1])(table.copy())),
+    }
+    names = list(nodes)
+    outs = v1.Executor([nodes[n][0] for n in names]).run(feed_dict={}, convert_to_numpy_ret_vals=True)
+    for n, got in zip(names, outs):
+        np.testing.assert_allclose(np.asarray(got, dtype=np.float64), np.asarray(nodes[n][1], dtype=np.float64), rtol=2e-5, atol=2e-5, err_msg=n)
+
+    # ALPT: the looked-up row passes the gradient straight through, the step gets dy * lsq
+    v1ex.reset_graph()
+    L2, S2 = var("look2", look, trainable=True), var("st2", step[ids], trainable=True)
+    y = v1.alpt_rounding_op(L2, S2, 0.25, 8)
+    gl, gs = v1.gradients(v1.reduce_sum_op(y * var("dy2", rows), [0, 1]), [L2, S2])
+    gl, gs = v1.Executor([gl, gs]).run(feed_dict={}, convert_to_numpy_ret_vals=True)
+    np.testing.assert_allclose(gl, rows * step[ids], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(gs, (rows * lsq).sum(1, keepdims=True), rtol=1e-4, atol=1e-4)
+
+    # MoE layout transforms: the hand-built gradient nodes equal autodiff of dispatch / combine
+    v1ex.reset_graph()
+    T, D, E, CAP = 6, 4, 3, 3
+    x = rng.randn(T, D).astype(np.float32)
+    expert = np.array([0, 2, 1, 0, 2, 0], np.int64)
+    loc = np.array([0, 0, 0, 1, 1, 2], np.int64)
+    gate = rng.rand(T).astype(np.float32)
+    X, IDX, LOC, GATE = var("mx", x, trainable=True), var("me", expert, "int64"), var("ml", loc, "int64"), var("mg", gate, trainable=True)
+    dslots = rng.randn(E * CAP, D).astype(np.float32)
+    DS = var("mds", dslots)
+    disp = v1.layout_transform_op(X, IDX, LOC, CAP, E)
+    auto_dx = v1.gradients(v1.reduce_sum_op(disp * DS, [0, 1]), [X])[0]
+    hand_dx = v1.layout_transform_gradient_op(DS, IDX, LOC, CAP)
+    Y = var("my", dslots, trainable=True)
+    dtok = rng.randn(T, D).astype(np.float32)
+    DT = var("mdt", dtok)
+    comb = v1.reverse_layout_transform_op(Y, IDX, LOC, GATE, CAP, E)
+    auto_dy, auto_dg = v1.gradients(v1.reduce_sum_op(comb * DT, [0, 1]), [Y, GATE])
+    hand_dy = v1.reverse_layout_transform_gradient_data_op(DT, IDX, LOC, GATE, CAP, E)
+    hand_dg = v1.reverse_layout_transform_gradient_gate_op(DT, Y, IDX, LOC, CAP)
+    hand_ng = v1.reverse_layout_transform_no_gate_gradient_op(DT, IDX, LOC, CAP, E)
+    r = v1.Executor([auto_dx, hand_dx, auto_dy, hand_dy, auto_dg, hand_dg, hand_ng]).run(feed_dict={}, convert_to_numpy_ret_vals=True)
+    np.testing.assert_allclose(r[1], r[0], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(r[3].reshape(r[2].shape), r[2], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(r[5].reshape(-1), r[4].reshape(-1), rtol=1e-5, atol=1e-6)
+    slots = expert * CAP + loc
+    want = np.zeros((E * CAP, D), np.float32)
+    want[slots] = dtok
+    np.testing.assert_allclose(r[6].reshape(E * CAP, D), want, rtol=1e-6, atol=1e-6)
+    v1ex.reset_graph()
+
+
+def test_v1_pipeline_send_and_receive_nodes_between_two_processes():
+    """ref: hetu/v1/python/hetu/gpu_ops/{PipelineSend,PipelineReceive}.py -- a hand-placed two-stage graph: the activation travels
+    through `pipeline_send_op` / `pipeline_receive_op` (graph ops over the runtime's P2P channel)"""
+    import json
+    import os
+    from dist_utils import run_workers
+    here = os.path.dirname(os.path.abspath(__file__))
+    ok, outs = run_workers(os.path.join(here, "workers", "v1_pipeline_p2p_worker.py"), 2, timeout=120)
+    assert ok, "\n-----\n".join(o[-3000:] for o in outs)
+    line = next(l for o in outs for l in o.splitlines() if l.startswith("P2P "))
+    r = json.loads(line[4:])
+    assert r["err"] < 1e-5 and r["raw"] == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0]

@@ -1,0 +1,29 @@
+"""two ranks, a hand-placed v1 pipeline: rank 0 computes h = relu(x @ w0) and hands it over with pipeline_send_op; rank 1 takes it
+with pipeline_receive_op and finishes y = h @ w1.  Also exercises the raw comm_send / comm_recv bindings."""
+import json
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import hetu_b200 as ht
+import hetu_b200.v1 as v1
+
+ht.init_comm_group()
+rank = dist.get_rank()
+rng = np.random.RandomState(0)
+x, w0, w1 = rng.randn(4, 6).astype(np.float32), rng.randn(6, 5).astype(np.float32), rng.randn(5, 3).astype(np.float32)
+if rank == 0:
+    h = v1.relu_op(v1.matmul_op(v1.Variable("x", value=x, trainable=False), v1.Variable("w0", value=w0, trainable=False)))
+    token = v1.pipeline_send_op(h, 1)
+    out = v1.Executor([token]).run(feed_dict={}, convert_to_numpy_ret_vals=True)[0]
+    assert out.shape == (1,)
+    ht._C.comm_send(torch.arange(6, dtype=torch.float32).reshape(2, 3), 1, 1)
+else:
+    h = v1.pipeline_receive_op(0, shape=[4, 5])
+    y = v1.matmul_op(h, v1.Variable("w1", value=w1, trainable=False))
+    got = v1.Executor([y]).run(feed_dict={}, convert_to_numpy_ret_vals=True)[0]
+    raw = ht._C.comm_recv([2, 3], "float32", 0, 1)
+    want = np.maximum(x @ w0, 0) @ w1
+    print("P2P " + json.dumps({"err": float(np.abs(got - want).max()), "raw": raw.reshape(-1).tolist()}), flush=True)
+dist.barrier()
