@@ -24,3 +24,6 @@ from ..models.moe import MoELayer, TopKGate, KTop1Gate, HashGate, BalanceGate, S
 from .ops import *  # noqa: F401,F403,E402  (the long tail of v1 `*_op` constructors)
 from .grad_ops import *  # noqa: F401,F403,E402  (explicit gradient-node constructors, quantised tables, pipeline send / receive)
 from . import ops as gpu_ops  # noqa: F401,E402
+from .runtime_api import (Communicator, wrapped_mpi_nccl_init, new_group_comm, get_mpi_communicate, get_nccl_communicate,  # noqa: F401,E402
+                          scheduler_init, scheduler_finish, server_init, server_finish, worker_init, worker_finish, get_worker_communicate,
+                          DistConfig, context, get_current_context, dispatch, softmax_func, random)

@@ -662,3 +662,43 @@ def test_v1_pipeline_send_and_receive_nodes_between_two_processes():
     line = next(l for o in outs for l in o.splitlines() if l.startswith("P2P "))
     r = json.loads(line[4:])
     assert r["err"] < 1e-5 and r["raw"] == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0]
+    c = json.loads(next(l for o in outs for l in o.splitlines() if l.startswith("COMM "))[5:])
+    assert c == {"sum": [3.0] * 3, "gather": [[0.0, 0.0], [1.0, 1.0]], "out": [4.0] * 3, "bc": [8.0]}
+
+
+def test_v1_role_functions_run_a_scheduler_two_servers_and_two_workers(tmp_path):
+    """ref: hetu/v1/python/hetu/gpu_ops/executor.py:100-137 -- scheduler_init / server_init / worker_init driven by the DMLC_*
+    environment (five processes, one program); the workers see both servers, BSP pushes land on every shard"""
+    import json
+    import os
+    import subprocess
+    import sys
+    from dist_utils import free_port
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "tests", "workers", "v1_roles_worker.py")
+    base = dict(os.environ, PYTHONPATH=root, HETU_B200_FORCE_CPU="1", CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1",
+                DMLC_PS_ROOT_URI="127.0.0.1", DMLC_PS_ROOT_PORT=str(free_port()), DMLC_NUM_SERVER="2", DMLC_NUM_WORKER="2")
+    for k in ("HETU_PS_SCHEDULER", "HETU_PS_ADDRESS"):
+        base.pop(k, None)
+    procs = []
+    for i, role in enumerate(["scheduler", "server", "server", "worker", "worker"]):
+        out = open(tmp_path / f"{role}{i}.log", "w")
+        procs.append((role, i, subprocess.Popen([sys.executable, script], env=dict(base, DMLC_ROLE=role), stdout=out, stderr=subprocess.STDOUT)))
+        if role == "scheduler":
+            import time
+            time.sleep(1.0)                     # the scheduler's port must be listening before the others dial it
+    codes = []
+    for role, i, p in procs:
+        try:
+            codes.append(p.wait(150))
+        except subprocess.TimeoutExpired:
+            p.kill()
+            codes.append(-9)
+    logs = {f"{role}{i}": (tmp_path / f"{role}{i}.log").read_text() for role, i, _ in procs}
+    assert codes == [0] * 5, json.dumps(logs)[-4000:]
+    res = [json.loads(l[6:]) for t in logs.values() for l in t.splitlines() if l.startswith("ROLES ")]
+    assert len(res) == 2 and all(r["servers"] == 2 and r["same"] for r in res)
+    # three steps, both workers' gradients (1 and 2) applied with lr 0.5 -> -4.5; rows 0 and 1 pushed once, row 5 by both workers
+    for r in res:
+        assert abs(r["w"] - (-4.5)) < 1e-6, r
+        assert r["emb"][0] == [-1.0, -1.0] and r["emb"][1] == [-1.0, -1.0] and r["emb"][2][0] <= -1.0

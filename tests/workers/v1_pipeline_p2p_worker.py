@@ -26,4 +26,16 @@ else:
     raw = ht._C.comm_recv([2, 3], "float32", 0, 1)
     want = np.maximum(x @ w0, 0) @ w1
     print("P2P " + json.dumps({"err": float(np.abs(got - want).max()), "raw": raw.reshape(-1).tolist()}), flush=True)
+# the v1 communicator handle: world + a collectively created sub-group, numpy in / numpy out, v1 spellings
+comm = v1.wrapped_mpi_nccl_init()
+assert comm.nrank == 2 and comm.rank == rank and v1.get_mpi_communicate() is comm
+total = comm.all_reduce(np.full(3, rank + 1.0, np.float32))
+gathered = comm.all_gather(np.full((1, 2), float(rank), np.float32))
+out = np.zeros(3, np.float32)
+comm.dlarrayNcclAllReduce(np.full(3, 2.0, np.float32), out)
+bc = comm.broadcast(np.array([7.0 + rank], np.float32), root=1)
+sub = v1.new_group_comm([0, 1])
+assert sub.nrank == 2
+if rank == 1:
+    print("COMM " + json.dumps({"sum": total.tolist(), "gather": gathered.tolist(), "out": out.tolist(), "bc": bc.tolist()}), flush=True)
 dist.barrier()
