@@ -84,6 +84,54 @@ static Ts sgd_update_compute(const OpDef& op, const Ts& in, RunCtx*) {
 HB_REGISTER_OP(sgd_update, "sgd_update", 1, kFlagOptimizerUpdate | kFlagNondiff | kFlagNoMetaExec | kFlagInplace,
                sgd_update_compute, nullptr, nullptr, scalar_out_infer);
 
+// rule_update: the rest of the optimizer family, one op with a `rule` attribute (ref: hetu/v1/python/hetu/optimizer.py AdaGrad /
+// AMSGrad / Lamb update ops and hetu/v1/src/ops/Optimizer*.cu).  inputs by rule:
+//   adagrad: param, grad, accumulator                       p -= lr * g / (sqrt(acc += g^2) + eps)
+//   amsgrad: param, grad, m, v, vhat, step                  Adam whose denominator uses the running maximum of v
+//   lamb   : param, grad, m, v, step                        Adam direction (+ decoupled decay) scaled by |p| / |update| per tensor
+// `l2` adds l2 * p to the gradient first (v1's l2reg); `weight_decay` is the decoupled form.
+static Ts rule_update_compute(const OpDef& op, const Ts& in, RunCtx*) {
+  at::Tensor param = in[0];
+  if (param.is_meta()) return {at::empty({1}, param.options().dtype(at::kFloat))};
+  const std::string rule = op.attrs.s("rule", "adagrad");
+  const double lr = op.attrs.f("lr", 0.01), eps = op.attrs.f("eps", 1e-7), l2 = op.attrs.f("l2", 0.0),
+               wd = op.attrs.f("weight_decay", 0.0), b1 = op.attrs.f("beta1", 0.9), b2 = op.attrs.f("beta2", 0.999);
+  at::NoGradGuard ng;
+  at::Tensor p = param.to(at::kFloat);
+  at::Tensor g = in[1].to(at::kFloat).to(param.device());
+  if (l2 != 0.0) g = g + l2 * p;
+  if (rule == "adagrad") {
+    at::Tensor acc = in[2];
+    acc.addcmul_(g, g);
+    p = p - lr * g / (acc.sqrt() + eps);
+  } else if (rule == "amsgrad") {
+    at::Tensor m = in[2], v = in[3], vhat = in[4], step = in[5];
+    step.add_(1);
+    const double t = (double)step.item<int64_t>();
+    m.mul_(b1).add_(g, 1 - b1);
+    v.mul_(b2).addcmul_(g, g, 1 - b2);
+    at::Tensor vc = v / (1 - std::pow(b2, t));
+    vhat.copy_(at::maximum(vhat, vc));
+    p = p - lr * (m / (1 - std::pow(b1, t))) / (vhat.sqrt() + eps) - lr * wd * p;
+  } else if (rule == "lamb") {
+    at::Tensor m = in[2], v = in[3], step = in[4];
+    step.add_(1);
+    const double t = (double)step.item<int64_t>();
+    m.mul_(b1).add_(g, 1 - b1);
+    v.mul_(b2).addcmul_(g, g, 1 - b2);
+    at::Tensor upd = (m / (1 - std::pow(b1, t))) / ((v / (1 - std::pow(b2, t))).sqrt() + eps) + wd * p;
+    const double pn = p.norm().item<double>(), un = upd.norm().item<double>();
+    const double trust = (pn > 0 && un > 0) ? pn / un : 1.0;
+    p = p - lr * trust * upd;
+  } else {
+    HB_CHECK(false) << "rule_update: unknown rule '" << rule << "'";
+  }
+  param.copy_(p);
+  return {at::zeros({1}, at::TensorOptions().dtype(at::kFloat))};
+}
+HB_REGISTER_OP(rule_update, "rule_update", 1, kFlagOptimizerUpdate | kFlagNondiff | kFlagNoMetaExec | kFlagInplace,
+               rule_update_compute, nullptr, nullptr, scalar_out_infer);
+
 // update_scale(scale, growth_tracker, found_inf): dynamic loss scaling (GradScaler)
 static Ts update_scale_compute(const OpDef& op, const Ts& in, RunCtx*) {
   at::Tensor scale = in[0], tracker = in[1];

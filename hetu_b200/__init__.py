@@ -21,7 +21,8 @@ from .core import (DeviceGroup, DeviceGroupUnion, DistributedStates, Distributed
 from .ops import *  # noqa: F401,F403
 from . import ops  # noqa: F401
 from .graph_api import gradients, run_graph  # noqa: F401
-from .optim import AdamOptimizer, SGDOptimizer, GradScaler  # noqa: F401
+from .optim import (AdamOptimizer, SGDOptimizer, GradScaler, AdaGradOptimizer, AMSGradOptimizer, AdamWOptimizer,  # noqa: F401
+                    LambOptimizer)
 from . import nn  # noqa: F401
 from . import logger  # noqa: F401  (module: hetu.logger.info(...), hetu.logger.get_logger(name))
 from .distributed import (init_comm_group, local_device, global_device_group, global_comm_barrier_rpc,  # noqa: F401

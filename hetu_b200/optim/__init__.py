@@ -277,6 +277,63 @@ class AdamOptimizer(Optimizer):
         return ins
 
 
+class _RuleOptimizer(Optimizer):
+    """optimizers served by the `rule_update` op (csrc/graph/ops_optim.cc): AdaGrad, AMSGrad, LAMB"""
+    update_type = "rule_update"
+    rule = "adagrad"
+
+    def __init__(self, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-7, weight_decay=0.0, l2reg=0.0, **kw):
+        super().__init__()
+        self.learning_rate, self.beta1, self.beta2, self.eps, self.weight_decay, self.l2reg = lr, beta1, beta2, eps, weight_decay, l2reg
+
+    def _attrs(self):
+        return {"rule": self.rule, "lr": float(self.learning_rate), "beta1": float(self.beta1), "beta2": float(self.beta2),
+                "eps": float(self.eps), "weight_decay": float(self.weight_decay), "l2": float(self.l2reg)}
+
+    def _named_states(self, param, ds_h, names, with_step=True):
+        st = {n: _state_var(param, n, ds_h) for n in names}
+        if with_step:
+            st["step"] = _state_var(param, "step", [], dtype="int64", shape=[1])
+        self.states[param.id] = st
+        return list(st.values())
+
+
+class AdaGradOptimizer(_RuleOptimizer):
+    """p -= lr * g / (sqrt(sum g^2) + eps)   (ref: hetu/v1/python/hetu/optimizer.py:418)"""
+    rule = "adagrad"
+
+    def __init__(self, lr=0.01, initial_accumulator_value=0.0, eps=1e-7, l2reg=0.0, **kw):
+        super().__init__(lr=lr, eps=eps, l2reg=l2reg)
+        self.initial_accumulator_value = float(initial_accumulator_value)
+
+    def _make_states(self, param, ds_h, dgh):
+        from ..core import constant_initializer
+        acc = _state_var(param, "accumulator", ds_h, init=constant_initializer(self.initial_accumulator_value)) \
+            if self.initial_accumulator_value else _state_var(param, "accumulator", ds_h)
+        self.states[param.id] = {"accumulator": acc}
+        return [acc]
+
+
+class AMSGradOptimizer(_RuleOptimizer):
+    """Adam with the running maximum of the second moment in the denominator (ref: optimizer.py:624)"""
+    rule = "amsgrad"
+
+    def _make_states(self, param, ds_h, dgh):
+        return self._named_states(param, ds_h, ["mean", "variance", "max_variance"])
+
+
+class LambOptimizer(_RuleOptimizer):
+    """layer-wise adaptive moments: the Adam(W) direction rescaled per tensor by |p| / |update| (ref: optimizer.py:730)"""
+    rule = "lamb"
+
+    def _make_states(self, param, ds_h, dgh):
+        return self._named_states(param, ds_h, ["mean", "variance"])
+
+
+class AdamWOptimizer(AdamOptimizer):
+    """Adam with decoupled weight decay -- what `adam_update` does with a non-zero weight_decay (ref: optimizer.py:671)"""
+
+
 class _CopyOf:
     """initializer that mirrors another parameter's (bf16-rounded) initial value: fp32 master weights.
     `zero_geom` = (interval, count) of the reduce-scatter group so the shard matches the collective's chunk order."""

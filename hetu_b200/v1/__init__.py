@@ -14,7 +14,8 @@ from .executor import (Variable, placeholder_op, Executor, HetuConfig, gradients
                        reduce_max_op, reduce_min_op, concatenate_op, split_op, sum_op, reset_graph)
 from . import initializers, initializers as init, layers, lr_scheduler, metrics, dataloader, onnx  # noqa: F401
 from .dataloader import Dataloader, dataloader_op  # noqa: F401
-from .optimizer import SGDOptimizer, MomentumOptimizer, AdaGradOptimizer, AdamOptimizer  # noqa: F401
+from .optimizer import (SGDOptimizer, MomentumOptimizer, AdaGradOptimizer, AdamOptimizer, AMSGradOptimizer, AdamWOptimizer,  # noqa: F401
+                        LambOptimizer)
 from . import optimizer as optim  # noqa: F401  (v1: ht.optim.SGDOptimizer)
 from .ps import PSContext, ShardedPSContext, CacheSparseTable  # noqa: F401
 from . import strategies as dist  # noqa: F401

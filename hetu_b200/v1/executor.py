@@ -41,8 +41,23 @@ def _g():
     return _graph
 
 
+_UPDATE_TYPES = ("adam_update", "sgd_update", "rule_update", "group")
+_notes: Dict = {}
+
+
+def annotate(t, key, value):
+    """side table for per-node facts the v1 API hangs on nodes (graph tensors are native objects without a __dict__)"""
+    _notes[(t.graph_id, t.id, key)] = value
+    return t
+
+
+def annotation(t, key, default=None):
+    return _notes.get((getattr(t, "graph_id", None), getattr(t, "id", None), key), default)
+
+
 def reset_graph():
     global _graph, _graph_ctx
+    _notes.clear()
     if _graph_ctx is not None:
         _graph_ctx.__exit__(None, None, None)
     _graph = _graph_ctx = None
@@ -199,6 +214,23 @@ class Executor:
         self._ps_plans[key] = (pairs, kind, lr)
         return self._ps_plans[key]
 
+    def _ps_explicit(self, node, grad, param, server_opt):
+        ps = self._ps_context()
+        kind, lr = server_opt
+        done = self.__dict__.setdefault("_ps_explicit_init", set())
+        if param.id not in done:
+            if getattr(ps, "worker_id", 0) == 0:
+                ps.init_dense(param.name, self.graph.get_param(param).float().cpu().numpy(), opt=kind, lr=lr)
+            if hasattr(ps, "_dense_len"):
+                ps._dense_len[param.name] = int(np.prod(param.shape))
+            ps.barrier()
+            done.add(param.id)
+        nw = max(int(getattr(ps, "num_workers", 1)), 1)
+        ps.push(param.name, grad.float().cpu().numpy().reshape(list(param.shape)) / nw)
+        ps.barrier()
+        self.graph.set_param(param, torch.as_tensor(ps.pull(param.name, list(param.shape))))
+        ps.barrier()
+
     def _ps_step(self, opt, grad_values):
         ps = self._ps_context()
         pairs, _, _ = self._ps_plan(opt)
@@ -242,12 +274,12 @@ class Executor:
             sched = getattr(opt, "v1_scheduler", None)
             if sched is not None:
                 opt.set_learning_rate(sched.get())
-        loss = next((n for n in nodes if isinstance(n, Tensor) and n.producer_type not in ("adam_update", "sgd_update", "group")), None)
+        loss = next((n for n in nodes if isinstance(n, Tensor) and n.producer_type not in _UPDATE_TYPES), None)
         dp = 1
         if self.comm_mode in ("AllReduce", "Hybrid"):
             from .. import distributed
             dp = max(distributed.world_size(), 1)
-        training = any(isinstance(n, Tensor) and n.producer_type in ("adam_update", "sgd_update", "group") for n in nodes)
+        training = any(isinstance(n, Tensor) and n.producer_type in _UPDATE_TYPES for n in nodes)
         ps_opts = []
         if training and self.comm_mode in ("PS", "Hybrid"):
             ps_opts = [o for o in self._optimizers() if any(n is o.v1_train_node or getattr(n, "id", None) == o.v1_train_node.id for n in nodes)]
@@ -269,8 +301,14 @@ class Executor:
             outs = [None if (self.comm_mode == "PS" and getattr(n, "id", None) in train_ids) else next(it) for n in nodes]
         else:
             outs = self.graph.run(loss if training else None, nodes, feed, grad_scale=1.0 / dp)
+        # explicit parameterServerCommunicate_op nodes: the fetched value is a gradient that goes to the server, which applies the
+        # node's optimizer; the fresh parameter comes back before the next step
+        for n, o in zip(nodes, outs):
+            target = annotation(n, "ps_target") if isinstance(n, Tensor) else None
+            if target is not None and o is not None:
+                self._ps_explicit(n, o, *target)
         self.step += 1
-        if any(isinstance(n, Tensor) and n.producer_type in ("adam_update", "sgd_update", "group") for n in nodes):
+        if any(isinstance(n, Tensor) and n.producer_type in _UPDATE_TYPES for n in nodes):
             for opt in self._optimizers():
                 if getattr(opt, "v1_scheduler", None) is not None:
                     opt.v1_scheduler.step()

@@ -302,13 +302,11 @@ def parameterServerCommunicate_op(node, parameter, optimizer):                  
     """push the gradient `node` of `parameter` to the server, which applies `optimizer` (the executor's comm_mode='PS' builds this
     itself; explicit use marks one parameter for the server path)"""
     from .optimizer import v1_server_opt
-    node.ps_target = (parameter, v1_server_opt(optimizer))
-    return node
+    return _ex.annotate(node, "ps_target", (parameter, v1_server_opt(optimizer)))
 def parameterServerSparsePull_op(parameter, deps_node):                                                    # noqa: N802
     """the rows of `parameter` named by `deps_node`, fetched from the server at run time"""
     out = ops.embedding_lookup(parameter, deps_node)
-    out.ps_sparse_pull = parameter
-    return out
+    return _ex.annotate(out, "ps_sparse_pull", parameter)
 def distgcn_15d_op(node_A, node_B, node_C, node_Count_Self=None, node_Count_All=None, size=1, replication=1, device_id=0, comm=None,   # noqa: E704,N803
                    comm_groups=(None, None), need_W=True):
     """one 1.5-D GCN layer A @ (H @ W) on the caller's row block (`models.gnn.DistGCN15D` is the partitioned trainer); on one rank

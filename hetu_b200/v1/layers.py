@@ -229,3 +229,117 @@ class BCELoss(BaseLayer):
 class MSELoss(BaseLayer):
     def __call__(self, p, y):
         return ops.mean(ops.mse_loss(p, y, reduction="none"))
+
+
+# ------------------------------------------------------------------ remaining v1 layer classes
+class _Reduced(BaseLayer):
+    """loss layers share the reduction switch (ref: layers/loss.py BaseLossLayer)"""
+
+    def __init__(self, reduction="mean"):
+        assert reduction in ("mean", "sum", "none", None)
+        self.reduction = reduction
+
+    def reduce(self, loss):
+        if self.reduction == "mean":
+            return ops.mean(loss, [0])
+        if self.reduction == "sum":
+            return ops.sum(loss, [0])
+        return loss
+
+
+class MAELoss(_Reduced):
+    def __call__(self, inputs, targets):
+        return self.reduce(ops.abs(inputs - targets))
+
+
+class BCEWithLogitsLoss(_Reduced):
+    def __call__(self, inputs, targets):
+        return self.reduce(ops.binary_cross_entropy(ops.sigmoid(inputs), targets, reduction="none"))
+
+
+class Concatenate(BaseLayer):
+    """concatenate the call's arguments along `axis` (ref: layers/concatenate.py)"""
+
+    def __init__(self, axis):
+        self.axis = axis
+
+    def __call__(self, *args):
+        return args[0] if len(args) == 1 else ops.concat(list(args), self.axis)
+
+
+class BatchSplitOnlyLayer(BaseLayer):
+    """a block that the v1 planners may only split along the batch dimension (ref: layers/batch_split_layer.py).  The wrapped
+    sequence runs unchanged; `split_dims` is what strategy searches read."""
+    split_dims = (0,)
+
+    def __init__(self, sequence, ctx=None):
+        self.sequence, self.ctx = sequence, ctx
+
+    def __call__(self, x):
+        y = self.sequence(x)
+        from .executor import annotate
+        return annotate(y, "layer_constraint", type(self).__name__)
+
+
+class ReserveSplitLayer(BatchSplitOnlyLayer):
+    """as above, and a split of the hidden dimension survives through the block's reshapes (attention-style head splits)"""
+    split_dims = (0, 1)
+
+
+def _moe():
+    from ..models import moe
+    return moe
+
+
+class Expert(BaseLayer):
+    """one feed-forward expert [*, d] -> [*, d] (ref: layers/moe_layer.py:7 -- two matmuls, optional bias, relu / gelu, dropout)"""
+
+    def __init__(self, embed_dim, ffn_dim, dropout_rate=0.0, initializer=None, bias=False, activation=None, name="expert"):
+        self.embed_dim, self.drop, self.activation = embed_dim, dropout_rate, activation
+        self.fc1 = Linear(embed_dim, ffn_dim, initializer=initializer, bias=bias, name=f"{name}_fc1") if initializer is not None \
+            else Linear(embed_dim, ffn_dim, bias=bias, name=f"{name}_fc1")
+        self.fc2 = Linear(ffn_dim, embed_dim, initializer=initializer, bias=bias, name=f"{name}_fc2") if initializer is not None \
+            else Linear(ffn_dim, embed_dim, bias=bias, name=f"{name}_fc2")
+
+    def __call__(self, x):
+        h = self.fc1(ops.reshape(x, [-1, self.embed_dim]))
+        h = _act(self.activation, h) if self.activation else h
+        if self.drop and self.drop > 0:
+            h = ops.dropout(h, float(self.drop))
+        return self.fc2(h)
+
+
+class _GatedMoE(BaseLayer):
+    """v1's MoE layers differ only in their gate; tokens [.., d] -> [.., d] through `models.moe.MoELayer`'s dispatch -> grouped
+    experts -> combine (all-to-alls fused in when `ep_ranks` spans ranks).  `l_aux` holds the gate's balance loss after a call."""
+    gate_type = "topk"
+
+    def __init__(self, embed_dim, ffn_dim, num_experts, top=1, capacity_factor=1.0, ep_ranks=(), activation="gelu", name=None, **_ignored):
+        self.embed_dim = embed_dim
+        self.inner = _moe().MoELayer(embed_dim, ffn_dim, num_experts, k=top, capacity_factor=capacity_factor, gate_type=self.gate_type,
+                                     ep_ranks=ep_ranks, act=activation, name=name or type(self).__name__.lower())
+        self.l_aux = None
+
+    def __call__(self, x):
+        shape = list(x.shape)
+        y = self.inner(ops.reshape(x, [-1, self.embed_dim]))
+        self.l_aux = self.inner.l_aux
+        return ops.reshape(y, shape)
+
+    def parameters(self):
+        return list(self.inner.parameters())
+
+
+class MoELayer(_GatedMoE): gate_type = "topk"          # noqa: E701
+class HashLayer(_GatedMoE): gate_type = "hash"         # noqa: E701
+class KTop1Layer(_GatedMoE): gate_type = "ktop1"       # noqa: E701
+class SAMLayer(_GatedMoE): gate_type = "sam"           # noqa: E701
+
+
+def __getattr__(name):
+    # the gates live with the MoE model family; v1 code reaches them as ht.layers.TopKGate etc.
+    alias = {"TopKGate": "TopKGate", "KTop1Gate": "KTop1Gate", "HashGate": "HashGate", "SAMGate": "SAMGate",
+             "BalanceAssignmentGate": "BalanceGate", "BalanceGate": "BalanceGate"}
+    if name in alias:
+        return getattr(_moe(), alias[name])
+    raise AttributeError(name)

@@ -50,22 +50,47 @@ class MomentumOptimizer(_Base):
 class AdaGradOptimizer(_Base):
     def __init__(self, learning_rate=0.01, initial_accumulator_value=0.0, eps=1e-7, l2reg=0.0):
         super().__init__(learning_rate, l2reg)
-        self.eps = eps
+        self.eps, self.initial_accumulator_value = eps, initial_accumulator_value
 
     def _server_opt(self):
         return ("adagrad", float(self.learning_rate))
 
-    def _make(self):     # AdaGrad == Adam with beta1 = 0, beta2 -> 1 without bias correction is close; use the exact SGD-family path
-        return optim.AdamOptimizer(lr=self.learning_rate, beta1=0.0, beta2=0.999, eps=self.eps, weight_decay=self.l2reg)
+    def _make(self):
+        return optim.AdaGradOptimizer(lr=self.learning_rate, initial_accumulator_value=self.initial_accumulator_value, eps=self.eps,
+                                      l2reg=self.l2reg)
 
 
 class AdamOptimizer(_Base):
     def __init__(self, learning_rate=0.01, beta1=0.9, beta2=0.999, epsilon=1e-7, l2reg=0.0, amsgrad=False):
         super().__init__(learning_rate, l2reg)
-        self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
+        self.beta1, self.beta2, self.epsilon, self.amsgrad = beta1, beta2, epsilon, amsgrad
 
     def _server_opt(self):
         return ("adam", float(self.learning_rate))
 
     def _make(self):
+        if self.amsgrad:
+            return optim.AMSGradOptimizer(lr=self.learning_rate, beta1=self.beta1, beta2=self.beta2, eps=self.epsilon, l2reg=self.l2reg)
         return optim.AdamOptimizer(lr=self.learning_rate, beta1=self.beta1, beta2=self.beta2, eps=self.epsilon, weight_decay=self.l2reg)
+
+
+class AMSGradOptimizer(AdamOptimizer):
+    def __init__(self, learning_rate=0.01, beta1=0.9, beta2=0.999, epsilon=1e-7, l2reg=0.0):
+        super().__init__(learning_rate, beta1, beta2, epsilon, l2reg, amsgrad=True)
+
+
+class AdamWOptimizer(_Base):
+    def __init__(self, learning_rate=0.01, beta1=0.9, beta2=0.999, epsilon=1e-7, weight_decay=0.0):
+        super().__init__(learning_rate, 0.0)
+        self.beta1, self.beta2, self.epsilon, self.weight_decay = beta1, beta2, epsilon, weight_decay
+
+    def _server_opt(self):
+        return ("adam", float(self.learning_rate))
+
+    def _make(self):
+        return optim.AdamWOptimizer(lr=self.learning_rate, beta1=self.beta1, beta2=self.beta2, eps=self.epsilon, weight_decay=self.weight_decay)
+
+
+class LambOptimizer(AdamWOptimizer):
+    def _make(self):
+        return optim.LambOptimizer(lr=self.learning_rate, beta1=self.beta1, beta2=self.beta2, eps=self.epsilon, weight_decay=self.weight_decay)

@@ -252,13 +252,13 @@ def dispatch(node, parts=None):
         return node
     split = {int(d): int(n) for d, n in (parts.items() if isinstance(parts, dict) else enumerate(parts)) if int(n) > 1}
     total = int(np.prod(list(split.values()))) if split else 1
-    node.dispatch_parts = dict(split)
+    from .executor import annotate
+    annotate(node, "dispatch_parts", dict(split))
     if total <= 1 or not _C.comm_initialized() or _C.comm_world() < total:
         return node
     ds = core.DistributedStates(total, split, sorted(split))
     out = ops.comm(node, [ds])
-    out.dispatch_parts = dict(split)
-    return out
+    return annotate(out, "dispatch_parts", dict(split))
 
 
 def softmax_func(y):

@@ -702,3 +702,97 @@ def test_v1_role_functions_run_a_scheduler_two_servers_and_two_workers(tmp_path)
     for r in res:
         assert abs(r["w"] - (-4.5)) < 1e-6, r
         assert r["emb"][0] == [-1.0, -1.0] and r["emb"][1] == [-1.0, -1.0] and r["emb"][2][0] <= -1.0
+
+
+def test_v1_remaining_layer_classes_train_and_reduce():
+    """ref: hetu/v1/python/hetu/layers/{moe_layer,hash_layer,ktop1_layer,sam_layer,loss,concatenate,batch_split_layer}.py -- the MoE
+    layer family trains under a v1 optimizer, the loss layers reduce as declared, the gates resolve from ht.layers"""
+    import numpy as np
+    import hetu_b200.v1 as v1
+    from hetu_b200.v1 import executor as v1ex
+    L = v1.layers
+    rng = np.random.RandomState(0)
+    xs, ys = rng.randn(16, 8).astype(np.float32), rng.randn(16, 8).astype(np.float32)
+    for cls, top in ((L.MoELayer, 2), (L.KTop1Layer, 1), (L.HashLayer, 1), (L.SAMLayer, 2)):
+        v1ex.reset_graph()
+        x, y = v1.placeholder_op("x", [16, 8]), v1.placeholder_op("y", [16, 8])
+        block = L.BatchSplitOnlyLayer(L.Sequence(cls(8, 16, 4, top=top, capacity_factor=2.0), L.Linear(8, 8, name=f"{cls.__name__}_head")))
+        out = block(x)
+        assert v1ex.annotation(out, "layer_constraint") == "BatchSplitOnlyLayer" and block.split_dims == (0,) and L.ReserveSplitLayer.split_dims == (0, 1)
+        loss = v1.reduce_mean_op(L.MSELoss()(out, y) if False else L.MAELoss("mean")(out, y), [0])
+        train = v1.optim.AdamOptimizer(0.02).minimize(loss)
+        ex = v1.Executor([loss, train])
+        hist = [float(ex.run(feed_dict={x: xs, y: ys}, convert_to_numpy_ret_vals=True)[0]) for _ in range(25)]
+        assert hist[-1] < 0.85 * hist[0], (cls.__name__, hist[0], hist[-1])
+    v1ex.reset_graph()
+    a, b = v1.Variable("la", value=xs, trainable=False), v1.Variable("lb", value=(ys > 0).astype(np.float32), trainable=False)
+    nodes = [L.MAELoss("sum")(a, b), L.MAELoss("none")(a, b), L.BCEWithLogitsLoss("mean")(a, b), L.Concatenate(1)(a, b), L.Concatenate(0)(a)]
+    r = v1.Executor(nodes).run(feed_dict={}, convert_to_numpy_ret_vals=True)
+    t = (ys > 0).astype(np.float32)
+    np.testing.assert_allclose(r[0], np.abs(xs - t).sum(0), rtol=1e-5)
+    np.testing.assert_allclose(r[1], np.abs(xs - t), rtol=1e-5)
+    np.testing.assert_allclose(r[2], (np.maximum(xs, 0) - xs * t + np.log1p(np.exp(-np.abs(xs)))).mean(0), rtol=1e-4, atol=1e-5)
+    assert r[3].shape == (16, 16) and r[4].shape == (16, 8)
+    from hetu_b200.models import moe
+    assert L.TopKGate is moe.TopKGate and L.BalanceAssignmentGate is moe.BalanceGate and L.SAMGate is moe.SAMGate and L.HashGate is moe.HashGate
+    v1ex.reset_graph()
+
+
+def test_v1_adagrad_amsgrad_adamw_and_lamb_follow_the_reference_update_rules():
+    """ref: hetu/v1/python/hetu/optimizer.py:335-760 -- four steps of every rule on a quadratic match torch.optim (AdaGrad, AMSGrad,
+    AdamW) and the written-out LAMB recurrence"""
+    import numpy as np
+    import torch
+    import hetu_b200.v1 as v1
+    from hetu_b200.v1 import executor as v1ex
+    rng = np.random.RandomState(3)
+    w0, a = rng.randn(5, 4).astype(np.float32), rng.randn(5, 4).astype(np.float32)
+
+    def ours(make):
+        v1ex.reset_graph()
+        w = v1.Variable("ow", value=w0.copy())
+        loss = v1.reduce_sum_op(v1.mul_op(v1.mul_op(w - v1.Variable("oa", value=a, trainable=False), w), w), [0, 1])     # sum (w - a) w^2
+        train = make().minimize(loss)
+        ex = v1.Executor([loss, train])
+        for _ in range(4):
+            ex.run(feed_dict={})
+        return ex.graph.get_param(w).float().numpy().copy()
+
+    def theirs(make):
+        w = torch.tensor(w0.copy(), requires_grad=True)
+        opt = make([w])
+        for _ in range(4):
+            opt.zero_grad()
+            ((w - torch.tensor(a)) * w * w).sum().backward()
+            opt.step()
+        return w.detach().numpy()
+
+    np.testing.assert_allclose(ours(lambda: v1.AdaGradOptimizer(0.1, eps=1e-10)), theirs(lambda p: torch.optim.Adagrad(p, lr=0.1, eps=1e-10)), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(ours(lambda: v1.AdaGradOptimizer(0.1, initial_accumulator_value=0.5, eps=1e-10)),
+                               theirs(lambda p: torch.optim.Adagrad(p, lr=0.1, initial_accumulator_value=0.5, eps=1e-10)), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(ours(lambda: v1.AdamWOptimizer(0.05, epsilon=1e-8, weight_decay=0.1)),
+                               theirs(lambda p: torch.optim.AdamW(p, lr=0.05, eps=1e-8, weight_decay=0.1)), rtol=2e-4, atol=2e-5)
+    # AMSGrad: running maximum of the bias-corrected second moment
+    def amsgrad_ref():
+        w = w0.astype(np.float64).copy()
+        m, v, vh = np.zeros_like(w), np.zeros_like(w), np.zeros_like(w)
+        for t in range(1, 5):
+            g = 3 * w * w - 2 * a * w
+            m, v = 0.9 * m + 0.1 * g, 0.999 * v + 0.001 * g * g
+            vh = np.maximum(vh, v / (1 - 0.999 ** t))
+            w = w - 0.05 * (m / (1 - 0.9 ** t)) / (np.sqrt(vh) + 1e-7)
+        return w
+    np.testing.assert_allclose(ours(lambda: v1.AMSGradOptimizer(0.05)), amsgrad_ref(), rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(ours(lambda: v1.AdamOptimizer(0.05, amsgrad=True)), amsgrad_ref(), rtol=2e-4, atol=2e-5)
+
+    def lamb_ref():
+        w = w0.astype(np.float64).copy()
+        m, v = np.zeros_like(w), np.zeros_like(w)
+        for t in range(1, 5):
+            g = 3 * w * w - 2 * a * w
+            m, v = 0.9 * m + 0.1 * g, 0.999 * v + 0.001 * g * g
+            upd = (m / (1 - 0.9 ** t)) / (np.sqrt(v / (1 - 0.999 ** t)) + 1e-7) + 0.01 * w
+            w = w - 0.05 * (np.linalg.norm(w) / np.linalg.norm(upd)) * upd
+        return w
+    np.testing.assert_allclose(ours(lambda: v1.LambOptimizer(0.05, weight_decay=0.01)), lamb_ref(), rtol=2e-4, atol=2e-5)
+    v1ex.reset_graph()
