@@ -19,6 +19,7 @@ from .optimizer import (SGDOptimizer, MomentumOptimizer, AdaGradOptimizer, AdamO
 from . import optimizer as optim  # noqa: F401  (v1: ht.optim.SGDOptimizer)
 from .ps import PSContext, ShardedPSContext, CacheSparseTable  # noqa: F401
 from . import strategies as dist  # noqa: F401
+from .profiler import HetuProfiler, NCCLProfiler, HetuSimulator, NCCLOP  # noqa: F401
 from .strategies import (DataParallel, ModelParallel4CNN, ModelParallel4LM, OneWeirdTrick4CNN, MegatronLM, FlexFlowSearching,  # noqa: F401
                          OptCNNSearching, GPipeSearching, PipeDreamSearching, PipeOptSearching)
 from ..models.moe import MoELayer, TopKGate, KTop1Gate, HashGate, BalanceGate, SAMGate  # noqa: F401

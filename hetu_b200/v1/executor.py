@@ -17,6 +17,17 @@ class _Ctx:
     def __init__(self, kind, index=0, host="localhost"):
         self.kind, self.index, self.host = kind, index, host
 
+    # the reference's DLContext spellings
+    device_id = property(lambda self: self.index)
+    hostname = property(lambda self: self.host)
+    local = property(lambda self: self.host in ("localhost", "127.0.0.1"))
+
+    def __eq__(self, other):
+        return isinstance(other, _Ctx) and (self.kind, self.index, self.host) == (other.kind, other.index, other.host)
+
+    def __hash__(self):
+        return hash((self.kind, self.index, self.host))
+
     def __repr__(self):
         return f"{self.host}:{self.kind}:{self.index}"
 

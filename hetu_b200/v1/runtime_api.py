@@ -22,19 +22,23 @@ class Communicator:
     def __init__(self, ranks: Optional[Sequence[int]] = None):
         from .. import _C
         self._C = _C
-        if not _C.comm_initialized():
-            core.init_comm_group()
-        self.ranks = [int(r) for r in ranks] if ranks is not None else list(range(_C.comm_world()))
-        if len(self.ranks) > 1:
+        if not _C.comm_initialized() and "RANK" in os.environ:
+            from .. import distributed
+            distributed.init_comm_group()
+        self._live = _C.comm_initialized()            # a lone process (no launcher environment) is a one-rank world
+        self.ranks = [int(r) for r in ranks] if ranks is not None else list(range(_C.comm_world() if self._live else 1))
+        if len(self.ranks) > 1 and self._live:
             _C.comm_create_group(self.ranks)
 
     # -- identity
     @property
-    def rank(self) -> int: return self.ranks.index(self._C.comm_rank()) if self._C.comm_rank() in self.ranks else -1    # noqa: E704
+    def rank(self) -> int:
+        me = self._C.comm_rank() if self._live else 0
+        return self.ranks.index(me) if me in self.ranks else -1
     @property
     def nrank(self) -> int: return len(self.ranks)                                                                        # noqa: E704
     @property
-    def local_rank(self) -> int: return int(os.environ.get("LOCAL_RANK", self._C.comm_rank()))                            # noqa: E704
+    def local_rank(self) -> int: return int(os.environ.get("LOCAL_RANK", self._C.comm_rank() if self._live else 0))        # noqa: E704
     @property
     def dev_id(self) -> int: return self.local_rank                                                                       # noqa: E704
     def getRank(self): return self.rank                                                                                   # noqa: E704,N802
@@ -61,7 +65,7 @@ class Communicator:
 
     def _run(self, fn, x, output=None):
         t, kind = self._in(x)
-        y = fn(t.contiguous()) if len(self.ranks) > 1 else t
+        y = fn(t.contiguous()) if (len(self.ranks) > 1 and self._live) else t
         if output is not None:                                          # v1 style: write into the caller's output array
             ot, okind = self._in(output)
             ot.copy_(y.reshape(ot.shape))
@@ -77,7 +81,7 @@ class Communicator:
     def all_to_all(self, x, output=None): return self._run(lambda t: self._C.comm_all_to_all(t, self.ranks, 0, 0), x, output)           # noqa: E704
     def send(self, x, dst, channel=0): self._C.comm_send(self._in(x)[0], self.ranks[dst], channel)                                        # noqa: E704
     def recv(self, shape, src, dtype="float32", channel=0): return self._C.comm_recv(list(shape), dtype, self.ranks[src], channel)        # noqa: E704
-    def barrier(self): self._C.comm_barrier()                                                                                             # noqa: E704
+    def barrier(self): self._live and self._C.comm_barrier()                                                                                             # noqa: E704
 
     def dlarrayNcclAllReduce(self, input_arr, output_arr, dtype=None, reduceop="sum", stream=None):                       # noqa: N802
         return self.all_reduce(input_arr, _op_name(reduceop), output_arr)

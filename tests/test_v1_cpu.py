@@ -796,3 +796,53 @@ def test_v1_adagrad_amsgrad_adamw_and_lamb_follow_the_reference_update_rules():
         return w
     np.testing.assert_allclose(ours(lambda: v1.LambOptimizer(0.05, weight_decay=0.01)), lamb_ref(), rtol=2e-4, atol=2e-5)
     v1ex.reset_graph()
+
+
+def test_v1_profiler_and_simulator_measure_cache_and_model_transfers(tmp_path):
+    """ref: hetu/v1/python/hetu/profiler.py -- HetuProfiler times nodes (whole and per op), HetuSimulator caches measured node times on
+    disk and prices transfers / collectives / re-sharding with its link model"""
+    import numpy as np
+    import hetu_b200.v1 as v1
+    from hetu_b200.v1 import executor as v1ex
+    v1ex.reset_graph()
+    x = v1.placeholder_op("px", [64, 128])
+    w = v1.Variable("pw", value=np.random.randn(128, 256).astype(np.float32) * 0.05)
+    y = v1.relu_op(v1.matmul_op(x, w))
+    prof = v1.HetuProfiler([y], {x: [64, 128]})
+    assert prof.profile(5) > 0
+    per_op = prof.profile_all(3)
+    assert any(k.startswith("matmul") for k in per_op) and any(k.startswith("unary_act") for k in per_op) and all(v >= 0 for v in per_op.values())
+    log = prof.profile_n_log(str(tmp_path / "ops.log"), num_iterations=2)
+    assert (tmp_path / "ops.log").read_text().count("ms") == len(log)
+    ids = prof.get_lookup_sampler(100, ignore_rate=0.5)([1000])
+    assert ids.max() < 100 and 0.3 < (ids == -1).mean() < 0.7
+    v1ex.reset_graph()
+
+    cache = str(tmp_path / "exetime.json")
+    sim = v1.HetuSimulator(cache_path=cache)
+    t1 = sim.get_node_time("matmul", [[64, 128], [128, 256]])
+    assert t1 > 0 and sim.get_node_time("matmul", [[64, 128], [128, 256]]) == t1           # second call: cached
+    assert sim.get_node_time("some_unknown_op", [[1024, 1024]], [1024, 1024]) > 0                  # memory-bound estimate
+    sim.write_cache()
+    again = v1.HetuSimulator(cache_path=cache)
+    assert again.get_node_time("matmul", [[64, 128], [128, 256]]) == t1                      # survives through the file
+    g0, g1 = v1.gpu(0), v1.gpu(1)
+    far = v1.rgpu("other-host", 0)
+    shape = [1024, 1024]
+    assert sim.get_dev_distance(g0, g0) == 0 and sim.get_dev_distance(g0, g1) == 1 and sim.get_dev_distance(g0, far) == 2
+    near_t, far_t = sim.get_comm_time(g0, g1, shape), sim.get_comm_time(g0, far, shape)
+    assert sim.get_comm_time(g0, g0, shape) == 0 and 0 < near_t < far_t
+    np.testing.assert_allclose(near_t, 8e-3 + 4 * 2 ** 20 / 900e9 * 1e3, rtol=1e-6)
+    ar2, ar8 = sim.get_allreduce_time(shape, [v1.gpu(i) for i in range(2)]), sim.get_allreduce_time(shape, [v1.gpu(i) for i in range(8)])
+    ag8 = sim.get_allreduce_time(shape, [v1.gpu(i) for i in range(8)], v1.NCCLOP.AllGather)
+    assert 0 < ar2 < ar8 and ag8 < ar8 and sim.get_allreduce_time(shape, [g0]) == 0
+    assert sim.get_split_shape({0: 2, 1: 4}, shape) == [512, 256] and sim.get_concatenate_shape([[2, 3], [5, 3]], 0) == [7, 3]
+    assert sim.get_split_time(shape, [0], [0], [2]) < sim.get_concatenate_time([shape, shape], 0)
+    assert sim.get_update_time(shape) > sim.get_update_time(shape, sparse_shape=[16, 1024])
+    # re-sharding: rows split over 2 devices -> columns split over the same 2: each target pulls the quarter it lacks from the peer
+    moved = sim.get_general_comm_time({0: 2}, {1: 2}, [g0, g1], [g0, g1], shape)
+    np.testing.assert_allclose(moved, sim.get_comm_time(g0, g1, [512, 512]), rtol=1e-9)
+    assert sim.get_general_comm_time({0: 2}, {0: 2}, [g0, g1], [g0, g1], shape) == 0
+    assert sim.get_group_comm_time([(g0, g1, shape), (g0, g1, shape)]) > sim.get_group_comm_time([(g0, g1, shape)])
+    prof2 = v1.NCCLProfiler()                                                                       # single process: nothing to move
+    assert prof2.profile_allreduce(1024, [0]) == 0.0 and prof2.profile_sendrecv(1024, [0, 0]) == 0.0

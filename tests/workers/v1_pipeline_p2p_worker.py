@@ -36,6 +36,11 @@ comm.dlarrayNcclAllReduce(np.full(3, 2.0, np.float32), out)
 bc = comm.broadcast(np.array([7.0 + rank], np.float32), root=1)
 sub = v1.new_group_comm([0, 1])
 assert sub.nrank == 2
+nprof = v1.NCCLProfiler()
+t_ar = nprof.profile_allreduce(4096, [0, 1], num_iterations=3)
+t_ag = nprof.profile_allreduce(4096, [0, 1], num_iterations=3, primitive=v1.NCCLOP.AllGather)
+t_p2p = nprof.profile_sendrecv(4096, [0, 1], num_iterations=3)
+assert t_ar > 0 and t_ag > 0 and t_p2p > 0, (t_ar, t_ag, t_p2p)
 if rank == 1:
     print("COMM " + json.dumps({"sum": total.tolist(), "gather": gathered.tolist(), "out": out.tolist(), "bc": bc.tolist()}), flush=True)
 dist.barrier()
