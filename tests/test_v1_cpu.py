@@ -846,3 +846,61 @@ def test_v1_profiler_and_simulator_measure_cache_and_model_transfers(tmp_path):
     assert sim.get_group_comm_time([(g0, g1, shape), (g0, g1, shape)]) > sim.get_group_comm_time([(g0, g1, shape)])
     prof2 = v1.NCCLProfiler()                                                                       # single process: nothing to move
     assert prof2.profile_allreduce(1024, [0]) == 0.0 and prof2.profile_sendrecv(1024, [0, 0]) == 0.0
+
+
+def test_v1_arrays_indexed_slices_device_groups_and_node_status(tmp_path):
+    """ref: hetu/v1/python/hetu/ndarray.py (array / sparse_array / IndexedSlices), context.py (DeviceGroup, NodeStatus), data.py"""
+    import gzip
+    import pickle
+    import numpy as np
+    import hetu_b200.v1 as v1
+    a = v1.array(np.arange(6.0).reshape(2, 3), v1.gpu(0))
+    assert a.shape == (2, 3) and a.asnumpy().dtype == np.float32 and v1.is_gpu_ctx(a.ctx) and not v1.is_gpu_ctx(v1.cpu(0))
+    b = v1.empty((2, 3), v1.cpu(0))
+    a.copyto(b)
+    b[0] = np.zeros(3)
+    np.testing.assert_array_equal(b.asnumpy(), [[0, 0, 0], [3, 4, 5]])
+    assert v1.empty_like(a).shape == (2, 3) and v1.array(np.array([1, 2], np.int64), v1.cpu(0)).asnumpy().dtype == np.int64
+    for form in ("csr", "coo"):
+        sp = v1.sparse_array([1.0, 2.0, 3.0], ([1, 0, 1], [0, 1, 2]), (2, 3), form=form)
+        np.testing.assert_array_equal(sp.to_dense().asnumpy(), [[0, 2, 0], [1, 0, 3]])
+        idx, val = sp.coo()
+        assert idx.shape == (2, 3) and val.numel() == 3
+    sl = v1.IndexedSlices(np.array([1, 3, 1, -1]), np.arange(8, dtype=np.float32).reshape(4, 2), (5, 2))
+    d = sl.deduplicate()
+    assert d.indices.tolist() == [1, 3] and d.values.tolist() == [[4.0, 6.0], [2.0, 3.0]] and sl.get_sparse_shape() == (4, 2)
+    np.testing.assert_array_equal(sl.asnumpy(), [[0, 0], [4, 6], [0, 0], [2, 3], [0, 0]])
+
+    g = v1.DeviceGroup([("gpu:0", "gpu:1"), ("node2:gpu:0", "node2:gpu:1"), "cpu:0"])
+    assert g.is_mp and g.mp_dev_num == 2 and g.worker_num == 2 and g.server_num == 1 and len(g.flat_workers()) == 4
+    assert g.index(v1.rgpu("node2", 1)) == 1 and g.workers[1][0].hostname == "node2" and g == v1.DeviceGroup(g)
+    g.check_mp_num(2)
+    assert v1.DeviceGroup("gpu:3").get_only() == v1.gpu(3) and v1.DeviceGroup([v1.gpu(1), v1.gpu(0)]).get_sorted()[0] == v1.gpu(0)
+
+    # row-split partial sums over 8 devices: 2 (split) x 2 (partial) x 2 (duplicate)
+    n = v1.NodeStatus({0: 2}, dev_num=8, partial=2)
+    assert (n.duplicate, n.partial, n.get_default_order(), n.get_loop_sizes()) == (2, 2, (-2, -1, 0), (4, 2, 1))
+    assert n.map_dev_to_index(5, True) == {-2: 1, -1: 0, 0: 1} and n.map_dev_to_index(5) == {0: 1} and n.get_devices_by_dim(0, 1) == [1, 3, 5, 7]
+    summed = n.remove_partial()
+    assert summed.duplicate == 4 and summed.partial == 1 and n.check_allreduce(summed) and not n.check_allgather(summed)
+    gathered = v1.NodeStatus({}, dev_num=8, duplicate=8)
+    assert summed.check_allgather(gathered) and v1.NodeStatus({0: 4}, dev_num=4).check_allgather(v1.NodeStatus({}, dev_num=4, duplicate=4))
+    rs_target = v1.NodeStatus({0: 4}, dev_num=8, duplicate=2, order=(-1, 0))
+    assert n.combine_state((-2, 0)) == ({0: 4}, 2, 1) and n.check_reducescatter(rs_target)
+    assert n.exchange_state(0, 1) == ({1: 2}, 2, 2) and n.exchange_order(0, 1) == (-2, -1, 1)
+    ds = n.to_distributed_states()
+    assert ds.device_num == 8 and dict(ds.states)[-2] == 2 and v1.NodeStatus.from_distributed_states(ds) == n
+    assert n.valid(True) and n.valid_state() and {n: 1}[v1.NodeStatus({0: 2}, dev_num=8, partial=2)] == 1
+
+    # data helpers: one-hot, augmentation, the MNIST archive format
+    assert v1.data.convert_to_one_hot([0, 2], 3).tolist() == [[1, 0, 0], [0, 0, 1]]
+    imgs = np.random.RandomState(0).rand(4, 3, 32, 32).astype(np.float32)
+    aug = v1.data.data_augmentation(imgs, "train", flip=True, crop=True, crop_shape=(24, 24), whiten=True, rng=np.random.RandomState(1))
+    assert aug.shape == (4, 3, 24, 24) and abs(aug.reshape(4, -1).mean(1)).max() < 1e-4
+    assert v1.data.data_augmentation(imgs, "test", crop=True).shape == (4, 3, 24, 24)
+    arch = tmp_path / "mnist.pkl.gz"
+    with gzip.open(arch, "wb") as f:
+        pickle.dump([(np.zeros((5, 784)), np.arange(5))] * 3, f)
+    (tx, ty), _, _ = v1.data.mnist(str(arch))
+    assert tx.shape == (5, 784) and ty.shape == (5, 10)
+    assert v1.lr is v1.lr_scheduler and v1.BertTokenizer is not None
