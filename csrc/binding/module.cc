@@ -794,6 +794,7 @@ PYBIND11_MODULE(_C, m) {
         .def_property_readonly("num_workers", &PsSchedulerClient::num_workers)
         .def_property_readonly("servers", &PsSchedulerClient::servers)
         .def("barrier", &PsSchedulerClient::barrier, py::arg("group") = (int)kAllGroup, nogil)
+        .def("preduce_partners", &PsSchedulerClient::preduce_partners, py::arg("key"), py::arg("rank"), py::arg("max_worker"), py::arg("wait_ms"), nogil)
         .def("heartbeat", &PsSchedulerClient::heartbeat, nogil)
         .def("dead_nodes", &PsSchedulerClient::dead_nodes, py::arg("timeout_s"), nogil)
         .def("key_ranges", &PsSchedulerClient::key_ranges, py::arg("total"))

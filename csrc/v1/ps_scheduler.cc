@@ -1,3 +1,4 @@
+#include <algorithm>
 #include "ps_scheduler.h"
 
 #include <arpa/inet.h>
@@ -10,7 +11,7 @@
 namespace hb {
 using namespace ps_wire;
 namespace {
-enum SOp : uint8_t { S_REGISTER = 1, S_BARRIER, S_HEARTBEAT, S_DEAD, S_FINALIZE };
+enum SOp : uint8_t { S_REGISTER = 1, S_BARRIER, S_HEARTBEAT, S_DEAD, S_FINALIZE, S_PREDUCE };
 
 void put_node(Writer& w, const PsNodeInfo& n) { w.put<int32_t>(n.role); w.put<int32_t>(n.rank); w.str(n.host); w.put<int32_t>(n.port); }
 PsNodeInfo get_node(Reader& r) {
@@ -126,6 +127,39 @@ void PsScheduler::serve(int fd) {
           cv_.notify_all();
           break;
         }
+        case S_PREDUCE: {
+          // partial reduce matchmaking: the first worker to ask under `key` opens a round; whoever asks before the round's
+          // deadline (or until `max_worker` have gathered) is in it, and all of them receive the same sorted member list
+          const int key = r.get<int32_t>(), rank = r.get<int32_t>(), max_worker = r.get<int32_t>();
+          const double wait_ms = r.get<double>();
+          auto& st = preduce_[key];
+          if (!st.open) {
+            st.open = true;
+            ++st.gen;
+            st.members.clear();
+            st.deadline = std::chrono::steady_clock::now() + std::chrono::microseconds((int64_t)(wait_ms * 1e3));
+          }
+          const uint64_t gen = st.gen;
+          st.members.push_back(rank);
+          auto close = [&] {
+            std::sort(st.members.begin(), st.members.end());
+            st.done[gen] = {st.members, (int)st.members.size()};
+            st.open = false;
+            cv_.notify_all();
+          };
+          if ((int)st.members.size() >= std::max(1, max_worker)) {
+            close();
+          } else {
+            cv_.wait_until(lk, st.deadline, [&] { return stop_ || st.done.count(gen) > 0; });
+            HB_CHECK(!stop_) << "scheduler stopped inside a partial-reduce round";
+            if (!st.done.count(gen)) close();          // the deadline passed: this waiter seals the round for everybody in it
+          }
+          auto& res = st.done[gen];
+          out.put<int32_t>((int32_t)res.first.size());
+          for (int m : res.first) out.put<int32_t>(m);
+          if (--res.second == 0) st.done.erase(gen);
+          break;
+        }
         default: HB_FAIL() << "unknown scheduler request " << (int)op;
       }
     } catch (const std::exception& e) {
@@ -226,6 +260,18 @@ void PsSchedulerClient::barrier(int group) {
   Writer w;
   w.put<uint8_t>(S_BARRIER); w.put<int32_t>(node_id_); w.put<int32_t>(group);
   roundtrip(w.b);
+}
+std::vector<int> PsSchedulerClient::preduce_partners(int key, int rank, int max_worker, double wait_ms) {
+  Writer w;
+  w.put<uint8_t>(S_PREDUCE); w.put<int32_t>(node_id_); w.put<int32_t>(key); w.put<int32_t>(rank); w.put<int32_t>(max_worker);
+  w.put<double>(wait_ms);
+  std::string rep = roundtrip(w.b);
+  Reader r(rep);
+  r.get<uint8_t>();
+  const int n = r.get<int32_t>();
+  std::vector<int> out(n);
+  for (int i = 0; i < n; ++i) out[i] = r.get<int32_t>();
+  return out;
 }
 void PsSchedulerClient::heartbeat() {
   Writer w;

@@ -48,6 +48,14 @@ class PsScheduler {
   std::condition_variable cv_;
   std::vector<Node> nodes_;                     // registration order
   std::map<int, std::pair<int, uint64_t>> barrier_;   // group -> (arrived, generation)
+  struct PReduceRound {
+    bool open = false;
+    uint64_t gen = 0;
+    std::vector<int> members;
+    std::chrono::steady_clock::time_point deadline;
+    std::map<uint64_t, std::pair<std::vector<int>, int>> done;   // sealed rounds: members + how many have not collected them yet
+  };
+  std::map<int, PReduceRound> preduce_;
   std::vector<std::thread> handlers_;
   std::vector<int> fds_;
 };
@@ -64,6 +72,8 @@ class PsSchedulerClient {
   int num_workers() const { return num_workers_; }
   const std::vector<PsNodeInfo>& servers() const { return servers_; }
   void barrier(int group);
+  // partial reduce: the workers that ask under `key` within `wait_ms` of the first one (at most `max_worker`) form a group
+  std::vector<int> preduce_partners(int key, int rank, int max_worker, double wait_ms);
   void heartbeat();
   std::vector<PsNodeInfo> dead_nodes(double timeout_s);
   // contiguous split of [0, total) over the servers: begin offsets (size num_servers + 1)

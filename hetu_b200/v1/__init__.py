@@ -22,6 +22,7 @@ from . import strategies as dist  # noqa: F401
 from . import lr_scheduler as lr, data  # noqa: F401
 from .ndarray import NDArray, ND_Sparse_Array, array, empty, empty_like, sparse_array, IndexedSlices, is_gpu_ctx  # noqa: F401
 from .context import DeviceGroup, NodeStatus, ContextStack  # noqa: F401
+from .preduce import PartialReduce  # noqa: F401
 from ..data.tokenizers.wordpiece import BertTokenizer  # noqa: F401
 from .profiler import HetuProfiler, NCCLProfiler, HetuSimulator, NCCLOP  # noqa: F401
 from .strategies import (DataParallel, ModelParallel4CNN, ModelParallel4LM, OneWeirdTrick4CNN, MegatronLM, FlexFlowSearching,  # noqa: F401

@@ -904,3 +904,43 @@ def test_v1_arrays_indexed_slices_device_groups_and_node_status(tmp_path):
     (tx, ty), _, _ = v1.data.mnist(str(arch))
     assert tx.shape == (5, 784) and ty.shape == (5, 10)
     assert v1.lr is v1.lr_scheduler and v1.BertTokenizer is not None
+
+
+def test_v1_partial_reduce_groups_the_workers_that_are_ready(tmp_path):
+    """ref: hetu/v1/python/hetu/preduce.py -- a late worker is left out of the round (the punctual two average among themselves),
+    a round with everybody on time averages over all three"""
+    import json
+    import os
+    import subprocess
+    import sys
+    import time
+    from dist_utils import free_port
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "tests", "workers", "v1_preduce_worker.py")
+    base = dict(os.environ, PYTHONPATH=root, HETU_B200_FORCE_CPU="1", CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1",
+                DMLC_PS_ROOT_URI="127.0.0.1", DMLC_PS_ROOT_PORT=str(free_port()), DMLC_NUM_SERVER="1", DMLC_NUM_WORKER="3",
+                MASTER_ADDR="127.0.0.1", MASTER_PORT=str(free_port()), WORLD_SIZE="3")
+    for k in ("HETU_PS_SCHEDULER", "HETU_PS_ADDRESS", "RANK", "LOCAL_RANK"):
+        base.pop(k, None)
+    procs = []
+    for i, role in enumerate(["scheduler", "server", "worker", "worker", "worker"]):
+        env = dict(base, DMLC_ROLE=role)
+        if role == "worker":
+            env.update(RANK=str(i - 2), LOCAL_RANK=str(i - 2))
+        out = open(tmp_path / f"{role}{i}.log", "w")
+        procs.append((role, i, subprocess.Popen([sys.executable, script], env=env, stdout=out, stderr=subprocess.STDOUT)))
+        if role == "scheduler":
+            time.sleep(1.0)
+    codes = []
+    for role, i, p in procs:
+        try:
+            codes.append(p.wait(150))
+        except subprocess.TimeoutExpired:
+            p.kill()
+            codes.append(-9)
+    logs = {f"{role}{i}": (tmp_path / f"{role}{i}.log").read_text() for role, i, _ in procs}
+    assert codes == [0] * 5, json.dumps(logs)[-4000:]
+    res = {r["rank"]: r for r in (json.loads(l[8:]) for t in logs.values() for l in t.splitlines() if l.startswith("PREDUCE "))}
+    assert res[0]["p1"] == res[1]["p1"] == [0, 1] and res[2]["p1"] == [2]
+    assert res[0]["first"] == res[1]["first"] == [1.5] * 4 and res[2]["first"] == [3.0] * 4
+    assert all(res[r]["p2"] == [0, 1, 2] and res[r]["second"] == [2.0] * 4 for r in range(3))
