@@ -23,6 +23,9 @@ from . import lr_scheduler as lr, data  # noqa: F401
 from .ndarray import NDArray, ND_Sparse_Array, array, empty, empty_like, sparse_array, IndexedSlices, is_gpu_ctx  # noqa: F401
 from .context import DeviceGroup, NodeStatus, ContextStack  # noqa: F401
 from .preduce import PartialReduce  # noqa: F401
+from .logger import HetuLogger, WandbLogger  # noqa: F401
+from .memory_pool import HetuMemoryPool  # noqa: F401
+from . import stream  # noqa: F401
 from ..data.tokenizers.wordpiece import BertTokenizer  # noqa: F401
 from .profiler import HetuProfiler, NCCLProfiler, HetuSimulator, NCCLOP  # noqa: F401
 from .strategies import (DataParallel, ModelParallel4CNN, ModelParallel4LM, OneWeirdTrick4CNN, MegatronLM, FlexFlowSearching,  # noqa: F401

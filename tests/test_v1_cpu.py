@@ -944,3 +944,68 @@ def test_v1_partial_reduce_groups_the_workers_that_are_ready(tmp_path):
     assert res[0]["p1"] == res[1]["p1"] == [0, 1] and res[2]["p1"] == [2]
     assert res[0]["first"] == res[1]["first"] == [1.5] * 4 and res[2]["first"] == [3.0] * 4
     assert all(res[r]["p2"] == [0, 1, 2] and res[r]["second"] == [2.0] * 4 for r in range(3))
+
+
+def test_v1_logger_memory_reuse_plan_and_stream_handles(tmp_path):
+    """ref: hetu/v1/python/hetu/{logger,memory_pool,stream}.py"""
+    import json
+    import numpy as np
+    import hetu_b200.v1 as v1
+    from hetu_b200.v1 import executor as v1ex
+    from hetu_b200.v1.memory_pool import nodes_of_graph
+    log = v1.HetuLogger(file=str(tmp_path / "m.jsonl"), echo=False)
+    log.log("loss", np.array([0.5]))
+    log.wrapped_log("acc", [[0.25]])
+    with pytest.raises(AssertionError):
+        log.log("loss", 1.0)
+    log.step()
+    log.log("loss", 0.4)
+    log.step()
+    recs = [json.loads(l) for l in open(tmp_path / "m.jsonl")]
+    assert [r["loss"] for r in recs] == [0.5, 0.4] and recs[0]["acc"] == 0.25 and recs[1]["_step"] == 1 and len(log.history) == 2
+    quiet = v1.HetuLogger(rank=1, nrank=2, echo=False)                  # not rank 0: buffers, never emits
+    quiet.log("x", 1.0)
+    quiet.step()
+    assert quiet.history == [] and not quiet.need_log
+    w = v1.WandbLogger("proj", "run", file=str(tmp_path / "w.jsonl"))
+    w.set_config({"lr": 0.1})
+    w.log("loss", 1.0)
+    w.step()
+    assert json.loads(open(tmp_path / "w.jsonl").read())["loss"] == 1.0 and w.config == {"lr": 0.1} and w.name == "run"
+
+    # a chain of same-shaped activations needs two buffers, not one per node; fetched nodes and parameters are never recycled
+    v1ex.reset_graph()
+    x = v1.placeholder_op("mx", [32, 64])
+    wgt = v1.Variable("mw", value=np.zeros((64, 64), np.float32))
+    h = x
+    for _ in range(6):
+        h = v1.relu_op(v1.matmul_op(h, wgt))
+    ex = v1.Executor([h])
+    pool = v1.HetuMemoryPool()
+    plan = pool.plan_graph(ex.graph, [h])
+    nodes = nodes_of_graph(ex.graph)
+    acts = [n for n in nodes if n.type in ("matmul", "unary_act")]
+    assert len(acts) == 12 and plan["buffers"] < len(nodes) and plan["allocated_bytes"] < plan["naive_bytes"]
+    owners = {n.id for n in acts if n.id not in plan["reuse"]}
+    assert len(owners) == 3 and h.id not in plan["reuse"].values() and all(v in {n.id for n in acts} for v in plan["reuse"].values())
+    # replaying the plan never hands a buffer to a node while an unfinished reader still needs it
+    owner_of = {n.id: plan["reuse"].get(n.id, n.id) for n in acts}
+    for i, n in enumerate(acts):
+        for later in acts[i + 1:]:
+            if owner_of[later.id] == owner_of[n.id]:
+                readers = [m for m in acts if n.id in m.inputs]
+                assert all(acts.index(m) < acts.index(later) or m is later for m in readers)
+                break
+    assert pool.test_memory(["gpu0"], {"gpu0": nodes}) and not pool.test_memory(["gpu0"], {"gpu0": nodes}, capacity_bytes=1024)
+    v1ex.reset_graph()
+
+    a, b = v1.stream.create_event_handle(v1.cpu(0)), v1.stream.create_event_handle(v1.cpu(0))
+    a.record()
+    b.record(v1.stream.create_stream_handle(v1.cpu(0)))
+    b.sync()
+    assert b.time_since(a) >= 0
+    ev = v1.stream.CSEvent(None, 3)
+    ev.update_ts(7)
+    assert ev.updated and ev.ts == 7
+    ev.sync()
+    assert not ev.updated
