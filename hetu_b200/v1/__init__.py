@@ -13,7 +13,7 @@ from .executor import (Variable, placeholder_op, Executor, HetuConfig, gradients
                        div_op, minus_op, opposite_op, abs_op, pow_op, rsqrt_op, leaky_relu_op, mish_op, silu_op, where_op, one_hot_op,
                        reduce_max_op, reduce_min_op, concatenate_op, split_op, sum_op, reset_graph)
 from . import initializers, initializers as init, layers, lr_scheduler, metrics, dataloader, onnx  # noqa: F401
-from .dataloader import Dataloader, dataloader_op  # noqa: F401
+from .dataloader import Dataloader, dataloader_op, GNNDataLoaderOp, BatchIndices, RawData  # noqa: F401
 from .optimizer import (SGDOptimizer, MomentumOptimizer, AdaGradOptimizer, AdamOptimizer, AMSGradOptimizer, AdamWOptimizer,  # noqa: F401
                         LambOptimizer)
 from . import optimizer as optim  # noqa: F401  (v1: ht.optim.SGDOptimizer)

@@ -88,3 +88,96 @@ def dataloader_op(dataloaders: Sequence, dtype="float32"):
 def loaders_of(nodes) -> List[DataloaderOp]:
     """the DataloaderOps among the transitive inputs the executor has to feed (all registered ones of the v1 graph)"""
     return list(_REGISTRY.values())
+
+
+class BatchIndices:
+    """the order in which batches are visited, shared by loaders that must stay aligned (features and labels): reshuffled every
+    time batch 0 is requested after a full pass (ref: dataloader.py:10)"""
+
+    def __init__(self, batch_num: int, need_shuffle: bool = False, seed: int = 0):
+        self.batch_num, self.need_shuffle = int(batch_num), bool(need_shuffle)
+        self.all_batch_indices = np.arange(self.batch_num)
+        self.last_key = self.batch_num - 1
+        self.rng = np.random.RandomState(seed)
+
+    def shuffle(self):
+        self.rng.shuffle(self.all_batch_indices)
+
+    def assert_attr(self, dataloader):
+        assert self.batch_num == dataloader.batch_num and self.need_shuffle == dataloader.shuffle
+
+    def __getitem__(self, key):
+        if key == 0 and self.last_key != key:
+            assert self.last_key == self.batch_num - 1, "a pass must finish before the next one starts"
+            if self.need_shuffle:
+                self.shuffle()
+        self.last_key = key
+        return int(self.all_batch_indices[key])
+
+
+class RawData:
+    """one logical array over several chunks (arrays / memmaps with equal trailing dims): rows are addressed globally and gathered
+    from the chunk that holds them, so a dataset larger than memory can stay memory-mapped (ref: dataloader.py:34)"""
+
+    def __init__(self, raw_data, dtype=np.float32, func=None):
+        self.dtype, self.func = dtype, (func or (lambda x: x))
+        chunks = raw_data if isinstance(raw_data, (list, tuple)) else [raw_data]
+        self.raw_data = [self._init_array(c) for c in chunks]
+        self._shape = list(self.raw_data[0].shape)
+        self._offsets = [0, self._shape[0]]
+        for d in self.raw_data[1:]:
+            assert list(d.shape[1:]) == self._shape[1:], "chunks must agree on every dimension but the first"
+            self._shape[0] += d.shape[0]
+            self._offsets.append(self._shape[0])
+
+    def _init_array(self, a):
+        a = self.func(a)
+        if not isinstance(a, (np.memmap, np.ndarray)):
+            return np.array(a, dtype=self.dtype)
+        return a if a.dtype == self.dtype else a.astype(self.dtype)
+
+    shape = property(lambda self: tuple(self._shape))
+
+    def __len__(self):
+        return self._shape[0]
+
+    def __getitem__(self, key):
+        if isinstance(key, (int, np.integer)):
+            c = int(np.searchsorted(self._offsets, key, side="right")) - 1
+            return self.raw_data[c][key - self._offsets[c]]
+        if isinstance(key, slice):
+            key = np.arange(*key.indices(len(self)))
+        key = np.asarray(key)
+        out = np.empty((key.size,) + tuple(self._shape[1:]), self.dtype)
+        which = np.searchsorted(self._offsets, key, side="right") - 1
+        for c in np.unique(which):
+            m = which == c
+            out[m] = self.raw_data[c][key[m] - self._offsets[c]]
+        return out
+
+
+class GNNDataLoaderOp:
+    """double-buffered graph feeder: `GNNDataLoaderOp.step(next_graph)` rotates (current <- next); every instance turns the current
+    graph into its array through `handler` (features, labels, adjacency ...) (ref: dataloader.py:253)"""
+    graph = None
+    nxt_graph = None
+
+    def __init__(self, handler, ctx=None, shape=None, dtype="float32", name="GNNDataloaderOp"):
+        from .executor import _g
+        _g()
+        self.handler, self.name = handler, name
+        self.node = core.placeholder(dtype, list(shape) if shape is not None else [1], name=name)
+        self.dataloaders = {}
+        _GNN_REGISTRY[self.node.id] = self
+
+    desc = property(lambda self: self.name)
+    def get_batch_num(self, name): return None                                  # noqa: E704
+    def get_arr(self, name=None): return self.handler(type(self).graph)         # noqa: E704
+    def get_next_arr(self, name=None): return self.handler(type(self).nxt_graph)   # noqa: E704
+
+    @classmethod
+    def step(cls, graph):
+        cls.graph, cls.nxt_graph = cls.nxt_graph, graph
+
+
+_GNN_REGISTRY: Dict[int, GNNDataLoaderOp] = {}

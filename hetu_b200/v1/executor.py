@@ -280,6 +280,9 @@ class Executor:
         for op in _dl.loaders_of(nodes):
             if op.node.id not in fed and name in op.dataloaders and op.node.graph_id == self.graph.id:
                 feed[op.node] = torch.as_tensor(op.get_arr(name))
+        for op in _dl._GNN_REGISTRY.values():         # graph feeders: the handler turns the current graph into this node's array
+            if op.node.id not in fed and op.node.graph_id == self.graph.id and type(op).graph is not None:
+                feed[op.node] = torch.as_tensor(np.asarray(op.get_arr(name)))
         # an lr scheduler object as the optimizer's learning rate: apply the current value, advance after the step
         for opt in self._optimizers():
             sched = getattr(opt, "v1_scheduler", None)

@@ -145,3 +145,25 @@ def GenHeNormal(): return HeNormalInit()                                  # noqa
 def GenHeUniform(): return HeUniformInit()                                # noqa: E704
 def GenLecunNormal(): return LecunNormalInit()                            # noqa: E704
 def GenLecunUniform(): return LecunUniformInit()                          # noqa: E704
+
+
+class ReversedTruncatedNormalInit(NormalInit):
+    """normal samples from OUTSIDE two standard deviations (|z| >= 2): the tails that TruncatedNormalInit rejects
+    (ref: hetu/v1/src/ops/Initializers.cu reversed_truncated_normal_kernel)"""
+
+    def __call__(self, shape=None, name=None, trainable=True, dtype="float32", ctx=None):
+        from .executor import Variable
+        from .runtime_api import random as _rnd
+        shape = list(shape or self.shape)
+        n = int(np.prod(shape))
+        rng = _rnd.get_np_rand(1)
+        out = np.empty(0, np.float64)
+        while out.size < n:                                      # ~4.6 % of draws land in the tails
+            z = rng.standard_normal(max(4096, 32 * (n - out.size)))
+            out = np.concatenate([out, z[np.abs(z) >= 2.0]])
+        data = (out[:n] * self.stddev + self.mean).astype(np.float32).reshape(shape)
+        return Variable(name or "reversed_truncated_normal_initializer", value=data, trainable=trainable, dtype=dtype)
+
+
+def reversed_truncated_normal(shape, mean=0.0, stddev=1.0, name=None, trainable=True, dtype="float32", ctx=None): return ReversedTruncatedNormalInit(mean, stddev)(shape, name, trainable, dtype)   # noqa: E704,E501
+def GenReversedTruncatedNormal(mean=0.0, stddev=1.0): return ReversedTruncatedNormalInit(mean, stddev)   # noqa: E704

@@ -1009,3 +1009,47 @@ def test_v1_logger_memory_reuse_plan_and_stream_handles(tmp_path):
     assert ev.updated and ev.ts == 7
     ev.sync()
     assert not ev.updated
+
+
+def test_v1_reversed_truncated_normal_raw_data_batch_indices_and_gnn_feeder(tmp_path):
+    """ref: hetu/v1/python/hetu/initializers.py:231, dataloader.py:10,34,253"""
+    import numpy as np
+    import hetu_b200.v1 as v1
+    from hetu_b200.v1 import executor as v1ex
+    v1ex.reset_graph()
+    v1.random.set_random_seed(5)
+    w = v1.init.reversed_truncated_normal([200, 50], mean=1.0, stddev=0.5, name="rtn")
+    gen = v1.init.GenReversedTruncatedNormal(0.0, 1.0)([64], name="rtn2")
+    vals = v1.Executor([w, gen]).run(feed_dict={}, convert_to_numpy_ret_vals=True)
+    z = (vals[0] - 1.0) / 0.5
+    assert np.abs(z).min() >= 2.0 - 1e-5 and abs((z > 0).mean() - 0.5) < 0.05 and np.abs(vals[1]).min() >= 2.0 - 1e-5
+
+    mm = np.memmap(tmp_path / "chunk.bin", dtype=np.float32, mode="w+", shape=(6, 3))
+    mm[:] = np.arange(18).reshape(6, 3) + 100
+    raw = v1.RawData([np.arange(12).reshape(4, 3), mm], dtype=np.float32)
+    assert len(raw) == 10 and raw.shape == (10, 3) and raw[5].tolist() == [103, 104, 105]
+    np.testing.assert_array_equal(raw[[0, 9, 4, 3]], [[0, 1, 2], [115, 116, 117], [100, 101, 102], [9, 10, 11]])
+    np.testing.assert_array_equal(raw[3:6], [[9, 10, 11], [100, 101, 102], [103, 104, 105]])
+    bi = v1.BatchIndices(5, need_shuffle=True, seed=1)
+    first = [bi[k] for k in range(5)]
+    second = [bi[k] for k in range(5)]
+    assert sorted(first) == sorted(second) == list(range(5)) and first != second
+    with pytest.raises(AssertionError):
+        bi[2], bi[0]                                           # a new pass before the previous one finished
+
+    # graph feeder: two nodes (features, normalised adjacency) read the CURRENT graph; step() rotates current <- next
+    v1ex.reset_graph()
+    v1.GNNDataLoaderOp.graph = v1.GNNDataLoaderOp.nxt_graph = None
+    feats = v1.GNNDataLoaderOp(lambda g: g["x"], shape=[4, 2], name="gnn_x")
+    adj = v1.GNNDataLoaderOp(lambda g: g["a"], shape=[4, 4], name="gnn_a")
+    out = v1.matmul_op(adj.node, feats.node)
+    ex = v1.Executor([out])
+    g1 = {"x": np.ones((4, 2), np.float32), "a": np.eye(4, dtype=np.float32) * 2}
+    g2 = {"x": np.full((4, 2), 3.0, np.float32), "a": np.eye(4, dtype=np.float32)}
+    v1.GNNDataLoaderOp.step(g1)
+    v1.GNNDataLoaderOp.step(g2)                               # current = g1, next = g2
+    np.testing.assert_array_equal(ex.run(feed_dict={}, convert_to_numpy_ret_vals=True)[0], np.full((4, 2), 2.0))
+    assert feats.get_next_arr()[0, 0] == 3.0
+    v1.GNNDataLoaderOp.step(None)
+    np.testing.assert_array_equal(ex.run(feed_dict={}, convert_to_numpy_ret_vals=True)[0], np.full((4, 2), 3.0))
+    v1ex.reset_graph()
