@@ -25,7 +25,9 @@ import yaml
 from .ps import PSContext
 
 
-def launch(command: Sequence[str], settings: Dict, log_dir: Optional[str] = None, wait: bool = True, timeout: Optional[float] = None):
+def launch(command, settings, log_dir: Optional[str] = None, wait: bool = True, timeout: Optional[float] = None):
+    if callable(command):                       # v1 form: launch(target, args) -- every role a process of this program
+        return launch_roles(command, settings, timeout)
     shared = {str(k): str(v) for k, v in (settings.get("shared") or {}).items()}
     lc = settings.get("launch") or {}
     n_worker, n_server = int(lc.get("worker", 1)), int(lc.get("server", 1))
@@ -96,3 +98,71 @@ def main(argv=None):
 
 if __name__ == "__main__":
     sys.exit(main())
+
+
+# ---- the function-style launcher of v1 programs (ref: hetu/v1/python/hetu/launcher.py): every role is a process of this program
+_procs: List = []
+
+
+def signal_handler(signum=None, frame=None):
+    print("SIGINT signal caught, stop Training")
+    for p in _procs:
+        if p.is_alive():
+            p.kill()
+    raise SystemExit(0)
+
+
+def start_sched():
+    os.environ["DMLC_ROLE"] = "scheduler"
+    from . import runtime_api as api
+    api.scheduler_init()
+    api.scheduler_finish()
+
+
+def start_server():
+    os.environ["DMLC_ROLE"] = "server"
+    from . import runtime_api as api
+    api.server_init()
+    api.server_finish()
+
+
+def start_worker(target, args):
+    os.environ["DMLC_ROLE"] = "worker"
+    from . import runtime_api as api
+    api.worker_init()
+    target(args)
+    api.worker_finish()
+
+
+def launch_roles(target, args, join_timeout: Optional[float] = None):
+    """`launch(target, args)` of v1: args.config names a yaml with `shared` (DMLC_* environment) and `launch` {worker, server,
+    scheduler}; runs `target(args)` in every worker process next to the server / scheduler roles and waits for all of them.
+    -> exit codes"""
+    import multiprocessing as mp
+
+    import yaml
+    settings = yaml.safe_load(open(args.config).read())
+    for k, v in (settings.get("shared") or {}).items():
+        os.environ[str(k)] = str(v)
+    lc = settings.get("launch") or {}
+    ctx = mp.get_context("spawn")
+    del _procs[:]
+    if int(lc.get("scheduler", 0)) != 0:
+        _procs.append(ctx.Process(target=start_sched))
+    for _ in range(int(lc.get("server", 0))):
+        _procs.append(ctx.Process(target=start_server))
+    for _ in range(int(lc.get("worker", 1))):
+        _procs.append(ctx.Process(target=start_worker, args=(target, args)))
+    signal.signal(signal.SIGINT, signal_handler)
+    for i, p in enumerate(_procs):
+        p.start()
+        if i == 0 and int(lc.get("scheduler", 0)) != 0:
+            import time
+            time.sleep(1.0)                     # the scheduler listens before the others dial it
+    for p in _procs:
+        p.join(join_timeout)
+    codes = [p.exitcode for p in _procs]
+    for p in _procs:
+        if p.is_alive():
+            p.kill()
+    return codes

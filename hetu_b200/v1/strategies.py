@@ -364,3 +364,29 @@ def strategy_to_ds_parallel_config(strategy: Strategy, num_layers: int, hidden: 
     cfg["searched_by"] = type(strategy).__name__
     cfg["estimated_step_s"] = strategy.total_time(layers, placements)
     return cfg
+
+
+class BaseSearchingStrategy(Strategy):
+    """what the searching strategies share in v1: a found plan can be saved and a saved plan loaded instead of searching again
+    (`save_path` / `load_path`).  Wraps any searcher: `BaseSearchingStrategy(FlexFlowSearching(8), save_path=...)`.
+    (ref: hetu/v1/python/hetu/distributed_strategies/base.py BaseSearchingStrategy)"""
+
+    def __init__(self, searcher: Strategy, save_path: Optional[str] = None, load_path: Optional[str] = None):
+        super().__init__(searcher.n, searcher.hw)
+        self.searcher, self.save_path, self.load_path = searcher, save_path, load_path
+        self.loaded = False
+
+    def assign(self, layers):
+        import json
+        import os
+        if self.load_path and os.path.exists(self.load_path):
+            raw = json.load(open(self.load_path))
+            assert len(raw["placements"]) == len(layers), "the saved plan belongs to a model with a different number of layers"
+            self.loaded = True
+            return [Placement(list(p["devices"]), {k: int(v) for k, v in p["split"].items()}) for p in raw["placements"]]
+        plan = self.searcher.assign(layers)
+        if self.save_path:
+            with open(self.save_path, "w") as f:
+                json.dump({"strategy": type(self.searcher).__name__, "num_devices": self.n, "estimated_step_s": self.total_time(layers, plan),
+                           "placements": [{"devices": list(p.devices), "split": dict(p.split)} for p in plan]}, f, indent=1)
+        return plan

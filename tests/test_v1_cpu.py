@@ -1053,3 +1053,46 @@ def test_v1_reversed_truncated_normal_raw_data_batch_indices_and_gnn_feeder(tmp_
     v1.GNNDataLoaderOp.step(None)
     np.testing.assert_array_equal(ex.run(feed_dict={}, convert_to_numpy_ret_vals=True)[0], np.full((4, 2), 3.0))
     v1ex.reset_graph()
+
+
+def test_v1_function_style_launcher_and_saved_search_plans(tmp_path):
+    """ref: hetu/v1/python/hetu/launcher.py (launch(target, args): scheduler + server + workers as processes of one program) and
+    distributed_strategies/base.py (BaseSearchingStrategy save / load)"""
+    import argparse
+    import json
+    import os
+    import sys
+    import yaml
+    from dist_utils import free_port
+    from hetu_b200.v1 import launcher
+    from hetu_b200.v1 import strategies as S
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests", "workers"))     # stays until the roles have started: spawn hands sys.path to the children
+    import v1_launch_roles_target as target_mod
+    cfg = tmp_path / "local.yml"
+    cfg.write_text(yaml.safe_dump({"shared": {"DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": free_port(), "DMLC_NUM_WORKER": 2, "DMLC_NUM_SERVER": 1,
+                                              "HETU_B200_FORCE_CPU": 1, "PYTHONPATH": root + os.pathsep + os.path.join(root, "tests", "workers")},
+                                   "launch": {"worker": 2, "server": 1, "scheduler": 1}}))
+    keep = dict(os.environ)
+    try:
+        for k in ("HETU_PS_SCHEDULER", "HETU_PS_ADDRESS"):
+            os.environ.pop(k, None)
+        codes = launcher.launch(target_mod.train, argparse.Namespace(config=str(cfg), out=str(tmp_path)), timeout=60)
+    finally:
+        os.environ.clear()
+        os.environ.update(keep)
+        sys.path.remove(os.path.join(root, "tests", "workers"))
+    assert codes == [0, 0, 0, 0], codes
+    for w in range(2):
+        r = json.load(open(tmp_path / f"worker{w}.json"))
+        assert r == {"w": [-2.0] * 4, "role": "worker"}
+
+    layers = [S.LayerSpec(f"l{i}", flops=4e12, params=2e8, act=6e7) for i in range(6)] if hasattr(S, "LayerSpec") else None
+    if layers is not None:
+        path = str(tmp_path / "plan.json")
+        first = S.BaseSearchingStrategy(S.FlexFlowSearching(8, budget=100), save_path=path)
+        plan = first.assign(layers)
+        saved = json.load(open(path))
+        assert saved["strategy"] == "FlexFlowSearching" and len(saved["placements"]) == 6 and saved["estimated_step_s"] > 0
+        again = S.BaseSearchingStrategy(S.FlexFlowSearching(8, budget=100, seed=9), load_path=path)
+        assert [p.key() for p in again.assign(layers)] == [p.key() for p in plan] and again.loaded and not first.loaded
