@@ -355,10 +355,154 @@ class CafeEmbedding(AdaptiveEmbedding):
         return out.reshape(ids.shape)
 
 
+class AutoSrhEmbedding(_Base):
+    """AutoSrh: rows are grouped (by frequency) into `nsplit` groups, every group has a learnable per-dimension gate alpha; after the
+    search the small gates are pruned and the table retrained with the mask frozen (`retrain()`), which is what makes it sparse
+    (ref: methods/layers/autosrh.py AutoSrhEmbedding / AutoSrhRetrainEmbedding)"""
+
+    def __init__(self, num_embeddings, dim, nsplit=4, group_indices=None, name="autosrh"):
+        super().__init__(num_embeddings, dim)
+        self.nsplit = int(nsplit)
+        self.weight = _table(num_embeddings, dim, f"{name}_weight")
+        groups = np.asarray(group_indices if group_indices is not None else np.arange(num_embeddings) * nsplit // max(num_embeddings, 1), np.int64)
+        assert groups.shape == (num_embeddings,) and groups.max() < nsplit
+        self.group_np = groups
+        self.groups = from_numpy(groups.reshape(-1, 1).astype(np.float32))
+        self.alpha = parallel_parameter(ones_initializer(), [self.nsplit, dim], None, requires_grad=True, name=f"{name}_alpha")
+        self.frozen_mask = None
+
+    def forward(self, ids):
+        f, shape = self._flat(ids)
+        w = ops.embedding_lookup(self.weight, f)
+        gid = ops.cast(ops.reshape(ops.embedding_lookup(self.groups, f), [-1]), "int64")
+        alpha = self.alpha if self.frozen_mask is None else self.frozen_mask
+        return self._shape_out(w * ops.embedding_lookup(alpha, gid), shape)
+
+    def l1_penalty(self):
+        """the sparsity pressure of the search phase: sum |alpha|"""
+        return ops.sum(ops.abs(self.alpha))
+
+    def retrain(self, alpha_values: np.ndarray, keep_rate: float):
+        """end of the search: keep the `keep_rate` largest gates (by magnitude), freeze them as a 0/1 mask"""
+        a = np.abs(np.asarray(alpha_values, np.float32))
+        k = max(int(round(a.size * keep_rate)), 1)
+        thr = np.sort(a.reshape(-1))[-k]
+        self.mask_np = (a >= thr).astype(np.float32)
+        self.frozen_mask = from_numpy(self.mask_np)
+        return float(self.mask_np.mean())
+
+    def num_parameters(self) -> int:
+        if self.frozen_mask is None:
+            return super().num_parameters()
+        mask = self.mask_np
+        return int(sum(int((self.group_np == g).sum()) * int(mask[g].sum()) for g in range(self.nsplit)))
+
+
+class DedupEmbedding(_Base):
+    """block-level de-duplication of a trained table: blocks of `nemb_per_block` consecutive rows that are (near-)identical are stored
+    once; `remap[block]` names the stored block (ref: methods/layers/deduplication.py; the LSH grouping of methods/scheduler)"""
+
+    def __init__(self, num_embeddings, dim, table: np.ndarray = None, nemb_per_block=4, tolerance=0.0, trainable=True, name="dedup"):
+        super().__init__(num_embeddings, dim)
+        assert table is not None and tuple(table.shape) == (num_embeddings, dim), "DedupEmbedding compresses an existing table"
+        self.block = int(nemb_per_block)
+        nblocks = -(-num_embeddings // self.block)
+        pad = np.zeros((nblocks * self.block, dim), np.float32)
+        pad[:num_embeddings] = table
+        blocks = pad.reshape(nblocks, self.block * dim)
+        stored, remap = [], np.zeros(nblocks, np.int64)
+        for b in range(nblocks):
+            hit = -1
+            for j, sblk in enumerate(stored):
+                if np.abs(sblk - blocks[b]).max() <= tolerance:
+                    hit = j
+                    break
+            if hit < 0:
+                stored.append(blocks[b])
+                hit = len(stored) - 1
+            remap[b] = hit
+        self.remap_np = remap
+        self.remap = from_numpy(remap.reshape(-1, 1).astype(np.float32))
+        data = np.stack(stored).reshape(len(stored) * self.block, dim)
+        from ...core import provided_initializer
+        self.weight = parallel_parameter(provided_initializer(data), list(data.shape), None, requires_grad=bool(trainable), name=f"{name}_weight")
+
+    def forward(self, ids):
+        f, shape = self._flat(ids)
+        fl = ops.cast(f, "float32")
+        blk = ops.floor(fl / float(self.block))
+        within = fl - blk * float(self.block)
+        stored_blk = ops.reshape(ops.embedding_lookup(self.remap, ops.cast(blk, "int64")), [-1])
+        real = ops.cast(stored_blk * float(self.block) + within, "int64")
+        return self._shape_out(ops.embedding_lookup(self.weight, real), shape)
+
+
+class QuantizedEmbedding(_Base):
+    """post-training / quantisation-aware uniform quantisation to `digit` bits: one (scale, zero point) for the table, or a pair per
+    row (`use_qparam`); the forward fake-quantises with a straight-through gradient so the table keeps training
+    (ref: methods/layers/quantize.py + src/ops/QuantizeEmbedding.cu)"""
+
+    def __init__(self, num_embeddings, dim, digit=8, scale=0.01, middle=0.0, use_qparam=False, name="quant"):
+        super().__init__(num_embeddings, dim)
+        assert digit in (8, 16)
+        self.digit, self.scale, self.middle, self.use_qparam = int(digit), float(scale), float(middle), bool(use_qparam)
+        self.weight = _table(num_embeddings, dim, f"{name}_weight")
+
+    def forward(self, ids):
+        f, shape = self._flat(ids)
+        w = ops.embedding_lookup(self.weight, f)
+        levels = float(2 ** self.digit - 1)
+        if self.use_qparam:
+            lo, hi = ops.min(w, [-1], True), ops.max(w, [-1], True)
+            step = (hi - lo) / levels
+            step = step + ops.equal(step, 0.0)
+            q = ops.floor((w - lo) / step + 0.5) * step + lo
+        else:
+            half = float(2 ** (self.digit - 1))
+            q = ops.clamp(ops.floor((w - self.middle) / self.scale + 0.5), -half, half - 1.0) * self.scale + self.middle
+        return self._shape_out(w + ops.stop_gradient(q - w), shape)
+
+    def num_parameters(self) -> int:
+        """in fp32 words: `digit` bits per entry (+ two floats per row with per-row parameters)"""
+        return int(math.ceil(self.num_embeddings * self.dim * self.digit / 32.0)) + (2 * self.num_embeddings if self.use_qparam else 2)
+
+
+class SparseEmbedding(_Base):
+    """inference form of a pruned table: only the non-zero entries are kept (CSR); lookups gather rows from the sparse matrix
+    (ref: methods/layers/sparse.py -- DeepLight / PEP / AutoSrh export to it)"""
+
+    def __init__(self, num_embeddings, dim, table: np.ndarray = None, form="csr", name="sparse"):
+        super().__init__(num_embeddings, dim)
+        assert table is not None and tuple(table.shape) == (num_embeddings, dim), "SparseEmbedding is built from a pruned table"
+        self.form = form
+        t = np.asarray(table, np.float32)
+        self.nnz = int((t != 0).sum())
+        self.indptr = np.concatenate([[0], np.cumsum((t != 0).sum(1))]).astype(np.int64)
+        self.indices = np.nonzero(t)[1].astype(np.int64)
+        self.values = t[t != 0].astype(np.float32)
+        self._dense = from_numpy(t)                                  # rows are rebuilt from (indptr, indices, values) in `rows()`
+
+    def rows(self, ids: np.ndarray) -> np.ndarray:
+        """host-side CSR gather (what the serving path does)"""
+        out = np.zeros((ids.size, self.dim), np.float32)
+        for k, i in enumerate(np.asarray(ids).reshape(-1)):
+            lo, hi = self.indptr[i], self.indptr[i + 1]
+            out[k, self.indices[lo:hi]] = self.values[lo:hi]
+        return out.reshape(tuple(np.asarray(ids).shape) + (self.dim,))
+
+    def forward(self, ids):
+        f, shape = self._flat(ids)
+        return self._shape_out(ops.embedding_lookup(self._dense, f), shape)
+
+    def num_parameters(self) -> int:
+        return int(2 * self.nnz + self.num_embeddings + 1)           # values + column indices + row pointers
+
+
 METHODS = {"hash": HashEmbedding, "compo": CompositionalEmbedding, "qr": CompositionalEmbedding, "tt": TensorTrainEmbedding,
            "dhe": DeepHashEmbedding, "robe": RobeEmbedding, "dpq": ProductQuantizedEmbedding, "mgqe": MGQEmbedding, "mde": MixedDimEmbedding,
            "autodim": AutoDimEmbedding, "pep": PrunedEmbedding, "deeplight": DeepLightEmbedding, "optembed": OptEmbedEmbedding,
-           "alpt": ALPTEmbedding, "adapt": AdaptiveEmbedding, "cafe": CafeEmbedding}
+           "alpt": ALPTEmbedding, "adapt": AdaptiveEmbedding, "cafe": CafeEmbedding, "autosrh": AutoSrhEmbedding, "dedup": DedupEmbedding,
+           "quantize": QuantizedEmbedding, "sparse": SparseEmbedding}
 
 
 def build_compressed_embedding(method: str, num_embeddings: int, dim: int, **kw):

@@ -78,6 +78,75 @@ def test_embedding_compression_methods_forward_backward(method, kw):
         assert emb.compression_ratio() > 1.5
 
 
+def test_autosrh_dedup_quantized_and_sparse_embeddings():
+    """ref: tools/EmbeddingMemoryCompression/methods/layers/{autosrh,deduplication,quantize,sparse}.py"""
+    rng = np.random.RandomState(0)
+    N, D = 64, 8
+    ids_np = rng.randint(0, N, (5, 3))
+    ids = torch.as_tensor(ids_np)
+    # AutoSrh: gates train with the table; after retrain() only the kept gates pass and the size accounts for the mask
+    with ht.graph("define_and_run", create_new=True) as g:
+        emb = build_compressed_embedding("autosrh", N, D, nsplit=4)
+        I = ht.placeholder("int64", [5, 3], name="ids")
+        e = emb(I)
+        loss = ht.mean(e * e, [0, 1, 2]) + emb.l1_penalty() * 1e-3
+        train = ht.SGDOptimizer(lr=0.1).minimize(loss)
+        a0 = g.get_param(emb.alpha).clone()
+        g.run(loss, [loss, train], {I: ids})
+        assert not torch.equal(g.get_param(emb.alpha), a0)
+        full = emb.num_parameters()
+        alpha = rng.rand(4, D).astype(np.float32)
+        kept = emb.retrain(alpha, keep_rate=0.25)
+        assert abs(kept - 0.25) < 0.05 and emb.num_parameters() < 0.4 * full
+        masked = g.run(None, [emb(I)], {I: ids})[0]
+        w = g.get_param(emb.weight)
+        thr = np.sort(alpha.reshape(-1))[-8]
+        want = w[ids_np.reshape(-1)].numpy() * (alpha >= thr)[emb.group_np[ids_np.reshape(-1)]]
+        np.testing.assert_allclose(masked.reshape(-1, D).numpy(), want, rtol=1e-6, atol=1e-7)
+    # Dedup: identical blocks are stored once and every id still reads its original row
+    table = rng.randn(N, D).astype(np.float32)
+    table[8:12] = table[0:4]
+    table[40:44] = table[0:4]
+    with ht.graph("define_and_run", create_new=True) as g:
+        emb = build_compressed_embedding("dedup", N, D, table=table, nemb_per_block=4)
+        I = ht.placeholder("int64", [5, 3], name="ids")
+        probe = torch.as_tensor(np.array([[0, 9, 42], [3, 11, 43], [5, 20, 63], [8, 40, 1], [10, 41, 2]]))
+        out = g.run(None, [emb(I)], {I: probe})[0]
+        np.testing.assert_allclose(out.numpy(), table[probe.numpy()], rtol=1e-6)
+        assert emb.weight.shape[0] == N - 8 and emb.compression_ratio() > 1.1 and emb.remap_np[2] == emb.remap_np[10] == 0
+    # Quantized: outputs sit on the grid, gradients pass straight through to the table
+    for kw in ({"digit": 8, "scale": 0.01, "middle": 0.0}, {"digit": 16, "scale": 1e-4}, {"digit": 8, "use_qparam": True}):
+        with ht.graph("define_and_run", create_new=True) as g:
+            emb = build_compressed_embedding("quantize", N, D, **kw)
+            I = ht.placeholder("int64", [5, 3], name="ids")
+            e = emb(I)
+            loss = ht.sum(e, [0, 1, 2])
+            gw = ht.gradients(loss, [emb.weight])[0]
+            out, grad = g.run(loss, [e, gw], {I: ids})
+            w = g.get_param(emb.weight).numpy()[ids_np.reshape(-1)]
+            got = out.reshape(-1, D).numpy()
+            if kw.get("use_qparam"):
+                step = (w.max(1, keepdims=True) - w.min(1, keepdims=True)) / 255.0
+                assert np.abs(got - w).max() <= step.max() / 2 + 1e-6
+                k = (got - w.min(1, keepdims=True)) / step
+            else:
+                assert np.abs(got - w).max() <= kw["scale"] / 2 + 1e-6
+                k = got / kw["scale"]
+            assert np.abs(k - np.round(k)).max() < 1e-2
+            counts = np.bincount(ids_np.reshape(-1), minlength=N).astype(np.float32)
+            np.testing.assert_allclose(grad.numpy(), np.repeat(counts[:, None], D, 1), rtol=1e-6)
+            assert emb.compression_ratio() > (3.5 if kw["digit"] == 8 and not kw.get("use_qparam") else 1.9)
+    # Sparse: CSR storage of a pruned table, the graph lookup and the host gather agree
+    pruned = table * (rng.rand(N, D) < 0.2)
+    with ht.graph("define_and_run", create_new=True) as g:
+        emb = build_compressed_embedding("sparse", N, D, table=pruned)
+        I = ht.placeholder("int64", [5, 3], name="ids")
+        out = g.run(None, [emb(I)], {I: ids})[0]
+        np.testing.assert_allclose(out.numpy(), pruned[ids_np], rtol=1e-6)
+        np.testing.assert_allclose(emb.rows(ids_np), pruned[ids_np], rtol=1e-6)
+        assert emb.nnz == int((pruned != 0).sum()) and emb.compression_ratio() > 1.5
+
+
 def test_cafe_hot_sketch_promotes_frequent_ids():
     with ht.graph("define_and_run", create_new=True):
         emb = METHODS["cafe"](1000, 8, hot=4, buckets=32)
