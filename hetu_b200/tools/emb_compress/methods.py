@@ -360,7 +360,7 @@ class AutoSrhEmbedding(_Base):
     search the small gates are pruned and the table retrained with the mask frozen (`retrain()`), which is what makes it sparse
     (ref: methods/layers/autosrh.py AutoSrhEmbedding / AutoSrhRetrainEmbedding)"""
 
-    def __init__(self, num_embeddings, dim, nsplit=4, group_indices=None, name="autosrh"):
+    def __init__(self, num_embeddings, dim, nsplit=4, group_indices=None, name="autosrh", frozen_alpha=None, keep_rate=None):
         super().__init__(num_embeddings, dim)
         self.nsplit = int(nsplit)
         self.weight = _table(num_embeddings, dim, f"{name}_weight")
@@ -370,6 +370,8 @@ class AutoSrhEmbedding(_Base):
         self.groups = from_numpy(groups.reshape(-1, 1).astype(np.float32))
         self.alpha = parallel_parameter(ones_initializer(), [self.nsplit, dim], None, requires_grad=True, name=f"{name}_alpha")
         self.frozen_mask = None
+        if frozen_alpha is not None:
+            self.retrain(frozen_alpha, float(keep_rate if keep_rate is not None else 0.5))
 
     def forward(self, ids):
         f, shape = self._flat(ids)
@@ -410,22 +412,23 @@ class DedupEmbedding(_Base):
         pad = np.zeros((nblocks * self.block, dim), np.float32)
         pad[:num_embeddings] = table
         blocks = pad.reshape(nblocks, self.block * dim)
-        stored, remap = [], np.zeros(nblocks, np.int64)
-        for b in range(nblocks):
-            hit = -1
-            for j, sblk in enumerate(stored):
-                if np.abs(sblk - blocks[b]).max() <= tolerance:
-                    hit = j
-                    break
-            if hit < 0:
-                stored.append(blocks[b])
-                hit = len(stored) - 1
-            remap[b] = hit
+        remap, stored = self.group_blocks(blocks, tolerance)
         self.remap_np = remap
         self.remap = from_numpy(remap.reshape(-1, 1).astype(np.float32))
         data = np.stack(stored).reshape(len(stored) * self.block, dim)
         from ...core import provided_initializer
         self.weight = parallel_parameter(provided_initializer(data), list(data.shape), None, requires_grad=bool(trainable), name=f"{name}_weight")
+
+    @staticmethod
+    def group_blocks(blocks: np.ndarray, tolerance: float):
+        """-> (remap [nblocks], stored blocks): blocks whose entries fall in the same cells of a grid of width 2 * tolerance share one
+        stored copy (the first seen); tolerance 0 merges exact duplicates only"""
+        keys = blocks if tolerance <= 0 else np.round(blocks / (2.0 * tolerance))
+        _, first, inverse = np.unique(np.ascontiguousarray(keys), axis=0, return_index=True, return_inverse=True)
+        order = np.argsort(first)                                     # stored blocks keep their order of first appearance
+        rank = np.empty_like(order)
+        rank[order] = np.arange(order.size)
+        return rank[inverse.reshape(-1)].astype(np.int64), [blocks[i] for i in first[order]]
 
     def forward(self, ids):
         f, shape = self._flat(ids)

@@ -170,6 +170,50 @@ def _pep_schedule() -> Schedule:
     return s
 
 
+_POST_TRAINING = ("dedup", "sparse", "quantize")     # compress a table that was trained at full size (methods/scheduler/{compressor,switchinference}.py)
+
+
+def _post_training_schedule(method: str, rate: float, kwargs: Dict) -> Schedule:
+    def compress(tr) -> Dict:
+        table = tr.value_of(tr.model.embedding.weight)
+        if method == "sparse":                                       # magnitude pruning down to the budget of a CSR table (2 words / entry)
+            keep = max(int((table.size * rate - table.shape[0] - 1) / 2.0), 1)      # values + column ids, after the row pointers
+            thr = np.sort(np.abs(table).reshape(-1))[-keep]
+            tr.schedule.report["sparsity"] = float((np.abs(table) < thr).mean())
+            return {"table": table * (np.abs(table) >= thr)}
+        if method == "dedup":                                        # widen the grid until the stored blocks fit the budget
+            from .methods import DedupEmbedding
+            block = int(kwargs.get("nemb_per_block", 4))
+            nblocks = -(-table.shape[0] // block)
+            pad = np.zeros((nblocks * block, table.shape[1]), np.float32)
+            pad[:table.shape[0]] = table
+            blocks = pad.reshape(nblocks, -1)
+            lo, hi = 0.0, float(np.abs(table).max()) + 1e-6
+            for _ in range(20):
+                mid = 0.5 * (lo + hi)
+                if len(DedupEmbedding.group_blocks(blocks, mid)[1]) > rate * nblocks:
+                    lo = mid
+                else:
+                    hi = mid
+            tr.schedule.report["tolerance"] = hi
+            return {"table": table, "nemb_per_block": block, "tolerance": hi}
+        tr.schedule.report["digit"] = int(kwargs.get("digit", 8))
+        span = float(np.abs(table).max()) or 1.0
+        tr.trained_table = table
+        return {"digit": int(kwargs.get("digit", 8)), "scale": 2.0 * span / (2 ** int(kwargs.get("digit", 8)) - 1), "middle": 0.0}
+    s = Schedule(stages=2, between_stages=compress, stage2_method=method)
+    return s
+
+
+def _autosrh_schedule(rate: float) -> Schedule:
+    def prune(tr) -> Dict:
+        emb = tr.embedding
+        alpha = tr.value_of(emb.alpha)
+        tr.schedule.report["alpha_abs_mean"] = float(np.abs(alpha).mean())
+        return {"nsplit": emb.nsplit, "group_indices": emb.group_np, "frozen_alpha": alpha, "keep_rate": rate}
+    return Schedule(stages=2, between_stages=prune, stage2_method="autosrh")
+
+
 def _cafe_schedule() -> Schedule:
     def after(tr, step, out):
         emb: CafeEmbedding = tr.embedding
@@ -216,12 +260,18 @@ class CompressionTrainer:
             return s
         if m == "adapt":
             return _adapt_schedule(self.data, self.kwargs.get("hot", 1))
+        if m == "autosrh":
+            return _autosrh_schedule(float(self.kwargs.pop("keep_rate", getattr(self, "rate", None) or 0.5)))
+        if m in _POST_TRAINING:
+            return _post_training_schedule(m, float(getattr(self, "rate", None) or 0.5), self.kwargs)
         return Schedule()
 
     # -- graph ----------------------------------------------------------------------------------------------------
     def _build(self, method: Optional[str], kwargs: Dict):
         kw = dict(kwargs)
         dim = int(kw.pop("_dim_override", self.dim))
+        if self.stage == 0 and method in _POST_TRAINING:             # these compress a trained table: stage 1 trains the full one
+            method, kw = None, {}
         with core.graph("define_and_run", create_new=True) as g:
             self.embedding = build_compressed_embedding(method, self.N, dim, **kw) if method else None
             if method == "optembed":
@@ -305,6 +355,9 @@ class CompressionTrainer:
                 carried = sched
                 self._build(sched.stage2_method, kw2)
                 self.method_stage2 = sched.stage2_method
+                table = getattr(self, "trained_table", None)         # post-training quantisation starts from the trained values
+                if table is not None and hasattr(self.embedding, "weight") and tuple(self.embedding.weight.shape) == tuple(table.shape):
+                    self.assign(self.embedding.weight, table)
                 self.schedule = _deeplight_schedule(every=10 ** 9) if sched.stage2_method == "deeplight" else Schedule()
                 self.schedule.report = carried.report                # keep what stage 1 found
                 if carried.after_step is not None and sched.stage2_method == "deeplight":

@@ -1096,3 +1096,19 @@ def test_v1_function_style_launcher_and_saved_search_plans(tmp_path):
         assert saved["strategy"] == "FlexFlowSearching" and len(saved["placements"]) == 6 and saved["estimated_step_s"] > 0
         again = S.BaseSearchingStrategy(S.FlexFlowSearching(8, budget=100, seed=9), load_path=path)
         assert [p.key() for p in again.assign(layers)] == [p.key() for p in plan] and again.loaded and not first.loaded
+
+
+def test_embedding_compression_post_training_and_autosrh_schedules():
+    """ref: tools/EmbeddingMemoryCompression/methods/scheduler/{compressor,switchinference,deduplication,quantize,autosrh}.py -- train
+    the full table, compress it to the requested rate (prune to CSR / merge near-identical blocks / quantise), keep training; AutoSrh
+    searches its gates then retrains under the frozen mask"""
+    from hetu_b200.tools.emb_compress.trainer import CompressionTrainer
+    common = dict(num_embeddings=1200, dim=8, num_fields=4, num_dense=3, batch_size=128, lr=0.02)
+    r = CompressionTrainer("sparse", "wdl", compress_rate=0.3, **common).run(steps=30, eval_batches=2)
+    assert r["stage1"]["ratio"] == 1.0 and 2.5 < r["ratio"] < 4.5 and r["schedule"]["sparsity"] > 0.8 and r["auc"] > 0.5
+    r = CompressionTrainer("dedup", "wdl", compress_rate=0.5, **common).run(steps=30, eval_batches=2)
+    assert 1.6 < r["ratio"] < 2.6 and r["schedule"]["tolerance"] > 0 and np.isfinite(r["stage2_loss"][1])
+    r = CompressionTrainer("quantize", "wdl", compress_rate=0.25, **common).run(steps=30, eval_batches=2)
+    assert 3.5 < r["ratio"] <= 4.0 and r["schedule"]["digit"] == 8 and abs(r["stage2_loss"][0] - r["stage1_loss"][1]) < 0.15
+    r = CompressionTrainer("autosrh", "wdl", compress_rate=0.25, method_kwargs={"nsplit": 4}, **common).run(steps=30, eval_batches=2)
+    assert r["stage1"]["ratio"] <= 1.0 and 3.0 < r["ratio"] < 5.0 and "alpha_abs_mean" in r["schedule"]
