@@ -52,6 +52,10 @@ TABLE = {
     "rpc.kv_store.producer_consumer": [("rpc.kv_store", ["ProducerConsumer"])],
     "rpc.kv_store.const": [("rpc.kv_store", ["TIMEOUT", "DEFAULT_PORT"])],
     "engine.sft_config": [("engine.trainer_config", ["SFTConfig"])],
+    "_binding": [("tools", [])],
+    "_binding.codegen": [("tools", [])],
+    "_binding.codegen.gen_py_ops": [("tools.gen_py_ops", ["gen_ops", "gen_stubs", "load_manifest", "check_manifest", "dump_registry", "main"])],
+    "_binding.codegen.args_bridge": [("tools.gen_py_ops", ["ArgType", "parse_args"])],
     "engine.utils": [("engine.strategy", ["Args", "TrainerCtxs", "TrainerDatasetArgs", "TrainerStrategyArgs", "TrainerCommArgs", "TrainerCommAllArgs",
                                           "TrainerEnvs"])],
     "data.tokenizers.utils": [("data.tokenizers", ["SpecialToken", "BaseTokenizer"])],

@@ -82,10 +82,10 @@ def test_reference_module_paths_resolve_under_the_hetu_alias():
              "hetu.rpc.pssh_start", "hetu.rpc.pssh_start_config", "hetu.rpc.pssh_start_elastic", "hetu.rpc.local_start", "hetu.rpc.pssh_workers",
              "hetu.rpc.elastic_arg_parser", "hetu.rpc.kv_store", "hetu.rpc.heturpc_elastic_server", "hetu.rpc.heturpc_polling_server",
              "hetu.rpc.heturpc_async_server"]
-    # every python module of the reference resolves (only its op-binding code generator has no counterpart): facades for the finer
+    # every python module of the reference resolves, its op-manifest tooling included: facades for the finer
     # grained reference layout -- nn.modules.*, nn.functional / init / parameter, optim.{optimizer,sgd}, engine.{utils,sft_config},
     # models.utils.*, data.tokenizers.{utils,pretrained_tokenizer}, rpc.kv_store.{client,server,const,producer_consumer}
-    more = ["hetu.nn.modules", "hetu.nn.modules.linear", "hetu.nn.modules.activation", "hetu.nn.modules.parallel_multi_ds", "hetu.nn.modules.parallel_utils",
+    more = ["hetu._binding.codegen.gen_py_ops", "hetu._binding.codegen.args_bridge", "hetu.nn.modules", "hetu.nn.modules.linear", "hetu.nn.modules.activation", "hetu.nn.modules.parallel_multi_ds", "hetu.nn.modules.parallel_utils",
             "hetu.nn.modules.container", "hetu.nn.functional", "hetu.nn.init", "hetu.nn.parameter", "hetu.optim.optimizer", "hetu.optim.sgd",
             "hetu.engine.utils", "hetu.engine.sft_config", "hetu.models.utils.model_utils", "hetu.models.utils.config_utils", "hetu.models.utils.hub",
             "hetu.models.utils.common_utils", "hetu.data.tokenizers.utils", "hetu.data.tokenizers.pretrained_tokenizer", "hetu.rpc.kv_store.client",
@@ -191,3 +191,30 @@ def test_galvatron_runtime_validates_describes_builds_and_checks_a_plan(tmp_path
     with ht.graph("define_and_run", create_new=True):
         model, cfg, run_kw = one.build(GPTLMHeadModel, GPTConfig(vocab_size=64, n_positions=16, n_embd=32, n_layer=2, n_head=2))
     assert run_kw == {"num_micro_batches": 2, "grad_scale": 1.0} and cfg["blocks"]["blocks1"]["recompute"] == [True]
+
+
+def test_op_manifest_tooling_parses_checks_and_emits_stubs(tmp_path):
+    """ref: python/hetu/_binding/codegen/{gen_py_ops,args_bridge}.py + ops.yml -- the manifest format is parsed, checked against the
+    framework's Python surface, and turned into editor stubs; the C++ registry can be dumped as a manifest"""
+    import yaml
+    from hetu._binding.codegen.args_bridge import parse_args
+    from hetu._binding.codegen.gen_py_ops import dump_registry, gen_ops
+    a = parse_args("Tensor input, HTAxes axes=None, bool keepdims=false, List[int] pads=[0, 0]")
+    assert [(x.type_str, x.name, x.default) for x in a] == [("Tensor", "input", None), ("HTAxes", "axes", "None"), ("bool", "keepdims", "false"),
+                                                           ("List[int]", "pads", "[0, 0]")]
+    assert a[2].signature() == "keepdims: bool = False" and a[0].py_type == "Tensor"
+    manifest = [{"name": "add", "op": "AddElewiseOp", "args": "Tensor input, Tensor other", "self": "input"},
+                {"name": "add", "op": "AddByConstOp", "args": "Tensor tensor, float value", "self": "tensor"},
+                {"name": "relu", "op": "ReluOp", "args": "Tensor input", "self": "input"},
+                {"name": "no_such_op_anywhere", "op": "NopeOp", "args": "Tensor x"}]
+    src = tmp_path / "ops.yml"
+    src.write_text(yaml.safe_dump(manifest))
+    rep = gen_ops(str(src), str(tmp_path / "out"))
+    assert rep["entries"] == 4 and rep["missing"] == ["no_such_op_anywhere"] and rep["bad_kwargs"] == []
+    stub = (tmp_path / "out" / "ops.pyi").read_text()
+    assert stub.count("@overload") == 2 and "def relu(input: Tensor, **op_meta: Any) -> Tensor: ...   # ReluOp" in stub
+    assert "    def add(self, other: Tensor, **op_meta: Any) -> Tensor: ..." in stub
+    compile(stub, "ops.pyi", "exec")
+    reg = yaml.safe_load((tmp_path / "out" / "registry.yml").read_text())
+    names = {r["op"] for r in reg}
+    assert {"matmul", "adam_update", "rule_update", "pipeline_send", "pipeline_recv", "comm"} <= names and len(dump_registry()) == len(reg)
