@@ -193,7 +193,8 @@ class Executor:
     def _ps_context(self):
         if self.ps is None:
             from . import ps as _ps
-            self.ps = _ps.connect()
+            from .runtime_api import get_worker_communicate
+            self.ps = get_worker_communicate() or _ps.connect()      # worker_init() already registered this process
         return self.ps
 
     def _ps_plan(self, opt):

@@ -301,8 +301,8 @@ def allreduceCommunicatep2p_op(node, comm=None): return ops.all_reduce(node)    
 def parameterServerCommunicate_op(node, parameter, optimizer):                                             # noqa: N802
     """push the gradient `node` of `parameter` to the server, which applies `optimizer` (the executor's comm_mode='PS' builds this
     itself; explicit use marks one parameter for the server path)"""
-    from .optimizer import v1_server_opt
-    return _ex.annotate(node, "ps_target", (parameter, v1_server_opt(optimizer)))
+    server_opt = optimizer._server_opt() if hasattr(optimizer, "_server_opt") else ("sgd", float(getattr(optimizer, "learning_rate", 0.01)))
+    return _ex.annotate(node, "ps_target", (parameter, server_opt))
 def parameterServerSparsePull_op(parameter, deps_node):                                                    # noqa: N802
     """the rows of `parameter` named by `deps_node`, fetched from the server at run time"""
     out = ops.embedding_lookup(parameter, deps_node)

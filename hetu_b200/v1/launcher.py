@@ -159,8 +159,12 @@ def launch_roles(target, args, join_timeout: Optional[float] = None):
         if i == 0 and int(lc.get("scheduler", 0)) != 0:
             import time
             time.sleep(1.0)                     # the scheduler listens before the others dial it
-    for p in _procs:
-        p.join(join_timeout)
+    import time
+    deadline = None if join_timeout is None else time.time() + float(join_timeout)
+    while any(p.is_alive() for p in _procs) and (deadline is None or time.time() < deadline):
+        if any(p.exitcode not in (None, 0) for p in _procs):      # a role died: the others would wait for it forever
+            break
+        time.sleep(0.2)
     codes = [p.exitcode for p in _procs]
     for p in _procs:
         if p.is_alive():

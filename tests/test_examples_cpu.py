@@ -33,6 +33,7 @@ CASES = [
     ("rec/train_ncf.py --steps 51", "auc"),
     ("nlp/train_transformer.py --steps 21 --batch 16 --seq 5 --vocab 12", "decoded"),
     ("hetero/convert_checkpoint.py examine .", "INCOMPLETE"),
+    ("v1/train_ps_roles.py --steps 12 --port 0", "cosine(w, w*)"),
 ]
 
 
